@@ -1,0 +1,789 @@
+// gdv_device_lib.cuh — device-side function library of the B200 expression engine.
+//
+// Replaces the reference's precompiled-bitcode function library (BASELINE.json
+// north_star: "a device-side function library that replaces the precompiled-bitcode
+// function_registry").  This header is prepended to every kernel the fuser emits and
+// compiled by NVRTC for sm_100a at Projector/Filter::Make(); every function is
+// __forceinline__ so the per-row body becomes straight-line SASS.  It is also compiled
+// by nvcc in __graft_entry__.build() (static_kernels.cu includes it) as a syntax gate.
+//
+// Naming follows the reference library: <base>_<param suffix>..., e.g. add_int32_int32.
+// Semantics decisions (the reference has no source in the mount) are
+// listed in DESIGN.md §"Semantics table"; oracle/gdv_oracle.cc restates each in scalar C++.
+#pragma once
+
+typedef signed char i8;
+typedef short i16;
+typedef int i32;
+typedef long long i64;
+typedef unsigned char u8;
+typedef unsigned short u16;
+typedef unsigned int u32;
+typedef unsigned long long u64;
+typedef float f32;
+typedef double f64;
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+
+#define GDV_FULL 0xffffffffu
+#define GDV_DEV __device__ __forceinline__
+
+// ---- error reporting (ExecutionError, P/include/arrow/status.h:100) -----------------
+#define GDV_ERR_NONE 0
+#define GDV_ERR_DIV_ZERO 1
+struct gdv_ctx {
+  int* err;
+};
+GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
+  if (c->err != nullptr) atomicCAS(c->err, 0, code);
+}
+
+// ---- strings: a view on Arrow bytes plus a lazy ASCII case map ------------------------
+// upper()/lower()/substr()/trim() never materialise: they return a view, and consumers read
+// bytes through gdv_ch().  xf: 0 = as stored, 1 = upper-cased, 2 = lower-cased.
+struct gdv_str {
+  const u8* p;
+  i32 len;
+  u32 xf;
+};
+GDV_DEV u8 gdv_ch(const gdv_str& s, i32 i) {
+  u8 c = s.p[i];
+  if (s.xf == 1u) {
+    if (c >= (u8)'a' && c <= (u8)'z') c = (u8)(c - 32);
+  } else if (s.xf == 2u) {
+    if (c >= (u8)'A' && c <= (u8)'Z') c = (u8)(c + 32);
+  }
+  return c;
+}
+GDV_DEV gdv_str gdv_make_str(const u8* p, i32 len) {
+  gdv_str s;
+  s.p = p;
+  s.len = len;
+  s.xf = 0u;
+  return s;
+}
+// Length in bytes of the UTF-8 glyph that starts with byte c (malformed lead bytes count 1).
+GDV_DEV i32 gdv_glyph_len(u8 c) {
+  if (c < 0x80u) return 1;
+  if ((c & 0xE0u) == 0xC0u) return 2;
+  if ((c & 0xF0u) == 0xE0u) return 3;
+  if ((c & 0xF8u) == 0xF0u) return 4;
+  return 1;
+}
+
+// ---- streaming loads / stores ----------------------------------------------------------
+// Inputs are read once and outputs written once: evict-first policy on both sides.
+template <typename T>
+GDV_DEV T gdv_ld(const void* base, i64 i) {
+  return __ldcs(reinterpret_cast<const T*>(base) + i);
+}
+template <>
+GDV_DEV i128 gdv_ld<i128>(const void* base, i64 i) {
+  const longlong2 v = __ldcs(reinterpret_cast<const longlong2*>(base) + i);
+  return (i128)(((u128)(u64)v.y << 64) | (u128)(u64)v.x);
+}
+template <>
+GDV_DEV i8 gdv_ld<i8>(const void* base, i64 i) {
+  return (i8)__ldcs(reinterpret_cast<const signed char*>(base) + i);
+}
+template <typename T>
+GDV_DEV void gdv_st(void* base, i64 i, T v) {
+  __stcs(reinterpret_cast<T*>(base) + i, v);
+}
+template <>
+GDV_DEV void gdv_st<i128>(void* base, i64 i, i128 v) {
+  longlong2 w;
+  w.x = (i64)(u64)(u128)v;
+  w.y = (i64)(u64)((u128)v >> 64);
+  __stcs(reinterpret_cast<longlong2*>(base) + i, w);
+}
+template <>
+GDV_DEV void gdv_st<i8>(void* base, i64 i, i8 v) {
+  __stcs(reinterpret_cast<signed char*>(base) + i, (signed char)v);
+}
+// Bit `i` (LSB-first, Arrow validity layout, P/include/arrow/util/bit_util.h:158) of a
+// bitmap that starts `sh` bits into byte *p.  p == nullptr means "all set".
+GDV_DEV bool gdv_ldbit(const u8* p, u32 sh, i64 i) {
+  if (p == nullptr) return true;
+  const i64 b = i + (i64)sh;
+  return ((p[b >> 3] >> (u32)(b & 7)) & 1u) != 0u;
+}
+GDV_DEV u32 gdv_lanemask_lt() {
+  u32 m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ---- arithmetic ------------------------------------------------------------------------
+// Integer add/subtract/multiply wrap in two's complement.
+#define GDV_INT_ARITH(T, UT, S)                                                              \
+  GDV_DEV T add_##S##_##S(T a, T b) { return (T)((UT)a + (UT)b); }                           \
+  GDV_DEV T subtract_##S##_##S(T a, T b) { return (T)((UT)a - (UT)b); }                      \
+  GDV_DEV T multiply_##S##_##S(T a, T b) { return (T)((UT)a * (UT)b); }
+GDV_INT_ARITH(i8, u32, int8)
+GDV_INT_ARITH(i16, u32, int16)
+GDV_INT_ARITH(i32, u32, int32)
+GDV_INT_ARITH(i64, u64, int64)
+GDV_INT_ARITH(u8, u32, uint8)
+GDV_INT_ARITH(u16, u32, uint16)
+GDV_INT_ARITH(u32, u32, uint32)
+GDV_INT_ARITH(u64, u64, uint64)
+#define GDV_SDIV(T, UT, S)                                        \
+  GDV_DEV T divide_##S##_##S(gdv_ctx* c, T a, T b) {              \
+    if (b == 0) {                                                 \
+      gdv_set_error(c, GDV_ERR_DIV_ZERO);                         \
+      return 0;                                                   \
+    }                                                             \
+    if (b == (T)-1) return (T)((UT)0 - (UT)a);                    \
+    return (T)(a / b);                                            \
+  }
+#define GDV_UDIV(T, S)                                            \
+  GDV_DEV T divide_##S##_##S(gdv_ctx* c, T a, T b) {              \
+    if (b == 0) {                                                 \
+      gdv_set_error(c, GDV_ERR_DIV_ZERO);                         \
+      return 0;                                                   \
+    }                                                             \
+    return (T)(a / b);                                            \
+  }
+GDV_SDIV(i8, u32, int8)
+GDV_SDIV(i16, u32, int16)
+GDV_SDIV(i32, u32, int32)
+GDV_SDIV(i64, u64, int64)
+GDV_UDIV(u8, uint8)
+GDV_UDIV(u16, uint16)
+GDV_UDIV(u32, uint32)
+GDV_UDIV(u64, uint64)
+// IEEE arithmetic, no contraction (the engine passes --fmad=false to NVRTC).
+#define GDV_FLT_ARITH(T, S)                                       \
+  GDV_DEV T add_##S##_##S(T a, T b) { return a + b; }             \
+  GDV_DEV T subtract_##S##_##S(T a, T b) { return a - b; }        \
+  GDV_DEV T multiply_##S##_##S(T a, T b) { return a * b; }        \
+  GDV_DEV T divide_##S##_##S(gdv_ctx* c, T a, T b) {              \
+    if (b == (T)0) {                                              \
+      gdv_set_error(c, GDV_ERR_DIV_ZERO);                         \
+      return (T)0;                                                \
+    }                                                             \
+    return a / b;                                                 \
+  }
+GDV_FLT_ARITH(f32, float32)
+GDV_FLT_ARITH(f64, float64)
+
+GDV_DEV i32 mod_int64_int32(i64 a, i32 b) {
+  if (b == 0) return (i32)a;
+  if (b == -1) return 0;
+  return (i32)(a % (i64)b);
+}
+GDV_DEV i64 mod_int64_int64(i64 a, i64 b) {
+  if (b == 0) return a;
+  if (b == -1) return 0;
+  return a % b;
+}
+GDV_DEV i32 abs_int32(i32 a) { return a < 0 ? (i32)(0u - (u32)a) : a; }
+GDV_DEV i64 abs_int64(i64 a) { return a < 0 ? (i64)(0ull - (u64)a) : a; }
+GDV_DEV f32 abs_float32(f32 a) { return fabsf(a); }
+GDV_DEV f64 abs_float64(f64 a) { return fabs(a); }
+GDV_DEV i32 negative_int32(i32 a) { return (i32)(0u - (u32)a); }
+GDV_DEV i64 negative_int64(i64 a) { return (i64)(0ull - (u64)a); }
+GDV_DEV f32 negative_float32(f32 a) { return -a; }
+GDV_DEV f64 negative_float64(f64 a) { return -a; }
+GDV_DEV f64 sqrt_float64(f64 a) { return sqrt(a); }
+#define GDV_BITWISE(T, S)                                                   \
+  GDV_DEV T bitwise_and_##S##_##S(T a, T b) { return a & b; }               \
+  GDV_DEV T bitwise_or_##S##_##S(T a, T b) { return a | b; }                \
+  GDV_DEV T bitwise_xor_##S##_##S(T a, T b) { return a ^ b; }               \
+  GDV_DEV T bitwise_not_##S(T a) { return ~a; }
+GDV_BITWISE(i32, int32)
+GDV_BITWISE(i64, int64)
+
+// ---- comparisons -----------------------------------------------------------------------
+#define GDV_RELOP(T, S)                                                               \
+  GDV_DEV bool equal_##S##_##S(T a, T b) { return a == b; }                           \
+  GDV_DEV bool not_equal_##S##_##S(T a, T b) { return a != b; }                       \
+  GDV_DEV bool less_than_##S##_##S(T a, T b) { return a < b; }                        \
+  GDV_DEV bool less_than_or_equal_to_##S##_##S(T a, T b) { return a <= b; }           \
+  GDV_DEV bool greater_than_##S##_##S(T a, T b) { return a > b; }                     \
+  GDV_DEV bool greater_than_or_equal_to_##S##_##S(T a, T b) { return a >= b; }
+GDV_RELOP(i8, int8)
+GDV_RELOP(i16, int16)
+GDV_RELOP(i32, int32)
+GDV_RELOP(i64, int64)
+GDV_RELOP(u8, uint8)
+GDV_RELOP(u16, uint16)
+GDV_RELOP(u32, uint32)
+GDV_RELOP(u64, uint64)
+GDV_RELOP(f32, float32)
+GDV_RELOP(f64, float64)
+GDV_RELOP(i32, date32)
+GDV_RELOP(i64, date64)
+GDV_RELOP(i64, timestamp)
+GDV_RELOP(i32, time32)
+GDV_DEV bool equal_boolean_boolean(bool a, bool b) { return a == b; }
+GDV_DEV bool not_equal_boolean_boolean(bool a, bool b) { return a != b; }
+GDV_DEV bool not_boolean(bool a) { return !a; }
+
+// Lexicographic byte comparison, shorter string first on a common prefix.
+GDV_DEV i32 gdv_mem_compare(const gdv_str& a, const gdv_str& b) {
+  const i32 n = a.len < b.len ? a.len : b.len;
+  for (i32 i = 0; i < n; ++i) {
+    const u8 x = gdv_ch(a, i), y = gdv_ch(b, i);
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return a.len == b.len ? 0 : (a.len < b.len ? -1 : 1);
+}
+#define GDV_STR_RELOP(S)                                                                           \
+  GDV_DEV bool equal_##S##_##S(gdv_str a, gdv_str b) {                                             \
+    return a.len == b.len && gdv_mem_compare(a, b) == 0;                                           \
+  }                                                                                                \
+  GDV_DEV bool not_equal_##S##_##S(gdv_str a, gdv_str b) {                                         \
+    return !(a.len == b.len && gdv_mem_compare(a, b) == 0);                                        \
+  }                                                                                                \
+  GDV_DEV bool less_than_##S##_##S(gdv_str a, gdv_str b) { return gdv_mem_compare(a, b) < 0; }     \
+  GDV_DEV bool less_than_or_equal_to_##S##_##S(gdv_str a, gdv_str b) {                             \
+    return gdv_mem_compare(a, b) <= 0;                                                             \
+  }                                                                                                \
+  GDV_DEV bool greater_than_##S##_##S(gdv_str a, gdv_str b) { return gdv_mem_compare(a, b) > 0; }  \
+  GDV_DEV bool greater_than_or_equal_to_##S##_##S(gdv_str a, gdv_str b) {                          \
+    return gdv_mem_compare(a, b) >= 0;                                                             \
+  }
+GDV_STR_RELOP(utf8)
+GDV_STR_RELOP(binary)
+
+// ---- null tests (NullMode::kNever: receive value + validity) -----------------------------
+#define GDV_NULLTEST(T, S)                                                   \
+  GDV_DEV bool isnull_##S(T, bool ok) { return !ok; }                        \
+  GDV_DEV bool isnotnull_##S(T, bool ok) { return ok; }
+GDV_NULLTEST(i8, int8)
+GDV_NULLTEST(i16, int16)
+GDV_NULLTEST(i32, int32)
+GDV_NULLTEST(i64, int64)
+GDV_NULLTEST(u8, uint8)
+GDV_NULLTEST(u16, uint16)
+GDV_NULLTEST(u32, uint32)
+GDV_NULLTEST(u64, uint64)
+GDV_NULLTEST(f32, float32)
+GDV_NULLTEST(f64, float64)
+GDV_NULLTEST(i32, date32)
+GDV_NULLTEST(i64, date64)
+GDV_NULLTEST(i64, timestamp)
+GDV_NULLTEST(i32, time32)
+GDV_NULLTEST(bool, boolean)
+GDV_NULLTEST(i128, decimal128)
+GDV_NULLTEST(gdv_str, utf8)
+GDV_NULLTEST(gdv_str, binary)
+GDV_DEV bool istrue_boolean(bool v, bool ok) { return ok && v; }
+GDV_DEV bool isfalse_boolean(bool v, bool ok) { return ok && !v; }
+GDV_DEV bool isnottrue_boolean(bool v, bool ok) { return !(ok && v); }
+GDV_DEV bool isnotfalse_boolean(bool v, bool ok) { return !(ok && !v); }
+#define GDV_DISTINCT(T, S)                                                                   \
+  GDV_DEV bool is_distinct_from_##S##_##S(T a, bool aok, T b, bool bok) {                    \
+    if (aok != bok) return true;                                                             \
+    if (!aok) return false;                                                                  \
+    return a != b;                                                                           \
+  }                                                                                          \
+  GDV_DEV bool is_not_distinct_from_##S##_##S(T a, bool aok, T b, bool bok) {                \
+    return !is_distinct_from_##S##_##S(a, aok, b, bok);                                      \
+  }
+GDV_DISTINCT(i8, int8)
+GDV_DISTINCT(i16, int16)
+GDV_DISTINCT(i32, int32)
+GDV_DISTINCT(i64, int64)
+GDV_DISTINCT(u8, uint8)
+GDV_DISTINCT(u16, uint16)
+GDV_DISTINCT(u32, uint32)
+GDV_DISTINCT(u64, uint64)
+GDV_DISTINCT(f32, float32)
+GDV_DISTINCT(f64, float64)
+GDV_DISTINCT(i32, date32)
+GDV_DISTINCT(i64, date64)
+GDV_DISTINCT(i64, timestamp)
+GDV_DISTINCT(i32, time32)
+GDV_DISTINCT(bool, boolean)
+
+// ---- casts -----------------------------------------------------------------------------
+GDV_DEV i64 castBIGINT_int32(i32 a) { return (i64)a; }
+GDV_DEV i32 castINT_int64(i64 a) { return (i32)(u32)(u64)a; }
+GDV_DEV f32 castFLOAT4_int32(i32 a) { return (f32)a; }
+GDV_DEV f32 castFLOAT4_int64(i64 a) { return (f32)a; }
+GDV_DEV f32 castFLOAT4_float64(f64 a) { return (f32)a; }
+GDV_DEV f64 castFLOAT8_int32(i32 a) { return (f64)a; }
+GDV_DEV f64 castFLOAT8_int64(i64 a) { return (f64)a; }
+GDV_DEV f64 castFLOAT8_float32(f32 a) { return (f64)a; }
+GDV_DEV i64 castDATE_int64(i64 a) { return a; }
+GDV_DEV i64 castTIMESTAMP_int64(i64 a) { return a; }
+GDV_DEV i64 castTIMESTAMP_date64(i64 a) { return a; }
+GDV_DEV i64 castBIGINT_date64(i64 a) { return a; }
+GDV_DEV i64 castBIGINT_timestamp(i64 a) { return a; }
+GDV_DEV i32 castINT_date32(i32 a) { return a; }
+GDV_DEV i32 castDATE_int32(i32 a) { return a; }
+// floor-divide helper for negative epochs
+GDV_DEV i64 gdv_floordiv(i64 a, i64 b) {
+  i64 q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+GDV_DEV i64 castDATE_timestamp(i64 ms) { return gdv_floordiv(ms, 86400000ll) * 86400000ll; }
+
+// ---- date / time extraction (proleptic Gregorian, days-from-civil inverse) ---------------
+struct gdv_ymd {
+  i64 y;
+  i32 m, d, doy;
+};
+GDV_DEV gdv_ymd gdv_civil_from_days(i64 z) {
+  z += 719468;
+  const i64 era = gdv_floordiv(z, 146097);
+  const i64 doe = z - era * 146097;
+  const i64 yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const i64 y = yoe + era * 400;
+  const i64 doy_mar = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const i64 mp = (5 * doy_mar + 2) / 153;
+  gdv_ymd r;
+  r.d = (i32)(doy_mar - (153 * mp + 2) / 5 + 1);
+  r.m = (i32)(mp < 10 ? mp + 3 : mp - 9);
+  r.y = y + (r.m <= 2 ? 1 : 0);
+  const bool leap = (r.y % 4 == 0) && ((r.y % 100 != 0) || (r.y % 400 == 0));
+  const i32 cum[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+  r.doy = cum[r.m - 1] + r.d + ((leap && r.m > 2) ? 1 : 0);
+  return r;
+}
+#define GDV_EXTRACT_MS(S)                                                                       \
+  GDV_DEV i64 extractYear_##S(i64 ms) {                                                         \
+    return gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).y;                                 \
+  }                                                                                             \
+  GDV_DEV i64 extractMonth_##S(i64 ms) {                                                        \
+    return gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).m;                                 \
+  }                                                                                             \
+  GDV_DEV i64 extractDay_##S(i64 ms) {                                                          \
+    return gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).d;                                 \
+  }                                                                                             \
+  GDV_DEV i64 extractDoy_##S(i64 ms) {                                                          \
+    return gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).doy;                               \
+  }                                                                                             \
+  GDV_DEV i64 extractQuarter_##S(i64 ms) {                                                      \
+    return (gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).m - 1) / 3 + 1;                   \
+  }                                                                                             \
+  GDV_DEV i64 extractDow_##S(i64 ms) {                                                          \
+    const i64 days = gdv_floordiv(ms, 86400000ll);                                              \
+    i64 w = (days + 4) % 7; /* 1970-01-01 was a Thursday; Sunday = 1 */                         \
+    if (w < 0) w += 7;                                                                          \
+    return w + 1;                                                                               \
+  }                                                                                             \
+  GDV_DEV i64 extractHour_##S(i64 ms) {                                                         \
+    return (ms - gdv_floordiv(ms, 86400000ll) * 86400000ll) / 3600000ll;                        \
+  }                                                                                             \
+  GDV_DEV i64 extractMinute_##S(i64 ms) {                                                       \
+    return ((ms - gdv_floordiv(ms, 86400000ll) * 86400000ll) / 60000ll) % 60;                   \
+  }                                                                                             \
+  GDV_DEV i64 extractSecond_##S(i64 ms) {                                                       \
+    return ((ms - gdv_floordiv(ms, 86400000ll) * 86400000ll) / 1000ll) % 60;                    \
+  }                                                                                             \
+  GDV_DEV i64 extractEpoch_##S(i64 ms) { return gdv_floordiv(ms, 1000ll); }
+GDV_EXTRACT_MS(date64)
+GDV_EXTRACT_MS(timestamp)
+GDV_DEV i64 extractYear_date32(i32 d) { return gdv_civil_from_days((i64)d).y; }
+GDV_DEV i64 extractMonth_date32(i32 d) { return gdv_civil_from_days((i64)d).m; }
+GDV_DEV i64 extractDay_date32(i32 d) { return gdv_civil_from_days((i64)d).d; }
+
+// ---- decimal128 ------------------------------------------------------------------------
+// Values are two's-complement 128-bit integers scaled by 10^scale (Arrow decimal128).
+// Rounding on scale reduction is half away from zero; a result that does not fit 38
+// digits yields 0 (the reference ignores the overflow flag of its decimal ops).
+GDV_DEV u128 gdv_pow10_u128(i32 e) {  // 0 <= e <= 38
+  const u64 p19 = 10000000000000000000ull;
+  const u64 t[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
+                     100000000ull, 1000000000ull, 10000000000ull, 100000000000ull,
+                     1000000000000ull, 10000000000000ull, 100000000000000ull,
+                     1000000000000000ull, 10000000000000000ull, 100000000000000000ull,
+                     1000000000000000000ull, 10000000000000000000ull};
+  if (e <= 19) return (u128)t[e];
+  return (u128)t[e - 19] * (u128)p19;
+}
+// 256-bit magnitude as four 64-bit limbs, little-endian.
+struct gdv_u256 {
+  u64 w[4];
+};
+GDV_DEV gdv_u256 gdv_mul_u128(u128 a, u128 b) {
+  const u64 a0 = (u64)a, a1 = (u64)(a >> 64), b0 = (u64)b, b1 = (u64)(b >> 64);
+  const u128 p00 = (u128)a0 * b0, p01 = (u128)a0 * b1, p10 = (u128)a1 * b0, p11 = (u128)a1 * b1;
+  gdv_u256 r;
+  r.w[0] = (u64)p00;
+  u128 mid = (p00 >> 64) + (u128)(u64)p01 + (u128)(u64)p10;
+  r.w[1] = (u64)mid;
+  u128 hi = (mid >> 64) + (p01 >> 64) + (p10 >> 64) + (u128)(u64)p11;
+  r.w[2] = (u64)hi;
+  r.w[3] = (u64)((hi >> 64) + (p11 >> 64));
+  return r;
+}
+GDV_DEV gdv_u256 gdv_add_u256(const gdv_u256& a, const gdv_u256& b) {
+  gdv_u256 r;
+  u128 c = 0;
+  for (int i = 0; i < 4; ++i) {
+    c += (u128)a.w[i] + (u128)b.w[i];
+    r.w[i] = (u64)c;
+    c >>= 64;
+  }
+  return r;
+}
+// a - b, requires a >= b
+GDV_DEV gdv_u256 gdv_sub_u256(const gdv_u256& a, const gdv_u256& b) {
+  gdv_u256 r;
+  u64 borrow = 0;
+  for (int i = 0; i < 4; ++i) {
+    const u64 bi = b.w[i];
+    const u64 d = a.w[i] - bi - borrow;
+    borrow = (a.w[i] < bi || (a.w[i] == bi && borrow)) ? 1ull : 0ull;
+    r.w[i] = d;
+  }
+  return r;
+}
+GDV_DEV int gdv_cmp_u256(const gdv_u256& a, const gdv_u256& b) {
+  for (int i = 3; i >= 0; --i) {
+    if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1;
+  }
+  return 0;
+}
+// Divide a 256-bit magnitude by a 64-bit divisor in place; returns the remainder.
+GDV_DEV u64 gdv_divmod_u256_u64(gdv_u256& a, u64 d) {
+  u128 rem = 0;
+  for (int i = 3; i >= 0; --i) {
+    const u128 cur = (rem << 64) | (u128)a.w[i];
+    a.w[i] = (u64)(cur / d);
+    rem = cur % d;
+  }
+  return (u64)rem;
+}
+// round-half-away(mag / 10^e), 0 <= e <= 38.
+GDV_DEV gdv_u256 gdv_div_pow10_round(gdv_u256 mag, i32 e) {
+  if (e == 0) return mag;
+  // add half of the divisor first, then truncate
+  const u128 half = gdv_pow10_u128(e) / 2u;  // 10^e is even for e >= 1
+  gdv_u256 h;
+  h.w[0] = (u64)half;
+  h.w[1] = (u64)(half >> 64);
+  h.w[2] = 0;
+  h.w[3] = 0;
+  mag = gdv_add_u256(mag, h);
+  i32 left = e;
+  while (left > 0) {
+    const i32 step = left > 19 ? 19 : left;
+    gdv_divmod_u256_u64(mag, (u64)gdv_pow10_u128(step));
+    left -= step;
+  }
+  return mag;
+}
+// Signed result from a 256-bit magnitude; 0 when it needs more than 38 digits.
+GDV_DEV i128 gdv_fit_decimal(const gdv_u256& mag, bool neg) {
+  if (mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+  const u128 m = ((u128)mag.w[1] << 64) | (u128)mag.w[0];
+  if (m >= gdv_pow10_u128(38)) return (i128)0;
+  return neg ? (i128)(~m + 1) : (i128)m;
+}
+GDV_DEV u128 gdv_abs_u128(i128 v) { return v < 0 ? (~(u128)v + 1) : (u128)v; }
+GDV_DEV gdv_u256 gdv_u256_from(u128 v) {
+  gdv_u256 r;
+  r.w[0] = (u64)v;
+  r.w[1] = (u64)(v >> 64);
+  r.w[2] = 0;
+  r.w[3] = 0;
+  return r;
+}
+
+// x (scale xs) + sign * y (scale ys) -> scale os.  Exact in 256 bits, then rounded.
+GDV_DEV i128 gdv_decimal_addsub(i128 x, i32 xs, i128 y, i32 ys, i32 os, bool subtract) {
+  const i32 ms = xs > ys ? xs : ys;
+  if (os == ms && xs == ys) {
+    // fast path: no rescale (covers TPC-H Q1); overflow past 38 digits -> 0
+    const i128 r = subtract ? (i128)((u128)x - (u128)y) : (i128)((u128)x + (u128)y);
+    const u128 m = gdv_abs_u128(r);
+    return m >= gdv_pow10_u128(38) ? (i128)0 : r;
+  }
+  const bool xneg = x < 0;
+  bool yneg = y < 0;
+  if (subtract) yneg = !yneg;
+  const gdv_u256 xm = gdv_mul_u128(gdv_abs_u128(x), gdv_pow10_u128(ms - xs));
+  const gdv_u256 ym = gdv_mul_u128(gdv_abs_u128(y), gdv_pow10_u128(ms - ys));
+  gdv_u256 mag;
+  bool neg;
+  if (xneg == yneg) {
+    mag = gdv_add_u256(xm, ym);
+    neg = xneg;
+  } else if (gdv_cmp_u256(xm, ym) >= 0) {
+    mag = gdv_sub_u256(xm, ym);
+    neg = xneg;
+  } else {
+    mag = gdv_sub_u256(ym, xm);
+    neg = yneg;
+  }
+  if (os < ms) mag = gdv_div_pow10_round(mag, ms - os);
+  // os > ms never happens with the reference's result-type rule; scale up if a caller asks
+  if (os > ms) {
+    if (mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+    mag = gdv_mul_u128(((u128)mag.w[1] << 64) | mag.w[0], gdv_pow10_u128(os - ms));
+  }
+  if (mag.w[0] == 0 && mag.w[1] == 0 && mag.w[2] == 0 && mag.w[3] == 0) neg = false;
+  return gdv_fit_decimal(mag, neg);
+}
+GDV_DEV i128 add_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys, i32 op,
+                                       i32 os) {
+  return gdv_decimal_addsub(x, xs, y, ys, os, false);
+}
+GDV_DEV i128 subtract_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys,
+                                            i32 op, i32 os) {
+  return gdv_decimal_addsub(x, xs, y, ys, os, true);
+}
+GDV_DEV i128 multiply_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys,
+                                            i32 op, i32 os) {
+  const bool neg = (x < 0) != (y < 0);
+  const i32 delta = xs + ys - os;
+  if (xp + yp <= 38 && delta == 0) {
+    // |x| < 10^xp, |y| < 10^yp  =>  |x*y| < 10^38 < 2^127: one 128-bit multiply is exact
+    return (i128)((u128)x * (u128)y);
+  }
+  gdv_u256 mag = gdv_mul_u128(gdv_abs_u128(x), gdv_abs_u128(y));
+  if (delta > 0) mag = gdv_div_pow10_round(mag, delta > 38 ? 38 : delta);
+  if (delta < 0) {
+    if (mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+    mag = gdv_mul_u128(((u128)mag.w[1] << 64) | mag.w[0], gdv_pow10_u128(-delta));
+  }
+  const bool zero = mag.w[0] == 0 && mag.w[1] == 0 && mag.w[2] == 0 && mag.w[3] == 0;
+  return gdv_fit_decimal(mag, neg && !zero);
+}
+GDV_DEV i128 abs_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) {
+  return x < 0 ? (i128)(~(u128)x + 1) : x;
+}
+GDV_DEV i128 negative_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) {
+  return (i128)(~(u128)x + 1);
+}
+// Compare after bringing both sides to the larger scale (exact, 256-bit).
+GDV_DEV i32 gdv_decimal_compare(i128 x, i32 xs, i128 y, i32 ys) {
+  if (xs == ys) return x < y ? -1 : (x > y ? 1 : 0);
+  const bool xneg = x < 0, yneg = y < 0;
+  if (xneg != yneg) return xneg ? -1 : 1;
+  const i32 ms = xs > ys ? xs : ys;
+  const gdv_u256 xm = gdv_mul_u128(gdv_abs_u128(x), gdv_pow10_u128(ms - xs));
+  const gdv_u256 ym = gdv_mul_u128(gdv_abs_u128(y), gdv_pow10_u128(ms - ys));
+  const int c = gdv_cmp_u256(xm, ym);
+  return xneg ? -c : c;
+}
+#define GDV_DEC_RELOP(NAME, OP)                                                                  \
+  GDV_DEV bool NAME##_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys) {    \
+    return gdv_decimal_compare(x, xs, y, ys) OP 0;                                               \
+  }
+GDV_DEC_RELOP(equal, ==)
+GDV_DEC_RELOP(not_equal, !=)
+GDV_DEC_RELOP(less_than, <)
+GDV_DEC_RELOP(less_than_or_equal_to, <=)
+GDV_DEC_RELOP(greater_than, >)
+GDV_DEC_RELOP(greater_than_or_equal_to, >=)
+// Rescale x from scale xs to (op, os): round half away; does not fit op digits -> 0.
+GDV_DEV i128 castDECIMAL_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) {
+  const bool neg = x < 0;
+  gdv_u256 mag = gdv_u256_from(gdv_abs_u128(x));
+  if (os > xs) mag = gdv_mul_u128(gdv_abs_u128(x), gdv_pow10_u128(os - xs));
+  if (os < xs) mag = gdv_div_pow10_round(mag, xs - os);
+  if (mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+  const u128 m = ((u128)mag.w[1] << 64) | (u128)mag.w[0];
+  if (m >= gdv_pow10_u128(op)) return (i128)0;
+  return (neg && m != 0) ? (i128)(~m + 1) : (i128)m;
+}
+GDV_DEV i128 castDECIMAL_int64(i64 v, i32 op, i32 os) {
+  return castDECIMAL_decimal128((i128)v, 19, 0, op, os);
+}
+GDV_DEV i128 castDECIMAL_int32(i32 v, i32 op, i32 os) {
+  return castDECIMAL_decimal128((i128)v, 10, 0, op, os);
+}
+// decimal -> int64: round half away at scale 0, then two's-complement truncation to 64 bits.
+GDV_DEV i64 castBIGINT_decimal128(i128 x, i32 xp, i32 xs) {
+  const i128 r = castDECIMAL_decimal128(x, xp, xs, 38, 0);
+  return (i64)(u64)(u128)r;
+}
+// decimal -> double: (hi * 2^64 + lo) / 10^scale with the IEEE operations written out,
+// so the oracle computes the identical sequence.
+GDV_DEV f64 castFLOAT8_decimal128(i128 x, i32 xp, i32 xs) {
+  const bool neg = x < 0;
+  const u128 m = gdv_abs_u128(x);
+  const f64 hi = (f64)(u64)(m >> 64), lo = (f64)(u64)m;
+  f64 v = hi * 18446744073709551616.0 + lo;
+  f64 p = 1.0;
+  for (i32 i = 0; i < xs; ++i) p = p * 10.0;
+  v = v / p;
+  return neg ? -v : v;
+}
+
+// ---- strings ---------------------------------------------------------------------------
+GDV_DEV gdv_str upper_utf8(gdv_str s) {
+  s.xf = 1u;
+  return s;
+}
+GDV_DEV gdv_str lower_utf8(gdv_str s) {
+  s.xf = 2u;
+  return s;
+}
+GDV_DEV i32 octet_length_utf8(gdv_str s) { return s.len; }
+GDV_DEV i32 octet_length_binary(gdv_str s) { return s.len; }
+GDV_DEV i32 bit_length_utf8(gdv_str s) { return s.len * 8; }
+GDV_DEV i32 bit_length_binary(gdv_str s) { return s.len * 8; }
+GDV_DEV i32 char_length_utf8(gdv_str s) {
+  i32 n = 0;
+  for (i32 i = 0; i < s.len; i += gdv_glyph_len(s.p[i])) ++n;
+  return n;
+}
+// 1-based, counts UTF-8 glyphs; offset 0 behaves as 1; negative offsets count from the end.
+GDV_DEV gdv_str substr_utf8_int64_int64(gdv_str s, i64 offset, i64 length) {
+  gdv_str r = s;
+  if (length <= 0 || s.len <= 0) {
+    r.len = 0;
+    return r;
+  }
+  i64 from_glyph;
+  if (offset > 0) {
+    from_glyph = offset - 1;
+  } else if (offset < 0) {
+    from_glyph = (i64)char_length_utf8(s) + offset;
+    if (from_glyph < 0) {
+      r.len = 0;
+      return r;
+    }
+  } else {
+    from_glyph = 0;
+  }
+  i32 pos = 0;
+  i64 g = 0;
+  while (pos < s.len && g < from_glyph) {
+    pos += gdv_glyph_len(s.p[pos]);
+    ++g;
+  }
+  if (pos >= s.len) {
+    r.len = 0;
+    return r;
+  }
+  const i32 start = pos;
+  i64 taken = 0;
+  while (pos < s.len && taken < length) {
+    pos += gdv_glyph_len(s.p[pos]);
+    ++taken;
+  }
+  if (pos > s.len) pos = s.len;
+  r.p = s.p + start;
+  r.len = pos - start;
+  return r;
+}
+GDV_DEV gdv_str substr_utf8_int64(gdv_str s, i64 offset) {
+  return substr_utf8_int64_int64(s, offset, (i64)s.len);
+}
+GDV_DEV bool starts_with_utf8_utf8(gdv_str s, gdv_str pre) {
+  if (pre.len > s.len) return false;
+  for (i32 i = 0; i < pre.len; ++i)
+    if (gdv_ch(s, i) != gdv_ch(pre, i)) return false;
+  return true;
+}
+GDV_DEV bool ends_with_utf8_utf8(gdv_str s, gdv_str suf) {
+  if (suf.len > s.len) return false;
+  const i32 d = s.len - suf.len;
+  for (i32 i = 0; i < suf.len; ++i)
+    if (gdv_ch(s, d + i) != gdv_ch(suf, i)) return false;
+  return true;
+}
+GDV_DEV bool is_substr_utf8_utf8(gdv_str s, gdv_str sub) {
+  if (sub.len == 0) return true;
+  for (i32 i = 0; i + sub.len <= s.len; ++i) {
+    i32 j = 0;
+    while (j < sub.len && gdv_ch(s, i + j) == gdv_ch(sub, j)) ++j;
+    if (j == sub.len) return true;
+  }
+  return false;
+}
+GDV_DEV gdv_str ltrim_utf8(gdv_str s) {
+  while (s.len > 0 && s.p[0] == (u8)' ') {
+    ++s.p;
+    --s.len;
+  }
+  return s;
+}
+GDV_DEV gdv_str rtrim_utf8(gdv_str s) {
+  while (s.len > 0 && s.p[s.len - 1] == (u8)' ') --s.len;
+  return s;
+}
+GDV_DEV gdv_str btrim_utf8(gdv_str s) { return rtrim_utf8(ltrim_utf8(s)); }
+
+// SQL LIKE over a pattern tokenised at Make(): each token is (kind << 8) | byte with
+// kind 0 = literal byte, 1 = '_' (exactly one glyph), 2 = '%' (any run of glyphs).
+// Iterative matcher with single-level backtracking to the last '%'.
+GDV_DEV bool gdv_like_match(const gdv_str& s, const u16* pat, i32 m) {
+  i32 i = 0, j = 0, star_j = -1, star_i = 0;
+  const i32 n = s.len;
+  while (i < n) {
+    if (j < m) {
+      const u32 tok = pat[j];
+      const u32 kind = tok >> 8;
+      if (kind == 2u) {
+        star_j = j++;
+        star_i = i;
+        continue;
+      }
+      if (kind == 1u) {
+        i += gdv_glyph_len(s.p[i]);
+        if (i > n) i = n;
+        ++j;
+        continue;
+      }
+      if (gdv_ch(s, i) == (u8)(tok & 0xffu)) {
+        ++i;
+        ++j;
+        continue;
+      }
+    }
+    if (star_j < 0) return false;
+    star_i += gdv_glyph_len(s.p[star_i]);
+    if (star_i > n) return false;
+    i = star_i;
+    j = star_j + 1;
+  }
+  while (j < m && (pat[j] >> 8) == 2u) ++j;
+  return j == m;
+}
+
+// ---- ordered stream compaction: decoupled look-back over CTA tiles ------------------------
+// One 64-bit descriptor per tile: flag (2 bits) | count (62 bits).  A tile publishes its own
+// count (AGGREGATE), looks back over its predecessors until it finds an INCLUSIVE prefix,
+// then publishes its own inclusive prefix.  Tiles are handed out by a global ticket so every
+// predecessor of a running tile has already started (no dependence on CTA scheduling order).
+#define GDV_TILE_INVALID 0ull
+#define GDV_TILE_AGGREGATE 1ull
+#define GDV_TILE_INCLUSIVE 2ull
+#define GDV_TILE_VALUE_MASK 0x3fffffffffffffffull
+GDV_DEV u64 gdv_ld_relaxed(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+GDV_DEV void gdv_st_relaxed(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Called by all 32 lanes of one warp.  Returns the exclusive prefix of `tile` (sum of the
+// counts of tiles 0..tile-1) in every lane and publishes this tile's inclusive prefix.
+GDV_DEV u64 gdv_tile_exclusive_prefix(u64* state, i64 tile, u64 count, u32 lane) {
+  if (tile == 0) {
+    if (lane == 0) gdv_st_relaxed(&state[0], (GDV_TILE_INCLUSIVE << 62) | count);
+    return 0ull;
+  }
+  if (lane == 0) gdv_st_relaxed(&state[tile], (GDV_TILE_AGGREGATE << 62) | count);
+  u64 excl = 0ull;
+  i64 look = tile - 1;
+  while (true) {
+    const i64 idx = look - (i64)lane;
+    u64 d = (GDV_TILE_INCLUSIVE << 62);  // tiles before 0 contribute an inclusive prefix of 0
+    if (idx >= 0) d = gdv_ld_relaxed(&state[idx]);
+    while (__any_sync(GDV_FULL, (d >> 62) == GDV_TILE_INVALID)) {
+      if (idx >= 0 && (d >> 62) == GDV_TILE_INVALID) d = gdv_ld_relaxed(&state[idx]);
+    }
+    const u32 incl = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INCLUSIVE);
+    const u32 first = incl != 0u ? (u32)(__ffs((int)incl) - 1) : 32u;
+    u64 contrib = (lane <= first) ? (d & GDV_TILE_VALUE_MASK) : 0ull;
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(GDV_FULL, contrib, o);
+    excl += contrib;
+    if (incl != 0u) break;
+    look -= 32;
+  }
+  if (lane == 0) gdv_st_relaxed(&state[tile], (GDV_TILE_INCLUSIVE << 62) | (excl + count));
+  return excl;
+}

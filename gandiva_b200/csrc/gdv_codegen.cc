@@ -1,0 +1,777 @@
+#include "gdv_codegen.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <map>
+#include <sstream>
+
+#include "gdv_registry.h"
+
+namespace gdv {
+
+// ======================================================================================
+// Validation (replaces the reference's expression validator)
+// ======================================================================================
+namespace {
+
+Status VErr(const std::string& m) { return Status::Make(GDV_EXPRESSION_VALIDATION_ERROR, m); }
+
+bool IsSupportedType(const DataType& t) {
+  switch (t.id) {
+    case GDV_TYPE_BOOL: case GDV_TYPE_UINT8: case GDV_TYPE_INT8: case GDV_TYPE_UINT16:
+    case GDV_TYPE_INT16: case GDV_TYPE_UINT32: case GDV_TYPE_INT32: case GDV_TYPE_UINT64:
+    case GDV_TYPE_INT64: case GDV_TYPE_FLOAT: case GDV_TYPE_DOUBLE: case GDV_TYPE_STRING:
+    case GDV_TYPE_BINARY: case GDV_TYPE_DATE32: case GDV_TYPE_DATE64: case GDV_TYPE_DECIMAL128:
+      return true;
+    case GDV_TYPE_TIMESTAMP: case GDV_TYPE_TIME32:
+      return t.precision == 1;  // milliseconds, as in the reference
+    default: return false;
+  }
+}
+
+Status ValidateNode(const Schema& schema, const Node& node) {
+  switch (node.kind()) {
+    case NodeKind::kField: {
+      const auto& f = static_cast<const FieldNode&>(node);
+      const int idx = schema.index_of(f.name());
+      if (idx < 0) return VErr("Field " + f.name() + " not in schema");
+      if (schema.fields()[idx].type != f.return_type())
+        return VErr("Field definition in schema " + schema.fields()[idx].name + ": " +
+                    schema.fields()[idx].type.ToString() +
+                    " different from field in expression " + f.ToString());
+      if (!IsSupportedType(f.return_type()))
+        return VErr("Field " + f.name() + " has unsupported data type " +
+                    f.return_type().ToString());
+      return Status::OK();
+    }
+    case NodeKind::kLiteral: {
+      if (!IsSupportedType(node.return_type()))
+        return VErr("Value " + node.ToString() + " has unsupported data type " +
+                    node.return_type().ToString());
+      return Status::OK();
+    }
+    case NodeKind::kFunction: {
+      const auto& fn = static_cast<const FunctionNode&>(node);
+      std::vector<DataType> params;
+      for (const auto& c : fn.children()) {
+        Status s = ValidateNode(schema, *c);
+        if (!s.ok()) return s;
+        params.push_back(c->return_type());
+      }
+      const FunctionDef* def = Registry::Get().Lookup(fn.name(), params);
+      if (def == nullptr) {
+        std::string sig = fn.return_type().ToString() + " " + fn.name() + "(";
+        for (size_t i = 0; i < params.size(); ++i)
+          sig += (i ? ", " : "") + params[i].ToString();
+        sig += ")";
+        return VErr("Function " + sig + " not supported yet. ");
+      }
+      if (def->ret.id != fn.return_type().id ||
+          (def->ret.id != GDV_TYPE_DECIMAL128 && def->ret != fn.return_type()))
+        return VErr("Function " + def->signature() + " not supported yet: return type " +
+                    fn.return_type().ToString() + " does not match");
+      if (def->flags & kLikeHolder) {
+        for (size_t i = 1; i < fn.children().size(); ++i) {
+          const Node& c = *fn.children()[i];
+          if (c.kind() != NodeKind::kLiteral || static_cast<const LiteralNode&>(c).is_null())
+            return VErr("'like' function requires a literal as the second parameter");
+        }
+        if (fn.children().size() == 3 &&
+            static_cast<const LiteralNode&>(*fn.children()[2]).bytes().size() != 1)
+          return VErr("The length of escape char in 'like' function must be 1");
+      }
+      return Status::OK();
+    }
+    case NodeKind::kIf: {
+      const auto& n = static_cast<const IfNode&>(node);
+      for (const NodePtr* c : {&n.condition(), &n.then_node(), &n.else_node()}) {
+        Status s = ValidateNode(schema, **c);
+        if (!s.ok()) return s;
+      }
+      if (n.condition()->return_type() != boolean())
+        return VErr("condition must be of boolean type, found type " +
+                    n.condition()->return_type().ToString());
+      if (n.then_node()->return_type() != n.return_type())
+        return VErr("return type of if " + n.return_type().ToString() + " and then " +
+                    n.then_node()->return_type().ToString() + " not matching.");
+      if (n.else_node()->return_type() != n.return_type())
+        return VErr("return type of if " + n.return_type().ToString() + " and else " +
+                    n.else_node()->return_type().ToString() + " not matching.");
+      return Status::OK();
+    }
+    case NodeKind::kBoolean: {
+      const auto& n = static_cast<const BooleanNode&>(node);
+      if (n.children().size() < 2)
+        return VErr("Boolean expression has " + std::to_string(n.children().size()) +
+                    " children, expected at least two");
+      for (const auto& c : n.children()) {
+        Status s = ValidateNode(schema, *c);
+        if (!s.ok()) return s;
+        if (c->return_type() != boolean())
+          return VErr("Boolean expression has a child with return type " +
+                      c->return_type().ToString() + ", expected return type boolean");
+      }
+      return Status::OK();
+    }
+    case NodeKind::kIn: {
+      const auto& n = static_cast<const InNode&>(node);
+      Status s = ValidateNode(schema, *n.child());
+      if (!s.ok()) return s;
+      if (n.child()->return_type() != n.value_type())
+        return VErr("Evaluation expression for IN clause returns " +
+                    n.child()->return_type().ToString() + " values are of type" +
+                    n.value_type().ToString());
+      const int id = n.value_type().id;
+      const bool ok = n.value_type().is_varlen() || id == GDV_TYPE_INT32 ||
+                      id == GDV_TYPE_INT64 || id == GDV_TYPE_DATE32 || id == GDV_TYPE_DATE64 ||
+                      id == GDV_TYPE_TIMESTAMP || id == GDV_TYPE_TIME32 || id == GDV_TYPE_TIME64;
+      if (!ok) return VErr("IN expression over " + n.value_type().ToString() + " not supported");
+      return Status::OK();
+    }
+  }
+  return VErr("unknown node kind");
+}
+
+}  // namespace
+
+Status ValidateExpression(const Schema& schema, const Expression& expr) {
+  if (expr.root() == nullptr) return VErr("Expression has no root node");
+  Status s = ValidateNode(schema, *expr.root());
+  if (!s.ok()) return s;
+  if (expr.root()->return_type() != expr.result().type)
+    return VErr("Return type of root node " + expr.root()->return_type().ToString() +
+                " does not match that of expression " + expr.result().type.ToString());
+  return Status::OK();
+}
+
+// ======================================================================================
+// Args layout
+// ======================================================================================
+ArgsLayout::ArgsLayout(int n_inputs, int n_outputs)
+    : ni(std::max(n_inputs, 1)), no(std::max(n_outputs, 1)) {
+  size_t o = 64;
+  off_in_val = o; o += 8u * ni;
+  off_in_vld = o; o += 8u * ni;
+  off_in_var = o; o += 8u * ni;
+  off_out_val = o; o += 8u * no;
+  off_out_vld = o; o += 8u * no;
+  off_out_var = o; o += 8u * no;
+  off_in_vsh = o; o += 4u * ni;
+  off_in_dsh = o; o += 4u * ni;
+  size = (o + 7u) & ~size_t(7);
+}
+
+// ======================================================================================
+// Body generation
+// ======================================================================================
+namespace {
+
+struct Val {
+  std::string v;   // C expression (usually a local variable name)
+  std::string ok;  // C expression of type bool; "true"/"false" when statically known
+  DataType type;
+};
+
+std::string HexLit(uint64_t bits) {
+  char b[40];
+  std::snprintf(b, sizeof(b), "0x%016llxull", static_cast<unsigned long long>(bits));
+  return b;
+}
+
+class BodyGen {
+ public:
+  BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots) : schema_(schema), slots_(slots) {}
+
+  std::string& globals() { return globals_; }
+  bool uses_ctx() const { return uses_ctx_; }
+
+  // Emit the statements that evaluate `node` for the row held in slot arrays at [k].
+  Val Gen(const Node& node, std::string* out, int indent) {
+    switch (node.kind()) {
+      case NodeKind::kField: return GenField(static_cast<const FieldNode&>(node));
+      case NodeKind::kLiteral: return GenLiteral(static_cast<const LiteralNode&>(node));
+      case NodeKind::kFunction:
+        return GenFunction(static_cast<const FunctionNode&>(node), out, indent);
+      case NodeKind::kIf: return GenIf(static_cast<const IfNode&>(node), out, indent);
+      case NodeKind::kBoolean:
+        return GenBoolean(static_cast<const BooleanNode&>(node), out, indent);
+      case NodeKind::kIn: return GenIn(static_cast<const InNode&>(node), out, indent);
+    }
+    return Val{"0", "false", node.return_type()};
+  }
+
+  int SlotFor(const FieldNode& f) {
+    const int idx = schema_.index_of(f.name());
+    for (size_t j = 0; j < slots_->size(); ++j)
+      if ((*slots_)[j].schema_index == idx) return static_cast<int>(j);
+    slots_->push_back(ColumnSlot{idx, f.return_type()});
+    return static_cast<int>(slots_->size()) - 1;
+  }
+
+  static bool CanFail(const Node& node) {
+    switch (node.kind()) {
+      case NodeKind::kField: case NodeKind::kLiteral: return false;
+      case NodeKind::kFunction: {
+        const auto& fn = static_cast<const FunctionNode&>(node);
+        std::vector<DataType> params;
+        for (const auto& c : fn.children()) params.push_back(c->return_type());
+        const FunctionDef* def = Registry::Get().Lookup(fn.name(), params);
+        if (def != nullptr && (def->flags & kCanFail)) return true;
+        for (const auto& c : fn.children())
+          if (CanFail(*c)) return true;
+        return false;
+      }
+      case NodeKind::kIf: {
+        const auto& n = static_cast<const IfNode&>(node);
+        return CanFail(*n.condition()) || CanFail(*n.then_node()) || CanFail(*n.else_node());
+      }
+      case NodeKind::kBoolean: {
+        for (const auto& c : static_cast<const BooleanNode&>(node).children())
+          if (CanFail(*c)) return true;
+        return false;
+      }
+      case NodeKind::kIn: return CanFail(*static_cast<const InNode&>(node).child());
+    }
+    return false;
+  }
+
+ private:
+  std::string NewVar(const char* prefix) { return std::string(prefix) + std::to_string(next_id_++); }
+  static std::string Ind(int n) { return std::string(static_cast<size_t>(n) * 2, ' '); }
+
+  static std::string AndOk(const std::vector<std::string>& oks) {
+    std::string r;
+    for (const auto& o : oks) {
+      if (o == "false") return "false";
+      if (o == "true") continue;
+      r += (r.empty() ? "" : " && ") + o;
+    }
+    return r.empty() ? "true" : r;
+  }
+
+  static std::string ZeroOf(const DataType& t) {
+    if (t.is_varlen()) return "gdv_make_str(nullptr, 0)";
+    if (t.is_bool()) return "false";
+    return std::string("(") + t.ctype() + ")0";
+  }
+
+  Val GenField(const FieldNode& f) {
+    const int j = SlotFor(f);
+    return Val{"f" + std::to_string(j) + "[k]", "k" + std::to_string(j) + "[k]", f.return_type()};
+  }
+
+  std::string BytesArray(const std::string& bytes, const char* prefix) {
+    const std::string name = NewVar(prefix);
+    std::string s = "__device__ const u8 " + name + "[" +
+                    std::to_string(std::max<size_t>(bytes.size(), 1)) + "] = {";
+    if (bytes.empty()) s += "0";
+    for (size_t i = 0; i < bytes.size(); ++i) {
+      if (i) s += ",";
+      s += std::to_string(static_cast<unsigned>(static_cast<uint8_t>(bytes[i])));
+    }
+    s += "};\n";
+    globals_ += s;
+    return name;
+  }
+
+  Val GenLiteral(const LiteralNode& lit) {
+    const DataType& t = lit.return_type();
+    if (lit.is_null()) return Val{ZeroOf(t), "false", t};
+    std::string v;
+    switch (t.id) {
+      case GDV_TYPE_BOOL: v = lit.raw()[0] ? "true" : "false"; break;
+      case GDV_TYPE_INT8: v = "(i8)" + std::to_string(static_cast<int>(lit.as<int8_t>())); break;
+      case GDV_TYPE_INT16: v = "(i16)" + std::to_string(lit.as<int16_t>()); break;
+      case GDV_TYPE_UINT8:
+        v = "(u8)" + std::to_string(static_cast<unsigned>(lit.as<uint8_t>()));
+        break;
+      case GDV_TYPE_UINT16: v = "(u16)" + std::to_string(lit.as<uint16_t>()); break;
+      case GDV_TYPE_UINT32: v = std::to_string(lit.as<uint32_t>()) + "u"; break;
+      case GDV_TYPE_INT32: case GDV_TYPE_DATE32: case GDV_TYPE_TIME32:
+        v = "(i32)" + HexLit(static_cast<uint64_t>(lit.as<uint32_t>()));
+        break;
+      case GDV_TYPE_UINT64: v = HexLit(lit.as<uint64_t>()); break;
+      case GDV_TYPE_INT64: case GDV_TYPE_DATE64: case GDV_TYPE_TIMESTAMP: case GDV_TYPE_TIME64:
+        v = "(i64)" + HexLit(lit.as<uint64_t>());
+        break;
+      case GDV_TYPE_FLOAT:
+        v = "__uint_as_float(" + std::to_string(lit.as<uint32_t>()) + "u)";
+        break;
+      case GDV_TYPE_DOUBLE: v = "__longlong_as_double((i64)" + HexLit(lit.as<uint64_t>()) + ")"; break;
+      case GDV_TYPE_DECIMAL128: {
+        uint64_t lo, hi;
+        std::memcpy(&lo, lit.raw(), 8);
+        std::memcpy(&hi, lit.raw() + 8, 8);
+        v = "(i128)(((u128)" + HexLit(hi) + " << 64) | (u128)" + HexLit(lo) + ")";
+        break;
+      }
+      case GDV_TYPE_STRING: case GDV_TYPE_BINARY: {
+        const std::string arr = BytesArray(lit.bytes(), "gdv_lit_");
+        v = "gdv_make_str(" + arr + ", " + std::to_string(lit.bytes().size()) + ")";
+        break;
+      }
+      default: v = "0"; break;
+    }
+    return Val{v, "true", t};
+  }
+
+  // Tokenise a SQL LIKE pattern: '%' any run, '_' one glyph, escape char quotes the next byte.
+  std::string LikePattern(const std::string& pat, bool has_escape, char esc, int* n_tokens) {
+    std::vector<unsigned> toks;
+    for (size_t i = 0; i < pat.size(); ++i) {
+      const unsigned char c = static_cast<unsigned char>(pat[i]);
+      if (has_escape && pat[i] == esc && i + 1 < pat.size()) {
+        toks.push_back(static_cast<unsigned char>(pat[++i]));
+      } else if (c == '%') {
+        if (toks.empty() || (toks.back() >> 8) != 2u) toks.push_back(2u << 8);
+      } else if (c == '_') {
+        toks.push_back(1u << 8);
+      } else {
+        toks.push_back(c);
+      }
+    }
+    *n_tokens = static_cast<int>(toks.size());
+    const std::string name = NewVar("gdv_pat_");
+    std::string s = "__device__ const u16 " + name + "[" +
+                    std::to_string(std::max<size_t>(toks.size(), 1)) + "] = {";
+    if (toks.empty()) s += "0";
+    for (size_t i = 0; i < toks.size(); ++i) s += (i ? "," : "") + std::to_string(toks[i]);
+    s += "};\n";
+    globals_ += s;
+    return name;
+  }
+
+  Val GenFunction(const FunctionNode& fn, std::string* out, int indent) {
+    std::vector<DataType> ptypes;
+    for (const auto& c : fn.children()) ptypes.push_back(c->return_type());
+    const FunctionDef* def = Registry::Get().Lookup(fn.name(), ptypes);
+    const DataType& rt = fn.return_type();
+
+    if (def->flags & kLikeHolder) {
+      Val s = Gen(*fn.children()[0], out, indent);
+      const auto& pat = static_cast<const LiteralNode&>(*fn.children()[1]);
+      bool has_esc = fn.children().size() == 3;
+      char esc = has_esc ? static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0] : 0;
+      int ntok = 0;
+      const std::string arr = LikePattern(pat.bytes(), has_esc, esc, &ntok);
+      const std::string v = NewVar("v");
+      *out += Ind(indent) + "const bool " + v + " = gdv_like_match(" + s.v + ", " + arr + ", " +
+              std::to_string(ntok) + ");\n";
+      return Val{v, s.ok, rt};
+    }
+
+    std::vector<Val> args;
+    for (const auto& c : fn.children()) args.push_back(Gen(*c, out, indent));
+
+    std::string call = def->device_name() + "(";
+    bool first = true;
+    auto add = [&](const std::string& a) {
+      if (!first) call += ", ";
+      call += a;
+      first = false;
+    };
+    if (def->flags & kCanFail) {
+      add("&ctx");
+      uses_ctx_ = true;
+    }
+    for (size_t i = 0; i < args.size(); ++i) {
+      add(args[i].v);
+      if (def->nulls != NullMode::kIfNull) add(args[i].ok);
+      if ((def->flags & kDecimalArgs) && args[i].type.is_decimal()) {
+        add(std::to_string(args[i].type.precision));
+        add(std::to_string(args[i].type.scale));
+      }
+    }
+    if ((def->flags & kDecimalArgs) && rt.is_decimal()) {
+      add(std::to_string(rt.precision));
+      add(std::to_string(rt.scale));
+    }
+    call += ")";
+
+    const std::string v = NewVar("v");
+    if (def->nulls == NullMode::kNever) {
+      *out += Ind(indent) + "const " + rt.ctype() + " " + v + " = " + call + ";\n";
+      return Val{v, "true", rt};
+    }
+    std::vector<std::string> oks;
+    for (const auto& a : args) oks.push_back(a.ok);
+    std::string ok = AndOk(oks);
+    if (ok != "true" && ok != "false" && ok.find("&&") != std::string::npos) {
+      const std::string okv = NewVar("ok");
+      *out += Ind(indent) + "const bool " + okv + " = " + ok + ";\n";
+      ok = okv;
+    }
+    if (def->flags & kCanFail) {
+      // functions that can raise are only called on valid rows (and on rows in range)
+      *out += Ind(indent) + rt.ctype() + " " + v + " = " + ZeroOf(rt) + ";\n";
+      *out += Ind(indent) + "if (in && (" + ok + ")) " + v + " = " + call + ";\n";
+    } else {
+      *out += Ind(indent) + "const " + rt.ctype() + " " + v + " = " + call + ";\n";
+    }
+    return Val{v, ok, rt};
+  }
+
+  Val GenIf(const IfNode& n, std::string* out, int indent) {
+    const DataType& rt = n.return_type();
+    Val c = Gen(*n.condition(), out, indent);
+    const std::string v = NewVar("v"), ok = NewVar("ok");
+    *out += Ind(indent) + rt.ctype() + " " + v + ";\n";
+    *out += Ind(indent) + "bool " + ok + ";\n";
+    *out += Ind(indent) + "if ((" + c.ok + ") && (" + c.v + ")) {\n";
+    Val t = Gen(*n.then_node(), out, indent + 1);
+    *out += Ind(indent + 1) + v + " = " + t.v + ";\n";
+    *out += Ind(indent + 1) + ok + " = " + t.ok + ";\n";
+    *out += Ind(indent) + "} else {\n";
+    Val e = Gen(*n.else_node(), out, indent + 1);
+    *out += Ind(indent + 1) + v + " = " + e.v + ";\n";
+    *out += Ind(indent + 1) + ok + " = " + e.ok + ";\n";
+    *out += Ind(indent) + "}\n";
+    return Val{v, ok, rt};
+  }
+
+  // SQL three-valued AND/OR.  AND: false if any child is (valid, false); else null if any
+  // child is null; else true.  OR is the dual.  Children after the first are evaluated
+  // lazily (only while the result is still undecided) when they contain a function that
+  // can raise, which is the reference's short-circuit behaviour.
+  Val GenBoolean(const BooleanNode& n, std::string* out, int indent) {
+    const bool is_and = n.op() == BooleanNode::kAnd;
+    const std::string dec = NewVar("dec");    // some child decided the result
+    const std::string allok = NewVar("aok");  // every child so far was valid
+    *out += Ind(indent) + "bool " + dec + " = false;\n";
+    *out += Ind(indent) + "bool " + allok + " = true;\n";
+    int opened = 0;
+    int ind = indent;
+    for (size_t i = 0; i < n.children().size(); ++i) {
+      const Node& c = *n.children()[i];
+      if (i > 0 && CanFail(c)) {
+        *out += Ind(ind) + "if (!" + dec + ") {\n";
+        ++opened;
+        ++ind;
+      }
+      Val cv = Gen(c, out, ind);
+      const std::string deciding = is_and ? ("!(" + cv.v + ")") : ("(" + cv.v + ")");
+      *out += Ind(ind) + dec + " = " + dec + " || ((" + cv.ok + ") && " + deciding + ");\n";
+      *out += Ind(ind) + allok + " = " + allok + " && (" + cv.ok + ");\n";
+    }
+    while (opened-- > 0) {
+      --ind;
+      *out += Ind(ind) + "}\n";
+    }
+    const std::string v = NewVar("v"), ok = NewVar("ok");
+    *out += Ind(indent) + "const bool " + v + " = " + (is_and ? "!" : "") + dec + ";\n";
+    *out += Ind(indent) + "const bool " + ok + " = " + dec + " || " + allok + ";\n";
+    return Val{v, ok, boolean()};
+  }
+
+  Val GenIn(const InNode& n, std::string* out, int indent) {
+    Val c = Gen(*n.child(), out, indent);
+    const std::string v = NewVar("v");
+    const DataType& t = n.value_type();
+    if (t.is_varlen()) {
+      std::string e;
+      std::vector<std::string> sorted = n.strs();
+      std::sort(sorted.begin(), sorted.end());
+      for (const auto& s : sorted) {
+        const std::string arr = BytesArray(s, "gdv_lit_");
+        e += (e.empty() ? "" : " || ") + std::string("equal_utf8_utf8(") + c.v +
+             ", gdv_make_str(" + arr + ", " + std::to_string(s.size()) + "))";
+      }
+      if (e.empty()) e = "false";
+      *out += Ind(indent) + "const bool " + v + " = " + e + ";\n";
+    } else {
+      std::vector<int64_t> vals = n.ints();
+      std::sort(vals.begin(), vals.end());
+      vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+      const char* ct = t.ctype();
+      if (vals.size() <= 8) {
+        std::string e;
+        for (auto x : vals)
+          e += (e.empty() ? "" : " || ") + std::string("(") + c.v + " == (" + ct + ")" +
+               HexLit(static_cast<uint64_t>(x)) + ")";
+        if (e.empty()) e = "false";
+        *out += Ind(indent) + "const bool " + v + " = " + e + ";\n";
+      } else {
+        const std::string arr = NewVar("gdv_in_");
+        std::string g = std::string("__device__ const ") + ct + " " + arr + "[" +
+                        std::to_string(vals.size()) + "] = {";
+        for (size_t i = 0; i < vals.size(); ++i)
+          g += (i ? "," : "") + std::string("(") + ct + ")" + HexLit(static_cast<uint64_t>(vals[i]));
+        g += "};\n";
+        globals_ += g;
+        // branch-free binary search over the sorted constants
+        *out += Ind(indent) + "bool " + v + ";\n";
+        *out += Ind(indent) + "{\n";
+        *out += Ind(indent + 1) + "int lo = 0, hi = " + std::to_string(vals.size()) + ";\n";
+        *out += Ind(indent + 1) + "while (lo < hi) { const int mid = (lo + hi) >> 1; if (" +
+                arr + "[mid] < " + c.v + ") lo = mid + 1; else hi = mid; }\n";
+        *out += Ind(indent + 1) + v + " = lo < " + std::to_string(vals.size()) + " && " + arr +
+                "[lo] == " + c.v + ";\n";
+        *out += Ind(indent) + "}\n";
+      }
+    }
+    return Val{v, c.ok, boolean()};
+  }
+
+  const Schema& schema_;
+  std::vector<ColumnSlot>* slots_;
+  std::string globals_;
+  int next_id_ = 0;
+  bool uses_ctx_ = false;
+};
+
+std::string EmitArgsStruct(const ArgsLayout& L) {
+  std::stringstream s;
+  s << "struct gdv_args {\n"
+    << "  i64 n;            // rows (or selection slots) to process\n"
+    << "  i64 row_base;     // added to every index a filter emits (row-range sharding)\n"
+    << "  const void* sel;  // project: input selection vector (or null)\n"
+    << "  void* out_idx;    // filter: output selection vector\n"
+    << "  u64* out_count;   // filter: number of indices written\n"
+    << "  u64* tile_state;  // filter: look-back descriptors, one per CTA tile\n"
+    << "  u64* ticket;      // filter: dynamic tile counter\n"
+    << "  int* err;         // first ExecutionError code raised by a device function\n"
+    << "  const void* in_val[" << L.ni << "];\n"
+    << "  const u8* in_vld[" << L.ni << "];\n"
+    << "  const u8* in_var[" << L.ni << "];\n"
+    << "  void* out_val[" << L.no << "];\n"
+    << "  u32* out_vld[" << L.no << "];\n"
+    << "  u8* out_var[" << L.no << "];\n"
+    << "  u32 in_vsh[" << L.ni << "];\n"
+    << "  u32 in_dsh[" << L.ni << "];\n"
+    << "};\n";
+  return s.str();
+}
+
+const char* SelCType(int mode) {
+  switch (mode) {
+    case GDV_SEL_UINT16: return "u16";
+    case GDV_SEL_UINT64: return "u64";
+    default: return "u32";
+  }
+}
+
+// Declarations + load phase shared by both kernel kinds.  `slot_expr` is the C expression
+// of the slot index for step k; with an input selection vector the row is sel[slot].
+void EmitLoadPhase(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R,
+                   std::string* o, int indent) {
+  const std::string I(static_cast<size_t>(indent) * 2, ' ');
+  for (size_t j = 0; j < slots.size(); ++j) {
+    const DataType& t = slots[j].type;
+    *o += I + t.ctype() + " f" + std::to_string(j) + "[" + std::to_string(R) + "];\n";
+    *o += I + "bool k" + std::to_string(j) + "[" + std::to_string(R) + "];\n";
+  }
+  *o += I + "#pragma unroll\n";
+  *o += I + "for (int k = 0; k < " + std::to_string(R) + "; ++k) {\n";
+  *o += I + "  const i64 s = base + 32 * k + (i64)lane;\n";
+  *o += I + "  const bool in = s < A.n;\n";
+  if (spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE) {
+    *o += I + "  const i64 r = in ? (i64)reinterpret_cast<const " +
+          SelCType(spec.selection_mode) + "*>(A.sel)[s] : 0;\n";
+  } else {
+    *o += I + "  const i64 r = in ? s : 0;\n";
+  }
+  for (size_t j = 0; j < slots.size(); ++j) {
+    const DataType& t = slots[j].type;
+    const std::string J = std::to_string(j);
+    if (t.is_bool()) {
+      *o += I + "  f" + J + "[k] = gdv_ldbit(reinterpret_cast<const u8*>(A.in_val[" + J +
+            "]), A.in_dsh[" + J + "], r);\n";
+    } else if (t.is_varlen()) {
+      *o += I + "  {\n";
+      *o += I + "    const i32* off = reinterpret_cast<const i32*>(A.in_val[" + J + "]);\n";
+      *o += I + "    const i32 b = in ? off[r] : 0;\n";
+      *o += I + "    const i32 e = in ? off[r + 1] : 0;\n";
+      *o += I + "    f" + J + "[k] = gdv_make_str(A.in_var[" + J + "] + b, e - b);\n";
+      *o += I + "  }\n";
+    } else {
+      *o += I + "  f" + J + "[k] = in ? gdv_ld<" + t.ctype() + ">(A.in_val[" + J + "], r) : (" +
+            t.ctype() + ")0;\n";
+    }
+    *o += I + "  k" + J + "[k] = in && gdv_ldbit(A.in_vld[" + J + "], A.in_vsh[" + J + "], r);\n";
+  }
+  *o += I + "}\n";
+}
+
+int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
+  // Keep roughly 64-128 bytes of loads in flight per thread without blowing the register
+  // budget (outputs are live in registers only one step at a time).
+  int bytes = std::max(in_bytes, 1);
+  int r = 96 / bytes;
+  if (kind == KernelKind::kFilter) r = std::max(r, 4);
+  r = std::max(1, std::min(r, 8));
+  // powers of two keep the index math cheap
+  int p = 1;
+  while (p * 2 <= r) p *= 2;
+  (void)out_bytes;
+  return p;
+}
+
+}  // namespace
+
+Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
+                      const KernelSpec& spec, GeneratedKernel* out) {
+  std::vector<ColumnSlot> slots;
+  BodyGen gen(schema, &slots);
+
+  // Per-row body (uses f<j>[k] / k<j>[k]); generated first so we know the slots.
+  std::string body;
+  std::vector<Val> results;
+  for (const auto& e : exprs) {
+    if (spec.kind == KernelKind::kProject && e->result().type.is_varlen())
+      return Status::Make(GDV_NOT_IMPLEMENTED,
+                          "variable-length projection outputs are handled by the two-pass "
+                          "string projector, not by GenerateKernel");
+    results.push_back(gen.Gen(*e->root(), &body, 3));
+  }
+
+  int in_bytes = 0, out_bytes = 0;
+  for (const auto& s : slots) in_bytes += s.type.is_varlen() ? 8 : std::max(s.type.width(), 1);
+  for (const auto& e : exprs) out_bytes += std::max(e->result().type.width(), 1);
+  if (spec.kind == KernelKind::kFilter) out_bytes = 0;
+
+  int R = spec.rows_per_thread > 0 ? spec.rows_per_thread
+                                   : PickRowsPerThread(in_bytes, out_bytes, spec.kind);
+  if (R > 32) R = 32;
+  const int BT = spec.block_threads > 0 ? spec.block_threads : 256;
+  if (BT % 32 != 0 || BT > 1024)
+    return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
+
+  const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
+  ArgsLayout L(static_cast<int>(slots.size()), n_out);
+
+  std::string src;
+  src += "// generated by gandiva_b200 kernel fuser; one fused kernel per ";
+  src += (spec.kind == KernelKind::kProject ? "Projector\n" : "Filter\n");
+  for (size_t i = 0; i < exprs.size(); ++i)
+    src += "// expr_" + std::to_string(i) + ": " + exprs[i]->ToString() + "\n";
+  src += "#include \"gdv_device_lib.cuh\"\n";
+  src += EmitArgsStruct(L);
+  src += gen.globals();
+  const std::string sR = std::to_string(R), sBT = std::to_string(BT);
+  src += "extern \"C\" __global__ void __launch_bounds__(" + sBT + ") " + spec.name +
+         "(const __grid_constant__ gdv_args A) {\n";
+  src += "  const u32 lane = threadIdx.x & 31u;\n";
+  src += "  const u32 wid = threadIdx.x >> 5;\n";
+  src += "  gdv_ctx ctx;\n  ctx.err = A.err;\n";
+
+  if (spec.kind == KernelKind::kProject) {
+    src += "  const i64 n_wtiles = (A.n + " + std::to_string(32 * R - 1) + ") / " +
+           std::to_string(32 * R) + ";\n";
+    src += "  const i64 wstride = (i64)gridDim.x * " + std::to_string(BT / 32) + ";\n";
+    src += "  for (i64 wt = (i64)blockIdx.x * " + std::to_string(BT / 32) +
+           " + wid; wt < n_wtiles; wt += wstride) {\n";
+    src += "    const i64 base = wt * " + std::to_string(32 * R) + ";\n";
+    EmitLoadPhase(slots, spec, R, &src, 2);
+    for (int o = 0; o < n_out; ++o) {
+      src += "    u32 vw" + std::to_string(o) + " = 0u;\n";
+      if (exprs[o]->result().type.is_bool()) src += "    u32 dw" + std::to_string(o) + " = 0u;\n";
+    }
+    src += "    #pragma unroll\n";
+    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "      const i64 s = base + 32 * k + (i64)lane;\n";
+    src += "      const bool in = s < A.n;\n";
+    src += body;
+    for (int o = 0; o < n_out; ++o) {
+      const DataType& t = exprs[o]->result().type;
+      const std::string O = std::to_string(o);
+      if (t.is_bool()) {
+        src += "      { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[o].v +
+               ")); if (lane == (u32)k) dw" + O + " = m; }\n";
+      } else {
+        src += "      if (in) gdv_st<" + std::string(t.ctype()) + ">(A.out_val[" + O + "], s, " +
+               results[o].v + ");\n";
+      }
+      src += "      { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[o].ok +
+             ")); if (lane == (u32)k) vw" + O + " = m; }\n";
+    }
+    src += "    }\n";
+    src += "    if (lane < " + sR + "u && base + 32 * (i64)lane < A.n) {\n";
+    src += "      const i64 w = (base >> 5) + (i64)lane;\n";
+    for (int o = 0; o < n_out; ++o) {
+      const std::string O = std::to_string(o);
+      src += "      if (A.out_vld[" + O + "] != nullptr) A.out_vld[" + O + "][w] = vw" + O + ";\n";
+      if (exprs[o]->result().type.is_bool())
+        src += "      reinterpret_cast<u32*>(A.out_val[" + O + "])[w] = dw" + O + ";\n";
+    }
+    src += "    }\n";
+    src += "  }\n";
+    src += "}\n";
+  } else {
+    const std::string IDX = SelCType(spec.selection_mode);
+    const int NW = BT / 32;
+    src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
+    src += "  __shared__ i64 s_tile;\n";
+    src += "  __shared__ u64 s_excl;\n";
+    src += "  const i64 n_tiles = (A.n + " + std::to_string(BT * R - 1) + ") / " +
+           std::to_string(BT * R) + ";\n";
+    src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
+    src += "  while (true) {\n";
+    src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
+    src += "    __syncthreads();\n";
+    src += "    const i64 tile = s_tile;\n";
+    src += "    if (tile >= n_tiles) break;\n";
+    src += "    const i64 base = tile * " + std::to_string(BT * R) + " + (i64)wid * " +
+           std::to_string(32 * R) + ";\n";
+    EmitLoadPhase(slots, spec, R, &src, 2);
+    src += "    u32 keep[" + sR + "];\n";
+    src += "    u32 wcount = 0u;\n";
+    src += "    #pragma unroll\n";
+    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "      const i64 s = base + 32 * k + (i64)lane;\n";
+    src += "      const bool in = s < A.n;\n";
+    src += body;
+    src += "      keep[k] = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
+           results[0].v + "));\n";
+    src += "      wcount += (u32)__popc(keep[k]);\n";
+    src += "    }\n";
+    src += "    if (lane == 0u) s_wcount[wid] = wcount;\n";
+    src += "    __syncthreads();\n";
+    src += "    if (wid == 0u) {\n";
+    src += "      const u32 c = lane < " + std::to_string(NW) + "u ? s_wcount[lane] : 0u;\n";
+    src += "      u32 incl = c;\n";
+    src += "      #pragma unroll\n";
+    src += "      for (int o = 1; o < 32; o <<= 1) {\n";
+    src += "        const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
+    src += "        if (lane >= (u32)o) incl += t;\n";
+    src += "      }\n";
+    src += "      const u32 total = __shfl_sync(GDV_FULL, incl, 31);\n";
+    src += "      if (lane < " + std::to_string(NW) + "u) s_wcount[lane] = incl - c;\n";
+    src += "      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);\n";
+    src += "      if (lane == 0u) {\n";
+    src += "        s_excl = excl;\n";
+    src += "        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;\n";
+    src += "      }\n";
+    src += "    }\n";
+    src += "    __syncthreads();\n";
+    src += "    u64 pos = s_excl + (u64)s_wcount[wid];\n";
+    src += "    const u32 lt = gdv_lanemask_lt();\n";
+    src += "    #pragma unroll\n";
+    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "      const u32 m = keep[k];\n";
+    src += "      if ((m >> lane) & 1u)\n";
+    src += "        out_idx[pos + (u64)__popc(m & lt)] = (" + IDX +
+           ")(A.row_base + base + 32 * k + (i64)lane);\n";
+    src += "      pos += (u64)__popc(m);\n";
+    src += "    }\n";
+    src += "  }\n";
+    src += "}\n";
+  }
+
+  out->source = std::move(src);
+  out->name = spec.name;
+  out->kind = spec.kind;
+  out->rows_per_thread = R;
+  out->block_threads = BT;
+  out->selection_mode = spec.selection_mode;
+  out->inputs = slots;
+  out->outputs.clear();
+  if (spec.kind == KernelKind::kProject)
+    for (const auto& e : exprs) out->outputs.push_back(e->result().type);
+  out->uses_ctx = gen.uses_ctx();
+  out->in_bytes_per_row = in_bytes;
+  out->out_bytes_per_row = out_bytes;
+  out->args_size = L.size;
+  return Status::OK();
+}
+
+}  // namespace gdv

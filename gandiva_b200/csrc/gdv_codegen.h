@@ -1,0 +1,77 @@
+// Kernel fuser: lowers a set of validated expression trees to ONE CUDA kernel
+// (source text) per Projector / Filter.  Replaces the reference's LLVMGenerator +
+// Annotator + BitmapAccumulator (named in BASELINE.json north_star):
+//   * Annotator        -> ColumnSlot table (which schema columns the kernel reads) and the
+//                         flat gdv_args pointer block the kernel indexes;
+//   * LLVMGenerator    -> EmitBody(): straight-line per-row code calling the device library;
+//   * BitmapAccumulator-> validity is ANDed in registers and written with one warp ballot
+//                         per 32 rows, inside the same kernel.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "gdv_node.h"
+
+namespace gdv {
+
+struct Status {
+  int code = GDV_OK;
+  std::string msg;
+  bool ok() const { return code == GDV_OK; }
+  static Status OK() { return Status(); }
+  static Status Make(int c, std::string m) {
+    Status s;
+    s.code = c;
+    s.msg = std::move(m);
+    return s;
+  }
+};
+
+// Validate one expression against the schema and the function registry
+// (ExpressionValidationError on failure).
+Status ValidateExpression(const Schema& schema, const Expression& expr);
+
+enum class KernelKind { kProject, kFilter };
+
+struct KernelSpec {
+  KernelKind kind = KernelKind::kProject;
+  int selection_mode = GDV_SEL_NONE;  // project: input selection; filter: output index width
+  int rows_per_thread = 0;            // 0 = pick from bytes/row
+  int block_threads = 256;
+  std::string name;                   // kernel symbol
+};
+
+struct ColumnSlot {
+  int schema_index;
+  DataType type;
+};
+
+struct GeneratedKernel {
+  std::string source;   // full translation unit (device library is #include'd by name)
+  std::string name;
+  KernelKind kind;
+  int rows_per_thread;
+  int block_threads;
+  int selection_mode;
+  std::vector<ColumnSlot> inputs;   // kernel input slot j reads schema column inputs[j]
+  std::vector<DataType> outputs;    // project: one per expression; filter: empty
+  bool uses_ctx = false;            // some function can raise an ExecutionError
+  int in_bytes_per_row = 0;         // algorithmic bytes (values only) read per row
+  int out_bytes_per_row = 0;
+  size_t args_size = 0;             // sizeof(gdv_args) for this kernel
+};
+
+// Byte offsets inside gdv_args; the host packs the same layout (see EmitArgsStruct()).
+struct ArgsLayout {
+  int ni, no;  // array extents (>= 1)
+  size_t off_n = 0, off_row_base = 8, off_sel = 16, off_out_idx = 24, off_out_count = 32,
+         off_tile_state = 40, off_ticket = 48, off_err = 56;
+  size_t off_in_val, off_in_vld, off_in_var, off_out_val, off_out_vld, off_out_var, off_in_vsh,
+      off_in_dsh, size;
+  ArgsLayout(int n_inputs, int n_outputs);
+};
+
+Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
+                      const KernelSpec& spec, GeneratedKernel* out);
+
+}  // namespace gdv

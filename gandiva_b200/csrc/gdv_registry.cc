@@ -1,0 +1,202 @@
+#include "gdv_registry.h"
+
+namespace gdv {
+
+std::string FunctionDef::device_name() const {
+  std::string s = device_base;
+  for (const auto& p : params) {
+    s += "_";
+    s += p.fn_suffix();
+  }
+  return s;
+}
+
+std::string FunctionDef::signature() const {
+  std::string s = ret.ToString() + " " + name + "(";
+  for (size_t i = 0; i < params.size(); ++i) {
+    if (i) s += ", ";
+    s += params[i].ToString();
+  }
+  return s + ")";
+}
+
+void Registry::Add(const std::string& name, std::vector<DataType> params, DataType ret,
+                   NullMode nulls, uint32_t flags, const std::vector<std::string>& aliases) {
+  FunctionDef d;
+  d.name = name;
+  d.device_base = name;
+  d.params = std::move(params);
+  d.ret = ret;
+  d.nulls = nulls;
+  d.flags = flags;
+  defs_.push_back(d);
+  for (const auto& a : aliases) {
+    FunctionDef e = d;
+    e.name = a;
+    defs_.push_back(e);
+  }
+}
+
+static bool ParamMatches(const DataType& want, const DataType& got) {
+  if (want.id != got.id) return false;
+  if (want.id == GDV_TYPE_DECIMAL128) return true;  // any precision/scale
+  if (want.id == GDV_TYPE_TIMESTAMP || want.id == GDV_TYPE_TIME32 || want.id == GDV_TYPE_TIME64)
+    return want.precision == got.precision;
+  return true;
+}
+
+const FunctionDef* Registry::Lookup(const std::string& name,
+                                    const std::vector<DataType>& params) const {
+  for (const auto& d : defs_) {
+    if (d.name != name || d.params.size() != params.size()) continue;
+    bool ok = true;
+    for (size_t i = 0; i < params.size() && ok; ++i) ok = ParamMatches(d.params[i], params[i]);
+    if (ok) return &d;
+  }
+  return nullptr;
+}
+
+const Registry& Registry::Get() {
+  static const Registry r;
+  return r;
+}
+
+Registry::Registry() {
+  const DataType B = boolean();
+  const DataType I8(GDV_TYPE_INT8), I16(GDV_TYPE_INT16), I32 = int32(), I64 = int64();
+  const DataType U8(GDV_TYPE_UINT8), U16(GDV_TYPE_UINT16), U32(GDV_TYPE_UINT32),
+      U64(GDV_TYPE_UINT64);
+  const DataType F32 = float32(), F64 = float64();
+  const DataType S = utf8(), BIN = binary();
+  const DataType D32 = date32(), D64 = date64(), TS = timestamp_ms(), T32 = time32_ms();
+  const DataType DEC = decimal128(0, 0);
+  const std::vector<DataType> numeric = {I8, I16, I32, I64, U8, U16, U32, U64, F32, F64};
+  const std::vector<DataType> dates = {D32, D64, TS, T32};
+
+  // ---- arithmetic -------------------------------------------------------------------
+  for (const auto& t : numeric) {
+    Add("add", {t, t}, t);
+    Add("subtract", {t, t}, t);
+    Add("multiply", {t, t}, t);
+    Add("divide", {t, t}, t, NullMode::kIfNull, kCanFail);
+  }
+  Add("mod", {I64, I32}, I32, NullMode::kIfNull, 0, {"modulo"});
+  Add("mod", {I64, I64}, I64, NullMode::kIfNull, 0, {"modulo"});
+  for (const auto& t : {I32, I64, F32, F64}) {
+    Add("abs", {t}, t);
+    Add("negative", {t}, t);
+  }
+  for (const auto& t : {I32, I64}) {
+    Add("bitwise_and", {t, t}, t);
+    Add("bitwise_or", {t, t}, t);
+    Add("bitwise_xor", {t, t}, t);
+    Add("bitwise_not", {t}, t);
+  }
+  Add("sqrt", {F64}, F64);
+
+  // ---- comparisons ------------------------------------------------------------------
+  std::vector<DataType> relop_types = numeric;
+  relop_types.insert(relop_types.end(), dates.begin(), dates.end());
+  relop_types.push_back(S);
+  relop_types.push_back(BIN);
+  for (const auto& t : relop_types) {
+    Add("equal", {t, t}, B, NullMode::kIfNull, 0, {"eq", "same"});
+    Add("not_equal", {t, t}, B);
+    Add("less_than", {t, t}, B);
+    Add("less_than_or_equal_to", {t, t}, B);
+    Add("greater_than", {t, t}, B);
+    Add("greater_than_or_equal_to", {t, t}, B);
+  }
+  Add("equal", {B, B}, B, NullMode::kIfNull, 0, {"eq", "same"});
+  Add("not_equal", {B, B}, B);
+  for (const char* op : {"equal", "not_equal", "less_than", "less_than_or_equal_to",
+                         "greater_than", "greater_than_or_equal_to"})
+    Add(op, {DEC, DEC}, B, NullMode::kIfNull, kDecimalArgs);
+
+  // ---- boolean / null tests ---------------------------------------------------------
+  Add("not", {B}, B);
+  std::vector<DataType> all_types = relop_types;
+  all_types.push_back(B);
+  all_types.push_back(DEC);
+  for (const auto& t : all_types) {
+    Add("isnull", {t}, B, NullMode::kNever);
+    Add("isnotnull", {t}, B, NullMode::kNever);
+  }
+  Add("istrue", {B}, B, NullMode::kNever);
+  Add("isfalse", {B}, B, NullMode::kNever);
+  Add("isnottrue", {B}, B, NullMode::kNever);
+  Add("isnotfalse", {B}, B, NullMode::kNever);
+  std::vector<DataType> distinct_types = numeric;
+  distinct_types.insert(distinct_types.end(), dates.begin(), dates.end());
+  distinct_types.push_back(B);
+  for (const auto& t : distinct_types) {
+    Add("is_distinct_from", {t, t}, B, NullMode::kNever);
+    Add("is_not_distinct_from", {t, t}, B, NullMode::kNever);
+  }
+
+  // ---- casts --------------------------------------------------------------------------
+  Add("castBIGINT", {I32}, I64);
+  Add("castINT", {I64}, I32);
+  Add("castFLOAT4", {I32}, F32);
+  Add("castFLOAT4", {I64}, F32);
+  Add("castFLOAT4", {F64}, F32);
+  Add("castFLOAT8", {I32}, F64);
+  Add("castFLOAT8", {I64}, F64);
+  Add("castFLOAT8", {F32}, F64);
+  Add("castDATE", {I64}, D64);
+  Add("castTIMESTAMP", {I64}, TS);
+  Add("castTIMESTAMP", {D64}, TS);
+  Add("castDATE", {TS}, D64);
+  Add("castBIGINT", {D64}, I64);
+  Add("castBIGINT", {TS}, I64);
+  Add("castINT", {D32}, I32);
+  Add("castDATE", {I32}, D32);
+
+  // ---- date / time extraction (date64 and timestamp are milliseconds since epoch) ----
+  for (const auto& t : {D64, TS}) {
+    for (const char* f : {"extractYear", "extractMonth", "extractDay", "extractHour",
+                          "extractMinute", "extractSecond", "extractDoy", "extractDow",
+                          "extractQuarter", "extractEpoch"})
+      Add(f, {t}, I64);
+  }
+  Add("extractYear", {D32}, I64);
+  Add("extractMonth", {D32}, I64);
+  Add("extractDay", {D32}, I64);
+
+  // ---- decimal128 ---------------------------------------------------------------------
+  Add("add", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("subtract", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("multiply", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("divide", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs | kCanFail);
+  Add("mod", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs | kCanFail, {"modulo"});
+  Add("abs", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("negative", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castDECIMAL", {I32}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castDECIMAL", {I64}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castDECIMAL", {F64}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castDECIMAL", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castBIGINT", {DEC}, I64, NullMode::kIfNull, kDecimalArgs);
+  Add("castFLOAT8", {DEC}, F64, NullMode::kIfNull, kDecimalArgs);
+
+  // ---- strings ------------------------------------------------------------------------
+  Add("like", {S, S}, B, NullMode::kIfNull, kLikeHolder);
+  Add("like", {S, S, S}, B, NullMode::kIfNull, kLikeHolder);
+  Add("substr", {S, I64, I64}, S, NullMode::kIfNull, kStringView, {"substring"});
+  Add("substr", {S, I64}, S, NullMode::kIfNull, kStringView, {"substring"});
+  Add("upper", {S}, S, NullMode::kIfNull, kStringView);
+  Add("lower", {S}, S, NullMode::kIfNull, kStringView);
+  Add("char_length", {S}, I32, NullMode::kIfNull, 0, {"length", "lengthUtf8"});
+  Add("octet_length", {S}, I32);
+  Add("octet_length", {BIN}, I32);
+  Add("bit_length", {S}, I32);
+  Add("bit_length", {BIN}, I32);
+  Add("starts_with", {S, S}, B);
+  Add("ends_with", {S, S}, B);
+  Add("is_substr", {S, S}, B);
+  Add("ltrim", {S}, S, NullMode::kIfNull, kStringView);
+  Add("rtrim", {S}, S, NullMode::kIfNull, kStringView);
+  Add("btrim", {S}, S, NullMode::kIfNull, kStringView, {"trim"});
+  Add("castVARCHAR", {S, I64}, S, NullMode::kIfNull, kStringView);
+}
+
+}  // namespace gdv

@@ -1,0 +1,698 @@
+#include "gdv_runtime.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace gdv {
+
+std::atomic<long long> g_launch_count{0};
+
+const char* ExecutionErrorMessage(int code) {
+  switch (code) {
+    case 1: return "divide by zero error";
+    default: return "execution error in device function";
+  }
+}
+
+// ======================================================================================
+// Device
+// ======================================================================================
+namespace {
+std::mutex g_dev_mu;
+Device* g_devices[64] = {nullptr};
+
+#define GDV_RETURN_NOT_OK(expr)      \
+  do {                               \
+    ::gdv::Status _s = (expr);       \
+    if (!_s.ok()) return _s;         \
+  } while (0)
+
+size_t RoundPool(size_t bytes) {
+  if (bytes < 512) return 512;
+  if (bytes <= (1u << 20)) {
+    size_t p = 512;
+    while (p < bytes) p <<= 1;
+    return p;
+  }
+  const size_t g = size_t(2) << 20;
+  return (bytes + g - 1) / g * g;
+}
+}  // namespace
+
+Status Device::Get(int ordinal, Device** out) {
+  const DriverApi& d = Driver();
+  if (!d.loaded)
+    return Status::Make(GDV_CUDA_ERROR, "CUDA driver unavailable: " + d.load_error);
+  if (ordinal < 0 || ordinal >= 64) return Status::Make(GDV_INVALID, "bad device ordinal");
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  if (g_devices[ordinal] == nullptr) {
+    int count = 0;
+    GDV_RETURN_NOT_OK(CuCheck(d.DeviceGetCount(&count), "cuDeviceGetCount"));
+    if (ordinal >= count)
+      return Status::Make(GDV_CUDA_ERROR, "device " + std::to_string(ordinal) +
+                                              " not present (" + std::to_string(count) +
+                                              " devices)");
+    std::unique_ptr<Device> dev(new Device());
+    dev->ordinal_ = ordinal;
+    GDV_RETURN_NOT_OK(CuCheck(d.DeviceGet(&dev->dev_, ordinal), "cuDeviceGet"));
+    GDV_RETURN_NOT_OK(
+        CuCheck(d.DevicePrimaryCtxRetain(&dev->ctx_, dev->dev_), "cuDevicePrimaryCtxRetain"));
+    GDV_RETURN_NOT_OK(CuCheck(d.CtxSetCurrent(dev->ctx_), "cuCtxSetCurrent"));
+    d.DeviceGetAttribute(&dev->sm_count_, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev->dev_);
+    d.DeviceGetAttribute(&dev->cc_major_, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, dev->dev_);
+    d.DeviceGetAttribute(&dev->cc_minor_, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, dev->dev_);
+    GDV_RETURN_NOT_OK(
+        CuCheck(d.StreamCreate(&dev->stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate"));
+    GDV_RETURN_NOT_OK(
+        CuCheck(d.StreamCreate(&dev->copy_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate"));
+    g_devices[ordinal] = dev.release();
+  }
+  *out = g_devices[ordinal];
+  return (*out)->MakeCurrent();
+}
+
+Status Device::MakeCurrent() const {
+  return CuCheck(Driver().CtxSetCurrent(ctx_), "cuCtxSetCurrent");
+}
+
+std::string Device::arch() const {
+  // This engine targets B200 only: sm_100a.  Other parts get their plain sm_XY so the
+  // test-suite can still run on whatever GPU a developer has, without arch-specific code.
+  if (cc_major_ == 10 && cc_minor_ == 0) return "sm_100a";
+  return "sm_" + std::to_string(cc_major_) + std::to_string(cc_minor_);
+}
+
+Status Device::Alloc(size_t bytes, CUdeviceptr* out) {
+  const size_t want = RoundPool(bytes);
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = free_.lower_bound(want);
+    if (it != free_.end() && it->first <= want * 2) {
+      *out = it->second;
+      free_.erase(it);
+      return Status::OK();
+    }
+  }
+  GDV_RETURN_NOT_OK(MakeCurrent());
+  CUdeviceptr p = 0;
+  CUresult r = Driver().MemAlloc(&p, want);
+  if (r == CUDA_ERROR_OUT_OF_MEMORY) {
+    // drop the cache and retry once
+    std::vector<CUdeviceptr> drop;
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      for (auto& kv : free_) {
+        drop.push_back(kv.second);
+        sizes_.erase(kv.second);
+      }
+      free_.clear();
+    }
+    for (auto q : drop) Driver().MemFree(q);
+    r = Driver().MemAlloc(&p, want);
+  }
+  if (r != CUDA_SUCCESS) {
+    Status s = CuCheck(r, "cuMemAlloc");
+    if (r == CUDA_ERROR_OUT_OF_MEMORY) s.code = GDV_OUT_OF_MEMORY;
+    return s;
+  }
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    sizes_[p] = want;
+  }
+  *out = p;
+  return Status::OK();
+}
+
+void Device::Free(CUdeviceptr p) {
+  if (p == 0) return;
+  std::lock_guard<std::mutex> lock(mu_);
+  auto it = sizes_.find(p);
+  if (it == sizes_.end()) return;
+  free_.emplace(it->second, p);
+}
+
+Status Device::StaticFunction(const char* name, CUfunction* out) {
+  std::lock_guard<std::mutex> lock(mu_);
+  GDV_RETURN_NOT_OK(MakeCurrent());
+  if (static_mod_ == nullptr) {
+    GDV_RETURN_NOT_OK(CuCheck(Driver().ModuleLoadData(&static_mod_, gdv_static_kernels_cubin),
+                              "cuModuleLoadData(static kernels)"));
+  }
+  auto it = static_fns_.find(name);
+  if (it == static_fns_.end()) {
+    CUfunction fn = nullptr;
+    GDV_RETURN_NOT_OK(
+        CuCheck(Driver().ModuleGetFunction(&fn, static_mod_, name), "cuModuleGetFunction"));
+    it = static_fns_.emplace(name, fn).first;
+  }
+  *out = it->second;
+  return Status::OK();
+}
+
+// ======================================================================================
+// CompiledKernel
+// ======================================================================================
+Status CompiledKernel::Load(Device* dev, Loaded* out) {
+  std::lock_guard<std::mutex> lock(mu_);
+  auto it = loaded_.find(dev->ordinal());
+  if (it != loaded_.end()) {
+    *out = it->second;
+    return Status::OK();
+  }
+  GDV_RETURN_NOT_OK(dev->MakeCurrent());
+  const DriverApi& d = Driver();
+  Loaded l;
+  GDV_RETURN_NOT_OK(CuCheck(d.ModuleLoadData(&l.mod, cubin.data()), "cuModuleLoadData"));
+  GDV_RETURN_NOT_OK(
+      CuCheck(d.ModuleGetFunction(&l.fn, l.mod, gen.name.c_str()), "cuModuleGetFunction"));
+  d.FuncGetAttribute(&l.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, l.fn);
+  d.FuncGetAttribute(&l.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, l.fn);
+  int b = 0;
+  if (d.OccupancyMaxActiveBlocksPerMultiprocessor(&b, l.fn, gen.block_threads, 0) ==
+          CUDA_SUCCESS &&
+      b > 0)
+    l.blocks_per_sm = b;
+  loaded_[dev->ordinal()] = l;
+  *out = l;
+  return Status::OK();
+}
+
+namespace {
+
+std::atomic<int> g_kernel_serial{0};
+
+Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
+                   KernelKind kind, int selection_mode, const Config& cfg,
+                   std::unique_ptr<CompiledKernel>* out) {
+  KernelSpec spec;
+  spec.kind = kind;
+  spec.selection_mode = selection_mode;
+  spec.rows_per_thread = cfg.rows_per_thread;
+  spec.block_threads = cfg.block_threads > 0 ? cfg.block_threads : 256;
+  spec.name = std::string(kind == KernelKind::kProject ? "gdv_project_expr_" : "gdv_filter_expr_") +
+              std::to_string(g_kernel_serial.fetch_add(1));
+  std::unique_ptr<CompiledKernel> k(new CompiledKernel());
+  GDV_RETURN_NOT_OK(GenerateKernel(schema, exprs, spec, &k->gen));
+  // Compile for the device we will run on when one is visible, else for B200.
+  std::string arch = "sm_100a";
+  Device* dev = nullptr;
+  if (Driver().loaded && Device::Get(cfg.device, &dev).ok()) arch = dev->arch();
+  GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
+                                   &k->ptx, &k->compile_log));
+  *out = std::move(k);
+  return Status::OK();
+}
+
+// One kernel input after staging: device addresses + bit shifts.
+struct ResolvedIn {
+  CUdeviceptr val = 0, vld = 0, var = 0;
+  uint32_t vsh = 0, dsh = 0;
+};
+
+inline int64_t BitBytes(int64_t bit_begin, int64_t nbits) {
+  // bytes that cover bits [bit_begin, bit_begin + nbits) counted from the byte of bit_begin
+  return ((bit_begin & 7) + nbits + 7) / 8;
+}
+
+Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t* batch,
+                     CUstream stream, ScratchScope* scratch, std::vector<ResolvedIn>* out) {
+  const DriverApi& d = Driver();
+  const bool host = batch->mem_space == GDV_MEM_HOST;
+  const int64_t n = batch->num_rows;
+  out->resize(gen.inputs.size());
+  for (size_t j = 0; j < gen.inputs.size(); ++j) {
+    const ColumnSlot& slot = gen.inputs[j];
+    if (slot.schema_index < 0 || slot.schema_index >= batch->num_columns)
+      return Status::Make(GDV_INVALID, "batch has fewer columns than the schema");
+    const gdv_column_t& c = batch->columns[slot.schema_index];
+    ResolvedIn r;
+    const int64_t off = c.offset;
+    const DataType& t = slot.type;
+    if (c.values == nullptr && n > 0)
+      return Status::Make(GDV_INVALID, "column " + std::to_string(slot.schema_index) +
+                                           " has no values buffer");
+    // ---- validity
+    if (c.validity != nullptr) {
+      const uint8_t* p = static_cast<const uint8_t*>(c.validity) + (off >> 3);
+      r.vsh = static_cast<uint32_t>(off & 7);
+      if (host) {
+        const size_t bytes = static_cast<size_t>(BitBytes(off, n));
+        CUdeviceptr dp;
+        GDV_RETURN_NOT_OK(scratch->Alloc(bytes + 8, &dp));
+        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D validity"));
+        r.vld = dp;
+      } else {
+        r.vld = reinterpret_cast<CUdeviceptr>(p);
+      }
+    }
+    // ---- values
+    if (t.is_bool()) {
+      const uint8_t* p = static_cast<const uint8_t*>(c.values) + (off >> 3);
+      r.dsh = static_cast<uint32_t>(off & 7);
+      if (host) {
+        const size_t bytes = static_cast<size_t>(BitBytes(off, n));
+        CUdeviceptr dp;
+        GDV_RETURN_NOT_OK(scratch->Alloc(bytes + 8, &dp));
+        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D bool values"));
+        r.val = dp;
+      } else {
+        r.val = reinterpret_cast<CUdeviceptr>(p);
+      }
+    } else if (t.is_varlen()) {
+      const int32_t* offs = static_cast<const int32_t*>(c.values) + off;
+      if (host) {
+        const size_t obytes = static_cast<size_t>(n + 1) * 4;
+        CUdeviceptr dp;
+        GDV_RETURN_NOT_OK(scratch->Alloc(obytes, &dp));
+        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, offs, obytes, stream), "H2D offsets"));
+        r.val = dp;
+        const int64_t first = n > 0 ? offs[0] : 0, last = n > 0 ? offs[n] : 0;
+        const size_t vbytes = static_cast<size_t>(last - first);
+        CUdeviceptr dv;
+        GDV_RETURN_NOT_OK(scratch->Alloc(vbytes + 16, &dv));
+        if (vbytes > 0)
+          GDV_RETURN_NOT_OK(CuCheck(
+              d.MemcpyHtoDAsync(dv, static_cast<const uint8_t*>(c.var_data) + first, vbytes,
+                                stream),
+              "H2D string bytes"));
+        // kernel addresses bytes as var + offs[r]; rebase so offs[0] lands on dv
+        r.var = dv - static_cast<CUdeviceptr>(first);
+      } else {
+        r.val = reinterpret_cast<CUdeviceptr>(offs);
+        r.var = reinterpret_cast<CUdeviceptr>(c.var_data);
+      }
+    } else {
+      const int w = t.width();
+      const uint8_t* p = static_cast<const uint8_t*>(c.values) + off * w;
+      if (host) {
+        const size_t bytes = static_cast<size_t>(n) * w;
+        CUdeviceptr dp;
+        GDV_RETURN_NOT_OK(scratch->Alloc(bytes + 16, &dp));
+        if (bytes > 0)
+          GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D values"));
+        r.val = dp;
+      } else {
+        if (reinterpret_cast<uintptr_t>(p) % static_cast<uintptr_t>(w) != 0)
+          return Status::Make(GDV_INVALID, "device values buffer of column " +
+                                               std::to_string(slot.schema_index) +
+                                               " is not aligned to its element width");
+        r.val = reinterpret_cast<CUdeviceptr>(p);
+      }
+    }
+    (*out)[j] = r;
+  }
+  return Status::OK();
+}
+
+template <typename T>
+void Put(std::vector<uint8_t>& buf, size_t off, T v) {
+  std::memcpy(buf.data() + off, &v, sizeof(T));
+}
+
+Status LaunchKernel(Device* dev, const CompiledKernel::Loaded& l, const GeneratedKernel& gen,
+                    std::vector<uint8_t>& args, unsigned grid, CUstream stream) {
+  void* params[] = {args.data()};
+  if (grid == 0) return Status::OK();
+  g_launch_count.fetch_add(1);
+  return CuCheck(Driver().LaunchKernel(l.fn, grid, 1, 1, static_cast<unsigned>(gen.block_threads),
+                                       1, 1, 0, stream, params, nullptr),
+                 "cuLaunchKernel");
+}
+
+int SelWidth(int mode) {
+  switch (mode) {
+    case GDV_SEL_UINT16: return 2;
+    case GDV_SEL_UINT32: return 4;
+    case GDV_SEL_UINT64: return 8;
+    default: return 0;
+  }
+}
+
+}  // namespace
+
+// ======================================================================================
+// Projector
+// ======================================================================================
+Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int selection_mode,
+                       const Config& cfg, std::shared_ptr<Projector>* out) {
+  if (schema == nullptr) return Status::Make(GDV_INVALID, "Schema cannot be null");
+  if (exprs.empty()) return Status::Make(GDV_INVALID, "Expressions cannot be empty");
+  for (const auto& e : exprs) {
+    if (e == nullptr) return Status::Make(GDV_INVALID, "Expression cannot be null");
+    GDV_RETURN_NOT_OK(ValidateExpression(*schema, *e));
+  }
+  std::shared_ptr<Projector> p(new Projector());
+  p->schema_ = schema;
+  p->exprs_ = std::move(exprs);
+  p->selection_mode_ = selection_mode;
+  p->cfg_ = cfg;
+  GDV_RETURN_NOT_OK(
+      BuildKernel(*schema, p->exprs_, KernelKind::kProject, selection_mode, cfg, &p->kernel_));
+  *out = std::move(p);
+  return Status::OK();
+}
+
+std::string Projector::DumpIR() const {
+  return kernel_->gen.source + (kernel_->ptx.empty() ? "" : "\n// ---- PTX ----\n" + kernel_->ptx);
+}
+
+Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
+                           gdv_out_column_t* outs, int n_outs, void* stream_v, bool async) {
+  if (batch == nullptr || outs == nullptr) return Status::Make(GDV_INVALID, "null argument");
+  if (n_outs != num_outputs())
+    return Status::Make(GDV_INVALID, "expected " + std::to_string(num_outputs()) +
+                                         " output columns, got " + std::to_string(n_outs));
+  if (batch->num_columns != static_cast<int>(schema_->fields().size()))
+    return Status::Make(GDV_INVALID, "RecordBatch schema must match the schema of Make()");
+  if (batch->num_rows <= 0) return Status::Make(GDV_INVALID, "RecordBatch must be non-empty.");
+  if (selection_mode_ != GDV_SEL_NONE) {
+    if (sel == nullptr) return Status::Make(GDV_INVALID, "selection vector required by Make()");
+    if (sel->mode != selection_mode_)
+      return Status::Make(GDV_INVALID, "selection vector mode differs from the mode given to Make()");
+    if (sel->mem_space != batch->mem_space)
+      return Status::Make(GDV_INVALID, "selection vector and batch must share a memory space");
+  } else if (sel != nullptr && sel->mode != GDV_SEL_NONE) {
+    return Status::Make(GDV_INVALID, "projector was built without a selection vector mode");
+  }
+  const bool host = batch->mem_space == GDV_MEM_HOST;
+  const int64_t n = selection_mode_ != GDV_SEL_NONE ? sel->num_slots : batch->num_rows;
+  if (n < 0) return Status::Make(GDV_INVALID, "negative slot count");
+
+  Device* dev = nullptr;
+  GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CompiledKernel::Loaded l;
+  GDV_RETURN_NOT_OK(kernel_->Load(dev, &l));
+  const DriverApi& d = Driver();
+  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
+  const GeneratedKernel& gen = kernel_->gen;
+
+  ScratchScope scratch(dev);
+  std::vector<ResolvedIn> ins;
+  GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
+
+  ArgsLayout L(static_cast<int>(gen.inputs.size()), n_outs);
+  std::vector<uint8_t> args(L.size, 0);
+  Put<int64_t>(args, L.off_n, n);
+  for (size_t j = 0; j < ins.size(); ++j) {
+    Put<CUdeviceptr>(args, L.off_in_val + 8 * j, ins[j].val);
+    Put<CUdeviceptr>(args, L.off_in_vld + 8 * j, ins[j].vld);
+    Put<CUdeviceptr>(args, L.off_in_var + 8 * j, ins[j].var);
+    Put<uint32_t>(args, L.off_in_vsh + 4 * j, ins[j].vsh);
+    Put<uint32_t>(args, L.off_in_dsh + 4 * j, ins[j].dsh);
+  }
+  // selection vector
+  if (selection_mode_ != GDV_SEL_NONE) {
+    CUdeviceptr dsel = reinterpret_cast<CUdeviceptr>(sel->indices);
+    if (host) {
+      const size_t bytes = static_cast<size_t>(n) * SelWidth(selection_mode_);
+      GDV_RETURN_NOT_OK(scratch.Alloc(bytes + 16, &dsel));
+      if (bytes > 0)
+        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dsel, sel->indices, bytes, stream), "H2D sel"));
+    }
+    Put<CUdeviceptr>(args, L.off_sel, dsel);
+  }
+  // outputs
+  struct OutStage {
+    CUdeviceptr val = 0, vld = 0;
+    size_t val_bytes = 0, vld_bytes = 0;
+  };
+  std::vector<OutStage> stage(n_outs);
+  const size_t words = static_cast<size_t>((n + 31) / 32);
+  for (int o = 0; o < n_outs; ++o) {
+    const DataType& t = gen.outputs[o];
+    if (outs[o].values == nullptr && n > 0)
+      return Status::Make(GDV_INVALID, "output values buffer is null");
+    OutStage& st = stage[o];
+    st.val_bytes = t.is_bool() ? static_cast<size_t>((n + 7) / 8) : static_cast<size_t>(n) * t.width();
+    st.vld_bytes = static_cast<size_t>((n + 7) / 8);
+    if (host) {
+      GDV_RETURN_NOT_OK(scratch.Alloc(t.is_bool() ? words * 4 + 8 : st.val_bytes + 16, &st.val));
+      if (outs[o].validity != nullptr) GDV_RETURN_NOT_OK(scratch.Alloc(words * 4 + 8, &st.vld));
+    } else {
+      st.val = reinterpret_cast<CUdeviceptr>(outs[o].values);
+      st.vld = reinterpret_cast<CUdeviceptr>(outs[o].validity);
+    }
+    Put<CUdeviceptr>(args, L.off_out_val + 8 * o, st.val);
+    Put<CUdeviceptr>(args, L.off_out_vld + 8 * o, st.vld);
+  }
+  // error flag
+  CUdeviceptr d_err = 0;
+  if (gen.uses_ctx) {
+    std::lock_guard<std::mutex> lock(mu_);
+    Pending& pend = pending_[stream];
+    if (pend.d_err == 0) {
+      pend.dev = dev;
+      pend.uses_ctx = true;
+      GDV_RETURN_NOT_OK(dev->Alloc(256, &pend.d_err));
+      GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(pend.d_err, 0, 256, stream), "memset err"));
+    }
+    d_err = pend.d_err;
+    Put<CUdeviceptr>(args, L.off_err, d_err);
+  }
+
+  const int R = gen.rows_per_thread, BT = gen.block_threads;
+  const int64_t wtiles = (n + 32 * R - 1) / (32 * R);
+  const int64_t blocks_needed = (wtiles + BT / 32 - 1) / (BT / 32);
+  const int64_t cap = static_cast<int64_t>(dev->sm_count()) * l.blocks_per_sm;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(blocks_needed, cap));
+  GDV_RETURN_NOT_OK(LaunchKernel(dev, l, gen, args, grid, stream));
+
+  if (host) {
+    for (int o = 0; o < n_outs; ++o) {
+      if (stage[o].val_bytes > 0)
+        GDV_RETURN_NOT_OK(CuCheck(
+            d.MemcpyDtoHAsync(outs[o].values, stage[o].val, stage[o].val_bytes, stream), "D2H values"));
+      if (outs[o].validity != nullptr && stage[o].vld_bytes > 0)
+        GDV_RETURN_NOT_OK(CuCheck(
+            d.MemcpyDtoHAsync(outs[o].validity, stage[o].vld, stage[o].vld_bytes, stream),
+            "D2H validity"));
+    }
+    return Sync(stream);
+  }
+  if (!async) return Sync(stream);
+  // async with device buffers: inputs were not staged, scratch holds nothing the kernel reads
+  return Status::OK();
+}
+
+Status Projector::Sync(void* stream_v) {
+  Device* dev = nullptr;
+  GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
+  const DriverApi& d = Driver();
+  Pending pend;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = pending_.find(stream);
+    if (it != pending_.end()) {
+      pend = it->second;
+      pending_.erase(it);
+      have = true;
+    }
+  }
+  int err = 0;
+  if (have && pend.d_err != 0)
+    GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(&err, pend.d_err, sizeof(int), stream), "D2H err"));
+  Status s = CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize");
+  if (have) {
+    if (pend.d_err != 0) dev->Free(pend.d_err);
+    for (auto p : pend.scratch) dev->Free(p);
+  }
+  GDV_RETURN_NOT_OK(s);
+  if (err != 0) return Status::Make(GDV_EXECUTION_ERROR, ExecutionErrorMessage(err));
+  return Status::OK();
+}
+
+// ======================================================================================
+// Filter
+// ======================================================================================
+Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
+                    std::shared_ptr<Filter>* out) {
+  if (schema == nullptr) return Status::Make(GDV_INVALID, "Schema cannot be null");
+  if (cond == nullptr) return Status::Make(GDV_INVALID, "Condition cannot be null");
+  GDV_RETURN_NOT_OK(ValidateExpression(*schema, *cond));
+  std::shared_ptr<Filter> f(new Filter());
+  f->schema_ = schema;
+  f->cond_ = cond;
+  f->cfg_ = cfg;
+  // The default Python/Cython path uses UINT32 indices: compile that variant eagerly so
+  // Make() surfaces code-generation errors, as the reference does.
+  CompiledKernel* k = nullptr;
+  GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, &k));
+  *out = std::move(f);
+  return Status::OK();
+}
+
+Status Filter::KernelFor(int mode, CompiledKernel** out) {
+  std::lock_guard<std::mutex> lock(mu_);
+  auto it = kernels_.find(mode);
+  if (it == kernels_.end()) {
+    std::unique_ptr<CompiledKernel> k;
+    std::vector<ExpressionPtr> exprs = {cond_};
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, cfg_, &k));
+    it = kernels_.emplace(mode, std::move(k)).first;
+  }
+  *out = it->second.get();
+  return Status::OK();
+}
+
+std::string Filter::DumpIR() const {
+  std::lock_guard<std::mutex> lock(mu_);
+  auto it = kernels_.find(GDV_SEL_UINT32);
+  if (it == kernels_.end()) return "";
+  return it->second->gen.source +
+         (it->second->ptx.empty() ? "" : "\n// ---- PTX ----\n" + it->second->ptx);
+}
+
+Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void* stream_v,
+                        bool async, void* d_count_user) {
+  if (batch == nullptr || out_sel == nullptr) return Status::Make(GDV_INVALID, "null argument");
+  if (batch->num_columns != static_cast<int>(schema_->fields().size()))
+    return Status::Make(GDV_INVALID, "RecordBatch schema must match the schema of Make()");
+  if (batch->num_rows <= 0) return Status::Make(GDV_INVALID, "RecordBatch must be non-empty.");
+  if (out_sel->mode < GDV_SEL_UINT16 || out_sel->mode > GDV_SEL_UINT64)
+    return Status::Make(GDV_INVALID, "invalid selection vector mode");
+  if (out_sel->max_slots < batch->num_rows)
+    return Status::Make(GDV_INVALID, "Selection vector max_slots " +
+                                         std::to_string(out_sel->max_slots) +
+                                         " is less than the number of rows " +
+                                         std::to_string(batch->num_rows));
+  if (out_sel->mem_space != batch->mem_space)
+    return Status::Make(GDV_INVALID, "selection vector and batch must share a memory space");
+  const int64_t n = batch->num_rows;
+  if (out_sel->mode == GDV_SEL_UINT16 && n > 65536)
+    return Status::Make(GDV_INVALID, "batch too large for a uint16 selection vector");
+  if (out_sel->mode == GDV_SEL_UINT32 && n > (int64_t(1) << 32))
+    return Status::Make(GDV_INVALID, "batch too large for a uint32 selection vector");
+  const bool host = batch->mem_space == GDV_MEM_HOST;
+
+  Device* dev = nullptr;
+  GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CompiledKernel* kernel = nullptr;
+  GDV_RETURN_NOT_OK(KernelFor(out_sel->mode, &kernel));
+  CompiledKernel::Loaded l;
+  GDV_RETURN_NOT_OK(kernel->Load(dev, &l));
+  const DriverApi& d = Driver();
+  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
+  const GeneratedKernel& gen = kernel->gen;
+
+  ScratchScope scratch(dev);
+  std::vector<ResolvedIn> ins;
+  GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
+
+  const int R = gen.rows_per_thread, BT = gen.block_threads;
+  const int64_t tile_rows = static_cast<int64_t>(R) * BT;
+  const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
+
+  // Per-stream persistent scratch: [ticket u64][count u64][tile_state n_tiles x u64]
+  const size_t state_bytes = 16 + static_cast<size_t>(n_tiles) * 8;
+  CUdeviceptr d_state = 0, d_err = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    Pending& pend = pending_[stream];
+    pend.dev = dev;
+    if (pend.state_cap < state_bytes) {
+      // earlier blocks stay alive until Sync(): launches still queued may be using them
+      GDV_RETURN_NOT_OK(dev->Alloc(state_bytes, &pend.d_state));
+      pend.scratch.push_back(pend.d_state);
+      pend.state_cap = state_bytes;
+    }
+    d_state = pend.d_state;
+    if (gen.uses_ctx) {
+      if (pend.d_err == 0) {
+        GDV_RETURN_NOT_OK(dev->Alloc(256, &pend.d_err));
+        GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(pend.d_err, 0, 256, stream), "memset err"));
+        pend.uses_ctx = true;
+      }
+      d_err = pend.d_err;
+    }
+    pend.d_count = d_count_user != nullptr ? reinterpret_cast<CUdeviceptr>(d_count_user)
+                                           : d_state + 8;
+  }
+  GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(d_state, 0, state_bytes, stream), "memset tile state"));
+  CUdeviceptr d_count = d_state + 8;
+  if (d_count_user != nullptr) {
+    d_count = reinterpret_cast<CUdeviceptr>(d_count_user);
+    GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(d_count, 0, 8, stream), "memset count"));
+  }
+
+  CUdeviceptr d_idx = reinterpret_cast<CUdeviceptr>(out_sel->indices);
+  const int iw = SelWidth(out_sel->mode);
+  if (host) GDV_RETURN_NOT_OK(scratch.Alloc(static_cast<size_t>(n) * iw + 16, &d_idx));
+
+  ArgsLayout L(static_cast<int>(gen.inputs.size()), 0);
+  std::vector<uint8_t> args(L.size, 0);
+  Put<int64_t>(args, L.off_n, n);
+  Put<int64_t>(args, L.off_row_base, out_sel->index_base);
+  Put<CUdeviceptr>(args, L.off_out_idx, d_idx);
+  Put<CUdeviceptr>(args, L.off_out_count, d_count);
+  Put<CUdeviceptr>(args, L.off_tile_state, d_state + 16);
+  Put<CUdeviceptr>(args, L.off_ticket, d_state);
+  Put<CUdeviceptr>(args, L.off_err, d_err);
+  for (size_t j = 0; j < ins.size(); ++j) {
+    Put<CUdeviceptr>(args, L.off_in_val + 8 * j, ins[j].val);
+    Put<CUdeviceptr>(args, L.off_in_vld + 8 * j, ins[j].vld);
+    Put<CUdeviceptr>(args, L.off_in_var + 8 * j, ins[j].var);
+    Put<uint32_t>(args, L.off_in_vsh + 4 * j, ins[j].vsh);
+    Put<uint32_t>(args, L.off_in_dsh + 4 * j, ins[j].dsh);
+  }
+  const int64_t cap = static_cast<int64_t>(dev->sm_count()) * l.blocks_per_sm;
+  const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, cap)));
+  GDV_RETURN_NOT_OK(LaunchKernel(dev, l, gen, args, grid, stream));
+
+  out_sel->num_slots = -1;
+  if (host) {
+    int64_t count = 0;
+    GDV_RETURN_NOT_OK(Sync(stream, &count));
+    if (count > 0) {
+      GDV_RETURN_NOT_OK(CuCheck(
+          d.MemcpyDtoHAsync(out_sel->indices, d_idx, static_cast<size_t>(count) * iw, stream),
+          "D2H selection"));
+      GDV_RETURN_NOT_OK(CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize"));
+    }
+    out_sel->num_slots = count;
+    return Status::OK();
+  }
+  if (!async) {
+    int64_t count = 0;
+    GDV_RETURN_NOT_OK(Sync(stream, &count));
+    out_sel->num_slots = count;
+  }
+  return Status::OK();
+}
+
+Status Filter::Sync(void* stream_v, int64_t* num_slots) {
+  Device* dev = nullptr;
+  GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
+  const DriverApi& d = Driver();
+  Pending pend;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = pending_.find(stream);
+    if (it != pending_.end()) {
+      pend = it->second;
+      pending_.erase(it);
+      have = true;
+    }
+  }
+  int err = 0;
+  uint64_t count = 0;
+  if (have && pend.d_err != 0)
+    GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(&err, pend.d_err, sizeof(int), stream), "D2H err"));
+  if (have && pend.d_count != 0)
+    GDV_RETURN_NOT_OK(
+        CuCheck(d.MemcpyDtoHAsync(&count, pend.d_count, sizeof(count), stream), "D2H count"));
+  Status s = CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize");
+  if (have) {
+    if (pend.d_err != 0) dev->Free(pend.d_err);
+    for (auto p : pend.scratch) dev->Free(p);
+  }
+  GDV_RETURN_NOT_OK(s);
+  if (err != 0) return Status::Make(GDV_EXECUTION_ERROR, ExecutionErrorMessage(err));
+  if (num_slots != nullptr) *num_slots = have ? static_cast<int64_t>(count) : -1;
+  return Status::OK();
+}
+
+}  // namespace gdv

@@ -1,0 +1,163 @@
+// Runtime behind Projector / Filter: device handles, scratch pool, compiled kernels,
+// buffer marshalling and launches.  Replaces the reference's Engine (module ownership,
+// compile, function pointers) and the evaluate-time half of its Annotator (RecordBatch ->
+// flat pointer block); SURVEY.md §3 call stacks A-D.
+#pragma once
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gdv_codegen.h"
+#include "gdv_cuda.h"
+
+namespace gdv {
+
+extern std::atomic<long long> g_launch_count;
+
+class Device {
+ public:
+  static Status Get(int ordinal, Device** out);
+  Status MakeCurrent() const;
+  int ordinal() const { return ordinal_; }
+  int sm_count() const { return sm_count_; }
+  std::string arch() const;
+  CUstream stream() const { return stream_; }
+  CUstream copy_stream() const { return copy_stream_; }
+
+  // Pooled device scratch: freed blocks are cached and reused (no cuMemFree on the hot path).
+  Status Alloc(size_t bytes, CUdeviceptr* out);
+  void Free(CUdeviceptr p);
+
+  // Kernels of device/static_kernels.cu (embedded sm_100a cubin).
+  Status StaticFunction(const char* name, CUfunction* out);
+
+ private:
+  Device() = default;
+  int ordinal_ = 0;
+  CUdevice dev_ = 0;
+  CUcontext ctx_ = nullptr;
+  CUstream stream_ = nullptr;
+  CUstream copy_stream_ = nullptr;
+  int sm_count_ = 0, cc_major_ = 0, cc_minor_ = 0;
+  std::mutex mu_;
+  std::multimap<size_t, CUdeviceptr> free_;
+  std::unordered_map<CUdeviceptr, size_t> sizes_;
+  CUmodule static_mod_ = nullptr;
+  std::map<std::string, CUfunction> static_fns_;
+};
+
+// RAII list of scratch blocks returned to the pool when the evaluation ends.
+class ScratchScope {
+ public:
+  explicit ScratchScope(Device* d) : dev_(d) {}
+  ~ScratchScope() {
+    for (auto p : blocks_) dev_->Free(p);
+  }
+  Status Alloc(size_t bytes, CUdeviceptr* out) {
+    Status s = dev_->Alloc(bytes, out);
+    if (s.ok()) blocks_.push_back(*out);
+    return s;
+  }
+  std::vector<CUdeviceptr> Release() {
+    std::vector<CUdeviceptr> b;
+    b.swap(blocks_);
+    return b;
+  }
+
+ private:
+  Device* dev_;
+  std::vector<CUdeviceptr> blocks_;
+};
+
+struct Config {
+  bool optimize = true;
+  bool dump_ir = false;
+  int device = 0;
+  int rows_per_thread = 0;
+  int block_threads = 0;
+  int loader = 0;
+};
+
+class CompiledKernel {
+ public:
+  GeneratedKernel gen;
+  std::vector<char> cubin;
+  std::string ptx;
+  std::string compile_log;
+
+  struct Loaded {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    int blocks_per_sm = 1;
+    int regs = 0;
+    int smem = 0;
+  };
+  // Lazily loads the cubin into `dev`'s context.
+  Status Load(Device* dev, Loaded* out);
+
+ private:
+  std::mutex mu_;
+  std::map<int, Loaded> loaded_;
+};
+
+// Pending asynchronous evaluation state (error flag / count readback) per stream.
+struct Pending {
+  Device* dev = nullptr;
+  std::vector<CUdeviceptr> scratch;  // returned to the pool at sync
+  CUdeviceptr d_err = 0;
+  CUdeviceptr d_count = 0;
+  CUdeviceptr d_state = 0;  // filter look-back state, reused by stream-ordered launches
+  size_t state_cap = 0;
+  bool uses_ctx = false;
+};
+
+class Projector {
+ public:
+  static Status Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int selection_mode,
+                     const Config& cfg, std::shared_ptr<Projector>* out);
+  Status Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel, gdv_out_column_t* outs,
+                  int n_outs, void* stream, bool async);
+  Status Sync(void* stream);
+  std::string DumpIR() const;
+  CompiledKernel& kernel() { return *kernel_; }
+  const Config& config() const { return cfg_; }
+  int num_outputs() const { return static_cast<int>(exprs_.size()); }
+
+ private:
+  SchemaPtr schema_;
+  std::vector<ExpressionPtr> exprs_;
+  int selection_mode_ = GDV_SEL_NONE;
+  Config cfg_;
+  std::unique_ptr<CompiledKernel> kernel_;
+  std::mutex mu_;
+  std::map<void*, Pending> pending_;
+};
+
+class Filter {
+ public:
+  static Status Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
+                     std::shared_ptr<Filter>* out);
+  Status Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void* stream, bool async,
+                  void* d_count);
+  Status Sync(void* stream, int64_t* num_slots);
+  std::string DumpIR() const;
+  // One kernel per selection-vector index width, compiled on first use.
+  Status KernelFor(int mode, CompiledKernel** out);
+  const Config& config() const { return cfg_; }
+
+ private:
+  SchemaPtr schema_;
+  ConditionPtr cond_;
+  Config cfg_;
+  mutable std::mutex mu_;
+  std::map<int, std::unique_ptr<CompiledKernel>> kernels_;
+  std::map<void*, Pending> pending_;
+};
+
+const char* ExecutionErrorMessage(int code);
+
+}  // namespace gdv

@@ -1,0 +1,270 @@
+/*
+ * gandiva_b200.h — C-ABI of the B200-native expression engine.
+ *
+ * This is the drop-in boundary for the Gandiva hot path (Projector / Filter
+ * Make + Evaluate over Arrow buffers).  Everything here is `extern "C"`, plain
+ * pointers and sizes; no C++ types, no torch types, no Arrow C++ types.  The
+ * C++ API in include/gandiva/ (namespace gandiva, the declarations that
+ * pyarrow/includes/libgandiva.pxd binds) is a thin layer over these calls; so
+ * is the Python mirror in gandiva_b200/__init__.py (ctypes).
+ *
+ * Reference interface each group replaces (the reference mount holds no
+ * source; citations are to the descendant's binding
+ * declarations shipped with pyarrow 24.0.0, `P` =
+ * site-packages/pyarrow):
+ *
+ *   gdv_node_*            <- gandiva::TreeExprBuilder::Make*      P/includes/libgandiva.pxd:110-212
+ *   gdv_expression_make   <- TreeExprBuilder::MakeExpression      P/includes/libgandiva.pxd:151-153
+ *   gdv_condition_make    <- TreeExprBuilder::MakeCondition       P/includes/libgandiva.pxd:172-174
+ *   gdv_projector_make    <- gandiva::Projector::Make             P/includes/libgandiva.pxd:230-240
+ *   gdv_projector_evaluate<- gandiva::Projector::Evaluate (both)  P/includes/libgandiva.pxd:218-226
+ *   gdv_projector_dump_ir <- gandiva::Projector::DumpIR           P/includes/libgandiva.pxd:228
+ *   gdv_filter_make       <- gandiva::Filter::Make                P/includes/libgandiva.pxd:252-256
+ *   gdv_filter_evaluate   <- gandiva::Filter::Evaluate            P/includes/libgandiva.pxd:246-248
+ *   gdv_filter_dump_ir    <- gandiva::Filter::DumpIR              P/includes/libgandiva.pxd:250
+ *   gdv_registry_*        <- GetRegisteredFunctionSignatures      P/includes/libgandiva.pxd:258-277
+ *   gdv_config_t          <- gandiva::Configuration               P/includes/libgandiva.pxd:279-298
+ *   GDV_SEL_*             <- gandiva::SelectionVector::Mode       P/includes/libgandiva.pxd:49-56
+ *   status codes          <- arrow::StatusCode (40/41/42)         P/include/arrow/status.h:97-100
+ *
+ * Ownership: every handle returned through an out-parameter is owned by the
+ * caller and released with the matching *_release call.  Nodes are
+ * reference-counted inside the library: a parent keeps its children alive, so
+ * a caller may release child handles right after building the parent.
+ * Threading: Make calls may run concurrently; a built projector/filter may be
+ * evaluated from several threads at once (per-call scratch, no per-object
+ * mutable state besides a lock-protected scratch pool).
+ * Errors: every call returns a gdv_status; gdv_last_error() returns the
+ * thread-local message of the last failing call on this thread.
+ */
+#ifndef GANDIVA_B200_H
+#define GANDIVA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (numerically equal to arrow::StatusCode) ------------- */
+typedef int32_t gdv_status;
+#define GDV_OK 0
+#define GDV_OUT_OF_MEMORY 1
+#define GDV_INVALID 4
+#define GDV_NOT_IMPLEMENTED 10
+#define GDV_CODEGEN_ERROR 40              /* arrow::StatusCode::CodeGenError */
+#define GDV_EXPRESSION_VALIDATION_ERROR 41 /* ExpressionValidationError */
+#define GDV_EXECUTION_ERROR 42            /* ExecutionError */
+#define GDV_CUDA_ERROR 100                /* driver / NVRTC unavailable or failed */
+
+/* ---- data types (ids numerically equal to arrow::Type::type) ----------- */
+#define GDV_TYPE_NA 0
+#define GDV_TYPE_BOOL 1
+#define GDV_TYPE_UINT8 2
+#define GDV_TYPE_INT8 3
+#define GDV_TYPE_UINT16 4
+#define GDV_TYPE_INT16 5
+#define GDV_TYPE_UINT32 6
+#define GDV_TYPE_INT32 7
+#define GDV_TYPE_UINT64 8
+#define GDV_TYPE_INT64 9
+#define GDV_TYPE_FLOAT 11
+#define GDV_TYPE_DOUBLE 12
+#define GDV_TYPE_STRING 13
+#define GDV_TYPE_BINARY 14
+#define GDV_TYPE_DATE32 16
+#define GDV_TYPE_DATE64 17
+#define GDV_TYPE_TIMESTAMP 18
+#define GDV_TYPE_TIME32 19
+#define GDV_TYPE_TIME64 20
+#define GDV_TYPE_DECIMAL128 23
+
+typedef struct gdv_type {
+  int32_t id;        /* GDV_TYPE_* */
+  int32_t precision; /* decimal128: precision; timestamp/time: arrow::TimeUnit (0=s,1=ms,2=us,3=ns) */
+  int32_t scale;     /* decimal128: scale */
+} gdv_type_t;
+
+/* ---- opaque handles ----------------------------------------------------- */
+typedef struct gdv_node_s* gdv_node_t;
+typedef struct gdv_expression_s* gdv_expression_t;
+typedef struct gdv_condition_s* gdv_condition_t;
+typedef struct gdv_schema_s* gdv_schema_t;
+typedef struct gdv_projector_s* gdv_projector_t;
+typedef struct gdv_filter_s* gdv_filter_t;
+
+/* ---- configuration (gandiva::Configuration + device placement) --------- */
+typedef struct gdv_config {
+  int32_t optimize;     /* reference option; here: ptxas -O3 (1) or -O0 (0) */
+  int32_t dump_ir;      /* keep generated CUDA source + PTX for DumpIR */
+  int32_t device;       /* CUDA device ordinal (default 0) */
+  int32_t rows_per_thread; /* 0 = engine picks; otherwise unroll factor override */
+  int32_t block_threads;   /* 0 = engine picks (256) */
+  int32_t loader;          /* 0 = engine picks; 1 = direct coalesced LDG; 2 = TMA bulk -> shared */
+  int32_t reserved[6];
+} gdv_config_t;
+void gdv_config_default(gdv_config_t* cfg);
+
+/* ---- selection-vector modes -------------------------------------------- */
+#define GDV_SEL_NONE 0
+#define GDV_SEL_UINT16 1
+#define GDV_SEL_UINT32 2
+#define GDV_SEL_UINT64 3
+
+/* ---- memory spaces of the buffers handed to Evaluate ------------------- */
+#define GDV_MEM_HOST 0   /* pageable or pinned host memory: engine stages H2D/D2H */
+#define GDV_MEM_DEVICE 1 /* buffers already live in the HBM of cfg.device */
+
+/* One Arrow array, as its raw buffers (arrow::ArrayData, P/include/arrow/array/data.h:468-474).
+ *  fixed width : validity | values                (values = buffers[1])
+ *  bool        : validity | bit-packed values
+ *  utf8/binary : validity | int32 offsets | bytes (values = offsets, var_data = bytes)
+ * `offset` is ArrayData::offset (in elements/bits), applied to every buffer.
+ * validity may be NULL (no nulls). */
+typedef struct gdv_column {
+  const void* validity;
+  const void* values;
+  const void* var_data;
+  int64_t offset;
+  int64_t var_data_size; /* bytes in var_data (needed to stage host strings); 0 otherwise */
+} gdv_column_t;
+
+typedef struct gdv_batch {
+  int64_t num_rows;
+  int32_t num_columns; /* must equal the schema's field count, same order */
+  int32_t mem_space;   /* GDV_MEM_* */
+  const gdv_column_t* columns;
+} gdv_batch_t;
+
+/* Caller-allocated output array (Projector::Evaluate allocates these from the
+ * MemoryPool in the C++ layer).  Output offset is always 0.
+ *  validity : ceil(n/8) bytes rounded up to 8; may be NULL -> validity not written
+ *  values   : n*width bytes (bool: ceil(n/8) rounded up to 8); utf8: (n+1) int32 offsets
+ *  var_data : utf8/binary outputs only, capacity var_capacity bytes */
+typedef struct gdv_out_column {
+  void* validity;
+  void* values;
+  void* var_data;
+  int64_t var_capacity;
+  int64_t var_size; /* out: bytes produced (utf8/binary) */
+} gdv_out_column_t;
+
+/* Selection vector storage (gandiva::SelectionVector): ascending row indices. */
+typedef struct gdv_selection {
+  void* indices;      /* uint16/uint32/uint64 per mode; host or device per mem_space */
+  int64_t max_slots;  /* capacity in indices */
+  int64_t num_slots;  /* in: slots to read (projector); out: slots written (filter) */
+  int32_t mode;       /* GDV_SEL_* */
+  int32_t mem_space;  /* GDV_MEM_* */
+  int64_t index_base; /* filter: added to every emitted index (row-range sharding: the
+                         shard's first global row); projector: ignored */
+} gdv_selection_t;
+
+/* ---- library / device ---------------------------------------------------- */
+const char* gdv_version(void);
+const char* gdv_last_error(void);
+/* 1 when libcuda + a device are usable, 0 otherwise (never fails). */
+int32_t gdv_cuda_available(void);
+int32_t gdv_device_count(void);
+
+/* ---- TreeExprBuilder ---------------------------------------------------- */
+gdv_status gdv_node_field(const char* name, gdv_type_t type, gdv_node_t* out);
+/* Literals: `value` points at the C value of the type (bool: uint8_t, intN: intN_t,
+ * float/double, date/time as their storage int; decimal128: 16 little-endian bytes;
+ * string/binary: bytes with `len`).  is_null != 0 makes a typed null literal. */
+gdv_status gdv_node_literal(gdv_type_t type, const void* value, int64_t len, int32_t is_null,
+                            gdv_node_t* out);
+gdv_status gdv_node_function(const char* name, const gdv_node_t* children, int32_t n_children,
+                             gdv_type_t return_type, gdv_node_t* out);
+gdv_status gdv_node_if(gdv_node_t condition, gdv_node_t then_node, gdv_node_t else_node,
+                       gdv_type_t return_type, gdv_node_t* out);
+gdv_status gdv_node_and(const gdv_node_t* children, int32_t n_children, gdv_node_t* out);
+gdv_status gdv_node_or(const gdv_node_t* children, int32_t n_children, gdv_node_t* out);
+/* IN expression.  Fixed-width: `values` is n_values packed values of `type`.
+ * string/binary: `values` is the concatenated bytes, `lengths` the n_values lengths. */
+gdv_status gdv_node_in(gdv_node_t child, gdv_type_t type, const void* values,
+                       const int32_t* lengths, int32_t n_values, gdv_node_t* out);
+gdv_status gdv_node_return_type(gdv_node_t node, gdv_type_t* out);
+/* Writes a NUL-terminated string; returns the full length needed (excluding NUL). */
+int64_t gdv_node_to_string(gdv_node_t node, char* buf, int64_t buf_len);
+void gdv_node_release(gdv_node_t node);
+
+gdv_status gdv_expression_make(gdv_node_t root, const char* result_name, gdv_type_t result_type,
+                               gdv_expression_t* out);
+int64_t gdv_expression_to_string(gdv_expression_t e, char* buf, int64_t buf_len);
+void gdv_expression_release(gdv_expression_t e);
+gdv_status gdv_condition_make(gdv_node_t root, gdv_condition_t* out);
+int64_t gdv_condition_to_string(gdv_condition_t c, char* buf, int64_t buf_len);
+void gdv_condition_release(gdv_condition_t c);
+
+/* ---- schema ------------------------------------------------------------- */
+gdv_status gdv_schema_make(const char* const* names, const gdv_type_t* types, int32_t n_fields,
+                           gdv_schema_t* out);
+void gdv_schema_release(gdv_schema_t s);
+
+/* ---- Projector ---------------------------------------------------------- */
+gdv_status gdv_projector_make(gdv_schema_t schema, const gdv_expression_t* exprs, int32_t n_exprs,
+                              int32_t selection_mode, const gdv_config_t* cfg,
+                              gdv_projector_t* out);
+/* Evaluate.  `selection` NULL (mode NONE) or a selection vector of the mode given at Make.
+ * `stream` is a CUstream/cudaStream_t (0 = the engine's own stream).  With host
+ * buffers the call is synchronous.  With device buffers and `async` != 0 it only
+ * enqueues work on `stream`; errors raised by device functions are then reported
+ * by gdv_projector_sync(). */
+gdv_status gdv_projector_evaluate(gdv_projector_t p, const gdv_batch_t* batch,
+                                  const gdv_selection_t* selection, gdv_out_column_t* outs,
+                                  int32_t n_outs, void* stream, int32_t async);
+gdv_status gdv_projector_sync(gdv_projector_t p, void* stream);
+/* Bytes needed for output i's var_data given the batch (utf8/binary outputs): runs the
+ * sizing pass only.  Fixed-width outputs return 0. */
+gdv_status gdv_projector_output_var_size(gdv_projector_t p, const gdv_batch_t* batch,
+                                         const gdv_selection_t* selection, int32_t out_index,
+                                         void* stream, int64_t* out_bytes);
+int64_t gdv_projector_dump_ir(gdv_projector_t p, char* buf, int64_t buf_len);
+/* Name of the generated kernel, its registers/thread and static shared memory. */
+gdv_status gdv_projector_kernel_info(gdv_projector_t p, char* name_buf, int64_t name_len,
+                                     int32_t* regs, int32_t* smem_bytes, int32_t* rows_per_thread,
+                                     int32_t* block_threads);
+void gdv_projector_release(gdv_projector_t p);
+
+/* ---- Filter --------------------------------------------------------------- */
+gdv_status gdv_filter_make(gdv_schema_t schema, gdv_condition_t condition, const gdv_config_t* cfg,
+                           gdv_filter_t* out);
+/* Fills `out_selection->indices` (capacity max_slots >= batch->num_rows) with the ascending
+ * indices of rows whose condition is true and valid; sets num_slots.  With device buffers and
+ * async != 0, num_slots is written to `d_count` (device uint64_t*, may be NULL) when the stream
+ * reaches that point and out_selection->num_slots is left at -1; gdv_filter_sync() returns it. */
+gdv_status gdv_filter_evaluate(gdv_filter_t f, const gdv_batch_t* batch,
+                               gdv_selection_t* out_selection, void* stream, int32_t async,
+                               void* d_count);
+gdv_status gdv_filter_sync(gdv_filter_t f, void* stream, int64_t* num_slots);
+int64_t gdv_filter_dump_ir(gdv_filter_t f, char* buf, int64_t buf_len);
+gdv_status gdv_filter_kernel_info(gdv_filter_t f, char* name_buf, int64_t name_len, int32_t* regs,
+                                  int32_t* smem_bytes, int32_t* rows_per_thread,
+                                  int32_t* block_threads);
+void gdv_filter_release(gdv_filter_t f);
+
+/* ---- function registry (ExpressionRegistry) ------------------------------ */
+int32_t gdv_registry_size(void);
+/* Signature i: name, return type, parameter types (up to max_params written; returns count). */
+gdv_status gdv_registry_get(int32_t i, const char** name, gdv_type_t* ret, gdv_type_t* params,
+                            int32_t max_params, int32_t* n_params);
+
+/* ---- device helpers used by the harness (bench.py, tests) ---------------- */
+/* Pinned host memory (cuMemHostAlloc) so H2D staging runs at PCIe speed. */
+gdv_status gdv_host_alloc(size_t bytes, void** out);
+gdv_status gdv_host_free(void* p);
+/* Synthetic TPC-H lineitem columns generated straight into device memory (counter-based
+ * hash RNG, identical stream to oracle/lineitem.c):
+ *  kind 0: l_shipdate date32  1: l_discount f64  2: l_quantity f64 ... see DESIGN.md */
+gdv_status gdv_generate_lineitem(int32_t device, int32_t column_kind, uint64_t seed,
+                                 int64_t first_row, int64_t num_rows, void* d_values,
+                                 void* d_validity, int32_t null_permille, void* stream);
+/* Number of kernels this library has launched since load (gpu_launches in bench.py). */
+int64_t gdv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANDIVA_B200_H */

@@ -1,0 +1,427 @@
+"""Expression catalogue + data generators shared by the CPU tests (oracle, NVRTC compile) and
+the GPU parity tests.  Each case is a function of a TreeExprBuilder-like `b` returning
+(schema, [(root_node, result_type)], kind) where kind is "project" or "filter"."""
+from __future__ import annotations
+
+import decimal
+
+import numpy as np
+import pyarrow as pa
+
+INT_TYPES = [pa.int8(), pa.int16(), pa.int32(), pa.int64(), pa.uint8(), pa.uint16(), pa.uint32(),
+             pa.uint64()]
+FLOAT_TYPES = [pa.float32(), pa.float64()]
+NUMERIC = INT_TYPES + FLOAT_TYPES
+RELOPS = ["equal", "not_equal", "less_than", "less_than_or_equal_to", "greater_than",
+          "greater_than_or_equal_to"]
+
+_NP = {pa.int8(): np.int8, pa.int16(): np.int16, pa.int32(): np.int32, pa.int64(): np.int64,
+       pa.uint8(): np.uint8, pa.uint16(): np.uint16, pa.uint32(): np.uint32,
+       pa.uint64(): np.uint64, pa.float32(): np.float32, pa.float64(): np.float64}
+
+WORDS = ["special", "requests", "spark", "park", "fire", "carefully", "final", "deposits", "ironic",
+         "blithely", "Quick", "BROWN", "fox", "a", "", "x_y", "100%", "naïve", "日本語", "ünï", "  pad  ",
+         "SPECIAL REQUESTS", "special packages requests"]
+
+
+def random_array(t: pa.DataType, n: int, rng: np.random.Generator, null_prob: float = 0.1,
+                 small: bool = False) -> pa.Array:
+    """Random Arrow array of type t with edge values sprinkled in and ~null_prob nulls."""
+    mask = rng.random(n) < null_prob if null_prob > 0 else None
+    if t in _NP:
+        npt = _NP[t]
+        if t in FLOAT_TYPES:
+            vals = (rng.standard_normal(n) * (10.0 if small else 1e6)).astype(npt)
+            edge = np.array([0.0, -0.0, 1.0, -1.0, 0.5, 1e-30, 3.5, 1000.0], dtype=npt)
+        else:
+            info = np.iinfo(npt)
+            if small:
+                lo, hi = max(info.min, -50), min(info.max, 50)
+                vals = rng.integers(lo, hi + 1, n, dtype=np.int64).astype(npt)
+                edge = np.array([0, 1, 2, 3], dtype=npt)
+            else:
+                vals = rng.integers(info.min, int(info.max) + 1, n, dtype=npt)
+                edge = np.array([info.min, info.max, 0, 1, info.max - 1, info.min + 1], dtype=npt)
+        k = min(n, len(edge))
+        if k:
+            pos = rng.choice(n, k, replace=False)
+            vals[pos] = edge[:k]
+        return pa.array(vals, type=t, mask=mask)
+    if pa.types.is_boolean(t):
+        return pa.array(rng.random(n) < 0.5, type=t, mask=mask)
+    if pa.types.is_date32(t):
+        return pa.array(rng.integers(-30000, 60000, n).astype(np.int32), type=pa.int32(), mask=mask).cast(t)
+    if pa.types.is_date64(t):
+        days = rng.integers(-30000, 60000, n).astype(np.int64)
+        return pa.array(days * 86400000, type=pa.int64(), mask=mask).cast(t)
+    if pa.types.is_timestamp(t):
+        ms = rng.integers(-2_000_000_000_000, 4_000_000_000_000, n).astype(np.int64)
+        return pa.array(ms, type=pa.int64(), mask=mask).cast(t)
+    if pa.types.is_time32(t):
+        return pa.array(rng.integers(0, 86400000, n).astype(np.int32), type=pa.int32(), mask=mask).cast(t)
+    if pa.types.is_decimal128(t):
+        digits = t.precision if not small else min(t.precision, 6)
+        out = []
+        for i in range(n):
+            if mask is not None and mask[i]:
+                out.append(None)
+                continue
+            nd = int(rng.integers(1, digits + 1))
+            mag = int("".join(str(int(d)) for d in rng.integers(0, 10, nd)))
+            if rng.random() < 0.5:
+                mag = -mag
+            out.append(decimal.Decimal(mag).scaleb(-t.scale))
+        return pa.array(out, type=t)
+    if pa.types.is_string(t) or pa.types.is_binary(t):
+        out = []
+        for i in range(n):
+            if mask is not None and mask[i]:
+                out.append(None)
+                continue
+            k = int(rng.integers(0, 5))
+            s = " ".join(WORDS[int(j)] for j in rng.integers(0, len(WORDS), k))
+            out.append(s if pa.types.is_string(t) else s.encode("utf-8"))
+        return pa.array(out, type=t)
+    raise NotImplementedError(str(t))
+
+
+def random_batch(schema: pa.Schema, n: int, seed: int, null_prob: float = 0.1, offset: int = 0,
+                 small: bool = False) -> pa.RecordBatch:
+    """Random batch; with offset > 0 every column is a slice (ArrayData.offset != 0)."""
+    rng = np.random.default_rng(seed)
+    cols = []
+    for f in schema:
+        arr = random_array(f.type, n + offset, rng, null_prob, small)
+        cols.append(arr.slice(offset) if offset else arr)
+    return pa.RecordBatch.from_arrays(cols, schema=schema)
+
+
+# ---- expression cases ----------------------------------------------------------------------
+def F(b, name, t):
+    return b.make_field(pa.field(name, t))
+
+
+def case_arith(op, t):
+    def build(b):
+        schema = pa.schema([("a", t), ("b", t)])
+        return schema, [(b.make_function(op, [F(b, "a", t), F(b, "b", t)], t), t)], "project"
+    build.__name__ = "%s_%s" % (op, t)
+    return build
+
+
+def case_relop(op, t):
+    def build(b):
+        schema = pa.schema([("a", t), ("b", t)])
+        return schema, [(b.make_function(op, [F(b, "a", t), F(b, "b", t)], pa.bool_()), pa.bool_())], "project"
+    build.__name__ = "%s_%s" % (op, t)
+    return build
+
+
+def case_if_else(b):
+    t = pa.int32()
+    schema = pa.schema([("a", t), ("b", t), ("c", t)])
+    a, bb, c = F(b, "a", t), F(b, "b", t), F(b, "c", t)
+    cond1 = b.make_function("greater_than", [a, bb], pa.bool_())
+    cond2 = b.make_function("less_than", [bb, c], pa.bool_())
+    inner = b.make_if(cond2, bb, b.make_function("add", [c, b.make_literal(7, t)], t), t)
+    root = b.make_if(cond1, a, inner, t)
+    return schema, [(root, t)], "project"
+
+
+def case_if_null_literal(b):
+    t = pa.int64()
+    schema = pa.schema([("a", t), ("b", t)])
+    a, bb = F(b, "a", t), F(b, "b", t)
+    cond = b.make_function("less_than", [a, bb], pa.bool_())
+    root = b.make_if(cond, a, b.make_literal(None, t), t)
+    return schema, [(root, t)], "project"
+
+
+def case_kleene(b):
+    t = pa.bool_()
+    schema = pa.schema([("x", t), ("y", t), ("z", t)])
+    x, y, z = F(b, "x", t), F(b, "y", t), F(b, "z", t)
+    return schema, [(b.make_and([x, y]), t), (b.make_or([x, y]), t), (b.make_and([x, y, z]), t),
+                    (b.make_or([b.make_and([x, y]), b.make_function("not", [z], t)]), t)], "project"
+
+
+def case_null_tests(b):
+    t = pa.float64()
+    schema = pa.schema([("a", t), ("b", t), ("x", pa.bool_())])
+    a, bb, x = F(b, "a", t), F(b, "b", t), F(b, "x", pa.bool_())
+    B = pa.bool_()
+    return schema, [(b.make_function("isnull", [a], B), B), (b.make_function("isnotnull", [bb], B), B),
+                    (b.make_function("is_distinct_from", [a, bb], B), B),
+                    (b.make_function("is_not_distinct_from", [a, bb], B), B),
+                    (b.make_function("istrue", [x], B), B), (b.make_function("isnotfalse", [x], B), B)], "project"
+
+
+def case_casts(b):
+    schema = pa.schema([("i", pa.int32()), ("l", pa.int64()), ("f", pa.float32()), ("d", pa.float64())])
+    i, l, f, d = F(b, "i", pa.int32()), F(b, "l", pa.int64()), F(b, "f", pa.float32()), F(b, "d", pa.float64())
+    return schema, [(b.make_function("castBIGINT", [i], pa.int64()), pa.int64()),
+                    (b.make_function("castINT", [l], pa.int32()), pa.int32()),
+                    (b.make_function("castFLOAT4", [l], pa.float32()), pa.float32()),
+                    (b.make_function("castFLOAT4", [d], pa.float32()), pa.float32()),
+                    (b.make_function("castFLOAT8", [l], pa.float64()), pa.float64()),
+                    (b.make_function("castFLOAT8", [f], pa.float64()), pa.float64()),
+                    (b.make_function("abs", [i], pa.int32()), pa.int32()),
+                    (b.make_function("negative", [d], pa.float64()), pa.float64()),
+                    (b.make_function("bitwise_xor", [l, l], pa.int64()), pa.int64())], "project"
+
+
+def case_mod(b):
+    schema = pa.schema([("l", pa.int64()), ("i", pa.int32()), ("m", pa.int64())])
+    l, i, m = F(b, "l", pa.int64()), F(b, "i", pa.int32()), F(b, "m", pa.int64())
+    return schema, [(b.make_function("mod", [l, i], pa.int32()), pa.int32()),
+                    (b.make_function("mod", [l, m], pa.int64()), pa.int64())], "project"
+
+
+def case_dates(b):
+    ts, d64, d32 = pa.timestamp("ms"), pa.date64(), pa.date32()
+    schema = pa.schema([("t", ts), ("d", d64), ("e", d32)])
+    t, d, e = F(b, "t", ts), F(b, "d", d64), F(b, "e", d32)
+    L = pa.int64()
+    outs = [(b.make_function(fn, [t], L), L) for fn in
+            ["extractYear", "extractMonth", "extractDay", "extractHour", "extractMinute",
+             "extractSecond", "extractDoy", "extractDow", "extractQuarter", "extractEpoch"]]
+    outs += [(b.make_function("extractYear", [d], L), L), (b.make_function("extractMonth", [e], L), L),
+             (b.make_function("extractDay", [e], L), L),
+             (b.make_function("castDATE", [t], d64), d64),
+             (b.make_function("less_than", [e, b.make_literal(9131, d32)], pa.bool_()), pa.bool_())]
+    return schema, outs, "project"
+
+
+def case_decimal(p1, s1, p2, s2, op, rp, rs):
+    def build(b):
+        t1, t2, rt = pa.decimal128(p1, s1), pa.decimal128(p2, s2), pa.decimal128(rp, rs)
+        schema = pa.schema([("x", t1), ("y", t2)])
+        return schema, [(b.make_function(op, [F(b, "x", t1), F(b, "y", t2)], rt), rt)], "project"
+    build.__name__ = "decimal_%s_%d_%d_%d_%d" % (op, p1, s1, p2, s2)
+    return build
+
+
+def case_decimal_misc(b):
+    t1, t2 = pa.decimal128(15, 2), pa.decimal128(20, 6)
+    schema = pa.schema([("x", t1), ("y", t2), ("l", pa.int64())])
+    x, y, l = F(b, "x", t1), F(b, "y", t2), F(b, "l", pa.int64())
+    B = pa.bool_()
+    one = b.make_literal(decimal.Decimal("1.00"), t1)
+    return schema, [(b.make_function("less_than", [x, y], B), B),
+                    (b.make_function("equal", [x, x], B), B),
+                    (b.make_function("greater_than_or_equal_to", [y, x], B), B),
+                    (b.make_function("castDECIMAL", [x], pa.decimal128(10, 0)), pa.decimal128(10, 0)),
+                    (b.make_function("castDECIMAL", [x], pa.decimal128(30, 8)), pa.decimal128(30, 8)),
+                    (b.make_function("castDECIMAL", [l], pa.decimal128(38, 4)), pa.decimal128(38, 4)),
+                    (b.make_function("castBIGINT", [y], pa.int64()), pa.int64()),
+                    (b.make_function("castFLOAT8", [x], pa.float64()), pa.float64()),
+                    (b.make_function("subtract", [one, x], pa.decimal128(16, 2)), pa.decimal128(16, 2)),
+                    (b.make_function("abs", [x], t1), t1), (b.make_function("negative", [y], t2), t2)], "project"
+
+
+def case_in_int(t, values):
+    def build(b):
+        schema = pa.schema([("a", t)])
+        return schema, [(b.make_in_expression(F(b, "a", t), values, t), pa.bool_())], "project"
+    build.__name__ = "in_%s_%d" % (t, len(values))
+    return build
+
+
+def case_in_string(b):
+    t = pa.string()
+    schema = pa.schema([("s", t)])
+    return schema, [(b.make_in_expression(F(b, "s", t), ["spark", "fox", "", "日本語 a"], t), pa.bool_())], "project"
+
+
+def case_like(pattern, escape=None):
+    def build(b):
+        t = pa.string()
+        schema = pa.schema([("s", t)])
+        args = [F(b, "s", t), b.make_literal(pattern, t)]
+        if escape is not None:
+            args.append(b.make_literal(escape, t))
+        return schema, [(b.make_function("like", args, pa.bool_()), pa.bool_())], "project"
+    build.__name__ = "like_%s" % pattern
+    return build
+
+
+def case_strings(b):
+    t = pa.string()
+    schema = pa.schema([("s", t), ("u", t), ("k", pa.int64())])
+    s, u, k = F(b, "s", t), F(b, "u", t), F(b, "k", pa.int64())
+    B, I = pa.bool_(), pa.int32()
+    L = lambda v: b.make_literal(v, pa.int64())
+    sub = lambda *a: b.make_function("substr", list(a), t)
+    outs = [
+        (b.make_function("char_length", [s], I), I),
+        (b.make_function("octet_length", [s], I), I),
+        (b.make_function("starts_with", [s, b.make_literal("sp", t)], B), B),
+        (b.make_function("ends_with", [s, b.make_literal("s", t)], B), B),
+        (b.make_function("is_substr", [s, b.make_literal("ar", t)], B), B),
+        (b.make_function("equal", [s, u], B), B),
+        (b.make_function("less_than", [s, u], B), B),
+        (b.make_function("greater_than_or_equal_to", [s, u], B), B),
+        (b.make_function("char_length", [sub(s, L(2), L(5))], I), I),
+        (b.make_function("char_length", [sub(s, L(-3), L(2))], I), I),
+        (b.make_function("octet_length", [sub(s, k, L(4))], I), I),
+        (b.make_function("equal", [b.make_function("upper", [s], t), b.make_function("upper", [u], t)], B), B),
+        (b.make_function("like", [b.make_function("upper", [sub(s, L(1), L(32))], t),
+                                  b.make_literal("%SPECIAL%REQUESTS%", t)], B), B),
+        (b.make_function("starts_with", [b.make_function("lower", [s], t), b.make_literal("quick", t)], B), B),
+        (b.make_function("octet_length", [b.make_function("btrim", [s], t)], I), I),
+        (b.make_function("equal", [b.make_function("ltrim", [s], t), b.make_function("rtrim", [s], t)], B), B),
+    ]
+    return schema, outs, "project"
+
+
+def case_literals_only(b):
+    t = pa.int32()
+    schema = pa.schema([("a", t)])
+    root = b.make_function("add", [b.make_literal(40, t), b.make_literal(2, t)], t)
+    return schema, [(root, t)], "project"
+
+
+def case_bool_io(b):
+    t = pa.bool_()
+    schema = pa.schema([("x", t), ("a", pa.int32())])
+    x, a = F(b, "x", t), F(b, "a", pa.int32())
+    return schema, [(b.make_function("not", [x], t), t),
+                    (b.make_if(x, a, b.make_function("negative", [a], pa.int32()), pa.int32()), pa.int32()),
+                    (b.make_function("equal", [x, b.make_function("greater_than", [a, b.make_literal(0, pa.int32())], t)], t), t)], "project"
+
+
+def q6_condition(b, d32=True):
+    """TPC-H Q6 predicate over (l_shipdate date32, l_discount f64, l_quantity f64)."""
+    sd, f = pa.date32(), pa.float64()
+    ship, disc, qty = F(b, "l_shipdate", sd), F(b, "l_discount", f), F(b, "l_quantity", f)
+    B = pa.bool_()
+    lit_d = lambda days: b.make_literal(days, sd)
+    lit_f = lambda v: b.make_literal(v, f)
+    conds = [
+        b.make_function("greater_than_or_equal_to", [ship, lit_d(8766)], B),   # 1994-01-01
+        b.make_function("less_than", [ship, lit_d(9131)], B),                  # 1995-01-01
+        b.make_function("greater_than_or_equal_to", [disc, lit_f(0.05)], B),
+        b.make_function("less_than_or_equal_to", [disc, lit_f(0.07)], B),
+        b.make_function("less_than", [qty, lit_f(24.0)], B),
+    ]
+    return b.make_and(conds)
+
+
+Q6_SCHEMA = pa.schema([("l_shipdate", pa.date32()), ("l_discount", pa.float64()),
+                       ("l_quantity", pa.float64())])
+
+
+def case_q6_filter(b):
+    return Q6_SCHEMA, [(q6_condition(b), pa.bool_())], "filter"
+
+
+def case_filter_float(b):
+    t = pa.float64()
+    schema = pa.schema([("a", t), ("b", t)])
+    a, bb = F(b, "a", t), F(b, "b", t)
+    B = pa.bool_()
+    c1 = b.make_function("less_than", [a, b.make_literal(50.0, t)], B)
+    c2 = b.make_function("greater_than", [a, bb], B)
+    c3 = b.make_function("less_than", [bb, b.make_literal(11.0, t)], B)
+    return schema, [(b.make_or([b.make_and([c1, c2]), c3]), B)], "filter"
+
+
+def case_filter_all(b):
+    t = pa.int32()
+    schema = pa.schema([("a", t)])
+    return schema, [(b.make_function("isnotnull", [F(b, "a", t)], pa.bool_()), pa.bool_())], "filter"
+
+
+def case_filter_none(b):
+    t = pa.int32()
+    schema = pa.schema([("a", t)])
+    a = F(b, "a", t)
+    return schema, [(b.make_and([b.make_function("isnull", [a], pa.bool_()),
+                                 b.make_function("isnotnull", [a], pa.bool_())]), pa.bool_())], "filter"
+
+
+def case_filter_string(b):
+    t = pa.string()
+    schema = pa.schema([("c", t)])
+    c = F(b, "c", t)
+    sub = b.make_function("substr", [c, b.make_literal(1, pa.int64()), b.make_literal(32, pa.int64())], t)
+    return schema, [(b.make_function("like", [b.make_function("upper", [sub], t),
+                                              b.make_literal("%SPECIAL%REQUESTS%", t)], pa.bool_()), pa.bool_())], "filter"
+
+
+def case_divide(t):
+    def build(b):
+        schema = pa.schema([("a", t), ("b", t)])
+        a, bb = F(b, "a", t), F(b, "b", t)
+        B = pa.bool_()
+        # guard: if b != 0 then a / b else a   (the untaken branch must not raise)
+        nz = b.make_function("not_equal", [bb, b.make_literal(0 if t not in FLOAT_TYPES else 0.0, t)], B)
+        return schema, [(b.make_if(nz, b.make_function("divide", [a, bb], t), a, t), t)], "project"
+    build.__name__ = "divide_guarded_%s" % t
+    return build
+
+
+def case_and_short_circuit(b):
+    t = pa.int32()
+    schema = pa.schema([("a", t), ("b", t)])
+    a, bb = F(b, "a", t), F(b, "b", t)
+    B = pa.bool_()
+    nz = b.make_function("not_equal", [bb, b.make_literal(0, t)], B)
+    q = b.make_function("greater_than", [b.make_function("divide", [a, bb], t), b.make_literal(1, t)], B)
+    return schema, [(b.make_and([nz, q]), B)], "project"
+
+
+def all_project_cases():
+    cases = []
+    for t in NUMERIC:
+        for op in ("add", "subtract", "multiply"):
+            cases.append(case_arith(op, t))
+    for t in [pa.int32(), pa.uint64(), pa.float32(), pa.float64(), pa.int8()]:
+        for op in RELOPS:
+            cases.append(case_relop(op, t))
+    for t in [pa.date32(), pa.date64(), pa.timestamp("ms")]:
+        cases.append(case_relop("less_than", t))
+        cases.append(case_relop("equal", t))
+    cases += [case_if_else, case_if_null_literal, case_kleene, case_null_tests, case_casts, case_mod,
+              case_dates, case_decimal_misc, case_in_string, case_strings, case_literals_only,
+              case_bool_io, case_and_short_circuit]
+    for t in [pa.int8(), pa.int32(), pa.int64(), pa.uint32(), pa.float32(), pa.float64()]:
+        cases.append(case_divide(t))
+    # decimal result types follow the reference's rule: add/sub: s=max(s1,s2),
+    # p=max(p1-s1,p2-s2)+s+1; multiply: p=p1+p2+1, s=s1+s2; capped at 38 with min scale 6
+    cases += [
+        case_decimal(12, 2, 12, 2, "multiply", 25, 4),
+        case_decimal(15, 2, 15, 2, "multiply", 31, 4),
+        case_decimal(31, 4, 16, 2, "multiply", 38, 6),
+        case_decimal(38, 10, 38, 10, "multiply", 38, 6),
+        case_decimal(30, 12, 20, 9, "multiply", 38, 8),
+        case_decimal(15, 2, 15, 2, "add", 16, 2),
+        case_decimal(15, 2, 20, 6, "add", 21, 6),
+        case_decimal(38, 10, 38, 4, "subtract", 38, 6),
+        case_decimal(38, 0, 38, 0, "add", 38, 0),
+        case_decimal(10, 5, 12, 1, "subtract", 17, 5),
+    ]
+    cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
+              case_in_int(pa.int32(), list(range(-20, 40, 3)))]
+    for pat in ["%spark%", "spark%", "%spark", "s_ark%", "%", "", "_", "%a%b%c%", "fire", "%日本%",
+                "_本%", "%%x%%", "a%a", "%ss"]:
+        cases.append(case_like(pat))
+    cases.append(case_like("100\\%%", "\\"))
+    cases.append(case_like("x\\_y%", "\\"))
+    return cases
+
+
+def all_filter_cases():
+    return [case_q6_filter, case_filter_float, case_filter_all, case_filter_none, case_filter_string]
+
+
+def q6_batch(n: int, seed: int = 42, null_permille: int = 0, oracle_mod=None) -> pa.RecordBatch:
+    """Synthetic lineitem from the CPU generator in oracle/."""
+    import oracle as _o
+    o = oracle_mod or _o
+    cols = []
+    for kind, t in ((0, pa.date32()), (1, pa.float64()), (2, pa.float64())):
+        vals, vld = o.generate_lineitem(kind, seed, 0, n, null_permille, threads=4)
+        bufs = [pa.py_buffer(vld) if vld is not None else None, pa.py_buffer(vals)]
+        cols.append(pa.Array.from_buffers(t, n, bufs))
+    return pa.RecordBatch.from_arrays(cols, schema=Q6_SCHEMA)

@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # build the native libraries once per session if they are missing (in-tree .so files
+    # normally travel with the snapshot)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "gdv_build", os.path.join(ROOT, "gandiva_b200", "build.py"))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
+    if not (os.path.exists(_build.LIB) and os.path.exists(_build.ORACLE_LIB)):
+        _build.build_all()
+
+
+@pytest.fixture(scope="session")
+def gandiva():
+    import gandiva_b200
+    return gandiva_b200
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle as _oracle
+    return _oracle

@@ -1,0 +1,274 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes mirror), against the
+CPU oracle on the same seeded inputs.  Bit-exact for integer / decimal / string / date /
+bool outputs and validity; float outputs within 0 ULP (BASELINE.json allows 1; kernels are
+compiled with --fmad=false so the IEEE sequence is identical)."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import cases
+from helpers import assert_arrays_match
+
+pytestmark = pytest.mark.gpu
+
+PROJECT_CASES = cases.all_project_cases()
+FILTER_CASES = cases.all_filter_cases()
+
+
+def _needs_small(name):
+    return name.startswith(("divide", "mod", "in_", "and_short"))
+
+
+def run_both(gandiva, oracle, build, n, seed, null_prob=0.15, offset=0, cfg=None):
+    b = gandiva.TreeExprBuilder()
+    schema, outs, kind = build(b)
+    batch = cases.random_batch(schema, n, seed, null_prob, offset, small=_needs_small(build.__name__))
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None, "NONE", cfg)
+    got = p.evaluate(batch)
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch, threads=4)
+    return got, want
+
+
+@pytest.mark.parametrize("case", PROJECT_CASES, ids=[c.__name__ for c in PROJECT_CASES])
+def test_project_parity(case, gandiva, oracle):
+    for n, offset, seed in [(1, 0, 1), (33, 0, 2), (1000, 3, 3), (20011, 13, 4)]:
+        got, want = run_both(gandiva, oracle, case, n, seed, offset=offset)
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert_arrays_match(g, w, "%s n=%d out=%d" % (case.__name__, n, i))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 255, 256, 257, 4095, 4096, 4097, 100003])
+def test_project_sizes_no_nulls(n, gandiva, oracle):
+    """Tail handling at warp / tile boundaries, absent validity buffers (buffers[0] == NULL)."""
+    got, want = run_both(gandiva, oracle, cases.case_arith("add", pa.int32()), n, seed=n, null_prob=0.0)
+    assert_arrays_match(got[0], want[0], "add int32 n=%d" % n)
+    assert got[0].null_count == 0
+
+
+@pytest.mark.parametrize("rpt", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("bt", [128, 256, 512])
+def test_project_tuning_knobs(rpt, bt, gandiva, oracle):
+    cfg = gandiva.Configuration(rows_per_thread=rpt, block_threads=bt)
+    got, want = run_both(gandiva, oracle, cases.case_if_else, 50021, seed=7, cfg=cfg)
+    assert_arrays_match(got[0], want[0], "if_else rpt=%d bt=%d" % (rpt, bt))
+
+
+def _filter_both(gandiva, oracle, build, batch, dtype="int32", cfg=None):
+    b = gandiva.TreeExprBuilder()
+    schema, outs, kind = build(b)
+    f = gandiva.make_filter(schema, b.make_condition(outs[0][0]), cfg)
+    sel = f.evaluate(batch, None, dtype)
+    want = oracle.filter_indices(outs[0][0], batch, threads=4)
+    return sel, want
+
+
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c.__name__ for c in FILTER_CASES])
+@pytest.mark.parametrize("n", [1, 32, 33, 2047, 2048, 2049, 65536, 300007])
+def test_filter_parity(case, n, gandiva, oracle):
+    b = gandiva.TreeExprBuilder()
+    schema, _, _ = case(b)
+    if case is cases.case_q6_filter:
+        batch = cases.q6_batch(n, seed=42, null_permille=10 if n % 2 else 0)
+    else:
+        batch = cases.random_batch(schema, n, seed=n, null_prob=0.1, offset=5 if n > 100 else 0, small=True)
+    sel, want = _filter_both(gandiva, oracle, case, batch)
+    got = sel.to_array().to_numpy()
+    assert got.dtype == np.uint32
+    assert sel.num_slots == len(want), "%s n=%d count %d != %d" % (case.__name__, n, sel.num_slots, len(want))
+    assert np.array_equal(got.astype(np.uint64), want)
+
+
+@pytest.mark.parametrize("dtype,npt", [("int16", np.uint16), ("int32", np.uint32), ("int64", np.uint64)])
+def test_filter_index_widths(dtype, npt, gandiva, oracle):
+    batch = cases.q6_batch(60000, seed=7)
+    sel, want = _filter_both(gandiva, oracle, cases.case_q6_filter, batch, dtype)
+    got = sel.to_array().to_numpy()
+    assert got.dtype == npt
+    assert np.array_equal(got.astype(np.uint64), want)
+
+
+@pytest.mark.parametrize("rpt,bt", [(1, 128), (2, 256), (4, 256), (8, 256), (8, 512), (16, 1024)])
+def test_filter_tuning_knobs(rpt, bt, gandiva, oracle):
+    cfg = gandiva.Configuration(rows_per_thread=rpt, block_threads=bt)
+    batch = cases.q6_batch(777777, seed=9, null_permille=20)
+    sel, want = _filter_both(gandiva, oracle, cases.case_q6_filter, batch, cfg=cfg)
+    assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
+
+
+def test_filter_selection_too_small(gandiva):
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_filter_all(b)
+    f = gandiva.make_filter(schema, b.make_condition(outs[0][0]))
+    batch = cases.random_batch(schema, 70000, seed=1)
+    with pytest.raises(pa.ArrowInvalid):
+        f.evaluate(batch, None, "int16")  # > 65536 rows cannot be indexed by uint16
+
+
+@pytest.mark.parametrize("mode,npt", [("UINT16", np.uint16), ("UINT32", np.uint32), ("UINT64", np.uint64)])
+def test_project_with_selection_vector(mode, npt, gandiva, oracle):
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_if_else(b)
+    n = 50000
+    batch = cases.random_batch(schema, n, seed=21, null_prob=0.2, offset=7)
+    rng = np.random.default_rng(5)
+    idx = np.sort(rng.choice(n, 12345, replace=False)).astype(npt)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None, mode)
+    sel = gandiva.SelectionVector(idx, len(idx), gandiva._SEL_MODE[mode])
+    got = p.evaluate(batch, sel)
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch, selection=idx.astype(np.int64))
+    assert len(got[0]) == len(idx)
+    assert_arrays_match(got[0], want[0], "selection %s" % mode)
+
+
+def test_multi_output_shares_inputs(gandiva, oracle):
+    """Eight outputs from one fused kernel (Q1-like mix of int64 / float64 / decimal / CASE)."""
+    import decimal
+    b = gandiva.TreeExprBuilder()
+    D, F64, I64, SD = pa.decimal128(15, 2), pa.float64(), pa.int64(), pa.date32()
+    schema = pa.schema([("qty", I64), ("ext", D), ("disc", D), ("tax", D), ("ext_f", F64),
+                        ("disc_f", F64), ("tax_f", F64), ("ship", SD)])
+    f = {x.name: b.make_field(x) for x in schema}
+    one_d = b.make_literal(decimal.Decimal("1.00"), D)
+    one_f = b.make_literal(1.0, F64)
+    d1 = b.make_function("multiply", [f["ext"], b.make_function("subtract", [one_d, f["disc"]], pa.decimal128(16, 2))], pa.decimal128(32, 4))
+    d2 = b.make_function("multiply", [d1, b.make_function("add", [one_d, f["tax"]], pa.decimal128(16, 2))], pa.decimal128(38, 6))
+    f1 = b.make_function("multiply", [f["ext_f"], b.make_function("subtract", [one_f, f["disc_f"]], F64)], F64)
+    f2 = b.make_function("multiply", [f1, b.make_function("add", [one_f, f["tax_f"]], F64)], F64)
+    q2 = b.make_function("add", [f["qty"], f["qty"]], I64)
+    c1 = b.make_if(b.make_function("greater_than", [f["disc_f"], b.make_literal(0.05, F64)], pa.bool_()), f["ext_f"], b.make_literal(0.0, F64), F64)
+    c2 = b.make_if(b.make_function("less_than", [f["qty"], b.make_literal(24, I64)], pa.bool_()), b.make_literal(1, I64), b.make_literal(0, I64), I64)
+    c3 = b.make_if(b.make_function("less_than_or_equal_to", [f["ship"], b.make_literal(10471, SD)], pa.bool_()), f["qty"], b.make_literal(None, I64), I64)
+    outs = [(d1, pa.decimal128(32, 4)), (d2, pa.decimal128(38, 6)), (f1, F64), (f2, F64), (q2, I64), (c1, F64), (c2, I64), (c3, I64)]
+    batch = cases.random_batch(schema, 30011, seed=33, null_prob=0.02, small=True)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None)
+    got = p.evaluate(batch)
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch, threads=4)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "q1 out %d" % i)
+
+
+@pytest.mark.parametrize("t", [pa.int32(), pa.int64(), pa.float64()], ids=str)
+def test_divide_by_zero_is_execution_error(t, gandiva, oracle):
+    b = gandiva.TreeExprBuilder()
+    schema = pa.schema([("a", t), ("b", t)])
+    root = b.make_function("divide", [cases.F(b, "a", t), cases.F(b, "b", t)], t)
+    p = gandiva.make_projector(schema, [b.make_expression(root, pa.field("r", t))], None)
+    av = pa.array([1, 2, 3, 4], t)
+    batch = pa.RecordBatch.from_arrays([av, pa.array([1, 0, 2, 1], t)], schema=schema)
+    with pytest.raises(gandiva.GandivaError, match="ExecutionError: divide by zero error"):
+        p.evaluate(batch)
+    with pytest.raises(Exception, match="divide by zero"):
+        oracle.project([root], [t], batch)
+    # the same projector keeps working afterwards, and a NULL divisor does not raise
+    batch = pa.RecordBatch.from_arrays([av, pa.array([1, None, 2, 1], t)], schema=schema)
+    got, = p.evaluate(batch)
+    want, = oracle.project([root], [t], batch)
+    assert_arrays_match(got, want, "divide with null divisor")
+
+
+def test_empty_batch_rejected(gandiva):
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_arith("add", pa.int32())(b)
+    p = gandiva.make_projector(schema, [b.make_expression(outs[0][0], pa.field("r", pa.int32()))], None)
+    batch = cases.random_batch(schema, 0, seed=1)
+    with pytest.raises(pa.ArrowInvalid, match="non-empty"):
+        p.evaluate(batch)
+
+
+def test_generator_matches_cpu_twin(gandiva, oracle):
+    """Device lineitem generator == oracle/lineitem.h for every column kind."""
+    import torch
+    n = 100003
+    for kind, npdt in [(0, np.int32), (1, np.float64), (2, np.float64), (3, np.int64), (7, np.float64),
+                       (8, np.float64), (9, np.int32)]:
+        vals = torch.zeros(n, dtype=getattr(torch, np.dtype(npdt).name), device="cuda")
+        vld = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+        gandiva._check(gandiva.lib.gdv_generate_lineitem(0, kind, 42, 1000, n, vals.data_ptr(), vld.data_ptr(), 15,
+                                                         torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        cv, cvld = oracle.generate_lineitem(kind, 42, 1000, n, 15)
+        assert np.array_equal(vals.cpu().numpy(), cv), kind
+        gbits = np.unpackbits(vld.cpu().numpy().view(np.uint8), bitorder="little")[:n]
+        cbits = np.unpackbits(cvld, bitorder="little")[:n]
+        assert np.array_equal(gbits, cbits), kind
+    for kind in (4, 5, 6):
+        vals = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+        gandiva._check(gandiva.lib.gdv_generate_lineitem(0, kind, 42, 0, n, vals.data_ptr(), None, 0,
+                                                         torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        cv, _ = oracle.generate_lineitem(kind, 42, 0, n)
+        assert np.array_equal(vals.cpu().numpy().view(np.uint64), cv), kind
+
+
+def test_device_resident_filter_and_properties(gandiva, oracle):
+    """Device-resident async API (the bench path): inputs generated in HBM, indices stay in HBM.
+    Checked exactly against the oracle on the first rows and by size-independent properties
+    (ascending, count == independent torch mask count, indices == torch.nonzero) on all rows."""
+    import torch
+    n = 20_000_003
+    dev = torch.device("cuda")
+    ship = torch.empty(n, dtype=torch.int32, device=dev)
+    disc = torch.empty(n, dtype=torch.float64, device=dev)
+    qty = torch.empty(n, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for kind, tns in ((0, ship), (1, disc), (2, qty)):
+        gandiva._check(gandiva.lib.gdv_generate_lineitem(0, kind, 42, 0, n, tns.data_ptr(), None, 0, st))
+    b = gandiva.TreeExprBuilder()
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)))
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
+    for _ in range(3):  # repeated async launches on one stream reuse the look-back scratch
+        f.evaluate_device(n, cols, out.data_ptr(), n, "UINT32", st, cnt.data_ptr())
+    count = f.sync(st)
+    assert count == int(cnt.item())
+    mask = (ship >= 8766) & (ship < 9131) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24)
+    assert count == int(mask.sum().item())
+    idx = out[:count].to(torch.int64)
+    assert bool((idx[1:] > idx[:-1]).all())
+    assert torch.equal(idx, torch.nonzero(mask).flatten())
+    # exact oracle parity on a prefix
+    m = 200_000
+    batch = cases.q6_batch(m, seed=42)
+    assert np.array_equal(ship[:m].cpu().numpy(), batch.column(0).to_numpy())
+    want = oracle.filter_indices(cases.q6_condition(b), batch, threads=4)
+    got = idx[idx < m].cpu().numpy().astype(np.uint64)
+    assert np.array_equal(got, want)
+
+
+def test_device_resident_projector(gandiva, oracle):
+    import torch
+    n = 3_000_001
+    dev = torch.device("cuda")
+    a = torch.empty(n, dtype=torch.int32, device=dev)
+    bb = torch.empty(n, dtype=torch.int32, device=dev)
+    av = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
+    bv = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gandiva._check(gandiva.lib.gdv_generate_lineitem(0, 9, 42, 0, n, a.data_ptr(), av.data_ptr(), 100, st))
+    gandiva._check(gandiva.lib.gdv_generate_lineitem(0, 10, 42, 0, n, bb.data_ptr(), bv.data_ptr(), 100, st))
+    bld = gandiva.TreeExprBuilder()
+    t = pa.int32()
+    schema = pa.schema([("a", t), ("b", t)])
+    root = bld.make_function("add", [cases.F(bld, "a", t), cases.F(bld, "b", t)], t)
+    p = gandiva.make_projector(schema, [bld.make_expression(root, pa.field("c", t))], None)
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    ov = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
+    p.evaluate_device(n, [(av.data_ptr(), a.data_ptr(), 0, 0), (bv.data_ptr(), bb.data_ptr(), 0, 0)],
+                      [(ov.data_ptr(), out.data_ptr())], st)
+    p.sync(st)
+    ca, cav = oracle.generate_lineitem(9, 42, 0, n, 100, threads=4)
+    cb, cbv = oracle.generate_lineitem(10, 42, 0, n, 100, threads=4)
+    batch = pa.RecordBatch.from_arrays(
+        [pa.Array.from_buffers(t, n, [pa.py_buffer(cav), pa.py_buffer(ca)]),
+         pa.Array.from_buffers(t, n, [pa.py_buffer(cbv), pa.py_buffer(cb)])], schema=schema)
+    want, = oracle.project([root], [t], batch, threads=4)
+    got = pa.Array.from_buffers(t, n, [pa.py_buffer(ov.cpu().numpy()), pa.py_buffer(out.cpu().numpy())])
+    assert_arrays_match(got, want, "device-resident add")
+
+
+def test_kernels_were_launched(gandiva):
+    assert gandiva.launch_count() > 0
