@@ -187,7 +187,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(dev)   # a real (non-default) stream: events, kernels and
+    torch.cuda.set_stream(stream)     # NCCL ops are all ordered on it
     st = stream.cuda_stream
 
     n = args.rows
@@ -203,8 +204,7 @@ def main():
     disc = torch.empty(n, dtype=torch.float64, device=dev)
     qty = torch.empty(n, dtype=torch.float64, device=dev)
     for kind, t in ((0, ship), (1, disc), (2, qty)):
-        gandiva._check(gandiva.lib.gdv_generate_lineitem(local_rank, kind, 42, first_row, n,
-                                                         t.data_ptr(), None, 0, st))
+        gandiva.generate_lineitem(local_rank, kind, 42, first_row, n, t.data_ptr(), 0, 0, st)
     out_idx = torch.empty(n, dtype=idx_dtype, device=dev)
     d_count = torch.zeros(1, dtype=torch.int64, device=dev)
     cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
@@ -389,7 +389,7 @@ def run_e2e(args, gandiva, cases, torch, np, dev, local_rank, rank, world, n, sh
                 sel = gandiva.gdv_selection_t(h_idx, chunk, 0, gandiva.GDV_SEL_UINT32,
                                               gandiva.GDV_MEM_HOST, 0)
                 gandiva._check(gandiva.lib.gdv_filter_evaluate(filt._h, C.byref(cb), C.byref(sel),
-                                                               C.c_void_p(stream.cuda_stream), 0, None))
+                                                               gandiva._stream_handle(stream.cuda_stream), 0, None))
                 total += sel.num_slots
             return total
         one_pass()

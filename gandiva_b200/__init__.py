@@ -534,6 +534,13 @@ class _SchemaHandle:
             pass
 
 
+def _stream_handle(stream: int) -> C.c_void_p:
+    """cudaStream_t value -> handle for the C-ABI.  The C-ABI reads NULL as "the engine's own
+    stream"; a caller that passes 0 here means CUDA's legacy default stream (torch's default
+    stream), whose explicit handle is CU_STREAM_LEGACY (0x1)."""
+    return C.c_void_p(stream if stream else 1)
+
+
 def _kernel_info(fn, handle) -> dict:
     name = C.create_string_buffer(256)
     regs, smem, rpt, bt = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -616,10 +623,10 @@ class Projector:
             s = gdv_selection_t(selection[0], selection[1], selection[1], self._mode, GDV_MEM_DEVICE)
             csel = C.byref(s)
         _check(lib.gdv_projector_evaluate(self._h, C.byref(cb), csel, outs, len(outputs),
-                                          C.c_void_p(stream), 0 if sync else 1))
+                                          _stream_handle(stream), 0 if sync else 1))
 
     def sync(self, stream: int = 0) -> None:
-        _check(lib.gdv_projector_sync(self._h, C.c_void_p(stream)))
+        _check(lib.gdv_projector_sync(self._h, _stream_handle(stream)))
 
 
 # ---- Filter ------------------------------------------------------------------------------
@@ -678,13 +685,13 @@ class Filter:
         cb = gdv_batch_t(num_rows, len(columns), GDV_MEM_DEVICE, cols)
         sel = gdv_selection_t(out_indices, max_slots, 0, _ensure_selection_mode(mode), GDV_MEM_DEVICE,
                               index_base)
-        _check(lib.gdv_filter_evaluate(self._h, C.byref(cb), C.byref(sel), C.c_void_p(stream),
+        _check(lib.gdv_filter_evaluate(self._h, C.byref(cb), C.byref(sel), _stream_handle(stream),
                                        0 if sync else 1, C.c_void_p(d_count) if d_count else None))
         return int(sel.num_slots)
 
     def sync(self, stream: int = 0) -> int:
         n = C.c_int64(-1)
-        _check(lib.gdv_filter_sync(self._h, C.c_void_p(stream), C.byref(n)))
+        _check(lib.gdv_filter_sync(self._h, _stream_handle(stream), C.byref(n)))
         return int(n.value)
 
 
@@ -749,6 +756,15 @@ class FunctionSignature:
 
     def __str__(self) -> str:
         return "%s %s(%s)" % (self._ret, self._name, ", ".join(str(p) for p in self._params))
+
+
+def generate_lineitem(device: int, kind: int, seed: int, first_row: int, num_rows: int,
+                      values_ptr: int, validity_ptr: int = 0, null_permille: int = 0,
+                      stream: int = 0) -> None:
+    """Synthetic TPC-H lineitem column written straight into device memory (harness helper;
+    column kinds in csrc/device/static_kernels.cu).  `stream` as in evaluate_device."""
+    _check(lib.gdv_generate_lineitem(device, kind, seed, first_row, num_rows, values_ptr,
+                                     validity_ptr or None, null_permille, _stream_handle(stream)))
 
 
 def get_registered_function_signatures() -> list:

@@ -208,7 +208,8 @@ gdv_status gdv_projector_make(gdv_schema_t schema, const gdv_expression_t* exprs
                               int32_t selection_mode, const gdv_config_t* cfg,
                               gdv_projector_t* out);
 /* Evaluate.  `selection` NULL (mode NONE) or a selection vector of the mode given at Make.
- * `stream` is a CUstream/cudaStream_t (0 = the engine's own stream).  With host
+ * `stream` is a CUstream/cudaStream_t; NULL = the engine's own non-blocking stream (pass
+ * CU_STREAM_LEGACY, (void*)0x1, to name CUDA's default stream explicitly).  With host
  * buffers the call is synchronous.  With device buffers and `async` != 0 it only
  * enqueues work on `stream`; errors raised by device functions are then reported
  * by gdv_projector_sync(). */
