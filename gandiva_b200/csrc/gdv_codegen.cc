@@ -632,6 +632,12 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   int R = spec.rows_per_thread > 0 ? spec.rows_per_thread
                                    : PickRowsPerThread(in_bytes, out_bytes, spec.kind);
   if (R > 32) R = 32;
+  if (spec.kind == KernelKind::kFilter) {
+    // the filter walks 32 steps per warp in groups of R: R must divide 32
+    int p = 1;
+    while (p * 2 <= R) p *= 2;
+    R = p;
+  }
   const int BT = spec.block_threads > 0 ? spec.block_threads : 256;
   if (BT % 32 != 0 || BT > 1024)
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
@@ -697,45 +703,65 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "  }\n";
     src += "}\n";
   } else {
+    // Filter: every warp owns 1024 consecutive rows of the CTA tile (32 steps of 32 rows).
+    // Step k's keep-mask is one ballot word, parked in lane k, so the whole tile costs one
+    // register per thread regardless of its size; loads are issued R steps at a time for
+    // memory-level parallelism.  Large tiles (BT/32 * 1024 rows) keep the number of
+    // look-back descriptors per launch small, which is what bounds ordered compaction at
+    // B200 bandwidth (DESIGN.md "Filter kernel").
     const std::string IDX = SelCType(spec.selection_mode);
     const int NW = BT / 32;
+    const int TILE = NW * 1024;
     src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
     src += "  __shared__ i64 s_tile;\n";
     src += "  __shared__ u64 s_excl;\n";
-    src += "  const i64 n_tiles = (A.n + " + std::to_string(BT * R - 1) + ") / " +
-           std::to_string(BT * R) + ";\n";
+    src += "  const i64 n_tiles = (A.n + " + std::to_string(TILE - 1) + ") / " +
+           std::to_string(TILE) + ";\n";
     src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
+    src += "  const u32 lt = gdv_lanemask_lt();\n";
     src += "  while (true) {\n";
     src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
     src += "    __syncthreads();\n";
     src += "    const i64 tile = s_tile;\n";
     src += "    if (tile >= n_tiles) break;\n";
-    src += "    const i64 base = tile * " + std::to_string(BT * R) + " + (i64)wid * " +
-           std::to_string(32 * R) + ";\n";
-    EmitLoadPhase(slots, spec, R, &src, 2);
-    src += "    u32 keep[" + sR + "];\n";
-    src += "    u32 wcount = 0u;\n";
-    src += "    #pragma unroll\n";
-    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
-    src += "      const i64 s = base + 32 * k + (i64)lane;\n";
-    src += "      const bool in = s < A.n;\n";
+    src += "    const i64 wbase = tile * " + std::to_string(TILE) + " + (i64)wid * 1024;\n";
+    src += "    u32 mymask = 0u;\n";
+    src += "    #pragma unroll 1\n";
+    src += "    for (int g = 0; g < 32; g += " + sR + ") {\n";
+    src += "      const i64 base = wbase + 32 * g;\n";
+    src += "      if (base >= A.n) break;\n";
+    EmitLoadPhase(slots, spec, R, &src, 3);
+    src += "      #pragma unroll\n";
+    src += "      for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "        const i64 s = base + 32 * k + (i64)lane;\n";
+    src += "        const bool in = s < A.n;\n";
     src += body;
-    src += "      keep[k] = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
+    src += "        const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
            results[0].v + "));\n";
-    src += "      wcount += (u32)__popc(keep[k]);\n";
+    src += "        if (lane == (u32)(g + k)) mymask = m;\n";
+    src += "      }\n";
     src += "    }\n";
-    src += "    if (lane == 0u) s_wcount[wid] = wcount;\n";
+    // lane k: c = selected rows of step k; exclusive scan over steps; warp total
+    src += "    const u32 c = (u32)__popc(mymask);\n";
+    src += "    u32 incl = c;\n";
+    src += "    #pragma unroll\n";
+    src += "    for (int o = 1; o < 32; o <<= 1) {\n";
+    src += "      const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
+    src += "      if (lane >= (u32)o) incl += t;\n";
+    src += "    }\n";
+    src += "    const u32 step_excl = incl - c;\n";
+    src += "    if (lane == 31u) s_wcount[wid] = incl;\n";
     src += "    __syncthreads();\n";
     src += "    if (wid == 0u) {\n";
-    src += "      const u32 c = lane < " + std::to_string(NW) + "u ? s_wcount[lane] : 0u;\n";
-    src += "      u32 incl = c;\n";
+    src += "      const u32 wc = lane < " + std::to_string(NW) + "u ? s_wcount[lane] : 0u;\n";
+    src += "      u32 winc = wc;\n";
     src += "      #pragma unroll\n";
     src += "      for (int o = 1; o < 32; o <<= 1) {\n";
-    src += "        const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
-    src += "        if (lane >= (u32)o) incl += t;\n";
+    src += "        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);\n";
+    src += "        if (lane >= (u32)o) winc += t;\n";
     src += "      }\n";
-    src += "      const u32 total = __shfl_sync(GDV_FULL, incl, 31);\n";
-    src += "      if (lane < " + std::to_string(NW) + "u) s_wcount[lane] = incl - c;\n";
+    src += "      const u32 total = __shfl_sync(GDV_FULL, winc, 31);\n";
+    src += "      if (lane < " + std::to_string(NW) + "u) s_wcount[lane] = winc - wc;\n";
     src += "      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);\n";
     src += "      if (lane == 0u) {\n";
     src += "        s_excl = excl;\n";
@@ -743,15 +769,17 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "      }\n";
     src += "    }\n";
     src += "    __syncthreads();\n";
-    src += "    u64 pos = s_excl + (u64)s_wcount[wid];\n";
-    src += "    const u32 lt = gdv_lanemask_lt();\n";
-    src += "    #pragma unroll\n";
-    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
-    src += "      const u32 m = keep[k];\n";
-    src += "      if ((m >> lane) & 1u)\n";
-    src += "        out_idx[pos + (u64)__popc(m & lt)] = (" + IDX +
-           ")(A.row_base + base + 32 * k + (i64)lane);\n";
-    src += "      pos += (u64)__popc(m);\n";
+    src += "    const u64 wpos = s_excl + (u64)s_wcount[wid];\n";
+    src += "    const u32 wtotal = __shfl_sync(GDV_FULL, incl, 31);\n";
+    src += "    if (wtotal != 0u) {\n";
+    src += "      #pragma unroll 4\n";
+    src += "      for (int k = 0; k < 32; ++k) {\n";
+    src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
+    src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
+    src += "        if ((m >> lane) & 1u)\n";
+    src += "          out_idx[wpos + (u64)off + (u64)__popc(m & lt)] = (" + IDX +
+           ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
+    src += "      }\n";
     src += "    }\n";
     src += "  }\n";
     src += "}\n";
@@ -771,6 +799,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->in_bytes_per_row = in_bytes;
   out->out_bytes_per_row = out_bytes;
   out->args_size = L.size;
+  out->tile_rows = spec.kind == KernelKind::kFilter ? static_cast<int64_t>(BT / 32) * 1024 : 0;
   return Status::OK();
 }
 

@@ -59,6 +59,7 @@ struct GeneratedKernel {
   int in_bytes_per_row = 0;         // algorithmic bytes (values only) read per row
   int out_bytes_per_row = 0;
   size_t args_size = 0;             // sizeof(gdv_args) for this kernel
+  int64_t tile_rows = 0;            // filter: rows per CTA tile (one look-back descriptor each)
 };
 
 // Byte offsets inside gdv_args; the host packs the same layout (see EmitArgsStruct()).

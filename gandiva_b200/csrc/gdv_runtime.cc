@@ -580,8 +580,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
 
-  const int R = gen.rows_per_thread, BT = gen.block_threads;
-  const int64_t tile_rows = static_cast<int64_t>(R) * BT;
+  const int64_t tile_rows = gen.tile_rows;
   const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
 
   // Per-stream persistent scratch: [ticket u64][count u64][tile_state n_tiles x u64]

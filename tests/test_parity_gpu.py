@@ -231,7 +231,7 @@ def test_device_resident_filter_and_properties(gandiva, oracle):
     # exact oracle parity on a prefix
     m = 200_000
     batch = cases.q6_batch(m, seed=42)
-    assert np.array_equal(ship[:m].cpu().numpy(), batch.column(0).to_numpy(zero_copy_only=False))
+    assert np.array_equal(ship[:m].cpu().numpy(), batch.column(0).cast(pa.int32()).to_numpy(zero_copy_only=False))
     want = oracle.filter_indices(cases.q6_condition(b), batch, threads=4)
     got = idx[idx < m].cpu().numpy().astype(np.uint64)
     assert np.array_equal(got, want)
