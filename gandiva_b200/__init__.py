@@ -504,7 +504,8 @@ def _batch_to_c(batch: pa.RecordBatch):
         bufs = arr.buffers()
         keep.append(bufs)
         c = cols[i]
-        c.validity = bufs[0].address if bufs[0] is not None else None
+        # a bitmap without any cleared bit is passed as "no validity" (selects the no-null kernel)
+        c.validity = bufs[0].address if bufs[0] is not None and arr.null_count > 0 else None
         t = arr.type
         if pa.types.is_string(t) or pa.types.is_binary(t):
             c.values = bufs[1].address if bufs[1] is not None else None

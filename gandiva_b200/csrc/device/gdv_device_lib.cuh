@@ -101,6 +101,36 @@ template <>
 GDV_DEV void gdv_st<i8>(void* base, i64 i, i8 v) {
   __stcs(reinterpret_cast<signed char*>(base) + i, (signed char)v);
 }
+// Pointer-based streaming load / store used by the fast path (one pointer per column, steps at
+// immediate offsets).
+template <typename T>
+GDV_DEV T gdv_ldp(const T* p) {
+  return __ldcs(p);
+}
+template <>
+GDV_DEV i128 gdv_ldp<i128>(const i128* p) {
+  const longlong2 v = __ldcs(reinterpret_cast<const longlong2*>(p));
+  return (i128)(((u128)(u64)v.y << 64) | (u128)(u64)v.x);
+}
+template <typename T>
+GDV_DEV void gdv_stp(T* p, T v) {
+  __stcs(p, v);
+}
+template <>
+GDV_DEV void gdv_stp<i128>(i128* p, i128 v) {
+  longlong2 w;
+  w.x = (i64)(u64)(u128)v;
+  w.y = (i64)(u64)((u128)v >> 64);
+  __stcs(reinterpret_cast<longlong2*>(p), w);
+}
+// 32 bitmap bits starting at bit (32 * widx + sh), sh in [0, 31], from a 4-byte aligned word
+// pointer.  Warp-uniform address: one broadcast transaction for the 32 rows of a step.
+GDV_DEV u32 gdv_ldwin(const u32* p, i64 widx, u32 sh) {
+  const u32 lo = __ldg(p + widx);
+  if (sh == 0u) return lo;
+  const u32 hi = __ldg(p + widx + 1);
+  return __funnelshift_r(lo, hi, sh);
+}
 // Bit `i` (LSB-first, Arrow validity layout, P/include/arrow/util/bit_util.h:158) of a
 // bitmap that starts `sh` bits into byte *p.  p == nullptr means "all set".
 GDV_DEV bool gdv_ldbit(const u8* p, u32 sh, i64 i) {

@@ -342,9 +342,11 @@ gdv_status gdv_filter_kernel_info(gdv_filter_t f, char* name_buf, int64_t name_l
                                   int32_t* block_threads) {
   if (f == nullptr) return Fail(GDV_INVALID, "null filter");
   auto& fl = *reinterpret_cast<FiltH*>(f)->p;
-  CompiledKernel* k = nullptr;
-  Status s = fl.KernelFor(GDV_SEL_UINT32, &k);
-  if (!s.ok()) return Fail(s);
+  CompiledKernel* k = fl.last_used();
+  if (k == nullptr) {
+    Status s = fl.KernelFor(GDV_SEL_UINT32, true, &k);
+    if (!s.ok()) return Fail(s);
+  }
   return KernelInfo(*k, fl.config(), name_buf, name_len, regs, smem_bytes, rows_per_thread,
                     block_threads);
 }

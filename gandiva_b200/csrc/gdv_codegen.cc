@@ -180,7 +180,8 @@ std::string HexLit(uint64_t bits) {
 
 class BodyGen {
  public:
-  BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots) : schema_(schema), slots_(slots) {}
+  BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots, bool nullable)
+      : schema_(schema), slots_(slots), nullable_(nullable) {}
 
   std::string& globals() { return globals_; }
   bool uses_ctx() const { return uses_ctx_; }
@@ -257,7 +258,8 @@ class BodyGen {
 
   Val GenField(const FieldNode& f) {
     const int j = SlotFor(f);
-    return Val{"f" + std::to_string(j) + "[k]", "k" + std::to_string(j) + "[k]", f.return_type()};
+    return Val{"f" + std::to_string(j) + "[k]",
+               nullable_ ? "k" + std::to_string(j) + "[k]" : std::string("true"), f.return_type()};
   }
 
   std::string BytesArray(const std::string& bytes, const char* prefix) {
@@ -514,6 +516,7 @@ class BodyGen {
 
   const Schema& schema_;
   std::vector<ColumnSlot>* slots_;
+  bool nullable_;
   std::string globals_;
   int next_id_ = 0;
   bool uses_ctx_ = false;
@@ -550,45 +553,114 @@ const char* SelCType(int mode) {
   }
 }
 
-// Declarations + load phase shared by both kernel kinds.  `slot_expr` is the C expression
-// of the slot index for step k; with an input selection vector the row is sel[slot].
-void EmitLoadPhase(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R,
-                   std::string* o, int indent) {
-  const std::string I(static_cast<size_t>(indent) * 2, ' ');
-  for (size_t j = 0; j < slots.size(); ++j) {
-    const DataType& t = slots[j].type;
-    *o += I + t.ctype() + " f" + std::to_string(j) + "[" + std::to_string(R) + "];\n";
-    *o += I + "bool k" + std::to_string(j) + "[" + std::to_string(R) + "];\n";
-  }
-  *o += I + "#pragma unroll\n";
-  *o += I + "for (int k = 0; k < " + std::to_string(R) + "; ++k) {\n";
-  *o += I + "  const i64 s = base + 32 * k + (i64)lane;\n";
-  *o += I + "  const bool in = s < A.n;\n";
-  if (spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE) {
-    *o += I + "  const i64 r = in ? (i64)reinterpret_cast<const " +
-          SelCType(spec.selection_mode) + "*>(A.sel)[s] : 0;\n";
-  } else {
-    *o += I + "  const i64 r = in ? s : 0;\n";
-  }
+// ---- kernel skeleton pieces ------------------------------------------------------------
+// Hoisted, typed views of the argument block (read once per thread, live in registers /
+// uniform registers for the whole kernel).
+void EmitPrologue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, std::string* o) {
   for (size_t j = 0; j < slots.size(); ++j) {
     const DataType& t = slots[j].type;
     const std::string J = std::to_string(j);
     if (t.is_bool()) {
-      *o += I + "  f" + J + "[k] = gdv_ldbit(reinterpret_cast<const u8*>(A.in_val[" + J +
-            "]), A.in_dsh[" + J + "], r);\n";
+      *o += "  const u32* in_dat" + J + " = reinterpret_cast<const u32*>(A.in_val[" + J + "]);\n";
+      *o += "  const u32 in_dsh" + J + " = A.in_dsh[" + J + "];\n";
     } else if (t.is_varlen()) {
-      *o += I + "  {\n";
-      *o += I + "    const i32* off = reinterpret_cast<const i32*>(A.in_val[" + J + "]);\n";
-      *o += I + "    const i32 b = in ? off[r] : 0;\n";
-      *o += I + "    const i32 e = in ? off[r + 1] : 0;\n";
-      *o += I + "    f" + J + "[k] = gdv_make_str(A.in_var[" + J + "] + b, e - b);\n";
-      *o += I + "  }\n";
+      *o += "  const i32* in_val" + J + " = reinterpret_cast<const i32*>(A.in_val[" + J + "]);\n";
+      *o += "  const u8* in_var" + J + " = A.in_var[" + J + "];\n";
     } else {
-      *o += I + "  f" + J + "[k] = in ? gdv_ld<" + t.ctype() + ">(A.in_val[" + J + "], r) : (" +
-            t.ctype() + ")0;\n";
+      *o += "  const " + std::string(t.ctype()) + "* in_val" + J + " = reinterpret_cast<const " +
+            t.ctype() + "*>(A.in_val[" + J + "]);\n";
     }
-    *o += I + "  k" + J + "[k] = in && gdv_ldbit(A.in_vld[" + J + "], A.in_vsh[" + J + "], r);\n";
+    if (spec.nullable) {
+      *o += "  const u32* in_vld" + J + " = reinterpret_cast<const u32*>(A.in_vld[" + J + "]);\n";
+      *o += "  const u32 in_vsh" + J + " = A.in_vsh[" + J + "];\n";
+      *o += "  const bool in_hv" + J + " = in_vld" + J + " != nullptr;\n";
+    }
   }
+  if (spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE)
+    *o += "  const " + std::string(SelCType(spec.selection_mode)) +
+          "* sel = reinterpret_cast<const " + SelCType(spec.selection_mode) + "*>(A.sel);\n";
+}
+
+// One group of R steps (32 rows each) starting at row `base` (a multiple of 32):
+// declarations, load phase, then the compute loop whose per-step tail is `step_tail`
+// (stores / ballots; may use `s`, `in`, `k`).  `fast` = every row of the group is in range
+// and rows are contiguous (no selection vector): loads are unconditional, back to back, with
+// immediate offsets from one pointer per column; validity arrives as one 32-bit window per
+// step (a warp-uniform load) instead of one byte load per row.
+void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R, bool fast,
+               const std::string& body, const std::string& step_tail, std::string* o, int indent) {
+  const std::string I(static_cast<size_t>(indent) * 2, ' ');
+  const std::string sR = std::to_string(R);
+  const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
+  for (size_t j = 0; j < slots.size(); ++j) {
+    const DataType& t = slots[j].type;
+    *o += I + t.ctype() + " f" + std::to_string(j) + "[" + sR + "];\n";
+    if (spec.nullable) *o += I + "bool k" + std::to_string(j) + "[" + sR + "];\n";
+  }
+  if (fast) {
+    for (size_t j = 0; j < slots.size(); ++j) {
+      const DataType& t = slots[j].type;
+      const std::string J = std::to_string(j);
+      if (!t.is_bool())
+        *o += I + "const " + (t.is_varlen() ? std::string("i32") : std::string(t.ctype())) +
+              "* ptr" + J + " = in_val" + J + " + base + (i64)lane;\n";
+    }
+    *o += I + "#pragma unroll\n";
+    *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
+    for (size_t j = 0; j < slots.size(); ++j) {
+      const DataType& t = slots[j].type;
+      const std::string J = std::to_string(j);
+      if (t.is_bool()) {
+        *o += I + "  f" + J + "[k] = ((gdv_ldwin(in_dat" + J + ", (base >> 5) + k, in_dsh" + J +
+              ") >> lane) & 1u) != 0u;\n";
+      } else if (t.is_varlen()) {
+        *o += I + "  { const i32 sb = ptr" + J + "[32 * k]; const i32 se = ptr" + J +
+              "[32 * k + 1]; f" + J + "[k] = gdv_make_str(in_var" + J + " + sb, se - sb); }\n";
+      } else {
+        *o += I + "  f" + J + "[k] = gdv_ldp(ptr" + J + " + 32 * k);\n";
+      }
+    }
+    *o += I + "}\n";
+    if (spec.nullable) {
+      *o += I + "#pragma unroll\n";
+      *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
+      for (size_t j = 0; j < slots.size(); ++j) {
+        const std::string J = std::to_string(j);
+        *o += I + "  k" + J + "[k] = !in_hv" + J + " || ((gdv_ldwin(in_vld" + J + ", (base >> 5) + k, in_vsh" +
+              J + ") >> lane) & 1u) != 0u;\n";
+      }
+      *o += I + "}\n";
+    }
+  } else {
+    *o += I + "#pragma unroll\n";
+    *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
+    *o += I + "  const i64 s = base + 32 * k + (i64)lane;\n";
+    *o += I + "  const bool in = s < A.n;\n";
+    *o += I + std::string("  const i64 r = in ? ") + (has_sel ? "(i64)sel[s]" : "s") + " : 0;\n";
+    for (size_t j = 0; j < slots.size(); ++j) {
+      const DataType& t = slots[j].type;
+      const std::string J = std::to_string(j);
+      if (t.is_bool()) {
+        *o += I + "  f" + J + "[k] = in && gdv_ldbit(reinterpret_cast<const u8*>(in_dat" + J + "), in_dsh" +
+              J + ", r);\n";
+      } else if (t.is_varlen()) {
+        *o += I + "  { const i32 sb = in ? in_val" + J + "[r] : 0; const i32 se = in ? in_val" + J +
+              "[r + 1] : 0; f" + J + "[k] = gdv_make_str(in_var" + J + " + sb, se - sb); }\n";
+      } else {
+        *o += I + "  f" + J + "[k] = in ? gdv_ldp(in_val" + J + " + r) : (" + t.ctype() + ")0;\n";
+      }
+      if (spec.nullable)
+        *o += I + "  k" + J + "[k] = in && (!in_hv" + J + " || gdv_ldbit(reinterpret_cast<const u8*>(in_vld" +
+              J + "), in_vsh" + J + ", r));\n";
+    }
+    *o += I + "}\n";
+  }
+  *o += I + "#pragma unroll\n";
+  *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
+  *o += I + "  const i64 s = base + 32 * k + (i64)lane;\n";
+  *o += I + (fast ? "  const bool in = true;\n" : "  const bool in = s < A.n;\n");
+  *o += body;
+  *o += step_tail;
   *o += I + "}\n";
 }
 
@@ -611,7 +683,7 @@ int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
 Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
                       const KernelSpec& spec, GeneratedKernel* out) {
   std::vector<ColumnSlot> slots;
-  BodyGen gen(schema, &slots);
+  BodyGen gen(schema, &slots, spec.nullable);
 
   // Per-row body (uses f<j>[k] / k<j>[k]); generated first so we know the slots.
   std::string body;
@@ -621,7 +693,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
       return Status::Make(GDV_NOT_IMPLEMENTED,
                           "variable-length projection outputs are handled by the two-pass "
                           "string projector, not by GenerateKernel");
-    results.push_back(gen.Gen(*e->root(), &body, 3));
+    results.push_back(gen.Gen(*e->root(), &body, 4));
   }
 
   int in_bytes = 0, out_bytes = 0;
@@ -643,54 +715,76 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
 
   const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
+  const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
   ArgsLayout L(static_cast<int>(slots.size()), n_out);
 
   std::string src;
   src += "// generated by gandiva_b200 kernel fuser; one fused kernel per ";
-  src += (spec.kind == KernelKind::kProject ? "Projector\n" : "Filter\n");
+  src += (spec.kind == KernelKind::kProject ? "Projector" : "Filter");
+  src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
   for (size_t i = 0; i < exprs.size(); ++i)
     src += "// expr_" + std::to_string(i) + ": " + exprs[i]->ToString() + "\n";
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
   const std::string sR = std::to_string(R), sBT = std::to_string(BT);
+  const std::string s32R = std::to_string(32 * R);
   src += "extern \"C\" __global__ void __launch_bounds__(" + sBT + ") " + spec.name +
          "(const __grid_constant__ gdv_args A) {\n";
   src += "  const u32 lane = threadIdx.x & 31u;\n";
   src += "  const u32 wid = threadIdx.x >> 5;\n";
   src += "  gdv_ctx ctx;\n  ctx.err = A.err;\n";
+  EmitPrologue(slots, spec, &src);
 
   if (spec.kind == KernelKind::kProject) {
-    src += "  const i64 n_wtiles = (A.n + " + std::to_string(32 * R - 1) + ") / " +
-           std::to_string(32 * R) + ";\n";
+    for (int o = 0; o < n_out; ++o) {
+      const DataType& t = exprs[o]->result().type;
+      const std::string O = std::to_string(o);
+      if (!t.is_bool())
+        src += "  " + std::string(t.ctype()) + "* out" + O + " = reinterpret_cast<" + t.ctype() +
+               "*>(A.out_val[" + O + "]);\n";
+    }
+    // per-step tails: stores + validity / bool-data ballots
+    auto tail = [&](bool fast) {
+      std::string t5;
+      for (int o = 0; o < n_out; ++o) {
+        const DataType& t = exprs[o]->result().type;
+        const std::string O = std::to_string(o);
+        if (t.is_bool()) {
+          t5 += "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[o].v +
+                ")); if (lane == (u32)k) dw" + O + " = m; }\n";
+        } else if (fast) {
+          t5 += "        gdv_stp(out" + O + " + s, (" + std::string(t.ctype()) + ")(" + results[o].v +
+                "));\n";
+        } else {
+          t5 += "        if (in) gdv_stp(out" + O + " + s, (" + std::string(t.ctype()) + ")(" +
+                results[o].v + "));\n";
+        }
+        t5 += "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[o].ok +
+              ")); if (lane == (u32)k) vw" + O + " = m; }\n";
+      }
+      return t5;
+    };
+    src += "  const i64 n_wtiles = (A.n + " + std::to_string(32 * R - 1) + ") / " + s32R + ";\n";
     src += "  const i64 wstride = (i64)gridDim.x * " + std::to_string(BT / 32) + ";\n";
     src += "  for (i64 wt = (i64)blockIdx.x * " + std::to_string(BT / 32) +
            " + wid; wt < n_wtiles; wt += wstride) {\n";
-    src += "    const i64 base = wt * " + std::to_string(32 * R) + ";\n";
-    EmitLoadPhase(slots, spec, R, &src, 2);
+    src += "    const i64 base = wt * " + s32R + ";\n";
     for (int o = 0; o < n_out; ++o) {
       src += "    u32 vw" + std::to_string(o) + " = 0u;\n";
       if (exprs[o]->result().type.is_bool()) src += "    u32 dw" + std::to_string(o) + " = 0u;\n";
     }
-    src += "    #pragma unroll\n";
-    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
-    src += "      const i64 s = base + 32 * k + (i64)lane;\n";
-    src += "      const bool in = s < A.n;\n";
-    src += body;
-    for (int o = 0; o < n_out; ++o) {
-      const DataType& t = exprs[o]->result().type;
-      const std::string O = std::to_string(o);
-      if (t.is_bool()) {
-        src += "      { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[o].v +
-               ")); if (lane == (u32)k) dw" + O + " = m; }\n";
-      } else {
-        src += "      if (in) gdv_st<" + std::string(t.ctype()) + ">(A.out_val[" + O + "], s, " +
-               results[o].v + ");\n";
-      }
-      src += "      { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[o].ok +
-             ")); if (lane == (u32)k) vw" + O + " = m; }\n";
+    if (!has_sel) {
+      src += "    if (base + " + s32R + " <= A.n) {\n";
+      EmitGroup(slots, spec, R, true, body, tail(true), &src, 3);
+      src += "    } else {\n";
+      EmitGroup(slots, spec, R, false, body, tail(false), &src, 3);
+      src += "    }\n";
+    } else {
+      src += "    {\n";
+      EmitGroup(slots, spec, R, false, body, tail(false), &src, 3);
+      src += "    }\n";
     }
-    src += "    }\n";
     src += "    if (lane < " + sR + "u && base + 32 * (i64)lane < A.n) {\n";
     src += "      const i64 w = (base >> 5) + (i64)lane;\n";
     for (int o = 0; o < n_out; ++o) {
@@ -712,6 +806,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     const std::string IDX = SelCType(spec.selection_mode);
     const int NW = BT / 32;
     const int TILE = NW * 1024;
+    const std::string step_tail =
+        "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
+        results[0].v + ")); if (lane == (u32)(g + k)) mymask = m; }\n";
     src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
     src += "  __shared__ i64 s_tile;\n";
     src += "  __shared__ u64 s_excl;\n";
@@ -730,15 +827,10 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "    for (int g = 0; g < 32; g += " + sR + ") {\n";
     src += "      const i64 base = wbase + 32 * g;\n";
     src += "      if (base >= A.n) break;\n";
-    EmitLoadPhase(slots, spec, R, &src, 3);
-    src += "      #pragma unroll\n";
-    src += "      for (int k = 0; k < " + sR + "; ++k) {\n";
-    src += "        const i64 s = base + 32 * k + (i64)lane;\n";
-    src += "        const bool in = s < A.n;\n";
-    src += body;
-    src += "        const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
-           results[0].v + "));\n";
-    src += "        if (lane == (u32)(g + k)) mymask = m;\n";
+    src += "      if (base + " + s32R + " <= A.n) {\n";
+    EmitGroup(slots, spec, R, true, body, step_tail, &src, 4);
+    src += "      } else {\n";
+    EmitGroup(slots, spec, R, false, body, step_tail, &src, 4);
     src += "      }\n";
     src += "    }\n";
     // lane k: c = selected rows of step k; exclusive scan over steps; warp total
@@ -791,6 +883,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->rows_per_thread = R;
   out->block_threads = BT;
   out->selection_mode = spec.selection_mode;
+  out->nullable = spec.nullable;
   out->inputs = slots;
   out->outputs.clear();
   if (spec.kind == KernelKind::kProject)

@@ -39,6 +39,7 @@ struct KernelSpec {
   int rows_per_thread = 0;            // 0 = pick from bytes/row
   int block_threads = 256;
   std::string name;                   // kernel symbol
+  bool nullable = true;               // false: specialised for batches where no input has nulls
 };
 
 struct ColumnSlot {
@@ -53,6 +54,7 @@ struct GeneratedKernel {
   int rows_per_thread;
   int block_threads;
   int selection_mode;
+  bool nullable = true;
   std::vector<ColumnSlot> inputs;   // kernel input slot j reads schema column inputs[j]
   std::vector<DataType> outputs;    // project: one per expression; filter: empty
   bool uses_ctx = false;            // some function can raise an ExecutionError

@@ -1,6 +1,8 @@
 #include "gdv_runtime.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace gdv {
@@ -182,10 +184,11 @@ namespace {
 std::atomic<int> g_kernel_serial{0};
 
 Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
-                   KernelKind kind, int selection_mode, const Config& cfg,
+                   KernelKind kind, int selection_mode, bool nullable, const Config& cfg,
                    std::unique_ptr<CompiledKernel>* out) {
   KernelSpec spec;
   spec.kind = kind;
+  spec.nullable = nullable;
   spec.selection_mode = selection_mode;
   spec.rows_per_thread = cfg.rows_per_thread;
   spec.block_threads = cfg.block_threads > 0 ? cfg.block_threads : 256;
@@ -199,6 +202,19 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
   if (Driver().loaded && Device::Get(cfg.device, &dev).ok()) arch = dev->arch();
   GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
                                    &k->ptx, &k->compile_log));
+  // GDV_DUMP_DIR=<dir>: write <kernel>.cu / <kernel>.cubin for offline SASS inspection
+  // (cuobjdump -sass) and so that ncu's source page can find the generated code.
+  if (const char* dir = std::getenv("GDV_DUMP_DIR")) {
+    const std::string base = std::string(dir) + "/" + k->gen.name;
+    if (FILE* f = std::fopen((base + ".cu").c_str(), "w")) {
+      std::fwrite(k->gen.source.data(), 1, k->gen.source.size(), f);
+      std::fclose(f);
+    }
+    if (FILE* f = std::fopen((base + ".cubin").c_str(), "wb")) {
+      std::fwrite(k->cubin.data(), 1, k->cubin.size(), f);
+      std::fclose(f);
+    }
+  }
   *out = std::move(k);
   return Status::OK();
 }
@@ -232,6 +248,7 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
       return Status::Make(GDV_INVALID, "column " + std::to_string(slot.schema_index) +
                                            " has no values buffer");
     // ---- validity
+    // Bitmaps reach the kernel as a 4-byte aligned word pointer plus a bit shift in [0, 31].
     if (c.validity != nullptr) {
       const uint8_t* p = static_cast<const uint8_t*>(c.validity) + (off >> 3);
       r.vsh = static_cast<uint32_t>(off & 7);
@@ -242,7 +259,9 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
         GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D validity"));
         r.vld = dp;
       } else {
-        r.vld = reinterpret_cast<CUdeviceptr>(p);
+        const uintptr_t mis = reinterpret_cast<uintptr_t>(p) & 3u;
+        r.vld = reinterpret_cast<CUdeviceptr>(p - mis);
+        r.vsh += static_cast<uint32_t>(8 * mis);
       }
     }
     // ---- values
@@ -256,7 +275,9 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
         GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D bool values"));
         r.val = dp;
       } else {
-        r.val = reinterpret_cast<CUdeviceptr>(p);
+        const uintptr_t mis = reinterpret_cast<uintptr_t>(p) & 3u;
+        r.val = reinterpret_cast<CUdeviceptr>(p - mis);
+        r.dsh += static_cast<uint32_t>(8 * mis);
       }
     } else if (t.is_varlen()) {
       const int32_t* offs = static_cast<const int32_t*>(c.values) + off;
@@ -346,10 +367,36 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
   p->exprs_ = std::move(exprs);
   p->selection_mode_ = selection_mode;
   p->cfg_ = cfg;
-  GDV_RETURN_NOT_OK(
-      BuildKernel(*schema, p->exprs_, KernelKind::kProject, selection_mode, cfg, &p->kernel_));
+  GDV_RETURN_NOT_OK(BuildKernel(*schema, p->exprs_, KernelKind::kProject, selection_mode, true, cfg,
+                                &p->kernel_));
+  if (std::getenv("GDV_EAGER_NONULL") != nullptr) {
+    CompiledKernel* k = nullptr;
+    GDV_RETURN_NOT_OK(p->KernelFor(false, &k));
+  }
   *out = std::move(p);
   return Status::OK();
+}
+
+Status Projector::KernelFor(bool nullable, CompiledKernel** out) {
+  if (nullable) {
+    *out = kernel_.get();
+    return Status::OK();
+  }
+  std::lock_guard<std::mutex> lock(mu_);
+  if (kernel_nonull_ == nullptr)
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs_, KernelKind::kProject, selection_mode_, false,
+                                  cfg_, &kernel_nonull_));
+  *out = kernel_nonull_.get();
+  return Status::OK();
+}
+
+// True when some column the kernel reads carries a validity bitmap.
+static bool AnyValidity(const GeneratedKernel& gen, const gdv_batch_t* batch) {
+  for (const auto& slot : gen.inputs)
+    if (slot.schema_index >= 0 && slot.schema_index < batch->num_columns &&
+        batch->columns[slot.schema_index].validity != nullptr)
+      return true;
+  return false;
 }
 
 std::string Projector::DumpIR() const {
@@ -380,11 +427,14 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
 
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CompiledKernel* kernel = nullptr;
+  GDV_RETURN_NOT_OK(KernelFor(AnyValidity(kernel_->gen, batch), &kernel));
+  last_used_ = kernel;
   CompiledKernel::Loaded l;
-  GDV_RETURN_NOT_OK(kernel_->Load(dev, &l));
+  GDV_RETURN_NOT_OK(kernel->Load(dev, &l));
   const DriverApi& d = Driver();
   CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
-  const GeneratedKernel& gen = kernel_->gen;
+  const GeneratedKernel& gen = kernel->gen;
 
   ScratchScope scratch(dev);
   std::vector<ResolvedIn> ins;
@@ -518,19 +568,22 @@ Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
   // The default Python/Cython path uses UINT32 indices: compile that variant eagerly so
   // Make() surfaces code-generation errors, as the reference does.
   CompiledKernel* k = nullptr;
-  GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, &k));
+  GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, true, &k));
+  if (std::getenv("GDV_EAGER_NONULL") != nullptr)
+    GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, false, &k));
   *out = std::move(f);
   return Status::OK();
 }
 
-Status Filter::KernelFor(int mode, CompiledKernel** out) {
+Status Filter::KernelFor(int mode, bool nullable, CompiledKernel** out) {
   std::lock_guard<std::mutex> lock(mu_);
-  auto it = kernels_.find(mode);
+  const int key = mode * 2 + (nullable ? 1 : 0);
+  auto it = kernels_.find(key);
   if (it == kernels_.end()) {
     std::unique_ptr<CompiledKernel> k;
     std::vector<ExpressionPtr> exprs = {cond_};
-    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, cfg_, &k));
-    it = kernels_.emplace(mode, std::move(k)).first;
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg_, &k));
+    it = kernels_.emplace(key, std::move(k)).first;
   }
   *out = it->second.get();
   return Status::OK();
@@ -538,7 +591,7 @@ Status Filter::KernelFor(int mode, CompiledKernel** out) {
 
 std::string Filter::DumpIR() const {
   std::lock_guard<std::mutex> lock(mu_);
-  auto it = kernels_.find(GDV_SEL_UINT32);
+  auto it = kernels_.find(GDV_SEL_UINT32 * 2 + 1);
   if (it == kernels_.end()) return "";
   return it->second->gen.source +
          (it->second->ptx.empty() ? "" : "\n// ---- PTX ----\n" + it->second->ptx);
@@ -568,8 +621,11 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
 
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CompiledKernel* general = nullptr;
+  GDV_RETURN_NOT_OK(KernelFor(GDV_SEL_UINT32, true, &general));
   CompiledKernel* kernel = nullptr;
-  GDV_RETURN_NOT_OK(KernelFor(out_sel->mode, &kernel));
+  GDV_RETURN_NOT_OK(KernelFor(out_sel->mode, AnyValidity(general->gen, batch), &kernel));
+  last_used_ = kernel;
   CompiledKernel::Loaded l;
   GDV_RETURN_NOT_OK(kernel->Load(dev, &l));
   const DriverApi& d = Driver();

@@ -123,7 +123,9 @@ class Projector {
                   int n_outs, void* stream, bool async);
   Status Sync(void* stream);
   std::string DumpIR() const;
-  CompiledKernel& kernel() { return *kernel_; }
+  CompiledKernel& kernel() { return last_used_ ? *last_used_ : *kernel_; }
+  // Variant specialised on whether any referenced input carries a validity bitmap.
+  Status KernelFor(bool nullable, CompiledKernel** out);
   const Config& config() const { return cfg_; }
   int num_outputs() const { return static_cast<int>(exprs_.size()); }
 
@@ -132,7 +134,9 @@ class Projector {
   std::vector<ExpressionPtr> exprs_;
   int selection_mode_ = GDV_SEL_NONE;
   Config cfg_;
-  std::unique_ptr<CompiledKernel> kernel_;
+  std::unique_ptr<CompiledKernel> kernel_;          // general (nullable) variant, built at Make()
+  std::unique_ptr<CompiledKernel> kernel_nonull_;   // built on first batch without nulls
+  CompiledKernel* last_used_ = nullptr;             // variant of the latest Evaluate (kernel_info)
   std::mutex mu_;
   std::map<void*, Pending> pending_;
 };
@@ -146,10 +150,12 @@ class Filter {
   Status Sync(void* stream, int64_t* num_slots);
   std::string DumpIR() const;
   // One kernel per selection-vector index width, compiled on first use.
-  Status KernelFor(int mode, CompiledKernel** out);
+  Status KernelFor(int mode, bool nullable, CompiledKernel** out);
   const Config& config() const { return cfg_; }
+  CompiledKernel* last_used() const { return last_used_; }
 
  private:
+  CompiledKernel* last_used_ = nullptr;
   SchemaPtr schema_;
   ConditionPtr cond_;
   Config cfg_;

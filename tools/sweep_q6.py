@@ -33,8 +33,8 @@ def main():
         cols = [(v.data_ptr() if v is not None else 0, t.data_ptr(), 0, 0) for t, v in zip((ship, disc, qty), vl)]
         results = []
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        for bt in (128, 256, 512, 1024):
-            for rpt in (1, 2, 4, 8, 16):
+        for bt in (256, 512, 1024):
+            for rpt in (2, 4, 8, 16):
                 cfg = gandiva.Configuration(rows_per_thread=rpt, block_threads=bt)
                 b = gandiva.TreeExprBuilder()
                 f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)), cfg)
