@@ -344,7 +344,7 @@ gdv_status gdv_filter_kernel_info(gdv_filter_t f, char* name_buf, int64_t name_l
   auto& fl = *reinterpret_cast<FiltH*>(f)->p;
   CompiledKernel* k = fl.last_used();
   if (k == nullptr) {
-    Status s = fl.KernelFor(GDV_SEL_UINT32, true, &k);
+    Status s = fl.KernelFor(GDV_SEL_UINT32, true, false, &k);
     if (!s.ok()) return Fail(s);
   }
   return KernelInfo(*k, fl.config(), name_buf, name_len, regs, smem_bytes, rows_per_thread,

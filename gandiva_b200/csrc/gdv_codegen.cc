@@ -665,16 +665,15 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
 }
 
 int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
-  // Keep roughly 64-128 bytes of loads in flight per thread without blowing the register
-  // budget (outputs are live in registers only one step at a time).
-  int bytes = std::max(in_bytes, 1);
-  int r = 96 / bytes;
-  if (kind == KernelKind::kFilter) r = std::max(r, 4);
-  r = std::max(1, std::min(r, 8));
-  // powers of two keep the index math cheap
+  // Measured on B200 (profiles/r01_sweeps.md): the map kernels want ~160-190 bytes of loads in
+  // flight per thread (add int32: R=16, Q6 predicate: R=8); the filter, whose tile is large
+  // and whose compaction tail needs registers, is best at R=2..4.
+  (void)out_bytes;
+  const int bytes = std::max(in_bytes, 1);
+  int r = kind == KernelKind::kFilter ? 64 / bytes : 192 / bytes;
+  r = std::max(kind == KernelKind::kFilter ? 2 : 1, std::min(r, 16));
   int p = 1;
   while (p * 2 <= r) p *= 2;
-  (void)out_bytes;
   return p;
 }
 

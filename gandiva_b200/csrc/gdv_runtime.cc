@@ -568,21 +568,26 @@ Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
   // The default Python/Cython path uses UINT32 indices: compile that variant eagerly so
   // Make() surfaces code-generation errors, as the reference does.
   CompiledKernel* k = nullptr;
-  GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, true, &k));
+  GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, true, false, &k));
   if (std::getenv("GDV_EAGER_NONULL") != nullptr)
-    GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, false, &k));
+    GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, false, true, &k));
   *out = std::move(f);
   return Status::OK();
 }
 
-Status Filter::KernelFor(int mode, bool nullable, CompiledKernel** out) {
+Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** out) {
   std::lock_guard<std::mutex> lock(mu_);
-  const int key = mode * 2 + (nullable ? 1 : 0);
+  const int key = mode * 4 + (nullable ? 1 : 0) + (large ? 2 : 0);
   auto it = kernels_.find(key);
   if (it == kernels_.end()) {
     std::unique_ptr<CompiledKernel> k;
     std::vector<ExpressionPtr> exprs = {cond_};
-    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg_, &k));
+    // Tile = block_threads / 32 * 1024 rows.  Big batches want big tiles (few look-back
+    // descriptors: 94% of HBM peak at 1024 threads vs 88% at 256 on Q6, profiles/r01_sweeps.md);
+    // small batches want enough tiles to occupy the 148 SMs.
+    Config cfg = cfg_;
+    if (cfg.block_threads == 0) cfg.block_threads = large ? (nullable ? 512 : 1024) : 256;
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg, &k));
     it = kernels_.emplace(key, std::move(k)).first;
   }
   *out = it->second.get();
@@ -591,7 +596,7 @@ Status Filter::KernelFor(int mode, bool nullable, CompiledKernel** out) {
 
 std::string Filter::DumpIR() const {
   std::lock_guard<std::mutex> lock(mu_);
-  auto it = kernels_.find(GDV_SEL_UINT32 * 2 + 1);
+  auto it = kernels_.find(GDV_SEL_UINT32 * 4 + 1);
   if (it == kernels_.end()) return "";
   return it->second->gen.source +
          (it->second->ptx.empty() ? "" : "\n// ---- PTX ----\n" + it->second->ptx);
@@ -622,9 +627,11 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
   CompiledKernel* general = nullptr;
-  GDV_RETURN_NOT_OK(KernelFor(GDV_SEL_UINT32, true, &general));
+  GDV_RETURN_NOT_OK(KernelFor(GDV_SEL_UINT32, true, false, &general));
   CompiledKernel* kernel = nullptr;
-  GDV_RETURN_NOT_OK(KernelFor(out_sel->mode, AnyValidity(general->gen, batch), &kernel));
+  const bool large = batch->num_rows >= (int64_t(32) << 20);
+  GDV_RETURN_NOT_OK(
+      KernelFor(out_sel->mode, AnyValidity(general->gen, batch), large, &kernel));
   last_used_ = kernel;
   CompiledKernel::Loaded l;
   GDV_RETURN_NOT_OK(kernel->Load(dev, &l));

@@ -150,7 +150,8 @@ class Filter {
   Status Sync(void* stream, int64_t* num_slots);
   std::string DumpIR() const;
   // One kernel per selection-vector index width, compiled on first use.
-  Status KernelFor(int mode, bool nullable, CompiledKernel** out);
+  // One kernel per (index width, nullable inputs?, large batch?), compiled on first use.
+  Status KernelFor(int mode, bool nullable, bool large, CompiledKernel** out);
   const Config& config() const { return cfg_; }
   CompiledKernel* last_used() const { return last_used_; }
 

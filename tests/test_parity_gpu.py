@@ -206,7 +206,7 @@ def test_device_resident_filter_and_properties(gandiva, oracle):
     Checked exactly against the oracle on the first rows and by size-independent properties
     (ascending, count == independent torch mask count, indices == torch.nonzero) on all rows."""
     import torch
-    n = 20_000_003
+    n = (32 << 20) + 3  # >= 32M rows: exercises the large-batch kernel variant (1024-thread tiles)
     dev = torch.device("cuda")
     ship = torch.empty(n, dtype=torch.int32, device=dev)
     disc = torch.empty(n, dtype=torch.float64, device=dev)
