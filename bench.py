@@ -298,8 +298,15 @@ def main():
     kernel_ms = kev[0].elapsed_time(kev[1]) / kreps
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     info = filt.kernel_info
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel/config
+        tj = json.load(open(os.path.join(ROOT, "profiles", "q6_filter_traffic.json")))
+        if int(tj["rows"]) == n and idx_mode == "UINT32":
+            traffic = float(tj["traffic_bytes_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": info["name"].rsplit("_", 1)[0], "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algo_bytes, "regs": info["regs"],
                 "rows_per_thread": info["rows_per_thread"], "block_threads": info["block_threads"]}
