@@ -371,6 +371,97 @@ def case_and_short_circuit(b):
     return schema, [(b.make_and([nz, q]), B)], "project"
 
 
+Q1_SCHEMA = pa.schema([("l_quantity", pa.int64()), ("l_extendedprice", pa.decimal128(15, 2)),
+                       ("l_discount", pa.decimal128(15, 2)), ("l_tax", pa.decimal128(15, 2)),
+                       ("l_extendedprice_f", pa.float64()), ("l_discount_f", pa.float64()),
+                       ("l_tax_f", pa.float64()), ("l_shipdate", pa.date32())])
+# generator column kinds (csrc/device/static_kernels.cu) of the Q1 schema, in field order
+Q1_KINDS = [3, 4, 5, 6, 7, 1, 8, 0]
+
+
+def q1_outputs(b):
+    """TPC-H Q1-style eight-output projector: decimal and float
+    `ext*(1-disc)` and `ext*(1-disc)*(1+tax)`, `qty+qty`, and three CASE expressions.
+    Decimal result types follow the reference's rule (p1+p2+1, s1+s2; capped at 38, min scale 6)."""
+    D, F64, I64, SD = pa.decimal128(15, 2), pa.float64(), pa.int64(), pa.date32()
+    f = {x.name: b.make_field(x) for x in Q1_SCHEMA}
+    one_d = b.make_literal(decimal.Decimal("1.00"), D)
+    one_f = b.make_literal(1.0, F64)
+    B = pa.bool_()
+    d1 = b.make_function("multiply", [f["l_extendedprice"],
+                                      b.make_function("subtract", [one_d, f["l_discount"]], pa.decimal128(16, 2))],
+                         pa.decimal128(32, 4))
+    d2 = b.make_function("multiply", [d1, b.make_function("add", [one_d, f["l_tax"]], pa.decimal128(16, 2))],
+                         pa.decimal128(38, 6))
+    f1 = b.make_function("multiply", [f["l_extendedprice_f"],
+                                      b.make_function("subtract", [one_f, f["l_discount_f"]], F64)], F64)
+    f2 = b.make_function("multiply", [f1, b.make_function("add", [one_f, f["l_tax_f"]], F64)], F64)
+    q2 = b.make_function("add", [f["l_quantity"], f["l_quantity"]], I64)
+    c1 = b.make_if(b.make_function("greater_than", [f["l_discount_f"], b.make_literal(0.05, F64)], B),
+                   f["l_extendedprice_f"], b.make_literal(0.0, F64), F64)
+    c2 = b.make_if(b.make_function("less_than", [f["l_quantity"], b.make_literal(24, I64)], B),
+                   b.make_literal(1, I64), b.make_literal(0, I64), I64)
+    c3 = b.make_if(b.make_function("less_than_or_equal_to", [f["l_shipdate"], b.make_literal(10471, SD)], B),
+                   f["l_quantity"], b.make_literal(None, I64), I64)
+    return [(d1, pa.decimal128(32, 4)), (d2, pa.decimal128(38, 6)), (f1, F64), (f2, F64), (q2, I64),
+            (c1, F64), (c2, I64), (c3, I64)]
+
+
+def case_q1_projector(b):
+    return Q1_SCHEMA, q1_outputs(b), "project"
+
+
+def q1_batch(n: int, seed: int = 42, null_permille: int = 20) -> pa.RecordBatch:
+    """Synthetic lineitem columns of the Q1 schema from the CPU generator (oracle/lineitem.h)."""
+    import oracle as o
+    cols = []
+    for kind, f in zip(Q1_KINDS, Q1_SCHEMA):
+        vals, vld = o.generate_lineitem(kind, seed, 0, n, null_permille, threads=4)
+        bufs = [pa.py_buffer(vld) if vld is not None else None, pa.py_buffer(vals)]
+        cols.append(pa.Array.from_buffers(f.type, n, bufs))
+    return pa.RecordBatch.from_arrays(cols, schema=Q1_SCHEMA)
+
+
+COMMENT_SCHEMA = pa.schema([("l_comment", pa.string())])
+_COMMENT_WORDS = ["furiously", "carefully", "quickly", "blithely", "slyly", "ironic", "final", "regular",
+                  "express", "bold", "pending", "even", "deposits", "accounts", "packages", "theodolites",
+                  "instructions", "foxes", "pinto", "beans", "platelets", "asymptotes", "dependencies",
+                  "sleep", "nag", "haggle", "wake", "cajole", "above", "the", "among", "about"]
+
+
+def comment_batch(n: int, seed: int = 42, null_prob: float = 0.01) -> pa.RecordBatch:
+    """l_comment-like utf8 column: ASCII words, length 10..43 bytes
+    (mean ~27), ~1 % of the rows contain "special" ... "requests", ~1 % nulls."""
+    rng = np.random.default_rng(seed)
+    pool = []
+    for i in range(4096):
+        target = int(rng.integers(10, 44))
+        words = []
+        if i % 100 == 7:
+            words = ["special", _COMMENT_WORDS[int(rng.integers(0, len(_COMMENT_WORDS)))], "requests"]
+        while len(" ".join(words)) < target:
+            words.append(_COMMENT_WORDS[int(rng.integers(0, len(_COMMENT_WORDS)))])
+        s = " ".join(words)[:43] if i % 100 != 7 else " ".join(words)[:43]
+        pool.append(s if len(s) >= 10 else s + " sleep nag")
+    pool_arr = pa.array(pool, type=pa.string())
+    idx = rng.integers(0, len(pool), n)
+    arr = pool_arr.take(pa.array(idx))
+    if null_prob > 0:
+        mask = rng.random(n) < null_prob
+        arr = pa.Array.from_buffers(pa.string(), n, [pa.py_buffer(np.packbits(~mask, bitorder="little")),
+                                                     arr.buffers()[1], arr.buffers()[2]])
+    return pa.RecordBatch.from_arrays([arr], schema=COMMENT_SCHEMA)
+
+
+def comment_condition(b):
+    """like(upper(substr(l_comment, 1, 32)), '%SPECIAL%REQUESTS%')"""
+    t = pa.string()
+    c = b.make_field(COMMENT_SCHEMA.field(0))
+    sub = b.make_function("substr", [c, b.make_literal(1, pa.int64()), b.make_literal(32, pa.int64())], t)
+    return b.make_function("like", [b.make_function("upper", [sub], t),
+                                    b.make_literal("%SPECIAL%REQUESTS%", t)], pa.bool_())
+
+
 def all_project_cases():
     cases = []
     for t in NUMERIC:
@@ -384,7 +475,7 @@ def all_project_cases():
         cases.append(case_relop("equal", t))
     cases += [case_if_else, case_if_null_literal, case_kleene, case_null_tests, case_casts, case_mod,
               case_dates, case_decimal_misc, case_in_string, case_strings, case_literals_only,
-              case_bool_io, case_and_short_circuit]
+              case_bool_io, case_and_short_circuit, case_q1_projector]
     for t in [pa.int8(), pa.int32(), pa.int64(), pa.uint32(), pa.float32(), pa.float64()]:
         cases.append(case_divide(t))
     # decimal result types follow the reference's rule: add/sub: s=max(s1,s2),

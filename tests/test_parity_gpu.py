@@ -122,32 +122,18 @@ def test_project_with_selection_vector(mode, npt, gandiva, oracle):
     assert_arrays_match(got[0], want[0], "selection %s" % mode)
 
 
-def test_multi_output_shares_inputs(gandiva, oracle):
-    """Eight outputs from one fused kernel (Q1-like mix of int64 / float64 / decimal / CASE)."""
-    import decimal
+def test_q1_projector_on_lineitem(gandiva, oracle):
+    """Eight outputs from one fused kernel (config 3 shape) on the synthetic lineitem columns."""
     b = gandiva.TreeExprBuilder()
-    D, F64, I64, SD = pa.decimal128(15, 2), pa.float64(), pa.int64(), pa.date32()
-    schema = pa.schema([("qty", I64), ("ext", D), ("disc", D), ("tax", D), ("ext_f", F64),
-                        ("disc_f", F64), ("tax_f", F64), ("ship", SD)])
-    f = {x.name: b.make_field(x) for x in schema}
-    one_d = b.make_literal(decimal.Decimal("1.00"), D)
-    one_f = b.make_literal(1.0, F64)
-    d1 = b.make_function("multiply", [f["ext"], b.make_function("subtract", [one_d, f["disc"]], pa.decimal128(16, 2))], pa.decimal128(32, 4))
-    d2 = b.make_function("multiply", [d1, b.make_function("add", [one_d, f["tax"]], pa.decimal128(16, 2))], pa.decimal128(38, 6))
-    f1 = b.make_function("multiply", [f["ext_f"], b.make_function("subtract", [one_f, f["disc_f"]], F64)], F64)
-    f2 = b.make_function("multiply", [f1, b.make_function("add", [one_f, f["tax_f"]], F64)], F64)
-    q2 = b.make_function("add", [f["qty"], f["qty"]], I64)
-    c1 = b.make_if(b.make_function("greater_than", [f["disc_f"], b.make_literal(0.05, F64)], pa.bool_()), f["ext_f"], b.make_literal(0.0, F64), F64)
-    c2 = b.make_if(b.make_function("less_than", [f["qty"], b.make_literal(24, I64)], pa.bool_()), b.make_literal(1, I64), b.make_literal(0, I64), I64)
-    c3 = b.make_if(b.make_function("less_than_or_equal_to", [f["ship"], b.make_literal(10471, SD)], pa.bool_()), f["qty"], b.make_literal(None, I64), I64)
-    outs = [(d1, pa.decimal128(32, 4)), (d2, pa.decimal128(38, 6)), (f1, F64), (f2, F64), (q2, I64), (c1, F64), (c2, I64), (c3, I64)]
-    batch = cases.random_batch(schema, 30011, seed=33, null_prob=0.02, small=True)
+    outs = cases.q1_outputs(b)
+    batch = cases.q1_batch(200_003, seed=42, null_permille=20)
     exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
-    p = gandiva.make_projector(schema, exprs, None)
+    p = gandiva.make_projector(cases.Q1_SCHEMA, exprs, None)
     got = p.evaluate(batch)
     want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch, threads=4)
     for i, (g, w) in enumerate(zip(got, want)):
         assert_arrays_match(g, w, "q1 out %d" % i)
+    assert got[0].null_count > 0 and got[7].null_count > got[4].null_count
 
 
 @pytest.mark.parametrize("t", [pa.int32(), pa.int64(), pa.float64()], ids=str)
