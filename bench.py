@@ -210,40 +210,18 @@ def main():
     cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
     torch.cuda.synchronize()
 
-    def gather_selection(count: int):
-        """N>1: reassemble the global SelectionVector on rank 0 (NCCL over NVLink): all-gather
-        of the 8 counts, then variable-length sends of each shard's ascending index run."""
-        counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        mine = torch.tensor([count], dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, mine)
-        c = counts.tolist()
-        if rank == 0:
-            total = sum(c)
-            if not hasattr(gather_selection, "buf") or gather_selection.buf.numel() < total:
-                gather_selection.buf = torch.empty(int(total * 1.1) + 16, dtype=idx_dtype, device=dev)
-            buf = gather_selection.buf
-            buf[: c[0]].copy_(out_idx[: c[0]])
-            off = c[0]
-            ops = []
-            for r in range(1, world):
-                if c[r] > 0:
-                    ops.append(dist.P2POp(dist.irecv, buf[off: off + c[r]], r))
-                off += c[r]
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            return total
-        if count > 0:
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, out_idx[:count], 0)]):
-                w.wait()
-        return sum(c)
+    from gandiva_b200.sharding import gather_selection
+    gathered = {"buf": None}
 
     def step():
         filt.evaluate_device(n, cols, out_idx.data_ptr(), n, idx_mode, st, d_count.data_ptr(),
                              sync=False, index_base=first_row)
         if world > 1 and not args.no_gather:
             cnt = int(d_count.item())  # the count is needed on the host to size the sends
-            return gather_selection(cnt)
+            out, total = gather_selection(out_idx, cnt, dst=0, out=gathered["buf"])
+            if rank == 0:
+                gathered["buf"] = out if gathered["buf"] is None or out.numel() > gathered["buf"].numel() else gathered["buf"]
+            return total
         return None
 
     for _ in range(max(args.warmup, 3)):

@@ -1,0 +1,76 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the row-range sharding + SelectionVector
+gather used by bench.py --gpus N (the filter itself is replaced by the oracle here)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cases
+    import gandiva_b200 as gandiva
+    import oracle
+    from gandiva_b200.sharding import gather_selection, shard_range
+    first, last = shard_range(n, world, rank)
+    batch = cases.q6_batch(n, seed=42).slice(first, last - first)
+    b = gandiva.TreeExprBuilder()
+    local = oracle.filter_indices(cases.q6_condition(b), batch) + np.uint64(first)   # global row numbers
+    t = torch.from_numpy(local.astype(np.int64))
+    out, total = gather_selection(t, len(local), dst=0)
+    if rank == 0:
+        q.put((out.numpy().copy(), total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_alignment():
+    from gandiva_b200.sharding import shard_range
+    n, world = 1_000_003, 8
+    edges = [shard_range(n, world, r) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+        assert a1 == b0 and b0 % 64 == 0
+    assert shard_range(10, 4, 3) == (10, 10)  # empty tail shard
+
+
+@pytest.mark.timeout(120)
+def test_gather_selection_world2():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cases
+    import gandiva_b200 as gandiva
+    import oracle
+    n, world = 300_001, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, total = q.get(timeout=100)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = gandiva.TreeExprBuilder()
+    want = oracle.filter_indices(cases.q6_condition(b), cases.q6_batch(n, seed=42))
+    assert total == len(want)
+    assert np.array_equal(got.astype(np.uint64), want)
