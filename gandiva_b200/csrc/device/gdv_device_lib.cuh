@@ -518,11 +518,15 @@ GDV_DEV gdv_u256 gdv_u256_from(u128 v) {
 }
 
 // x (scale xs) + sign * y (scale ys) -> scale os.  Exact in 256 bits, then rounded.
-GDV_DEV i128 gdv_decimal_addsub(i128 x, i32 xs, i128 y, i32 ys, i32 os, bool subtract) {
+GDV_DEV i128 gdv_decimal_addsub(i128 x, i32 xs, i128 y, i32 ys, i32 os, bool subtract,
+                                bool headroom) {
   const i32 ms = xs > ys ? xs : ys;
   if (os == ms && xs == ys) {
-    // fast path: no rescale (covers TPC-H Q1); overflow past 38 digits -> 0
+    // fast path: no rescale (covers TPC-H Q1).  When the declared precisions leave headroom
+    // (max(xp, yp) + 1 <= 38) the sum of two in-contract values cannot pass 38 digits and the
+    // overflow test is dropped, as the reference's fast path does.
     const i128 r = subtract ? (i128)((u128)x - (u128)y) : (i128)((u128)x + (u128)y);
+    if (headroom) return r;
     const u128 m = gdv_abs_u128(r);
     return m >= gdv_pow10_u128(38) ? (i128)0 : r;
   }
@@ -554,11 +558,11 @@ GDV_DEV i128 gdv_decimal_addsub(i128 x, i32 xs, i128 y, i32 ys, i32 os, bool sub
 }
 GDV_DEV i128 add_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys, i32 op,
                                        i32 os) {
-  return gdv_decimal_addsub(x, xs, y, ys, os, false);
+  return gdv_decimal_addsub(x, xs, y, ys, os, false, (xp > yp ? xp : yp) + 1 <= 38);
 }
 GDV_DEV i128 subtract_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys,
                                             i32 op, i32 os) {
-  return gdv_decimal_addsub(x, xs, y, ys, os, true);
+  return gdv_decimal_addsub(x, xs, y, ys, os, true, (xp > yp ? xp : yp) + 1 <= 38);
 }
 GDV_DEV i128 multiply_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys,
                                             i32 op, i32 os) {
@@ -567,6 +571,11 @@ GDV_DEV i128 multiply_decimal128_decimal128(i128 x, i32 xp, i32 xs, i128 y, i32 
   if (xp + yp <= 38 && delta == 0) {
     // |x| < 10^xp, |y| < 10^yp  =>  |x*y| < 10^38 < 2^127: one 128-bit multiply is exact
     return (i128)((u128)x * (u128)y);
+  }
+  if (delta == 0 && x == (i128)(i64)x && y == (i128)(i64)y) {
+    // both operands fit 64 bits (the usual case whatever the declared precision):
+    // |x*y| < 2^126 < 10^38, so one signed 64x64->128 multiply is exact and cannot overflow
+    return (i128)(i64)x * (i128)(i64)y;
   }
   gdv_u256 mag = gdv_mul_u128(gdv_abs_u128(x), gdv_abs_u128(y));
   if (delta > 0) mag = gdv_div_pow10_round(mag, delta > 38 ? 38 : delta);
