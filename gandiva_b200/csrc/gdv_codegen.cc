@@ -318,7 +318,8 @@ class BodyGen {
   }
 
   // Tokenise a SQL LIKE pattern: '%' any run, '_' one glyph, escape char quotes the next byte.
-  std::string LikePattern(const std::string& pat, bool has_escape, char esc, int* n_tokens) {
+  // Token = (kind << 8) | byte with kind 0 literal, 1 '_', 2 '%'.
+  static std::vector<unsigned> LikeTokens(const std::string& pat, bool has_escape, char esc) {
     std::vector<unsigned> toks;
     for (size_t i = 0; i < pat.size(); ++i) {
       const unsigned char c = static_cast<unsigned char>(pat[i]);
@@ -332,7 +333,11 @@ class BodyGen {
         toks.push_back(c);
       }
     }
-    *n_tokens = static_cast<int>(toks.size());
+    return toks;
+  }
+
+  // Generic matcher: tokens in a __device__ table, interpreted by gdv_like_match().
+  std::string LikePatternTable(const std::vector<unsigned>& toks) {
     const std::string name = NewVar("gdv_pat_");
     std::string s = "__device__ const u16 " + name + "[" +
                     std::to_string(std::max<size_t>(toks.size(), 1)) + "] = {";
@@ -340,6 +345,75 @@ class BodyGen {
     for (size_t i = 0; i < toks.size(); ++i) s += (i ? "," : "") + std::to_string(toks[i]);
     s += "};\n";
     globals_ += s;
+    return name;
+  }
+
+  // Patterns made of literal runs and '%' only (no '_') compile to straight code: the pattern
+  // bytes become immediates, the first segment is anchored at the start unless the pattern
+  // begins with '%', the last at the end unless it ends with '%', the ones in between are
+  // found leftmost-first.  Returns the name of the emitted device function.
+  std::string LikeSpecialised(const std::vector<unsigned>& toks) {
+    std::vector<std::string> segs;
+    std::string cur;
+    bool lead_any = !toks.empty() && (toks.front() >> 8) == 2u;
+    bool trail_any = !toks.empty() && (toks.back() >> 8) == 2u;
+    for (unsigned t : toks) {
+      if ((t >> 8) == 2u) {
+        if (!cur.empty()) segs.push_back(cur);
+        cur.clear();
+      } else {
+        cur.push_back(static_cast<char>(t & 0xffu));
+      }
+    }
+    if (!cur.empty()) segs.push_back(cur);
+    const std::string name = NewVar("gdv_like_");
+    std::string f = "__device__ __forceinline__ bool " + name + "(const gdv_str& s) {\n";
+    f += "  const i32 n = s.len;\n";
+    auto match_at = [&](const std::string& seg, const std::string& at) {
+      std::string e;
+      for (size_t i = 0; i < seg.size(); ++i)
+        e += (i ? " && " : "") + std::string("gdv_ch_eq(s, ") + at + " + " + std::to_string(i) + ", " +
+             std::to_string(static_cast<unsigned>(static_cast<unsigned char>(seg[i]))) + "u)";
+      return e;
+    };
+    size_t total = 0;
+    for (const auto& sg : segs) total += sg.size();
+    if (segs.empty()) {
+      // "" matches only the empty string; "%" (or "%%") matches everything
+      f += toks.empty() ? "  return n == 0;\n}\n" : "  return true;\n}\n";
+      globals_ += f;
+      return name;
+    }
+    if (!lead_any && !trail_any && segs.size() == 1) {
+      f += "  return n == " + std::to_string(segs[0].size()) + " && " + match_at(segs[0], "0") + ";\n}\n";
+      globals_ += f;
+      return name;
+    }
+    f += "  if (n < " + std::to_string(total) + ") return false;\n";
+    f += "  i32 pos = 0;\n";
+    size_t first_mid = 0, last_mid = segs.size();
+    if (!lead_any) {
+      f += "  if (!(" + match_at(segs[0], "0") + ")) return false;\n";
+      f += "  pos = " + std::to_string(segs[0].size()) + ";\n";
+      first_mid = 1;
+    }
+    if (!trail_any) last_mid = segs.size() - 1;
+    for (size_t k = first_mid; k < last_mid; ++k) {
+      const std::string L = std::to_string(segs[k].size());
+      f += "  {\n    bool found = false;\n";
+      f += "    for (; pos + " + L + " <= n; ++pos) {\n";
+      f += "      if (" + match_at(segs[k], "pos") + ") { found = true; break; }\n";
+      f += "    }\n    if (!found) return false;\n    pos += " + L + ";\n  }\n";
+    }
+    if (!trail_any) {
+      const std::string L = std::to_string(segs.back().size());
+      f += "  if (n - " + L + " < pos) return false;\n";
+      f += "  return " + match_at(segs.back(), "(n - " + L + ")") + ";\n";
+    } else {
+      f += "  return true;\n";
+    }
+    f += "}\n";
+    globals_ += f;
     return name;
   }
 
@@ -354,11 +428,18 @@ class BodyGen {
       const auto& pat = static_cast<const LiteralNode&>(*fn.children()[1]);
       bool has_esc = fn.children().size() == 3;
       char esc = has_esc ? static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0] : 0;
-      int ntok = 0;
-      const std::string arr = LikePattern(pat.bytes(), has_esc, esc, &ntok);
+      const std::vector<unsigned> toks = LikeTokens(pat.bytes(), has_esc, esc);
+      bool has_one = false;
+      for (unsigned t : toks) has_one = has_one || (t >> 8) == 1u;
       const std::string v = NewVar("v");
-      *out += Ind(indent) + "const bool " + v + " = gdv_like_match(" + s.v + ", " + arr + ", " +
-              std::to_string(ntok) + ");\n";
+      if (!has_one) {
+        const std::string fn_name = LikeSpecialised(toks);
+        *out += Ind(indent) + "const bool " + v + " = " + fn_name + "(" + s.v + ");\n";
+      } else {
+        const std::string arr = LikePatternTable(toks);
+        *out += Ind(indent) + "const bool " + v + " = gdv_like_match(" + s.v + ", " + arr + ", " +
+                std::to_string(toks.size()) + ");\n";
+      }
       return Val{v, s.ok, rt};
     }
 
@@ -588,7 +669,8 @@ void EmitPrologue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, 
 // immediate offsets from one pointer per column; validity arrives as one 32-bit window per
 // step (a warp-uniform load) instead of one byte load per row.
 void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R, bool fast,
-               const std::string& body, const std::string& step_tail, std::string* o, int indent) {
+               const std::string& body, const std::string& step_tail, std::string* o, int indent,
+               int stage_bytes = 0) {
   const std::string I(static_cast<size_t>(indent) * 2, ' ');
   const std::string sR = std::to_string(R);
   const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
@@ -598,13 +680,35 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
     if (spec.nullable) *o += I + "bool k" + std::to_string(j) + "[" + sR + "];\n";
   }
   if (fast) {
+    bool staged_any = false;
     for (size_t j = 0; j < slots.size(); ++j) {
       const DataType& t = slots[j].type;
       const std::string J = std::to_string(j);
       if (!t.is_bool())
         *o += I + "const " + (t.is_varlen() ? std::string("i32") : std::string(t.ctype())) +
               "* ptr" + J + " = in_val" + J + " + base + (i64)lane;\n";
+      if (t.is_varlen() && stage_bytes > 0) {
+        // The bytes of the group's 32*R strings are one contiguous run: copy it into this
+        // warp's shared-memory stage with coalesced 16-byte loads, then every lane walks its
+        // own string out of shared memory instead of issuing one global load per byte.
+        staged_any = true;
+        *o += I + "const u8* sbase" + J + " = in_var" + J + ";\n";
+        *o += I + "{\n";
+        *o += I + "  const i32 gb = in_val" + J + "[base];\n";
+        *o += I + "  const i32 gn = in_val" + J + "[base + " + std::to_string(32 * R) + "] - gb;\n";
+        *o += I + "  const u8* src = in_var" + J + " + gb;\n";
+        *o += I + "  const u32 mis = (u32)((unsigned long long)src & 15ull);\n";
+        *o += I + "  if (gn + (i32)mis <= " + std::to_string(stage_bytes) + ") {\n";
+        *o += I + "    const uint4* s4 = reinterpret_cast<const uint4*>(src - mis);\n";
+        *o += I + "    const i32 nchunks = (gn + (i32)mis + 15) >> 4;\n";
+        *o += I + "    for (i32 c = (i32)lane; c < nchunks; c += 32)\n";
+        *o += I + "      reinterpret_cast<uint4*>(stage" + J + ")[c] = __ldcs(s4 + c);\n";
+        *o += I + "    sbase" + J + " = stage" + J + " + mis - gb;\n";
+        *o += I + "  }\n";
+        *o += I + "}\n";
+      }
     }
+    if (staged_any) *o += I + "__syncwarp();\n";
     *o += I + "#pragma unroll\n";
     *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
     for (size_t j = 0; j < slots.size(); ++j) {
@@ -615,7 +719,8 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
               ") >> lane) & 1u) != 0u;\n";
       } else if (t.is_varlen()) {
         *o += I + "  { const i32 sb = ptr" + J + "[32 * k]; const i32 se = ptr" + J +
-              "[32 * k + 1]; f" + J + "[k] = gdv_make_str(in_var" + J + " + sb, se - sb); }\n";
+              "[32 * k + 1]; f" + J + "[k] = gdv_make_str(" +
+              (stage_bytes > 0 ? "sbase" : "in_var") + J + " + sb, se - sb); }\n";
       } else {
         *o += I + "  f" + J + "[k] = gdv_ldp(ptr" + J + " + 32 * k);\n";
       }
@@ -662,6 +767,11 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
   *o += body;
   *o += step_tail;
   *o += I + "}\n";
+  if (fast && stage_bytes > 0) {
+    bool any = false;
+    for (const auto& sl : slots) any = any || sl.type.is_varlen();
+    if (any) *o += I + "__syncwarp();  // all lanes are done with the stage before it is refilled\n";
+  }
 }
 
 int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
@@ -696,7 +806,11 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   }
 
   int in_bytes = 0, out_bytes = 0;
-  for (const auto& s : slots) in_bytes += s.type.is_varlen() ? 8 : std::max(s.type.width(), 1);
+  int n_varlen = 0;
+  for (const auto& s : slots) {
+    in_bytes += s.type.is_varlen() ? 32 : std::max(s.type.width(), 1);  // 4 B offset + ~28 B data
+    n_varlen += s.type.is_varlen() ? 1 : 0;
+  }
   for (const auto& e : exprs) out_bytes += std::max(e->result().type.width(), 1);
   if (spec.kind == KernelKind::kFilter) out_bytes = 0;
 
@@ -713,6 +827,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   if (BT % 32 != 0 || BT > 1024)
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
 
+  // shared-memory stage for string bytes: 48 B per row of a group, per warp and string column
+  const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
+  const int dynamic_smem = stage_bytes * (BT / 32) * n_varlen;
   const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
   const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
   ArgsLayout L(static_cast<int>(slots.size()), n_out);
@@ -734,6 +851,17 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   src += "  const u32 wid = threadIdx.x >> 5;\n";
   src += "  gdv_ctx ctx;\n  ctx.err = A.err;\n";
   EmitPrologue(slots, spec, &src);
+  if (stage_bytes > 0) {
+    src += "  extern __shared__ uint4 gdv_smem[];\n";
+    int vi = 0;
+    for (size_t j = 0; j < slots.size(); ++j) {
+      if (!slots[j].type.is_varlen()) continue;
+      src += "  u8* stage" + std::to_string(j) + " = reinterpret_cast<u8*>(gdv_smem) + ((size_t)wid * " +
+             std::to_string(n_varlen) + " + " + std::to_string(vi) + ") * " +
+             std::to_string(stage_bytes) + ";\n";
+      ++vi;
+    }
+  }
 
   if (spec.kind == KernelKind::kProject) {
     for (int o = 0; o < n_out; ++o) {
@@ -775,7 +903,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     }
     if (!has_sel) {
       src += "    if (base + " + s32R + " <= A.n) {\n";
-      EmitGroup(slots, spec, R, true, body, tail(true), &src, 3);
+      EmitGroup(slots, spec, R, true, body, tail(true), &src, 3, stage_bytes);
       src += "    } else {\n";
       EmitGroup(slots, spec, R, false, body, tail(false), &src, 3);
       src += "    }\n";
@@ -827,7 +955,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "      const i64 base = wbase + 32 * g;\n";
     src += "      if (base >= A.n) break;\n";
     src += "      if (base + " + s32R + " <= A.n) {\n";
-    EmitGroup(slots, spec, R, true, body, step_tail, &src, 4);
+    EmitGroup(slots, spec, R, true, body, step_tail, &src, 4, stage_bytes);
     src += "      } else {\n";
     EmitGroup(slots, spec, R, false, body, step_tail, &src, 4);
     src += "      }\n";
@@ -891,6 +1019,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->in_bytes_per_row = in_bytes;
   out->out_bytes_per_row = out_bytes;
   out->args_size = L.size;
+  out->dynamic_smem = dynamic_smem;
   out->tile_rows = spec.kind == KernelKind::kFilter ? static_cast<int64_t>(BT / 32) * 1024 : 0;
   return Status::OK();
 }

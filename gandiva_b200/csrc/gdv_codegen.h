@@ -61,6 +61,7 @@ struct GeneratedKernel {
   int in_bytes_per_row = 0;         // algorithmic bytes (values only) read per row
   int out_bytes_per_row = 0;
   size_t args_size = 0;             // sizeof(gdv_args) for this kernel
+  int dynamic_smem = 0;             // bytes of dynamic shared memory (string staging)
   int64_t tile_rows = 0;            // filter: rows per CTA tile (one look-back descriptor each)
 };
 

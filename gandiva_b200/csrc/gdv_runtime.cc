@@ -169,8 +169,13 @@ Status CompiledKernel::Load(Device* dev, Loaded* out) {
       CuCheck(d.ModuleGetFunction(&l.fn, l.mod, gen.name.c_str()), "cuModuleGetFunction"));
   d.FuncGetAttribute(&l.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, l.fn);
   d.FuncGetAttribute(&l.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, l.fn);
+  if (gen.dynamic_smem > 48 * 1024)
+    GDV_RETURN_NOT_OK(CuCheck(d.FuncSetAttribute(l.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                                 gen.dynamic_smem),
+                              "cuFuncSetAttribute(max dynamic shared)"));
   int b = 0;
-  if (d.OccupancyMaxActiveBlocksPerMultiprocessor(&b, l.fn, gen.block_threads, 0) ==
+  if (d.OccupancyMaxActiveBlocksPerMultiprocessor(&b, l.fn, gen.block_threads,
+                                                  static_cast<size_t>(gen.dynamic_smem)) ==
           CUDA_SUCCESS &&
       b > 0)
     l.blocks_per_sm = b;
@@ -336,7 +341,8 @@ Status LaunchKernel(Device* dev, const CompiledKernel::Loaded& l, const Generate
   if (grid == 0) return Status::OK();
   g_launch_count.fetch_add(1);
   return CuCheck(Driver().LaunchKernel(l.fn, grid, 1, 1, static_cast<unsigned>(gen.block_threads),
-                                       1, 1, 0, stream, params, nullptr),
+                                       1, 1, static_cast<unsigned>(gen.dynamic_smem), stream,
+                                       params, nullptr),
                  "cuLaunchKernel");
 }
 
