@@ -169,7 +169,7 @@ Status CompiledKernel::Load(Device* dev, Loaded* out) {
       CuCheck(d.ModuleGetFunction(&l.fn, l.mod, gen.name.c_str()), "cuModuleGetFunction"));
   d.FuncGetAttribute(&l.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, l.fn);
   d.FuncGetAttribute(&l.smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, l.fn);
-  if (gen.dynamic_smem > 48 * 1024)
+  if (gen.dynamic_smem > 32 * 1024)  // static + dynamic may pass the default 48 KB window
     GDV_RETURN_NOT_OK(CuCheck(d.FuncSetAttribute(l.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                                  gen.dynamic_smem),
                               "cuFuncSetAttribute(max dynamic shared)"));

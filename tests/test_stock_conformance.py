@@ -33,7 +33,14 @@ def test_stock_host_side_tests_pass_without_gpu():
 @pytest.mark.gpu
 @pytest.mark.skipif(not _stock_built(), reason="stock binding not built")
 def test_stock_binding_tests_pass_on_gpu():
-    """All of test_gandiva.py (11 tests + 1 skipped upstream) passes on the CUDA path."""
+    """test_gandiva.py on the CUDA path: every test that checks RESULTS passes (9 + 1 skipped
+    upstream).  The two known divergences are the assertions that DumpIR
+    contains LLVM's "@expr_" symbol: here DumpIR is CUDA source + PTX (kernel
+    gdv_project_expr_N / gdv_filter_expr_N); output is not shaped to satisfy them."""
     rc, out = _run([])
-    assert rc == 0, out[-4000:]
-    assert re.search(r"11 passed, 1 skipped", out), out[-2000:]
+    assert re.search(r"2 failed, 9 passed, 1 skipped", out), out[-4000:]
+    failed = re.findall(r"^FAILED .*::(\w+)", out, flags=re.M)
+    assert sorted(failed) == ["test_filter", "test_tree_exp_builder"], failed
+    # both failures are the llvm_ir "@expr_" assertion and nothing else
+    assert len(re.findall(r'llvm_ir\.find\("@expr_"\) != -1', out)) >= 2
+    assert "Error" not in "".join(l for l in out.splitlines() if l.startswith("E  ") and "AssertionError" not in l and "assert -1" not in l and "where" not in l)
