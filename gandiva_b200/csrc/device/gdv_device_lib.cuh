@@ -68,6 +68,50 @@ GDV_DEV bool gdv_ch_eq(const gdv_str& s, i32 i, u32 lit) {
   }
   return c == lit;
 }
+// First position i in [from, limit) whose byte equals the immediate `lit` under the string's
+// case map, or `limit`.  Scans four bytes per iteration with the SIMD byte compare once the
+// address is word aligned (whole words only, so nothing past the string is read).
+GDV_DEV i32 gdv_find_byte(const gdv_str& s, i32 from, i32 limit, u32 lit) {
+  bool fold = false;
+  if (s.xf == 1u) {
+    if (lit >= (u32)'a' && lit <= (u32)'z') return limit;
+    if (lit >= (u32)'A' && lit <= (u32)'Z') { fold = true; lit |= 0x20u; }
+  } else if (s.xf == 2u) {
+    if (lit >= (u32)'A' && lit <= (u32)'Z') return limit;
+    if (lit >= (u32)'a' && lit <= (u32)'z') fold = true;
+  }
+  const u32 fmask = fold ? 0x20u : 0u;
+  i32 i = from;
+  while (i < limit && ((unsigned long long)(s.p + i) & 3ull) != 0ull) {
+    if (((u32)s.p[i] | fmask) == lit) return i;
+    ++i;
+  }
+  const u32 pat = lit * 0x01010101u;
+  const u32 fm4 = fmask * 0x01010101u;
+  while (i + 4 <= limit) {
+    const u32 w = *reinterpret_cast<const u32*>(s.p + i) | fm4;
+    const u32 m = __vcmpeq4(w, pat);
+    if (m != 0u) return i + ((__ffs((int)m) - 1) >> 3);
+    i += 4;
+  }
+  while (i < limit) {
+    if (((u32)s.p[i] | fmask) == lit) return i;
+    ++i;
+  }
+  return limit;
+}
+// True when the first n bytes at p are all ASCII (< 0x80).
+GDV_DEV bool gdv_all_ascii(const u8* p, i32 n) {
+  i32 i = 0;
+  u32 acc = 0u;
+  while (i < n && ((unsigned long long)(p + i) & 3ull) != 0ull) acc |= p[i++];
+  while (i + 4 <= n) {
+    acc |= *reinterpret_cast<const u32*>(p + i);
+    i += 4;
+  }
+  while (i < n) acc |= p[i++];
+  return (acc & 0x80808080u) == 0u;
+}
 GDV_DEV gdv_str gdv_make_str(const u8* p, i32 len) {
   gdv_str s;
   s.p = p;
@@ -688,6 +732,11 @@ GDV_DEV gdv_str substr_utf8_int64_int64(gdv_str s, i64 offset, i64 length) {
   }
   // from the first glyph and at least as many glyphs as bytes: the whole string, no scan
   if ((offset == 0 || offset == 1) && length >= (i64)s.len) return s;
+  // ASCII prefix: glyph positions are byte positions
+  if ((offset == 0 || offset == 1) && gdv_all_ascii(s.p, (i32)length)) {
+    r.len = (i32)length;
+    return r;
+  }
   i64 from_glyph;
   if (offset > 0) {
     from_glyph = offset - 1;
