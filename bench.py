@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: gather inside each step, no pipelining")
+    ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs left free for NCCL (default: 16 when N>1)")
     return ap.parse_args()
 
 
@@ -195,8 +197,9 @@ def main():
     first_row = rank * n
     idx_mode = "UINT32" if (world == 1 and n <= (1 << 32)) else "UINT64"
     idx_dtype = torch.int32 if idx_mode == "UINT32" else torch.int64
+    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (16 if world > 1 and not args.no_gather else 0)
     cfg = gandiva.Configuration(device=local_rank, rows_per_thread=args.rows_per_thread,
-                                block_threads=args.block_threads)
+                                block_threads=args.block_threads, sm_reserve=sm_reserve)
     filt, _ = q6_filter(gandiva, cases, cfg)
 
     # ---- inputs resident in HBM (generated on device; same stream as oracle/lineitem.h) -----
@@ -211,21 +214,64 @@ def main():
     torch.cuda.synchronize()
 
     from gandiva_b200.sharding import gather_selection
+    pipelined = world > 1 and not args.no_gather and not args.no_overlap
+    # N>1: the gather of batch i runs on a second stream while the filter kernel of batch i+1
+    # runs (double-buffered index buffers).  The filter was built with sm_reserve so that NCCL's
+    # copy CTAs find free slots next to the persistent filter CTAs.
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    bufs = [out_idx, torch.empty(n, dtype=idx_dtype, device=dev) if pipelined else out_idx]
+    cnts = [d_count, torch.zeros(1, dtype=torch.int64, device=dev)]
+    host_cnt = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
+    ev_k = [torch.cuda.Event() for _ in range(2)]
+    ev_g = [torch.cuda.Event() for _ in range(2)]
     gathered = {"buf": None}
 
-    def step():
-        filt.evaluate_device(n, cols, out_idx.data_ptr(), n, idx_mode, st, d_count.data_ptr(),
+    def launch(i):
+        b = i % 2
+        filt.evaluate_device(n, cols, bufs[b].data_ptr(), n, idx_mode, st, cnts[b].data_ptr(),
                              sync=False, index_base=first_row)
         if world > 1 and not args.no_gather:
-            cnt = int(d_count.item())  # the count is needed on the host to size the sends
-            out, total = gather_selection(out_idx, cnt, dst=0, out=gathered["buf"])
-            if rank == 0:
-                gathered["buf"] = out if gathered["buf"] is None or out.numel() > gathered["buf"].numel() else gathered["buf"]
-            return total
-        return None
+            host_cnt[b].copy_(cnts[b], non_blocking=True)
+            ev_k[b].record(stream)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def gather(i):
+        b = i % 2
+        ev_k[b].synchronize()              # kernel i and its count copy are done
+        cnt = int(host_cnt[b][0])
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ev_k[b])
+            out, total = gather_selection(bufs[b], cnt, dst=0, out=gathered["buf"])
+            if rank == 0 and (gathered["buf"] is None or out.numel() > gathered["buf"].numel()):
+                gathered["buf"] = torch.empty(int(total * 1.1) + 16, dtype=idx_dtype, device=dev)
+            ev_g[b].record(comm_stream)
+        return total
+
+    def run_steps(k, events=None):
+        """k passes of the hot path; with N>1 each pass ends with the SelectionVector on rank 0."""
+        total = None
+        for i in range(k):
+            if pipelined and i >= 2:
+                stream.wait_event(ev_g[i % 2])      # buffer i%2 is free again
+            launch(i)
+            if world > 1 and not args.no_gather:
+                if pipelined:
+                    if i >= 1:
+                        total = gather(i - 1)
+                else:
+                    total = gather(i)
+                    stream.wait_event(ev_g[i % 2])
+            if events is not None:
+                events[i + 1].record(stream)
+        if pipelined and k >= 1:
+            total = gather(k - 1)
+            stream.wait_event(ev_g[(k - 1) % 2])
+            if k >= 2:
+                stream.wait_event(ev_g[k % 2])
+            if events is not None:
+                events[k].record(stream)          # the last event closes after the last gather
+        return total
+
+    run_steps(max(args.warmup, 3))
     count = filt.sync(st)
     torch.cuda.synchronize()
     if world > 1:
@@ -238,9 +284,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
     ev[0].record(stream)
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record(stream)
+    run_steps(args.steps, ev)
     torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(ev[args.steps])
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -317,7 +361,7 @@ def main():
             "config": {"workload": "TPC-H Q6 filter (BASELINE.json configs[1]%s)" %
                                    ("; configs[4] sharding" if world > 1 else ""),
                        "rows_per_gpu": n, "total_rows": n * world, "selectivity": total_selected / (n * world),
-                       "selection_vector": idx_mode + (" gathered to rank 0 over NCCL" if world > 1 and not args.no_gather else ""),
+                       "selection_vector": idx_mode + ((" gathered to rank 0 over NCCL" + (", overlapped with the next batch's kernel (sm_reserve=%d)" % sm_reserve if pipelined else "")) if world > 1 and not args.no_gather else ""),
                        "l2_policy": "inputs (20 B/row x %d rows) larger than L2; no flush" % n,
                        "parallelism": "row-range shards, %d" % world},
             "hbm_gbs": achieved, "per_step_ms": per_step,

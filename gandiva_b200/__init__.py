@@ -62,7 +62,7 @@ class gdv_type_t(C.Structure):
 class gdv_config_t(C.Structure):
     _fields_ = [("optimize", C.c_int32), ("dump_ir", C.c_int32), ("device", C.c_int32),
                 ("rows_per_thread", C.c_int32), ("block_threads", C.c_int32),
-                ("loader", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("loader", C.c_int32), ("sm_reserve", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class gdv_column_t(C.Structure):
@@ -445,13 +445,15 @@ class Configuration:
     """gandiva::Configuration (optimize, dump_ir) plus device placement / tuning knobs."""
 
     def __init__(self, optimize: bool = True, dump_ir: bool = False, device: int = 0,
-                 rows_per_thread: int = 0, block_threads: int = 0, loader: int = 0):
+                 rows_per_thread: int = 0, block_threads: int = 0, loader: int = 0,
+                 sm_reserve: int = 0):
         self.optimize = bool(optimize)
         self.dump_ir = bool(dump_ir)
         self.device = int(device)
         self.rows_per_thread = int(rows_per_thread)
         self.block_threads = int(block_threads)
         self.loader = int(loader)
+        self.sm_reserve = int(sm_reserve)
 
     def _c(self) -> gdv_config_t:
         c = gdv_config_t()
@@ -462,6 +464,7 @@ class Configuration:
         c.rows_per_thread = self.rows_per_thread
         c.block_threads = self.block_threads
         c.loader = self.loader
+        c.sm_reserve = self.sm_reserve
         return c
 
 

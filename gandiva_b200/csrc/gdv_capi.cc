@@ -50,6 +50,7 @@ Config FromC(const gdv_config_t* c) {
     cfg.rows_per_thread = c->rows_per_thread;
     cfg.block_threads = c->block_threads;
     cfg.loader = c->loader;
+    cfg.sm_reserve = c->sm_reserve;
   }
   return cfg;
 }

@@ -509,7 +509,8 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   const int R = gen.rows_per_thread, BT = gen.block_threads;
   const int64_t wtiles = (n + 32 * R - 1) / (32 * R);
   const int64_t blocks_needed = (wtiles + BT / 32 - 1) / (BT / 32);
-  const int64_t cap = static_cast<int64_t>(dev->sm_count()) * l.blocks_per_sm;
+  const int64_t cap =
+      static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * l.blocks_per_sm;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(blocks_needed, cap));
   GDV_RETURN_NOT_OK(LaunchKernel(dev, l, gen, args, grid, stream));
 
@@ -704,7 +705,8 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
     Put<uint32_t>(args, L.off_in_vsh + 4 * j, ins[j].vsh);
     Put<uint32_t>(args, L.off_in_dsh + 4 * j, ins[j].dsh);
   }
-  const int64_t cap = static_cast<int64_t>(dev->sm_count()) * l.blocks_per_sm;
+  const int64_t cap =
+      static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * l.blocks_per_sm;
   const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, cap)));
   GDV_RETURN_NOT_OK(LaunchKernel(dev, l, gen, args, grid, stream));
 
