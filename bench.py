@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: gather inside each step, no pipelining")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: NCCL send/recv instead of copy-engine peer writes")
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs left free for NCCL (default: 16 when N>1)")
     return ap.parse_args()
 
@@ -197,7 +198,7 @@ def main():
     first_row = rank * n
     idx_mode = "UINT32" if (world == 1 and n <= (1 << 32)) else "UINT64"
     idx_dtype = torch.int32 if idx_mode == "UINT32" else torch.int64
-    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (16 if world > 1 and not args.no_gather else 0)
+    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else 0
     cfg = gandiva.Configuration(device=local_rank, rows_per_thread=args.rows_per_thread,
                                 block_threads=args.block_threads, sm_reserve=sm_reserve)
     filt, _ = q6_filter(gandiva, cases, cfg)
@@ -225,6 +226,15 @@ def main():
     ev_k = [torch.cuda.Event() for _ in range(2)]
     ev_g = [torch.cuda.Event() for _ in range(2)]
     gathered = {"buf": None}
+    peer = None
+    if pipelined and not args.nccl_gather:
+        try:   # copy-engine gather into rank 0's IPC-mapped buffer (no SMs: overlaps the next kernel)
+            from gandiva_b200.sharding import PeerGather
+            peer = PeerGather(int(n * world * 0.03) + 1024, idx_dtype, dev, dst=0)
+        except Exception as e:  # pragma: no cover - fall back to NCCL send/recv
+            if rank == 0:
+                print("PeerGather unavailable (%s); using NCCL send/recv" % e, file=sys.stderr)
+            peer = None
 
     def launch(i):
         b = i % 2
@@ -238,6 +248,11 @@ def main():
         b = i % 2
         ev_k[b].synchronize()              # kernel i and its count copy are done
         cnt = int(host_cnt[b][0])
+        if peer is not None:
+            peer.finish()                  # previous batch's vector is complete on rank 0
+            total = peer.start(bufs[b], cnt, after=ev_k[b])
+            ev_g[b] = peer.done
+            return total
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(ev_k[b])
             out, total = gather_selection(bufs[b], cnt, dst=0, out=gathered["buf"])
@@ -264,6 +279,8 @@ def main():
                 events[i + 1].record(stream)
         if pipelined and k >= 1:
             total = gather(k - 1)
+            if peer is not None:
+                peer.finish()
             stream.wait_event(ev_g[(k - 1) % 2])
             if k >= 2:
                 stream.wait_event(ev_g[k % 2])
@@ -361,7 +378,7 @@ def main():
             "config": {"workload": "TPC-H Q6 filter (BASELINE.json configs[1]%s)" %
                                    ("; configs[4] sharding" if world > 1 else ""),
                        "rows_per_gpu": n, "total_rows": n * world, "selectivity": total_selected / (n * world),
-                       "selection_vector": idx_mode + ((" gathered to rank 0 over NCCL" + (", overlapped with the next batch's kernel (sm_reserve=%d)" % sm_reserve if pipelined else "")) if world > 1 and not args.no_gather else ""),
+                       "selection_vector": idx_mode + ((" gathered to rank 0 over NVLink" + ((", copy-engine peer writes into rank 0 (CUDA IPC)" if peer is not None else ", NCCL send/recv") + ", overlapped with the next batch's kernel" if pipelined else ", NCCL send/recv")) if world > 1 and not args.no_gather else ""),
                        "l2_policy": "inputs (20 B/row x %d rows) larger than L2; no flush" % n,
                        "parallelism": "row-range shards, %d" % world},
             "hbm_gbs": achieved, "per_step_ms": per_step,

@@ -55,3 +55,59 @@ def gather_selection(local_indices: torch.Tensor, count: int, dst: int = 0,
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_indices[:count].contiguous(), dst, group)]):
             w.wait()
     return None, total
+
+
+class PeerGather:
+    """SelectionVector gather without SMs: every rank writes its index run straight into rank
+    `dst`'s buffer over NVLink with the copy engines (peer memory mapped through CUDA IPC), so
+    the transfer runs underneath the persistent filter kernel of the next batch -- an NCCL
+    send/recv kernel cannot (it finds no free CTA slot until the filter kernel ends).
+    Counts travel host-side over a gloo group; the data never touches the host.
+
+    Protocol per batch: `start(local, count)` -> all-gather of counts (gloo), then one async
+    device-to-peer copy at this rank's prefix offset on `copy_stream`; `finish()` -> every rank
+    waits for its own copy, then a gloo barrier tells `dst` that the vector is complete."""
+
+    def __init__(self, capacity: int, dtype: torch.dtype, device: torch.device, dst: int = 0):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.rank, self.world, self.dst = dist.get_rank(), dist.get_world_size(), dst
+        self.device = device
+        self.cpu_group = dist.new_group(backend="gloo")
+        self.copy_stream = torch.cuda.Stream(device)
+        self.done = torch.cuda.Event()
+        self.buf = None
+        payload = [None]
+        if self.rank == dst:
+            self.buf = torch.empty(capacity, dtype=dtype, device=device)
+            fn, args = reduce_tensor(self.buf)
+            payload = [(fn, args)]
+        dist.broadcast_object_list(payload, src=dst, group=self.cpu_group)
+        if self.rank != dst:
+            fn, args = payload[0]
+            self.buf = fn(*args)          # rank dst's memory, mapped into this process
+        self.total = 0
+        self._pending = False
+
+    def start(self, local: torch.Tensor, count: int, after: Optional[torch.cuda.Event] = None) -> int:
+        counts = [None] * self.world
+        dist.all_gather_object(counts, int(count), group=self.cpu_group)
+        off = sum(counts[: self.rank])
+        self.total = sum(counts)
+        if self.total > self.buf.numel():
+            raise RuntimeError("PeerGather capacity %d < %d selected rows" % (self.buf.numel(), self.total))
+        with torch.cuda.stream(self.copy_stream):
+            if after is not None:
+                self.copy_stream.wait_event(after)
+            if count > 0:
+                self.buf[off: off + count].copy_(local[:count], non_blocking=True)
+            self.done.record(self.copy_stream)
+        self._pending = True
+        return self.total
+
+    def finish(self) -> Optional[torch.Tensor]:
+        """Blocks the host until every rank's run has landed; returns the vector on `dst`."""
+        if self._pending:
+            self.done.synchronize()
+            dist.barrier(group=self.cpu_group)
+            self._pending = False
+        return self.buf[: self.total] if self.rank == self.dst else None
