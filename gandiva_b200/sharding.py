@@ -89,8 +89,11 @@ class PeerGather:
         self._pending = False
 
     def start(self, local: torch.Tensor, count: int, after: Optional[torch.cuda.Event] = None) -> int:
-        counts = [None] * self.world
-        dist.all_gather_object(counts, int(count), group=self.cpu_group)
+        # plain CPU tensors over gloo (the *_object collectives pickle and take milliseconds)
+        mine = torch.tensor([int(count)], dtype=torch.int64)
+        gathered = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=self.cpu_group)
+        counts = [int(t[0]) for t in gathered]
         off = sum(counts[: self.rank])
         self.total = sum(counts)
         if self.total > self.buf.numel():
@@ -108,6 +111,7 @@ class PeerGather:
         """Blocks the host until every rank's run has landed; returns the vector on `dst`."""
         if self._pending:
             self.done.synchronize()
-            dist.barrier(group=self.cpu_group)
+            flag = torch.ones(1, dtype=torch.int32)
+            dist.all_reduce(flag, group=self.cpu_group)   # acts as the barrier
             self._pending = False
         return self.buf[: self.total] if self.rank == self.dst else None
