@@ -53,7 +53,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: gather inside each step, no pipelining")
-    ap.add_argument("--nccl-gather", action="store_true", help="N>1: NCCL send/recv instead of copy-engine peer writes")
+    ap.add_argument("--peer-gather", action="store_true",
+                    help="N>1: experimental copy-engine peer writes (CUDA IPC) instead of NCCL send/recv; "
+                         "measured slower in round 1 (host-side gloo sync), see DESIGN.md")
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs left free for NCCL (default: 16 when N>1)")
     return ap.parse_args()
 
@@ -227,7 +229,7 @@ def main():
     ev_g = [torch.cuda.Event() for _ in range(2)]
     gathered = {"buf": None}
     peer = None
-    if pipelined and not args.nccl_gather:
+    if pipelined and args.peer_gather:
         try:   # copy-engine gather into rank 0's IPC-mapped buffer (no SMs: overlaps the next kernel)
             from gandiva_b200.sharding import PeerGather
             peer = PeerGather(int(n * world * 0.03) + 1024, idx_dtype, dev, dst=0)
