@@ -62,7 +62,8 @@ class gdv_type_t(C.Structure):
 class gdv_config_t(C.Structure):
     _fields_ = [("optimize", C.c_int32), ("dump_ir", C.c_int32), ("device", C.c_int32),
                 ("rows_per_thread", C.c_int32), ("block_threads", C.c_int32),
-                ("loader", C.c_int32), ("sm_reserve", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("loader", C.c_int32), ("sm_reserve", C.c_int32), ("stages", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class gdv_column_t(C.Structure):
@@ -131,6 +132,8 @@ def _load() -> C.CDLL:
         "gdv_filter_sync": (i32, [vp, vp, P(i64)]),
         "gdv_filter_dump_ir": (i64, [vp, C.c_char_p, i64]),
         "gdv_filter_kernel_info": (i32, [vp, C.c_char_p, i64, P(i32), P(i32), P(i32), P(i32)]),
+        "gdv_projector_kernel_attr": (i32, [vp, C.c_char_p, P(i64)]),
+        "gdv_filter_kernel_attr": (i32, [vp, C.c_char_p, P(i64)]),
         "gdv_filter_release": (None, [vp]),
         "gdv_registry_size": (i32, []),
         "gdv_registry_get": (i32, [i32, P(C.c_char_p), P(gdv_type_t), P(gdv_type_t), i32, P(i32)]),
@@ -446,7 +449,8 @@ class Configuration:
 
     def __init__(self, optimize: bool = True, dump_ir: bool = False, device: int = 0,
                  rows_per_thread: int = 0, block_threads: int = 0, loader: int = 0,
-                 sm_reserve: int = 0):
+                 sm_reserve: int = 0, stages: int = 0):
+        self.stages = int(stages)
         self.optimize = bool(optimize)
         self.dump_ir = bool(dump_ir)
         self.device = int(device)
@@ -465,6 +469,7 @@ class Configuration:
         c.block_threads = self.block_threads
         c.loader = self.loader
         c.sm_reserve = self.sm_reserve
+        c.stages = self.stages
         return c
 
 
@@ -545,12 +550,21 @@ def _stream_handle(stream: int) -> C.c_void_p:
     return C.c_void_p(stream if stream else 1)
 
 
-def _kernel_info(fn, handle) -> dict:
+def _kernel_info(fn, handle, attr_fn=None) -> dict:
     name = C.create_string_buffer(256)
     regs, smem, rpt, bt = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     _check(fn(handle, name, 256, C.byref(regs), C.byref(smem), C.byref(rpt), C.byref(bt)))
-    return {"name": name.value.decode(), "regs": regs.value, "smem_bytes": smem.value,
+    info = {"name": name.value.decode(), "regs": regs.value, "smem_bytes": smem.value,
             "rows_per_thread": rpt.value, "block_threads": bt.value}
+    if attr_fn is not None:
+        keys = ["staged", "stages", "dynamic_smem", "cta_tile_rows", "tile_rows", "nullable"]
+        if regs.value >= 0:
+            keys.append("blocks_per_sm")
+        for key in keys:
+            v = C.c_int64()
+            if attr_fn(handle, key.encode(), C.byref(v)) == 0:
+                info[key] = v.value
+    return info
 
 
 # ---- Projector ---------------------------------------------------------------------------
@@ -578,7 +592,7 @@ class Projector:
 
     @property
     def kernel_info(self) -> dict:
-        return _kernel_info(lib.gdv_projector_kernel_info, self._h)
+        return _kernel_info(lib.gdv_projector_kernel_info, self._h, lib.gdv_projector_kernel_attr)
 
     def evaluate(self, batch: pa.RecordBatch, selection: SelectionVector | None = None) -> list:
         if not isinstance(batch, pa.RecordBatch):
@@ -656,7 +670,7 @@ class Filter:
 
     @property
     def kernel_info(self) -> dict:
-        return _kernel_info(lib.gdv_filter_kernel_info, self._h)
+        return _kernel_info(lib.gdv_filter_kernel_info, self._h, lib.gdv_filter_kernel_attr)
 
     def evaluate(self, batch: pa.RecordBatch, pool: Any = None, dtype: Any = "int32") -> SelectionVector:
         if not isinstance(batch, pa.RecordBatch):

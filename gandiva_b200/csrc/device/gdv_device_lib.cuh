@@ -195,6 +195,71 @@ GDV_DEV bool gdv_ldbit(const u8* p, u32 sh, i64 i) {
   const i64 b = i + (i64)sh;
   return ((p[b >> 3] >> (u32)(b & 7)) & 1u) != 0u;
 }
+// ---- TMA bulk copies into shared memory (cp.async.bulk + mbarrier) ------------------------
+// Wide projectors stage each CTA tile of every input column through shared memory with one
+// bulk copy per column (SASS UBLKCP): the loads of the next tiles are in flight while the
+// current tile computes, at no register cost.  Source and destination must be 16-byte aligned
+// and the size a multiple of 16; the codegen aligns column pointers down and keeps the
+// misalignment as a constant byte offset into the stage.
+GDV_DEV u32 gdv_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+GDV_DEV void gdv_mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gdv_smem_addr(bar)), "r"(count)
+               : "memory");
+}
+GDV_DEV void gdv_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+GDV_DEV void gdv_mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gdv_smem_addr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+GDV_DEV u64 gdv_policy_evict_first() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+GDV_DEV void gdv_bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar, u64 policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(gdv_smem_addr(dst)),
+      "l"(src), "r"(bytes), "r"(gdv_smem_addr(bar)), "l"(policy)
+      : "memory");
+}
+GDV_DEV bool gdv_mbar_try_wait(u64* bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(gdv_smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+GDV_DEV void gdv_mbar_wait(u64* bar, u32 parity) {
+  while (!gdv_mbar_try_wait(bar, parity)) {
+  }
+}
+// Shared-memory element load (i128 as one LDS.128).
+template <typename T>
+GDV_DEV T gdv_lds(const T* p) {
+  return *p;
+}
+template <>
+GDV_DEV i128 gdv_lds<i128>(const i128* p) {
+  const longlong2 v = *reinterpret_cast<const longlong2*>(p);
+  return (i128)(((u128)(u64)v.y << 64) | (u128)(u64)v.x);
+}
+// gdv_ldwin() over a bitmap window that was staged into shared memory.
+GDV_DEV u32 gdv_ldwin_s(const u32* p, u32 widx, u32 sh) {
+  const u32 lo = p[widx];
+  if (sh == 0u) return lo;
+  return __funnelshift_r(lo, p[widx + 1], sh);
+}
+
 GDV_DEV u32 gdv_lanemask_lt() {
   u32 m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

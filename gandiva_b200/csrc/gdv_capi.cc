@@ -50,6 +50,7 @@ Config FromC(const gdv_config_t* c) {
     cfg.rows_per_thread = c->rows_per_thread;
     cfg.block_threads = c->block_threads;
     cfg.loader = c->loader;
+    cfg.stages = c->stages;
     cfg.sm_reserve = c->sm_reserve;
   }
   return cfg;
@@ -303,6 +304,35 @@ gdv_status gdv_projector_kernel_info(gdv_projector_t p, char* name_buf, int64_t 
                     block_threads);
 }
 
+static gdv_status KernelAttr(CompiledKernel& k, const Config& cfg, const char* key, int64_t* out) {
+  if (key == nullptr || out == nullptr) return Fail(GDV_INVALID, "null argument");
+  const std::string kk(key);
+  if (kk == "staged") { *out = k.gen.staged ? 1 : 0; return GDV_OK; }
+  if (kk == "stages") { *out = k.gen.stages; return GDV_OK; }
+  if (kk == "dynamic_smem") { *out = k.gen.dynamic_smem; return GDV_OK; }
+  if (kk == "cta_tile_rows") { *out = k.gen.cta_tile_rows; return GDV_OK; }
+  if (kk == "tile_rows") { *out = k.gen.tile_rows; return GDV_OK; }
+  if (kk == "nullable") { *out = k.gen.nullable ? 1 : 0; return GDV_OK; }
+  if (kk == "in_bytes_per_row") { *out = k.gen.in_bytes_per_row; return GDV_OK; }
+  if (kk == "blocks_per_sm") {
+    Device* dev = nullptr;
+    Status s = Device::Get(cfg.device, &dev);
+    if (!s.ok()) return Fail(s);
+    CompiledKernel::Loaded l;
+    s = k.Load(dev, &l);
+    if (!s.ok()) return Fail(s);
+    *out = l.blocks_per_sm;
+    return GDV_OK;
+  }
+  return Fail(GDV_INVALID, "unknown kernel attribute " + kk);
+}
+
+gdv_status gdv_projector_kernel_attr(gdv_projector_t p, const char* key, int64_t* out) {
+  if (p == nullptr) return Fail(GDV_INVALID, "null projector");
+  auto& pr = *reinterpret_cast<ProjH*>(p)->p;
+  return KernelAttr(pr.kernel(), pr.config(), key, out);
+}
+
 void gdv_projector_release(gdv_projector_t p) { delete reinterpret_cast<ProjH*>(p); }
 
 // ---- Filter -------------------------------------------------------------------------------
@@ -350,6 +380,17 @@ gdv_status gdv_filter_kernel_info(gdv_filter_t f, char* name_buf, int64_t name_l
   }
   return KernelInfo(*k, fl.config(), name_buf, name_len, regs, smem_bytes, rows_per_thread,
                     block_threads);
+}
+
+gdv_status gdv_filter_kernel_attr(gdv_filter_t f, const char* key, int64_t* out) {
+  if (f == nullptr) return Fail(GDV_INVALID, "null filter");
+  auto& fl = *reinterpret_cast<FiltH*>(f)->p;
+  CompiledKernel* k = fl.last_used();
+  if (k == nullptr) {
+    Status s = fl.KernelFor(GDV_SEL_UINT32, true, false, &k);
+    if (!s.ok()) return Fail(s);
+  }
+  return KernelAttr(*k, fl.config(), key, out);
 }
 
 void gdv_filter_release(gdv_filter_t f) { delete reinterpret_cast<FiltH*>(f); }

@@ -670,9 +670,14 @@ void EmitPrologue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, 
 // and rows are contiguous (no selection vector): loads are unconditional, back to back, with
 // immediate offsets from one pointer per column; validity arrives as one 32-bit window per
 // step (a warp-uniform load) instead of one byte load per row.
-void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R, bool fast,
+// Group modes: kPred = per-row range predicates (tail group / selection vector), kFast = whole
+// group in range, direct global loads, kStaged = whole CTA tile already in shared memory (TMA).
+enum GroupMode { kPred = 0, kFast = 1, kStaged = 2 };
+
+void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R, int mode,
                const std::string& body, const std::string& step_tail, std::string* o, int indent,
-               int stage_bytes = 0) {
+               int stage_bytes = 0, const std::string& after_loads = std::string()) {
+  const bool fast = mode != kPred;
   const std::string I(static_cast<size_t>(indent) * 2, ' ');
   const std::string sR = std::to_string(R);
   const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
@@ -681,7 +686,19 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
     *o += I + t.ctype() + " f" + std::to_string(j) + "[" + sR + "];\n";
     if (spec.nullable) *o += I + "bool k" + std::to_string(j) + "[" + sR + "];\n";
   }
-  if (fast) {
+  if (mode == kStaged) {
+    *o += I + "#pragma unroll\n";
+    *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
+    for (size_t j = 0; j < slots.size(); ++j) {
+      const std::string J = std::to_string(j);
+      *o += I + "  f" + J + "[k] = gdv_lds(sp" + J + " + 32 * k);\n";
+      if (spec.nullable)
+        *o += I + "  k" + J + "[k] = !in_hv" + J + " || ((gdv_ldwin_s(sv" + J + ", wid * " + sR +
+              "u + (u32)k, in_vsh" + J + ") >> lane) & 1u) != 0u;\n";
+    }
+    *o += I + "}\n";
+    *o += after_loads;
+  } else if (fast) {
     bool staged_any = false;
     for (size_t j = 0; j < slots.size(); ++j) {
       const DataType& t = slots[j].type;
@@ -816,8 +833,15 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   for (const auto& e : exprs) out_bytes += std::max(e->result().type.width(), 1);
   if (spec.kind == KernelKind::kFilter) out_bytes = 0;
 
+  // The TMA loader is the default for wide-row projectors (measured on the Q1 projector, 166 B/row:
+  // 0.97 of the HBM copy peak at BT=256, R=2, 4 stages vs 0.73 for the best direct-load variant,
+  // profiles/r01_q1_tma_sweep.md).
+  bool want_staged = spec.kind == KernelKind::kProject && spec.selection_mode == GDV_SEL_NONE &&
+                     spec.loader != 1 && !slots.empty() && (spec.loader == 2 || in_bytes >= 48);
+  for (const auto& sl : slots)
+    if (sl.type.is_varlen() || sl.type.is_bool()) want_staged = false;
   int R = spec.rows_per_thread > 0 ? spec.rows_per_thread
-                                   : PickRowsPerThread(in_bytes, out_bytes, spec.kind);
+                                   : (want_staged ? 2 : PickRowsPerThread(in_bytes, out_bytes, spec.kind));
   if (R > 32) R = 32;
   if (spec.kind == KernelKind::kFilter) {
     // the filter walks 32 steps per warp in groups of R: R must divide 32
@@ -831,9 +855,40 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
 
   // shared-memory stage for string bytes: 48 B per row of a group, per warp and string column
   const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
-  const int dynamic_smem = stage_bytes * (BT / 32) * n_varlen;
+  int dynamic_smem = stage_bytes * (BT / 32) * n_varlen;
   const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
   const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
+
+  // ---- TMA loader (projector, fixed-width inputs, no selection vector) -------------------------
+  // Each CTA tile (BT * R rows) of every input column is copied into a shared-memory stage by one
+  // cp.async.bulk; S stages per CTA keep (S - 1) tiles in flight per CTA while one computes.
+  // Picked by default for wide rows (>= 48 B of inputs), where the direct path runs out of
+  // registers before it has enough loads in flight (profiles/r01_configs_3_4.md).
+  bool staged = want_staged && (BT * R) % 128 == 0;
+  std::vector<int> val_off(slots.size(), 0), vld_off(slots.size(), 0);
+  int stage_total = 0, val_tx = 0, S = 0;
+  const int vld_copy = BT * R / 8 + 32;
+  if (staged) {
+    int o = 0;
+    for (size_t j = 0; j < slots.size(); ++j) {
+      val_off[j] = o;
+      o += BT * R * slots[j].type.width() + 16;
+      val_tx += BT * R * slots[j].type.width() + 16;
+    }
+    if (spec.nullable)
+      for (size_t j = 0; j < slots.size(); ++j) {
+        vld_off[j] = o;
+        o += vld_copy;
+      }
+    stage_total = (o + 127) / 128 * 128;
+    S = spec.stages > 0 ? spec.stages : 4;
+    while (S > 2 && S * stage_total > 220 * 1024) --S;
+    if (S < 2 || S * stage_total > 220 * 1024) {
+      staged = false;
+    } else {
+      dynamic_smem = S * stage_total;
+    }
+  }
   ArgsLayout L(static_cast<int>(slots.size()), n_out);
 
   std::string src;
@@ -894,9 +949,99 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
       }
       return t5;
     };
+    const int NWP = BT / 32;
+    const int T = BT * R;  // rows per CTA tile
+    std::string wt_first = "0";
+    if (staged) {
+      // ---- TMA-staged full tiles: persistent CTAs, S stages, one bulk copy per column and tile
+      const std::string sS = std::to_string(S), sT = std::to_string(T);
+      src += "  extern __shared__ uint4 gdv_smem[];\n";
+      src += "  __shared__ u64 gdv_full[" + sS + "];\n";
+      src += "  u8* const stage0 = reinterpret_cast<u8*>(gdv_smem);\n";
+      std::string tx = std::to_string(val_tx) + "u";
+      for (size_t j = 0; j < slots.size(); ++j) {
+        const std::string J = std::to_string(j);
+        src += "  const u32 mis" + J + " = (u32)((unsigned long long)in_val" + J + " & 15ull);\n";
+        if (spec.nullable) {
+          src += "  const u32 vmis" + J + " = (u32)((unsigned long long)in_vld" + J + " & 15ull);\n";
+          tx += " + (in_hv" + J + " ? " + std::to_string(vld_copy) + "u : 0u)";
+        }
+      }
+      src += "  const u32 tx_bytes = " + tx + ";\n";
+      src += "  const u64 pol = gdv_policy_evict_first();\n";
+      // a bulk copy may read up to 32 bytes past its tile: the last 256 rows are never staged
+      src += "  const i64 n_st = A.n > 256 ? (A.n - 256) / " + sT + " : 0;\n";
+      src += "  if (threadIdx.x == 0) {\n";
+      src += "    for (u32 s = 0; s < " + sS + "u; ++s) gdv_mbar_init(&gdv_full[s], 1u);\n";
+      src += "    gdv_fence_mbar_init();\n";
+      src += "  }\n";
+      src += "  __syncthreads();\n";
+      src += "  auto issue = [&](i64 t, u32 s) {\n";
+      src += "    u8* sb = stage0 + (size_t)s * " + std::to_string(stage_total) + "u;\n";
+      src += "    gdv_mbar_expect_tx(&gdv_full[s], tx_bytes);\n";
+      for (size_t j = 0; j < slots.size(); ++j) {
+        const std::string J = std::to_string(j);
+        const int w = slots[j].type.width();
+        src += "    gdv_bulk_g2s(sb + " + std::to_string(val_off[j]) + ", reinterpret_cast<const u8*>(in_val" +
+               J + ") - mis" + J + " + t * " + std::to_string(static_cast<long long>(T) * w) + "ll, " +
+               std::to_string(T * w + 16) + "u, &gdv_full[s], pol);\n";
+        if (spec.nullable)
+          src += "    if (in_hv" + J + ") gdv_bulk_g2s(sb + " + std::to_string(vld_off[j]) +
+                 ", reinterpret_cast<const u8*>(in_vld" + J + ") - vmis" + J + " + t * " +
+                 std::to_string(T / 8) + "ll, " + std::to_string(vld_copy) + "u, &gdv_full[s], pol);\n";
+      }
+      src += "  };\n";
+      src += "  if (threadIdx.x == 0) {\n";
+      src += "    for (u32 s = 0; s < " + sS + "u; ++s) {\n";
+      src += "      const i64 t = (i64)blockIdx.x + (i64)s * gridDim.x;\n";
+      src += "      if (t < n_st) issue(t, s);\n";
+      src += "    }\n";
+      src += "  }\n";
+      src += "  u32 it = 0u;\n";
+      src += "  for (i64 t = blockIdx.x; t < n_st; t += gridDim.x, ++it) {\n";
+      src += "    const u32 s = it % " + sS + "u;\n";
+      src += "    const u32 par = (it / " + sS + "u) & 1u;\n";
+      src += "    const u8* sb = stage0 + (size_t)s * " + std::to_string(stage_total) + "u;\n";
+      src += "    const i64 base = t * " + sT + " + (i64)wid * " + s32R + ";\n";
+      for (size_t j = 0; j < slots.size(); ++j) {
+        const std::string J = std::to_string(j);
+        const std::string ct = slots[j].type.ctype();
+        src += "    const " + ct + "* sp" + J + " = reinterpret_cast<const " + ct + "*>(sb + " +
+               std::to_string(val_off[j]) + " + mis" + J + ") + wid * " + s32R + "u + lane;\n";
+        if (spec.nullable)
+          src += "    const u32* sv" + J + " = reinterpret_cast<const u32*>(sb + " +
+                 std::to_string(vld_off[j]) + " + vmis" + J + ");\n";
+      }
+      for (int o = 0; o < n_out; ++o) {
+        src += "    u32 vw" + std::to_string(o) + " = 0u;\n";
+        if (exprs[o]->result().type.is_bool()) src += "    u32 dw" + std::to_string(o) + " = 0u;\n";
+      }
+      src += "    gdv_mbar_wait(&gdv_full[s], par);\n";
+      src += "    {\n";
+      std::string after;
+      after += "      __syncthreads();  // every thread holds its rows: the stage can be refilled\n";
+      after += "      if (threadIdx.x == 0) {\n";
+      after += "        const i64 tn = t + (i64)" + sS + " * gridDim.x;\n";
+      after += "        if (tn < n_st) issue(tn, s);\n";
+      after += "      }\n";
+      EmitGroup(slots, spec, R, kStaged, body, tail(true), &src, 3, 0, after);
+      src += "    }\n";
+      src += "    if (lane < " + sR + "u) {\n";
+      src += "      const i64 w = (base >> 5) + (i64)lane;\n";
+      for (int o = 0; o < n_out; ++o) {
+        const std::string O = std::to_string(o);
+        src += "      if (A.out_vld[" + O + "] != nullptr) A.out_vld[" + O + "][w] = vw" + O + ";\n";
+        if (exprs[o]->result().type.is_bool())
+          src += "      reinterpret_cast<u32*>(A.out_val[" + O + "])[w] = dw" + O + ";\n";
+      }
+      src += "    }\n";
+      src += "  }\n";
+      // rows after the staged tiles take the direct path below
+      wt_first = "n_st * " + std::to_string(NWP);
+    }
     src += "  const i64 n_wtiles = (A.n + " + std::to_string(32 * R - 1) + ") / " + s32R + ";\n";
-    src += "  const i64 wstride = (i64)gridDim.x * " + std::to_string(BT / 32) + ";\n";
-    src += "  for (i64 wt = (i64)blockIdx.x * " + std::to_string(BT / 32) +
+    src += "  const i64 wstride = (i64)gridDim.x * " + std::to_string(NWP) + ";\n";
+    src += "  for (i64 wt = " + wt_first + " + (i64)blockIdx.x * " + std::to_string(NWP) +
            " + wid; wt < n_wtiles; wt += wstride) {\n";
     src += "    const i64 base = wt * " + s32R + ";\n";
     for (int o = 0; o < n_out; ++o) {
@@ -905,13 +1050,13 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     }
     if (!has_sel) {
       src += "    if (base + " + s32R + " <= A.n) {\n";
-      EmitGroup(slots, spec, R, true, body, tail(true), &src, 3, stage_bytes);
+      EmitGroup(slots, spec, R, kFast, body, tail(true), &src, 3, stage_bytes);
       src += "    } else {\n";
-      EmitGroup(slots, spec, R, false, body, tail(false), &src, 3);
+      EmitGroup(slots, spec, R, kPred, body, tail(false), &src, 3);
       src += "    }\n";
     } else {
       src += "    {\n";
-      EmitGroup(slots, spec, R, false, body, tail(false), &src, 3);
+      EmitGroup(slots, spec, R, kPred, body, tail(false), &src, 3);
       src += "    }\n";
     }
     src += "    if (lane < " + sR + "u && base + 32 * (i64)lane < A.n) {\n";
@@ -957,9 +1102,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "      const i64 base = wbase + 32 * g;\n";
     src += "      if (base >= A.n) break;\n";
     src += "      if (base + " + s32R + " <= A.n) {\n";
-    EmitGroup(slots, spec, R, true, body, step_tail, &src, 4, stage_bytes);
+    EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes);
     src += "      } else {\n";
-    EmitGroup(slots, spec, R, false, body, step_tail, &src, 4);
+    EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 4);
     src += "      }\n";
     src += "    }\n";
     // lane k: c = selected rows of step k; exclusive scan over steps; warp total
@@ -1023,6 +1168,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->args_size = L.size;
   out->dynamic_smem = dynamic_smem;
   out->tile_rows = spec.kind == KernelKind::kFilter ? static_cast<int64_t>(BT / 32) * 1024 : 0;
+  out->staged = staged;
+  out->stages = staged ? S : 0;
+  out->cta_tile_rows = static_cast<int64_t>(BT) * R;
   return Status::OK();
 }
 

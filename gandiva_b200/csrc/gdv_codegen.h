@@ -40,6 +40,8 @@ struct KernelSpec {
   int block_threads = 256;
   std::string name;                   // kernel symbol
   bool nullable = true;               // false: specialised for batches where no input has nulls
+  int loader = 0;                     // 0 = engine picks, 1 = direct LDG, 2 = TMA bulk -> shared
+  int stages = 0;                     // TMA loader: shared-memory stages per CTA (0 = pick)
 };
 
 struct ColumnSlot {
@@ -63,6 +65,9 @@ struct GeneratedKernel {
   size_t args_size = 0;             // sizeof(gdv_args) for this kernel
   int dynamic_smem = 0;             // bytes of dynamic shared memory (string staging)
   int64_t tile_rows = 0;            // filter: rows per CTA tile (one look-back descriptor each)
+  bool staged = false;              // project: inputs staged through shared memory by TMA bulk copies
+  int stages = 0;                   // staged: shared-memory stages per CTA
+  int64_t cta_tile_rows = 0;        // staged: rows per CTA tile (block_threads * rows_per_thread)
 };
 
 // Byte offsets inside gdv_args; the host packs the same layout (see EmitArgsStruct()).

@@ -80,6 +80,7 @@ struct Config {
   int rows_per_thread = 0;
   int block_threads = 0;
   int loader = 0;
+  int stages = 0;
   int sm_reserve = 0;
 };
 

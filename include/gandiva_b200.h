@@ -105,7 +105,8 @@ typedef struct gdv_config {
   int32_t sm_reserve;      /* SMs left without CTAs of the persistent kernels, so that a
                               concurrent stream (e.g. NCCL's gather of the previous batch's
                               SelectionVector) can run; default 0 */
-  int32_t reserved[5];
+  int32_t stages;          /* TMA loader: shared-memory stages per CTA (0 = engine picks) */
+  int32_t reserved[4];
 } gdv_config_t;
 void gdv_config_default(gdv_config_t* cfg);
 
@@ -230,6 +231,10 @@ int64_t gdv_projector_dump_ir(gdv_projector_t p, char* buf, int64_t buf_len);
 gdv_status gdv_projector_kernel_info(gdv_projector_t p, char* name_buf, int64_t name_len,
                                      int32_t* regs, int32_t* smem_bytes, int32_t* rows_per_thread,
                                      int32_t* block_threads);
+/* Integer attribute of the kernel variant used by the latest Evaluate: "staged" (1 = TMA bulk
+ * loader), "stages", "dynamic_smem", "cta_tile_rows", "tile_rows", "nullable",
+ * "in_bytes_per_row", "blocks_per_sm" (needs a device). */
+gdv_status gdv_projector_kernel_attr(gdv_projector_t p, const char* key, int64_t* out);
 void gdv_projector_release(gdv_projector_t p);
 
 /* ---- Filter --------------------------------------------------------------- */
@@ -247,6 +252,7 @@ int64_t gdv_filter_dump_ir(gdv_filter_t f, char* buf, int64_t buf_len);
 gdv_status gdv_filter_kernel_info(gdv_filter_t f, char* name_buf, int64_t name_len, int32_t* regs,
                                   int32_t* smem_bytes, int32_t* rows_per_thread,
                                   int32_t* block_threads);
+gdv_status gdv_filter_kernel_attr(gdv_filter_t f, const char* key, int64_t* out);
 void gdv_filter_release(gdv_filter_t f);
 
 /* ---- function registry (ExpressionRegistry) ------------------------------ */

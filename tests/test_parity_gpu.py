@@ -54,6 +54,44 @@ def test_project_tuning_knobs(rpt, bt, gandiva, oracle):
     assert_arrays_match(got[0], want[0], "if_else rpt=%d bt=%d" % (rpt, bt))
 
 
+@pytest.mark.parametrize("n", [255, 256, 257, 511, 512, 513, 767, 768, 769, 1024, 5000, 100003, 1_000_003])
+@pytest.mark.parametrize("null_prob", [0.0, 0.2])
+def test_project_tma_loader_sizes(n, null_prob, gandiva, oracle):
+    """TMA bulk loader (loader=2): staged full tiles + direct tail, at tile boundaries; array
+    offsets make every column pointer misaligned by a different amount."""
+    cfg = gandiva.Configuration(rows_per_thread=2, block_threads=256, loader=2)
+    for offset in (0, 3):
+        got, want = run_both(gandiva, oracle, cases.case_if_else, n, seed=n + offset, null_prob=null_prob,
+                             offset=offset, cfg=cfg)
+        assert_arrays_match(got[0], want[0], "tma if_else n=%d off=%d" % (n, offset))
+
+
+@pytest.mark.parametrize("rpt,bt,stages", [(1, 128, 2), (1, 256, 3), (2, 256, 2), (2, 256, 4), (4, 128, 3),
+                                           (4, 256, 2), (2, 512, 2), (8, 128, 2)])
+def test_project_tma_loader_knobs(rpt, bt, stages, gandiva, oracle):
+    cfg = gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, loader=2, stages=stages)
+    b = gandiva.TreeExprBuilder()
+    outs = cases.q1_outputs(b)
+    batch = cases.q1_batch(150_001, seed=rpt * 1000 + bt + stages, null_permille=20)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(cases.Q1_SCHEMA, exprs, None, "NONE", cfg)
+    got = p.evaluate(batch)
+    assert p.kernel_info["staged"] == 1
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch, threads=4)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "q1 tma out %d" % i)
+
+
+@pytest.mark.parametrize("case", PROJECT_CASES[::3], ids=[c.__name__ for c in PROJECT_CASES[::3]])
+def test_project_tma_loader_cases(case, gandiva, oracle):
+    """Same cases as test_project_parity through the staged loader (falls back to the direct
+    path by itself when a column is bool / varlen)."""
+    cfg = gandiva.Configuration(loader=2)
+    got, want = run_both(gandiva, oracle, case, 20011, 4, offset=13, cfg=cfg)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "%s tma out=%d" % (case.__name__, i))
+
+
 def _filter_both(gandiva, oracle, build, batch, dtype="int32", cfg=None):
     b = gandiva.TreeExprBuilder()
     schema, outs, kind = build(b)

@@ -60,12 +60,18 @@ def bench_q1(n, passes):
             outs.append((vl.data_ptr(), v.data_ptr()))
         in_bytes = 8 + 3 * 16 + 3 * 8 + 4 + 8 / 8.0
         out_bytes = 2 * 16 + 6 * 8 + 8 / 8.0
-        for bt in (128, 256, 512):
-            for rpt in (1, 2, 4):
+        combos = [(bt, rpt, 1, 0) for bt in (128, 256) for rpt in (2, 4)]
+        combos += [(bt, rpt, 2, st_) for bt, rpt in ((128, 1), (128, 2), (256, 1), (256, 2), (128, 4), (512, 1))
+                   for st_ in (2, 3, 4)]
+        if os.environ.get("GDV_Q1_COMBOS"):
+            combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_Q1_COMBOS"].split(";")]
+        for bt, rpt, loader, stages in combos:
+            if True:
                 b = gandiva.TreeExprBuilder()
                 exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(cases.q1_outputs(b))]
                 p = gandiva.make_projector(cases.Q1_SCHEMA, exprs, None, "NONE",
-                                           gandiva.Configuration(rows_per_thread=rpt, block_threads=bt))
+                                           gandiva.Configuration(rows_per_thread=rpt, block_threads=bt,
+                                                                 loader=loader, stages=stages))
 
                 def run():
                     for _ in range(passes):
@@ -76,7 +82,10 @@ def bench_q1(n, passes):
                 gbs = rows * (in_bytes + out_bytes) / ms / 1e6
                 r = {"config": "q1_projector_8_outputs", "block_threads": bt, "rows_per_thread": rpt, "rows": rows,
                      "ms": ms, "rows_per_s": rows / ms * 1e3, "gbs": gbs, "frac": gbs / PEAK,
-                     "bytes_per_row": in_bytes + out_bytes, "regs": p.kernel_info["regs"]}
+                     "bytes_per_row": in_bytes + out_bytes, "regs": p.kernel_info["regs"],
+                     "loader": "tma" if p.kernel_info.get("staged") else "ldg",
+                     "stages": p.kernel_info.get("stages"), "smem": p.kernel_info.get("dynamic_smem"),
+                     "ctas_per_sm": p.kernel_info.get("blocks_per_sm")}
                 results.append(r)
                 print(json.dumps(r), flush=True)
     json.dump(results, open(os.path.join(ROOT, "gpurun_out", "bench_q1.json"), "w"), indent=1)
