@@ -52,11 +52,17 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: gather inside each step, no pipelining")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl"],
+                    help="N>1: how the SelectionVector reaches rank 0.  push (default): "
+                         "gdv_selection_push, device-side NVLink stores into rank 0's vector, no host "
+                         "sync; nccl: all-gather of counts + send/recv (host reads the count)")
+    ap.add_argument("--no-overlap", action="store_true", help="--gather nccl: gather inside each step, no pipelining")
     ap.add_argument("--peer-gather", action="store_true",
-                    help="N>1: experimental copy-engine peer writes (CUDA IPC) instead of NCCL send/recv; "
+                    help="--gather nccl: copy-engine peer writes (CUDA IPC) instead of NCCL send/recv; "
                          "measured slower in round 1 (host-side gloo sync), see DESIGN.md")
-    ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs left free for NCCL (default: 16 when N>1)")
+    ap.add_argument("--push-ctas", type=int, default=4, help="--gather push: CTAs of the push kernel")
+    ap.add_argument("--sm-reserve", type=int, default=-1,
+                    help="SMs left free for the push / NCCL kernels (default: --push-ctas when N>1)")
     return ap.parse_args()
 
 
@@ -200,7 +206,8 @@ def main():
     first_row = rank * n
     idx_mode = "UINT32" if (world == 1 and n <= (1 << 32)) else "UINT64"
     idx_dtype = torch.int32 if idx_mode == "UINT32" else torch.int64
-    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else 0
+    use_push = world > 1 and not args.no_gather and args.gather == "push"
+    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if use_push else 0)
     cfg = gandiva.Configuration(device=local_rank, rows_per_thread=args.rows_per_thread,
                                 block_threads=args.block_threads, sm_reserve=sm_reserve)
     filt, _ = q6_filter(gandiva, cases, cfg)
@@ -211,17 +218,25 @@ def main():
     qty = torch.empty(n, dtype=torch.float64, device=dev)
     for kind, t in ((0, ship), (1, disc), (2, qty)):
         gandiva.generate_lineitem(local_rank, kind, 42, first_row, n, t.data_ptr(), 0, 0, st)
-    out_idx = torch.empty(n, dtype=idx_dtype, device=dev)
+    out_idx = None if use_push else torch.empty(n, dtype=idx_dtype, device=dev)
     d_count = torch.zeros(1, dtype=torch.int64, device=dev)
     cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
     torch.cuda.synchronize()
 
     from gandiva_b200.sharding import gather_selection
-    pipelined = world > 1 and not args.no_gather and not args.no_overlap
+    pipelined = world > 1 and not args.no_gather and not args.no_overlap and not use_push
+    ps = None
+    if use_push:
+        from gandiva_b200.sharding import PeerSelection
+        ps = PeerSelection(capacity=int(n * world * 0.03) + 4096, local_rows=n, mode=idx_mode, device=dev,
+                           slots=2, ctas=args.push_ctas)
+    gstep = {"i": 0}
     # N>1: the gather of batch i runs on a second stream while the filter kernel of batch i+1
     # runs (double-buffered index buffers).  The filter was built with sm_reserve so that NCCL's
     # copy CTAs find free slots next to the persistent filter CTAs.
     comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    if use_push:                       # the kernel-only timing below writes here
+        out_idx = ps.local[0] if rank != 0 else torch.empty(n, dtype=idx_dtype, device=dev)
     bufs = [out_idx, torch.empty(n, dtype=idx_dtype, device=dev) if pipelined else out_idx]
     cnts = [d_count, torch.zeros(1, dtype=torch.int64, device=dev)]
     host_cnt = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
@@ -263,8 +278,28 @@ def main():
             ev_g[b].record(comm_stream)
         return total
 
+    def run_steps_push(k, events=None):
+        """N>1, --gather push: filter kernel i+1 overlaps the NVLink push of run i; nothing
+        touches the host between steps."""
+        for i in range(k):
+            g = gstep["i"]
+            gstep["i"] += 1
+            ps.before_filter(g, stream)
+            ptr, cap, mode, cnt_ptr = ps.filter_target(g)
+            filt.evaluate_device(n, cols, ptr, cap, mode, st, cnt_ptr, sync=False, index_base=first_row)
+            # the last run of the job has no filter kernel to hide under: push it with the whole GPU
+            ps.after_filter(g, stream, ctas=(2 * 148 if i == k - 1 else 0))
+            if events is not None and i + 1 < k:
+                events[i + 1].record(stream)
+        ps.finish(stream)                          # the last step closes after its push landed
+        if events is not None:
+            events[k].record(stream)
+        return None
+
     def run_steps(k, events=None):
         """k passes of the hot path; with N>1 each pass ends with the SelectionVector on rank 0."""
+        if use_push:
+            return run_steps_push(k, events)
         total = None
         for i in range(k):
             if pipelined and i >= 2:
@@ -321,6 +356,19 @@ def main():
         total_selected = count
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3)
+    gather_check = None
+    if use_push:
+        # outside the timed region: the last step's vector on rank 0 is complete, ascending and
+        # holds exactly the rows all ranks selected
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            vec, total = ps.result(gstep["i"] - 1)
+            ok = (total == total_selected) and not ps.overflowed()
+            if ok and total > 1:
+                ok = bool((vec[1:] > vec[:-1]).all().item())
+            ok = ok and int(vec[-1].item()) < n * world and int(vec[0].item()) >= 0
+            gather_check = "ok: %d ascending global indices on rank 0" % total if ok else "FAILED"
 
     # ---- roofline of the dominant (only) kernel ----------------------------------------------
     peak, peak_src = measured_peak_gbs()
@@ -380,7 +428,8 @@ def main():
             "config": {"workload": "TPC-H Q6 filter (BASELINE.json configs[1]%s)" %
                                    ("; configs[4] sharding" if world > 1 else ""),
                        "rows_per_gpu": n, "total_rows": n * world, "selectivity": total_selected / (n * world),
-                       "selection_vector": idx_mode + ((" gathered to rank 0 over NVLink" + ((", copy-engine peer writes into rank 0 (CUDA IPC)" if peer is not None else ", NCCL send/recv") + ", overlapped with the next batch's kernel" if pipelined else ", NCCL send/recv")) if world > 1 and not args.no_gather else ""),
+                       "selection_vector": idx_mode + ((" reassembled on rank 0 over NVLink" + (", gdv_selection_push: device-side stores into rank 0's vector (CUDA IPC), counts exchanged through a board in rank 0's HBM, no host sync, overlapped with the next batch's kernel (%d SMs reserved)" % sm_reserve if use_push else ((", copy-engine peer writes into rank 0 (CUDA IPC)" if peer is not None else ", NCCL send/recv") + ", overlapped with the next batch's kernel" if pipelined else ", NCCL send/recv"))) if world > 1 and not args.no_gather else ""),
+                       "gather_check": gather_check,
                        "l2_policy": "inputs (20 B/row x %d rows) larger than L2; no flush" % n,
                        "parallelism": "row-range shards, %d" % world},
             "hbm_gbs": achieved, "per_step_ms": per_step,
@@ -389,6 +438,8 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if ps is not None:
+            ps.close()
         dist.barrier()
         dist.destroy_process_group()
 

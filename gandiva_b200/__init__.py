@@ -41,6 +41,9 @@ GDV_EXECUTION_ERROR = 42
 GDV_CUDA_ERROR = 100
 
 GDV_SEL_NONE, GDV_SEL_UINT16, GDV_SEL_UINT32, GDV_SEL_UINT64 = 0, 1, 2, 3
+GDV_SEL_BOUNDED = 0x100
+GDV_BOARD_MAX_WORLD, GDV_BOARD_SLOTS = 16, 4
+GDV_BOARD_BYTES = (2 * GDV_BOARD_SLOTS * GDV_BOARD_MAX_WORLD + GDV_BOARD_SLOTS + 1) * 8
 GDV_MEM_HOST, GDV_MEM_DEVICE = 0, 1
 
 
@@ -132,6 +135,13 @@ def _load() -> C.CDLL:
         "gdv_filter_sync": (i32, [vp, vp, P(i64)]),
         "gdv_filter_dump_ir": (i64, [vp, C.c_char_p, i64]),
         "gdv_filter_kernel_info": (i32, [vp, C.c_char_p, i64, P(i32), P(i32), P(i32), P(i32)]),
+        "gdv_selection_push": (i32, [i32, vp, vp, vp, i64, vp, i32, i32, i32, C.c_uint64, C.c_uint64, i32,
+                                     i32, vp, C.c_uint64, vp, vp]),
+        "gdv_selection_release": (i32, [i32, vp, i32, C.c_uint64, vp]),
+        "gdv_enable_peer_access": (i32, [i32, i32]),
+        "gdv_ipc_export": (i32, [i32, vp, C.c_char_p, P(i64)]),
+        "gdv_ipc_open": (i32, [i32, C.c_char_p, i64, P(vp)]),
+        "gdv_ipc_close": (i32, [i32, vp, i64]),
         "gdv_projector_kernel_attr": (i32, [vp, C.c_char_p, P(i64)]),
         "gdv_filter_kernel_attr": (i32, [vp, C.c_char_p, P(i64)]),
         "gdv_filter_release": (None, [vp]),
@@ -481,7 +491,10 @@ _SEL_NP = {GDV_SEL_UINT16: np.uint16, GDV_SEL_UINT32: np.uint32, GDV_SEL_UINT64:
 
 def _ensure_selection_mode(name: str) -> int:
     try:
-        return _SEL_MODE[name.upper()]
+        name = name.upper()
+        if name.endswith("|BOUNDED"):   # device-resident Filter only (GDV_SEL_BOUNDED)
+            return _SEL_MODE[name[:-8]] | GDV_SEL_BOUNDED
+        return _SEL_MODE[name]
     except KeyError:
         raise ValueError("Invalid value for Selection Mode: %r" % (name,))
 

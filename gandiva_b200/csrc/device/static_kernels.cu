@@ -82,3 +82,101 @@ extern "C" __global__ void __launch_bounds__(256) gdv_fill_u32(u32* p, i64 words
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) p[i] = v;
 }
+
+// ---- SelectionVector reassembly across row-range shards (DESIGN.md "Multi-GPU") ------------
+// One process per GPU filters its row range into a LOCAL index run (global row numbers).  This
+// kernel, launched on a side stream next to the following batch's filter kernel, moves the run
+// into its final position of the root's SelectionVector with plain stores over NVLink (the root
+// buffer is peer-mapped through CUDA IPC).  The only thing the ranks exchange besides the runs
+// is a "board" of 64-bit words in the root's memory:
+//   count[q]  = (seq << 40) | rows selected by rank q in step seq   (published at kernel start)
+//   done[q]   = seq once rank q's run has landed in the root buffer
+//   consumed  = seq of the last step whose vector the root has released for reuse
+// seq increases by one per step, so no word is ever reset and no host round trip is needed:
+// rank r's offset is the sum of count[q], q < r, read with acquire loads once they carry seq.
+#define GDV_BOARD_SEQ_SHIFT 40
+#define GDV_BOARD_COUNT_MASK ((1ull << GDV_BOARD_SEQ_SHIFT) - 1ull)
+__device__ __forceinline__ u64 gdv_ld_acquire_sys(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void gdv_st_release_sys(u64* p, u64 v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void gdv_copy_run(const T* __restrict__ src, T* dst, u64 n) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  // eight independent local loads in flight per thread, then eight fire-and-forget peer stores:
+  // a few CTAs are enough to move one run per step while the next filter kernel owns the GPU
+  for (; i + 7 * stride < n; i += 8 * stride) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[i + k * stride] = v[k];
+  }
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+
+extern "C" __global__ void __launch_bounds__(1024)
+gdv_sel_push(const void* src, const u64* d_count, void* dst, i64 dst_cap, u64* board_count,
+             u64* board_done, u64* board_consumed, u64* board_err, int rank, int world, u64 seq,
+             u64 need_consumed, int elem_bytes, u64* local_ctr, u64 done_target, u64* total_out) {
+  __shared__ u64 s_off, s_cnt;
+  if (threadIdx.x == 0) {
+    const u64 cnt = *d_count;
+    if (blockIdx.x == 0) gdv_st_release_sys(&board_count[rank], (seq << GDV_BOARD_SEQ_SHIFT) | cnt);
+    if (need_consumed != 0ull)
+      while (gdv_ld_acquire_sys(board_consumed) < need_consumed) {
+      }
+    u64 off = 0;
+    for (int q = 0; q < rank; ++q) {
+      u64 v;
+      do {
+        v = gdv_ld_acquire_sys(&board_count[q]);
+      } while ((v >> GDV_BOARD_SEQ_SHIFT) != seq);
+      off += v & GDV_BOARD_COUNT_MASK;
+    }
+    s_off = off;
+    s_cnt = cnt;
+  }
+  __syncthreads();
+  const u64 off = s_off, cnt = s_cnt;
+  if (rank != 0) {
+    if (off + cnt <= (u64)dst_cap) {
+      if (elem_bytes == 8)
+        gdv_copy_run(reinterpret_cast<const u64*>(src), reinterpret_cast<u64*>(dst) + off, cnt);
+      else if (elem_bytes == 4)
+        gdv_copy_run(reinterpret_cast<const u32*>(src), reinterpret_cast<u32*>(dst) + off, cnt);
+      else
+        gdv_copy_run(reinterpret_cast<const u16*>(src), reinterpret_cast<u16*>(dst) + off, cnt);
+    } else if (threadIdx.x == 0 && blockIdx.x == 0) {
+      gdv_st_release_sys(board_err, seq);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const u64 prev = atomicAdd(reinterpret_cast<unsigned long long*>(local_ctr), 1ull);
+      if (prev + 1ull == done_target) gdv_st_release_sys(&board_done[rank], seq);
+    }
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // root: its own run was written in place by the filter kernel (offset 0)
+    if (cnt > (u64)dst_cap) gdv_st_release_sys(board_err, seq);
+    gdv_st_release_sys(&board_done[0], seq);
+    u64 total = cnt;
+    for (int q = 1; q < world; ++q) {
+      while (gdv_ld_acquire_sys(&board_done[q]) != seq) {
+      }
+      total += gdv_ld_acquire_sys(&board_count[q]) & GDV_BOARD_COUNT_MASK;
+    }
+    if (total_out != nullptr) *total_out = total;
+  }
+}
+
+// root: stamps `consumed` once the consumer of step seq's vector is done with it.
+extern "C" __global__ void gdv_sel_release(u64* board_consumed, u64 seq) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) gdv_st_release_sys(board_consumed, seq);
+}

@@ -451,6 +451,139 @@ gdv_status gdv_generate_lineitem(int32_t device, int32_t column_kind, uint64_t s
   return s.ok() ? GDV_OK : Fail(s);
 }
 
+gdv_status gdv_enable_peer_access(int32_t device, int32_t peer_device) {
+  if (device == peer_device) return GDV_OK;
+  const DriverApi& d = Driver();
+  if (!d.loaded) return Fail(GDV_CUDA_ERROR, d.load_error);
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  CUdevice cu_dev = 0, cu_peer = 0;
+  s = CuCheck(d.DeviceGet(&cu_dev, device), "cuDeviceGet");
+  if (s.ok()) s = CuCheck(d.DeviceGet(&cu_peer, peer_device), "cuDeviceGet(peer)");
+  if (!s.ok()) return Fail(s);
+  int can = 0;
+  s = CuCheck(d.DeviceCanAccessPeer(&can, cu_dev, cu_peer), "cuDeviceCanAccessPeer");
+  if (!s.ok()) return Fail(s);
+  if (!can)
+    return Fail(GDV_CUDA_ERROR, "device " + std::to_string(device) + " cannot access device " +
+                                    std::to_string(peer_device) + " (no NVLink / PCIe P2P path)");
+  CUcontext peer_ctx = nullptr;
+  s = CuCheck(d.DevicePrimaryCtxRetain(&peer_ctx, cu_peer), "cuDevicePrimaryCtxRetain(peer)");
+  if (!s.ok()) return Fail(s);
+  s = dev->MakeCurrent();
+  if (!s.ok()) return Fail(s);
+  const CUresult r = d.CtxEnablePeerAccess(peer_ctx, 0);
+  if (r != CUDA_SUCCESS && r != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED)
+    return Fail(CuCheck(r, "cuCtxEnablePeerAccess"));
+  return GDV_OK;
+}
+
+// CUDA IPC: the root exports the allocation behind its SelectionVector / board, every other rank
+// opens it with ITS OWN device context current and CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS, which maps
+// the memory into that device's address space and enables NVLink peer access to the root GPU.
+gdv_status gdv_ipc_export(int32_t device, const void* d_ptr, uint8_t* handle64, int64_t* offset) {
+  static_assert(sizeof(CUipcMemHandle) == 64, "CUipcMemHandle is 64 bytes");
+  if (d_ptr == nullptr || handle64 == nullptr || offset == nullptr)
+    return Fail(GDV_INVALID, "gdv_ipc_export: null argument");
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  const DriverApi& d = Driver();
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  s = CuCheck(d.MemGetAddressRange(&base, &size, reinterpret_cast<CUdeviceptr>(d_ptr)),
+              "cuMemGetAddressRange");
+  if (!s.ok()) return Fail(s);
+  CUipcMemHandle h;
+  s = CuCheck(d.IpcGetMemHandle(&h, base), "cuIpcGetMemHandle");
+  if (!s.ok()) return Fail(s);
+  std::memcpy(handle64, &h, 64);
+  *offset = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(d_ptr) - base);
+  return GDV_OK;
+}
+
+gdv_status gdv_ipc_open(int32_t device, const uint8_t* handle64, int64_t offset, void** out_ptr) {
+  if (handle64 == nullptr || out_ptr == nullptr) return Fail(GDV_INVALID, "gdv_ipc_open: null argument");
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);  // makes the context of `device` current
+  if (!s.ok()) return Fail(s);
+  CUipcMemHandle h;
+  std::memcpy(&h, handle64, 64);
+  CUdeviceptr base = 0;
+  s = CuCheck(Driver().IpcOpenMemHandle(&base, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS),
+              "cuIpcOpenMemHandle");
+  if (!s.ok()) return Fail(s);
+  *out_ptr = reinterpret_cast<void*>(base + static_cast<CUdeviceptr>(offset));
+  return GDV_OK;
+}
+
+gdv_status gdv_ipc_close(int32_t device, void* d_ptr, int64_t offset) {
+  if (d_ptr == nullptr) return GDV_OK;
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  s = CuCheck(Driver().IpcCloseMemHandle(reinterpret_cast<CUdeviceptr>(d_ptr) -
+                                          static_cast<CUdeviceptr>(offset)),
+              "cuIpcCloseMemHandle");
+  return s.ok() ? GDV_OK : Fail(s);
+}
+
+gdv_status gdv_selection_push(int32_t device, const void* d_src, const void* d_count, void* d_dst,
+                              int64_t dst_capacity, void* board, int32_t board_slot, int32_t rank,
+                              int32_t world, uint64_t seq, uint64_t need_consumed, int32_t mode,
+                              int32_t ctas, void* d_local_counter, uint64_t done_target,
+                              void* d_total_out, void* stream) {
+  if (world < 1 || world > GDV_BOARD_MAX_WORLD || rank < 0 || rank >= world || board == nullptr ||
+      d_count == nullptr || board_slot < 0 || board_slot >= GDV_BOARD_SLOTS)
+    return Fail(GDV_INVALID, "gdv_selection_push: bad arguments");
+  const int sel = mode & ~GDV_SEL_BOUNDED;
+  const int elem = sel == GDV_SEL_UINT16 ? 2 : sel == GDV_SEL_UINT32 ? 4 : sel == GDV_SEL_UINT64 ? 8 : 0;
+  if (elem == 0) return Fail(GDV_INVALID, "gdv_selection_push: invalid selection vector mode");
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  CUfunction fn = nullptr;
+  s = dev->StaticFunction("gdv_sel_push", &fn);
+  if (!s.ok()) return Fail(s);
+  CUstream st = stream != nullptr ? static_cast<CUstream>(stream) : dev->stream();
+  uint64_t* b = static_cast<uint64_t*>(board);
+  uint64_t* b_count = b + static_cast<size_t>(board_slot) * GDV_BOARD_MAX_WORLD;
+  uint64_t* b_done = b + static_cast<size_t>(GDV_BOARD_SLOTS + board_slot) * GDV_BOARD_MAX_WORLD;
+  uint64_t* b_cons = b + static_cast<size_t>(2 * GDV_BOARD_SLOTS) * GDV_BOARD_MAX_WORLD + board_slot;
+  uint64_t* b_err = b + static_cast<size_t>(2 * GDV_BOARD_SLOTS) * GDV_BOARD_MAX_WORLD + GDV_BOARD_SLOTS;
+  int elem_bytes = elem;
+  void* params[] = {&d_src, &d_count, &d_dst, &dst_capacity, &b_count, &b_done, &b_cons, &b_err,
+                    &rank, &world, &seq, &need_consumed, &elem_bytes, &d_local_counter, &done_target,
+                    &d_total_out};
+  const unsigned grid = rank == 0 ? 1u : static_cast<unsigned>(std::max(1, ctas));
+  const unsigned threads = rank == 0 ? 32u : 1024u;
+  g_launch_count.fetch_add(1);
+  s = CuCheck(Driver().LaunchKernel(fn, grid, 1, 1, threads, 1, 1, 0, st, params, nullptr),
+              "cuLaunchKernel(gdv_sel_push)");
+  return s.ok() ? GDV_OK : Fail(s);
+}
+
+gdv_status gdv_selection_release(int32_t device, void* board, int32_t board_slot, uint64_t seq,
+                                 void* stream) {
+  if (board == nullptr || board_slot < 0 || board_slot >= GDV_BOARD_SLOTS)
+    return Fail(GDV_INVALID, "gdv_selection_release: bad arguments");
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  CUfunction fn = nullptr;
+  s = dev->StaticFunction("gdv_sel_release", &fn);
+  if (!s.ok()) return Fail(s);
+  CUstream st = stream != nullptr ? static_cast<CUstream>(stream) : dev->stream();
+  uint64_t* b_cons = static_cast<uint64_t*>(board) +
+                     static_cast<size_t>(2 * GDV_BOARD_SLOTS) * GDV_BOARD_MAX_WORLD + board_slot;
+  void* params[] = {&b_cons, &seq};
+  g_launch_count.fetch_add(1);
+  s = CuCheck(Driver().LaunchKernel(fn, 1, 1, 1, 32, 1, 1, 0, st, params, nullptr),
+              "cuLaunchKernel(gdv_sel_release)");
+  return s.ok() ? GDV_OK : Fail(s);
+}
+
 int64_t gdv_launch_count(void) { return g_launch_count.load(); }
 
 }  // extern "C"

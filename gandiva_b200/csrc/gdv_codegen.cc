@@ -149,7 +149,7 @@ Status ValidateExpression(const Schema& schema, const Expression& expr) {
 // ======================================================================================
 ArgsLayout::ArgsLayout(int n_inputs, int n_outputs)
     : ni(std::max(n_inputs, 1)), no(std::max(n_outputs, 1)) {
-  size_t o = 64;
+  size_t o = 72;
   off_in_val = o; o += 8u * ni;
   off_in_vld = o; o += 8u * ni;
   off_in_var = o; o += 8u * ni;
@@ -616,6 +616,7 @@ std::string EmitArgsStruct(const ArgsLayout& L) {
     << "  u64* tile_state;  // filter: look-back descriptors, one per CTA tile\n"
     << "  u64* ticket;      // filter: dynamic tile counter\n"
     << "  int* err;         // first ExecutionError code raised by a device function\n"
+    << "  i64 out_cap;      // filter: capacity of out_idx; selected rows past it are counted, not stored\n"
     << "  const void* in_val[" << L.ni << "];\n"
     << "  const u8* in_vld[" << L.ni << "];\n"
     << "  const u8* in_var[" << L.ni << "];\n"
@@ -1142,9 +1143,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "      for (int k = 0; k < 32; ++k) {\n";
     src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
     src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
-    src += "        if ((m >> lane) & 1u)\n";
-    src += "          out_idx[wpos + (u64)off + (u64)__popc(m & lt)] = (" + IDX +
-           ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
+    src += "        const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
+    src += "        if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
+    src += "          out_idx[pos] = (" + IDX + ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
     src += "      }\n";
     src += "    }\n";
     src += "  }\n";

@@ -63,7 +63,13 @@ void LoadDriver() {
                 &d.OccupancyMaxActiveBlocksPerMultiprocessor, &e) &&
             Sym(h, "cuLaunchKernel", &d.LaunchKernel, &e) &&
             Sym(h, "cuGetErrorString", &d.GetErrorString, &e) &&
-            Sym(h, "cuPointerGetAttribute", &d.PointerGetAttribute, &e);
+            Sym(h, "cuPointerGetAttribute", &d.PointerGetAttribute, &e) &&
+            Sym(h, "cuCtxEnablePeerAccess", &d.CtxEnablePeerAccess, &e) &&
+            Sym(h, "cuDeviceCanAccessPeer", &d.DeviceCanAccessPeer, &e) &&
+            Sym(h, "cuIpcGetMemHandle", &d.IpcGetMemHandle, &e) &&
+            Sym(h, "cuIpcOpenMemHandle_v2", &d.IpcOpenMemHandle, &e) &&
+            Sym(h, "cuIpcCloseMemHandle", &d.IpcCloseMemHandle, &e) &&
+            Sym(h, "cuMemGetAddressRange_v2", &d.MemGetAddressRange, &e);
   if (!ok) {
     d.load_error = "libcuda.so.1: " + e;
     return;

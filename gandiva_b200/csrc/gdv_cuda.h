@@ -50,6 +50,12 @@ struct DriverApi {
                            unsigned, CUstream, void**, void**);
   CUresult (*GetErrorString)(CUresult, const char**);
   CUresult (*PointerGetAttribute)(void*, CUpointer_attribute, CUdeviceptr);
+  CUresult (*CtxEnablePeerAccess)(CUcontext, unsigned int);
+  CUresult (*DeviceCanAccessPeer)(int*, CUdevice, CUdevice);
+  CUresult (*IpcGetMemHandle)(CUipcMemHandle*, CUdeviceptr);
+  CUresult (*IpcOpenMemHandle)(CUdeviceptr*, CUipcMemHandle, unsigned int);
+  CUresult (*IpcCloseMemHandle)(CUdeviceptr);
+  CUresult (*MemGetAddressRange)(CUdeviceptr*, size_t*, CUdeviceptr);
 };
 // Loads libcuda.so.1 and calls cuInit(0) once.  Returns nullptr-safe struct; check .loaded.
 const DriverApi& Driver();

@@ -617,9 +617,16 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   if (batch->num_columns != static_cast<int>(schema_->fields().size()))
     return Status::Make(GDV_INVALID, "RecordBatch schema must match the schema of Make()");
   if (batch->num_rows <= 0) return Status::Make(GDV_INVALID, "RecordBatch must be non-empty.");
-  if (out_sel->mode < GDV_SEL_UINT16 || out_sel->mode > GDV_SEL_UINT64)
+  // GDV_SEL_BOUNDED: the caller sized the index buffer for the rows it expects to be selected
+  // (row-range shards writing into a shared SelectionVector); rows past max_slots are counted
+  // but not stored, so count > max_slots tells the caller that the vector overflowed.
+  const bool bounded = (out_sel->mode & GDV_SEL_BOUNDED) != 0;
+  const int sel_mode = out_sel->mode & ~GDV_SEL_BOUNDED;
+  if (sel_mode < GDV_SEL_UINT16 || sel_mode > GDV_SEL_UINT64)
     return Status::Make(GDV_INVALID, "invalid selection vector mode");
-  if (out_sel->max_slots < batch->num_rows)
+  if (bounded && (batch->mem_space != GDV_MEM_DEVICE || out_sel->max_slots < 0))
+    return Status::Make(GDV_INVALID, "a bounded selection vector needs device buffers");
+  if (!bounded && out_sel->max_slots < batch->num_rows)
     return Status::Make(GDV_INVALID, "Selection vector max_slots " +
                                          std::to_string(out_sel->max_slots) +
                                          " is less than the number of rows " +
@@ -627,9 +634,9 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   if (out_sel->mem_space != batch->mem_space)
     return Status::Make(GDV_INVALID, "selection vector and batch must share a memory space");
   const int64_t n = batch->num_rows;
-  if (out_sel->mode == GDV_SEL_UINT16 && n > 65536)
+  if (sel_mode == GDV_SEL_UINT16 && n > 65536)
     return Status::Make(GDV_INVALID, "batch too large for a uint16 selection vector");
-  if (out_sel->mode == GDV_SEL_UINT32 && n > (int64_t(1) << 32))
+  if (sel_mode == GDV_SEL_UINT32 && n > (int64_t(1) << 32))
     return Status::Make(GDV_INVALID, "batch too large for a uint32 selection vector");
   const bool host = batch->mem_space == GDV_MEM_HOST;
 
@@ -640,7 +647,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   CompiledKernel* kernel = nullptr;
   const bool large = batch->num_rows >= (int64_t(32) << 20);
   GDV_RETURN_NOT_OK(
-      KernelFor(out_sel->mode, AnyValidity(general->gen, batch), large, &kernel));
+      KernelFor(sel_mode, AnyValidity(general->gen, batch), large, &kernel));
   last_used_ = kernel;
   CompiledKernel::Loaded l;
   GDV_RETURN_NOT_OK(kernel->Load(dev, &l));
@@ -688,7 +695,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   }
 
   CUdeviceptr d_idx = reinterpret_cast<CUdeviceptr>(out_sel->indices);
-  const int iw = SelWidth(out_sel->mode);
+  const int iw = SelWidth(sel_mode);
   if (host) GDV_RETURN_NOT_OK(scratch.Alloc(static_cast<size_t>(n) * iw + 16, &d_idx));
 
   ArgsLayout L(static_cast<int>(gen.inputs.size()), 0);
@@ -700,6 +707,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   Put<CUdeviceptr>(args, L.off_tile_state, d_state + 16);
   Put<CUdeviceptr>(args, L.off_ticket, d_state);
   Put<CUdeviceptr>(args, L.off_err, d_err);
+  Put<int64_t>(args, L.off_out_cap, bounded ? out_sel->max_slots : n);
   for (size_t j = 0; j < ins.size(); ++j) {
     Put<CUdeviceptr>(args, L.off_in_val + 8 * j, ins[j].val);
     Put<CUdeviceptr>(args, L.off_in_vld + 8 * j, ins[j].vld);

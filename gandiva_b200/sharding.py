@@ -115,3 +115,135 @@ class PeerGather:
             dist.all_reduce(flag, group=self.cpu_group)   # acts as the barrier
             self._pending = False
         return self.buf[: self.total] if self.rank == self.dst else None
+
+
+class PeerSelection:
+    """SelectionVector reassembly with no host in the loop (C-ABI `gdv_selection_push`).
+
+    Rank 0 (the root) owns a ring of `slots` SelectionVector buffers and a small "board" of
+    64-bit words; both are mapped into every other rank through CUDA IPC (`gdv_ipc_export` /
+    `gdv_ipc_open`: opened with the rank's own device current, which also enables NVLink peer
+    access to the root GPU).  Per step:
+
+      * every rank runs its Filter on its row range (`index_base` = first row).  The root writes
+        straight into the step's vector (its run starts at offset 0, bounded by the vector's
+        capacity: GDV_SEL_BOUNDED); the other ranks write a local run;
+      * on a side stream, ordered after the filter kernel by an event, `gdv_selection_push`
+        publishes the rank's count on the board, reads the lower ranks' counts from it and stores
+        the run at its final offset in the root's vector over NVLink.  The filter is built with
+        `sm_reserve` so this copy kernel finds free SMs while the NEXT batch's filter kernel runs;
+      * the root's push call waits (on the device) for every rank's `done` word and writes the
+        total count next to the vector.
+
+    Nothing is synchronised through the host; `torch.distributed` (gloo) is used once, at
+    construction, to hand the IPC handles around."""
+
+    def __init__(self, capacity: int, local_rows: int, mode: str, device: torch.device,
+                 slots: int = 2, ctas: int = 8, root: int = 0):
+        import ctypes as C
+        import gandiva_b200 as gandiva
+        assert root == 0, "the root is rank 0 (its run has offset 0 and is written in place)"
+        self.g = gandiva
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        assert self.world <= gandiva.GDV_BOARD_MAX_WORLD and 1 <= slots <= gandiva.GDV_BOARD_SLOTS
+        self.device, self.slots, self.ctas = device, slots, ctas
+        self.mode = mode
+        self.dtype = {"UINT16": torch.int16, "UINT32": torch.int32, "UINT64": torch.int64}[mode]
+        self.capacity = int(capacity)
+        self.cpu_group = dist.new_group(backend="gloo")
+        payload = [None]
+        self._opened = []
+        if self.rank == 0:
+            self.vectors = [torch.empty(self.capacity, dtype=self.dtype, device=device) for _ in range(slots)]
+            self.board = torch.zeros(gandiva.GDV_BOARD_BYTES // 8, dtype=torch.int64, device=device)
+            torch.cuda.synchronize(device)
+            handles = []
+            for t in self.vectors + [self.board]:
+                h = C.create_string_buffer(64)
+                off = C.c_int64()
+                gandiva._check(gandiva.lib.gdv_ipc_export(device.index, t.data_ptr(), h, C.byref(off)))
+                handles.append((h.raw, off.value))
+            payload = [handles]
+            self.vector_ptrs = [t.data_ptr() for t in self.vectors]
+            self.board_ptr = self.board.data_ptr()
+        dist.broadcast_object_list(payload, src=0, group=self.cpu_group)
+        if self.rank != 0:
+            ptrs = []
+            seen = {}
+            for raw, off in payload[0]:   # several tensors may live in one exported allocation
+                if raw not in seen:
+                    p = C.c_void_p()
+                    gandiva._check(gandiva.lib.gdv_ipc_open(device.index, raw, 0, C.byref(p)))
+                    seen[raw] = p.value
+                    self._opened.append(p.value)
+                ptrs.append(seen[raw] + off)
+            self.vector_ptrs, self.board_ptr = ptrs[:-1], ptrs[-1]
+            self.local = [torch.empty(local_rows, dtype=self.dtype, device=device) for _ in range(slots)]
+        self.counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(slots)]
+        self.totals = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(slots)]
+        self.local_ctr = torch.zeros(1, dtype=torch.int64, device=device)
+        self.side = torch.cuda.Stream(device)
+        self.ev_filter = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_pushed = [torch.cuda.Event() for _ in range(slots)]
+        self.local_rows = int(local_rows)
+        self.ctas_issued = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.cpu_group)
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.cpu_group)
+        for p in self._opened:
+            self.g.lib.gdv_ipc_close(self.device.index, p, 0)
+        self._opened = []
+        dist.barrier(group=self.cpu_group)
+
+    def filter_target(self, step: int):
+        """(device pointer, max_slots, mode string, count pointer) for this step's Filter call."""
+        b = step % self.slots
+        if self.rank == 0:
+            return self.vector_ptrs[b], self.capacity, self.mode + "|BOUNDED", self.counts[b].data_ptr()
+        return self.local[b].data_ptr(), self.local_rows, self.mode, self.counts[b].data_ptr()
+
+    def before_filter(self, step: int, stream: torch.cuda.Stream) -> None:
+        """The step's buffers are free again once the push that last used them has finished."""
+        if step >= self.slots:
+            stream.wait_event(self.ev_pushed[step % self.slots])
+
+    def after_filter(self, step: int, stream: torch.cuda.Stream, ctas: int = 0) -> None:
+        """Enqueue the push of this step's run (and, on the root, the wait for all runs).
+        `ctas` overrides the copy kernel's grid for this call (e.g. the whole GPU for the last
+        step of a job, when no filter kernel follows)."""
+        g, b, seq = self.g, step % self.slots, step + 1
+        ctas = ctas or self.ctas
+        self.ctas_issued += ctas
+        self.ev_filter[b].record(stream)
+        self.side.wait_event(self.ev_filter[b])
+        need = seq - self.slots if (self.rank != 0 and seq > self.slots) else 0
+        src = self.vector_ptrs[b] if self.rank == 0 else self.local[b].data_ptr()
+        g._check(g.lib.gdv_selection_push(
+            self.device.index, src, self.counts[b].data_ptr(), self.vector_ptrs[b], self.capacity,
+            self.board_ptr, b, self.rank, self.world, seq, need, g._SEL_MODE[self.mode], ctas,
+            self.local_ctr.data_ptr(), self.ctas_issued, self.totals[b].data_ptr(),
+            g._stream_handle(self.side.cuda_stream)))
+        if self.rank == 0:
+            # bench / tests have no consumer: the vector is released as soon as it is complete
+            g._check(g.lib.gdv_selection_release(self.device.index, self.board_ptr, b, seq,
+                                                 g._stream_handle(self.side.cuda_stream)))
+        self.ev_pushed[b].record(self.side)
+
+    def finish(self, stream: torch.cuda.Stream) -> None:
+        """Make `stream` wait for every push issued so far."""
+        for e in self.ev_pushed:
+            stream.wait_event(e)
+
+    def result(self, step: int):
+        """Root only, after synchronisation: (vector, total) of `step`."""
+        b = step % self.slots
+        total = int(self.totals[b].item())
+        return self.vectors[b][:min(total, self.capacity)], total
+
+    def overflowed(self) -> bool:
+        """Root only: some step's runs did not fit the vector's capacity."""
+        g = self.g
+        return bool(self.board[2 * g.GDV_BOARD_SLOTS * g.GDV_BOARD_MAX_WORLD + g.GDV_BOARD_SLOTS].item() != 0)

@@ -115,6 +115,11 @@ void gdv_config_default(gdv_config_t* cfg);
 #define GDV_SEL_UINT16 1
 #define GDV_SEL_UINT32 2
 #define GDV_SEL_UINT64 3
+/* OR'ed into gdv_selection_t.mode for Filter evaluation with device buffers: max_slots may be
+ * smaller than num_rows; selected rows past max_slots are counted but not stored (the caller
+ * detects overflow by num_slots > max_slots).  Used by row-range shards that write into one
+ * shared SelectionVector. */
+#define GDV_SEL_BOUNDED 0x100
 
 /* ---- memory spaces of the buffers handed to Evaluate ------------------- */
 #define GDV_MEM_HOST 0   /* pageable or pinned host memory: engine stages H2D/D2H */
@@ -271,6 +276,48 @@ gdv_status gdv_host_free(void* p);
 gdv_status gdv_generate_lineitem(int32_t device, int32_t column_kind, uint64_t seed,
                                  int64_t first_row, int64_t num_rows, void* d_values,
                                  void* d_validity, int32_t null_permille, void* stream);
+/* ---- SelectionVector reassembly across row-range shards (one process per GPU) -----------
+ * Replaces nothing in the reference (it is single-node CPU); BASELINE.json north_star asks for
+ * "row-range-shards a batch across the 8 GPUs of one box, with an optional ... gather over
+ * NVLink to reassemble the SelectionVector".  Each rank filters its row range with
+ * gdv_filter_evaluate (index_base = first row of the range) into a local run, then calls
+ * gdv_selection_push on a side stream: the kernel reads the lower ranks' counts from the board,
+ * and stores the run at its final offset of the root's vector `d_dst` (peer-mapped memory of the
+ * root GPU, e.g. through CUDA IPC) over NVLink.  No host round trip, no collective library.
+ *  board       : GDV_BOARD_BYTES of zero-initialised memory on the root GPU, mapped by every rank
+ *  board_slot  : which of the GDV_BOARD_SLOTS in-flight steps this is (step % slots)
+ *  seq         : step number + 1 (strictly increasing; board words are never reset)
+ *  need_consumed: 0, or the seq the root must have released for this slot before d_dst is
+ *                overwritten (seq - GDV_BOARD_SLOTS in a ring of buffers)
+ *  rank 0 (root): its filter wrote straight into d_dst (offset 0); the call waits on the device
+ *                for every rank's run and writes the total to d_total_out (device uint64).
+ *  ctas        : CTAs of the copy kernel on non-root ranks (leave that many SMs free with
+ *                gdv_config_t.sm_reserve so it overlaps the next batch's filter kernel)
+ *  d_local_counter: zero-initialised device uint64 owned by the calling rank; every CTA of every
+ *                push adds one to it.  done_target: the value it reaches when this call's last
+ *                CTA has finished (= sum of `ctas` over all pushes issued so far, this one
+ *                included), so `ctas` may differ from call to call. */
+/* Lets kernels running on `device` dereference memory of `peer_device` (cuCtxEnablePeerAccess);
+ * required once per process before gdv_selection_push stores into the root's vector. */
+gdv_status gdv_enable_peer_access(int32_t device, int32_t peer_device);
+/* CUDA IPC plumbing for the above (one process per GPU).  The root exports the allocation that
+ * holds `d_ptr` (64-byte handle + byte offset of d_ptr inside it); every other rank opens it with
+ * its own device current: the memory is mapped into that device's address space with NVLink peer
+ * access to the root GPU enabled (CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS). */
+gdv_status gdv_ipc_export(int32_t device, const void* d_ptr, uint8_t* handle64, int64_t* offset);
+gdv_status gdv_ipc_open(int32_t device, const uint8_t* handle64, int64_t offset, void** out_ptr);
+gdv_status gdv_ipc_close(int32_t device, void* d_ptr, int64_t offset);
+#define GDV_BOARD_MAX_WORLD 16
+#define GDV_BOARD_SLOTS 4
+#define GDV_BOARD_BYTES ((2 * GDV_BOARD_SLOTS * GDV_BOARD_MAX_WORLD + GDV_BOARD_SLOTS + 1) * 8)
+gdv_status gdv_selection_push(int32_t device, const void* d_src, const void* d_count, void* d_dst,
+                              int64_t dst_capacity, void* board, int32_t board_slot, int32_t rank,
+                              int32_t world, uint64_t seq, uint64_t need_consumed, int32_t mode,
+                              int32_t ctas, void* d_local_counter, uint64_t done_target,
+                              void* d_total_out, void* stream);
+/* root: marks slot `board_slot`'s vector of step `seq` as consumed (its buffer may be reused). */
+gdv_status gdv_selection_release(int32_t device, void* board, int32_t board_slot, uint64_t seq,
+                                 void* stream);
 /* Number of kernels this library has launched since load (gpu_launches in bench.py). */
 int64_t gdv_launch_count(void);
 

@@ -294,3 +294,49 @@ def test_device_resident_projector(gandiva, oracle):
 
 def test_kernels_were_launched(gandiva):
     assert gandiva.launch_count() > 0
+
+
+def test_filter_bounded_selection_vector(gandiva, oracle):
+    """GDV_SEL_BOUNDED: capacity smaller than the number of selected rows -> the count is still
+    exact, the first max_slots indices are stored, nothing is written past the capacity."""
+    import torch
+    n = 1_000_003
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ship = torch.empty(n, dtype=torch.int32, device=dev)
+    disc = torch.empty(n, dtype=torch.float64, device=dev)
+    qty = torch.empty(n, dtype=torch.float64, device=dev)
+    for kind, t in ((0, ship), (1, disc), (2, qty)):
+        gandiva.generate_lineitem(0, kind, 42, 0, n, t.data_ptr(), 0, 0, st)
+    b = gandiva.TreeExprBuilder()
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)))
+    want = oracle.filter_indices(cases.q6_condition(b), cases.q6_batch(n, seed=42), threads=4)
+    cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
+    for cap in (len(want) + 100, len(want) // 2, 7):
+        out = torch.full((cap + 64,), -1, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        f.evaluate_device(n, cols, out.data_ptr(), cap, "UINT64|BOUNDED", st, cnt.data_ptr(), index_base=5)
+        count = f.sync(st)
+        assert count == len(want)
+        k = min(cap, count)
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:k].astype(np.uint64), want[:k] + 5)
+        assert (got[max(cap, k):] == -1).all()
+    with pytest.raises(pa.ArrowInvalid):   # without the flag the reference rule holds
+        f.evaluate_device(n, cols, out.data_ptr(), 7, "UINT64", st, cnt.data_ptr())
+
+
+def test_peer_selection_push(gandiva):
+    """Multi-GPU reassembly of the SelectionVector (needs >= 2 GPUs on the box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "peer_push_worker.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "PEER_PUSH_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
