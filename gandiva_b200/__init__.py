@@ -66,7 +66,7 @@ class gdv_config_t(C.Structure):
     _fields_ = [("optimize", C.c_int32), ("dump_ir", C.c_int32), ("device", C.c_int32),
                 ("rows_per_thread", C.c_int32), ("block_threads", C.c_int32),
                 ("loader", C.c_int32), ("sm_reserve", C.c_int32), ("stages", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("string_scan", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class gdv_column_t(C.Structure):
@@ -459,8 +459,9 @@ class Configuration:
 
     def __init__(self, optimize: bool = True, dump_ir: bool = False, device: int = 0,
                  rows_per_thread: int = 0, block_threads: int = 0, loader: int = 0,
-                 sm_reserve: int = 0, stages: int = 0):
+                 sm_reserve: int = 0, stages: int = 0, string_scan: int = 0):
         self.stages = int(stages)
+        self.string_scan = int(string_scan)
         self.optimize = bool(optimize)
         self.dump_ir = bool(dump_ir)
         self.device = int(device)
@@ -480,6 +481,7 @@ class Configuration:
         c.loader = self.loader
         c.sm_reserve = self.sm_reserve
         c.stages = self.stages
+        c.string_scan = self.string_scan
         return c
 
 

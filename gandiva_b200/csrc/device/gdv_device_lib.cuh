@@ -40,7 +40,11 @@ GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
 
 // ---- strings: a view on Arrow bytes plus a lazy ASCII case map ------------------------
 // upper()/lower()/substr()/trim() never materialise: they return a view, and consumers read
-// bytes through gdv_ch().  xf: 0 = as stored, 1 = upper-cased, 2 = lower-cased.
+// bytes through gdv_ch().  xf bits 0-1: 0 = as stored, 1 = upper-cased, 2 = lower-cased;
+// GDV_XF_ASCII: every stored byte of the row is known to be < 0x80 (set by the cooperative
+// scan of the staged bytes), so glyph positions are byte positions.
+#define GDV_XF_CASE 3u
+#define GDV_XF_ASCII 0x100u
 struct gdv_str {
   const u8* p;
   i32 len;
@@ -48,9 +52,10 @@ struct gdv_str {
 };
 GDV_DEV u8 gdv_ch(const gdv_str& s, i32 i) {
   u8 c = s.p[i];
-  if (s.xf == 1u) {
+  const u32 cm = s.xf & GDV_XF_CASE;
+  if (cm == 1u) {
     if (c >= (u8)'a' && c <= (u8)'z') c = (u8)(c - 32);
-  } else if (s.xf == 2u) {
+  } else if (cm == 2u) {
     if (c >= (u8)'A' && c <= (u8)'Z') c = (u8)(c + 32);
   }
   return c;
@@ -59,10 +64,11 @@ GDV_DEV u8 gdv_ch(const gdv_str& s, i32 i) {
 // the constant instead of transforming the text byte (2 instructions instead of 4).
 GDV_DEV bool gdv_ch_eq(const gdv_str& s, i32 i, u32 lit) {
   const u32 c = s.p[i];
-  if (s.xf == 1u) {
+  const u32 cm = s.xf & GDV_XF_CASE;
+  if (cm == 1u) {
     if (lit >= (u32)'a' && lit <= (u32)'z') return false;  // upper-cased text has no a-z
     if (lit >= (u32)'A' && lit <= (u32)'Z') return (c | 0x20u) == (lit | 0x20u);
-  } else if (s.xf == 2u) {
+  } else if (cm == 2u) {
     if (lit >= (u32)'A' && lit <= (u32)'Z') return false;
     if (lit >= (u32)'a' && lit <= (u32)'z') return (c | 0x20u) == lit;
   }
@@ -73,10 +79,11 @@ GDV_DEV bool gdv_ch_eq(const gdv_str& s, i32 i, u32 lit) {
 // address is word aligned (whole words only, so nothing past the string is read).
 GDV_DEV i32 gdv_find_byte(const gdv_str& s, i32 from, i32 limit, u32 lit) {
   bool fold = false;
-  if (s.xf == 1u) {
+  const u32 cm = s.xf & GDV_XF_CASE;
+  if (cm == 1u) {
     if (lit >= (u32)'a' && lit <= (u32)'z') return limit;
     if (lit >= (u32)'A' && lit <= (u32)'Z') { fold = true; lit |= 0x20u; }
-  } else if (s.xf == 2u) {
+  } else if (cm == 2u) {
     if (lit >= (u32)'A' && lit <= (u32)'Z') return limit;
     if (lit >= (u32)'a' && lit <= (u32)'z') fold = true;
   }
@@ -258,6 +265,21 @@ GDV_DEV u32 gdv_ldwin_s(const u32* p, u32 widx, u32 sh) {
   const u32 lo = p[widx];
   if (sh == 0u) return lo;
   return __funnelshift_r(lo, p[widx + 1], sh);
+}
+
+// Bytes of x equal to the matching byte of pat, as 0x80 in that byte.  A byte directly above a
+// true match can be flagged too (borrow of the subtraction): callers verify candidates.
+GDV_DEV u32 gdv_eqbytes_msb(u32 x, u32 pat) {
+  const u32 z = x ^ pat;
+  return (z - 0x01010101u) & ~z & 0x80808080u;
+}
+// Four per-word byte-hit masks (bit 7 of every hit byte) of one 16-byte chunk -> one bit per byte.
+GDV_DEV u32 gdv_mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
+  const u32 n0 = ((m0 & 0x80808080u) * 0x00204081u) >> 28;
+  const u32 n1 = ((m1 & 0x80808080u) * 0x00204081u) >> 28;
+  const u32 n2 = ((m2 & 0x80808080u) * 0x00204081u) >> 28;
+  const u32 n3 = ((m3 & 0x80808080u) * 0x00204081u) >> 28;
+  return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
 }
 
 GDV_DEV u32 gdv_lanemask_lt() {
@@ -772,11 +794,11 @@ GDV_DEV f64 castFLOAT8_decimal128(i128 x, i32 xp, i32 xs) {
 
 // ---- strings ---------------------------------------------------------------------------
 GDV_DEV gdv_str upper_utf8(gdv_str s) {
-  s.xf = 1u;
+  s.xf = (s.xf & ~GDV_XF_CASE) | 1u;
   return s;
 }
 GDV_DEV gdv_str lower_utf8(gdv_str s) {
-  s.xf = 2u;
+  s.xf = (s.xf & ~GDV_XF_CASE) | 2u;
   return s;
 }
 GDV_DEV i32 octet_length_utf8(gdv_str s) { return s.len; }
@@ -784,6 +806,7 @@ GDV_DEV i32 octet_length_binary(gdv_str s) { return s.len; }
 GDV_DEV i32 bit_length_utf8(gdv_str s) { return s.len * 8; }
 GDV_DEV i32 bit_length_binary(gdv_str s) { return s.len * 8; }
 GDV_DEV i32 char_length_utf8(gdv_str s) {
+  if ((s.xf & GDV_XF_ASCII) != 0u) return s.len;
   i32 n = 0;
   for (i32 i = 0; i < s.len; i += gdv_glyph_len(s.p[i])) ++n;
   return n;
@@ -797,6 +820,20 @@ GDV_DEV gdv_str substr_utf8_int64_int64(gdv_str s, i64 offset, i64 length) {
   }
   // from the first glyph and at least as many glyphs as bytes: the whole string, no scan
   if ((offset == 0 || offset == 1) && length >= (i64)s.len) return s;
+  // known-ASCII row: glyph positions are byte positions, pure arithmetic
+  if ((s.xf & GDV_XF_ASCII) != 0u) {
+    i64 from = 0;
+    if (offset > 0) from = offset - 1;
+    if (offset < 0) from = (i64)s.len + offset;
+    if (from < 0 || from >= (i64)s.len) {
+      r.len = 0;
+      return r;
+    }
+    const i64 rest = (i64)s.len - from;
+    r.p = s.p + from;
+    r.len = (i32)(length < rest ? length : rest);
+    return r;
+  }
   // ASCII prefix: glyph positions are byte positions
   if ((offset == 0 || offset == 1) && gdv_all_ascii(s.p, (i32)length)) {
     r.len = (i32)length;

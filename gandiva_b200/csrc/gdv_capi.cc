@@ -51,6 +51,7 @@ Config FromC(const gdv_config_t* c) {
     cfg.block_threads = c->block_threads;
     cfg.loader = c->loader;
     cfg.stages = c->stages;
+    cfg.string_scan = c->string_scan;
     cfg.sm_reserve = c->sm_reserve;
   }
   return cfg;

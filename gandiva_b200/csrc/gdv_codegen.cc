@@ -178,12 +178,24 @@ std::string HexLit(uint64_t bits) {
   return b;
 }
 
+// One '%'-delimited middle segment of a LIKE pattern that the cooperative scan of column `slot`
+// looks for: occurrences are recorded as (id << 24 | stage byte offset) in the warp's hit list.
+struct CoopSeg {
+  int slot = 0;
+  unsigned xf = 0;     // case map of the view the pattern is matched against
+  std::string bytes;
+  int id = 0;          // unique per slot
+  int rare = 0;        // index of the byte the scan compares (the rarest of the segment)
+};
+constexpr int kHitCap = 64;  // hits per warp and group; more -> the group falls back per lane
+
 class BodyGen {
  public:
-  BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots, bool nullable)
-      : schema_(schema), slots_(slots), nullable_(nullable) {}
+  BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots, bool nullable, bool coop)
+      : schema_(schema), slots_(slots), nullable_(nullable), coop_(coop) {}
 
   std::string& globals() { return globals_; }
+  const std::vector<CoopSeg>& coop_segs() const { return coop_segs_; }
   bool uses_ctx() const { return uses_ctx_; }
 
   // Emit the statements that evaluate `node` for the row held in slot arrays at [k].
@@ -352,20 +364,158 @@ class BodyGen {
   // bytes become immediates, the first segment is anchored at the start unless the pattern
   // begins with '%', the last at the end unless it ends with '%', the ones in between are
   // found leftmost-first.  Returns the name of the emitted device function.
-  std::string LikeSpecialised(const std::vector<unsigned>& toks) {
-    std::vector<std::string> segs;
+  static void LikeSegments(const std::vector<unsigned>& toks, std::vector<std::string>* segs,
+                           bool* lead_any, bool* trail_any) {
     std::string cur;
-    bool lead_any = !toks.empty() && (toks.front() >> 8) == 2u;
-    bool trail_any = !toks.empty() && (toks.back() >> 8) == 2u;
+    *lead_any = !toks.empty() && (toks.front() >> 8) == 2u;
+    *trail_any = !toks.empty() && (toks.back() >> 8) == 2u;
     for (unsigned t : toks) {
       if ((t >> 8) == 2u) {
-        if (!cur.empty()) segs.push_back(cur);
+        if (!cur.empty()) segs->push_back(cur);
         cur.clear();
       } else {
         cur.push_back(static_cast<char>(t & 0xffu));
       }
     }
-    if (!cur.empty()) segs.push_back(cur);
+    if (!cur.empty()) segs->push_back(cur);
+  }
+
+  // A "view chain": upper/lower/substr/trim applied (in any order) to a string column.  The
+  // result is a sub-range of the row's stored bytes under a statically known ASCII case map,
+  // which is what the cooperative LIKE scan needs.
+  bool ViewChain(const Node& node, int* slot, unsigned* xf) {
+    if (node.kind() == NodeKind::kField) {
+      if (!node.return_type().is_varlen()) return false;
+      *slot = SlotFor(static_cast<const FieldNode&>(node));
+      *xf = 0u;
+      return true;
+    }
+    if (node.kind() != NodeKind::kFunction) return false;
+    const auto& fn = static_cast<const FunctionNode&>(node);
+    const std::string& n = fn.name();
+    const bool is_case = n == "upper" || n == "lower";
+    const bool is_view = n == "substr" || n == "substring" || n == "ltrim" || n == "rtrim" ||
+                         n == "btrim" || n == "trim";
+    if (!is_case && !is_view) return false;
+    if (fn.children().empty() || !fn.children()[0]->return_type().is_varlen()) return false;
+    if (!ViewChain(*fn.children()[0], slot, xf)) return false;
+    if (n == "upper") *xf = 1u;
+    if (n == "lower") *xf = 2u;
+    return true;
+  }
+
+  // Static byte-rarity score (English text; lower = rarer) used to pick the byte of a segment
+  // the cooperative scan looks for.
+  static double ByteScore(unsigned char c, unsigned xf) {
+    static const double letter[26] = {8.2, 1.5, 2.8, 4.3, 12.7, 2.2, 2.0, 6.1, 7.0, 0.15, 0.77,
+                                      4.0, 2.4, 6.7, 7.5, 1.9, 0.095, 6.0, 6.3, 9.1, 2.8, 0.98,
+                                      2.4, 0.15, 2.0, 0.074};
+    if (c >= 'a' && c <= 'z') return letter[c - 'a'];
+    if (c >= 'A' && c <= 'Z') return xf != 0u ? letter[c - 'A'] : letter[c - 'A'] * 0.05;
+    if (c == ' ') return 15.0;
+    if (c >= 0x80) return 0.3;
+    if (c >= '0' && c <= '9') return 1.0;
+    return 0.5;
+  }
+
+  static bool FoldedLetter(unsigned char c, unsigned xf) {
+    return (xf == 1u && c >= 'A' && c <= 'Z') || (xf == 2u && c >= 'a' && c <= 'z');
+  }
+
+  // `stage[at + i] == seg[i]` under case map xf, as a C expression on raw staged bytes.
+  static std::string StageByteEq(const std::string& stage, const std::string& at, int i,
+                                 unsigned char lit, unsigned xf) {
+    const std::string ld = "(u32)" + stage + "[" + at + " + " + std::to_string(i) + "]";
+    if (FoldedLetter(lit, xf))
+      return "((" + ld + " | 0x20u) == " + std::to_string(static_cast<unsigned>(lit | 0x20u)) + "u)";
+    return "(" + ld + " == " + std::to_string(static_cast<unsigned>(lit)) + "u)";
+  }
+
+  // LIKE over a view chain of column `slot` whose '%'-separated middle segments are all >= 3
+  // bytes: the warp scans the staged bytes of a whole group for segment occurrences once
+  // (EmitGroup, "cooperative scan") and leaves the verified hits in shared memory; this emits the
+  // per-row function that chains those hits leftmost-first inside the row's view instead of
+  // walking the row's bytes.  Returns "" when the pattern does not qualify.
+  std::string LikeFromHits(const std::vector<unsigned>& toks, int slot, unsigned xf) {
+    std::vector<std::string> segs;
+    bool lead_any, trail_any;
+    LikeSegments(toks, &segs, &lead_any, &trail_any);
+    size_t first_mid = lead_any ? 0 : 1;
+    size_t last_mid = trail_any ? segs.size() : (segs.empty() ? 0 : segs.size() - 1);
+    if (segs.empty() || first_mid >= last_mid) return "";
+    size_t total = 0;
+    for (const auto& sg : segs) {
+      total += sg.size();
+      for (unsigned char c : sg) {
+        // a literal the case map can never produce: the per-lane matcher already answers false
+        if ((xf == 1u && c >= 'a' && c <= 'z') || (xf == 2u && c >= 'A' && c <= 'Z')) return "";
+      }
+    }
+    for (size_t k = first_mid; k < last_mid; ++k)
+      if (segs[k].size() < 3) return "";
+    int n_slot_segs = 0;
+    for (const auto& cs : coop_segs_) n_slot_segs += cs.slot == slot ? 1 : 0;
+    if (n_slot_segs + static_cast<int>(last_mid - first_mid) > 8) return "";
+
+    const std::string name = NewVar("gdv_likeh_");
+    std::string f = "__device__ __forceinline__ bool " + name +
+                    "(const gdv_str& s, const u8* stage, const u32* hits, u32 nh) {\n";
+    f += "  if (s.len < " + std::to_string(total) + ") return false;\n";
+    f += "  i32 cur = (i32)(s.p - stage);\n";
+    f += "  i32 lim = cur + s.len;\n";
+    auto match_at = [&](const std::string& seg, const std::string& at) {
+      std::string e;
+      for (size_t i = 0; i < seg.size(); ++i)
+        e += (i ? " && " : "") + std::string("gdv_ch_eq(s, ") + at + " + " + std::to_string(i) + ", " +
+             std::to_string(static_cast<unsigned>(static_cast<unsigned char>(seg[i]))) + "u)";
+      return e;
+    };
+    if (!lead_any) {
+      f += "  if (!(" + match_at(segs[0], "0") + ")) return false;\n";
+      f += "  cur += " + std::to_string(segs[0].size()) + ";\n";
+    }
+    if (!trail_any) {
+      const std::string L = std::to_string(segs.back().size());
+      f += "  if (!(" + match_at(segs.back(), "(s.len - " + L + ")") + ")) return false;\n";
+      f += "  lim -= " + L + ";\n";
+    }
+    for (size_t k = first_mid; k < last_mid; ++k) {
+      CoopSeg cs;
+      cs.slot = slot;
+      cs.xf = xf;
+      cs.bytes = segs[k];
+      cs.id = -1;
+      for (const auto& o : coop_segs_)
+        if (o.slot == slot && o.xf == xf && o.bytes == segs[k]) cs.id = o.id;
+      if (cs.id < 0) {
+        cs.id = n_slot_segs++;
+        cs.rare = 0;
+        for (size_t i = 1; i < cs.bytes.size(); ++i)
+          if (ByteScore(static_cast<unsigned char>(cs.bytes[i]), xf) <
+              ByteScore(static_cast<unsigned char>(cs.bytes[cs.rare]), xf))
+            cs.rare = static_cast<int>(i);
+        coop_segs_.push_back(cs);
+      }
+      const std::string L = std::to_string(segs[k].size());
+      f += "  {\n    i32 best = 0x7fffffff;\n";
+      f += "    for (u32 h = 0u; h < nh; ++h) {\n";
+      f += "      const u32 e = hits[h];\n";
+      f += "      const i32 p = (i32)(e & 0xffffffu);\n";
+      f += "      if ((e >> 24) == " + std::to_string(cs.id) + "u && p >= cur && p + " + L +
+           " <= lim && p < best) best = p;\n";
+      f += "    }\n";
+      f += "    if (best == 0x7fffffff) return false;\n";
+      f += "    cur = best + " + L + ";\n  }\n";
+    }
+    f += "  return true;\n}\n";
+    globals_ += f;
+    return name;
+  }
+
+  std::string LikeSpecialised(const std::vector<unsigned>& toks) {
+    std::vector<std::string> segs;
+    bool lead_any, trail_any;
+    LikeSegments(toks, &segs, &lead_any, &trail_any);
     const std::string name = NewVar("gdv_like_");
     std::string f = "__device__ __forceinline__ bool " + name + "(const gdv_str& s) {\n";
     f += "  const i32 n = s.len;\n";
@@ -436,7 +586,17 @@ class BodyGen {
       const std::string v = NewVar("v");
       if (!has_one) {
         const std::string fn_name = LikeSpecialised(toks);
-        *out += Ind(indent) + "const bool " + v + " = " + fn_name + "(" + s.v + ");\n";
+        int slot = -1;
+        unsigned xf = 0u;
+        std::string hits_fn;
+        if (coop_ && ViewChain(*fn.children()[0], &slot, &xf)) hits_fn = LikeFromHits(toks, slot, xf);
+        if (!hits_fn.empty()) {
+          const std::string J = std::to_string(slot);
+          *out += Ind(indent) + "const bool " + v + " = coop" + J + " ? " + hits_fn + "(" + s.v +
+                  ", stage" + J + ", hits" + J + ", nh" + J + ") : " + fn_name + "(" + s.v + ");\n";
+        } else {
+          *out += Ind(indent) + "const bool " + v + " = " + fn_name + "(" + s.v + ");\n";
+        }
       } else {
         const std::string arr = LikePatternTable(toks);
         *out += Ind(indent) + "const bool " + v + " = gdv_like_match(" + s.v + ", " + arr + ", " +
@@ -600,6 +760,8 @@ class BodyGen {
   const Schema& schema_;
   std::vector<ColumnSlot>* slots_;
   bool nullable_;
+  bool coop_;
+  std::vector<CoopSeg> coop_segs_;
   std::string globals_;
   int next_id_ = 0;
   bool uses_ctx_ = false;
@@ -675,9 +837,95 @@ void EmitPrologue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, 
 // group in range, direct global loads, kStaged = whole CTA tile already in shared memory (TMA).
 enum GroupMode { kPred = 0, kFast = 1, kStaged = 2 };
 
+// Cooperative scan of the staged bytes of column J for the LIKE segments registered on it
+// (BodyGen::LikeFromHits).  Every lane takes 16-byte chunks of the group's byte run, compares all
+// 16 bytes against each segment's rarest byte with four word-wide zero-byte tests, and only on a
+// candidate verifies the whole segment and appends (id << 24 | stage offset) to the warp's hit
+// list.  More than kHitCap hits: the group falls back to the per-lane matcher.
+bool ScanFolds(const CoopSeg& cs, unsigned char c) {
+  return (cs.xf == 1u && c >= 'A' && c <= 'Z') || (cs.xf == 2u && c >= 'a' && c <= 'z');
+}
+
+std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, const std::string& I) {
+  const std::string J = std::to_string(j);
+  std::string o;
+  bool any_fold = false;
+  for (const auto& cs : segs)
+    if (cs.slot == j)
+      any_fold = any_fold || ScanFolds(cs, static_cast<unsigned char>(cs.bytes[cs.rare]));
+  o += I + "if (lane == 0u) hctr" + J + "[0] = 0u;\n";
+  o += I + "__syncwarp();\n";
+  o += I + "{\n";
+  o += I + "  const i32 lo = (i32)mis, hi = (i32)mis + gn;\n";
+  o += I + "  for (i32 c = (i32)lane; c < nchunks; c += 32) {\n";
+  o += I + "    const uint4 v = reinterpret_cast<const uint4*>(stage" + J + ")[c];\n";
+  if (any_fold)
+    o += I + "    const u32 x0 = v.x | 0x20202020u, x1 = v.y | 0x20202020u, x2 = v.z | 0x20202020u, "
+             "x3 = v.w | 0x20202020u;\n";
+  std::string any;
+  for (const auto& cs : segs) {
+    if (cs.slot != j) continue;
+    const std::string S = std::to_string(cs.id);
+    const unsigned char rb = static_cast<unsigned char>(cs.bytes[cs.rare]);
+    const bool fold = ScanFolds(cs, rb);
+    const unsigned b = fold ? (rb | 0x20u) : rb;
+    char pat[16];
+    std::snprintf(pat, sizeof(pat), "0x%08xu", b * 0x01010101u);
+    const char* w[4] = {fold ? "x0" : "v.x", fold ? "x1" : "v.y", fold ? "x2" : "v.z",
+                        fold ? "x3" : "v.w"};
+    for (int q = 0; q < 4; ++q) {
+      o += I + "    const u32 a" + S + "_" + std::to_string(q) + " = gdv_eqbytes_msb(" + w[q] + ", " + pat +
+           ");\n";
+      any += (any.empty() ? "" : " | ") + std::string("a") + S + "_" + std::to_string(q);
+    }
+  }
+  o += I + "    if ((" + any + ") != 0u) {\n";
+  for (const auto& cs : segs) {
+    if (cs.slot != j) continue;
+    const std::string S = std::to_string(cs.id);
+    const std::string L = std::to_string(cs.bytes.size());
+    std::string verify;
+    for (size_t i = 0; i < cs.bytes.size(); ++i) {
+      const unsigned char lit = static_cast<unsigned char>(cs.bytes[i]);
+      const std::string ld = "(u32)stage" + J + "[st + " + std::to_string(i) + "]";
+      verify += " && ";
+      if (ScanFolds(cs, lit))
+        verify += "((" + ld + " | 0x20u) == " + std::to_string(static_cast<unsigned>(lit | 0x20u)) + "u)";
+      else
+        verify += "(" + ld + " == " + std::to_string(static_cast<unsigned>(lit)) + "u)";
+    }
+    o += I + "      {\n";
+    o += I + "        u32 mk = gdv_mask16(a" + S + "_0, a" + S + "_1, a" + S + "_2, a" + S + "_3);\n";
+    o += I + "        while (mk != 0u) {\n";
+    o += I + "          const i32 st = 16 * c + (__ffs((int)mk) - 1) - " + std::to_string(cs.rare) + ";\n";
+    o += I + "          mk &= mk - 1u;\n";
+    o += I + "          if (st >= lo && st + " + L + " <= hi" + verify + ") {\n";
+    o += I + "            const u32 hx = atomicAdd(hctr" + J + ", 1u);\n";
+    o += I + "            if (hx < " + std::to_string(kHitCap) + "u) hits" + J + "[hx] = (" + S +
+         "u << 24) | (u32)st;\n";
+    o += I + "          }\n";
+    o += I + "        }\n";
+    o += I + "      }\n";
+  }
+  o += I + "    }\n";
+  o += I + "  }\n";
+  o += I + "}\n";
+  o += I + "__syncwarp();\n";
+  o += I + "nh" + J + " = hctr" + J + "[0];\n";
+  o += I + "coop" + J + " = nh" + J + " <= " + std::to_string(kHitCap) + "u;\n";
+  return o;
+}
+
+bool SlotHasCoop(const std::vector<CoopSeg>& segs, int j) {
+  for (const auto& cs : segs)
+    if (cs.slot == j) return true;
+  return false;
+}
+
 void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R, int mode,
                const std::string& body, const std::string& step_tail, std::string* o, int indent,
-               int stage_bytes = 0, const std::string& after_loads = std::string()) {
+               int stage_bytes = 0, const std::string& after_loads = std::string(),
+               const std::vector<CoopSeg>& coop = std::vector<CoopSeg>()) {
   const bool fast = mode != kPred;
   const std::string I(static_cast<size_t>(indent) * 2, ' ');
   const std::string sR = std::to_string(R);
@@ -686,6 +934,14 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
     const DataType& t = slots[j].type;
     *o += I + t.ctype() + " f" + std::to_string(j) + "[" + sR + "];\n";
     if (spec.nullable) *o += I + "bool k" + std::to_string(j) + "[" + sR + "];\n";
+    if (t.is_varlen()) {
+      // group state of the string stage: rows known to be ASCII, cooperative-scan hit list usable
+      *o += I + "u32 ascii" + std::to_string(j) + " = 0u;\n";
+      if (SlotHasCoop(coop, static_cast<int>(j))) {
+        *o += I + "bool coop" + std::to_string(j) + " = false;\n";
+        *o += I + "u32 nh" + std::to_string(j) + " = 0u;\n";
+      }
+    }
   }
   if (mode == kStaged) {
     *o += I + "#pragma unroll\n";
@@ -721,14 +977,33 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
         *o += I + "  if (gn + (i32)mis <= " + std::to_string(stage_bytes) + ") {\n";
         *o += I + "    const uint4* s4 = reinterpret_cast<const uint4*>(src - mis);\n";
         *o += I + "    const i32 nchunks = (gn + (i32)mis + 15) >> 4;\n";
-        *o += I + "    for (i32 c = (i32)lane; c < nchunks; c += 32)\n";
-        *o += I + "      reinterpret_cast<uint4*>(stage" + J + ")[c] = __ldcs(s4 + c);\n";
+        // four 16-byte loads in flight per lane, then the stores; the OR of all words tells
+        // whether the whole run is ASCII
+        *o += I + "    u32 hibits = 0u;\n";
+        *o += I + "    for (i32 c0 = (i32)lane; c0 < nchunks; c0 += 128) {\n";
+        *o += I + "      uint4 t4[4];\n";
+        *o += I + "      #pragma unroll\n";
+        *o += I + "      for (int u = 0; u < 4; ++u)\n";
+        *o += I + "        if (c0 + 32 * u < nchunks) t4[u] = __ldcs(s4 + c0 + 32 * u);\n";
+        *o += I + "      #pragma unroll\n";
+        *o += I + "      for (int u = 0; u < 4; ++u)\n";
+        *o += I + "        if (c0 + 32 * u < nchunks) {\n";
+        *o += I + "          reinterpret_cast<uint4*>(stage" + J + ")[c0 + 32 * u] = t4[u];\n";
+        *o += I + "          hibits |= t4[u].x | t4[u].y | t4[u].z | t4[u].w;\n";
+        *o += I + "        }\n";
+        *o += I + "    }\n";
         *o += I + "    sbase" + J + " = stage" + J + " + mis - gb;\n";
+        *o += I + "    ascii" + J + " = __any_sync(GDV_FULL, (hibits & 0x80808080u) != 0u) ? 0u : GDV_XF_ASCII;\n";
+        if (SlotHasCoop(coop, static_cast<int>(j))) {
+          *o += EmitCoopScan(static_cast<int>(j), coop, I + "    ");
+        } else {
+          *o += I + "    __syncwarp();\n";
+        }
         *o += I + "  }\n";
         *o += I + "}\n";
       }
     }
-    if (staged_any) *o += I + "__syncwarp();\n";
+    (void)staged_any;
     *o += I + "#pragma unroll\n";
     *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
     for (size_t j = 0; j < slots.size(); ++j) {
@@ -740,7 +1015,8 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
       } else if (t.is_varlen()) {
         *o += I + "  { const i32 sb = ptr" + J + "[32 * k]; const i32 se = ptr" + J +
               "[32 * k + 1]; f" + J + "[k] = gdv_make_str(" +
-              (stage_bytes > 0 ? "sbase" : "in_var") + J + " + sb, se - sb); }\n";
+              (stage_bytes > 0 ? "sbase" : "in_var") + J + " + sb, se - sb); f" + J +
+              "[k].xf = ascii" + J + "; }\n";
       } else {
         *o += I + "  f" + J + "[k] = gdv_ldp(ptr" + J + " + 32 * k);\n";
       }
@@ -812,7 +1088,7 @@ int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
 Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
                       const KernelSpec& spec, GeneratedKernel* out) {
   std::vector<ColumnSlot> slots;
-  BodyGen gen(schema, &slots, spec.nullable);
+  BodyGen gen(schema, &slots, spec.nullable, spec.string_scan != 1);
 
   // Per-row body (uses f<j>[k] / k<j>[k]); generated first so we know the slots.
   std::string body;
@@ -856,7 +1132,11 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
 
   // shared-memory stage for string bytes: 48 B per row of a group, per warp and string column
   const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
-  int dynamic_smem = stage_bytes * (BT / 32) * n_varlen;
+  // per warp and string column: [stage bytes][hit list + counter of the cooperative LIKE scan]
+  const std::vector<CoopSeg>& coop = gen.coop_segs();
+  const int hit_bytes = coop.empty() ? 0 : 4 * kHitCap + 16;
+  const int col_block = stage_bytes + hit_bytes;
+  int dynamic_smem = col_block * (BT / 32) * n_varlen;
   const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
   const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
 
@@ -916,7 +1196,13 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
       if (!slots[j].type.is_varlen()) continue;
       src += "  u8* stage" + std::to_string(j) + " = reinterpret_cast<u8*>(gdv_smem) + ((size_t)wid * " +
              std::to_string(n_varlen) + " + " + std::to_string(vi) + ") * " +
-             std::to_string(stage_bytes) + ";\n";
+             std::to_string(col_block) + ";\n";
+      if (SlotHasCoop(coop, static_cast<int>(j))) {
+        src += "  u32* hits" + std::to_string(j) + " = reinterpret_cast<u32*>(stage" + std::to_string(j) +
+               " + " + std::to_string(stage_bytes) + ");\n";
+        src += "  u32* hctr" + std::to_string(j) + " = hits" + std::to_string(j) + " + " +
+               std::to_string(kHitCap) + ";\n";
+      }
       ++vi;
     }
   }
@@ -1025,7 +1311,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
       after += "        const i64 tn = t + (i64)" + sS + " * gridDim.x;\n";
       after += "        if (tn < n_st) issue(tn, s);\n";
       after += "      }\n";
-      EmitGroup(slots, spec, R, kStaged, body, tail(true), &src, 3, 0, after);
+      EmitGroup(slots, spec, R, kStaged, body, tail(true), &src, 3, 0, after, coop);
       src += "    }\n";
       src += "    if (lane < " + sR + "u) {\n";
       src += "      const i64 w = (base >> 5) + (i64)lane;\n";
@@ -1051,13 +1337,13 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     }
     if (!has_sel) {
       src += "    if (base + " + s32R + " <= A.n) {\n";
-      EmitGroup(slots, spec, R, kFast, body, tail(true), &src, 3, stage_bytes);
+      EmitGroup(slots, spec, R, kFast, body, tail(true), &src, 3, stage_bytes, std::string(), coop);
       src += "    } else {\n";
-      EmitGroup(slots, spec, R, kPred, body, tail(false), &src, 3);
+      EmitGroup(slots, spec, R, kPred, body, tail(false), &src, 3, 0, std::string(), coop);
       src += "    }\n";
     } else {
       src += "    {\n";
-      EmitGroup(slots, spec, R, kPred, body, tail(false), &src, 3);
+      EmitGroup(slots, spec, R, kPred, body, tail(false), &src, 3, 0, std::string(), coop);
       src += "    }\n";
     }
     src += "    if (lane < " + sR + "u && base + 32 * (i64)lane < A.n) {\n";
@@ -1103,9 +1389,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "      const i64 base = wbase + 32 * g;\n";
     src += "      if (base >= A.n) break;\n";
     src += "      if (base + " + s32R + " <= A.n) {\n";
-    EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes);
+    EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes, std::string(), coop);
     src += "      } else {\n";
-    EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 4);
+    EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 4, 0, std::string(), coop);
     src += "      }\n";
     src += "    }\n";
     // lane k: c = selected rows of step k; exclusive scan over steps; warp total

@@ -42,6 +42,7 @@ struct KernelSpec {
   bool nullable = true;               // false: specialised for batches where no input has nulls
   int loader = 0;                     // 0 = engine picks, 1 = direct LDG, 2 = TMA bulk -> shared
   int stages = 0;                     // TMA loader: shared-memory stages per CTA (0 = pick)
+  int string_scan = 0;                // 0 = engine picks (cooperative LIKE scan), 1 = per-lane only
 };
 
 struct ColumnSlot {

@@ -199,6 +199,7 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
   spec.block_threads = cfg.block_threads > 0 ? cfg.block_threads : 256;
   spec.loader = cfg.loader;
   spec.stages = cfg.stages;
+  spec.string_scan = cfg.string_scan;
   spec.name = std::string(kind == KernelKind::kProject ? "gdv_project_expr_" : "gdv_filter_expr_") +
               std::to_string(g_kernel_serial.fetch_add(1));
   std::unique_ptr<CompiledKernel> k(new CompiledKernel());

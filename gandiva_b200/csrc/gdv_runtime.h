@@ -82,6 +82,7 @@ struct Config {
   int loader = 0;
   int stages = 0;
   int sm_reserve = 0;
+  int string_scan = 0;
 };
 
 class CompiledKernel {

@@ -106,7 +106,9 @@ typedef struct gdv_config {
                               concurrent stream (e.g. NCCL's gather of the previous batch's
                               SelectionVector) can run; default 0 */
   int32_t stages;          /* TMA loader: shared-memory stages per CTA (0 = engine picks) */
-  int32_t reserved[4];
+  int32_t string_scan;     /* LIKE over string columns: 0 = engine picks (warp-cooperative scan of
+                              the staged bytes), 1 = per-lane matcher only */
+  int32_t reserved[3];
 } gdv_config_t;
 void gdv_config_default(gdv_config_t* cfg);
 

@@ -274,6 +274,81 @@ def case_strings(b):
     return schema, outs, "project"
 
 
+# ---- LIKE through the warp-cooperative scan (DESIGN.md "String path") --------------------------
+LIKE_SCAN_PATTERNS = ["%special%requests%", "%spark%", "spa%ark%fire", "%park%park%", "%requests%special%",
+                      "%日本語%", "%fire%fox", "x_y%100%%%park%"]
+LIKE_SCAN_VIEWS = ["plain", "upper_substr32", "lower", "substr_3_20", "btrim", "upper"]
+
+
+def like_scan_view(b, s, view):
+    t = pa.string()
+    L = lambda v: b.make_literal(v, pa.int64())
+    if view == "plain":
+        return s
+    if view == "upper_substr32":
+        return b.make_function("upper", [b.make_function("substr", [s, L(1), L(32)], t)], t)
+    if view == "lower":
+        return b.make_function("lower", [s], t)
+    if view == "upper":
+        return b.make_function("upper", [s], t)
+    if view == "substr_3_20":
+        return b.make_function("substr", [s, L(3), L(20)], t)
+    if view == "btrim":
+        return b.make_function("btrim", [s], t)
+    raise KeyError(view)
+
+
+def case_like_scan(pattern, view, kind="project"):
+    """like(<view>(s), pattern): patterns whose '%'-delimited middle segments are >= 3 bytes go
+    through the cooperative scan; the pattern is upper/lower-cased to match the view's case map."""
+    def build(b):
+        t = pa.string()
+        schema = pa.schema([("s", t)])
+        pat = pattern.upper() if view in ("upper", "upper_substr32") else pattern
+        if pattern.startswith("x_y"):
+            args = [like_scan_view(b, F(b, "s", t), view), b.make_literal(pat.replace("_", "\\_"), t),
+                    b.make_literal("\\", t)]
+        else:
+            args = [like_scan_view(b, F(b, "s", t), view), b.make_literal(pat, t)]
+        return schema, [(b.make_function("like", args, pa.bool_()), pa.bool_())], kind
+    build.__name__ = "like_scan_%s_%s_%s" % (pattern, view, kind)
+    return build
+
+
+def like_scan_batch(n: int, seed: int, null_prob: float = 0.05, offset: int = 0, dense: bool = False,
+                    long_rows: bool = False) -> pa.RecordBatch:
+    """Strings for the cooperative scan: WORDS mixtures (ASCII and not), optionally rows that are
+    nothing but matches (hit-list overflow -> per-lane fallback) and rows longer than the stage."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n + offset):
+        if null_prob > 0 and rng.random() < null_prob:
+            out.append(None)
+            continue
+        if dense and i % 97 < 40:
+            out.append("special requests park spark fire " * int(rng.integers(1, 3)))
+            continue
+        if long_rows and i % 251 == 17:
+            out.append(("blithely ironic deposits " * 150) + "special final requests park fire")
+            continue
+        k = int(rng.integers(0, 7))
+        out.append(" ".join(WORDS[int(j)] for j in rng.integers(0, len(WORDS), k)))
+    arr = pa.array(out, type=pa.string())
+    if offset:
+        arr = arr.slice(offset)
+    return pa.RecordBatch.from_arrays([arr], schema=pa.schema([("s", pa.string())]))
+
+
+def all_like_scan_cases():
+    out = []
+    for pat in LIKE_SCAN_PATTERNS:
+        for view in LIKE_SCAN_VIEWS:
+            if view in ("upper", "upper_substr32") and pat == "%日本語%":
+                continue
+            out.append(case_like_scan(pat, view))
+    return out
+
+
 def case_literals_only(b):
     t = pa.int32()
     schema = pa.schema([("a", t)])

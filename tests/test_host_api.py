@@ -154,6 +154,29 @@ def test_make_compiles_for_sm100a(case, gandiva):
         assert "gdv_tile_exclusive_prefix" in f.llvm_ir
 
 
+def test_like_scan_kernels_compile(gandiva):
+    """LIKE over view chains lowers to the warp-cooperative scan (hit list + per-row chain);
+    string_scan=1 keeps the per-lane matcher only.  Both variants compile for sm_100a."""
+    for case in cases.all_like_scan_cases()[::5] + [cases.case_like_scan("%special%requests%", "upper_substr32", "filter")]:
+        b = gandiva.TreeExprBuilder()
+        schema, outs, kind = case(b)
+        for scan in (0, 1):
+            cfg = gandiva.Configuration(string_scan=scan)
+            if kind == "project":
+                src = gandiva.make_projector(schema, [b.make_expression(outs[0][0], pa.field("o", pa.bool_()))],
+                                             None, "NONE", cfg).llvm_ir
+            else:
+                src = gandiva.make_filter(schema, b.make_condition(outs[0][0]), cfg).llvm_ir
+            assert ("gdv_likeh_" in src) == (scan == 0), case.__name__
+            assert ("gdv_eqbytes_msb(" in src) == (scan == 0)
+    # patterns that do not qualify (a middle segment shorter than 3 bytes, '_' wildcards) stay per lane
+    for pat in ["%a%b%c%", "s_ark%", "spark%", "%ss"]:
+        b = gandiva.TreeExprBuilder()
+        schema, outs, _ = cases.case_like(pat)(b)
+        src = gandiva.make_projector(schema, [b.make_expression(outs[0][0], pa.field("o", pa.bool_()))], None).llvm_ir
+        assert "gdv_likeh_" not in src
+
+
 def test_selection_mode_names(gandiva):
     b = gandiva.TreeExprBuilder()
     fa = pa.field('a', pa.int32())

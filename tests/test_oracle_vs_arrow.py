@@ -167,6 +167,25 @@ def test_decimal_rescale_rounds_half_away(oracle, gandiva):
     assert got.to_pylist() == want
 
 
+def test_like_scan_patterns(oracle, gandiva):
+    """The patterns/views of the cooperative-scan GPU tests, oracle against pyarrow.compute."""
+    batch = cases.like_scan_batch(3000, seed=11, dense=True, long_rows=True)
+    s = batch.column(0)
+    for pat in cases.LIKE_SCAN_PATTERNS:
+        if pat.startswith("x_y"):
+            continue  # match_like has no escape argument
+        got, = run_oracle(oracle, gandiva, cases.case_like_scan(pat, "plain"), batch)
+        assert_arrays_match(got, pc.match_like(s, pat), "like " + pat)
+        got, = run_oracle(oracle, gandiva, cases.case_like_scan(pat, "lower"), batch)
+        assert_arrays_match(got, pc.match_like(pc.ascii_lower(s), pat), "like lower " + pat)
+        if pat != "%日本語%":
+            got, = run_oracle(oracle, gandiva, cases.case_like_scan(pat, "upper_substr32"), batch)
+            want = pc.match_like(pc.ascii_upper(pc.utf8_slice_codeunits(s, 0, 32)), pat.upper())
+            assert_arrays_match(got, want, "like upper substr " + pat)
+        got, = run_oracle(oracle, gandiva, cases.case_like_scan(pat, "btrim"), batch)
+        assert_arrays_match(got, pc.match_like(pc.ascii_trim(s, " "), pat), "like btrim " + pat)
+
+
 def test_like_and_strings(oracle, gandiva):
     t = pa.string()
     schema = pa.schema([("s", t)])

@@ -92,6 +92,47 @@ def test_project_tma_loader_cases(case, gandiva, oracle):
         assert_arrays_match(g, w, "%s tma out=%d" % (case.__name__, i))
 
 
+LIKE_SCAN_CASES = cases.all_like_scan_cases()
+
+
+@pytest.mark.parametrize("case", LIKE_SCAN_CASES, ids=[c.__name__ for c in LIKE_SCAN_CASES])
+def test_like_cooperative_scan(case, gandiva, oracle):
+    """LIKE through the warp-cooperative scan of the staged bytes (hit list + per-row chain),
+    against the oracle: plain rows, rows that overflow the hit list (per-lane fallback), rows
+    longer than the shared-memory stage, non-ASCII rows, sliced arrays."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = case(b)
+    expr = b.make_expression(outs[0][0], pa.field("o", pa.bool_()))
+    p = gandiva.make_projector(schema, [expr], None)
+    assert "gdv_likeh_" in p.llvm_ir
+    p_lane = gandiva.make_projector(schema, [expr], None, "NONE", gandiva.Configuration(string_scan=1))
+    for n, seed, offset, dense, long_rows in [(64, 1, 0, False, False), (5000, 2, 0, False, False),
+                                              (20011, 3, 7, True, False), (9000, 4, 1, False, True),
+                                              (4097, 5, 3, True, True)]:
+        batch = cases.like_scan_batch(n, seed, offset=offset, dense=dense, long_rows=long_rows)
+        want, = oracle.project([outs[0][0]], [pa.bool_()], batch, threads=4)
+        got, = p.evaluate(batch)
+        assert_arrays_match(got, want, "%s n=%d" % (case.__name__, n))
+        got_lane, = p_lane.evaluate(batch)
+        assert_arrays_match(got_lane, want, "%s per-lane n=%d" % (case.__name__, n))
+
+
+@pytest.mark.parametrize("bt,rpt", [(256, 2), (512, 2), (1024, 2), (512, 4), (256, 1)])
+def test_like_scan_filter(bt, rpt, gandiva, oracle):
+    """The config-4 condition as a Filter on l_comment-like rows, block sizes and rows/thread."""
+    b = gandiva.TreeExprBuilder()
+    cond = cases.comment_condition(b)
+    f = gandiva.make_filter(cases.COMMENT_SCHEMA, b.make_condition(cond),
+                            gandiva.Configuration(rows_per_thread=rpt, block_threads=bt))
+    assert "gdv_likeh_" in f.llvm_ir
+    for n in (70_001, 300_000):
+        batch = cases.comment_batch(n, seed=bt + rpt)
+        sel = f.evaluate(batch)
+        want = oracle.filter_indices(cond, batch, threads=4)
+        assert sel.num_slots == len(want) and len(want) > 0
+        assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
+
+
 def _filter_both(gandiva, oracle, build, batch, dtype="int32", cfg=None):
     b = gandiva.TreeExprBuilder()
     schema, outs, kind = build(b)

@@ -119,11 +119,14 @@ def bench_str(rows_per_batch, batches):
         out = torch.empty(n, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         cols = [(d_vld.data_ptr(), d_offs.data_ptr(), d_bytes.data_ptr(), 0)]
-        for bt in (256, 512, 1024):
-            for rpt in (1, 2, 4):
+        combos = [(bt, rpt, 0) for bt in (256, 512, 1024) for rpt in (1, 2, 4)] + [(1024, 2, 1), (512, 2, 1)]
+        if os.environ.get("GDV_STR_COMBOS"):
+            combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_STR_COMBOS"].split(";")]
+        for bt, rpt, scan in combos:
+            if True:
                 b = gandiva.TreeExprBuilder()
                 f = gandiva.make_filter(cases.COMMENT_SCHEMA, b.make_condition(cases.comment_condition(b)),
-                                        gandiva.Configuration(rows_per_thread=rpt, block_threads=bt))
+                                        gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, string_scan=scan))
 
                 def run():
                     for _ in range(batches):
@@ -134,8 +137,10 @@ def bench_str(rows_per_batch, batches):
                 bytes_ = batches * (4.0 * n + block_bytes * reps + n / 8.0 + 4.0 * count)
                 gbs = bytes_ / ms / 1e6
                 r = {"config": "string_filter_like_upper_substr", "block_threads": bt, "rows_per_thread": rpt,
+                     "matcher": "per-lane" if scan == 1 else "cooperative scan",
                      "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "gbs": gbs, "frac": gbs / PEAK,
-                     "bytes_per_row": bytes_ / rows, "selected_per_batch": count, "regs": f.kernel_info["regs"]}
+                     "bytes_per_row": bytes_ / rows, "selected_per_batch": count, "regs": f.kernel_info["regs"],
+                     "smem": f.kernel_info.get("dynamic_smem"), "ctas_per_sm": f.kernel_info.get("blocks_per_sm")}
                 results.append(r)
                 print(json.dumps(r), flush=True)
         # parity of the device-resident string path on the first block against the oracle
