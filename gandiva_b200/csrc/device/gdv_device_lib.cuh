@@ -792,6 +792,261 @@ GDV_DEV f64 castFLOAT8_decimal128(i128 x, i32 xp, i32 xs) {
   return neg ? -v : v;
 }
 
+// ---- decimal128 divide / mod / from double ---------------------------------------------------
+GDV_DEV bool gdv_u256_is_zero(const gdv_u256& a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) == 0ull; }
+GDV_DEV bool gdv_u256_fits128(const gdv_u256& a) { return (a.w[2] | a.w[3]) == 0ull; }
+GDV_DEV u128 gdv_u256_low128(const gdv_u256& a) { return ((u128)a.w[1] << 64) | (u128)a.w[0]; }
+// a * b for a 256-bit a and a 128-bit b; *overflow when the product needs more than 256 bits.
+GDV_DEV gdv_u256 gdv_mul_u256_u128(const gdv_u256& a, u128 b, bool* overflow) {
+  const gdv_u256 lo = gdv_mul_u128(gdv_u256_low128(a), b);
+  const gdv_u256 hi = gdv_mul_u128(((u128)a.w[3] << 64) | (u128)a.w[2], b);  // weight 2^128
+  gdv_u256 r;
+  r.w[0] = lo.w[0];
+  r.w[1] = lo.w[1];
+  u128 c = (u128)lo.w[2] + (u128)hi.w[0];
+  r.w[2] = (u64)c;
+  c = (c >> 64) + (u128)lo.w[3] + (u128)hi.w[1];
+  r.w[3] = (u64)c;
+  *overflow = (c >> 64) != 0 || hi.w[2] != 0ull || hi.w[3] != 0ull;
+  return r;
+}
+// Restoring division, one bit per iteration: n = q * d + r, r < d.  d != 0 and d < 2^255.
+GDV_DEV void gdv_divmod_u256(const gdv_u256& n, const gdv_u256& d, gdv_u256* q, gdv_u256* r) {
+  if (gdv_u256_fits128(n) && gdv_u256_fits128(d)) {
+    const u128 nn = gdv_u256_low128(n), dd = gdv_u256_low128(d);
+    *q = gdv_u256_from(nn / dd);
+    *r = gdv_u256_from(nn % dd);
+    return;
+  }
+  gdv_u256 quo, rem;
+  for (int i = 0; i < 4; ++i) quo.w[i] = rem.w[i] = 0ull;
+  int top = 255;
+  while (top > 0 && ((n.w[top >> 6] >> (top & 63)) & 1ull) == 0ull) --top;
+  for (int b = top; b >= 0; --b) {
+    rem.w[3] = (rem.w[3] << 1) | (rem.w[2] >> 63);
+    rem.w[2] = (rem.w[2] << 1) | (rem.w[1] >> 63);
+    rem.w[1] = (rem.w[1] << 1) | (rem.w[0] >> 63);
+    rem.w[0] = (rem.w[0] << 1) | ((n.w[b >> 6] >> (b & 63)) & 1ull);
+    if (gdv_cmp_u256(rem, d) >= 0) {
+      rem = gdv_sub_u256(rem, d);
+      quo.w[b >> 6] |= 1ull << (b & 63);
+    }
+  }
+  *q = quo;
+  *r = rem;
+}
+// |x| * 10^e in 256 bits (e >= 0, any size); *overflow when it does not fit.
+GDV_DEV gdv_u256 gdv_scale_up_u256(u128 x, i32 e, bool* overflow) {
+  *overflow = false;
+  gdv_u256 r = gdv_mul_u128(x, gdv_pow10_u128(e > 38 ? 38 : e));
+  i32 left = e > 38 ? e - 38 : 0;
+  while (left > 0) {
+    const i32 step = left > 38 ? 38 : left;
+    bool o = false;
+    r = gdv_mul_u256_u128(r, gdv_pow10_u128(step), &o);
+    *overflow = *overflow || o;
+    left -= step;
+  }
+  return r;
+}
+// x / y at the declared output scale: |x| * 10^(os - xs + ys) / |y|, rounded half away from zero;
+// y == 0 raises "divide by zero error"; a quotient of more than 38 digits yields 0.
+GDV_DEV i128 divide_decimal128_decimal128(gdv_ctx* c, i128 x, i32 xp, i32 xs, i128 y, i32 yp,
+                                          i32 ys, i32 op, i32 os) {
+  if (y == 0) {
+    gdv_set_error(c, GDV_ERR_DIV_ZERO);
+    return (i128)0;
+  }
+  const bool neg = (x < 0) != (y < 0);
+  const i32 delta = os - xs + ys;
+  bool overflow = false;
+  gdv_u256 num = gdv_scale_up_u256(gdv_abs_u128(x), delta > 0 ? delta : 0, &overflow);
+  if (overflow) return (i128)0;  // the quotient then has more than 38 digits whatever y is
+  bool o2 = false;
+  const gdv_u256 den = gdv_scale_up_u256(gdv_abs_u128(y), delta < 0 ? -delta : 0, &o2);
+  if (o2) return (i128)0;  // |x / den| < 1/2: rounds to 0
+  gdv_u256 q, r;
+  gdv_divmod_u256(num, den, &q, &r);
+  // round half away from zero: 2 * r >= den
+  const gdv_u256 r2 = gdv_add_u256(r, r);
+  if (gdv_cmp_u256(r2, den) >= 0) q = gdv_add_u256(q, gdv_u256_from((u128)1));
+  return gdv_fit_decimal(q, neg && !gdv_u256_is_zero(q));
+}
+// x mod y with both sides brought to the larger scale; the sign follows the dividend (C's %).
+GDV_DEV i128 mod_decimal128_decimal128(gdv_ctx* c, i128 x, i32 xp, i32 xs, i128 y, i32 yp, i32 ys,
+                                       i32 op, i32 os) {
+  if (y == 0) {
+    gdv_set_error(c, GDV_ERR_DIV_ZERO);
+    return (i128)0;
+  }
+  const i32 ms = xs > ys ? xs : ys;
+  const gdv_u256 xm = gdv_mul_u128(gdv_abs_u128(x), gdv_pow10_u128(ms - xs));
+  const gdv_u256 ym = gdv_mul_u128(gdv_abs_u128(y), gdv_pow10_u128(ms - ys));
+  gdv_u256 q, r;
+  gdv_divmod_u256(xm, ym, &q, &r);
+  if (os < ms) r = gdv_div_pow10_round(r, ms - os);
+  if (os > ms) {
+    if (!gdv_u256_fits128(r)) return (i128)0;
+    r = gdv_mul_u128(gdv_u256_low128(r), gdv_pow10_u128(os - ms));
+  }
+  return gdv_fit_decimal(r, x < 0 && !gdv_u256_is_zero(r));
+}
+// double -> decimal(op, os): v * 10^os (the power built by repeated IEEE multiplication, as in
+// castFLOAT8_decimal128), rounded half away from zero; NaN, infinities and values of more than
+// `op` digits yield 0.
+GDV_DEV i128 castDECIMAL_float64(f64 v, i32 op, i32 os) {
+  f64 p = 1.0;
+  for (i32 i = 0; i < os; ++i) p = p * 10.0;
+  const f64 s = v * p;
+  const f64 a = fabs(s);
+  if (!(a < 1.0e38)) return (i128)0;
+  f64 t = floor(a);
+  if (a - t >= 0.5) t = t + 1.0;
+  u128 m;
+  if (t < 18446744073709551616.0) {
+    m = (u128)(u64)t;
+  } else {
+    const u64 bits = (u64)__double_as_longlong(t);
+    const i32 e = (i32)((bits >> 52) & 0x7ffull) - 1075;  // >= 12 here
+    const u64 mant = (bits & 0xfffffffffffffull) | 0x10000000000000ull;
+    m = (u128)mant << e;
+  }
+  if (m >= gdv_pow10_u128(op)) return (i128)0;
+  return (s < 0.0 && m != 0) ? (i128)(~m + 1) : (i128)m;
+}
+GDV_DEV i128 castDECIMAL_float32(f32 v, i32 op, i32 os) { return castDECIMAL_float64((f64)v, op, os); }
+
+// ---- hashes (MurmurHash3; numeric values are hashed as the 8 bytes of their double) ------------
+// hash32 = MurmurHash3_x86_32, hash64 = the low word of MurmurHash3_x64_128.  A null input yields
+// the seed (0 without one); the result is never null.
+GDV_DEV u64 gdv_rotl64(u64 v, int d) { return (v << d) | (v >> (64 - d)); }
+GDV_DEV u32 gdv_rotl32(u32 v, int d) { return (v << d) | (v >> (32 - d)); }
+GDV_DEV u64 gdv_fmix64(u64 k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+GDV_DEV u32 gdv_fmix32(u32 h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+GDV_DEV u32 gdv_mm32_k(u32 k) { return gdv_rotl32(k * 0xcc9e2d51u, 15) * 0x1b873593u; }
+GDV_DEV u32 gdv_mm32_h(u32 h, u32 k) { return gdv_rotl32(h ^ gdv_mm32_k(k), 13) * 5u + 0xe6546b64u; }
+GDV_DEV u64 gdv_mm64_k1(u64 k) { return gdv_rotl64(k * 0x87c37b91114253d5ull, 31) * 0x4cf5ad432745937full; }
+GDV_DEV u64 gdv_mm64_k2(u64 k) { return gdv_rotl64(k * 0x4cf5ad432745937full, 33) * 0x87c37b91114253d5ull; }
+// one 8-byte key
+GDV_DEV u32 gdv_murmur3_32(u64 val, i32 seed) {
+  u32 h = (u32)seed;
+  h = gdv_mm32_h(h, (u32)val);
+  h = gdv_mm32_h(h, (u32)(val >> 32));
+  return gdv_fmix32(h ^ 8u);
+}
+GDV_DEV u64 gdv_murmur3_64(u64 val, i32 seed) {
+  u64 h1 = (u64)(i64)seed, h2 = (u64)(i64)seed;
+  h1 ^= gdv_mm64_k1(val);
+  h1 ^= 8ull;
+  h2 ^= 8ull;
+  h1 += h2;
+  h2 += h1;
+  h1 = gdv_fmix64(h1);
+  h2 = gdv_fmix64(h2);
+  return h1 + h2;
+}
+// byte strings (through the view's case map)
+GDV_DEV u32 gdv_murmur3_32_buf(const gdv_str& s, i32 seed) {
+  u32 h = (u32)seed;
+  const i32 nb = s.len / 4;
+  for (i32 b = 0; b < nb; ++b) {
+    const u32 k = (u32)gdv_ch(s, 4 * b) | ((u32)gdv_ch(s, 4 * b + 1) << 8) |
+                  ((u32)gdv_ch(s, 4 * b + 2) << 16) | ((u32)gdv_ch(s, 4 * b + 3) << 24);
+    h = gdv_mm32_h(h, k);
+  }
+  u32 k = 0u;
+  const i32 t = 4 * nb;
+  switch (s.len & 3) {
+    case 3: k ^= (u32)gdv_ch(s, t + 2) << 16;
+    case 2: k ^= (u32)gdv_ch(s, t + 1) << 8;
+    case 1: k ^= (u32)gdv_ch(s, t);
+            h ^= gdv_mm32_k(k);
+  }
+  return gdv_fmix32(h ^ (u32)s.len);
+}
+GDV_DEV u64 gdv_ld64_str(const gdv_str& s, i32 at, i32 n) {  // n <= 8 bytes, little endian
+  u64 k = 0ull;
+  for (i32 i = 0; i < n; ++i) k |= (u64)gdv_ch(s, at + i) << (8 * i);
+  return k;
+}
+GDV_DEV u64 gdv_murmur3_64_buf(const gdv_str& s, i32 seed) {
+  u64 h1 = (u64)(i64)seed, h2 = (u64)(i64)seed;
+  const i32 nb = s.len / 16;
+  for (i32 b = 0; b < nb; ++b) {
+    h1 ^= gdv_mm64_k1(gdv_ld64_str(s, 16 * b, 8));
+    h1 = (gdv_rotl64(h1, 27) + h2) * 5ull + 0x52dce729ull;
+    h2 ^= gdv_mm64_k2(gdv_ld64_str(s, 16 * b + 8, 8));
+    h2 = (gdv_rotl64(h2, 31) + h1) * 5ull + 0x38495ab5ull;
+  }
+  const i32 t = 16 * nb, rest = s.len & 15;
+  if (rest > 8) h2 ^= gdv_mm64_k2(gdv_ld64_str(s, t + 8, rest - 8));
+  if (rest > 0) h1 ^= gdv_mm64_k1(gdv_ld64_str(s, t, rest > 8 ? 8 : rest));
+  h1 ^= (u64)(u32)s.len;
+  h2 ^= (u64)(u32)s.len;
+  h1 += h2;
+  h2 += h1;
+  h1 = gdv_fmix64(h1);
+  h2 = gdv_fmix64(h2);
+  return h1 + h2;
+}
+#define GDV_HASH_NUM(T, S)                                                                        \
+  GDV_DEV i32 hash32_##S(T v, bool ok) {                                                          \
+    return ok ? (i32)gdv_murmur3_32((u64)__double_as_longlong((f64)v), 0) : 0;                    \
+  }                                                                                               \
+  GDV_DEV i32 hash32_##S##_int32(T v, bool ok, i32 seed, bool sok) {                              \
+    const i32 sd = sok ? seed : 0;                                                                \
+    return ok ? (i32)gdv_murmur3_32((u64)__double_as_longlong((f64)v), sd) : sd;                  \
+  }                                                                                               \
+  GDV_DEV i64 hash64_##S(T v, bool ok) {                                                          \
+    return ok ? (i64)gdv_murmur3_64((u64)__double_as_longlong((f64)v), 0) : 0;                    \
+  }                                                                                               \
+  GDV_DEV i64 hash64_##S##_int64(T v, bool ok, i64 seed, bool sok) {                              \
+    const i64 sd = sok ? seed : 0;                                                                \
+    return ok ? (i64)gdv_murmur3_64((u64)__double_as_longlong((f64)v), (i32)(u32)(u64)sd) : sd;   \
+  }
+GDV_HASH_NUM(i8, int8)
+GDV_HASH_NUM(i16, int16)
+GDV_HASH_NUM(i32, int32)
+GDV_HASH_NUM(i64, int64)
+GDV_HASH_NUM(u8, uint8)
+GDV_HASH_NUM(u16, uint16)
+GDV_HASH_NUM(u32, uint32)
+GDV_HASH_NUM(u64, uint64)
+GDV_HASH_NUM(f32, float32)
+GDV_HASH_NUM(f64, float64)
+GDV_HASH_NUM(bool, boolean)
+GDV_HASH_NUM(i32, date32)
+GDV_HASH_NUM(i64, date64)
+GDV_HASH_NUM(i64, timestamp)
+GDV_HASH_NUM(i32, time32)
+#define GDV_HASH_STR(S)                                                                           \
+  GDV_DEV i32 hash32_##S(gdv_str v, bool ok) { return ok ? (i32)gdv_murmur3_32_buf(v, 0) : 0; }   \
+  GDV_DEV i32 hash32_##S##_int32(gdv_str v, bool ok, i32 seed, bool sok) {                        \
+    const i32 sd = sok ? seed : 0;                                                                \
+    return ok ? (i32)gdv_murmur3_32_buf(v, sd) : sd;                                              \
+  }                                                                                               \
+  GDV_DEV i64 hash64_##S(gdv_str v, bool ok) { return ok ? (i64)gdv_murmur3_64_buf(v, 0) : 0; }   \
+  GDV_DEV i64 hash64_##S##_int64(gdv_str v, bool ok, i64 seed, bool sok) {                        \
+    const i64 sd = sok ? seed : 0;                                                                \
+    return ok ? (i64)gdv_murmur3_64_buf(v, (i32)(u32)(u64)sd) : sd;                               \
+  }
+GDV_HASH_STR(utf8)
+GDV_HASH_STR(binary)
+
 // ---- strings ---------------------------------------------------------------------------
 GDV_DEV gdv_str upper_utf8(gdv_str s) {
   s.xf = (s.xf & ~GDV_XF_CASE) | 1u;
@@ -875,6 +1130,8 @@ GDV_DEV gdv_str substr_utf8_int64_int64(gdv_str s, i64 offset, i64 length) {
 GDV_DEV gdv_str substr_utf8_int64(gdv_str s, i64 offset) {
   return substr_utf8_int64_int64(s, offset, (i64)s.len);
 }
+// castVARCHAR(s, n): the first n glyphs (n <= 0: empty).
+GDV_DEV gdv_str castVARCHAR_utf8_int64(gdv_str s, i64 n) { return substr_utf8_int64_int64(s, 1, n); }
 GDV_DEV bool starts_with_utf8_utf8(gdv_str s, gdv_str pre) {
   if (pre.len > s.len) return false;
   for (i32 i = 0; i < pre.len; ++i)

@@ -174,9 +174,28 @@ Registry::Registry() {
   Add("castDECIMAL", {I32}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castDECIMAL", {I64}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castDECIMAL", {F64}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castDECIMAL", {F32}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castDECIMAL", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castBIGINT", {DEC}, I64, NullMode::kIfNull, kDecimalArgs);
   Add("castFLOAT8", {DEC}, F64, NullMode::kIfNull, kDecimalArgs);
+
+  // ---- hashes (never null: a null input yields the seed) --------------------------------
+  std::vector<DataType> hash_types = numeric;
+  hash_types.insert(hash_types.end(), dates.begin(), dates.end());
+  hash_types.push_back(B);
+  hash_types.push_back(S);
+  hash_types.push_back(BIN);
+  for (const auto& t : hash_types) {
+    const bool num = !t.is_varlen();
+    Add("hash32", {t}, I32, NullMode::kNever, 0,
+        num ? std::vector<std::string>{"hash", "hash32AsDouble"} : std::vector<std::string>{"hash"});
+    Add("hash32", {t, I32}, I32, NullMode::kNever, 0,
+        num ? std::vector<std::string>{"hash32AsDouble"} : std::vector<std::string>{});
+    Add("hash64", {t}, I64, NullMode::kNever, 0,
+        num ? std::vector<std::string>{"hash64AsDouble"} : std::vector<std::string>{});
+    Add("hash64", {t, I64}, I64, NullMode::kNever, 0,
+        num ? std::vector<std::string>{"hash64AsDouble"} : std::vector<std::string>{});
+  }
 
   // ---- strings ------------------------------------------------------------------------
   Add("like", {S, S}, B, NullMode::kIfNull, kLikeHolder);

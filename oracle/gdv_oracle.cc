@@ -410,6 +410,38 @@ struct Big {
     return r;
   }
   void MulPow10(int e) { for (int k = 0; k < e; ++k) MulSmall(10); }
+  // *this *= 10^e; false when a carry left the 256 bits
+  bool MulPow10Checked(int e) {
+    for (int k = 0; k < e; ++k) {
+      uint64_t carry = 0;
+      for (int j = 0; j < 8; ++j) {
+        uint64_t cur = static_cast<uint64_t>(w[j]) * 10u + carry;
+        w[j] = static_cast<uint32_t>(cur);
+        carry = cur >> 32;
+      }
+      if (carry) return false;
+    }
+    return true;
+  }
+  bool Bit(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+  // schoolbook binary long division: n = q * d + r  (d != 0, d < 2^255)
+  static void DivMod(const Big& n, const Big& d, Big* q, Big* r) {
+    Big quo, rem;
+    for (int i = 255; i >= 0; --i) {
+      uint32_t carry = n.Bit(i) ? 1u : 0u;
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t top = rem.w[j] >> 31;
+        rem.w[j] = (rem.w[j] << 1) | carry;
+        carry = top;
+      }
+      if (rem.Cmp(d) >= 0) {
+        rem.Sub(d);
+        quo.w[i >> 5] |= 1u << (i & 31);
+      }
+    }
+    *q = quo;
+    *r = rem;
+  }
   bool FitsDigits(int digits) const {
     Big lim = Big::From(1);
     lim.MulPow10(digits);
@@ -510,6 +542,133 @@ i128 DecimalRescale(i128 x, int xs, int op, int os) {
   if (os > xs) a.mag.MulPow10(os - xs);
   if (os < xs) a.mag = DivPow10HalfUp(a.mag, xs - os);
   return FromSigned(a, op);
+}
+
+// x / y at scale os: |x| * 10^(os - xs + ys) / |y| rounded half away from zero; 0 on overflow.
+// *div_zero is set when y == 0.
+i128 DecimalDivide(i128 x, int xs, i128 y, int ys, int os, bool* div_zero) {
+  if (y == 0) { *div_zero = true; return 0; }
+  SignedBig a = ToSigned(x), b = ToSigned(y);
+  const int delta = os - xs + ys;
+  if (delta > 0 && !a.mag.MulPow10Checked(delta)) return 0;
+  if (delta < 0 && !b.mag.MulPow10Checked(-delta)) return 0;
+  Big q, r;
+  Big::DivMod(a.mag, b.mag, &q, &r);
+  Big r2 = r;
+  r2.Add(r);
+  if (r2.Cmp(b.mag) >= 0) q.Add(Big::From(1));
+  SignedBig res;
+  res.neg = a.neg != b.neg;
+  res.mag = q;
+  return FromSigned(res, 38);
+}
+
+i128 DecimalMod(i128 x, int xs, i128 y, int ys, int os, bool* div_zero) {
+  if (y == 0) { *div_zero = true; return 0; }
+  const int ms = std::max(xs, ys);
+  SignedBig a = ToSigned(x), b = ToSigned(y);
+  a.mag.MulPow10(ms - xs);
+  b.mag.MulPow10(ms - ys);
+  Big q, r;
+  Big::DivMod(a.mag, b.mag, &q, &r);
+  if (os < ms) r = DivPow10HalfUp(r, ms - os);
+  if (os > ms) {
+    if (!r.FitsDigits(38)) return 0;
+    r.MulPow10(os - ms);
+  }
+  SignedBig res;
+  res.neg = a.neg;
+  res.mag = r;
+  return FromSigned(res, 38);
+}
+
+// double -> decimal(op, os); the IEEE operation sequence is the one DESIGN.md states.
+i128 DecimalFromDouble(double v, int op, int os) {
+  double p = 1.0;
+  for (int k = 0; k < os; ++k) p = p * 10.0;
+  const double s = v * p;
+  const double a = std::fabs(s);
+  if (!(a < 1.0e38)) return 0;
+  double t = std::floor(a);
+  if (a - t >= 0.5) t = t + 1.0;
+  // integer-valued double -> 128-bit integer, by peeling 32-bit digits from the top
+  u128 m = 0;
+  {
+    int e = 0;
+    const double fr = std::frexp(t, &e);  // t = fr * 2^e, fr in [0.5, 1)
+    double f = fr;
+    int bits_left = e;
+    while (bits_left > 0) {
+      const int take = bits_left >= 32 ? 32 : bits_left;
+      f = std::ldexp(f, take);
+      const double ip = std::floor(f);
+      m = (m << take) | static_cast<u128>(static_cast<uint64_t>(ip));
+      f -= ip;
+      bits_left -= take;
+    }
+  }
+  Big lim = Big::From(1);
+  lim.MulPow10(op);
+  if (Big::From(m).Cmp(lim) >= 0) return 0;
+  if (m == 0) return 0;
+  return s < 0.0 ? static_cast<i128>(~m + 1) : static_cast<i128>(m);
+}
+
+// ---- MurmurHash3 over byte buffers (Austin Appleby's published algorithm) ---------------------
+uint32_t Rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+uint64_t Rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+uint32_t Murmur3_x86_32(const unsigned char* data, int len, uint32_t seed) {
+  const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
+  uint32_t h1 = seed;
+  const int nblocks = len / 4;
+  for (int i = 0; i < nblocks; ++i) {
+    uint32_t k1;
+    std::memcpy(&k1, data + 4 * i, 4);
+    k1 *= c1; k1 = Rotl32(k1, 15); k1 *= c2;
+    h1 ^= k1; h1 = Rotl32(h1, 13); h1 = h1 * 5 + 0xe6546b64u;
+  }
+  const unsigned char* tail = data + nblocks * 4;
+  uint32_t k1 = 0;
+  switch (len & 3) {
+    case 3: k1 ^= static_cast<uint32_t>(tail[2]) << 16;  // fall through
+    case 2: k1 ^= static_cast<uint32_t>(tail[1]) << 8;   // fall through
+    case 1: k1 ^= tail[0];
+            k1 *= c1; k1 = Rotl32(k1, 15); k1 *= c2; h1 ^= k1;
+  }
+  h1 ^= static_cast<uint32_t>(len);
+  h1 ^= h1 >> 16; h1 *= 0x85ebca6bu; h1 ^= h1 >> 13; h1 *= 0xc2b2ae35u; h1 ^= h1 >> 16;
+  return h1;
+}
+uint64_t Fmix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+// low 64 bits (h1) of MurmurHash3_x64_128; the seed initialises both lanes
+uint64_t Murmur3_x64_128_lo(const unsigned char* data, int len, uint64_t seed) {
+  const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
+  uint64_t h1 = seed, h2 = seed;
+  const int nblocks = len / 16;
+  for (int i = 0; i < nblocks; ++i) {
+    uint64_t k1, k2;
+    std::memcpy(&k1, data + 16 * i, 8);
+    std::memcpy(&k2, data + 16 * i + 8, 8);
+    k1 *= c1; k1 = Rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    h1 = Rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+    k2 *= c2; k2 = Rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    h2 = Rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+  }
+  const unsigned char* tail = data + nblocks * 16;
+  uint64_t k1 = 0, k2 = 0;
+  const int rest = len & 15;
+  for (int i = rest - 1; i >= 8; --i) k2 ^= static_cast<uint64_t>(tail[i]) << (8 * (i - 8));
+  if (rest > 8) { k2 *= c2; k2 = Rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+  for (int i = std::min(rest, 8) - 1; i >= 0; --i) k1 ^= static_cast<uint64_t>(tail[i]) << (8 * i);
+  if (rest > 0) { k1 *= c1; k1 = Rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+  h1 ^= static_cast<uint64_t>(len); h2 ^= static_cast<uint64_t>(len);
+  h1 += h2; h2 += h1;
+  h1 = Fmix64(h1); h2 = Fmix64(h2);
+  h1 += h2;
+  return h1;
 }
 
 double DecimalToDouble(i128 x, int xs) {
@@ -657,6 +816,34 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
 
+  if (f == "hash" || f == "hash32" || f == "hash32AsDouble" || f == "hash64" || f == "hash64AsDouble") {
+    const bool is64 = f == "hash64" || f == "hash64AsDouble";
+    const int64_t seed = (na >= 2 && a[1].ok) ? a[1].i : 0;
+    out->ok = true;
+    if (!a[0].ok) { out->i = seed; return; }
+    std::string bytes;
+    if (t0.is_string()) {
+      bytes = a[0].s;
+    } else {
+      double d;
+      if (t0.id == T_BOOL) d = a[0].b ? 1.0 : 0.0;
+      else if (t0.id == T_FLOAT) d = static_cast<double>(a[0].f);
+      else if (t0.id == T_DOUBLE) d = a[0].d;
+      else if (t0.is_unsigned_int()) d = static_cast<double>(a[0].u);
+      else d = static_cast<double>(a[0].i);
+      bytes.assign(reinterpret_cast<const char*>(&d), 8);
+    }
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(bytes.data());
+    const int32_t seed32 = static_cast<int32_t>(static_cast<uint32_t>(static_cast<uint64_t>(seed)));
+    if (is64)
+      out->i = static_cast<int64_t>(Murmur3_x64_128_lo(p, static_cast<int>(bytes.size()),
+                                                       static_cast<uint64_t>(static_cast<int64_t>(seed32))));
+    else
+      out->i = static_cast<int32_t>(Murmur3_x86_32(p, static_cast<int>(bytes.size()),
+                                                   static_cast<uint32_t>(seed32)));
+    return;
+  }
+
   // ---- null-if-null functions -------------------------------------------------------------
   bool ok = true;
   for (size_t k = 0; k < na && k < 3; ++k) {
@@ -683,6 +870,18 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
       uint64_t r = f == "add" ? x + y : (f == "subtract" ? x - y : x * y);
       out->i = WrapSigned(static_cast<int64_t>(r), rt.bits());
     }
+    return;
+  }
+  if (f == "divide" && rt.id == T_DECIMAL) {
+    bool dz = false;
+    out->dec = DecimalDivide(a[0].dec, t0.scale, a[1].dec, n.kids[1]->type.scale, rt.scale, &dz);
+    if (dz) cx.error = 1;
+    return;
+  }
+  if ((f == "mod" || f == "modulo") && rt.id == T_DECIMAL) {
+    bool dz = false;
+    out->dec = DecimalMod(a[0].dec, t0.scale, a[1].dec, n.kids[1]->type.scale, rt.scale, &dz);
+    if (dz) cx.error = 1;
     return;
   }
   if (f == "divide") {
@@ -779,6 +978,8 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   if (f == "castTIMESTAMP") { out->i = a[0].i; return; }
   if (f == "castDECIMAL") {
     if (t0.id == T_DECIMAL) out->dec = DecimalRescale(a[0].dec, t0.scale, rt.precision, rt.scale);
+    else if (t0.id == T_DOUBLE) out->dec = DecimalFromDouble(a[0].d, rt.precision, rt.scale);
+    else if (t0.id == T_FLOAT) out->dec = DecimalFromDouble(static_cast<double>(a[0].f), rt.precision, rt.scale);
     else out->dec = DecimalRescale(static_cast<i128>(a[0].i), 0, rt.precision, rt.scale);
     return;
   }
@@ -818,6 +1019,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
                      : Substr(a[0].s, a[1].i, static_cast<int64_t>(a[0].s.size()));
     return;
   }
+  if (f == "castVARCHAR") { out->s = Substr(a[0].s, 1, a[1].i); return; }
   if (f == "char_length" || f == "length" || f == "lengthUtf8") {
     out->i = static_cast<int64_t>(GlyphStarts(a[0].s).size());
     return;

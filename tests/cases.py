@@ -219,6 +219,99 @@ def case_decimal_misc(b):
                     (b.make_function("abs", [x], t1), t1), (b.make_function("negative", [y], t2), t2)], "project"
 
 
+def decimal_divide_type(p1, s1, p2, s2):
+    """The reference's result type for decimal divide (DESIGN.md semantics table):
+    scale = max(6, s1 + p2 + 1), precision = p1 - s1 + s2 + scale, capped at 38 by giving up
+    scale down to min(scale, 6)."""
+    scale = max(6, s1 + p2 + 1)
+    prec = p1 - s1 + s2 + scale
+    if prec > 38:
+        delta = prec - 38
+        scale = max(scale - delta, min(scale, 6))
+        prec = 38
+    return prec, scale
+
+
+def decimal_mod_type(p1, s1, p2, s2):
+    scale = max(s1, s2)
+    return min(p1 - s1, p2 - s2) + scale, scale
+
+
+def case_decimal_divide(p1, s1, p2, s2, guarded=True):
+    """x / y (decimal128); guarded: `if y != 0 then x / y else x_cast` so random zeros do not raise."""
+    def build(b):
+        t1, t2 = pa.decimal128(p1, s1), pa.decimal128(p2, s2)
+        rt = pa.decimal128(*decimal_divide_type(p1, s1, p2, s2))
+        schema = pa.schema([("x", t1), ("y", t2)])
+        x, y = F(b, "x", t1), F(b, "y", t2)
+        div = b.make_function("divide", [x, y], rt)
+        if not guarded:
+            return schema, [(div, rt)], "project"
+        nz = b.make_function("not_equal", [y, b.make_literal(decimal.Decimal(0).scaleb(-s2), t2)], pa.bool_())
+        return schema, [(b.make_if(nz, div, b.make_literal(None, rt), rt), rt)], "project"
+    build.__name__ = "decimal_divide_%d_%d_%d_%d" % (p1, s1, p2, s2)
+    return build
+
+
+def case_decimal_mod(p1, s1, p2, s2):
+    def build(b):
+        t1, t2 = pa.decimal128(p1, s1), pa.decimal128(p2, s2)
+        rt = pa.decimal128(*decimal_mod_type(p1, s1, p2, s2))
+        schema = pa.schema([("x", t1), ("y", t2)])
+        x, y = F(b, "x", t1), F(b, "y", t2)
+        nz = b.make_function("not_equal", [y, b.make_literal(decimal.Decimal(0).scaleb(-s2), t2)], pa.bool_())
+        return schema, [(b.make_if(nz, b.make_function("mod", [x, y], rt), b.make_literal(None, rt), rt), rt)], "project"
+    build.__name__ = "decimal_mod_%d_%d_%d_%d" % (p1, s1, p2, s2)
+    return build
+
+
+def case_decimal_from_double(b):
+    schema = pa.schema([("d", pa.float64()), ("f", pa.float32())])
+    d, f = F(b, "d", pa.float64()), F(b, "f", pa.float32())
+    outs = []
+    for p, s in [(38, 6), (20, 2), (10, 0), (38, 30), (9, 4)]:
+        t = pa.decimal128(p, s)
+        outs.append((b.make_function("castDECIMAL", [d], t), t))
+    t = pa.decimal128(30, 8)
+    outs.append((b.make_function("castDECIMAL", [f], t), t))
+    return schema, outs, "project"
+
+
+HASH_TYPES = [pa.int8(), pa.int32(), pa.int64(), pa.uint16(), pa.uint64(), pa.float32(), pa.float64(),
+              pa.bool_(), pa.date32(), pa.date64(), pa.timestamp("ms"), pa.string(), pa.binary()]
+
+
+def case_hash(t):
+    def build(b):
+        schema = pa.schema([("v", t), ("s32", pa.int32()), ("s64", pa.int64())])
+        v, s32, s64 = F(b, "v", t), F(b, "s32", pa.int32()), F(b, "s64", pa.int64())
+        I, L = pa.int32(), pa.int64()
+        outs = [(b.make_function("hash32", [v], I), I), (b.make_function("hash", [v], I), I),
+                (b.make_function("hash64", [v], L), L),
+                (b.make_function("hash32", [v, s32], I), I), (b.make_function("hash64", [v, s64], L), L),
+                (b.make_function("hash32", [v, b.make_literal(7, I)], I), I),
+                (b.make_function("hash64", [v, b.make_literal(-3, L)], L), L)]
+        if pa.types.is_string(t):
+            outs.append((b.make_function("hash64", [b.make_function("upper", [v], t)], L), L))
+            outs.append((b.make_function("hash32", [b.make_function("substr", [v, b.make_literal(2, L), b.make_literal(9, L)], t)], I), I))
+        return schema, outs, "project"
+    build.__name__ = "hash_%s" % t
+    return build
+
+
+def case_cast_varchar(b):
+    t = pa.string()
+    schema = pa.schema([("s", t), ("k", pa.int64())])
+    s, k = F(b, "s", t), F(b, "k", pa.int64())
+    I = pa.int32()
+    L = lambda v: b.make_literal(v, pa.int64())
+    cv = lambda n: b.make_function("castVARCHAR", [s, n], t)
+    return schema, [(b.make_function("octet_length", [cv(L(5))], I), I),
+                    (b.make_function("char_length", [cv(k)], I), I),
+                    (b.make_function("like", [cv(L(7)), b.make_literal("%spa%", t)], pa.bool_()), pa.bool_()),
+                    (b.make_function("equal", [cv(L(0)), b.make_literal("", t)], pa.bool_()), pa.bool_())], "project"
+
+
 def case_in_int(t, values):
     def build(b):
         schema = pa.schema([("a", t)])
@@ -567,6 +660,12 @@ def all_project_cases():
         case_decimal(38, 0, 38, 0, "add", 38, 0),
         case_decimal(10, 5, 12, 1, "subtract", 17, 5),
     ]
+    cases += [case_decimal_divide(15, 2, 15, 2), case_decimal_divide(38, 10, 20, 4),
+              case_decimal_divide(10, 0, 5, 3), case_decimal_divide(30, 20, 38, 2),
+              case_decimal_divide(38, 30, 12, 0),
+              case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
+              case_decimal_from_double, case_cast_varchar]
+    cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]
     for pat in ["%spark%", "spark%", "%spark", "s_ark%", "%", "", "_", "%a%b%c%", "fire", "%日本%",

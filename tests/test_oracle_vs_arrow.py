@@ -264,3 +264,198 @@ def test_lineitem_generator_ranges(oracle):
     # Q6 selectivity of the synthetic data is ~1.8%
     sel = ((ship >= 8766) & (ship < 9131) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24)).mean()
     assert 0.014 < sel < 0.023
+
+
+# ---- decimal divide / mod / from double against Python's decimal module -------------------------
+def _dec_ctx():
+    return decimal.Context(prec=120, rounding=decimal.ROUND_HALF_UP)
+
+
+def _fit(v, precision, scale):
+    """Quantise to `scale`; values that need more than 38 digits become 0."""
+    q = v.quantize(decimal.Decimal(1).scaleb(-scale), rounding=decimal.ROUND_HALF_UP, context=_dec_ctx())
+    return q if abs(int(q.scaleb(scale))) < 10 ** 38 else decimal.Decimal(0).scaleb(-scale)
+
+
+@pytest.mark.parametrize("p1,s1,p2,s2", [(15, 2, 15, 2), (38, 10, 20, 4), (10, 0, 5, 3), (30, 20, 38, 2),
+                                         (38, 30, 12, 0), (38, 0, 38, 37)])
+def test_decimal_divide(p1, s1, p2, s2, oracle, gandiva):
+    build = cases.case_decimal_divide(p1, s1, p2, s2)
+    schema = pa.schema([("x", pa.decimal128(p1, s1)), ("y", pa.decimal128(p2, s2))])
+    batch = cases.random_batch(schema, 2000, seed=31)
+    got, = run_oracle(oracle, gandiva, build, batch)
+    rp, rs = cases.decimal_divide_type(p1, s1, p2, s2)
+    want = []
+    ctx = _dec_ctx()
+    for x, y in zip(batch.column(0).to_pylist(), batch.column(1).to_pylist()):
+        if x is None or y is None or y == 0:
+            want.append(None)
+        else:
+            want.append(_fit(ctx.divide(x, y), rp, rs))
+    assert_arrays_match(got, pa.array(want, type=pa.decimal128(rp, rs)), "decimal divide")
+    assert got.null_count < len(got)
+
+
+@pytest.mark.parametrize("p1,s1,p2,s2", [(15, 2, 15, 2), (38, 10, 20, 4), (20, 0, 38, 30), (12, 6, 9, 1)])
+def test_decimal_mod(p1, s1, p2, s2, oracle, gandiva):
+    build = cases.case_decimal_mod(p1, s1, p2, s2)
+    schema = pa.schema([("x", pa.decimal128(p1, s1)), ("y", pa.decimal128(p2, s2))])
+    batch = cases.random_batch(schema, 2000, seed=32)
+    got, = run_oracle(oracle, gandiva, build, batch)
+    rp, rs = cases.decimal_mod_type(p1, s1, p2, s2)
+    ctx = _dec_ctx()
+    want = []
+    for x, y in zip(batch.column(0).to_pylist(), batch.column(1).to_pylist()):
+        want.append(None if x is None or y is None or y == 0 else _fit(ctx.remainder(x, y), rp, rs))
+    assert_arrays_match(got, pa.array(want, type=pa.decimal128(rp, rs)), "decimal mod")
+
+
+def test_decimal_divide_by_zero_raises(oracle, gandiva):
+    build = cases.case_decimal_divide(15, 2, 15, 2, guarded=False)
+    schema = pa.schema([("x", pa.decimal128(15, 2)), ("y", pa.decimal128(15, 2))])
+    D = decimal.Decimal
+    batch = pa.RecordBatch.from_arrays([pa.array([D("1.00"), D("2.00")], schema.field(0).type),
+                                        pa.array([D("3.00"), D("0.00")], schema.field(1).type)], schema=schema)
+    with pytest.raises(Exception, match="divide by zero"):
+        run_oracle(oracle, gandiva, build, batch)
+
+
+def test_decimal_from_double(oracle, gandiva):
+    schema = pa.schema([("d", pa.float64()), ("f", pa.float32())])
+    rng = np.random.default_rng(5)
+    n = 4000
+    d = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 30, n)
+    d[:8] = [0.0, -0.0, 0.5, -0.5, 2.5, 1e37, -1e38, 123456.789]
+    d[8:11] = [np.nan, np.inf, -np.inf]
+    f = (rng.standard_normal(n) * 10.0 ** rng.integers(-4, 12, n)).astype(np.float32)
+    batch = pa.RecordBatch.from_arrays([pa.array(d), pa.array(f)], schema=schema)
+    got = run_oracle(oracle, gandiva, cases.case_decimal_from_double, batch)
+    specs = [(38, 6, d), (20, 2, d), (10, 0, d), (38, 30, d), (9, 4, d), (30, 8, f.astype(np.float64))]
+    for g, (p, s, src) in zip(got, specs):
+        want = []
+        for v in src:
+            pw = 1.0
+            for _ in range(s):
+                pw = pw * 10.0
+            sc = float(v) * pw
+            if not (abs(sc) < 1e38):
+                want.append(decimal.Decimal(0).scaleb(-s))
+                continue
+            r = decimal.Decimal(sc).quantize(decimal.Decimal(1), rounding=decimal.ROUND_HALF_UP, context=_dec_ctx())
+            if abs(int(r)) >= 10 ** p:
+                r = decimal.Decimal(0)
+            want.append(decimal.Decimal(int(r)).scaleb(-s, context=_dec_ctx()))
+        assert_arrays_match(g, pa.array(want, type=pa.decimal128(p, s)), "castDECIMAL(double) -> (%d,%d)" % (p, s))
+
+
+# ---- MurmurHash3: scikit-learn's x86_32 and a plain-Python x64_128 ------------------------------
+def _mm3_x64_128_lo(data: bytes, seed: int) -> int:
+    M = (1 << 64) - 1
+    c1, c2 = 0x87c37b91114253d5, 0x4cf5ad432745937f
+    rotl = lambda x, r: ((x << r) | (x >> (64 - r))) & M
+
+    def fmix(k):
+        k ^= k >> 33
+        k = (k * 0xff51afd7ed558ccd) & M
+        k ^= k >> 33
+        k = (k * 0xc4ceb9fe1a85ec53) & M
+        return k ^ (k >> 33)
+    h1 = h2 = seed & M
+    nb = len(data) // 16
+    for i in range(nb):
+        k1 = int.from_bytes(data[16 * i:16 * i + 8], "little")
+        k2 = int.from_bytes(data[16 * i + 8:16 * i + 16], "little")
+        k1 = (rotl((k1 * c1) & M, 31) * c2) & M
+        h1 ^= k1
+        h1 = ((rotl(h1, 27) + h2) * 5 + 0x52dce729) & M
+        k2 = (rotl((k2 * c2) & M, 33) * c1) & M
+        h2 ^= k2
+        h2 = ((rotl(h2, 31) + h1) * 5 + 0x38495ab5) & M
+    tail = data[16 * nb:]
+    if len(tail) > 8:
+        k2 = int.from_bytes(tail[8:], "little")
+        h2 ^= (rotl((k2 * c2) & M, 33) * c1) & M
+    if len(tail) > 0:
+        k1 = int.from_bytes(tail[:8], "little")
+        h1 ^= (rotl((k1 * c1) & M, 31) * c2) & M
+    h1 ^= len(data)
+    h2 ^= len(data)
+    h1 = (h1 + h2) & M
+    h2 = (h2 + h1) & M
+    h1, h2 = fmix(h1), fmix(h2)
+    h1 = (h1 + h2) & M
+    h2 = (h2 + h1) & M
+    return h1, h2
+
+
+def test_murmur_reference_known_answers():
+    """Pin the plain-Python x64_128 to the published answers for "foo" (mmh3.hash64 /
+    mmh3.hash128 documentation) and "" with seed 0."""
+    h1, h2 = _mm3_x64_128_lo(b"foo", 0)
+    assert (h2 << 64 | h1) == 168394135621993849475852668931176482145
+    assert h1 - (1 << 64) == -2129773440516405919 and h2 == 9128664383759220103
+    assert _mm3_x64_128_lo(b"", 0) == (0, 0)
+
+
+def _signed(v, bits):
+    return v - (1 << bits) if v >> (bits - 1) else v
+
+
+@pytest.mark.parametrize("t", cases.HASH_TYPES, ids=str)
+def test_hash_functions(t, oracle, gandiva):
+    import struct
+    from sklearn.utils import murmurhash3_32
+    schema = pa.schema([("v", t), ("s32", pa.int32()), ("s64", pa.int64())])
+    batch = cases.random_batch(schema, 1500, seed=41, null_prob=0.1)
+    got = run_oracle(oracle, gandiva, cases.case_hash(t), batch)
+    vals = batch.column(0).to_pylist()
+    if pa.types.is_date32(t):
+        raw = batch.column(0).cast(pa.int32()).to_pylist()
+    elif pa.types.is_temporal(t):
+        raw = batch.column(0).cast(pa.int64()).to_pylist()
+    else:
+        raw = vals
+    s32 = batch.column(1).to_pylist()
+    s64 = batch.column(2).to_pylist()
+
+    def key(v, xf=None):
+        if isinstance(v, str):
+            v = v.encode("utf-8")
+        if isinstance(v, bytes):
+            return v
+        return struct.pack("<d", float(v))
+
+    def h32(v, seed):
+        seed = 0 if seed is None else seed
+        if v is None:
+            return seed
+        return _signed(murmurhash3_32(key(v), seed=seed & 0xffffffff, positive=True), 32)
+
+    def h64(v, seed):
+        seed = 0 if seed is None else seed
+        if v is None:
+            return seed
+        s = _signed(seed & 0xffffffff, 32)
+        return _signed(_mm3_x64_128_lo(key(v), s)[0], 64)
+
+    want = [[h32(v, 0) for v in raw], [h32(v, 0) for v in raw], [h64(v, 0) for v in raw],
+            [h32(v, s) for v, s in zip(raw, s32)], [h64(v, s) for v, s in zip(raw, s64)],
+            [h32(v, 7) for v in raw], [h64(v, -3) for v in raw]]
+    types = [pa.int32(), pa.int32(), pa.int64(), pa.int32(), pa.int64(), pa.int32(), pa.int64()]
+    if pa.types.is_string(t):
+        want.append([h64(None if v is None else "".join(c.upper() if "a" <= c <= "z" else c for c in v), 0) for v in raw])
+        want.append([h32(None if v is None else v[1:10], 0) for v in raw])
+        types += [pa.int64(), pa.int32()]
+    for i, (g, w, ty) in enumerate(zip(got, want, types)):
+        assert g.null_count == 0
+        assert_arrays_match(g, pa.array(w, type=ty), "hash out %d of %s" % (i, t))
+
+
+def test_cast_varchar(oracle, gandiva):
+    schema = pa.schema([("s", pa.string()), ("k", pa.int64())])
+    batch = cases.random_batch(schema, 2000, seed=43, small=True)
+    got = run_oracle(oracle, gandiva, cases.case_cast_varchar, batch)
+    s, k = batch.column(0), batch.column(1)
+    assert_arrays_match(got[0], pc.binary_length(pc.utf8_slice_codeunits(s, 0, 5)), "castVARCHAR 5")
+    want = [None if a is None or b is None else len(a[:max(b, 0)]) for a, b in zip(s.to_pylist(), k.to_pylist())]
+    assert_arrays_match(got[1], pa.array(want, type=pa.int32()), "castVARCHAR k")

@@ -234,6 +234,26 @@ def test_divide_by_zero_is_execution_error(t, gandiva, oracle):
     assert_arrays_match(got, want, "divide with null divisor")
 
 
+def test_decimal_divide_by_zero_is_execution_error(gandiva, oracle):
+    import decimal
+    D = decimal.Decimal
+    for build in (cases.case_decimal_divide(15, 2, 15, 2, guarded=False),):
+        b = gandiva.TreeExprBuilder()
+        schema, outs, _ = build(b)
+        p = gandiva.make_projector(schema, [b.make_expression(outs[0][0], pa.field("r", outs[0][1]))], None)
+        batch = pa.RecordBatch.from_arrays([pa.array([D("1.00"), D("2.00"), D("7.25")], schema.field(0).type),
+                                            pa.array([D("3.00"), D("0.00"), D("-0.50")], schema.field(1).type)],
+                                           schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: divide by zero error"):
+            p.evaluate(batch)
+        batch = pa.RecordBatch.from_arrays([batch.column(0), pa.array([D("3.00"), None, D("-0.50")], schema.field(1).type)],
+                                           schema=schema)
+        got, = p.evaluate(batch)
+        want, = oracle.project([outs[0][0]], [outs[0][1]], batch)
+        assert_arrays_match(got, want, "decimal divide with a null divisor")
+        assert got.to_pylist()[2] == D("-14.5")
+
+
 def test_empty_batch_rejected(gandiva):
     b = gandiva.TreeExprBuilder()
     schema, outs, _ = cases.case_arith("add", pa.int32())(b)
