@@ -273,6 +273,21 @@ GDV_DEV u32 gdv_eqbytes_msb(u32 x, u32 pat) {
   const u32 z = x ^ pat;
   return (z - 0x01010101u) & ~z & 0x80808080u;
 }
+// Halfwords of x equal to the matching halfword of pat, as 0x8000 in that halfword (the upper one
+// can be flagged falsely when the lower one matches: callers verify candidates).
+GDV_DEV u32 gdv_eqhalf_msb(u32 x, u32 pat) {
+  const u32 z = x ^ pat;
+  return (z - 0x00010001u) & ~z & 0x80008000u;
+}
+// Digram hit masks of the four words of a chunk (e: pair starts at byte 0 / 2 of the word, o: at
+// byte 1 / 3) -> one bit per start byte of the 16-byte chunk.
+GDV_DEV u32 gdv_nib_half(u32 e, u32 o) {
+  return ((e >> 15) & 1u) | ((o >> 14) & 2u) | ((e >> 29) & 4u) | ((o >> 28) & 8u);
+}
+GDV_DEV u32 gdv_mask16_half(u32 e0, u32 o0, u32 e1, u32 o1, u32 e2, u32 o2, u32 e3, u32 o3) {
+  return gdv_nib_half(e0, o0) | (gdv_nib_half(e1, o1) << 4) | (gdv_nib_half(e2, o2) << 8) |
+         (gdv_nib_half(e3, o3) << 12);
+}
 // Four per-word byte-hit masks (bit 7 of every hit byte) of one 16-byte chunk -> one bit per byte.
 GDV_DEV u32 gdv_mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
   const u32 n0 = ((m0 & 0x80808080u) * 0x00204081u) >> 28;

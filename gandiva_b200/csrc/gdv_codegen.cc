@@ -185,7 +185,9 @@ struct CoopSeg {
   unsigned xf = 0;     // case map of the view the pattern is matched against
   std::string bytes;
   int id = 0;          // unique per slot
-  int rare = 0;        // index of the byte the scan compares (the rarest of the segment)
+  int like = 0;        // which LIKE node of the slot the segment belongs to
+  bool is_key = false; // the segment of its LIKE the scan looks for (rarest digram)
+  int digram = 0;      // key: index of the first byte of the adjacent pair the scan tests
 };
 constexpr int kHitCap = 64;  // hits per warp and group; more -> the group falls back per lane
 
@@ -479,23 +481,36 @@ class BodyGen {
       f += "  if (!(" + match_at(segs.back(), "(s.len - " + L + ")") + ")) return false;\n";
       f += "  lim -= " + L + ";\n";
     }
+    // ids are unique per slot; the key of this LIKE is the middle segment with the rarest digram
+    int like_idx = 0;
+    for (const auto& cs : coop_segs_)
+      if (cs.slot == slot) like_idx = std::max(like_idx, cs.like + 1);
+    size_t key_k = first_mid;
+    int key_d = 0;
+    double key_score = 1e300;
+    for (size_t k = first_mid; k < last_mid; ++k) {
+      if (segs[k].size() > 32) continue;  // lane i verifies byte i of the key
+      for (size_t i = 0; i + 1 < segs[k].size(); ++i) {
+        const double sc = ByteScore(static_cast<unsigned char>(segs[k][i]), xf) *
+                          ByteScore(static_cast<unsigned char>(segs[k][i + 1]), xf);
+        if (sc < key_score) {
+          key_score = sc;
+          key_k = k;
+          key_d = static_cast<int>(i);
+        }
+      }
+    }
+    if (key_score == 1e300) return "";
     for (size_t k = first_mid; k < last_mid; ++k) {
       CoopSeg cs;
       cs.slot = slot;
       cs.xf = xf;
       cs.bytes = segs[k];
-      cs.id = -1;
-      for (const auto& o : coop_segs_)
-        if (o.slot == slot && o.xf == xf && o.bytes == segs[k]) cs.id = o.id;
-      if (cs.id < 0) {
-        cs.id = n_slot_segs++;
-        cs.rare = 0;
-        for (size_t i = 1; i < cs.bytes.size(); ++i)
-          if (ByteScore(static_cast<unsigned char>(cs.bytes[i]), xf) <
-              ByteScore(static_cast<unsigned char>(cs.bytes[cs.rare]), xf))
-            cs.rare = static_cast<int>(i);
-        coop_segs_.push_back(cs);
-      }
+      cs.id = n_slot_segs++;
+      cs.like = like_idx;
+      cs.is_key = k == key_k;
+      cs.digram = cs.is_key ? key_d : 0;
+      coop_segs_.push_back(cs);
       const std::string L = std::to_string(segs[k].size());
       f += "  {\n    i32 best = 0x7fffffff;\n";
       f += "    for (u32 h = 0u; h < nh; ++h) {\n";
@@ -837,82 +852,169 @@ void EmitPrologue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, 
 // group in range, direct global loads, kStaged = whole CTA tile already in shared memory (TMA).
 enum GroupMode { kPred = 0, kFast = 1, kStaged = 2 };
 
-// Cooperative scan of the staged bytes of column J for the LIKE segments registered on it
-// (BodyGen::LikeFromHits).  Every lane takes 16-byte chunks of the group's byte run, compares all
-// 16 bytes against each segment's rarest byte with four word-wide zero-byte tests, and only on a
-// candidate verifies the whole segment and appends (id << 24 | stage offset) to the warp's hit
-// list.  More than kHitCap hits: the group falls back to the per-lane matcher.
+// Cooperative LIKE scan of the staged bytes of column J (BodyGen::LikeFromHits registers the
+// segments).  Level 1: every lane takes 16-byte chunks of the group's byte run and tests all 16
+// byte positions for the rarest adjacent byte pair (digram) of each LIKE's key segment with two
+// halfword zero tests per word; the (rare) candidates go to a list.  Level 2, per candidate and
+// warp-uniform: lane i verifies byte i of the key segment, the row that holds the occurrence is
+// found with a ballot over the lanes' row ranges, and the row's bytes are searched for the
+// LIKE's other segments, 32 positions at a time.  Verified occurrences are appended to the hit
+// list as (segment id << 24 | stage offset); the per-row function chains them.  More than
+// kHitCap candidates or hits: the group falls back to the per-lane matcher.
 bool ScanFolds(const CoopSeg& cs, unsigned char c) {
   return (cs.xf == 1u && c >= 'A' && c <= 'Z') || (cs.xf == 2u && c >= 'a' && c <= 'z');
 }
 
-std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, const std::string& I) {
+std::string SegVerifyExpr(const CoopSeg& cs, const std::string& stage, const std::string& at) {
+  std::string e;
+  for (size_t i = 0; i < cs.bytes.size(); ++i) {
+    const unsigned char lit = static_cast<unsigned char>(cs.bytes[i]);
+    const std::string ld = "(u32)" + stage + "[" + at + " + " + std::to_string(i) + "]";
+    if (!e.empty()) e += " && ";
+    if (ScanFolds(cs, lit))
+      e += "((" + ld + " | 0x20u) == " + std::to_string(static_cast<unsigned>(lit | 0x20u)) + "u)";
+    else
+      e += "(" + ld + " == " + std::to_string(static_cast<unsigned>(lit)) + "u)";
+  }
+  return e;
+}
+
+std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, int R, const std::string& I,
+                         std::string* globals_unused = nullptr) {
+  (void)globals_unused;
   const std::string J = std::to_string(j);
+  const std::string CAP = std::to_string(kHitCap) + "u";
   std::string o;
-  bool any_fold = false;
+  std::vector<const CoopSeg*> keys;
   for (const auto& cs : segs)
-    if (cs.slot == j)
-      any_fold = any_fold || ScanFolds(cs, static_cast<unsigned char>(cs.bytes[cs.rare]));
-  o += I + "if (lane == 0u) hctr" + J + "[0] = 0u;\n";
+    if (cs.slot == j && cs.is_key) keys.push_back(&cs);
+  o += I + "if (lane < 2u) hctr" + J + "[lane] = 0u;\n";
   o += I + "__syncwarp();\n";
-  o += I + "{\n";
-  o += I + "  const i32 lo = (i32)mis, hi = (i32)mis + gn;\n";
-  o += I + "  for (i32 c = (i32)lane; c < nchunks; c += 32) {\n";
-  o += I + "    const uint4 v = reinterpret_cast<const uint4*>(stage" + J + ")[c];\n";
-  if (any_fold)
-    o += I + "    const u32 x0 = v.x | 0x20202020u, x1 = v.y | 0x20202020u, x2 = v.z | 0x20202020u, "
-             "x3 = v.w | 0x20202020u;\n";
+  o += I + "const i32 lo = (i32)mis, hi = (i32)mis + gn;\n";
+  // ---- level 1: digram candidates
+  o += I + "for (i32 c = (i32)lane; c < nchunks; c += 32) {\n";
+  o += I + "  const uint4 v = reinterpret_cast<const uint4*>(stage" + J + ")[c];\n";
+  o += I + "  const u32 vn = reinterpret_cast<const u32*>(stage" + J + ")[4 * c + 4];\n";
   std::string any;
-  for (const auto& cs : segs) {
-    if (cs.slot != j) continue;
-    const std::string S = std::to_string(cs.id);
-    const unsigned char rb = static_cast<unsigned char>(cs.bytes[cs.rare]);
-    const bool fold = ScanFolds(cs, rb);
-    const unsigned b = fold ? (rb | 0x20u) : rb;
-    char pat[16];
-    std::snprintf(pat, sizeof(pat), "0x%08xu", b * 0x01010101u);
-    const char* w[4] = {fold ? "x0" : "v.x", fold ? "x1" : "v.y", fold ? "x2" : "v.z",
-                        fold ? "x3" : "v.w"};
+  for (const CoopSeg* k : keys) {
+    const std::string S = std::to_string(k->id);
+    const unsigned char c1 = static_cast<unsigned char>(k->bytes[k->digram]);
+    const unsigned char c2 = static_cast<unsigned char>(k->bytes[k->digram + 1]);
+    const bool f1 = ScanFolds(*k, c1), f2 = ScanFolds(*k, c2);
+    const unsigned b1 = f1 ? (c1 | 0x20u) : c1, b2 = f2 ? (c2 | 0x20u) : c2;
+    const unsigned fold = (f1 ? 0x20u : 0u) | (f2 ? 0x2000u : 0u);
+    char pat[16], fm[16];
+    std::snprintf(pat, sizeof(pat), "0x%08xu", (b1 | (b2 << 8)) * 0x00010001u);
+    std::snprintf(fm, sizeof(fm), "0x%08xu", fold * 0x00010001u);
+    // the odd-offset test sees the bytes rotated by one: the fold mask and pattern stay aligned
+    // with (first, second) because the word is shifted, not the pattern
+    const char* w[5] = {"v.x", "v.y", "v.z", "v.w", "vn"};
+    // Both bytes fold (or neither): fold the words once, before the byte shift of the odd test.
+    // Mixed: the fold mask must line up with (first, second) byte, so it is applied after it.
+    const bool uniform = f1 == f2;
+    const std::string orfm = fold != 0u ? std::string(" | ") + fm : std::string();
+    for (int q = 0; q < 5; ++q)
+      o += I + "  const u32 x" + S + "_" + std::to_string(q) + " = " + w[q] + (uniform ? orfm : std::string()) +
+           ";\n";
     for (int q = 0; q < 4; ++q) {
-      o += I + "    const u32 a" + S + "_" + std::to_string(q) + " = gdv_eqbytes_msb(" + w[q] + ", " + pat +
-           ");\n";
-      any += (any.empty() ? "" : " | ") + std::string("a") + S + "_" + std::to_string(q);
+      const std::string Q = std::to_string(q), Qn = std::to_string(q + 1);
+      o += I + "  const u32 e" + S + "_" + Q + " = gdv_eqhalf_msb(x" + S + "_" + Q + (uniform ? std::string() : orfm) +
+           ", " + pat + ");\n";
+      o += I + "  const u32 o" + S + "_" + Q + " = gdv_eqhalf_msb(__funnelshift_r(x" + S + "_" + Q + ", x" +
+           S + "_" + Qn + ", 8)" + (uniform ? std::string() : orfm) + ", " + pat + ");\n";
+      any += (any.empty() ? "" : " | ") + std::string("e") + S + "_" + Q + " | o" + S + "_" + Q;
     }
   }
-  o += I + "    if ((" + any + ") != 0u) {\n";
-  for (const auto& cs : segs) {
-    if (cs.slot != j) continue;
-    const std::string S = std::to_string(cs.id);
-    const std::string L = std::to_string(cs.bytes.size());
-    std::string verify;
-    for (size_t i = 0; i < cs.bytes.size(); ++i) {
-      const unsigned char lit = static_cast<unsigned char>(cs.bytes[i]);
-      const std::string ld = "(u32)stage" + J + "[st + " + std::to_string(i) + "]";
-      verify += " && ";
-      if (ScanFolds(cs, lit))
-        verify += "((" + ld + " | 0x20u) == " + std::to_string(static_cast<unsigned>(lit | 0x20u)) + "u)";
-      else
-        verify += "(" + ld + " == " + std::to_string(static_cast<unsigned>(lit)) + "u)";
-    }
-    o += I + "      {\n";
-    o += I + "        u32 mk = gdv_mask16(a" + S + "_0, a" + S + "_1, a" + S + "_2, a" + S + "_3);\n";
-    o += I + "        while (mk != 0u) {\n";
-    o += I + "          const i32 st = 16 * c + (__ffs((int)mk) - 1) - " + std::to_string(cs.rare) + ";\n";
-    o += I + "          mk &= mk - 1u;\n";
-    o += I + "          if (st >= lo && st + " + L + " <= hi" + verify + ") {\n";
-    o += I + "            const u32 hx = atomicAdd(hctr" + J + ", 1u);\n";
-    o += I + "            if (hx < " + std::to_string(kHitCap) + "u) hits" + J + "[hx] = (" + S +
+  o += I + "  if ((" + any + ") != 0u) {\n";
+  for (const CoopSeg* k : keys) {
+    const std::string S = std::to_string(k->id);
+    o += I + "    {\n";
+    o += I + "      u32 mk = gdv_mask16_half(e" + S + "_0, o" + S + "_0, e" + S + "_1, o" + S + "_1, e" + S +
+         "_2, o" + S + "_2, e" + S + "_3, o" + S + "_3);\n";
+    o += I + "      while (mk != 0u) {\n";
+    o += I + "        const i32 st = 16 * c + (__ffs((int)mk) - 1) - " + std::to_string(k->digram) + ";\n";
+    o += I + "        mk &= mk - 1u;\n";
+    o += I + "        if (st >= lo && st + " + std::to_string(k->bytes.size()) + " <= hi) {\n";
+    o += I + "          const u32 cx = atomicAdd(hctr" + J + " + 1, 1u);\n";
+    o += I + "          if (cx < " + CAP + ") cand" + J + "[cx] = (" + std::to_string(k->like) +
          "u << 24) | (u32)st;\n";
-    o += I + "          }\n";
     o += I + "        }\n";
     o += I + "      }\n";
+    o += I + "    }\n";
   }
-  o += I + "    }\n";
   o += I + "  }\n";
   o += I + "}\n";
   o += I + "__syncwarp();\n";
+  // ---- level 2: verify candidates, find their rows, search the rows for the other segments
+  o += I + "const u32 ncand = hctr" + J + "[1];\n";
+  o += I + "if (ncand != 0u && ncand <= " + CAP + ") {\n";
+  o += I + "  for (u32 h = 0u; h < ncand; ++h) {\n";
+  o += I + "    const u32 ce = cand" + J + "[h];\n";
+  o += I + "    const i32 p = (i32)(ce & 0xffffffu);\n";
+  for (const CoopSeg* k : keys) {
+    const std::string KL = std::to_string(k->bytes.size());
+    // per-lane byte of the key: immediate select chain would be long; use a packed table
+    o += I + "    if ((ce >> 24) == " + std::to_string(k->like) + "u) {\n";
+    o += I + "      bool good = true;\n";
+    o += I + "      if (lane < " + KL + "u) {\n";
+    o += I + "        const u32 kb = gdv_key" + J + "_" + std::to_string(k->id) + "[lane];\n";
+    o += I + "        good = (((u32)stage" + J + "[p + (i32)lane]) | (kb >> 8)) == (kb & 0xffu);\n";
+    o += I + "      }\n";
+    o += I + "      if (__all_sync(GDV_FULL, good)) {\n";
+    o += I + "        i32 rs = 0, re = -1;\n";
+    o += I + "        #pragma unroll\n";
+    o += I + "        for (int k = 0; k < " + std::to_string(R) + "; ++k) {\n";
+    o += I + "          const i32 a = ptr" + J + "[32 * k] - gb + (i32)mis;\n";
+    o += I + "          const i32 b = ptr" + J + "[32 * k + 1] - gb + (i32)mis;\n";
+    o += I + "          const u32 own = __ballot_sync(GDV_FULL, a <= p && p + " + KL + " <= b);\n";
+    o += I + "          if (own != 0u) {\n";
+    o += I + "            const int src = __ffs((int)own) - 1;\n";
+    o += I + "            rs = __shfl_sync(GDV_FULL, a, src);\n";
+    o += I + "            re = __shfl_sync(GDV_FULL, b, src);\n";
+    o += I + "          }\n";
+    o += I + "        }\n";
+    o += I + "        if (re >= 0) {\n";
+    o += I + "          if (lane == 0u) {\n";
+    o += I + "            const u32 hx = atomicAdd(hctr" + J + ", 1u);\n";
+    o += I + "            if (hx < " + CAP + ") hits" + J + "[hx] = (" + std::to_string(k->id) + "u << 24) | (u32)p;\n";
+    o += I + "          }\n";
+    for (const auto& os : segs) {
+      if (os.slot != j || os.like != k->like || os.id == k->id) continue;
+      const std::string L = std::to_string(os.bytes.size());
+      o += I + "          for (i32 q = rs + (i32)lane; q + " + L + " <= re; q += 32) {\n";
+      o += I + "            if (" + SegVerifyExpr(os, "stage" + J, "q") + ") {\n";
+      o += I + "              const u32 hx = atomicAdd(hctr" + J + ", 1u);\n";
+      o += I + "              if (hx < " + CAP + ") hits" + J + "[hx] = (" + std::to_string(os.id) + "u << 24) | (u32)q;\n";
+      o += I + "            }\n";
+      o += I + "          }\n";
+    }
+    o += I + "        }\n";
+    o += I + "      }\n";
+    o += I + "    }\n";
+  }
+  o += I + "  }\n";
+  o += I + "  __syncwarp();\n";
+  o += I + "}\n";
   o += I + "nh" + J + " = hctr" + J + "[0];\n";
-  o += I + "coop" + J + " = nh" + J + " <= " + std::to_string(kHitCap) + "u;\n";
+  o += I + "coop" + J + " = ncand <= " + CAP + " && nh" + J + " <= " + CAP + ";\n";
+  return o;
+}
+
+// __device__ tables of the key segments: byte i as (fold mask << 8) | folded byte.
+std::string EmitCoopKeyTables(const std::vector<CoopSeg>& segs) {
+  std::string o;
+  for (const auto& cs : segs) {
+    if (!cs.is_key) continue;
+    o += "__device__ const u16 gdv_key" + std::to_string(cs.slot) + "_" + std::to_string(cs.id) + "[" +
+         std::to_string(cs.bytes.size()) + "] = {";
+    for (size_t i = 0; i < cs.bytes.size(); ++i) {
+      const unsigned char c = static_cast<unsigned char>(cs.bytes[i]);
+      const bool f = ScanFolds(cs, c);
+      const unsigned v = (f ? 0x2000u : 0u) | (f ? (c | 0x20u) : c);
+      o += (i ? "," : "") + std::to_string(v);
+    }
+    o += "};\n";
+  }
   return o;
 }
 
@@ -995,7 +1097,7 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
         *o += I + "    sbase" + J + " = stage" + J + " + mis - gb;\n";
         *o += I + "    ascii" + J + " = __any_sync(GDV_FULL, (hibits & 0x80808080u) != 0u) ? 0u : GDV_XF_ASCII;\n";
         if (SlotHasCoop(coop, static_cast<int>(j))) {
-          *o += EmitCoopScan(static_cast<int>(j), coop, I + "    ");
+          *o += EmitCoopScan(static_cast<int>(j), coop, R, I + "    ");
         } else {
           *o += I + "    __syncwarp();\n";
         }
@@ -1134,7 +1236,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
   // per warp and string column: [stage bytes][hit list + counter of the cooperative LIKE scan]
   const std::vector<CoopSeg>& coop = gen.coop_segs();
-  const int hit_bytes = coop.empty() ? 0 : 4 * kHitCap + 16;
+  const int hit_bytes = coop.empty() ? 0 : 8 * kHitCap + 16;  // candidates, hits, two counters
   const int col_block = stage_bytes + hit_bytes;
   int dynamic_smem = col_block * (BT / 32) * n_varlen;
   const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
@@ -1181,6 +1283,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
+  src += EmitCoopKeyTables(gen.coop_segs());
   const std::string sR = std::to_string(R), sBT = std::to_string(BT);
   const std::string s32R = std::to_string(32 * R);
   src += "extern \"C\" __global__ void __launch_bounds__(" + sBT + ") " + spec.name +
@@ -1198,10 +1301,12 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
              std::to_string(n_varlen) + " + " + std::to_string(vi) + ") * " +
              std::to_string(col_block) + ";\n";
       if (SlotHasCoop(coop, static_cast<int>(j))) {
-        src += "  u32* hits" + std::to_string(j) + " = reinterpret_cast<u32*>(stage" + std::to_string(j) +
+        src += "  u32* cand" + std::to_string(j) + " = reinterpret_cast<u32*>(stage" + std::to_string(j) +
                " + " + std::to_string(stage_bytes) + ");\n";
-        src += "  u32* hctr" + std::to_string(j) + " = hits" + std::to_string(j) + " + " +
+        src += "  u32* hits" + std::to_string(j) + " = cand" + std::to_string(j) + " + " +
                std::to_string(kHitCap) + ";\n";
+        src += "  u32* hctr" + std::to_string(j) + " = hits" + std::to_string(j) + " + " +
+               std::to_string(kHitCap) + ";  // [0] hits, [1] candidates\n";
       }
       ++vi;
     }
