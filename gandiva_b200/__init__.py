@@ -616,26 +616,38 @@ class Projector:
         n = batch.num_rows if selection is None else selection.num_slots
         outs = (gdv_out_column_t * len(self._exprs))()
         holders = []
-        for i, e in enumerate(self._exprs):
-            t = e.result().type
-            vbytes = (n + 7) // 8
-            vbuf = np.zeros((vbytes + 7) // 8 * 8, dtype=np.uint8)
-            if pa.types.is_boolean(t):
-                dbuf = np.zeros((vbytes + 7) // 8 * 8, dtype=np.uint8)
-            else:
-                dbuf = np.zeros(max(n * (t.bit_width // 8), 8), dtype=np.uint8)
-            holders.append((vbuf, dbuf))
-            outs[i].validity = vbuf.ctypes.data_as(C.c_void_p)
-            outs[i].values = dbuf.ctypes.data_as(C.c_void_p)
         csel = None
         if selection is not None:
             s = selection._c()
             csel = C.byref(s)
+        for i, e in enumerate(self._exprs):
+            t = e.result().type
+            vbytes = (n + 7) // 8
+            vbuf = np.zeros((vbytes + 7) // 8 * 8, dtype=np.uint8)
+            var = None
+            if pa.types.is_string(t) or pa.types.is_binary(t):
+                # utf8/binary: size the data buffer with the sizing pass, as the C++ layer does
+                need = C.c_int64(0)
+                _check(lib.gdv_projector_output_var_size(self._h, C.byref(cb), csel, i, None, C.byref(need)))
+                dbuf = np.zeros(n + 1, dtype=np.int32)
+                var = np.zeros(max(need.value, 8), dtype=np.uint8)
+                outs[i].var_data = var.ctypes.data_as(C.c_void_p)
+                outs[i].var_capacity = need.value
+            elif pa.types.is_boolean(t):
+                dbuf = np.zeros((vbytes + 7) // 8 * 8, dtype=np.uint8)
+            else:
+                dbuf = np.zeros(max(n * (t.bit_width // 8), 8), dtype=np.uint8)
+            holders.append((vbuf, dbuf, var))
+            outs[i].validity = vbuf.ctypes.data_as(C.c_void_p)
+            outs[i].values = dbuf.ctypes.data_as(C.c_void_p)
         _check(lib.gdv_projector_evaluate(self._h, C.byref(cb), csel, outs, len(self._exprs), None, 0))
         result = []
-        for (vbuf, dbuf), e in zip(holders, self._exprs):
+        for (vbuf, dbuf, var), e in zip(holders, self._exprs):
             t = e.result().type
-            result.append(pa.Array.from_buffers(t, n, [pa.py_buffer(vbuf), pa.py_buffer(dbuf)]))
+            bufs = [pa.py_buffer(vbuf), pa.py_buffer(dbuf)]
+            if var is not None:
+                bufs.append(pa.py_buffer(var))
+            result.append(pa.Array.from_buffers(t, n, bufs))
         return result
 
     # -- device-resident path (bench / multi-GPU): raw pointers in HBM, caller-owned stream ----

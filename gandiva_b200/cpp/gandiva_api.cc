@@ -510,29 +510,6 @@ Status Projector::Evaluate(const arrow::RecordBatch& batch, const SelectionVecto
   const int64_t n = selection_vector != nullptr && mode_ != SelectionVector::MODE_NONE
                         ? selection_vector->GetNumSlots()
                         : batch.num_rows();
-  std::vector<gdv_out_column_t> outs(output_fields_.size());
-  std::vector<ArrayDataPtr> datas;
-  for (size_t i = 0; i < outs.size(); ++i) {
-    std::memset(&outs[i], 0, sizeof(outs[i]));
-    const DataTypePtr& t = output_fields_[i]->type();
-    const int64_t bitmap_bytes = arrow::bit_util::RoundUpToMultipleOf8(arrow::bit_util::BytesForBits(n)) + 8;
-    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> validity, arrow::AllocateBuffer(bitmap_bytes, pool));
-    std::memset(validity->mutable_data(), 0, static_cast<size_t>(bitmap_bytes));
-    int64_t value_bytes;
-    if (t->id() == arrow::Type::BOOL) {
-      value_bytes = bitmap_bytes;
-    } else if (t->id() == arrow::Type::STRING || t->id() == arrow::Type::BINARY) {
-      return Status::NotImplemented("variable-length projection outputs are not implemented yet");
-    } else {
-      value_bytes = n * (t->bit_width() / 8) + 8;
-    }
-    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> values, arrow::AllocateBuffer(value_bytes, pool));
-    if (t->id() == arrow::Type::BOOL) std::memset(values->mutable_data(), 0, static_cast<size_t>(value_bytes));
-    outs[i].validity = validity->mutable_data();
-    outs[i].values = values->mutable_data();
-    datas.push_back(arrow::ArrayData::Make(
-        t, n, {std::shared_ptr<arrow::Buffer>(std::move(validity)), std::shared_ptr<arrow::Buffer>(std::move(values))}));
-  }
   gdv_selection_t sel;
   std::memset(&sel, 0, sizeof(sel));
   const gdv_selection_t* psel = nullptr;
@@ -543,6 +520,43 @@ Status Projector::Evaluate(const arrow::RecordBatch& batch, const SelectionVecto
     sel.mode = SelModeToC(selection_vector->GetMode());
     sel.mem_space = GDV_MEM_HOST;
     psel = &sel;
+  }
+  std::vector<gdv_out_column_t> outs(output_fields_.size());
+  std::vector<ArrayDataPtr> datas;
+  for (size_t i = 0; i < outs.size(); ++i) {
+    std::memset(&outs[i], 0, sizeof(outs[i]));
+    const DataTypePtr& t = output_fields_[i]->type();
+    const int64_t bitmap_bytes = arrow::bit_util::RoundUpToMultipleOf8(arrow::bit_util::BytesForBits(n)) + 8;
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> validity, arrow::AllocateBuffer(bitmap_bytes, pool));
+    std::memset(validity->mutable_data(), 0, static_cast<size_t>(bitmap_bytes));
+    outs[i].validity = validity->mutable_data();
+    if (t->id() == arrow::Type::STRING || t->id() == arrow::Type::BINARY) {
+      // utf8/binary: the sizing pass says how many bytes the data buffer needs, then the
+      // offsets (n + 1 int32) and the bytes are allocated from the caller's pool
+      int64_t need = 0;
+      ARROW_RETURN_NOT_OK(ToStatus(gdv_projector_output_var_size(
+          static_cast<gdv_projector_t>(handle_), &b, psel, static_cast<int32_t>(i), nullptr, &need)));
+      ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> offsets, arrow::AllocateBuffer((n + 1) * 4 + 8, pool));
+      ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> bytes, arrow::AllocateBuffer(need + 8, pool));
+      outs[i].values = offsets->mutable_data();
+      outs[i].var_data = bytes->mutable_data();
+      outs[i].var_capacity = need;
+      datas.push_back(arrow::ArrayData::Make(
+          t, n, {std::shared_ptr<arrow::Buffer>(std::move(validity)), std::shared_ptr<arrow::Buffer>(std::move(offsets)),
+                 std::shared_ptr<arrow::Buffer>(std::move(bytes))}));
+      continue;
+    }
+    int64_t value_bytes;
+    if (t->id() == arrow::Type::BOOL) {
+      value_bytes = bitmap_bytes;
+    } else {
+      value_bytes = n * (t->bit_width() / 8) + 8;
+    }
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> values, arrow::AllocateBuffer(value_bytes, pool));
+    if (t->id() == arrow::Type::BOOL) std::memset(values->mutable_data(), 0, static_cast<size_t>(value_bytes));
+    outs[i].values = values->mutable_data();
+    datas.push_back(arrow::ArrayData::Make(
+        t, n, {std::shared_ptr<arrow::Buffer>(std::move(validity)), std::shared_ptr<arrow::Buffer>(std::move(values))}));
   }
   ARROW_RETURN_NOT_OK(ToStatus(gdv_projector_evaluate(static_cast<gdv_projector_t>(handle_), &b, psel,
                                                       outs.data(), static_cast<int32_t>(outs.size()),

@@ -31,6 +31,8 @@ typedef unsigned __int128 u128;
 // ---- error reporting (ExecutionError, P/include/arrow/status.h:100) -----------------
 #define GDV_ERR_NONE 0
 #define GDV_ERR_DIV_ZERO 1
+#define GDV_ERR_OFFSET_OVERFLOW 2  /* a utf8/binary output needs more than 2^31 - 1 bytes */
+#define GDV_ERR_VAR_CAPACITY 3     /* the caller's var_data buffer is too small */
 struct gdv_ctx {
   int* err;
 };

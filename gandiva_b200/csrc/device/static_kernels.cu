@@ -83,6 +83,49 @@ extern "C" __global__ void __launch_bounds__(256) gdv_fill_u32(u32* p, i64 words
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) p[i] = v;
 }
 
+// ---- string-producing projections: exclusive scan of the per-tile byte counts -------------------
+// One CTA of 1024 threads walks the tile array in blocks of 1024 (a 1e9-row batch has ~2M tiles of
+// 512 rows: a few hundred microseconds next to the two passes over the string bytes).  Writes the
+// total to *total and raises GDV_ERR_OFFSET_OVERFLOW when it exceeds `limit` (int32 offsets).
+extern "C" __global__ void __launch_bounds__(1024)
+gdv_scan_tiles(u64* tiles, i64 n_tiles, u64* total, int* err, u64 limit) {
+  __shared__ u64 s_warp[32];
+  __shared__ u64 s_carry;
+  const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0ull;
+  __syncthreads();
+  for (i64 b = 0; b < n_tiles; b += 1024) {
+    const i64 i = b + (i64)threadIdx.x;
+    const u64 v = i < n_tiles ? tiles[i] : 0ull;
+    u64 x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(GDV_FULL, x, o);
+      if (lane >= (u32)o) x += t;
+    }
+    if (lane == 31u) s_warp[wid] = x;
+    __syncthreads();
+    if (wid == 0u) {
+      u64 w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(GDV_FULL, w, o);
+        if (lane >= (u32)o) w += t;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const u64 carry = s_carry;
+    const u64 wexcl = wid == 0u ? 0ull : s_warp[wid - 1];
+    if (i < n_tiles) tiles[i] = carry + wexcl + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + wexcl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total = s_carry;
+    if (s_carry > limit && err != nullptr) atomicCAS(err, 0, GDV_ERR_OFFSET_OVERFLOW);
+  }
+}
+
 // ---- SelectionVector reassembly across row-range shards (DESIGN.md "Multi-GPU") ------------
 // One process per GPU filters its row range into a LOCAL index run (global row numbers).  This
 // kernel, launched on a side stream next to the following batch's filter kernel, moves the run

@@ -267,10 +267,12 @@ gdv_status gdv_projector_sync(gdv_projector_t p, void* stream) {
   return s.ok() ? GDV_OK : Fail(s);
 }
 
-gdv_status gdv_projector_output_var_size(gdv_projector_t, const gdv_batch_t*,
-                                         const gdv_selection_t*, int32_t, void*, int64_t* out) {
-  if (out != nullptr) *out = 0;
-  return Fail(GDV_NOT_IMPLEMENTED, "variable-length projection outputs are not implemented yet");
+gdv_status gdv_projector_output_var_size(gdv_projector_t p, const gdv_batch_t* batch,
+                                         const gdv_selection_t* selection, int32_t out_index,
+                                         void* stream, int64_t* out) {
+  if (p == nullptr) return Fail(GDV_INVALID, "null projector");
+  Status s = reinterpret_cast<ProjH*>(p)->p->OutputVarSize(batch, selection, out_index, stream, out);
+  return s.ok() ? GDV_OK : Fail(s);
 }
 
 int64_t gdv_projector_dump_ir(gdv_projector_t p, char* buf, int64_t buf_len) {

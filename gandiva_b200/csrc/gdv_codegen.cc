@@ -1185,10 +1185,194 @@ int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
   return p;
 }
 
+// ---- string-producing projections ---------------------------------------------------------------
+// One utf8/binary output expression = two kernels around a tile scan (DESIGN.md "String outputs"):
+//   gdv_strsize_*  : bytes produced by every CTA tile -> tile_state[tile]
+//   gdv_scan_tiles : (static kernel) exclusive scan of tile_state, total -> out_count
+//   gdv_strwrite_* : re-evaluates the rows (the values are views, so this is cheap), scans the
+//                    row lengths inside the tile, writes the int32 offsets and copies the bytes
+//                    (through the view's case map) warp-cooperatively, row by row.
+// No CTA waits on another one; the host may read the total between the scan and the write to
+// size the data buffer (Projector::Evaluate with host batches does).
+Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, const KernelSpec& spec,
+                            GeneratedKernel* out) {
+  const bool is_size = spec.kind == KernelKind::kStringSize;
+  std::vector<ColumnSlot> slots;
+  BodyGen gen(schema, &slots, spec.nullable, spec.string_scan != 1);
+  std::string body;
+  const Val res = gen.Gen(*expr->root(), &body, 4);
+  int n_varlen = 0, in_bytes = 0;
+  for (const auto& s : slots) {
+    n_varlen += s.type.is_varlen() ? 1 : 0;
+    in_bytes += s.type.is_varlen() ? 32 : std::max(s.type.width(), 1);
+  }
+  const int R = spec.rows_per_thread > 0 ? std::min(spec.rows_per_thread, 8) : 2;
+  const int BT = spec.block_threads > 0 ? spec.block_threads : 256;
+  if (BT % 32 != 0 || BT > 1024)
+    return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
+  const int NW = BT / 32;
+  const int T = BT * R;
+  const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
+  const std::vector<CoopSeg>& coop = gen.coop_segs();
+  const int hit_bytes = coop.empty() ? 0 : 8 * kHitCap + 16;
+  const int col_block = stage_bytes + hit_bytes;
+  const int dynamic_smem = col_block * NW * n_varlen;
+  const bool has_sel = spec.selection_mode != GDV_SEL_NONE;
+  ArgsLayout L(static_cast<int>(slots.size()), 1);
+  const std::string sR = std::to_string(R), s32R = std::to_string(32 * R), sT = std::to_string(T);
+
+  std::string src;
+  src += std::string("// generated by gandiva_b200 kernel fuser; string projection, ") +
+         (is_size ? "sizing pass" : "write pass") +
+         (spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n");
+  src += "// expr_0: " + expr->ToString() + "\n";
+  src += "#include \"gdv_device_lib.cuh\"\n";
+  src += EmitArgsStruct(L);
+  src += gen.globals();
+  src += EmitCoopKeyTables(coop);
+  src += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(BT) + ") " + spec.name +
+         "(const __grid_constant__ gdv_args A) {\n";
+  src += "  const u32 lane = threadIdx.x & 31u;\n";
+  src += "  const u32 wid = threadIdx.x >> 5;\n";
+  src += "  gdv_ctx ctx;\n  ctx.err = A.err;\n";
+  KernelSpec pspec = spec;
+  pspec.kind = KernelKind::kProject;  // prologue / group emitters key on project vs filter only
+  EmitPrologue(slots, pspec, &src);
+  if (stage_bytes > 0) {
+    src += "  extern __shared__ uint4 gdv_smem[];\n";
+    int vi = 0;
+    for (size_t j = 0; j < slots.size(); ++j) {
+      if (!slots[j].type.is_varlen()) continue;
+      const std::string J = std::to_string(j);
+      src += "  u8* stage" + J + " = reinterpret_cast<u8*>(gdv_smem) + ((size_t)wid * " +
+             std::to_string(n_varlen) + " + " + std::to_string(vi) + ") * " + std::to_string(col_block) + ";\n";
+      if (SlotHasCoop(coop, static_cast<int>(j))) {
+        src += "  u32* cand" + J + " = reinterpret_cast<u32*>(stage" + J + " + " + std::to_string(stage_bytes) + ");\n";
+        src += "  u32* hits" + J + " = cand" + J + " + " + std::to_string(kHitCap) + ";\n";
+        src += "  u32* hctr" + J + " = hits" + J + " + " + std::to_string(kHitCap) + ";\n";
+      }
+      ++vi;
+    }
+  }
+  src += "  __shared__ u64 s_part[" + std::to_string(NW) + "];\n";
+  src += "  const i64 n_tiles = (A.n + " + std::to_string(T - 1) + ") / " + sT + ";\n";
+  src += "  for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n";
+  src += "    const i64 base = tile * " + sT + " + (i64)wid * " + s32R + ";\n";
+  std::string tail;
+  if (is_size) {
+    src += "    u32 tsum = 0u;\n";
+    tail = "        tsum += (in && (" + res.ok + ")) ? (u32)(" + res.v + ").len : 0u;\n";
+  } else {
+    src += "    u32 slen[" + sR + "];\n    gdv_str sv[" + sR + "];\n    u32 vw0 = 0u;\n";
+    tail = "        { const bool okk = in && (" + res.ok + "); slen[k] = okk ? (u32)(" + res.v +
+           ").len : 0u; sv[k] = " + res.v + "; const u32 m = __ballot_sync(GDV_FULL, okk); "
+           "if (lane == (u32)k) vw0 = m; }\n";
+  }
+  if (!has_sel) {
+    src += "    if (base + " + s32R + " <= A.n) {\n";
+    EmitGroup(slots, pspec, R, kFast, body, tail, &src, 3, stage_bytes, std::string(), coop);
+    src += "    } else {\n";
+    EmitGroup(slots, pspec, R, kPred, body, tail, &src, 3, 0, std::string(), coop);
+    src += "    }\n";
+  } else {
+    src += "    {\n";
+    EmitGroup(slots, pspec, R, kPred, body, tail, &src, 3, 0, std::string(), coop);
+    src += "    }\n";
+  }
+  if (is_size) {
+    src += "    u64 ws = (u64)tsum;\n";
+    src += "    for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(GDV_FULL, ws, o);\n";
+    src += "    if (lane == 0u) s_part[wid] = ws;\n";
+    src += "    __syncthreads();\n";
+    src += "    if (threadIdx.x == 0) {\n";
+    src += "      u64 t = 0ull;\n";
+    src += "      for (int w = 0; w < " + std::to_string(NW) + "; ++w) t += s_part[w];\n";
+    src += "      A.tile_state[tile] = t;\n";
+    src += "    }\n";
+    src += "    __syncthreads();\n";
+  } else {
+    // lengths -> inclusive offsets inside the warp (row order: step k, then lane), then across warps
+    src += "    u32 incl[" + sR + "];\n";
+    src += "    u32 run = 0u;\n";
+    src += "    #pragma unroll\n";
+    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "      u32 x = slen[k];\n";
+    src += "      #pragma unroll\n";
+    src += "      for (int o = 1; o < 32; o <<= 1) {\n";
+    src += "        const u32 t = __shfl_up_sync(GDV_FULL, x, o);\n";
+    src += "        if (lane >= (u32)o) x += t;\n";
+    src += "      }\n";
+    src += "      incl[k] = run + x;\n";
+    src += "      run += __shfl_sync(GDV_FULL, x, 31);\n";
+    src += "    }\n";
+    src += "    if (lane == 0u) s_part[wid] = (u64)run;\n";
+    src += "    __syncthreads();\n";
+    src += "    u64 wbase = A.tile_state[tile];\n";
+    src += "    for (u32 w = 0u; w < wid; ++w) wbase += s_part[w];\n";
+    src += "    __syncthreads();\n";
+    src += "    i32* offs = reinterpret_cast<i32*>(A.out_val[0]);\n";
+    src += "    u8* data = A.out_var[0];\n";
+    src += "    #pragma unroll\n";
+    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "      const i64 s = base + 32 * k + (i64)lane;\n";
+    src += "      if (s < A.n) offs[s + 1] = (i32)(wbase + (u64)incl[k]);\n";
+    src += "    }\n";
+    src += "    if (tile == 0 && threadIdx.x == 0) offs[0] = 0;\n";
+    src += "    #pragma unroll\n";
+    src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
+    src += "      const u64 dst0 = wbase + (u64)(incl[k] - slen[k]);\n";
+    src += "      const u32 nonempty = __ballot_sync(GDV_FULL, slen[k] != 0u);\n";
+    src += "      for (u32 rest = nonempty; rest != 0u; rest &= rest - 1u) {\n";
+    src += "        const int j = __ffs((int)rest) - 1;\n";
+    src += "        gdv_str v;\n";
+    src += "        v.p = reinterpret_cast<const u8*>(__shfl_sync(GDV_FULL, (u64)sv[k].p, j));\n";
+    src += "        v.len = (i32)__shfl_sync(GDV_FULL, slen[k], j);\n";
+    src += "        v.xf = __shfl_sync(GDV_FULL, sv[k].xf, j);\n";
+    src += "        const u64 d = __shfl_sync(GDV_FULL, dst0, j);\n";
+    src += "        if (d + (u64)v.len <= (u64)A.out_cap) {\n";
+    src += "          for (i32 i = (i32)lane; i < v.len; i += 32) data[d + (u64)i] = gdv_ch(v, i);\n";
+    src += "        } else if (lane == 0u) {\n";
+    src += "          gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";
+    src += "        }\n";
+    src += "      }\n";
+    src += "    }\n";
+    src += "    if (lane < " + sR + "u && base + 32 * (i64)lane < A.n && A.out_vld[0] != nullptr)\n";
+    src += "      A.out_vld[0][(base >> 5) + (i64)lane] = vw0;\n";
+    src += "    __syncwarp();  // the views may point into this warp's stage: done before it is refilled\n";
+  }
+  src += "  }\n";
+  src += "}\n";
+
+  out->source = std::move(src);
+  out->name = spec.name;
+  out->kind = spec.kind;
+  out->rows_per_thread = R;
+  out->block_threads = BT;
+  out->selection_mode = spec.selection_mode;
+  out->nullable = spec.nullable;
+  out->inputs = slots;
+  out->outputs = {expr->result().type};
+  out->uses_ctx = gen.uses_ctx() || !is_size;
+  out->in_bytes_per_row = in_bytes;
+  out->out_bytes_per_row = 4;
+  out->args_size = L.size;
+  out->dynamic_smem = dynamic_smem;
+  out->tile_rows = T;
+  out->staged = false;
+  out->stages = 0;
+  out->cta_tile_rows = T;
+  return Status::OK();
+}
+
 }  // namespace
 
 Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
                       const KernelSpec& spec, GeneratedKernel* out) {
+  if (spec.kind == KernelKind::kStringSize || spec.kind == KernelKind::kStringWrite) {
+    if (exprs.size() != 1 || !exprs[0]->result().type.is_varlen())
+      return Status::Make(GDV_INVALID, "a string kernel takes exactly one utf8/binary expression");
+    return GenerateStringKernel(schema, exprs[0], spec, out);
+  }
   std::vector<ColumnSlot> slots;
   BodyGen gen(schema, &slots, spec.nullable, spec.string_scan != 1);
 

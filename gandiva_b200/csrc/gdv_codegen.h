@@ -31,7 +31,7 @@ struct Status {
 // (ExpressionValidationError on failure).
 Status ValidateExpression(const Schema& schema, const Expression& expr);
 
-enum class KernelKind { kProject, kFilter };
+enum class KernelKind { kProject, kFilter, kStringSize, kStringWrite };
 
 struct KernelSpec {
   KernelKind kind = KernelKind::kProject;

@@ -12,6 +12,8 @@ std::atomic<long long> g_launch_count{0};
 const char* ExecutionErrorMessage(int code) {
   switch (code) {
     case 1: return "divide by zero error";
+    case 2: return "a utf8/binary output needs more than 2^31 - 1 bytes (int32 offsets)";
+    case 3: return "var_data capacity of a utf8/binary output is too small";
     default: return "execution error in device function";
   }
 }
@@ -376,9 +378,26 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
   p->exprs_ = std::move(exprs);
   p->selection_mode_ = selection_mode;
   p->cfg_ = cfg;
-  GDV_RETURN_NOT_OK(BuildKernel(*schema, p->exprs_, KernelKind::kProject, selection_mode, true, cfg,
-                                &p->kernel_));
-  if (std::getenv("GDV_EAGER_NONULL") != nullptr) {
+  // Fixed-width outputs share ONE fused kernel; every utf8/binary output gets its own
+  // sizing + write kernel pair (its bytes cannot be placed before all lengths are known).
+  for (size_t i = 0; i < p->exprs_.size(); ++i) {
+    if (p->exprs_[i]->result().type.is_varlen()) {
+      StringKernels sk;
+      sk.out_index = static_cast<int>(i);
+      p->strings_.push_back(std::move(sk));
+    } else {
+      p->fixed_exprs_.push_back(p->exprs_[i]);
+      p->fixed_idx_.push_back(static_cast<int>(i));
+    }
+  }
+  if (!p->fixed_exprs_.empty())
+    GDV_RETURN_NOT_OK(BuildKernel(*schema, p->fixed_exprs_, KernelKind::kProject, selection_mode, true,
+                                  cfg, &p->kernel_));
+  for (auto& sk : p->strings_) {
+    CompiledKernel *a = nullptr, *b = nullptr;
+    GDV_RETURN_NOT_OK(p->StringKernelsFor(&sk, true, &a, &b));
+  }
+  if (std::getenv("GDV_EAGER_NONULL") != nullptr && p->kernel_ != nullptr) {
     CompiledKernel* k = nullptr;
     GDV_RETURN_NOT_OK(p->KernelFor(false, &k));
   }
@@ -386,7 +405,32 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
   return Status::OK();
 }
 
+CompiledKernel& Projector::kernel() {
+  if (last_used_ != nullptr) return *last_used_;
+  if (kernel_ != nullptr) return *kernel_;
+  return *strings_.front().write[0];
+}
+
+Status Projector::StringKernelsFor(StringKernels* sk, bool nullable, CompiledKernel** size,
+                                   CompiledKernel** write) {
+  std::lock_guard<std::mutex> lock(mu_);
+  const int v = nullable ? 0 : 1;
+  if (sk->size[v] == nullptr) {
+    std::vector<ExpressionPtr> one = {exprs_[static_cast<size_t>(sk->out_index)]};
+    Config cfg = cfg_;
+    cfg.loader = 1;
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, one, KernelKind::kStringSize, selection_mode_, nullable, cfg,
+                                  &sk->size[v]));
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, one, KernelKind::kStringWrite, selection_mode_, nullable, cfg,
+                                  &sk->write[v]));
+  }
+  *size = sk->size[v].get();
+  *write = sk->write[v].get();
+  return Status::OK();
+}
+
 Status Projector::KernelFor(bool nullable, CompiledKernel** out) {
+  if (kernel_ == nullptr) return Status::Make(GDV_INVALID, "projector has no fixed-width output");
   if (nullable) {
     *out = kernel_.get();
     return Status::OK();
@@ -409,15 +453,18 @@ static bool AnyValidity(const GeneratedKernel& gen, const gdv_batch_t* batch) {
 }
 
 std::string Projector::DumpIR() const {
-  return kernel_->gen.source + (kernel_->ptx.empty() ? "" : "\n// ---- PTX ----\n" + kernel_->ptx);
+  std::string ir;
+  if (kernel_ != nullptr)
+    ir += kernel_->gen.source + (kernel_->ptx.empty() ? "" : "\n// ---- PTX ----\n" + kernel_->ptx);
+  for (const auto& sk : strings_)
+    for (const auto* k : {sk.size[0].get(), sk.write[0].get()})
+      if (k != nullptr) ir += "\n" + k->gen.source + (k->ptx.empty() ? "" : "\n// ---- PTX ----\n" + k->ptx);
+  return ir;
 }
 
-Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
-                           gdv_out_column_t* outs, int n_outs, void* stream_v, bool async) {
-  if (batch == nullptr || outs == nullptr) return Status::Make(GDV_INVALID, "null argument");
-  if (n_outs != num_outputs())
-    return Status::Make(GDV_INVALID, "expected " + std::to_string(num_outputs()) +
-                                         " output columns, got " + std::to_string(n_outs));
+Status Projector::CheckEvaluateArgs(const gdv_batch_t* batch, const gdv_selection_t* sel,
+                                    int64_t* n) const {
+  if (batch == nullptr) return Status::Make(GDV_INVALID, "null argument");
   if (batch->num_columns != static_cast<int>(schema_->fields().size()))
     return Status::Make(GDV_INVALID, "RecordBatch schema must match the schema of Make()");
   if (batch->num_rows <= 0) return Status::Make(GDV_INVALID, "RecordBatch must be non-empty.");
@@ -430,9 +477,183 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   } else if (sel != nullptr && sel->mode != GDV_SEL_NONE) {
     return Status::Make(GDV_INVALID, "projector was built without a selection vector mode");
   }
+  *n = selection_mode_ != GDV_SEL_NONE ? sel->num_slots : batch->num_rows;
+  if (*n < 0) return Status::Make(GDV_INVALID, "negative slot count");
+  return Status::OK();
+}
+
+Status Projector::OutputVarSize(const gdv_batch_t* batch, const gdv_selection_t* sel, int out_index,
+                                void* stream, int64_t* bytes) {
+  if (bytes == nullptr) return Status::Make(GDV_INVALID, "null argument");
+  *bytes = 0;
+  if (out_index < 0 || out_index >= num_outputs())
+    return Status::Make(GDV_INVALID, "output index out of range");
+  for (auto& sk : strings_)
+    if (sk.out_index == out_index)
+      return EvaluateString(&sk, batch, sel, nullptr, stream, false, true, bytes);
+  return Status::OK();  // fixed-width output
+}
+
+// One utf8/binary output: sizing kernel -> tile scan -> (host: read the total, size the staging
+// buffers) -> write kernel.  size_only stops after the scan and returns the total.
+Status Projector::EvaluateString(StringKernels* sk, const gdv_batch_t* batch,
+                                 const gdv_selection_t* sel, gdv_out_column_t* out, void* stream_v,
+                                 bool async, bool size_only, int64_t* total_out) {
+  int64_t n = 0;
+  GDV_RETURN_NOT_OK(CheckEvaluateArgs(batch, sel, &n));
   const bool host = batch->mem_space == GDV_MEM_HOST;
-  const int64_t n = selection_mode_ != GDV_SEL_NONE ? sel->num_slots : batch->num_rows;
-  if (n < 0) return Status::Make(GDV_INVALID, "negative slot count");
+  Device* dev = nullptr;
+  GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
+  CompiledKernel *ksize = nullptr, *kwrite = nullptr;
+  GDV_RETURN_NOT_OK(StringKernelsFor(sk, AnyValidity(sk->size[0]->gen, batch), &ksize, &kwrite));
+  CompiledKernel::Loaded lsize, lwrite;
+  GDV_RETURN_NOT_OK(ksize->Load(dev, &lsize));
+  GDV_RETURN_NOT_OK(kwrite->Load(dev, &lwrite));
+  last_used_ = kwrite;
+  const DriverApi& d = Driver();
+  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
+  const GeneratedKernel& gen = ksize->gen;  // both kernels read the same input slots
+
+  ScratchScope scratch(dev);
+  std::vector<ResolvedIn> ins;
+  GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
+  ArgsLayout L(static_cast<int>(gen.inputs.size()), 1);
+  std::vector<uint8_t> args(L.size, 0);
+  Put<int64_t>(args, L.off_n, n);
+  for (size_t j = 0; j < ins.size(); ++j) {
+    Put<CUdeviceptr>(args, L.off_in_val + 8 * j, ins[j].val);
+    Put<CUdeviceptr>(args, L.off_in_vld + 8 * j, ins[j].vld);
+    Put<CUdeviceptr>(args, L.off_in_var + 8 * j, ins[j].var);
+    Put<uint32_t>(args, L.off_in_vsh + 4 * j, ins[j].vsh);
+    Put<uint32_t>(args, L.off_in_dsh + 4 * j, ins[j].dsh);
+  }
+  if (selection_mode_ != GDV_SEL_NONE) {
+    CUdeviceptr dsel = reinterpret_cast<CUdeviceptr>(sel->indices);
+    if (host) {
+      const size_t bytes = static_cast<size_t>(n) * SelWidth(selection_mode_);
+      GDV_RETURN_NOT_OK(scratch.Alloc(bytes + 16, &dsel));
+      if (bytes > 0)
+        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dsel, sel->indices, bytes, stream), "H2D sel"));
+    }
+    Put<CUdeviceptr>(args, L.off_sel, dsel);
+  }
+  // [total u64][pad u64][one u64 per CTA tile]; lives until the stream is synchronised
+  const int64_t T = gen.tile_rows;
+  const int64_t n_tiles = (n + T - 1) / T;
+  CUdeviceptr d_state = 0, d_err = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    Pending& pend = pending_[stream];
+    pend.dev = dev;
+    GDV_RETURN_NOT_OK(dev->Alloc(16 + static_cast<size_t>(n_tiles) * 8, &d_state));
+    pend.scratch.push_back(d_state);
+    if (pend.d_err == 0) {
+      pend.uses_ctx = true;
+      GDV_RETURN_NOT_OK(dev->Alloc(256, &pend.d_err));
+      GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(pend.d_err, 0, 256, stream), "memset err"));
+    }
+    d_err = pend.d_err;
+  }
+  Put<CUdeviceptr>(args, L.off_err, d_err);
+  Put<CUdeviceptr>(args, L.off_tile_state, d_state + 16);
+  Put<CUdeviceptr>(args, L.off_out_count, d_state);
+  const int64_t cap_blocks =
+      static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * lsize.blocks_per_sm;
+  unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, cap_blocks)));
+  GDV_RETURN_NOT_OK(LaunchKernel(dev, lsize, ksize->gen, args, grid, stream));
+  {
+    CUfunction scan = nullptr;
+    GDV_RETURN_NOT_OK(dev->StaticFunction("gdv_scan_tiles", &scan));
+    CUdeviceptr tiles = d_state + 16, total = d_state, errp = d_err;
+    int64_t nt = n_tiles;
+    uint64_t limit = 0x7fffffffull;
+    void* params[] = {&tiles, &nt, &total, &errp, &limit};
+    g_launch_count.fetch_add(1);
+    GDV_RETURN_NOT_OK(CuCheck(d.LaunchKernel(scan, 1, 1, 1, 1024, 1, 1, 0, stream, params, nullptr),
+                              "cuLaunchKernel(gdv_scan_tiles)"));
+  }
+  uint64_t total = 0;
+  if (size_only || host || !async) {
+    GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(&total, d_state, 8, stream), "D2H total"));
+    GDV_RETURN_NOT_OK(CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize"));
+    if (total > 0x7fffffffull) {
+      Sync(stream);  // releases the pending blocks; reports the overflow below
+      return Status::Make(GDV_EXECUTION_ERROR, ExecutionErrorMessage(2));
+    }
+    if (total_out != nullptr) *total_out = static_cast<int64_t>(total);
+  }
+  if (size_only) return Sync(stream);
+
+  if (out == nullptr || out->values == nullptr)
+    return Status::Make(GDV_INVALID, "output offsets buffer is null");
+  const size_t words = static_cast<size_t>((n + 31) / 32);
+  CUdeviceptr d_offs = reinterpret_cast<CUdeviceptr>(out->values);
+  CUdeviceptr d_data = reinterpret_cast<CUdeviceptr>(out->var_data);
+  CUdeviceptr d_vld = reinterpret_cast<CUdeviceptr>(out->validity);
+  int64_t out_cap = out->var_capacity;
+  if (host) {
+    out->var_size = static_cast<int64_t>(total);
+    if (static_cast<int64_t>(total) > out->var_capacity || (total > 0 && out->var_data == nullptr)) {
+      Sync(stream);
+      return Status::Make(GDV_INVALID, "var_data capacity " + std::to_string(out->var_capacity) +
+                                           " is smaller than the " + std::to_string(total) +
+                                           " bytes the output needs (see var_size)");
+    }
+    GDV_RETURN_NOT_OK(scratch.Alloc(static_cast<size_t>(n + 1) * 4 + 16, &d_offs));
+    GDV_RETURN_NOT_OK(scratch.Alloc(static_cast<size_t>(total) + 16, &d_data));
+    if (out->validity != nullptr) GDV_RETURN_NOT_OK(scratch.Alloc(words * 4 + 8, &d_vld));
+    out_cap = static_cast<int64_t>(total);
+  } else {
+    out->var_size = async ? -1 : static_cast<int64_t>(total);
+    if (out->var_data == nullptr && out->var_capacity > 0)
+      return Status::Make(GDV_INVALID, "output var_data buffer is null");
+  }
+  Put<CUdeviceptr>(args, L.off_out_val, d_offs);
+  Put<CUdeviceptr>(args, L.off_out_vld, d_vld);
+  Put<CUdeviceptr>(args, L.off_out_var, d_data);
+  Put<int64_t>(args, L.off_out_cap, out_cap);
+  const int64_t cap_w =
+      static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * lwrite.blocks_per_sm;
+  grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, cap_w)));
+  GDV_RETURN_NOT_OK(LaunchKernel(dev, lwrite, kwrite->gen, args, grid, stream));
+  if (host) {
+    GDV_RETURN_NOT_OK(CuCheck(
+        d.MemcpyDtoHAsync(out->values, d_offs, static_cast<size_t>(n + 1) * 4, stream), "D2H offsets"));
+    if (total > 0)
+      GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(out->var_data, d_data, static_cast<size_t>(total), stream),
+                                "D2H string bytes"));
+    if (out->validity != nullptr)
+      GDV_RETURN_NOT_OK(CuCheck(
+          d.MemcpyDtoHAsync(out->validity, d_vld, static_cast<size_t>((n + 7) / 8), stream), "D2H validity"));
+    // the staging blocks go back to the pool when `scratch` dies: wait for the copies first
+    GDV_RETURN_NOT_OK(CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize"));
+  }
+  return Status::OK();
+}
+
+Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
+                           gdv_out_column_t* all_outs, int n_all_outs, void* stream_v, bool async) {
+  if (batch == nullptr || all_outs == nullptr) return Status::Make(GDV_INVALID, "null argument");
+  if (n_all_outs != num_outputs())
+    return Status::Make(GDV_INVALID, "expected " + std::to_string(num_outputs()) +
+                                         " output columns, got " + std::to_string(n_all_outs));
+  int64_t n = 0;
+  GDV_RETURN_NOT_OK(CheckEvaluateArgs(batch, sel, &n));
+  const bool host = batch->mem_space == GDV_MEM_HOST;
+  // utf8/binary outputs first (each runs its own kernel pair), then the fused fixed-width kernel
+  for (auto& sk : strings_) {
+    int64_t total = 0;
+    GDV_RETURN_NOT_OK(EvaluateString(&sk, batch, sel, &all_outs[sk.out_index], stream_v, async, false,
+                                     &total));
+  }
+  if (fixed_exprs_.empty()) {
+    if (host || !async) return Sync(stream_v);
+    return Status::OK();
+  }
+  std::vector<gdv_out_column_t> fixed_outs;
+  for (int idx : fixed_idx_) fixed_outs.push_back(all_outs[idx]);
+  gdv_out_column_t* outs = fixed_outs.data();
+  const int n_outs = static_cast<int>(fixed_outs.size());
 
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));

@@ -124,17 +124,35 @@ class Projector {
                      const Config& cfg, std::shared_ptr<Projector>* out);
   Status Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel, gdv_out_column_t* outs,
                   int n_outs, void* stream, bool async);
+  // Bytes output `out_index` (utf8/binary) produces for this batch: runs the sizing pass only.
+  Status OutputVarSize(const gdv_batch_t* batch, const gdv_selection_t* sel, int out_index,
+                       void* stream, int64_t* bytes);
   Status Sync(void* stream);
   std::string DumpIR() const;
-  CompiledKernel& kernel() { return last_used_ ? *last_used_ : *kernel_; }
+  CompiledKernel& kernel();
   // Variant specialised on whether any referenced input carries a validity bitmap.
   Status KernelFor(bool nullable, CompiledKernel** out);
   const Config& config() const { return cfg_; }
   int num_outputs() const { return static_cast<int>(exprs_.size()); }
 
  private:
+  // One utf8/binary output expression: sizing + write kernels, [0] nullable inputs, [1] no nulls.
+  struct StringKernels {
+    int out_index = 0;
+    std::unique_ptr<CompiledKernel> size[2], write[2];
+  };
+  Status StringKernelsFor(StringKernels* sk, bool nullable, CompiledKernel** size,
+                          CompiledKernel** write);
+  Status CheckEvaluateArgs(const gdv_batch_t* batch, const gdv_selection_t* sel, int64_t* n) const;
+  Status EvaluateString(StringKernels* sk, const gdv_batch_t* batch, const gdv_selection_t* sel,
+                        gdv_out_column_t* out, void* stream, bool async, bool size_only,
+                        int64_t* total);
+
   SchemaPtr schema_;
   std::vector<ExpressionPtr> exprs_;
+  std::vector<ExpressionPtr> fixed_exprs_;  // fixed-width outputs: one fused kernel
+  std::vector<int> fixed_idx_;              // their positions in exprs_
+  std::vector<StringKernels> strings_;      // utf8/binary outputs
   int selection_mode_ = GDV_SEL_NONE;
   Config cfg_;
   std::unique_ptr<CompiledKernel> kernel_;          // general (nullable) variant, built at Make()

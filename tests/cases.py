@@ -442,6 +442,38 @@ def all_like_scan_cases():
     return out
 
 
+def case_string_outputs(b):
+    """utf8 outputs (two-pass string projection): views, case maps, if/else, literals, plus a
+    fixed-width output from the same projector."""
+    t = pa.string()
+    schema = pa.schema([("s", t), ("u", t), ("k", pa.int64()), ("a", pa.int32())])
+    s, u, k, a = F(b, "s", t), F(b, "u", t), F(b, "k", pa.int64()), F(b, "a", pa.int32())
+    L = lambda v: b.make_literal(v, pa.int64())
+    B = pa.bool_()
+    up = b.make_function("upper", [s], t)
+    cond = b.make_function("greater_than", [a, b.make_literal(0, pa.int32())], B)
+    outs = [
+        (s, t),
+        (up, t),
+        (b.make_function("lower", [b.make_function("substr", [s, L(2), L(9)], t)], t), t),
+        (b.make_function("btrim", [u], t), t),
+        (b.make_if(cond, up, b.make_function("castVARCHAR", [u, k], t), t), t),
+        (b.make_if(b.make_function("like", [s, b.make_literal("%spark%", t)], B),
+                   b.make_literal("SPARK!", t), b.make_if(cond, b.make_literal("", t), b.make_literal(None, t), t), t), t),
+        (b.make_function("char_length", [s], pa.int32()), pa.int32()),
+        (b.make_function("substr", [u, k], t), t),
+    ]
+    return schema, outs, "project"
+
+
+def case_binary_output(b):
+    t = pa.binary()
+    schema = pa.schema([("x", t), ("a", pa.int32())])
+    x, a = F(b, "x", t), F(b, "a", pa.int32())
+    cond = b.make_function("less_than", [a, b.make_literal(10, pa.int32())], pa.bool_())
+    return schema, [(b.make_if(cond, x, b.make_literal(b"\xfe\xffraw", t), t), t)], "project"
+
+
 def case_literals_only(b):
     t = pa.int32()
     schema = pa.schema([("a", t)])
@@ -664,7 +696,7 @@ def all_project_cases():
               case_decimal_divide(10, 0, 5, 3), case_decimal_divide(30, 20, 38, 2),
               case_decimal_divide(38, 30, 12, 0),
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
-              case_decimal_from_double, case_cast_varchar]
+              case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

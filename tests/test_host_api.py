@@ -168,7 +168,7 @@ def test_like_scan_kernels_compile(gandiva):
             else:
                 src = gandiva.make_filter(schema, b.make_condition(outs[0][0]), cfg).llvm_ir
             assert ("gdv_likeh_" in src) == (scan == 0), case.__name__
-            assert ("gdv_eqbytes_msb(" in src) == (scan == 0)
+            assert ("gdv_eqhalf_msb(" in src) == (scan == 0)
     # patterns that do not qualify (a middle segment shorter than 3 bytes, '_' wildcards) stay per lane
     for pat in ["%a%b%c%", "s_ark%", "spark%", "%ss"]:
         b = gandiva.TreeExprBuilder()

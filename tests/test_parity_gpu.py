@@ -254,6 +254,31 @@ def test_decimal_divide_by_zero_is_execution_error(gandiva, oracle):
         assert got.to_pylist()[2] == D("-14.5")
 
 
+@pytest.mark.parametrize("n,offset", [(1, 0), (40, 0), (513, 2), (30011, 5)])
+def test_string_outputs(n, offset, gandiva, oracle):
+    """utf8 outputs (sizing pass, tile scan, write pass) next to a fixed-width output, small
+    substr / castVARCHAR arguments, sliced inputs; plus the sizing entry point on its own."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_string_outputs(b)
+    batch = cases.random_batch(schema, n, seed=n, null_prob=0.15, offset=offset, small=True)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None)
+    got = p.evaluate(batch)
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "string outputs n=%d out=%d" % (n, i))
+        if pa.types.is_string(g.type):
+            g.validate(full=True)
+    # a projector with only string outputs, and with a selection vector
+    p2 = gandiva.make_projector(schema, exprs[1:3], None, "UINT32")
+    idx = np.sort(np.random.default_rng(n).choice(n, max(1, n // 3), replace=False)).astype(np.uint32)
+    sel = gandiva.SelectionVector(idx, len(idx), gandiva._SEL_MODE["UINT32"])
+    got2 = p2.evaluate(batch, sel)
+    want2 = oracle.project([r for r, _ in outs[1:3]], [t for _, t in outs[1:3]], batch, selection=idx.astype(np.int64))
+    for g, w in zip(got2, want2):
+        assert_arrays_match(g, w, "string outputs with selection n=%d" % n)
+
+
 def test_empty_batch_rejected(gandiva):
     b = gandiva.TreeExprBuilder()
     schema, outs, _ = cases.case_arith("add", pa.int32())(b)
