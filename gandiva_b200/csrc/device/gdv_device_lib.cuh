@@ -252,6 +252,17 @@ GDV_DEV void gdv_mbar_wait(u64* bar, u32 parity) {
   while (!gdv_mbar_try_wait(bar, parity)) {
   }
 }
+// 16-byte asynchronous global -> shared copies (LDGSTS): the filter's string stage is filled one
+// group ahead with these, so the copy needs no registers and overlaps the scan of the current group.
+GDV_DEV void gdv_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gdv_smem_addr(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+GDV_DEV void gdv_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+GDV_DEV void gdv_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // Shared-memory element load (i128 as one LDS.128).
 template <typename T>
 GDV_DEV T gdv_lds(const T* p) {

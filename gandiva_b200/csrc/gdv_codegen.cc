@@ -420,6 +420,33 @@ class BodyGen {
     return 0.5;
   }
 
+  // Frequency estimate (percent) of the adjacent pair (a, b): independent letters, floored by a
+  // table of the digrams English text is known to repeat (or that are perfectly correlated,
+  // like "qu"), so that the scan does not pick a pair that looks rare but is not.
+  static double DigramScore(unsigned char a, unsigned char b, unsigned xf) {
+    double sc = ByteScore(a, xf) * ByteScore(b, xf) / 100.0;
+    auto low = [&](unsigned char c) -> char {
+      if (c >= 'A' && c <= 'Z') return static_cast<char>(c + 32);
+      return static_cast<char>(c);
+    };
+    const bool letters = ((a | 0x20) >= 'a' && (a | 0x20) <= 'z') && ((b | 0x20) >= 'a' && (b | 0x20) <= 'z');
+    const bool lower_ctx = xf != 0u || ((a >= 'a' && a <= 'z') && (b >= 'a' && b <= 'z'));
+    if (letters && lower_ctx) {
+      static const struct { const char* d; double f; } known[] = {
+          {"th", 3.56}, {"he", 3.07}, {"in", 2.43}, {"er", 2.05}, {"an", 1.99}, {"re", 1.85}, {"on", 1.76},
+          {"at", 1.49}, {"en", 1.45}, {"nd", 1.35}, {"ti", 1.34}, {"es", 1.34}, {"or", 1.28}, {"te", 1.20},
+          {"of", 1.17}, {"ed", 1.17}, {"is", 1.13}, {"it", 1.12}, {"al", 1.09}, {"ar", 1.07}, {"st", 1.05},
+          {"to", 1.05}, {"nt", 1.04}, {"ng", 0.95}, {"se", 0.93}, {"ha", 0.93}, {"as", 0.87}, {"ou", 0.87},
+          {"io", 0.83}, {"le", 0.83}, {"ve", 0.83}, {"co", 0.79}, {"me", 0.79}, {"de", 0.76}, {"hi", 0.76},
+          {"ri", 0.73}, {"ro", 0.73}, {"ic", 0.70}, {"ne", 0.69}, {"ea", 0.69}, {"ra", 0.69}, {"ce", 0.65},
+          {"li", 0.62}, {"ch", 0.60}, {"ll", 0.58}, {"be", 0.58}, {"ma", 0.57}, {"si", 0.55}, {"om", 0.55},
+          {"ur", 0.54}, {"qu", 0.095}, {"ly", 0.43}, {"ck", 0.12}, {"ss", 0.41}, {"ee", 0.38}, {"oo", 0.21}};
+      for (const auto& kd : known)
+        if (kd.d[0] == low(a) && kd.d[1] == low(b)) sc = std::max(sc, kd.f);
+    }
+    return sc;
+  }
+
   static bool FoldedLetter(unsigned char c, unsigned xf) {
     return (xf == 1u && c >= 'A' && c <= 'Z') || (xf == 2u && c >= 'a' && c <= 'z');
   }
@@ -491,8 +518,8 @@ class BodyGen {
     for (size_t k = first_mid; k < last_mid; ++k) {
       if (segs[k].size() > 32) continue;  // lane i verifies byte i of the key
       for (size_t i = 0; i + 1 < segs[k].size(); ++i) {
-        const double sc = ByteScore(static_cast<unsigned char>(segs[k][i]), xf) *
-                          ByteScore(static_cast<unsigned char>(segs[k][i + 1]), xf);
+        const double sc = DigramScore(static_cast<unsigned char>(segs[k][i]),
+                                      static_cast<unsigned char>(segs[k][i + 1]), xf);
         if (sc < key_score) {
           key_score = sc;
           key_k = k;
@@ -880,8 +907,7 @@ std::string SegVerifyExpr(const CoopSeg& cs, const std::string& stage, const std
 }
 
 std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, int R, const std::string& I,
-                         std::string* globals_unused = nullptr) {
-  (void)globals_unused;
+                         bool accumulate_hibits = false) {
   const std::string J = std::to_string(j);
   const std::string CAP = std::to_string(kHitCap) + "u";
   std::string o;
@@ -895,6 +921,7 @@ std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, int R, const s
   o += I + "for (i32 c = (i32)lane; c < nchunks; c += 32) {\n";
   o += I + "  const uint4 v = reinterpret_cast<const uint4*>(stage" + J + ")[c];\n";
   o += I + "  const u32 vn = reinterpret_cast<const u32*>(stage" + J + ")[4 * c + 4];\n";
+  if (accumulate_hibits) o += I + "  hibits |= v.x | v.y | v.z | v.w;\n";
   std::string any;
   for (const CoopSeg* k : keys) {
     const std::string S = std::to_string(k->id);
@@ -934,7 +961,8 @@ std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, int R, const s
     o += I + "      while (mk != 0u) {\n";
     o += I + "        const i32 st = 16 * c + (__ffs((int)mk) - 1) - " + std::to_string(k->digram) + ";\n";
     o += I + "        mk &= mk - 1u;\n";
-    o += I + "        if (st >= lo && st + " + std::to_string(k->bytes.size()) + " <= hi) {\n";
+    o += I + "        if (st >= lo && st + " + std::to_string(k->bytes.size()) + " <= hi && " +
+         SegVerifyExpr(*k, "stage" + J, "st") + ") {\n";
     o += I + "          const u32 cx = atomicAdd(hctr" + J + " + 1, 1u);\n";
     o += I + "          if (cx < " + CAP + ") cand" + J + "[cx] = (" + std::to_string(k->like) +
          "u << 24) | (u32)st;\n";
@@ -955,12 +983,7 @@ std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, int R, const s
     const std::string KL = std::to_string(k->bytes.size());
     // per-lane byte of the key: immediate select chain would be long; use a packed table
     o += I + "    if ((ce >> 24) == " + std::to_string(k->like) + "u) {\n";
-    o += I + "      bool good = true;\n";
-    o += I + "      if (lane < " + KL + "u) {\n";
-    o += I + "        const u32 kb = gdv_key" + J + "_" + std::to_string(k->id) + "[lane];\n";
-    o += I + "        good = (((u32)stage" + J + "[p + (i32)lane]) | (kb >> 8)) == (kb & 0xffu);\n";
-    o += I + "      }\n";
-    o += I + "      if (__all_sync(GDV_FULL, good)) {\n";
+    o += I + "      {\n";
     o += I + "        i32 rs = 0, re = -1;\n";
     o += I + "        #pragma unroll\n";
     o += I + "        for (int k = 0; k < " + std::to_string(R) + "; ++k) {\n";
@@ -1000,24 +1023,6 @@ std::string EmitCoopScan(int j, const std::vector<CoopSeg>& segs, int R, const s
   return o;
 }
 
-// __device__ tables of the key segments: byte i as (fold mask << 8) | folded byte.
-std::string EmitCoopKeyTables(const std::vector<CoopSeg>& segs) {
-  std::string o;
-  for (const auto& cs : segs) {
-    if (!cs.is_key) continue;
-    o += "__device__ const u16 gdv_key" + std::to_string(cs.slot) + "_" + std::to_string(cs.id) + "[" +
-         std::to_string(cs.bytes.size()) + "] = {";
-    for (size_t i = 0; i < cs.bytes.size(); ++i) {
-      const unsigned char c = static_cast<unsigned char>(cs.bytes[i]);
-      const bool f = ScanFolds(cs, c);
-      const unsigned v = (f ? 0x2000u : 0u) | (f ? (c | 0x20u) : c);
-      o += (i ? "," : "") + std::to_string(v);
-    }
-    o += "};\n";
-  }
-  return o;
-}
-
 bool SlotHasCoop(const std::vector<CoopSeg>& segs, int j) {
   for (const auto& cs : segs)
     if (cs.slot == j) return true;
@@ -1027,7 +1032,7 @@ bool SlotHasCoop(const std::vector<CoopSeg>& segs, int j) {
 void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int R, int mode,
                const std::string& body, const std::string& step_tail, std::string* o, int indent,
                int stage_bytes = 0, const std::string& after_loads = std::string(),
-               const std::vector<CoopSeg>& coop = std::vector<CoopSeg>()) {
+               const std::vector<CoopSeg>& coop = std::vector<CoopSeg>(), bool prefetched = false) {
   const bool fast = mode != kPred;
   const std::string I(static_cast<size_t>(indent) * 2, ' ');
   const std::string sR = std::to_string(R);
@@ -1077,30 +1082,39 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
         *o += I + "  const u8* src = in_var" + J + " + gb;\n";
         *o += I + "  const u32 mis = (u32)((unsigned long long)src & 15ull);\n";
         *o += I + "  if (gn + (i32)mis <= " + std::to_string(stage_bytes) + ") {\n";
-        *o += I + "    const uint4* s4 = reinterpret_cast<const uint4*>(src - mis);\n";
         *o += I + "    const i32 nchunks = (gn + (i32)mis + 15) >> 4;\n";
-        // four 16-byte loads in flight per lane, then the stores; the OR of all words tells
-        // whether the whole run is ASCII
         *o += I + "    u32 hibits = 0u;\n";
-        *o += I + "    for (i32 c0 = (i32)lane; c0 < nchunks; c0 += 128) {\n";
-        *o += I + "      uint4 t4[4];\n";
-        *o += I + "      #pragma unroll\n";
-        *o += I + "      for (int u = 0; u < 4; ++u)\n";
-        *o += I + "        if (c0 + 32 * u < nchunks) t4[u] = __ldcs(s4 + c0 + 32 * u);\n";
-        *o += I + "      #pragma unroll\n";
-        *o += I + "      for (int u = 0; u < 4; ++u)\n";
-        *o += I + "        if (c0 + 32 * u < nchunks) {\n";
-        *o += I + "          reinterpret_cast<uint4*>(stage" + J + ")[c0 + 32 * u] = t4[u];\n";
-        *o += I + "          hibits |= t4[u].x | t4[u].y | t4[u].z | t4[u].w;\n";
-        *o += I + "        }\n";
-        *o += I + "    }\n";
+        if (!prefetched) {
+          // four 16-byte loads in flight per lane, then the stores; the OR of all words tells
+          // whether the whole run is ASCII
+          *o += I + "    const uint4* s4 = reinterpret_cast<const uint4*>(src - mis);\n";
+          *o += I + "    for (i32 c0 = (i32)lane; c0 < nchunks; c0 += 128) {\n";
+          *o += I + "      uint4 t4[4];\n";
+          *o += I + "      #pragma unroll\n";
+          *o += I + "      for (int u = 0; u < 4; ++u)\n";
+          *o += I + "        if (c0 + 32 * u < nchunks) t4[u] = __ldcs(s4 + c0 + 32 * u);\n";
+          *o += I + "      #pragma unroll\n";
+          *o += I + "      for (int u = 0; u < 4; ++u)\n";
+          *o += I + "        if (c0 + 32 * u < nchunks) {\n";
+          *o += I + "          reinterpret_cast<uint4*>(stage" + J + ")[c0 + 32 * u] = t4[u];\n";
+          *o += I + "          hibits |= t4[u].x | t4[u].y | t4[u].z | t4[u].w;\n";
+          *o += I + "        }\n";
+          *o += I + "    }\n";
+        }
+        // prefetched: the bytes were copied by cp.async one group ahead (filter kernel) and the
+        // caller has waited for them; the ASCII test rides on the scan's pass over the stage
         *o += I + "    sbase" + J + " = stage" + J + " + mis - gb;\n";
-        *o += I + "    ascii" + J + " = __any_sync(GDV_FULL, (hibits & 0x80808080u) != 0u) ? 0u : GDV_XF_ASCII;\n";
         if (SlotHasCoop(coop, static_cast<int>(j))) {
-          *o += EmitCoopScan(static_cast<int>(j), coop, R, I + "    ");
+          *o += EmitCoopScan(static_cast<int>(j), coop, R, I + "    ", prefetched);
+        } else if (prefetched) {
+          *o += I + "    for (i32 c = (i32)lane; c < nchunks; c += 32) {\n";
+          *o += I + "      const uint4 v = reinterpret_cast<const uint4*>(stage" + J + ")[c];\n";
+          *o += I + "      hibits |= v.x | v.y | v.z | v.w;\n";
+          *o += I + "    }\n";
         } else {
           *o += I + "    __syncwarp();\n";
         }
+        *o += I + "    ascii" + J + " = __any_sync(GDV_FULL, (hibits & 0x80808080u) != 0u) ? 0u : GDV_XF_ASCII;\n";
         *o += I + "  }\n";
         *o += I + "}\n";
       }
@@ -1198,7 +1212,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
                             GeneratedKernel* out) {
   const bool is_size = spec.kind == KernelKind::kStringSize;
   std::vector<ColumnSlot> slots;
-  BodyGen gen(schema, &slots, spec.nullable, spec.string_scan != 1);
+  BodyGen gen(schema, &slots, spec.nullable, (spec.string_scan & 1) == 0);
   std::string body;
   const Val res = gen.Gen(*expr->root(), &body, 4);
   int n_varlen = 0, in_bytes = 0;
@@ -1229,7 +1243,6 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
-  src += EmitCoopKeyTables(coop);
   src += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(BT) + ") " + spec.name +
          "(const __grid_constant__ gdv_args A) {\n";
   src += "  const u32 lane = threadIdx.x & 31u;\n";
@@ -1374,7 +1387,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     return GenerateStringKernel(schema, exprs[0], spec, out);
   }
   std::vector<ColumnSlot> slots;
-  BodyGen gen(schema, &slots, spec.nullable, spec.string_scan != 1);
+  BodyGen gen(schema, &slots, spec.nullable, (spec.string_scan & 1) == 0);
 
   // Per-row body (uses f<j>[k] / k<j>[k]); generated first so we know the slots.
   std::string body;
@@ -1418,10 +1431,15 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
 
   // shared-memory stage for string bytes: 48 B per row of a group, per warp and string column
   const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
-  // per warp and string column: [stage bytes][hit list + counter of the cooperative LIKE scan]
+  // Filters copy the string bytes of the NEXT group into a second stage with cp.async while the
+  // current group is scanned (per-warp double buffering): the copy costs no registers and its
+  // latency is hidden behind the scan instead of behind other warps.
+  const bool prefetch = spec.kind == KernelKind::kFilter && n_varlen > 0 && (spec.string_scan & 2) == 0;
+  const int n_stages = prefetch ? 2 : 1;
+  // per warp and string column: [stage bytes x stages][hit list + counters of the cooperative scan]
   const std::vector<CoopSeg>& coop = gen.coop_segs();
   const int hit_bytes = coop.empty() ? 0 : 8 * kHitCap + 16;  // candidates, hits, two counters
-  const int col_block = stage_bytes + hit_bytes;
+  const int col_block = n_stages * stage_bytes + hit_bytes;
   int dynamic_smem = col_block * (BT / 32) * n_varlen;
   const int n_out = spec.kind == KernelKind::kProject ? static_cast<int>(exprs.size()) : 0;
   const bool has_sel = spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE;
@@ -1467,7 +1485,6 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
-  src += EmitCoopKeyTables(gen.coop_segs());
   const std::string sR = std::to_string(R), sBT = std::to_string(BT);
   const std::string s32R = std::to_string(32 * R);
   src += "extern \"C\" __global__ void __launch_bounds__(" + sBT + ") " + spec.name +
@@ -1481,12 +1498,13 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     int vi = 0;
     for (size_t j = 0; j < slots.size(); ++j) {
       if (!slots[j].type.is_varlen()) continue;
-      src += "  u8* stage" + std::to_string(j) + " = reinterpret_cast<u8*>(gdv_smem) + ((size_t)wid * " +
+      const std::string SJ = "stage" + std::to_string(j) + (prefetch ? "_0" : "");
+      src += "  u8* const " + SJ + " = reinterpret_cast<u8*>(gdv_smem) + ((size_t)wid * " +
              std::to_string(n_varlen) + " + " + std::to_string(vi) + ") * " +
              std::to_string(col_block) + ";\n";
       if (SlotHasCoop(coop, static_cast<int>(j))) {
-        src += "  u32* cand" + std::to_string(j) + " = reinterpret_cast<u32*>(stage" + std::to_string(j) +
-               " + " + std::to_string(stage_bytes) + ");\n";
+        src += "  u32* cand" + std::to_string(j) + " = reinterpret_cast<u32*>(" + SJ +
+               " + " + std::to_string(n_stages * stage_bytes) + ");\n";
         src += "  u32* hits" + std::to_string(j) + " = cand" + std::to_string(j) + " + " +
                std::to_string(kHitCap) + ";\n";
         src += "  u32* hctr" + std::to_string(j) + " = hits" + std::to_string(j) + " + " +
@@ -1673,12 +1691,52 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "    if (tile >= n_tiles) break;\n";
     src += "    const i64 wbase = tile * " + std::to_string(TILE) + " + (i64)wid * 1024;\n";
     src += "    u32 mymask = 0u;\n";
+    if (prefetch) {
+      // issue(b, par): cp.async the bytes of the full group that starts at row b into stage `par`
+      src += "    auto issue = [&](i64 b, u32 par) {\n";
+      for (size_t j = 0; j < slots.size(); ++j) {
+        if (!slots[j].type.is_varlen()) continue;
+        const std::string J = std::to_string(j);
+        src += "      {\n";
+        src += "        const i32 gb = in_val" + J + "[b];\n";
+        src += "        const i32 gn = in_val" + J + "[b + " + s32R + "] - gb;\n";
+        src += "        const u8* src = in_var" + J + " + gb;\n";
+        src += "        const u32 mis = (u32)((unsigned long long)src & 15ull);\n";
+        src += "        if (gn + (i32)mis <= " + std::to_string(stage_bytes) + ") {\n";
+        src += "          const i32 nchunks = (gn + (i32)mis + 15) >> 4;\n";
+        src += "          u8* dst = stage" + J + "_0 + (size_t)par * " + std::to_string(stage_bytes) + "u;\n";
+        src += "          for (i32 c = (i32)lane; c < nchunks; c += 32)\n";
+        src += "            gdv_cp_async16(dst + 16 * c, src - mis + 16 * c);\n";
+        src += "        }\n";
+        src += "      }\n";
+      }
+      src += "      gdv_cp_async_commit();\n";
+      src += "    };\n";
+      src += "    u32 par = 0u;\n";
+      src += "    if (wbase + " + s32R + " <= A.n) issue(wbase, 0u);\n";
+    }
     src += "    #pragma unroll 1\n";
     src += "    for (int g = 0; g < 32; g += " + sR + ") {\n";
     src += "      const i64 base = wbase + 32 * g;\n";
     src += "      if (base >= A.n) break;\n";
+    if (prefetch) {
+      for (size_t j = 0; j < slots.size(); ++j)
+        if (slots[j].type.is_varlen())
+          src += "      u8* const stage" + std::to_string(j) + " = stage" + std::to_string(j) +
+                 "_0 + (size_t)par * " + std::to_string(stage_bytes) + "u;\n";
+    }
     src += "      if (base + " + s32R + " <= A.n) {\n";
-    EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes, std::string(), coop);
+    if (prefetch) {
+      src += "        if (g + " + sR + " < 32 && base + " + std::to_string(64 * R) + " <= A.n) {\n";
+      src += "          issue(base + " + s32R + ", par ^ 1u);\n";
+      src += "          gdv_cp_async_wait<1>();\n";
+      src += "        } else {\n";
+      src += "          gdv_cp_async_wait<0>();\n";
+      src += "        }\n";
+      src += "        __syncwarp();\n";
+      src += "        par ^= 1u;\n";
+    }
+    EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes, std::string(), coop, prefetch);
     src += "      } else {\n";
     EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 4, 0, std::string(), coop);
     src += "      }\n";

@@ -106,8 +106,9 @@ typedef struct gdv_config {
                               concurrent stream (e.g. NCCL's gather of the previous batch's
                               SelectionVector) can run; default 0 */
   int32_t stages;          /* TMA loader: shared-memory stages per CTA (0 = engine picks) */
-  int32_t string_scan;     /* LIKE over string columns: 0 = engine picks (warp-cooperative scan of
-                              the staged bytes), 1 = per-lane matcher only */
+  int32_t string_scan;     /* string columns, bit mask; 0 = engine picks (everything on):
+                              bit 0: LIKE with the per-lane matcher only (no warp-cooperative scan),
+                              bit 1: filters stage string bytes without the cp.async prefetch */
   int32_t reserved[3];
 } gdv_config_t;
 void gdv_config_default(gdv_config_t* cfg);

@@ -137,7 +137,7 @@ def bench_str(rows_per_batch, batches):
                 bytes_ = batches * (4.0 * n + block_bytes * reps + n / 8.0 + 4.0 * count)
                 gbs = bytes_ / ms / 1e6
                 r = {"config": "string_filter_like_upper_substr", "block_threads": bt, "rows_per_thread": rpt,
-                     "matcher": "per-lane" if scan == 1 else "cooperative scan",
+                     "matcher": ("per-lane" if scan & 1 else "cooperative scan") + (", no prefetch" if scan & 2 else ", cp.async prefetch"),
                      "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "gbs": gbs, "frac": gbs / PEAK,
                      "bytes_per_row": bytes_ / rows, "selected_per_batch": count, "regs": f.kernel_info["regs"],
                      "smem": f.kernel_info.get("dynamic_smem"), "ctas_per_sm": f.kernel_info.get("blocks_per_sm")}
