@@ -396,6 +396,7 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
   for (auto& sk : p->strings_) {
     CompiledKernel *a = nullptr, *b = nullptr;
     GDV_RETURN_NOT_OK(p->StringKernelsFor(&sk, true, &a, &b));
+    if (std::getenv("GDV_EAGER_NONULL") != nullptr) GDV_RETURN_NOT_OK(p->StringKernelsFor(&sk, false, &a, &b));
   }
   if (std::getenv("GDV_EAGER_NONULL") != nullptr && p->kernel_ != nullptr) {
     CompiledKernel* k = nullptr;
@@ -437,7 +438,7 @@ Status Projector::KernelFor(bool nullable, CompiledKernel** out) {
   }
   std::lock_guard<std::mutex> lock(mu_);
   if (kernel_nonull_ == nullptr)
-    GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs_, KernelKind::kProject, selection_mode_, false,
+    GDV_RETURN_NOT_OK(BuildKernel(*schema_, fixed_exprs_, KernelKind::kProject, selection_mode_, false,
                                   cfg_, &kernel_nonull_));
   *out = kernel_nonull_.get();
   return Status::OK();
@@ -817,7 +818,12 @@ Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** o
     // descriptors: 94% of HBM peak at 1024 threads vs 88% at 256 on Q6, profiles/r01_sweeps.md);
     // small batches want enough tiles to occupy the 148 SMs.
     Config cfg = cfg_;
-    if (cfg.block_threads == 0) cfg.block_threads = large ? (nullable ? 512 : 1024) : 256;
+    // String predicates are instruction-bound and stage bytes per warp in shared memory: 512
+    // threads measured best at every batch size (profiles/r01_string_filter.md).
+    bool has_varlen = false;
+    for (const auto& f : schema_->fields()) has_varlen = has_varlen || f.type.is_varlen();
+    if (cfg.block_threads == 0)
+      cfg.block_threads = large ? ((nullable || has_varlen) ? 512 : 1024) : 256;
     GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg, &k));
     it = kernels_.emplace(key, std::move(k)).first;
   }

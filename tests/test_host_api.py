@@ -154,6 +154,25 @@ def test_make_compiles_for_sm100a(case, gandiva):
         assert "gdv_tile_exclusive_prefix" in f.llvm_ir
 
 
+NONULL_CASES = ALL_CASES[::6] + [cases.case_string_outputs, cases.case_binary_output, cases.case_q1_projector,
+                                 cases.case_filter_string]
+
+
+@pytest.mark.parametrize("case", NONULL_CASES, ids=[c.__name__ for c in NONULL_CASES])
+def test_nonull_variants_compile(case, gandiva, monkeypatch):
+    """The kernel variants specialised for batches without validity bitmaps are built lazily at
+    the first Evaluate; GDV_EAGER_NONULL builds them at Make() so that they are compile-checked
+    here, without a GPU (fixed-width, string-size / string-write and filter variants)."""
+    monkeypatch.setenv("GDV_EAGER_NONULL", "1")
+    b = gandiva.TreeExprBuilder()
+    schema, outs, kind = case(b)
+    if kind == "project":
+        exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+        assert "__global__" in gandiva.make_projector(schema, exprs, None).llvm_ir
+    else:
+        assert "__global__" in gandiva.make_filter(schema, b.make_condition(outs[0][0])).llvm_ir
+
+
 def test_like_scan_kernels_compile(gandiva):
     """LIKE over view chains lowers to the warp-cooperative scan (hit list + per-row chain);
     string_scan=1 keeps the per-lane matcher only.  Both variants compile for sm_100a."""
