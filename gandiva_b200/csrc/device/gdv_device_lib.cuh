@@ -1263,11 +1263,17 @@ GDV_DEV u64 gdv_tile_exclusive_prefix(u64* state, i64 tile, u64 count, u32 lane)
     const i64 idx = look - (i64)lane;
     u64 d = (GDV_TILE_INCLUSIVE << 62);  // tiles before 0 contribute an inclusive prefix of 0
     if (idx >= 0) d = gdv_ld_relaxed(&state[idx]);
-    while (__any_sync(GDV_FULL, (d >> 62) == GDV_TILE_INVALID)) {
+    // Lane 0 holds the nearest predecessor.  Only the descriptors up to the nearest INCLUSIVE one
+    // are needed: wait while one of THOSE is still unpublished, not for the whole window.
+    u32 incl, first;
+    while (true) {
+      const u32 inv = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INVALID);
+      incl = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INCLUSIVE);
+      first = incl != 0u ? (u32)(__ffs((int)incl) - 1) : 32u;
+      const u32 need = first >= 32u ? inv : (inv & ((1u << first) - 1u));
+      if (need == 0u) break;
       if (idx >= 0 && (d >> 62) == GDV_TILE_INVALID) d = gdv_ld_relaxed(&state[idx]);
     }
-    const u32 incl = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INCLUSIVE);
-    const u32 first = incl != 0u ? (u32)(__ffs((int)incl) - 1) : 32u;
     u64 contrib = (lane <= first) ? (d & GDV_TILE_VALUE_MASK) : 0ull;
     for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(GDV_FULL, contrib, o);
     excl += contrib;

@@ -1673,7 +1673,11 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     // B200 bandwidth (DESIGN.md "Filter kernel").
     const std::string IDX = SelCType(spec.selection_mode);
     const int NW = BT / 32;
-    const int TILE = NW * 1024;
+    // String filters are instruction-bound and their warps finish at very different times (hits
+    // are rare and expensive): every warp is its own 1024-row tile with its own ticket and
+    // look-back, so no warp ever waits at a CTA barrier (string_scan bit 2 turns this off).
+    const bool warp_tiles = n_varlen > 0 && (spec.string_scan & 4) == 0;
+    const int TILE = warp_tiles ? 1024 : NW * 1024;
     const std::string step_tail =
         "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
         results[0].v + ")); if (lane == (u32)(g + k)) mymask = m; }\n";
@@ -1685,11 +1689,19 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
     src += "  const u32 lt = gdv_lanemask_lt();\n";
     src += "  while (true) {\n";
-    src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
-    src += "    __syncthreads();\n";
-    src += "    const i64 tile = s_tile;\n";
-    src += "    if (tile >= n_tiles) break;\n";
-    src += "    const i64 wbase = tile * " + std::to_string(TILE) + " + (i64)wid * 1024;\n";
+    if (warp_tiles) {
+      src += "    i64 tile = 0;\n";
+      src += "    if (lane == 0u) tile = (i64)atomicAdd(A.ticket, 1ull);\n";
+      src += "    tile = __shfl_sync(GDV_FULL, tile, 0);\n";
+      src += "    if (tile >= n_tiles) break;\n";
+      src += "    const i64 wbase = tile * 1024;\n";
+    } else {
+      src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
+      src += "    __syncthreads();\n";
+      src += "    const i64 tile = s_tile;\n";
+      src += "    if (tile >= n_tiles) break;\n";
+      src += "    const i64 wbase = tile * " + std::to_string(TILE) + " + (i64)wid * 1024;\n";
+    }
     src += "    u32 mymask = 0u;\n";
     if (prefetch) {
       // issue(b, par): cp.async the bytes of the full group that starts at row b into stage `par`
@@ -1750,6 +1762,23 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "      if (lane >= (u32)o) incl += t;\n";
     src += "    }\n";
     src += "    const u32 step_excl = incl - c;\n";
+    if (warp_tiles) {
+      src += "    const u32 wtotal = __shfl_sync(GDV_FULL, incl, 31);\n";
+      src += "    const u64 wpos = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)wtotal, lane);\n";
+      src += "    if (lane == 0u && tile == n_tiles - 1) *A.out_count = wpos + (u64)wtotal;\n";
+      src += "    if (wtotal != 0u) {\n";
+      src += "      #pragma unroll 4\n";
+      src += "      for (int k = 0; k < 32; ++k) {\n";
+      src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
+      src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
+      src += "        const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
+      src += "        if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
+      src += "          out_idx[pos] = (" + IDX + ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
+      src += "      }\n";
+      src += "    }\n";
+      src += "  }\n";
+      src += "}\n";
+    } else {
     src += "    if (lane == 31u) s_wcount[wid] = incl;\n";
     src += "    __syncthreads();\n";
     src += "    if (wid == 0u) {\n";
@@ -1783,6 +1812,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "    }\n";
     src += "  }\n";
     src += "}\n";
+    }  // !warp_tiles
   }
 
   out->source = std::move(src);
@@ -1801,7 +1831,9 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->out_bytes_per_row = out_bytes;
   out->args_size = L.size;
   out->dynamic_smem = dynamic_smem;
-  out->tile_rows = spec.kind == KernelKind::kFilter ? static_cast<int64_t>(BT / 32) * 1024 : 0;
+  out->tile_rows = spec.kind == KernelKind::kFilter
+                       ? ((n_varlen > 0 && (spec.string_scan & 4) == 0) ? 1024 : static_cast<int64_t>(BT / 32) * 1024)
+                       : 0;
   out->staged = staged;
   out->stages = staged ? S : 0;
   out->cta_tile_rows = static_cast<int64_t>(BT) * R;
