@@ -151,6 +151,7 @@ def _load() -> C.CDLL:
         "gdv_host_free": (i32, [vp]),
         "gdv_generate_lineitem": (i32, [i32, i32, C.c_uint64, i64, i64, vp, vp, i32, vp]),
         "gdv_launch_count": (i64, []),
+        "gdv_compile_count": (i64, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -178,6 +179,11 @@ def _check(status: int) -> None:
 
 def cuda_available() -> bool:
     return bool(lib.gdv_cuda_available())
+
+
+def compile_count() -> int:
+    """NVRTC compilations so far (Make() calls served from the cubin cache do not count)."""
+    return int(lib.gdv_compile_count())
 
 
 def launch_count() -> int:

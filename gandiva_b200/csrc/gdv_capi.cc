@@ -588,5 +588,6 @@ gdv_status gdv_selection_release(int32_t device, void* board, int32_t board_slot
 }
 
 int64_t gdv_launch_count(void) { return g_launch_count.load(); }
+int64_t gdv_compile_count(void) { return g_compile_count.load(); }
 
 }  // extern "C"

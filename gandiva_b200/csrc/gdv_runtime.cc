@@ -8,6 +8,7 @@
 namespace gdv {
 
 std::atomic<long long> g_launch_count{0};
+std::atomic<long long> g_compile_count{0};
 
 const char* ExecutionErrorMessage(int code) {
   switch (code) {
@@ -188,7 +189,35 @@ Status CompiledKernel::Load(Device* dev, Loaded* out) {
 
 namespace {
 
-std::atomic<int> g_kernel_serial{0};
+// Compiled-kernel cache (the reference keeps an LRU of built projectors / filters keyed on schema +
+// expressions + configuration): here the key is the generated translation unit
+// itself plus the compile options, so two Make() calls that lower to the same kernel share one
+// NVRTC compilation whatever objects they came from.  Kernel symbols are named after the hash of
+// the source, which keeps the source text (and so the key) independent of creation order.
+struct CachedCubin {
+  std::vector<char> cubin;
+  std::string ptx, log;
+};
+std::mutex g_cache_mu;
+std::unordered_map<std::string, std::shared_ptr<const CachedCubin>> g_cubin_cache;
+constexpr size_t kCubinCacheEntries = 512;
+
+uint64_t Fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+const char* KernelPrefix(KernelKind kind) {
+  switch (kind) {
+    case KernelKind::kProject: return "gdv_project_expr_";
+    case KernelKind::kFilter: return "gdv_filter_expr_";
+    case KernelKind::kStringSize: return "gdv_strsize_expr_";
+    default: return "gdv_strwrite_expr_";
+  }
+}
 
 Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
                    KernelKind kind, int selection_mode, bool nullable, const Config& cfg,
@@ -202,16 +231,44 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
   spec.loader = cfg.loader;
   spec.stages = cfg.stages;
   spec.string_scan = cfg.string_scan;
-  spec.name = std::string(kind == KernelKind::kProject ? "gdv_project_expr_" : "gdv_filter_expr_") +
-              std::to_string(g_kernel_serial.fetch_add(1));
+  const std::string placeholder = std::string(KernelPrefix(kind)) + "PLACEHOLDER";
+  spec.name = placeholder;
   std::unique_ptr<CompiledKernel> k(new CompiledKernel());
   GDV_RETURN_NOT_OK(GenerateKernel(schema, exprs, spec, &k->gen));
   // Compile for the device we will run on when one is visible, else for B200.
   std::string arch = "sm_100a";
   Device* dev = nullptr;
   if (Driver().loaded && Device::Get(cfg.device, &dev).ok()) arch = dev->arch();
-  GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
-                                   &k->ptx, &k->compile_log));
+  // name the kernel after its own text
+  char hex[24];
+  std::snprintf(hex, sizeof(hex), "%016llx", static_cast<unsigned long long>(Fnv1a(arch, Fnv1a(k->gen.source))));
+  const std::string name = std::string(KernelPrefix(kind)) + hex;
+  for (size_t pos = 0; (pos = k->gen.source.find(placeholder, pos)) != std::string::npos;)
+    k->gen.source.replace(pos, placeholder.size(), name);
+  k->gen.name = name;
+  const std::string key = arch + (cfg.optimize ? "|O3|" : "|O0|") + (cfg.dump_ir ? "ptx|" : "|") + k->gen.source;
+  std::shared_ptr<const CachedCubin> hit;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    auto it = g_cubin_cache.find(key);
+    if (it != g_cubin_cache.end()) hit = it->second;
+  }
+  if (hit != nullptr) {
+    k->cubin = hit->cubin;
+    k->ptx = hit->ptx;
+    k->compile_log = hit->log;
+  } else {
+    g_compile_count.fetch_add(1);
+    GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
+                                     &k->ptx, &k->compile_log));
+    auto entry = std::make_shared<CachedCubin>();
+    entry->cubin = k->cubin;
+    entry->ptx = k->ptx;
+    entry->log = k->compile_log;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (g_cubin_cache.size() >= kCubinCacheEntries) g_cubin_cache.clear();
+    g_cubin_cache.emplace(key, std::move(entry));
+  }
   // GDV_DUMP_DIR=<dir>: write <kernel>.cu / <kernel>.cubin for offline SASS inspection
   // (cuobjdump -sass) and so that ncu's source page can find the generated code.
   if (const char* dir = std::getenv("GDV_DUMP_DIR")) {

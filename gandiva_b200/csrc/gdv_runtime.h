@@ -17,6 +17,7 @@
 namespace gdv {
 
 extern std::atomic<long long> g_launch_count;
+extern std::atomic<long long> g_compile_count;  // NVRTC compilations (cache misses)
 
 class Device {
  public:

@@ -323,6 +323,10 @@ gdv_status gdv_selection_release(int32_t device, void* board, int32_t board_slot
                                  void* stream);
 /* Number of kernels this library has launched since load (gpu_launches in bench.py). */
 int64_t gdv_launch_count(void);
+/* Number of NVRTC compilations since load.  Make() calls that lower to a kernel already built in
+ * this process (same generated source, architecture and options) reuse its cubin: the counterpart
+ * of the reference's projector / filter cache. */
+int64_t gdv_compile_count(void);
 
 #ifdef __cplusplus
 }

@@ -196,6 +196,29 @@ def test_like_scan_kernels_compile(gandiva):
         assert "gdv_likeh_" not in src
 
 
+def test_cubin_cache(gandiva):
+    """Two Make() calls that lower to the same kernel share one NVRTC compilation (the reference
+    caches built projectors / filters); a different expression or configuration compiles anew."""
+    def make(lit, cfg=None):
+        b = gandiva.TreeExprBuilder()
+        t = pa.int32()
+        schema = pa.schema([("cache_a", t), ("cache_b", t)])
+        root = b.make_function("add", [b.make_function("multiply", [cases.F(b, "cache_a", t), b.make_literal(lit, t)], t),
+                                       cases.F(b, "cache_b", t)], t)
+        return gandiva.make_projector(schema, [b.make_expression(root, pa.field("r", t))], None, "NONE", cfg)
+    c0 = gandiva.compile_count()
+    p1 = make(12345)
+    c1 = gandiva.compile_count()
+    assert c1 == c0 + 1
+    p2 = make(12345)
+    assert gandiva.compile_count() == c1
+    assert p1.kernel_info["name"] == p2.kernel_info["name"]
+    p3 = make(54321)
+    assert gandiva.compile_count() == c1 + 1 and p3.kernel_info["name"] != p1.kernel_info["name"]
+    make(12345, gandiva.Configuration(rows_per_thread=4))
+    assert gandiva.compile_count() == c1 + 2
+
+
 def test_selection_mode_names(gandiva):
     b = gandiva.TreeExprBuilder()
     fa = pa.field('a', pa.int32())
