@@ -1270,7 +1270,11 @@ GDV_DEV u64 gdv_tile_exclusive_prefix(u64* state, i64 tile, u64 count, u32 lane)
       const u32 inv = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INVALID);
       incl = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INCLUSIVE);
       first = incl != 0u ? (u32)(__ffs((int)incl) - 1) : 32u;
+#ifdef GDV_LOOKBACK_STRICT
+      const u32 need = inv;  // A/B switch (string_scan bit 3): wait for the whole 32-tile window
+#else
       const u32 need = first >= 32u ? inv : (inv & ((1u << first) - 1u));
+#endif
       if (need == 0u) break;
       if (idx >= 0 && (d >> 62) == GDV_TILE_INVALID) d = gdv_ld_relaxed(&state[idx]);
     }

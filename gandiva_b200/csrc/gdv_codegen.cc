@@ -1482,6 +1482,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
   for (size_t i = 0; i < exprs.size(); ++i)
     src += "// expr_" + std::to_string(i) + ": " + exprs[i]->ToString() + "\n";
+  if ((spec.string_scan & 8) != 0) src += "#define GDV_LOOKBACK_STRICT 1\n";
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
@@ -1673,10 +1674,11 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     // B200 bandwidth (DESIGN.md "Filter kernel").
     const std::string IDX = SelCType(spec.selection_mode);
     const int NW = BT / 32;
-    // String filters are instruction-bound and their warps finish at very different times (hits
-    // are rare and expensive): every warp is its own 1024-row tile with its own ticket and
-    // look-back, so no warp ever waits at a CTA barrier (string_scan bit 2 turns this off).
-    const bool warp_tiles = n_varlen > 0 && (spec.string_scan & 4) == 0;
+    // Optional (string_scan bit 2): every warp of a string filter is its own 1024-row tile with
+    // its own ticket and look-back, so no warp waits at a CTA barrier.  Measured slower than CTA
+    // tiles at 256/512 threads (0.268 vs 0.289 of peak, profiles/r01_string_filter.md): the barrier
+    // was not what bounds the kernel, and 16x more look-back descriptors cost more than it saves.
+    const bool warp_tiles = n_varlen > 0 && (spec.string_scan & 4) != 0;
     const int TILE = warp_tiles ? 1024 : NW * 1024;
     const std::string step_tail =
         "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
@@ -1832,7 +1834,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->args_size = L.size;
   out->dynamic_smem = dynamic_smem;
   out->tile_rows = spec.kind == KernelKind::kFilter
-                       ? ((n_varlen > 0 && (spec.string_scan & 4) == 0) ? 1024 : static_cast<int64_t>(BT / 32) * 1024)
+                       ? ((n_varlen > 0 && (spec.string_scan & 4) != 0) ? 1024 : static_cast<int64_t>(BT / 32) * 1024)
                        : 0;
   out->staged = staged;
   out->stages = staged ? S : 0;

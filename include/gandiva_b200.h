@@ -108,7 +108,9 @@ typedef struct gdv_config {
   int32_t stages;          /* TMA loader: shared-memory stages per CTA (0 = engine picks) */
   int32_t string_scan;     /* string columns, bit mask; 0 = engine picks (everything on):
                               bit 0: LIKE with the per-lane matcher only (no warp-cooperative scan),
-                              bit 1: filters stage string bytes without the cp.async prefetch */
+                              bit 1: filters stage string bytes without the cp.async prefetch,
+                              bit 2: string filters use one 1024-row tile per warp,
+                              bit 3: look-back waits for its whole 32-tile window (A/B switch) */
   int32_t reserved[3];
 } gdv_config_t;
 void gdv_config_default(gdv_config_t* cfg);
