@@ -170,6 +170,9 @@ struct Val {
   std::string v;   // C expression (usually a local variable name)
   std::string ok;  // C expression of type bool; "true"/"false" when statically known
   DataType type;
+  // concat() results are ropes: the C expressions (type gdv_str) of the pieces, in order.  Only
+  // a string output, another concat or an if/else may consume one; `v` is unused then.
+  std::vector<std::string> parts;
 };
 
 std::string HexLit(uint64_t bits) {
@@ -199,6 +202,7 @@ class BodyGen {
   std::string& globals() { return globals_; }
   const std::vector<CoopSeg>& coop_segs() const { return coop_segs_; }
   bool uses_ctx() const { return uses_ctx_; }
+  const std::string& error() const { return error_; }
 
   // Emit the statements that evaluate `node` for the row held in slot arrays at [k].
   Val Gen(const Node& node, std::string* out, int indent) {
@@ -619,6 +623,7 @@ class BodyGen {
 
     if (def->flags & kLikeHolder) {
       Val s = Gen(*fn.children()[0], out, indent);
+      if (!s.parts.empty() && error_.empty()) error_ = "like(concat(...)) is not supported yet";
       const auto& pat = static_cast<const LiteralNode&>(*fn.children()[1]);
       bool has_esc = fn.children().size() == 3;
       char esc = has_esc ? static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0] : 0;
@@ -649,6 +654,43 @@ class BodyGen {
 
     std::vector<Val> args;
     for (const auto& c : fn.children()) args.push_back(Gen(*c, out, indent));
+
+    if (def->flags & kConcat) {
+      // concat: a null argument counts as the empty string, the result is never null;
+      // concatOperator: null if any argument is null.  Either way no byte moves here: the
+      // result is the list of its arguments' views, copied piece by piece by the write pass.
+      const bool null_as_empty = fn.name() == "concat";
+      Val r;
+      r.type = rt;
+      std::vector<std::string> oks;
+      for (const auto& a : args) {
+        oks.push_back(a.ok);
+        if (!a.parts.empty()) {
+          for (const auto& p : a.parts) r.parts.push_back(p);
+        } else if (null_as_empty && a.ok != "true") {
+          const std::string pv = NewVar("v");
+          *out += Ind(indent) + "const gdv_str " + pv + " = (" + a.ok + ") ? " + a.v +
+                  " : gdv_make_str(nullptr, 0);\n";
+          r.parts.push_back(pv);
+        } else {
+          r.parts.push_back(a.v);
+        }
+      }
+      if (r.parts.size() > 8 && error_.empty())
+        error_ = "concat of more than 8 pieces is not supported";
+      r.ok = null_as_empty ? std::string("true") : AndOk(oks);
+      if (r.ok != "true" && r.ok != "false" && r.ok.find("&&") != std::string::npos) {
+        const std::string okv = NewVar("ok");
+        *out += Ind(indent) + "const bool " + okv + " = " + r.ok + ";\n";
+        r.ok = okv;
+      }
+      r.v = "gdv_make_str(nullptr, 0)";
+      return r;
+    }
+    for (const auto& a : args)
+      if (!a.parts.empty() && error_.empty())
+        error_ = "the result of concat can only be projected, concatenated again or chosen by if/else; " +
+                 fn.name() + "(concat(...)) is not supported yet";
 
     std::string call = def->device_name() + "(";
     bool first = true;
@@ -702,18 +744,40 @@ class BodyGen {
     const DataType& rt = n.return_type();
     Val c = Gen(*n.condition(), out, indent);
     const std::string v = NewVar("v"), ok = NewVar("ok");
-    *out += Ind(indent) + rt.ctype() + " " + v + ";\n";
+    // Branches are generated into side buffers first: when one of them is a concat rope the
+    // result needs one variable per piece, and the number of pieces is only known afterwards.
+    std::string tb, eb;
+    Val t = Gen(*n.then_node(), &tb, indent + 1);
+    Val e = Gen(*n.else_node(), &eb, indent + 1);
+    const size_t np = std::max(t.parts.size(), e.parts.size());
+    if (np == 0) {
+      *out += Ind(indent) + rt.ctype() + " " + v + ";\n";
+    } else {
+      for (size_t i = 0; i < np; ++i)
+        *out += Ind(indent) + "gdv_str " + v + "_" + std::to_string(i) + " = gdv_make_str(nullptr, 0);\n";
+    }
     *out += Ind(indent) + "bool " + ok + ";\n";
     *out += Ind(indent) + "if ((" + c.ok + ") && (" + c.v + ")) {\n";
-    Val t = Gen(*n.then_node(), out, indent + 1);
-    *out += Ind(indent + 1) + v + " = " + t.v + ";\n";
-    *out += Ind(indent + 1) + ok + " = " + t.ok + ";\n";
+    auto assign = [&](const Val& b, const std::string& code) {
+      *out += code;
+      if (np == 0) {
+        *out += Ind(indent + 1) + v + " = " + b.v + ";\n";
+      } else if (b.parts.empty()) {
+        *out += Ind(indent + 1) + v + "_0 = " + b.v + ";\n";
+      } else {
+        for (size_t i = 0; i < b.parts.size(); ++i)
+          *out += Ind(indent + 1) + v + "_" + std::to_string(i) + " = " + b.parts[i] + ";\n";
+      }
+      *out += Ind(indent + 1) + ok + " = " + b.ok + ";\n";
+    };
+    assign(t, tb);
     *out += Ind(indent) + "} else {\n";
-    Val e = Gen(*n.else_node(), out, indent + 1);
-    *out += Ind(indent + 1) + v + " = " + e.v + ";\n";
-    *out += Ind(indent + 1) + ok + " = " + e.ok + ";\n";
+    assign(e, eb);
     *out += Ind(indent) + "}\n";
-    return Val{v, ok, rt};
+    Val r{v, ok, rt, {}};
+    for (size_t i = 0; i < np; ++i) r.parts.push_back(v + "_" + std::to_string(i));
+    if (np != 0) r.v = "gdv_make_str(nullptr, 0)";
+    return r;
   }
 
   // SQL three-valued AND/OR.  AND: false if any child is (valid, false); else null if any
@@ -752,6 +816,7 @@ class BodyGen {
 
   Val GenIn(const InNode& n, std::string* out, int indent) {
     Val c = Gen(*n.child(), out, indent);
+    if (!c.parts.empty() && error_.empty()) error_ = "IN over concat(...) is not supported yet";
     const std::string v = NewVar("v");
     const DataType& t = n.value_type();
     if (t.is_varlen()) {
@@ -803,6 +868,7 @@ class BodyGen {
   std::vector<ColumnSlot>* slots_;
   bool nullable_;
   bool coop_;
+  std::string error_;  // first construct the fuser cannot lower (reported by GenerateKernel)
   std::vector<CoopSeg> coop_segs_;
   std::string globals_;
   int next_id_ = 0;
@@ -1215,6 +1281,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
   BodyGen gen(schema, &slots, spec.nullable, (spec.string_scan & 1) == 0);
   std::string body;
   const Val res = gen.Gen(*expr->root(), &body, 4);
+  if (!gen.error().empty()) return Status::Make(GDV_NOT_IMPLEMENTED, gen.error());
   int n_varlen = 0, in_bytes = 0;
   for (const auto& s : slots) {
     n_varlen += s.type.is_varlen() ? 1 : 0;
@@ -1271,15 +1338,23 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
   src += "  const i64 n_tiles = (A.n + " + std::to_string(T - 1) + ") / " + sT + ";\n";
   src += "  for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n";
   src += "    const i64 base = tile * " + sT + " + (i64)wid * " + s32R + ";\n";
+  // a plain string value is a rope of one piece
+  std::vector<std::string> parts = res.parts;
+  if (parts.empty()) parts.push_back(res.v);
+  const int K = static_cast<int>(parts.size());
+  const std::string sK = std::to_string(K);
+  std::string total_len;
+  for (int i = 0; i < K; ++i) total_len += (i ? " + " : "") + std::string("(u32)(") + parts[i] + ").len";
   std::string tail;
   if (is_size) {
     src += "    u32 tsum = 0u;\n";
-    tail = "        tsum += (in && (" + res.ok + ")) ? (u32)(" + res.v + ").len : 0u;\n";
+    tail = "        tsum += (in && (" + res.ok + ")) ? (" + total_len + ") : 0u;\n";
   } else {
-    src += "    u32 slen[" + sR + "];\n    gdv_str sv[" + sR + "];\n    u32 vw0 = 0u;\n";
-    tail = "        { const bool okk = in && (" + res.ok + "); slen[k] = okk ? (u32)(" + res.v +
-           ").len : 0u; sv[k] = " + res.v + "; const u32 m = __ballot_sync(GDV_FULL, okk); "
-           "if (lane == (u32)k) vw0 = m; }\n";
+    src += "    u32 slen[" + sR + "];\n    gdv_str sv[" + sR + "][" + sK + "];\n    u32 vw0 = 0u;\n";
+    tail = "        { const bool okk = in && (" + res.ok + "); slen[k] = okk ? (" + total_len + ") : 0u;\n";
+    for (int i = 0; i < K; ++i)
+      tail += "          sv[k][" + std::to_string(i) + "] = " + parts[i] + ";\n";
+    tail += "          const u32 m = __ballot_sync(GDV_FULL, okk); if (lane == (u32)k) vw0 = m; }\n";
   }
   if (!has_sel) {
     src += "    if (base + " + s32R + " <= A.n) {\n";
@@ -1333,20 +1408,26 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     src += "    if (tile == 0 && threadIdx.x == 0) offs[0] = 0;\n";
     src += "    #pragma unroll\n";
     src += "    for (int k = 0; k < " + sR + "; ++k) {\n";
-    src += "      const u64 dst0 = wbase + (u64)(incl[k] - slen[k]);\n";
-    src += "      const u32 nonempty = __ballot_sync(GDV_FULL, slen[k] != 0u);\n";
-    src += "      for (u32 rest = nonempty; rest != 0u; rest &= rest - 1u) {\n";
-    src += "        const int j = __ffs((int)rest) - 1;\n";
-    src += "        gdv_str v;\n";
-    src += "        v.p = reinterpret_cast<const u8*>(__shfl_sync(GDV_FULL, (u64)sv[k].p, j));\n";
-    src += "        v.len = (i32)__shfl_sync(GDV_FULL, slen[k], j);\n";
-    src += "        v.xf = __shfl_sync(GDV_FULL, sv[k].xf, j);\n";
-    src += "        const u64 d = __shfl_sync(GDV_FULL, dst0, j);\n";
-    src += "        if (d + (u64)v.len <= (u64)A.out_cap) {\n";
-    src += "          for (i32 i = (i32)lane; i < v.len; i += 32) data[d + (u64)i] = gdv_ch(v, i);\n";
-    src += "        } else if (lane == 0u) {\n";
-    src += "          gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";
+    src += "      u64 dst0 = wbase + (u64)(incl[k] - slen[k]);\n";
+    src += "      const bool rowok = slen[k] != 0u;\n";
+    src += "      #pragma unroll\n";
+    src += "      for (int piece = 0; piece < " + sK + "; ++piece) {\n";
+    src += "        const u32 plen = rowok ? (u32)sv[k][piece].len : 0u;\n";
+    src += "        const u32 nonempty = __ballot_sync(GDV_FULL, plen != 0u);\n";
+    src += "        for (u32 rest = nonempty; rest != 0u; rest &= rest - 1u) {\n";
+    src += "          const int j = __ffs((int)rest) - 1;\n";
+    src += "          gdv_str v;\n";
+    src += "          v.p = reinterpret_cast<const u8*>(__shfl_sync(GDV_FULL, (u64)sv[k][piece].p, j));\n";
+    src += "          v.len = (i32)__shfl_sync(GDV_FULL, plen, j);\n";
+    src += "          v.xf = __shfl_sync(GDV_FULL, sv[k][piece].xf, j);\n";
+    src += "          const u64 d = __shfl_sync(GDV_FULL, dst0, j);\n";
+    src += "          if (d + (u64)v.len <= (u64)A.out_cap) {\n";
+    src += "            for (i32 i = (i32)lane; i < v.len; i += 32) data[d + (u64)i] = gdv_ch(v, i);\n";
+    src += "          } else if (lane == 0u) {\n";
+    src += "            gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";
+    src += "          }\n";
     src += "        }\n";
+    src += "        dst0 += (u64)plen;\n";
     src += "      }\n";
     src += "    }\n";
     src += "    if (lane < " + sR + "u && base + 32 * (i64)lane < A.n && A.out_vld[0] != nullptr)\n";
@@ -1399,6 +1480,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
                           "string projector, not by GenerateKernel");
     results.push_back(gen.Gen(*e->root(), &body, 4));
   }
+  if (!gen.error().empty()) return Status::Make(GDV_NOT_IMPLEMENTED, gen.error());
 
   int in_bytes = 0, out_bytes = 0;
   int n_varlen = 0;
@@ -1802,8 +1884,19 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
     src += "    __syncthreads();\n";
     src += "    const u64 wpos = s_excl + (u64)s_wcount[wid];\n";
     src += "    const u32 wtotal = __shfl_sync(GDV_FULL, incl, 31);\n";
-    src += "    if (wtotal != 0u) {\n";
+    // The whole run of this warp fits the vector (always, unless GDV_SEL_BOUNDED): 32-bit offsets
+    // from one 64-bit base and no per-row capacity test.
+    src += "    if (wtotal != 0u && wpos + (u64)wtotal <= (u64)A.out_cap) {\n";
+    src += "      " + IDX + "* const wout = out_idx + wpos;\n";
     src += "      #pragma unroll 4\n";
+    src += "      for (int k = 0; k < 32; ++k) {\n";
+    src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
+    src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
+    src += "        if ((m >> lane) & 1u)\n";
+    src += "          wout[off + (u32)__popc(m & lt)] = (" + IDX + ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
+    src += "      }\n";
+    src += "    } else if (wtotal != 0u) {\n";
+    src += "      #pragma unroll 1\n";
     src += "      for (int k = 0; k < 32; ++k) {\n";
     src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
     src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";

@@ -216,6 +216,11 @@ Registry::Registry() {
   Add("rtrim", {S}, S, NullMode::kIfNull, kStringView);
   Add("btrim", {S}, S, NullMode::kIfNull, kStringView, {"trim"});
   Add("castVARCHAR", {S, I64}, S, NullMode::kIfNull, kStringView);
+  // concat: null arguments are empty strings, never null; concatOperator: null if any is null
+  for (int n = 2; n <= 6; ++n) {
+    Add("concat", std::vector<DataType>(static_cast<size_t>(n), S), S, NullMode::kNever, kConcat);
+    Add("concatOperator", std::vector<DataType>(static_cast<size_t>(n), S), S, NullMode::kIfNull, kConcat);
+  }
 }
 
 }  // namespace gdv

@@ -22,6 +22,7 @@ enum FnFlags : uint32_t {
   kLikeHolder = 1u << 1,   // second (third) arg must be a literal pattern, compiled at Make()
   kDecimalArgs = 1u << 2,  // decimal params are followed by (precision, scale); out (p, s) appended
   kStringView = 1u << 3,   // returns a view/transform of its first argument (no new bytes)
+  kConcat = 1u << 4,       // result = the pieces of its arguments in order (a rope, see the fuser)
 };
 
 struct FunctionDef {

@@ -786,6 +786,22 @@ bool RelopNum(const std::string& name, T a, T b) {
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
+  if (f == "concat" || f == "concatOperator") {
+    // concat: null arguments are empty strings, never null; concatOperator: null if any is null
+    out->ok = true;
+    out->s.clear();
+    for (const auto& k : n.kids) {
+      Val v;
+      Eval(*k, cx, row, &v);
+      if (!v.ok) {
+        if (f == "concatOperator") out->ok = false;
+        continue;
+      }
+      out->s += v.s;
+    }
+    if (!out->ok) out->s.clear();
+    return;
+  }
   Val a[3];
   for (size_t k = 0; k < na && k < 3; ++k) {
     // LIKE patterns are literals handled at parse time

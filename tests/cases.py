@@ -466,6 +466,28 @@ def case_string_outputs(b):
     return schema, outs, "project"
 
 
+def case_concat_outputs(b):
+    """concat / concatOperator results (ropes of views) projected as utf8 outputs."""
+    t = pa.string()
+    schema = pa.schema([("s", t), ("u", t), ("a", pa.int32())])
+    s, u, a = F(b, "s", t), F(b, "u", t), F(b, "a", pa.int32())
+    L = lambda v: b.make_literal(v, pa.int64())
+    lit = lambda v: b.make_literal(v, t)
+    cond = b.make_function("greater_than", [a, b.make_literal(0, pa.int32())], pa.bool_())
+    cc = lambda *x: b.make_function("concat", list(x), t)
+    co = lambda *x: b.make_function("concatOperator", list(x), t)
+    up = b.make_function("upper", [s], t)
+    outs = [
+        (cc(s, u), t),
+        (co(s, lit(" | "), u), t),
+        (cc(up, lit("-"), b.make_function("lower", [b.make_function("substr", [u, L(1), L(3)], t)], t), lit("!")), t),
+        (cc(cc(s, lit("/")), co(u, lit("/"), s)), t),
+        (b.make_if(cond, cc(s, lit("+"), u), up, t), t),
+        (b.make_if(cond, lit("x"), co(u, s), t), t),
+    ]
+    return schema, outs, "project"
+
+
 def case_binary_output(b):
     t = pa.binary()
     schema = pa.schema([("x", t), ("a", pa.int32())])
@@ -696,7 +718,8 @@ def all_project_cases():
               case_decimal_divide(10, 0, 5, 3), case_decimal_divide(30, 20, 38, 2),
               case_decimal_divide(38, 30, 12, 0),
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
-              case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output]
+              case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
+              case_concat_outputs]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

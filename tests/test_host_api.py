@@ -196,6 +196,21 @@ def test_like_scan_kernels_compile(gandiva):
         assert "gdv_likeh_" not in src
 
 
+def test_concat_consumers_are_rejected(gandiva):
+    """concat() results are ropes of views: they can be projected, concatenated again or chosen by
+    if/else; feeding one to another function is a Make()-time error, not a wrong answer."""
+    b = gandiva.TreeExprBuilder()
+    t = pa.string()
+    schema = pa.schema([("s", t), ("u", t)])
+    cc = b.make_function("concat", [cases.F(b, "s", t), cases.F(b, "u", t)], t)
+    bad = b.make_function("octet_length", [cc], pa.int32())
+    with pytest.raises(pa.ArrowNotImplementedError, match="concat"):
+        gandiva.make_projector(schema, [b.make_expression(bad, pa.field("r", pa.int32()))], None)
+    like = b.make_function("like", [cc, b.make_literal("%ab%", t)], pa.bool_())
+    with pytest.raises(pa.ArrowNotImplementedError, match="concat"):
+        gandiva.make_filter(schema, b.make_condition(like))
+
+
 def test_cubin_cache(gandiva):
     """Two Make() calls that lower to the same kernel share one NVRTC compilation (the reference
     caches built projectors / filters); a different expression or configuration compiles anew."""

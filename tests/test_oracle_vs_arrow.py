@@ -459,3 +459,25 @@ def test_cast_varchar(oracle, gandiva):
     assert_arrays_match(got[0], pc.binary_length(pc.utf8_slice_codeunits(s, 0, 5)), "castVARCHAR 5")
     want = [None if a is None or b is None else len(a[:max(b, 0)]) for a, b in zip(s.to_pylist(), k.to_pylist())]
     assert_arrays_match(got[1], pa.array(want, type=pa.int32()), "castVARCHAR k")
+
+
+def test_concat(oracle, gandiva):
+    schema = pa.schema([("s", pa.string()), ("u", pa.string()), ("a", pa.int32())])
+    batch = cases.random_batch(schema, 1500, seed=51, null_prob=0.2)
+    got = run_oracle(oracle, gandiva, cases.case_concat_outputs, batch)
+    s, u, a = [c.to_pylist() for c in batch.columns]
+    e = lambda x: "" if x is None else x
+    up = lambda x: None if x is None else "".join(c.upper() if "a" <= c <= "z" else c for c in x)
+    low3 = lambda x: None if x is None else "".join(c.lower() if "A" <= c <= "Z" else c for c in x[:3])
+    nn = lambda *xs: None if any(x is None for x in xs) else "".join(xs)
+    cond = [x is not None and x > 0 for x in a]
+    want = [
+        [e(x) + e(y) for x, y in zip(s, u)],
+        [nn(x, " | ", y) for x, y in zip(s, u)],
+        [e(up(x)) + "-" + e(low3(y)) + "!" for x, y in zip(s, u)],
+        [e(x) + "/" + e(nn(y, "/", x)) for x, y in zip(s, u)],
+        [(e(x) + "+" + e(y)) if c else up(x) for x, y, c in zip(s, u, cond)],
+        ["x" if c else nn(y, x) for x, y, c in zip(s, u, cond)],
+    ]
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, pa.array(w, type=pa.string()), "concat out %d" % i)
