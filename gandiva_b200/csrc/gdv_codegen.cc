@@ -219,6 +219,32 @@ class BodyGen {
     return Val{"0", "false", node.return_type()};
   }
 
+  // "valid and true" of a boolean expression, for consumers that need nothing else (a Filter
+  // keeps a row iff its condition is valid and true).  Under SQL three-valued logic
+  //   truth(a AND b) = truth(a) && truth(b),   truth(a OR b) = truth(a) || truth(b),
+  // so the Kleene bookkeeping (decided / all-valid flags per child) of GenBoolean is not needed
+  // on this path: a nullable Q6 predicate drops from ~6 to ~2 instructions per comparison.
+  // Children that can raise keep the general, lazily evaluated form.
+  Val GenTruth(const Node& node, std::string* out, int indent) {
+    if (node.kind() == NodeKind::kBoolean && !CanFail(node)) {
+      const auto& n = static_cast<const BooleanNode&>(node);
+      const bool is_and = n.op() == BooleanNode::kAnd;
+      std::string e;
+      for (const auto& c : n.children()) {
+        const Val cv = GenTruth(*c, out, indent);
+        e += (e.empty() ? "" : (is_and ? " && " : " || ")) + std::string("(") + cv.v + ")";
+      }
+      const std::string v = NewVar("v");
+      *out += Ind(indent) + "const bool " + v + " = " + e + ";\n";
+      return Val{v, "true", boolean(), {}};
+    }
+    const Val r = Gen(node, out, indent);
+    if (r.ok == "true") return r;
+    const std::string v = NewVar("v");
+    *out += Ind(indent) + "const bool " + v + " = (" + r.ok + ") && (" + r.v + ");\n";
+    return Val{v, "true", boolean(), {}};
+  }
+
   int SlotFor(const FieldNode& f) {
     const int idx = schema_.index_of(f.name());
     for (size_t j = 0; j < slots_->size(); ++j)
@@ -1478,7 +1504,8 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
       return Status::Make(GDV_NOT_IMPLEMENTED,
                           "variable-length projection outputs are handled by the two-pass "
                           "string projector, not by GenerateKernel");
-    results.push_back(gen.Gen(*e->root(), &body, 4));
+    results.push_back(spec.kind == KernelKind::kFilter ? gen.GenTruth(*e->root(), &body, 4)
+                                                       : gen.Gen(*e->root(), &body, 4));
   }
   if (!gen.error().empty()) return Status::Make(GDV_NOT_IMPLEMENTED, gen.error());
 
