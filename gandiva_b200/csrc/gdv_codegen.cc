@@ -692,7 +692,17 @@ class BodyGen {
       for (const auto& a : args) {
         oks.push_back(a.ok);
         if (!a.parts.empty()) {
-          for (const auto& p : a.parts) r.parts.push_back(p);
+          // a rope argument that is null (a null concatOperator result) contributes nothing
+          for (const auto& p : a.parts) {
+            if (null_as_empty && a.ok != "true") {
+              const std::string pv = NewVar("v");
+              *out += Ind(indent) + "const gdv_str " + pv + " = (" + a.ok + ") ? " + p +
+                      " : gdv_make_str(nullptr, 0);\n";
+              r.parts.push_back(pv);
+            } else {
+              r.parts.push_back(p);
+            }
+          }
         } else if (null_as_empty && a.ok != "true") {
           const std::string pv = NewVar("v");
           *out += Ind(indent) + "const gdv_str " + pv + " = (" + a.ok + ") ? " + a.v +
