@@ -585,6 +585,84 @@ GDV_DEV i64 extractYear_date32(i32 d) { return gdv_civil_from_days((i64)d).y; }
 GDV_DEV i64 extractMonth_date32(i32 d) { return gdv_civil_from_days((i64)d).m; }
 GDV_DEV i64 extractDay_date32(i32 d) { return gdv_civil_from_days((i64)d).d; }
 
+// ---- rounding (exact IEEE operations; half away from zero like C's round()) ------------------
+GDV_DEV f64 round_float64(f64 a) { return round(a); }
+GDV_DEV f32 round_float32(f32 a) { return roundf(a); }
+GDV_DEV f64 ceil_float64(f64 a) { return ceil(a); }
+GDV_DEV f64 floor_float64(f64 a) { return floor(a); }
+GDV_DEV f64 truncate_float64(f64 a) { return trunc(a); }
+GDV_DEV i32 round_int32(i32 a) { return a; }
+GDV_DEV i64 round_int64(i64 a) { return a; }
+// round(x, s): s >= 0: round(x * 10^s) / 10^s; s < 0: round(x / 10^-s) * 10^-s; a value that is
+// already a multiple of 10^-s is returned unchanged; the power is built by repeated
+// multiplication (exact up to 10^22); |s| is clamped to 308.
+GDV_DEV f64 gdv_pow10_f64(i32 e) {
+  f64 p = 1.0;
+  for (i32 i = 0; i < e; ++i) p = p * 10.0;
+  return p;
+}
+GDV_DEV f64 round_float64_int32(f64 a, i32 s) {
+  if (s >= 0) {
+    const f64 p = gdv_pow10_f64(s > 308 ? 308 : s);
+    const f64 v = a * p;
+    if (!(fabs(v) < 1.7976931348623157e308)) return a;  // overflow or NaN: nothing to round
+    if (v == floor(v)) return a;  // already a multiple of 10^-s: do not disturb the value
+    return round(v) / p;
+  }
+  const f64 p = gdv_pow10_f64(-s > 308 ? 308 : -s);
+  const f64 q = a / p;
+  if (q == floor(q)) return a;
+  return round(q) * p;
+}
+
+// ---- date / time arithmetic (date64 and timestamp are milliseconds since the epoch) -----------
+GDV_DEV i64 gdv_days_from_civil(i64 y, i32 m, i32 d) {
+  y -= m <= 2 ? 1 : 0;
+  const i64 era = gdv_floordiv(y, 400);
+  const i64 yoe = y - era * 400;
+  const i64 doy = (153 * (i64)(m + (m > 2 ? -3 : 9)) + 2) / 5 + (i64)d - 1;
+  const i64 doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + doe - 719468;
+}
+// Calendar month arithmetic: the day of month is clamped to the length of the target month
+// (Jan 31 + 1 month = Feb 28/29); the time of day is kept.
+GDV_DEV i64 gdv_add_months(i64 ms, i64 months) {
+  const i64 days = gdv_floordiv(ms, 86400000ll);
+  const i64 in_day = ms - days * 86400000ll;
+  const gdv_ymd c = gdv_civil_from_days(days);
+  const i64 total = c.y * 12 + (i64)(c.m - 1) + months;
+  const i64 ny = gdv_floordiv(total, 12);
+  const i32 nm = (i32)(total - ny * 12) + 1;
+  const bool leap = (ny % 4 == 0) && ((ny % 100 != 0) || (ny % 400 == 0));
+  const i32 mlen[12] = {31, leap ? 29 : 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  const i32 nd = c.d < mlen[nm - 1] ? c.d : mlen[nm - 1];
+  return gdv_days_from_civil(ny, nm, nd) * 86400000ll + in_day;
+}
+#define GDV_TSADD(NAME, UNIT_MS)                                                                  \
+  GDV_DEV i64 NAME##_int32_timestamp(i32 n, i64 ts) { return (i64)((u64)ts + (u64)((i64)n * (UNIT_MS))); } \
+  GDV_DEV i64 NAME##_int64_timestamp(i64 n, i64 ts) { return (i64)((u64)ts + (u64)n * (u64)(UNIT_MS)); }
+GDV_TSADD(timestampaddSecond, 1000ll)
+GDV_TSADD(timestampaddMinute, 60000ll)
+GDV_TSADD(timestampaddHour, 3600000ll)
+GDV_TSADD(timestampaddDay, 86400000ll)
+GDV_TSADD(timestampaddWeek, 604800000ll)
+GDV_DEV i64 timestampaddMonth_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, (i64)n); }
+GDV_DEV i64 timestampaddQuarter_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, 3 * (i64)n); }
+GDV_DEV i64 timestampaddYear_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, 12 * (i64)n); }
+GDV_DEV i64 date_add_date64_int32(i64 d, i32 n) { return (i64)((u64)d + (u64)((i64)n * 86400000ll)); }
+GDV_DEV i64 date_sub_date64_int32(i64 d, i32 n) { return (i64)((u64)d - (u64)((i64)n * 86400000ll)); }
+GDV_DEV i64 date_add_timestamp_int32(i64 d, i32 n) { return date_add_date64_int32(d, n); }
+GDV_DEV i64 date_sub_timestamp_int32(i64 d, i32 n) { return date_sub_date64_int32(d, n); }
+#define GDV_TSDIFF(NAME, UNIT_MS)                                                                 \
+  GDV_DEV i32 NAME##_timestamp_timestamp(i64 a, i64 b) {                                          \
+    return (i32)(u32)(u64)((i64)((u64)b - (u64)a) / (UNIT_MS));                                   \
+  }
+GDV_TSDIFF(timestampdiffSecond, 1000ll)
+GDV_TSDIFF(timestampdiffMinute, 60000ll)
+GDV_TSDIFF(timestampdiffHour, 3600000ll)
+GDV_TSDIFF(timestampdiffDay, 86400000ll)
+GDV_TSDIFF(timestampdiffWeek, 604800000ll)
+
 // ---- decimal128 ------------------------------------------------------------------------
 // Values are two's-complement 128-bit integers scaled by 10^scale (Arrow decimal128).
 // Rounding on scale reduction is half away from zero; a result that does not fit 38

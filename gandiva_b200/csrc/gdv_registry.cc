@@ -163,6 +163,31 @@ Registry::Registry() {
   Add("extractMonth", {D32}, I64);
   Add("extractDay", {D32}, I64);
 
+  // ---- rounding ------------------------------------------------------------------------
+  Add("round", {F64}, F64);
+  Add("round", {F32}, F32);
+  Add("round", {I32}, I32);
+  Add("round", {I64}, I64);
+  Add("round", {F64, I32}, F64);
+  Add("ceil", {F64}, F64);
+  Add("floor", {F64}, F64);
+  Add("truncate", {F64}, F64, NullMode::kIfNull, 0, {"trunc"});
+
+  // ---- date / time arithmetic -------------------------------------------------------------
+  for (const char* f : {"timestampaddSecond", "timestampaddMinute", "timestampaddHour", "timestampaddDay",
+                        "timestampaddWeek"}) {
+    Add(f, {I32, TS}, TS);
+    Add(f, {I64, TS}, TS);
+  }
+  for (const char* f : {"timestampaddMonth", "timestampaddQuarter", "timestampaddYear"}) Add(f, {I32, TS}, TS);
+  Add("date_add", {D64, I32}, D64);
+  Add("date_sub", {D64, I32}, D64);
+  Add("date_add", {TS, I32}, TS);
+  Add("date_sub", {TS, I32}, TS);
+  for (const char* f : {"timestampdiffSecond", "timestampdiffMinute", "timestampdiffHour", "timestampdiffDay",
+                        "timestampdiffWeek"})
+    Add(f, {TS, TS}, I32);
+
   // ---- decimal128 ---------------------------------------------------------------------
   Add("add", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("subtract", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);

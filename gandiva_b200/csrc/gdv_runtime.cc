@@ -880,7 +880,7 @@ Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** o
     bool has_varlen = false;
     for (const auto& f : schema_->fields()) has_varlen = has_varlen || f.type.is_varlen();
     if (cfg.block_threads == 0)
-      cfg.block_threads = large ? ((nullable || has_varlen) ? 512 : 1024) : 256;
+      cfg.block_threads = large ? (has_varlen ? 512 : 1024) : 256;
     GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg, &k));
     it = kernels_.emplace(key, std::move(k)).first;
   }

@@ -1000,6 +1000,80 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
 
+  // ---- rounding ---------------------------------------------------------------------------
+  if (f == "round") {
+    if (na == 2) {
+      const int s = static_cast<int>(a[1].i);
+      double p = 1.0;
+      const int e = std::min(std::abs(s), 308);
+      for (int k = 0; k < e; ++k) p = p * 10.0;
+      if (s >= 0) {
+        const double v = a[0].d * p;
+        if (!(std::fabs(v) < 1.7976931348623157e308) || v == std::floor(v)) out->d = a[0].d;
+        else out->d = std::round(v) / p;
+      } else {
+        const double q = a[0].d / p;
+        out->d = (q == std::floor(q)) ? a[0].d : std::round(q) * p;
+      }
+    } else if (rt.id == T_DOUBLE) out->d = std::round(a[0].d);
+    else if (rt.id == T_FLOAT) out->f = std::round(a[0].f);
+    else out->i = a[0].i;
+    return;
+  }
+  if (f == "ceil") { out->d = std::ceil(a[0].d); return; }
+  if (f == "floor") { out->d = std::floor(a[0].d); return; }
+  if (f == "truncate" || f == "trunc") { out->d = std::trunc(a[0].d); return; }
+
+  // ---- date/time arithmetic -----------------------------------------------------------------
+  if (f.rfind("timestampadd", 0) == 0) {
+    const std::string unit = f.substr(12);
+    const int64_t n = a[0].i, ts = a[1].i;
+    int64_t unit_ms = 0;
+    if (unit == "Second") unit_ms = 1000;
+    else if (unit == "Minute") unit_ms = 60000;
+    else if (unit == "Hour") unit_ms = 3600000;
+    else if (unit == "Day") unit_ms = 86400000;
+    else if (unit == "Week") unit_ms = 604800000;
+    if (unit_ms != 0) {
+      out->i = static_cast<int64_t>(static_cast<uint64_t>(ts) + static_cast<uint64_t>(n) * static_cast<uint64_t>(unit_ms));
+      return;
+    }
+    const int64_t months = unit == "Month" ? n : (unit == "Quarter" ? 3 * n : 12 * n);
+    const int64_t days = FloorDiv(ts, 86400000);
+    const int64_t in_day = ts - days * 86400000;
+    const Ymd c = CivilFromDays(days);
+    const int64_t total = c.y * 12 + (c.m - 1) + months;
+    const int64_t ny = FloorDiv(total, 12);
+    const int nm = static_cast<int>(total - ny * 12) + 1;
+    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    const int len = mdays[nm - 1] + ((nm == 2 && IsLeap(ny)) ? 1 : 0);
+    const int nd = std::min(c.d, len);
+    // days since epoch of (ny, nm, nd): walk from the first day of the year
+    int64_t y1 = ny - 1;
+    int64_t dn = y1 * 365 + FloorDiv(y1, 4) - FloorDiv(y1, 100) + FloorDiv(y1, 400) - 719162;  // Jan 1 of ny
+    for (int m = 1; m < nm; ++m) dn += mdays[m - 1] + ((m == 2 && IsLeap(ny)) ? 1 : 0);
+    dn += nd - 1;
+    out->i = dn * 86400000 + in_day;
+    return;
+  }
+  if (f == "date_add" || f == "date_sub") {
+    const uint64_t delta = static_cast<uint64_t>(a[1].i) * 86400000ull;
+    out->i = static_cast<int64_t>(f == "date_add" ? static_cast<uint64_t>(a[0].i) + delta
+                                                  : static_cast<uint64_t>(a[0].i) - delta);
+    return;
+  }
+  if (f.rfind("timestampdiff", 0) == 0) {
+    const std::string unit = f.substr(13);
+    int64_t unit_ms = 1000;
+    if (unit == "Minute") unit_ms = 60000;
+    else if (unit == "Hour") unit_ms = 3600000;
+    else if (unit == "Day") unit_ms = 86400000;
+    else if (unit == "Week") unit_ms = 604800000;
+    const int64_t diff = static_cast<int64_t>(static_cast<uint64_t>(a[1].i) - static_cast<uint64_t>(a[0].i));
+    out->i = WrapSigned(diff / unit_ms, 32);
+    return;
+  }
+
   // ---- date/time -------------------------------------------------------------------------
   if (f.rfind("extract", 0) == 0) {
     const bool is_d32 = t0.id == T_DATE32;

@@ -192,6 +192,54 @@ def case_dates(b):
     return schema, outs, "project"
 
 
+def case_rounding(b):
+    schema = pa.schema([("d", pa.float64()), ("f", pa.float32()), ("s", pa.int32()), ("l", pa.int64())])
+    d, f, s, l = F(b, "d", pa.float64()), F(b, "f", pa.float32()), F(b, "s", pa.int32()), F(b, "l", pa.int64())
+    D = pa.float64()
+    outs = [(b.make_function("round", [d], D), D), (b.make_function("round", [f], pa.float32()), pa.float32()),
+            (b.make_function("ceil", [d], D), D), (b.make_function("floor", [d], D), D),
+            (b.make_function("truncate", [d], D), D), (b.make_function("round", [l], pa.int64()), pa.int64())]
+    for k in (0, 1, 2, 5, -1, -3):
+        outs.append((b.make_function("round", [d, b.make_literal(k, pa.int32())], D), D))
+    outs.append((b.make_function("round", [d, s], D), D))
+    return schema, outs, "project"
+
+
+def case_date_arith(b):
+    ts, d64 = pa.timestamp("ms"), pa.date64()
+    schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
+    t, u, d, n, m = F(b, "t", ts), F(b, "u", ts), F(b, "d", d64), F(b, "n", pa.int32()), F(b, "m", pa.int64())
+    outs = []
+    for fn in ("timestampaddSecond", "timestampaddMinute", "timestampaddHour", "timestampaddDay", "timestampaddWeek",
+               "timestampaddMonth", "timestampaddQuarter", "timestampaddYear"):
+        outs.append((b.make_function(fn, [n, t], ts), ts))
+    outs.append((b.make_function("timestampaddDay", [m, t], ts), ts))
+    outs.append((b.make_function("timestampaddMonth", [b.make_literal(1, pa.int32()), t], ts), ts))
+    outs.append((b.make_function("date_add", [d, n], d64), d64))
+    outs.append((b.make_function("date_sub", [d, n], d64), d64))
+    outs.append((b.make_function("date_add", [t, n], ts), ts))
+    for fn in ("timestampdiffSecond", "timestampdiffMinute", "timestampdiffHour", "timestampdiffDay", "timestampdiffWeek"):
+        outs.append((b.make_function(fn, [t, u], pa.int32()), pa.int32()))
+    return schema, outs, "project"
+
+
+def date_arith_batch(n: int, seed: int, null_prob: float = 0.1) -> pa.RecordBatch:
+    """timestamps around 1600..2400, month-end days included, small signed counts."""
+    rng = np.random.default_rng(seed)
+    ts, d64 = pa.timestamp("ms"), pa.date64()
+    mk = lambda: rng.integers(-11_676_096_000_000, 13_569_465_600_000, n).astype(np.int64)
+    t, u = mk(), mk()
+    ends = np.array([951782400000, 1706659200000, 1709164800000, 1711843200000, -2203891200000], dtype=np.int64)
+    t[: len(ends)] = ends + rng.integers(0, 86400000, len(ends))   # 2000-02-29, 2024-01-31, 2024-02-29, 2024-03-31, 1900-03-01
+    dd = (rng.integers(-150000, 150000, n).astype(np.int64)) * 86400000
+    cnt = rng.integers(-400, 400, n).astype(np.int32)
+    big = rng.integers(-40000, 40000, n).astype(np.int64)
+    mask = lambda: (rng.random(n) < null_prob) if null_prob > 0 else None
+    cols = [pa.array(t, pa.int64(), mask=mask()).cast(ts), pa.array(u, pa.int64(), mask=mask()).cast(ts),
+            pa.array(dd, pa.int64(), mask=mask()).cast(d64), pa.array(cnt, mask=mask()), pa.array(big, mask=mask())]
+    return pa.RecordBatch.from_arrays(cols, names=["t", "u", "d", "n", "m"])
+
+
 def case_decimal(p1, s1, p2, s2, op, rp, rs):
     def build(b):
         t1, t2, rt = pa.decimal128(p1, s1), pa.decimal128(p2, s2), pa.decimal128(rp, rs)
@@ -719,7 +767,7 @@ def all_project_cases():
               case_decimal_divide(38, 30, 12, 0),
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
-              case_concat_outputs]
+              case_concat_outputs, case_rounding, case_date_arith]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

@@ -481,3 +481,64 @@ def test_concat(oracle, gandiva):
     ]
     for i, (g, w) in enumerate(zip(got, want)):
         assert_arrays_match(g, pa.array(w, type=pa.string()), "concat out %d" % i)
+
+
+def test_rounding(oracle, gandiva):
+    rng = np.random.default_rng(61)
+    n = 4000
+    d = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 7, n)
+    d[:10] = [0.5, -0.5, 1.5, 2.5, -2.5, 0.0, -0.0, 1e300, 123.456, -987.654321]
+    f = (rng.standard_normal(n) * 100).astype(np.float32)
+    sc = rng.integers(-4, 8, n).astype(np.int32)
+    l = rng.integers(-10**12, 10**12, n)
+    batch = pa.RecordBatch.from_arrays([pa.array(d), pa.array(f), pa.array(sc), pa.array(l)], names=["d", "f", "s", "l"])
+    got = run_oracle(oracle, gandiva, cases.case_rounding, batch)
+    half_away = lambda x: np.sign(x) * np.floor(np.abs(x) + 0.5)
+    assert_arrays_match(got[0], pc.round(batch.column(0), round_mode="half_towards_infinity"), "round(double)")
+    assert_arrays_match(got[1], pc.round(batch.column(1), round_mode="half_towards_infinity"), "round(float)")
+    assert_arrays_match(got[2], pc.ceil(batch.column(0)), "ceil")
+    assert_arrays_match(got[3], pc.floor(batch.column(0)), "floor")
+    assert_arrays_match(got[4], pc.trunc(batch.column(0)), "truncate")
+    assert_arrays_match(got[5], batch.column(3), "round(int64)")
+    for g, k in zip(got[6:12], (0, 1, 2, 5, -1, -3)):
+        assert_arrays_match(g, pc.round(batch.column(0), ndigits=k, round_mode="half_towards_infinity"), "round(d, %d)" % k)
+
+
+def test_date_arithmetic(oracle, gandiva):
+    import pandas as pd
+    batch = cases.date_arith_batch(3000, seed=71)
+    got = run_oracle(oracle, gandiva, cases.case_date_arith, batch)
+    t = batch.column(0).cast(pa.int64()).to_pylist()
+    u = batch.column(1).cast(pa.int64()).to_pylist()
+    d = batch.column(2).cast(pa.int64()).to_pylist()
+    n = batch.column(3).to_pylist()
+    m = batch.column(4).to_pylist()
+    unit = {"Second": 1000, "Minute": 60000, "Hour": 3600000, "Day": 86400000, "Week": 604800000}
+
+    def add_months(ms, k):
+        ts = pd.Timestamp(ms, unit="ms") + pd.DateOffset(months=k)
+        return int(ts.as_unit("ms").asm8.view("i8"))
+    want = []
+    for name in ("Second", "Minute", "Hour", "Day", "Week"):
+        want.append([None if a is None or b is None else b + a * unit[name] for a, b in zip(n, t)])
+    for mult in (1, 3, 12):
+        want.append([None if a is None or b is None else add_months(b, mult * a) for a, b in zip(n, t)])
+    want.append([None if a is None or b is None else b + a * 86400000 for a, b in zip(m, t)])
+    want.append([None if b is None else add_months(b, 1) for b in t])
+    want.append([None if a is None or b is None else b + a * 86400000 for a, b in zip(n, d)])
+    want.append([None if a is None or b is None else b - a * 86400000 for a, b in zip(n, d)])
+    want.append([None if a is None or b is None else b + a * 86400000 for a, b in zip(n, t)])
+    trunc_div = lambda x, y: abs(x) // y * (1 if x >= 0 else -1)
+    for name in ("Second", "Minute", "Hour", "Day", "Week"):
+        w = []
+        for a, b in zip(t, u):
+            if a is None or b is None:
+                w.append(None)
+            else:
+                q = trunc_div(b - a, unit[name]) & 0xffffffff
+                w.append(q - (1 << 32) if q >> 31 else q)
+        want.append(w)
+    schema_b = cases.case_date_arith(gandiva.TreeExprBuilder())[1]
+    for i, (g, w, (_, ty)) in enumerate(zip(got, want, schema_b)):
+        exp = pa.array(w, type=pa.int64()).cast(ty) if not pa.types.is_int32(ty) else pa.array(w, type=pa.int32())
+        assert_arrays_match(g, exp, "date arithmetic out %d" % i)
