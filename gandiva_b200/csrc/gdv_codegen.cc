@@ -175,6 +175,23 @@ struct Val {
   std::vector<std::string> parts;
 };
 
+// Text that is safe inside a `//` comment of the generated source: bytes outside printable ASCII
+// (a binary literal's 0xff made NVRTC drop the rest of the translation unit) and backslashes (a
+// trailing one would splice the next line into the comment) are written as \\xNN.
+std::string CommentSafe(const std::string& s) {
+  std::string o;
+  for (unsigned char c : s) {
+    if (c < 0x20 || c >= 0x7f || c == '\\') {
+      char b[8];
+      std::snprintf(b, sizeof(b), "<%02x>", static_cast<unsigned>(c));
+      o += b;
+    } else {
+      o.push_back(static_cast<char>(c));
+    }
+  }
+  return o;
+}
+
 std::string HexLit(uint64_t bits) {
   char b[40];
   std::snprintf(b, sizeof(b), "0x%016llxull", static_cast<unsigned long long>(bits));
@@ -1342,7 +1359,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
   src += std::string("// generated by gandiva_b200 kernel fuser; string projection, ") +
          (is_size ? "sizing pass" : "write pass") +
          (spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n");
-  src += "// expr_0: " + expr->ToString() + "\n";
+  src += "// expr_0: " + CommentSafe(expr->ToString()) + "\n";
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
@@ -1600,7 +1617,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   src += (spec.kind == KernelKind::kProject ? "Projector" : "Filter");
   src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
   for (size_t i = 0; i < exprs.size(); ++i)
-    src += "// expr_" + std::to_string(i) + ": " + exprs[i]->ToString() + "\n";
+    src += "// expr_" + std::to_string(i) + ": " + CommentSafe(exprs[i]->ToString()) + "\n";
   if ((spec.string_scan & 8) != 0) src += "#define GDV_LOOKBACK_STRICT 1\n";
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);

@@ -261,6 +261,11 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
     g_compile_count.fetch_add(1);
     GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
                                      &k->ptx, &k->compile_log));
+    // a translation unit can compile "successfully" without the kernel in it (e.g. when the
+    // front end stops at a stray byte): make that a code-generation error here, not a missing
+    // symbol at the first Evaluate on a GPU
+    if (std::search(k->cubin.begin(), k->cubin.end(), name.begin(), name.end()) == k->cubin.end())
+      return Status::Make(GDV_CODEGEN_ERROR, "NVRTC produced a module without the kernel " + name);
     auto entry = std::make_shared<CachedCubin>();
     entry->cubin = k->cubin;
     entry->ptx = k->ptx;

@@ -541,7 +541,7 @@ def case_binary_output(b):
     schema = pa.schema([("x", t), ("a", pa.int32())])
     x, a = F(b, "x", t), F(b, "a", pa.int32())
     cond = b.make_function("less_than", [a, b.make_literal(10, pa.int32())], pa.bool_())
-    return schema, [(b.make_if(cond, x, b.make_literal(b"\xfe\xffraw", t), t), t)], "project"
+    return schema, [(b.make_if(cond, x, b.make_literal(b"\x00\xffraw", t), t), t)], "project"
 
 
 def case_literals_only(b):
