@@ -76,39 +76,6 @@ GDV_DEV bool gdv_ch_eq(const gdv_str& s, i32 i, u32 lit) {
   }
   return c == lit;
 }
-// First position i in [from, limit) whose byte equals the immediate `lit` under the string's
-// case map, or `limit`.  Scans four bytes per iteration with the SIMD byte compare once the
-// address is word aligned (whole words only, so nothing past the string is read).
-GDV_DEV i32 gdv_find_byte(const gdv_str& s, i32 from, i32 limit, u32 lit) {
-  bool fold = false;
-  const u32 cm = s.xf & GDV_XF_CASE;
-  if (cm == 1u) {
-    if (lit >= (u32)'a' && lit <= (u32)'z') return limit;
-    if (lit >= (u32)'A' && lit <= (u32)'Z') { fold = true; lit |= 0x20u; }
-  } else if (cm == 2u) {
-    if (lit >= (u32)'A' && lit <= (u32)'Z') return limit;
-    if (lit >= (u32)'a' && lit <= (u32)'z') fold = true;
-  }
-  const u32 fmask = fold ? 0x20u : 0u;
-  i32 i = from;
-  while (i < limit && ((unsigned long long)(s.p + i) & 3ull) != 0ull) {
-    if (((u32)s.p[i] | fmask) == lit) return i;
-    ++i;
-  }
-  const u32 pat = lit * 0x01010101u;
-  const u32 fm4 = fmask * 0x01010101u;
-  while (i + 4 <= limit) {
-    const u32 w = *reinterpret_cast<const u32*>(s.p + i) | fm4;
-    const u32 m = __vcmpeq4(w, pat);
-    if (m != 0u) return i + ((__ffs((int)m) - 1) >> 3);
-    i += 4;
-  }
-  while (i < limit) {
-    if (((u32)s.p[i] | fmask) == lit) return i;
-    ++i;
-  }
-  return limit;
-}
 // True when the first n bytes at p are all ASCII (< 0x80).
 GDV_DEV bool gdv_all_ascii(const u8* p, i32 n) {
   i32 i = 0;
@@ -139,19 +106,6 @@ GDV_DEV i32 gdv_glyph_len(u8 c) {
 
 // ---- streaming loads / stores ----------------------------------------------------------
 // Inputs are read once and outputs written once: evict-first policy on both sides.
-template <typename T>
-GDV_DEV T gdv_ld(const void* base, i64 i) {
-  return __ldcs(reinterpret_cast<const T*>(base) + i);
-}
-template <>
-GDV_DEV i128 gdv_ld<i128>(const void* base, i64 i) {
-  const longlong2 v = __ldcs(reinterpret_cast<const longlong2*>(base) + i);
-  return (i128)(((u128)(u64)v.y << 64) | (u128)(u64)v.x);
-}
-template <>
-GDV_DEV i8 gdv_ld<i8>(const void* base, i64 i) {
-  return (i8)__ldcs(reinterpret_cast<const signed char*>(base) + i);
-}
 template <typename T>
 GDV_DEV void gdv_st(void* base, i64 i, T v) {
   __stcs(reinterpret_cast<T*>(base) + i, v);
@@ -280,12 +234,6 @@ GDV_DEV u32 gdv_ldwin_s(const u32* p, u32 widx, u32 sh) {
   return __funnelshift_r(lo, p[widx + 1], sh);
 }
 
-// Bytes of x equal to the matching byte of pat, as 0x80 in that byte.  A byte directly above a
-// true match can be flagged too (borrow of the subtraction): callers verify candidates.
-GDV_DEV u32 gdv_eqbytes_msb(u32 x, u32 pat) {
-  const u32 z = x ^ pat;
-  return (z - 0x01010101u) & ~z & 0x80808080u;
-}
 // Halfwords of x equal to the matching halfword of pat, as 0x8000 in that halfword (the upper one
 // can be flagged falsely when the lower one matches: callers verify candidates).
 GDV_DEV u32 gdv_eqhalf_msb(u32 x, u32 pat) {
@@ -301,15 +249,6 @@ GDV_DEV u32 gdv_mask16_half(u32 e0, u32 o0, u32 e1, u32 o1, u32 e2, u32 o2, u32 
   return gdv_nib_half(e0, o0) | (gdv_nib_half(e1, o1) << 4) | (gdv_nib_half(e2, o2) << 8) |
          (gdv_nib_half(e3, o3) << 12);
 }
-// Four per-word byte-hit masks (bit 7 of every hit byte) of one 16-byte chunk -> one bit per byte.
-GDV_DEV u32 gdv_mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
-  const u32 n0 = ((m0 & 0x80808080u) * 0x00204081u) >> 28;
-  const u32 n1 = ((m1 & 0x80808080u) * 0x00204081u) >> 28;
-  const u32 n2 = ((m2 & 0x80808080u) * 0x00204081u) >> 28;
-  const u32 n3 = ((m3 & 0x80808080u) * 0x00204081u) >> 28;
-  return n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
-}
-
 GDV_DEV u32 gdv_lanemask_lt() {
   u32 m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -494,18 +494,6 @@ class BodyGen {
     return sc;
   }
 
-  static bool FoldedLetter(unsigned char c, unsigned xf) {
-    return (xf == 1u && c >= 'A' && c <= 'Z') || (xf == 2u && c >= 'a' && c <= 'z');
-  }
-
-  // `stage[at + i] == seg[i]` under case map xf, as a C expression on raw staged bytes.
-  static std::string StageByteEq(const std::string& stage, const std::string& at, int i,
-                                 unsigned char lit, unsigned xf) {
-    const std::string ld = "(u32)" + stage + "[" + at + " + " + std::to_string(i) + "]";
-    if (FoldedLetter(lit, xf))
-      return "((" + ld + " | 0x20u) == " + std::to_string(static_cast<unsigned>(lit | 0x20u)) + "u)";
-    return "(" + ld + " == " + std::to_string(static_cast<unsigned>(lit)) + "u)";
-  }
 
   // LIKE over a view chain of column `slot` whose '%'-separated middle segments are all >= 3
   // bytes: the warp scans the staged bytes of a whole group for segment occurrences once
@@ -639,8 +627,7 @@ class BodyGen {
     if (!trail_any) last_mid = segs.size() - 1;
     for (size_t k = first_mid; k < last_mid; ++k) {
       const std::string L = std::to_string(segs[k].size());
-      // Byte-at-a-time leftmost search.  (A word-wise first-byte scan, gdv_find_byte, measured
-      // slower on l_comment-like text: the first byte of a segment is too common a letter.)
+      // Byte-at-a-time leftmost search (the fallback of the cooperative scan).
       f += "  {\n    bool found = false;\n";
       f += "    for (; pos + " + L + " <= n; ++pos) {\n";
       f += "      if (" + match_at(segs[k], "pos") + ") { found = true; break; }\n";
