@@ -164,6 +164,7 @@ GDV_DEV bool gdv_ldbit(const u8* p, u32 sh, i64 i) {
 // current tile computes, at no register cost.  Source and destination must be 16-byte aligned
 // and the size a multiple of 16; the codegen aligns column pointers down and keeps the
 // misalignment as a constant byte offset into the stage.
+#ifndef GDV_HOST_EMU  // tests/emu/gdv_emu.h restates these primitives for the host-side simulator
 GDV_DEV u32 gdv_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 GDV_DEV void gdv_mbar_init(u64* bar, u32 count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gdv_smem_addr(bar)), "r"(count)
@@ -217,6 +218,7 @@ template <int N>
 GDV_DEV void gdv_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+#endif  // GDV_HOST_EMU
 // Shared-memory element load (i128 as one LDS.128).
 template <typename T>
 GDV_DEV T gdv_lds(const T* p) {
@@ -249,11 +251,13 @@ GDV_DEV u32 gdv_mask16_half(u32 e0, u32 o0, u32 e1, u32 o1, u32 e2, u32 o2, u32 
   return gdv_nib_half(e0, o0) | (gdv_nib_half(e1, o1) << 4) | (gdv_nib_half(e2, o2) << 8) |
          (gdv_nib_half(e3, o3) << 12);
 }
+#ifndef GDV_HOST_EMU
 GDV_DEV u32 gdv_lanemask_lt() {
   u32 m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
 }
+#endif
 
 // ---- arithmetic ------------------------------------------------------------------------
 // Integer add/subtract/multiply wrap in two's complement.
@@ -541,14 +545,15 @@ GDV_DEV f64 gdv_pow10_f64(i32 e) {
   return p;
 }
 GDV_DEV f64 round_float64_int32(f64 a, i32 s) {
+  s = s > 308 ? 308 : (s < -308 ? -308 : s);  // clamp first: -s must not overflow for INT32_MIN
   if (s >= 0) {
-    const f64 p = gdv_pow10_f64(s > 308 ? 308 : s);
+    const f64 p = gdv_pow10_f64(s);
     const f64 v = a * p;
     if (!(fabs(v) < 1.7976931348623157e308)) return a;  // overflow or NaN: nothing to round
     if (v == floor(v)) return a;  // already a multiple of 10^-s: do not disturb the value
     return round(v) / p;
   }
-  const f64 p = gdv_pow10_f64(-s > 308 ? 308 : -s);
+  const f64 p = gdv_pow10_f64(-s);
   const f64 q = a / p;
   if (q == floor(q)) return a;
   return round(q) * p;
@@ -1258,6 +1263,7 @@ GDV_DEV bool gdv_like_match(const gdv_str& s, const u16* pat, i32 m) {
 #define GDV_TILE_AGGREGATE 1ull
 #define GDV_TILE_INCLUSIVE 2ull
 #define GDV_TILE_VALUE_MASK 0x3fffffffffffffffull
+#ifndef GDV_HOST_EMU
 GDV_DEV u64 gdv_ld_relaxed(const u64* p) {
   u64 v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1266,6 +1272,7 @@ GDV_DEV u64 gdv_ld_relaxed(const u64* p) {
 GDV_DEV void gdv_st_relaxed(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 // Called by all 32 lanes of one warp.  Returns the exclusive prefix of `tile` (sum of the
 // counts of tiles 0..tile-1) in every lane and publishes this tile's inclusive prefix.
 GDV_DEV u64 gdv_tile_exclusive_prefix(u64* state, i64 tile, u64 count, u32 lane) {

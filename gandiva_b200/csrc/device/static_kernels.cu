@@ -139,6 +139,7 @@ gdv_scan_tiles(u64* tiles, i64 n_tiles, u64* total, int* err, u64 limit) {
 // rank r's offset is the sum of count[q], q < r, read with acquire loads once they carry seq.
 #define GDV_BOARD_SEQ_SHIFT 40
 #define GDV_BOARD_COUNT_MASK ((1ull << GDV_BOARD_SEQ_SHIFT) - 1ull)
+#ifndef GDV_HOST_EMU
 __device__ __forceinline__ u64 gdv_ld_acquire_sys(const u64* p) {
   u64 v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -147,6 +148,7 @@ __device__ __forceinline__ u64 gdv_ld_acquire_sys(const u64* p) {
 __device__ __forceinline__ void gdv_st_release_sys(u64* p, u64 v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 
 template <typename T>
 __device__ __forceinline__ void gdv_copy_run(const T* __restrict__ src, T* dst, u64 n) {

@@ -1003,9 +1003,9 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   // ---- rounding ---------------------------------------------------------------------------
   if (f == "round") {
     if (na == 2) {
-      const int s = static_cast<int>(a[1].i);
+      const int s = static_cast<int>(std::max<int64_t>(-308, std::min<int64_t>(308, a[1].i)));
       double p = 1.0;
-      const int e = std::min(std::abs(s), 308);
+      const int e = std::abs(s);
       for (int k = 0; k < e; ++k) p = p * 10.0;
       if (s >= 0) {
         const double v = a[0].d * p;

@@ -7,6 +7,7 @@ import pyarrow as pa
 import pytest
 
 import cases
+import devmem
 from helpers import assert_arrays_match
 
 pytestmark = pytest.mark.gpu
@@ -290,83 +291,91 @@ def test_empty_batch_rejected(gandiva):
 
 def test_generator_matches_cpu_twin(gandiva, oracle):
     """Device lineitem generator == oracle/lineitem.h for every column kind."""
-    import torch
     n = 100003
+    st = devmem.stream()
     for kind, npdt in [(0, np.int32), (1, np.float64), (2, np.float64), (3, np.int64), (7, np.float64),
                        (8, np.float64), (9, np.int32)]:
-        vals = torch.zeros(n, dtype=getattr(torch, np.dtype(npdt).name), device="cuda")
-        vld = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
-        gandiva.generate_lineitem(0, kind, 42, 1000, n, vals.data_ptr(), vld.data_ptr(), 15, torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
+        vals = devmem.DevBuf(n, npdt, fill=0)
+        vld = devmem.DevBuf((n + 31) // 32, np.int32, fill=0)
+        gandiva.generate_lineitem(0, kind, 42, 1000, n, vals.ptr, vld.ptr, 15, st)
+        devmem.synchronize()
         cv, cvld = oracle.generate_lineitem(kind, 42, 1000, n, 15)
-        assert np.array_equal(vals.cpu().numpy(), cv), kind
-        gbits = np.unpackbits(vld.cpu().numpy().view(np.uint8), bitorder="little")[:n]
+        assert np.array_equal(vals.numpy(), cv), kind
+        gbits = np.unpackbits(vld.numpy().view(np.uint8), bitorder="little")[:n]
         cbits = np.unpackbits(cvld, bitorder="little")[:n]
         assert np.array_equal(gbits, cbits), kind
     for kind in (4, 5, 6):
-        vals = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
-        gandiva.generate_lineitem(0, kind, 42, 0, n, vals.data_ptr(), 0, 0, torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
+        vals = devmem.DevBuf((n, 2), np.int64, fill=0)
+        gandiva.generate_lineitem(0, kind, 42, 0, n, vals.ptr, 0, 0, st)
+        devmem.synchronize()
         cv, _ = oracle.generate_lineitem(kind, 42, 0, n)
-        assert np.array_equal(vals.cpu().numpy().view(np.uint64), cv), kind
+        assert np.array_equal(vals.numpy().view(np.uint64), cv), kind
 
 
 def test_device_resident_filter_and_properties(gandiva, oracle):
     """Device-resident async API (the bench path): inputs generated in HBM, indices stay in HBM.
     Checked exactly against the oracle on the first rows and by size-independent properties
-    (ascending, count == independent torch mask count, indices == torch.nonzero) on all rows."""
-    import torch
-    n = (32 << 20) + 3  # >= 32M rows: exercises the large-batch kernel variant (1024-thread tiles)
-    dev = torch.device("cuda")
-    ship = torch.empty(n, dtype=torch.int32, device=dev)
-    disc = torch.empty(n, dtype=torch.float64, device=dev)
-    qty = torch.empty(n, dtype=torch.float64, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    (ascending, count == independent mask count, indices == nonzero(mask)) on all rows."""
+    # >= 32M rows: exercises the large-batch kernel variant (1024-thread tiles); the simulator
+    # takes a batch it finishes in seconds (that variant is reached there through block_threads)
+    n = 300_007 if devmem.EMU else (32 << 20) + 3
+    ship = devmem.DevBuf(n, np.int32)
+    disc = devmem.DevBuf(n, np.float64)
+    qty = devmem.DevBuf(n, np.float64)
+    st = devmem.stream()
     for kind, tns in ((0, ship), (1, disc), (2, qty)):
-        gandiva.generate_lineitem(0, kind, 42, 0, n, tns.data_ptr(), 0, 0, st)
+        gandiva.generate_lineitem(0, kind, 42, 0, n, tns.ptr, 0, 0, st)
     b = gandiva.TreeExprBuilder()
-    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)))
-    out = torch.empty(n, dtype=torch.int32, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-    cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
+    cfg = gandiva.Configuration(block_threads=1024) if devmem.EMU else None
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)), cfg)
+    out = devmem.DevBuf(n, np.int32)
+    cnt = devmem.DevBuf(1, np.int64, fill=0)
+    cols = [(0, ship.ptr, 0, 0), (0, disc.ptr, 0, 0), (0, qty.ptr, 0, 0)]
     for _ in range(3):  # repeated async launches on one stream reuse the look-back scratch
-        f.evaluate_device(n, cols, out.data_ptr(), n, "UINT32", st, cnt.data_ptr())
+        f.evaluate_device(n, cols, out.ptr, n, "UINT32", st, cnt.ptr)
     count = f.sync(st)
-    assert count == int(cnt.item())
-    mask = (ship >= 8766) & (ship < 9131) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24)
-    assert count == int(mask.sum().item())
-    idx = out[:count].to(torch.int64)
-    assert bool((idx[1:] > idx[:-1]).all())
-    assert torch.equal(idx, torch.nonzero(mask).flatten())
+    assert count == int(cnt.numpy()[0])
+    if devmem.EMU:
+        shipn, discn, qtyn = ship.numpy(), disc.numpy(), qty.numpy()
+        mask = (shipn >= 8766) & (shipn < 9131) & (discn >= 0.05) & (discn <= 0.07) & (qtyn < 24)
+        assert count == int(mask.sum())
+        idx = out.numpy()[:count].astype(np.int64)
+        assert bool((idx[1:] > idx[:-1]).all())
+        assert np.array_equal(idx, np.nonzero(mask)[0])
+    else:
+        import torch
+        mask = (ship.a >= 8766) & (ship.a < 9131) & (disc.a >= 0.05) & (disc.a <= 0.07) & (qty.a < 24)
+        assert count == int(mask.sum().item())
+        tidx = out.a[:count].to(torch.int64)
+        assert bool((tidx[1:] > tidx[:-1]).all())
+        assert torch.equal(tidx, torch.nonzero(mask).flatten())
+        idx = tidx.cpu().numpy()
     # exact oracle parity on a prefix
     m = 200_000
     batch = cases.q6_batch(m, seed=42)
-    assert np.array_equal(ship[:m].cpu().numpy(), batch.column(0).cast(pa.int32()).to_numpy(zero_copy_only=False))
+    assert np.array_equal(ship.numpy()[:m], batch.column(0).cast(pa.int32()).to_numpy(zero_copy_only=False))
     want = oracle.filter_indices(cases.q6_condition(b), batch, threads=4)
-    got = idx[idx < m].cpu().numpy().astype(np.uint64)
+    got = idx[idx < m].astype(np.uint64)
     assert np.array_equal(got, want)
 
 
 def test_device_resident_projector(gandiva, oracle):
-    import torch
-    n = 3_000_001
-    dev = torch.device("cuda")
-    a = torch.empty(n, dtype=torch.int32, device=dev)
-    bb = torch.empty(n, dtype=torch.int32, device=dev)
-    av = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
-    bv = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    gandiva.generate_lineitem(0, 9, 42, 0, n, a.data_ptr(), av.data_ptr(), 100, st)
-    gandiva.generate_lineitem(0, 10, 42, 0, n, bb.data_ptr(), bv.data_ptr(), 100, st)
+    n = 300_001 if devmem.EMU else 3_000_001
+    a = devmem.DevBuf(n, np.int32)
+    bb = devmem.DevBuf(n, np.int32)
+    av = devmem.DevBuf((n + 31) // 32, np.int32)
+    bv = devmem.DevBuf((n + 31) // 32, np.int32)
+    st = devmem.stream()
+    gandiva.generate_lineitem(0, 9, 42, 0, n, a.ptr, av.ptr, 100, st)
+    gandiva.generate_lineitem(0, 10, 42, 0, n, bb.ptr, bv.ptr, 100, st)
     bld = gandiva.TreeExprBuilder()
     t = pa.int32()
     schema = pa.schema([("a", t), ("b", t)])
     root = bld.make_function("add", [cases.F(bld, "a", t), cases.F(bld, "b", t)], t)
     p = gandiva.make_projector(schema, [bld.make_expression(root, pa.field("c", t))], None)
-    out = torch.empty(n, dtype=torch.int32, device=dev)
-    ov = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
-    p.evaluate_device(n, [(av.data_ptr(), a.data_ptr(), 0, 0), (bv.data_ptr(), bb.data_ptr(), 0, 0)],
-                      [(ov.data_ptr(), out.data_ptr())], st)
+    out = devmem.DevBuf(n, np.int32)
+    ov = devmem.DevBuf((n + 31) // 32, np.int32)
+    p.evaluate_device(n, [(av.ptr, a.ptr, 0, 0), (bv.ptr, bb.ptr, 0, 0)], [(ov.ptr, out.ptr)], st)
     p.sync(st)
     ca, cav = oracle.generate_lineitem(9, 42, 0, n, 100, threads=4)
     cb, cbv = oracle.generate_lineitem(10, 42, 0, n, 100, threads=4)
@@ -374,7 +383,7 @@ def test_device_resident_projector(gandiva, oracle):
         [pa.Array.from_buffers(t, n, [pa.py_buffer(cav), pa.py_buffer(ca)]),
          pa.Array.from_buffers(t, n, [pa.py_buffer(cbv), pa.py_buffer(cb)])], schema=schema)
     want, = oracle.project([root], [t], batch, threads=4)
-    got = pa.Array.from_buffers(t, n, [pa.py_buffer(ov.cpu().numpy()), pa.py_buffer(out.cpu().numpy())])
+    got = pa.Array.from_buffers(t, n, [pa.py_buffer(ov.numpy()), pa.py_buffer(out.numpy())])
     assert_arrays_match(got, want, "device-resident add")
 
 
@@ -385,31 +394,29 @@ def test_kernels_were_launched(gandiva):
 def test_filter_bounded_selection_vector(gandiva, oracle):
     """GDV_SEL_BOUNDED: capacity smaller than the number of selected rows -> the count is still
     exact, the first max_slots indices are stored, nothing is written past the capacity."""
-    import torch
-    n = 1_000_003
-    dev = torch.device("cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    ship = torch.empty(n, dtype=torch.int32, device=dev)
-    disc = torch.empty(n, dtype=torch.float64, device=dev)
-    qty = torch.empty(n, dtype=torch.float64, device=dev)
+    n = 200_003 if devmem.EMU else 1_000_003
+    st = devmem.stream()
+    ship = devmem.DevBuf(n, np.int32)
+    disc = devmem.DevBuf(n, np.float64)
+    qty = devmem.DevBuf(n, np.float64)
     for kind, t in ((0, ship), (1, disc), (2, qty)):
-        gandiva.generate_lineitem(0, kind, 42, 0, n, t.data_ptr(), 0, 0, st)
+        gandiva.generate_lineitem(0, kind, 42, 0, n, t.ptr, 0, 0, st)
     b = gandiva.TreeExprBuilder()
     f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)))
     want = oracle.filter_indices(cases.q6_condition(b), cases.q6_batch(n, seed=42), threads=4)
-    cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
+    cols = [(0, ship.ptr, 0, 0), (0, disc.ptr, 0, 0), (0, qty.ptr, 0, 0)]
     for cap in (len(want) + 100, len(want) // 2, 7):
-        out = torch.full((cap + 64,), -1, dtype=torch.int64, device=dev)
-        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-        f.evaluate_device(n, cols, out.data_ptr(), cap, "UINT64|BOUNDED", st, cnt.data_ptr(), index_base=5)
+        out = devmem.DevBuf(cap + 64, np.int64, fill=-1)
+        cnt = devmem.DevBuf(1, np.int64, fill=0)
+        f.evaluate_device(n, cols, out.ptr, cap, "UINT64|BOUNDED", st, cnt.ptr, index_base=5)
         count = f.sync(st)
         assert count == len(want)
         k = min(cap, count)
-        got = out.cpu().numpy()
+        got = out.numpy()
         assert np.array_equal(got[:k].astype(np.uint64), want[:k] + 5)
         assert (got[max(cap, k):] == -1).all()
     with pytest.raises(pa.ArrowInvalid):   # without the flag the reference rule holds
-        f.evaluate_device(n, cols, out.data_ptr(), 7, "UINT64", st, cnt.data_ptr())
+        f.evaluate_device(n, cols, out.ptr, 7, "UINT64", st, cnt.ptr)
 
 
 def test_peer_selection_push(gandiva):
