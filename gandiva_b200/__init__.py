@@ -152,6 +152,16 @@ def _load() -> C.CDLL:
         "gdv_generate_lineitem": (i32, [i32, i32, C.c_uint64, i64, i64, vp, vp, i32, vp]),
         "gdv_launch_count": (i64, []),
         "gdv_compile_count": (i64, []),
+        # include/gandiva_b200_arrow.h
+        "gdv_schema_from_arrow": (i32, [vp, P(vp)]),
+        "gdv_arrow_batch_import": (i32, [vp, vp, P(vp)]),
+        "gdv_arrow_batch_view": (P(gdv_batch_t), [vp]),
+        "gdv_arrow_batch_wait": (i32, [vp, vp]),
+        "gdv_arrow_batch_release": (None, [vp]),
+        "gdv_projector_output_schema_arrow": (i32, [vp, vp]),
+        "gdv_projector_evaluate_arrow": (i32, [vp, vp, vp, vp]),
+        "gdv_filter_evaluate_arrow": (i32, [vp, vp, i32, vp, vp]),
+        "gdv_memcpy": (i32, [i32, vp, vp, C.c_size_t, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -744,6 +754,143 @@ class Filter:
         n = C.c_int64(-1)
         _check(lib.gdv_filter_sync(self._h, _stream_handle(stream), C.byref(n)))
         return int(n.value)
+
+
+# ---- Arrow C Device Data interface (include/gandiva_b200_arrow.h) -----------------------------
+class ArrowSchemaC(C.Structure):
+    pass
+
+
+ArrowSchemaC._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p),
+                         ("flags", C.c_int64), ("n_children", C.c_int64),
+                         ("children", C.POINTER(C.POINTER(ArrowSchemaC))), ("dictionary", C.POINTER(ArrowSchemaC)),
+                         ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArrayC(C.Structure):
+    pass
+
+
+ArrowArrayC._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64),
+                        ("n_buffers", C.c_int64), ("n_children", C.c_int64),
+                        ("buffers", C.POINTER(C.c_void_p)), ("children", C.POINTER(C.POINTER(ArrowArrayC))),
+                        ("dictionary", C.POINTER(ArrowArrayC)), ("release", C.c_void_p),
+                        ("private_data", C.c_void_p)]
+
+ARROW_DEVICE_CPU, ARROW_DEVICE_CUDA, ARROW_DEVICE_CUDA_HOST = 1, 2, 3
+
+
+class ArrowDeviceArrayC(C.Structure):
+    _fields_ = [("array", ArrowArrayC), ("device_id", C.c_int64), ("device_type", C.c_int32),
+                ("sync_event", C.c_void_p), ("reserved", C.c_int64 * 3)]
+
+
+_RELEASE_ARRAY = C.CFUNCTYPE(None, C.POINTER(ArrowArrayC))
+_RELEASE_SCHEMA = C.CFUNCTYPE(None, C.POINTER(ArrowSchemaC))
+
+
+class ArrowDeviceBatch:
+    """A record batch imported from a struct-typed ArrowDeviceArray (zero copy; device buffers
+    stay in HBM).  `address` is the address of the producer's `struct ArrowDeviceArray`, which is
+    MOVED (marked released) by the import."""
+
+    def __init__(self, address: int, schema: pa.Schema):
+        self._schema_handle = _SchemaHandle(schema)
+        self._h = C.c_void_p()
+        _check(lib.gdv_arrow_batch_import(C.c_void_p(address), self._schema_handle._h, C.byref(self._h)))
+
+    @classmethod
+    def from_record_batch(cls, batch: pa.RecordBatch) -> "ArrowDeviceBatch":
+        """Host batch through pyarrow's own exporter (device type ARROW_DEVICE_CPU)."""
+        arr = ArrowDeviceArrayC()
+        sch = ArrowSchemaC()
+        batch._export_to_c_device(C.addressof(arr), C.addressof(sch))
+        try:
+            return cls(C.addressof(arr), batch.schema)
+        finally:
+            if sch.release:
+                _RELEASE_SCHEMA(sch.release)(C.byref(sch))
+            if arr.array.release:  # import failed: the array was not moved
+                _RELEASE_ARRAY(arr.array.release)(C.byref(arr.array))
+
+    @property
+    def num_rows(self) -> int:
+        return int(lib.gdv_arrow_batch_view(self._h).contents.num_rows)
+
+    @property
+    def mem_space(self) -> int:
+        return int(lib.gdv_arrow_batch_view(self._h).contents.mem_space)
+
+    def release(self) -> None:
+        if self._h:
+            lib.gdv_arrow_batch_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class ArrowDeviceResult:
+    """An ArrowDeviceArray exported by the engine (+ its ArrowSchema for projector results);
+    the buffers go back to the engine's pool on release()."""
+
+    def __init__(self):
+        self.array = ArrowDeviceArrayC()
+        self.schema = None
+
+    @property
+    def address(self) -> int:
+        return C.addressof(self.array)
+
+    def to_record_batch(self) -> pa.RecordBatch:
+        """Host results only: hands array + schema to pyarrow's importer (which takes ownership)."""
+        if self.array.device_type != ARROW_DEVICE_CPU:
+            raise pa.ArrowNotImplementedError("pyarrow in this image cannot import CUDA device arrays")
+        rb = pa.RecordBatch._import_from_c_device(C.addressof(self.array), C.addressof(self.schema))
+        return rb
+
+    def release(self) -> None:
+        if self.array.array.release:
+            _RELEASE_ARRAY(self.array.array.release)(C.byref(self.array.array))
+        if self.schema is not None and self.schema.release:
+            _RELEASE_SCHEMA(self.schema.release)(C.byref(self.schema))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def _projector_evaluate_arrow(self, batch: ArrowDeviceBatch, stream: int = 0) -> ArrowDeviceResult:
+    res = ArrowDeviceResult()
+    res.schema = ArrowSchemaC()
+    _check(lib.gdv_projector_output_schema_arrow(self._h, C.addressof(res.schema)))
+    _check(lib.gdv_projector_evaluate_arrow(self._h, batch._h, _stream_handle(stream) if stream else None,
+                                            C.addressof(res.array)))
+    return res
+
+
+def _filter_evaluate_arrow(self, batch: ArrowDeviceBatch, mode: str = "UINT32", stream: int = 0) -> ArrowDeviceResult:
+    res = ArrowDeviceResult()
+    _check(lib.gdv_filter_evaluate_arrow(self._h, batch._h, _ensure_selection_mode(mode),
+                                         _stream_handle(stream) if stream else None, C.addressof(res.array)))
+    return res
+
+
+Projector.evaluate_arrow = _projector_evaluate_arrow
+Filter.evaluate_arrow = _filter_evaluate_arrow
+
+
+def memcpy_dtoh(device: int, dst: np.ndarray, src_ptr: int) -> None:
+    _check(lib.gdv_memcpy(device, dst.ctypes.data_as(C.c_void_p), C.c_void_p(src_ptr), dst.nbytes, 2))
+
+
+def memcpy_htod(device: int, dst_ptr: int, src: np.ndarray) -> None:
+    _check(lib.gdv_memcpy(device, C.c_void_p(dst_ptr), src.ctypes.data_as(C.c_void_p), src.nbytes, 1))
 
 
 # ---- factories ---------------------------------------------------------------------------

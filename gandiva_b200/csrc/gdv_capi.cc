@@ -4,16 +4,20 @@
 #include <vector>
 
 #include "gandiva_b200.h"
+#include "gdv_capi_internal.h"
 #include "gdv_node.h"
 #include "gdv_registry.h"
 #include "gdv_runtime.h"
 
 using namespace gdv;
+using namespace gdv::capi;
 
 namespace {
-
 thread_local std::string tl_error;
+}
 
+namespace gdv {
+namespace capi {
 gdv_status Fail(const Status& s) {
   tl_error = s.msg;
   return s.code;
@@ -22,13 +26,10 @@ gdv_status Fail(int code, const std::string& msg) {
   tl_error = msg;
   return code;
 }
+}  // namespace capi
+}  // namespace gdv
 
-struct NodeH { NodePtr p; };
-struct ExprH { ExpressionPtr p; };
-struct CondH { ConditionPtr p; };
-struct SchemaH { SchemaPtr p; };
-struct ProjH { std::shared_ptr<Projector> p; };
-struct FiltH { std::shared_ptr<Filter> p; };
+namespace {
 
 NodeH* N(gdv_node_t h) { return reinterpret_cast<NodeH*>(h); }
 

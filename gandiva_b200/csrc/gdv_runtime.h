@@ -135,6 +135,8 @@ class Projector {
   Status KernelFor(bool nullable, CompiledKernel** out);
   const Config& config() const { return cfg_; }
   int num_outputs() const { return static_cast<int>(exprs_.size()); }
+  const SchemaPtr& schema() const { return schema_; }
+  const std::vector<ExpressionPtr>& expressions() const { return exprs_; }
 
  private:
   // One utf8/binary output expression: sizing + write kernels, [0] nullable inputs, [1] no nulls.
@@ -175,6 +177,7 @@ class Filter {
   // One kernel per (index width, nullable inputs?, large batch?), compiled on first use.
   Status KernelFor(int mode, bool nullable, bool large, CompiledKernel** out);
   const Config& config() const { return cfg_; }
+  const SchemaPtr& schema() const { return schema_; }
   CompiledKernel* last_used() const { return last_used_; }
 
  private:
