@@ -33,6 +33,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_DIV_ZERO 1
 #define GDV_ERR_OFFSET_OVERFLOW 2  /* a utf8/binary output needs more than 2^31 - 1 bytes */
 #define GDV_ERR_VAR_CAPACITY 3     /* the caller's var_data buffer is too small */
+#define GDV_ERR_CAST_INT 4         /* castINT / castBIGINT of a string that is not an integer */
 struct gdv_ctx {
   int* err;
 };
@@ -340,6 +341,50 @@ GDV_DEV f64 sqrt_float64(f64 a) { return sqrt(a); }
 GDV_BITWISE(i32, int32)
 GDV_BITWISE(i64, int64)
 
+// div: truncating integer division (x / 0 raises like divide); pmod: modulo with the sign of the
+// divisor (Hive's ((x % y) + y) % y), pmod(x, 0) = x like mod; sign: -1 / 0 / 1 (floats: +-0 and
+// NaN pass through).
+#define GDV_INTDIV(T, UT, S)                                      \
+  GDV_DEV T div_##S##_##S(gdv_ctx* c, T a, T b) {                 \
+    if (b == 0) {                                                 \
+      gdv_set_error(c, GDV_ERR_DIV_ZERO);                         \
+      return (T)0;                                                \
+    }                                                             \
+    if (b == (T)-1) return (T)((UT)0 - (UT)a);                    \
+    return (T)(a / b);                                            \
+  }                                                               \
+  GDV_DEV T pmod_##S##_##S(T a, T b) {                            \
+    if (b == 0) return a;                                         \
+    if (b == (T)-1) return (T)0;                                  \
+    T r = (T)(a % b);                                             \
+    if (r != 0 && ((r < 0) != (b < 0))) r = (T)(r + b);           \
+    return r;                                                     \
+  }                                                               \
+  GDV_DEV T sign_##S(T a) { return (T)((a > 0) - (a < 0)); }
+GDV_INTDIV(i32, u32, int32)
+GDV_INTDIV(i64, u64, int64)
+GDV_DEV f32 sign_float32(f32 a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : a); }
+GDV_DEV f64 sign_float64(f64 a) { return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : a); }
+// greatest / least of 2..4 arguments, folded left to right with > / <: a NaN that is not the
+// first argument never wins, a leading NaN is only displaced by a comparison that is true.
+#define GDV_GREATEST_LEAST(T, S)                                                                  \
+  GDV_DEV T greatest_##S##_##S(T a, T b) { return b > a ? b : a; }                                \
+  GDV_DEV T greatest_##S##_##S##_##S(T a, T b, T c) {                                             \
+    return greatest_##S##_##S(greatest_##S##_##S(a, b), c);                                       \
+  }                                                                                               \
+  GDV_DEV T greatest_##S##_##S##_##S##_##S(T a, T b, T c, T d) {                                  \
+    return greatest_##S##_##S(greatest_##S##_##S##_##S(a, b, c), d);                              \
+  }                                                                                               \
+  GDV_DEV T least_##S##_##S(T a, T b) { return b < a ? b : a; }                                   \
+  GDV_DEV T least_##S##_##S##_##S(T a, T b, T c) { return least_##S##_##S(least_##S##_##S(a, b), c); } \
+  GDV_DEV T least_##S##_##S##_##S##_##S(T a, T b, T c, T d) {                                     \
+    return least_##S##_##S(least_##S##_##S##_##S(a, b, c), d);                                    \
+  }
+GDV_GREATEST_LEAST(i32, int32)
+GDV_GREATEST_LEAST(i64, int64)
+GDV_GREATEST_LEAST(f32, float32)
+GDV_GREATEST_LEAST(f64, float64)
+
 // ---- comparisons -----------------------------------------------------------------------
 #define GDV_RELOP(T, S)                                                               \
   GDV_DEV bool equal_##S##_##S(T a, T b) { return a == b; }                           \
@@ -559,6 +604,41 @@ GDV_DEV f64 round_float64_int32(f64 a, i32 s) {
   return round(q) * p;
 }
 
+// truncate(x, s): like round(x, s) with trunc() in place of round().
+GDV_DEV f64 truncate_float64_int32(f64 a, i32 s) {
+  s = s > 308 ? 308 : (s < -308 ? -308 : s);
+  if (s >= 0) {
+    const f64 p = gdv_pow10_f64(s);
+    const f64 v = a * p;
+    if (!(fabs(v) < 1.7976931348623157e308)) return a;
+    if (v == floor(v)) return a;
+    return trunc(v) / p;
+  }
+  const f64 p = gdv_pow10_f64(-s);
+  const f64 q = a / p;
+  if (q == floor(q)) return a;
+  return trunc(q) * p;
+}
+// round / truncate of an integer to 10^-s, s < 0 (s >= 0: unchanged); half away from zero; the
+// arithmetic is done in 128 bits and the result wraps into the output type like a cast.
+GDV_DEV i128 gdv_round_int128(i128 x, i32 s, bool half_away) {
+  if (s >= 0) return x;
+  if (s < -38) return (i128)0;
+  i128 p = 1;
+  for (i32 i = 0; i < -s; ++i) p = p * 10;
+  const i128 r = x % p;
+  i128 base = x - r;
+  if (half_away) {
+    const i128 ar = r < 0 ? -r : r;
+    if (ar >= p - ar) base = base + (x < 0 ? -p : p);
+  }
+  return base;
+}
+GDV_DEV i32 round_int32_int32(i32 a, i32 s) { return (i32)(u32)(u128)gdv_round_int128((i128)a, s, true); }
+GDV_DEV i64 round_int64_int32(i64 a, i32 s) { return (i64)(u64)(u128)gdv_round_int128((i128)a, s, true); }
+GDV_DEV i32 truncate_int32_int32(i32 a, i32 s) { return (i32)(u32)(u128)gdv_round_int128((i128)a, s, false); }
+GDV_DEV i64 truncate_int64_int32(i64 a, i32 s) { return (i64)(u64)(u128)gdv_round_int128((i128)a, s, false); }
+
 // ---- date / time arithmetic (date64 and timestamp are milliseconds since the epoch) -----------
 GDV_DEV i64 gdv_days_from_civil(i64 y, i32 m, i32 d) {
   y -= m <= 2 ? 1 : 0;
@@ -606,6 +686,83 @@ GDV_TSDIFF(timestampdiffMinute, 60000ll)
 GDV_TSDIFF(timestampdiffHour, 3600000ll)
 GDV_TSDIFF(timestampdiffDay, 86400000ll)
 GDV_TSDIFF(timestampdiffWeek, 604800000ll)
+
+// ---- calendar fields and truncation -------------------------------------------------------------
+// ISO 8601 week of the year (weeks start on Monday, week 1 holds the year's first Thursday).
+GDV_DEV i64 gdv_iso_week(i64 days) {
+  const gdv_ymd c = gdv_civil_from_days(days);
+  i64 wd = (days + 3) % 7;  // 1970-01-01 was a Thursday: Monday = 0
+  if (wd < 0) wd += 7;
+  const i64 week = ((i64)c.doy - (wd + 1) + 10) / 7;
+  if (week >= 1 && week <= 52) return week;
+  // weekday of Jan 1 of year y (Monday = 0), and whether y has 53 ISO weeks
+  const i64 jan1 = days - ((i64)c.doy - 1);
+  if (week < 1) {
+    const i64 py = c.y - 1;
+    const bool pleap = (py % 4 == 0) && ((py % 100 != 0) || (py % 400 == 0));
+    const i64 pjan1 = jan1 - (pleap ? 366 : 365);
+    i64 pw = (pjan1 + 3) % 7;
+    if (pw < 0) pw += 7;
+    return (pw == 3 || (pleap && pw == 2)) ? 53 : 52;
+  }
+  const bool leap = (c.y % 4 == 0) && ((c.y % 100 != 0) || (c.y % 400 == 0));
+  i64 jw = (jan1 + 3) % 7;
+  if (jw < 0) jw += 7;
+  return (jw == 3 || (leap && jw == 2)) ? 53 : 1;
+}
+// date_trunc: the first instant of the enclosing unit; weeks start on Monday; decades start in
+// years divisible by 10, centuries / millennia in years ...01 (C truncating division on the year).
+GDV_DEV i64 gdv_trunc_year_to(i64 ms, i64 span, i64 first) {
+  const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));
+  const i64 y = span == 10 ? (c.y / 10) * 10 : ((c.y - 1) / span) * span + first;
+  return gdv_days_from_civil(span == 1 ? c.y : y, 1, 1) * 86400000ll;
+}
+#define GDV_CALENDAR(S)                                                                           \
+  GDV_DEV i64 extractWeek_##S(i64 ms) { return gdv_iso_week(gdv_floordiv(ms, 86400000ll)); }      \
+  GDV_DEV i64 extractDecade_##S(i64 ms) {                                                         \
+    return gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).y / 10;                              \
+  }                                                                                               \
+  GDV_DEV i64 extractCentury_##S(i64 ms) {                                                        \
+    return (gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).y - 1) / 100 + 1;                   \
+  }                                                                                               \
+  GDV_DEV i64 extractMillennium_##S(i64 ms) {                                                     \
+    return (gdv_civil_from_days(gdv_floordiv(ms, 86400000ll)).y - 1) / 1000 + 1;                  \
+  }                                                                                               \
+  GDV_DEV i64 date_trunc_Second_##S(i64 ms) { return gdv_floordiv(ms, 1000ll) * 1000ll; }         \
+  GDV_DEV i64 date_trunc_Minute_##S(i64 ms) { return gdv_floordiv(ms, 60000ll) * 60000ll; }       \
+  GDV_DEV i64 date_trunc_Hour_##S(i64 ms) { return gdv_floordiv(ms, 3600000ll) * 3600000ll; }     \
+  GDV_DEV i64 date_trunc_Day_##S(i64 ms) { return gdv_floordiv(ms, 86400000ll) * 86400000ll; }    \
+  GDV_DEV i64 date_trunc_Week_##S(i64 ms) {                                                       \
+    const i64 days = gdv_floordiv(ms, 86400000ll);                                                \
+    i64 wd = (days + 3) % 7;                                                                      \
+    if (wd < 0) wd += 7;                                                                          \
+    return (days - wd) * 86400000ll;                                                              \
+  }                                                                                               \
+  GDV_DEV i64 date_trunc_Month_##S(i64 ms) {                                                      \
+    const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));                          \
+    return gdv_days_from_civil(c.y, c.m, 1) * 86400000ll;                                         \
+  }                                                                                               \
+  GDV_DEV i64 date_trunc_Quarter_##S(i64 ms) {                                                    \
+    const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));                          \
+    return gdv_days_from_civil(c.y, ((c.m - 1) / 3) * 3 + 1, 1) * 86400000ll;                     \
+  }                                                                                               \
+  GDV_DEV i64 date_trunc_Year_##S(i64 ms) { return gdv_trunc_year_to(ms, 1, 0); }                 \
+  GDV_DEV i64 date_trunc_Decade_##S(i64 ms) { return gdv_trunc_year_to(ms, 10, 0); }              \
+  GDV_DEV i64 date_trunc_Century_##S(i64 ms) { return gdv_trunc_year_to(ms, 100, 1); }            \
+  GDV_DEV i64 date_trunc_Millennium_##S(i64 ms) { return gdv_trunc_year_to(ms, 1000, 1); }        \
+  GDV_DEV i64 last_day_##S(i64 ms) {                                                              \
+    const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));                          \
+    const i64 ny = c.m == 12 ? c.y + 1 : c.y;                                                     \
+    const i32 nm = c.m == 12 ? 1 : c.m + 1;                                                       \
+    return (gdv_days_from_civil(ny, nm, 1) - 1) * 86400000ll;                                     \
+  }
+GDV_CALENDAR(date64)
+GDV_CALENDAR(timestamp)
+// time of day (time32[ms]) of a timestamp, and its fields
+GDV_DEV i32 castTIME_timestamp(i64 ms) { return (i32)(ms - gdv_floordiv(ms, 86400000ll) * 86400000ll); }
+GDV_DEV i64 extractHour_time32(i32 t) { return (i64)(t / 3600000); }
+GDV_DEV i64 extractMinute_time32(i32 t) { return (i64)((t / 60000) % 60); }
+GDV_DEV i64 extractSecond_time32(i32 t) { return (i64)((t / 1000) % 60); }
 
 // ---- decimal128 ------------------------------------------------------------------------
 // Values are two's-complement 128-bit integers scaled by 10^scale (Arrow decimal128).
@@ -1216,6 +1373,101 @@ GDV_DEV gdv_str rtrim_utf8(gdv_str s) {
   return s;
 }
 GDV_DEV gdv_str btrim_utf8(gdv_str s) { return rtrim_utf8(ltrim_utf8(s)); }
+
+// ascii(s): the first byte as seen through the case map (0 for the empty string).
+GDV_DEV i32 ascii_utf8(gdv_str s) { return s.len > 0 ? (i32)gdv_ch(s, 0) : 0; }
+// left(s, n): the first n glyphs, n < 0: all but the last |n|; right(s, n): the last n glyphs,
+// n < 0: all but the first |n|.  Views, like substr.
+GDV_DEV gdv_str left_utf8_int32(gdv_str s, i32 n) {
+  if (n > 0) return substr_utf8_int64_int64(s, 1, (i64)n);
+  gdv_str r = s;
+  r.len = 0;
+  if (n == 0) return r;
+  const i64 keep = (i64)char_length_utf8(s) + (i64)n;
+  if (keep <= 0) return r;
+  return substr_utf8_int64_int64(s, 1, keep);
+}
+GDV_DEV gdv_str right_utf8_int32(gdv_str s, i32 n) {
+  gdv_str r = s;
+  r.len = 0;
+  if (n == 0) return r;
+  if (n < 0) return substr_utf8_int64_int64(s, 1 - (i64)n, (i64)s.len);
+  const i64 g = (i64)char_length_utf8(s);
+  if ((i64)n >= g) return s;
+  return substr_utf8_int64_int64(s, g - (i64)n + 1, (i64)n);
+}
+// locate(sub, s[, start]): 1-based glyph position of the first occurrence of sub in s at or after
+// glyph `start`, 0 when there is none (or start < 1); the empty string is found at `start`.
+GDV_DEV i32 locate_utf8_utf8_int32(gdv_str sub, gdv_str s, i32 start) {
+  if (start < 1) return 0;
+  i32 pos = 0, g = 1;
+  while (pos < s.len && g < start) {
+    pos += gdv_glyph_len(s.p[pos]);
+    ++g;
+  }
+  if (g < start) return 0;  // start lies beyond the end (start == length + 1 still finds "")
+  if (pos > s.len) pos = s.len;
+  while (true) {
+    if (pos + sub.len <= s.len) {
+      i32 j = 0;
+      while (j < sub.len && gdv_ch(s, pos + j) == gdv_ch(sub, j)) ++j;
+      if (j == sub.len) return g;
+    } else {
+      return 0;
+    }
+    if (pos >= s.len) return 0;
+    pos += gdv_glyph_len(s.p[pos]);
+    ++g;
+  }
+}
+GDV_DEV i32 locate_utf8_utf8(gdv_str sub, gdv_str s) { return locate_utf8_utf8_int32(sub, s, 1); }
+GDV_DEV i32 strpos_utf8_utf8(gdv_str s, gdv_str sub) { return locate_utf8_utf8_int32(sub, s, 1); }
+// byte_substr(b, offset, length): substr over bytes (1-based, offset 0 acts as 1, negative offsets
+// count from the end, out-of-range -> empty).
+GDV_DEV gdv_str byte_substr_binary_int32_int32(gdv_str s, i32 offset, i32 length) {
+  gdv_str r = s;
+  r.len = 0;
+  if (length <= 0 || s.len <= 0) return r;
+  i64 from = 0;
+  if (offset > 0) from = (i64)offset - 1;
+  if (offset < 0) from = (i64)s.len + (i64)offset;
+  if (from < 0 || from >= (i64)s.len) return r;
+  const i64 rest = (i64)s.len - from;
+  r.p = s.p + from;
+  r.len = (i32)((i64)length < rest ? (i64)length : rest);
+  return r;
+}
+// castINT / castBIGINT of a string: optional surrounding spaces, optional sign, decimal digits;
+// anything else, or a value outside the type, raises an ExecutionError.
+GDV_DEV i64 gdv_parse_int(gdv_ctx* c, const gdv_str& s, i64 lo, i64 hi) {
+  i32 b = 0, e = s.len;
+  while (b < e && s.p[b] == (u8)' ') ++b;
+  while (e > b && s.p[e - 1] == (u8)' ') --e;
+  bool neg = false;
+  if (b < e && (s.p[b] == (u8)'-' || s.p[b] == (u8)'+')) {
+    neg = s.p[b] == (u8)'-';
+    ++b;
+  }
+  if (b >= e) {
+    gdv_set_error(c, GDV_ERR_CAST_INT);
+    return 0;
+  }
+  const u64 limit = neg ? (u64)0 - (u64)lo : (u64)hi;  // magnitude the type can hold
+  u64 v = 0;
+  for (i32 i = b; i < e; ++i) {
+    const u32 d = (u32)s.p[i] - (u32)'0';
+    if (d > 9u || v > (limit - d) / 10ull) {
+      gdv_set_error(c, GDV_ERR_CAST_INT);
+      return 0;
+    }
+    v = v * 10ull + d;
+  }
+  return neg ? (i64)((u64)0 - v) : (i64)v;
+}
+GDV_DEV i64 castBIGINT_utf8(gdv_ctx* c, gdv_str s) {
+  return gdv_parse_int(c, s, (i64)0x8000000000000000ull, 0x7fffffffffffffffll);
+}
+GDV_DEV i32 castINT_utf8(gdv_ctx* c, gdv_str s) { return (i32)gdv_parse_int(c, s, -2147483648ll, 2147483647ll); }
 
 // SQL LIKE over a pattern tokenised at Make(): each token is (kind << 8) | byte with
 // kind 0 = literal byte, 1 = '_' (exactly one glyph), 2 = '%' (any run of glyphs).

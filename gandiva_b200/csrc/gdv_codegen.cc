@@ -444,7 +444,7 @@ class BodyGen {
     const std::string& n = fn.name();
     const bool is_case = n == "upper" || n == "lower";
     const bool is_view = n == "substr" || n == "substring" || n == "ltrim" || n == "rtrim" ||
-                         n == "btrim" || n == "trim";
+                         n == "btrim" || n == "trim" || n == "left" || n == "right";
     if (!is_case && !is_view) return false;
     if (fn.children().empty() || !fn.children()[0]->return_type().is_varlen()) return false;
     if (!ViewChain(*fn.children()[0], slot, xf)) return false;
@@ -731,6 +731,19 @@ class BodyGen {
       if (!a.parts.empty() && error_.empty())
         error_ = "the result of concat can only be projected, concatenated again or chosen by if/else; " +
                  fn.name() + "(concat(...)) is not supported yet";
+
+    if (fn.name() == "nvl") {
+      // nvl(a, b) = a where a is valid, else b: a select on a's validity, no device function
+      const Val& a = args[0];
+      const Val& b = args[1];
+      if (a.ok == "true") return a;
+      const std::string v = NewVar("v");
+      *out += Ind(indent) + "const " + rt.ctype() + " " + v + " = (" + a.ok + ") ? " + a.v + " : " + b.v + ";\n";
+      if (b.ok == "true") return Val{v, "true", rt};
+      const std::string okv = NewVar("ok");
+      *out += Ind(indent) + "const bool " + okv + " = (" + a.ok + ") || (" + b.ok + ");\n";
+      return Val{v, okv, rt};
+    }
 
     std::string call = def->device_name() + "(";
     bool first = true;
@@ -1500,8 +1513,81 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
 
 }  // namespace
 
+namespace {
+
+// Functions that are spelled in terms of others are rewritten before lowering:
+//   ilike(s, 'pattern') -> like(lower(s), 'lower-cased pattern')   (ASCII case folding)
+// Returns the node itself when nothing below it changes.
+NodePtr RewriteAliases(const NodePtr& node) {
+  switch (node->kind()) {
+    case NodeKind::kFunction: {
+      const auto& fn = static_cast<const FunctionNode&>(*node);
+      NodeVector kids;
+      bool changed = false;
+      for (const auto& c : fn.children()) {
+        kids.push_back(RewriteAliases(c));
+        changed = changed || kids.back() != c;
+      }
+      if (fn.name() == "ilike" && kids.size() == 2 && kids[1]->kind() == NodeKind::kLiteral) {
+        const auto& pat = static_cast<const LiteralNode&>(*kids[1]);
+        std::string low = pat.bytes();
+        for (auto& ch : low)
+          if (ch >= 'A' && ch <= 'Z') ch = static_cast<char>(ch + 32);
+        NodePtr text = std::make_shared<FunctionNode>("lower", NodeVector{kids[0]}, utf8());
+        NodePtr lit = std::make_shared<LiteralNode>(utf8(), low.data(), static_cast<int64_t>(low.size()),
+                                                    pat.is_null());
+        return std::make_shared<FunctionNode>("like", NodeVector{text, lit}, boolean());
+      }
+      if (!changed) return node;
+      return std::make_shared<FunctionNode>(fn.name(), std::move(kids), fn.return_type());
+    }
+    case NodeKind::kIf: {
+      const auto& n = static_cast<const IfNode&>(*node);
+      NodePtr c = RewriteAliases(n.condition()), t = RewriteAliases(n.then_node()),
+              e = RewriteAliases(n.else_node());
+      if (c == n.condition() && t == n.then_node() && e == n.else_node()) return node;
+      return std::make_shared<IfNode>(c, t, e, n.return_type());
+    }
+    case NodeKind::kBoolean: {
+      const auto& n = static_cast<const BooleanNode&>(*node);
+      NodeVector kids;
+      bool changed = false;
+      for (const auto& c : n.children()) {
+        kids.push_back(RewriteAliases(c));
+        changed = changed || kids.back() != c;
+      }
+      if (!changed) return node;
+      return std::make_shared<BooleanNode>(n.op(), std::move(kids));
+    }
+    case NodeKind::kIn: {
+      const auto& n = static_cast<const InNode&>(*node);
+      NodePtr c = RewriteAliases(n.child());
+      if (c == n.child()) return node;
+      return std::make_shared<InNode>(c, n.value_type(), n.ints(), n.strs());
+    }
+    default: return node;
+  }
+}
+
+Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
+                          const KernelSpec& spec, GeneratedKernel* out);
+
+}  // namespace
+
 Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
                       const KernelSpec& spec, GeneratedKernel* out) {
+  std::vector<ExpressionPtr> lowered;
+  for (const auto& e : exprs) {
+    NodePtr r = RewriteAliases(e->root());
+    lowered.push_back(r == e->root() ? e : std::make_shared<Expression>(r, e->result()));
+  }
+  return GenerateKernelImpl(schema, lowered, spec, out);
+}
+
+namespace {
+
+Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>& exprs,
+                          const KernelSpec& spec, GeneratedKernel* out) {
   if (spec.kind == KernelKind::kStringSize || spec.kind == KernelKind::kStringWrite) {
     if (exprs.size() != 1 || !exprs[0]->result().type.is_varlen())
       return Status::Make(GDV_INVALID, "a string kernel takes exactly one utf8/binary expression");
@@ -1975,5 +2061,7 @@ Status GenerateKernel(const Schema& schema, const std::vector<ExpressionPtr>& ex
   out->cta_tile_rows = static_cast<int64_t>(BT) * R;
   return Status::OK();
 }
+
+}  // namespace
 
 }  // namespace gdv

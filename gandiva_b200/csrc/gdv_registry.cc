@@ -93,6 +93,17 @@ Registry::Registry() {
     Add("bitwise_not", {t}, t);
   }
   Add("sqrt", {F64}, F64);
+  for (const auto& t : {I32, I64}) {
+    Add("div", {t, t}, t, NullMode::kIfNull, kCanFail);
+    Add("pmod", {t, t}, t);
+  }
+  for (const auto& t : {I32, I64, F32, F64}) {
+    Add("sign", {t}, t);
+    for (size_t n = 2; n <= 4; ++n) {
+      Add("greatest", std::vector<DataType>(n, t), t);
+      Add("least", std::vector<DataType>(n, t), t);
+    }
+  }
 
   // ---- comparisons ------------------------------------------------------------------
   std::vector<DataType> relop_types = numeric;
@@ -172,6 +183,11 @@ Registry::Registry() {
   Add("ceil", {F64}, F64);
   Add("floor", {F64}, F64);
   Add("truncate", {F64}, F64, NullMode::kIfNull, 0, {"trunc"});
+  Add("truncate", {F64, I32}, F64, NullMode::kIfNull, 0, {"trunc"});
+  Add("round", {I32, I32}, I32);
+  Add("round", {I64, I32}, I64);
+  Add("truncate", {I32, I32}, I32, NullMode::kIfNull, 0, {"trunc"});
+  Add("truncate", {I64, I32}, I64, NullMode::kIfNull, 0, {"trunc"});
 
   // ---- date / time arithmetic -------------------------------------------------------------
   for (const char* f : {"timestampaddSecond", "timestampaddMinute", "timestampaddHour", "timestampaddDay",
@@ -187,6 +203,19 @@ Registry::Registry() {
   for (const char* f : {"timestampdiffSecond", "timestampdiffMinute", "timestampdiffHour", "timestampdiffDay",
                         "timestampdiffWeek"})
     Add(f, {TS, TS}, I32);
+
+  // ---- calendar fields, truncation, time of day ----------------------------------------------
+  for (const auto& t : {D64, TS}) {
+    for (const char* f : {"extractWeek", "extractDecade", "extractCentury", "extractMillennium"}) Add(f, {t}, I64);
+    for (const char* u : {"Second", "Minute", "Hour", "Day", "Week", "Month", "Quarter", "Year", "Decade",
+                          "Century", "Millennium"})
+      Add(std::string("date_trunc_") + u, {t}, t);
+    Add("last_day", {t}, D64);
+  }
+  Add("castTIME", {TS}, T32);
+  Add("extractHour", {T32}, I64);
+  Add("extractMinute", {T32}, I64);
+  Add("extractSecond", {T32}, I64);
 
   // ---- decimal128 ---------------------------------------------------------------------
   Add("add", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
@@ -241,6 +270,27 @@ Registry::Registry() {
   Add("rtrim", {S}, S, NullMode::kIfNull, kStringView);
   Add("btrim", {S}, S, NullMode::kIfNull, kStringView, {"trim"});
   Add("castVARCHAR", {S, I64}, S, NullMode::kIfNull, kStringView);
+  Add("ascii", {S}, I32);
+  Add("left", {S, I32}, S, NullMode::kIfNull, kStringView);
+  Add("right", {S, I32}, S, NullMode::kIfNull, kStringView);
+  Add("locate", {S, S}, I32, NullMode::kIfNull, 0, {"position"});
+  Add("locate", {S, S, I32}, I32);
+  Add("strpos", {S, S}, I32);
+  Add("byte_substr", {BIN, I32, I32}, BIN, NullMode::kIfNull, kStringView, {"bytesubstring"});
+  Add("castBIGINT", {S}, I64, NullMode::kIfNull, kCanFail);
+  Add("castINT", {S}, I32, NullMode::kIfNull, kCanFail);
+  // ilike(s, pattern): like() over lower-cased text and pattern (ASCII case folding); rewritten
+  // at Make() (RewriteAliases), never called as a device function
+  Add("ilike", {S, S}, B, NullMode::kIfNull, kLikeHolder);
+  // nvl(a, b): a when a is valid, else b; lowered by the fuser itself
+  {
+    std::vector<DataType> nvl_types = numeric;
+    nvl_types.insert(nvl_types.end(), dates.begin(), dates.end());
+    nvl_types.push_back(B);
+    nvl_types.push_back(S);
+    nvl_types.push_back(BIN);
+    for (const auto& t : nvl_types) Add("nvl", {t, t}, t, NullMode::kInternal);
+  }
   // concat: null arguments are empty strings, never null; concatOperator: null if any is null
   for (int n = 2; n <= 6; ++n) {
     Add("concat", std::vector<DataType>(static_cast<size_t>(n), S), S, NullMode::kNever, kConcat);

@@ -88,7 +88,7 @@ struct Column {  // same layout as gdv_column_t
 
 struct EvalCtx {
   const Column* cols;
-  int error = 0;  // 1 = divide by zero
+  int error = 0;  // 1 = divide by zero, 4 = string is not an integer of the target type
 };
 
 enum Kind { K_FIELD, K_LIT, K_FN, K_IF, K_AND, K_OR, K_IN };
@@ -802,16 +802,18 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     if (!out->ok) out->s.clear();
     return;
   }
-  Val a[3];
-  for (size_t k = 0; k < na && k < 3; ++k) {
+  Val a[6];
+  const bool is_like = f == "like" || f == "ilike";
+  for (size_t k = 0; k < na && k < 6; ++k) {
     // LIKE patterns are literals handled at parse time
-    if (f == "like" && k >= 1) break;
+    if (is_like && k >= 1) break;
     Eval(*n.kids[k], cx, row, &a[k]);
   }
   const Type& rt = n.type;
   const Type& t0 = n.kids[0]->type;
 
   // ---- never-null functions -------------------------------------------------------------
+  if (f == "nvl") { *out = a[0].ok ? a[0] : a[1]; return; }
   if (f == "isnull") { out->ok = true; out->b = !a[0].ok; return; }
   if (f == "isnotnull") { out->ok = true; out->b = a[0].ok; return; }
   if (f == "istrue") { out->ok = true; out->b = a[0].ok && a[0].b; return; }
@@ -862,8 +864,8 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
 
   // ---- null-if-null functions -------------------------------------------------------------
   bool ok = true;
-  for (size_t k = 0; k < na && k < 3; ++k) {
-    if (f == "like" && k >= 1) break;
+  for (size_t k = 0; k < na && k < 6; ++k) {
+    if (is_like && k >= 1) break;
     ok = ok && a[k].ok;
   }
   out->ok = ok;
@@ -926,6 +928,43 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     out->i = WrapSigned(r, rt.bits());
     return;
   }
+  if (f == "div") {
+    if (a[1].i == 0) { cx.error = 1; return; }
+    if (a[1].i == -1) out->i = WrapSigned(static_cast<int64_t>(0 - static_cast<uint64_t>(a[0].i)), rt.bits());
+    else out->i = a[0].i / a[1].i;
+    return;
+  }
+  if (f == "pmod") {
+    const int64_t x = a[0].i, y = a[1].i;
+    int64_t r;
+    if (y == 0) r = x;
+    else if (y == -1) r = 0;
+    else {
+      r = x % y;
+      if (r != 0 && ((r < 0) != (y < 0))) r += y;
+    }
+    out->i = WrapSigned(r, rt.bits());
+    return;
+  }
+  if (f == "sign") {
+    if (rt.id == T_FLOAT) out->f = a[0].f > 0.0f ? 1.0f : (a[0].f < 0.0f ? -1.0f : a[0].f);
+    else if (rt.id == T_DOUBLE) out->d = a[0].d > 0.0 ? 1.0 : (a[0].d < 0.0 ? -1.0 : a[0].d);
+    else out->i = (a[0].i > 0) - (a[0].i < 0);
+    return;
+  }
+  if (f == "greatest" || f == "least") {
+    const bool g = f == "greatest";
+    *out = a[0];
+    for (size_t k = 1; k < na; ++k) {
+      bool take;
+      if (rt.id == T_FLOAT) take = g ? a[k].f > out->f : a[k].f < out->f;
+      else if (rt.id == T_DOUBLE) take = g ? a[k].d > out->d : a[k].d < out->d;
+      else take = g ? a[k].i > out->i : a[k].i < out->i;
+      if (take) *out = a[k];
+    }
+    out->ok = true;
+    return;
+  }
   if (f == "abs") {
     if (rt.id == T_FLOAT) out->f = std::fabs(a[0].f);
     else if (rt.id == T_DOUBLE) out->d = std::fabs(a[0].d);
@@ -967,6 +1006,28 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   }
 
   // ---- casts ---------------------------------------------------------------------------
+  if ((f == "castINT" || f == "castBIGINT") && t0.id == T_STRING) {
+    // optional spaces, optional sign, digits; anything else or out of range -> error 4
+    const std::string& str = a[0].s;
+    size_t b = 0, e = str.size();
+    while (b < e && str[b] == ' ') ++b;
+    while (e > b && str[e - 1] == ' ') --e;
+    bool neg = false;
+    if (b < e && (str[b] == '-' || str[b] == '+')) { neg = str[b] == '-'; ++b; }
+    if (b >= e) { cx.error = 4; return; }
+    __int128 v = 0;
+    for (size_t k = b; k < e; ++k) {
+      if (str[k] < '0' || str[k] > '9') { cx.error = 4; return; }
+      v = v * 10 + (str[k] - '0');
+      if (v > (static_cast<__int128>(1) << 64)) { cx.error = 4; return; }
+    }
+    if (neg) v = -v;
+    const __int128 lo = f == "castINT" ? -2147483648ll : static_cast<__int128>(INT64_MIN);
+    const __int128 hi = f == "castINT" ? 2147483647ll : static_cast<__int128>(INT64_MAX);
+    if (v < lo || v > hi) { cx.error = 4; return; }
+    out->i = static_cast<int64_t>(v);
+    return;
+  }
   if (f == "castBIGINT") {
     if (t0.id == T_DECIMAL) {
       const i128 r = DecimalRescale(a[0].dec, t0.scale, 38, 0);
@@ -1001,6 +1062,39 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   }
 
   // ---- rounding ---------------------------------------------------------------------------
+  if ((f == "round" || f == "truncate" || f == "trunc") && na == 2 && rt.id != T_DOUBLE) {
+    // integers: to a multiple of 10^-s for s < 0, in 128 bits, wrapped into the output type
+    const int64_t sc = a[1].i;
+    __int128 x = a[0].i, res;
+    if (sc >= 0) res = x;
+    else if (sc < -38) res = 0;
+    else {
+      __int128 p = 1;
+      for (int64_t k = 0; k < -sc; ++k) p *= 10;
+      const __int128 r = x % p;
+      res = x - r;
+      if (f == "round") {
+        const __int128 ar = r < 0 ? -r : r;
+        if (ar >= p - ar) res += x < 0 ? -p : p;
+      }
+    }
+    out->i = WrapSigned(static_cast<int64_t>(static_cast<uint64_t>(static_cast<unsigned __int128>(res))), rt.bits());
+    return;
+  }
+  if ((f == "truncate" || f == "trunc") && na == 2) {
+    const int s = static_cast<int>(std::max<int64_t>(-308, std::min<int64_t>(308, a[1].i)));
+    double p = 1.0;
+    for (int k = 0; k < std::abs(s); ++k) p = p * 10.0;
+    if (s >= 0) {
+      const double v = a[0].d * p;
+      if (!(std::fabs(v) < 1.7976931348623157e308) || v == std::floor(v)) out->d = a[0].d;
+      else out->d = std::trunc(v) / p;
+    } else {
+      const double q = a[0].d / p;
+      out->d = (q == std::floor(q)) ? a[0].d : std::trunc(q) * p;
+    }
+    return;
+  }
   if (f == "round") {
     if (na == 2) {
       const int s = static_cast<int>(std::max<int64_t>(-308, std::min<int64_t>(308, a[1].i)));
@@ -1075,6 +1169,59 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   }
 
   // ---- date/time -------------------------------------------------------------------------
+  if (t0.id == T_TIME32 && f.rfind("extract", 0) == 0) {
+    const int64_t t = a[0].i;
+    if (f == "extractHour") out->i = t / 3600000;
+    else if (f == "extractMinute") out->i = (t / 60000) % 60;
+    else out->i = (t / 1000) % 60;
+    return;
+  }
+  if (f == "castTIME") { out->i = a[0].i - FloorDiv(a[0].i, 86400000) * 86400000; return; }
+  if (f == "extractWeek" || f == "extractDecade" || f == "extractCentury" || f == "extractMillennium" ||
+      f.rfind("date_trunc_", 0) == 0 || f == "last_day") {
+    const int64_t ms = a[0].i;
+    const int64_t days = FloorDiv(ms, 86400000);
+    const Ymd c = CivilFromDays(days);
+    auto jan1_of = [&](int64_t y) {  // days since epoch of January 1st of year y
+      const int64_t y1 = y - 1;
+      return y1 * 365 + FloorDiv(y1, 4) - FloorDiv(y1, 100) + FloorDiv(y1, 400) - 719162;
+    };
+    auto monday0 = [](int64_t d) { int64_t w = (d + 3) % 7; return w < 0 ? w + 7 : w; };
+    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    auto first_of_month = [&](int64_t y, int m) {
+      int64_t d = jan1_of(y);
+      for (int k = 1; k < m; ++k) d += mdays[k - 1] + ((k == 2 && IsLeap(y)) ? 1 : 0);
+      return d;
+    };
+    if (f == "extractDecade") { out->i = c.y / 10; return; }
+    if (f == "extractCentury") { out->i = (c.y - 1) / 100 + 1; return; }
+    if (f == "extractMillennium") { out->i = (c.y - 1) / 1000 + 1; return; }
+    if (f == "extractWeek") {
+      // ISO 8601: the week with the year's first Thursday is week 1; walk it out explicitly
+      const int64_t thursday = days - monday0(days) + 3;       // Thursday of this row's week
+      const Ymd ty = CivilFromDays(thursday);                   // its year owns the week
+      out->i = (thursday - jan1_of(ty.y)) / 7 + 1;
+      return;
+    }
+    if (f == "last_day") {
+      const int len = mdays[c.m - 1] + ((c.m == 2 && IsLeap(c.y)) ? 1 : 0);
+      out->i = (first_of_month(c.y, c.m) + len - 1) * 86400000;
+      return;
+    }
+    const std::string unit = f.substr(11);
+    if (unit == "Second") out->i = FloorDiv(ms, 1000) * 1000;
+    else if (unit == "Minute") out->i = FloorDiv(ms, 60000) * 60000;
+    else if (unit == "Hour") out->i = FloorDiv(ms, 3600000) * 3600000;
+    else if (unit == "Day") out->i = days * 86400000;
+    else if (unit == "Week") out->i = (days - monday0(days)) * 86400000;
+    else if (unit == "Month") out->i = first_of_month(c.y, c.m) * 86400000;
+    else if (unit == "Quarter") out->i = first_of_month(c.y, ((c.m - 1) / 3) * 3 + 1) * 86400000;
+    else if (unit == "Year") out->i = jan1_of(c.y) * 86400000;
+    else if (unit == "Decade") out->i = jan1_of((c.y / 10) * 10) * 86400000;
+    else if (unit == "Century") out->i = jan1_of(((c.y - 1) / 100) * 100 + 1) * 86400000;
+    else out->i = jan1_of(((c.y - 1) / 1000) * 1000 + 1) * 86400000;  // Millennium
+    return;
+  }
   if (f.rfind("extract", 0) == 0) {
     const bool is_d32 = t0.id == T_DATE32;
     const int64_t ms = is_d32 ? a[0].i * 86400000 : a[0].i;
@@ -1133,6 +1280,47 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     out->s = a[0].s.substr(b, e - b);
     return;
   }
+  if (f == "ilike") {
+    std::string low = a[0].s;
+    for (auto& ch : low)
+      if (ch >= 'A' && ch <= 'Z') ch = static_cast<char>(ch + 32);
+    out->b = LikeRec(low, 0, n.like, 0);
+    return;
+  }
+  if (f == "ascii") { out->i = a[0].s.empty() ? 0 : static_cast<unsigned char>(a[0].s[0]); return; }
+  if (f == "left" || f == "right") {
+    const int64_t k = a[1].i;
+    const int64_t g = static_cast<int64_t>(GlyphStarts(a[0].s).size());
+    if (k == 0) out->s.clear();
+    else if (f == "left") out->s = k > 0 ? Substr(a[0].s, 1, k) : (g + k <= 0 ? std::string() : Substr(a[0].s, 1, g + k));
+    else if (k < 0) out->s = Substr(a[0].s, 1 - k, g + 1);
+    else out->s = k >= g ? a[0].s : Substr(a[0].s, g - k + 1, k);
+    return;
+  }
+  if (f == "locate" || f == "position" || f == "strpos") {
+    const std::string& sub = f == "strpos" ? a[1].s : a[0].s;
+    const std::string& str = f == "strpos" ? a[0].s : a[1].s;
+    const int64_t start = na == 3 ? a[2].i : 1;
+    out->i = 0;
+    if (start < 1) return;
+    const std::vector<size_t> st = GlyphStarts(str);
+    const int64_t g = static_cast<int64_t>(st.size());
+    if (start > g + 1) return;
+    for (int64_t k = start; k <= g + 1; ++k) {   // candidate glyph positions, incl. one past the end
+      const size_t pos = k <= g ? st[static_cast<size_t>(k - 1)] : str.size();
+      if (pos + sub.size() <= str.size() && str.compare(pos, sub.size(), sub) == 0) { out->i = k; return; }
+    }
+    return;
+  }
+  if (f == "byte_substr" || f == "bytesubstring") {
+    const int64_t off = a[1].i, len = a[2].i, size = static_cast<int64_t>(a[0].s.size());
+    out->s.clear();
+    if (len <= 0 || size == 0) return;
+    const int64_t from = off > 0 ? off - 1 : (off < 0 ? size + off : 0);
+    if (from < 0 || from >= size) return;
+    out->s = a[0].s.substr(static_cast<size_t>(from), static_cast<size_t>(std::min(len, size - from)));
+    return;
+  }
   cx.error = 100;  // unknown function
 }
 
@@ -1184,11 +1372,15 @@ void Eval(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
 bool Prepare(Node* n, std::string* err) {
   for (auto& k : n->kids)
     if (!Prepare(k.get(), err)) return false;
-  if (n->kind == K_FN && n->name == "like") {
+  if (n->kind == K_FN && (n->name == "like" || n->name == "ilike")) {
     if (n->kids.size() < 2 || n->kids[1]->kind != K_LIT) { *err = "like needs a literal pattern"; return false; }
     const bool has_esc = n->kids.size() == 3;
     const char esc = has_esc ? n->kids[2]->lit.s[0] : 0;
-    n->like = CompileLike(n->kids[1]->lit.s, has_esc, esc);
+    std::string pat = n->kids[1]->lit.s;
+    if (n->name == "ilike")  // ASCII case folding of pattern and text
+      for (auto& ch : pat)
+        if (ch >= 'A' && ch <= 'Z') ch = static_cast<char>(ch + 32);
+    n->like = CompileLike(pat, has_esc, esc);
   }
   return true;
 }

@@ -205,6 +205,89 @@ def case_rounding(b):
     return schema, outs, "project"
 
 
+def case_intmath(b):
+    """div / pmod / sign / greatest / least / nvl / round and truncate with a scale."""
+    I, L, F32, D, B = pa.int32(), pa.int64(), pa.float32(), pa.float64(), pa.bool_()
+    schema = pa.schema([("i", I), ("j", I), ("l", L), ("m", L), ("f", F32), ("g", F32), ("d", D), ("e", D)])
+    i, j, l, m = F(b, "i", I), F(b, "j", I), F(b, "l", L), F(b, "m", L)
+    f, g, d, e = F(b, "f", F32), F(b, "g", F32), F(b, "d", D), F(b, "e", D)
+    fn = b.make_function
+    lit = b.make_literal
+    outs = [
+        (b.make_if(fn("not_equal", [j, lit(0, I)], B), fn("div", [i, j], I), i, I), I),
+        (b.make_if(fn("not_equal", [m, lit(0, L)], B), fn("div", [l, m], L), l, L), L),
+        (fn("pmod", [i, j], I), I), (fn("pmod", [l, m], L), L),
+        (fn("pmod", [i, lit(7, I)], I), I), (fn("pmod", [l, lit(-7, L)], L), L),
+        (fn("sign", [i], I), I), (fn("sign", [l], L), L), (fn("sign", [f], F32), F32), (fn("sign", [d], D), D),
+        (fn("greatest", [i, j], I), I), (fn("least", [i, j, lit(0, I)], I), I),
+        (fn("greatest", [l, m, lit(5, L), l], L), L), (fn("least", [l, m], L), L),
+        (fn("greatest", [f, g], F32), F32), (fn("least", [d, e, lit(0.5, D)], D), D),
+        (fn("greatest", [d, e], D), D), (fn("least", [f, g, f, g], F32), F32),
+        (fn("nvl", [i, j], I), I), (fn("nvl", [d, lit(-1.5, D)], D), D), (fn("nvl", [l, fn("add", [m, m], L)], L), L),
+        (fn("round", [i, lit(-2, I)], I), I), (fn("round", [l, lit(-5, I)], L), L), (fn("round", [l, j], L), L),
+        (fn("round", [i, lit(3, I)], I), I), (fn("round", [l, lit(-19, I)], L), L), (fn("round", [l, lit(-40, I)], L), L),
+        (fn("truncate", [l, lit(-3, I)], L), L), (fn("truncate", [i, lit(-1, I)], I), I),
+        (fn("truncate", [d, lit(2, I)], D), D), (fn("truncate", [d, lit(-2, I)], D), D), (fn("trunc", [d, j], D), D),
+    ]
+    return schema, outs, "project"
+
+
+def case_calendar(b):
+    """ISO week, decade / century / millennium, date_trunc_*, last_day, time of day."""
+    ts, d64, t32, L = pa.timestamp("ms"), pa.date64(), pa.time32("ms"), pa.int64()
+    schema = pa.schema([("t", ts), ("d", d64), ("c", t32)])
+    t, d, c = F(b, "t", ts), F(b, "d", d64), F(b, "c", t32)
+    fn = b.make_function
+    outs = []
+    for name in ("extractWeek", "extractDecade", "extractCentury", "extractMillennium"):
+        outs.append((fn(name, [t], L), L))
+        outs.append((fn(name, [d], L), L))
+    for unit in ("Second", "Minute", "Hour", "Day", "Week", "Month", "Quarter", "Year", "Decade", "Century",
+                 "Millennium"):
+        outs.append((fn("date_trunc_" + unit, [t], ts), ts))
+    outs.append((fn("date_trunc_Month", [d], d64), d64))
+    outs.append((fn("date_trunc_Week", [d], d64), d64))
+    outs.append((fn("last_day", [t], d64), d64))
+    outs.append((fn("last_day", [d], d64), d64))
+    outs.append((fn("castTIME", [t], t32), t32))
+    for name in ("extractHour", "extractMinute", "extractSecond"):
+        outs.append((fn(name, [c], L), L))
+    outs.append((fn("extractHour", [fn("castTIME", [t], t32)], L), L))
+    return schema, outs, "project"
+
+
+def case_string_positions(b):
+    """ascii / left / right / locate / strpos / byte_substr / ilike / nvl over strings."""
+    S, BIN, I, B = pa.string(), pa.binary(), pa.int32(), pa.bool_()
+    schema = pa.schema([("s", S), ("u", S), ("z", BIN), ("k", I)])
+    s, u, z, k = F(b, "s", S), F(b, "u", S), F(b, "z", BIN), F(b, "k", I)
+    fn = b.make_function
+    lit = b.make_literal
+    clen = lambda x: fn("char_length", [x], I)
+    small_k = fn("castINT", [fn("mod", [fn("castBIGINT", [k], pa.int64()), lit(9, I)], I)], I) if False else None
+    kk = fn("subtract", [fn("castINT", [fn("mod", [fn("castBIGINT", [k], pa.int64()), lit(9, pa.int64())], pa.int64())], I),
+                         lit(4, I)], I)   # k mod 9 - 4: a small signed count
+    outs = [
+        (fn("ascii", [s], I), I), (fn("ascii", [fn("upper", [s], S)], I), I),
+        (clen(fn("left", [s, lit(3, I)], S)), I), (clen(fn("left", [s, lit(-2, I)], S)), I),
+        (clen(fn("right", [s, lit(4, I)], S)), I), (clen(fn("right", [s, lit(-3, I)], S)), I),
+        (fn("equal", [fn("left", [s, kk], S), fn("right", [u, kk], S)], B), B),
+        (fn("octet_length", [fn("right", [s, kk], S)], I), I),
+        (fn("locate", [lit("ar", S), s], I), I), (fn("locate", [lit("", S), s], I), I),
+        (fn("locate", [lit("本", S), s], I), I), (fn("locate", [lit("e", S), s, lit(3, I)], I), I),
+        (fn("locate", [lit("s", S), s, kk], I), I), (fn("locate", [u, s], I), I),
+        (fn("position", [lit("re", S), s], I), I),
+        (fn("strpos", [s, lit("re", S)], I), I), (fn("strpos", [fn("upper", [s], S), lit("RE", S)], I), I),
+        (fn("octet_length", [fn("byte_substr", [z, lit(2, I), lit(5, I)], BIN)], I), I),
+        (fn("octet_length", [fn("byte_substr", [z, lit(-3, I), lit(2, I)], BIN)], I), I),
+        (fn("equal", [fn("byte_substr", [z, kk, lit(3, I)], BIN), fn("byte_substr", [z, lit(1, I), lit(3, I)], BIN)], B), B),
+        (fn("ilike", [s, lit("%SPecial%Requests%", S)], B), B), (fn("ilike", [s, lit("quick%", S)], B), B),
+        (fn("ilike", [fn("substr", [s, lit(1, pa.int64()), lit(12, pa.int64())], S), lit("%BROWN%", S)], B), B),
+        (clen(fn("nvl", [s, u], S)), I), (fn("equal", [fn("nvl", [s, lit("none", S)], S), u], B), B),
+    ]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -767,7 +850,8 @@ def all_project_cases():
               case_decimal_divide(38, 30, 12, 0),
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
-              case_concat_outputs, case_rounding, case_date_arith]
+              case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
+              case_string_positions]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

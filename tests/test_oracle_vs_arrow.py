@@ -542,3 +542,223 @@ def test_date_arithmetic(oracle, gandiva):
     for i, (g, w, (_, ty)) in enumerate(zip(got, want, schema_b)):
         exp = pa.array(w, type=pa.int64()).cast(ty) if not pa.types.is_int32(ty) else pa.array(w, type=pa.int32())
         assert_arrays_match(g, exp, "date arithmetic out %d" % i)
+
+
+def _trunc_div(x, y):
+    q = abs(x) // abs(y)
+    return q if (x < 0) == (y < 0) else -q
+
+
+def _wrap(v, bits):
+    v &= (1 << bits) - 1
+    return v - (1 << bits) if v >> (bits - 1) else v
+
+
+def test_integer_math_family(oracle, gandiva):
+    """div / pmod / sign / greatest / least / nvl / round + truncate with a scale against Python
+    integers, `decimal` (ROUND_HALF_UP / ROUND_DOWN) and Arrow's element-wise max / min / round."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_intmath(b)
+    batch = cases.random_batch(schema, N, seed=11, null_prob=0.15)
+    got = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
+    col = {f.name: batch.column(k).to_pylist() for k, f in enumerate(schema)}
+    i, j, l, m, f, g, d, e = (col[k] for k in "ijlmfgde")
+    none = lambda *a: any(x is None for x in a)
+
+    def expect(k, fn, bits=None):
+        want = [fn(r) for r in range(N)]
+        gl = got[k].to_pylist()
+        for r in range(N):
+            w = want[r]
+            if w is not None and bits:
+                w = _wrap(w, bits)
+            assert gl[r] == w or (w is not None and w != w and gl[r] != gl[r]), (k, r, gl[r], w)
+
+    # if (y != 0) div(x, y) else x: a null or zero divisor takes the else branch
+    guarded = lambda x, y: x if (y is None or y == 0) else (None if x is None else _trunc_div(x, y))
+    expect(0, lambda r: guarded(i[r], j[r]), 32)
+    expect(1, lambda r: guarded(l[r], m[r]), 64)
+    expect(2, lambda r: None if none(i[r], j[r]) else (i[r] % j[r] if j[r] != 0 else i[r]))   # Python % = sign of divisor
+    expect(3, lambda r: None if none(l[r], m[r]) else (l[r] % m[r] if m[r] != 0 else l[r]))
+    expect(4, lambda r: None if none(i[r]) else i[r] % 7)
+    expect(5, lambda r: None if none(l[r]) else l[r] % -7)
+    expect(6, lambda r: None if none(i[r]) else (i[r] > 0) - (i[r] < 0))
+    expect(7, lambda r: None if none(l[r]) else (l[r] > 0) - (l[r] < 0))
+    assert_arrays_match(got[8], pc.sign(batch.column(4)), "sign f32")
+    assert_arrays_match(got[9], pc.sign(batch.column(6)), "sign f64")
+    I, L, D = pa.int32(), pa.int64(), pa.float64()
+    ci, cj, cl, cm, cf, cg, cd, ce = batch.columns
+    mx = lambda *a: pc.max_element_wise(*a, skip_nulls=False)
+    mn = lambda *a: pc.min_element_wise(*a, skip_nulls=False)
+    assert_arrays_match(got[10], mx(ci, cj), "greatest i32")
+    assert_arrays_match(got[11], mn(ci, cj, pa.scalar(0, I)), "least i32 x3")
+    assert_arrays_match(got[12], mx(cl, cm, pa.scalar(5, L), cl), "greatest i64 x4")
+    assert_arrays_match(got[13], mn(cl, cm), "least i64")
+    assert_arrays_match(got[14], mx(cf, cg), "greatest f32")   # no NaNs in the random data
+    assert_arrays_match(got[15], mn(cd, ce, pa.scalar(0.5, D)), "least f64 x3")
+    assert_arrays_match(got[16], mx(cd, ce), "greatest f64")
+    assert_arrays_match(got[17], mn(cf, cg, cf, cg), "least f32 x4")
+    assert_arrays_match(got[18], pc.coalesce(ci, cj), "nvl i32")
+    assert_arrays_match(got[19], pc.coalesce(cd, pa.scalar(-1.5, D)), "nvl f64 literal")
+    assert_arrays_match(got[20], pc.coalesce(cl, pc.add(cm, cm)), "nvl i64 expr")
+
+    def dec_round(v, s, mode):
+        if s >= 0:
+            return v
+        q = decimal.Decimal(v).scaleb(s).quantize(decimal.Decimal(1), rounding=mode)
+        return int(q.scaleb(-s))
+
+    with decimal.localcontext() as ctx:
+        ctx.prec = 80
+        up, down = decimal.ROUND_HALF_UP, decimal.ROUND_DOWN
+        expect(21, lambda r: None if none(i[r]) else dec_round(i[r], -2, up), 32)
+        expect(22, lambda r: None if none(l[r]) else dec_round(l[r], -5, up), 64)
+        expect(23, lambda r: None if none(l[r], j[r]) else (dec_round(l[r], max(j[r], -60), up)), 64)
+        expect(24, lambda r: i[r])
+        expect(25, lambda r: None if none(l[r]) else dec_round(l[r], -19, up), 64)
+        expect(26, lambda r: None if none(l[r]) else 0)
+        expect(27, lambda r: None if none(l[r]) else dec_round(l[r], -3, down), 64)
+        expect(28, lambda r: None if none(i[r]) else dec_round(i[r], -1, down), 32)
+    assert_arrays_match(got[29], pc.round(cd, 2, round_mode="towards_zero"), "truncate(d, 2)")
+    assert_arrays_match(got[30], pc.round(cd, -2, round_mode="towards_zero"), "truncate(d, -2)")
+
+
+def test_calendar_functions(oracle, gandiva):
+    """ISO week / date_trunc / last_day against Arrow's temporal kernels and Python's calendar."""
+    import calendar
+    import datetime
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_calendar(b)
+    rng = np.random.default_rng(5)
+    n = N
+    # 0001-01-01 .. 9999: inside datetime's range so Python can be the referee
+    ms = rng.integers(-62_135_596_800_000 + 86_400_000 * 400, 253_402_300_799_000 - 86_400_000 * 400, n).astype(np.int64)
+    # week-53 / week-1 boundaries and leap days
+    for k, (y, mo, dd) in enumerate([(2020, 12, 31), (2021, 1, 1), (2021, 1, 3), (2021, 1, 4), (2015, 12, 31),
+                                     (2016, 1, 1), (2024, 2, 29), (2024, 12, 30), (1999, 12, 31), (2000, 1, 1),
+                                     (1900, 2, 28), (1, 1, 1), (100, 12, 31), (2001, 1, 1), (1000, 12, 31)]):
+        ms[k] = int((datetime.date(y, mo, dd) - datetime.date(1970, 1, 1)).days) * 86400000 + int(rng.integers(0, 86400000))
+    days = rng.integers(-700000, 2900000, n).astype(np.int64) * 86400000
+    tod = rng.integers(0, 86400000, n).astype(np.int32)
+    mask = lambda: rng.random(n) < 0.1
+    ts, d64, t32 = pa.timestamp("ms"), pa.date64(), pa.time32("ms")
+    ct = pa.array(ms, pa.int64(), mask=mask()).cast(ts)
+    cd = pa.array(days, pa.int64(), mask=mask()).cast(d64)
+    cc = pa.array(tod, pa.int32(), mask=mask()).cast(t32)
+    batch = pa.RecordBatch.from_arrays([ct, cd, cc], schema=schema)
+    got = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
+    L = pa.int64()
+    assert_arrays_match(got[0], pc.iso_week(ct).cast(L), "extractWeek ts")
+    assert_arrays_match(got[1], pc.iso_week(cd.cast(ts)).cast(L), "extractWeek date64")
+    year_t, year_d = pc.year(ct).cast(L), pc.year(cd.cast(ts)).cast(L)
+    py = lambda arr, fn: pa.array([None if v is None else fn(v) for v in arr.to_pylist()], L)
+    assert_arrays_match(got[2], py(year_t, lambda y: y // 10), "decade")
+    assert_arrays_match(got[3], py(year_d, lambda y: y // 10), "decade d")
+    assert_arrays_match(got[4], py(year_t, lambda y: (y - 1) // 100 + 1), "century")
+    assert_arrays_match(got[5], py(year_d, lambda y: (y - 1) // 100 + 1), "century d")
+    assert_arrays_match(got[6], py(year_t, lambda y: (y - 1) // 1000 + 1), "millennium")
+    assert_arrays_match(got[7], py(year_d, lambda y: (y - 1) // 1000 + 1), "millennium d")
+    k = 8
+    for unit in ("second", "minute", "hour", "day", "week", "month", "quarter", "year"):
+        want = pc.floor_temporal(ct, unit=unit, week_starts_monday=True)
+        assert_arrays_match(got[k], want, "date_trunc_" + unit)
+        k += 1
+
+    def first_of(span, first):
+        def fn(v):
+            if v is None:
+                return None
+            y = v.year
+            y0 = (y // 10) * 10 if span == 10 else ((y - 1) // span) * span + first
+            return int((datetime.date(max(y0, 1), 1, 1) - datetime.date(1970, 1, 1)).days) * 86400000
+        return fn
+    tl = ct.to_pylist()
+    for span, first in ((10, 0), (100, 1), (1000, 1)):
+        fn = first_of(span, first)
+        want = pa.array([fn(v) for v in tl], pa.int64()).cast(ts)
+        # decade 0 would need year 0: the random range starts in year 2, rows of years 1..9 are skipped
+        ok = np.array([v is None or v.year >= 10 for v in tl])
+        assert_arrays_match(got[k].filter(pa.array(ok)), want.filter(pa.array(ok)), "date_trunc span %d" % span)
+        k += 1
+    assert_arrays_match(got[k], pc.floor_temporal(cd.cast(ts), unit="month").cast(d64), "date_trunc_Month date64"); k += 1
+    assert_arrays_match(got[k], pc.floor_temporal(cd.cast(ts), unit="week", week_starts_monday=True).cast(d64), "week d64"); k += 1
+
+    def last_day(v):
+        if v is None:
+            return None
+        v = v.date() if isinstance(v, datetime.datetime) else v
+        last = datetime.date(v.year, v.month, calendar.monthrange(v.year, v.month)[1])
+        return (last - datetime.date(1970, 1, 1)).days * 86400000
+    assert_arrays_match(got[k], pa.array([last_day(v) for v in tl], pa.int64()).cast(d64), "last_day ts"); k += 1
+    assert_arrays_match(got[k], pa.array([last_day(v) for v in cd.to_pylist()], pa.int64()).cast(d64), "last_day d64"); k += 1
+    want_tod = pa.array([None if v is None else ((v - datetime.datetime(1970, 1, 1)) // datetime.timedelta(milliseconds=1)) % 86400000
+                         for v in tl], pa.int32()).cast(t32)
+    assert_arrays_match(got[k], want_tod, "castTIME"); k += 1
+    assert_arrays_match(got[k], pc.hour(cc).cast(L), "hour(time32)"); k += 1
+    assert_arrays_match(got[k], pc.minute(cc).cast(L), "minute(time32)"); k += 1
+    assert_arrays_match(got[k], pc.second(cc).cast(L), "second(time32)"); k += 1
+    assert_arrays_match(got[k], pc.hour(ct).cast(L), "hour(castTIME(ts))")
+
+
+def test_string_position_functions(oracle, gandiva):
+    """ascii / left / right / locate / strpos / byte_substr / ilike / nvl against Python str and bytes."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_string_positions(b)
+    batch = cases.random_batch(schema, N, seed=21, null_prob=0.15)
+    got = [g.to_pylist() for g in oracle.project([r for r, _ in outs], [t for _, t in outs], batch)]
+    s, u, z, k = (batch.column(c).to_pylist() for c in range(4))
+
+    def left(x, n):
+        return x[:n] if n > 0 else ("" if n == 0 else x[:max(len(x) + n, 0)])
+
+    def right(x, n):
+        return (x[-n:] if n < len(x) else x) if n > 0 else ("" if n == 0 else x[-n:])
+
+    def locate(sub, x, start=1):
+        if start < 1 or start > len(x) + 1:
+            return 0
+        return x.find(sub, start - 1) + 1
+
+    def bsub(x, off, ln):
+        if ln <= 0 or not x:
+            return b""
+        frm = off - 1 if off > 0 else (len(x) + off if off < 0 else 0)
+        return b"" if frm < 0 or frm >= len(x) else x[frm:frm + ln]
+
+    import re
+
+    def ilike(x, pat):
+        rx = "".join(".*" if c == "%" else ("." if c == "_" else re.escape(c)) for c in pat)
+        low = lambda t: "".join(chr(ord(c) + 32) if "A" <= c <= "Z" else c for c in t)
+        return re.fullmatch(low(rx) if False else rx, low(x), flags=re.S) is not None
+
+    def lowpat(p):
+        return "".join(chr(ord(c) + 32) if "A" <= c <= "Z" else c for c in p)
+
+    for r in range(N):
+        kk = None if k[r] is None else (abs(k[r]) % 9) * (1 if k[r] >= 0 else -1) - 4   # C remainder, then - 4
+        sv, uv, zv = s[r], u[r], z[r]
+        exp = [
+            None if sv is None else (sv.encode()[0] if sv else 0),
+            None if sv is None else (sv.upper().encode()[0] if sv and sv[0].isascii() else (sv.encode()[0] if sv else 0)),
+            None if sv is None else len(left(sv, 3)), None if sv is None else len(left(sv, -2)),
+            None if sv is None else len(right(sv, 4)), None if sv is None else len(right(sv, -3)),
+            None if None in (sv, uv, kk) else left(sv, kk) == right(uv, kk),
+            None if None in (sv, kk) else len(right(sv, kk).encode()),
+            None if sv is None else locate("ar", sv), None if sv is None else locate("", sv),
+            None if sv is None else locate("本", sv), None if sv is None else locate("e", sv, 3),
+            None if None in (sv, kk) else locate("s", sv, kk), None if None in (sv, uv) else locate(uv, sv),
+            None if sv is None else locate("re", sv), None if sv is None else locate("re", sv),
+            None if sv is None else locate("RE", "".join(c.upper() if c.isascii() else c for c in sv)),
+            None if zv is None else len(bsub(zv, 2, 5)), None if zv is None else len(bsub(zv, -3, 2)),
+            None if None in (zv, kk) else bsub(zv, kk, 3) == bsub(zv, 1, 3),
+            None if sv is None else ilike(sv, lowpat("%SPecial%Requests%")),
+            None if sv is None else ilike(sv, lowpat("quick%")),
+            None if sv is None else ilike(sv[:12], lowpat("%BROWN%")),
+            None if (sv is None and uv is None) else len(sv if sv is not None else uv),
+            None if uv is None else (sv if sv is not None else "none") == uv,
+        ]
+        for c, w in enumerate(exp):
+            assert got[c][r] == w, (c, r, got[c][r], w, sv, uv, zv, kk)
+    # Arrow's case-insensitive LIKE agrees as well
+    assert got[20] == pc.match_like(batch.column(0), "%special%requests%", ignore_case=True).to_pylist()

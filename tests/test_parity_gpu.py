@@ -433,3 +433,43 @@ def test_peer_selection_push(gandiva):
                           os.path.join(root, "tests", "peer_push_worker.py")],
                          capture_output=True, text=True, timeout=600)
     assert "PEER_PUSH_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def _int_strings(n, seed, bits):
+    rng = np.random.default_rng(seed)
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    vals = [int(v) for v in rng.integers(lo, hi, n, dtype=np.int64, endpoint=True)]
+    vals[:4] = [lo, hi, 0, -1][:n]
+    out = []
+    for k, v in enumerate(vals):
+        t = str(v) if k % 5 else ("+" + str(v) if v >= 0 else str(v))
+        t = (" " * (k % 3)) + t + (" " * (k % 2))
+        out.append(None if k % 11 == 7 else t)
+    return out, vals
+
+
+@pytest.mark.parametrize("fn_name,t,bits", [("castINT", pa.int32(), 32), ("castBIGINT", pa.int64(), 64)])
+def test_cast_string_to_integer(fn_name, t, bits, gandiva, oracle):
+    """castINT / castBIGINT(utf8): spaces, signs, the extreme values; strings that are not integers
+    of the type raise an ExecutionError (in the kernel and in the oracle), a NULL row does not."""
+    b = gandiva.TreeExprBuilder()
+    S = pa.string()
+    schema = pa.schema([("s", S)])
+    root = b.make_function(fn_name, [cases.F(b, "s", S)], t)
+    p = gandiva.make_projector(schema, [b.make_expression(root, pa.field("v", t))], None)
+    for n in (1, 40, 3001):
+        strs, vals = _int_strings(n, n, bits)
+        batch = pa.RecordBatch.from_arrays([pa.array(strs, S)], schema=schema)
+        got, = p.evaluate(batch)
+        want, = oracle.project([root], [t], batch)
+        assert_arrays_match(got, want, "%s n=%d" % (fn_name, n))
+        assert got.to_pylist() == [None if s is None else v for s, v in zip(strs, vals)]
+    too_big = str(1 << (bits - 1))
+    for bad in ("12a", "", "  ", "-", "1 2", too_big, "-" + str((1 << (bits - 1)) + 1), "9" * 30, "１２"):
+        batch = pa.RecordBatch.from_arrays([pa.array(["7", None, bad, "8"], S)], schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: Failed to cast"):
+            p.evaluate(batch)
+        with pytest.raises(Exception, match="Failed to cast"):
+            oracle.project([root], [t], batch)
+    batch = pa.RecordBatch.from_arrays([pa.array(["7", None, "-8"], S)], schema=schema)
+    assert p.evaluate(batch)[0].to_pylist() == [7, None, -8]
