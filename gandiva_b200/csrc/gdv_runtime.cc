@@ -71,10 +71,36 @@ Status Device::Get(int ordinal, Device** out) {
         CuCheck(d.StreamCreate(&dev->stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate"));
     GDV_RETURN_NOT_OK(
         CuCheck(d.StreamCreate(&dev->copy_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate"));
+    dev->owner_thread_ = std::this_thread::get_id();
     g_devices[ordinal] = dev.release();
   }
   *out = g_devices[ordinal];
   return (*out)->MakeCurrent();
+}
+
+namespace {
+// Streams of the threads that did not create the Device; released at thread exit.
+struct ThreadStreams {
+  CUstream by_device[64] = {nullptr};
+  ~ThreadStreams() {
+    const DriverApi& d = Driver();
+    if (!d.loaded) return;
+    for (CUstream s : by_device)
+      if (s != nullptr) d.StreamDestroy(s);  // fails harmlessly once the context is gone
+  }
+};
+thread_local ThreadStreams tl_streams;
+}  // namespace
+
+CUstream Device::stream() const {
+  if (std::this_thread::get_id() == owner_thread_) return stream_;
+  CUstream& s = tl_streams.by_device[ordinal_];
+  if (s == nullptr) {
+    if (!MakeCurrent().ok() ||
+        Driver().StreamCreate(&s, CU_STREAM_NON_BLOCKING) != CUDA_SUCCESS)
+      return stream_;  // out of streams: fall back to the shared one
+  }
+  return s;
 }
 
 Status Device::MakeCurrent() const {

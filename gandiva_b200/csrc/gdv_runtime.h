@@ -8,6 +8,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -26,7 +27,11 @@ class Device {
   int ordinal() const { return ordinal_; }
   int sm_count() const { return sm_count_; }
   std::string arch() const;
-  CUstream stream() const { return stream_; }
+  // The engine's own stream for calls that pass stream == NULL: one non-blocking stream per
+  // (host thread, device), so that concurrent Evaluate calls from different threads never share
+  // stream-ordered scratch or error / count read-backs.  The thread that created the Device uses
+  // stream_; other threads get theirs on first use (destroyed when the thread exits).
+  CUstream stream() const;
   CUstream copy_stream() const { return copy_stream_; }
 
   // Pooled device scratch: freed blocks are cached and reused (no cuMemFree on the hot path).
@@ -43,6 +48,7 @@ class Device {
   CUcontext ctx_ = nullptr;
   CUstream stream_ = nullptr;
   CUstream copy_stream_ = nullptr;
+  std::thread::id owner_thread_;
   int sm_count_ = 0, cc_major_ = 0, cc_minor_ = 0;
   std::mutex mu_;
   std::multimap<size_t, CUdeviceptr> free_;
@@ -160,7 +166,7 @@ class Projector {
   Config cfg_;
   std::unique_ptr<CompiledKernel> kernel_;          // general (nullable) variant, built at Make()
   std::unique_ptr<CompiledKernel> kernel_nonull_;   // built on first batch without nulls
-  CompiledKernel* last_used_ = nullptr;             // variant of the latest Evaluate (kernel_info)
+  std::atomic<CompiledKernel*> last_used_{nullptr};  // variant of the latest Evaluate (kernel_info)
   std::mutex mu_;
   std::map<void*, Pending> pending_;
 };
@@ -178,10 +184,10 @@ class Filter {
   Status KernelFor(int mode, bool nullable, bool large, CompiledKernel** out);
   const Config& config() const { return cfg_; }
   const SchemaPtr& schema() const { return schema_; }
-  CompiledKernel* last_used() const { return last_used_; }
+  CompiledKernel* last_used() const { return last_used_.load(); }
 
  private:
-  CompiledKernel* last_used_ = nullptr;
+  std::atomic<CompiledKernel*> last_used_{nullptr};
   SchemaPtr schema_;
   ConditionPtr cond_;
   Config cfg_;

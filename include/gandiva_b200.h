@@ -32,8 +32,12 @@
  * reference-counted inside the library: a parent keeps its children alive, so
  * a caller may release child handles right after building the parent.
  * Threading: Make calls may run concurrently; a built projector/filter may be
- * evaluated from several threads at once (per-call scratch, no per-object
- * mutable state besides a lock-protected scratch pool).
+ * evaluated from several threads at once (per-call scratch; the engine's own
+ * stream -- the one a NULL `stream` argument names -- is per host thread, so
+ * stream-ordered scratch and error / count read-backs are never shared).  A
+ * caller-provided stream must not be used from two threads at the same time,
+ * and an asynchronous Evaluate on the NULL stream is completed by *_sync() on
+ * the same thread.
  * Errors: every call returns a gdv_status; gdv_last_error() returns the
  * thread-local message of the last failing call on this thread.
  */

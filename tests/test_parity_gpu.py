@@ -473,3 +473,41 @@ def test_cast_string_to_integer(fn_name, t, bits, gandiva, oracle):
             oracle.project([root], [t], batch)
     batch = pa.RecordBatch.from_arrays([pa.array(["7", None, "-8"], S)], schema=schema)
     assert p.evaluate(batch)[0].to_pylist() == [7, None, -8]
+
+
+def test_concurrent_evaluate_from_threads(gandiva, oracle):
+    """One Projector and one Filter evaluated from several host threads at once on different
+    batches (include/gandiva_b200.h "Threading"): every call gets its own results."""
+    import threading
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_string_outputs(b)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None)
+    cond = cases.q6_condition(b)
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cond))
+    work = []
+    for k in range(6):
+        pb = cases.random_batch(schema, 1500 + 517 * k, seed=100 + k, null_prob=0.1, small=True)
+        fb = cases.q6_batch(20_000 + 1111 * k, seed=200 + k, null_permille=10)
+        work.append((pb, oracle.project([r for r, _ in outs], [t for _, t in outs], pb),
+                     fb, oracle.filter_indices(cond, fb)))
+    errors = []
+
+    def run(tid):
+        try:
+            for it in range(4 if devmem.EMU else 16):
+                pb, pwant, fb, fwant = work[(tid + it) % len(work)]
+                got = p.evaluate(pb)
+                for i, (g, w) in enumerate(zip(got, pwant)):
+                    assert_arrays_match(g, w, "thread %d it %d out %d" % (tid, it, i))
+                sel = f.evaluate(fb, None)
+                assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), fwant), (tid, it)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e)[:500])
+
+    threads = [threading.Thread(target=run, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert errors == [], errors[:3]
