@@ -1506,6 +1506,25 @@ GDV_DEV bool gdv_like_match(const gdv_str& s, const u16* pat, i32 m) {
   return j == m;
 }
 
+// Largest row r in [lo, n) with offs[r] <= pos, given offs[lo] <= pos < offs[n] (Arrow int32
+// offsets are non-decreasing): gallop from `lo`, then bisect.  Used by the key-scan string filter
+// to map a byte position of the data buffer back to its row.
+GDV_DEV i64 gdv_row_of_byte(const i32* offs, i64 lo, i64 n, i64 pos) {
+  i64 step = 32, hi = lo + step;
+  while (hi < n && (i64)__ldg(offs + hi) <= pos) {
+    lo = hi;
+    step <<= 1;
+    hi = lo + step;
+  }
+  if (hi > n) hi = n;
+  while (hi - lo > 1) {
+    const i64 mid = (lo + hi) >> 1;
+    if ((i64)__ldg(offs + mid) <= pos) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
 // ---- ordered stream compaction: decoupled look-back over CTA tiles ------------------------
 // One 64-bit descriptor per tile: flag (2 bits) | count (62 bits).  A tile publishes its own
 // count (AGGREGATE), looks back over its predecessors until it finds an INCLUSIVE prefix,

@@ -211,6 +211,16 @@ struct CoopSeg {
 };
 constexpr int kHitCap = 64;  // hits per warp and group; more -> the group falls back per lane
 
+// Plan of the key-scan string filter (EmitKeyScanFilter): the condition holds only in rows whose
+// string column `slot` contains `key` (a literal segment of a top-level LIKE conjunct), compared
+// through the ASCII case map `xf` of the view chain; the scan looks for the digram at key[digram].
+struct KeyScanPlan {
+  int slot = -1;
+  unsigned xf = 0u;
+  std::string key;
+  int digram = 0;
+};
+
 class BodyGen {
  public:
   BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots, bool nullable, bool coop)
@@ -268,6 +278,63 @@ class BodyGen {
       if ((*slots_)[j].schema_index == idx) return static_cast<int>(j);
     slots_->push_back(ColumnSlot{idx, f.return_type()});
     return static_cast<int>(slots_->size()) - 1;
+  }
+
+  // Finds a LIKE on the AND-spine of a filter condition whose pattern has a literal segment of
+  // >= 3 bytes over a view chain of a string column: the filter can then be driven by the
+  // occurrences of that segment in the column's bytes instead of by rows.
+  bool PlanKeyScan(const Node& cond, KeyScanPlan* plan) {
+    std::vector<const Node*> conj;
+    std::vector<const Node*> todo = {&cond};
+    while (!todo.empty()) {
+      const Node* n = todo.back();
+      todo.pop_back();
+      if (n->kind() == NodeKind::kBoolean &&
+          static_cast<const BooleanNode*>(n)->op() == BooleanNode::kAnd) {
+        for (const auto& c : static_cast<const BooleanNode*>(n)->children()) todo.push_back(c.get());
+      } else {
+        conj.push_back(n);
+      }
+    }
+    double best = 1e300;
+    for (const Node* n : conj) {
+      if (n->kind() != NodeKind::kFunction) continue;
+      const auto& fn = *static_cast<const FunctionNode*>(n);
+      if (fn.name() != "like" || fn.children().size() < 2) continue;
+      if (fn.children()[1]->kind() != NodeKind::kLiteral) continue;
+      const auto& pat = static_cast<const LiteralNode&>(*fn.children()[1]);
+      const bool has_esc = fn.children().size() == 3;
+      const char esc = has_esc ? static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0] : 0;
+      const std::vector<unsigned> toks = LikeTokens(pat.bytes(), has_esc, esc);
+      bool has_one = false;
+      for (unsigned t : toks) has_one = has_one || (t >> 8) == 1u;
+      if (has_one) continue;
+      int slot = -1;
+      unsigned xf = 0u;
+      if (!ViewChain(*fn.children()[0], &slot, &xf)) continue;
+      std::vector<std::string> segs;
+      bool lead_any, trail_any;
+      LikeSegments(toks, &segs, &lead_any, &trail_any);
+      for (const auto& sg : segs) {
+        if (sg.size() < 3 || sg.size() > 64) continue;
+        bool possible = true;
+        for (unsigned char c : sg)
+          if ((xf == 1u && c >= 'a' && c <= 'z') || (xf == 2u && c >= 'A' && c <= 'Z')) possible = false;
+        if (!possible) continue;
+        for (size_t i = 0; i + 1 < sg.size(); ++i) {
+          const double sc = DigramScore(static_cast<unsigned char>(sg[i]),
+                                        static_cast<unsigned char>(sg[i + 1]), xf);
+          if (sc < best) {
+            best = sc;
+            plan->slot = slot;
+            plan->xf = xf;
+            plan->key = sg;
+            plan->digram = static_cast<int>(i);
+          }
+        }
+      }
+    }
+    return plan->slot >= 0;
   }
 
   static bool CanFail(const Node& node) {
@@ -1305,6 +1372,265 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
   }
 }
 
+// ---- key-scan string filter (opt-in: string_scan bit 4) ---------------------------------------
+// A filter whose condition implies "column J contains KEY" (PlanKeyScan) does not have to look at
+// rows at all: it streams the column's BYTES, 16 per lane and load, tests every position for the
+// rarest digram of the key with a few ALU operations per word, verifies the rare candidates, and
+// only then maps a hit back to its row (gallop + bisect in the offsets), checks that it is the
+// leftmost occurrence in that row (so every row is reported once, by one warp) and evaluates the
+// full condition for that one row.  Rows without an occurrence cost no instruction and their
+// offsets are never read.  Tiles are byte ranges; every warp owns one contiguous segment of its
+// CTA's tile and keeps the rows it accepts in a shared-memory list, so the output stays ascending:
+// segments, warps and tiles are all in byte order.  A list that overflows (dense matches) makes
+// the CTA scan its tile a second time after the look-back, writing directly.
+std::string KeyMatchExpr(const std::string& key, const std::string& view, const std::string& at) {
+  std::string e;
+  for (size_t i = 0; i < key.size(); ++i)
+    e += (i ? " && " : "") + std::string("gdv_ch_eq(") + view + ", " + at + " + " + std::to_string(i) + ", " +
+         std::to_string(static_cast<unsigned>(static_cast<unsigned char>(key[i]))) + "u)";
+  return e;
+}
+
+void ReplaceAll(std::string* s, const std::string& from, const std::string& to) {
+  for (size_t pos = 0; (pos = s->find(from, pos)) != std::string::npos; pos += to.size())
+    s->replace(pos, from.size(), to);
+}
+
+constexpr int kKeyScanListCap = 1024;  // accepted rows per warp and tile kept in shared memory
+
+std::string EmitKeyScanFilter(const std::vector<ColumnSlot>& slots, const KernelSpec& spec,
+                              const KeyScanPlan& plan, const std::string& body, const Val& result,
+                              int BT, int seg_bytes) {
+  const int NW = BT / 32;
+  const unsigned char d0 = static_cast<unsigned char>(plan.key[static_cast<size_t>(plan.digram)]);
+  const unsigned char d1 = static_cast<unsigned char>(plan.key[static_cast<size_t>(plan.digram) + 1]);
+  auto is_letter = [](unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); };
+  const unsigned f0 = (plan.xf != 0u && is_letter(d0)) ? 0x20u : 0u;
+  const unsigned f1 = (plan.xf != 0u && is_letter(d1)) ? 0x20u : 0u;
+  const unsigned half = (d0 | f0) | ((d1 | f1) << 8);
+  const unsigned fold = f0 | (f1 << 8);
+  char hex[16];
+  std::snprintf(hex, sizeof(hex), "0x%08xu", half | (half << 16));
+  const std::string PAT = hex;
+  std::snprintf(hex, sizeof(hex), "0x%08xu", fold | (fold << 16));
+  const std::string FOLD = hex;
+  const std::string fold_or = (fold != 0u) ? (" | " + FOLD) : std::string();
+
+  // the condition of ONE row per lane: EmitGroup's per-row path with base chosen so that row s is
+  // the candidate's row (lanes without a candidate get s = A.n, i.e. out of range)
+  std::string pred;
+  const std::string tail = "          { km = __ballot_sync(GDV_FULL, in && (" + result.ok + ") && (" + result.v + ")); }\n";
+  EmitGroup(slots, spec, 1, kPred, body, tail, &pred, 5);
+
+  std::string k = R"K(// one bit per byte of a 16-byte chunk where the key's digram may start (vn = the word after it)
+__device__ __forceinline__ u32 gdv_ks_mask(const uint4& v, const u32 vn) {
+  const u32 x0 = v.x@FOLDOR@, x1 = v.y@FOLDOR@, x2 = v.z@FOLDOR@, x3 = v.w@FOLDOR@, x4 = vn@FOLDOR@;
+  const u32 e0 = gdv_eqhalf_msb(x0, @PAT@), o0 = gdv_eqhalf_msb(__funnelshift_r(x0, x1, 8), @PAT@);
+  const u32 e1 = gdv_eqhalf_msb(x1, @PAT@), o1 = gdv_eqhalf_msb(__funnelshift_r(x1, x2, 8), @PAT@);
+  const u32 e2 = gdv_eqhalf_msb(x2, @PAT@), o2 = gdv_eqhalf_msb(__funnelshift_r(x2, x3, 8), @PAT@);
+  const u32 e3 = gdv_eqhalf_msb(x3, @PAT@), o3 = gdv_eqhalf_msb(__funnelshift_r(x3, x4, 8), @PAT@);
+  if ((e0 | o0 | e1 | o1 | e2 | o2 | e3 | o3) == 0u) return 0u;
+  return gdv_mask16_half(e0, o0, e1, o1, e2, o2, e3, o3);
+}
+extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant__ gdv_args A) {
+  const u32 lane = threadIdx.x & 31u;
+  const u32 wid = threadIdx.x >> 5;
+  gdv_ctx ctx;
+  ctx.err = A.err;
+@PROLOGUE@  extern __shared__ uint4 gdv_smem[];
+  u32* const wrows = reinterpret_cast<u32*>(gdv_smem) + (size_t)wid * (@LCAP@ + 256);  // rows this warp accepted
+  u16* const wcand = reinterpret_cast<u16*>(wrows + @LCAP@);  // candidates of one 512-byte block
+  __shared__ u32 s_wcount[@NW@];
+  __shared__ i64 s_tile;
+  __shared__ u64 s_excl;
+  __shared__ u32 s_over;
+  const i32* const offs = in_val@J@;
+  const u8* const data = in_var@J@;
+  const i64 b_begin = (i64)offs[0], b_end = (i64)offs[A.n];
+  i64 n_tiles = (b_end - b_begin + @TILE@ - 1) / @TILE@;
+  if (n_tiles < 1) n_tiles = 1;
+  const i64 mis = (i64)((unsigned long long)data & 15ull);  // aligned coordinate = byte position + mis
+  const u8* const abase = data - mis;
+  const i64 a_limit = (b_end + mis + 15) & ~15ll;  // end of the last 16-byte chunk that holds a byte
+  @IDX@* out_idx = reinterpret_cast<@IDX@*>(A.out_idx);
+  const u32 lt = gdv_lanemask_lt();
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);
+    __syncthreads();
+    const i64 tile = s_tile;
+    if (tile >= n_tiles) break;
+    // this warp's segment [g0, g1) of the tile: it owns the occurrences whose digram starts in it
+    i64 g0 = b_begin + tile * @TILE@ + (i64)wid * @SEG@;
+    i64 g1 = g0 + @SEG@;
+    if (g0 > b_end) g0 = b_end;
+    if (g1 > b_end) g1 = b_end;
+    // scan(direct, wstart): walks the segment; direct == false keeps accepted rows in wrows[]
+    // (counting past its capacity), direct == true stores them at out_idx[wstart + ...]
+    auto scan = [&](const bool direct, const u64 wstart) -> u32 {
+      u32 cnt = 0u;
+      if (g0 >= g1) return cnt;
+      i64 first = g0 - @KD@;
+      if (first < b_begin) first = b_begin;
+      i64 row_lo = gdv_row_of_byte(offs, 0, A.n, first);  // no later occurrence starts before this row
+      // 32-bit coordinates relative to the first 512-byte block of the segment
+      const i64 a0 = g0 + mis, a1 = g1 + mis;
+      const i64 abs0 = a0 & ~511ll;
+      const u8* const sp = abase + abs0;
+      const i32 rel0 = (i32)(a0 - abs0), rel1 = (i32)(a1 - abs0);
+      const i32 rlim = a_limit - abs0 > 0x7fffffffll ? 0x7fffffff : (i32)(a_limit - abs0);
+      // digram hits of one lane's chunk that start inside the segment and verify as the key
+      auto verify = [&](u32 mk, const i32 rc) -> u32 {
+        u32 vm = 0u;
+        while (mk != 0u) {
+          const int bit = __ffs((int)mk) - 1;
+          mk &= mk - 1u;
+          const i64 d = abs0 + (i64)(rc + bit) - mis;  // byte position of the digram
+          const i64 st = d - @KD@;                      // where the key would start
+          if (d >= g0 && d < g1 && st >= b_begin && st + @KL@ <= b_end) {
+            gdv_str kv = gdv_make_str(data + st, @KL@);
+            kv.xf = @XF@u;
+            if (@KEYMATCH_KV@) vm |= 1u << bit;
+          }
+        }
+        return vm;
+      };
+      for (i32 rb = 0; rb < rel1; rb += 512) {
+        const i32 rc = rb + 16 * (i32)lane;  // this lane's chunk
+        u32 vm = 0u;
+        if (rb >= rel0 && rb + 528 <= rel1) {
+          // interior block: every chunk and the word after the last one lie inside the segment
+          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + rc));
+          u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
+          if (lane == 31u) vn = __ldg(reinterpret_cast<const u32*>(sp + rc + 16));
+          const u32 mk = gdv_ks_mask(v, vn);
+          if (mk != 0u) vm = verify(mk, rc);
+        } else {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          const bool mine = rc < rel1 && rc + 16 > rel0;
+          // one chunk past the segment is loaded too: it holds the second byte of a digram that
+          // starts at the segment's last byte
+          if (rc + 16 > rel0 && rc < rel1 + 16 && rc < rlim) v = __ldcs(reinterpret_cast<const uint4*>(sp + rc));
+          u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
+          if (lane == 31u) vn = (mine && rc + 16 < rlim) ? __ldg(reinterpret_cast<const u32*>(sp + rc + 16)) : 0u;
+          if (mine) {
+            const u32 mk = gdv_ks_mask(v, vn);
+            if (mk != 0u) vm = verify(mk, rc);
+          }
+        }
+        if (__ballot_sync(GDV_FULL, vm != 0u) == 0u) continue;
+        // ordinals of the block's occurrences, in byte order
+        const u32 c = (u32)__popc(vm);
+        u32 incl = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(GDV_FULL, incl, o);
+          if (lane >= (u32)o) incl += t;
+        }
+        const u32 total = __shfl_sync(GDV_FULL, incl, 31);
+        {
+          u32 at = incl - c;
+          for (u32 m = vm; m != 0u; m &= m - 1u) wcand[at++] = (u16)(16u * lane + (u32)(__ffs((int)m) - 1));
+        }
+        __syncwarp();
+        for (u32 q0 = 0u; q0 < total; q0 += 32u) {
+          const bool has = q0 + lane < total;
+          const i64 st = has ? abs0 + (i64)rb + (i64)wcand[q0 + lane] - mis - @KD@ : b_begin;
+          i64 r = A.n;
+          bool cand_ok = false;
+          if (has) {
+            r = gdv_row_of_byte(offs, row_lo, A.n, st);
+            const i64 rowb = (i64)offs[r], rowe = (i64)offs[r + 1];
+            if (st + @KL@ <= rowe) {
+              // leftmost occurrence in its row? (an earlier one reports the row, here or elsewhere)
+              gdv_str rv = gdv_make_str(data + rowb, (i32)(rowe - rowb));
+              rv.xf = @XF@u;
+              cand_ok = true;
+              const i32 upto = (i32)(st - rowb);
+              for (i32 q = 0; q < upto; ++q)
+                if (@KEYMATCH_RV@) {
+                  cand_ok = false;
+                  break;
+                }
+            }
+          }
+          row_lo = __shfl_sync(GDV_FULL, r, 0);  // occurrences come in byte order
+          u32 km = 0u;
+          {
+            const i64 base = (cand_ok ? r : A.n) - (i64)lane;
+@PRED@          }
+          const u32 kc = (u32)__popc(km);
+          if ((km >> lane) & 1u) {
+            const u32 at = cnt + (u32)__popc(km & lt);
+            if (!direct) {
+              if (at < @LCAP@u) wrows[at] = (u32)r;
+            } else {
+              const u64 pos = wstart + (u64)at;
+              if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + r);
+            }
+          }
+          cnt += kc;
+        }
+        __syncwarp();  // wcand is rewritten by the next block
+      }
+      return cnt;
+    };
+    const u32 cnt = scan(false, 0ull);
+    if (lane == 0u) s_wcount[wid] = cnt;
+    __syncthreads();
+    if (wid == 0u) {
+      const u32 wc = lane < @NW@u ? s_wcount[lane] : 0u;
+      u32 winc = wc;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);
+        if (lane >= (u32)o) winc += t;
+      }
+      const u32 total = __shfl_sync(GDV_FULL, winc, 31);
+      const u32 over = __ballot_sync(GDV_FULL, wc > @LCAP@u);
+      if (lane < @NW@u) s_wcount[lane] = winc - wc;
+      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);
+      if (lane == 0u) {
+        s_excl = excl;
+        s_over = over;
+        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;
+      }
+    }
+    __syncthreads();
+    const u64 wpos = s_excl + (u64)s_wcount[wid];
+    if (s_over == 0u) {
+      for (u32 i = lane; i < cnt; i += 32u) {
+        const u64 pos = wpos + (u64)i;
+        if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + (i64)wrows[i]);
+      }
+    } else {
+      scan(true, wpos);  // some list overflowed: the offsets are known now, write directly
+    }
+  }
+}
+)K";
+  std::string prologue;
+  EmitPrologue(slots, spec, &prologue);
+  ReplaceAll(&k, "@PROLOGUE@", prologue);
+  ReplaceAll(&k, "@PRED@", pred);
+  ReplaceAll(&k, "@KEYMATCH_KV@", KeyMatchExpr(plan.key, "kv", "0"));
+  ReplaceAll(&k, "@KEYMATCH_RV@", "q + " + std::to_string(plan.key.size()) + " <= rv.len && " +
+                                       KeyMatchExpr(plan.key, "rv", "q"));
+  ReplaceAll(&k, "@BT@", std::to_string(BT));
+  ReplaceAll(&k, "@NW@", std::to_string(NW));
+  ReplaceAll(&k, "@NAME@", spec.name);
+  ReplaceAll(&k, "@LCAP@", std::to_string(kKeyScanListCap));
+  ReplaceAll(&k, "@J@", std::to_string(plan.slot));
+  ReplaceAll(&k, "@TILE@", std::to_string(static_cast<long long>(seg_bytes) * NW) + "ll");
+  ReplaceAll(&k, "@SEG@", std::to_string(seg_bytes) + "ll");
+  ReplaceAll(&k, "@IDX@", SelCType(spec.selection_mode));
+  ReplaceAll(&k, "@KD@", std::to_string(plan.digram));
+  ReplaceAll(&k, "@KL@", std::to_string(plan.key.size()));
+  ReplaceAll(&k, "@XF@", std::to_string(plan.xf));
+  ReplaceAll(&k, "@PAT@", PAT);
+  ReplaceAll(&k, "@FOLDOR@", fold_or);
+  return k;
+}
+
 int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
   // Measured on B200 (profiles/r01_sweeps.md): the map kernels want ~160-190 bytes of loads in
   // flight per thread (add int32: R=16, Q6 predicate: R=8); the filter, whose tile is large
@@ -1592,6 +1918,54 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     if (exprs.size() != 1 || !exprs[0]->result().type.is_varlen())
       return Status::Make(GDV_INVALID, "a string kernel takes exactly one utf8/binary expression");
     return GenerateStringKernel(schema, exprs[0], spec, out);
+  }
+  // Key-scan string filter (opt-in, string_scan bit 4): driven by the occurrences of a literal
+  // LIKE segment in the column's bytes; conditions that can raise keep the row-driven kernel so
+  // that errors are reported for the same rows.
+  if (spec.kind == KernelKind::kFilter && (spec.string_scan & 16) != 0 && exprs.size() == 1) {
+    std::vector<ColumnSlot> kslots;
+    BodyGen kgen(schema, &kslots, spec.nullable, /*coop=*/false);
+    std::string kbody;
+    const Val kres = kgen.GenTruth(*exprs[0]->root(), &kbody, 6);
+    KeyScanPlan plan;
+    const int kBT = spec.block_threads > 0 ? spec.block_threads : 256;
+    if (kgen.error().empty() && !kgen.uses_ctx() && kBT % 32 == 0 && kBT <= 1024 &&
+        kgen.PlanKeyScan(*exprs[0]->root(), &plan)) {
+      const int seg = spec.key_scan_seg > 0 ? spec.key_scan_seg : 4096;
+      ArgsLayout KL(static_cast<int>(kslots.size()), 0);
+      std::string src = "// generated by gandiva_b200 kernel fuser; key-scan string Filter";
+      src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
+      src += "// expr_0: " + CommentSafe(exprs[0]->ToString()) + "\n";
+      src += "// key: '" + CommentSafe(plan.key) + "' in column slot " + std::to_string(plan.slot) +
+             ", case map " + std::to_string(plan.xf) + ", digram at " + std::to_string(plan.digram) + "\n";
+      if ((spec.string_scan & 8) != 0) src += "#define GDV_LOOKBACK_STRICT 1\n";
+      src += "#include \"gdv_device_lib.cuh\"\n";
+      src += EmitArgsStruct(KL);
+      src += kgen.globals();
+      src += EmitKeyScanFilter(kslots, spec, plan, kbody, kres, kBT, seg);
+      int in_bytes = 0;
+      for (const auto& sl : kslots) in_bytes += sl.type.is_varlen() ? 32 : std::max(sl.type.width(), 1);
+      out->source = std::move(src);
+      out->name = spec.name;
+      out->kind = spec.kind;
+      out->rows_per_thread = 1;
+      out->block_threads = kBT;
+      out->selection_mode = spec.selection_mode;
+      out->nullable = spec.nullable;
+      out->inputs = kslots;
+      out->outputs.clear();
+      out->uses_ctx = false;
+      out->in_bytes_per_row = in_bytes;
+      out->out_bytes_per_row = 0;
+      out->args_size = KL.size;
+      out->dynamic_smem = (kBT / 32) * (kKeyScanListCap + 256) * 4;
+      out->tile_rows = 0;
+      out->tile_bytes = static_cast<int64_t>(seg) * (kBT / 32);
+      out->staged = false;
+      out->stages = 0;
+      out->cta_tile_rows = 0;
+      return Status::OK();
+    }
   }
   std::vector<ColumnSlot> slots;
   BodyGen gen(schema, &slots, spec.nullable, (spec.string_scan & 1) == 0);

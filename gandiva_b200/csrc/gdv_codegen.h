@@ -43,6 +43,7 @@ struct KernelSpec {
   int loader = 0;                     // 0 = engine picks, 1 = direct LDG, 2 = TMA bulk -> shared
   int stages = 0;                     // TMA loader: shared-memory stages per CTA (0 = pick)
   int string_scan = 0;                // 0 = engine picks (cooperative LIKE scan), 1 = per-lane only
+  int key_scan_seg = 0;               // key-scan filter: bytes of the data buffer per warp and tile
 };
 
 struct ColumnSlot {
@@ -66,6 +67,7 @@ struct GeneratedKernel {
   size_t args_size = 0;             // sizeof(gdv_args) for this kernel
   int dynamic_smem = 0;             // bytes of dynamic shared memory (string staging)
   int64_t tile_rows = 0;            // filter: rows per CTA tile (one look-back descriptor each)
+  int64_t tile_bytes = 0;           // key-scan filter: bytes of the string column per CTA tile (tile_rows == 0)
   bool staged = false;              // project: inputs staged through shared memory by TMA bulk copies
   int stages = 0;                   // staged: shared-memory stages per CTA
   int64_t cta_tile_rows = 0;        // staged: rows per CTA tile (block_threads * rows_per_thread)

@@ -258,6 +258,7 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
   spec.loader = cfg.loader;
   spec.stages = cfg.stages;
   spec.string_scan = cfg.string_scan;
+  spec.key_scan_seg = cfg.key_scan_seg;
   const std::string placeholder = std::string(KernelPrefix(kind)) + "PLACEHOLDER";
   spec.name = placeholder;
   std::unique_ptr<CompiledKernel> k(new CompiledKernel());
@@ -913,6 +914,9 @@ Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** o
     for (const auto& f : schema_->fields()) has_varlen = has_varlen || f.type.is_varlen();
     if (cfg.block_threads == 0)
       cfg.block_threads = large ? (has_varlen ? 512 : 1024) : 256;
+    // key-scan filters (string_scan bit 4): 64 KB of the string column per warp and tile on big
+    // batches (few look-back descriptors), 4 KB on small ones (enough tiles for 148 SMs)
+    cfg.key_scan_seg = large ? 65536 : 4096;
     GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg, &k));
     it = kernels_.emplace(key, std::move(k)).first;
   }
@@ -976,8 +980,11 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
 
+  // Row tiles: ceil(n / tile_rows) descriptors.  Key-scan kernels tile the BYTES of a string
+  // column, whose amount the host does not know for device batches: int32 offsets bound it.
   const int64_t tile_rows = gen.tile_rows;
-  const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
+  const int64_t n_tiles = tile_rows > 0 ? (n + tile_rows - 1) / tile_rows
+                                        : ((int64_t(1) << 31) / gen.tile_bytes + 2);
 
   // Per-stream persistent scratch: [ticket u64][count u64][tile_state n_tiles x u64]
   const size_t state_bytes = 16 + static_cast<size_t>(n_tiles) * 8;

@@ -90,6 +90,7 @@ struct Config {
   int stages = 0;
   int sm_reserve = 0;
   int string_scan = 0;
+  int key_scan_seg = 0;  // set per kernel variant by Filter::KernelFor
 };
 
 class CompiledKernel {

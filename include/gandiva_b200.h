@@ -114,7 +114,10 @@ typedef struct gdv_config {
                               bit 0: LIKE with the per-lane matcher only (no warp-cooperative scan),
                               bit 1: filters stage string bytes without the cp.async prefetch,
                               bit 2: string filters use one 1024-row tile per warp,
-                              bit 3: look-back waits for its whole 32-tile window (A/B switch) */
+                              bit 3: look-back waits for its whole 32-tile window (A/B switch),
+                              bit 4: key-scan filter: a condition with a LIKE conjunct over a literal
+                                     segment is driven by that segment's occurrences in the column's
+                                     bytes instead of by rows (opt-in until measured on B200) */
   int32_t reserved[3];
 } gdv_config_t;
 void gdv_config_default(gdv_config_t* cfg);

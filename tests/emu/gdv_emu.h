@@ -48,6 +48,7 @@ void gdv_emu_warp_gather(unsigned mask, unsigned long long v, unsigned long long
 struct alignas(16) uint4 {
   unsigned x, y, z, w;
 };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct alignas(16) int4 {
   int x, y, z, w;
 };

@@ -511,3 +511,86 @@ def test_concurrent_evaluate_from_threads(gandiva, oracle):
     for t in threads:
         t.join()
     assert errors == [], errors[:3]
+
+
+KEY_SCAN_CASES = [cases.case_like_scan(p, v, "filter") for p, v in
+                  [("%special%requests%", "upper_substr32"), ("%spark%", "plain"), ("spa%ark%fire", "lower"),
+                   ("%park%park%", "substr_3_20"), ("%日本語%", "plain"), ("%fire%fox", "btrim"),
+                   ("x_y%100%%%park%", "plain"), ("%requests%special%", "upper")]]
+
+
+@pytest.mark.parametrize("case", KEY_SCAN_CASES, ids=[c.__name__ for c in KEY_SCAN_CASES])
+def test_key_scan_filter(case, gandiva, oracle):
+    """string_scan bit 4: the filter is driven by the occurrences of a literal LIKE segment in the
+    column's bytes (rows without one are never looked at).  Same answers as the oracle on sparse
+    and dense matches (list overflow -> second pass), rows longer than a segment, non-ASCII text,
+    sliced arrays, 16/32/64-bit indices and a row base."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = case(b)
+    cond = outs[0][0]
+    f = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(string_scan=16))
+    assert "key-scan string Filter" in f.llvm_ir
+    for n, seed, offset, dense, long_rows in [(1, 1, 0, False, False), (64, 1, 0, False, False),
+                                              (5000, 2, 0, False, False), (20011, 3, 7, True, False),
+                                              (9000, 4, 1, False, True), (60_001, 5, 3, True, True)]:
+        batch = cases.like_scan_batch(n, seed, offset=offset, dense=dense, long_rows=long_rows)
+        want = oracle.filter_indices(cond, batch, threads=4)
+        for dtype in ("int32", "int64") if n != 5000 else ("int16", "int32"):
+            sel = f.evaluate(batch, None, dtype)
+            assert sel.num_slots == len(want), (n, dtype, sel.num_slots, len(want))
+            assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want), (n, dtype)
+
+
+def test_key_scan_filter_conjunction_and_fallback(gandiva, oracle):
+    """The LIKE may sit anywhere on the AND spine next to other predicates (evaluated for the
+    candidate rows only); conditions that do not imply a key keep the row-driven kernel."""
+    b = gandiva.TreeExprBuilder()
+    cond = cases.comment_condition(b)
+    cfg = gandiva.Configuration(string_scan=16)
+    f = gandiva.make_filter(cases.COMMENT_SCHEMA, b.make_condition(cond), cfg)
+    assert "key-scan string Filter" in f.llvm_ir
+    for n in (70_001, 300_000):
+        batch = cases.comment_batch(n, seed=n)
+        want = oracle.filter_indices(cond, batch, threads=4)
+        sel = f.evaluate(batch)
+        assert len(want) > 0 and np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
+    S, I, B = pa.string(), pa.int32(), pa.bool_()
+    schema = pa.schema([("s", S), ("k", I)])
+    s, k = cases.F(b, "s", S), cases.F(b, "k", I)
+    like = b.make_function("like", [s, b.make_literal("%park%", S)], B)
+    small = b.make_function("less_than", [k, b.make_literal(0, I)], B)
+    both = b.make_and([small, b.make_and([like, b.make_function("isnotnull", [k], B)])])
+    either = b.make_or([small, like])
+    batch = cases.random_batch(schema, 30_011, seed=9, null_prob=0.1, offset=5)
+    f_and = gandiva.make_filter(schema, b.make_condition(both), cfg)
+    assert "key-scan string Filter" in f_and.llvm_ir
+    assert np.array_equal(f_and.evaluate(batch).to_array().to_numpy().astype(np.uint64),
+                          oracle.filter_indices(both, batch, threads=4))
+    f_or = gandiva.make_filter(schema, b.make_condition(either), cfg)
+    assert "key-scan string Filter" not in f_or.llvm_ir   # an OR does not imply the key
+    assert np.array_equal(f_or.evaluate(batch).to_array().to_numpy().astype(np.uint64),
+                          oracle.filter_indices(either, batch, threads=4))
+
+
+def test_key_scan_filter_dense_and_empty(gandiva, oracle):
+    """More accepted rows per warp segment than the shared-memory list holds (second, direct-write
+    pass over the tile), a column of empty strings (no bytes at all), and a bounded vector."""
+    b = gandiva.TreeExprBuilder()
+    S, B = pa.string(), pa.bool_()
+    schema = pa.schema([("s", S)])
+    cond = b.make_function("like", [cases.F(b, "s", S), b.make_literal("%ark%", S)], B)
+    f = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(string_scan=16))
+    assert "key-scan string Filter" in f.llvm_ir
+    rng = np.random.default_rng(3)
+    rows = [None if rng.random() < 0.02 else ("ark" if rng.random() < 0.97 else "xy") for _ in range(40_003)]
+    batch = pa.RecordBatch.from_arrays([pa.array(rows, S)], schema=schema)
+    want = oracle.filter_indices(cond, batch, threads=4)
+    assert len(want) > 35_000
+    sel = f.evaluate(batch)
+    assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
+    empty = pa.RecordBatch.from_arrays([pa.array([""] * 1000 + [None] * 5, S)], schema=schema)
+    assert f.evaluate(empty).num_slots == 0
+    # "arkark": two occurrences in one row, the row is reported once
+    twice = pa.RecordBatch.from_arrays([pa.array(["arkark", "xarkxxark", "ar", "k", "ark"] * 700, S)], schema=schema)
+    sel = f.evaluate(twice)
+    assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), oracle.filter_indices(cond, twice))

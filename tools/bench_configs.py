@@ -120,6 +120,7 @@ def bench_str(rows_per_batch, batches):
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         cols = [(d_vld.data_ptr(), d_offs.data_ptr(), d_bytes.data_ptr(), 0)]
         combos = [(bt, rpt, 0) for bt in (256, 512, 1024) for rpt in (1, 2, 4)] + [(1024, 2, 1), (512, 2, 1)]
+        combos += [(bt, 1, 16) for bt in (128, 256, 512, 1024)]   # key-scan filter (string_scan bit 4)
         if os.environ.get("GDV_STR_COMBOS"):
             combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_STR_COMBOS"].split(";")]
         for bt, rpt, scan in combos:
@@ -137,7 +138,8 @@ def bench_str(rows_per_batch, batches):
                 bytes_ = batches * (4.0 * n + block_bytes * reps + n / 8.0 + 4.0 * count)
                 gbs = bytes_ / ms / 1e6
                 r = {"config": "string_filter_like_upper_substr", "block_threads": bt, "rows_per_thread": rpt,
-                     "matcher": ("per-lane" if scan & 1 else "cooperative scan") + (", no prefetch" if scan & 2 else ", cp.async prefetch"),
+                     "matcher": "key scan over the column bytes" if scan & 16 else
+                     ("per-lane" if scan & 1 else "cooperative scan") + (", no prefetch" if scan & 2 else ", cp.async prefetch"),
                      "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "gbs": gbs, "frac": gbs / PEAK,
                      "bytes_per_row": bytes_ / rows, "selected_per_batch": count, "regs": f.kernel_info["regs"],
                      "smem": f.kernel_info.get("dynamic_smem"), "ctas_per_sm": f.kernel_info.get("blocks_per_sm")}

@@ -1,0 +1,16 @@
+#!/bin/bash
+# First gpurun call of the next round: everything built while no GPU minutes were left.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r02_gpu_plan.sh'
+# 1. the -m gpu suite on the real device (new: Arrow C device interface, new functions, key-scan
+#    filter, concurrent Evaluate);  2. config-4 sweep: cooperative scan vs key-scan filter;
+# 3. ncu of the key-scan kernel and of the nullable Q6 filter (no capture exists for either);
+# 4. the default bench line.
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
+GDV_STR_COMBOS="512,2,0;128,1,16;256,1,16;512,1,16;1024,1,16" python tools/bench_configs.py str > gpurun_out/r02_str_sweep.log 2>&1
+tail -8 gpurun_out/r02_str_sweep.log
+GDV_STR_COMBOS="512,1,16" ncu --set full --clock-control none --import-source on -k regex:gdv_filter_expr -c 1 \
+  -o gpurun_out/r02_keyscan python tools/bench_configs.py str 16000000 1 > gpurun_out/r02_keyscan_ncu.log 2>&1
+python tools/sweep_q6.py > gpurun_out/r02_q6_sweep.log 2>&1; tail -12 gpurun_out/r02_q6_sweep.log
+python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -c 1500 gpurun_out/r02_bench_n1.json
