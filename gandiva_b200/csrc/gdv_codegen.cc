@@ -1931,7 +1931,9 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     const int kBT = spec.block_threads > 0 ? spec.block_threads : 256;
     if (kgen.error().empty() && !kgen.uses_ctx() && kBT % 32 == 0 && kBT <= 1024 &&
         kgen.PlanKeyScan(*exprs[0]->root(), &plan)) {
-      const int seg = spec.key_scan_seg > 0 ? spec.key_scan_seg : 4096;
+      // bytes per warp segment: rows_per_thread, meaningless here, doubles as the override in KB
+      const int seg = spec.rows_per_thread > 0 ? std::min(spec.rows_per_thread, 1024) * 1024
+                                               : (spec.key_scan_seg > 0 ? spec.key_scan_seg : 4096);
       ArgsLayout KL(static_cast<int>(kslots.size()), 0);
       std::string src = "// generated by gandiva_b200 kernel fuser; key-scan string Filter";
       src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";

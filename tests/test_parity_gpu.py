@@ -590,6 +590,11 @@ def test_key_scan_filter_dense_and_empty(gandiva, oracle):
     assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
     empty = pa.RecordBatch.from_arrays([pa.array([""] * 1000 + [None] * 5, S)], schema=schema)
     assert f.evaluate(empty).num_slots == 0
+    # big segments / big CTAs (the variant large batches get): rows_per_thread = KB per warp segment
+    for bt, seg_kb in ((1024, 64), (64, 1), (512, 16)):
+        f2 = gandiva.make_filter(schema, b.make_condition(cond),
+                                 gandiva.Configuration(string_scan=16, block_threads=bt, rows_per_thread=seg_kb))
+        assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want), (bt, seg_kb)
     # "arkark": two occurrences in one row, the row is reported once
     twice = pa.RecordBatch.from_arrays([pa.array(["arkark", "xarkxxark", "ar", "k", "ark"] * 700, S)], schema=schema)
     sel = f.evaluate(twice)

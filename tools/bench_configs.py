@@ -120,7 +120,8 @@ def bench_str(rows_per_batch, batches):
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         cols = [(d_vld.data_ptr(), d_offs.data_ptr(), d_bytes.data_ptr(), 0)]
         combos = [(bt, rpt, 0) for bt in (256, 512, 1024) for rpt in (1, 2, 4)] + [(1024, 2, 1), (512, 2, 1)]
-        combos += [(bt, 1, 16) for bt in (128, 256, 512, 1024)]   # key-scan filter (string_scan bit 4)
+        # key-scan filter (string_scan bit 4): rows_per_thread = KB of the column per warp segment (0 = 64)
+        combos += [(bt, kb, 16) for bt in (128, 256, 512, 1024) for kb in (0, 16, 256)]
         if os.environ.get("GDV_STR_COMBOS"):
             combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_STR_COMBOS"].split(";")]
         for bt, rpt, scan in combos:
