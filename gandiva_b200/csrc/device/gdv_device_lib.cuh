@@ -144,13 +144,16 @@ GDV_DEV void gdv_stp<i128>(i128* p, i128 v) {
   w.y = (i64)(u64)((u128)v >> 64);
   __stcs(reinterpret_cast<longlong2*>(p), w);
 }
+// What a column without a validity bitmap reads on the branch-free fast path (index 0, and
+// index 1 when the column's bit shift is not 0).
+__device__ const u32 gdv_all_ones[2] = {0xffffffffu, 0xffffffffu};
 // 32 bitmap bits starting at bit (32 * widx + sh), sh in [0, 31], from a 4-byte aligned word
 // pointer.  Warp-uniform address: one broadcast transaction for the 32 rows of a step.
 GDV_DEV u32 gdv_ldwin(const u32* p, i64 widx, u32 sh) {
   const u32 lo = __ldg(p + widx);
-  if (sh == 0u) return lo;
-  const u32 hi = __ldg(p + widx + 1);
-  return __funnelshift_r(lo, hi, sh);
+  u32 hi = 0u;
+  if (sh != 0u) hi = __ldg(p + widx + 1);  // a predicated load: the word after the last one is never touched
+  return __funnelshift_r(lo, hi, sh);      // sh == 0 yields lo
 }
 // Bit `i` (LSB-first, Arrow validity layout, P/include/arrow/util/bit_util.h:158) of a
 // bitmap that starts `sh` bits into byte *p.  p == nullptr means "all set".

@@ -1048,6 +1048,11 @@ void EmitPrologue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, 
       *o += "  const u32* in_vld" + J + " = reinterpret_cast<const u32*>(A.in_vld[" + J + "]);\n";
       *o += "  const u32 in_vsh" + J + " = A.in_vsh[" + J + "];\n";
       *o += "  const bool in_hv" + J + " = in_vld" + J + " != nullptr;\n";
+      // branch-free validity windows on the fast path: a column without a bitmap reads an all-ones
+      // word at index 0, so the window loads of all columns issue back to back with the value
+      // loads instead of sitting behind one uniform branch (and one load latency) each
+      *o += "  const u32* const in_vp" + J + " = in_hv" + J + " ? in_vld" + J + " : gdv_all_ones;\n";
+      *o += "  const i64 in_vm" + J + " = in_hv" + J + " ? -1ll : 0ll;\n";
     }
   }
   if (spec.kind == KernelKind::kProject && spec.selection_mode != GDV_SEL_NONE)
@@ -1329,7 +1334,7 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
       *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
       for (size_t j = 0; j < slots.size(); ++j) {
         const std::string J = std::to_string(j);
-        *o += I + "  k" + J + "[k] = !in_hv" + J + " || ((gdv_ldwin(in_vld" + J + ", (base >> 5) + k, in_vsh" +
+        *o += I + "  k" + J + "[k] = ((gdv_ldwin(in_vp" + J + ", ((base >> 5) + k) & in_vm" + J + ", in_vsh" +
               J + ") >> lane) & 1u) != 0u;\n";
       }
       *o += I + "}\n";
@@ -2073,7 +2078,13 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   src += gen.globals();
   const std::string sR = std::to_string(R), sBT = std::to_string(BT);
   const std::string s32R = std::to_string(32 * R);
-  src += "extern \"C\" __global__ void __launch_bounds__(" + sBT + ") " + spec.name +
+  // Fixed-width filters are bandwidth-bound and want every warp slot of the SM: ask for
+  // 2048 / BT resident CTAs, which caps the kernel at 32 registers per thread (what it needs).
+  std::string bounds = sBT;
+  if (spec.kind == KernelKind::kFilter && n_varlen == 0 && BT >= 256 && 2048 % BT == 0 &&
+      !gen.uses_ctx())
+    bounds += ", " + std::to_string(2048 / BT);
+  src += "extern \"C\" __global__ void __launch_bounds__(" + bounds + ") " + spec.name +
          "(const __grid_constant__ gdv_args A) {\n";
   src += "  const u32 lane = threadIdx.x & 31u;\n";
   src += "  const u32 wid = threadIdx.x >> 5;\n";
