@@ -1424,8 +1424,8 @@ std::string EmitKeyScanFilter(const std::vector<ColumnSlot>& slots, const Kernel
   // the condition of ONE row per lane: EmitGroup's per-row path with base chosen so that row s is
   // the candidate's row (lanes without a candidate get s = A.n, i.e. out of range)
   std::string pred;
-  const std::string tail = "          { km = __ballot_sync(GDV_FULL, in && (" + result.ok + ") && (" + result.v + ")); }\n";
-  EmitGroup(slots, spec, 1, kPred, body, tail, &pred, 5);
+  const std::string tail = "              { km = __ballot_sync(GDV_FULL, in && (" + result.ok + ") && (" + result.v + ")); }\n";
+  EmitGroup(slots, spec, 1, kPred, body, tail, &pred, 7);
 
   std::string k = R"K(// one bit per byte of a 16-byte chunk where the key's digram may start (vn = the word after it)
 __device__ __forceinline__ u32 gdv_ks_mask(const uint4& v, const u32 vn) {
@@ -1469,146 +1469,143 @@ extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant_
     i64 g1 = g0 + @SEG@;
     if (g0 > b_end) g0 = b_end;
     if (g1 > b_end) g1 = b_end;
-    // scan(direct, wstart): walks the segment; direct == false keeps accepted rows in wrows[]
-    // (counting past its capacity), direct == true stores them at out_idx[wstart + ...]
-    auto scan = [&](const bool direct, const u64 wstart) -> u32 {
-      u32 cnt = 0u;
-      if (g0 >= g1) return cnt;
-      i64 first = g0 - @KD@;
-      if (first < b_begin) first = b_begin;
-      i64 row_lo = gdv_row_of_byte(offs, 0, A.n, first);  // no later occurrence starts before this row
-      // 32-bit coordinates relative to the first 512-byte block of the segment
-      const i64 a0 = g0 + mis, a1 = g1 + mis;
-      const i64 abs0 = a0 & ~511ll;
-      const u8* const sp = abase + abs0;
-      const i32 rel0 = (i32)(a0 - abs0), rel1 = (i32)(a1 - abs0);
-      const i32 rlim = a_limit - abs0 > 0x7fffffffll ? 0x7fffffff : (i32)(a_limit - abs0);
-      // digram hits of one lane's chunk that start inside the segment and verify as the key
-      auto verify = [&](u32 mk, const i32 rc) -> u32 {
-        u32 vm = 0u;
-        while (mk != 0u) {
-          const int bit = __ffs((int)mk) - 1;
-          mk &= mk - 1u;
-          const i64 d = abs0 + (i64)(rc + bit) - mis;  // byte position of the digram
-          const i64 st = d - @KD@;                      // where the key would start
-          if (d >= g0 && d < g1 && st >= b_begin && st + @KL@ <= b_end) {
-            gdv_str kv = gdv_make_str(data + st, @KL@);
-            kv.xf = @XF@u;
-            if (@KEYMATCH_KV@) vm |= 1u << bit;
+    // Pass 0 walks the segment and keeps the accepted rows in wrows[] (counting past its
+    // capacity); if some list of the CTA overflowed, pass 1 walks it again after the look-back and
+    // stores the rows at their final positions directly.
+    u32 cnt = 0u;
+    u64 wpos = 0ull;
+    bool direct = false;
+    for (int pass = 0; pass < 2; ++pass) {
+      cnt = 0u;
+      if (g0 < g1) {
+        i64 first = g0 - @KD@;
+        if (first < b_begin) first = b_begin;
+        i64 row_lo = gdv_row_of_byte(offs, 0, A.n, first);  // no later occurrence starts before this row
+        // 32-bit coordinates relative to the first 512-byte block of the segment
+        const i64 a0 = g0 + mis, a1 = g1 + mis;
+        const i64 abs0 = a0 & ~511ll;
+        const u8* const sp = abase + abs0 + 16 * (i64)lane;  // this lane's chunk of block 0
+        const i32 rel0 = (i32)(a0 - abs0), rel1 = (i32)(a1 - abs0);
+        const i32 rlim = a_limit - abs0 > 0x7fffffffll ? 0x7fffffff : (i32)(a_limit - abs0);
+        const i32 rc0 = 16 * (i32)lane;
+        for (i32 rb = 0; rb < rel1; rb += 512) {
+          const i32 rc = rb + rc0;  // this lane's chunk
+          u32 mk = 0u;
+          if (rb >= rel0 && rb + 528 <= rel1) {
+            // interior block: every chunk and the word after the last one lie inside the segment
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + rb));
+            u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
+            if (lane == 31u) vn = __ldg(reinterpret_cast<const u32*>(sp + rb + 16));
+            mk = gdv_ks_mask(v, vn);
+          } else {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            const bool mine = rc < rel1 && rc + 16 > rel0;
+            // one chunk past the segment is loaded too: it holds the second byte of a digram that
+            // starts at the segment's last byte
+            if (rc + 16 > rel0 && rc < rel1 + 16 && rc < rlim) v = __ldcs(reinterpret_cast<const uint4*>(sp + rb));
+            u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
+            if (lane == 31u) vn = (mine && rc + 16 < rlim) ? __ldg(reinterpret_cast<const u32*>(sp + rb + 16)) : 0u;
+            if (mine) mk = gdv_ks_mask(v, vn);
           }
-        }
-        return vm;
-      };
-      for (i32 rb = 0; rb < rel1; rb += 512) {
-        const i32 rc = rb + 16 * (i32)lane;  // this lane's chunk
-        u32 vm = 0u;
-        if (rb >= rel0 && rb + 528 <= rel1) {
-          // interior block: every chunk and the word after the last one lie inside the segment
-          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + rc));
-          u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
-          if (lane == 31u) vn = __ldg(reinterpret_cast<const u32*>(sp + rc + 16));
-          const u32 mk = gdv_ks_mask(v, vn);
-          if (mk != 0u) vm = verify(mk, rc);
-        } else {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          const bool mine = rc < rel1 && rc + 16 > rel0;
-          // one chunk past the segment is loaded too: it holds the second byte of a digram that
-          // starts at the segment's last byte
-          if (rc + 16 > rel0 && rc < rel1 + 16 && rc < rlim) v = __ldcs(reinterpret_cast<const uint4*>(sp + rc));
-          u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
-          if (lane == 31u) vn = (mine && rc + 16 < rlim) ? __ldg(reinterpret_cast<const u32*>(sp + rc + 16)) : 0u;
-          if (mine) {
-            const u32 mk = gdv_ks_mask(v, vn);
-            if (mk != 0u) vm = verify(mk, rc);
+          // digram hits that start inside the segment and verify as the key
+          u32 vm = 0u;
+          while (mk != 0u) {
+            const int bit = __ffs((int)mk) - 1;
+            mk &= mk - 1u;
+            const i64 d = abs0 + (i64)(rc + bit) - mis;  // byte position of the digram
+            const i64 st = d - @KD@;                      // where the key would start
+            if (d >= g0 && d < g1 && st >= b_begin && st + @KL@ <= b_end) {
+              gdv_str kv = gdv_make_str(data + st, @KL@);
+              kv.xf = @XF@u;
+              if (@KEYMATCH_KV@) vm |= 1u << bit;
+            }
           }
+          if (__ballot_sync(GDV_FULL, vm != 0u) == 0u) continue;
+          // ordinals of the block's occurrences, in byte order
+          const u32 c = (u32)__popc(vm);
+          u32 incl = c;
+          #pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(GDV_FULL, incl, o);
+            if (lane >= (u32)o) incl += t;
+          }
+          const u32 total = __shfl_sync(GDV_FULL, incl, 31);
+          {
+            u32 at = incl - c;
+            for (u32 m = vm; m != 0u; m &= m - 1u) wcand[at++] = (u16)(16u * lane + (u32)(__ffs((int)m) - 1));
+          }
+          __syncwarp();
+          for (u32 q0 = 0u; q0 < total; q0 += 32u) {
+            const bool has = q0 + lane < total;
+            const i64 st = has ? abs0 + (i64)rb + (i64)wcand[q0 + lane] - mis - @KD@ : b_begin;
+            i64 r = A.n;
+            bool cand_ok = false;
+            if (has) {
+              r = gdv_row_of_byte(offs, row_lo, A.n, st);
+              const i64 rowb = (i64)offs[r], rowe = (i64)offs[r + 1];
+              if (st + @KL@ <= rowe) {
+                // leftmost occurrence in its row? (an earlier one reports the row, here or elsewhere)
+                gdv_str rv = gdv_make_str(data + rowb, (i32)(rowe - rowb));
+                rv.xf = @XF@u;
+                cand_ok = true;
+                const i32 upto = (i32)(st - rowb);
+                for (i32 q = 0; q < upto; ++q)
+                  if (@KEYMATCH_RV@) {
+                    cand_ok = false;
+                    break;
+                  }
+              }
+            }
+            row_lo = __shfl_sync(GDV_FULL, r, 0);  // occurrences come in byte order
+            u32 km = 0u;
+            {
+              const i64 base = (cand_ok ? r : A.n) - (i64)lane;
+@PRED@            }
+            if ((km >> lane) & 1u) {
+              const u32 at = cnt + (u32)__popc(km & lt);
+              if (!direct) {
+                if (at < @LCAP@u) wrows[at] = (u32)r;
+              } else {
+                const u64 pos = wpos + (u64)at;
+                if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + r);
+              }
+            }
+            cnt += (u32)__popc(km);
+          }
+          __syncwarp();  // wcand is rewritten by the next block
         }
-        if (__ballot_sync(GDV_FULL, vm != 0u) == 0u) continue;
-        // ordinals of the block's occurrences, in byte order
-        const u32 c = (u32)__popc(vm);
-        u32 incl = c;
+      }
+      if (pass == 1) break;
+      if (lane == 0u) s_wcount[wid] = cnt;
+      __syncthreads();
+      if (wid == 0u) {
+        const u32 wc = lane < @NW@u ? s_wcount[lane] : 0u;
+        u32 winc = wc;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const u32 t = __shfl_up_sync(GDV_FULL, incl, o);
-          if (lane >= (u32)o) incl += t;
+          const u32 t = __shfl_up_sync(GDV_FULL, winc, o);
+          if (lane >= (u32)o) winc += t;
         }
-        const u32 total = __shfl_sync(GDV_FULL, incl, 31);
-        {
-          u32 at = incl - c;
-          for (u32 m = vm; m != 0u; m &= m - 1u) wcand[at++] = (u16)(16u * lane + (u32)(__ffs((int)m) - 1));
+        const u32 total = __shfl_sync(GDV_FULL, winc, 31);
+        const u32 over = __ballot_sync(GDV_FULL, wc > @LCAP@u);
+        if (lane < @NW@u) s_wcount[lane] = winc - wc;
+        const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);
+        if (lane == 0u) {
+          s_excl = excl;
+          s_over = over;
+          if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;
         }
-        __syncwarp();
-        for (u32 q0 = 0u; q0 < total; q0 += 32u) {
-          const bool has = q0 + lane < total;
-          const i64 st = has ? abs0 + (i64)rb + (i64)wcand[q0 + lane] - mis - @KD@ : b_begin;
-          i64 r = A.n;
-          bool cand_ok = false;
-          if (has) {
-            r = gdv_row_of_byte(offs, row_lo, A.n, st);
-            const i64 rowb = (i64)offs[r], rowe = (i64)offs[r + 1];
-            if (st + @KL@ <= rowe) {
-              // leftmost occurrence in its row? (an earlier one reports the row, here or elsewhere)
-              gdv_str rv = gdv_make_str(data + rowb, (i32)(rowe - rowb));
-              rv.xf = @XF@u;
-              cand_ok = true;
-              const i32 upto = (i32)(st - rowb);
-              for (i32 q = 0; q < upto; ++q)
-                if (@KEYMATCH_RV@) {
-                  cand_ok = false;
-                  break;
-                }
-            }
-          }
-          row_lo = __shfl_sync(GDV_FULL, r, 0);  // occurrences come in byte order
-          u32 km = 0u;
-          {
-            const i64 base = (cand_ok ? r : A.n) - (i64)lane;
-@PRED@          }
-          const u32 kc = (u32)__popc(km);
-          if ((km >> lane) & 1u) {
-            const u32 at = cnt + (u32)__popc(km & lt);
-            if (!direct) {
-              if (at < @LCAP@u) wrows[at] = (u32)r;
-            } else {
-              const u64 pos = wstart + (u64)at;
-              if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + r);
-            }
-          }
-          cnt += kc;
+      }
+      __syncthreads();
+      wpos = s_excl + (u64)s_wcount[wid];
+      if (s_over == 0u) {
+        for (u32 i = lane; i < cnt; i += 32u) {
+          const u64 pos = wpos + (u64)i;
+          if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + (i64)wrows[i]);
         }
-        __syncwarp();  // wcand is rewritten by the next block
+        break;
       }
-      return cnt;
-    };
-    const u32 cnt = scan(false, 0ull);
-    if (lane == 0u) s_wcount[wid] = cnt;
-    __syncthreads();
-    if (wid == 0u) {
-      const u32 wc = lane < @NW@u ? s_wcount[lane] : 0u;
-      u32 winc = wc;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);
-        if (lane >= (u32)o) winc += t;
-      }
-      const u32 total = __shfl_sync(GDV_FULL, winc, 31);
-      const u32 over = __ballot_sync(GDV_FULL, wc > @LCAP@u);
-      if (lane < @NW@u) s_wcount[lane] = winc - wc;
-      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);
-      if (lane == 0u) {
-        s_excl = excl;
-        s_over = over;
-        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;
-      }
-    }
-    __syncthreads();
-    const u64 wpos = s_excl + (u64)s_wcount[wid];
-    if (s_over == 0u) {
-      for (u32 i = lane; i < cnt; i += 32u) {
-        const u64 pos = wpos + (u64)i;
-        if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + (i64)wrows[i]);
-      }
-    } else {
-      scan(true, wpos);  // some list overflowed: the offsets are known now, write directly
+      direct = true;  // some list overflowed: the offsets are known now, walk the tile again
     }
   }
 }
