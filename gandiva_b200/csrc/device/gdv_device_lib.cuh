@@ -514,7 +514,10 @@ GDV_DEV i64 gdv_floordiv(i64 a, i64 b) {
   if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
   return q;
 }
-GDV_DEV i64 castDATE_timestamp(i64 ms) { return gdv_floordiv(ms, 86400000ll) * 86400000ll; }
+// days -> milliseconds with two's-complement wrap (dates within 86400 s of the int64 limits have
+// month / year starts outside the range: the result is then defined, and the oracle's, not UB)
+GDV_DEV i64 gdv_days_to_ms(i64 days) { return (i64)((u64)days * 86400000ull); }
+GDV_DEV i64 castDATE_timestamp(i64 ms) { return gdv_days_to_ms(gdv_floordiv(ms, 86400000ll)); }
 
 // ---- date / time extraction (proleptic Gregorian, days-from-civil inverse) ---------------
 struct gdv_ymd {
@@ -663,7 +666,7 @@ GDV_DEV i64 gdv_add_months(i64 ms, i64 months) {
   const bool leap = (ny % 4 == 0) && ((ny % 100 != 0) || (ny % 400 == 0));
   const i32 mlen[12] = {31, leap ? 29 : 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
   const i32 nd = c.d < mlen[nm - 1] ? c.d : mlen[nm - 1];
-  return gdv_days_from_civil(ny, nm, nd) * 86400000ll + in_day;
+  return (i64)((u64)gdv_days_to_ms(gdv_days_from_civil(ny, nm, nd)) + (u64)in_day);
 }
 #define GDV_TSADD(NAME, UNIT_MS)                                                                  \
   GDV_DEV i64 NAME##_int32_timestamp(i32 n, i64 ts) { return (i64)((u64)ts + (u64)((i64)n * (UNIT_MS))); } \
@@ -718,7 +721,7 @@ GDV_DEV i64 gdv_iso_week(i64 days) {
 GDV_DEV i64 gdv_trunc_year_to(i64 ms, i64 span, i64 first) {
   const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));
   const i64 y = span == 10 ? (c.y / 10) * 10 : ((c.y - 1) / span) * span + first;
-  return gdv_days_from_civil(span == 1 ? c.y : y, 1, 1) * 86400000ll;
+  return gdv_days_to_ms(gdv_days_from_civil(span == 1 ? c.y : y, 1, 1));
 }
 #define GDV_CALENDAR(S)                                                                           \
   GDV_DEV i64 extractWeek_##S(i64 ms) { return gdv_iso_week(gdv_floordiv(ms, 86400000ll)); }      \
@@ -734,20 +737,20 @@ GDV_DEV i64 gdv_trunc_year_to(i64 ms, i64 span, i64 first) {
   GDV_DEV i64 date_trunc_Second_##S(i64 ms) { return gdv_floordiv(ms, 1000ll) * 1000ll; }         \
   GDV_DEV i64 date_trunc_Minute_##S(i64 ms) { return gdv_floordiv(ms, 60000ll) * 60000ll; }       \
   GDV_DEV i64 date_trunc_Hour_##S(i64 ms) { return gdv_floordiv(ms, 3600000ll) * 3600000ll; }     \
-  GDV_DEV i64 date_trunc_Day_##S(i64 ms) { return gdv_floordiv(ms, 86400000ll) * 86400000ll; }    \
+  GDV_DEV i64 date_trunc_Day_##S(i64 ms) { return gdv_days_to_ms(gdv_floordiv(ms, 86400000ll)); } \
   GDV_DEV i64 date_trunc_Week_##S(i64 ms) {                                                       \
     const i64 days = gdv_floordiv(ms, 86400000ll);                                                \
     i64 wd = (days + 3) % 7;                                                                      \
     if (wd < 0) wd += 7;                                                                          \
-    return (days - wd) * 86400000ll;                                                              \
+    return gdv_days_to_ms(days - wd);                                                             \
   }                                                                                               \
   GDV_DEV i64 date_trunc_Month_##S(i64 ms) {                                                      \
     const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));                          \
-    return gdv_days_from_civil(c.y, c.m, 1) * 86400000ll;                                         \
+    return gdv_days_to_ms(gdv_days_from_civil(c.y, c.m, 1));                                      \
   }                                                                                               \
   GDV_DEV i64 date_trunc_Quarter_##S(i64 ms) {                                                    \
     const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));                          \
-    return gdv_days_from_civil(c.y, ((c.m - 1) / 3) * 3 + 1, 1) * 86400000ll;                     \
+    return gdv_days_to_ms(gdv_days_from_civil(c.y, ((c.m - 1) / 3) * 3 + 1, 1));                  \
   }                                                                                               \
   GDV_DEV i64 date_trunc_Year_##S(i64 ms) { return gdv_trunc_year_to(ms, 1, 0); }                 \
   GDV_DEV i64 date_trunc_Decade_##S(i64 ms) { return gdv_trunc_year_to(ms, 10, 0); }              \
@@ -757,7 +760,7 @@ GDV_DEV i64 gdv_trunc_year_to(i64 ms, i64 span, i64 first) {
     const gdv_ymd c = gdv_civil_from_days(gdv_floordiv(ms, 86400000ll));                          \
     const i64 ny = c.m == 12 ? c.y + 1 : c.y;                                                     \
     const i32 nm = c.m == 12 ? 1 : c.m + 1;                                                       \
-    return (gdv_days_from_civil(ny, nm, 1) - 1) * 86400000ll;                                     \
+    return gdv_days_to_ms(gdv_days_from_civil(ny, nm, 1) - 1);                                    \
   }
 GDV_CALENDAR(date64)
 GDV_CALENDAR(timestamp)

@@ -312,6 +312,9 @@ int64_t FloorDiv(int64_t a, int64_t b) {
   if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
   return q;
 }
+// days -> ms with two's-complement wrap: month / year starts of dates at the very ends of the
+// int64 range fall outside it; the result is defined (and equal to the kernel's), not UB
+int64_t DaysToMs(int64_t days) { return static_cast<int64_t>(static_cast<uint64_t>(days) * 86400000ull); }
 
 // Gregorian calendar from days since 1970-01-01 (independent formulation: walk via
 // 400/100/4/1-year cycles instead of the era/doe closed form used on the GPU).
@@ -1048,7 +1051,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "castDATE") {
-    if (t0.id == T_TIMESTAMP) out->i = FloorDiv(a[0].i, 86400000) * 86400000;
+    if (t0.id == T_TIMESTAMP) out->i = DaysToMs(FloorDiv(a[0].i, 86400000));
     else out->i = a[0].i;
     return;
   }
@@ -1147,7 +1150,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     int64_t dn = y1 * 365 + FloorDiv(y1, 4) - FloorDiv(y1, 100) + FloorDiv(y1, 400) - 719162;  // Jan 1 of ny
     for (int m = 1; m < nm; ++m) dn += mdays[m - 1] + ((m == 2 && IsLeap(ny)) ? 1 : 0);
     dn += nd - 1;
-    out->i = dn * 86400000 + in_day;
+    out->i = static_cast<int64_t>(static_cast<uint64_t>(DaysToMs(dn)) + static_cast<uint64_t>(in_day));
     return;
   }
   if (f == "date_add" || f == "date_sub") {
@@ -1205,21 +1208,21 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     }
     if (f == "last_day") {
       const int len = mdays[c.m - 1] + ((c.m == 2 && IsLeap(c.y)) ? 1 : 0);
-      out->i = (first_of_month(c.y, c.m) + len - 1) * 86400000;
+      out->i = DaysToMs(first_of_month(c.y, c.m) + len - 1);
       return;
     }
     const std::string unit = f.substr(11);
     if (unit == "Second") out->i = FloorDiv(ms, 1000) * 1000;
     else if (unit == "Minute") out->i = FloorDiv(ms, 60000) * 60000;
     else if (unit == "Hour") out->i = FloorDiv(ms, 3600000) * 3600000;
-    else if (unit == "Day") out->i = days * 86400000;
-    else if (unit == "Week") out->i = (days - monday0(days)) * 86400000;
-    else if (unit == "Month") out->i = first_of_month(c.y, c.m) * 86400000;
-    else if (unit == "Quarter") out->i = first_of_month(c.y, ((c.m - 1) / 3) * 3 + 1) * 86400000;
-    else if (unit == "Year") out->i = jan1_of(c.y) * 86400000;
-    else if (unit == "Decade") out->i = jan1_of((c.y / 10) * 10) * 86400000;
-    else if (unit == "Century") out->i = jan1_of(((c.y - 1) / 100) * 100 + 1) * 86400000;
-    else out->i = jan1_of(((c.y - 1) / 1000) * 1000 + 1) * 86400000;  // Millennium
+    else if (unit == "Day") out->i = DaysToMs(days);
+    else if (unit == "Week") out->i = DaysToMs(days - monday0(days));
+    else if (unit == "Month") out->i = DaysToMs(first_of_month(c.y, c.m));
+    else if (unit == "Quarter") out->i = DaysToMs(first_of_month(c.y, ((c.m - 1) / 3) * 3 + 1));
+    else if (unit == "Year") out->i = DaysToMs(jan1_of(c.y));
+    else if (unit == "Decade") out->i = DaysToMs(jan1_of((c.y / 10) * 10));
+    else if (unit == "Century") out->i = DaysToMs(jan1_of(((c.y - 1) / 100) * 100 + 1));
+    else out->i = DaysToMs(jan1_of(((c.y - 1) / 1000) * 1000 + 1));  // Millennium
     return;
   }
   if (f.rfind("extract", 0) == 0) {
