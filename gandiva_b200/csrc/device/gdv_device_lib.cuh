@@ -34,6 +34,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_OFFSET_OVERFLOW 2  /* a utf8/binary output needs more than 2^31 - 1 bytes */
 #define GDV_ERR_VAR_CAPACITY 3     /* the caller's var_data buffer is too small */
 #define GDV_ERR_CAST_INT 4         /* castINT / castBIGINT of a string that is not an integer */
+#define GDV_ERR_CAST_DATE 5        /* castDATE / castTIMESTAMP of a string that is not a date / timestamp */
 struct gdv_ctx {
   int* err;
 };
@@ -1474,6 +1475,83 @@ GDV_DEV i64 castBIGINT_utf8(gdv_ctx* c, gdv_str s) {
   return gdv_parse_int(c, s, (i64)0x8000000000000000ull, 0x7fffffffffffffffll);
 }
 GDV_DEV i32 castINT_utf8(gdv_ctx* c, gdv_str s) { return (i32)gdv_parse_int(c, s, -2147483648ll, 2147483647ll); }
+
+// castDATE / castTIMESTAMP of a string: [spaces] Y-M-D [(' ' | 'T') h:m[:s[.fraction]]] [spaces],
+// 1..9 digit year (optional leading '-'), 1..2 digit fields, fraction truncated to milliseconds;
+// month 1..12, day valid for the month (proleptic Gregorian), h < 24, m < 60, s < 60.  castDATE
+// drops the time of day.  Anything else raises an ExecutionError.
+GDV_DEV bool gdv_parse_uint(const gdv_str& s, i32* pos, i32 end, i32 min_digits, i32 max_digits, i64* out) {
+  i64 v = 0;
+  i32 n = 0;
+  while (*pos < end && n < max_digits) {
+    const u32 d = (u32)s.p[*pos] - (u32)'0';
+    if (d > 9u) break;
+    v = v * 10 + (i64)d;
+    ++*pos;
+    ++n;
+  }
+  *out = v;
+  return n >= min_digits;
+}
+GDV_DEV i64 gdv_parse_timestamp(gdv_ctx* c, const gdv_str& s, bool date_only) {
+  i32 b = 0, e = s.len;
+  while (b < e && s.p[b] == (u8)' ') ++b;
+  while (e > b && s.p[e - 1] == (u8)' ') --e;
+  bool ok = true, neg = false;
+  if (b < e && s.p[b] == (u8)'-') {
+    neg = true;
+    ++b;
+  }
+  i64 y = 0, mo = 0, d = 0, hh = 0, mi = 0, ss = 0, ms = 0;
+  ok = ok && gdv_parse_uint(s, &b, e, 1, 9, &y);
+  ok = ok && b < e && s.p[b] == (u8)'-';
+  ++b;
+  ok = ok && gdv_parse_uint(s, &b, e, 1, 2, &mo);
+  ok = ok && b < e && s.p[b] == (u8)'-';
+  ++b;
+  ok = ok && gdv_parse_uint(s, &b, e, 1, 2, &d);
+  if (ok && b < e) {
+    ok = s.p[b] == (u8)' ' || s.p[b] == (u8)'T';
+    ++b;
+    ok = ok && gdv_parse_uint(s, &b, e, 1, 2, &hh);
+    ok = ok && b < e && s.p[b] == (u8)':';
+    ++b;
+    ok = ok && gdv_parse_uint(s, &b, e, 1, 2, &mi);
+    if (ok && b < e) {
+      ok = s.p[b] == (u8)':';
+      ++b;
+      ok = ok && gdv_parse_uint(s, &b, e, 1, 2, &ss);
+      if (ok && b < e) {
+        ok = s.p[b] == (u8)'.';
+        ++b;
+        i32 nd = 0;
+        while (b < e && (u32)s.p[b] - (u32)'0' <= 9u) {
+          if (nd < 3) ms = ms * 10 + (i64)((u32)s.p[b] - (u32)'0');
+          ++nd;
+          ++b;
+        }
+        ok = ok && nd >= 1 && b == e;
+        for (; nd < 3; ++nd) ms *= 10;
+      }
+    }
+  }
+  if (neg) y = -y;
+  ok = ok && b >= e && mo >= 1 && mo <= 12 && d >= 1 && hh < 24 && mi < 60 && ss < 60;
+  if (ok) {
+    const bool leap = (y % 4 == 0) && ((y % 100 != 0) || (y % 400 == 0));
+    const i32 mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    ok = d <= (i64)mdays[mo - 1] + ((mo == 2 && leap) ? 1 : 0);
+  }
+  if (!ok) {
+    gdv_set_error(c, GDV_ERR_CAST_DATE);
+    return 0;
+  }
+  const i64 day_ms = gdv_days_to_ms(gdv_days_from_civil(y, (i32)mo, (i32)d));
+  if (date_only) return day_ms;
+  return day_ms + ((hh * 60 + mi) * 60 + ss) * 1000 + ms;
+}
+GDV_DEV i64 castDATE_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_timestamp(c, s, true); }
+GDV_DEV i64 castTIMESTAMP_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_timestamp(c, s, false); }
 
 // SQL LIKE over a pattern tokenised at Make(): each token is (kind << 8) | byte with
 // kind 0 = literal byte, 1 = '_' (exactly one glyph), 2 = '%' (any run of glyphs).

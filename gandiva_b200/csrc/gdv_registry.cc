@@ -279,6 +279,8 @@ Registry::Registry() {
   Add("byte_substr", {BIN, I32, I32}, BIN, NullMode::kIfNull, kStringView, {"bytesubstring"});
   Add("castBIGINT", {S}, I64, NullMode::kIfNull, kCanFail);
   Add("castINT", {S}, I32, NullMode::kIfNull, kCanFail);
+  Add("castDATE", {S}, D64, NullMode::kIfNull, kCanFail);
+  Add("castTIMESTAMP", {S}, TS, NullMode::kIfNull, kCanFail);
   // ilike(s, pattern): like() over lower-cased text and pattern (ASCII case folding); rewritten
   // at Make() (RewriteAliases), never called as a device function
   Add("ilike", {S, S}, B, NullMode::kIfNull, kLikeHolder);

@@ -16,6 +16,7 @@ const char* ExecutionErrorMessage(int code) {
     case 2: return "a utf8/binary output needs more than 2^31 - 1 bytes (int32 offsets)";
     case 3: return "var_data capacity of a utf8/binary output is too small";
     case 4: return "Failed to cast the string to an integer of the requested type";
+    case 5: return "Failed to cast the string to a date / timestamp (not a valid date / timestamp)";
     default: return "execution error in device function";
   }
 }

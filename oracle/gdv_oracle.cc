@@ -88,7 +88,7 @@ struct Column {  // same layout as gdv_column_t
 
 struct EvalCtx {
   const Column* cols;
-  int error = 0;  // 1 = divide by zero, 4 = string is not an integer of the target type
+  int error = 0;  // 1 = divide by zero, 4 = not an integer of the target type, 5 = not a date / timestamp
 };
 
 enum Kind { K_FIELD, K_LIT, K_FN, K_IF, K_AND, K_OR, K_IN };
@@ -1048,6 +1048,57 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     if (t0.id == T_FLOAT) out->d = static_cast<double>(a[0].f);
     else if (t0.id == T_DECIMAL) out->d = DecimalToDouble(a[0].dec, t0.scale);
     else out->d = static_cast<double>(a[0].i);
+    return;
+  }
+  if ((f == "castDATE" || f == "castTIMESTAMP") && t0.id == T_STRING) {
+    // [spaces] [-]Y-M-D [(' '|'T') h:m[:s[.frac]]] [spaces]; sscanf-free, field by field
+    std::string str = a[0].s;
+    while (!str.empty() && str.front() == ' ') str.erase(str.begin());
+    while (!str.empty() && str.back() == ' ') str.pop_back();
+    size_t pos = 0;
+    bool neg = false;
+    if (pos < str.size() && str[pos] == '-') { neg = true; ++pos; }
+    auto field = [&](int maxd, int64_t* v) {
+      int n = 0;
+      *v = 0;
+      while (pos < str.size() && n < maxd && str[pos] >= '0' && str[pos] <= '9') { *v = *v * 10 + (str[pos] - '0'); ++pos; ++n; }
+      return n >= 1;
+    };
+    auto expect = [&](const char* any) {
+      if (pos >= str.size() || std::strchr(any, str[pos]) == nullptr) return false;
+      ++pos;
+      return true;
+    };
+    int64_t y = 0, mo = 0, d = 0, hh = 0, mi = 0, ss = 0, ms = 0;
+    bool good = field(9, &y) && expect("-") && field(2, &mo) && expect("-") && field(2, &d);
+    if (good && pos < str.size()) {
+      good = expect(" T") && field(2, &hh) && expect(":") && field(2, &mi);
+      if (good && pos < str.size()) {
+        good = expect(":") && field(2, &ss);
+        if (good && pos < str.size()) {
+          good = expect(".");
+          int nd = 0;
+          while (good && pos < str.size() && str[pos] >= '0' && str[pos] <= '9') {
+            if (nd < 3) ms = ms * 10 + (str[pos] - '0');
+            ++nd;
+            ++pos;
+          }
+          good = good && nd >= 1;
+          for (; nd < 3; ++nd) ms *= 10;
+        }
+      }
+    }
+    if (neg) y = -y;
+    good = good && pos == str.size() && mo >= 1 && mo <= 12 && d >= 1 && hh < 24 && mi < 60 && ss < 60;
+    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    if (good) good = d <= mdays[mo - 1] + ((mo == 2 && IsLeap(y)) ? 1 : 0);
+    if (!good) { cx.error = 5; return; }
+    const int64_t y1 = y - 1;
+    int64_t dn = y1 * 365 + FloorDiv(y1, 4) - FloorDiv(y1, 100) + FloorDiv(y1, 400) - 719162;
+    for (int m = 1; m < mo; ++m) dn += mdays[m - 1] + ((m == 2 && IsLeap(y)) ? 1 : 0);
+    dn += d - 1;
+    out->i = DaysToMs(dn);
+    if (f == "castTIMESTAMP") out->i += ((hh * 60 + mi) * 60 + ss) * 1000 + ms;
     return;
   }
   if (f == "castDATE") {

@@ -599,3 +599,57 @@ def test_key_scan_filter_dense_and_empty(gandiva, oracle):
     twice = pa.RecordBatch.from_arrays([pa.array(["arkark", "xarkxxark", "ar", "k", "ark"] * 700, S)], schema=schema)
     sel = f.evaluate(twice)
     assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), oracle.filter_indices(cond, twice))
+
+
+def test_cast_string_to_date_and_timestamp(gandiva, oracle):
+    """castDATE / castTIMESTAMP(utf8): the accepted spellings against Python's calendar, bit-exact
+    with the oracle; malformed or impossible dates raise an ExecutionError in both."""
+    import datetime
+    rng = np.random.default_rng(12)
+    S, D64, TS = pa.string(), pa.date64(), pa.timestamp("ms")
+    schema = pa.schema([("s", S)])
+    b = gandiva.TreeExprBuilder()
+    root_d = b.make_function("castDATE", [cases.F(b, "s", S)], D64)
+    root_t = b.make_function("castTIMESTAMP", [cases.F(b, "s", S)], TS)
+    p = gandiva.make_projector(schema, [b.make_expression(root_d, pa.field("d", D64)),
+                                        b.make_expression(root_t, pa.field("t", TS))], None)
+    epoch = datetime.datetime(1970, 1, 1)
+    strs, want_d, want_t = [], [], []
+    for k in range(3000):
+        dt = datetime.datetime(int(rng.integers(1, 9999)), 1, 1) + datetime.timedelta(
+            days=int(rng.integers(0, 365)), milliseconds=int(rng.integers(0, 86400000)))
+        y, mo, d, hh, mi, ss, ms = dt.year, dt.month, dt.day, dt.hour, dt.minute, dt.second, dt.microsecond // 1000
+        style = k % 6
+        if style == 0:
+            t, tod = "%04d-%02d-%02d" % (y, mo, d), 0
+        elif style == 1:
+            t, tod = "%d-%d-%d %d:%d" % (y, mo, d, hh, mi), (hh * 60 + mi) * 60000
+        elif style == 2:
+            t, tod = "%04d-%02d-%02dT%02d:%02d:%02d" % (y, mo, d, hh, mi, ss), ((hh * 60 + mi) * 60 + ss) * 1000
+        elif style == 3:
+            t, tod = "  %04d-%02d-%02d %02d:%02d:%02d.%03d " % (y, mo, d, hh, mi, ss, ms), ((hh * 60 + mi) * 60 + ss) * 1000 + ms
+        elif style == 4:
+            t, tod = "%04d-%02d-%02d %02d:%02d:%02d.%d" % (y, mo, d, hh, mi, ss, ms // 100), ((hh * 60 + mi) * 60 + ss) * 1000 + (ms // 100) * 100
+        else:
+            t, tod = "%04d-%02d-%02d %02d:%02d:%02d.%03d987" % (y, mo, d, hh, mi, ss, ms), ((hh * 60 + mi) * 60 + ss) * 1000 + ms
+        day_ms = (datetime.datetime(y, mo, d) - epoch).days * 86400000
+        strs.append(None if k % 13 == 5 else t)
+        want_d.append(None if k % 13 == 5 else day_ms)
+        want_t.append(None if k % 13 == 5 else day_ms + tod)
+    batch = pa.RecordBatch.from_arrays([pa.array(strs, S)], schema=schema)
+    got = p.evaluate(batch)
+    want = oracle.project([root_d, root_t], [D64, TS], batch)
+    for g, w in zip(got, want):
+        assert_arrays_match(g, w, "cast string to date/timestamp")
+    assert got[0].view(pa.int64()).to_pylist() == want_d
+    assert got[1].view(pa.int64()).to_pylist() == want_t
+    neg = pa.RecordBatch.from_arrays([pa.array(["-0044-03-15", "0000-02-29", "1900-03-01"], S)], schema=schema)
+    assert_arrays_match(p.evaluate(neg)[0], oracle.project([root_d], [D64], neg)[0], "BC dates")
+    for bad in ("2024-02-30", "2023-02-29", "2024-13-01", "2024-00-10", "2024-01-00", "2024-1-1x", "20240101", "",
+                "2024-01-01 24:00", "2024-01-01 12:60", "2024-01-01 12:00:60", "2024-01-01 12", "2024-01-01 12:00:00.",
+                "2024-01-01  12:00", "2024/01/01", "1-2", "+2024-01-01"):
+        one = pa.RecordBatch.from_arrays([pa.array(["2024-01-01", None, bad], S)], schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: Failed to cast the string to a date"):
+            p.evaluate(one)
+        with pytest.raises(Exception, match="Failed to cast the string to a date"):
+            oracle.project([root_t], [TS], one)
