@@ -49,6 +49,8 @@ GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
 // scan of the staged bytes), so glyph positions are byte positions.
 #define GDV_XF_CASE 3u
 #define GDV_XF_ASCII 0x100u
+#define GDV_XF_LOCAL 0x200u  /* bytes live in the producing thread's scratch slot: only that thread may read them */
+#define GDV_SCRATCH_SLOT 32  /* bytes per (row, call site) of a function that writes its result as text */
 struct gdv_str {
   const u8* p;
   i32 len;
@@ -1552,6 +1554,72 @@ GDV_DEV i64 gdv_parse_timestamp(gdv_ctx* c, const gdv_str& s, bool date_only) {
 }
 GDV_DEV i64 castDATE_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_timestamp(c, s, true); }
 GDV_DEV i64 castTIMESTAMP_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_timestamp(c, s, false); }
+
+// ---- numbers and dates as text (castVARCHAR): bytes are produced into a thread-private slot -----
+GDV_DEV gdv_str gdv_scratch_str(u8* scr, i32 len, i64 maxlen) {
+  gdv_str r;
+  r.p = scr;
+  r.len = maxlen <= 0 ? 0 : ((i64)len > maxlen ? (i32)maxlen : len);
+  r.xf = GDV_XF_ASCII | GDV_XF_LOCAL;
+  return r;
+}
+GDV_DEV i32 gdv_put_uint(u8* scr, i32 at, u64 v, i32 min_digits) {
+  u8 tmp[20];
+  i32 n = 0;
+  do {
+    tmp[n++] = (u8)((u32)'0' + (u32)(v % 10ull));
+    v /= 10ull;
+  } while (v != 0ull);
+  for (i32 pad = n; pad < min_digits; ++pad) scr[at++] = (u8)'0';
+  while (n > 0) scr[at++] = tmp[--n];
+  return at;
+}
+GDV_DEV gdv_str castVARCHAR_int64_int64(i64 v, i64 maxlen, u8* scr) {
+  i32 at = 0;
+  if (v < 0) scr[at++] = (u8)'-';
+  at = gdv_put_uint(scr, at, v < 0 ? (u64)0 - (u64)v : (u64)v, 1);
+  return gdv_scratch_str(scr, at, maxlen);
+}
+GDV_DEV gdv_str castVARCHAR_int32_int64(i32 v, i64 maxlen, u8* scr) {
+  return castVARCHAR_int64_int64((i64)v, maxlen, scr);
+}
+// "YYYY-MM-DD" (years outside 0..9999: a leading '-' and / or more digits)
+GDV_DEV i32 gdv_put_date(u8* scr, i64 days) {
+  const gdv_ymd c = gdv_civil_from_days(days);
+  i32 at = 0;
+  if (c.y < 0) scr[at++] = (u8)'-';
+  at = gdv_put_uint(scr, at, c.y < 0 ? (u64)0 - (u64)c.y : (u64)c.y, 4);
+  scr[at++] = (u8)'-';
+  at = gdv_put_uint(scr, at, (u64)c.m, 2);
+  scr[at++] = (u8)'-';
+  return gdv_put_uint(scr, at, (u64)c.d, 2);
+}
+GDV_DEV gdv_str castVARCHAR_date64_int64(i64 ms, i64 maxlen, u8* scr) {
+  return gdv_scratch_str(scr, gdv_put_date(scr, gdv_floordiv(ms, 86400000ll)), maxlen);
+}
+// "YYYY-MM-DD hh:mm:ss.mmm"
+GDV_DEV gdv_str castVARCHAR_timestamp_int64(i64 ms, i64 maxlen, u8* scr) {
+  const i64 days = gdv_floordiv(ms, 86400000ll);
+  const i64 in_day = (i64)((u64)ms - (u64)gdv_days_to_ms(days));
+  i32 at = gdv_put_date(scr, days);
+  scr[at++] = (u8)' ';
+  at = gdv_put_uint(scr, at, (u64)(in_day / 3600000ll), 2);
+  scr[at++] = (u8)':';
+  at = gdv_put_uint(scr, at, (u64)((in_day / 60000ll) % 60), 2);
+  scr[at++] = (u8)':';
+  at = gdv_put_uint(scr, at, (u64)((in_day / 1000ll) % 60), 2);
+  scr[at++] = (u8)'.';
+  at = gdv_put_uint(scr, at, (u64)(in_day % 1000ll), 3);
+  return gdv_scratch_str(scr, at, maxlen);
+}
+__device__ const u8 gdv_true_false[9] = {'t', 'r', 'u', 'e', 'f', 'a', 'l', 's', 'e'};
+GDV_DEV gdv_str castVARCHAR_boolean_int64(bool v, i64 maxlen) {
+  gdv_str r = gdv_make_str(v ? gdv_true_false : gdv_true_false + 4, v ? 4 : 5);
+  if (maxlen <= 0) r.len = 0;
+  else if ((i64)r.len > maxlen) r.len = (i32)maxlen;
+  r.xf = GDV_XF_ASCII;
+  return r;
+}
 
 // SQL LIKE over a pattern tokenised at Make(): each token is (kind << 8) | byte with
 // kind 0 = literal byte, 1 = '_' (exactly one glyph), 2 = '%' (any run of glyphs).

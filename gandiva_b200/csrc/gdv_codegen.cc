@@ -226,7 +226,16 @@ class BodyGen {
   BodyGen(const Schema& schema, std::vector<ColumnSlot>* slots, bool nullable, bool coop)
       : schema_(schema), slots_(slots), nullable_(nullable), coop_(coop) {}
 
-  std::string& globals() { return globals_; }
+  // Device-scope definitions the body needs; GDV_NS = call sites that write text into scratch slots.
+  std::string globals() const {
+    return n_scratch_ > 0 ? "#define GDV_NS " + std::to_string(n_scratch_) + "\n" + globals_ : globals_;
+  }
+  int scratch_sites() const { return n_scratch_; }
+  // Declaration of the thread-private scratch slots of a kernel that evaluates R rows per group.
+  std::string ScratchDecl(int R) const {
+    if (n_scratch_ == 0) return std::string();
+    return "  u8 gdv_scr[" + std::to_string(R) + " * GDV_NS * GDV_SCRATCH_SLOT];  // text written by castVARCHAR(number)\n";
+  }
   const std::vector<CoopSeg>& coop_segs() const { return coop_segs_; }
   bool uses_ctx() const { return uses_ctx_; }
   const std::string& error() const { return error_; }
@@ -835,6 +844,8 @@ class BodyGen {
       add(std::to_string(rt.precision));
       add(std::to_string(rt.scale));
     }
+    if (def->flags & kScratch)
+      add("gdv_scr + ((size_t)k * GDV_NS + " + std::to_string(n_scratch_++) + ") * GDV_SCRATCH_SLOT");
     call += ")";
 
     const std::string v = NewVar("v");
@@ -991,6 +1002,7 @@ class BodyGen {
   std::string error_;  // first construct the fuser cannot lower (reported by GenerateKernel)
   std::vector<CoopSeg> coop_segs_;
   std::string globals_;
+  int n_scratch_ = 0;
   int next_id_ = 0;
   bool uses_ctx_ = false;
 };
@@ -1405,7 +1417,7 @@ constexpr int kKeyScanListCap = 1024;  // accepted rows per warp and tile kept i
 
 std::string EmitKeyScanFilter(const std::vector<ColumnSlot>& slots, const KernelSpec& spec,
                               const KeyScanPlan& plan, const std::string& body, const Val& result,
-                              int BT, int seg_bytes) {
+                              int BT, int seg_bytes, const std::string& scratch_decl) {
   const int NW = BT / 32;
   const unsigned char d0 = static_cast<unsigned char>(plan.key[static_cast<size_t>(plan.digram)]);
   const unsigned char d1 = static_cast<unsigned char>(plan.key[static_cast<size_t>(plan.digram) + 1]);
@@ -1612,6 +1624,7 @@ extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant_
 )K";
   std::string prologue;
   EmitPrologue(slots, spec, &prologue);
+  prologue += scratch_decl;
   ReplaceAll(&k, "@PROLOGUE@", prologue);
   ReplaceAll(&k, "@PRED@", pred);
   ReplaceAll(&k, "@KEYMATCH_KV@", KeyMatchExpr(plan.key, "kv", "0"));
@@ -1699,6 +1712,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
   KernelSpec pspec = spec;
   pspec.kind = KernelKind::kProject;  // prologue / group emitters key on project vs filter only
   EmitPrologue(slots, pspec, &src);
+  src += gen.ScratchDecl(R);
   if (stage_bytes > 0) {
     src += "  extern __shared__ uint4 gdv_smem[];\n";
     int vi = 0;
@@ -1794,7 +1808,16 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     src += "      #pragma unroll\n";
     src += "      for (int piece = 0; piece < " + sK + "; ++piece) {\n";
     src += "        const u32 plen = rowok ? (u32)sv[k][piece].len : 0u;\n";
-    src += "        const u32 nonempty = __ballot_sync(GDV_FULL, plen != 0u);\n";
+    src += "        // text in a thread-private scratch slot is copied by its owner, everything else by the warp\n";
+    src += "        const bool mine_only = (sv[k][piece].xf & GDV_XF_LOCAL) != 0u;\n";
+    src += "        if (plen != 0u && mine_only) {\n";
+    src += "          if (dst0 + (u64)plen <= (u64)A.out_cap) {\n";
+    src += "            for (u32 i = 0u; i < plen; ++i) data[dst0 + (u64)i] = gdv_ch(sv[k][piece], (i32)i);\n";
+    src += "          } else {\n";
+    src += "            gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";
+    src += "          }\n";
+    src += "        }\n";
+    src += "        const u32 nonempty = __ballot_sync(GDV_FULL, plen != 0u && !mine_only);\n";
     src += "        for (u32 rest = nonempty; rest != 0u; rest &= rest - 1u) {\n";
     src += "          const int j = __ffs((int)rest) - 1;\n";
     src += "          gdv_str v;\n";
@@ -1946,7 +1969,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
       src += "#include \"gdv_device_lib.cuh\"\n";
       src += EmitArgsStruct(KL);
       src += kgen.globals();
-      src += EmitKeyScanFilter(kslots, spec, plan, kbody, kres, kBT, seg);
+      src += EmitKeyScanFilter(kslots, spec, plan, kbody, kres, kBT, seg, kgen.ScratchDecl(1));
       int in_bytes = 0;
       for (const auto& sl : kslots) in_bytes += sl.type.is_varlen() ? 32 : std::max(sl.type.width(), 1);
       out->source = std::move(src);
@@ -2087,6 +2110,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   src += "  const u32 wid = threadIdx.x >> 5;\n";
   src += "  gdv_ctx ctx;\n  ctx.err = A.err;\n";
   EmitPrologue(slots, spec, &src);
+  src += gen.ScratchDecl(R);
   if (stage_bytes > 0) {
     src += "  extern __shared__ uint4 gdv_smem[];\n";
     int vi = 0;

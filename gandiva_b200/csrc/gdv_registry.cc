@@ -270,6 +270,12 @@ Registry::Registry() {
   Add("rtrim", {S}, S, NullMode::kIfNull, kStringView);
   Add("btrim", {S}, S, NullMode::kIfNull, kStringView, {"trim"});
   Add("castVARCHAR", {S, I64}, S, NullMode::kIfNull, kStringView);
+  // numbers / dates as text: the digits are written into a thread-private scratch slot
+  Add("castVARCHAR", {I32, I64}, S, NullMode::kIfNull, kScratch);
+  Add("castVARCHAR", {I64, I64}, S, NullMode::kIfNull, kScratch);
+  Add("castVARCHAR", {D64, I64}, S, NullMode::kIfNull, kScratch);
+  Add("castVARCHAR", {TS, I64}, S, NullMode::kIfNull, kScratch);
+  Add("castVARCHAR", {B, I64}, S);
   Add("ascii", {S}, I32);
   Add("left", {S, I32}, S, NullMode::kIfNull, kStringView);
   Add("right", {S, I32}, S, NullMode::kIfNull, kStringView);

@@ -23,6 +23,7 @@ enum FnFlags : uint32_t {
   kDecimalArgs = 1u << 2,  // decimal params are followed by (precision, scale); out (p, s) appended
   kStringView = 1u << 3,   // returns a view/transform of its first argument (no new bytes)
   kConcat = 1u << 4,       // result = the pieces of its arguments in order (a rope, see the fuser)
+  kScratch = 1u << 5,      // writes its result bytes into a per-row scratch slot passed as last argument
 };
 
 struct FunctionDef {

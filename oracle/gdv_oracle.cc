@@ -1310,6 +1310,28 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
                      : Substr(a[0].s, a[1].i, static_cast<int64_t>(a[0].s.size()));
     return;
   }
+  if (f == "castVARCHAR" && t0.id != T_STRING) {
+    // numbers / booleans / dates as text, then the first `len` characters
+    char buf[64];
+    std::string text;
+    if (t0.id == T_BOOL) text = a[0].b ? "true" : "false";
+    else if (t0.id == T_DATE64 || t0.id == T_TIMESTAMP) {
+      const int64_t days = FloorDiv(a[0].i, 86400000);
+      const Ymd c = CivilFromDays(days);
+      std::snprintf(buf, sizeof(buf), "%s%04lld-%02d-%02d", c.y < 0 ? "-" : "",
+                    static_cast<long long>(c.y < 0 ? -c.y : c.y), c.m, c.d);
+      text = buf;
+      if (t0.id == T_TIMESTAMP) {
+        const int64_t in_day = static_cast<int64_t>(static_cast<uint64_t>(a[0].i) - static_cast<uint64_t>(DaysToMs(days)));
+        std::snprintf(buf, sizeof(buf), " %02d:%02d:%02d.%03d", static_cast<int>(in_day / 3600000),
+                      static_cast<int>((in_day / 60000) % 60), static_cast<int>((in_day / 1000) % 60),
+                      static_cast<int>(in_day % 1000));
+        text += buf;
+      }
+    } else text = std::to_string(static_cast<long long>(a[0].i));
+    out->s = Substr(text, 1, a[1].i);
+    return;
+  }
   if (f == "castVARCHAR") { out->s = Substr(a[0].s, 1, a[1].i); return; }
   if (f == "char_length" || f == "length" || f == "lengthUtf8") {
     out->i = static_cast<int64_t>(GlyphStarts(a[0].s).size());

@@ -288,6 +288,33 @@ def case_string_positions(b):
     return schema, outs, "project"
 
 
+def case_number_to_text(b):
+    """castVARCHAR of integers / booleans / dates / timestamps: text written into a thread-private
+    scratch slot, consumed per lane (lengths, LIKE, compares, hashes) or projected (alone, inside a
+    concat rope, chosen by if/else)."""
+    S, I, L, B, TS, D64 = pa.string(), pa.int32(), pa.int64(), pa.bool_(), pa.timestamp("ms"), pa.date64()
+    schema = pa.schema([("i", I), ("l", L), ("p", B), ("t", TS), ("w", D64), ("s", S)])
+    i, l, pp, t, w, s = F(b, "i", I), F(b, "l", L), F(b, "p", B), F(b, "t", TS), F(b, "w", D64), F(b, "s", S)
+    fn = b.make_function
+    n = lambda v: b.make_literal(v, L)
+    txt = lambda x, k: fn("castVARCHAR", [x, n(k)], S)
+    outs = [
+        (txt(i, 20), S), (txt(l, 30), S), (txt(l, 5), S), (txt(l, 0), S), (txt(pp, 10), S), (txt(pp, 3), S),
+        (txt(t, 30), S), (txt(t, 16), S), (txt(w, 10), S), (txt(w, 40), S),
+        (fn("concat", [b.make_literal("id-", S), txt(l, 30), b.make_literal("/", S), txt(i, 4)], S), S),
+        (fn("concatOperator", [s, txt(pp, 10)], S), S),
+        (b.make_if(pp, txt(i, 12), fn("upper", [s], S), S), S),
+        (fn("upper", [txt(pp, 10)], S), S),
+        (fn("char_length", [txt(l, 30)], I), I), (fn("octet_length", [txt(t, 30)], I), I),
+        (fn("like", [txt(l, 30), b.make_literal("%12%", S)], B), B),
+        (fn("equal", [txt(i, 12), fn("castVARCHAR", [s, n(12)], S)], B), B),
+        (fn("hash32", [txt(l, 30)], I), I),
+        (fn("castBIGINT", [txt(l, 30)], L), L),   # text -> number again: the round trip is the identity
+        (fn("substr", [txt(t, 30), n(12), n(8)], S), S),
+    ]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -851,7 +878,7 @@ def all_project_cases():
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
-              case_string_positions]
+              case_string_positions, case_number_to_text]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

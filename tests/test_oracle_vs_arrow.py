@@ -762,3 +762,38 @@ def test_string_position_functions(oracle, gandiva):
             assert got[c][r] == w, (c, r, got[c][r], w, sv, uv, zv, kk)
     # Arrow's case-insensitive LIKE agrees as well
     assert got[20] == pc.match_like(batch.column(0), "%special%requests%", ignore_case=True).to_pylist()
+
+
+def test_number_to_text(oracle, gandiva):
+    """castVARCHAR(int / bool / date64 / timestamp, n) against Python's str() and datetime."""
+    import datetime
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_number_to_text(b)
+    batch = cases.random_batch(schema, N, seed=31, null_prob=0.1)
+    got = [g.to_pylist() for g in oracle.project([r for r, _ in outs], [t for _, t in outs], batch)]
+    i, l, p, t, w, s = (batch.column(c) for c in range(6))
+    il, ll, pl = i.to_pylist(), l.to_pylist(), p.to_pylist()
+    tl = t.cast(pa.int64()).to_pylist()
+    wl = w.cast(pa.int64()).to_pylist()
+    sl = s.to_pylist()
+    ep = datetime.datetime(1970, 1, 1)
+
+    def ts_text(ms):
+        dt = ep + datetime.timedelta(milliseconds=ms)
+        return dt.strftime("%Y-%m-%d %H:%M:%S.") + "%03d" % (dt.microsecond // 1000)
+
+    def d_text(ms):
+        return (ep + datetime.timedelta(milliseconds=ms)).strftime("%Y-%m-%d")
+    bt = lambda v: "true" if v else "false"
+    for r in range(N):
+        exp = [None if il[r] is None else str(il[r])[:20], None if ll[r] is None else str(ll[r])[:30],
+               None if ll[r] is None else str(ll[r])[:5], None if ll[r] is None else "",
+               None if pl[r] is None else bt(pl[r]), None if pl[r] is None else bt(pl[r])[:3],
+               None if tl[r] is None else ts_text(tl[r]), None if tl[r] is None else ts_text(tl[r])[:16],
+               None if wl[r] is None else d_text(wl[r]), None if wl[r] is None else d_text(wl[r]),
+               "id-" + ("" if ll[r] is None else str(ll[r])) + "/" + ("" if il[r] is None else str(il[r])[:4]),
+               None if (sl[r] is None or pl[r] is None) else sl[r] + bt(pl[r])]
+        for c, wv in enumerate(exp):
+            assert got[c][r] == wv, (c, r, got[c][r], wv)
+        if ll[r] is not None:
+            assert got[14][r] == len(str(ll[r])) and got[19][r] == ll[r]
