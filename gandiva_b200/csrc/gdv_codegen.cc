@@ -1500,25 +1500,47 @@ extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant_
         const i32 rel0 = (i32)(a0 - abs0), rel1 = (i32)(a1 - abs0);
         const i32 rlim = a_limit - abs0 > 0x7fffffffll ? 0x7fffffff : (i32)(a_limit - abs0);
         const i32 rc0 = 16 * (i32)lane;
-        for (i32 rb = 0; rb < rel1; rb += 512) {
-          const i32 rc = rb + rc0;  // this lane's chunk
-          u32 mk = 0u;
-          if (rb >= rel0 && rb + 528 <= rel1) {
+        for (i32 rb0 = 0; rb0 < rel1;) {
+          // digram masks of one or two 512-byte blocks; two loads are in flight per lane whenever
+          // two whole blocks lie inside the segment (one load per lane does not cover the HBM latency)
+          u32 mkA = 0u, mkB = 0u;
+          int nblk = 1;
+          if (rb0 >= rel0 && rb0 + 1040 <= rel1) {
+            nblk = 2;
+            const uint4 va = __ldcs(reinterpret_cast<const uint4*>(sp + rb0));
+            const uint4 vb = __ldcs(reinterpret_cast<const uint4*>(sp + rb0 + 512));
+            u32 na = __shfl_down_sync(GDV_FULL, va.x, 1);
+            u32 nb = __shfl_down_sync(GDV_FULL, vb.x, 1);
+            const u32 b_first = __shfl_sync(GDV_FULL, vb.x, 0);  // the word after block A's last chunk
+            if (lane == 31u) {
+              na = b_first;
+              nb = __ldg(reinterpret_cast<const u32*>(sp + rb0 + 528));
+            }
+            mkA = gdv_ks_mask(va, na);
+            mkB = gdv_ks_mask(vb, nb);
+          } else if (rb0 >= rel0 && rb0 + 528 <= rel1) {
             // interior block: every chunk and the word after the last one lie inside the segment
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + rb));
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + rb0));
             u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
-            if (lane == 31u) vn = __ldg(reinterpret_cast<const u32*>(sp + rb + 16));
-            mk = gdv_ks_mask(v, vn);
+            if (lane == 31u) vn = __ldg(reinterpret_cast<const u32*>(sp + rb0 + 16));
+            mkA = gdv_ks_mask(v, vn);
           } else {
+            const i32 rc = rb0 + rc0;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             const bool mine = rc < rel1 && rc + 16 > rel0;
             // one chunk past the segment is loaded too: it holds the second byte of a digram that
             // starts at the segment's last byte
-            if (rc + 16 > rel0 && rc < rel1 + 16 && rc < rlim) v = __ldcs(reinterpret_cast<const uint4*>(sp + rb));
+            if (rc + 16 > rel0 && rc < rel1 + 16 && rc < rlim) v = __ldcs(reinterpret_cast<const uint4*>(sp + rb0));
             u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
-            if (lane == 31u) vn = (mine && rc + 16 < rlim) ? __ldg(reinterpret_cast<const u32*>(sp + rb + 16)) : 0u;
-            if (mine) mk = gdv_ks_mask(v, vn);
+            if (lane == 31u) vn = (mine && rc + 16 < rlim) ? __ldg(reinterpret_cast<const u32*>(sp + rb0 + 16)) : 0u;
+            if (mine) mkA = gdv_ks_mask(v, vn);
           }
+          const i32 rb_first = rb0;
+          rb0 += 512 * nblk;
+          for (int half = 0; half < nblk; ++half) {
+          const i32 rb = rb_first + 512 * half;
+          const i32 rc = rb + rc0;  // this lane's chunk
+          u32 mk = half == 0 ? mkA : mkB;
           // digram hits that start inside the segment and verify as the key
           u32 vm = 0u;
           while (mk != 0u) {
@@ -1585,6 +1607,7 @@ extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant_
             cnt += (u32)__popc(km);
           }
           __syncwarp();  // wcand is rewritten by the next block
+          }
         }
       }
       if (pass == 1) break;
