@@ -2124,9 +2124,10 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   // Fixed-width filters are bandwidth-bound and want every warp slot of the SM: ask for
   // 2048 / BT resident CTAs, which caps the kernel at 32 registers per thread (what it needs).
   std::string bounds = sBT;
-  if (spec.kind == KernelKind::kFilter && n_varlen == 0 && BT >= 256 && 2048 % BT == 0 &&
-      !gen.uses_ctx())
-    bounds += ", " + std::to_string(2048 / BT);
+  bool light = spec.kind == KernelKind::kFilter && n_varlen == 0 && BT >= 256 && 2048 % BT == 0 &&
+               !gen.uses_ctx() && body.size() < 6000;
+  for (const auto& sl : slots) light = light && !sl.type.is_decimal();  // 128-bit math wants registers
+  if (light) bounds += ", " + std::to_string(2048 / BT);
   src += "extern \"C\" __global__ void __launch_bounds__(" + bounds + ") " + spec.name +
          "(const __grid_constant__ gdv_args A) {\n";
   src += "  const u32 lane = threadIdx.x & 31u;\n";
