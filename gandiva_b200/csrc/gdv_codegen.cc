@@ -309,8 +309,34 @@ class BodyGen {
     for (const Node* n : conj) {
       if (n->kind() != NodeKind::kFunction) continue;
       const auto& fn = *static_cast<const FunctionNode*>(n);
-      if (fn.name() != "like" || fn.children().size() < 2) continue;
-      if (fn.children()[1]->kind() != NodeKind::kLiteral) continue;
+      if (fn.children().size() < 2 || fn.children()[1]->kind() != NodeKind::kLiteral) continue;
+      if (fn.name() == "is_substr" || fn.name() == "starts_with" || fn.name() == "ends_with" ||
+          fn.name() == "equal" || fn.name() == "eq" || fn.name() == "same") {
+        // s contains / starts with / ends with / equals a literal: the literal itself is the key
+        // (comparisons see the view through its case map, like LIKE does)
+        const auto& lit = static_cast<const LiteralNode&>(*fn.children()[1]);
+        if (lit.is_null() || !lit.return_type().is_varlen()) continue;
+        const std::string& sg = lit.bytes();
+        int slot = -1;
+        unsigned xf = 0u;
+        if (sg.size() < 3 || sg.size() > 64 || !ViewChain(*fn.children()[0], &slot, &xf)) continue;
+        bool possible = true;
+        for (unsigned char c : sg)
+          if ((xf == 1u && c >= 'a' && c <= 'z') || (xf == 2u && c >= 'A' && c <= 'Z')) possible = false;
+        if (!possible) continue;
+        for (size_t i = 0; i + 1 < sg.size(); ++i) {
+          const double sc = DigramScore(static_cast<unsigned char>(sg[i]), static_cast<unsigned char>(sg[i + 1]), xf);
+          if (sc < best) {
+            best = sc;
+            plan->slot = slot;
+            plan->xf = xf;
+            plan->key = sg;
+            plan->digram = static_cast<int>(i);
+          }
+        }
+        continue;
+      }
+      if (fn.name() != "like") continue;
       const auto& pat = static_cast<const LiteralNode&>(*fn.children()[1]);
       const bool has_esc = fn.children().size() == 3;
       const char esc = has_esc ? static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0] : 0;

@@ -566,6 +566,15 @@ def test_key_scan_filter_conjunction_and_fallback(gandiva, oracle):
     assert "key-scan string Filter" in f_and.llvm_ir
     assert np.array_equal(f_and.evaluate(batch).to_array().to_numpy().astype(np.uint64),
                           oracle.filter_indices(both, batch, threads=4))
+    # other ways of saying "the column holds this literal": is_substr / starts_with / ends_with / equal
+    for fname, lit, view in (("is_substr", "park", None), ("starts_with", "SPECIAL", "upper"),
+                             ("ends_with", "fire", "btrim"), ("equal", "special requests", "lower")):
+        arg = s if view is None else b.make_function(view, [s], S)
+        c2 = b.make_and([b.make_function(fname, [arg, b.make_literal(lit, S)], B), b.make_function("isnotnull", [k], B)])
+        f2 = gandiva.make_filter(schema, b.make_condition(c2), cfg)
+        assert "key-scan string Filter" in f2.llvm_ir, fname
+        want2 = oracle.filter_indices(c2, batch, threads=4)
+        assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want2), fname
     f_or = gandiva.make_filter(schema, b.make_condition(either), cfg)
     assert "key-scan string Filter" not in f_or.llvm_ir   # an OR does not imply the key
     assert np.array_equal(f_or.evaluate(batch).to_array().to_numpy().astype(np.uint64),
