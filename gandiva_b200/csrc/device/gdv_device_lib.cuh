@@ -35,6 +35,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_VAR_CAPACITY 3     /* the caller's var_data buffer is too small */
 #define GDV_ERR_CAST_INT 4         /* castINT / castBIGINT of a string that is not an integer */
 #define GDV_ERR_CAST_DATE 5        /* castDATE / castTIMESTAMP of a string that is not a date / timestamp */
+#define GDV_ERR_SPLIT_INDEX 6      /* split_part with an index < 1 */
 struct gdv_ctx {
   int* err;
 };
@@ -1555,6 +1556,100 @@ GDV_DEV i64 gdv_parse_timestamp(gdv_ctx* c, const gdv_str& s, bool date_only) {
 GDV_DEV i64 castDATE_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_timestamp(c, s, true); }
 GDV_DEV i64 castTIMESTAMP_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_timestamp(c, s, false); }
 
+// ltrim / rtrim / btrim(s, chars): strips glyphs that occur in `chars` (both sides compared as
+// stored bytes: case maps of the operands are ignored for the set test only when they differ per
+// byte, i.e. bytes are read through gdv_ch).
+GDV_DEV bool gdv_glyph_in_set(const gdv_str& s, i32 at, i32 glen, const gdv_str& set) {
+  for (i32 j = 0; j < set.len;) {
+    const i32 sl = gdv_glyph_len(set.p[j]);
+    if (sl == glen && j + sl <= set.len) {
+      i32 t = 0;
+      while (t < glen && gdv_ch(s, at + t) == gdv_ch(set, j + t)) ++t;
+      if (t == glen) return true;
+    }
+    j += sl;
+  }
+  return false;
+}
+GDV_DEV gdv_str ltrim_utf8_utf8(gdv_str s, gdv_str chars) {
+  i32 at = 0;
+  while (at < s.len) {
+    i32 gl = gdv_glyph_len(s.p[at]);
+    if (at + gl > s.len) gl = s.len - at;
+    if (!gdv_glyph_in_set(s, at, gl, chars)) break;
+    at += gl;
+  }
+  s.p += at;
+  s.len -= at;
+  return s;
+}
+GDV_DEV gdv_str rtrim_utf8_utf8(gdv_str s, gdv_str chars) {
+  while (s.len > 0) {
+    i32 st = s.len - 1;  // start of the last glyph: skip back over continuation bytes
+    while (st > 0 && (s.p[st] & 0xC0u) == 0x80u && s.len - st < 4) --st;
+    i32 gl = s.len - st;
+    if (gdv_glyph_len(s.p[st]) != gl) {  // malformed tail: treat the last byte as a glyph of its own
+      st = s.len - 1;
+      gl = 1;
+    }
+    if (!gdv_glyph_in_set(s, st, gl, chars)) break;
+    s.len = st;
+  }
+  return s;
+}
+GDV_DEV gdv_str btrim_utf8_utf8(gdv_str s, gdv_str chars) { return rtrim_utf8_utf8(ltrim_utf8_utf8(s, chars), chars); }
+// split_part(s, delimiter, k): the k-th (1-based) piece of s split at every occurrence of the
+// delimiter (leftmost, non-overlapping); empty when there are fewer pieces; k < 1 raises; an empty
+// delimiter never matches (the whole string is piece 1).  A view.
+GDV_DEV gdv_str split_part_utf8_utf8_int32(gdv_ctx* c, gdv_str s, gdv_str delim, i32 k) {
+  gdv_str r = s;
+  r.len = 0;
+  if (k < 1) {
+    gdv_set_error(c, GDV_ERR_SPLIT_INDEX);
+    return r;
+  }
+  i32 piece = 1, start = 0, i = 0;
+  while (delim.len > 0 && i + delim.len <= s.len) {
+    i32 j = 0;
+    while (j < delim.len && gdv_ch(s, i + j) == gdv_ch(delim, j)) ++j;
+    if (j == delim.len) {
+      if (piece == k) {
+        r.p = s.p + start;
+        r.len = i - start;
+        return r;
+      }
+      ++piece;
+      i += delim.len;
+      start = i;
+    } else {
+      ++i;
+    }
+  }
+  if (piece == k) {
+    r.p = s.p + start;
+    r.len = s.len - start;
+  }
+  return r;
+}
+// crc32 (IEEE 802.3, reflected polynomial 0xEDB88320) of the bytes seen through the view.
+GDV_DEV i64 gdv_crc32(const gdv_str& s) {
+  u32 crc = 0xffffffffu;
+  for (i32 i = 0; i < s.len; ++i) {
+    crc ^= (u32)gdv_ch(s, i);
+    for (int b = 0; b < 8; ++b) crc = (crc >> 1) ^ (0xEDB88320u & (0u - (crc & 1u)));
+  }
+  return (i64)(crc ^ 0xffffffffu);
+}
+GDV_DEV i64 crc32_utf8(gdv_str s) { return gdv_crc32(s); }
+GDV_DEV i64 crc32_binary(gdv_str s) { return gdv_crc32(s); }
+GDV_DEV f64 degrees_float64(f64 a) { return a * 180.0 / 3.14159265358979323846; }
+GDV_DEV f64 radians_float64(f64 a) { return a * 3.14159265358979323846 / 180.0; }
+// datediff(a, b): whole days between the calendar days of a and b (a - b)
+GDV_DEV i32 datediff_timestamp_timestamp(i64 a, i64 b) {
+  return (i32)(gdv_floordiv(a, 86400000ll) - gdv_floordiv(b, 86400000ll));
+}
+GDV_DEV i32 datediff_date64_date64(i64 a, i64 b) { return datediff_timestamp_timestamp(a, b); }
+
 // ---- numbers and dates as text (castVARCHAR): bytes are produced into a thread-private slot -----
 GDV_DEV gdv_str gdv_scratch_str(u8* scr, i32 len, i64 maxlen) {
   gdv_str r;
@@ -1583,6 +1678,21 @@ GDV_DEV gdv_str castVARCHAR_int64_int64(i64 v, i64 maxlen, u8* scr) {
 GDV_DEV gdv_str castVARCHAR_int32_int64(i32 v, i64 maxlen, u8* scr) {
   return castVARCHAR_int64_int64((i64)v, maxlen, scr);
 }
+// to_hex(int): upper-case hexadecimal digits of the two's-complement bits, no leading zeros
+GDV_DEV gdv_str gdv_to_hex(u64 v, u8* scr) {
+  i32 n = 0;
+  u8 tmp[16];
+  do {
+    const u32 d = (u32)(v & 15ull);
+    tmp[n++] = (u8)(d < 10u ? (u32)'0' + d : (u32)'A' + d - 10u);
+    v >>= 4;
+  } while (v != 0ull);
+  i32 at = 0;
+  while (n > 0) scr[at++] = tmp[--n];
+  return gdv_scratch_str(scr, at, 64);
+}
+GDV_DEV gdv_str to_hex_int64(i64 v, u8* scr) { return gdv_to_hex((u64)v, scr); }
+GDV_DEV gdv_str to_hex_int32(i32 v, u8* scr) { return gdv_to_hex((u64)(u32)v, scr); }
 // "YYYY-MM-DD" (years outside 0..9999: a leading '-' and / or more digits)
 GDV_DEV i32 gdv_put_date(u8* scr, i64 days) {
   const gdv_ymd c = gdv_civil_from_days(days);

@@ -93,6 +93,8 @@ Registry::Registry() {
     Add("bitwise_not", {t}, t);
   }
   Add("sqrt", {F64}, F64);
+  Add("degrees", {F64}, F64);
+  Add("radians", {F64}, F64);
   for (const auto& t : {I32, I64}) {
     Add("div", {t, t}, t, NullMode::kIfNull, kCanFail);
     Add("pmod", {t, t}, t);
@@ -212,6 +214,8 @@ Registry::Registry() {
       Add(std::string("date_trunc_") + u, {t}, t);
     Add("last_day", {t}, D64);
   }
+  Add("datediff", {TS, TS}, I32);
+  Add("datediff", {D64, D64}, I32);
   Add("castTIME", {TS}, T32);
   Add("extractHour", {T32}, I64);
   Add("extractMinute", {T32}, I64);
@@ -283,6 +287,14 @@ Registry::Registry() {
   Add("locate", {S, S, I32}, I32);
   Add("strpos", {S, S}, I32);
   Add("byte_substr", {BIN, I32, I32}, BIN, NullMode::kIfNull, kStringView, {"bytesubstring"});
+  Add("ltrim", {S, S}, S, NullMode::kIfNull, kStringView);
+  Add("rtrim", {S, S}, S, NullMode::kIfNull, kStringView);
+  Add("btrim", {S, S}, S, NullMode::kIfNull, kStringView, {"trim"});
+  Add("split_part", {S, S, I32}, S, NullMode::kIfNull, kStringView | kCanFail);
+  Add("crc32", {S}, I64);
+  Add("crc32", {BIN}, I64);
+  Add("to_hex", {I64}, S, NullMode::kIfNull, kScratch);
+  Add("to_hex", {I32}, S, NullMode::kIfNull, kScratch);
   Add("castBIGINT", {S}, I64, NullMode::kIfNull, kCanFail);
   Add("castINT", {S}, I32, NullMode::kIfNull, kCanFail);
   Add("castDATE", {S}, D64, NullMode::kIfNull, kCanFail);

@@ -17,6 +17,7 @@ const char* ExecutionErrorMessage(int code) {
     case 3: return "var_data capacity of a utf8/binary output is too small";
     case 4: return "Failed to cast the string to an integer of the requested type";
     case 5: return "Failed to cast the string to a date / timestamp (not a valid date / timestamp)";
+    case 6: return "Index in split_part must be positive";
     default: return "execution error in device function";
   }
 }

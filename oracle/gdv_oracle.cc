@@ -1230,6 +1230,9 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     else out->i = (t / 1000) % 60;
     return;
   }
+  if (f == "datediff") { out->i = WrapSigned(FloorDiv(a[0].i, 86400000) - FloorDiv(a[1].i, 86400000), 32); return; }
+  if (f == "degrees") { out->d = a[0].d * 180.0 / 3.14159265358979323846; return; }
+  if (f == "radians") { out->d = a[0].d * 3.14159265358979323846 / 180.0; return; }
   if (f == "castTIME") { out->i = a[0].i - FloorDiv(a[0].i, 86400000) * 86400000; return; }
   if (f == "extractWeek" || f == "extractDecade" || f == "extractCentury" || f == "extractMillennium" ||
       f.rfind("date_trunc_", 0) == 0 || f == "last_day") {
@@ -1349,6 +1352,67 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "is_substr") { out->b = a[0].s.find(a[1].s) != std::string::npos; return; }
+  if ((f == "ltrim" || f == "rtrim" || f == "btrim" || f == "trim") && na == 2) {
+    // glyph-wise: strip glyphs of a[0] that are one of the glyphs of a[1]
+    const std::vector<size_t> st = GlyphStarts(a[0].s), cs = GlyphStarts(a[1].s);
+    auto glyph = [](const std::string& str, const std::vector<size_t>& starts, size_t k) {
+      const size_t b = starts[k], e = k + 1 < starts.size() ? starts[k + 1] : str.size();
+      return str.substr(b, e - b);
+    };
+    auto in_set = [&](const std::string& g) {
+      for (size_t k = 0; k < cs.size(); ++k)
+        if (glyph(a[1].s, cs, k) == g) return true;
+      return false;
+    };
+    size_t lo = 0, hi = st.size();
+    if (f != "rtrim") while (lo < hi && in_set(glyph(a[0].s, st, lo))) ++lo;
+    if (f != "ltrim") while (hi > lo && in_set(glyph(a[0].s, st, hi - 1))) --hi;
+    const size_t b = lo < st.size() ? st[lo] : a[0].s.size();
+    const size_t e = hi < st.size() ? st[hi] : a[0].s.size();
+    out->s = a[0].s.substr(b, e - b);
+    return;
+  }
+  if (f == "split_part") {
+    if (a[2].i < 1) { cx.error = 6; return; }
+    std::vector<std::string> pieces;
+    if (a[1].s.empty()) pieces.push_back(a[0].s);
+    else {
+      size_t from = 0;
+      while (true) {
+        const size_t hit = a[0].s.find(a[1].s, from);
+        if (hit == std::string::npos) { pieces.push_back(a[0].s.substr(from)); break; }
+        pieces.push_back(a[0].s.substr(from, hit - from));
+        from = hit + a[1].s.size();
+      }
+    }
+    out->s = static_cast<size_t>(a[2].i) <= pieces.size() ? pieces[static_cast<size_t>(a[2].i) - 1] : std::string();
+    return;
+  }
+  if (f == "crc32") {
+    // table-driven here (the kernel is bitwise): same polynomial, different code
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+      for (uint32_t n = 0; n < 256; ++n) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        table[n] = c;
+      }
+      init = true;
+    }
+    uint32_t crc = 0xffffffffu;
+    for (unsigned char ch : a[0].s) crc = table[(crc ^ ch) & 0xffu] ^ (crc >> 8);
+    out->i = static_cast<int64_t>(crc ^ 0xffffffffu);
+    return;
+  }
+  if (f == "to_hex") {
+    char buf[32];
+    const unsigned long long v = t0.id == T_INT32 ? static_cast<unsigned long long>(static_cast<uint32_t>(a[0].i))
+                                                  : static_cast<unsigned long long>(a[0].i);
+    std::snprintf(buf, sizeof(buf), "%llX", v);
+    out->s = buf;
+    return;
+  }
   if (f == "ltrim" || f == "rtrim" || f == "btrim" || f == "trim") {
     size_t b = 0, e = a[0].s.size();
     if (f != "rtrim") while (b < e && a[0].s[b] == ' ') ++b;

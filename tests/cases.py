@@ -315,6 +315,31 @@ def case_number_to_text(b):
     return schema, outs, "project"
 
 
+def case_string_misc(b):
+    """trim with a character set, split_part, crc32, to_hex, degrees / radians, datediff."""
+    S, BIN, I, L, B, D, TS, D64 = (pa.string(), pa.binary(), pa.int32(), pa.int64(), pa.bool_(), pa.float64(),
+                                   pa.timestamp("ms"), pa.date64())
+    schema = pa.schema([("s", S), ("u", S), ("z", BIN), ("i", I), ("l", L), ("d", D), ("t", TS), ("v", TS), ("w", D64)])
+    s, u, z, i, l, d, t, v, w = (F(b, n, ty) for n, ty in zip("suzildtvw", (S, S, BIN, I, L, D, TS, TS, D64)))
+    fn = b.make_function
+    lit = b.make_literal
+    olen = lambda x: fn("octet_length", [x], I)
+    kk = fn("add", [fn("castINT", [fn("pmod", [l, lit(4, L)], L)], I), lit(1, I)], I)   # 1..4
+    outs = [
+        (fn("ltrim", [s, lit("sp ", S)], S), S), (fn("rtrim", [s, lit("se ", S)], S), S),
+        (fn("btrim", [s, lit(" ü日", S)], S), S), (olen(fn("trim", [s, u], S)), I),
+        (fn("split_part", [s, lit(" ", S), lit(1, I)], S), S), (fn("split_part", [s, lit(" ", S), lit(3, I)], S), S),
+        (olen(fn("split_part", [s, lit("e", S), kk], S)), I), (fn("split_part", [s, lit("", S), lit(1, I)], S), S),
+        (fn("upper", [fn("split_part", [s, lit("re", S), lit(2, I)], S)], S), S),
+        (fn("crc32", [s], L), L), (fn("crc32", [z], L), L), (fn("crc32", [fn("upper", [s], S)], L), L),
+        (fn("to_hex", [l], S), S), (fn("to_hex", [i], S), S),
+        (fn("concat", [lit("0x", S), fn("to_hex", [i], S)], S), S),
+        (fn("degrees", [d], D), D), (fn("radians", [d], D), D),
+        (fn("datediff", [t, v], I), I), (fn("datediff", [w, fn("castDATE", [t], D64)], I), I),
+    ]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -878,7 +903,7 @@ def all_project_cases():
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
-              case_string_positions, case_number_to_text]
+              case_string_positions, case_number_to_text, case_string_misc]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

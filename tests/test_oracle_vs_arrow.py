@@ -797,3 +797,40 @@ def test_number_to_text(oracle, gandiva):
             assert got[c][r] == wv, (c, r, got[c][r], wv)
         if ll[r] is not None:
             assert got[14][r] == len(str(ll[r])) and got[19][r] == ll[r]
+
+
+def test_string_misc(oracle, gandiva):
+    """trim(chars) / split_part / crc32 / to_hex / degrees / radians / datediff against Python's
+    str.strip, str.split, zlib.crc32, format(x, "X"), math and integer day arithmetic."""
+    import math
+    import zlib
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_string_misc(b)
+    batch = cases.random_batch(schema, N, seed=41, null_prob=0.1)
+    got = [g.to_pylist() for g in oracle.project([r for r, _ in outs], [t for _, t in outs], batch)]
+    s, u, z, i, l, d = (batch.column(c).to_pylist() for c in range(6))
+    t, v, w = (batch.column(c).cast(pa.int64()).to_pylist() for c in (6, 7, 8))
+
+    def piece(x, delim, k):
+        parts = x.split(delim) if delim else [x]
+        return parts[k - 1] if k <= len(parts) else ""
+    up = lambda x: "".join(c.upper() if c.isascii() else c for c in x)
+    for r in range(N):
+        sv, uv, zv = s[r], u[r], z[r]
+        kk = None if l[r] is None else (l[r] % 4) + 1
+        exp = [None if sv is None else sv.lstrip("sp "), None if sv is None else sv.rstrip("se "),
+               None if sv is None else sv.strip(" ü日"),
+               None if None in (sv, uv) else len(sv.strip(uv).encode()) if uv else len(sv.encode()),
+               None if sv is None else piece(sv, " ", 1), None if sv is None else piece(sv, " ", 3),
+               None if None in (sv, kk) else len(piece(sv, "e", kk).encode()), None if sv is None else sv,
+               None if sv is None else up(piece(sv, "re", 2)),
+               None if sv is None else zlib.crc32(sv.encode()), None if zv is None else zlib.crc32(zv),
+               None if sv is None else zlib.crc32(up(sv).encode()),
+               None if l[r] is None else format(l[r] & (2**64 - 1), "X"),
+               None if i[r] is None else format(i[r] & (2**32 - 1), "X"),
+               "0x" + ("" if i[r] is None else format(i[r] & (2**32 - 1), "X")),
+               None if d[r] is None else d[r] * 180.0 / math.pi, None if d[r] is None else d[r] * math.pi / 180.0,
+               None if None in (t[r], v[r]) else t[r] // 86400000 - v[r] // 86400000,
+               None if None in (w[r], t[r]) else w[r] // 86400000 - t[r] // 86400000]
+        for c, wv in enumerate(exp):
+            assert got[c][r] == wv, (c, r, got[c][r], wv, sv, uv)

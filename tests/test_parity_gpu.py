@@ -662,3 +662,19 @@ def test_cast_string_to_date_and_timestamp(gandiva, oracle):
             p.evaluate(one)
         with pytest.raises(Exception, match="Failed to cast the string to a date"):
             oracle.project([root_t], [TS], one)
+
+
+def test_split_part_index_must_be_positive(gandiva, oracle):
+    b = gandiva.TreeExprBuilder()
+    S, I = pa.string(), pa.int32()
+    schema = pa.schema([("s", S), ("k", I)])
+    root = b.make_function("split_part", [cases.F(b, "s", S), b.make_literal("-", S), cases.F(b, "k", I)], S)
+    p = gandiva.make_projector(schema, [b.make_expression(root, pa.field("o", S))], None)
+    ok = pa.RecordBatch.from_arrays([pa.array(["a-b-c", "x", None, "p-q"], S), pa.array([2, 1, 0, 5], I)], schema=schema)
+    got, = p.evaluate(ok)   # the row with k = 0 has a NULL string: not evaluated, no error
+    assert got.to_pylist() == ["b", "x", None, ""]
+    bad = pa.RecordBatch.from_arrays([pa.array(["a-b-c", "x"], S), pa.array([2, 0], I)], schema=schema)
+    with pytest.raises(gandiva.GandivaError, match="ExecutionError: Index in split_part must be positive"):
+        p.evaluate(bad)
+    with pytest.raises(Exception, match="split_part"):
+        oracle.project([root], [S], bad)
