@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=0, help="cpu_baseline sample rows (0 = auto)")
     ap.add_argument("--rows-per-thread", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--filter-loader", type=int, default=0,
+                    help="Configuration.loader of the Q6 Filter: 0 = fused filter kernel, 3 = two-pass "
+                         "(projector -> truth bitmap, gdv_bitmap_to_sel -> SelectionVector)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
@@ -209,7 +212,8 @@ def main():
     use_push = world > 1 and not args.no_gather and args.gather == "push"
     sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if use_push else 0)
     cfg = gandiva.Configuration(device=local_rank, rows_per_thread=args.rows_per_thread,
-                                block_threads=args.block_threads, sm_reserve=sm_reserve)
+                                block_threads=args.block_threads, sm_reserve=sm_reserve,
+                                loader=args.filter_loader)
     filt, _ = q6_filter(gandiva, cases, cfg)
 
     # ---- inputs resident in HBM (generated on device; same stream as oracle/lineitem.h) -----

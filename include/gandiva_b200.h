@@ -105,7 +105,10 @@ typedef struct gdv_config {
   int32_t device;       /* CUDA device ordinal (default 0) */
   int32_t rows_per_thread; /* 0 = engine picks; otherwise unroll factor override */
   int32_t block_threads;   /* 0 = engine picks (256) */
-  int32_t loader;          /* 0 = engine picks; 1 = direct coalesced LDG; 2 = TMA bulk -> shared */
+  int32_t loader;          /* Projector: 0 = engine picks; 1 = direct coalesced LDG; 2 = TMA bulk -> shared.
+                              Filter: 3 = two-pass on device batches (condition -> truth bitmap by the
+                              projector kernel, bitmap -> SelectionVector by gdv_bitmap_to_sel); opt-in
+                              until measured against the fused filter kernel */
   int32_t sm_reserve;      /* SMs left without CTAs of the persistent kernels, so that a
                               concurrent stream (e.g. NCCL's gather of the previous batch's
                               SelectionVector) can run; default 0 */

@@ -678,3 +678,41 @@ def test_split_part_index_must_be_positive(gandiva, oracle):
         p.evaluate(bad)
     with pytest.raises(Exception, match="split_part"):
         oracle.project([root], [S], bad)
+
+
+@pytest.mark.parametrize("nullp", [0, 15])
+def test_two_pass_filter(nullp, gandiva, oracle):
+    """Configuration(loader=3) on device batches: condition -> truth bitmap with the projector
+    kernel, bitmap -> ordered SelectionVector with gdv_bitmap_to_sel.  Same indices as the oracle
+    for every index width, with a row base and a bounded vector, at tile and word boundaries."""
+    b = gandiva.TreeExprBuilder()
+    cond = cases.q6_condition(b)
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cond), gandiva.Configuration(loader=3))
+    st = devmem.stream()
+    for n in (1, 31, 32, 33, 4095, 131072, 131073, 300_011):
+        ship, disc, qty = devmem.DevBuf(n, np.int32), devmem.DevBuf(n, np.float64), devmem.DevBuf(n, np.float64)
+        vl = [devmem.DevBuf((n + 31) // 32, np.int32) if nullp else None for _ in range(3)]
+        for kind, t, v in ((0, ship, vl[0]), (1, disc, vl[1]), (2, qty, vl[2])):
+            gandiva.generate_lineitem(0, kind, 42, 0, n, t.ptr, v.ptr if v is not None else 0, nullp, st)
+        cols = [(v.ptr if v is not None else 0, t.ptr, 0, 0) for t, v in zip((ship, disc, qty), vl)]
+        batch = cases.q6_batch(n, seed=42, null_permille=nullp)
+        want = oracle.filter_indices(cond, batch, threads=4)
+        modes = [("UINT32", np.uint32, 0), ("UINT64", np.uint64, 7_000_000_000)]
+        if n <= 65536:
+            modes.append(("UINT16", np.uint16, 0))
+        for mode, npdt, base in modes:
+            out = devmem.DevBuf(n + 8, npdt, fill=0)
+            cnt = devmem.DevBuf(1, np.int64, fill=0)
+            f.evaluate_device(n, cols, out.ptr, n, mode, st, cnt.ptr, index_base=base)
+            count = f.sync(st)
+            assert count == len(want) == int(cnt.numpy()[0]), (n, mode)
+            assert np.array_equal(out.numpy()[:count].astype(np.uint64), want + base), (n, mode)
+        if n > 1000:
+            cap = max(1, len(want) // 2)
+            out = devmem.DevBuf(cap + 16, np.int64, fill=-1)
+            cnt = devmem.DevBuf(1, np.int64, fill=0)
+            f.evaluate_device(n, cols, out.ptr, cap, "UINT64|BOUNDED", st, cnt.ptr)
+            assert f.sync(st) == len(want)
+            got = out.numpy()
+            assert np.array_equal(got[:cap].astype(np.uint64), want[:cap]) and (got[cap:] == -1).all()
+    assert "gdv_project_expr_" in f.kernel_info["name"]
