@@ -233,11 +233,31 @@ CUresult cuMemAlloc_v2(CUdeviceptr* p, size_t n) {
   *p = static_cast<CUdeviceptr>(user);
   EMU_OK;
 }
+// Guard bands: the kPad bytes on either side of every allocation keep their 0xCD fill unless a
+// kernel (or a copy) wrote out of bounds.  Checked after every launch and at free.
+static bool GuardsIntact(const char* when) {
+  bool ok = true;
+  for (const auto& kv : g_allocs) {
+    const unsigned char* lo = reinterpret_cast<const unsigned char*>(kv.first - kPad);
+    const unsigned char* hi = reinterpret_cast<const unsigned char*>(kv.first + kv.second);
+    for (size_t i = 0; i < kPad; ++i) {
+      if (lo[i] != 0xCD || hi[i] != 0xCD) {
+        std::fprintf(stderr, "gdv_emu: out-of-bounds WRITE detected %s: allocation of %zu bytes at %p, guard byte %s%zu\n",
+                     when, kv.second, reinterpret_cast<void*>(kv.first), lo[i] != 0xCD ? "-" : "+",
+                     lo[i] != 0xCD ? kPad - i : i);
+        ok = false;
+        break;
+      }
+    }
+  }
+  return ok;
+}
 CUresult cuMemFree_v2(CUdeviceptr p) {
   std::lock_guard<std::recursive_mutex> lock(g_mu);
   if (p == 0) EMU_OK;
   auto it = g_allocs.find(static_cast<uintptr_t>(p));
   if (it == g_allocs.end()) return CUDA_ERROR_INVALID_VALUE;
+  if (!GuardsIntact("at cuMemFree")) return CUDA_ERROR_ILLEGAL_ADDRESS;
   g_allocs.erase(it);
   std::free(reinterpret_cast<void*>(static_cast<uintptr_t>(p) - kPad));
   EMU_OK;
@@ -364,6 +384,7 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
         ok = RunCta(fn, gdv_emu_uint3{x, y, z}, bdim, gdim, dyn, params);
       }
   std::free(dyn);
+  if (ok && !GuardsIntact(("after kernel " + fn->name).c_str())) return CUDA_ERROR_ILLEGAL_ADDRESS;
   return ok ? CUDA_SUCCESS : CUDA_ERROR_LAUNCH_TIMEOUT;
 }
 CUresult cuGetErrorString(CUresult r, const char** s) {
