@@ -51,7 +51,7 @@ GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
 #define GDV_XF_CASE 3u
 #define GDV_XF_ASCII 0x100u
 #define GDV_XF_LOCAL 0x200u  /* bytes live in the producing thread's scratch slot: only that thread may read them */
-#define GDV_SCRATCH_SLOT 32  /* bytes per (row, call site) of a function that writes its result as text */
+#define GDV_SCRATCH_SLOT 64  /* bytes per (row, call site) of a function that writes its result as text */
 struct gdv_str {
   const u8* p;
   i32 len;
@@ -1730,6 +1730,145 @@ GDV_DEV gdv_str castVARCHAR_boolean_int64(bool v, i64 maxlen) {
   r.xf = GDV_XF_ASCII;
   return r;
 }
+
+// ---- message digests as lower-case hex text: hashMD5 / hashSHA1 / hashSHA256 (RFC 1321, FIPS 180-4) --
+// Byte `pos` of the padded message: the text, 0x80, zeros, then the bit length in the last 8 bytes
+// (little endian for MD5, big endian for SHA).
+GDV_DEV u32 gdv_md_byte(const gdv_str& s, i64 pos, i64 padded, bool big_endian_len) {
+  if (pos < (i64)s.len) return (u32)gdv_ch(s, (i32)pos);
+  if (pos == (i64)s.len) return 0x80u;
+  if (pos < padded - 8) return 0u;
+  const u64 bits = (u64)s.len * 8ull;
+  const int k = (int)(pos - (padded - 8));  // 0..7
+  return (u32)((bits >> (big_endian_len ? 8 * (7 - k) : 8 * k)) & 0xffull);
+}
+GDV_DEV i32 gdv_put_hex32(u8* scr, i32 at, u32 v, bool big_endian) {
+  for (int b = 0; b < 4; ++b) {
+    const u32 byte = big_endian ? (v >> (24 - 8 * b)) & 0xffu : (v >> (8 * b)) & 0xffu;
+    const u32 hi = byte >> 4, lo = byte & 15u;
+    scr[at++] = (u8)(hi < 10u ? (u32)'0' + hi : (u32)'a' + hi - 10u);
+    scr[at++] = (u8)(lo < 10u ? (u32)'0' + lo : (u32)'a' + lo - 10u);
+  }
+  return at;
+}
+__device__ const u32 gdv_sha256_k[64] = {
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+GDV_DEV u32 gdv_rotr32(u32 v, int d) { return (v >> d) | (v << (32 - d)); }
+GDV_DEV gdv_str gdv_sha256_hex(const gdv_str& s, u8* scr) {
+  u32 h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+  const i64 padded = (((i64)s.len + 8) / 64 + 1) * 64;
+  for (i64 blk = 0; blk < padded; blk += 64) {
+    u32 w[16];
+    for (int t = 0; t < 16; ++t) {
+      u32 x = 0u;
+      for (int b = 0; b < 4; ++b) x = (x << 8) | gdv_md_byte(s, blk + 4 * t + b, padded, true);
+      w[t] = x;
+    }
+    u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int t = 0; t < 64; ++t) {
+      if (t >= 16) {
+        const u32 w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+        const u32 s0 = gdv_rotr32(w15, 7) ^ gdv_rotr32(w15, 18) ^ (w15 >> 3);
+        const u32 s1 = gdv_rotr32(w2, 17) ^ gdv_rotr32(w2, 19) ^ (w2 >> 10);
+        w[t & 15] = w[t & 15] + s0 + w[(t + 9) & 15] + s1;
+      }
+      const u32 S1 = gdv_rotr32(e, 6) ^ gdv_rotr32(e, 11) ^ gdv_rotr32(e, 25);
+      const u32 ch = (e & f) ^ (~e & g);
+      const u32 t1 = hh + S1 + ch + gdv_sha256_k[t] + w[t & 15];
+      const u32 S0 = gdv_rotr32(a, 2) ^ gdv_rotr32(a, 13) ^ gdv_rotr32(a, 22);
+      const u32 mj = (a & b) ^ (a & c) ^ (b & c);
+      const u32 t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  i32 at = 0;
+  for (int k = 0; k < 8; ++k) at = gdv_put_hex32(scr, at, h[k], true);
+  return gdv_scratch_str(scr, at, 64);
+}
+GDV_DEV gdv_str gdv_sha1_hex(const gdv_str& s, u8* scr) {
+  u32 h[5] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u, 0xc3d2e1f0u};
+  const i64 padded = (((i64)s.len + 8) / 64 + 1) * 64;
+  for (i64 blk = 0; blk < padded; blk += 64) {
+    u32 w[16];
+    for (int t = 0; t < 16; ++t) {
+      u32 x = 0u;
+      for (int b = 0; b < 4; ++b) x = (x << 8) | gdv_md_byte(s, blk + 4 * t + b, padded, true);
+      w[t] = x;
+    }
+    u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+    for (int t = 0; t < 80; ++t) {
+      if (t >= 16) {
+        const u32 x = w[(t + 13) & 15] ^ w[(t + 8) & 15] ^ w[(t + 2) & 15] ^ w[t & 15];
+        w[t & 15] = (x << 1) | (x >> 31);
+      }
+      u32 f, k;
+      if (t < 20) { f = (b & c) | (~b & d); k = 0x5a827999u; }
+      else if (t < 40) { f = b ^ c ^ d; k = 0x6ed9eba1u; }
+      else if (t < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8f1bbcdcu; }
+      else { f = b ^ c ^ d; k = 0xca62c1d6u; }
+      const u32 tmp = ((a << 5) | (a >> 27)) + f + e + k + w[t & 15];
+      e = d; d = c; c = (b << 30) | (b >> 2); b = a; a = tmp;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+  }
+  i32 at = 0;
+  for (int k = 0; k < 5; ++k) at = gdv_put_hex32(scr, at, h[k], true);
+  return gdv_scratch_str(scr, at, 64);
+}
+__device__ const u8 gdv_md5_s[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9,
+                                     14, 20, 5, 9, 14, 20, 5, 9, 14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                                     4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+__device__ const u32 gdv_md5_k[64] = {
+    0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u,
+    0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u,
+    0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau, 0xd62f105du, 0x02441453u, 0xd8a1e681u, 0xe7d3fbc8u,
+    0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au,
+    0xfffa3942u, 0x8771f681u, 0x6d9d6122u, 0xfde5380cu, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u,
+    0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u,
+    0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u,
+    0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u};
+GDV_DEV gdv_str gdv_md5_hex(const gdv_str& s, u8* scr) {
+  u32 h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+  const i64 padded = (((i64)s.len + 8) / 64 + 1) * 64;
+  for (i64 blk = 0; blk < padded; blk += 64) {
+    u32 m[16];
+    for (int t = 0; t < 16; ++t) {
+      u32 x = 0u;
+      for (int b = 3; b >= 0; --b) x = (x << 8) | gdv_md_byte(s, blk + 4 * t + b, padded, false);
+      m[t] = x;
+    }
+    u32 a = h[0], b = h[1], c = h[2], d = h[3];
+    for (int t = 0; t < 64; ++t) {
+      u32 f;
+      int g;
+      if (t < 16) { f = (b & c) | (~b & d); g = t; }
+      else if (t < 32) { f = (d & b) | (~d & c); g = (5 * t + 1) & 15; }
+      else if (t < 48) { f = b ^ c ^ d; g = (3 * t + 5) & 15; }
+      else { f = c ^ (b | ~d); g = (7 * t) & 15; }
+      const u32 x = a + f + gdv_md5_k[t] + m[g];
+      const int r = (int)gdv_md5_s[t];
+      a = d; d = c; c = b; b = b + ((x << r) | (x >> (32 - r)));
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+  }
+  i32 at = 0;
+  for (int k = 0; k < 4; ++k) at = gdv_put_hex32(scr, at, h[k], false);
+  return gdv_scratch_str(scr, at, 64);
+}
+GDV_DEV gdv_str hashSHA256_utf8(gdv_str s, u8* scr) { return gdv_sha256_hex(s, scr); }
+GDV_DEV gdv_str hashSHA256_binary(gdv_str s, u8* scr) { return gdv_sha256_hex(s, scr); }
+GDV_DEV gdv_str hashSHA1_utf8(gdv_str s, u8* scr) { return gdv_sha1_hex(s, scr); }
+GDV_DEV gdv_str hashSHA1_binary(gdv_str s, u8* scr) { return gdv_sha1_hex(s, scr); }
+GDV_DEV gdv_str hashMD5_utf8(gdv_str s, u8* scr) { return gdv_md5_hex(s, scr); }
+GDV_DEV gdv_str hashMD5_binary(gdv_str s, u8* scr) { return gdv_md5_hex(s, scr); }
 
 // SQL LIKE over a pattern tokenised at Make(): each token is (kind << 8) | byte with
 // kind 0 = literal byte, 1 = '_' (exactly one glyph), 2 = '%' (any run of glyphs).

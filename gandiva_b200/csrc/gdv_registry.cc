@@ -291,6 +291,11 @@ Registry::Registry() {
   Add("rtrim", {S, S}, S, NullMode::kIfNull, kStringView);
   Add("btrim", {S, S}, S, NullMode::kIfNull, kStringView, {"trim"});
   Add("split_part", {S, S, I32}, S, NullMode::kIfNull, kStringView | kCanFail);
+  for (const auto& t : {S, BIN}) {   // digests as lower-case hex text
+    Add("hashSHA256", {t}, S, NullMode::kIfNull, kScratch, {"sha256"});
+    Add("hashSHA1", {t}, S, NullMode::kIfNull, kScratch, {"sha1"});
+    Add("hashMD5", {t}, S, NullMode::kIfNull, kScratch, {"md5"});
+  }
   Add("crc32", {S}, I64);
   Add("crc32", {BIN}, I64);
   Add("to_hex", {I64}, S, NullMode::kIfNull, kScratch);

@@ -786,6 +786,121 @@ bool RelopNum(const std::string& name, T a, T b) {
   return a >= b;
 }
 
+// ---- message digests (RFC 1321 MD5, FIPS 180-4 SHA-1 / SHA-256): whole padded message in a
+// vector, full message schedules -- written for clarity, unlike the kernel's rolling windows.
+std::vector<uint8_t> PadMessage(const std::string& m, bool big_endian_len) {
+  std::vector<uint8_t> p(m.begin(), m.end());
+  p.push_back(0x80);
+  while (p.size() % 64 != 56) p.push_back(0);
+  const uint64_t bits = static_cast<uint64_t>(m.size()) * 8;
+  for (int k = 0; k < 8; ++k)
+    p.push_back(static_cast<uint8_t>(bits >> (big_endian_len ? 8 * (7 - k) : 8 * k)));
+  return p;
+}
+uint32_t Rol(uint32_t v, int d) { return (v << d) | (v >> (32 - d)); }
+uint32_t Ror(uint32_t v, int d) { return (v >> d) | (v << (32 - d)); }
+std::string HexOfWords(const uint32_t* w, int n, bool big_endian) {
+  static const char* digits = "0123456789abcdef";
+  std::string out;
+  for (int k = 0; k < n; ++k)
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t byte = big_endian ? (w[k] >> (24 - 8 * b)) & 0xff : (w[k] >> (8 * b)) & 0xff;
+      out.push_back(digits[byte >> 4]);
+      out.push_back(digits[byte & 15]);
+    }
+  return out;
+}
+std::string Sha256Hex(const std::string& m) {
+  uint32_t K[64];
+  {  // K[i] = first 32 bits of the fractional part of the cube root of the i-th prime
+    int count = 0;
+    for (int p = 2; count < 64; ++p) {
+      bool prime = true;
+      for (int q = 2; q * q <= p; ++q) prime = prime && p % q != 0;
+      if (!prime) continue;
+      const long double r = cbrtl(static_cast<long double>(p));
+      K[count++] = static_cast<uint32_t>((r - floorl(r)) * 4294967296.0L);
+    }
+  }
+  uint32_t H[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  const std::vector<uint8_t> p = PadMessage(m, true);
+  for (size_t off = 0; off < p.size(); off += 64) {
+    uint32_t W[64];
+    for (int t = 0; t < 16; ++t)
+      W[t] = (uint32_t(p[off + 4 * t]) << 24) | (uint32_t(p[off + 4 * t + 1]) << 16) |
+             (uint32_t(p[off + 4 * t + 2]) << 8) | uint32_t(p[off + 4 * t + 3]);
+    for (int t = 16; t < 64; ++t) {
+      const uint32_t s0 = Ror(W[t - 15], 7) ^ Ror(W[t - 15], 18) ^ (W[t - 15] >> 3);
+      const uint32_t s1 = Ror(W[t - 2], 17) ^ Ror(W[t - 2], 19) ^ (W[t - 2] >> 10);
+      W[t] = W[t - 16] + s0 + W[t - 7] + s1;
+    }
+    uint32_t v[8];
+    std::memcpy(v, H, sizeof(v));
+    for (int t = 0; t < 64; ++t) {
+      const uint32_t t1 = v[7] + (Ror(v[4], 6) ^ Ror(v[4], 11) ^ Ror(v[4], 25)) + ((v[4] & v[5]) ^ (~v[4] & v[6])) + K[t] + W[t];
+      const uint32_t t2 = (Ror(v[0], 2) ^ Ror(v[0], 13) ^ Ror(v[0], 22)) + ((v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]));
+      for (int k = 7; k > 0; --k) v[k] = v[k - 1];
+      v[4] += t1;
+      v[0] = t1 + t2;
+    }
+    for (int k = 0; k < 8; ++k) H[k] += v[k];
+  }
+  return HexOfWords(H, 8, true);
+}
+std::string Sha1Hex(const std::string& m) {
+  uint32_t H[5] = {0x67452301, 0xefcdab89, 0x98badcfe, 0x10325476, 0xc3d2e1f0};
+  const std::vector<uint8_t> p = PadMessage(m, true);
+  for (size_t off = 0; off < p.size(); off += 64) {
+    uint32_t W[80];
+    for (int t = 0; t < 16; ++t)
+      W[t] = (uint32_t(p[off + 4 * t]) << 24) | (uint32_t(p[off + 4 * t + 1]) << 16) |
+             (uint32_t(p[off + 4 * t + 2]) << 8) | uint32_t(p[off + 4 * t + 3]);
+    for (int t = 16; t < 80; ++t) W[t] = Rol(W[t - 3] ^ W[t - 8] ^ W[t - 14] ^ W[t - 16], 1);
+    uint32_t a = H[0], b = H[1], c = H[2], d = H[3], e = H[4];
+    for (int t = 0; t < 80; ++t) {
+      uint32_t f, k;
+      if (t < 20) { f = (b & c) | (~b & d); k = 0x5a827999; }
+      else if (t < 40) { f = b ^ c ^ d; k = 0x6ed9eba1; }
+      else if (t < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8f1bbcdc; }
+      else { f = b ^ c ^ d; k = 0xca62c1d6; }
+      const uint32_t tmp = Rol(a, 5) + f + e + k + W[t];
+      e = d; d = c; c = Rol(b, 30); b = a; a = tmp;
+    }
+    H[0] += a; H[1] += b; H[2] += c; H[3] += d; H[4] += e;
+  }
+  return HexOfWords(H, 5, true);
+}
+std::string Md5Hex(const std::string& m) {
+  uint32_t K[64];
+  for (int i = 0; i < 64; ++i)  // K[i] = floor(2^32 * |sin(i + 1)|)
+    K[i] = static_cast<uint32_t>(floorl(fabsl(sinl(static_cast<long double>(i + 1))) * 4294967296.0L));
+  static const int S[4][4] = {{7, 12, 17, 22}, {5, 9, 14, 20}, {4, 11, 16, 23}, {6, 10, 15, 21}};
+  uint32_t H[4] = {0x67452301, 0xefcdab89, 0x98badcfe, 0x10325476};
+  const std::vector<uint8_t> p = PadMessage(m, false);
+  for (size_t off = 0; off < p.size(); off += 64) {
+    uint32_t M[16];
+    for (int t = 0; t < 16; ++t)
+      M[t] = uint32_t(p[off + 4 * t]) | (uint32_t(p[off + 4 * t + 1]) << 8) | (uint32_t(p[off + 4 * t + 2]) << 16) |
+             (uint32_t(p[off + 4 * t + 3]) << 24);
+    uint32_t a = H[0], b = H[1], c = H[2], d = H[3];
+    for (int i = 0; i < 64; ++i) {
+      uint32_t f;
+      int g;
+      switch (i / 16) {
+        case 0: f = (b & c) | (~b & d); g = i; break;
+        case 1: f = (d & b) | (~d & c); g = (5 * i + 1) % 16; break;
+        case 2: f = b ^ c ^ d; g = (3 * i + 5) % 16; break;
+        default: f = c ^ (b | ~d); g = (7 * i) % 16; break;
+      }
+      const uint32_t x = a + f + K[i] + M[g];
+      a = d; d = c; c = b;
+      b = b + Rol(x, S[i / 16][i % 4]);
+    }
+    H[0] += a; H[1] += b; H[2] += c; H[3] += d;
+  }
+  return HexOfWords(H, 4, false);
+}
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
@@ -1388,6 +1503,9 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     out->s = static_cast<size_t>(a[2].i) <= pieces.size() ? pieces[static_cast<size_t>(a[2].i) - 1] : std::string();
     return;
   }
+  if (f == "hashSHA256" || f == "sha256") { out->s = Sha256Hex(a[0].s); return; }
+  if (f == "hashSHA1" || f == "sha1") { out->s = Sha1Hex(a[0].s); return; }
+  if (f == "hashMD5" || f == "md5") { out->s = Md5Hex(a[0].s); return; }
   if (f == "crc32") {
     // table-driven here (the kernel is bitwise): same polynomial, different code
     static uint32_t table[256];

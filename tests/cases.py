@@ -340,6 +340,38 @@ def case_string_misc(b):
     return schema, outs, "project"
 
 
+def case_digests(b):
+    """hashSHA256 / hashSHA1 / hashMD5 of utf8 and binary (lower-case hex), alone and consumed."""
+    S, BIN, I, B = pa.string(), pa.binary(), pa.int32(), pa.bool_()
+    schema = pa.schema([("s", S), ("z", BIN)])
+    s, z = F(b, "s", S), F(b, "z", BIN)
+    fn = b.make_function
+    outs = [(fn("hashSHA256", [s], S), S), (fn("hashSHA1", [s], S), S), (fn("hashMD5", [s], S), S),
+            (fn("sha256", [z], S), S), (fn("sha1", [z], S), S), (fn("md5", [z], S), S),
+            (fn("hashSHA256", [fn("upper", [s], S)], S), S),
+            (fn("concat", [fn("md5", [s], S), b.make_literal(":", S), fn("sha1", [s], S)], S), S),
+            (fn("like", [fn("hashMD5", [s], S), b.make_literal("%a%f%", S)], B), B),
+            (fn("char_length", [fn("hashSHA256", [z], S)], I), I)]
+    return schema, outs, "project"
+
+
+def digest_batch(n: int, seed: int, offset: int = 0) -> pa.RecordBatch:
+    """Messages around the 55 / 56 / 64-byte padding boundaries, multi-block ones, empty, nulls."""
+    rng = np.random.default_rng(seed)
+    lens = [0, 1, 3, 55, 56, 57, 63, 64, 65, 111, 112, 119, 120, 128, 200]
+    ss, zz = [], []
+    for k in range(n + offset):
+        ln = lens[k % len(lens)] if k < 4 * len(lens) else int(rng.integers(0, 180))
+        raw = bytes(rng.integers(32, 127, ln).astype(np.uint8))
+        ss.append(None if k % 17 == 11 else raw.decode("ascii"))
+        zz.append(None if k % 19 == 7 else bytes(rng.integers(0, 256, ln).astype(np.uint8)))
+    ss[0] = "abc"
+    a, zc = pa.array(ss, pa.string()), pa.array(zz, pa.binary())
+    if offset:
+        a, zc = a.slice(offset), zc.slice(offset)
+    return pa.RecordBatch.from_arrays([a, zc], names=["s", "z"])
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])

@@ -834,3 +834,29 @@ def test_string_misc(oracle, gandiva):
                None if None in (w[r], t[r]) else w[r] // 86400000 - t[r] // 86400000]
         for c, wv in enumerate(exp):
             assert got[c][r] == wv, (c, r, got[c][r], wv, sv, uv)
+
+
+def test_digests_against_hashlib(oracle, gandiva):
+    """hashSHA256 / hashSHA1 / hashMD5: the published standards (FIPS 180-4, RFC 1321) pin these
+    bit for bit -- checked against the known answers for "abc" and against hashlib."""
+    import hashlib
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_digests(b)
+    batch = cases.digest_batch(600, seed=3)
+    got = [g.to_pylist() for g in oracle.project([r for r, _ in outs], [t for _, t in outs], batch)]
+    assert got[0][0] == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    assert got[1][0] == "a9993e364706816aba3e25717850c26c9cd0d89d"
+    assert got[2][0] == "900150983cd24fb0d6963f7d28e17f72"
+    s, z = batch.column(0).to_pylist(), batch.column(1).to_pylist()
+    for r in range(len(s)):
+        if s[r] is not None:
+            m = s[r].encode()
+            assert got[0][r] == hashlib.sha256(m).hexdigest() and got[1][r] == hashlib.sha1(m).hexdigest()
+            assert got[2][r] == hashlib.md5(m).hexdigest()
+            assert got[6][r] == hashlib.sha256(s[r].upper().encode()).hexdigest()
+            assert got[7][r] == hashlib.md5(m).hexdigest() + ":" + hashlib.sha1(m).hexdigest()
+        else:
+            assert got[0][r] is None and got[7][r] == ":"
+        if z[r] is not None:
+            assert got[3][r] == hashlib.sha256(z[r]).hexdigest() and got[4][r] == hashlib.sha1(z[r]).hexdigest()
+            assert got[5][r] == hashlib.md5(z[r]).hexdigest() and got[9][r] == 64

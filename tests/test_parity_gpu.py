@@ -716,3 +716,22 @@ def test_two_pass_filter(nullp, gandiva, oracle):
             got = out.numpy()
             assert np.array_equal(got[:cap].astype(np.uint64), want[:cap]) and (got[cap:] == -1).all()
     assert "gdv_project_expr_" in f.kernel_info["name"]
+
+
+@pytest.mark.parametrize("n,offset", [(1, 0), (45, 0), (700, 3)])
+def test_digests(n, offset, gandiva, oracle):
+    """hashSHA256 / hashSHA1 / hashMD5 in the kernels against the oracle (itself pinned to hashlib
+    and the published known answers): block-boundary message lengths, multi-block messages, nulls."""
+    import hashlib
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_digests(b)
+    batch = cases.digest_batch(n, seed=n, offset=offset)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None)
+    got = p.evaluate(batch)
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "digests n=%d out=%d" % (n, i))
+    s0 = batch.column(0)[0].as_py()
+    if s0 is not None:
+        assert got[0][0].as_py() == hashlib.sha256(s0.encode()).hexdigest()
