@@ -102,7 +102,7 @@ def _batch(n, seed):
     return cases.random_batch(SCHEMA, n, seed=seed, null_prob=0.12, offset=seed % 5)
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(16))
 def test_random_projector_trees(seed, gandiva, oracle):
     rng = np.random.default_rng(1000 + seed)
     b = gandiva.TreeExprBuilder()
@@ -119,7 +119,7 @@ def test_random_projector_trees(seed, gandiva, oracle):
             assert_arrays_match(gv, wv, "seed %d n=%d out %d: %s" % (seed, n, i, roots[i]))
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(10))
 def test_random_filter_trees(seed, gandiva, oracle):
     rng = np.random.default_rng(5000 + seed)
     b = gandiva.TreeExprBuilder()
