@@ -1,5 +1,7 @@
 #include "gdv_runtime.h"
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -283,6 +285,33 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
     auto it = g_cubin_cache.find(key);
     if (it != g_cubin_cache.end()) hit = it->second;
   }
+  // GDV_CUBIN_CACHE_DIR=<dir>: cubins also persist across processes (the counterpart of the
+  // reference's object-code cache): <dir>/<fnv64 of arch|options|source>.cubin, written atomically.
+  std::string disk_path;
+  if (const char* cdir = std::getenv("GDV_CUBIN_CACHE_DIR")) {
+    if (!cfg.dump_ir) {  // DumpIR wants the PTX too: always compile
+      char kh[24];
+      std::snprintf(kh, sizeof(kh), "%016llx", static_cast<unsigned long long>(Fnv1a(key)));
+      disk_path = std::string(cdir) + "/" + kh + ".cubin";
+    }
+  }
+  if (hit == nullptr && !disk_path.empty()) {
+    if (FILE* f = std::fopen(disk_path.c_str(), "rb")) {
+      std::vector<char> blob;
+      char buf[65536];
+      size_t got;
+      while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) blob.insert(blob.end(), buf, buf + got);
+      std::fclose(f);
+      if (std::search(blob.begin(), blob.end(), name.begin(), name.end()) != blob.end()) {
+        auto entry = std::make_shared<CachedCubin>();
+        entry->cubin = std::move(blob);
+        hit = entry;
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (g_cubin_cache.size() >= kCubinCacheEntries) g_cubin_cache.clear();
+        g_cubin_cache.emplace(key, entry);
+      }
+    }
+  }
   if (hit != nullptr) {
     k->cubin = hit->cubin;
     k->ptx = hit->ptx;
@@ -291,6 +320,15 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
     g_compile_count.fetch_add(1);
     GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
                                      &k->ptx, &k->compile_log));
+    if (!disk_path.empty()) {
+      const std::string tmp = disk_path + ".tmp" + std::to_string(static_cast<long long>(::getpid()));
+      if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
+        const bool ok = std::fwrite(k->cubin.data(), 1, k->cubin.size(), f) == k->cubin.size();
+        std::fclose(f);
+        if (ok) std::rename(tmp.c_str(), disk_path.c_str());
+        else std::remove(tmp.c_str());
+      }
+    }
     // a translation unit can compile "successfully" without the kernel in it (e.g. when the
     // front end stops at a stray byte): make that a code-generation error here, not a missing
     // symbol at the first Evaluate on a GPU

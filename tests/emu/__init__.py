@@ -80,4 +80,5 @@ def env(sms: int = 4) -> dict:
     e["GDV_EMU_STATIC_LIB"] = libs["static"]
     e["GDV_EMU_SMS"] = str(sms)
     e["GDV_EMU"] = "1"  # tests/ read this to pick simulator-sized inputs
+    e.pop("GDV_CUBIN_CACHE_DIR", None)  # the simulator's "cubins" must never reach a real cache
     return e

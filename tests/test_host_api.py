@@ -255,3 +255,22 @@ def test_evaluate_without_gpu_fails_loudly(gandiva):
     batch = pa.RecordBatch.from_arrays([pa.array([1, 2, 3], pa.int32())], names=['a'])
     with pytest.raises(gandiva.GandivaError, match="CUDA"):
         p.evaluate(batch)
+
+
+def test_disk_cubin_cache(tmp_path):
+    import os
+    """GDV_CUBIN_CACHE_DIR: a second process that lowers to the same kernel compiles nothing."""
+    import subprocess
+    import sys
+    prog = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import gandiva_b200 as g, cases\n"
+            "b = g.TreeExprBuilder()\n"
+            "f = g.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)))\n"
+            "print('COMPILED', g.compile_count())\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                          os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GDV_CUBIN_CACHE_DIR=str(tmp_path))
+    first = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True)
+    second = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True)
+    assert "COMPILED 1" in first.stdout, first.stdout + first.stderr
+    assert "COMPILED 0" in second.stdout, second.stdout + second.stderr
+    assert len([p for p in os.listdir(tmp_path) if p.endswith(".cubin")]) == 1
