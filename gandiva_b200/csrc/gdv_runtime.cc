@@ -302,7 +302,8 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
       size_t got;
       while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) blob.insert(blob.end(), buf, buf + got);
       std::fclose(f);
-      if (std::search(blob.begin(), blob.end(), name.begin(), name.end()) != blob.end()) {
+      const bool elf = blob.size() > 4 && blob[0] == 0x7f && blob[1] == 'E' && blob[2] == 'L' && blob[3] == 'F';
+      if (elf && std::search(blob.begin(), blob.end(), name.begin(), name.end()) != blob.end()) {
         auto entry = std::make_shared<CachedCubin>();
         entry->cubin = std::move(blob);
         hit = entry;
@@ -320,7 +321,8 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
     g_compile_count.fetch_add(1);
     GDV_RETURN_NOT_OK(CompileToCubin(k->gen.source, arch, cfg.optimize, cfg.dump_ir, &k->cubin,
                                      &k->ptx, &k->compile_log));
-    if (!disk_path.empty()) {
+    const bool elf_out = k->cubin.size() > 4 && k->cubin[0] == 0x7f && k->cubin[1] == 'E';
+    if (!disk_path.empty() && elf_out) {
       const std::string tmp = disk_path + ".tmp" + std::to_string(static_cast<long long>(::getpid()));
       if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
         const bool ok = std::fwrite(k->cubin.data(), 1, k->cubin.size(), f) == k->cubin.size();

@@ -8,6 +8,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Kernels compiled before (here, without a GPU: NVRTC needs none) are loaded instead of recompiled:
+# tools/populate_cubin_cache.py fills this in-tree directory, which travels to the GPU box with
+# the snapshot like the built .so files (*.cubin is git-ignored).
+_CUBIN_CACHE = os.path.join(ROOT, "gandiva_b200", "_cubin_cache")
+if os.path.isdir(_CUBIN_CACHE) and os.environ.get("GDV_EMU") != "1":
+    os.environ.setdefault("GDV_CUBIN_CACHE_DIR", _CUBIN_CACHE)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # build the native libraries once per session if they are missing (in-tree .so files

@@ -12,7 +12,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.path.join(HERE, "lib")              # libcuda.so.1 stand-in: goes on LD_LIBRARY_PATH
+NVRTC_DIR = os.path.join(HERE, "lib_nvrtc")     # libnvrtc.so.12 stand-in: named by GDV_NVRTC_PATH only (a
+#                                                 real NVRTC must never find it on the loader path)
 CACHE = os.path.join(HERE, "cache")
 CUDA_INC = "/usr/local/cuda/include"
 DEVICE_DIR = os.path.join(ROOT, "gandiva_b200", "csrc", "device")
@@ -32,9 +34,13 @@ def _cxx(out: str, src: str, extra: list[str]) -> None:
 
 def build() -> dict:
     os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(NVRTC_DIR, exist_ok=True)
     os.makedirs(CACHE, exist_ok=True)
     cuda = os.path.join(LIBDIR, "libcuda.so.1")
-    nvrtc = os.path.join(LIBDIR, "libnvrtc.so.12")
+    nvrtc = os.path.join(NVRTC_DIR, "libnvrtc.so.12")
+    stale = os.path.join(LIBDIR, "libnvrtc.so.12")
+    if os.path.exists(stale):
+        os.remove(stale)
     if not _newer(cuda, os.path.join(HERE, "fake_cuda.cc")):
         _cxx(cuda, os.path.join(HERE, "fake_cuda.cc"), ["-ldl"])
     if not _newer(nvrtc, os.path.join(HERE, "fake_nvrtc.cc")):
