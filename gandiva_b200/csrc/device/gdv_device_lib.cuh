@@ -51,6 +51,8 @@ GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
 #define GDV_XF_CASE 3u
 #define GDV_XF_ASCII 0x100u
 #define GDV_XF_LOCAL 0x200u  /* bytes live in the producing thread's scratch slot: only that thread may read them */
+#define GDV_XF_REP 0x400u    /* periodic: byte i is p[i % (xf >> 12)]; only the string write pass reads these */
+#define GDV_XF_REV 0x800u    /* glyph-reversed: copied by the owning lane in the string write pass */
 #define GDV_SCRATCH_SLOT 64  /* bytes per (row, call site) of a function that writes its result as text */
 struct gdv_str {
   const u8* p;
@@ -1649,6 +1651,72 @@ GDV_DEV i32 datediff_timestamp_timestamp(i64 a, i64 b) {
   return (i32)(gdv_floordiv(a, 86400000ll) - gdv_floordiv(b, 86400000ll));
 }
 GDV_DEV i32 datediff_date64_date64(i64 a, i64 b) { return datediff_timestamp_timestamp(a, b); }
+
+// ---- virtual pieces: repeat / space / lpad / rpad / reverse ----------------------------------------
+// A periodic view: `total` bytes that repeat the `period` bytes at p (period < 2^20).
+GDV_DEV gdv_str gdv_rep_view(const u8* p, i64 period, i64 total) {
+  gdv_str r = gdv_make_str(p, 0);
+  if (period <= 0 || total <= 0 || period >= (1ll << 20)) return r;
+  r.len = total > 0x7fffffffll ? 0x7fffffff : (i32)total;  // > 2^31 - 1 bytes: the tile scan raises
+  r.xf = GDV_XF_REP | ((u32)period << 12);
+  return r;
+}
+__device__ const u8 gdv_one_space[1] = {' '};
+GDV_DEV gdv_str repeat_utf8_int32(gdv_str s, i32 n) {
+  // the case map of s travels with the piece (xf low bits), its bytes repeat
+  gdv_str r = gdv_rep_view(s.p, (i64)s.len, (i64)s.len * (i64)(n > 0 ? n : 0));
+  r.xf |= s.xf & (GDV_XF_CASE | GDV_XF_LOCAL);
+  return r;
+}
+GDV_DEV gdv_str space_int32(i32 n) { return gdv_rep_view(gdv_one_space, 1, (i64)(n > 0 ? n : 0)); }
+GDV_DEV gdv_str reverse_utf8(gdv_str s) {
+  s.xf = (s.xf & (GDV_XF_CASE | GDV_XF_LOCAL)) | GDV_XF_REV;
+  return s;
+}
+// lpad / rpad(s, n, fill): the result has n glyphs: s cut to n glyphs, padded with the glyphs of
+// `fill` repeated cyclically (an empty fill pads nothing; n <= 0 gives the empty string).
+// gdv_pad_text = the text piece, gdv_pad_fill = the padding piece (a periodic view of fill).
+GDV_DEV gdv_str gdv_pad_text(gdv_str s, i32 n) {
+  gdv_str r = s;
+  r.len = 0;
+  if (n <= 0) return r;
+  return substr_utf8_int64_int64(s, 1, (i64)n);
+}
+GDV_DEV gdv_str gdv_pad_fill(gdv_str s, i32 n, gdv_str fill) {
+  gdv_str none = gdv_make_str(fill.p, 0);
+  if (n <= 0 || fill.len <= 0) return none;
+  const i64 need = (i64)n - (i64)char_length_utf8(s);  // glyphs of padding
+  if (need <= 0) return none;
+  const i64 fg = (i64)char_length_utf8(fill);
+  if (fg <= 0) return none;
+  i64 bytes = (need / fg) * (i64)fill.len;
+  i64 rest = need % fg;
+  for (i32 pos = 0; rest > 0 && pos < fill.len; --rest) {
+    const i32 gl = gdv_glyph_len(fill.p[pos]);
+    bytes += gl;
+    pos += gl;
+  }
+  gdv_str r = gdv_rep_view(fill.p, (i64)fill.len, bytes);
+  r.xf |= fill.xf & (GDV_XF_CASE | GDV_XF_LOCAL);
+  return r;
+}
+// Byte i of a piece as the string write pass sees it (periodic pieces wrap around).
+GDV_DEV u8 gdv_piece_byte(const gdv_str& v, i32 i) {
+  if ((v.xf & GDV_XF_REP) != 0u) i = i % (i32)(v.xf >> 12);
+  return gdv_ch(v, i);
+}
+// Copies a glyph-reversed piece (owner lane only): glyphs from the last to the first, the bytes
+// of every glyph in their own order.
+GDV_DEV void gdv_copy_reversed(u8* dst, const gdv_str& v) {
+  i32 out = 0;
+  for (i32 end = v.len; end > 0;) {
+    i32 st = end - 1;
+    while (st > 0 && (v.p[st] & 0xC0u) == 0x80u && end - st < 4) --st;
+    if (gdv_glyph_len(v.p[st]) != end - st) st = end - 1;  // malformed: single bytes
+    for (i32 i = st; i < end; ++i) dst[out++] = gdv_ch(v, i);
+    end = st;
+  }
+}
 
 // ---- numbers and dates as text (castVARCHAR): bytes are produced into a thread-private slot -----
 GDV_DEV gdv_str gdv_scratch_str(u8* scr, i32 len, i64 maxlen) {

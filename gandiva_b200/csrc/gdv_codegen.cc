@@ -831,8 +831,43 @@ class BodyGen {
     }
     for (const auto& a : args)
       if (!a.parts.empty() && error_.empty())
-        error_ = "the result of concat can only be projected, concatenated again or chosen by if/else; " +
-                 fn.name() + "(concat(...)) is not supported yet";
+        error_ = "the result of concat / repeat / space / lpad / rpad / reverse can only be projected, "
+                 "concatenated again or chosen by if/else; " + fn.name() + "(...) over it is not supported yet";
+
+    if (def->flags & kVirtual) {
+      // repeat / space / reverse: one virtual piece; lpad / rpad: the padding piece and the text
+      // piece.  Pieces are plain gdv_str values whose xf marks them periodic / reversed; only the
+      // string write pass knows how to read those, so the result is a rope like concat's.
+      std::vector<std::string> oks;
+      for (const auto& a : args) oks.push_back(a.ok);
+      Val r;
+      r.type = rt;
+      r.ok = AndOk(oks);
+      if (r.ok != "true" && r.ok != "false" && r.ok.find("&&") != std::string::npos) {
+        const std::string okv = NewVar("ok");
+        *out += Ind(indent) + "const bool " + okv + " = " + r.ok + ";\n";
+        r.ok = okv;
+      }
+      r.v = "gdv_make_str(nullptr, 0)";
+      auto piece = [&](const std::string& expr) {
+        const std::string pv = NewVar("v");
+        *out += Ind(indent) + "const gdv_str " + pv + " = " + expr + ";\n";
+        r.parts.push_back(pv);
+      };
+      const std::string& nm = fn.name();
+      if (nm == "lpad" || nm == "rpad") {
+        const std::string fill = args.size() == 3 ? args[2].v : std::string("gdv_make_str(gdv_one_space, 1)");
+        const std::string pad = "gdv_pad_fill(" + args[0].v + ", " + args[1].v + ", " + fill + ")";
+        const std::string text = "gdv_pad_text(" + args[0].v + ", " + args[1].v + ")";
+        if (nm == "lpad") { piece(pad); piece(text); }
+        else { piece(text); piece(pad); }
+      } else {
+        std::string call = def->device_name() + "(";
+        for (size_t i = 0; i < args.size(); ++i) call += (i ? ", " : "") + args[i].v;
+        piece(call + ")");
+      }
+      return r;
+    }
 
     if (fn.name() == "nvl") {
       // nvl(a, b) = a where a is valid, else b: a select on a's validity, no device function
@@ -1858,10 +1893,11 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     src += "      for (int piece = 0; piece < " + sK + "; ++piece) {\n";
     src += "        const u32 plen = rowok ? (u32)sv[k][piece].len : 0u;\n";
     src += "        // text in a thread-private scratch slot is copied by its owner, everything else by the warp\n";
-    src += "        const bool mine_only = (sv[k][piece].xf & GDV_XF_LOCAL) != 0u;\n";
+    src += "        const bool mine_only = (sv[k][piece].xf & (GDV_XF_LOCAL | GDV_XF_REV)) != 0u;\n";
     src += "        if (plen != 0u && mine_only) {\n";
     src += "          if (dst0 + (u64)plen <= (u64)A.out_cap) {\n";
-    src += "            for (u32 i = 0u; i < plen; ++i) data[dst0 + (u64)i] = gdv_ch(sv[k][piece], (i32)i);\n";
+    src += "            if ((sv[k][piece].xf & GDV_XF_REV) != 0u) gdv_copy_reversed(data + dst0, sv[k][piece]);\n";
+    src += "            else for (u32 i = 0u; i < plen; ++i) data[dst0 + (u64)i] = gdv_piece_byte(sv[k][piece], (i32)i);\n";
     src += "          } else {\n";
     src += "            gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";
     src += "          }\n";
@@ -1875,7 +1911,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     src += "          v.xf = __shfl_sync(GDV_FULL, sv[k][piece].xf, j);\n";
     src += "          const u64 d = __shfl_sync(GDV_FULL, dst0, j);\n";
     src += "          if (d + (u64)v.len <= (u64)A.out_cap) {\n";
-    src += "            for (i32 i = (i32)lane; i < v.len; i += 32) data[d + (u64)i] = gdv_ch(v, i);\n";
+    src += "            for (i32 i = (i32)lane; i < v.len; i += 32) data[d + (u64)i] = gdv_piece_byte(v, i);\n";
     src += "          } else if (lane == 0u) {\n";
     src += "            gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";
     src += "          }\n";

@@ -280,6 +280,14 @@ Registry::Registry() {
   Add("castVARCHAR", {D64, I64}, S, NullMode::kIfNull, kScratch);
   Add("castVARCHAR", {TS, I64}, S, NullMode::kIfNull, kScratch);
   Add("castVARCHAR", {B, I64}, S);
+  // new bytes without a bound: virtual pieces (periodic / reversed views) read by the write pass only
+  Add("repeat", {S, I32}, S, NullMode::kIfNull, kVirtual);
+  Add("space", {I32}, S, NullMode::kIfNull, kVirtual);
+  Add("reverse", {S}, S, NullMode::kIfNull, kVirtual);
+  Add("lpad", {S, I32, S}, S, NullMode::kIfNull, kVirtual);
+  Add("rpad", {S, I32, S}, S, NullMode::kIfNull, kVirtual);
+  Add("lpad", {S, I32}, S, NullMode::kIfNull, kVirtual);
+  Add("rpad", {S, I32}, S, NullMode::kIfNull, kVirtual);
   Add("ascii", {S}, I32);
   Add("left", {S, I32}, S, NullMode::kIfNull, kStringView);
   Add("right", {S, I32}, S, NullMode::kIfNull, kStringView);

@@ -1506,6 +1506,39 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   if (f == "hashSHA256" || f == "sha256") { out->s = Sha256Hex(a[0].s); return; }
   if (f == "hashSHA1" || f == "sha1") { out->s = Sha1Hex(a[0].s); return; }
   if (f == "hashMD5" || f == "md5") { out->s = Md5Hex(a[0].s); return; }
+  if (f == "repeat") {
+    out->s.clear();
+    for (int64_t k = 0; k < a[1].i; ++k) out->s += a[0].s;
+    return;
+  }
+  if (f == "space") { out->s.assign(static_cast<size_t>(std::max<int64_t>(a[0].i, 0)), ' '); return; }
+  if (f == "reverse") {
+    const std::vector<size_t> st = GlyphStarts(a[0].s);
+    out->s.clear();
+    for (size_t k = st.size(); k-- > 0;) {
+      const size_t e = k + 1 < st.size() ? st[k + 1] : a[0].s.size();
+      out->s += a[0].s.substr(st[k], e - st[k]);
+    }
+    return;
+  }
+  if (f == "lpad" || f == "rpad") {
+    const int64_t want = a[1].i;
+    const std::string fill = na == 3 ? a[2].s : std::string(" ");
+    out->s.clear();
+    if (want <= 0) return;
+    const std::string text = Substr(a[0].s, 1, want);
+    const int64_t have = static_cast<int64_t>(GlyphStarts(a[0].s).size());
+    std::string pad;
+    const std::vector<size_t> fs = GlyphStarts(fill);
+    if (!fs.empty())
+      for (int64_t k = 0; k < want - have; ++k) {
+        const size_t g = static_cast<size_t>(k) % fs.size();
+        const size_t e = g + 1 < fs.size() ? fs[g + 1] : fill.size();
+        pad += fill.substr(fs[g], e - fs[g]);
+      }
+    out->s = f == "lpad" ? pad + text : text + pad;
+    return;
+  }
   if (f == "crc32") {
     // table-driven here (the kernel is bitwise): same polynomial, different code
     static uint32_t table[256];

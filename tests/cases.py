@@ -372,6 +372,30 @@ def digest_batch(n: int, seed: int, offset: int = 0) -> pa.RecordBatch:
     return pa.RecordBatch.from_arrays([a, zc], names=["s", "z"])
 
 
+def case_virtual_strings(b):
+    """repeat / space / reverse / lpad / rpad: periodic and reversed pieces that only the string write
+    pass reads; alone, inside concat ropes, chosen by if/else, over scratch-slot text."""
+    S, I, L, B = pa.string(), pa.int32(), pa.int64(), pa.bool_()
+    schema = pa.schema([("s", S), ("u", S), ("k", I), ("l", L), ("p", B)])
+    s, u, k, l, pp = F(b, "s", S), F(b, "u", S), F(b, "k", I), F(b, "l", L), F(b, "p", B)
+    fn = b.make_function
+    lit = b.make_literal
+    kk = fn("subtract", [fn("castINT", [fn("pmod", [fn("castBIGINT", [k], L), lit(23, L)], L)], I), lit(3, I)], I)   # -3..19
+    outs = [
+        (fn("repeat", [s, lit(3, I)], S), S), (fn("repeat", [fn("upper", [s], S), kk], S), S),
+        (fn("space", [kk], S), S), (fn("reverse", [s], S), S), (fn("reverse", [fn("lower", [u], S)], S), S),
+        (fn("lpad", [s, lit(12, I)], S), S), (fn("rpad", [s, lit(12, I), lit("*", S)], S), S),
+        (fn("lpad", [s, kk, lit("ab", S)], S), S), (fn("rpad", [s, kk, lit("日本x", S)], S), S),
+        (fn("lpad", [s, lit(7, I), u], S), S), (fn("rpad", [u, lit(9, I), lit("", S)], S), S),
+        (fn("concat", [lit("[", S), fn("lpad", [fn("castVARCHAR", [l, lit(30, L)], S), lit(8, I), lit("0", S)], S), lit("]", S)], S), S),
+        (fn("concat", [fn("reverse", [s], S), fn("space", [lit(2, I)], S), fn("repeat", [lit("-", S), lit(4, I)], S)], S), S),
+        (b.make_if(pp, fn("repeat", [u, lit(2, I)], S), fn("reverse", [u], S), S), S),
+        (fn("reverse", [fn("castVARCHAR", [l, lit(30, L)], S)], S), S),
+        (fn("repeat", [fn("castVARCHAR", [k, lit(4, L)], S), lit(2, I)], S), S),
+    ]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -935,7 +959,7 @@ def all_project_cases():
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
-              case_string_positions, case_number_to_text, case_string_misc]
+              case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

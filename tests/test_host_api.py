@@ -209,6 +209,12 @@ def test_concat_consumers_are_rejected(gandiva):
     like = b.make_function("like", [cc, b.make_literal("%ab%", t)], pa.bool_())
     with pytest.raises(pa.ArrowNotImplementedError, match="concat"):
         gandiva.make_filter(schema, b.make_condition(like))
+    # the same holds for the virtual pieces of repeat / space / lpad / rpad / reverse
+    for inner in (b.make_function("repeat", [cases.F(b, "s", t), b.make_literal(2, pa.int32())], t),
+                  b.make_function("reverse", [cases.F(b, "s", t)], t),
+                  b.make_function("lpad", [cases.F(b, "s", t), b.make_literal(9, pa.int32())], t)):
+        with pytest.raises(pa.ArrowNotImplementedError, match="only be projected"):
+            gandiva.make_projector(schema, [b.make_expression(b.make_function("upper", [inner], t), pa.field("r", t))], None)
 
 
 def test_cubin_cache(gandiva):

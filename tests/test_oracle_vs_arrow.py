@@ -860,3 +860,37 @@ def test_digests_against_hashlib(oracle, gandiva):
         if z[r] is not None:
             assert got[3][r] == hashlib.sha256(z[r]).hexdigest() and got[4][r] == hashlib.sha1(z[r]).hexdigest()
             assert got[5][r] == hashlib.md5(z[r]).hexdigest() and got[9][r] == 64
+
+
+def test_virtual_strings(oracle, gandiva):
+    """repeat / space / reverse / lpad / rpad against Python str operations (glyph = code point)."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_virtual_strings(b)
+    batch = cases.random_batch(schema, N, seed=51, null_prob=0.1)
+    got = [g.to_pylist() for g in oracle.project([r for r, _ in outs], [t for _, t in outs], batch)]
+    s, u, k, l, p = (batch.column(c).to_pylist() for c in range(5))
+    up = lambda x: "".join(c.upper() if c.isascii() else c for c in x)
+    low = lambda x: "".join(c.lower() if c.isascii() else c for c in x)
+
+    def pad(x, n, fill, left):
+        if n <= 0:
+            return ""
+        text = x[:n]
+        padding = "".join(fill[i % len(fill)] for i in range(max(n - len(x), 0))) if fill else ""
+        return padding + text if left else text + padding
+    for r in range(N):
+        sv, uv, lv = s[r], u[r], l[r]
+        kk = None if k[r] is None else (k[r] % 23) - 3
+        num = None if lv is None else str(lv)[:30]
+        exp = [None if sv is None else sv * 3, None if None in (sv, kk) else up(sv) * max(kk, 0),
+               None if kk is None else " " * max(kk, 0), None if sv is None else sv[::-1],
+               None if uv is None else low(uv)[::-1],
+               None if sv is None else pad(sv, 12, " ", True), None if sv is None else pad(sv, 12, "*", False),
+               None if None in (sv, kk) else pad(sv, kk, "ab", True), None if None in (sv, kk) else pad(sv, kk, "日本x", False),
+               None if None in (sv, uv) else pad(sv, 7, uv, True), None if uv is None else pad(uv, 9, "", False),
+               "[" + ("" if num is None else pad(num, 8, "0", True)) + "]",
+               ("" if sv is None else sv[::-1]) + "  " + "----",
+               (None if uv is None else uv * 2) if p[r] else (None if uv is None else uv[::-1]),
+               None if num is None else num[::-1], None if k[r] is None else str(k[r])[:4] * 2]
+        for c, w in enumerate(exp):
+            assert got[c][r] == w, (c, r, got[c][r], w, sv, uv, kk)
