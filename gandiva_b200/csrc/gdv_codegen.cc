@@ -2189,6 +2189,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   bool light = spec.kind == KernelKind::kFilter && n_varlen == 0 && BT >= 256 && 2048 % BT == 0 &&
                !gen.uses_ctx() && body.size() < 6000;
   for (const auto& sl : slots) light = light && !sl.type.is_decimal();  // 128-bit math wants registers
+  if (spec.stages == 2 || spec.stages == 4 || spec.stages == 8) light = false;  // W-walk keeps 2 W more registers
   if (light) bounds += ", " + std::to_string(2048 / BT);
   src += "extern \"C\" __global__ void __launch_bounds__(" + bounds + ") " + spec.name +
          "(const __grid_constant__ gdv_args A) {\n";
@@ -2382,6 +2383,99 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     // tiles at 256/512 threads (0.268 vs 0.289 of peak, profiles/r01_string_filter.md): the barrier
     // was not what bounds the kernel, and 16x more look-back descriptors cost more than it saves.
     const bool warp_tiles = n_varlen > 0 && (spec.string_scan & 4) != 0;
+    // Optional (Configuration.stages = 2 / 4 / 8 on a fixed-width filter): every warp walks W
+    // consecutive 1024-row chunks per tile, so a 32K-row tile needs 256 / W ... threads instead of
+    // 1024 and eight small CTAs share an SM: while one of them sits in its tile-end barriers and
+    // look-back, seven keep streaming (with two 1024-thread CTAs per SM it is one of two).  Same
+    // single fused kernel, same descriptors per row; costs 2 W registers.  Not yet measured.
+    const int W = (n_varlen == 0 && (spec.stages == 2 || spec.stages == 4 || spec.stages == 8)) ? spec.stages : 1;
+    if (W > 1) {
+      const int WT = NW * 1024 * W;
+      const std::string sW = std::to_string(W);
+      const std::string walk_tail =
+          "          { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
+          results[0].v + ")); if (lane == (u32)(g + k)) cur = m; }\n";
+      src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
+      src += "  __shared__ i64 s_tile;\n";
+      src += "  __shared__ u64 s_excl;\n";
+      src += "  const i64 n_tiles = (A.n + " + std::to_string(WT - 1) + ") / " + std::to_string(WT) + ";\n";
+      src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
+      src += "  const u32 lt = gdv_lanemask_lt();\n";
+      src += "  while (true) {\n";
+      src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
+      src += "    __syncthreads();\n";
+      src += "    const i64 tile = s_tile;\n";
+      src += "    if (tile >= n_tiles) break;\n";
+      src += "    const i64 wbase0 = tile * " + std::to_string(WT) + " + (i64)wid * " + std::to_string(1024 * W) + ";\n";
+      src += "    u32 mymask[" + sW + "];\n";
+      src += "    #pragma unroll\n";
+      src += "    for (int w = 0; w < " + sW + "; ++w) {\n";
+      src += "      const i64 wbase = wbase0 + 1024 * w;\n";
+      src += "      u32 cur = 0u;\n";
+      src += "      #pragma unroll 1\n";
+      src += "      for (int g = 0; g < 32; g += " + sR + ") {\n";
+      src += "        const i64 base = wbase + 32 * g;\n";
+      src += "        if (base >= A.n) break;\n";
+      src += "        if (base + " + s32R + " <= A.n) {\n";
+      EmitGroup(slots, spec, R, kFast, body, walk_tail, &src, 5, 0, std::string(), coop);
+      src += "        } else {\n";
+      EmitGroup(slots, spec, R, kPred, body, walk_tail, &src, 5, 0, std::string(), coop);
+      src += "        }\n";
+      src += "      }\n";
+      src += "      mymask[w] = cur;\n";
+      src += "    }\n";
+      // per chunk: lane k holds step k's mask; exclusive positions run over chunks, then steps
+      src += "    u32 step_excl[" + sW + "];\n";
+      src += "    u32 run = 0u;\n";
+      src += "    #pragma unroll\n";
+      src += "    for (int w = 0; w < " + sW + "; ++w) {\n";
+      src += "      const u32 c = (u32)__popc(mymask[w]);\n";
+      src += "      u32 incl = c;\n";
+      src += "      #pragma unroll\n";
+      src += "      for (int o = 1; o < 32; o <<= 1) {\n";
+      src += "        const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
+      src += "        if (lane >= (u32)o) incl += t;\n";
+      src += "      }\n";
+      src += "      step_excl[w] = run + incl - c;\n";
+      src += "      run += __shfl_sync(GDV_FULL, incl, 31);\n";
+      src += "    }\n";
+      src += "    if (lane == 0u) s_wcount[wid] = run;\n";
+      src += "    __syncthreads();\n";
+      src += "    if (wid == 0u) {\n";
+      src += "      const u32 wc = lane < " + std::to_string(NW) + "u ? s_wcount[lane] : 0u;\n";
+      src += "      u32 winc = wc;\n";
+      src += "      #pragma unroll\n";
+      src += "      for (int o = 1; o < 32; o <<= 1) {\n";
+      src += "        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);\n";
+      src += "        if (lane >= (u32)o) winc += t;\n";
+      src += "      }\n";
+      src += "      const u32 total = __shfl_sync(GDV_FULL, winc, 31);\n";
+      src += "      if (lane < " + std::to_string(NW) + "u) s_wcount[lane] = winc - wc;\n";
+      src += "      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);\n";
+      src += "      if (lane == 0u) {\n";
+      src += "        s_excl = excl;\n";
+      src += "        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;\n";
+      src += "      }\n";
+      src += "    }\n";
+      src += "    __syncthreads();\n";
+      src += "    const u64 wpos = s_excl + (u64)s_wcount[wid];\n";
+      src += "    if (run != 0u) {\n";
+      src += "      #pragma unroll\n";
+      src += "      for (int w = 0; w < " + sW + "; ++w) {\n";
+      src += "        if (__ballot_sync(GDV_FULL, mymask[w] != 0u) == 0u) continue;\n";
+      src += "        #pragma unroll 4\n";
+      src += "        for (int k = 0; k < 32; ++k) {\n";
+      src += "          const u32 m = __shfl_sync(GDV_FULL, mymask[w], k);\n";
+      src += "          const u32 off = __shfl_sync(GDV_FULL, step_excl[w], k);\n";
+      src += "          const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
+      src += "          if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
+      src += "            out_idx[pos] = (" + IDX + ")(A.row_base + wbase0 + 1024 * w + 32 * k + (i64)lane);\n";
+      src += "        }\n";
+      src += "      }\n";
+      src += "    }\n";
+      src += "  }\n";
+      src += "}\n";
+    } else {
     const int TILE = warp_tiles ? 1024 : NW * 1024;
     const std::string step_tail =
         "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
@@ -2529,6 +2623,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     src += "  }\n";
     src += "}\n";
     }  // !warp_tiles
+    }  // W == 1
   }
 
   out->source = std::move(src);
@@ -2547,8 +2642,10 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   out->out_bytes_per_row = out_bytes;
   out->args_size = L.size;
   out->dynamic_smem = dynamic_smem;
+  const int walk = (spec.kind == KernelKind::kFilter && n_varlen == 0 &&
+                    (spec.stages == 2 || spec.stages == 4 || spec.stages == 8)) ? spec.stages : 1;
   out->tile_rows = spec.kind == KernelKind::kFilter
-                       ? ((n_varlen > 0 && (spec.string_scan & 4) != 0) ? 1024 : static_cast<int64_t>(BT / 32) * 1024)
+                       ? ((n_varlen > 0 && (spec.string_scan & 4) != 0) ? 1024 : static_cast<int64_t>(BT / 32) * 1024 * walk)
                        : 0;
   out->staged = staged;
   out->stages = staged ? S : 0;

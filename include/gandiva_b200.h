@@ -112,7 +112,9 @@ typedef struct gdv_config {
   int32_t sm_reserve;      /* SMs left without CTAs of the persistent kernels, so that a
                               concurrent stream (e.g. NCCL's gather of the previous batch's
                               SelectionVector) can run; default 0 */
-  int32_t stages;          /* TMA loader: shared-memory stages per CTA (0 = engine picks) */
+  int32_t stages;          /* Projector, TMA loader: shared-memory stages per CTA (0 = engine picks).
+                              Fixed-width Filter: 2 / 4 / 8 = 1024-row chunks every warp walks per tile
+                              (smaller CTAs for the same tile; opt-in until measured) */
   int32_t string_scan;     /* string columns, bit mask; 0 = engine picks (everything on):
                               bit 0: LIKE with the per-lane matcher only (no warp-cooperative scan),
                               bit 1: filters stage string bytes without the cp.async prefetch,

@@ -735,3 +735,19 @@ def test_digests(n, offset, gandiva, oracle):
     s0 = batch.column(0)[0].as_py()
     if s0 is not None:
         assert got[0][0].as_py() == hashlib.sha256(s0.encode()).hexdigest()
+
+
+@pytest.mark.parametrize("walk,bt", [(2, 256), (4, 256), (8, 128), (4, 64)])
+def test_filter_walk_variant(walk, bt, gandiva, oracle):
+    """Configuration(stages = W) on a fixed-width filter: every warp walks W 1024-row chunks per
+    tile (same fused kernel, smaller CTAs).  Same indices as the oracle, tails and bounded vectors."""
+    b = gandiva.TreeExprBuilder()
+    cond = cases.q6_condition(b)
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cond), gandiva.Configuration(stages=walk, block_threads=bt))
+    assert "mymask[%d]" % walk in f.llvm_ir
+    for n, nullp in ((1, 0), (1023, 10), (1024 * walk * (bt // 32) + 5, 0), (300_007, 15)):
+        batch = cases.q6_batch(n, seed=7, null_permille=nullp)
+        want = oracle.filter_indices(cond, batch, threads=4)
+        for dtype in ("int32", "int64"):
+            sel = f.evaluate(batch, None, dtype)
+            assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want), (n, nullp, dtype)

@@ -12,9 +12,9 @@ GDV_STR_COMBOS="512,2,0;128,1,16;256,1,16;512,1,16;1024,1,16" python tools/bench
 tail -8 gpurun_out/r02_str_sweep.log
 GDV_STR_COMBOS="512,1,16" ncu --set full --clock-control none --import-source on -k regex:gdv_filter_expr -c 1 \
   -o gpurun_out/r02_keyscan python tools/bench_configs.py str 16000000 1 > gpurun_out/r02_keyscan_ncu.log 2>&1
-GDV_Q6_COMBOS="1024,2,0;512,2,0;512,4,0;256,0,0,3;256,8,0,3;128,8,0,3;512,4,0,3" python tools/sweep_q6.py 1000000000 0 > gpurun_out/r02_q6_sweep.log 2>&1; tail -4 gpurun_out/r02_q6_sweep.log
+GDV_Q6_COMBOS="1024,2,0;512,2,0;512,4,0;256,0,0,3;256,8,0,3;128,8,0,3;512,4,0,3;256,2,0,0,4;256,4,0,0,4;512,2,0,0,2;128,2,0,0,8" python tools/sweep_q6.py 1000000000 0 > gpurun_out/r02_q6_sweep.log 2>&1; tail -4 gpurun_out/r02_q6_sweep.log
 # nullable variant after the branch-free validity loads (round 1: 0.837 at 1024 x 2)
-GDV_Q6_COMBOS="1024,2,0;512,2,0;512,4,0;256,0,0,3;256,8,0,3;128,8,0,3" python tools/sweep_q6.py 1000000000 10 > gpurun_out/r02_q6_nulls_sweep.log 2>&1; tail -4 gpurun_out/r02_q6_nulls_sweep.log
+GDV_Q6_COMBOS="1024,2,0;512,2,0;512,4,0;256,0,0,3;256,8,0,3;128,8,0,3;256,2,0,0,4;256,4,0,0,4" python tools/sweep_q6.py 1000000000 10 > gpurun_out/r02_q6_nulls_sweep.log 2>&1; tail -4 gpurun_out/r02_q6_nulls_sweep.log
 GDV_Q6_COMBOS="1024,2,0" ncu --set full --clock-control none --import-source on -k regex:gdv_filter_expr -c 1 \
   -o gpurun_out/r02_q6_nulls python tools/sweep_q6.py 200000000 10 > gpurun_out/r02_q6_nulls_ncu.log 2>&1
 python bench.py --filter-loader 3 --no-e2e --no-cpu > gpurun_out/r02_bench_n1_twopass.json 2> gpurun_out/r02_bench_n1_twopass.err; tail -c 600 gpurun_out/r02_bench_n1_twopass.json
