@@ -699,6 +699,41 @@ GDV_TSDIFF(timestampdiffHour, 3600000ll)
 GDV_TSDIFF(timestampdiffDay, 86400000ll)
 GDV_TSDIFF(timestampdiffWeek, 604800000ll)
 
+// timestampdiff{Month,Quarter,Year}(a, b): whole calendar months from a to b, consistent with
+// timestampaddMonth: the largest |k| such that a + k months (day clamped to the month's length,
+// time of day kept) does not pass b; quarters and years are that count / 3 and / 12, truncated.
+GDV_DEV i64 gdv_months_between_whole(i64 a, i64 b) {
+  const gdv_ymd ca = gdv_civil_from_days(gdv_floordiv(a, 86400000ll));
+  const gdv_ymd cb = gdv_civil_from_days(gdv_floordiv(b, 86400000ll));
+  i64 k = (cb.y - ca.y) * 12 + (i64)(cb.m - ca.m);
+  if (b >= a) {
+    if (k > 0 && gdv_add_months(a, k) > b) --k;
+    if (k < 0) k = 0;
+  } else {
+    if (k < 0 && gdv_add_months(a, k) < b) ++k;
+    if (k > 0) k = 0;
+  }
+  return k;
+}
+GDV_DEV i32 timestampdiffMonth_timestamp_timestamp(i64 a, i64 b) { return (i32)gdv_months_between_whole(a, b); }
+GDV_DEV i32 timestampdiffQuarter_timestamp_timestamp(i64 a, i64 b) { return (i32)(gdv_months_between_whole(a, b) / 3); }
+GDV_DEV i32 timestampdiffYear_timestamp_timestamp(i64 a, i64 b) { return (i32)(gdv_months_between_whole(a, b) / 12); }
+// months_between(a, b) (Hive / Oracle): a - b in months; whole when both are the same day of the
+// month or both the last day of theirs, else the month difference plus (day and time of day
+// difference) / 31 days; IEEE double operations in a fixed order.
+GDV_DEV f64 gdv_months_between(i64 a, i64 b) {
+  const i64 da = gdv_floordiv(a, 86400000ll), db = gdv_floordiv(b, 86400000ll);
+  const gdv_ymd ca = gdv_civil_from_days(da), cb = gdv_civil_from_days(db);
+  const f64 months = (f64)((ca.y - cb.y) * 12 + (i64)(ca.m - cb.m));
+  const bool last_a = gdv_civil_from_days(da + 1).d == 1, last_b = gdv_civil_from_days(db + 1).d == 1;
+  if (ca.d == cb.d || (last_a && last_b)) return months;
+  const i64 ta = a - da * 86400000ll, tb = b - db * 86400000ll;
+  const f64 secs = (f64)((i64)(ca.d - cb.d) * 86400ll) + (f64)(ta - tb) / 1000.0;
+  return months + secs / 2678400.0;
+}
+GDV_DEV f64 months_between_timestamp_timestamp(i64 a, i64 b) { return gdv_months_between(a, b); }
+GDV_DEV f64 months_between_date64_date64(i64 a, i64 b) { return gdv_months_between(a, b); }
+
 // ---- calendar fields and truncation -------------------------------------------------------------
 // ISO 8601 week of the year (weeks start on Monday, week 1 holds the year's first Thursday).
 GDV_DEV i64 gdv_iso_week(i64 days) {

@@ -214,6 +214,9 @@ Registry::Registry() {
       Add(std::string("date_trunc_") + u, {t}, t);
     Add("last_day", {t}, D64);
   }
+  for (const char* f : {"timestampdiffMonth", "timestampdiffQuarter", "timestampdiffYear"}) Add(f, {TS, TS}, I32);
+  Add("months_between", {TS, TS}, F64);
+  Add("months_between", {D64, D64}, F64);
   Add("datediff", {TS, TS}, I32);
   Add("datediff", {D64, D64}, I32);
   Add("castTIME", {TS}, T32);

@@ -1325,6 +1325,51 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
                                                   : static_cast<uint64_t>(a[0].i) - delta);
     return;
   }
+  if (f == "timestampdiffMonth" || f == "timestampdiffQuarter" || f == "timestampdiffYear" || f == "months_between") {
+    // calendar arithmetic on (year, month, day, ms of day) tuples, Python-style
+    struct Cal { int64_t y; int m, d; int64_t tod; };
+    auto cal = [&](int64_t ms) {
+      const int64_t days = FloorDiv(ms, 86400000);
+      const Ymd c = CivilFromDays(days);
+      return Cal{c.y, c.m, c.d, ms - days * 86400000};
+    };
+    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    auto mlen = [&](int64_t y, int m) { return mdays[m - 1] + ((m == 2 && IsLeap(y)) ? 1 : 0); };
+    const Cal A = cal(a[0].i), B = cal(a[1].i);
+    if (f == "months_between") {
+      const double months = static_cast<double>((A.y - B.y) * 12 + (A.m - B.m));
+      if (A.d == B.d || (A.d == mlen(A.y, A.m) && B.d == mlen(B.y, B.m))) { out->d = months; return; }
+      const double secs = static_cast<double>(static_cast<int64_t>(A.d - B.d) * 86400) +
+                          static_cast<double>(A.tod - B.tod) / 1000.0;
+      out->d = months + secs / 2678400.0;
+      return;
+    }
+    // a + k months as a comparable tuple (day clamped), compared with b lexicographically
+    auto plus = [&](int64_t k) {
+      const int64_t total = A.y * 12 + (A.m - 1) + k;
+      const int64_t y = FloorDiv(total, 12);
+      const int m = static_cast<int>(total - y * 12) + 1;
+      return Cal{y, m, std::min(A.d, mlen(y, m)), A.tod};
+    };
+    auto less = [](const Cal& x, const Cal& y) {
+      if (x.y != y.y) return x.y < y.y;
+      if (x.m != y.m) return x.m < y.m;
+      if (x.d != y.d) return x.d < y.d;
+      return x.tod < y.tod;
+    };
+    int64_t k = (B.y - A.y) * 12 + (B.m - A.m);
+    if (a[1].i >= a[0].i) {
+      if (k > 0 && less(B, plus(k))) --k;
+      if (k < 0) k = 0;
+    } else {
+      if (k < 0 && less(plus(k), B)) ++k;
+      if (k > 0) k = 0;
+    }
+    if (f == "timestampdiffQuarter") k /= 3;
+    else if (f == "timestampdiffYear") k /= 12;
+    out->i = WrapSigned(k, 32);
+    return;
+  }
   if (f.rfind("timestampdiff", 0) == 0) {
     const std::string unit = f.substr(13);
     int64_t unit_ms = 1000;

@@ -409,8 +409,11 @@ def case_date_arith(b):
     outs.append((b.make_function("date_add", [d, n], d64), d64))
     outs.append((b.make_function("date_sub", [d, n], d64), d64))
     outs.append((b.make_function("date_add", [t, n], ts), ts))
-    for fn in ("timestampdiffSecond", "timestampdiffMinute", "timestampdiffHour", "timestampdiffDay", "timestampdiffWeek"):
+    for fn in ("timestampdiffSecond", "timestampdiffMinute", "timestampdiffHour", "timestampdiffDay", "timestampdiffWeek",
+               "timestampdiffMonth", "timestampdiffQuarter", "timestampdiffYear"):
         outs.append((b.make_function(fn, [t, u], pa.int32()), pa.int32()))
+    outs.append((b.make_function("months_between", [t, u], pa.float64()), pa.float64()))
+    outs.append((b.make_function("months_between", [d, b.make_function("castDATE", [t], d64)], pa.float64()), pa.float64()))
     return schema, outs, "project"
 
 

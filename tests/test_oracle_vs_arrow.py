@@ -894,3 +894,47 @@ def test_virtual_strings(oracle, gandiva):
                None if num is None else num[::-1], None if k[r] is None else str(k[r])[:4] * 2]
         for c, w in enumerate(exp):
             assert got[c][r] == w, (c, r, got[c][r], w, sv, uv, kk)
+
+
+def test_month_differences(oracle, gandiva):
+    """timestampdiff{Month,Quarter,Year}: the largest |k| with a + k months (pandas DateOffset, the
+    referee of timestampaddMonth) not past b; months_between: the Hive / Oracle formula in Python floats."""
+    import calendar
+    import pandas as pd
+    batch = cases.date_arith_batch(2000, seed=77)
+    got = run_oracle(oracle, gandiva, cases.case_date_arith, batch)
+    t = batch.column(0).cast(pa.int64()).to_pylist()
+    u = batch.column(1).cast(pa.int64()).to_pylist()
+    d = batch.column(2).cast(pa.int64()).to_pylist()
+    first = len(got) - 5   # Month, Quarter, Year, months_between(t, u), months_between(d, castDATE(t))
+
+    def plus(ms, k):
+        return int((pd.Timestamp(ms, unit="ms") + pd.DateOffset(months=k)).as_unit("ms").asm8.view("i8"))
+
+    def whole_months(a, b):
+        ta, tb = pd.Timestamp(a, unit="ms"), pd.Timestamp(b, unit="ms")
+        k0 = (tb.year - ta.year) * 12 + tb.month - ta.month
+        if b >= a:
+            return max(k for k in (0, k0 - 1, k0) if k >= 0 and plus(a, k) <= b)
+        return min(k for k in (0, k0 + 1, k0) if k <= 0 and plus(a, k) >= b)
+
+    def months_between(a, b):
+        ta, tb = pd.Timestamp(a, unit="ms"), pd.Timestamp(b, unit="ms")
+        months = float((ta.year - tb.year) * 12 + ta.month - tb.month)
+        last = lambda x: x.day == calendar.monthrange(x.year, x.month)[1]
+        if ta.day == tb.day or (last(ta) and last(tb)):
+            return months
+        tod = lambda x, ms: ms - (ms // 86400000) * 86400000
+        secs = float((ta.day - tb.day) * 86400) + float(tod(ta, a) - tod(tb, b)) / 1000.0
+        return months + secs / 2678400.0
+    tq = lambda k, q: abs(k) // q * (1 if k >= 0 else -1)
+    gm, gq, gy, gb1, gb2 = (got[first + i].to_pylist() for i in range(5))
+    for r in range(len(t)):
+        if t[r] is None or u[r] is None:
+            assert gm[r] is None and gb1[r] is None
+        else:
+            k = whole_months(t[r], u[r])
+            assert (gm[r], gq[r], gy[r]) == (k, tq(k, 3), tq(k, 12)), (r, t[r], u[r], gm[r], k)
+            assert gb1[r] == months_between(t[r], u[r]), (r, gb1[r])
+        if d[r] is not None and t[r] is not None:
+            assert gb2[r] == months_between(d[r], (t[r] // 86400000) * 86400000), r

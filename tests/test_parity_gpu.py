@@ -751,3 +751,17 @@ def test_filter_walk_variant(walk, bt, gandiva, oracle):
         for dtype in ("int32", "int64"):
             sel = f.evaluate(batch, None, dtype)
             assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want), (n, nullp, dtype)
+
+
+def test_date_arithmetic_month_ends(gandiva, oracle):
+    """Calendar arithmetic on month-end days (Jan 31 + 1 month, leap days, diffs across them)."""
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_date_arith(b)
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None)
+    for n, seed in ((40, 1), (5003, 2)):
+        batch = cases.date_arith_batch(n, seed)
+        got = p.evaluate(batch)
+        want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert_arrays_match(g, w, "date arithmetic n=%d out=%d" % (n, i))
