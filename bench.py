@@ -361,6 +361,27 @@ def main():
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3)
     gather_check = None
+    full_check = None
+    if world == 1:
+        # outside the timed region, at the full bench size: the SelectionVector of the last step is
+        # ascending, its length is the count of an independent torch evaluation of the predicate,
+        # and it holds exactly torch.nonzero of that mask
+        try:
+            torch.cuda.synchronize()
+            mask = (ship >= 8766) & (ship < 9131) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24)
+            want_n = int(mask.sum().item())
+            idx = out_idx[:count].to(torch.int64)
+            if idx_mode == "UINT32":
+                idx = idx & 0xFFFFFFFF
+            ok = (count == want_n)
+            if ok and count > 1:
+                ok = bool((idx[1:] > idx[:-1]).all().item())
+            ok = ok and bool(torch.equal(idx, torch.nonzero(mask).flatten()))
+            full_check = ("ok: %d rows == torch mask count, ascending, == nonzero(mask)" % count) if ok else \
+                         ("FAILED: count %d, torch %d" % (count, want_n))
+            del mask, idx
+        except Exception as e:  # noqa: BLE001 - the bench line must still be printed
+            full_check = "not run: %r" % (e,)
     if use_push:
         # outside the timed region: the last step's vector on rank 0 is complete, ascending and
         # holds exactly the rows all ranks selected
@@ -433,7 +454,7 @@ def main():
                                    ("; configs[4] sharding" if world > 1 else ""),
                        "rows_per_gpu": n, "total_rows": n * world, "selectivity": total_selected / (n * world),
                        "selection_vector": idx_mode + ((" reassembled on rank 0 over NVLink" + (", gdv_selection_push: device-side stores into rank 0's vector (CUDA IPC), counts exchanged through a board in rank 0's HBM, no host sync, overlapped with the next batch's kernel (%d SMs reserved)" % sm_reserve if use_push else ((", copy-engine peer writes into rank 0 (CUDA IPC)" if peer is not None else ", NCCL send/recv") + ", overlapped with the next batch's kernel" if pipelined else ", NCCL send/recv"))) if world > 1 and not args.no_gather else ""),
-                       "gather_check": gather_check,
+                       "gather_check": gather_check, "full_size_check": full_check,
                        "l2_policy": "inputs (20 B/row x %d rows) larger than L2; no flush" % n,
                        "parallelism": "row-range shards, %d" % world},
             "hbm_gbs": achieved, "per_step_ms": per_step,
