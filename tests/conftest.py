@@ -39,3 +39,14 @@ def gandiva():
 def oracle():
     import oracle as _oracle
     return _oracle
+
+
+def pytest_collection_modifyitems(config, items):
+    """A kernel that never finishes must fail its test, not hang the GPU box until the runner's own
+    limit: every gpu-marked test gets a generous pytest-timeout (thread method: the process exits,
+    the driver tears the context down)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
