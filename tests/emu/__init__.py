@@ -86,5 +86,9 @@ def env(sms: int = 4) -> dict:
     e["GDV_EMU_STATIC_LIB"] = libs["static"]
     e["GDV_EMU_SMS"] = str(sms)
     e["GDV_EMU"] = "1"  # tests/ read this to pick simulator-sized inputs
+    # three CTAs resident at once (each on its own copy of the kernel's shared object), scheduled in
+    # a pseudo-random order: look-back waits and ticket order are exercised, not just sequential tiles
+    e.setdefault("GDV_EMU_CTAS", "3")
+    e.setdefault("GDV_EMU_SCHED", "2")
     e.pop("GDV_CUBIN_CACHE_DIR", None)  # the simulator's "cubins" must never reach a real cache
     return e

@@ -11,7 +11,9 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <ucontext.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +32,8 @@ struct gdv_emu_thread {
   unsigned lane, warp;
 };
 
+extern "C" gdv_emu_thread* gdv_emu_cur;
+
 namespace {
 
 constexpr size_t kStackBytes = 256 * 1024;
@@ -39,31 +43,43 @@ struct WarpSync {
   unsigned long long vals[32];
   unsigned long long snap[32];
 };
+struct CtaRun;
 struct Fiber {
   ucontext_t ctx;
   gdv_emu_thread th;
+  CtaRun* cta = nullptr;
   bool done = false;
 };
+// One resident CTA.  Several may be resident at once (GDV_EMU_CTAS): each runs its own copy of the
+// kernel's shared object, because `__shared__` variables are function-local statics there.
 struct CtaRun {
   std::vector<Fiber> fibers;
   std::vector<WarpSync> warps;
+  std::vector<char*> stacks;
   unsigned live = 0, bar_arrived = 0, bar_gen = 0;
-  ucontext_t sched;
   void (*entry)(void**) = nullptr;
   void** params = nullptr;
+  void* dyn_smem = nullptr;
+  bool active = false;
 };
-CtaRun* g_cta = nullptr;
-std::vector<char*> g_stacks;
+ucontext_t g_sched;
 std::recursive_mutex g_mu;
+int g_resident_ctas = 1;   // GDV_EMU_CTAS: CTAs resident at once (> 1 exercises look-back waits)
+int g_sched_policy = 0;    // GDV_EMU_SCHED: 0 = lowest CTA first, 1 = highest CTA first, 2 = xorshift
 
 struct Module {
-  void* handle = nullptr;
+  std::vector<void*> handles;  // [0] the shared object, [i] private copies for concurrently resident CTAs
+  std::string path;
 };
 struct Function {
-  void (*entry)(void**) = nullptr;
+  std::vector<void (*)(void**)> entries;  // one per copy
   std::string name;
   int max_dyn_smem = 48 * 1024;
 };
+
+Fiber* CurFiber() {
+  return reinterpret_cast<Fiber*>(reinterpret_cast<char*>(gdv_emu_cur) - offsetof(Fiber, th));
+}
 
 }  // namespace
 
@@ -71,13 +87,12 @@ extern "C" {
 gdv_emu_thread* gdv_emu_cur = nullptr;
 
 void gdv_emu_yield() {
-  CtaRun* c = g_cta;
-  Fiber* f = reinterpret_cast<Fiber*>(reinterpret_cast<char*>(gdv_emu_cur) - offsetof(Fiber, th));
-  swapcontext(&f->ctx, &c->sched);
+  Fiber* f = CurFiber();
+  swapcontext(&f->ctx, &g_sched);
 }
 
 void gdv_emu_syncthreads() {
-  CtaRun* c = g_cta;
+  CtaRun* c = CurFiber()->cta;
   const unsigned my = c->bar_gen;
   if (++c->bar_arrived >= c->live) {
     c->bar_arrived = 0;
@@ -88,7 +103,7 @@ void gdv_emu_syncthreads() {
 }
 
 void gdv_emu_warp_gather(unsigned mask, unsigned long long v, unsigned long long* out) {
-  CtaRun* c = g_cta;
+  CtaRun* c = CurFiber()->cta;
   gdv_emu_thread* t = gdv_emu_cur;
   WarpSync& w = c->warps[t->warp];
   if (((mask >> t->lane) & 1u) == 0u) {
@@ -116,8 +131,8 @@ void gdv_emu_warp_gather(unsigned mask, unsigned long long v, unsigned long long
 namespace {
 
 void FiberEntry() {
-  CtaRun* c = g_cta;
-  Fiber* f = reinterpret_cast<Fiber*>(reinterpret_cast<char*>(gdv_emu_cur) - offsetof(Fiber, th));
+  Fiber* f = CurFiber();
+  CtaRun* c = f->cta;
   c->entry(c->params);
   f->done = true;
   --c->live;
@@ -126,57 +141,99 @@ void FiberEntry() {
     c->bar_arrived = 0;
     ++c->bar_gen;
   }
-  swapcontext(&f->ctx, &c->sched);
+  swapcontext(&f->ctx, &g_sched);
 }
 
-bool RunCta(Function* fn, const gdv_emu_uint3& bid, const gdv_emu_uint3& bdim,
-            const gdv_emu_uint3& gdim, void* dyn_smem, void** params) {
+void StartCta(CtaRun* cta, void (*entry)(void**), void** params, const gdv_emu_uint3& bid,
+              const gdv_emu_uint3& bdim, const gdv_emu_uint3& gdim, size_t smem) {
   const unsigned nthreads = bdim.x * bdim.y * bdim.z;
-  CtaRun cta;
-  cta.fibers.resize(nthreads);
-  cta.warps.resize((nthreads + 31) / 32);
-  cta.live = nthreads;
-  cta.entry = fn->entry;
-  cta.params = params;
-  while (g_stacks.size() < nthreads) g_stacks.push_back(static_cast<char*>(std::malloc(kStackBytes)));
-  g_cta = &cta;
+  cta->fibers.assign(nthreads, Fiber());
+  cta->warps.assign((nthreads + 31) / 32, WarpSync());
+  cta->live = nthreads;
+  cta->bar_arrived = 0;
+  cta->bar_gen = 0;
+  cta->entry = entry;
+  cta->params = params;
+  cta->active = true;
+  while (cta->stacks.size() < nthreads) cta->stacks.push_back(static_cast<char*>(std::malloc(kStackBytes)));
+  std::memset(cta->dyn_smem, 0xA5, smem + 1024);  // shared memory starts undefined
   for (unsigned i = 0; i < nthreads; ++i) {
-    Fiber& f = cta.fibers[i];
+    Fiber& f = cta->fibers[i];
+    f.cta = cta;
     f.th.tid = {i % bdim.x, (i / bdim.x) % bdim.y, i / (bdim.x * bdim.y)};
     f.th.bid = bid;
     f.th.bdim = bdim;
     f.th.gdim = gdim;
-    f.th.dyn_smem = dyn_smem;
+    f.th.dyn_smem = cta->dyn_smem;
     f.th.lane = i & 31u;
     f.th.warp = i >> 5;
     getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = g_stacks[i];
+    f.ctx.uc_stack.ss_sp = cta->stacks[i];
     f.ctx.uc_stack.ss_size = kStackBytes;
-    f.ctx.uc_link = &cta.sched;
+    f.ctx.uc_link = &g_sched;
     makecontext(&f.ctx, FiberEntry, 0);
   }
-  unsigned long long idle_rounds = 0;
-  while (cta.live > 0) {
-    const unsigned live_before = cta.live;
-    const unsigned gen_before = cta.bar_gen;
-    for (unsigned i = 0; i < nthreads; ++i) {
-      Fiber& f = cta.fibers[i];
-      if (f.done) continue;
-      gdv_emu_cur = &f.th;
-      swapcontext(&cta.sched, &f.ctx);
+}
+
+std::vector<CtaRun*> g_slots;  // reused across launches (stacks are expensive)
+
+// Runs the grid with up to `resident` CTAs at a time; CTA i uses copy (slot index) of the kernel.
+bool RunGrid(Function* fn, const gdv_emu_uint3& gdim, const gdv_emu_uint3& bdim, size_t smem, void** params) {
+  const unsigned long long total = 1ull * gdim.x * gdim.y * gdim.z;
+  const unsigned resident = static_cast<unsigned>(
+      std::min<unsigned long long>(total, std::min<size_t>(fn->entries.size(), static_cast<size_t>(g_resident_ctas))));
+  while (g_slots.size() < resident) g_slots.push_back(new CtaRun());
+  for (unsigned s = 0; s < resident; ++s) {
+    std::free(g_slots[s]->dyn_smem);
+    g_slots[s]->dyn_smem = nullptr;
+    if (posix_memalign(&g_slots[s]->dyn_smem, 1024, smem + 1024) != 0) return false;
+    g_slots[s]->active = false;
+  }
+  unsigned long long next = 0, finished = 0, idle_rounds = 0, rng = 0x9E3779B97F4A7C15ull;
+  auto bid_of = [&](unsigned long long i) {
+    return gdv_emu_uint3{static_cast<unsigned>(i % gdim.x), static_cast<unsigned>((i / gdim.x) % gdim.y),
+                         static_cast<unsigned>(i / (1ull * gdim.x * gdim.y))};
+  };
+  while (finished < total) {
+    for (unsigned s = 0; s < resident; ++s)
+      if (!g_slots[s]->active && next < total) {
+        StartCta(g_slots[s], fn->entries[s], params, bid_of(next), bdim, gdim, smem);
+        ++next;
+      }
+    bool progressed = false;
+    for (unsigned k = 0; k < resident; ++k) {
+      unsigned s = k;
+      if (g_sched_policy == 1) s = resident - 1 - k;
+      else if (g_sched_policy == 2) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        s = static_cast<unsigned>(rng % resident);
+      }
+      CtaRun* cta = g_slots[s];
+      if (!cta->active) continue;
+      const unsigned live_before = cta->live, gen_before = cta->bar_gen;
+      for (Fiber& f : cta->fibers) {
+        if (f.done) continue;
+        gdv_emu_cur = &f.th;
+        swapcontext(&g_sched, &f.ctx);
+      }
+      if (cta->live != live_before || cta->bar_gen != gen_before) progressed = true;
+      if (cta->live == 0) {
+        cta->active = false;
+        ++finished;
+        progressed = true;
+      }
     }
-    // crude hang detector: nothing exits and no barrier completes for a very long time
-    if (cta.live == live_before && cta.bar_gen == gen_before) {
-      if (++idle_rounds > 100'000ull) {
-        std::fprintf(stderr, "gdv_emu: kernel %s appears to hang (CTA %u)\n", fn->name.c_str(), bid.x);
-        g_cta = nullptr;
+    // crude hang detector: no thread exits and no CTA barrier completes for a very long time
+    if (!progressed) {
+      if (++idle_rounds > 200'000ull) {
+        std::fprintf(stderr, "gdv_emu: kernel %s appears to hang\n", fn->name.c_str());
+        gdv_emu_cur = nullptr;
         return false;
       }
     } else {
       idle_rounds = 0;
     }
   }
-  g_cta = nullptr;
   gdv_emu_cur = nullptr;
   return true;
 }
@@ -193,6 +250,8 @@ extern "C" {
 CUresult cuInit(unsigned int) {
   if (const char* e = std::getenv("GDV_EMU_DEVICES")) g_device_count = std::atoi(e);
   if (const char* e = std::getenv("GDV_EMU_SMS")) g_sm_count = std::atoi(e);
+  if (const char* e = std::getenv("GDV_EMU_CTAS")) g_resident_ctas = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("GDV_EMU_SCHED")) g_sched_policy = std::atoi(e);
   EMU_OK;
 }
 CUresult cuDeviceGetCount(int* n) { *n = g_device_count; EMU_OK; }
@@ -310,6 +369,24 @@ CUresult cuEventRecord(CUevent, CUstream) { EMU_OK; }
 CUresult cuEventSynchronize(CUevent) { EMU_OK; }
 CUresult cuEventDestroy_v2(CUevent) { EMU_OK; }
 
+// A private copy of the shared object: dlopen of a different path gives different statics.
+static void* OpenCopy(const std::string& path, int copy) {
+  if (copy == 0) return dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  const std::string cp = path + ".c" + std::to_string(copy) + ".so";
+  if (access(cp.c_str(), R_OK) != 0) {
+    const std::string tmp = cp + ".tmp" + std::to_string(getpid());
+    FILE* in = std::fopen(path.c_str(), "rb");
+    FILE* out = std::fopen(tmp.c_str(), "wb");
+    if (in == nullptr || out == nullptr) return nullptr;
+    char buf[65536];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), in)) > 0) std::fwrite(buf, 1, n, out);
+    std::fclose(in);
+    std::fclose(out);
+    std::rename(tmp.c_str(), cp.c_str());
+  }
+  return dlopen(cp.c_str(), RTLD_NOW | RTLD_LOCAL);
+}
 CUresult cuModuleLoadData(CUmodule* m, const void* image) {
   std::lock_guard<std::recursive_mutex> lock(g_mu);
   std::string path;
@@ -320,27 +397,36 @@ CUresult cuModuleLoadData(CUmodule* m, const void* image) {
     if (s == nullptr) return CUDA_ERROR_INVALID_IMAGE;
     path = s;
   }
-  void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
-  if (h == nullptr) {
-    std::fprintf(stderr, "gdv_emu: dlopen(%s): %s\n", path.c_str(), dlerror());
-    return CUDA_ERROR_INVALID_IMAGE;
-  }
   Module* mod = new Module();
-  mod->handle = h;
+  mod->path = path;
+  for (int c = 0; c < g_resident_ctas; ++c) {
+    void* h = OpenCopy(path, c);
+    if (h == nullptr) {
+      std::fprintf(stderr, "gdv_emu: dlopen(%s, copy %d): %s\n", path.c_str(), c, dlerror());
+      delete mod;
+      return CUDA_ERROR_INVALID_IMAGE;
+    }
+    mod->handles.push_back(h);
+  }
   *m = reinterpret_cast<CUmodule>(mod);
   EMU_OK;
 }
 CUresult cuModuleUnload(CUmodule m) {
-  delete reinterpret_cast<Module*>(m);  // the .so stays mapped: kernels keep function-local statics
+  delete reinterpret_cast<Module*>(m);  // the objects stay mapped: kernels keep function-local statics
   EMU_OK;
 }
 CUresult cuModuleGetFunction(CUfunction* f, CUmodule m, const char* name) {
   Module* mod = reinterpret_cast<Module*>(m);
   const std::string tramp = std::string(name) + "__emu";
-  void* p = dlsym(mod->handle, tramp.c_str());
-  if (p == nullptr) return CUDA_ERROR_NOT_FOUND;
   Function* fn = new Function();
-  fn->entry = reinterpret_cast<void (*)(void**)>(p);
+  for (void* h : mod->handles) {
+    void* p = dlsym(h, tramp.c_str());
+    if (p == nullptr) {
+      delete fn;
+      return CUDA_ERROR_NOT_FOUND;
+    }
+    fn->entries.push_back(reinterpret_cast<void (*)(void**)>(p));
+  }
   fn->name = name;
   *f = reinterpret_cast<CUfunction>(fn);
   EMU_OK;
@@ -373,17 +459,7 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
   Function* fn = reinterpret_cast<Function*>(f);
   if (bx * by * bz == 0 || bx * by * bz > 1024 || gx * gy * gz == 0) return CUDA_ERROR_INVALID_VALUE;
   if (static_cast<int>(smem) > fn->max_dyn_smem) return CUDA_ERROR_INVALID_VALUE;
-  void* dyn = nullptr;
-  if (posix_memalign(&dyn, 1024, smem + 1024) != 0) return CUDA_ERROR_OUT_OF_MEMORY;
-  const gdv_emu_uint3 bdim{bx, by, bz}, gdim{gx, gy, gz};
-  bool ok = true;
-  for (unsigned z = 0; z < gz && ok; ++z)
-    for (unsigned y = 0; y < gy && ok; ++y)
-      for (unsigned x = 0; x < gx && ok; ++x) {
-        std::memset(dyn, 0xA5, smem + 1024);  // shared memory starts undefined
-        ok = RunCta(fn, gdv_emu_uint3{x, y, z}, bdim, gdim, dyn, params);
-      }
-  std::free(dyn);
+  const bool ok = RunGrid(fn, gdv_emu_uint3{gx, gy, gz}, gdv_emu_uint3{bx, by, bz}, smem, params);
   if (ok && !GuardsIntact(("after kernel " + fn->name).c_str())) return CUDA_ERROR_ILLEGAL_ADDRESS;
   return ok ? CUDA_SUCCESS : CUDA_ERROR_LAUNCH_TIMEOUT;
 }
