@@ -52,6 +52,8 @@ GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
 #define GDV_XF_ASCII 0x100u
 #define GDV_XF_LOCAL 0x200u  /* bytes live in the producing thread's scratch slot: only that thread may read them */
 #define GDV_XF_REP 0x400u    /* periodic: byte i is p[i % (xf >> 12)]; only the string write pass reads these */
+#define GDV_XF_REPL 0x4u     /* replace(): the view is the SOURCE text, (xf >> 12) & 0xff the call site whose
+                                literals gdv_repl_len / gdv_repl_copy (generated per kernel) apply */
 #define GDV_XF_REV 0x800u    /* glyph-reversed: copied by the owning lane in the string write pass */
 #define GDV_SCRATCH_SLOT 64  /* bytes per (row, call site) of a function that writes its result as text */
 struct gdv_str {
@@ -1734,6 +1736,54 @@ GDV_DEV gdv_str gdv_pad_fill(gdv_str s, i32 n, gdv_str fill) {
   gdv_str r = gdv_rep_view(fill.p, (i64)fill.len, bytes);
   r.xf |= fill.xf & (GDV_XF_CASE | GDV_XF_LOCAL);
   return r;
+}
+// replace(s, from, to) with literal from / to: the piece is the source view; its output length and
+// bytes come from these two (leftmost, non-overlapping occurrences; an empty `from` replaces
+// nothing).  Bytes are compared and copied through the view's case map.
+GDV_DEV i32 gdv_replace_len(const gdv_str& s, const u8* from, i32 fl, i32 tl) {
+  if (fl <= 0) return s.len;
+  i64 out = 0;
+  for (i32 i = 0; i < s.len;) {
+    bool hit = i + fl <= s.len;
+    for (i32 j = 0; hit && j < fl; ++j) hit = gdv_ch(s, i + j) == from[j];
+    if (hit) {
+      out += tl;
+      i += fl;
+    } else {
+      ++out;
+      ++i;
+    }
+  }
+  return out > 0x7fffffffll ? 0x7fffffff : (i32)out;
+}
+GDV_DEV void gdv_replace_copy(u8* dst, const gdv_str& s, const u8* from, i32 fl, const u8* to, i32 tl) {
+  i64 out = 0;
+  for (i32 i = 0; i < s.len;) {
+    bool hit = fl > 0 && i + fl <= s.len;
+    for (i32 j = 0; hit && j < fl; ++j) hit = gdv_ch(s, i + j) == from[j];
+    if (hit) {
+      for (i32 j = 0; j < tl; ++j) dst[out++] = to[j];
+      i += fl;
+    } else {
+      dst[out++] = gdv_ch(s, i);
+      ++i;
+    }
+  }
+}
+GDV_DEV gdv_str gdv_repl_view(gdv_str s, u32 site) {
+  s.xf = (s.xf & (GDV_XF_CASE | GDV_XF_LOCAL)) | GDV_XF_REPL | (site << 12);
+  return s;
+}
+#ifdef GDV_HAS_REPL  /* the fuser defines both after this header, one switch over the call sites */
+GDV_DEV i32 gdv_repl_len(const gdv_str& v);
+GDV_DEV void gdv_repl_copy(u8* dst, const gdv_str& v);
+#else
+GDV_DEV i32 gdv_repl_len(const gdv_str& v) { return v.len; }
+GDV_DEV void gdv_repl_copy(u8*, const gdv_str&) {}
+#endif
+// Output bytes of a piece (everything but replace(): the view's own length).
+GDV_DEV u32 gdv_piece_len(const gdv_str& v) {
+  return (v.xf & GDV_XF_REPL) != 0u ? (u32)gdv_repl_len(v) : (u32)v.len;
 }
 // Byte i of a piece as the string write pass sees it (periodic pieces wrap around).
 GDV_DEV u8 gdv_piece_byte(const gdv_str& v, i32 i) {

@@ -228,8 +228,23 @@ class BodyGen {
 
   // Device-scope definitions the body needs; GDV_NS = call sites that write text into scratch slots.
   std::string globals() const {
-    return n_scratch_ > 0 ? "#define GDV_NS " + std::to_string(n_scratch_) + "\n" + globals_ : globals_;
+    std::string g = n_scratch_ > 0 ? "#define GDV_NS " + std::to_string(n_scratch_) + "\n" + globals_ : globals_;
+    if (!repl_sites_.empty()) {
+      // replace() call sites: one switch each for the output length and the copy
+      std::string len = "__device__ __forceinline__ i32 gdv_repl_len(const gdv_str& v) {\n  switch ((v.xf >> 12) & 0xffu) {\n";
+      std::string cpy = "__device__ __forceinline__ void gdv_repl_copy(u8* dst, const gdv_str& v) {\n  switch ((v.xf >> 12) & 0xffu) {\n";
+      for (size_t i = 0; i < repl_sites_.size(); ++i) {
+        const ReplSite& r = repl_sites_[i];
+        len += "    case " + std::to_string(i) + ": return gdv_replace_len(v, " + r.from + ", " + std::to_string(r.fl) +
+               ", " + std::to_string(r.tl) + ");\n";
+        cpy += "    case " + std::to_string(i) + ": gdv_replace_copy(dst, v, " + r.from + ", " + std::to_string(r.fl) +
+               ", " + r.to + ", " + std::to_string(r.tl) + "); return;\n";
+      }
+      g += len + "  }\n  return v.len;\n}\n" + cpy + "  }\n}\n";
+    }
+    return g;
   }
+  bool has_replace() const { return !repl_sites_.empty(); }
   int scratch_sites() const { return n_scratch_; }
   // Declaration of the thread-private scratch slots of a kernel that evaluates R rows per group.
   std::string ScratchDecl(int R) const {
@@ -855,7 +870,22 @@ class BodyGen {
         r.parts.push_back(pv);
       };
       const std::string& nm = fn.name();
-      if (nm == "lpad" || nm == "rpad") {
+      if (nm == "replace") {
+        const Node& fnode = *fn.children()[1];
+        const Node& tnode = *fn.children()[2];
+        if (fnode.kind() != NodeKind::kLiteral || tnode.kind() != NodeKind::kLiteral ||
+            static_cast<const LiteralNode&>(fnode).is_null() || static_cast<const LiteralNode&>(tnode).is_null()) {
+          if (error_.empty()) error_ = "replace(s, from, to) needs literal, non-null from / to strings";
+          return r;
+        }
+        if (repl_sites_.size() >= 256 && error_.empty()) error_ = "more than 256 replace() calls in one kernel";
+        const std::string& fb = static_cast<const LiteralNode&>(fnode).bytes();
+        const std::string& tb = static_cast<const LiteralNode&>(tnode).bytes();
+        ReplSite site{BytesArray(fb, "gdv_rfrom_"), BytesArray(tb, "gdv_rto_"), static_cast<int>(fb.size()),
+                      static_cast<int>(tb.size())};
+        piece("gdv_repl_view(" + args[0].v + ", " + std::to_string(repl_sites_.size()) + "u)");
+        repl_sites_.push_back(site);
+      } else if (nm == "lpad" || nm == "rpad") {
         const std::string fill = args.size() == 3 ? args[2].v : std::string("gdv_make_str(gdv_one_space, 1)");
         const std::string pad = "gdv_pad_fill(" + args[0].v + ", " + args[1].v + ", " + fill + ")";
         const std::string text = "gdv_pad_text(" + args[0].v + ", " + args[1].v + ")";
@@ -1063,6 +1093,11 @@ class BodyGen {
   std::string error_;  // first construct the fuser cannot lower (reported by GenerateKernel)
   std::vector<CoopSeg> coop_segs_;
   std::string globals_;
+  struct ReplSite {
+    std::string from, to;  // names of the literal byte arrays
+    int fl, tl;
+  };
+  std::vector<ReplSite> repl_sites_;
   int n_scratch_ = 0;
   int next_id_ = 0;
   bool uses_ctx_ = false;
@@ -1785,6 +1820,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
          (is_size ? "sizing pass" : "write pass") +
          (spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n");
   src += "// expr_0: " + CommentSafe(expr->ToString()) + "\n";
+  if (gen.has_replace()) src += "#define GDV_HAS_REPL 1\n";
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
@@ -1823,7 +1859,7 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
   const int K = static_cast<int>(parts.size());
   const std::string sK = std::to_string(K);
   std::string total_len;
-  for (int i = 0; i < K; ++i) total_len += (i ? " + " : "") + std::string("(u32)(") + parts[i] + ").len";
+  for (int i = 0; i < K; ++i) total_len += (i ? " + " : "") + std::string("gdv_piece_len(") + parts[i] + ")";
   std::string tail;
   if (is_size) {
     src += "    u32 tsum = 0u;\n";
@@ -1891,12 +1927,13 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     src += "      const bool rowok = slen[k] != 0u;\n";
     src += "      #pragma unroll\n";
     src += "      for (int piece = 0; piece < " + sK + "; ++piece) {\n";
-    src += "        const u32 plen = rowok ? (u32)sv[k][piece].len : 0u;\n";
+    src += "        const u32 plen = rowok ? gdv_piece_len(sv[k][piece]) : 0u;\n";
     src += "        // text in a thread-private scratch slot is copied by its owner, everything else by the warp\n";
-    src += "        const bool mine_only = (sv[k][piece].xf & (GDV_XF_LOCAL | GDV_XF_REV)) != 0u;\n";
+    src += "        const bool mine_only = (sv[k][piece].xf & (GDV_XF_LOCAL | GDV_XF_REV | GDV_XF_REPL)) != 0u;\n";
     src += "        if (plen != 0u && mine_only) {\n";
     src += "          if (dst0 + (u64)plen <= (u64)A.out_cap) {\n";
-    src += "            if ((sv[k][piece].xf & GDV_XF_REV) != 0u) gdv_copy_reversed(data + dst0, sv[k][piece]);\n";
+    src += "            if ((sv[k][piece].xf & GDV_XF_REPL) != 0u) gdv_repl_copy(data + dst0, sv[k][piece]);\n";
+    src += "            else if ((sv[k][piece].xf & GDV_XF_REV) != 0u) gdv_copy_reversed(data + dst0, sv[k][piece]);\n";
     src += "            else for (u32 i = 0u; i < plen; ++i) data[dst0 + (u64)i] = gdv_piece_byte(sv[k][piece], (i32)i);\n";
     src += "          } else {\n";
     src += "            gdv_set_error(&ctx, GDV_ERR_VAR_CAPACITY);\n";

@@ -284,6 +284,7 @@ Registry::Registry() {
   Add("castVARCHAR", {TS, I64}, S, NullMode::kIfNull, kScratch);
   Add("castVARCHAR", {B, I64}, S);
   // new bytes without a bound: virtual pieces (periodic / reversed views) read by the write pass only
+  Add("replace", {S, S, S}, S, NullMode::kIfNull, kVirtual);   // from / to must be literals
   Add("repeat", {S, I32}, S, NullMode::kIfNull, kVirtual);
   Add("space", {I32}, S, NullMode::kIfNull, kVirtual);
   Add("reverse", {S}, S, NullMode::kIfNull, kVirtual);

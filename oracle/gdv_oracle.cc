@@ -1551,6 +1551,18 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   if (f == "hashSHA256" || f == "sha256") { out->s = Sha256Hex(a[0].s); return; }
   if (f == "hashSHA1" || f == "sha1") { out->s = Sha1Hex(a[0].s); return; }
   if (f == "hashMD5" || f == "md5") { out->s = Md5Hex(a[0].s); return; }
+  if (f == "replace") {
+    out->s.clear();
+    if (a[1].s.empty()) { out->s = a[0].s; return; }
+    size_t from = 0;
+    while (true) {
+      const size_t hit = a[0].s.find(a[1].s, from);
+      if (hit == std::string::npos) { out->s += a[0].s.substr(from); break; }
+      out->s += a[0].s.substr(from, hit - from) + a[2].s;
+      from = hit + a[1].s.size();
+    }
+    return;
+  }
   if (f == "repeat") {
     out->s.clear();
     for (int64_t k = 0; k < a[1].i; ++k) out->s += a[0].s;

@@ -392,6 +392,12 @@ def case_virtual_strings(b):
         (b.make_if(pp, fn("repeat", [u, lit(2, I)], S), fn("reverse", [u], S), S), S),
         (fn("reverse", [fn("castVARCHAR", [l, lit(30, L)], S)], S), S),
         (fn("repeat", [fn("castVARCHAR", [k, lit(4, L)], S), lit(2, I)], S), S),
+        (fn("replace", [s, lit("re", S), lit("<RE>", S)], S), S), (fn("replace", [s, lit(" ", S), lit("", S)], S), S),
+        (fn("replace", [fn("upper", [s], S), lit("SPECIAL", S), lit("日本", S)], S), S),
+        (fn("replace", [u, lit("", S), lit("x", S)], S), S), (fn("replace", [u, lit("ss", S), lit("s", S)], S), S),
+        (fn("concat", [fn("replace", [s, lit("a", S), lit("aa", S)], S), lit("|", S),
+                       fn("replace", [fn("castVARCHAR", [l, lit(30, L)], S), lit("1", S), lit("one", S)], S)], S), S),
+        (b.make_if(pp, fn("replace", [s, lit("e", S), lit("", S)], S), fn("replace", [s, lit("e", S), lit("EE", S)], S), S), S),
     ]
     return schema, outs, "project"
 

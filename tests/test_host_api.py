@@ -209,6 +209,10 @@ def test_concat_consumers_are_rejected(gandiva):
     like = b.make_function("like", [cc, b.make_literal("%ab%", t)], pa.bool_())
     with pytest.raises(pa.ArrowNotImplementedError, match="concat"):
         gandiva.make_filter(schema, b.make_condition(like))
+    # replace() needs literal from / to
+    with pytest.raises(pa.ArrowNotImplementedError, match="literal"):
+        gandiva.make_projector(schema, [b.make_expression(
+            b.make_function("replace", [cases.F(b, "s", t), cases.F(b, "u", t), b.make_literal("x", t)], t), pa.field("r", t))], None)
     # the same holds for the virtual pieces of repeat / space / lpad / rpad / reverse
     for inner in (b.make_function("repeat", [cases.F(b, "s", t), b.make_literal(2, pa.int32())], t),
                   b.make_function("reverse", [cases.F(b, "s", t)], t),

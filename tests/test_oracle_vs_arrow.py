@@ -891,7 +891,12 @@ def test_virtual_strings(oracle, gandiva):
                "[" + ("" if num is None else pad(num, 8, "0", True)) + "]",
                ("" if sv is None else sv[::-1]) + "  " + "----",
                (None if uv is None else uv * 2) if p[r] else (None if uv is None else uv[::-1]),
-               None if num is None else num[::-1], None if k[r] is None else str(k[r])[:4] * 2]
+               None if num is None else num[::-1], None if k[r] is None else str(k[r])[:4] * 2,
+               None if sv is None else sv.replace("re", "<RE>"), None if sv is None else sv.replace(" ", ""),
+               None if sv is None else up(sv).replace("SPECIAL", "日本"),
+               uv, None if uv is None else uv.replace("ss", "s"),
+               ("" if sv is None else sv.replace("a", "aa")) + "|" + ("" if num is None else num.replace("1", "one")),
+               None if sv is None else (sv.replace("e", "") if p[r] else sv.replace("e", "EE"))]
         for c, w in enumerate(exp):
             assert got[c][r] == w, (c, r, got[c][r], w, sv, uv, kk)
 

@@ -24,7 +24,7 @@ TYPES = [I32, I64, F32, F64, B, S, BIN, D64, TS, T32, D32]
 # special form, build ropes, produce NaN (sqrt), or hit signed-overflow corners whose result is
 # unspecified in both implementations (calendar arithmetic with arbitrary 32-bit month counts)
 SKIP = {"divide", "div", "like", "ilike", "concat", "concatOperator", "sqrt", "castDECIMAL", "split_part",
-        "repeat", "space", "reverse", "lpad", "rpad",
+        "repeat", "space", "reverse", "lpad", "rpad", "replace",
         "timestampaddMonth", "timestampaddQuarter", "timestampaddYear", "mod", "modulo"}
 LIKE_PATTERNS = ["%spark%", "s%", "%s", "%special%requests%", "_a%", "%", "", "%re%e%", "fire", "%日本%"]
 STR_LITS = ["", "s", "re", "park", "special", "日本", " ", "Quick", "x_y"]
