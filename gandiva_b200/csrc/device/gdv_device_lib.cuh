@@ -1105,6 +1105,56 @@ GDV_DEV gdv_u256 gdv_scale_up_u256(u128 x, i32 e, bool* overflow) {
   }
   return r;
 }
+// round / truncate / ceil / floor of a decimal: drop `d` = xs - rs digits under `mode` (0 half away
+// from zero, 1 toward zero, 2 toward +inf, 3 toward -inf), then express the result (scale rs) at the
+// declared output (op, os).  rs >= xs: nothing to drop.  More than 38 digits -> 0, like the others.
+GDV_DEV i128 gdv_decimal_round_to(i128 x, i32 xs, i32 rs, i32 mode, i32 op, i32 os) {
+  const bool neg = x < 0;
+  gdv_u256 mag = gdv_u256_from(gdv_abs_u128(x));
+  i32 cur = xs;  // scale of `mag`
+  if (rs < xs) {
+    const i32 d = xs - rs;
+    if (d > 39) {
+      mag = gdv_u256_from((u128)0);
+      if ((mode == 2 && !neg && x != 0) || (mode == 3 && neg)) mag = gdv_u256_from((u128)1);
+    } else if (mode == 0) {
+      mag = gdv_div_pow10_round(mag, d > 38 ? 38 : d);
+      if (d > 38) gdv_divmod_u256_u64(mag, 10ull);  // 10^39 > any 38-digit magnitude: 0 (half of it too)
+    } else {
+      bool rem_any = false;
+      i32 left = d;
+      while (left > 0) {
+        const i32 step = left > 19 ? 19 : left;
+        rem_any = (gdv_divmod_u256_u64(mag, (u64)gdv_pow10_u128(step)) != 0ull) || rem_any;
+        left -= step;
+      }
+      if (rem_any && ((mode == 2 && !neg) || (mode == 3 && neg))) mag = gdv_add_u256(mag, gdv_u256_from((u128)1));
+    }
+    cur = rs;
+  }
+  if (os > cur) {
+    bool overflow = false;
+    if (mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+    mag = gdv_scale_up_u256(gdv_u256_low128(mag), os - cur, &overflow);
+    if (overflow) return (i128)0;
+  } else if (os < cur) {
+    mag = gdv_div_pow10_round(mag, cur - os > 38 ? 38 : cur - os);
+  }
+  if (mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+  const u128 m = ((u128)mag.w[1] << 64) | (u128)mag.w[0];
+  if (m >= gdv_pow10_u128(op)) return (i128)0;
+  return (neg && m != 0) ? (i128)(~m + 1) : (i128)m;
+}
+GDV_DEV i128 round_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return gdv_decimal_round_to(x, xs, 0, 0, op, os); }
+GDV_DEV i128 round_decimal128_int32(i128 x, i32 xp, i32 xs, i32 rs, i32 op, i32 os) {
+  return gdv_decimal_round_to(x, xs, rs < -38 ? -39 : rs, 0, op, os);
+}
+GDV_DEV i128 truncate_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return gdv_decimal_round_to(x, xs, 0, 1, op, os); }
+GDV_DEV i128 truncate_decimal128_int32(i128 x, i32 xp, i32 xs, i32 rs, i32 op, i32 os) {
+  return gdv_decimal_round_to(x, xs, rs < -38 ? -39 : rs, 1, op, os);
+}
+GDV_DEV i128 ceil_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return gdv_decimal_round_to(x, xs, 0, 2, op, os); }
+GDV_DEV i128 floor_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return gdv_decimal_round_to(x, xs, 0, 3, op, os); }
 // x / y at the declared output scale: |x| * 10^(os - xs + ys) / |y|, rounded half away from zero;
 // y == 0 raises "divide by zero error"; a quotient of more than 38 digits yields 0.
 GDV_DEV i128 divide_decimal128_decimal128(gdv_ctx* c, i128 x, i32 xp, i32 xs, i128 y, i32 yp,

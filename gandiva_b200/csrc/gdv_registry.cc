@@ -230,6 +230,12 @@ Registry::Registry() {
   Add("multiply", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("divide", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs | kCanFail);
   Add("mod", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs | kCanFail, {"modulo"});
+  Add("round", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("round", {DEC, I32}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("truncate", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs, {"trunc"});
+  Add("truncate", {DEC, I32}, DEC, NullMode::kIfNull, kDecimalArgs, {"trunc"});
+  Add("ceil", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("floor", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("abs", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("negative", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castDECIMAL", {I32}, DEC, NullMode::kIfNull, kDecimalArgs);

@@ -540,6 +540,36 @@ int DecimalCompare(i128 x, int xs, i128 y, int ys) {
   return a.neg ? -c : c;
 }
 
+// Drops xs - rs digits under `mode` (0 half away from zero, 1 toward zero, 2 toward +inf, 3 toward
+// -inf), then expresses the result at (op, os): digit by digit, with a sticky remainder.
+i128 DecimalRoundTo(i128 x, int xs, int64_t rs64, int mode, int op, int os) {
+  SignedBig a = ToSigned(x);
+  const int rs = static_cast<int>(std::max<int64_t>(rs64, -39));
+  int cur = xs;
+  if (rs < xs) {
+    const int d = xs - rs;
+    bool sticky = false;
+    uint32_t last = 0;
+    for (int k = 0; k < d; ++k) {
+      sticky = sticky || last != 0;
+      last = a.mag.DivSmall(10);
+    }
+    bool up;
+    if (mode == 0) up = last >= 5;
+    else if (mode == 1) up = false;
+    else if (mode == 2) up = !a.neg && (last != 0 || sticky);
+    else up = a.neg && (last != 0 || sticky);
+    if (up) a.mag.Add(Big::From(1));
+    cur = rs;
+  }
+  if (os > cur) {
+    if (!a.mag.MulPow10Checked(os - cur)) return 0;
+  } else if (os < cur) {
+    a.mag = DivPow10HalfUp(a.mag, std::min(cur - os, 38));
+  }
+  return FromSigned(a, op);
+}
+
 i128 DecimalRescale(i128 x, int xs, int op, int os) {
   SignedBig a = ToSigned(x);
   if (os > xs) a.mag.MulPow10(os - xs);
@@ -1231,6 +1261,11 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   }
 
   // ---- rounding ---------------------------------------------------------------------------
+  if (rt.id == T_DECIMAL && (f == "round" || f == "truncate" || f == "trunc" || f == "ceil" || f == "floor")) {
+    const int mode = f == "round" ? 0 : (f == "ceil" ? 2 : (f == "floor" ? 3 : 1));
+    out->dec = DecimalRoundTo(a[0].dec, t0.scale, na == 2 ? a[1].i : 0, mode, rt.precision, rt.scale);
+    return;
+  }
   if ((f == "round" || f == "truncate" || f == "trunc") && na == 2 && rt.id != T_DOUBLE) {
     // integers: to a multiple of 10^-s for s < 0, in 128 bits, wrapped into the output type
     const int64_t sc = a[1].i;

@@ -467,6 +467,28 @@ def case_decimal_misc(b):
                     (b.make_function("abs", [x], t1), t1), (b.make_function("negative", [y], t2), t2)], "project"
 
 
+def case_decimal_rounding(b):
+    """round / truncate / ceil / floor of decimal128: to scale 0, to a literal scale (positive, zero,
+    negative, larger than the input's), with result types as the caller declares them."""
+    t1, t2 = pa.decimal128(15, 4), pa.decimal128(38, 10)
+    schema = pa.schema([("x", t1), ("y", t2)])
+    x, y = F(b, "x", t1), F(b, "y", t2)
+    fn = b.make_function
+    I = pa.int32()
+    D = pa.decimal128
+    outs = [
+        (fn("round", [x], D(12, 0)), D(12, 0)), (fn("truncate", [x], D(12, 0)), D(12, 0)),
+        (fn("ceil", [x], D(12, 0)), D(12, 0)), (fn("floor", [x], D(12, 0)), D(12, 0)),
+        (fn("round", [x, b.make_literal(2, I)], D(15, 2)), D(15, 2)), (fn("round", [x, b.make_literal(-2, I)], D(12, 0)), D(12, 0)),
+        (fn("truncate", [x, b.make_literal(1, I)], D(13, 1)), D(13, 1)), (fn("trunc", [x, b.make_literal(-3, I)], D(12, 0)), D(12, 0)),
+        (fn("round", [x, b.make_literal(6, I)], D(17, 6)), D(17, 6)),
+        (fn("round", [y], D(29, 0)), D(29, 0)), (fn("ceil", [y], D(29, 0)), D(29, 0)), (fn("floor", [y], D(29, 0)), D(29, 0)),
+        (fn("round", [y, b.make_literal(3, I)], D(32, 3)), D(32, 3)), (fn("truncate", [y, b.make_literal(-5, I)], D(29, 0)), D(29, 0)),
+        (fn("round", [y, b.make_literal(-40, I)], D(29, 0)), D(29, 0)),
+    ]
+    return schema, outs, "project"
+
+
 def decimal_divide_type(p1, s1, p2, s2):
     """The reference's result type for decimal divide (DESIGN.md semantics table):
     scale = max(6, s1 + p2 + 1), precision = p1 - s1 + s2 + scale, capped at 38 by giving up
@@ -968,7 +990,8 @@ def all_project_cases():
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
-              case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings]
+              case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
+              case_decimal_rounding]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

@@ -943,3 +943,33 @@ def test_month_differences(oracle, gandiva):
             assert gb1[r] == months_between(t[r], u[r]), (r, gb1[r])
         if d[r] is not None and t[r] is not None:
             assert gb2[r] == months_between(d[r], (t[r] // 86400000) * 86400000), r
+
+
+def test_decimal_rounding(oracle, gandiva):
+    """round / truncate / ceil / floor of decimal128 against Python's `decimal` quantize
+    (ROUND_HALF_UP / ROUND_DOWN / ROUND_CEILING / ROUND_FLOOR)."""
+    D = decimal.Decimal
+    b = gandiva.TreeExprBuilder()
+    schema, outs, _ = cases.case_decimal_rounding(b)
+    batch = cases.random_batch(schema, 3000, seed=61, null_prob=0.1)
+    got = [g.to_pylist() for g in oracle.project([r for r, _ in outs], [t for _, t in outs], batch)]
+    x, y = batch.column(0).to_pylist(), batch.column(1).to_pylist()
+
+    def q(v, digits, mode):
+        if v is None:
+            return None
+        with decimal.localcontext() as ctx:
+            ctx.prec = 80
+            r = v.quantize(D(1).scaleb(-digits), rounding=mode)
+            return r
+    HU, DN, CE, FL = decimal.ROUND_HALF_UP, decimal.ROUND_DOWN, decimal.ROUND_CEILING, decimal.ROUND_FLOOR
+    plan = [(x, 0, HU), (x, 0, DN), (x, 0, CE), (x, 0, FL), (x, 2, HU), (x, -2, HU), (x, 1, DN), (x, -3, DN), (x, 6, HU),
+            (y, 0, HU), (y, 0, CE), (y, 0, FL), (y, 3, HU), (y, -5, DN), (y, -40, HU)]
+    for c, (col, digits, mode) in enumerate(plan):
+        for r in range(len(col)):
+            want = q(col[r], digits, mode)
+            g = got[c][r]
+            if want is None:
+                assert g is None, (c, r)
+            else:
+                assert g is not None and D(g) == want, (c, r, col[r], g, want)
