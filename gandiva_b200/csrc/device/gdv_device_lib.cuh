@@ -36,6 +36,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_CAST_INT 4         /* castINT / castBIGINT of a string that is not an integer */
 #define GDV_ERR_CAST_DATE 5        /* castDATE / castTIMESTAMP of a string that is not a date / timestamp */
 #define GDV_ERR_SPLIT_INDEX 6      /* split_part with an index < 1 */
+#define GDV_ERR_CAST_DECIMAL 7     /* castDECIMAL of a string that is not a decimal number */
 struct gdv_ctx {
   int* err;
 };
@@ -1155,6 +1156,65 @@ GDV_DEV i128 truncate_decimal128_int32(i128 x, i32 xp, i32 xs, i32 rs, i32 op, i
 }
 GDV_DEV i128 ceil_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return gdv_decimal_round_to(x, xs, 0, 2, op, os); }
 GDV_DEV i128 floor_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return gdv_decimal_round_to(x, xs, 0, 3, op, os); }
+// castDECIMAL(utf8): [spaces][+-]digits[.digits][spaces] (at least one digit), rounded half away
+// from zero to the declared scale; anything else raises; a value that needs more than the declared
+// precision yields 0 like the other decimal producers.  Digits beyond 76 are not accumulated
+// (they cannot change a 38-digit result except through the sticky rounding digit, which is kept).
+GDV_DEV i128 castDECIMAL_utf8(gdv_ctx* c, gdv_str s, i32 op, i32 os) {
+  i32 b = 0, e = s.len;
+  while (b < e && s.p[b] == (u8)' ') ++b;
+  while (e > b && s.p[e - 1] == (u8)' ') --e;
+  bool neg = false;
+  if (b < e && (s.p[b] == (u8)'-' || s.p[b] == (u8)'+')) {
+    neg = s.p[b] == (u8)'-';
+    ++b;
+  }
+  gdv_u256 mag = gdv_u256_from((u128)0);
+  i32 digits = 0, frac = 0;  // digits seen, fractional digits accumulated into mag
+  bool seen_point = false, overflow = false, ok = true;
+  u32 round_digit = 0u;      // first fractional digit beyond the target scale
+  bool have_round = false;
+  for (i32 i = b; i < e && ok; ++i) {
+    const u32 ch = (u32)s.p[i];
+    if (ch == (u32)'.') {
+      ok = !seen_point;
+      seen_point = true;
+      continue;
+    }
+    const u32 d = ch - (u32)'0';
+    if (d > 9u) {
+      ok = false;
+      break;
+    }
+    ++digits;
+    if (seen_point && frac >= os) {
+      if (!have_round) {
+        round_digit = d;
+        have_round = true;
+      }
+      continue;  // digits past the rounding digit cannot matter for half-away rounding
+    }
+    bool o = false;
+    mag = gdv_mul_u256_u128(mag, (u128)10, &o);
+    overflow = overflow || o;
+    mag = gdv_add_u256(mag, gdv_u256_from((u128)d));
+    if (seen_point) ++frac;
+  }
+  if (!ok || digits == 0) {
+    gdv_set_error(c, GDV_ERR_CAST_DECIMAL);
+    return (i128)0;
+  }
+  if (frac < os) {  // fewer fractional digits than the target scale: scale up
+    bool o = false;
+    mag = gdv_mul_u256_u128(mag, gdv_pow10_u128(os - frac), &o);
+    overflow = overflow || o;
+  }
+  if (have_round && round_digit >= 5u) mag = gdv_add_u256(mag, gdv_u256_from((u128)1));
+  if (overflow || mag.w[2] != 0 || mag.w[3] != 0) return (i128)0;
+  const u128 m = ((u128)mag.w[1] << 64) | (u128)mag.w[0];
+  if (m >= gdv_pow10_u128(op)) return (i128)0;
+  return (neg && m != 0) ? (i128)(~m + 1) : (i128)m;
+}
 // x / y at the declared output scale: |x| * 10^(os - xs + ys) / |y|, rounded half away from zero;
 // y == 0 raises "divide by zero error"; a quotient of more than 38 digits yields 0.
 GDV_DEV i128 divide_decimal128_decimal128(gdv_ctx* c, i128 x, i32 xp, i32 xs, i128 y, i32 yp,
@@ -1880,6 +1940,24 @@ GDV_DEV gdv_str castVARCHAR_int64_int64(i64 v, i64 maxlen, u8* scr) {
 }
 GDV_DEV gdv_str castVARCHAR_int32_int64(i32 v, i64 maxlen, u8* scr) {
   return castVARCHAR_int64_int64((i64)v, maxlen, scr);
+}
+// castVARCHAR(decimal(p, s), n): [-]integer digits[.s fractional digits], then the first n characters
+GDV_DEV gdv_str castVARCHAR_decimal128_int64(i128 x, i32 xp, i32 xs, i64 maxlen, u8* scr) {
+  u8 tmp[40];
+  i32 n = 0;
+  u128 m = gdv_abs_u128(x);
+  do {
+    tmp[n++] = (u8)((u32)'0' + (u32)(m % 10u));
+    m /= 10u;
+  } while (m != 0u);
+  while (n <= xs) tmp[n++] = (u8)'0';  // at least one digit before the point
+  i32 at = 0;
+  if (x < 0) scr[at++] = (u8)'-';
+  for (i32 k = n - 1; k >= 0; --k) {
+    scr[at++] = tmp[k];
+    if (k == xs && xs > 0) scr[at++] = (u8)'.';
+  }
+  return gdv_scratch_str(scr, at, maxlen);
 }
 // to_hex(int): upper-case hexadecimal digits of the two's-complement bits, no leading zeros
 GDV_DEV gdv_str gdv_to_hex(u64 v, u8* scr) {

@@ -243,6 +243,8 @@ Registry::Registry() {
   Add("castDECIMAL", {F64}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castDECIMAL", {F32}, DEC, NullMode::kIfNull, kDecimalArgs);
   Add("castDECIMAL", {DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
+  Add("castDECIMAL", {S}, DEC, NullMode::kIfNull, kDecimalArgs | kCanFail);
+  Add("castVARCHAR", {DEC, I64}, S, NullMode::kIfNull, kDecimalArgs | kScratch);
   Add("castBIGINT", {DEC}, I64, NullMode::kIfNull, kDecimalArgs);
   Add("castFLOAT8", {DEC}, F64, NullMode::kIfNull, kDecimalArgs);
 

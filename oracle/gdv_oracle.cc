@@ -1252,6 +1252,36 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "castTIMESTAMP") { out->i = a[0].i; return; }
+  if (f == "castDECIMAL" && t0.id == T_STRING) {
+    // [spaces][+-]digits[.digits][spaces]; half away from zero at the declared scale
+    std::string str = a[0].s;
+    while (!str.empty() && str.front() == ' ') str.erase(str.begin());
+    while (!str.empty() && str.back() == ' ') str.pop_back();
+    bool neg = false;
+    size_t pos = 0;
+    if (pos < str.size() && (str[pos] == '-' || str[pos] == '+')) { neg = str[pos] == '-'; ++pos; }
+    std::string ip, fp;
+    bool point = false, good = true;
+    for (; pos < str.size(); ++pos) {
+      if (str[pos] == '.') { good = good && !point; point = true; }
+      else if (str[pos] >= '0' && str[pos] <= '9') (point ? fp : ip).push_back(str[pos]);
+      else good = false;
+    }
+    if (!good || ip.size() + fp.size() == 0) { cx.error = 7; return; }
+    const size_t scale = static_cast<size_t>(rt.scale);
+    const bool up = fp.size() > scale && fp[scale] >= '5';
+    fp.resize(scale, '0');   // cut or pad to exactly `scale` fractional digits
+    Big mag;
+    bool overflow = false;
+    for (char ch : ip + fp) {
+      if (!mag.MulPow10Checked(1)) overflow = true;
+      mag.Add(Big::From(static_cast<u128>(ch - '0')));
+    }
+    if (up) mag.Add(Big::From(1));
+    SignedBig sb{neg, mag};
+    out->dec = overflow ? 0 : FromSigned(sb, rt.precision);
+    return;
+  }
   if (f == "castDECIMAL") {
     if (t0.id == T_DECIMAL) out->dec = DecimalRescale(a[0].dec, t0.scale, rt.precision, rt.scale);
     else if (t0.id == T_DOUBLE) out->dec = DecimalFromDouble(a[0].d, rt.precision, rt.scale);
@@ -1506,6 +1536,18 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   if (f == "substr" || f == "substring") {
     out->s = na == 3 ? Substr(a[0].s, a[1].i, a[2].i)
                      : Substr(a[0].s, a[1].i, static_cast<int64_t>(a[0].s.size()));
+    return;
+  }
+  if (f == "castVARCHAR" && t0.id == T_DECIMAL) {
+    // unscaled digits with the point `scale` places from the right
+    u128 m = a[0].dec < 0 ? (~static_cast<u128>(a[0].dec) + 1) : static_cast<u128>(a[0].dec);
+    std::string digits;
+    do { digits.insert(digits.begin(), static_cast<char>('0' + static_cast<int>(m % 10))); m /= 10; } while (m != 0);
+    const size_t sc = static_cast<size_t>(t0.scale);
+    if (digits.size() <= sc) digits.insert(0, sc + 1 - digits.size(), '0');
+    if (sc > 0) digits.insert(digits.size() - sc, ".");
+    if (a[0].dec < 0) digits.insert(digits.begin(), '-');
+    out->s = Substr(digits, 1, a[1].i);
     return;
   }
   if (f == "castVARCHAR" && t0.id != T_STRING) {

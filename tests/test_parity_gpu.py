@@ -765,3 +765,54 @@ def test_date_arithmetic_month_ends(gandiva, oracle):
         want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
         for i, (g, w) in enumerate(zip(got, want)):
             assert_arrays_match(g, w, "date arithmetic n=%d out=%d" % (n, i))
+
+
+def test_decimal_text_round_trip(gandiva, oracle):
+    """castVARCHAR(decimal, n) and castDECIMAL(utf8): kernels against the oracle and both against
+    Python's `decimal`; text -> decimal -> text is the identity at the same scale; malformed numbers
+    raise an ExecutionError."""
+    D = decimal = __import__("decimal").Decimal
+    t1, t2, S, L = pa.decimal128(15, 4), pa.decimal128(38, 10), pa.string(), pa.int64()
+    schema = pa.schema([("x", t1), ("y", t2), ("s", S)])
+    b = gandiva.TreeExprBuilder()
+    x, y, s = cases.F(b, "x", t1), cases.F(b, "y", t2), cases.F(b, "s", S)
+    fn = b.make_function
+    n = lambda v: b.make_literal(v, L)
+    outs = [(fn("castVARCHAR", [x, n(64)], S), S), (fn("castVARCHAR", [y, n(64)], S), S), (fn("castVARCHAR", [x, n(5)], S), S),
+            (fn("castDECIMAL", [s], pa.decimal128(20, 3)), pa.decimal128(20, 3)),
+            (fn("castDECIMAL", [s], pa.decimal128(38, 0)), pa.decimal128(38, 0)),
+            (fn("castDECIMAL", [fn("castVARCHAR", [y, n(64)], S)], t2), t2)]
+    exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(outs)]
+    p = gandiva.make_projector(schema, exprs, None)
+    rng = np.random.default_rng(4)
+    base = cases.random_batch(pa.schema([("x", t1), ("y", t2)]), 2000, seed=9, null_prob=0.1)
+    texts = []
+    for k in range(2000):
+        ip = "".join(str(int(d)) for d in rng.integers(0, 10, int(rng.integers(0, 12))))
+        fp = "".join(str(int(d)) for d in rng.integers(0, 10, int(rng.integers(0, 8))))
+        t = ("-" if k % 3 == 0 else ("+" if k % 7 == 0 else "")) + ip + ("." + fp if (fp or k % 5 == 0) else "")
+        if not (ip or fp):
+            t = "0"
+        texts.append(None if k % 19 == 3 else (" " * (k % 2)) + t + (" " * (k % 3)))
+    batch = pa.RecordBatch.from_arrays([base.column(0), base.column(1), pa.array(texts, S)], schema=schema)
+    got = p.evaluate(batch)
+    want = oracle.project([r for r, _ in outs], [t for _, t in outs], batch)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "decimal text out %d" % i)
+    xs, ys = batch.column(0).to_pylist(), batch.column(1).to_pylist()
+    g0, g1, g3, g5 = got[0].to_pylist(), got[1].to_pylist(), got[3].to_pylist(), got[5].to_pylist()
+    for r in range(2000):
+        if xs[r] is not None:
+            assert D(g0[r]) == xs[r] and g0[r] == format(xs[r], "f")
+        if ys[r] is not None:
+            assert g1[r] == format(ys[r], "f") and g5[r] == ys[r]
+        if texts[r] is not None:
+            q = D(texts[r].strip()).quantize(D("0.001"), rounding="ROUND_HALF_UP")
+            assert g3[r] == q, (r, texts[r], g3[r], q)
+    for bad in ("", " ", "-", "1.2.3", "12a", "1e5", ".", "--1", "1 2"):
+        one = pa.RecordBatch.from_arrays([base.column(0).slice(0, 2), base.column(1).slice(0, 2), pa.array(["1.5", bad], S)],
+                                         schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: Failed to cast the string to a decimal"):
+            p.evaluate(one)
+        with pytest.raises(Exception, match="decimal"):
+            oracle.project([outs[3][0]], [outs[3][1]], one)
