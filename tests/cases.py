@@ -264,7 +264,6 @@ def case_string_positions(b):
     fn = b.make_function
     lit = b.make_literal
     clen = lambda x: fn("char_length", [x], I)
-    small_k = fn("castINT", [fn("mod", [fn("castBIGINT", [k], pa.int64()), lit(9, I)], I)], I) if False else None
     kk = fn("subtract", [fn("castINT", [fn("mod", [fn("castBIGINT", [k], pa.int64()), lit(9, pa.int64())], pa.int64())], I),
                          lit(4, I)], I)   # k mod 9 - 4: a small signed count
     outs = [
