@@ -397,6 +397,160 @@ GDV_GREATEST_LEAST(i64, int64)
 GDV_GREATEST_LEAST(f32, float32)
 GDV_GREATEST_LEAST(f64, float64)
 
+// ---- exp / log / log10 / cbrt: explicit IEEE sequences ------------------------------------------------
+// CUDA's libm and the host's differ in the last bit(s), so these are not library calls: each is the
+// classic fdlibm (Sun Microsystems, 1993, freely usable) argument reduction + polynomial written out
+// as a fixed sequence of IEEE double operations, which oracle/gdv_oracle.cc repeats operation for
+// operation (the engine compiles with --fmad=false, the oracle with -ffp-contract=off): bit-exact
+// parity, < 1 ULP from the exact result (measured against the host libm in tests/).
+GDV_DEV f64 gdv_f64_from_bits(u64 b) { return __longlong_as_double((i64)b); }
+GDV_DEV u64 gdv_f64_bits(f64 d) { return (u64)__double_as_longlong(d); }
+GDV_DEV f64 exp_float64(f64 x) {
+  const f64 ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
+  const f64 P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+            P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+  if (x != x) return x;
+  if (x > 7.09782712893383973096e+02) return gdv_f64_from_bits(0x7ff0000000000000ull);
+  if (x < -7.45133219101941108420e+02) return 0.0;
+  const f64 ax = x < 0.0 ? -x : x;
+  f64 hi = 0.0, lo = 0.0;
+  i32 k = 0;
+  if (ax > 0.34657359027997264) {          // |x| > 0.5 ln2
+    if (ax < 1.0397207708399179) {         // |x| < 1.5 ln2
+      k = x < 0.0 ? -1 : 1;
+    } else {
+      k = (i32)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+    }
+    hi = x - (f64)k * ln2hi;
+    lo = (f64)k * ln2lo;
+    x = hi - lo;
+  } else if (ax < 3.7252902984619141e-09) {  // |x| < 2^-28
+    return 1.0 + x;
+  }
+  const f64 t = x * x;
+  const f64 c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+  const f64 y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+  // y * 2^k through the exponent field (y is in [0.5, 2))
+  if (k == 1024) return (y * 2.0) * 8.98846567431157953865e+307;  // 2^1023: the field would overflow
+  if (k >= -1021) return gdv_f64_from_bits(gdv_f64_bits(y) + ((u64)(i64)k << 52));
+  return gdv_f64_from_bits(gdv_f64_bits(y) + ((u64)(i64)(k + 1000) << 52)) * 9.33263618503218878990e-302;  // 2^-1000
+}
+GDV_DEV f64 log_float64(f64 x) {
+  const f64 ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10;
+  const f64 Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+            Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+            Lg7 = 1.479819860511658591e-01;
+  if (x != x) return x;
+  if (x < 0.0) return gdv_f64_from_bits(0x7ff8000000000000ull);
+  if (x == 0.0) return gdv_f64_from_bits(0xfff0000000000000ull);
+  u64 bits = gdv_f64_bits(x);
+  if (bits == 0x7ff0000000000000ull) return x;
+  i32 k = 0;
+  if ((bits >> 52) == 0ull) {  // subnormal: scale up by 2^54
+    x = x * 18014398509481984.0;
+    bits = gdv_f64_bits(x);
+    k = -54;
+  }
+  i32 hx = (i32)(bits >> 32);
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const i32 i = (hx + 0x95f64) & 0x100000;
+  x = gdv_f64_from_bits(((u64)(u32)(hx | (i ^ 0x3ff00000)) << 32) | (bits & 0xffffffffull));  // x in [sqrt(2)/2, sqrt(2))
+  k += i >> 20;
+  const f64 f = x - 1.0;
+  const f64 dk = (f64)k;
+  if ((0x000fffff & (2 + hx)) < 3) {  // |f| < 2^-20
+    if (f == 0.0) return k == 0 ? 0.0 : dk * ln2hi + dk * ln2lo;
+    const f64 R = f * f * (0.5 - 0.33333333333333333 * f);
+    if (k == 0) return f - R;
+    return dk * ln2hi - ((R - dk * ln2lo) - f);
+  }
+  const f64 s = f / (2.0 + f);
+  const f64 z = s * s;
+  const f64 w = z * z;
+  const f64 t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  const f64 t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  const f64 R = t2 + t1;
+  if (((hx - 0x6147a) | (0x6b851 - hx)) > 0) {
+    const f64 hfsq = 0.5 * f * f;
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    return dk * ln2hi - ((hfsq - (s * (hfsq + R) + dk * ln2lo)) - f);
+  }
+  if (k == 0) return f - s * (f - R);
+  return dk * ln2hi - ((s * (f - R) - dk * ln2lo) - f);
+}
+GDV_DEV f64 log10_float64(f64 x) {
+  // FreeBSD msun's e_log10: log(1 + f) kept as a hi + lo pair, multiplied by 1 / ln 10 (hi + lo too)
+  const f64 ivln10hi = 4.34294481878168880939e-01, ivln10lo = 2.50829467116452752298e-11;
+  const f64 log10_2hi = 3.01029995663611771306e-01, log10_2lo = 3.69423907715893078616e-13;
+  const f64 Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+            Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+            Lg7 = 1.479819860511658591e-01;
+  if (x != x) return x;
+  if (x < 0.0) return gdv_f64_from_bits(0x7ff8000000000000ull);
+  if (x == 0.0) return gdv_f64_from_bits(0xfff0000000000000ull);
+  u64 bits = gdv_f64_bits(x);
+  if (bits == 0x7ff0000000000000ull) return x;
+  if (x == 1.0) return 0.0;
+  i32 k = 0;
+  if ((bits >> 52) == 0ull) {
+    x = x * 18014398509481984.0;
+    bits = gdv_f64_bits(x);
+    k = -54;
+  }
+  i32 hx = (i32)(bits >> 32);
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const i32 i = (hx + 0x95f64) & 0x100000;
+  x = gdv_f64_from_bits(((u64)(u32)(hx | (i ^ 0x3ff00000)) << 32) | (bits & 0xffffffffull));
+  k += i >> 20;
+  const f64 dk = (f64)k;
+  const f64 f = x - 1.0;
+  const f64 hfsq = 0.5 * f * f;
+  const f64 s = f / (2.0 + f);
+  const f64 z = s * s;
+  const f64 w = z * z;
+  const f64 t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  const f64 t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  const f64 r = s * (hfsq + (t2 + t1));  // log(1 + f) - f + f * f / 2
+  f64 hi = f - hfsq;
+  hi = gdv_f64_from_bits(gdv_f64_bits(hi) & 0xffffffff00000000ull);
+  const f64 lo = (f - hi) - hfsq + r;
+  f64 val_hi = hi * ivln10hi;
+  const f64 y2 = dk * log10_2hi;
+  f64 val_lo = dk * log10_2lo + (lo + hi) * ivln10lo + lo * ivln10hi;
+  const f64 ww = y2 + val_hi;
+  val_lo += (y2 - ww) + val_hi;
+  val_hi = ww;
+  return val_lo + val_hi;
+}
+GDV_DEV f64 cbrt_float64(f64 x) {
+  const f64 P0 = 1.87595182427177009643, P1 = -1.88497979543377169875, P2 = 1.621429720105354466140,
+            P3 = -0.758397934778766047437, P4 = 0.145996192886612446982;
+  const u64 bits = gdv_f64_bits(x);
+  const u64 sign = bits & 0x8000000000000000ull;
+  const u32 hx = (u32)(bits >> 32) & 0x7fffffffu;
+  if (hx >= 0x7ff00000u) return x + x;  // inf / NaN
+  f64 t;
+  if (hx < 0x00100000u) {               // zero or subnormal
+    if ((bits & 0x7fffffffffffffffull) == 0ull) return x;
+    const f64 sc = gdv_f64_from_bits(bits & 0x7fffffffffffffffull) * 18014398509481984.0;  // |x| * 2^54
+    const u32 h2 = (u32)(gdv_f64_bits(sc) >> 32) & 0x7fffffffu;
+    t = gdv_f64_from_bits(sign | ((u64)(h2 / 3u + 696219795u) << 32));
+  } else {
+    t = gdv_f64_from_bits(sign | ((u64)(hx / 3u + 715094163u) << 32));
+  }
+  f64 r = (t * t) * (t / x);
+  t = t * ((P0 + r * (P1 + r * P2)) + ((r * r) * r) * (P3 + r * P4));
+  t = gdv_f64_from_bits((gdv_f64_bits(t) + 0x80000000ull) & 0xffffffffc0000000ull);  // 23 significant bits
+  const f64 s2 = t * t;
+  r = x / s2;
+  const f64 w = t + t;
+  r = (r - t) / (w + r);
+  return t + t * r;
+}
+
 // ---- comparisons -----------------------------------------------------------------------
 #define GDV_RELOP(T, S)                                                               \
   GDV_DEV bool equal_##S##_##S(T a, T b) { return a == b; }                           \

@@ -93,6 +93,10 @@ Registry::Registry() {
     Add("bitwise_not", {t}, t);
   }
   Add("sqrt", {F64}, F64);
+  Add("exp", {F64}, F64);
+  Add("log", {F64}, F64, NullMode::kIfNull, 0, {"ln"});
+  Add("log10", {F64}, F64);
+  Add("cbrt", {F64}, F64);
   Add("degrees", {F64}, F64);
   Add("radians", {F64}, F64);
   for (const auto& t : {I32, I64}) {

@@ -931,6 +931,153 @@ std::string Md5Hex(const std::string& m) {
   return HexOfWords(H, 4, false);
 }
 
+// ---- exp / log / log10 / cbrt: the same IEEE operation sequences as the device library (fdlibm's
+// reductions and polynomials, Sun Microsystems 1993); the two must agree bit for bit, and both are
+// measured against the host libm in tests/test_oracle_vs_arrow.py.
+double F64FromBits(uint64_t b) { double d; std::memcpy(&d, &b, 8); return d; }
+uint64_t F64Bits(double d) { uint64_t b; std::memcpy(&b, &d, 8); return b; }
+double OrcExp(double x) {
+  const double ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
+  const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+  if (x != x) return x;
+  if (x > 7.09782712893383973096e+02) return F64FromBits(0x7ff0000000000000ull);
+  if (x < -7.45133219101941108420e+02) return 0.0;
+  const double ax = x < 0.0 ? -x : x;
+  double hi = 0.0, lo = 0.0;
+  int32_t k = 0;
+  if (ax > 0.34657359027997264) {
+    if (ax < 1.0397207708399179) k = x < 0.0 ? -1 : 1;
+    else k = static_cast<int32_t>(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+    hi = x - static_cast<double>(k) * ln2hi;
+    lo = static_cast<double>(k) * ln2lo;
+    x = hi - lo;
+  } else if (ax < 3.7252902984619141e-09) {
+    return 1.0 + x;
+  }
+  const double t = x * x;
+  const double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+  const double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+  if (k == 1024) return (y * 2.0) * 8.98846567431157953865e+307;
+  if (k >= -1021) return F64FromBits(F64Bits(y) + (static_cast<uint64_t>(static_cast<int64_t>(k)) << 52));
+  return F64FromBits(F64Bits(y) + (static_cast<uint64_t>(static_cast<int64_t>(k + 1000)) << 52)) * 9.33263618503218878990e-302;
+}
+double OrcLog(double x) {
+  const double ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10;
+  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+               Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+               Lg7 = 1.479819860511658591e-01;
+  if (x != x) return x;
+  if (x < 0.0) return F64FromBits(0x7ff8000000000000ull);
+  if (x == 0.0) return F64FromBits(0xfff0000000000000ull);
+  uint64_t bits = F64Bits(x);
+  if (bits == 0x7ff0000000000000ull) return x;
+  int32_t k = 0;
+  if ((bits >> 52) == 0) {
+    x = x * 18014398509481984.0;
+    bits = F64Bits(x);
+    k = -54;
+  }
+  int32_t hx = static_cast<int32_t>(bits >> 32);
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int32_t i = (hx + 0x95f64) & 0x100000;
+  x = F64FromBits((static_cast<uint64_t>(static_cast<uint32_t>(hx | (i ^ 0x3ff00000))) << 32) | (bits & 0xffffffffull));
+  k += i >> 20;
+  const double f = x - 1.0;
+  const double dk = static_cast<double>(k);
+  if ((0x000fffff & (2 + hx)) < 3) {
+    if (f == 0.0) return k == 0 ? 0.0 : dk * ln2hi + dk * ln2lo;
+    const double R = f * f * (0.5 - 0.33333333333333333 * f);
+    if (k == 0) return f - R;
+    return dk * ln2hi - ((R - dk * ln2lo) - f);
+  }
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  const double R = t2 + t1;
+  if (((hx - 0x6147a) | (0x6b851 - hx)) > 0) {
+    const double hfsq = 0.5 * f * f;
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    return dk * ln2hi - ((hfsq - (s * (hfsq + R) + dk * ln2lo)) - f);
+  }
+  if (k == 0) return f - s * (f - R);
+  return dk * ln2hi - ((s * (f - R) - dk * ln2lo) - f);
+}
+double OrcLog10(double x) {
+  // FreeBSD msun's e_log10: log(1 + f) kept as a hi + lo pair, multiplied by 1 / ln 10 (hi + lo too)
+  const double ivln10hi = 4.34294481878168880939e-01, ivln10lo = 2.50829467116452752298e-11;
+  const double log10_2hi = 3.01029995663611771306e-01, log10_2lo = 3.69423907715893078616e-13;
+  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+            Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+            Lg7 = 1.479819860511658591e-01;
+  if (x != x) return x;
+  if (x < 0.0) return F64FromBits(0x7ff8000000000000ull);
+  if (x == 0.0) return F64FromBits(0xfff0000000000000ull);
+  uint64_t bits = F64Bits(x);
+  if (bits == 0x7ff0000000000000ull) return x;
+  if (x == 1.0) return 0.0;
+  int32_t k = 0;
+  if ((bits >> 52) == 0ull) {
+    x = x * 18014398509481984.0;
+    bits = F64Bits(x);
+    k = -54;
+  }
+  int32_t hx = (int32_t)(bits >> 32);
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int32_t i = (hx + 0x95f64) & 0x100000;
+  x = F64FromBits(((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (bits & 0xffffffffull));
+  k += i >> 20;
+  const double dk = (double)k;
+  const double f = x - 1.0;
+  const double hfsq = 0.5 * f * f;
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  const double r = s * (hfsq + (t2 + t1));  // log(1 + f) - f + f * f / 2
+  double hi = f - hfsq;
+  hi = F64FromBits(F64Bits(hi) & 0xffffffff00000000ull);
+  const double lo = (f - hi) - hfsq + r;
+  double val_hi = hi * ivln10hi;
+  const double y2 = dk * log10_2hi;
+  double val_lo = dk * log10_2lo + (lo + hi) * ivln10lo + lo * ivln10hi;
+  const double ww = y2 + val_hi;
+  val_lo += (y2 - ww) + val_hi;
+  val_hi = ww;
+  return val_lo + val_hi;
+}
+double OrcCbrt(double x) {
+  const double P0 = 1.87595182427177009643, P1 = -1.88497979543377169875, P2 = 1.621429720105354466140,
+               P3 = -0.758397934778766047437, P4 = 0.145996192886612446982;
+  const uint64_t bits = F64Bits(x);
+  const uint64_t sign = bits & 0x8000000000000000ull;
+  const uint32_t hx = static_cast<uint32_t>(bits >> 32) & 0x7fffffffu;
+  if (hx >= 0x7ff00000u) return x + x;
+  double t;
+  if (hx < 0x00100000u) {
+    if ((bits & 0x7fffffffffffffffull) == 0) return x;
+    const double sc = F64FromBits(bits & 0x7fffffffffffffffull) * 18014398509481984.0;
+    const uint32_t h2 = static_cast<uint32_t>(F64Bits(sc) >> 32) & 0x7fffffffu;
+    t = F64FromBits(sign | (static_cast<uint64_t>(h2 / 3u + 696219795u) << 32));
+  } else {
+    t = F64FromBits(sign | (static_cast<uint64_t>(hx / 3u + 715094163u) << 32));
+  }
+  double r = (t * t) * (t / x);
+  t = t * ((P0 + r * (P1 + r * P2)) + ((r * r) * r) * (P3 + r * P4));
+  t = F64FromBits((F64Bits(t) + 0x80000000ull) & 0xffffffffc0000000ull);
+  const double s2 = t * t;
+  r = x / s2;
+  const double w = t + t;
+  r = (r - t) / (w + r);
+  return t + t * r;
+}
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
@@ -1128,6 +1275,10 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "sqrt") { out->d = std::sqrt(a[0].d); return; }
+  if (f == "exp") { out->d = OrcExp(a[0].d); return; }
+  if (f == "log" || f == "ln") { out->d = OrcLog(a[0].d); return; }
+  if (f == "log10") { out->d = OrcLog10(a[0].d); return; }
+  if (f == "cbrt") { out->d = OrcCbrt(a[0].d); return; }
   if (f == "bitwise_and") { out->i = a[0].i & a[1].i; return; }
   if (f == "bitwise_or") { out->i = a[0].i | a[1].i; return; }
   if (f == "bitwise_xor") { out->i = a[0].i ^ a[1].i; return; }

@@ -401,6 +401,19 @@ def case_virtual_strings(b):
     return schema, outs, "project"
 
 
+def case_math(b):
+    """exp / log / ln / log10 / cbrt (explicit IEEE sequences, bit-exact against the oracle)."""
+    D = pa.float64()
+    schema = pa.schema([("d", D), ("e", D)])
+    d, e = F(b, "d", D), F(b, "e", D)
+    fn = b.make_function
+    small = fn("divide", [d, b.make_literal(1.0e5, D)], D)            # ~N(0, 10): exp stays finite
+    outs = [(fn("exp", [small], D), D), (fn("exp", [d], D), D), (fn("log", [fn("abs", [d], D)], D), D),
+            (fn("ln", [e], D), D), (fn("log10", [fn("abs", [e], D)], D), D), (fn("cbrt", [d], D), D),
+            (fn("log", [fn("exp", [small], D)], D), D), (fn("cbrt", [fn("multiply", [e, fn("multiply", [e, e], D)], D)], D), D)]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -990,7 +1003,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding]
+              case_decimal_rounding, case_math]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]
