@@ -27,6 +27,9 @@ typedef unsigned __int128 u128;
 
 #define GDV_FULL 0xffffffffu
 #define GDV_DEV __device__ __forceinline__
+// big, rarely hot helpers (digests, parsers, decimal rounding): one copy per kernel instead of one
+// per call site keeps Make() latency (ptxas time) in check
+#define GDV_DEV_BIG __device__ __noinline__
 
 // ---- error reporting (ExecutionError, P/include/arrow/status.h:100) -----------------
 #define GDV_ERR_NONE 0
@@ -859,7 +862,7 @@ GDV_TSDIFF(timestampdiffWeek, 604800000ll)
 // timestampdiff{Month,Quarter,Year}(a, b): whole calendar months from a to b, consistent with
 // timestampaddMonth: the largest |k| such that a + k months (day clamped to the month's length,
 // time of day kept) does not pass b; quarters and years are that count / 3 and / 12, truncated.
-GDV_DEV i64 gdv_months_between_whole(i64 a, i64 b) {
+GDV_DEV_BIG i64 gdv_months_between_whole(i64 a, i64 b) {
   const gdv_ymd ca = gdv_civil_from_days(gdv_floordiv(a, 86400000ll));
   const gdv_ymd cb = gdv_civil_from_days(gdv_floordiv(b, 86400000ll));
   i64 k = (cb.y - ca.y) * 12 + (i64)(cb.m - ca.m);
@@ -878,7 +881,7 @@ GDV_DEV i32 timestampdiffYear_timestamp_timestamp(i64 a, i64 b) { return (i32)(g
 // months_between(a, b) (Hive / Oracle): a - b in months; whole when both are the same day of the
 // month or both the last day of theirs, else the month difference plus (day and time of day
 // difference) / 31 days; IEEE double operations in a fixed order.
-GDV_DEV f64 gdv_months_between(i64 a, i64 b) {
+GDV_DEV_BIG f64 gdv_months_between(i64 a, i64 b) {
   const i64 da = gdv_floordiv(a, 86400000ll), db = gdv_floordiv(b, 86400000ll);
   const gdv_ymd ca = gdv_civil_from_days(da), cb = gdv_civil_from_days(db);
   const f64 months = (f64)((ca.y - cb.y) * 12 + (i64)(ca.m - cb.m));
@@ -1263,7 +1266,7 @@ GDV_DEV gdv_u256 gdv_scale_up_u256(u128 x, i32 e, bool* overflow) {
 // round / truncate / ceil / floor of a decimal: drop `d` = xs - rs digits under `mode` (0 half away
 // from zero, 1 toward zero, 2 toward +inf, 3 toward -inf), then express the result (scale rs) at the
 // declared output (op, os).  rs >= xs: nothing to drop.  More than 38 digits -> 0, like the others.
-GDV_DEV i128 gdv_decimal_round_to(i128 x, i32 xs, i32 rs, i32 mode, i32 op, i32 os) {
+GDV_DEV_BIG i128 gdv_decimal_round_to(i128 x, i32 xs, i32 rs, i32 mode, i32 op, i32 os) {
   const bool neg = x < 0;
   gdv_u256 mag = gdv_u256_from(gdv_abs_u128(x));
   i32 cur = xs;  // scale of `mag`
@@ -1314,7 +1317,7 @@ GDV_DEV i128 floor_decimal128(i128 x, i32 xp, i32 xs, i32 op, i32 os) { return g
 // from zero to the declared scale; anything else raises; a value that needs more than the declared
 // precision yields 0 like the other decimal producers.  Digits beyond 76 are not accumulated
 // (they cannot change a 38-digit result except through the sticky rounding digit, which is kept).
-GDV_DEV i128 castDECIMAL_utf8(gdv_ctx* c, gdv_str s, i32 op, i32 os) {
+GDV_DEV_BIG i128 castDECIMAL_utf8(gdv_ctx* c, gdv_str s, i32 op, i32 os) {
   i32 b = 0, e = s.len;
   while (b < e && s.p[b] == (u8)' ') ++b;
   while (e > b && s.p[e - 1] == (u8)' ') --e;
@@ -1752,7 +1755,7 @@ GDV_DEV gdv_str byte_substr_binary_int32_int32(gdv_str s, i32 offset, i32 length
 }
 // castINT / castBIGINT of a string: optional surrounding spaces, optional sign, decimal digits;
 // anything else, or a value outside the type, raises an ExecutionError.
-GDV_DEV i64 gdv_parse_int(gdv_ctx* c, const gdv_str& s, i64 lo, i64 hi) {
+GDV_DEV_BIG i64 gdv_parse_int(gdv_ctx* c, const gdv_str& s, i64 lo, i64 hi) {
   i32 b = 0, e = s.len;
   while (b < e && s.p[b] == (u8)' ') ++b;
   while (e > b && s.p[e - 1] == (u8)' ') --e;
@@ -1799,7 +1802,7 @@ GDV_DEV bool gdv_parse_uint(const gdv_str& s, i32* pos, i32 end, i32 min_digits,
   *out = v;
   return n >= min_digits;
 }
-GDV_DEV i64 gdv_parse_timestamp(gdv_ctx* c, const gdv_str& s, bool date_only) {
+GDV_DEV_BIG i64 gdv_parse_timestamp(gdv_ctx* c, const gdv_str& s, bool date_only) {
   i32 b = 0, e = s.len;
   while (b < e && s.p[b] == (u8)' ') ++b;
   while (e > b && s.p[e - 1] == (u8)' ') --e;
@@ -1904,7 +1907,7 @@ GDV_DEV gdv_str btrim_utf8_utf8(gdv_str s, gdv_str chars) { return rtrim_utf8_ut
 // split_part(s, delimiter, k): the k-th (1-based) piece of s split at every occurrence of the
 // delimiter (leftmost, non-overlapping); empty when there are fewer pieces; k < 1 raises; an empty
 // delimiter never matches (the whole string is piece 1).  A view.
-GDV_DEV gdv_str split_part_utf8_utf8_int32(gdv_ctx* c, gdv_str s, gdv_str delim, i32 k) {
+GDV_DEV_BIG gdv_str split_part_utf8_utf8_int32(gdv_ctx* c, gdv_str s, gdv_str delim, i32 k) {
   gdv_str r = s;
   r.len = 0;
   if (k < 1) {
@@ -2004,7 +2007,7 @@ GDV_DEV gdv_str gdv_pad_fill(gdv_str s, i32 n, gdv_str fill) {
 // replace(s, from, to) with literal from / to: the piece is the source view; its output length and
 // bytes come from these two (leftmost, non-overlapping occurrences; an empty `from` replaces
 // nothing).  Bytes are compared and copied through the view's case map.
-GDV_DEV i32 gdv_replace_len(const gdv_str& s, const u8* from, i32 fl, i32 tl) {
+GDV_DEV_BIG i32 gdv_replace_len(const gdv_str& s, const u8* from, i32 fl, i32 tl) {
   if (fl <= 0) return s.len;
   i64 out = 0;
   for (i32 i = 0; i < s.len;) {
@@ -2020,7 +2023,7 @@ GDV_DEV i32 gdv_replace_len(const gdv_str& s, const u8* from, i32 fl, i32 tl) {
   }
   return out > 0x7fffffffll ? 0x7fffffff : (i32)out;
 }
-GDV_DEV void gdv_replace_copy(u8* dst, const gdv_str& s, const u8* from, i32 fl, const u8* to, i32 tl) {
+GDV_DEV_BIG void gdv_replace_copy(u8* dst, const gdv_str& s, const u8* from, i32 fl, const u8* to, i32 tl) {
   i64 out = 0;
   for (i32 i = 0; i < s.len;) {
     bool hit = fl > 0 && i + fl <= s.len;
@@ -2096,7 +2099,7 @@ GDV_DEV gdv_str castVARCHAR_int32_int64(i32 v, i64 maxlen, u8* scr) {
   return castVARCHAR_int64_int64((i64)v, maxlen, scr);
 }
 // castVARCHAR(decimal(p, s), n): [-]integer digits[.s fractional digits], then the first n characters
-GDV_DEV gdv_str castVARCHAR_decimal128_int64(i128 x, i32 xp, i32 xs, i64 maxlen, u8* scr) {
+GDV_DEV_BIG gdv_str castVARCHAR_decimal128_int64(i128 x, i32 xp, i32 xs, i64 maxlen, u8* scr) {
   u8 tmp[40];
   i32 n = 0;
   u128 m = gdv_abs_u128(x);
@@ -2143,7 +2146,7 @@ GDV_DEV gdv_str castVARCHAR_date64_int64(i64 ms, i64 maxlen, u8* scr) {
   return gdv_scratch_str(scr, gdv_put_date(scr, gdv_floordiv(ms, 86400000ll)), maxlen);
 }
 // "YYYY-MM-DD hh:mm:ss.mmm"
-GDV_DEV gdv_str castVARCHAR_timestamp_int64(i64 ms, i64 maxlen, u8* scr) {
+GDV_DEV_BIG gdv_str castVARCHAR_timestamp_int64(i64 ms, i64 maxlen, u8* scr) {
   const i64 days = gdv_floordiv(ms, 86400000ll);
   const i64 in_day = (i64)((u64)ms - (u64)gdv_days_to_ms(days));
   i32 at = gdv_put_date(scr, days);
@@ -2196,7 +2199,7 @@ __device__ const u32 gdv_sha256_k[64] = {
     0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
     0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
 GDV_DEV u32 gdv_rotr32(u32 v, int d) { return (v >> d) | (v << (32 - d)); }
-GDV_DEV gdv_str gdv_sha256_hex(const gdv_str& s, u8* scr) {
+GDV_DEV_BIG gdv_str gdv_sha256_hex(const gdv_str& s, u8* scr) {
   u32 h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
   const i64 padded = (((i64)s.len + 8) / 64 + 1) * 64;
   for (i64 blk = 0; blk < padded; blk += 64) {
@@ -2228,7 +2231,7 @@ GDV_DEV gdv_str gdv_sha256_hex(const gdv_str& s, u8* scr) {
   for (int k = 0; k < 8; ++k) at = gdv_put_hex32(scr, at, h[k], true);
   return gdv_scratch_str(scr, at, 64);
 }
-GDV_DEV gdv_str gdv_sha1_hex(const gdv_str& s, u8* scr) {
+GDV_DEV_BIG gdv_str gdv_sha1_hex(const gdv_str& s, u8* scr) {
   u32 h[5] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u, 0xc3d2e1f0u};
   const i64 padded = (((i64)s.len + 8) / 64 + 1) * 64;
   for (i64 blk = 0; blk < padded; blk += 64) {
@@ -2270,7 +2273,7 @@ __device__ const u32 gdv_md5_k[64] = {
     0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u,
     0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u,
     0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u};
-GDV_DEV gdv_str gdv_md5_hex(const gdv_str& s, u8* scr) {
+GDV_DEV_BIG gdv_str gdv_md5_hex(const gdv_str& s, u8* scr) {
   u32 h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
   const i64 padded = (((i64)s.len + 8) / 64 + 1) * 64;
   for (i64 blk = 0; blk < padded; blk += 64) {

@@ -18,6 +18,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ inline __attribute__((noinline))
 #define __shared__ static
 #define __grid_constant__
 #define __launch_bounds__(...)
