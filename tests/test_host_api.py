@@ -136,7 +136,12 @@ def test_dump_ir_is_cuda_source(gandiva):
     assert info["name"].startswith("gdv_project_expr_") and info["rows_per_thread"] >= 1
 
 
-ALL_CASES = cases.all_project_cases() + cases.all_filter_cases()
+# the arithmetic / comparison type matrix at the head of the list differs only in a type name:
+# every third one is enough for the compile gate (the GPU parity suite still runs them all)
+_PROJECT = cases.all_project_cases()
+_MATRIX = [c for c in _PROJECT if c.__name__.startswith(("add_", "subtract_", "multiply_", "equal_", "not_equal_", "less_than_",
+                                                          "greater_than_", "less_than_or_equal_to_", "greater_than_or_equal_to_"))]
+ALL_CASES = [c for c in _PROJECT if c not in _MATRIX] + _MATRIX[::3] + cases.all_filter_cases()
 
 
 @pytest.mark.parametrize("case", ALL_CASES, ids=[c.__name__ for c in ALL_CASES])
