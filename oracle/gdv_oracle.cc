@@ -15,6 +15,11 @@
 // (the "precompiled function library"), validity computed per row, then for filters a pass
 // that turns the boolean result into an ascending index list.
 //
+// Pinned beyond those vectors by published standards: MurmurHash3 (reference answers), MD5 / SHA-1 /
+// SHA-256 (RFC 1321, FIPS 180-4 known answers + hashlib), CRC-32 (zlib).  exp / log / log10 / cbrt
+// are, on purpose, the same IEEE operation sequences as the device library (no libm on either
+// side), measured against the host libm in tests/.
+//
 // Deliberately naive and independent of the GPU implementation: strings are materialised
 // as std::string (the GPU uses lazy views), decimals use 32-bit-limb schoolbook arithmetic
 // (the GPU uses 64-bit limbs), the tree is parsed from an s-expression emitted by the test
