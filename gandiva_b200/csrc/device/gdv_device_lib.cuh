@@ -40,6 +40,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_CAST_DATE 5        /* castDATE / castTIMESTAMP of a string that is not a date / timestamp */
 #define GDV_ERR_SPLIT_INDEX 6      /* split_part with an index < 1 */
 #define GDV_ERR_CAST_DECIMAL 7     /* castDECIMAL of a string that is not a decimal number */
+#define GDV_ERR_CAST_FLOAT 8       /* castFLOAT4 / castFLOAT8 of a string that is not a number */
 struct gdv_ctx {
   int* err;
 };
@@ -1263,6 +1264,154 @@ GDV_DEV gdv_u256 gdv_scale_up_u256(u128 x, i32 e, bool* overflow) {
   }
   return r;
 }
+// castFLOAT8 / castFLOAT4(utf8): [spaces][+-]digits[.digits][(e|E)[+-]digits][spaces].  Up to 19
+// significant digits m (further digits only make the value "inexact") and a decimal exponent e10.
+// m * 10^e10 is carried as X * 2^exp2 with X a 256-bit integer: multiplied by 10^k (k <= 19) after
+// X is cut to its top 192 bits, or divided by 10^k after X is shifted up to bit 255, so every step
+// keeps >= 192 significant bits (relative error < 2^-190 after the <= 22 steps the double range
+// needs) -- far below the 2^-120 by which a 64-bit decimal significand can approach a rounding
+// boundary, and exact whenever the value is a dyadic rational.  One round-to-nearest-even at the end,
+// subnormals, overflow to infinity and underflow to zero included: the result strtod / Python
+// float() give.  The oracle does the same steps on 32-bit limbs, bit by bit and digit by digit.
+GDV_DEV int gdv_u256_top(const gdv_u256& x) {  // index of the highest set bit (x != 0)
+  for (int w = 3; w > 0; --w)
+    if (x.w[w] != 0ull) return w * 64 + 63 - __clzll((long long)x.w[w]);
+  return 63 - __clzll((long long)x.w[0]);
+}
+GDV_DEV void gdv_u256_shr_sticky(gdv_u256& x, int s, bool& sticky) {  // 0 <= s <= 255
+  if (s <= 0) return;
+  const int ws = s >> 6, bs = s & 63;
+  gdv_u256 r;
+  for (int i = 0; i < 4; ++i) {
+    if (i < ws) sticky = sticky || x.w[i] != 0ull;
+    const u64 lo = i + ws < 4 ? x.w[i + ws] : 0ull;
+    const u64 hi = i + ws + 1 < 4 ? x.w[i + ws + 1] : 0ull;
+    r.w[i] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+  }
+  if (bs) sticky = sticky || (x.w[ws] & ((1ull << bs) - 1ull)) != 0ull;
+  x = r;
+}
+GDV_DEV void gdv_u256_shl(gdv_u256& x, int s) {  // 0 <= s <= 255, no bit is shifted out by callers
+  if (s <= 0) return;
+  const int ws = s >> 6, bs = s & 63;
+  gdv_u256 r;
+  for (int i = 3; i >= 0; --i) {
+    const u64 hi = i - ws >= 0 ? x.w[i - ws] : 0ull;
+    const u64 lo = i - ws - 1 >= 0 ? x.w[i - ws - 1] : 0ull;
+    r.w[i] = bs ? (hi << bs) | (lo >> (64 - bs)) : hi;
+  }
+  x = r;
+}
+GDV_DEV f64 gdv_u256_to_f64(gdv_u256 x, bool sticky, i32 exp2) {  // x != 0: RNE(x * 2^exp2) as an IEEE double
+  const int p = gdv_u256_top(x);
+  const i32 be = p + exp2;  // x * 2^exp2 in [2^be, 2^(be+1))
+  if (be > 1023) return gdv_f64_from_bits(0x7ff0000000000000ull);
+  const i32 nb = be >= -1022 ? 53 : be + 1075;  // significand bits the format has at this magnitude
+  if (nb < 0) return 0.0;
+  const i32 drop = p + 1 - nb;
+  u64 mant;
+  bool round = false;
+  if (drop <= 0) {
+    mant = x.w[0] << (-drop);
+  } else {
+    gdv_u256_shr_sticky(x, drop - 1, sticky);  // nb + 1 bits left, all in w[0]
+    round = (x.w[0] & 1ull) != 0ull;
+    mant = x.w[0] >> 1;
+  }
+  if (round && (sticky || (mant & 1ull) != 0ull)) ++mant;
+  // mant * 2^(exp2 + drop): normal numbers carry the hidden bit into the exponent field, subnormals
+  // (exp2 + drop == -1074, mant < 2^52) come out as the bare fraction, 2^53 / 2^1024 carry upwards
+  return gdv_f64_from_bits(((u64)(i64)(exp2 + drop + 1075) << 52) + mant - (1ull << 52));
+}
+GDV_DEV_BIG f64 gdv_parse_f64(gdv_ctx* c, const gdv_str& s) {
+  i32 b = 0, e = s.len;
+  while (b < e && s.p[b] == (u8)' ') ++b;
+  while (e > b && s.p[e - 1] == (u8)' ') --e;
+  bool neg = false;
+  if (b < e && (s.p[b] == (u8)'-' || s.p[b] == (u8)'+')) {
+    neg = s.p[b] == (u8)'-';
+    ++b;
+  }
+  u64 m = 0ull;
+  i32 sig = 0, e10 = 0, ndig = 0;
+  bool point = false, sticky = false, ok = true;
+  i32 i = b;
+  for (; i < e; ++i) {
+    const u32 ch = (u32)s.p[i];
+    if (ch == (u32)'.') {
+      if (point) ok = false;
+      point = true;
+      continue;
+    }
+    const u32 d = ch - (u32)'0';
+    if (d > 9u) break;
+    ++ndig;
+    if (sig < 19) {
+      if (m != 0ull || d != 0u) {
+        m = m * 10ull + d;
+        ++sig;
+      }
+      if (point) --e10;
+    } else {
+      sticky = sticky || d != 0u;
+      if (!point) ++e10;
+    }
+  }
+  if (ok && ndig > 0 && i < e && (s.p[i] == (u8)'e' || s.p[i] == (u8)'E')) {
+    ++i;
+    bool eneg = false;
+    if (i < e && (s.p[i] == (u8)'-' || s.p[i] == (u8)'+')) {
+      eneg = s.p[i] == (u8)'-';
+      ++i;
+    }
+    i32 ev = 0, edig = 0;
+    for (; i < e; ++i) {
+      const u32 d = (u32)s.p[i] - (u32)'0';
+      if (d > 9u) break;
+      if (ev < 100000) ev = ev * 10 + (i32)d;
+      ++edig;
+    }
+    ok = ok && edig > 0;
+    e10 += eneg ? -ev : ev;
+  }
+  if (!ok || ndig == 0 || i != e) {
+    gdv_set_error(c, GDV_ERR_CAST_FLOAT);
+    return 0.0;
+  }
+  if (m == 0ull) return neg ? -0.0 : 0.0;
+  if (e10 > 400) e10 = 400;
+  if (e10 < -400) e10 = -400;
+  gdv_u256 x;
+  x.w[0] = m;
+  x.w[1] = 0ull;
+  x.w[2] = 0ull;
+  x.w[3] = 0ull;
+  i32 exp2 = 0, rest = e10;
+  while (rest > 0) {
+    const i32 k = rest > 19 ? 19 : rest;
+    const int p = gdv_u256_top(x);
+    if (p > 191) {
+      gdv_u256_shr_sticky(x, p - 191, sticky);
+      exp2 += p - 191;
+    }
+    bool o = false;
+    x = gdv_mul_u256_u128(x, gdv_pow10_u128(k), &o);  // < 2^192 * 2^64
+    rest -= k;
+  }
+  while (rest < 0) {
+    const i32 k = -rest > 19 ? 19 : -rest;
+    const int up = 255 - gdv_u256_top(x);
+    gdv_u256_shl(x, up);
+    exp2 -= up;
+    sticky = (gdv_divmod_u256_u64(x, (u64)gdv_pow10_u128(k)) != 0ull) || sticky;
+    rest += k;
+  }
+  const f64 d = gdv_u256_to_f64(x, sticky, exp2);
+  return neg ? -d : d;
+}
+GDV_DEV f64 castFLOAT8_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_f64(c, s); }
+GDV_DEV f32 castFLOAT4_utf8(gdv_ctx* c, gdv_str s) { return (f32)gdv_parse_f64(c, s); }
+
 // round / truncate / ceil / floor of a decimal: drop `d` = xs - rs digits under `mode` (0 half away
 // from zero, 1 toward zero, 2 toward +inf, 3 toward -inf), then express the result (scale rs) at the
 // declared output (op, os).  rs >= xs: nothing to drop.  More than 38 digits -> 0, like the others.

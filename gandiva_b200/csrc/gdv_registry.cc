@@ -326,6 +326,8 @@ Registry::Registry() {
   Add("to_hex", {I32}, S, NullMode::kIfNull, kScratch);
   Add("castBIGINT", {S}, I64, NullMode::kIfNull, kCanFail);
   Add("castINT", {S}, I32, NullMode::kIfNull, kCanFail);
+  Add("castFLOAT8", {S}, F64, NullMode::kIfNull, kCanFail);
+  Add("castFLOAT4", {S}, F32, NullMode::kIfNull, kCanFail);
   Add("castDATE", {S}, D64, NullMode::kIfNull, kCanFail);
   Add("castTIMESTAMP", {S}, TS, NullMode::kIfNull, kCanFail);
   // ilike(s, pattern): like() over lower-cased text and pattern (ASCII case folding); rewritten

@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
 #include <thread>
@@ -1083,6 +1084,102 @@ double OrcCbrt(double x) {
   return t + t * r;
 }
 
+// ---- castFLOAT8 / castFLOAT4(utf8): m * 10^e10 (m <= 19 digits) carried as X * 2^exp2, X < 2^256:
+// times ten, k <= 19 times, after X is cut to its top 192 bits; or shifted up to bit 255 and divided
+// by ten k times.  The same cuts as the kernel (gdv_parse_f64), made here one bit / one digit at a
+// time on the 32-bit-limb Big; the final round-to-nearest-even goes through ldexp.
+int BigTop(const Big& x) {
+  int p = 255;
+  while (p > 0 && !x.Bit(p)) --p;
+  return p;
+}
+void BigShr1(Big* x, bool* sticky) {
+  *sticky = *sticky || (x->w[0] & 1u);
+  for (int j = 0; j < 8; ++j) x->w[j] = (x->w[j] >> 1) | (j + 1 < 8 ? x->w[j + 1] << 31 : 0u);
+}
+void BigShl1(Big* x) {
+  for (int j = 7; j >= 0; --j) x->w[j] = (x->w[j] << 1) | (j > 0 ? x->w[j - 1] >> 31 : 0u);
+}
+double BigToDouble(Big x, bool sticky, int exp2) {  // x != 0: RNE(x * 2^exp2)
+  const int p = BigTop(x);
+  const int be = p + exp2;
+  if (be > 1023) return std::numeric_limits<double>::infinity();
+  const int nb = be >= -1022 ? 53 : be + 1075;
+  if (nb < 0) return 0.0;
+  int e2 = exp2;
+  bool round = false;
+  for (int k = 0; k < p + 1 - nb; ++k) {  // drop the low bits: the last one dropped is the round bit
+    sticky = sticky || round;
+    round = x.w[0] & 1u;
+    bool unused = false;
+    BigShr1(&x, &unused);
+    ++e2;
+  }
+  uint64_t mant = (static_cast<uint64_t>(x.w[1]) << 32) | x.w[0];
+  if (round && (sticky || (mant & 1))) ++mant;
+  return std::ldexp(static_cast<double>(mant), e2);
+}
+bool ParseDouble(const std::string& text, double* out) {
+  std::string str = text;
+  while (!str.empty() && str.front() == ' ') str.erase(str.begin());
+  while (!str.empty() && str.back() == ' ') str.pop_back();
+  size_t pos = 0;
+  bool neg = false;
+  if (pos < str.size() && (str[pos] == '-' || str[pos] == '+')) { neg = str[pos] == '-'; ++pos; }
+  uint64_t m = 0;
+  int sig = 0, ndig = 0;
+  int64_t e10 = 0;
+  bool point = false, sticky = false;
+  for (; pos < str.size(); ++pos) {
+    const char ch = str[pos];
+    if (ch == '.') { if (point) return false; point = true; continue; }
+    if (ch < '0' || ch > '9') break;
+    ++ndig;
+    if (sig < 19) {
+      if (m != 0 || ch != '0') { m = m * 10 + static_cast<uint64_t>(ch - '0'); ++sig; }
+      if (point) --e10;
+    } else {
+      sticky = sticky || ch != '0';
+      if (!point) ++e10;
+    }
+  }
+  if (ndig == 0) return false;
+  if (pos < str.size() && (str[pos] == 'e' || str[pos] == 'E')) {
+    ++pos;
+    bool eneg = false;
+    if (pos < str.size() && (str[pos] == '-' || str[pos] == '+')) { eneg = str[pos] == '-'; ++pos; }
+    int64_t ev = 0;
+    int edig = 0;
+    for (; pos < str.size() && str[pos] >= '0' && str[pos] <= '9'; ++pos) {
+      if (ev < 100000) ev = ev * 10 + (str[pos] - '0');
+      ++edig;
+    }
+    if (edig == 0) return false;
+    e10 += eneg ? -ev : ev;
+  }
+  if (pos != str.size()) return false;
+  if (m == 0) { *out = neg ? -0.0 : 0.0; return true; }
+  e10 = std::max<int64_t>(-400, std::min<int64_t>(400, e10));
+  Big x = Big::From(m);
+  int exp2 = 0;
+  int64_t rest = e10;
+  while (rest > 0) {
+    const int k = static_cast<int>(std::min<int64_t>(19, rest));
+    while (BigTop(x) > 191) { BigShr1(&x, &sticky); ++exp2; }
+    x.MulPow10(k);
+    rest -= k;
+  }
+  while (rest < 0) {
+    const int k = static_cast<int>(std::min<int64_t>(19, -rest));
+    while (BigTop(x) < 255) { BigShl1(&x); --exp2; }
+    for (int j = 0; j < k; ++j) sticky = (x.DivSmall(10) != 0) || sticky;
+    rest += k;
+  }
+  const double d = BigToDouble(x, sticky, exp2);
+  *out = neg ? -d : d;
+  return true;
+}
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
@@ -1340,6 +1437,13 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "castINT") { out->i = WrapSigned(a[0].i, 32); return; }
+  if ((f == "castFLOAT8" || f == "castFLOAT4") && t0.id == T_STRING) {
+    double v = 0.0;
+    if (!ParseDouble(a[0].s, &v)) { cx.error = 8; return; }
+    if (f == "castFLOAT8") out->d = v;
+    else out->f = static_cast<float>(v);
+    return;
+  }
   if (f == "castFLOAT4") {
     if (t0.id == T_DOUBLE) out->f = static_cast<float>(a[0].d);
     else out->f = static_cast<float>(a[0].i);

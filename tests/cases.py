@@ -309,6 +309,8 @@ def case_number_to_text(b):
         (fn("equal", [txt(i, 12), fn("castVARCHAR", [s, n(12)], S)], B), B),
         (fn("hash32", [txt(l, 30)], I), I),
         (fn("castBIGINT", [txt(l, 30)], L), L),   # text -> number again: the round trip is the identity
+        (fn("castFLOAT8", [txt(l, 30)], pa.float64()), pa.float64()),   # == castFLOAT8(l) up to 2^53, RNE beyond
+        (fn("castFLOAT4", [txt(i, 12)], pa.float32()), pa.float32()),
         (fn("substr", [txt(t, 30), n(12), n(8)], S), S),
     ]
     return schema, outs, "project"

@@ -475,6 +475,85 @@ def test_cast_string_to_integer(fn_name, t, bits, gandiva, oracle):
     assert p.evaluate(batch)[0].to_pylist() == [7, None, -8]
 
 
+def _float_strings(n, seed):
+    rng = np.random.default_rng(seed)
+    out = ["0", "-0", "+0.0", "1", "-1.5", " 2.5 ", "1e0", "1E+2", "1.e2", ".5", "5.", "-.5e-1", "1e22", "1e23",
+           "9007199254740993", "9007199254740992.5", "0.1", "0.3", "1e-38", "1.7976931348623157e308", "1e309",
+           "-1e400", "4.9e-324", "2.2250738585072014e-308", "1e-400", "123456789012345678901234567890",
+           "0.000000000000000000000000000000000000001", "3.4028235e38", "1.17549435e-38", "1e-45",
+           "0000000000000000000000000001", "0.00000", "100000000000000000000000000000.00000000001e-29",
+           "2.2250738585072011e-308", "2.2250738585072012e-308", "4.9406564584124654e-324", "2.4703282292062327e-324",
+           "2.4703282292062328e-324", "7.4109846876186982e-324", "1.7976931348623158e308", "1.7976931348623159e308",
+           "17976931348623158079e289", "8.98846567431158e307", "9007199254740992", "9007199254740994", "9007199254740995",
+           "0.500000000000000166533453693773481063544750213623046875", "6.2230152778611417e-1",
+           "8.5e-324", "1e-323", "3e-324", "2e-324", "5e-324", "1.0000000000000002", "1.00000000000000011102230246251565",
+           "1.00000000000000033306690738754696", "9.5e-1", "4.35e0", "1e+400", "1e-99999999999", "1e99999999999",
+           "0e99999999999", "7450580596923828125e-27", "14901161193847656250e-28", "1e-5", "5e-1", "123456789e-9"]
+    while len(out) < n:
+        style = int(rng.integers(0, 5))
+        digits = "".join(str(int(d)) for d in rng.integers(0, 10, size=int(rng.integers(1, 22))))
+        if style == 0:
+            t = digits
+        elif style == 1:
+            cut = int(rng.integers(0, len(digits) + 1))
+            t = digits[:cut] + "." + digits[cut:]
+        elif style == 2:
+            t = digits[:1] + "." + digits[1:] + "e%d" % int(rng.integers(-45, 46))
+        elif style == 3:
+            t = digits + "E%+d" % int(rng.integers(-330, 310))
+        else:
+            t = repr(abs(float(rng.standard_normal() * 10.0 ** int(rng.integers(-30, 30)))))
+        if rng.integers(0, 2):
+            t = "-" + t
+        if rng.integers(0, 8) == 0:
+            t = " " + t + "  "
+        out.append(t)
+    out = out[:n]
+    for k in range(3, n, 11):
+        out[k] = None
+    return out
+
+
+def _sig_digits(text):
+    t = text.strip().lstrip("+-").lower().partition("e")[0].replace(".", "")
+    return len(t.lstrip("0").rstrip("0"))
+
+
+def test_cast_string_to_float(gandiva, oracle):
+    """castFLOAT8 / castFLOAT4(utf8): kernel == oracle bit for bit; both == Python's correctly
+    rounded float() over the whole double range (subnormals, overflow to inf, underflow to 0) when
+    the text has <= 19 significant digits, within 1 ULP with more; malformed text raises in both."""
+    b = gandiva.TreeExprBuilder()
+    S, F8, F4 = pa.string(), pa.float64(), pa.float32()
+    schema = pa.schema([("s", S)])
+    root8 = b.make_function("castFLOAT8", [cases.F(b, "s", S)], F8)
+    root4 = b.make_function("castFLOAT4", [cases.F(b, "s", S)], F4)
+    p = gandiva.make_projector(schema, [b.make_expression(root8, pa.field("d", F8)),
+                                        b.make_expression(root4, pa.field("f", F4))], None)
+    for n, seed in ((1, 1), (33, 2), (2500, 3)):
+        strs = _float_strings(n, seed)
+        batch = pa.RecordBatch.from_arrays([pa.array(strs, S)], schema=schema)
+        got8, got4 = p.evaluate(batch)
+        want8, want4 = oracle.project([root8, root4], [F8, F4], batch)
+        assert_arrays_match(got8, want8, "castFLOAT8 n=%d" % n)
+        assert_arrays_match(got4, want4, "castFLOAT4 n=%d" % n)
+        for text, v in zip(strs, got8.to_pylist()):
+            if text is None:
+                assert v is None
+                continue
+            ref = float(text)
+            if _sig_digits(text) <= 19:
+                assert np.float64(v).tobytes() == np.float64(ref).tobytes(), (text, v, ref)
+            else:
+                assert v == ref or v in (np.nextafter(ref, np.inf), np.nextafter(ref, -np.inf)), (text, v, ref)
+    for bad in ("", " ", "-", ".", "e5", "1e", "1e+", "1.2.3", "1 2", "0x10", "nan", "inf", "1f", "--1", "１"):
+        batch = pa.RecordBatch.from_arrays([pa.array(["7", None, bad, "8"], S)], schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: Failed to cast the string to a float"):
+            p.evaluate(batch)
+        with pytest.raises(Exception, match="Failed to cast the string to a float"):
+            oracle.project([root8], [F8], batch)
+
+
 def test_concurrent_evaluate_from_threads(gandiva, oracle):
     """One Projector and one Filter evaluated from several host threads at once on different
     batches (include/gandiva_b200.h "Threading"): every call gets its own results."""

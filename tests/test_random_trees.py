@@ -39,7 +39,7 @@ def _signatures(gandiva):
         params = sig.param_types()
         if any(p not in TYPES for p in params) or sig.return_type() not in TYPES:
             continue
-        if sig.name() in ("castINT", "castBIGINT", "castDATE", "castTIMESTAMP") and params and params[0] == S:
+        if sig.name() in ("castINT", "castBIGINT", "castFLOAT4", "castFLOAT8", "castDATE", "castTIMESTAMP") and params and params[0] == S:
             continue   # raises on strings that are not numbers / dates
         by_ret.setdefault(sig.return_type(), []).append((sig.name(), params))
     return by_ret
