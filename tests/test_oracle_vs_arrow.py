@@ -797,6 +797,9 @@ def test_number_to_text(oracle, gandiva):
             assert got[c][r] == wv, (c, r, got[c][r], wv)
         if ll[r] is not None:
             assert got[14][r] == len(str(ll[r])) and got[19][r] == ll[r]
+            assert got[20][r] == float(ll[r])   # int -> text -> double: the correctly rounded conversion
+        if il[r] is not None:
+            assert got[21][r] == float(np.float32(il[r]))
 
 
 def test_string_misc(oracle, gandiva):
@@ -999,3 +1002,35 @@ def test_math_functions_within_one_ulp_of_libm(oracle, gandiva):
         assert np.array_equal(np.isnan(got), np.isnan(want)), name
         ok = ~np.isnan(want)
         assert int(ulp_diff(np.ascontiguousarray(got[ok]), np.ascontiguousarray(want[ok])).max()) <= 1, name
+
+
+def test_float_parsing_against_python_float(oracle, gandiva):
+    """castFLOAT8(utf8): bit-identical to Python's (correctly rounded) float() for texts of <= 19
+    significant digits over the whole double range; castFLOAT4 is that double rounded to float."""
+    from test_parity_gpu import _float_strings, _sig_digits
+    b = gandiva.TreeExprBuilder()
+    S, F8, F4 = pa.string(), pa.float64(), pa.float32()
+    schema = pa.schema([("s", S)])
+    s = cases.F(b, "s", S)
+    rng = np.random.default_rng(77)
+    strs = [t for t in _float_strings(60_000, 9) if t is not None]
+    # halfway-adjacent texts: a double's exact midpoint to its neighbour, cut to 19 digits, +- 1 in the last
+    import decimal
+    ctx = decimal.Context(prec=60)
+    for _ in range(4000):
+        v = float(np.ldexp(rng.uniform(1, 2), int(rng.integers(-1070, 1020))))
+        mid = (decimal.Decimal(v) + decimal.Decimal(float(np.nextafter(v, np.inf)))) / 2
+        q = ctx.create_decimal(mid).normalize(decimal.Context(prec=19, rounding=decimal.ROUND_DOWN))
+        strs += ["%e" % 0 if q == 0 else format(q, "e"), format(q.next_plus(decimal.Context(prec=19)), "e")]
+    batch = pa.RecordBatch.from_arrays([pa.array(strs, S)], schema=schema)
+    got8, got4 = oracle.project([b.make_function("castFLOAT8", [s], F8), b.make_function("castFLOAT4", [s], F4)],
+                                [F8, F4], batch, threads=4)
+    g8 = got8.to_numpy(zero_copy_only=False)
+    g4 = got4.to_numpy(zero_copy_only=False)
+    ref = np.array([float(t) for t in strs])
+    few = np.array([_sig_digits(t) <= 19 for t in strs])
+    assert np.array_equal(g8[few].view(np.uint64), ref[few].view(np.uint64))
+    lo, hi = np.nextafter(ref, -np.inf), np.nextafter(ref, np.inf)
+    assert np.all((g8 == ref) | (g8 == lo) | (g8 == hi))
+    with np.errstate(over="ignore"):
+        assert np.array_equal(g4.view(np.uint32), g8.astype(np.float32).view(np.uint32))
