@@ -97,6 +97,8 @@ Registry::Registry() {
   Add("log", {F64}, F64, NullMode::kIfNull, 0, {"ln"});
   Add("log10", {F64}, F64);
   Add("cbrt", {F64}, F64);
+  for (const auto& t : {I32, I64, F32, F64})
+    for (const char* f : {"sin", "cos", "tan", "cot"}) Add(f, {t}, F64);
   Add("degrees", {F64}, F64);
   Add("radians", {F64}, F64);
   for (const auto& t : {I32, I64}) {

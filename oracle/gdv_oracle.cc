@@ -942,6 +942,147 @@ std::string Md5Hex(const std::string& m) {
 // measured against the host libm in tests/test_oracle_vs_arrow.py.
 double F64FromBits(uint64_t b) { double d; std::memcpy(&d, &b, 8); return d; }
 uint64_t F64Bits(double d) { uint64_t b; std::memcpy(&b, &d, 8); return b; }
+// ---- sin / cos / tan / cot: the kernel's sequence (device/gdv_device_lib.cuh gdv_trig), operation for
+// operation: integer Payne-Hanek reduction against 1280 bits of 2/pi, Taylor kernels, double-double
+// quotient for tan / cot.  Constants from tools/derive_trig_constants.py.  Checked against the host
+// libm (<= 1 ULP) and against exact rational evaluation in tests/test_oracle_vs_arrow.py.
+const uint64_t kTwoOverPi[20] = {
+    0xa2f9836e4e441529ull, 0xfc2757d1f534ddc0ull, 0xdb6295993c439041ull, 0xfe5163abdebbc561ull,
+    0xb7246e3a424dd2e0ull, 0x06492eea09d1921cull, 0xfe1deb1cb129a73eull, 0xe88235f52ebb4484ull,
+    0xe99c7026b45f7e41ull, 0x3991d639835339f4ull, 0x9c845f8bbdf9283bull, 0x1ff897ffde05980full,
+    0xef2f118b5a0a6d1full, 0x6d367ecf27cb09b7ull, 0x4f463f669e5fea2dull, 0x7527bac7ebe5f17bull,
+    0x3d0739f78a5292eaull, 0x6bfb5fb11f8d5d08ull, 0x56033046fc7b6babull, 0xf0cfbc209af4361dull};
+// ax finite, > pi/4: ax = quad * pi/2 + (y0 + y1), |y0 + y1| <= pi/4
+void OrcRemPio2(double ax, double* y0, double* y1, int32_t* quad) {
+  const uint64_t bits = F64Bits(ax);
+  const int32_t e = (int32_t)(bits >> 52) - 1075;  // ax = M * 2^e, M in [2^52, 2^53)
+  const uint64_t M = (bits & 0x000fffffffffffffull) | 0x0010000000000000ull;
+  const int32_t i0 = e >= 2 ? e - 1 : 1;       // first bit of 2/pi (1 = the 2^-1 bit) that matters mod 4
+  const int32_t s = e >= 2 ? 190 : 192 - e;    // the product below is (ax * 2/pi mod 4) * 2^s
+  const int32_t j = (i0 - 1) >> 6, sh = (i0 - 1) & 63;
+  uint64_t w[3];
+  for (int32_t k = 0; k < 3; ++k)
+    w[k] = sh ? (kTwoOverPi[j + k] << sh) | (kTwoOverPi[j + k + 1] >> (64 - sh)) : kTwoOverPi[j + k];
+  const unsigned __int128 p2 = (unsigned __int128)M * w[2], p1 = (unsigned __int128)M * w[1], p0 = (unsigned __int128)M * w[0];
+  uint64_t P[4];
+  P[0] = (uint64_t)p2;
+  unsigned __int128 acc = (p2 >> 64) + (unsigned __int128)(uint64_t)p1;
+  P[1] = (uint64_t)acc;
+  acc = (acc >> 64) + (p1 >> 64) + (unsigned __int128)(uint64_t)p0;
+  P[2] = (uint64_t)acc;
+  acc = (acc >> 64) + (p0 >> 64);
+  P[3] = (uint64_t)acc;
+  int32_t q = (int32_t)((P[s >> 6] >> (s & 63)) & 1ull) | ((int32_t)((P[(s + 1) >> 6] >> ((s + 1) & 63)) & 1ull) << 1);
+  const bool half = ((P[(s - 1) >> 6] >> ((s - 1) & 63)) & 1ull) != 0ull;
+  // keep the s fraction bits; past one half, go to the next quadrant and negate the fraction
+  const uint64_t top_mask = (1ull << (s & 63)) - 1ull;
+  for (int32_t k = 0; k < 4; ++k) {
+    if (half) P[k] = ~P[k];
+    if (k == (s >> 6)) P[k] &= top_mask;
+    if (k > (s >> 6)) P[k] = 0ull;
+  }
+  if (half) {  // two's complement: + 1 (cannot carry out of s bits: the fraction was not zero)
+    ++q;
+    for (int32_t k = 0; k < 4; ++k) {
+      P[k] += 1ull;
+      if (P[k] != 0ull) break;
+    }
+  }
+  *quad = q & 3;
+  int32_t p = -1;
+  for (int32_t k = 3; k >= 0 && p < 0; --k)
+    if (P[k] != 0ull) p = k * 64 + 63 - __builtin_clzll(P[k]);
+  if (p < 0) {
+    *y0 = 0.0;
+    *y1 = 0.0;
+    return;
+  }
+  // the top 106 bits of the fraction as two 53-bit integers
+  const int32_t up = 255 - p, uw = up >> 6, ub = up & 63;
+  uint64_t G[4];
+  for (int32_t k = 3; k >= 0; --k) {
+    const uint64_t hi = k - uw >= 0 ? P[k - uw] : 0ull;
+    const uint64_t lo = k - uw - 1 >= 0 ? P[k - uw - 1] : 0ull;
+    G[k] = ub ? (hi << ub) | (lo >> (64 - ub)) : hi;
+  }
+  const uint64_t H = G[3] >> 11, L = ((G[3] & 0x7ffull) << 42) | (G[2] >> 22);
+  const double sc = F64FromBits((uint64_t)(int64_t)(1023 + p - 52 - s) << 52);
+  const double fh = (double)(int64_t)H * sc, fl = ((double)(int64_t)L * sc) * 1.1102230246251565e-16;  // * 2^-53
+  const double ph = 1.5707963267948966, pl = 6.123233995736766e-17;
+  const double t = fh * ph;
+  const double err = std::fma(fh, ph, -t);
+  const double lo = err + (fh * pl + fl * ph);
+  double r0 = t + lo;
+  double r1 = (t - r0) + lo;
+  if (half) {
+    r0 = -r0;
+    r1 = -r1;
+  }
+  *y0 = r0;
+  *y1 = r1;
+}
+double OrcKSinPoly(double z) {  // (sin(x) - x + x^3/6) / x^5, z = x^2
+  const double S2 = 0.008333333333333333, S3 = -0.0001984126984126984, S4 = 2.7557319223985893e-06,
+            S5 = -2.505210838544172e-08, S6 = 1.6059043836821613e-10, S7 = -7.647163731819816e-13,
+            S8 = 2.8114572543455206e-15;
+  return S2 + z * (S3 + z * (S4 + z * (S5 + z * (S6 + z * (S7 + z * S8)))));
+}
+double OrcKCosPoly(double z) {
+  const double C1 = 0.041666666666666664, C2 = -0.001388888888888889, C3 = 2.48015873015873e-05,
+            C4 = -2.755731922398589e-07, C5 = 2.08767569878681e-09, C6 = -1.1470745597729725e-11,
+            C7 = 4.779477332387385e-14, C8 = -1.5619206968586225e-16;
+  return z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * (C6 + z * (C7 + z * C8)))))));
+}
+// fn: 0 sin, 1 cos, 2 tan, 3 cot
+double OrcTrig(double x, int32_t fn) {
+  const uint64_t bits = F64Bits(x);
+  const uint64_t ab = bits & 0x7fffffffffffffffull;
+  if (ab >= 0x7ff0000000000000ull) return x - x;  // inf, nan -> nan
+  const bool neg = (bits >> 63) != 0ull;
+  const double ax = F64FromBits(ab);
+  if (ab < 0x3e40000000000000ull) {  // |x| < 2^-27
+    if (fn == 1) return 1.0;
+    if (fn == 3) return 1.0 / x;
+    return x;
+  }
+  double y0 = ax, y1 = 0.0;
+  int32_t q = 0;
+  if (ax > 0.7853981633974483) OrcRemPio2(ax, &y0, &y1, &q);
+  // sin = y0 - (y0 + y1)^3 / 6 + ..., cos = 1 - (y0 + y1)^2 / 2 + ...: the squares, the cube and 1/6
+  // carry their rounding errors along, so that both come out as double-doubles good to ~2^-58
+  const double S1 = -0.16666666666666666, S1L = -9.25185853854297e-18;
+  const double z = y0 * y0;
+  const double zl = std::fma(y0, y0, -z) + (2.0 * y0) * y1;
+  const double v = z * y0;
+  const double vl = std::fma(z, y0, -v) + (zl * y0 + z * y1);
+  const double t3 = v * S1;
+  const double t3l = (std::fma(v, S1, -t3) + v * S1L) + vl * S1;
+  const double s_rest = (t3l + y1) + ((z * z) * y0) * OrcKSinPoly(z);
+  const double s_a = y0 + t3, s_b = ((y0 - s_a) + t3) + s_rest;
+  const double s_hi = s_a + s_b, s_lo = (s_a - s_hi) + s_b;
+  const double ch = -0.5 * z;
+  const double c_rest = z * OrcKCosPoly(z) - 0.5 * zl;
+  const double c_a = 1.0 + ch, c_b = ((1.0 - c_a) + ch) + c_rest;
+  const double c_hi = c_a + c_b, c_lo = (c_a - c_hi) + c_b;
+  double res;
+  if (fn <= 1) {
+    const int32_t k = (q + fn) & 3;  // cos(t) = sin(t + pi/2)
+    res = (k & 1) ? c_hi : s_hi;
+    if (k & 2) res = -res;
+    if (fn == 0 && neg) res = -res;
+    return res;
+  }
+  // tan / cot: one double-double divided by the other
+  const bool sin_over_cos = ((q & 1) != 0) == (fn == 3);
+  const double n_hi = sin_over_cos ? s_hi : c_hi, n_lo = sin_over_cos ? s_lo : c_lo;
+  const double d_hi = sin_over_cos ? c_hi : s_hi, d_lo = sin_over_cos ? c_lo : s_lo;
+  const double q0 = n_hi / d_hi;
+  const double rem = std::fma(-q0, d_hi, n_hi);
+  const double q1 = ((rem + n_lo) - q0 * d_lo) / d_hi;
+  res = q0 + q1;
+  if (q & 1) res = -res;
+  return neg ? -res : res;
+}
 double OrcExp(double x) {
   const double ln2hi = 6.93147180369123816490e-01, ln2lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
   const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
@@ -1377,6 +1518,12 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "sqrt") { out->d = std::sqrt(a[0].d); return; }
+  if (f == "sin" || f == "cos" || f == "tan" || f == "cot") {
+    const double x = (t0.id == T_INT32 || t0.id == T_INT64) ? static_cast<double>(a[0].i)
+                     : t0.id == T_FLOAT ? static_cast<double>(a[0].f) : a[0].d;
+    out->d = OrcTrig(x, f == "sin" ? 0 : f == "cos" ? 1 : f == "tan" ? 2 : 3);
+    return;
+  }
   if (f == "exp") { out->d = OrcExp(a[0].d); return; }
   if (f == "log" || f == "ln") { out->d = OrcLog(a[0].d); return; }
   if (f == "log10") { out->d = OrcLog10(a[0].d); return; }

@@ -416,6 +416,24 @@ def case_math(b):
     return schema, outs, "project"
 
 
+def case_trig(b):
+    """sin / cos / tan / cot of doubles (ordinary, tiny, huge: the integer Payne-Hanek reduction), floats and
+    integers; bit-exact against the oracle."""
+    D, F4, I, L = pa.float64(), pa.float32(), pa.int32(), pa.int64()
+    schema = pa.schema([("d", D), ("f", F4), ("i", I), ("l", L)])
+    d, f, i, l = F(b, "d", D), F(b, "f", F4), F(b, "i", I), F(b, "l", L)
+    fn = b.make_function
+    small = fn("divide", [d, b.make_literal(1.0e6, D)], D)
+    tiny = fn("divide", [d, b.make_literal(1.0e20, D)], D)
+    huge = fn("multiply", [fn("multiply", [d, b.make_literal(1.0e150, D)], D), b.make_literal(1.0e140, D)], D)
+    outs = []
+    for name in ("sin", "cos", "tan", "cot"):
+        outs += [(fn(name, [x], D), D) for x in (d, small, tiny, huge, f, i, l)]
+    outs.append((fn("add", [fn("multiply", [fn("sin", [d], D), fn("sin", [d], D)], D),
+                            fn("multiply", [fn("cos", [d], D), fn("cos", [d], D)], D)], D), D))
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1005,7 +1023,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math]
+              case_decimal_rounding, case_math, case_trig]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]
