@@ -654,7 +654,7 @@ GDV_DEV f64 gdv_kcos_poly(f64 z) {
 GDV_DEV_BIG f64 gdv_trig(f64 x, i32 fn) {
   const u64 bits = gdv_f64_bits(x);
   const u64 ab = bits & 0x7fffffffffffffffull;
-  if (ab >= 0x7ff0000000000000ull) return x - x;  // inf, nan -> nan
+  if (ab >= 0x7ff0000000000000ull) return gdv_f64_from_bits(0x7ff8000000000000ull);  // inf, nan -> the canonical nan
   const bool neg = (bits >> 63) != 0ull;
   const f64 ax = gdv_f64_from_bits(ab);
   if (ab < 0x3e40000000000000ull) {  // |x| < 2^-27
@@ -2650,6 +2650,25 @@ GDV_DEV bool gdv_like_match(const gdv_str& s, const u16* pat, i32 m) {
   }
   while (j < m && (pat[j] >> 8) == 2u) ++j;
   return j == m;
+}
+
+// regexp_matches: the position automaton built at Make() (gdv_regex.h), run bit-parallel.  `live` holds
+// the positions whose byte was just read; the next set is the union of their follow sets (plus the
+// start positions wherever a match may begin) restricted to the positions that accept the next byte.
+// prog: [0] first, [1] last, [2] flags (1 matches "", 2 '^', 4 '$'), [3..66] follow, [67..322] classes.
+GDV_DEV_BIG bool gdv_regex_match(const gdv_str& s, const u64* prog) {
+  const u64 first = prog[0], last = prog[1], flags = prog[2];
+  const bool at_start = (flags & 2ull) != 0ull, at_end = (flags & 4ull) != 0ull;
+  if ((flags & 1ull) != 0ull && (!at_start || !at_end || s.len == 0)) return true;
+  u64 live = 0ull;
+  for (i32 i = 0; i < s.len; ++i) {
+    u64 next = (i == 0 || !at_start) ? first : 0ull;
+    for (u64 t = live; t != 0ull; t &= t - 1ull) next |= prog[3 + (__ffsll((long long)t) - 1)];
+    live = next & prog[67 + (u32)gdv_ch(s, i)];
+    if (!at_end && (live & last) != 0ull) return true;
+    if (at_start && live == 0ull) return false;
+  }
+  return (live & last) != 0ull;
 }
 
 // Largest row r in [lo, n) with offs[r] <= pos, given offs[lo] <= pos < offs[n] (Arrow int32

@@ -1,4 +1,5 @@
 #include "gdv_codegen.h"
+#include "gdv_regex.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -70,6 +71,16 @@ Status ValidateNode(const Schema& schema, const Node& node) {
           (def->ret.id != GDV_TYPE_DECIMAL128 && def->ret != fn.return_type()))
         return VErr("Function " + def->signature() + " not supported yet: return type " +
                     fn.return_type().ToString() + " does not match");
+      if (def->flags & kRegexHolder) {
+        const Node& c = *fn.children()[1];
+        if (c.kind() != NodeKind::kLiteral || static_cast<const LiteralNode&>(c).is_null())
+          return VErr("'" + fn.name() + "' function requires a literal as the second parameter");
+        RegexProgram prog;
+        std::string why;
+        const int rc = CompileRegex(static_cast<const LiteralNode&>(c).bytes(), &prog, &why);
+        if (rc == 1) return VErr(why);
+        if (rc != 0) return Status::Make(GDV_NOT_IMPLEMENTED, why);
+      }
       if (def->flags & kLikeHolder) {
         for (size_t i = 1; i < fn.children().size(); ++i) {
           const Node& c = *fn.children()[i];
@@ -767,6 +778,32 @@ class BodyGen {
     for (const auto& c : fn.children()) ptypes.push_back(c->return_type());
     const FunctionDef* def = Registry::Get().Lookup(fn.name(), ptypes);
     const DataType& rt = fn.return_type();
+
+    if (def->flags & kRegexHolder) {
+      Val s = Gen(*fn.children()[0], out, indent);
+      if (!s.parts.empty() && error_.empty()) error_ = fn.name() + "(concat(...)) is not supported yet";
+      RegexProgram prog;
+      std::string why;
+      if (CompileRegex(static_cast<const LiteralNode&>(*fn.children()[1]).bytes(), &prog, &why) != 0 && error_.empty())
+        error_ = why;
+      // program block: first, last, flags, follow[64], byte classes[256]
+      const std::string arr = NewVar("gdv_re_");
+      std::string t = "__device__ const u64 " + arr + "[323] = {";
+      auto hex = [](uint64_t v) {
+        char buf[32];
+        std::snprintf(buf, sizeof buf, "0x%llxull", static_cast<unsigned long long>(v));
+        return std::string(buf);
+      };
+      t += hex(prog.first) + "," + hex(prog.last) + "," +
+           hex((prog.nullable ? 1u : 0u) | (prog.anchor_start ? 2u : 0u) | (prog.anchor_end ? 4u : 0u));
+      for (int k = 0; k < 64; ++k) t += "," + hex(prog.follow[k]);
+      for (int k = 0; k < 256; ++k) t += (k % 16 == 0 ? ",\n    " : ",") + hex(prog.cls[k]);
+      t += "};\n";
+      globals_ += t;
+      const std::string v = NewVar("v");
+      *out += Ind(indent) + "const bool " + v + " = gdv_regex_match(" + s.v + ", " + arr + ");\n";
+      return Val{v, s.ok, rt};
+    }
 
     if (def->flags & kLikeHolder) {
       Val s = Gen(*fn.children()[0], out, indent);

@@ -273,6 +273,7 @@ Registry::Registry() {
   }
 
   // ---- strings ------------------------------------------------------------------------
+  Add("regexp_matches", {S, S}, B, NullMode::kIfNull, kRegexHolder, {"regexp_like"});
   Add("like", {S, S}, B, NullMode::kIfNull, kLikeHolder);
   Add("like", {S, S, S}, B, NullMode::kIfNull, kLikeHolder);
   Add("substr", {S, I64, I64}, S, NullMode::kIfNull, kStringView, {"substring"});

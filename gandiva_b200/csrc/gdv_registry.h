@@ -24,6 +24,7 @@ enum FnFlags : uint32_t {
   kStringView = 1u << 3,   // returns a view/transform of its first argument (no new bytes)
   kConcat = 1u << 4,       // result = the pieces of its arguments in order (a rope, see the fuser)
   kScratch = 1u << 5,      // writes its result bytes into a per-row scratch slot passed as last argument
+  kRegexHolder = 1u << 7,  // second arg is a literal regular expression, compiled at Make() (gdv_regex.h)
   kVirtual = 1u << 6,      // result is a rope of "virtual" pieces (repeated / reversed bytes) that only the
                            // string write pass can read: projectable, concat-able, if/else-able, nothing else
 };

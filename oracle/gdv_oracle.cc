@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <string>
@@ -110,6 +111,7 @@ struct Node {
   std::vector<std::string> in_strs;
   // LIKE pattern tokens: 0..255 literal byte, 256 = '_', 257 = '%'
   std::vector<int> like;
+  std::shared_ptr<struct OrcRe> regex;  // regexp_matches: parsed pattern
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1037,7 +1039,7 @@ double OrcKCosPoly(double z) {
 double OrcTrig(double x, int32_t fn) {
   const uint64_t bits = F64Bits(x);
   const uint64_t ab = bits & 0x7fffffffffffffffull;
-  if (ab >= 0x7ff0000000000000ull) return x - x;  // inf, nan -> nan
+  if (ab >= 0x7ff0000000000000ull) return F64FromBits(0x7ff8000000000000ull);  // inf, nan -> the canonical nan
   const bool neg = (bits >> 63) != 0ull;
   const double ax = F64FromBits(ab);
   if (ab < 0x3e40000000000000ull) {  // |x| < 2^-27
@@ -1223,6 +1225,180 @@ double OrcCbrt(double x) {
   const double w = t + t;
   r = (r - t) / (w + r);
   return t + t * r;
+}
+
+// ---- regexp_matches / regexp_like: RE2's partial-match semantics (the reference's holder), restated as
+// a plain backtracking matcher over CODE POINTS -- nothing like the kernel's byte automaton.  '.' is any
+// code point but '\n'; \d \w \s are ASCII; '^' / '$' match at the ends of the text only.
+struct OrcRe {
+  enum K { CHAR, ANY, CLASS, CAT, ALT, REP, BOL, EOL } k = CAT;
+  uint32_t cp = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> ranges;
+  bool neg = false;
+  std::vector<std::shared_ptr<OrcRe>> kids;
+  int lo = 0, hi = -1;
+};
+using OrcReP = std::shared_ptr<OrcRe>;
+std::vector<uint32_t> DecodeUtf8(const std::string& t) {
+  std::vector<uint32_t> out;
+  for (size_t i = 0; i < t.size();) {
+    const unsigned char c = static_cast<unsigned char>(t[i]);
+    const int n = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+    uint32_t cp = n == 1 ? c : c & (0xffu >> (n + 1));
+    for (int k = 1; k < n && i + k < t.size(); ++k) cp = (cp << 6) | (static_cast<unsigned char>(t[i + k]) & 0x3fu);
+    out.push_back(cp);
+    i += static_cast<size_t>(n);
+  }
+  return out;
+}
+struct OrcReParser {
+  std::vector<uint32_t> p;
+  size_t i = 0;
+  bool bad = false;
+  OrcReP Node(OrcRe::K k) { auto r = std::make_shared<OrcRe>(); r->k = k; return r; }
+  void Shorthand(uint32_t c, OrcRe* cls) {
+    if (c == 'd' || c == 'D') cls->ranges.push_back({'0', '9'});
+    if (c == 'w' || c == 'W') { cls->ranges.push_back({'0', '9'}); cls->ranges.push_back({'a', 'z'}); cls->ranges.push_back({'A', 'Z'}); cls->ranges.push_back({'_', '_'}); }
+    if (c == 's' || c == 'S') for (uint32_t ch : {' ', '\t', '\n', '\f', '\r'}) cls->ranges.push_back({ch, ch});
+  }
+  static uint32_t Unescape(uint32_t c) {
+    switch (c) { case 'n': return '\n'; case 't': return '\t'; case 'r': return '\r'; case 'f': return '\f'; case 'v': return '\v'; case 'a': return 7; default: return c; }
+  }
+  OrcReP Alt() {
+    auto alt = Node(OrcRe::ALT);
+    alt->kids.push_back(Cat());
+    while (i < p.size() && p[i] == '|') { ++i; alt->kids.push_back(Cat()); }
+    return alt->kids.size() == 1 ? alt->kids[0] : alt;
+  }
+  OrcReP Cat() {
+    auto cat = Node(OrcRe::CAT);
+    while (i < p.size() && p[i] != '|' && p[i] != ')') cat->kids.push_back(Rep());
+    return cat;
+  }
+  bool Num(int* v) {
+    if (i >= p.size() || p[i] < '0' || p[i] > '9') return false;
+    *v = 0;
+    while (i < p.size() && p[i] >= '0' && p[i] <= '9') { *v = std::min(1000, *v * 10 + static_cast<int>(p[i] - '0')); ++i; }
+    return true;
+  }
+  OrcReP Rep() {
+    OrcReP a = Atom();
+    while (i < p.size()) {
+      int lo, hi;
+      if (p[i] == '*') { lo = 0; hi = -1; ++i; }
+      else if (p[i] == '+') { lo = 1; hi = -1; ++i; }
+      else if (p[i] == '?') { lo = 0; hi = 1; ++i; }
+      else if (p[i] == '{') {
+        const size_t save = i++;
+        if (!Num(&lo)) { i = save; break; }
+        hi = lo;
+        if (i < p.size() && p[i] == ',') { ++i; if (!Num(&hi)) hi = -1; }
+        if (i >= p.size() || p[i] != '}') { i = save; break; }
+        ++i;
+      } else break;
+      if (i < p.size() && p[i] == '?') ++i;
+      auto r = Node(OrcRe::REP);
+      r->kids.push_back(a);
+      r->lo = lo;
+      r->hi = hi;
+      a = r;
+    }
+    return a;
+  }
+  OrcReP Atom() {
+    const uint32_t c = p[i++];
+    if (c == '(') {
+      if (i + 1 < p.size() && p[i] == '?' && p[i + 1] == ':') i += 2;
+      OrcReP r = Alt();
+      if (i >= p.size() || p[i] != ')') bad = true; else ++i;
+      return r;
+    }
+    if (c == '.') return Node(OrcRe::ANY);
+    if (c == '^') return Node(OrcRe::BOL);
+    if (c == '$') return Node(OrcRe::EOL);
+    if (c == '[') {
+      auto cls = Node(OrcRe::CLASS);
+      if (i < p.size() && p[i] == '^') { cls->neg = true; ++i; }
+      bool first = true;
+      while (true) {
+        if (i >= p.size()) { bad = true; return cls; }
+        uint32_t lo = p[i++];
+        if (lo == ']' && !first) break;
+        first = false;
+        if (lo == '\\') {
+          if (i >= p.size()) { bad = true; return cls; }
+          const uint32_t e = p[i++];
+          if (e == 'd' || e == 'w' || e == 's') { Shorthand(e, cls.get()); continue; }
+          lo = Unescape(e);
+        }
+        uint32_t hi = lo;
+        if (i + 1 < p.size() && p[i] == '-' && p[i + 1] != ']') {
+          ++i;
+          hi = p[i++];
+          if (hi == '\\' && i < p.size()) hi = Unescape(p[i++]);
+        }
+        cls->ranges.push_back({lo, hi});
+      }
+      return cls;
+    }
+    if (c == '\\') {
+      if (i >= p.size()) { bad = true; return Node(OrcRe::CAT); }
+      const uint32_t e = p[i++];
+      if (e == 'd' || e == 'w' || e == 's' || e == 'D' || e == 'W' || e == 'S') {
+        auto cls = Node(OrcRe::CLASS);
+        Shorthand(e, cls.get());
+        cls->neg = e == 'D' || e == 'W' || e == 'S';
+        return cls;
+      }
+      auto ch = Node(OrcRe::CHAR);
+      ch->cp = Unescape(e);
+      return ch;
+    }
+    auto ch = Node(OrcRe::CHAR);
+    ch->cp = c;
+    return ch;
+  }
+};
+using OrcReCont = std::function<bool(size_t)>;
+bool OrcReMatch(const OrcRe* r, const std::vector<uint32_t>& t, size_t pos, const OrcReCont& k);
+bool OrcReCat(const OrcRe* r, size_t idx, const std::vector<uint32_t>& t, size_t pos, const OrcReCont& k) {
+  if (idx == r->kids.size()) return k(pos);
+  return OrcReMatch(r->kids[idx].get(), t, pos, [&](size_t p2) { return OrcReCat(r, idx + 1, t, p2, k); });
+}
+bool OrcReRep(const OrcRe* r, int count, const std::vector<uint32_t>& t, size_t pos, const OrcReCont& k) {
+  if (count >= r->lo && k(pos)) return true;
+  if (r->hi >= 0 && count >= r->hi) return false;
+  return OrcReMatch(r->kids[0].get(), t, pos, [&](size_t p2) {
+    if (p2 == pos) return count < r->lo ? k(pos) : false;  // an empty iteration: the remaining ones can be empty too
+    return OrcReRep(r, count + 1, t, p2, k);
+  });
+}
+bool OrcReMatch(const OrcRe* r, const std::vector<uint32_t>& t, size_t pos, const OrcReCont& k) {
+  switch (r->k) {
+    case OrcRe::CHAR: return pos < t.size() && t[pos] == r->cp && k(pos + 1);
+    case OrcRe::ANY: return pos < t.size() && t[pos] != '\n' && k(pos + 1);
+    case OrcRe::CLASS: {
+      if (pos >= t.size()) return false;
+      bool in = false;
+      for (const auto& rg : r->ranges) in = in || (t[pos] >= rg.first && t[pos] <= rg.second);
+      return in != r->neg && k(pos + 1);
+    }
+    case OrcRe::CAT: return OrcReCat(r, 0, t, pos, k);
+    case OrcRe::ALT:
+      for (const auto& kid : r->kids)
+        if (OrcReMatch(kid.get(), t, pos, k)) return true;
+      return false;
+    case OrcRe::REP: return OrcReRep(r, 0, t, pos, k);
+    case OrcRe::BOL: return pos == 0 && k(pos);
+    case OrcRe::EOL: return pos == t.size() && k(pos);
+  }
+  return false;
+}
+bool OrcReSearch(const OrcRe* r, const std::string& text) {
+  const std::vector<uint32_t> t = DecodeUtf8(text);
+  for (size_t start = 0; start <= t.size(); ++start)
+    if (OrcReMatch(r, t, start, [](size_t) { return true; })) return true;
+  return false;
 }
 
 // ---- castFLOAT8 / castFLOAT4(utf8): m * 10^e10 (m <= 19 digits) carried as X * 2^exp2, X < 2^256:
@@ -1932,6 +2108,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
 
   // ---- strings ---------------------------------------------------------------------------
   if (f == "like") { out->b = LikeRec(a[0].s, 0, n.like, 0); return; }
+  if (f == "regexp_matches" || f == "regexp_like") { out->b = OrcReSearch(n.regex.get(), a[0].s); return; }
   if (f == "upper" || f == "lower") {
     out->s = a[0].s;
     for (auto& ch : out->s) {
@@ -2204,6 +2381,13 @@ void Eval(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
 bool Prepare(Node* n, std::string* err) {
   for (auto& k : n->kids)
     if (!Prepare(k.get(), err)) return false;
+  if (n->kind == K_FN && (n->name == "regexp_matches" || n->name == "regexp_like")) {
+    if (n->kids.size() != 2 || n->kids[1]->kind != K_LIT) { *err = "regexp_matches needs a literal pattern"; return false; }
+    OrcReParser rp;
+    rp.p = DecodeUtf8(n->kids[1]->lit.s);
+    n->regex = rp.Alt();
+    if (rp.bad || rp.i != rp.p.size()) { *err = "malformed regular expression"; return false; }
+  }
   if (n->kind == K_FN && (n->name == "like" || n->name == "ilike")) {
     if (n->kids.size() < 2 || n->kids[1]->kind != K_LIT) { *err = "like needs a literal pattern"; return false; }
     const bool has_esc = n->kids.size() == 3;

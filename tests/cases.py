@@ -434,6 +434,22 @@ def case_trig(b):
     return schema, outs, "project"
 
 
+def case_regexp(b):
+    """regexp_matches / regexp_like on the generic string columns (tests/test_parity_gpu.py::test_regexp_matches
+    holds the pattern matrix)."""
+    S, B = pa.string(), pa.bool_()
+    schema = pa.schema([("s", S), ("u", S)])
+    s, u = F(b, "s", S), F(b, "u", S)
+    fn = b.make_function
+    lit = lambda v: b.make_literal(v, S)
+    outs = [(fn("regexp_matches", [s, lit(p)], B), B) for p in
+            ("^[a-z]+$", "[0-9]{2,}", "(spec|requ).*s$", "^\\s*$", "[^ -~]", "a.e", "\\w+\\s\\w+")]
+    outs.append((fn("regexp_like", [fn("upper", [u], S), lit("^[A-Z ]*$")], B), B))
+    outs.append((b.make_if(fn("regexp_matches", [s, lit("e")], B), fn("char_length", [s], pa.int32()),
+                           b.make_literal(-1, pa.int32()), pa.int32()), pa.int32()))
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1023,7 +1039,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math, case_trig]
+              case_decimal_rounding, case_math, case_trig, case_regexp]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]
@@ -1049,3 +1065,26 @@ def q6_batch(n: int, seed: int = 42, null_permille: int = 0, oracle_mod=None) ->
         bufs = [pa.py_buffer(vld) if vld is not None else None, pa.py_buffer(vals)]
         cols.append(pa.Array.from_buffers(t, n, bufs))
     return pa.RecordBatch.from_arrays(cols, schema=Q6_SCHEMA)
+
+
+REGEX_PATTERNS = [
+    "abc", "a.c", "^abc", "abc$", "^abc$", "a*", "^a*$", "a+b", "ab?c", "a|b", "^(a|bc)+$", "(ab)*c", "[abc]+", "[^abc]", "^[^abc]*$",
+    "[a-c0-2]{2,3}", "a{3}", "a{2,}", "^.{3}$", ".*", "^.*$", "", "^$", "\\d+", "\\w+\\s\\w+", "\\D", "^\\S+$", "\\.", "a\\|b", "[.]", "[]a]", "[a\\]]",
+    "[\\d_]+", "é", "^é+$", "日.語", "[é日]", "[^a]é", "a.*b.*c", "(a|b)*abb", "(?:ab|cd)+e", "x?y?z?$", "^(a?){3}b", "(a*)*b", "(a|ab)(c|bcd)(d*)",
+    "[a-c]+[0-2]*$", "\\n", "a\\nb", "^[^\\n]*$", "\\t", "-", "[a-]", "[-a]", "_+", "a{1,2}b{0,1}", "((a))", "(a|)", "(|a)b", "0[01]*1", "^\\w*$",
+    "(ab|a)(bc|c)?$", "^(?:[a-c]|é)+$", ".\\W.", "\\s$", "^\\s", "c.{2}c", "[0-9]+(\\.[0-9]+)?$", "^-?\\d+$",
+]
+
+
+def regex_texts(n, seed):
+    """Short texts over a small alphabet (so that the patterns above hit often), some multi-byte, some NULL."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    alphabet = list("aaabbbccc012 _-.\n\t") + ["é", "日", "語", "x", "y", "z", "d", "e", "|", "]", "A"]
+    out = ["", "abc", "aabbcc", "abb", "日本語", "a\nb", "é", "ééé"]
+    while len(out) < n:
+        out.append("".join(rng.choice(alphabet, size=int(rng.integers(0, 12)))))
+    out = out[:n]
+    for k in range(5, n, 13):
+        out[k] = None
+    return out

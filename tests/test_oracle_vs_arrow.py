@@ -1122,3 +1122,27 @@ def test_trig_functions_within_one_ulp_of_libm(oracle, gandiva):
                 continue
             ulp = Fraction(float(np.spacing(abs(g)))) if g != 0 else Fraction(5e-324)
             assert abs(Fraction(g) - exact) < ulp, (nm, sample[i], g, float(exact))
+
+
+def test_regexp_matches_against_python_re(oracle, gandiva):
+    """regexp_matches / regexp_like (RE2 partial match): the oracle's backtracking matcher against
+    Python's re.search with re.ASCII ('$' spelled \\Z there: Python's '$' also matches before a final
+    newline, RE2's does not)."""
+    import re
+    b = gandiva.TreeExprBuilder()
+    S, B = pa.string(), pa.bool_()
+    schema = pa.schema([("s", S)])
+    s = cases.F(b, "s", S)
+    texts = cases.regex_texts(3000, 21)
+    batch = pa.RecordBatch.from_arrays([pa.array(texts, S)], schema=schema)
+    for pat in cases.REGEX_PATTERNS:
+        root = b.make_function("regexp_matches", [s, b.make_literal(pat, S)], B)
+        got = oracle.project([root], [B], batch)[0].to_pylist()
+        py = pat
+        if py.endswith("$") and not py.endswith("\\$"):
+            py = py[:-1] + "\\Z"
+        rx = re.compile(py, re.ASCII)
+        want = [None if t is None else rx.search(t) is not None for t in texts]
+        assert got == want, (pat, [(t, g, w) for t, g, w in zip(texts, got, want) if g != w][:5])
+    root = b.make_function("regexp_like", [s, b.make_literal("^a", S)], B)
+    assert oracle.project([root], [B], batch)[0].to_pylist() == [None if t is None else t.startswith("a") for t in texts]

@@ -554,6 +554,53 @@ def test_cast_string_to_float(gandiva, oracle):
             oracle.project([root8], [F8], batch)
 
 
+@pytest.mark.parametrize("chunk", range(6))
+def test_regexp_matches(chunk, gandiva, oracle):
+    """regexp_matches / regexp_like: the byte automaton built at Make() against the oracle's
+    backtracking matcher over code points -- literals, classes, repetition, alternation, anchors,
+    multi-byte text, NULLs; plain column, lower() view and substr() view as the subject."""
+    b = gandiva.TreeExprBuilder()
+    S, B, L = pa.string(), pa.bool_(), pa.int64()
+    schema = pa.schema([("s", S)])
+    s = cases.F(b, "s", S)
+    pats = cases.REGEX_PATTERNS[chunk::6]
+    roots = [b.make_function("regexp_matches", [s, b.make_literal(p, S)], B) for p in pats]
+    roots.append(b.make_function("regexp_like", [b.make_function("lower", [s], S), b.make_literal(pats[0], S)], B))
+    roots.append(b.make_function("regexp_matches", [b.make_function("substr", [s, b.make_literal(2, L), b.make_literal(4, L)], S),
+                                                    b.make_literal(pats[-1], S)], B))
+    p = gandiva.make_projector(schema, [b.make_expression(r, pa.field("m%d" % i, B)) for i, r in enumerate(roots)], None)
+    for n, seed in ((1, 1), (70, 2), (2000, 3 + chunk)):
+        batch = pa.RecordBatch.from_arrays([pa.array(cases.regex_texts(n, seed), S)], schema=schema)
+        got = p.evaluate(batch)
+        want = oracle.project(roots, [B] * len(roots), batch)
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert_arrays_match(g, w, "regexp %r n=%d" % (pats[i] if i < len(pats) else "view", n))
+    cond = b.make_condition(roots[0])
+    f = gandiva.make_filter(schema, cond)
+    batch = pa.RecordBatch.from_arrays([pa.array(cases.regex_texts(3000, 40 + chunk), S)], schema=schema)
+    sel = f.evaluate(batch, None).to_array().to_numpy()
+    assert np.array_equal(sel.astype(np.uint64), oracle.filter_indices(roots[0], batch))
+
+
+def test_regexp_pattern_errors(gandiva):
+    b = gandiva.TreeExprBuilder()
+    S, B = pa.string(), pa.bool_()
+    schema = pa.schema([("s", S), ("t", S)])
+    s, t = cases.F(b, "s", S), cases.F(b, "t", S)
+
+    def make(pat_node):
+        root = b.make_function("regexp_matches", [s, pat_node], B)
+        return gandiva.make_projector(schema, [b.make_expression(root, pa.field("m", B))], None)
+    for bad in ("(ab", "ab)", "[abc", "a**b(", "*a", "a\\"):
+        with pytest.raises(Exception, match="regular expression"):
+            make(b.make_literal(bad, S))
+    for unsupported in ("\\bword\\b", "(?i)abc", "(?=a)b", "a^b", "(a$)|b", "[α-ω]", "(a)\\1", "a{100}b{100}", "[[:alpha:]]"):
+        with pytest.raises(pa.ArrowNotImplementedError):
+            make(b.make_literal(unsupported, S))
+    with pytest.raises(Exception, match="requires a literal"):
+        make(t)
+
+
 def test_concurrent_evaluate_from_threads(gandiva, oracle):
     """One Projector and one Filter evaluated from several host threads at once on different
     batches (include/gandiva_b200.h "Threading"): every call gets its own results."""
