@@ -12,6 +12,14 @@ if ROOT not in sys.path:
 # tools/populate_cubin_cache.py fills this in-tree directory, which travels to the GPU box with
 # the snapshot like the built .so files (*.cubin is git-ignored).
 _CUBIN_CACHE = os.path.join(ROOT, "gandiva_b200", "_cubin_cache")
+if (not os.path.isdir(_CUBIN_CACHE) and os.path.exists(_CUBIN_CACHE + ".tar.xz") and os.environ.get("GDV_EMU") != "1"
+        and os.environ.get("PYTEST_XDIST_WORKER") is None):
+    import tarfile
+    try:   # the packed form tools/populate_cubin_cache.py --pack leaves (a few seconds to unpack)
+        with tarfile.open(_CUBIN_CACHE + ".tar.xz") as _tar:
+            _tar.extractall(os.path.dirname(_CUBIN_CACHE), filter="data")
+    except Exception as _e:   # a broken archive only costs the compilations
+        print("cubin cache archive not usable: %s" % _e)
 if os.path.isdir(_CUBIN_CACHE) and os.environ.get("GDV_EMU") != "1":
     os.environ.setdefault("GDV_CUBIN_CACHE_DIR", _CUBIN_CACHE)
 
