@@ -41,6 +41,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_SPLIT_INDEX 6      /* split_part with an index < 1 */
 #define GDV_ERR_CAST_DECIMAL 7     /* castDECIMAL of a string that is not a decimal number */
 #define GDV_ERR_CAST_FLOAT 8       /* castFLOAT4 / castFLOAT8 of a string that is not a number */
+#define GDV_ERR_CAST_BOOL 9        /* castBIT / castBOOLEAN of a string that is not true / false / 1 / 0 */
 struct gdv_ctx {
   int* err;
 };
@@ -1124,6 +1125,34 @@ GDV_DEV i64 gdv_trunc_year_to(i64 ms, i64 span, i64 first) {
   }
 GDV_CALENDAR(date64)
 GDV_CALENDAR(timestamp)
+// float -> integer casts: round half away from zero, then saturate at the ends of the type; NaN -> 0
+GDV_DEV i64 castBIGINT_float64(f64 x) {
+  if (x != x) return 0ll;
+  const f64 r = round(x);
+  if (r >= 9223372036854775808.0) return 0x7fffffffffffffffll;
+  if (r <= -9223372036854775808.0) return (i64)0x8000000000000000ull;
+  return (i64)r;
+}
+GDV_DEV i64 castBIGINT_float32(f32 x) { return castBIGINT_float64((f64)x); }
+GDV_DEV i32 castINT_float64(f64 x) {
+  if (x != x) return 0;
+  const f64 r = round(x);
+  if (r >= 2147483647.0) return 2147483647;
+  if (r <= -2147483648.0) return (i32)0x80000000u;
+  return (i32)r;
+}
+GDV_DEV i32 castINT_float32(f32 x) { return castINT_float64((f64)x); }
+// to_timestamp(seconds since the epoch) / to_time(seconds): milliseconds, fractions truncated toward
+// zero; to_time keeps the time of day in [0, 86 400 000)
+GDV_DEV i64 to_timestamp_int64(i64 sec) { return (i64)((u64)sec * 1000ull); }
+GDV_DEV i64 to_timestamp_int32(i32 sec) { return (i64)sec * 1000ll; }
+GDV_DEV i64 to_timestamp_float64(f64 sec) { return castBIGINT_float64(trunc(sec * 1000.0)); }
+GDV_DEV i64 to_timestamp_float32(f32 sec) { return to_timestamp_float64((f64)sec); }
+GDV_DEV i32 gdv_ms_of_day(i64 ms) { return (i32)(ms - gdv_floordiv(ms, 86400000ll) * 86400000ll); }
+GDV_DEV i32 to_time_int64(i64 sec) { return gdv_ms_of_day(to_timestamp_int64(sec)); }
+GDV_DEV i32 to_time_int32(i32 sec) { return gdv_ms_of_day(to_timestamp_int32(sec)); }
+GDV_DEV i32 to_time_float64(f64 sec) { return gdv_ms_of_day(to_timestamp_float64(sec)); }
+GDV_DEV i32 to_time_float32(f32 sec) { return gdv_ms_of_day(to_timestamp_float64((f64)sec)); }
 // time of day (time32[ms]) of a timestamp, and its fields
 GDV_DEV i32 castTIME_timestamp(i64 ms) { return (i32)(ms - gdv_floordiv(ms, 86400000ll) * 86400000ll); }
 GDV_DEV i64 extractHour_time32(i32 t) { return (i64)(t / 3600000); }
@@ -2086,6 +2115,41 @@ GDV_DEV_BIG i64 gdv_parse_int(gdv_ctx* c, const gdv_str& s, i64 lo, i64 hi) {
     v = v * 10ull + d;
   }
   return neg ? (i64)((u64)0 - v) : (i64)v;
+}
+// castBIT / castBOOLEAN of a string: surrounding spaces ignored; "true" / "false" in any case, "1", "0";
+// anything else raises an ExecutionError.
+GDV_DEV_BIG bool castBIT_utf8(gdv_ctx* c, gdv_str s) {
+  i32 b = 0, e = s.len;
+  while (b < e && s.p[b] == (u8)' ') ++b;
+  while (e > b && s.p[e - 1] == (u8)' ') --e;
+  const i32 n = e - b;
+  if (n == 1 && (s.p[b] == (u8)'1' || s.p[b] == (u8)'0')) return s.p[b] == (u8)'1';
+  if (n == 4 && (s.p[b] | 0x20) == 't' && (s.p[b + 1] | 0x20) == 'r' && (s.p[b + 2] | 0x20) == 'u' && (s.p[b + 3] | 0x20) == 'e')
+    return true;
+  if (n == 5 && (s.p[b] | 0x20) == 'f' && (s.p[b + 1] | 0x20) == 'a' && (s.p[b + 2] | 0x20) == 'l' && (s.p[b + 3] | 0x20) == 's' &&
+      (s.p[b + 4] | 0x20) == 'e')
+    return false;
+  gdv_set_error(c, GDV_ERR_CAST_BOOL);
+  return false;
+}
+// find_in_set(s, list): 1-based index of s among the comma-separated items of list, 0 when it is
+// not there or s itself contains a comma
+GDV_DEV_BIG i32 find_in_set_utf8_utf8(gdv_str s, gdv_str list) {
+  for (i32 i = 0; i < s.len; ++i)
+    if (gdv_ch(s, i) == (u8)',') return 0;
+  i32 item = 1, start = 0;
+  for (i32 i = 0; i <= list.len; ++i) {
+    if (i == list.len || gdv_ch(list, i) == (u8)',') {
+      if (i - start == s.len) {
+        bool same = true;
+        for (i32 k = 0; k < s.len && same; ++k) same = gdv_ch(list, start + k) == gdv_ch(s, k);
+        if (same) return item;
+      }
+      ++item;
+      start = i + 1;
+    }
+  }
+  return 0;
 }
 GDV_DEV i64 castBIGINT_utf8(gdv_ctx* c, gdv_str s) {
   return gdv_parse_int(c, s, (i64)0x8000000000000000ull, 0x7fffffffffffffffll);

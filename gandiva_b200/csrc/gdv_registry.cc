@@ -312,7 +312,7 @@ Registry::Registry() {
   Add("right", {S, I32}, S, NullMode::kIfNull, kStringView);
   Add("locate", {S, S}, I32, NullMode::kIfNull, 0, {"position"});
   Add("locate", {S, S, I32}, I32);
-  Add("strpos", {S, S}, I32);
+  Add("strpos", {S, S}, I32, NullMode::kIfNull, 0, {"instr"});
   Add("byte_substr", {BIN, I32, I32}, BIN, NullMode::kIfNull, kStringView, {"bytesubstring"});
   Add("ltrim", {S, S}, S, NullMode::kIfNull, kStringView);
   Add("rtrim", {S, S}, S, NullMode::kIfNull, kStringView);
@@ -327,6 +327,16 @@ Registry::Registry() {
   Add("crc32", {BIN}, I64);
   Add("to_hex", {I64}, S, NullMode::kIfNull, kScratch);
   Add("to_hex", {I32}, S, NullMode::kIfNull, kScratch);
+  Add("castBIT", {S}, B, NullMode::kIfNull, kCanFail, {"castBOOLEAN"});
+  Add("find_in_set", {S, S}, I32);
+  for (const auto& t : {F32, F64}) {
+    Add("castBIGINT", {t}, I64);
+    Add("castINT", {t}, I32);
+  }
+  for (const auto& t : {I32, I64, F32, F64}) {
+    Add("to_timestamp", {t}, TS);
+    Add("to_time", {t}, T32);
+  }
   Add("castBIGINT", {S}, I64, NullMode::kIfNull, kCanFail);
   Add("castINT", {S}, I32, NullMode::kIfNull, kCanFail);
   Add("castFLOAT8", {S}, F64, NullMode::kIfNull, kCanFail);

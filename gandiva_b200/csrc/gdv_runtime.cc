@@ -22,6 +22,7 @@ const char* ExecutionErrorMessage(int code) {
     case 6: return "Index in split_part must be positive";
     case 7: return "Failed to cast the string to a decimal (not a decimal number)";
     case 8: return "Failed to cast the string to a float (not a number)";
+    case 9: return "Invalid value for boolean";
     default: return "execution error in device function";
   }
 }

@@ -1752,6 +1752,50 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     out->i = static_cast<int64_t>(v);
     return;
   }
+  if ((f == "castBIGINT" || f == "castINT" || f == "to_timestamp" || f == "to_time") && (t0.id == T_FLOAT || t0.id == T_DOUBLE)) {
+    // round half away from zero (to_timestamp / to_time: milliseconds, truncated), saturate, NaN -> 0
+    double x = t0.id == T_FLOAT ? static_cast<double>(a[0].f) : a[0].d;
+    const bool is32 = f == "castINT";
+    if (f == "to_timestamp" || f == "to_time") x = std::trunc(x * 1000.0);
+    int64_t v;
+    if (x != x) v = 0;
+    else {
+      const double r = std::round(x);
+      const double top = is32 ? 2147483647.0 : 9223372036854775808.0, bottom = is32 ? -2147483648.0 : -9223372036854775808.0;
+      if (r >= top) v = is32 ? INT32_MAX : INT64_MAX;
+      else if (r <= bottom) v = is32 ? INT32_MIN : INT64_MIN;
+      else v = static_cast<int64_t>(r);
+    }
+    out->i = f == "to_time" ? v - FloorDiv(v, 86400000) * 86400000 : v;
+    return;
+  }
+  if (f == "to_timestamp" || f == "to_time") {
+    const int64_t ms = static_cast<int64_t>(static_cast<uint64_t>(a[0].i) * 1000ull);
+    out->i = f == "to_time" ? ms - FloorDiv(ms, 86400000) * 86400000 : ms;
+    return;
+  }
+  if (f == "castBIT" || f == "castBOOLEAN") {
+    std::string t = a[0].s;
+    while (!t.empty() && t.front() == ' ') t.erase(t.begin());
+    while (!t.empty() && t.back() == ' ') t.pop_back();
+    for (auto& ch : t) if (ch >= 'A' && ch <= 'Z') ch = static_cast<char>(ch + 32);
+    if (t == "1" || t == "true") out->b = true;
+    else if (t == "0" || t == "false") out->b = false;
+    else cx.error = 9;
+    return;
+  }
+  if (f == "find_in_set") {
+    out->i = 0;
+    if (a[0].s.find(',') != std::string::npos) return;
+    size_t start = 0;
+    for (int64_t item = 1;; ++item) {
+      const size_t comma = a[1].s.find(',', start);
+      const std::string piece = a[1].s.substr(start, comma == std::string::npos ? std::string::npos : comma - start);
+      if (piece == a[0].s) { out->i = item; return; }
+      if (comma == std::string::npos) return;
+      start = comma + 1;
+    }
+  }
   if (f == "castBIGINT") {
     if (t0.id == T_DECIMAL) {
       const i128 r = DecimalRescale(a[0].dec, t0.scale, 38, 0);
@@ -2306,9 +2350,10 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     else out->s = k >= g ? a[0].s : Substr(a[0].s, g - k + 1, k);
     return;
   }
-  if (f == "locate" || f == "position" || f == "strpos") {
-    const std::string& sub = f == "strpos" ? a[1].s : a[0].s;
-    const std::string& str = f == "strpos" ? a[0].s : a[1].s;
+  if (f == "locate" || f == "position" || f == "strpos" || f == "instr") {
+    const bool text_first = f == "strpos" || f == "instr";
+    const std::string& sub = text_first ? a[1].s : a[0].s;
+    const std::string& str = text_first ? a[0].s : a[1].s;
     const int64_t start = na == 3 ? a[2].i : 1;
     out->i = 0;
     if (start < 1) return;

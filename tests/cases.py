@@ -450,6 +450,27 @@ def case_regexp(b):
     return schema, outs, "project"
 
 
+def case_misc_casts(b):
+    """castINT / castBIGINT of floats (round half away, saturating), to_timestamp / to_time, find_in_set, instr."""
+    D, F4, I, L, S, TS, T32 = pa.float64(), pa.float32(), pa.int32(), pa.int64(), pa.string(), pa.timestamp("ms"), pa.time32("ms")
+    schema = pa.schema([("d", D), ("f", F4), ("i", I), ("l", L), ("s", S), ("u", S)])
+    d, f, i, l, s, u = (F(b, n, t) for n, t in zip("dfilsu", (D, F4, I, L, S, S)))
+    fn = b.make_function
+    half = fn("add", [fn("divide", [d, b.make_literal(2.0, D)], D), b.make_literal(0.5, D)], D)
+    huge = fn("multiply", [d, b.make_literal(1.0e13, D)], D)
+    outs = [(fn("castBIGINT", [d], L), L), (fn("castBIGINT", [half], L), L), (fn("castBIGINT", [huge], L), L), (fn("castBIGINT", [f], L), L),
+            (fn("castINT", [d], I), I), (fn("castINT", [half], I), I), (fn("castINT", [huge], I), I), (fn("castINT", [f], I), I),
+            (fn("castINT", [fn("sqrt", [d], D)], I), I),   # NaN for negative d -> 0
+            (fn("to_timestamp", [i], TS), TS), (fn("to_timestamp", [l], TS), TS), (fn("to_timestamp", [d], TS), TS),
+            (fn("to_timestamp", [f], TS), TS), (fn("to_time", [i], T32), T32), (fn("to_time", [l], T32), T32),
+            (fn("to_time", [d], T32), T32), (fn("to_time", [f], T32), T32),
+            (fn("find_in_set", [s, b.make_literal("fox,special,,requests,日本語,the", S)], I), I),
+            (fn("find_in_set", [b.make_literal("", S), u], I), I), (fn("find_in_set", [s, u], I), I),
+            (fn("find_in_set", [fn("lower", [s], S), fn("lower", [u], S)], I), I),
+            (fn("instr", [s, b.make_literal("e", S)], I), I), (fn("instr", [u, s], I), I)]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1039,7 +1060,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math, case_trig, case_regexp]
+              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

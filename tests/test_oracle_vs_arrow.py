@@ -1146,3 +1146,58 @@ def test_regexp_matches_against_python_re(oracle, gandiva):
         assert got == want, (pat, [(t, g, w) for t, g, w in zip(texts, got, want) if g != w][:5])
     root = b.make_function("regexp_like", [s, b.make_literal("^a", S)], B)
     assert oracle.project([root], [B], batch)[0].to_pylist() == [None if t is None else t.startswith("a") for t in texts]
+
+
+def test_misc_casts_against_python(oracle, gandiva):
+    """Float -> integer casts (round half away from zero, saturating, NaN -> 0), to_timestamp / to_time,
+    find_in_set, instr, castBIT against plain Python."""
+    import math
+    b = gandiva.TreeExprBuilder()
+    D, I, L, S, TS, T32, B = pa.float64(), pa.int32(), pa.int64(), pa.string(), pa.timestamp("ms"), pa.time32("ms"), pa.bool_()
+    vals = [0.5, -0.5, 1.5, 2.5, -2.5, 0.49999999999999994, 2147483646.5, 2147483647.4, -2147483648.5, 3e9, -3e9, 9.3e18, -9.3e18,
+            9223372036854775807.0, 1e300, -1e300, math.inf, -math.inf, math.nan, 123456.789, -123456.789, 86399.9995, -0.0004, None]
+    rng = np.random.default_rng(3)
+    vals += (rng.standard_normal(2000) * 10.0 ** rng.integers(0, 12, 2000)).tolist()
+    schema = pa.schema([("d", D), ("s", S), ("u", S)])
+    items = ["a", "b", "fox", "", "日本", "a,b", None]
+    strs = [items[k % len(items)] for k in range(len(vals))]
+    lists = [",".join(rng.choice(["a", "b", "fox", "", "日本", "zz"], size=int(rng.integers(0, 5)))) for _ in vals]
+    batch = pa.RecordBatch.from_arrays([pa.array(vals, D), pa.array(strs, S), pa.array(lists, S)], schema=schema)
+    d, s, u = (cases.F(b, n, t) for n, t in (("d", D), ("s", S), ("u", S)))
+    fn = b.make_function
+    roots = [fn("castBIGINT", [d], L), fn("castINT", [d], I), fn("to_timestamp", [d], TS), fn("to_time", [d], T32),
+             fn("find_in_set", [s, u], I), fn("instr", [u, s], I)]
+    res = oracle.project(roots, [L, I, TS, T32, I, I], batch)
+    got = [res[0].to_pylist(), res[1].to_pylist(), res[2].cast(pa.int64()).to_pylist(), res[3].cast(pa.int32()).to_pylist(),
+           res[4].to_pylist(), res[5].to_pylist()]
+
+    def rnd(x, lo, hi):
+        if x != x:
+            return 0
+        if math.isinf(x):
+            return hi if x > 0 else lo
+        return min(hi, max(lo, int(decimal.Decimal(x).to_integral_value(rounding=decimal.ROUND_HALF_UP))))
+    for r, x in enumerate(vals):
+        if x is None:
+            assert got[0][r] is None and got[1][r] is None
+            continue
+        assert got[0][r] == rnd(x, -2 ** 63, 2 ** 63 - 1), (x, got[0][r])
+        assert got[1][r] == rnd(x, -2 ** 31, 2 ** 31 - 1), (x, got[1][r])
+        ms = x * 1000.0
+        want_ms = 0 if ms != ms else (2 ** 63 - 1 if ms >= 2.0 ** 63 else -2 ** 63 if ms <= -2.0 ** 63 else int(ms))
+        assert got[2][r] == want_ms, (x, got[2][r], want_ms)
+        assert got[3][r] == want_ms % 86400000, (x, got[3][r])
+    for r, (item, lst) in enumerate(zip(strs, lists)):
+        if item is None:
+            assert got[4][r] is None
+            continue
+        parts = lst.split(",")
+        assert got[4][r] == (0 if "," in item or item not in parts else parts.index(item) + 1), (item, lst, got[4][r])
+        assert got[5][r] == lst.find(item) + 1 if item.isascii() and lst.isascii() else True
+    sb = pa.RecordBatch.from_arrays([pa.array(["true", " FALSE ", "1", "0", "True", None, "tRuE  "], S)], schema=pa.schema([("s", S)]))
+    root = fn("castBIT", [cases.F(b, "s", S)], B)
+    assert oracle.project([root], [B], sb)[0].to_pylist() == [True, False, True, False, True, None, True]
+    for bad in ("yes", "", "t", "10", "truee", "fals"):
+        bb = pa.RecordBatch.from_arrays([pa.array(["1", bad], S)], schema=pa.schema([("s", S)]))
+        with pytest.raises(Exception, match="Invalid value for boolean"):
+            oracle.project([fn("castBOOLEAN", [cases.F(b, "s", S)], B)], [B], bb)

@@ -601,6 +601,29 @@ def test_regexp_pattern_errors(gandiva):
         make(t)
 
 
+def test_cast_string_to_boolean(gandiva, oracle):
+    """castBIT / castBOOLEAN(utf8): kernel == oracle; anything but true / false / 1 / 0 raises in both."""
+    b = gandiva.TreeExprBuilder()
+    S, B = pa.string(), pa.bool_()
+    schema = pa.schema([("s", S)])
+    root = b.make_function("castBIT", [cases.F(b, "s", S)], B)
+    root2 = b.make_function("castBOOLEAN", [b.make_function("btrim", [cases.F(b, "s", S)], S)], B)
+    p = gandiva.make_projector(schema, [b.make_expression(root, pa.field("v", B)), b.make_expression(root2, pa.field("w", B))], None)
+    words = ["true", " FALSE ", "1", "0", "True", None, "tRuE  ", "false", " 0"]
+    for n in (1, 9, 1000):
+        batch = pa.RecordBatch.from_arrays([pa.array([words[k % len(words)] for k in range(n)], S)], schema=schema)
+        got = p.evaluate(batch)
+        want = oracle.project([root, root2], [B, B], batch)
+        assert_arrays_match(got[0], want[0], "castBIT")
+        assert_arrays_match(got[1], want[1], "castBOOLEAN(btrim)")
+    for bad in ("yes", "", "t", "10", "truee", "fals", "ｔrue"):
+        batch = pa.RecordBatch.from_arrays([pa.array(["1", None, bad], S)], schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: Invalid value for boolean"):
+            p.evaluate(batch)
+        with pytest.raises(Exception, match="Invalid value for boolean"):
+            oracle.project([root], [B], batch)
+
+
 def test_concurrent_evaluate_from_threads(gandiva, oracle):
     """One Projector and one Filter evaluated from several host threads at once on different
     batches (include/gandiva_b200.h "Threading"): every call gets its own results."""
