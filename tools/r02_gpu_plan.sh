@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
 # memcheck + racecheck of the kernels that have never run on hardware (small cases only)
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_z_optin_kernels.py -m gpu -x -q \
-  -k "key_scan_filter_dense or two_pass or filter_walk or virtual_strings or number_to_text or digests or cast_string" > gpurun_out/r02_memcheck.log 2>&1; tail -4 gpurun_out/r02_memcheck.log
+  -k "key_scan_filter_dense or two_pass or filter_walk or virtual_strings or number_to_text or digests or cast_string or regexp or case_trig or misc_casts" > gpurun_out/r02_memcheck.log 2>&1; tail -4 gpurun_out/r02_memcheck.log
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_z_optin_kernels.py -m gpu -x -q \
   -k "key_scan_filter_dense or two_pass or filter_walk" > gpurun_out/r02_racecheck.log 2>&1; tail -4 gpurun_out/r02_racecheck.log
 GDV_STR_COMBOS="512,2,0;128,1,16;256,1,16;512,1,16;1024,1,16" python tools/bench_configs.py str > gpurun_out/r02_str_sweep.log 2>&1
