@@ -1097,6 +1097,40 @@ REGEX_PATTERNS = [
 ]
 
 
+def _random_regex(rng, depth=0):
+    """A random pattern of the supported subset over the alphabet regex_texts() draws from."""
+    atoms = ["a", "b", "c", "0", "1", " ", "_", "-", "\\.", ".", "é", "日", "x", "[abc]", "[^ab]", "[a-c0-2]", "[^\\n0-9]", "\\d", "\\w", "\\s",
+             "\\D", "\\W", "\\S", "[é_-]", "\\|", "\\n", "[\\d\\s]"]
+    parts = []
+    for _ in range(int(rng.integers(1, 4 if depth else 5))):
+        k = int(rng.integers(0, 10))
+        if k < 6 or depth >= 2:
+            atom = str(rng.choice(atoms))
+        elif k < 8:
+            atom = "(" + _random_regex(rng, depth + 1) + ")"
+        else:
+            atom = "(?:" + _random_regex(rng, depth + 1) + "|" + _random_regex(rng, depth + 1) + ")"
+        q = int(rng.integers(0, 12))
+        atom += ["", "", "", "", "", "*", "+", "?", "{2}", "{1,2}", "{0,1}", "*?"][q]
+        parts.append(atom)
+    return "".join(parts)
+
+
+def _random_regexes(n, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        p = _random_regex(rng)
+        k = int(rng.integers(0, 8))
+        p = ("^" + p if k in (0, 2) else p) + ("$" if k in (1, 2) else "")
+        out.append(p)
+    return out
+
+
+REGEX_PATTERNS += _random_regexes(61, 2024)
+
+
 def regex_texts(n, seed):
     """Short texts over a small alphabet (so that the patterns above hit often), some multi-byte, some NULL."""
     import numpy as np

@@ -563,12 +563,20 @@ def test_regexp_matches(chunk, gandiva, oracle):
     S, B, L = pa.string(), pa.bool_(), pa.int64()
     schema = pa.schema([("s", S)])
     s = cases.F(b, "s", S)
-    pats = cases.REGEX_PATTERNS[chunk::6]
-    roots = [b.make_function("regexp_matches", [s, b.make_literal(p, S)], B) for p in pats]
-    roots.append(b.make_function("regexp_like", [b.make_function("lower", [s], S), b.make_literal(pats[0], S)], B))
-    roots.append(b.make_function("regexp_matches", [b.make_function("substr", [s, b.make_literal(2, L), b.make_literal(4, L)], S),
-                                                    b.make_literal(pats[-1], S)], B))
-    p = gandiva.make_projector(schema, [b.make_expression(r, pa.field("m%d" % i, B)) for i, r in enumerate(roots)], None)
+    pats = list(cases.REGEX_PATTERNS[chunk::6])
+    while True:   # the random patterns may need more than 64 automaton positions: Make() names the first that does
+        roots = [b.make_function("regexp_matches", [s, b.make_literal(p, S)], B) for p in pats]
+        roots.append(b.make_function("regexp_like", [b.make_function("lower", [s], S), b.make_literal(pats[0], S)], B))
+        roots.append(b.make_function("regexp_matches", [b.make_function("substr", [s, b.make_literal(2, L), b.make_literal(4, L)], S),
+                                                        b.make_literal(pats[-1], S)], B))
+        try:
+            p = gandiva.make_projector(schema, [b.make_expression(r, pa.field("m%d" % i, B)) for i, r in enumerate(roots)], None)
+            break
+        except pa.ArrowNotImplementedError as e:
+            too_big = [q for q in pats if "'%s' needs more than 64 automaton positions" % q in str(e)]
+            assert len(too_big) >= 1, str(e)
+            pats = [q for q in pats if q not in too_big]
+    assert len(pats) >= 14, pats
     for n, seed in ((1, 1), (70, 2), (2000, 3 + chunk)):
         batch = pa.RecordBatch.from_arrays([pa.array(cases.regex_texts(n, seed), S)], schema=schema)
         got = p.evaluate(batch)
