@@ -1599,6 +1599,124 @@ GDV_DEV_BIG f64 gdv_parse_f64(gdv_ctx* c, const gdv_str& s) {
 GDV_DEV f64 castFLOAT8_utf8(gdv_ctx* c, gdv_str s) { return gdv_parse_f64(c, s); }
 GDV_DEV f32 castFLOAT4_utf8(gdv_ctx* c, gdv_str s) { return (f32)gdv_parse_f64(c, s); }
 
+// ---- power(x, y) = 2^(y * log2 x), in integers -------------------------------------------------------
+// log2 of the significand bit by bit (square; if >= 2, halve and emit a 1) in Q2.126 for 120 bits:
+// absolute error < 2^-118, also when x is next to 1 and log2 x ~ 2^-53.  y * log2 x is an exact
+// integer product (53 x 131 bits); its fraction F goes through e^(F ln 2) as a 34-term Taylor sum in
+// Q1.127, and the 128-bit significand is rounded once (nearest-even, subnormals and overflow
+// included) by gdv_u256_to_f64.  Total error before that rounding < 2^-57 relative: the result is the
+// correctly rounded one except within 2^-57 of a tie.  IEEE 754 pow special cases up front.  The
+// oracle repeats the same steps; both are checked against Python's decimal at 60 digits.
+GDV_DEV u128 gdv_mulshr127(u128 a, u128 b) {  // (a * b) >> 127, the result fits 128 bits
+  const gdv_u256 p = gdv_mul_u128(a, b);
+  return ((u128)p.w[3] << 65) | ((u128)p.w[2] << 1) | (u128)(p.w[1] >> 63);
+}
+GDV_DEV_BIG f64 power_float64_float64(f64 x, f64 y) {
+  const u64 xb = gdv_f64_bits(x), yb = gdv_f64_bits(y);
+  const u64 xa = xb & 0x7fffffffffffffffull, ya = yb & 0x7fffffffffffffffull;
+  const u64 inf = 0x7ff0000000000000ull;
+  const bool xneg = (xb >> 63) != 0ull, yneg = (yb >> 63) != 0ull;
+  if (ya == 0ull || xb == 0x3ff0000000000000ull) return 1.0;  // pow(x, +-0) = pow(1, y) = 1, NaNs included
+  if (xa > inf || ya > inf) return gdv_f64_from_bits(0x7ff8000000000000ull);
+  // y as an integer M_y * 2^ey; is it an integer, an odd one?
+  const i32 yexp = (i32)(ya >> 52);
+  const u64 my = yexp == 0 ? (ya & 0x000fffffffffffffull) : ((ya & 0x000fffffffffffffull) | 0x0010000000000000ull);
+  const i32 ey = (yexp == 0 ? 1 : yexp) - 1075;
+  bool y_int = false, y_odd = false;
+  if (ya < inf) {
+    if (ey >= 0) {
+      y_int = true;
+      y_odd = ey == 0 && (my & 1ull) != 0ull;
+    } else if (ey >= -52) {
+      y_int = (my & ((1ull << (-ey)) - 1ull)) == 0ull;
+      y_odd = y_int && ((my >> (-ey)) & 1ull) != 0ull;
+    }
+  }
+  const bool res_neg = xneg && y_odd;
+  if (xa == 0ull) {  // +-0
+    if (yneg) return gdv_f64_from_bits((res_neg ? 0x8000000000000000ull : 0ull) | inf);
+    return gdv_f64_from_bits(res_neg ? 0x8000000000000000ull : 0ull);
+  }
+  if (ya == inf) {
+    if (xa == 0x3ff0000000000000ull) return 1.0;  // pow(-1, +-inf)
+    return ((xa > 0x3ff0000000000000ull) != yneg) ? gdv_f64_from_bits(inf) : 0.0;
+  }
+  if (xa == inf) {
+    if (yneg) return gdv_f64_from_bits(res_neg ? 0x8000000000000000ull : 0ull);
+    return gdv_f64_from_bits((res_neg ? 0x8000000000000000ull : 0ull) | inf);
+  }
+  if (xneg && !y_int) return gdv_f64_from_bits(0x7ff8000000000000ull);
+  // |x| = m * 2^k, m in [1, 2)
+  const i32 xexp = (i32)(xa >> 52);
+  u64 mx = xexp == 0 ? (xa & 0x000fffffffffffffull) : ((xa & 0x000fffffffffffffull) | 0x0010000000000000ull);
+  i32 k = (xexp == 0 ? 1 : xexp) - 1023;
+  if (xexp == 0) {
+    const i32 up = __clzll((long long)mx) - 11;
+    mx <<= up;
+    k -= up;
+  }
+  u128 m = (u128)mx << 74;  // Q2.126
+  u128 frac = 0;            // 120 bits of log2 m
+  for (i32 i = 0; i < 120; ++i) {
+    const gdv_u256 p = gdv_mul_u128(m, m);
+    const u128 sq = ((u128)p.w[3] << 66) | ((u128)p.w[2] << 2) | (u128)(p.w[1] >> 62);  // >> 126: in [1, 4)
+    const bool two = (sq >> 127) != 0;
+    m = two ? sq >> 1 : sq;
+    frac = (frac << 1) | (two ? 1u : 0u);
+  }
+  // |log2 |x|| = ip + fp / 2^120
+  const bool lneg = k < 0;
+  u64 ip = (u64)(lneg ? -k : k);
+  u128 fp = frac;
+  if (lneg && frac != 0) {
+    ip -= 1ull;
+    fp = ((u128)1 << 120) - frac;
+  }
+  if (ip == 0ull && fp == 0) return res_neg ? -1.0 : 1.0;  // |x| = 1
+  // P = M_y * (ip * 2^120 + fp);  |y log2|x|| = P * 2^(ey - 120)
+  gdv_u256 P = gdv_mul_u128((u128)my, fp);
+  {
+    const u64 v = my * ip;  // < 2^53 * 2^11
+    gdv_u256 add;
+    add.w[0] = 0ull;
+    add.w[1] = v << 56;
+    add.w[2] = v >> 8;
+    add.w[3] = 0ull;
+    P = gdv_add_u256(P, add);
+  }
+  const bool tneg = lneg != yneg;
+  const i32 s = 120 - ey;
+  if (s > 250) return res_neg ? -1.0 : 1.0;  // |t| < 2^-66
+  const f64 big = gdv_f64_from_bits((res_neg ? 0x8000000000000000ull : 0ull) | (tneg ? 0ull : inf));  // overflow / underflow
+  if (s <= 0) return big;
+  gdv_u256 ipart = P;
+  bool dropped = false;
+  gdv_u256_shr_sticky(ipart, s, dropped);
+  if ((ipart.w[1] | ipart.w[2] | ipart.w[3]) != 0ull || ipart.w[0] >= 1100ull) return big;
+  gdv_u256 fr = P;
+  gdv_u256_shl(fr, 256 - s);
+  u128 fq = ((u128)fr.w[3] << 64) | (u128)fr.w[2];  // Q0.128 fraction of |t|
+  i32 e2 = (i32)ipart.w[0];
+  if (tneg) {
+    if (fq != 0) {
+      e2 = -e2 - 1;
+      fq = (u128)0 - fq;
+    } else {
+      e2 = -e2;
+    }
+  }
+  // 2^fq = e^z, z = fq * ln 2 in Q1.127
+  const u128 ln2 = ((u128)0x58b90bfbe8e7bcd5ull << 64) | (u128)0xe4f1d9cc01f97b57ull;
+  const gdv_u256 zp = gdv_mul_u128(fq, ln2);
+  const u128 z = ((u128)zp.w[3] << 64) | (u128)zp.w[2];
+  const u128 one = (u128)1 << 127;
+  u128 acc = 0;
+  for (u32 n = 34u; n >= 2u; --n) acc = gdv_mulshr127(one + acc, z) / (u128)n;
+  const u128 mant = one + gdv_mulshr127(one + acc, z);  // Q1.127 in [1, 2)
+  const f64 r = gdv_u256_to_f64(gdv_u256_from(mant), true, e2 - 127);
+  return res_neg ? -r : r;
+}
+
 // round / truncate / ceil / floor of a decimal: drop `d` = xs - rs digits under `mode` (0 half away
 // from zero, 1 toward zero, 2 toward +inf, 3 toward -inf), then express the result (scale rs) at the
 // declared output (op, os).  rs >= xs: nothing to drop.  More than 38 digits -> 0, like the others.

@@ -99,6 +99,7 @@ Registry::Registry() {
   Add("cbrt", {F64}, F64);
   for (const auto& t : {I32, I64, F32, F64})
     for (const char* f : {"sin", "cos", "tan", "cot"}) Add(f, {t}, F64);
+  Add("power", {F64, F64}, F64, NullMode::kIfNull, 0, {"pow"});
   Add("degrees", {F64}, F64);
   Add("radians", {F64}, F64);
   for (const auto& t : {I32, I64}) {

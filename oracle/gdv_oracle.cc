@@ -1497,6 +1497,93 @@ bool ParseDouble(const std::string& text, double* out) {
   return true;
 }
 
+// ---- power(x, y): the kernel's integer algorithm (device/gdv_device_lib.cuh power_float64_float64) on
+// the 32-bit-limb Big: log2 of the significand bit by bit in Q2.126 (120 bits), the exact product with
+// y's significand, e^(F ln 2) as a 34-term sum in Q1.127, one final rounding through BigToDouble.
+unsigned __int128 BigBits128(const Big& b, int shift) {  // bits [shift, shift + 128) of b
+  unsigned __int128 r = 0;
+  for (int i = 127; i >= 0; --i) r = (r << 1) | (shift + i < 256 && b.Bit(shift + i) ? 1u : 0u);
+  return r;
+}
+unsigned __int128 MulShr(unsigned __int128 a, unsigned __int128 b, int shift) {
+  return BigBits128(Big::Mul(Big::From(a), Big::From(b)), shift);
+}
+double OrcPow(double x, double y) {
+  const uint64_t xb = F64Bits(x), yb = F64Bits(y);
+  const uint64_t xa = xb & 0x7fffffffffffffffull, ya = yb & 0x7fffffffffffffffull;
+  const uint64_t inf = 0x7ff0000000000000ull, one_bits = 0x3ff0000000000000ull, sign = 0x8000000000000000ull;
+  const bool xneg = (xb >> 63) != 0, yneg = (yb >> 63) != 0;
+  if (ya == 0 || xb == one_bits) return 1.0;
+  if (xa > inf || ya > inf) return F64FromBits(0x7ff8000000000000ull);
+  const int yexp = static_cast<int>(ya >> 52);
+  const uint64_t my = (ya & 0x000fffffffffffffull) | (yexp == 0 ? 0 : 0x0010000000000000ull);
+  const int ey = (yexp == 0 ? 1 : yexp) - 1075;
+  bool y_int = false, y_odd = false;
+  if (ya < inf) {
+    if (ey >= 0) { y_int = true; y_odd = ey == 0 && (my & 1); }
+    else if (ey >= -52) {
+      y_int = (my & ((1ull << (-ey)) - 1)) == 0;
+      y_odd = y_int && ((my >> (-ey)) & 1);
+    }
+  }
+  const bool res_neg = xneg && y_odd;
+  const uint64_t sbit = res_neg ? sign : 0;
+  if (xa == 0) return F64FromBits(sbit | (yneg ? inf : 0));
+  if (ya == inf) {
+    if (xa == one_bits) return 1.0;
+    return ((xa > one_bits) != yneg) ? F64FromBits(inf) : 0.0;
+  }
+  if (xa == inf) return F64FromBits(sbit | (yneg ? 0 : inf));
+  if (xneg && !y_int) return F64FromBits(0x7ff8000000000000ull);
+  const int xexp = static_cast<int>(xa >> 52);
+  uint64_t mx = (xa & 0x000fffffffffffffull) | (xexp == 0 ? 0 : 0x0010000000000000ull);
+  int k = (xexp == 0 ? 1 : xexp) - 1023;
+  while ((mx >> 52) == 0) { mx <<= 1; --k; }
+  using u128 = unsigned __int128;
+  u128 m = static_cast<u128>(mx) << 74;
+  u128 frac = 0;
+  for (int i = 0; i < 120; ++i) {
+    const u128 sq = MulShr(m, m, 126);
+    const bool two = (sq >> 127) != 0;
+    m = two ? sq >> 1 : sq;
+    frac = (frac << 1) | (two ? 1u : 0u);
+  }
+  const bool lneg = k < 0;
+  uint64_t ip = static_cast<uint64_t>(lneg ? -k : k);
+  u128 fp = frac;
+  if (lneg && frac != 0) { ip -= 1; fp = (static_cast<u128>(1) << 120) - frac; }
+  if (ip == 0 && fp == 0) return res_neg ? -1.0 : 1.0;
+  // P = M_y * (ip * 2^120 + fp)
+  Big lq = Big::From(static_cast<u128>(ip));
+  for (int i = 0; i < 120; ++i) BigShl1(&lq);
+  lq.Add(Big::From(fp));
+  const Big P = Big::Mul(Big::From(static_cast<u128>(my)), lq);
+  const bool tneg = lneg != yneg;
+  const int s = 120 - ey;
+  if (s > 250) return res_neg ? -1.0 : 1.0;
+  const double big = F64FromBits(sbit | (tneg ? 0 : inf));
+  if (s <= 0) return big;
+  // integer part: bits [s, 256); fraction: the 128 bits below bit s
+  for (int i = s + 11; i < 256; ++i) if (P.Bit(i)) return big;
+  int e2 = 0;
+  for (int i = s + 10; i >= s; --i) e2 = (e2 << 1) | (P.Bit(i) ? 1 : 0);
+  if (e2 >= 1100) return big;
+  u128 fq = 0;
+  for (int i = 1; i <= 128; ++i) fq = (fq << 1) | (s - i >= 0 && P.Bit(s - i) ? 1u : 0u);
+  if (tneg) {
+    if (fq != 0) { e2 = -e2 - 1; fq = static_cast<u128>(0) - fq; }
+    else e2 = -e2;
+  }
+  const u128 ln2 = (static_cast<u128>(0x58b90bfbe8e7bcd5ull) << 64) | 0xe4f1d9cc01f97b57ull;
+  const u128 z = MulShr(fq, ln2, 128);
+  const u128 one = static_cast<u128>(1) << 127;
+  u128 acc = 0;
+  for (unsigned n = 34; n >= 2; --n) acc = MulShr(one + acc, z, 127) / n;
+  const u128 mant = one + MulShr(one + acc, z, 127);
+  const double r = BigToDouble(Big::From(mant), true, e2 - 127);
+  return res_neg ? -r : r;
+}
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
@@ -1700,6 +1787,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     out->d = OrcTrig(x, f == "sin" ? 0 : f == "cos" ? 1 : f == "tan" ? 2 : 3);
     return;
   }
+  if (f == "power" || f == "pow") { out->d = OrcPow(a[0].d, a[1].d); return; }
   if (f == "exp") { out->d = OrcExp(a[0].d); return; }
   if (f == "log" || f == "ln") { out->d = OrcLog(a[0].d); return; }
   if (f == "log10") { out->d = OrcLog10(a[0].d); return; }

@@ -471,6 +471,24 @@ def case_misc_casts(b):
     return schema, outs, "project"
 
 
+def case_power(b):
+    """power / pow: ordinary, huge, tiny and negative bases, integer and fractional exponents."""
+    D = pa.float64()
+    schema = pa.schema([("d", D), ("e", D)])
+    d, e = F(b, "d", D), F(b, "e", D)
+    fn = b.make_function
+    lit = lambda v: b.make_literal(v, D)
+    small = fn("divide", [d, lit(2.0e5)], D)
+    near1 = fn("add", [lit(1.0), fn("divide", [e, lit(1.0e18)], D)], D)
+    outs = [(fn("power", [fn("abs", [d], D), fn("divide", [e, lit(1.0e6)], D)], D), D),
+            (fn("power", [d, fn("round", [fn("divide", [e, lit(3.0e5)], D)], D)], D), D),       # negative bases, integer exponents
+            (fn("power", [d, small], D), D),                                                         # mostly NaN / huge
+            (fn("pow", [near1, lit(1.0e15)], D), D), (fn("pow", [lit(2.0), small], D), D),
+            (fn("power", [fn("abs", [small], D), lit(0.5)], D), D), (fn("power", [d, lit(2.0)], D), D),
+            (fn("power", [d, lit(-3.0)], D), D), (fn("power", [lit(10.0), fn("divide", [e, lit(4.0e3)], D)], D), D)]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1060,7 +1078,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts]
+              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

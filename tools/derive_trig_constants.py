@@ -48,3 +48,11 @@ for n in range(2, 19):
         coef_c.append(rn(Fraction((-1) ** (n // 2), fact)))
 print("S1..S8 =", ", ".join(repr(c) for c in coef_s))
 print("C1..C7 =", ", ".join(repr(c) for c in coef_c))
+
+# ln 2 in Q1.127 for power(): sum 1 / (k 2^k) in integers with 200 guard bits
+G = 200
+total, k = 0, 1
+while (1 << (127 + G)) // (k << k):
+    total += (1 << (127 + G)) // (k << k)
+    k += 1
+print("ln 2 * 2^127 = 0x%032x" % (total >> G))
