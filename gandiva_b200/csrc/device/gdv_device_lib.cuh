@@ -1611,6 +1611,46 @@ GDV_DEV u128 gdv_mulshr127(u128 a, u128 b) {  // (a * b) >> 127, the result fits
   const gdv_u256 p = gdv_mul_u128(a, b);
   return ((u128)p.w[3] << 65) | ((u128)p.w[2] << 1) | (u128)(p.w[1] >> 63);
 }
+// 2^(+-(ip + fq / 2^128)) as a 128-bit significand: value = mant * 2^(e2 - 127), mant in [2^127, 2^128)
+struct gdv_bigf {
+  u128 mant;
+  i32 e2;
+};
+GDV_DEV_BIG gdv_bigf gdv_exp2_q(bool tneg, i32 ip, u128 fq) {
+  i32 e2 = ip;
+  if (tneg) {
+    if (fq != 0) {
+      e2 = -e2 - 1;
+      fq = (u128)0 - fq;
+    } else {
+      e2 = -e2;
+    }
+  }
+  // 2^fq = e^z, z = fq * ln 2 in Q1.127
+  const u128 ln2 = ((u128)0x58b90bfbe8e7bcd5ull << 64) | (u128)0xe4f1d9cc01f97b57ull;
+  const gdv_u256 zp = gdv_mul_u128(fq, ln2);
+  const u128 z = ((u128)zp.w[3] << 64) | (u128)zp.w[2];
+  const u128 one = (u128)1 << 127;
+  u128 acc = 0;
+  for (u32 n = 34u; n >= 2u; --n) acc = gdv_mulshr127(one + acc, z) / (u128)n;
+  gdv_bigf r;
+  r.mant = one + gdv_mulshr127(one + acc, z);  // Q1.127 in [1, 2)
+  r.e2 = e2;
+  return r;
+}
+// |t| = P * 2^-s split into its integer part (false when it is >= 1100: certain overflow / underflow)
+// and the top 128 bits of its fraction; 1 <= s <= 250
+GDV_DEV bool gdv_split_fixed(const gdv_u256& P, i32 s, i32* ip, u128* fq) {
+  gdv_u256 ipart = P;
+  bool dropped = false;
+  gdv_u256_shr_sticky(ipart, s, dropped);
+  if ((ipart.w[1] | ipart.w[2] | ipart.w[3]) != 0ull || ipart.w[0] >= 1100ull) return false;
+  gdv_u256 fr = P;
+  gdv_u256_shl(fr, 256 - s);
+  *fq = ((u128)fr.w[3] << 64) | (u128)fr.w[2];
+  *ip = (i32)ipart.w[0];
+  return true;
+}
 GDV_DEV_BIG f64 power_float64_float64(f64 x, f64 y) {
   const u64 xb = gdv_f64_bits(x), yb = gdv_f64_bits(y);
   const u64 xa = xb & 0x7fffffffffffffffull, ya = yb & 0x7fffffffffffffffull;
@@ -1689,33 +1729,74 @@ GDV_DEV_BIG f64 power_float64_float64(f64 x, f64 y) {
   if (s > 250) return res_neg ? -1.0 : 1.0;  // |t| < 2^-66
   const f64 big = gdv_f64_from_bits((res_neg ? 0x8000000000000000ull : 0ull) | (tneg ? 0ull : inf));  // overflow / underflow
   if (s <= 0) return big;
-  gdv_u256 ipart = P;
-  bool dropped = false;
-  gdv_u256_shr_sticky(ipart, s, dropped);
-  if ((ipart.w[1] | ipart.w[2] | ipart.w[3]) != 0ull || ipart.w[0] >= 1100ull) return big;
-  gdv_u256 fr = P;
-  gdv_u256_shl(fr, 256 - s);
-  u128 fq = ((u128)fr.w[3] << 64) | (u128)fr.w[2];  // Q0.128 fraction of |t|
-  i32 e2 = (i32)ipart.w[0];
-  if (tneg) {
-    if (fq != 0) {
-      e2 = -e2 - 1;
-      fq = (u128)0 - fq;
-    } else {
-      e2 = -e2;
-    }
-  }
-  // 2^fq = e^z, z = fq * ln 2 in Q1.127
-  const u128 ln2 = ((u128)0x58b90bfbe8e7bcd5ull << 64) | (u128)0xe4f1d9cc01f97b57ull;
-  const gdv_u256 zp = gdv_mul_u128(fq, ln2);
-  const u128 z = ((u128)zp.w[3] << 64) | (u128)zp.w[2];
-  const u128 one = (u128)1 << 127;
-  u128 acc = 0;
-  for (u32 n = 34u; n >= 2u; --n) acc = gdv_mulshr127(one + acc, z) / (u128)n;
-  const u128 mant = one + gdv_mulshr127(one + acc, z);  // Q1.127 in [1, 2)
-  const f64 r = gdv_u256_to_f64(gdv_u256_from(mant), true, e2 - 127);
+  i32 ipow = 0;
+  u128 fq = 0;
+  if (!gdv_split_fixed(P, s, &ipow, &fq)) return big;
+  const gdv_bigf v = gdv_exp2_q(tneg, ipow, fq);
+  const f64 r = gdv_u256_to_f64(gdv_u256_from(v.mant), true, v.e2 - 127);
   return res_neg ? -r : r;
 }
+// sinh / cosh / tanh from the same pieces: a = e^|x| and b = e^-|x| as 128-bit significands (|x| log2 e
+// is an exact 53 x 127-bit product), a +- b aligned in 256 bits, tanh as their 128-bit quotient; one
+// rounding at the end.  fn: 0 sinh, 1 cosh, 2 tanh
+GDV_DEV_BIG f64 gdv_hyperbolic(f64 x, i32 fn) {
+  const u64 xb = gdv_f64_bits(x);
+  const u64 xa = xb & 0x7fffffffffffffffull;
+  const bool neg = (xb >> 63) != 0ull && fn != 1;
+  if (xa > 0x7ff0000000000000ull) return gdv_f64_from_bits(0x7ff8000000000000ull);
+  if (xa < 0x3e30000000000000ull) return fn == 1 ? 1.0 : x;  // |x| < 2^-28
+  const f64 top = fn == 2 ? 1.0 : gdv_f64_from_bits(0x7ff0000000000000ull);
+  if (xa == 0x7ff0000000000000ull) return neg ? -top : top;
+  const u64 mx = (xa & 0x000fffffffffffffull) | 0x0010000000000000ull;
+  const i32 ex = (i32)(xa >> 52) - 1075;  // |x| = mx * 2^ex, ex >= -80 here
+  const u128 log2e = ((u128)0x5c551d94ae0bf85dull << 64) | (u128)0xdf43ff68348e9f44ull;  // Q2.126
+  const gdv_u256 P = gdv_mul_u128((u128)mx, log2e);  // |x| log2 e = P * 2^(ex - 126)
+  const i32 s = 126 - ex;
+  i32 ip = 0;
+  u128 fq = 0;
+  if (s <= 0 || !gdv_split_fixed(P, s, &ip, &fq)) return neg ? -top : top;
+  const gdv_bigf a = gdv_exp2_q(false, ip, fq), b = gdv_exp2_q(true, ip, fq);
+  // A = a.mant * 2^126, B = b aligned to it: a + b < 2^255
+  gdv_u256 A, B;
+  A.w[0] = 0ull;
+  A.w[1] = (u64)(a.mant << 62);
+  A.w[2] = (u64)(a.mant >> 2);
+  A.w[3] = (u64)(a.mant >> 66);
+  B.w[0] = 0ull;
+  B.w[1] = (u64)(b.mant << 62);
+  B.w[2] = (u64)(b.mant >> 2);
+  B.w[3] = (u64)(b.mant >> 66);
+  bool sticky = true;  // a and b are themselves inexact
+  const i32 d = a.e2 - b.e2;
+  if (d > 255) {
+    B.w[0] = B.w[1] = B.w[2] = B.w[3] = 0ull;
+  } else {
+    gdv_u256_shr_sticky(B, d, sticky);
+  }
+  const gdv_u256 sum = gdv_add_u256(A, B), dif = gdv_sub_u256(A, B);
+  f64 r;
+  if (fn == 2) {
+    // (a - b) / (a + b) from the top 128 bits of each
+    gdv_u256 num, den, q, rem;
+    num.w[0] = 0ull;
+    num.w[1] = 0ull;
+    num.w[2] = (dif.w[1] >> 63) | (dif.w[2] << 1);  // (a - b) >> 127, times 2^128
+    num.w[3] = (dif.w[2] >> 63) | (dif.w[3] << 1);
+    den.w[0] = (sum.w[1] >> 63) | (sum.w[2] << 1);  // (a + b) >> 127 < 2^128
+    den.w[1] = (sum.w[2] >> 63) | (sum.w[3] << 1);
+    den.w[2] = 0ull;
+    den.w[3] = 0ull;
+    gdv_divmod_u256(num, den, &q, &rem);
+    r = gdv_u256_is_zero(q) ? 0.0 : gdv_u256_to_f64(q, true, -128);
+  } else {
+    // value = (A +- B) * 2^(a.e2 - 127 - 126) / 2
+    r = gdv_u256_to_f64(fn == 1 ? sum : dif, sticky, a.e2 - 254);
+  }
+  return neg ? -r : r;
+}
+GDV_DEV f64 sinh_float64(f64 x) { return gdv_hyperbolic(x, 0); }
+GDV_DEV f64 cosh_float64(f64 x) { return gdv_hyperbolic(x, 1); }
+GDV_DEV f64 tanh_float64(f64 x) { return gdv_hyperbolic(x, 2); }
 
 // round / truncate / ceil / floor of a decimal: drop `d` = xs - rs digits under `mode` (0 half away
 // from zero, 1 toward zero, 2 toward +inf, 3 toward -inf), then express the result (scale rs) at the

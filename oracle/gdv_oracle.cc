@@ -1508,6 +1508,21 @@ unsigned __int128 BigBits128(const Big& b, int shift) {  // bits [shift, shift +
 unsigned __int128 MulShr(unsigned __int128 a, unsigned __int128 b, int shift) {
   return BigBits128(Big::Mul(Big::From(a), Big::From(b)), shift);
 }
+struct OrcBigF { unsigned __int128 mant; int e2; };  // mant * 2^(e2 - 127), mant in [2^127, 2^128)
+OrcBigF OrcExp2Q(bool tneg, int ip, unsigned __int128 fq) {  // 2^(+-(ip + fq / 2^128))
+  using u128 = unsigned __int128;
+  int e2 = ip;
+  if (tneg) {
+    if (fq != 0) { e2 = -e2 - 1; fq = static_cast<u128>(0) - fq; }
+    else e2 = -e2;
+  }
+  const u128 ln2 = (static_cast<u128>(0x58b90bfbe8e7bcd5ull) << 64) | 0xe4f1d9cc01f97b57ull;
+  const u128 z = MulShr(fq, ln2, 128);
+  const u128 one = static_cast<u128>(1) << 127;
+  u128 acc = 0;
+  for (unsigned n = 34; n >= 2; --n) acc = MulShr(one + acc, z, 127) / n;
+  return OrcBigF{one + MulShr(one + acc, z, 127), e2};
+}
 double OrcPow(double x, double y) {
   const uint64_t xb = F64Bits(x), yb = F64Bits(y);
   const uint64_t xa = xb & 0x7fffffffffffffffull, ya = yb & 0x7fffffffffffffffull;
@@ -1570,18 +1585,56 @@ double OrcPow(double x, double y) {
   if (e2 >= 1100) return big;
   u128 fq = 0;
   for (int i = 1; i <= 128; ++i) fq = (fq << 1) | (s - i >= 0 && P.Bit(s - i) ? 1u : 0u);
-  if (tneg) {
-    if (fq != 0) { e2 = -e2 - 1; fq = static_cast<u128>(0) - fq; }
-    else e2 = -e2;
-  }
-  const u128 ln2 = (static_cast<u128>(0x58b90bfbe8e7bcd5ull) << 64) | 0xe4f1d9cc01f97b57ull;
-  const u128 z = MulShr(fq, ln2, 128);
-  const u128 one = static_cast<u128>(1) << 127;
-  u128 acc = 0;
-  for (unsigned n = 34; n >= 2; --n) acc = MulShr(one + acc, z, 127) / n;
-  const u128 mant = one + MulShr(one + acc, z, 127);
-  const double r = BigToDouble(Big::From(mant), true, e2 - 127);
+  const OrcBigF v = OrcExp2Q(tneg, e2, fq);
+  const double r = BigToDouble(Big::From(v.mant), true, v.e2 - 127);
   return res_neg ? -r : r;
+}
+
+// sinh / cosh / tanh (the kernel's gdv_hyperbolic): e^|x| and e^-|x| as 128-bit significands, combined in
+// 256-bit integers, one rounding.  fn: 0 sinh, 1 cosh, 2 tanh
+double OrcHyperbolic(double x, int fn) {
+  using u128 = unsigned __int128;
+  const uint64_t xb = F64Bits(x), xa = xb & 0x7fffffffffffffffull, inf = 0x7ff0000000000000ull;
+  const bool neg = (xb >> 63) != 0 && fn != 1;
+  if (xa > inf) return F64FromBits(0x7ff8000000000000ull);
+  if (xa < 0x3e30000000000000ull) return fn == 1 ? 1.0 : x;
+  const double top = fn == 2 ? 1.0 : F64FromBits(inf);
+  if (xa == inf) return neg ? -top : top;
+  const uint64_t mx = (xa & 0x000fffffffffffffull) | 0x0010000000000000ull;
+  const int ex = static_cast<int>(xa >> 52) - 1075;
+  const u128 log2e = (static_cast<u128>(0x5c551d94ae0bf85dull) << 64) | 0xdf43ff68348e9f44ull;
+  const Big P = Big::Mul(Big::From(static_cast<u128>(mx)), Big::From(log2e));
+  const int s = 126 - ex;
+  if (s <= 0) return neg ? -top : top;
+  for (int i = s + 11; i < 256; ++i) if (P.Bit(i)) return neg ? -top : top;
+  int ip = 0;
+  for (int i = s + 10; i >= s; --i) ip = (ip << 1) | (P.Bit(i) ? 1 : 0);
+  if (ip >= 1100) return neg ? -top : top;
+  u128 fq = 0;
+  for (int i = 1; i <= 128; ++i) fq = (fq << 1) | (s - i >= 0 && P.Bit(s - i) ? 1u : 0u);
+  const OrcBigF a = OrcExp2Q(false, ip, fq), b = OrcExp2Q(true, ip, fq);
+  Big A = Big::From(a.mant), B = Big::From(b.mant);
+  for (int i = 0; i < 126; ++i) { BigShl1(&A); BigShl1(&B); }
+  bool sticky = true;
+  for (int i = 0; i < a.e2 - b.e2; ++i) {
+    if (B.IsZero()) break;
+    BigShr1(&B, &sticky);
+  }
+  Big sum = A, dif = A;
+  sum.Add(B);
+  dif.Sub(B);
+  double r;
+  if (fn == 2) {
+    const Big num = Big::From(BigBits128(dif, 127)), den = Big::From(BigBits128(sum, 127));
+    Big shifted = num;
+    for (int i = 0; i < 128; ++i) BigShl1(&shifted);
+    Big q, rem;
+    Big::DivMod(shifted, den, &q, &rem);
+    r = q.IsZero() ? 0.0 : BigToDouble(q, true, -128);
+  } else {
+    r = BigToDouble(fn == 1 ? sum : dif, sticky, a.e2 - 254);
+  }
+  return neg ? -r : r;
 }
 
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
@@ -1788,6 +1841,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "power" || f == "pow") { out->d = OrcPow(a[0].d, a[1].d); return; }
+  if (f == "sinh" || f == "cosh" || f == "tanh") { out->d = OrcHyperbolic(a[0].d, f == "sinh" ? 0 : f == "cosh" ? 1 : 2); return; }
   if (f == "exp") { out->d = OrcExp(a[0].d); return; }
   if (f == "log" || f == "ln") { out->d = OrcLog(a[0].d); return; }
   if (f == "log10") { out->d = OrcLog10(a[0].d); return; }

@@ -56,3 +56,4 @@ while (1 << (127 + G)) // (k << k):
     total += (1 << (127 + G)) // (k << k)
     k += 1
 print("ln 2 * 2^127 = 0x%032x" % (total >> G))
+print("log2(e) * 2^126 = 0x%032x" % ((1 << (126 + 127 + G)) // total))
