@@ -1797,6 +1797,178 @@ GDV_DEV_BIG f64 gdv_hyperbolic(f64 x, i32 fn) {
 GDV_DEV f64 sinh_float64(f64 x) { return gdv_hyperbolic(x, 0); }
 GDV_DEV f64 cosh_float64(f64 x) { return gdv_hyperbolic(x, 1); }
 GDV_DEV f64 tanh_float64(f64 x) { return gdv_hyperbolic(x, 2); }
+// ---- atan / atan2 / asin / acos: CORDIC in 128-bit integers ---------------------------------------------
+// The vector (X, Y) is rotated onto the x axis through the angles atan(2^-i), i = 0..119, accumulated
+// in Q2.126 (table derived by tools/derive_trig_constants.py; below i = 42 the angle is 2^-i itself):
+// absolute error < 2^-118, relative < 2^-86 for the smallest angles that come here (2^-32; smaller
+// ones are y / x).  asin / acos feed it (sqrt(1 - v^2), v) with the square root taken exactly
+// (digit by digit) of the 248-bit integer 2^248 - V^2.  One nearest-even rounding of the 128-bit angle.
+__device__ const u64 gdv_atan_tab[43][2] = {
+      {0x3243f6a8885a308dull, 0x313198a2e0370734ull},
+      {0x1dac670561bb4f68ull, 0xadfc88bd978751a0ull},
+      {0x0fadbafc96406eb1ull, 0x56dc79ef5f7a217eull},
+      {0x07f56ea6ab0bdb71ull, 0x9644bcc4f9f44477ull},
+      {0x03feab76e59fbd38ull, 0xdb2c9e4b7038b835ull},
+      {0x01ffd55bba97624aull, 0x84ef3aeedbb518c4ull},
+      {0x00fffaaadddb94d5ull, 0xbbe78c564015f760ull},
+      {0x007fff5556eeea5cull, 0xb40311a8fddf3057ull},
+      {0x003fffeaaab7776eull, 0x52ec4abedadb53dfull},
+      {0x001ffffd5555bbbbull, 0xa9729ab7aac08947ull},
+      {0x000fffffaaaaadddull, 0xddb94b968067ef3aull},
+      {0x0007fffff555556eull, 0xeeeea5ca5d895892ull},
+      {0x0003fffffeaaaaabull, 0x777776e52e5356f5ull},
+      {0x0001ffffffd55555ull, 0x5bbbbbba972972d0ull},
+      {0x0000fffffffaaaaaull, 0xaadddddddb94b94bull},
+      {0x00007fffffff5555ull, 0x5556eeeeeeea5ca5ull},
+      {0x00003fffffffeaaaull, 0xaaaab77777776e52ull},
+      {0x00001ffffffffd55ull, 0x555555bbbbbbbba9ull},
+      {0x00000fffffffffaaull, 0xaaaaaaadddddddddull},
+      {0x000007fffffffff5ull, 0x555555556eeeeeeeull},
+      {0x000003fffffffffeull, 0xaaaaaaaaab777777ull},
+      {0x000001ffffffffffull, 0xd5555555555bbbbbull},
+      {0x000000ffffffffffull, 0xfaaaaaaaaaaaddddull},
+      {0x0000007fffffffffull, 0xff555555555556eeull},
+      {0x0000003fffffffffull, 0xffeaaaaaaaaaaab7ull},
+      {0x0000001fffffffffull, 0xfffd555555555555ull},
+      {0x0000000fffffffffull, 0xffffaaaaaaaaaaaaull},
+      {0x00000007ffffffffull, 0xfffff55555555555ull},
+      {0x00000003ffffffffull, 0xfffffeaaaaaaaaaaull},
+      {0x00000001ffffffffull, 0xffffffd555555555ull},
+      {0x00000000ffffffffull, 0xfffffffaaaaaaaaaull},
+      {0x000000007fffffffull, 0xffffffff55555555ull},
+      {0x000000003fffffffull, 0xffffffffeaaaaaaaull},
+      {0x000000001fffffffull, 0xfffffffffd555555ull},
+      {0x000000000fffffffull, 0xffffffffffaaaaaaull},
+      {0x0000000007ffffffull, 0xfffffffffff55555ull},
+      {0x0000000003ffffffull, 0xfffffffffffeaaaaull},
+      {0x0000000001ffffffull, 0xffffffffffffd555ull},
+      {0x0000000000ffffffull, 0xfffffffffffffaaaull},
+      {0x00000000007fffffull, 0xffffffffffffff55ull},
+      {0x00000000003fffffull, 0xffffffffffffffeaull},
+      {0x00000000001fffffull, 0xfffffffffffffffdull},
+      {0x00000000000fffffull, 0xffffffffffffffffull}};
+GDV_DEV u128 gdv_mul_hi128(u128 a, u128 b) {
+  const gdv_u256 p = gdv_mul_u128(a, b);
+  return ((u128)p.w[3] << 64) | (u128)p.w[2];
+}
+GDV_DEV u128 gdv_mul_lo128(u128 a, u128 b) {
+  const gdv_u256 p = gdv_mul_u128(a, b);
+  return ((u128)p.w[1] << 64) | (u128)p.w[0];
+}
+// atan(y0 / x0) in Q2.126 for 0 <= x0, y0 < 2^125, not both zero
+GDV_DEV_BIG i128 gdv_cordic_atan(u128 x0, u128 y0) {
+  i128 X = (i128)x0, Y = (i128)y0, Z = 0;
+  for (i32 i = 0; i < 120; ++i) {
+    const i128 dx = X >> i, dy = Y >> i;
+    const i128 a = i < 43 ? (i128)(((u128)gdv_atan_tab[i][0] << 64) | (u128)gdv_atan_tab[i][1]) : (i128)1 << (126 - i);
+    if (Y > 0) {
+      X += dy;
+      Y -= dx;
+      Z += a;
+    } else {
+      X -= dy;
+      Y += dx;
+      Z -= a;
+    }
+  }
+  return Z < 0 ? (i128)0 : Z;
+}
+GDV_DEV u128 gdv_pi_q126() { return ((u128)0xc90fdaa22168c234ull << 64) | (u128)0xc4c6628b80dc1cd1ull; }
+GDV_DEV f64 gdv_angle_to_f64(u128 z, bool neg) {  // Q2.126 -> double
+  if (z == 0) return neg ? -0.0 : 0.0;
+  const f64 r = gdv_u256_to_f64(gdv_u256_from(z), true, -126);
+  return neg ? -r : r;
+}
+// a finite nonzero double as M * 2^e with M in [2^52, 2^53)
+GDV_DEV void gdv_split_f64(u64 abits, u64* m, i32* e) {
+  const i32 ex = (i32)(abits >> 52);
+  u64 mm = abits & 0x000fffffffffffffull;
+  i32 ee = (ex == 0 ? 1 : ex) - 1075;
+  if (ex != 0) {
+    mm |= 0x0010000000000000ull;
+  } else {
+    while ((mm >> 52) == 0ull) {
+      mm <<= 1;
+      --ee;
+    }
+  }
+  *m = mm;
+  *e = ee;
+}
+GDV_DEV_BIG f64 atan2_float64_float64(f64 y, f64 x) {
+  const u64 yb = gdv_f64_bits(y), xb = gdv_f64_bits(x);
+  const u64 ya = yb & 0x7fffffffffffffffull, xa = xb & 0x7fffffffffffffffull, inf = 0x7ff0000000000000ull;
+  const bool yneg = (yb >> 63) != 0ull, xneg = (xb >> 63) != 0ull;
+  if (ya > inf || xa > inf) return gdv_f64_from_bits(0x7ff8000000000000ull);
+  const f64 pi = 3.141592653589793, pi_lo = 1.2246467991473532e-16, pio2 = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
+  f64 r;
+  if (ya == 0ull) r = xneg ? pi : 0.0;
+  else if (xa == 0ull) r = pio2;
+  else if (ya == inf) r = xa == inf ? (xneg ? 2.356194490192345 : 0.7853981633974483) : pio2;
+  else if (xa == inf) r = xneg ? pi : 0.0;
+  else {
+    u64 my, mx;
+    i32 ey, ex;
+    gdv_split_f64(ya, &my, &ey);
+    gdv_split_f64(xa, &mx, &ex);
+    const i32 d = ey - ex;
+    if (d > 70) {
+      const f64 t = x / (yneg ? -y : y);  // signed, tiny
+      r = pio2 + (pio2_lo - t);
+    } else if (d < -32) {
+      const f64 t = (yneg ? -y : y) / (xneg ? -x : x);
+      r = xneg ? pi + (pi_lo - t) : t;
+    } else {
+      u128 X0 = (u128)mx << 71, Y0 = (u128)my << 71;
+      if (d > 0) X0 >>= d;
+      else Y0 >>= -d;
+      u128 z = (u128)gdv_cordic_atan(X0, Y0);
+      if (xneg) z = gdv_pi_q126() - z;
+      r = gdv_angle_to_f64(z, false);
+    }
+  }
+  return yneg ? -r : r;
+}
+GDV_DEV f64 atan_float64(f64 v) { return atan2_float64_float64(v, 1.0); }
+// fn: 0 asin, 1 acos
+GDV_DEV_BIG f64 gdv_asin_acos(f64 v, i32 fn) {
+  const u64 vb = gdv_f64_bits(v), va = vb & 0x7fffffffffffffffull;
+  const bool neg = (vb >> 63) != 0ull;
+  if (va > 0x3ff0000000000000ull) return gdv_f64_from_bits(0x7ff8000000000000ull);  // |v| > 1, nan
+  const f64 pi = 3.141592653589793, pio2 = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
+  if (va < 0x3e10000000000000ull) return fn == 0 ? v : pio2 + (pio2_lo - v);  // |v| < 2^-30
+  u64 mv;
+  i32 ev;
+  gdv_split_f64(va, &mv, &ev);
+  const u128 V = (u128)mv << (124 + ev);  // |v| in Q0.124
+  // W = 2^248 - V^2, S = floor(sqrt(W)): sqrt(1 - v^2) in Q0.124
+  const u128 sq_hi = gdv_mul_hi128(V, V), sq_lo = gdv_mul_lo128(V, V);
+  const u128 w_lo = (u128)0 - sq_lo;
+  const u128 w_hi = ((u128)1 << 120) - sq_hi - (sq_lo != 0 ? 1u : 0u);
+  u128 res = 0, rem = 0;
+  for (i32 i = 123; i >= 0; --i) {
+    const i32 bit = 2 * i;  // the pair (bit + 1, bit) of W
+    const u128 pair = bit >= 128 ? (w_hi >> (bit - 128)) & 3u : (w_lo >> bit) & 3u;
+    rem = (rem << 2) | pair;
+    const u128 trial = (res << 2) | 1u;
+    if (rem >= trial) {
+      rem -= trial;
+      res = (res << 1) | 1u;
+    } else {
+      res <<= 1;
+    }
+  }
+  if (res == 0) {  // |v| = 1
+    if (fn == 0) return neg ? -pio2 : pio2;
+    return neg ? pi : 0.0;
+  }
+  if (fn == 0) return gdv_angle_to_f64((u128)gdv_cordic_atan(res, V), neg);
+  u128 z = (u128)gdv_cordic_atan(V, res);
+  if (neg) z = gdv_pi_q126() - z;
+  return gdv_angle_to_f64(z, false);
+}
+GDV_DEV f64 asin_float64(f64 v) { return gdv_asin_acos(v, 0); }
+GDV_DEV f64 acos_float64(f64 v) { return gdv_asin_acos(v, 1); }
 
 // round / truncate / ceil / floor of a decimal: drop `d` = xs - rs digits under `mode` (0 half away
 // from zero, 1 toward zero, 2 toward +inf, 3 toward -inf), then express the result (scale rs) at the

@@ -100,7 +100,8 @@ Registry::Registry() {
   for (const auto& t : {I32, I64, F32, F64})
     for (const char* f : {"sin", "cos", "tan", "cot"}) Add(f, {t}, F64);
   Add("power", {F64, F64}, F64, NullMode::kIfNull, 0, {"pow"});
-  for (const char* f : {"sinh", "cosh", "tanh"}) Add(f, {F64}, F64);
+  for (const char* f : {"sinh", "cosh", "tanh", "asin", "acos", "atan"}) Add(f, {F64}, F64);
+  Add("atan2", {F64, F64}, F64);
   Add("degrees", {F64}, F64);
   Add("radians", {F64}, F64);
   for (const auto& t : {I32, I64}) {

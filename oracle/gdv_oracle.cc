@@ -1637,6 +1637,171 @@ double OrcHyperbolic(double x, int fn) {
   return neg ? -r : r;
 }
 
+// ---- atan / atan2 / asin / acos: the kernel's CORDIC (device/gdv_device_lib.cuh), step for step
+// The vector (X, Y) is rotated onto the x axis through the angles atan(2^-i), i = 0..119, accumulated
+// in Q2.126 (table derived by tools/derive_trig_constants.py; below i = 42 the angle is 2^-i itself):
+// absolute error < 2^-118, relative < 2^-86 for the smallest angles that come here (2^-32; smaller
+// ones are y / x).  asin / acos feed it (sqrt(1 - v^2), v) with the square root taken exactly
+// (digit by digit) of the 248-bit integer 2^248 - V^2.  One nearest-even rounding of the 128-bit angle.
+const uint64_t kAtanTab[43][2] = {
+      {0x3243f6a8885a308dull, 0x313198a2e0370734ull},
+      {0x1dac670561bb4f68ull, 0xadfc88bd978751a0ull},
+      {0x0fadbafc96406eb1ull, 0x56dc79ef5f7a217eull},
+      {0x07f56ea6ab0bdb71ull, 0x9644bcc4f9f44477ull},
+      {0x03feab76e59fbd38ull, 0xdb2c9e4b7038b835ull},
+      {0x01ffd55bba97624aull, 0x84ef3aeedbb518c4ull},
+      {0x00fffaaadddb94d5ull, 0xbbe78c564015f760ull},
+      {0x007fff5556eeea5cull, 0xb40311a8fddf3057ull},
+      {0x003fffeaaab7776eull, 0x52ec4abedadb53dfull},
+      {0x001ffffd5555bbbbull, 0xa9729ab7aac08947ull},
+      {0x000fffffaaaaadddull, 0xddb94b968067ef3aull},
+      {0x0007fffff555556eull, 0xeeeea5ca5d895892ull},
+      {0x0003fffffeaaaaabull, 0x777776e52e5356f5ull},
+      {0x0001ffffffd55555ull, 0x5bbbbbba972972d0ull},
+      {0x0000fffffffaaaaaull, 0xaadddddddb94b94bull},
+      {0x00007fffffff5555ull, 0x5556eeeeeeea5ca5ull},
+      {0x00003fffffffeaaaull, 0xaaaab77777776e52ull},
+      {0x00001ffffffffd55ull, 0x555555bbbbbbbba9ull},
+      {0x00000fffffffffaaull, 0xaaaaaaadddddddddull},
+      {0x000007fffffffff5ull, 0x555555556eeeeeeeull},
+      {0x000003fffffffffeull, 0xaaaaaaaaab777777ull},
+      {0x000001ffffffffffull, 0xd5555555555bbbbbull},
+      {0x000000ffffffffffull, 0xfaaaaaaaaaaaddddull},
+      {0x0000007fffffffffull, 0xff555555555556eeull},
+      {0x0000003fffffffffull, 0xffeaaaaaaaaaaab7ull},
+      {0x0000001fffffffffull, 0xfffd555555555555ull},
+      {0x0000000fffffffffull, 0xffffaaaaaaaaaaaaull},
+      {0x00000007ffffffffull, 0xfffff55555555555ull},
+      {0x00000003ffffffffull, 0xfffffeaaaaaaaaaaull},
+      {0x00000001ffffffffull, 0xffffffd555555555ull},
+      {0x00000000ffffffffull, 0xfffffffaaaaaaaaaull},
+      {0x000000007fffffffull, 0xffffffff55555555ull},
+      {0x000000003fffffffull, 0xffffffffeaaaaaaaull},
+      {0x000000001fffffffull, 0xfffffffffd555555ull},
+      {0x000000000fffffffull, 0xffffffffffaaaaaaull},
+      {0x0000000007ffffffull, 0xfffffffffff55555ull},
+      {0x0000000003ffffffull, 0xfffffffffffeaaaaull},
+      {0x0000000001ffffffull, 0xffffffffffffd555ull},
+      {0x0000000000ffffffull, 0xfffffffffffffaaaull},
+      {0x00000000007fffffull, 0xffffffffffffff55ull},
+      {0x00000000003fffffull, 0xffffffffffffffeaull},
+      {0x00000000001fffffull, 0xfffffffffffffffdull},
+      {0x00000000000fffffull, 0xffffffffffffffffull}};
+// atan(y0 / x0) in Q2.126 for 0 <= x0, y0 < 2^125, not both zero
+__int128 OrcCordicAtan(unsigned __int128 x0, unsigned __int128 y0) {
+  __int128 X = (__int128)x0, Y = (__int128)y0, Z = 0;
+  for (int32_t i = 0; i < 120; ++i) {
+    const __int128 dx = X >> i, dy = Y >> i;
+    const __int128 a = i < 43 ? (__int128)(((unsigned __int128)kAtanTab[i][0] << 64) | (unsigned __int128)kAtanTab[i][1]) : (__int128)1 << (126 - i);
+    if (Y > 0) {
+      X += dy;
+      Y -= dx;
+      Z += a;
+    } else {
+      X -= dy;
+      Y += dx;
+      Z -= a;
+    }
+  }
+  return Z < 0 ? (__int128)0 : Z;
+}
+unsigned __int128 OrcPiQ126() { return ((unsigned __int128)0xc90fdaa22168c234ull << 64) | (unsigned __int128)0xc4c6628b80dc1cd1ull; }
+double OrcAngleToF64(unsigned __int128 z, bool neg) {  // Q2.126 -> double
+  if (z == 0) return neg ? -0.0 : 0.0;
+  const double r = BigToDouble(Big::From(z), true, -126);
+  return neg ? -r : r;
+}
+// a finite nonzero double as M * 2^e with M in [2^52, 2^53)
+void OrcSplitF64(uint64_t abits, uint64_t* m, int32_t* e) {
+  const int32_t ex = (int32_t)(abits >> 52);
+  uint64_t mm = abits & 0x000fffffffffffffull;
+  int32_t ee = (ex == 0 ? 1 : ex) - 1075;
+  if (ex != 0) {
+    mm |= 0x0010000000000000ull;
+  } else {
+    while ((mm >> 52) == 0ull) {
+      mm <<= 1;
+      --ee;
+    }
+  }
+  *m = mm;
+  *e = ee;
+}
+double OrcAtan2(double y, double x) {
+  const uint64_t yb = F64Bits(y), xb = F64Bits(x);
+  const uint64_t ya = yb & 0x7fffffffffffffffull, xa = xb & 0x7fffffffffffffffull, inf = 0x7ff0000000000000ull;
+  const bool yneg = (yb >> 63) != 0ull, xneg = (xb >> 63) != 0ull;
+  if (ya > inf || xa > inf) return F64FromBits(0x7ff8000000000000ull);
+  const double pi = 3.141592653589793, pi_lo = 1.2246467991473532e-16, pio2 = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
+  double r;
+  if (ya == 0ull) r = xneg ? pi : 0.0;
+  else if (xa == 0ull) r = pio2;
+  else if (ya == inf) r = xa == inf ? (xneg ? 2.356194490192345 : 0.7853981633974483) : pio2;
+  else if (xa == inf) r = xneg ? pi : 0.0;
+  else {
+    uint64_t my, mx;
+    int32_t ey, ex;
+    OrcSplitF64(ya, &my, &ey);
+    OrcSplitF64(xa, &mx, &ex);
+    const int32_t d = ey - ex;
+    if (d > 70) {
+      const double t = x / (yneg ? -y : y);  // signed, tiny
+      r = pio2 + (pio2_lo - t);
+    } else if (d < -32) {
+      const double t = (yneg ? -y : y) / (xneg ? -x : x);
+      r = xneg ? pi + (pi_lo - t) : t;
+    } else {
+      unsigned __int128 X0 = (unsigned __int128)mx << 71, Y0 = (unsigned __int128)my << 71;
+      if (d > 0) X0 >>= d;
+      else Y0 >>= -d;
+      unsigned __int128 z = (unsigned __int128)OrcCordicAtan(X0, Y0);
+      if (xneg) z = OrcPiQ126() - z;
+      r = OrcAngleToF64(z, false);
+    }
+  }
+  return yneg ? -r : r;
+}
+double OrcAtan(double v) { return OrcAtan2(v, 1.0); }
+// fn: 0 asin, 1 acos
+double OrcAsinAcos(double v, int32_t fn) {
+  const uint64_t vb = F64Bits(v), va = vb & 0x7fffffffffffffffull;
+  const bool neg = (vb >> 63) != 0ull;
+  if (va > 0x3ff0000000000000ull) return F64FromBits(0x7ff8000000000000ull);  // |v| > 1, nan
+  const double pi = 3.141592653589793, pio2 = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
+  if (va < 0x3e10000000000000ull) return fn == 0 ? v : pio2 + (pio2_lo - v);  // |v| < 2^-30
+  uint64_t mv;
+  int32_t ev;
+  OrcSplitF64(va, &mv, &ev);
+  const unsigned __int128 V = (unsigned __int128)mv << (124 + ev);  // |v| in Q0.124
+  // W = 2^248 - V^2, S = floor(sqrt(W)): sqrt(1 - v^2) in Q0.124
+  const unsigned __int128 sq_hi = MulShr(V, V, 128), sq_lo = MulShr(V, V, 0);
+  const unsigned __int128 w_lo = (unsigned __int128)0 - sq_lo;
+  const unsigned __int128 w_hi = ((unsigned __int128)1 << 120) - sq_hi - (sq_lo != 0 ? 1u : 0u);
+  unsigned __int128 res = 0, rem = 0;
+  for (int32_t i = 123; i >= 0; --i) {
+    const int32_t bit = 2 * i;  // the pair (bit + 1, bit) of W
+    const unsigned __int128 pair = bit >= 128 ? (w_hi >> (bit - 128)) & 3u : (w_lo >> bit) & 3u;
+    rem = (rem << 2) | pair;
+    const unsigned __int128 trial = (res << 2) | 1u;
+    if (rem >= trial) {
+      rem -= trial;
+      res = (res << 1) | 1u;
+    } else {
+      res <<= 1;
+    }
+  }
+  if (res == 0) {  // |v| = 1
+    if (fn == 0) return neg ? -pio2 : pio2;
+    return neg ? pi : 0.0;
+  }
+  if (fn == 0) return OrcAngleToF64((unsigned __int128)OrcCordicAtan(res, V), neg);
+  unsigned __int128 z = (unsigned __int128)OrcCordicAtan(V, res);
+  if (neg) z = OrcPiQ126() - z;
+  return OrcAngleToF64(z, false);
+}
+double OrcAsin(double v) { return OrcAsinAcos(v, 0); }
+double OrcAcos(double v) { return OrcAsinAcos(v, 1); }
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
@@ -1841,6 +2006,10 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     return;
   }
   if (f == "power" || f == "pow") { out->d = OrcPow(a[0].d, a[1].d); return; }
+  if (f == "atan2") { out->d = OrcAtan2(a[0].d, a[1].d); return; }
+  if (f == "atan") { out->d = OrcAtan(a[0].d); return; }
+  if (f == "asin") { out->d = OrcAsin(a[0].d); return; }
+  if (f == "acos") { out->d = OrcAcos(a[0].d); return; }
   if (f == "sinh" || f == "cosh" || f == "tanh") { out->d = OrcHyperbolic(a[0].d, f == "sinh" ? 0 : f == "cosh" ? 1 : 2); return; }
   if (f == "exp") { out->d = OrcExp(a[0].d); return; }
   if (f == "log" || f == "ln") { out->d = OrcLog(a[0].d); return; }

@@ -492,6 +492,23 @@ def case_power(b):
     return schema, outs, "project"
 
 
+def case_inverse_trig(b):
+    """atan / atan2 / asin / acos: ordinary, tiny and huge ratios, all quadrants, |v| <= 1 and beyond (NaN)."""
+    D = pa.float64()
+    schema = pa.schema([("d", D), ("e", D)])
+    d, e = F(b, "d", D), F(b, "e", D)
+    fn = b.make_function
+    lit = lambda v: b.make_literal(v, D)
+    unit = fn("sin", [d], D)                                  # in [-1, 1]
+    outs = [(fn("atan2", [d, e], D), D), (fn("atan2", [d, fn("multiply", [e, lit(1.0e12)], D)], D), D),
+            (fn("atan2", [fn("multiply", [d, lit(1.0e25)], D), e], D), D), (fn("atan2", [d, lit(0.0)], D), D),
+            (fn("atan2", [lit(0.0), e], D), D), (fn("atan", [d], D), D), (fn("atan", [fn("divide", [d, lit(1.0e17)], D)], D), D),
+            (fn("asin", [unit], D), D), (fn("acos", [unit], D), D), (fn("asin", [fn("divide", [d, lit(1.0e6)], D)], D), D),
+            (fn("acos", [fn("divide", [d, lit(1.0e6)], D)], D), D), (fn("acos", [fn("divide", [unit, lit(1.0e12)], D)], D), D),
+            (fn("asin", [fn("cos", [fn("divide", [d, lit(1.0e14)], D)], D)], D), D)]       # next to 1
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1081,7 +1098,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power]
+              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power, case_inverse_trig]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

@@ -57,3 +57,22 @@ while (1 << (127 + G)) // (k << k):
     k += 1
 print("ln 2 * 2^127 = 0x%032x" % (total >> G))
 print("log2(e) * 2^126 = 0x%032x" % ((1 << (126 + 127 + G)) // total))
+
+# atan(2^-i) in Q2.126 for the CORDIC of atan / atan2 / asin / acos (i = 0..42; below that 2^-i itself),
+# and pi in Q2.126
+def atan_pow2(i, scale):   # atan(2^-i) * scale; i = 0: pi / 4
+    if i == 0:
+        return pi_scaled * scale // (4 << (BITS + GUARD))
+    return arctan_inv(1 << i, scale)
+
+
+S126 = 1 << (126 + 64)
+print("atan(2^-i) * 2^126:")
+for i in range(43):
+    v = atan_pow2(i, S126) >> 64
+    print("  ((u128)0x%016xull << 64) | 0x%016xull,  // i = %d" % (v >> 64, v & ((1 << 64) - 1), i))
+pi_q = (pi_scaled >> (BITS + GUARD - 126 - 8)) >> 8
+print("pi * 2^126 = ((u128)0x%016xull << 64) | 0x%016xull" % (pi_q >> 64, pi_q & ((1 << 64) - 1)))
+for name, fr in (("pi", Fraction(pi_scaled, scale)), ("pi/2", Fraction(pi_scaled, 2 * scale)), ("pi/4", Fraction(pi_scaled, 4 * scale)),
+                 ("3pi/4", Fraction(3 * pi_scaled, 4 * scale))):
+    print("RN(%s) = %r" % (name, rn(fr)))
