@@ -485,6 +485,15 @@ GDV_DEV f64 log_float64(f64 x) {
   if (k == 0) return f - s * (f - R);
   return dk * ln2hi - ((s * (f - R) - dk * ln2lo) - f);
 }
+// log(base, value) = ln(value) / ln(base); a base whose logarithm is zero (1) raises "divide by zero"
+GDV_DEV f64 log_float64_float64(gdv_ctx* c, f64 base, f64 v) {
+  const f64 lb = log_float64(base);
+  if (lb == 0.0) {
+    gdv_set_error(c, GDV_ERR_DIV_ZERO);
+    return 0.0;
+  }
+  return log_float64(v) / lb;
+}
 GDV_DEV f64 log10_float64(f64 x) {
   // FreeBSD msun's e_log10: log(1 + f) kept as a hi + lo pair, multiplied by 1 / ln 10 (hi + lo too)
   const f64 ivln10hi = 4.34294481878168880939e-01, ivln10lo = 2.50829467116452752298e-11;

@@ -96,6 +96,7 @@ Registry::Registry() {
   Add("exp", {F64}, F64);
   Add("log", {F64}, F64, NullMode::kIfNull, 0, {"ln"});
   Add("log10", {F64}, F64);
+  Add("log", {F64, F64}, F64, NullMode::kIfNull, kCanFail);
   Add("cbrt", {F64}, F64);
   for (const auto& t : {I32, I64, F32, F64})
     for (const char* f : {"sin", "cos", "tan", "cot"}) Add(f, {t}, F64);

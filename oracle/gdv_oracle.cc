@@ -2012,6 +2012,12 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   if (f == "acos") { out->d = OrcAcos(a[0].d); return; }
   if (f == "sinh" || f == "cosh" || f == "tanh") { out->d = OrcHyperbolic(a[0].d, f == "sinh" ? 0 : f == "cosh" ? 1 : 2); return; }
   if (f == "exp") { out->d = OrcExp(a[0].d); return; }
+  if (f == "log" && na == 2) {
+    const double lb = OrcLog(a[0].d);
+    if (lb == 0.0) { cx.error = 1; return; }
+    out->d = OrcLog(a[1].d) / lb;
+    return;
+  }
   if (f == "log" || f == "ln") { out->d = OrcLog(a[0].d); return; }
   if (f == "log10") { out->d = OrcLog10(a[0].d); return; }
   if (f == "cbrt") { out->d = OrcCbrt(a[0].d); return; }

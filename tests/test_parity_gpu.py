@@ -609,6 +609,29 @@ def test_regexp_pattern_errors(gandiva):
         make(t)
 
 
+def test_log_with_base(gandiva, oracle):
+    """log(base, value) = ln(value) / ln(base), bit-exact with the oracle; base 1 raises like a division by zero."""
+    b = gandiva.TreeExprBuilder()
+    D = pa.float64()
+    schema = pa.schema([("b", D), ("v", D)])
+    root = b.make_function("log", [cases.F(b, "b", D), cases.F(b, "v", D)], D)
+    p = gandiva.make_projector(schema, [b.make_expression(root, pa.field("r", D))], None)
+    rng = np.random.default_rng(4)
+    bases = np.concatenate([rng.uniform(1.5, 100, 500), [2.0, 10.0, 0.5, 1e-300, 7.0]])
+    vals = np.concatenate([np.exp(rng.uniform(-300, 300, 500)), [8.0, 1000.0, 0.25, 1e300, 0.0]])
+    batch = pa.RecordBatch.from_arrays([pa.array(bases, D), pa.array(vals, D)], schema=schema)
+    got, = p.evaluate(batch)
+    want, = oracle.project([root], [D], batch)
+    assert_arrays_match(got, want, "log(base, value)")
+    g = got.to_pylist()
+    assert abs(g[500] - 3.0) < 1e-15 and abs(g[501] - 3.0) < 1e-15 and abs(g[502] - 2.0) < 1e-15 and g[504] == -np.inf
+    bad = pa.RecordBatch.from_arrays([pa.array([2.0, 1.0], D), pa.array([4.0, 4.0], D)], schema=schema)
+    with pytest.raises(gandiva.GandivaError, match="ExecutionError: divide by zero error"):
+        p.evaluate(bad)
+    with pytest.raises(Exception, match="divide by zero"):
+        oracle.project([root], [D], bad)
+
+
 def test_cast_string_to_boolean(gandiva, oracle):
     """castBIT / castBOOLEAN(utf8): kernel == oracle; anything but true / false / 1 / 0 raises in both."""
     b = gandiva.TreeExprBuilder()
