@@ -13,7 +13,7 @@ if ROOT not in sys.path:
 # the snapshot like the built .so files (*.cubin is git-ignored).
 _CUBIN_CACHE = os.path.join(ROOT, "gandiva_b200", "_cubin_cache")
 if (not os.path.isdir(_CUBIN_CACHE) and os.path.exists(_CUBIN_CACHE + ".tar.xz") and os.environ.get("GDV_EMU") != "1"
-        and os.environ.get("PYTEST_XDIST_WORKER") is None):
+        and os.environ.get("PYTEST_XDIST_WORKER") is None and os.path.exists("/dev/nvidiactl")):   # only where a GPU is
     import tarfile
     try:   # the packed form tools/populate_cubin_cache.py --pack leaves (a few seconds to unpack)
         with tarfile.open(_CUBIN_CACHE + ".tar.xz") as _tar:
