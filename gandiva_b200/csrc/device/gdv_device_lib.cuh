@@ -1519,6 +1519,28 @@ GDV_DEV f64 gdv_u256_to_f64(gdv_u256 x, bool sticky, i32 exp2) {  // x != 0: RNE
   // (exp2 + drop == -1074, mant < 2^52) come out as the bare fraction, 2^53 / 2^1024 carry upwards
   return gdv_f64_from_bits(((u64)(i64)(exp2 + drop + 1075) << 52) + mant - (1ull << 52));
 }
+// x * 2^exp2 times 10^rest, 19 decimal digits at a time, keeping >= 192 significant bits (see below)
+GDV_DEV void gdv_scale_pow10(gdv_u256& x, i32& exp2, bool& sticky, i32 rest) {
+  while (rest > 0) {
+    const i32 k = rest > 19 ? 19 : rest;
+    const int p = gdv_u256_top(x);
+    if (p > 191) {
+      gdv_u256_shr_sticky(x, p - 191, sticky);
+      exp2 += p - 191;
+    }
+    bool o = false;
+    x = gdv_mul_u256_u128(x, gdv_pow10_u128(k), &o);  // < 2^192 * 2^64
+    rest -= k;
+  }
+  while (rest < 0) {
+    const i32 k = -rest > 19 ? 19 : -rest;
+    const int up = 255 - gdv_u256_top(x);
+    gdv_u256_shl(x, up);
+    exp2 -= up;
+    sticky = (gdv_divmod_u256_u64(x, (u64)gdv_pow10_u128(k)) != 0ull) || sticky;
+    rest += k;
+  }
+}
 GDV_DEV_BIG f64 gdv_parse_f64(gdv_ctx* c, const gdv_str& s) {
   i32 b = 0, e = s.len;
   while (b < e && s.p[b] == (u8)' ') ++b;
@@ -1582,26 +1604,8 @@ GDV_DEV_BIG f64 gdv_parse_f64(gdv_ctx* c, const gdv_str& s) {
   x.w[1] = 0ull;
   x.w[2] = 0ull;
   x.w[3] = 0ull;
-  i32 exp2 = 0, rest = e10;
-  while (rest > 0) {
-    const i32 k = rest > 19 ? 19 : rest;
-    const int p = gdv_u256_top(x);
-    if (p > 191) {
-      gdv_u256_shr_sticky(x, p - 191, sticky);
-      exp2 += p - 191;
-    }
-    bool o = false;
-    x = gdv_mul_u256_u128(x, gdv_pow10_u128(k), &o);  // < 2^192 * 2^64
-    rest -= k;
-  }
-  while (rest < 0) {
-    const i32 k = -rest > 19 ? 19 : -rest;
-    const int up = 255 - gdv_u256_top(x);
-    gdv_u256_shl(x, up);
-    exp2 -= up;
-    sticky = (gdv_divmod_u256_u64(x, (u64)gdv_pow10_u128(k)) != 0ull) || sticky;
-    rest += k;
-  }
+  i32 exp2 = 0;
+  gdv_scale_pow10(x, exp2, sticky, e10);
   const f64 d = gdv_u256_to_f64(x, sticky, exp2);
   return neg ? -d : d;
 }
@@ -2848,6 +2852,175 @@ GDV_DEV gdv_str castVARCHAR_int64_int64(i64 v, i64 maxlen, u8* scr) {
 }
 GDV_DEV gdv_str castVARCHAR_int32_int64(i32 v, i64 maxlen, u8* scr) {
   return castVARCHAR_int64_int64((i64)v, maxlen, scr);
+}
+// castVARCHAR(float32 / float64, n): the SHORTEST decimal digits that read back as the same value
+// (nearest to it when several do), laid out the way the reference's formatter does (Java's
+// Double.toString): plain notation for 10^-3 <= |v| < 10^7 with at least one digit after the point,
+// otherwise d.dddE[-]x; "NaN", "Infinity", "-Infinity", "0.0", "-0.0".
+// v = M * 2^e is scaled to W = v * 10^(16 - k) in [10^16, 10^17) as a 57.128 fixed-point number (the
+// 19-digit stepping of gdv_parse_f64: relative error < 2^-185); the rounding interval of v is
+// W -+ W / (2M) (half of that below a power of two); for p = 1, 2, ... the multiples of 10^(17 - p)
+// around W are tried against that interval -- end points count when M is even, as round-to-nearest-even
+// reads them.  17 digits always suffice for a double, 9 for a float.
+GDV_DEV_BIG void gdv_shortest_digits(u64 M, i32 e, bool lower_half, u64* digits, i32* ndig, i32* k10) {
+  const int nb = 64 - __clzll((long long)M);
+  i32 k = (i32)gdv_floordiv((i64)(e + nb - 1) * 1233ll, 4096ll);  // floor(log10 v) or one less
+  gdv_u256 W;
+  for (;;) {
+    W.w[0] = M;
+    W.w[1] = 0ull;
+    W.w[2] = 0ull;
+    W.w[3] = 0ull;
+    i32 exp2 = e;
+    bool sticky = false;
+    gdv_scale_pow10(W, exp2, sticky, 16 - k);
+    const i32 sh = exp2 + 128;  // W * 2^128 as an integer
+    if (sh >= 0) gdv_u256_shl(W, sh);
+    else gdv_u256_shr_sticky(W, -sh > 255 ? 255 : -sh, sticky);
+    const u128 ip = ((u128)W.w[3] << 64) | (u128)W.w[2];
+    if (ip < (u128)10000000000000000ull) {
+      --k;
+      continue;
+    }
+    if (ip >= (u128)100000000000000000ull) {
+      ++k;
+      continue;
+    }
+    break;
+  }
+  gdv_u256 h = W;
+  gdv_divmod_u256_u64(h, 2ull * M);
+  gdv_u256 hlo = h;
+  if (lower_half) {
+    bool unused = false;
+    gdv_u256_shr_sticky(hlo, 1, unused);
+  }
+  const gdv_u256 whi = gdv_add_u256(W, h), wlo = gdv_sub_u256(W, hlo);
+  const bool even = (M & 1ull) == 0ull;  // round-to-nearest-even reads the end points of the interval back as v
+  // Integer parts (< 2^58: w[3] is 0) and 128-bit fractions.  The fixed-point values carry an error of a
+  // few units of 2^-128, while a boundary that does not coincide with a candidate stays more than 2^-70
+  // away from it (the 124-bit bound of shortest-digit printing): anything within 2^-104 is a coincidence.
+  const u64 I = W.w[2], Il = wlo.w[2], Ih = whi.w[2];
+  const u128 f = ((u128)W.w[1] << 64) | (u128)W.w[0];
+  const u128 fl = ((u128)wlo.w[1] << 64) | (u128)wlo.w[0], fh = ((u128)whi.w[1] << 64) | (u128)whi.w[0];
+  const u128 tol = (u128)1 << 24, near_one = (u128)0 - tol;
+  u64 unit = 10000000000000000ull;
+  for (i32 p = 1; p <= 17; ++p, unit /= 10ull) {
+    const u64 cdn = (I / unit) * unit, cup = cdn + unit;
+    bool dn_ok, up_ok;
+    if ((cdn == Il && fl <= tol) || (cdn == Il + 1ull && fl >= near_one)) dn_ok = even;  // on the lower boundary
+    else dn_ok = cdn > Il;
+    if ((cup == Ih && fh <= tol) || (cup == Ih + 1ull && fh >= near_one)) up_ok = even;  // on the upper boundary
+    else up_ok = cup <= Ih;
+    if (!dn_ok && !up_ok) continue;
+    u64 pick = dn_ok ? cdn : cup;
+    if (dn_ok && up_ok) {
+      // distances W - cdn and cup - W as (integer, 128-bit fraction)
+      const u64 a_i = I - cdn;
+      const u64 b_i = f == 0 ? cup - I : cup - I - 1ull;
+      const u128 b_f = (u128)0 - f;
+      const bool tie = a_i == b_i && (f > b_f ? f - b_f : b_f - f) <= tol;
+      const bool up_closer = b_i < a_i || (b_i == a_i && b_f < f);
+      if (tie ? ((cdn / unit) & 1ull) != 0ull : up_closer) pick = cup;
+    }
+    if (pick == 100000000000000000ull) {
+      *digits = 1ull;
+      *ndig = 1;
+      *k10 = k + 1;
+    } else {
+      *digits = pick / unit;
+      *ndig = p;
+      *k10 = k;
+    }
+    return;
+  }
+  *digits = I;  // not reached: 17 digits always fit
+  *ndig = 17;
+  *k10 = k;
+}
+GDV_DEV_BIG i32 gdv_put_float(u8* scr, bool neg, u64 M, i32 e, bool lower_half) {
+  u64 digits = 0ull;
+  i32 nd = 0, k = 0;
+  gdv_shortest_digits(M, e, lower_half, &digits, &nd, &k);
+  u8 d[20];
+  for (i32 i = nd - 1; i >= 0; --i) {
+    d[i] = (u8)((u32)'0' + (u32)(digits % 10ull));
+    digits /= 10ull;
+  }
+  i32 at = 0;
+  if (neg) scr[at++] = (u8)'-';
+  if (k >= -3 && k < 7) {
+    if (k >= 0) {
+      for (i32 i = 0; i <= k; ++i) scr[at++] = i < nd ? d[i] : (u8)'0';
+      scr[at++] = (u8)'.';
+      if (nd > k + 1) {
+        for (i32 i = k + 1; i < nd; ++i) scr[at++] = d[i];
+      } else {
+        scr[at++] = (u8)'0';
+      }
+    } else {
+      scr[at++] = (u8)'0';
+      scr[at++] = (u8)'.';
+      for (i32 i = 0; i < -k - 1; ++i) scr[at++] = (u8)'0';
+      for (i32 i = 0; i < nd; ++i) scr[at++] = d[i];
+    }
+  } else {
+    scr[at++] = d[0];
+    scr[at++] = (u8)'.';
+    if (nd > 1) {
+      for (i32 i = 1; i < nd; ++i) scr[at++] = d[i];
+    } else {
+      scr[at++] = (u8)'0';
+    }
+    scr[at++] = (u8)'E';
+    if (k < 0) scr[at++] = (u8)'-';
+    at = gdv_put_uint(scr, at, (u64)(k < 0 ? -k : k), 1);
+  }
+  return at;
+}
+GDV_DEV i32 gdv_put_text(u8* scr, i32 at, const char* t, i32 n) {
+  for (i32 i = 0; i < n; ++i) scr[at++] = (u8)t[i];
+  return at;
+}
+GDV_DEV_BIG gdv_str castVARCHAR_float64_int64(f64 v, i64 maxlen, u8* scr) {
+  const u64 b = gdv_f64_bits(v), a = b & 0x7fffffffffffffffull;
+  const bool neg = (b >> 63) != 0ull;
+  i32 at = 0;
+  if (a > 0x7ff0000000000000ull) {
+    at = gdv_put_text(scr, 0, "NaN", 3);
+  } else if (a == 0x7ff0000000000000ull) {
+    if (neg) scr[at++] = (u8)'-';
+    at = gdv_put_text(scr, at, "Infinity", 8);
+  } else if (a == 0ull) {
+    if (neg) scr[at++] = (u8)'-';
+    at = gdv_put_text(scr, at, "0.0", 3);
+  } else {
+    const i32 ex = (i32)(a >> 52);
+    const u64 frac = a & 0x000fffffffffffffull;
+    const u64 M = ex == 0 ? frac : (frac | 0x0010000000000000ull);
+    at = gdv_put_float(scr, neg, M, (ex == 0 ? 1 : ex) - 1075, frac == 0ull && ex > 1);
+  }
+  return gdv_scratch_str(scr, at, maxlen);
+}
+GDV_DEV_BIG gdv_str castVARCHAR_float32_int64(f32 v, i64 maxlen, u8* scr) {
+  const u32 b = (u32)__float_as_int(v), a = b & 0x7fffffffu;
+  const bool neg = (b >> 31) != 0u;
+  i32 at = 0;
+  if (a > 0x7f800000u) {
+    at = gdv_put_text(scr, 0, "NaN", 3);
+  } else if (a == 0x7f800000u) {
+    if (neg) scr[at++] = (u8)'-';
+    at = gdv_put_text(scr, at, "Infinity", 8);
+  } else if (a == 0u) {
+    if (neg) scr[at++] = (u8)'-';
+    at = gdv_put_text(scr, at, "0.0", 3);
+  } else {
+    const i32 ex = (i32)(a >> 23);
+    const u32 frac = a & 0x007fffffu;
+    const u64 M = ex == 0 ? (u64)frac : (u64)(frac | 0x00800000u);
+    at = gdv_put_float(scr, neg, M, (ex == 0 ? 1 : ex) - 150, frac == 0u && ex > 1);
+  }
+  return gdv_scratch_str(scr, at, maxlen);
 }
 // castVARCHAR(decimal(p, s), n): [-]integer digits[.s fractional digits], then the first n characters
 GDV_DEV_BIG gdv_str castVARCHAR_decimal128_int64(i128 x, i32 xp, i32 xs, i64 maxlen, u8* scr) {

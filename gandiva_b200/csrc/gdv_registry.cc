@@ -297,6 +297,8 @@ Registry::Registry() {
   Add("btrim", {S}, S, NullMode::kIfNull, kStringView, {"trim"});
   Add("castVARCHAR", {S, I64}, S, NullMode::kIfNull, kStringView);
   // numbers / dates as text: the digits are written into a thread-private scratch slot
+  Add("castVARCHAR", {F32, I64}, S, NullMode::kIfNull, kScratch);
+  Add("castVARCHAR", {F64, I64}, S, NullMode::kIfNull, kScratch);
   Add("castVARCHAR", {I32, I64}, S, NullMode::kIfNull, kScratch);
   Add("castVARCHAR", {I64, I64}, S, NullMode::kIfNull, kScratch);
   Add("castVARCHAR", {D64, I64}, S, NullMode::kIfNull, kScratch);

@@ -28,6 +28,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -1802,6 +1803,63 @@ double OrcAsinAcos(double v, int32_t fn) {
 double OrcAsin(double v) { return OrcAsinAcos(v, 0); }
 double OrcAcos(double v) { return OrcAsinAcos(v, 1); }
 
+// ---- castVARCHAR(float32 / float64): shortest round-trip digits found with the C library (printf gives
+// the nearest p-digit decimal, strtod / strtof read it back) -- nothing like the kernel's fixed-point
+// interval test -- then Java's Double.toString layout, which the reference's formatter follows.
+std::string OrcFloatText(double v, bool is_float) {
+  if (v != v) return "NaN";
+  const bool neg = std::signbit(v);
+  const double a = std::fabs(v);
+  std::string out = neg ? "-" : "";
+  if (std::isinf(a)) return out + "Infinity";
+  if (a == 0.0) return out + "0.0";
+  auto reads_back = [&](const std::string& text) {
+    return is_float ? static_cast<double>(std::strtof(text.c_str(), nullptr)) == a : std::strtod(text.c_str(), nullptr) == a;
+  };
+  auto read = [&](const std::string& text) {
+    return is_float ? static_cast<double>(std::strtof(text.c_str(), nullptr)) : std::strtod(text.c_str(), nullptr);
+  };
+  std::string digits;
+  int x10 = 0;
+  for (int p = 1; p <= 17 && digits.empty(); ++p) {
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%.*e", p - 1, a);
+    std::string mant;
+    for (const char* q = buf; *q && *q != 'e'; ++q) if (*q != '.') mant.push_back(*q);
+    const int x = std::atoi(std::strchr(buf, 'e') + 1);
+    if (reads_back(buf)) { digits = mant; x10 = x; break; }
+    // the nearest p-digit decimal reads back as a neighbour: try the next one on the other side of v
+    unsigned long long d = std::strtoull(mant.c_str(), nullptr, 10);
+    unsigned long long top = 1;
+    for (int k = 0; k < p; ++k) top *= 10;
+    int xo = x;
+    if (read(buf) > a) {
+      if (d == top / 10) continue;   // would drop to p - 1 digits, already tried
+      d -= 1;
+    } else {
+      d += 1;
+      if (d == top) { d = top / 10; xo += 1; }
+    }
+    char other[64];
+    std::snprintf(other, sizeof other, "%llue%d", d, xo - (p - 1));
+    if (reads_back(other)) { digits = std::to_string(d); x10 = xo; }
+  }
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  const int nd = static_cast<int>(digits.size());
+  if (x10 >= -3 && x10 < 7) {
+    if (x10 >= 0) {
+      std::string ip = digits.substr(0, std::min(nd, x10 + 1));
+      ip.append(static_cast<size_t>(x10 + 1 - static_cast<int>(ip.size())), '0');
+      out += ip + "." + (nd > x10 + 1 ? digits.substr(static_cast<size_t>(x10 + 1)) : "0");
+    } else {
+      out += "0." + std::string(static_cast<size_t>(-x10 - 1), '0') + digits;
+    }
+  } else {
+    out += digits.substr(0, 1) + "." + (nd > 1 ? digits.substr(1) : "0") + "E" + std::to_string(x10);
+  }
+  return out;
+}
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   const std::string& f = n.name;
   const size_t na = n.kids.size();
@@ -2493,6 +2551,10 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     if (sc > 0) digits.insert(digits.size() - sc, ".");
     if (a[0].dec < 0) digits.insert(digits.begin(), '-');
     out->s = Substr(digits, 1, a[1].i);
+    return;
+  }
+  if (f == "castVARCHAR" && (t0.id == T_FLOAT || t0.id == T_DOUBLE)) {
+    out->s = Substr(OrcFloatText(t0.id == T_FLOAT ? static_cast<double>(a[0].f) : a[0].d, t0.id == T_FLOAT), 1, a[1].i);
     return;
   }
   if (f == "castVARCHAR" && t0.id != T_STRING) {

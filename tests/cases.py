@@ -312,6 +312,8 @@ def case_number_to_text(b):
         (fn("castFLOAT8", [txt(l, 30)], pa.float64()), pa.float64()),   # == castFLOAT8(l) up to 2^53, RNE beyond
         (fn("castFLOAT4", [txt(i, 12)], pa.float32()), pa.float32()),
         (fn("substr", [txt(t, 30), n(12), n(8)], S), S),
+        (txt(fn("castFLOAT8", [l], pa.float64()), 30), S), (txt(fn("castFLOAT4", [i], pa.float32()), 30), S),
+        (txt(fn("divide", [fn("castFLOAT8", [l], pa.float64()), b.make_literal(3.0e9, pa.float64())], pa.float64()), 12), S),
     ]
     return schema, outs, "project"
 

@@ -1375,3 +1375,81 @@ def test_inverse_trig_against_libm_and_exact(oracle, gandiva):
             assert ch < vy < cl, (name, ys[i])
         else:   # angle t of (vx, vy): the cross product with the direction of an angle below / above t has a known sign
             assert vy * cl - vx * sl > 0 and vy * ch - vx * sh < 0, (name, ys[i], xs[i])
+
+
+def _java_layout(sci, neg):
+    """'d.ddde[+-]x' (shortest digits) -> Java's Double.toString layout."""
+    mant, _, ex = sci.partition("e")
+    digits = mant.replace(".", "").rstrip("0") or "0"
+    k = int(ex)
+    if -3 <= k < 7:
+        if k >= 0:
+            ip = digits[:k + 1].ljust(k + 1, "0")
+            text = ip + "." + (digits[k + 1:] or "0")
+        else:
+            text = "0." + "0" * (-k - 1) + digits
+    else:
+        text = digits[0] + "." + (digits[1:] or "0") + "E" + str(k)
+    return ("-" if neg else "") + text
+
+
+def float_text_reference(values, is_float):
+    out = []
+    for v in values:
+        if v is None:
+            out.append(None)
+        elif v != v:
+            out.append("NaN")
+        elif v in (np.inf, -np.inf):
+            out.append("Infinity" if v > 0 else "-Infinity")
+        elif v == 0:
+            out.append("-0.0" if np.signbit(v) else "0.0")
+        else:
+            a = abs(v)
+            sci = np.format_float_scientific(np.float32(a), unique=True, trim="-") if is_float else "%e" % 0
+            if not is_float:
+                r = repr(float(a))
+                sci = np.format_float_scientific(float(a), unique=True, trim="-") if "e" not in r and "." not in r else None
+                if sci is None:   # repr() is the shortest round-trip form: bring it to d.ddde+x
+                    import decimal as _d
+                    t = _d.Decimal(r).as_tuple()
+                    digs = "".join(map(str, t.digits)).rstrip("0") or "0"
+                    k = len(t.digits) - 1 + t.exponent
+                    sci = digs[0] + "." + (digs[1:] or "0") + "e%d" % k
+            out.append(_java_layout(sci, bool(np.signbit(v))))
+    return out
+
+
+def float_text_values(n, seed):
+    rng = np.random.default_rng(seed)
+    vals = [1.0, -1.0, 0.0, -0.0, 1e7, 9999999.0, 1e-3, 9.999e-4, 0.001, 123456.789, 1.5e300, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+            np.inf, -np.inf, np.nan, 0.1, 0.3, 2.0 ** 53, 2.0 ** -1022, 2.0 ** 100, 9007199254740993.0, 1e22, 1e23, 4.35, 0.5, 100.0, 1e-7, 123.0,
+            9.5367431640625e-07, 8.41e21, 2.0 ** 62, 1.0000000000000002, 0.9999999999999999, 1e21, 299792458.0, 6.02214076e23, 1.2345678e-5]
+    vals += (2.0 ** rng.integers(-1074, 1024, 200)).tolist()                      # binade boundaries: the lower half-ulp is narrower
+    vals += (rng.standard_normal(n) * 10.0 ** rng.integers(-300, 300, n)).tolist()
+    vals += (rng.integers(-10 ** 9, 10 ** 9, n) / 10.0 ** rng.integers(0, 9, n)).tolist()
+    vals += rng.uniform(-1e7, 1e7, n).round(2).tolist()
+    return vals
+
+
+def test_float_to_text_against_python_repr(oracle, gandiva):
+    """castVARCHAR(float64 / float32, n): shortest round-trip digits in Java's Double.toString layout.
+    The oracle (C library printf / strtod search) against Python's repr() / numpy's unique float32
+    formatting."""
+    b = gandiva.TreeExprBuilder()
+    D, F4, S, L = pa.float64(), pa.float32(), pa.string(), pa.int64()
+    vals = float_text_values(20000, 5)
+    batch = pa.RecordBatch.from_arrays([pa.array(vals, D)], schema=pa.schema([("d", D)]))
+    root = b.make_function("castVARCHAR", [cases.F(b, "d", D), b.make_literal(40, L)], S)
+    got = oracle.project([root], [S], batch, threads=4)[0].to_pylist()
+    want = float_text_reference(vals, False)
+    bad = [(v, g, w) for v, g, w in zip(vals, got, want) if g != w]
+    assert not bad, bad[:8]
+    with np.errstate(over="ignore"):
+        f32 = np.array(vals, dtype=np.float64).astype(np.float32)
+    batch = pa.RecordBatch.from_arrays([pa.array(f32, F4)], schema=pa.schema([("f", F4)]))
+    root = b.make_function("castVARCHAR", [cases.F(b, "f", F4), b.make_literal(40, L)], S)
+    got = oracle.project([root], [S], batch, threads=4)[0].to_pylist()
+    want = float_text_reference(f32.tolist(), True)
+    bad = [(v, g, w) for v, g, w in zip(f32.tolist(), got, want) if g != w]
+    assert not bad, bad[:8]

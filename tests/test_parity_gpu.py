@@ -609,6 +609,42 @@ def test_regexp_pattern_errors(gandiva):
         make(t)
 
 
+@pytest.mark.parametrize("n", [1, 100, 4000])
+def test_cast_float_to_string(n, gandiva, oracle):
+    """castVARCHAR(float64 / float32, len): the kernel's fixed-point interval search for the shortest
+    digits against the oracle's C-library search (which tests/test_oracle_vs_arrow.py pins to Python's
+    repr); binade boundaries, subnormals, the layout thresholds 10^-3 and 10^7, truncation to len."""
+    from test_oracle_vs_arrow import float_text_values
+    b = gandiva.TreeExprBuilder()
+    D, F4, S, L = pa.float64(), pa.float32(), pa.string(), pa.int64()
+    schema = pa.schema([("d", D), ("f", F4)])
+    vals = float_text_values(max(n // 3, 1), 17 + n)[-n:] if n < 100 else float_text_values(n // 3, 17 + n)
+    with np.errstate(over="ignore"):
+        f32 = np.array(vals, dtype=np.float64).astype(np.float32)
+    nulls = np.arange(len(vals)) % 9 == 4
+    batch = pa.RecordBatch.from_arrays([pa.array(vals, D, mask=nulls), pa.array(f32, F4, mask=nulls)], schema=schema)
+    d, f = cases.F(b, "d", D), cases.F(b, "f", F4)
+    fn = b.make_function
+    roots = [fn("castVARCHAR", [d, b.make_literal(40, L)], S), fn("castVARCHAR", [f, b.make_literal(40, L)], S),
+             fn("castVARCHAR", [d, b.make_literal(5, L)], S),
+             fn("concat", [b.make_literal("v=", S), fn("castVARCHAR", [d, b.make_literal(30, L)], S)], S),
+             fn("castFLOAT8", [fn("castVARCHAR", [d, b.make_literal(40, L)], S)], D)]
+    types = [S, S, S, S, D]
+    # the round trip text -> double only parses plain / exponent spellings: NaN and the infinities are left out of it
+    finite = pa.RecordBatch.from_arrays([pa.array([v if np.isfinite(v) else 1.0 for v in vals], D, mask=nulls), batch.column(1)], schema=schema)
+    p = gandiva.make_projector(schema, [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(zip(roots, types))], None)
+    got = p.evaluate(finite)
+    want = oracle.project(roots, types, finite, threads=4)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_arrays_match(g, w, "castVARCHAR(float) out=%d n=%d" % (i, n))
+    back = got[4].to_numpy(zero_copy_only=False)
+    src = finite.column(0).to_numpy(zero_copy_only=False)
+    ok = ~nulls[:len(src)]
+    assert np.array_equal(back[ok].view(np.uint64), src[ok].view(np.uint64))   # shortest digits read back exactly
+    p2 = gandiva.make_projector(schema, [b.make_expression(roots[0], pa.field("o", S))], None)
+    assert_arrays_match(p2.evaluate(batch)[0], oracle.project(roots[:1], [S], batch)[0], "NaN / Infinity spellings")
+
+
 def test_log_with_base(gandiva, oracle):
     """log(base, value) = ln(value) / ln(base), bit-exact with the oracle; base 1 raises like a division by zero."""
     b = gandiva.TreeExprBuilder()
