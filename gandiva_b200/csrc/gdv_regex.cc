@@ -46,19 +46,14 @@ ReP Clone(const ReP& r) {
   c->b = Clone(r->b);
   return c;
 }
-// every well-formed multi-byte code point (2, 3 and 4 byte forms)
-ReP MultiByte() {
-  const ReP cont = MkSet(Range(0x80, 0xbf));
-  ReP two = Cat(MkSet(Range(0xc2, 0xdf)), Clone(cont));
-  ReP three = Cat(MkSet(Range(0xe0, 0xef)), Cat(Clone(cont), Clone(cont)));
-  ReP four = Cat(MkSet(Range(0xf0, 0xf4)), Cat(Clone(cont), Cat(Clone(cont), Clone(cont))));
-  return Mk(Re::kAlt, two, Mk(Re::kAlt, three, four));
-}
-// one code point whose ASCII members are `ascii`; with_multibyte adds every non-ASCII code point
+// One code point whose ASCII members are `ascii`; with_multibyte adds every non-ASCII code point.
+// A multi-byte character costs two positions, not one per UTF-8 form: a lead byte (folded into the
+// ASCII position) followed by any run of continuation bytes.  On well-formed UTF-8 that run is exactly
+// the rest of the character -- no atom of the automaton can begin at a continuation byte, so the run
+// can neither stop early nor swallow part of the next character.
 ReP CodePoint(const ByteSet& ascii, bool with_multibyte) {
-  ReP r = ascii.any() ? MkSet(ascii) : nullptr;
-  if (!with_multibyte) return r ? r : MkSet(ByteSet());  // an empty set never matches
-  return r ? Mk(Re::kAlt, r, MultiByte()) : MultiByte();
+  if (!with_multibyte) return MkSet(ascii);  // an empty set never matches
+  return Cat(MkSet(ascii | Range(0xc2, 0xf4)), Mk(Re::kStar, MkSet(Range(0x80, 0xbf))));
 }
 ByteSet Digits() { return Range('0', '9'); }
 ByteSet Word() { return Range('0', '9') | Range('a', 'z') | Range('A', 'Z') | Range('_', '_'); }
