@@ -2,6 +2,7 @@
 #include "gdv_regex.h"
 
 #include <bitset>
+#include <cctype>
 #include <memory>
 #include <vector>
 
@@ -70,6 +71,10 @@ class Parser {
   int code = 0;  // 0 ok, 1 invalid, 2 not implemented
 
   ReP Parse() {
+    if (p_.compare(0, 4, "(?i)") == 0) {  // ASCII case-insensitive matching for the whole pattern
+      icase_ = true;
+      i_ = 4;
+    }
     ReP r = Alt();
     if (code == 0 && i_ < p_.size()) Fail(1, "unmatched ')'");
     return r;
@@ -79,6 +84,27 @@ class Parser {
   const std::string& p_;
   size_t i_ = 0;
   std::string* err_;
+  bool icase_ = false;
+
+  // a position accepting `set` (both cases of its ASCII letters under (?i))
+  ReP Pos(ByteSet set) const {
+    if (icase_) {
+      for (int c = 'a'; c <= 'z'; ++c) {
+        const size_t lo = static_cast<size_t>(c), up = static_cast<size_t>(c - 32);
+        if (set.test(lo) || set.test(up)) { set.set(lo); set.set(up); }
+      }
+    }
+    return MkSet(set);
+  }
+  ByteSet Fold(ByteSet set) const {
+    if (icase_) {
+      for (int c = 'a'; c <= 'z'; ++c) {
+        const size_t lo = static_cast<size_t>(c), up = static_cast<size_t>(c - 32);
+        if (set.test(lo) || set.test(up)) { set.set(lo); set.set(up); }
+      }
+    }
+    return set;
+  }
 
   void Fail(int c, const std::string& m) {
     if (code == 0) {
@@ -164,7 +190,7 @@ class Parser {
     for (int k = 0; k < n; ++k) {
       const unsigned char b = static_cast<unsigned char>(p_[i_ + static_cast<size_t>(k)]);
       if (k > 0 && (b & 0xc0) != 0x80) { Fail(1, "invalid UTF-8"); break; }
-      r = Cat(r, MkSet(Range(b, b)));
+      r = Cat(r, Pos(Range(b, b)));
     }
     i_ += static_cast<size_t>(n);
     return r;
@@ -194,6 +220,19 @@ class Parser {
       case 'f': lit = '\f'; break;
       case 'v': lit = '\v'; break;
       case 'a': lit = 7; break;
+      case 'x': {
+        int v = 0, nd = 0;
+        while (nd < 2 && More() && std::isxdigit(Peek())) {
+          const unsigned char h = Peek();
+          v = v * 16 + (h <= '9' ? h - '0' : (h | 0x20) - 'a' + 10);
+          ++i_;
+          ++nd;
+        }
+        if (nd != 2) { Fail(1, "\\x needs two hexadecimal digits"); return false; }
+        if (v >= 0x80) { Fail(2, "\\x escape above 7f"); return false; }
+        lit = v;
+        break;
+      }
       default:
         if ((c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z')) {
           Fail(2, std::string("escape \\") + static_cast<char>(c));  // \b \B \A \z \1 \p{..} \x.. \Q ...
@@ -216,7 +255,30 @@ class Parser {
       unsigned char c = Peek();
       if (c == ']' && !first) { ++i_; break; }
       first = false;
-      if (c == '[' && i_ + 1 < p_.size() && p_[i_ + 1] == ':') { Fail(2, "[:class:]"); return Mk(Re::kEmpty); }
+      if (c == '[' && i_ + 1 < p_.size() && p_[i_ + 1] == ':') {
+        const size_t end = p_.find(":]", i_ + 2);
+        if (end == std::string::npos) { Fail(1, "missing ':]'"); return Mk(Re::kEmpty); }
+        const std::string name = p_.substr(i_ + 2, end - i_ - 2);
+        ByteSet cls;
+        if (name == "alpha") cls = Range('a', 'z') | Range('A', 'Z');
+        else if (name == "digit") cls = Digits();
+        else if (name == "alnum") cls = Range('a', 'z') | Range('A', 'Z') | Digits();
+        else if (name == "upper") cls = Range('A', 'Z');
+        else if (name == "lower") cls = Range('a', 'z');
+        else if (name == "space") cls = Space() | Range('\v', '\v');
+        else if (name == "blank") cls = Range(' ', ' ') | Range('\t', '\t');
+        else if (name == "punct") cls = Range('!', '/') | Range(':', '@') | Range('[', '`') | Range('{', '~');
+        else if (name == "xdigit") cls = Digits() | Range('a', 'f') | Range('A', 'F');
+        else if (name == "word") cls = Word();
+        else if (name == "print") cls = Range(' ', '~');
+        else if (name == "graph") cls = Range('!', '~');
+        else if (name == "cntrl") cls = Range(0, 31) | Range(127, 127);
+        else if (name == "ascii") cls = Range(0, 127);
+        else { Fail(1, "unknown class [:" + name + ":]"); return Mk(Re::kEmpty); }
+        ascii |= cls;
+        i_ = end + 2;
+        continue;
+      }
       int lo = -1;
       if (c == '\\') {
         ++i_;
@@ -259,6 +321,7 @@ class Parser {
       }
       ascii |= Range(lo, hi);
     }
+    ascii = Fold(ascii);
     if (neg) {
       if (!wide.empty()) { Fail(2, "negated class with non-ASCII members"); return Mk(Re::kEmpty); }
       return CodePoint(AsciiNot(ascii), true);
@@ -274,7 +337,7 @@ class Parser {
         ++i_;
         if (More() && Peek() == '?') {
           if (i_ + 1 < p_.size() && p_[i_ + 1] == ':') i_ += 2;
-          else { Fail(2, "group flags / look-around"); return Mk(Re::kEmpty); }
+          else { Fail(2, "group flags / look-around ((?i) is accepted at the very start only)"); return Mk(Re::kEmpty); }
         }
         ReP r = Alt();
         if (!More() || Peek() != ')') { Fail(1, "missing ')'"); return r; }
@@ -292,7 +355,7 @@ class Parser {
         bool n = false, is_class = false;
         if (!Escape(&s, &n, &is_class)) return Mk(Re::kEmpty);
         if (is_class && n) return CodePoint(AsciiNot(s), true);
-        return MkSet(s);
+        return Pos(s);
       }
       default:
         return Utf8Char();

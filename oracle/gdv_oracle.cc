@@ -25,6 +25,7 @@
 // (the GPU uses 64-bit limbs), the tree is parsed from an s-expression emitted by the test
 // harness rather than shared with the product's node classes.
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1236,6 +1237,7 @@ struct OrcRe {
   uint32_t cp = 0;
   std::vector<std::pair<uint32_t, uint32_t>> ranges;
   bool neg = false;
+  bool icase = false;  // (?i): ASCII letters match in both cases
   std::vector<std::shared_ptr<OrcRe>> kids;
   int lo = 0, hi = -1;
 };
@@ -1256,7 +1258,41 @@ struct OrcReParser {
   std::vector<uint32_t> p;
   size_t i = 0;
   bool bad = false;
-  OrcReP Node(OrcRe::K k) { auto r = std::make_shared<OrcRe>(); r->k = k; return r; }
+  bool icase = false;
+  OrcReP Node(OrcRe::K k) { auto r = std::make_shared<OrcRe>(); r->k = k; r->icase = icase; return r; }
+  bool Posix(OrcRe* cls) {   // at "[:", inside a bracket expression
+    size_t e = i + 2;
+    std::string name;
+    while (e + 1 < p.size() && !(p[e] == ':' && p[e + 1] == ']')) name.push_back(static_cast<char>(p[e++]));
+    if (e + 1 >= p.size()) return false;
+    auto add = [&](uint32_t lo, uint32_t hi) { cls->ranges.push_back({lo, hi}); };
+    if (name == "alpha") { add('a', 'z'); add('A', 'Z'); }
+    else if (name == "digit") add('0', '9');
+    else if (name == "alnum") { add('a', 'z'); add('A', 'Z'); add('0', '9'); }
+    else if (name == "upper") add('A', 'Z');
+    else if (name == "lower") add('a', 'z');
+    else if (name == "space") { add(9, 13); add(' ', ' '); }
+    else if (name == "blank") { add(' ', ' '); add(9, 9); }
+    else if (name == "punct") { add('!', '/'); add(':', '@'); add('[', '`'); add('{', '~'); }
+    else if (name == "xdigit") { add('0', '9'); add('a', 'f'); add('A', 'F'); }
+    else if (name == "word") { add('a', 'z'); add('A', 'Z'); add('0', '9'); add('_', '_'); }
+    else if (name == "print") add(' ', '~');
+    else if (name == "graph") add('!', '~');
+    else if (name == "cntrl") { add(0, 31); add(127, 127); }
+    else if (name == "ascii") add(0, 127);
+    else return false;
+    i = e + 2;
+    return true;
+  }
+  uint32_t Hex2() {   // after "\\x"
+    uint32_t v = 0;
+    for (int k = 0; k < 2; ++k) {
+      if (i >= p.size() || !std::isxdigit(static_cast<int>(p[i]))) { bad = true; return 0; }
+      const uint32_t h = p[i++];
+      v = v * 16 + (h <= '9' ? h - '0' : (h | 0x20) - 'a' + 10);
+    }
+    return v;
+  }
   void Shorthand(uint32_t c, OrcRe* cls) {
     if (c == 'd' || c == 'D') cls->ranges.push_back({'0', '9'});
     if (c == 'w' || c == 'W') { cls->ranges.push_back({'0', '9'}); cls->ranges.push_back({'a', 'z'}); cls->ranges.push_back({'A', 'Z'}); cls->ranges.push_back({'_', '_'}); }
@@ -1323,6 +1359,11 @@ struct OrcReParser {
       bool first = true;
       while (true) {
         if (i >= p.size()) { bad = true; return cls; }
+        if (p[i] == '[' && i + 1 < p.size() && p[i + 1] == ':' && !(first && false)) {
+          first = false;
+          if (!Posix(cls.get())) { bad = true; return cls; }
+          continue;
+        }
         uint32_t lo = p[i++];
         if (lo == ']' && !first) break;
         first = false;
@@ -1330,13 +1371,16 @@ struct OrcReParser {
           if (i >= p.size()) { bad = true; return cls; }
           const uint32_t e = p[i++];
           if (e == 'd' || e == 'w' || e == 's') { Shorthand(e, cls.get()); continue; }
-          lo = Unescape(e);
+          lo = e == 'x' ? Hex2() : Unescape(e);
         }
         uint32_t hi = lo;
         if (i + 1 < p.size() && p[i] == '-' && p[i + 1] != ']') {
           ++i;
           hi = p[i++];
-          if (hi == '\\' && i < p.size()) hi = Unescape(p[i++]);
+          if (hi == '\\' && i < p.size()) {
+            const uint32_t e2 = p[i++];
+            hi = e2 == 'x' ? Hex2() : Unescape(e2);
+          }
         }
         cls->ranges.push_back({lo, hi});
       }
@@ -1352,7 +1396,7 @@ struct OrcReParser {
         return cls;
       }
       auto ch = Node(OrcRe::CHAR);
-      ch->cp = Unescape(e);
+      ch->cp = e == 'x' ? Hex2() : Unescape(e);
       return ch;
     }
     auto ch = Node(OrcRe::CHAR);
@@ -1376,12 +1420,20 @@ bool OrcReRep(const OrcRe* r, int count, const std::vector<uint32_t>& t, size_t 
 }
 bool OrcReMatch(const OrcRe* r, const std::vector<uint32_t>& t, size_t pos, const OrcReCont& k) {
   switch (r->k) {
-    case OrcRe::CHAR: return pos < t.size() && t[pos] == r->cp && k(pos + 1);
+    case OrcRe::CHAR: {
+      if (pos >= t.size()) return false;
+      auto low = [](uint32_t c) { return c >= 'A' && c <= 'Z' ? c + 32 : c; };
+      return (r->icase ? low(t[pos]) == low(r->cp) : t[pos] == r->cp) && k(pos + 1);
+    }
     case OrcRe::ANY: return pos < t.size() && t[pos] != '\n' && k(pos + 1);
     case OrcRe::CLASS: {
       if (pos >= t.size()) return false;
       bool in = false;
-      for (const auto& rg : r->ranges) in = in || (t[pos] >= rg.first && t[pos] <= rg.second);
+      uint32_t other = t[pos];   // the same letter in the other case, under (?i)
+      if (r->icase && other >= 'a' && other <= 'z') other -= 32;
+      else if (r->icase && other >= 'A' && other <= 'Z') other += 32;
+      for (const auto& rg : r->ranges)
+        in = in || (t[pos] >= rg.first && t[pos] <= rg.second) || (other >= rg.first && other <= rg.second);
       return in != r->neg && k(pos + 1);
     }
     case OrcRe::CAT: return OrcReCat(r, 0, t, pos, k);
@@ -2809,6 +2861,7 @@ bool Prepare(Node* n, std::string* err) {
     if (n->kids.size() != 2 || n->kids[1]->kind != K_LIT) { *err = "regexp_matches needs a literal pattern"; return false; }
     OrcReParser rp;
     rp.p = DecodeUtf8(n->kids[1]->lit.s);
+    if (n->kids[1]->lit.s.compare(0, 4, "(?i)") == 0) { rp.icase = true; rp.i = 4; }
     n->regex = rp.Alt();
     if (rp.bad || rp.i != rp.p.size()) { *err = "malformed regular expression"; return false; }
   }

@@ -1170,6 +1170,8 @@ def _random_regexes(n, seed):
 
 
 REGEX_PATTERNS += _random_regexes(61, 2024)
+REGEX_PATTERNS += ["(?i)abc", "(?i)^[a-c]+$", "(?i)é|日本", "(?i)[^a]b", "(?i)A\\wC$", "\\x61\\x62", "[\\x30-\\x32]+$", "[[:alpha:]]+", "^[[:digit:][:space:]]+$",
+                   "[^[:alnum:]_]", "[[:upper:]][[:lower:]]", "(?i)[[:upper:]]{2}", "[[:punct:]]{2,}", "^[[:word:]-]*$", "[[:xdigit:]]{3}"]
 
 
 def regex_texts(n, seed):

@@ -1139,6 +1139,9 @@ def test_regexp_matches_against_python_re(oracle, gandiva):
         root = b.make_function("regexp_matches", [s, b.make_literal(pat, S)], B)
         got = oracle.project([root], [B], batch)[0].to_pylist()
         py = pat
+        for name, cls in (("alpha", "a-zA-Z"), ("digit", "0-9"), ("alnum", "a-zA-Z0-9"), ("upper", "A-Z"), ("lower", "a-z"),
+                          ("space", " \\t-\\r"), ("punct", "!-/:-@\\[-`{-~"), ("word", "\\w"), ("xdigit", "0-9a-fA-F")):
+            py = py.replace("[:%s:]" % name, cls)   # Python's re has no POSIX classes
         if py.endswith("$") and not py.endswith("\\$"):
             py = py[:-1] + "\\Z"
         rx = re.compile(py, re.ASCII)
