@@ -281,7 +281,12 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
   for (size_t pos = 0; (pos = k->gen.source.find(placeholder, pos)) != std::string::npos;)
     k->gen.source.replace(pos, placeholder.size(), name);
   k->gen.name = name;
-  const std::string key = arch + (cfg.optimize ? "|O3|" : "|O0|") + (cfg.dump_ir ? "ptx|" : "|") + k->gen.source;
+  // the device function library is part of every translation unit: its text is part of the key, so a
+  // persisted cubin can never outlive the library it was compiled against
+  static const uint64_t lib_hash = Fnv1a(std::string(gdv_device_lib_text, static_cast<size_t>(gdv_device_lib_text_len)));
+  char lib_hex[24];
+  std::snprintf(lib_hex, sizeof(lib_hex), "%016llx", static_cast<unsigned long long>(lib_hash));
+  const std::string key = arch + (cfg.optimize ? "|O3|" : "|O0|") + (cfg.dump_ir ? "ptx|" : "|") + lib_hex + "|" + k->gen.source;
   std::shared_ptr<const CachedCubin> hit;
   {
     std::lock_guard<std::mutex> lock(g_cache_mu);

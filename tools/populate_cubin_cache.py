@@ -4,7 +4,7 @@ GDV_EAGER_NONULL=1 (the no-null variants are built at Make() too); every Make() 
 real NVRTC and lands in the cache, every test then fails at its first Evaluate (no driver), which is
 expected and ignored.  The GPU box finds the cubins through GDV_CUBIN_CACHE_DIR (tests/conftest.py)
 and skips those compilations; kernels that are only built at Evaluate (other index widths, the
-large-batch variants) are still compiled there.  Entries are keyed by the full generated source
+large-batch variants) are still compiled there.  Entries are keyed by the full generated source, the device library text
 and options, so a stale entry can never be picked up.
 
 `--pack` stores the result as gandiva_b200/_cubin_cache.tar.xz (about 27 MB instead of 170 MB; git-ignored
