@@ -448,6 +448,12 @@ class TreeExprBuilder:
             _check(lib.gdv_node_in(node._h, _to_c_type(t), C.cast(buf, C.c_void_p), lens, len(raws),
                                    C.byref(out)))
             return Node(out.value, "in", pa.bool_(), [node], payload=(t, raws))
+        if pa.types.is_floating(t) and t.bit_width in (32, 64):
+            # C++ MakeInExpressionFloat / Double: the constants travel as bit patterns
+            ft, it = (np.float32, np.int32) if t.bit_width == 32 else (np.float64, np.int64)
+            arr = np.ascontiguousarray(np.array(values, dtype=ft)).view(it)
+            _check(lib.gdv_node_in(node._h, _to_c_type(t), arr.ctypes.data_as(C.c_void_p), None, len(arr), C.byref(out)))
+            return Node(out.value, "in", pa.bool_(), [node], payload=(t, [float(x) for x in np.array(values, dtype=ft)]))
         if t.bit_width == 32:
             arr = np.array(pa.array(values, type=t).cast(pa.int32()).to_numpy(), dtype=np.int32) \
                 if values else np.zeros(0, np.int32)

@@ -135,7 +135,8 @@ Status ValidateNode(const Schema& schema, const Node& node) {
       const int id = n.value_type().id;
       const bool ok = n.value_type().is_varlen() || id == GDV_TYPE_INT32 ||
                       id == GDV_TYPE_INT64 || id == GDV_TYPE_DATE32 || id == GDV_TYPE_DATE64 ||
-                      id == GDV_TYPE_TIMESTAMP || id == GDV_TYPE_TIME32 || id == GDV_TYPE_TIME64;
+                      id == GDV_TYPE_TIMESTAMP || id == GDV_TYPE_TIME32 || id == GDV_TYPE_TIME64 ||
+                      id == GDV_TYPE_FLOAT || id == GDV_TYPE_DOUBLE;
       if (!ok) return VErr("IN expression over " + n.value_type().ToString() + " not supported");
       return Status::OK();
     }
@@ -1086,6 +1087,20 @@ class BodyGen {
         const std::string arr = BytesArray(s, "gdv_lit_");
         e += (e.empty() ? "" : " || ") + std::string("equal_utf8_utf8(") + c.v +
              ", gdv_make_str(" + arr + ", " + std::to_string(s.size()) + "))";
+      }
+      if (e.empty()) e = "false";
+      *out += Ind(indent) + "const bool " + v + " = " + e + ";\n";
+    } else if (t.id == GDV_TYPE_FLOAT || t.id == GDV_TYPE_DOUBLE) {
+      // the constants arrive as bit patterns; membership is IEEE equality (-0.0 is in {0.0}, NaN is in nothing)
+      std::vector<int64_t> vals = n.ints();
+      std::sort(vals.begin(), vals.end());
+      vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+      std::string e;
+      for (auto x : vals) {
+        const std::string lit = t.id == GDV_TYPE_DOUBLE
+                                    ? "gdv_f64_from_bits(" + HexLit(static_cast<uint64_t>(x)) + ")"
+                                    : "__int_as_float((int)" + HexLit(static_cast<uint64_t>(x) & 0xffffffffull) + ")";
+        e += (e.empty() ? "" : " || ") + std::string("(") + c.v + " == " + lit + ")";
       }
       if (e.empty()) e = "false";
       *out += Ind(indent) + "const bool " + v + " = " + e + ";\n";

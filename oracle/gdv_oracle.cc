@@ -111,6 +111,7 @@ struct Node {
   std::vector<std::unique_ptr<Node>> kids;
   std::vector<int64_t> in_ints;
   std::vector<std::string> in_strs;
+  std::vector<double> in_dbls;   // IN over float32 / float64
   // LIKE pattern tokens: 0..255 literal byte, 256 = '_', 257 = '%'
   std::vector<int> like;
   std::shared_ptr<struct OrcRe> regex;  // regexp_matches: parsed pattern
@@ -241,6 +242,8 @@ struct Parser {
         Val v;
         if (!value(vt, &v)) return nullptr;
         if (vt.is_string()) n->in_strs.push_back(v.s);
+        else if (vt.id == T_FLOAT) n->in_dbls.push_back(static_cast<double>(v.f));
+        else if (vt.id == T_DOUBLE) n->in_dbls.push_back(v.d);
         else n->in_ints.push_back(v.i);
         ws();
       }
@@ -2845,6 +2848,9 @@ void Eval(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
       bool hit = false;
       if (n.kids[0]->type.is_string()) {
         for (const auto& s : n.in_strs) hit = hit || s == c.s;
+      } else if (n.kids[0]->type.id == T_FLOAT || n.kids[0]->type.id == T_DOUBLE) {
+        const double x = n.kids[0]->type.id == T_FLOAT ? static_cast<double>(c.f) : c.d;
+        for (double v : n.in_dbls) hit = hit || v == x;   // IEEE equality: NaN matches nothing, -0.0 == 0.0
       } else {
         for (auto v : n.in_ints) hit = hit || v == c.i;
       }

@@ -512,6 +512,20 @@ def case_inverse_trig(b):
     return schema, outs, "project"
 
 
+def case_in_floats(b):
+    """IN over float64 / float32 (C++ MakeInExpressionDouble / Float): IEEE equality, -0.0 is in {0.0}, NaN in nothing."""
+    D, F4, B = pa.float64(), pa.float32(), pa.bool_()
+    schema = pa.schema([("d", D), ("f", F4)])
+    d, f = F(b, "d", D), F(b, "f", F4)
+    fn = b.make_function
+    small = fn("round", [fn("divide", [d, b.make_literal(2.0e5, D)], D)], D)      # small integers, some -0.0
+    outs = [(b.make_in_expression(small, [0.0, 1.0, -2.0, 3.5, float("nan")], D), B),
+            (b.make_in_expression(d, [], D), B),
+            (b.make_in_expression(fn("castFLOAT4", [small], F4), [-0.0, 2.0, 5.0, 1e30, -1.0, 7.0, 8.0, 9.0, 10.0, 11.0], F4), B),
+            (b.make_in_expression(fn("multiply", [small, b.make_literal(0.5, D)], D), [0.5, -0.5, 1.5], D), B)]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1101,7 +1115,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power, case_inverse_trig]
+              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power, case_inverse_trig, case_in_floats]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]

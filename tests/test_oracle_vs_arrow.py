@@ -1456,3 +1456,20 @@ def test_float_to_text_against_python_repr(oracle, gandiva):
     want = float_text_reference(f32.tolist(), True)
     bad = [(v, g, w) for v, g, w in zip(f32.tolist(), got, want) if g != w]
     assert not bad, bad[:8]
+
+
+def test_in_expression_over_floats(oracle, gandiva):
+    """IN over float64 / float32 against numpy.isin (IEEE equality: NaN is in nothing, -0.0 is in {0.0})."""
+    b = gandiva.TreeExprBuilder()
+    D, F4, B = pa.float64(), pa.float32(), pa.bool_()
+    vals = [0.0, -0.0, 1.0, 3.5, float("nan"), -2.0, 1e30, None, 0.1, float("inf")] * 50
+    schema = pa.schema([("d", D), ("f", F4)])
+    batch = pa.RecordBatch.from_arrays([pa.array(vals, D), pa.array(vals, F4)], schema=schema)
+    consts = [0.0, 3.5, float("nan"), 0.1, float("inf")]
+    roots = [b.make_in_expression(cases.F(b, "d", D), consts, D), b.make_in_expression(cases.F(b, "f", F4), consts, F4)]
+    got = oracle.project(roots, [B, B], batch)
+    a64 = np.array([np.nan if v is None else v for v in vals])
+    want64 = np.isin(a64, np.array(consts))
+    want32 = np.isin(a64.astype(np.float32), np.array(consts, dtype=np.float32))
+    for g, w in zip(got, (want64, want32)):
+        assert g.to_pylist() == [None if v is None else bool(x) for v, x in zip(vals, w)]
