@@ -353,6 +353,12 @@ NodePtr TreeExprBuilder::MakeInExpressionInt32(NodePtr node, const std::unordere
 NodePtr TreeExprBuilder::MakeInExpressionInt64(NodePtr node, const std::unordered_set<int64_t>& c) {
   return MakeIn(std::move(node), arrow::int64(), c);
 }
+NodePtr TreeExprBuilder::MakeInExpressionFloat(NodePtr node, const std::unordered_set<float>& c) {
+  return MakeIn(std::move(node), arrow::float32(), c);
+}
+NodePtr TreeExprBuilder::MakeInExpressionDouble(NodePtr node, const std::unordered_set<double>& c) {
+  return MakeIn(std::move(node), arrow::float64(), c);
+}
 NodePtr TreeExprBuilder::MakeInExpressionString(NodePtr node, const std::unordered_set<std::string>& c) {
   return MakeInBytes(std::move(node), arrow::utf8(), c);
 }

@@ -45,6 +45,8 @@ class GANDIVA_EXPORT TreeExprBuilder {
 
   static NodePtr MakeInExpressionInt32(NodePtr node, const std::unordered_set<int32_t>& constants);
   static NodePtr MakeInExpressionInt64(NodePtr node, const std::unordered_set<int64_t>& constants);
+  static NodePtr MakeInExpressionFloat(NodePtr node, const std::unordered_set<float>& constants);
+  static NodePtr MakeInExpressionDouble(NodePtr node, const std::unordered_set<double>& constants);
   static NodePtr MakeInExpressionString(NodePtr node, const std::unordered_set<std::string>& constants);
   static NodePtr MakeInExpressionBinary(NodePtr node, const std::unordered_set<std::string>& constants);
   static NodePtr MakeInExpressionDate32(NodePtr node, const std::unordered_set<int32_t>& constants);
