@@ -2063,6 +2063,33 @@ NodePtr RewriteAliases(const NodePtr& node) {
                                                     pat.is_null());
         return std::make_shared<FunctionNode>("like", NodeVector{text, lit}, boolean());
       }
+      // A concat result is a rope that only projection / concat / if-else can read.  Two consumers
+      // distribute over its pieces instead: the ASCII case maps, and the length functions.
+      if (kids.size() == 1 && kids[0]->kind() == NodeKind::kFunction) {
+        const auto& inner = static_cast<const FunctionNode&>(*kids[0]);
+        const bool is_concat = inner.name() == "concat" || inner.name() == "concatOperator";
+        if (is_concat && (fn.name() == "upper" || fn.name() == "lower")) {
+          NodeVector parts;
+          for (const auto& c : inner.children())
+            parts.push_back(RewriteAliases(std::make_shared<FunctionNode>(fn.name(), NodeVector{c}, c->return_type())));
+          return std::make_shared<FunctionNode>(inner.name(), std::move(parts), inner.return_type());
+        }
+        const bool is_len = fn.name() == "char_length" || fn.name() == "length" || fn.name() == "lengthUtf8" ||
+                            fn.name() == "octet_length" || fn.name() == "bit_length";
+        if (is_concat && is_len && !inner.children().empty()) {
+          // concat counts a NULL argument as the empty string; concatOperator is NULL if any argument is
+          NodePtr sum;
+          const int32_t zero = 0;
+          for (const auto& c : inner.children()) {
+            NodePtr len = RewriteAliases(std::make_shared<FunctionNode>(fn.name(), NodeVector{c}, fn.return_type()));
+            if (inner.name() == "concat")
+              len = std::make_shared<FunctionNode>(
+                  "nvl", NodeVector{len, std::make_shared<LiteralNode>(fn.return_type(), &zero, 4, false)}, fn.return_type());
+            sum = sum == nullptr ? len : std::make_shared<FunctionNode>("add", NodeVector{sum, len}, fn.return_type());
+          }
+          return sum;
+        }
+      }
       if (!changed) return node;
       return std::make_shared<FunctionNode>(fn.name(), std::move(kids), fn.return_type());
     }

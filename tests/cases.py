@@ -526,6 +526,24 @@ def case_in_floats(b):
     return schema, outs, "project"
 
 
+def case_concat_consumers(b):
+    """upper / lower and the length functions over concat / concatOperator: rewritten to act on the pieces
+    (the oracle evaluates the tree as written)."""
+    S, I = pa.string(), pa.int32()
+    schema = pa.schema([("s", S), ("u", S)])
+    s, u = F(b, "s", S), F(b, "u", S)
+    fn = b.make_function
+    lit = lambda v: b.make_literal(v, S)
+    cc = fn("concat", [s, lit(" - "), u], S)
+    co = fn("concatOperator", [s, u], S)
+    nested = fn("concat", [fn("upper", [co], S), lit("日本"), fn("lower", [cc], S)], S)
+    outs = [(fn("upper", [cc], S), S), (fn("lower", [co], S), S), (fn("char_length", [cc], I), I), (fn("octet_length", [co], I), I),
+            (fn("bit_length", [nested], I), I), (fn("length", [fn("upper", [cc], S)], I), I), (nested, S),
+            (fn("char_length", [fn("concat", [lit("é"), s], S)], I), I),
+            (b.make_if(fn("greater_than", [fn("char_length", [co], I), b.make_literal(60, I)], pa.bool_()), fn("upper", [co], S), cc, S), S)]
+    return schema, outs, "project"
+
+
 def case_date_arith(b):
     ts, d64 = pa.timestamp("ms"), pa.date64()
     schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
@@ -1115,7 +1133,7 @@ def all_project_cases():
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
               case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
-              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power, case_inverse_trig, case_in_floats]
+              case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power, case_inverse_trig, case_in_floats, case_concat_consumers]
     cases += [case_hash(t) for t in HASH_TYPES]
     cases += [case_in_int(pa.int32(), [1, 5]), case_in_int(pa.int64(), [1, 5, -3]),
               case_in_int(pa.int32(), list(range(-20, 40, 3)))]
