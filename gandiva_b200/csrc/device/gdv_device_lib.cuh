@@ -336,6 +336,20 @@ GDV_DEV i32 mod_int64_int32(i64 a, i32 b) {
   if (b == -1) return 0;
   return (i32)(a % (i64)b);
 }
+GDV_DEV i32 mod_int32_int32(i32 a, i32 b) {
+  if (b == 0) return a;
+  if (b == -1) return 0;
+  return a % b;
+}
+// mod of doubles: the exact IEEE remainder with the sign of x (fmod); a zero divisor raises like `divide`
+GDV_DEV f64 mod_float64_float64(gdv_ctx* c, f64 x, f64 y) {
+  if (y == 0.0) {
+    gdv_set_error(c, GDV_ERR_DIV_ZERO);
+    return 0.0;
+  }
+  const f64 r = fmod(x, y);
+  return r != r ? __longlong_as_double(0x7ff8000000000000ll) : r;
+}
 GDV_DEV i64 mod_int64_int64(i64 a, i64 b) {
   if (b == 0) return a;
   if (b == -1) return 0;

@@ -82,6 +82,8 @@ Registry::Registry() {
   }
   Add("mod", {I64, I32}, I32, NullMode::kIfNull, 0, {"modulo"});
   Add("mod", {I64, I64}, I64, NullMode::kIfNull, 0, {"modulo"});
+  Add("mod", {I32, I32}, I32, NullMode::kIfNull, 0, {"modulo"});
+  Add("mod", {F64, F64}, F64, NullMode::kIfNull, kCanFail, {"modulo"});
   for (const auto& t : {I32, I64, F32, F64}) {
     Add("abs", {t}, t);
     Add("negative", {t}, t);

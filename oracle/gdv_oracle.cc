@@ -2051,6 +2051,12 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     }
     return;
   }
+  if ((f == "mod" || f == "modulo") && t0.id == T_DOUBLE) {
+    if (a[1].d == 0.0) { cx.error = 1; return; }
+    const double r = std::fmod(a[0].d, a[1].d);
+    out->d = r != r ? F64FromBits(0x7ff8000000000000ull) : r;
+    return;
+  }
   if (f == "mod" || f == "modulo") {
     const int64_t x = a[0].i, y = a[1].i;
     int64_t r;

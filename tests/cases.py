@@ -488,6 +488,9 @@ def case_power(b):
             (fn("pow", [near1, lit(1.0e15)], D), D), (fn("pow", [lit(2.0), small], D), D),
             (fn("power", [fn("abs", [small], D), lit(0.5)], D), D), (fn("power", [d, lit(2.0)], D), D),
             (fn("power", [d, lit(-3.0)], D), D), (fn("power", [lit(10.0), fn("divide", [e, lit(4.0e3)], D)], D), D)]
+    nz = fn("add", [fn("abs", [e], D), lit(0.25)], D)
+    outs += [(fn("mod", [d, nz], D), D), (fn("modulo", [fn("multiply", [d, lit(1.0e200)], D), lit(3.0)], D), D),
+             (fn("mod", [lit(5.5), fn("subtract", [lit(0.0), nz], D)], D), D)]
     outs += [(fn("log", [lit(10.0), fn("abs", [d], D)], D), D), (fn("log", [fn("add", [fn("abs", [e], D), lit(2.0)], D), fn("abs", [d], D)], D), D)]
     tiny = fn("divide", [d, lit(1.0e14)], D)
     for name in ("sinh", "cosh", "tanh"):

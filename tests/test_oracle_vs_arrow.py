@@ -1473,3 +1473,28 @@ def test_in_expression_over_floats(oracle, gandiva):
     want32 = np.isin(a64.astype(np.float32), np.array(consts, dtype=np.float32))
     for g, w in zip(got, (want64, want32)):
         assert g.to_pylist() == [None if v is None else bool(x) for v, x in zip(vals, w)]
+
+
+def test_mod_of_doubles_against_math_fmod(oracle, gandiva):
+    """mod / modulo (float64): the exact IEEE remainder (math.fmod); a zero divisor raises; mod(int32, int32)."""
+    import math
+    b = gandiva.TreeExprBuilder()
+    D, I = pa.float64(), pa.int32()
+    rng = np.random.default_rng(2)
+    xs = np.concatenate([rng.standard_normal(3000) * 10.0 ** rng.integers(-5, 300, 3000), [5.5, -5.5, 0.0, -0.0, np.inf, 1e308]])
+    ys = np.concatenate([rng.standard_normal(3000) * 10.0 ** rng.integers(-5, 20, 3000), [2.0, 2.0, 3.0, 3.0, 2.0, 1e-300]])
+    schema = pa.schema([("x", D), ("y", D), ("i", I), ("j", I)])
+    ii = rng.integers(-2 ** 31, 2 ** 31, len(xs)).astype(np.int32)
+    jj = rng.choice([0, -1, 1, 7, -13, 2 ** 31 - 1, -2 ** 31], len(xs)).astype(np.int32)
+    batch = pa.RecordBatch.from_arrays([pa.array(xs, D), pa.array(ys, D), pa.array(ii, I), pa.array(jj, I)], schema=schema)
+    x, y, i, j = (cases.F(b, n, t) for n, t in (("x", D), ("y", D), ("i", I), ("j", I)))
+    got, gi = oracle.project([b.make_function("mod", [x, y], D), b.make_function("mod", [i, j], I)], [D, I], batch)
+    for a, c, g in zip(xs.tolist(), ys.tolist(), got.to_pylist()):
+        want = math.fmod(a, c) if math.isfinite(a) else math.nan
+        assert (g != g and want != want) or (g == want and math.copysign(1, g) == math.copysign(1, want)), (a, c, g, want)
+    for a, c, g in zip(ii.tolist(), jj.tolist(), gi.to_pylist()):
+        want = a if c == 0 else 0 if c == -1 else int(math.fmod(a, c))
+        assert g == want, (a, c, g, want)
+    bad = pa.RecordBatch.from_arrays([pa.array([1.0], D), pa.array([0.0], D), pa.array([1], I), pa.array([1], I)], schema=schema)
+    with pytest.raises(Exception, match="divide by zero"):
+        oracle.project([b.make_function("modulo", [x, y], D)], [D], bad)
