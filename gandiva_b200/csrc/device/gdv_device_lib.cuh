@@ -3302,6 +3302,35 @@ GDV_DEV_BIG bool gdv_regex_match(const gdv_str& s, const u64* prog) {
   return (live & last) != 0ull;
 }
 
+// The same automaton with up to 128 positions (two words per set).
+// prog: [0..1] first, [2..3] last, [4] flags, [5..260] follow (128 x 2), [261..772] classes (256 x 2).
+GDV_DEV_BIG bool gdv_regex_match2(const gdv_str& s, const u64* prog) {
+  const u64 flags = prog[4];
+  const bool at_start = (flags & 2ull) != 0ull, at_end = (flags & 4ull) != 0ull;
+  if ((flags & 1ull) != 0ull && (!at_start || !at_end || s.len == 0)) return true;
+  u64 l0 = 0ull, l1 = 0ull;
+  for (i32 i = 0; i < s.len; ++i) {
+    const bool start = i == 0 || !at_start;
+    u64 n0 = start ? prog[0] : 0ull, n1 = start ? prog[1] : 0ull;
+    for (u64 t = l0; t != 0ull; t &= t - 1ull) {
+      const i32 k = __ffsll((long long)t) - 1;
+      n0 |= prog[5 + 2 * k];
+      n1 |= prog[6 + 2 * k];
+    }
+    for (u64 t = l1; t != 0ull; t &= t - 1ull) {
+      const i32 k = 64 + __ffsll((long long)t) - 1;
+      n0 |= prog[5 + 2 * k];
+      n1 |= prog[6 + 2 * k];
+    }
+    const u32 c = (u32)gdv_ch(s, i);
+    l0 = n0 & prog[261 + 2 * c];
+    l1 = n1 & prog[262 + 2 * c];
+    if (!at_end && ((l0 & prog[2]) | (l1 & prog[3])) != 0ull) return true;
+    if (at_start && (l0 | l1) == 0ull) return false;
+  }
+  return ((l0 & prog[2]) | (l1 & prog[3])) != 0ull;
+}
+
 // Largest row r in [lo, n) with offs[r] <= pos, given offs[lo] <= pos < offs[n] (Arrow int32
 // offsets are non-decreasing): gallop from `lo`, then bisect.  Used by the key-scan string filter
 // to map a byte position of the data buffer back to its row.

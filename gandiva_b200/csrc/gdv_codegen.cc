@@ -787,22 +787,28 @@ class BodyGen {
       std::string why;
       if (CompileRegex(static_cast<const LiteralNode&>(*fn.children()[1]).bytes(), &prog, &why) != 0 && error_.empty())
         error_ = why;
-      // program block: first, last, flags, follow[64], byte classes[256]
+      // program block: first, last, flags, follow, byte classes -- one u64 per set for <= 64 positions
+      // (gdv_regex_match), two for up to 128 (gdv_regex_match2)
+      const bool wide = prog.positions > 64;
+      const int W = wide ? 2 : 1, NP = wide ? 128 : 64;
       const std::string arr = NewVar("gdv_re_");
-      std::string t = "__device__ const u64 " + arr + "[323] = {";
       auto hex = [](uint64_t v) {
         char buf[32];
         std::snprintf(buf, sizeof buf, "0x%llxull", static_cast<unsigned long long>(v));
         return std::string(buf);
       };
-      t += hex(prog.first) + "," + hex(prog.last) + "," +
-           hex((prog.nullable ? 1u : 0u) | (prog.anchor_start ? 2u : 0u) | (prog.anchor_end ? 4u : 0u));
-      for (int k = 0; k < 64; ++k) t += "," + hex(prog.follow[k]);
-      for (int k = 0; k < 256; ++k) t += (k % 16 == 0 ? ",\n    " : ",") + hex(prog.cls[k]);
+      std::string t = "__device__ const u64 " + arr + "[" + std::to_string(2 * W + 1 + NP * W + 256 * W) + "] = {";
+      for (int w = 0; w < W; ++w) t += hex(prog.first[w]) + ",";
+      for (int w = 0; w < W; ++w) t += hex(prog.last[w]) + ",";
+      t += hex((prog.nullable ? 1u : 0u) | (prog.anchor_start ? 2u : 0u) | (prog.anchor_end ? 4u : 0u));
+      for (int k = 0; k < NP; ++k)
+        for (int w = 0; w < W; ++w) t += "," + hex(prog.follow[k][w]);
+      for (int k = 0; k < 256; ++k)
+        for (int w = 0; w < W; ++w) t += ((k % 16 == 0 && w == 0) ? ",\n    " : ",") + hex(prog.cls[k][w]);
       t += "};\n";
       globals_ += t;
       const std::string v = NewVar("v");
-      *out += Ind(indent) + "const bool " + v + " = gdv_regex_match(" + s.v + ", " + arr + ");\n";
+      *out += Ind(indent) + "const bool " + v + " = " + (wide ? "gdv_regex_match2(" : "gdv_regex_match(") + s.v + ", " + arr + ");\n";
       return Val{v, s.ok, rt};
     }
 

@@ -363,15 +363,18 @@ class Parser {
   }
 };
 
+using PosSet = std::bitset<RegexProgram::kMaxPositions>;
+
 struct Info {
   bool nullable = false;
-  uint64_t first = 0, last = 0;
+  PosSet first, last;
 };
 
 struct Builder {
   RegexProgram* prog;
   bool overflow = false;
   bool inner_anchor = false;
+  PosSet follow[RegexProgram::kMaxPositions];
 
   Info Walk(const ReP& r) {
     Info o;
@@ -379,18 +382,20 @@ struct Builder {
       case Re::kEmpty: o.nullable = true; return o;
       case Re::kBol: case Re::kEol: inner_anchor = true; o.nullable = true; return o;
       case Re::kSet: {
-        if (prog->positions >= 64) { overflow = true; return o; }
+        if (prog->positions >= RegexProgram::kMaxPositions) { overflow = true; return o; }
         const int p = prog->positions++;
-        for (int b = 0; b < 256; ++b) if (r->set.test(static_cast<size_t>(b))) prog->cls[b] |= 1ull << p;
-        o.first = o.last = 1ull << p;
+        for (int b = 0; b < 256; ++b)
+          if (r->set.test(static_cast<size_t>(b))) prog->cls[b][p >> 6] |= 1ull << (p & 63);
+        o.first.set(static_cast<size_t>(p));
+        o.last = o.first;
         return o;
       }
       case Re::kCat: {
         const Info x = Walk(r->a), y = Walk(r->b);
         Link(x.last, y.first);
         o.nullable = x.nullable && y.nullable;
-        o.first = x.first | (x.nullable ? y.first : 0);
-        o.last = y.last | (y.nullable ? x.last : 0);
+        o.first = x.first | (x.nullable ? y.first : PosSet());
+        o.last = y.last | (y.nullable ? x.last : PosSet());
         return o;
       }
       case Re::kAlt: {
@@ -411,8 +416,14 @@ struct Builder {
     }
     return o;
   }
-  void Link(uint64_t from, uint64_t to) {
-    for (int p = 0; p < 64; ++p) if ((from >> p) & 1ull) prog->follow[p] |= to;
+  void Link(const PosSet& from, const PosSet& to) {
+    for (int p = 0; p < RegexProgram::kMaxPositions; ++p)
+      if (from.test(static_cast<size_t>(p))) follow[p] |= to;
+  }
+  static void Words(const PosSet& s, uint64_t out[2]) {
+    out[0] = out[1] = 0;
+    for (int p = 0; p < RegexProgram::kMaxPositions; ++p)
+      if (s.test(static_cast<size_t>(p))) out[p >> 6] |= 1ull << (p & 63);
   }
 };
 
@@ -441,19 +452,21 @@ int CompileRegex(const std::string& pattern, RegexProgram* out, std::string* err
   if (lo < hi && chain[hi - 1]->kind == Re::kEol) { out->anchor_end = true; --hi; }
   ReP body = Mk(Re::kEmpty);
   for (size_t k = lo; k < hi; ++k) body = Cat(body, chain[k]);
-  Builder b{out};
+  Builder b;
+  b.prog = out;
   const Info info = b.Walk(body);
   if (b.inner_anchor) {
     *error = "'^' / '$' inside the pattern are not supported (regular expression '" + pattern + "')";
     return 2;
   }
   if (b.overflow) {
-    *error = "regular expression '" + pattern + "' needs more than 64 automaton positions";
+    *error = "regular expression '" + pattern + "' needs more than 128 automaton positions";
     return 2;
   }
   out->nullable = info.nullable;
-  out->first = info.first;
-  out->last = info.last;
+  Builder::Words(info.first, out->first);
+  Builder::Words(info.last, out->last);
+  for (int p = 0; p < out->positions; ++p) Builder::Words(b.follow[p], out->follow[p]);
   return 0;
 }
 

@@ -1206,7 +1206,9 @@ def _random_regexes(n, seed):
 
 REGEX_PATTERNS += _random_regexes(61, 2024)
 REGEX_PATTERNS += ["(?i)abc", "(?i)^[a-c]+$", "(?i)é|日本", "(?i)[^a]b", "(?i)A\\wC$", "\\x61\\x62", "[\\x30-\\x32]+$", "[[:alpha:]]+", "^[[:digit:][:space:]]+$",
-                   "[^[:alnum:]_]", "[[:upper:]][[:lower:]]", "(?i)[[:upper:]]{2}", "[[:punct:]]{2,}", "^[[:word:]-]*$", "[[:xdigit:]]{3}"]
+                   "[^[:alnum:]_]", "[[:upper:]][[:lower:]]", "(?i)[[:upper:]]{2}", "[[:punct:]]{2,}", "^[[:word:]-]*$", "[[:xdigit:]]{3}",
+                   # more than 64 automaton positions: the two-word matcher
+                   "^(?:[a-c][0-2 .]?_?){1,24}", "^(?:\\w|\\s|é){1,20}$", "(?:a|b|c|0|1|2| |_|-|x|y|z|d|e){3}[|\\]A.]?(?:ab|bc|ca|é日|語x){10}"]
 
 
 def regex_texts(n, seed):
