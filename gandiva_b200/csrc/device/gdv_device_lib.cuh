@@ -176,6 +176,16 @@ GDV_DEV bool gdv_ldbit(const u8* p, u32 sh, i64 i) {
   const i64 b = i + (i64)sh;
   return ((p[b >> 3] >> (u32)(b & 7)) & 1u) != 0u;
 }
+// The 32 bitmap bits of rows [rb, rb + 32), rb % 32 == 0, of a bitmap whose row 0 is bit `sh` of the
+// 4-byte aligned word *p; rows >= n read as 0 and no byte past the one that holds row n - 1 is touched.
+// (Filter epilogue: one word per lane and 1024-row chunk, ColumnSlot::hoist.)
+GDV_DEV u32 gdv_ldwin_rows(const u32* p, u32 sh, i64 rb, i64 n) {
+  if (rb + 64 <= n) return gdv_ldwin(p, rb >> 5, sh);  // word rb / 32 + 1 still holds rows < n
+  u32 w = 0u;
+  const u8* b = reinterpret_cast<const u8*>(p);
+  for (int i = 0; i < 32 && rb + i < n; ++i) w |= (u32)gdv_ldbit(b, sh, rb + i) << i;
+  return w;
+}
 // ---- TMA bulk copies into shared memory (cp.async.bulk + mbarrier) ------------------------
 // Wide projectors stage each CTA tile of every input column through shared memory with one
 // bulk copy per column (SASS UBLKCP): the loads of the next tiles are in flight while the
@@ -3390,11 +3400,7 @@ GDV_DEV u64 gdv_tile_exclusive_prefix(u64* state, i64 tile, u64 count, u32 lane)
       const u32 inv = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INVALID);
       incl = __ballot_sync(GDV_FULL, (d >> 62) == GDV_TILE_INCLUSIVE);
       first = incl != 0u ? (u32)(__ffs((int)incl) - 1) : 32u;
-#ifdef GDV_LOOKBACK_STRICT
-      const u32 need = inv;  // A/B switch (string_scan bit 3): wait for the whole 32-tile window
-#else
       const u32 need = first >= 32u ? inv : (inv & ((1u << first) - 1u));
-#endif
       if (need == 0u) break;
       if (idx >= 0 && (d >> 62) == GDV_TILE_INVALID) d = gdv_ld_relaxed(&state[idx]);
     }

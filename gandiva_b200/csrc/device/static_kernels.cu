@@ -126,120 +126,6 @@ gdv_scan_tiles(u64* tiles, i64 n_tiles, u64* total, int* err, u64 limit) {
   }
 }
 
-// ---- two-pass filter (Configuration.loader = 3): truth bitmap -> ordered SelectionVector ---------
-// Pass 1 is the condition evaluated by the PROJECTOR kernel into a bit-packed boolean column
-// (value bits + validity bits, one ballot word per 32 rows: the map runs at copy speed because no
-// tile ever waits for another).  This kernel is pass 2: it reads the two bitmaps (1/80 of the bytes
-// pass 1 read for Q6), keeps value & validity, and writes the ascending row indices with the same
-// ticket-ordered decoupled look-back the fused filter uses.  256 threads x 16 words = 131072 rows
-// per CTA tile.
-#define GDV_B2S_WPT 16
-extern "C" __global__ void __launch_bounds__(256)
-gdv_bitmap_to_sel(const u32* data, const u32* vld, i64 n, i64 row_base, void* out_idx, int elem_bytes,
-                  i64 out_cap, u64* out_count, u64* tile_state, u64* ticket) {
-  __shared__ u32 s_wcount[8];
-  __shared__ i64 s_tile;
-  __shared__ u64 s_excl;
-  const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const i64 n_words = (n + 31) / 32;
-  const i64 tile_words = 256 * GDV_B2S_WPT;
-  const i64 n_tiles = (n_words + tile_words - 1) / tile_words;
-  while (true) {
-    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(reinterpret_cast<unsigned long long*>(ticket), 1ull);
-    __syncthreads();
-    const i64 tile = s_tile;
-    if (tile >= n_tiles) break;
-    const i64 w0 = tile * tile_words + (i64)threadIdx.x * GDV_B2S_WPT;
-    u32 m[GDV_B2S_WPT];
-    if (w0 + GDV_B2S_WPT <= n_words) {
-      const uint4* d4 = reinterpret_cast<const uint4*>(data + w0);
-#pragma unroll
-      for (int q = 0; q < GDV_B2S_WPT / 4; ++q) {
-        const uint4 v = __ldcs(d4 + q);
-        m[4 * q + 0] = v.x;
-        m[4 * q + 1] = v.y;
-        m[4 * q + 2] = v.z;
-        m[4 * q + 3] = v.w;
-      }
-      if (vld != nullptr) {
-        const uint4* v4 = reinterpret_cast<const uint4*>(vld + w0);
-#pragma unroll
-        for (int q = 0; q < GDV_B2S_WPT / 4; ++q) {
-          const uint4 v = __ldcs(v4 + q);
-          m[4 * q + 0] &= v.x;
-          m[4 * q + 1] &= v.y;
-          m[4 * q + 2] &= v.z;
-          m[4 * q + 3] &= v.w;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < GDV_B2S_WPT; ++j) {
-        const i64 w = w0 + j;
-        u32 x = 0u;
-        if (w < n_words) {
-          x = data[w];
-          if (vld != nullptr) x &= vld[w];
-        }
-        m[j] = x;
-      }
-    }
-    // bits past the last row of the batch are not rows
-    if ((w0 + GDV_B2S_WPT) * 32 > n) {
-#pragma unroll
-      for (int j = 0; j < GDV_B2S_WPT; ++j) {
-        const i64 first = (w0 + j) * 32;
-        if (first >= n) m[j] = 0u;
-        else if (first + 32 > n) m[j] &= (1u << (u32)(n - first)) - 1u;
-      }
-    }
-    u32 c = 0u;
-#pragma unroll
-    for (int j = 0; j < GDV_B2S_WPT; ++j) c += (u32)__popc(m[j]);
-    u32 incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 t = __shfl_up_sync(GDV_FULL, incl, o);
-      if (lane >= (u32)o) incl += t;
-    }
-    if (lane == 31u) s_wcount[wid] = incl;
-    __syncthreads();
-    if (wid == 0u) {
-      const u32 wc = lane < 8u ? s_wcount[lane] : 0u;
-      u32 winc = wc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);
-        if (lane >= (u32)o) winc += t;
-      }
-      const u32 total = __shfl_sync(GDV_FULL, winc, 31);
-      if (lane < 8u) s_wcount[lane] = winc - wc;
-      const u64 excl = gdv_tile_exclusive_prefix(tile_state, tile, (u64)total, lane);
-      if (lane == 0u) {
-        s_excl = excl;
-        if (tile == n_tiles - 1) *out_count = excl + (u64)total;
-      }
-    }
-    __syncthreads();
-    u64 pos = s_excl + (u64)s_wcount[wid] + (u64)(incl - c);
-    if (c != 0u) {
-#pragma unroll 1
-      for (int j = 0; j < GDV_B2S_WPT; ++j) {
-        const i64 first = row_base + (w0 + j) * 32;
-        for (u32 x = m[j]; x != 0u; x &= x - 1u) {
-          const i64 row = first + (i64)(__ffs((int)x) - 1);
-          if (pos < (u64)out_cap) {
-            if (elem_bytes == 4) reinterpret_cast<u32*>(out_idx)[pos] = (u32)row;
-            else if (elem_bytes == 8) reinterpret_cast<u64*>(out_idx)[pos] = (u64)row;
-            else reinterpret_cast<u16*>(out_idx)[pos] = (u16)row;
-          }
-          ++pos;
-        }
-      }
-    }
-  }
-}
-
 // ---- SelectionVector reassembly across row-range shards (DESIGN.md "Multi-GPU") ------------
 // One process per GPU filters its row range into a LOCAL index run (global row numbers).  This
 // kernel, launched on a side stream next to the following batch's filter kernel, moves the run

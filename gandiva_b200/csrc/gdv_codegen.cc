@@ -222,15 +222,16 @@ struct CoopSeg {
   int digram = 0;      // key: index of the first byte of the adjacent pair the scan tests
 };
 constexpr int kHitCap = 64;  // hits per warp and group; more -> the group falls back per lane
+constexpr int kKeyAnchorCap = 256;  // key-driven filter: anchors a warp queues between two drains
 
-// Plan of the key-scan string filter (EmitKeyScanFilter): the condition holds only in rows whose
-// string column `slot` contains `key` (a literal segment of a top-level LIKE conjunct), compared
-// through the ASCII case map `xf` of the view chain; the scan looks for the digram at key[digram].
-struct KeyScanPlan {
+// Plan of the key-driven string filter (EmitKeyFilter): the condition holds only in rows whose
+// string column `slot` contains `key` (a literal segment of a LIKE / is_substr / starts_with /
+// ends_with / equal conjunct on the condition's AND spine), compared through the ASCII case map
+// `xf` of the view chain.
+struct KeyPlan {
   int slot = -1;
   unsigned xf = 0u;
   std::string key;
-  int digram = 0;
 };
 
 class BodyGen {
@@ -316,10 +317,12 @@ class BodyGen {
     return static_cast<int>(slots_->size()) - 1;
   }
 
-  // Finds a LIKE on the AND-spine of a filter condition whose pattern has a literal segment of
-  // >= 3 bytes over a view chain of a string column: the filter can then be driven by the
-  // occurrences of that segment in the column's bytes instead of by rows.
-  bool PlanKeyScan(const Node& cond, KeyScanPlan* plan) {
+  // Finds, on the AND spine of a filter condition, a conjunct that can only be true in rows whose
+  // string column contains a literal of >= 3 bytes (a '%'-free segment of a LIKE pattern, or the
+  // literal of is_substr / starts_with / ends_with / equal) seen through a view chain: the filter is
+  // then driven by the occurrences of that literal in the column's bytes (EmitKeyFilter).  The
+  // longest literal wins (>= 7 bytes allows the aligned-word test), ties go to the rarer digrams.
+  bool PlanKey(const Node& cond, KeyPlan* plan) {
     std::vector<const Node*> conj;
     std::vector<const Node*> todo = {&cond};
     while (!todo.empty()) {
@@ -332,72 +335,111 @@ class BodyGen {
         conj.push_back(n);
       }
     }
-    double best = 1e300;
+    double best = -1.0;
+    auto offer = [&](const std::string& sg, int slot, unsigned xf) {
+      if (sg.size() < 3 || sg.size() > 64) return;
+      double rare = 1e300;
+      for (unsigned char c : sg)
+        if ((xf == 1u && c >= 'a' && c <= 'z') || (xf == 2u && c >= 'A' && c <= 'Z')) return;  // can never match
+      for (size_t i = 0; i + 1 < sg.size(); ++i)
+        rare = std::min(rare, DigramScore(static_cast<unsigned char>(sg[i]), static_cast<unsigned char>(sg[i + 1]), xf));
+      const double score = static_cast<double>(std::min<size_t>(sg.size(), 16)) * 100.0 - std::min(rare, 50.0);
+      if (score > best) {
+        best = score;
+        plan->slot = slot;
+        plan->xf = xf;
+        plan->key = sg;
+      }
+    };
     for (const Node* n : conj) {
       if (n->kind() != NodeKind::kFunction) continue;
       const auto& fn = *static_cast<const FunctionNode*>(n);
       if (fn.children().size() < 2 || fn.children()[1]->kind() != NodeKind::kLiteral) continue;
+      int slot = -1;
+      unsigned xf = 0u;
       if (fn.name() == "is_substr" || fn.name() == "starts_with" || fn.name() == "ends_with" ||
           fn.name() == "equal" || fn.name() == "eq" || fn.name() == "same") {
         // s contains / starts with / ends with / equals a literal: the literal itself is the key
         // (comparisons see the view through its case map, like LIKE does)
         const auto& lit = static_cast<const LiteralNode&>(*fn.children()[1]);
         if (lit.is_null() || !lit.return_type().is_varlen()) continue;
-        const std::string& sg = lit.bytes();
-        int slot = -1;
-        unsigned xf = 0u;
-        if (sg.size() < 3 || sg.size() > 64 || !ViewChain(*fn.children()[0], &slot, &xf)) continue;
-        bool possible = true;
-        for (unsigned char c : sg)
-          if ((xf == 1u && c >= 'a' && c <= 'z') || (xf == 2u && c >= 'A' && c <= 'Z')) possible = false;
-        if (!possible) continue;
-        for (size_t i = 0; i + 1 < sg.size(); ++i) {
-          const double sc = DigramScore(static_cast<unsigned char>(sg[i]), static_cast<unsigned char>(sg[i + 1]), xf);
-          if (sc < best) {
-            best = sc;
-            plan->slot = slot;
-            plan->xf = xf;
-            plan->key = sg;
-            plan->digram = static_cast<int>(i);
-          }
-        }
+        if (!ViewChain(*fn.children()[0], &slot, &xf)) continue;
+        offer(lit.bytes(), slot, xf);
         continue;
       }
       if (fn.name() != "like") continue;
       const auto& pat = static_cast<const LiteralNode&>(*fn.children()[1]);
+      if (pat.is_null()) continue;
       const bool has_esc = fn.children().size() == 3;
       const char esc = has_esc ? static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0] : 0;
       const std::vector<unsigned> toks = LikeTokens(pat.bytes(), has_esc, esc);
-      bool has_one = false;
-      for (unsigned t : toks) has_one = has_one || (t >> 8) == 1u;
-      if (has_one) continue;
-      int slot = -1;
-      unsigned xf = 0u;
       if (!ViewChain(*fn.children()[0], &slot, &xf)) continue;
-      std::vector<std::string> segs;
-      bool lead_any, trail_any;
-      LikeSegments(toks, &segs, &lead_any, &trail_any);
-      for (const auto& sg : segs) {
-        if (sg.size() < 3 || sg.size() > 64) continue;
-        bool possible = true;
-        for (unsigned char c : sg)
-          if ((xf == 1u && c >= 'a' && c <= 'z') || (xf == 2u && c >= 'A' && c <= 'Z')) possible = false;
-        if (!possible) continue;
-        for (size_t i = 0; i + 1 < sg.size(); ++i) {
-          const double sc = DigramScore(static_cast<unsigned char>(sg[i]),
-                                        static_cast<unsigned char>(sg[i + 1]), xf);
-          if (sc < best) {
-            best = sc;
-            plan->slot = slot;
-            plan->xf = xf;
-            plan->key = sg;
-            plan->digram = static_cast<int>(i);
-          }
+      // literal runs between wildcards ('%' and '_' both end a run)
+      std::string cur;
+      for (unsigned t : toks) {
+        if ((t >> 8) == 0u) {
+          cur.push_back(static_cast<char>(t & 0xffu));
+        } else {
+          offer(cur, slot, xf);
+          cur.clear();
         }
       }
+      offer(cur, slot, xf);
     }
     return plan->slot >= 0;
   }
+
+  // Schema columns whose NULL makes `node` not-true (truth context: a Filter keeps a row iff its
+  // condition is valid and true).  AND needs every child true (union), OR one of them
+  // (intersection); everything else is true only if valid, and a function with the default null
+  // rule is null as soon as one argument is.
+  void TruthStrict(const Node& node, std::vector<int>* cols) const {
+    if (node.kind() == NodeKind::kBoolean && !CanFail(node)) {
+      const auto& n = static_cast<const BooleanNode&>(node);
+      const bool is_and = n.op() == BooleanNode::kAnd;
+      bool first = true;
+      for (const auto& c : n.children()) {
+        std::vector<int> cc;
+        TruthStrict(*c, &cc);
+        if (is_and) {
+          for (int x : cc)
+            if (std::find(cols->begin(), cols->end(), x) == cols->end()) cols->push_back(x);
+        } else if (first) {
+          *cols = cc;
+        } else {
+          std::vector<int> both;
+          for (int x : *cols)
+            if (std::find(cc.begin(), cc.end(), x) != cc.end()) both.push_back(x);
+          *cols = both;
+        }
+        first = false;
+      }
+      return;
+    }
+    ValueStrict(node, cols);
+  }
+  void ValueStrict(const Node& node, std::vector<int>* cols) const {
+    auto add = [&](int x) {
+      if (std::find(cols->begin(), cols->end(), x) == cols->end()) cols->push_back(x);
+    };
+    switch (node.kind()) {
+      case NodeKind::kField: add(schema_.index_of(static_cast<const FieldNode&>(node).name())); return;
+      case NodeKind::kIn: ValueStrict(*static_cast<const InNode&>(node).child(), cols); return;
+      case NodeKind::kFunction: {
+        const auto& fn = static_cast<const FunctionNode&>(node);
+        std::vector<DataType> params;
+        for (const auto& c : fn.children()) params.push_back(c->return_type());
+        const FunctionDef* def = Registry::Get().Lookup(fn.name(), params);
+        if (def == nullptr || def->nulls != NullMode::kIfNull || (def->flags & (kConcat | kVirtual)) || fn.name() == "nvl")
+          return;
+        for (const auto& c : fn.children()) ValueStrict(*c, cols);
+        return;
+      }
+      default: return;  // literals, if/else, Kleene and/or as values: no column is strict
+    }
+  }
+
+  static double PairScore(unsigned char a, unsigned char b, unsigned xf) { return DigramScore(a, b, xf); }
 
   static bool CanFail(const Node& node) {
     switch (node.kind()) {
@@ -1413,7 +1455,9 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
     for (size_t j = 0; j < slots.size(); ++j) {
       const std::string J = std::to_string(j);
       *o += I + "  f" + J + "[k] = gdv_lds(sp" + J + " + 32 * k);\n";
-      if (spec.nullable)
+      if (spec.nullable && slots[j].hoist)
+        *o += I + "  k" + J + "[k] = true;\n";
+      else if (spec.nullable)
         *o += I + "  k" + J + "[k] = !in_hv" + J + " || ((gdv_ldwin_s(sv" + J + ", wid * " + sR +
               "u + (u32)k, in_vsh" + J + ") >> lane) & 1u) != 0u;\n";
     }
@@ -1500,8 +1544,11 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
       *o += I + "for (int k = 0; k < " + sR + "; ++k) {\n";
       for (size_t j = 0; j < slots.size(); ++j) {
         const std::string J = std::to_string(j);
-        *o += I + "  k" + J + "[k] = ((gdv_ldwin(in_vp" + J + ", ((base >> 5) + k) & in_vm" + J + ", in_vsh" +
-              J + ") >> lane) & 1u) != 0u;\n";
+        if (slots[j].hoist)  // validity ANDed into the keep-mask after the row loop (EmitHoistedValidity)
+          *o += I + "  k" + J + "[k] = true;\n";
+        else
+          *o += I + "  k" + J + "[k] = ((gdv_ldwin(in_vp" + J + ", ((base >> 5) + k) & in_vm" + J + ", in_vsh" +
+                J + ") >> lane) & 1u) != 0u;\n";
       }
       *o += I + "}\n";
     }
@@ -1523,7 +1570,9 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
       } else {
         *o += I + "  f" + J + "[k] = in ? gdv_ldp(in_val" + J + " + r) : (" + t.ctype() + ")0;\n";
       }
-      if (spec.nullable)
+      if (spec.nullable && slots[j].hoist)
+        *o += I + "  k" + J + "[k] = in;\n";
+      else if (spec.nullable)
         *o += I + "  k" + J + "[k] = in && (!in_hv" + J + " || gdv_ldbit(reinterpret_cast<const u8*>(in_vld" +
               J + "), in_vsh" + J + ", r));\n";
     }
@@ -1543,86 +1592,233 @@ void EmitGroup(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int
   }
 }
 
-// ---- key-scan string filter (opt-in: string_scan bit 4) ---------------------------------------
-// A filter whose condition implies "column J contains KEY" (PlanKeyScan) does not have to look at
-// rows at all: it streams the column's BYTES, 16 per lane and load, tests every position for the
-// rarest digram of the key with a few ALU operations per word, verifies the rare candidates, and
-// only then maps a hit back to its row (gallop + bisect in the offsets), checks that it is the
-// leftmost occurrence in that row (so every row is reported once, by one warp) and evaluates the
-// full condition for that one row.  Rows without an occurrence cost no instruction and their
-// offsets are never read.  Tiles are byte ranges; every warp owns one contiguous segment of its
-// CTA's tile and keeps the rows it accepts in a shared-memory list, so the output stays ascending:
-// segments, warps and tiles are all in byte order.  A list that overflows (dense matches) makes
-// the CTA scan its tile a second time after the look-back, writing directly.
-std::string KeyMatchExpr(const std::string& key, const std::string& view, const std::string& at) {
-  std::string e;
-  for (size_t i = 0; i < key.size(); ++i)
-    e += (i ? " && " : "") + std::string("gdv_ch_eq(") + view + ", " + at + " + " + std::to_string(i) + ", " +
-         std::to_string(static_cast<unsigned>(static_cast<unsigned char>(key[i]))) + "u)";
-  return e;
-}
-
 void ReplaceAll(std::string* s, const std::string& from, const std::string& to) {
   for (size_t pos = 0; (pos = s->find(from, pos)) != std::string::npos; pos += to.size())
     s->replace(pos, from.size(), to);
 }
 
-constexpr int kKeyScanListCap = 1024;  // accepted rows per warp and tile kept in shared memory
-
-std::string EmitKeyScanFilter(const std::vector<ColumnSlot>& slots, const KernelSpec& spec,
-                              const KeyScanPlan& plan, const std::string& body, const Val& result,
-                              int BT, int seg_bytes, const std::string& scratch_decl) {
-  const int NW = BT / 32;
-  const unsigned char d0 = static_cast<unsigned char>(plan.key[static_cast<size_t>(plan.digram)]);
-  const unsigned char d1 = static_cast<unsigned char>(plan.key[static_cast<size_t>(plan.digram) + 1]);
-  auto is_letter = [](unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); };
-  const unsigned f0 = (plan.xf != 0u && is_letter(d0)) ? 0x20u : 0u;
-  const unsigned f1 = (plan.xf != 0u && is_letter(d1)) ? 0x20u : 0u;
-  const unsigned half = (d0 | f0) | ((d1 | f1) << 8);
-  const unsigned fold = f0 | (f1 << 8);
-  char hex[16];
-  std::snprintf(hex, sizeof(hex), "0x%08xu", half | (half << 16));
-  const std::string PAT = hex;
-  std::snprintf(hex, sizeof(hex), "0x%08xu", fold | (fold << 16));
-  const std::string FOLD = hex;
-  const std::string fold_or = (fold != 0u) ? (" | " + FOLD) : std::string();
-
-  // the condition of ONE row per lane: EmitGroup's per-row path with base chosen so that row s is
-  // the candidate's row (lanes without a candidate get s = A.n, i.e. out of range)
-  std::string pred;
-  const std::string tail = "              { km = __ballot_sync(GDV_FULL, in && (" + result.ok + ") && (" + result.v + ")); }\n";
-  EmitGroup(slots, spec, 1, kPred, body, tail, &pred, 7);
-
-  std::string k = R"K(// one bit per byte of a 16-byte chunk where the key's digram may start (vn = the word after it)
-__device__ __forceinline__ u32 gdv_ks_mask(const uint4& v, const u32 vn) {
-  const u32 x0 = v.x@FOLDOR@, x1 = v.y@FOLDOR@, x2 = v.z@FOLDOR@, x3 = v.w@FOLDOR@, x4 = vn@FOLDOR@;
-  const u32 e0 = gdv_eqhalf_msb(x0, @PAT@), o0 = gdv_eqhalf_msb(__funnelshift_r(x0, x1, 8), @PAT@);
-  const u32 e1 = gdv_eqhalf_msb(x1, @PAT@), o1 = gdv_eqhalf_msb(__funnelshift_r(x1, x2, 8), @PAT@);
-  const u32 e2 = gdv_eqhalf_msb(x2, @PAT@), o2 = gdv_eqhalf_msb(__funnelshift_r(x2, x3, 8), @PAT@);
-  const u32 e3 = gdv_eqhalf_msb(x3, @PAT@), o3 = gdv_eqhalf_msb(__funnelshift_r(x3, x4, 8), @PAT@);
-  if ((e0 | o0 | e1 | o1 | e2 | o2 | e3 | o3) == 0u) return 0u;
-  return gdv_mask16_half(e0, o0, e1, o1, e2, o2, e3, o3);
+// After the row loops of a filter tile: lane k of the warp holds, in mymask[w], the keep-mask of
+// step k of its w-th 1024-row chunk (first row of chunk 0: wbase0).  ANDs in the validity words of
+// the hoisted columns (ColumnSlot::hoist: one coalesced word load per lane and chunk instead of one
+// warp-uniform window load per step and column inside the row loop), then positions the kept rows —
+// scan over chunks and steps inside the warp, over warps inside the CTA, decoupled look-back over
+// tiles — and writes the ascending indices.
+void EmitFilterEpilogue(const std::vector<ColumnSlot>& slots, const KernelSpec& spec, int NW, int W,
+                        const std::string& IDX, std::string* o) {
+  const std::string sW = std::to_string(W), sNW = std::to_string(NW);
+  std::string& src = *o;
+  if (spec.nullable) {
+    bool any = false;
+    for (const auto& sl : slots) any = any || sl.hoist;
+    if (any) {
+      src += "    #pragma unroll\n";
+      src += "    for (int w = 0; w < " + sW + "; ++w) {\n";
+      src += "      const i64 rb = wbase0 + 1024 * w + 32 * (i64)lane;  // first row of the step whose mask this lane holds\n";
+      for (size_t j = 0; j < slots.size(); ++j) {
+        if (!slots[j].hoist) continue;
+        const std::string J = std::to_string(j);
+        src += "      if (in_hv" + J + " && rb < A.n) mymask[w] &= gdv_ldwin_rows(in_vld" + J + ", in_vsh" + J + ", rb, A.n);\n";
+      }
+      src += "    }\n";
+    }
+  }
+  // per chunk: exclusive positions run over chunks, then steps
+  src += "    u32 step_excl[" + sW + "];\n";
+  src += "    u32 run = 0u;\n";
+  src += "    #pragma unroll\n";
+  src += "    for (int w = 0; w < " + sW + "; ++w) {\n";
+  src += "      const u32 c = (u32)__popc(mymask[w]);\n";
+  src += "      u32 incl = c;\n";
+  src += "      #pragma unroll\n";
+  src += "      for (int o = 1; o < 32; o <<= 1) {\n";
+  src += "        const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
+  src += "        if (lane >= (u32)o) incl += t;\n";
+  src += "      }\n";
+  src += "      step_excl[w] = run + incl - c;\n";
+  src += "      run += __shfl_sync(GDV_FULL, incl, 31);\n";
+  src += "    }\n";
+  src += "    if (lane == 0u) s_wcount[wid] = run;\n";
+  src += "    __syncthreads();\n";
+  src += "    if (wid == 0u) {\n";
+  src += "      const u32 wc = lane < " + sNW + "u ? s_wcount[lane] : 0u;\n";
+  src += "      u32 winc = wc;\n";
+  src += "      #pragma unroll\n";
+  src += "      for (int o = 1; o < 32; o <<= 1) {\n";
+  src += "        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);\n";
+  src += "        if (lane >= (u32)o) winc += t;\n";
+  src += "      }\n";
+  src += "      const u32 total = __shfl_sync(GDV_FULL, winc, 31);\n";
+  src += "      if (lane < " + sNW + "u) s_wcount[lane] = winc - wc;\n";
+  src += "      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);\n";
+  src += "      if (lane == 0u) {\n";
+  src += "        s_excl = excl;\n";
+  src += "        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;\n";
+  src += "      }\n";
+  src += "    }\n";
+  src += "    __syncthreads();\n";
+  src += "    const u64 wpos = s_excl + (u64)s_wcount[wid];\n";
+  // The whole run of this warp fits the vector (always, unless GDV_SEL_BOUNDED): 32-bit offsets
+  // from one 64-bit base and no per-row capacity test.
+  src += "    if (run != 0u && wpos + (u64)run <= (u64)A.out_cap) {\n";
+  src += "      " + IDX + "* const wout = out_idx + wpos;\n";
+  src += "      #pragma unroll\n";
+  src += "      for (int w = 0; w < " + sW + "; ++w) {\n";
+  src += "        if (__ballot_sync(GDV_FULL, mymask[w] != 0u) == 0u) continue;\n";
+  src += "        #pragma unroll 4\n";
+  src += "        for (int k = 0; k < 32; ++k) {\n";
+  src += "          const u32 m = __shfl_sync(GDV_FULL, mymask[w], k);\n";
+  src += "          const u32 off = __shfl_sync(GDV_FULL, step_excl[w], k);\n";
+  src += "          if ((m >> lane) & 1u)\n";
+  src += "            wout[off + (u32)__popc(m & lt)] = (" + IDX + ")(A.row_base + wbase0 + 1024 * w + 32 * k + (i64)lane);\n";
+  src += "        }\n";
+  src += "      }\n";
+  src += "    } else if (run != 0u) {\n";
+  src += "      #pragma unroll\n";
+  src += "      for (int w = 0; w < " + sW + "; ++w) {\n";
+  src += "        #pragma unroll 1\n";
+  src += "        for (int k = 0; k < 32; ++k) {\n";
+  src += "          const u32 m = __shfl_sync(GDV_FULL, mymask[w], k);\n";
+  src += "          const u32 off = __shfl_sync(GDV_FULL, step_excl[w], k);\n";
+  src += "          const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
+  src += "          if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
+  src += "            out_idx[pos] = (" + IDX + ")(A.row_base + wbase0 + 1024 * w + 32 * k + (i64)lane);\n";
+  src += "        }\n";
+  src += "      }\n";
+  src += "    }\n";
 }
-extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant__ gdv_args A) {
+
+// ---- key-driven string filter ---------------------------------------------------------------------
+// A filter whose condition implies "column J contains KEY" (BodyGen::PlanKey) does not have to look
+// at rows: every warp streams the BYTES of its 1024 rows (one contiguous run of the Arrow data
+// buffer) straight from global memory, 4 x 16 bytes per lane in flight, and tests aligned machine
+// words against the key's bytes:
+//   * KEY of >= 7 bytes: wherever it starts, one of its aligned 4-byte words is key[o .. o+4) for
+//     o = start phase 0..3: four compares per loaded word, nothing else (no case-fold arithmetic
+//     beyond one OR, no cross-word shifts);
+//   * KEY of 3..6 bytes: the same with aligned halfwords (key[o .. o+2), o = 0, 1), verified against
+//     the whole key before it counts (two bytes alone are too common).
+// A match is only an *anchor*: its byte position goes to a small per-warp list; when the list fills
+// or the run ends, the lanes take one anchor each, bisect the row it lies in (int32 offsets of the
+// warp's 1024 rows), and evaluate the FULL condition for that row with the ordinary per-row body
+// (substr, upper, the exact LIKE matcher, other conjuncts, validity).  Rows without an anchor cost
+// no instruction and their offsets are never read.  Bytes that share a 16-byte chunk with memory
+// outside the column (first / last chunk of the batch) are not loaded as chunks: every such byte is
+// an anchor.  More anchors than the list holds between two drains: the warp evaluates all its rows.
+std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec& spec,
+                          const KeyPlan& plan, const std::string& body, const Val& result, int BT,
+                          const std::string& scratch_decl) {
+  const int NW = BT / 32;
+  const int L = static_cast<int>(plan.key.size());
+  const bool words = L >= 7;
+  const int unit = words ? 4 : 2;  // bytes per tested unit = start phases that need their own pattern
+  auto is_letter = [](unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); };
+  // pattern of phase o: the rarest unit among key[o + unit * j ..) (they share the alignment)
+  std::vector<unsigned> pats, folds;
+  std::vector<int> pat_at;
+  for (int o = 0; o < unit; ++o) {
+    int best_at = o;
+    double best = 1e300;
+    for (int at = o; at + unit <= L; at += unit) {
+      double sc = 0.0;
+      for (int i = 0; i + 1 < unit; ++i)
+        sc += BodyGen::PairScore(static_cast<unsigned char>(plan.key[static_cast<size_t>(at + i)]),
+                                   static_cast<unsigned char>(plan.key[static_cast<size_t>(at + i + 1)]), plan.xf);
+      if (sc < best) {
+        best = sc;
+        best_at = at;
+      }
+    }
+    unsigned pat = 0u, fold = 0u;
+    for (int i = 0; i < unit; ++i) {
+      const unsigned char c = static_cast<unsigned char>(plan.key[static_cast<size_t>(best_at + i)]);
+      const unsigned f = (plan.xf != 0u && is_letter(c)) ? 0x20u : 0u;
+      pat |= static_cast<unsigned>(c | f) << (8 * i);
+      fold |= f << (8 * i);
+    }
+    pats.push_back(pat);
+    folds.push_back(fold);
+    pat_at.push_back(best_at);
+  }
+  auto hex = [](unsigned v) {
+    char b[16];
+    std::snprintf(b, sizeof(b), "0x%08xu", v);
+    return std::string(b);
+  };
+  // mask function: bit i = unit i of a 16-byte chunk equals some phase pattern.  Branch-free: four
+  // compares per word into one predicate (the compiler must not turn them into a decision tree: the
+  // lanes of a warp would take different paths through it), one test of the four predicates.
+  std::string mk = "// units of a 16-byte chunk (bit i = unit i) that equal a phase pattern of the key '" +
+                   CommentSafe(plan.key) + "'\n";
+  const char* comp[4] = {"v.x", "v.y", "v.z", "v.w"};
+  if (words) {
+    mk += "__device__ __forceinline__ u32 gdv_key_word(u32 x) {\n";
+    std::string e;
+    for (int o = 0; o < unit; ++o)
+      e += (o ? " | " : "") + std::string("(u32)((x") + (folds[o] ? " | " + hex(folds[o]) : "") + ") == " + hex(pats[o]) + ")";
+    mk += "  return " + e + ";\n}\n";
+    mk += "__device__ __forceinline__ u32 gdv_key_mask(const uint4& v) {\n";
+    mk += "  const u32 a = gdv_key_word(v.x), b = gdv_key_word(v.y), c = gdv_key_word(v.z), d = gdv_key_word(v.w);\n";
+    mk += "  return a | (b << 1) | (c << 2) | (d << 3);\n}\n";
+    // the streaming loop only needs "some unit of the chunk matches": 16 compares chained into ONE predicate
+    std::string eb;
+    for (int o = 0; o < unit; ++o)
+      eb += (o ? " | " : "") + std::string("((x") + (folds[o] ? " | " + hex(folds[o]) : "") + ") == " + hex(pats[o]) + ")";
+    mk += "__device__ __forceinline__ bool gdv_key_wordb(u32 x) {\n  return " + eb + ";\n}\n";
+    mk += "__device__ __forceinline__ bool gdv_key_any(const uint4& v) {\n";
+    mk += "  return gdv_key_wordb(v.x) | gdv_key_wordb(v.y) | gdv_key_wordb(v.z) | gdv_key_wordb(v.w);\n}\n";
+  } else {
+    mk += "__device__ __forceinline__ u32 gdv_key_mask(const uint4& v) {\n";
+    mk += "  u32 h[4];\n";
+    for (int wi = 0; wi < 4; ++wi) {
+      std::string e;
+      for (int o = 0; o < unit; ++o) {
+        const unsigned p2 = pats[o] | (pats[o] << 16), f2 = folds[o] | (folds[o] << 16);
+        e += (o ? " | " : "") + std::string("gdv_eqhalf_msb(") + comp[wi] + (f2 ? " | " + hex(f2) : "") + ", " + hex(p2) + ")";
+      }
+      mk += "  h[" + std::to_string(wi) + "] = " + e + ";\n";
+    }
+    // 0x8000 flags halfword 0, 0x80000000 halfword 1 (the upper one may be flagged falsely: anchors are verified)
+    mk += "  if ((h[0] | h[1] | h[2] | h[3]) == 0u) return 0u;\n";
+    mk += "  u32 m = 0u;\n";
+    mk += "  #pragma unroll\n";
+    mk += "  for (int i = 0; i < 4; ++i) m |= (((h[i] >> 15) & 1u) | ((h[i] >> 30) & 2u)) << (2 * i);\n";
+    mk += "  return m;\n}\n";
+    mk += "__device__ __forceinline__ bool gdv_key_any(const uint4& v) {\n";
+    std::string eh;
+    for (int wi = 0; wi < 4; ++wi)
+      for (int o = 0; o < unit; ++o) {
+        const unsigned p2 = pats[o] | (pats[o] << 16), f2 = folds[o] | (folds[o] << 16);
+        eh += (eh.empty() ? "" : " | ") + std::string("gdv_eqhalf_msb(") + comp[wi] + (f2 ? " | " + hex(f2) : "") + ", " + hex(p2) + ")";
+      }
+    mk += "  return (" + eh + ") != 0u;\n}\n";
+  }
+
+  // the condition of ONE row per lane: EmitGroup's per-row path with `base` chosen so that row s is
+  // the anchor's row (lanes without one get s = A.n, i.e. out of range)
+  std::string pred;
+  EmitGroup(slots, spec, 1, kPred, body,
+            "              { keep = in && (" + result.ok + ") && (" + result.v + "); }\n", &pred, 7);
+  std::string k = mk + R"K(extern "C" __global__ void __launch_bounds__(@BT@, @MINB@) @NAME@(const __grid_constant__ gdv_args A) {
   const u32 lane = threadIdx.x & 31u;
   const u32 wid = threadIdx.x >> 5;
   gdv_ctx ctx;
   ctx.err = A.err;
 @PROLOGUE@  extern __shared__ uint4 gdv_smem[];
-  u32* const wrows = reinterpret_cast<u32*>(gdv_smem) + (size_t)wid * (@LCAP@ + 256);  // rows this warp accepted
-  u16* const wcand = reinterpret_cast<u16*>(wrows + @LCAP@);  // candidates of one 512-byte block
+  u32* const wmask = reinterpret_cast<u32*>(gdv_smem) + (size_t)wid * (@CAP@ + 36);  // keep-mask of step k of this warp's rows
+  u32* const wctr = wmask + 32;   // [0] anchors queued since the last drain
+  u32* const wanch = wmask + 36;  // their byte positions in the column's data buffer
   __shared__ u32 s_wcount[@NW@];
   __shared__ i64 s_tile;
   __shared__ u64 s_excl;
-  __shared__ u32 s_over;
   const i32* const offs = in_val@J@;
   const u8* const data = in_var@J@;
-  const i64 b_begin = (i64)offs[0], b_end = (i64)offs[A.n];
-  i64 n_tiles = (b_end - b_begin + @TILE@ - 1) / @TILE@;
-  if (n_tiles < 1) n_tiles = 1;
-  const i64 mis = (i64)((unsigned long long)data & 15ull);  // aligned coordinate = byte position + mis
-  const u8* const abase = data - mis;
-  const i64 a_limit = (b_end + mis + 15) & ~15ll;  // end of the last 16-byte chunk that holds a byte
+  const i64 n_tiles = (A.n + @TILE@ - 1) / @TILE@;
+  const i64 B0 = (i64)offs[0], B1 = (i64)offs[A.n];
+  // chunk c holds the bytes [16 c - mis, 16 c - mis + 16) of the data buffer
+  const i64 mis = (i64)((unsigned long long)data & 15ull);
+  const uint4* const abase = reinterpret_cast<const uint4*>(data - mis);
+  const i64 c_safe_lo = (B0 + mis + 15) >> 4;  // chunks that lie entirely inside the column's bytes
+  const i64 c_safe_hi = (B1 + mis) >> 4;
   @IDX@* out_idx = reinterpret_cast<@IDX@*>(A.out_idx);
   const u32 lt = gdv_lanemask_lt();
   while (true) {
@@ -1630,197 +1826,185 @@ extern "C" __global__ void __launch_bounds__(@BT@) @NAME@(const __grid_constant_
     __syncthreads();
     const i64 tile = s_tile;
     if (tile >= n_tiles) break;
-    // this warp's segment [g0, g1) of the tile: it owns the occurrences whose digram starts in it
-    i64 g0 = b_begin + tile * @TILE@ + (i64)wid * @SEG@;
-    i64 g1 = g0 + @SEG@;
-    if (g0 > b_end) g0 = b_end;
-    if (g1 > b_end) g1 = b_end;
-    // Pass 0 walks the segment and keeps the accepted rows in wrows[] (counting past its
-    // capacity); if some list of the CTA overflowed, pass 1 walks it again after the look-back and
-    // stores the rows at their final positions directly.
-    u32 cnt = 0u;
-    u64 wpos = 0ull;
-    bool direct = false;
-    for (int pass = 0; pass < 2; ++pass) {
-      cnt = 0u;
-      if (g0 < g1) {
-        i64 first = g0 - @KD@;
-        if (first < b_begin) first = b_begin;
-        i64 row_lo = gdv_row_of_byte(offs, 0, A.n, first);  // no later occurrence starts before this row
-        // 32-bit coordinates relative to the first 512-byte block of the segment
-        const i64 a0 = g0 + mis, a1 = g1 + mis;
-        const i64 abs0 = a0 & ~511ll;
-        const u8* const sp = abase + abs0 + 16 * (i64)lane;  // this lane's chunk of block 0
-        const i32 rel0 = (i32)(a0 - abs0), rel1 = (i32)(a1 - abs0);
-        const i32 rlim = a_limit - abs0 > 0x7fffffffll ? 0x7fffffff : (i32)(a_limit - abs0);
-        const i32 rc0 = 16 * (i32)lane;
-        for (i32 rb0 = 0; rb0 < rel1;) {
-          // digram masks of one or two 512-byte blocks; two loads are in flight per lane whenever
-          // two whole blocks lie inside the segment (one load per lane does not cover the HBM latency)
-          u32 mkA = 0u, mkB = 0u;
-          int nblk = 1;
-          if (rb0 >= rel0 && rb0 + 1040 <= rel1) {
-            nblk = 2;
-            const uint4 va = __ldcs(reinterpret_cast<const uint4*>(sp + rb0));
-            const uint4 vb = __ldcs(reinterpret_cast<const uint4*>(sp + rb0 + 512));
-            u32 na = __shfl_down_sync(GDV_FULL, va.x, 1);
-            u32 nb = __shfl_down_sync(GDV_FULL, vb.x, 1);
-            const u32 b_first = __shfl_sync(GDV_FULL, vb.x, 0);  // the word after block A's last chunk
-            if (lane == 31u) {
-              na = b_first;
-              nb = __ldg(reinterpret_cast<const u32*>(sp + rb0 + 528));
+    const i64 wbase0 = tile * @TILE@ + (i64)wid * 1024;
+    wmask[lane] = 0u;
+    if (lane == 0u) wctr[0] = 0u;
+    __syncwarp();
+    if (wbase0 < A.n) {
+      const i64 r0 = wbase0;
+      const i64 r1 = r0 + 1024 < A.n ? r0 + 1024 : A.n;
+      const i64 b0 = (i64)offs[r0], b1 = (i64)offs[r1];
+      auto push = [&](i64 pos) {
+        const u32 ix = atomicAdd(wctr, 1u);
+        if (ix < @CAP@u) wanch[ix] = (u32)pos;
+      };
+      // bytes of this run that share a chunk with memory outside the column: every one is an anchor
+      i64 c_lo = (b0 + mis) >> 4, c_hi = (b1 + mis + 15) >> 4;
+      if (c_lo < c_safe_lo) {
+        const i64 e = b1 < (c_safe_lo << 4) - mis ? b1 : (c_safe_lo << 4) - mis;
+        for (i64 q = b0 + (i64)lane; q < e; q += 32) push(q);
+        c_lo = c_safe_lo;
+      }
+      if (c_hi > c_safe_hi) {
+        const i64 s = b0 > (c_safe_hi << 4) - mis ? b0 : (c_safe_hi << 4) - mis;
+        for (i64 q = s + (i64)lane; q < b1; q += 32) push(q);
+        c_hi = c_safe_hi;
+      }
+      // Blocks of 128 chunks (2 KB): 4 x 16 bytes in flight per lane; 32-bit chunk indices relative to
+      // the run's first chunk, positions are only formed for the (rare) matches.  After every block
+      // the queued anchors are drained if the list is half full (or the run is over): one anchor per
+      // lane, row of the anchor, then the full condition for that row — the only copy of the per-row
+      // body in this kernel.  Should a block ever queue more anchors than the list holds (every word
+      // of it a match), the warp goes over its rows a second time, 128 rows per step, with the first
+      // byte of every non-empty row as its anchor.
+      const uint4* const cp = abase + c_lo + (i64)lane;
+      const i32 nch = c_hi > c_lo ? (i32)(c_hi - c_lo) : 0;
+      i32 ci = 0;
+      i64 redo_row = r0;
+      bool redo = false, lost = false;
+      while (true) {
+        bool last;
+        if (!redo) {
+          if (ci < nch) {
+            bool any[4];
+            if (ci + 128 <= nch) {
+              uint4 v[4];
+              #pragma unroll
+              for (int u = 0; u < 4; ++u) v[u] = __ldcs(cp + ci + 32 * u);
+              #pragma unroll
+              for (int u = 0; u < 4; ++u) any[u] = gdv_key_any(v[u]);
+            } else {
+              #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                any[u] = false;
+                if (ci + 32 * u + (i32)lane < nch) any[u] = gdv_key_any(__ldcs(cp + ci + 32 * u));
+              }
             }
-            mkA = gdv_ks_mask(va, na);
-            mkB = gdv_ks_mask(vb, nb);
-          } else if (rb0 >= rel0 && rb0 + 528 <= rel1) {
-            // interior block: every chunk and the word after the last one lie inside the segment
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + rb0));
-            u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
-            if (lane == 31u) vn = __ldg(reinterpret_cast<const u32*>(sp + rb0 + 16));
-            mkA = gdv_ks_mask(v, vn);
-          } else {
-            const i32 rc = rb0 + rc0;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            const bool mine = rc < rel1 && rc + 16 > rel0;
-            // one chunk past the segment is loaded too: it holds the second byte of a digram that
-            // starts at the segment's last byte
-            if (rc + 16 > rel0 && rc < rel1 + 16 && rc < rlim) v = __ldcs(reinterpret_cast<const uint4*>(sp + rb0));
-            u32 vn = __shfl_down_sync(GDV_FULL, v.x, 1);
-            if (lane == 31u) vn = (mine && rc + 16 < rlim) ? __ldg(reinterpret_cast<const u32*>(sp + rb0 + 16)) : 0u;
-            if (mine) mkA = gdv_ks_mask(v, vn);
-          }
-          const i32 rb_first = rb0;
-          rb0 += 512 * nblk;
-          for (int half = 0; half < nblk; ++half) {
-          const i32 rb = rb_first + 512 * half;
-          const i32 rc = rb + rc0;  // this lane's chunk
-          u32 mk = half == 0 ? mkA : mkB;
-          // digram hits that start inside the segment and verify as the key
-          u32 vm = 0u;
-          while (mk != 0u) {
-            const int bit = __ffs((int)mk) - 1;
-            mk &= mk - 1u;
-            const i64 d = abs0 + (i64)(rc + bit) - mis;  // byte position of the digram
-            const i64 st = d - @KD@;                      // where the key would start
-            if (d >= g0 && d < g1 && st >= b_begin && st + @KL@ <= b_end) {
-              gdv_str kv = gdv_make_str(data + st, @KL@);
-              kv.xf = @XF@u;
-              if (@KEYMATCH_KV@) vm |= 1u << bit;
+            if (any[0] | any[1] | any[2] | any[3]) {
+              #pragma unroll 1
+              for (int u = 0; u < 4; ++u) {
+                if (!any[u]) continue;
+                // the chunk is read again (it is in L2 / L1): keeping 64 loaded bytes per lane alive for
+                // this rare path would cost the streaming loop 16 registers
+                u32 mm = gdv_key_mask(__ldg(cp + ci + 32 * u));
+                while (mm != 0u) {
+                  const int bit = __ffs((int)mm) - 1;
+                  mm &= mm - 1u;
+                  const i64 pos = ((c_lo + (i64)(ci + 32 * u) + (i64)lane) << 4) - mis + @UNIT@ * bit;
+@VERIFY@                  push(pos);
+                }
+              }
             }
           }
-          if (__ballot_sync(GDV_FULL, vm != 0u) == 0u) continue;
-          // ordinals of the block's occurrences, in byte order
-          const u32 c = (u32)__popc(vm);
-          u32 incl = c;
+          ci += 128;
+          last = ci >= nch;
+        } else {
           #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const u32 t = __shfl_up_sync(GDV_FULL, incl, o);
-            if (lane >= (u32)o) incl += t;
+          for (int u = 0; u < 4; ++u) {
+            const i64 row = redo_row + 32 * u + (i64)lane;
+            if (row < r1) {
+              const i32 a = __ldg(offs + row);
+              if (__ldg(offs + row + 1) > a) push((i64)a);
+            }
           }
-          const u32 total = __shfl_sync(GDV_FULL, incl, 31);
-          {
-            u32 at = incl - c;
-            for (u32 m = vm; m != 0u; m &= m - 1u) wcand[at++] = (u16)(16u * lane + (u32)(__ffs((int)m) - 1));
+          redo_row += 128;
+          last = redo_row >= r1;
+        }
+        __syncwarp();
+        // one lane reads the count and broadcasts it: a lane that read it on its own could see the
+        // pushes faster lanes already make for the next block
+        const u32 queued = __shfl_sync(GDV_FULL, wctr[0], 0);
+        if (queued >= @CAP@u / 2u || (last && queued != 0u)) {
+          if (queued > @CAP@u) lost = true;
+          const u32 nc = queued < @CAP@u ? queued : @CAP@u;
+          for (u32 i0 = 0u; i0 < nc; i0 += 32u) {
+            const bool has = i0 + lane < nc;
+            const i64 pos = has ? (i64)wanch[i0 + lane] : b0;
+            // last row r in [r0, r1) with offs[r] <= pos (offsets are non-decreasing; empty rows are skipped)
+            i64 lo = r0, hi = r1;
+            while (hi - lo > 1) {
+              const i64 mid = (lo + hi) >> 1;
+              if ((i64)__ldg(offs + mid) <= pos) lo = mid;
+              else hi = mid;
+            }
+            const u32 rr = (u32)(lo - r0);
+            const bool cand = has && pos >= b0 && pos < b1 && ((wmask[rr >> 5] >> (rr & 31u)) & 1u) == 0u;
+            bool keep = false;
+            {
+              const i64 base = (cand ? lo : A.n) - (i64)lane;
+@PRED@            }
+            if (keep) atomicOr(&wmask[rr >> 5], 1u << (rr & 31u));
           }
           __syncwarp();
-          for (u32 q0 = 0u; q0 < total; q0 += 32u) {
-            const bool has = q0 + lane < total;
-            const i64 st = has ? abs0 + (i64)rb + (i64)wcand[q0 + lane] - mis - @KD@ : b_begin;
-            i64 r = A.n;
-            bool cand_ok = false;
-            if (has) {
-              r = gdv_row_of_byte(offs, row_lo, A.n, st);
-              const i64 rowb = (i64)offs[r], rowe = (i64)offs[r + 1];
-              if (st + @KL@ <= rowe) {
-                // leftmost occurrence in its row? (an earlier one reports the row, here or elsewhere)
-                gdv_str rv = gdv_make_str(data + rowb, (i32)(rowe - rowb));
-                rv.xf = @XF@u;
-                cand_ok = true;
-                const i32 upto = (i32)(st - rowb);
-                for (i32 q = 0; q < upto; ++q)
-                  if (@KEYMATCH_RV@) {
-                    cand_ok = false;
-                    break;
-                  }
-              }
-            }
-            row_lo = __shfl_sync(GDV_FULL, r, 0);  // occurrences come in byte order
-            u32 km = 0u;
-            {
-              const i64 base = (cand_ok ? r : A.n) - (i64)lane;
-@PRED@            }
-            if ((km >> lane) & 1u) {
-              const u32 at = cnt + (u32)__popc(km & lt);
-              if (!direct) {
-                if (at < @LCAP@u) wrows[at] = (u32)r;
-              } else {
-                const u64 pos = wpos + (u64)at;
-                if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + r);
-              }
-            }
-            cnt += (u32)__popc(km);
-          }
-          __syncwarp();  // wcand is rewritten by the next block
-          }
+          if (lane == 0u) wctr[0] = 0u;
+          __syncwarp();
+        }
+        if (last) {
+          if (redo || !lost) break;
+          redo = true;
         }
       }
-      if (pass == 1) break;
-      if (lane == 0u) s_wcount[wid] = cnt;
-      __syncthreads();
-      if (wid == 0u) {
-        const u32 wc = lane < @NW@u ? s_wcount[lane] : 0u;
-        u32 winc = wc;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const u32 t = __shfl_up_sync(GDV_FULL, winc, o);
-          if (lane >= (u32)o) winc += t;
-        }
-        const u32 total = __shfl_sync(GDV_FULL, winc, 31);
-        const u32 over = __ballot_sync(GDV_FULL, wc > @LCAP@u);
-        if (lane < @NW@u) s_wcount[lane] = winc - wc;
-        const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);
-        if (lane == 0u) {
-          s_excl = excl;
-          s_over = over;
-          if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;
-        }
-      }
-      __syncthreads();
-      wpos = s_excl + (u64)s_wcount[wid];
-      if (s_over == 0u) {
-        for (u32 i = lane; i < cnt; i += 32u) {
-          const u64 pos = wpos + (u64)i;
-          if (pos < (u64)A.out_cap) out_idx[pos] = (@IDX@)(A.row_base + (i64)wrows[i]);
-        }
-        break;
-      }
-      direct = true;  // some list overflowed: the offsets are known now, walk the tile again
     }
-  }
+    u32 mymask[1];
+    mymask[0] = wmask[lane];
+    __syncwarp();
+@EPILOGUE@  }
 }
 )K";
-  std::string prologue;
+  // halfword mode: an anchor counts only if the whole key is there (two bytes alone are too common):
+  // the matched halfword is key[at .. at+2) for the phase pattern it equals, so the key would start
+  // at pos - at for one of the (at most two) pattern offsets
+  std::string verify;
+  if (!words) {
+    std::string e;
+    for (int i = 0; i < L; ++i)
+      e += (i ? " && " : "") + std::string("gdv_ch_eq(kv, ") + std::to_string(i) + ", " +
+           std::to_string(static_cast<unsigned>(static_cast<unsigned char>(plan.key[static_cast<size_t>(i)]))) + "u)";
+    verify += "            {\n";
+    verify += "              bool hit = false;\n";
+    for (int o = 0; o < unit; ++o) {
+      if (o == 1 && pat_at[1] == pat_at[0]) continue;
+      verify += "              {\n";
+      verify += "                const i64 st = pos - " + std::to_string(pat_at[static_cast<size_t>(o)]) + ";\n";
+      verify += "                if (st >= B0 && st + " + std::to_string(L) + " <= B1) {\n";
+      verify += "                  gdv_str kv = gdv_make_str(data + st, " + std::to_string(L) + ");\n";
+      verify += "                  kv.xf = " + std::to_string(plan.xf) + "u;\n";
+      verify += "                  if (" + e + ") hit = true;\n";
+      verify += "                }\n";
+      verify += "              }\n";
+    }
+    verify += "              if (!hit) continue;\n";
+    verify += "            }\n";
+  }
+  std::string prologue, epilogue;
   EmitPrologue(slots, spec, &prologue);
   prologue += scratch_decl;
+  EmitFilterEpilogue(slots, spec, NW, 1, SelCType(spec.selection_mode), &epilogue);
   ReplaceAll(&k, "@PROLOGUE@", prologue);
+  ReplaceAll(&k, "@EPILOGUE@", epilogue);
   ReplaceAll(&k, "@PRED@", pred);
-  ReplaceAll(&k, "@KEYMATCH_KV@", KeyMatchExpr(plan.key, "kv", "0"));
-  ReplaceAll(&k, "@KEYMATCH_RV@", "q + " + std::to_string(plan.key.size()) + " <= rv.len && " +
-                                       KeyMatchExpr(plan.key, "rv", "q"));
+  ReplaceAll(&k, "@VERIFY@", verify);
   ReplaceAll(&k, "@BT@", std::to_string(BT));
+  // the streaming loop needs ~40 registers; the per-row body (rare) may spill: ask for 48 warps per SM
+  ReplaceAll(&k, "@MINB@", std::to_string(std::max(1, 1536 / BT)));
   ReplaceAll(&k, "@NW@", std::to_string(NW));
   ReplaceAll(&k, "@NAME@", spec.name);
-  ReplaceAll(&k, "@LCAP@", std::to_string(kKeyScanListCap));
+  ReplaceAll(&k, "@CAP@", std::to_string(kKeyAnchorCap));
   ReplaceAll(&k, "@J@", std::to_string(plan.slot));
-  ReplaceAll(&k, "@TILE@", std::to_string(static_cast<long long>(seg_bytes) * NW) + "ll");
-  ReplaceAll(&k, "@SEG@", std::to_string(seg_bytes) + "ll");
+  ReplaceAll(&k, "@TILE@", std::to_string(static_cast<long long>(NW) * 1024) + "ll");
   ReplaceAll(&k, "@IDX@", SelCType(spec.selection_mode));
-  ReplaceAll(&k, "@KD@", std::to_string(plan.digram));
-  ReplaceAll(&k, "@KL@", std::to_string(plan.key.size()));
-  ReplaceAll(&k, "@XF@", std::to_string(plan.xf));
-  ReplaceAll(&k, "@PAT@", PAT);
-  ReplaceAll(&k, "@FOLDOR@", fold_or);
+  ReplaceAll(&k, "@UNIT@", std::to_string(unit));
   return k;
+}
+
+// Filter kernels: columns whose NULL makes the condition not-true (BodyGen::TruthStrict) have their
+// validity ANDed into the keep-mask one 32-row word at a time after the row loop; inside the loop
+// they count as valid (no function of the kernel can raise, so a null slot's value is harmless).
+void MarkHoisted(const BodyGen& gen, const Node& cond, std::vector<ColumnSlot>* slots) {
+  std::vector<int> strict;
+  gen.TruthStrict(cond, &strict);
+  for (auto& sl : *slots)
+    if (std::find(strict.begin(), strict.end(), sl.schema_index) != strict.end()) sl.hoist = true;
 }
 
 int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
@@ -1829,8 +2013,8 @@ int PickRowsPerThread(int in_bytes, int out_bytes, KernelKind kind) {
   // and whose compaction tail needs registers, is best at R=2..4.
   (void)out_bytes;
   const int bytes = std::max(in_bytes, 1);
-  int r = kind == KernelKind::kFilter ? 64 / bytes : 192 / bytes;
-  r = std::max(kind == KernelKind::kFilter ? 2 : 1, std::min(r, 16));
+  int r = kind == KernelKind::kFilter ? 96 / bytes : 192 / bytes;
+  r = std::max(kind == KernelKind::kFilter ? 2 : 1, std::min(r, kind == KernelKind::kFilter ? 8 : 16));
   int p = 1;
   while (p * 2 <= r) p *= 2;
   return p;
@@ -1859,7 +2043,10 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     in_bytes += s.type.is_varlen() ? 32 : std::max(s.type.width(), 1);
   }
   const int R = spec.rows_per_thread > 0 ? std::min(spec.rows_per_thread, 8) : 2;
-  const int BT = spec.block_threads > 0 ? spec.block_threads : 256;
+  // String predicates are instruction-bound and stage bytes per warp in shared memory: 512 threads
+  // measured best on big batches (profiles/r01_string_filter.md); everything else runs 256.
+  const int BT = spec.block_threads > 0 ? spec.block_threads
+                                        : (spec.kind == KernelKind::kFilter && n_varlen > 0 && spec.large_batch ? 512 : 256);
   if (BT % 32 != 0 || BT > 1024)
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
   const int NW = BT / 32;
@@ -2151,54 +2338,53 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
       return Status::Make(GDV_INVALID, "a string kernel takes exactly one utf8/binary expression");
     return GenerateStringKernel(schema, exprs[0], spec, out);
   }
-  // Key-scan string filter (opt-in, string_scan bit 4): driven by the occurrences of a literal
-  // LIKE segment in the column's bytes; conditions that can raise keep the row-driven kernel so
-  // that errors are reported for the same rows.
-  if (spec.kind == KernelKind::kFilter && (spec.string_scan & 16) != 0 && exprs.size() == 1) {
+  // Key-driven string filter (default wherever it applies; string_scan bit 2 keeps the row-driven
+  // kernel): driven by the occurrences of a literal of the condition in the column's bytes.
+  // Conditions that can raise keep the row-driven kernel so that errors come from the same rows.
+  if (spec.kind == KernelKind::kFilter && (spec.string_scan & 4) == 0 && exprs.size() == 1 &&
+      !BodyGen::CanFail(*exprs[0]->root())) {
     std::vector<ColumnSlot> kslots;
     BodyGen kgen(schema, &kslots, spec.nullable, /*coop=*/false);
-    std::string kbody;
-    const Val kres = kgen.GenTruth(*exprs[0]->root(), &kbody, 6);
-    KeyScanPlan plan;
+    KeyPlan plan;
     const int kBT = spec.block_threads > 0 ? spec.block_threads : 256;
-    if (kgen.error().empty() && !kgen.uses_ctx() && kBT % 32 == 0 && kBT <= 1024 &&
-        kgen.PlanKeyScan(*exprs[0]->root(), &plan)) {
-      // bytes per warp segment: rows_per_thread, meaningless here, doubles as the override in KB
-      const int seg = spec.rows_per_thread > 0 ? std::min(spec.rows_per_thread, 1024) * 1024
-                                               : (spec.key_scan_seg > 0 ? spec.key_scan_seg : 4096);
-      ArgsLayout KL(static_cast<int>(kslots.size()), 0);
-      std::string src = "// generated by gandiva_b200 kernel fuser; key-scan string Filter";
-      src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
-      src += "// expr_0: " + CommentSafe(exprs[0]->ToString()) + "\n";
-      src += "// key: '" + CommentSafe(plan.key) + "' in column slot " + std::to_string(plan.slot) +
-             ", case map " + std::to_string(plan.xf) + ", digram at " + std::to_string(plan.digram) + "\n";
-      if ((spec.string_scan & 8) != 0) src += "#define GDV_LOOKBACK_STRICT 1\n";
-      src += "#include \"gdv_device_lib.cuh\"\n";
-      src += EmitArgsStruct(KL);
-      src += kgen.globals();
-      src += EmitKeyScanFilter(kslots, spec, plan, kbody, kres, kBT, seg, kgen.ScratchDecl(1));
-      int in_bytes = 0;
-      for (const auto& sl : kslots) in_bytes += sl.type.is_varlen() ? 32 : std::max(sl.type.width(), 1);
-      out->source = std::move(src);
-      out->name = spec.name;
-      out->kind = spec.kind;
-      out->rows_per_thread = 1;
-      out->block_threads = kBT;
-      out->selection_mode = spec.selection_mode;
-      out->nullable = spec.nullable;
-      out->inputs = kslots;
-      out->outputs.clear();
-      out->uses_ctx = false;
-      out->in_bytes_per_row = in_bytes;
-      out->out_bytes_per_row = 0;
-      out->args_size = KL.size;
-      out->dynamic_smem = (kBT / 32) * (kKeyScanListCap + 256) * 4;
-      out->tile_rows = 0;
-      out->tile_bytes = static_cast<int64_t>(seg) * (kBT / 32);
-      out->staged = false;
-      out->stages = 0;
-      out->cta_tile_rows = 0;
-      return Status::OK();
+    if (kBT % 32 == 0 && kBT <= 1024 && kgen.PlanKey(*exprs[0]->root(), &plan)) {
+      std::string kbody;
+      const Val kres = kgen.GenTruth(*exprs[0]->root(), &kbody, 6);
+      if (kgen.error().empty() && !kgen.uses_ctx()) {
+        if (spec.nullable) MarkHoisted(kgen, *exprs[0]->root(), &kslots);
+        ArgsLayout KL(static_cast<int>(kslots.size()), 0);
+        std::string src = "// generated by gandiva_b200 kernel fuser; key-driven string Filter";
+        src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
+        src += "// expr_0: " + CommentSafe(exprs[0]->ToString()) + "\n";
+        src += "// key: '" + CommentSafe(plan.key) + "' in column slot " + std::to_string(plan.slot) +
+               ", case map " + std::to_string(plan.xf) + "\n";
+        src += "#include \"gdv_device_lib.cuh\"\n";
+        src += EmitArgsStruct(KL);
+        src += kgen.globals();
+        src += EmitKeyFilter(kslots, spec, plan, kbody, kres, kBT, kgen.ScratchDecl(1));
+        int in_bytes = 0;
+        for (const auto& sl : kslots) in_bytes += sl.type.is_varlen() ? 32 : std::max(sl.type.width(), 1);
+        out->source = std::move(src);
+        out->name = spec.name;
+        out->kind = spec.kind;
+        out->rows_per_thread = 1;
+        out->block_threads = kBT;
+        out->selection_mode = spec.selection_mode;
+        out->nullable = spec.nullable;
+        out->inputs = kslots;
+        out->outputs.clear();
+        out->uses_ctx = false;
+        out->in_bytes_per_row = in_bytes;
+        out->out_bytes_per_row = 0;
+        out->args_size = KL.size;
+        out->dynamic_smem = (kBT / 32) * (kKeyAnchorCap + 36) * 4;
+        out->tile_rows = static_cast<int64_t>(kBT / 32) * 1024;
+        out->key_driven = true;
+        out->staged = false;
+        out->stages = 0;
+        out->cta_tile_rows = 0;
+        return Status::OK();
+      }
     }
   }
   std::vector<ColumnSlot> slots;
@@ -2216,6 +2402,8 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
                                                        : gen.Gen(*e->root(), &body, 4));
   }
   if (!gen.error().empty()) return Status::Make(GDV_NOT_IMPLEMENTED, gen.error());
+  if (spec.kind == KernelKind::kFilter && spec.nullable && !gen.uses_ctx() && exprs.size() == 1)
+    MarkHoisted(gen, *exprs[0]->root(), &slots);
 
   int in_bytes = 0, out_bytes = 0;
   int n_varlen = 0;
@@ -2242,7 +2430,10 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     while (p * 2 <= R) p *= 2;
     R = p;
   }
-  const int BT = spec.block_threads > 0 ? spec.block_threads : 256;
+  // String predicates are instruction-bound and stage bytes per warp in shared memory: 512 threads
+  // measured best on big batches (profiles/r01_string_filter.md); everything else runs 256.
+  const int BT = spec.block_threads > 0 ? spec.block_threads
+                                        : (spec.kind == KernelKind::kFilter && n_varlen > 0 && spec.large_batch ? 512 : 256);
   if (BT % 32 != 0 || BT > 1024)
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
 
@@ -2251,8 +2442,12 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   // Filters copy the string bytes of the NEXT group into a second stage with cp.async while the
   // current group is scanned (per-warp double buffering): the copy costs no registers and its
   // latency is hidden behind the scan instead of behind other warps.
-  const bool prefetch = spec.kind == KernelKind::kFilter && n_varlen > 0 && (spec.string_scan & 2) == 0;
+  const bool prefetch = spec.kind == KernelKind::kFilter && n_varlen > 0;
   const int n_stages = prefetch ? 2 : 1;
+  // fixed-width filters: 1024-row chunks every warp walks per tile (Configuration.stages; 1 unless asked)
+  const int W = (spec.kind != KernelKind::kFilter || n_varlen != 0) ? 1
+                : (spec.stages == 1 || spec.stages == 2 || spec.stages == 4 || spec.stages == 8) ? spec.stages
+                : (spec.large_batch ? 4 : 1);
   // per warp and string column: [stage bytes x stages][hit list + counters of the cooperative scan]
   const std::vector<CoopSeg>& coop = gen.coop_segs();
   const int hit_bytes = coop.empty() ? 0 : 8 * kHitCap + 16;  // candidates, hits, two counters
@@ -2299,7 +2494,6 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   src += spec.nullable ? " (inputs may carry validity bitmaps)\n" : " (no input has nulls)\n";
   for (size_t i = 0; i < exprs.size(); ++i)
     src += "// expr_" + std::to_string(i) + ": " + CommentSafe(exprs[i]->ToString()) + "\n";
-  if ((spec.string_scan & 8) != 0) src += "#define GDV_LOOKBACK_STRICT 1\n";
   src += "#include \"gdv_device_lib.cuh\"\n";
   src += EmitArgsStruct(L);
   src += gen.globals();
@@ -2311,7 +2505,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   bool light = spec.kind == KernelKind::kFilter && n_varlen == 0 && BT >= 256 && 2048 % BT == 0 &&
                !gen.uses_ctx() && body.size() < 6000;
   for (const auto& sl : slots) light = light && !sl.type.is_decimal();  // 128-bit math wants registers
-  if (spec.stages == 2 || spec.stages == 4 || spec.stages == 8) light = false;  // W-walk keeps 2 W more registers
+  if (W > 1) light = false;  // W chunks keep 2 W more registers
   if (light) bounds += ", " + std::to_string(2048 / BT);
   src += "extern \"C\" __global__ void __launch_bounds__(" + bounds + ") " + spec.name +
          "(const __grid_constant__ gdv_args A) {\n";
@@ -2492,44 +2686,36 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     src += "  }\n";
     src += "}\n";
   } else {
-    // Filter: every warp owns 1024 consecutive rows of the CTA tile (32 steps of 32 rows).
-    // Step k's keep-mask is one ballot word, parked in lane k, so the whole tile costs one
-    // register per thread regardless of its size; loads are issued R steps at a time for
-    // memory-level parallelism.  Large tiles (BT/32 * 1024 rows) keep the number of
-    // look-back descriptors per launch small, which is what bounds ordered compaction at
-    // B200 bandwidth (DESIGN.md "Filter kernel").
+    // Filter: every warp owns 1024 consecutive rows per chunk (32 steps of 32 rows).  Step k's
+    // keep-mask is one ballot word, parked in lane k, so a chunk costs one register per thread
+    // regardless of its size; loads are issued R steps at a time for memory-level parallelism.
+    // Large tiles keep the number of look-back descriptors per launch small, which is what bounds
+    // ordered compaction at B200 bandwidth (DESIGN.md "Filter kernel").
     const std::string IDX = SelCType(spec.selection_mode);
     const int NW = BT / 32;
-    // Optional (string_scan bit 2): every warp of a string filter is its own 1024-row tile with
-    // its own ticket and look-back, so no warp waits at a CTA barrier.  Measured slower than CTA
-    // tiles at 256/512 threads (0.268 vs 0.289 of peak, profiles/r01_string_filter.md): the barrier
-    // was not what bounds the kernel, and 16x more look-back descriptors cost more than it saves.
-    const bool warp_tiles = n_varlen > 0 && (spec.string_scan & 4) != 0;
-    // Optional (Configuration.stages = 2 / 4 / 8 on a fixed-width filter): every warp walks W
-    // consecutive 1024-row chunks per tile, so a 32K-row tile needs 256 / W ... threads instead of
-    // 1024 and eight small CTAs share an SM: while one of them sits in its tile-end barriers and
-    // look-back, seven keep streaming (with two 1024-thread CTAs per SM it is one of two).  Same
-    // single fused kernel, same descriptors per row; costs 2 W registers.  Not yet measured.
-    const int W = (n_varlen == 0 && (spec.stages == 2 || spec.stages == 4 || spec.stages == 8)) ? spec.stages : 1;
-    if (W > 1) {
-      const int WT = NW * 1024 * W;
-      const std::string sW = std::to_string(W);
-      const std::string walk_tail =
-          "          { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
-          results[0].v + ")); if (lane == (u32)(g + k)) cur = m; }\n";
-      src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
-      src += "  __shared__ i64 s_tile;\n";
-      src += "  __shared__ u64 s_excl;\n";
-      src += "  const i64 n_tiles = (A.n + " + std::to_string(WT - 1) + ") / " + std::to_string(WT) + ";\n";
-      src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
-      src += "  const u32 lt = gdv_lanemask_lt();\n";
-      src += "  while (true) {\n";
-      src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
-      src += "    __syncthreads();\n";
-      src += "    const i64 tile = s_tile;\n";
-      src += "    if (tile >= n_tiles) break;\n";
-      src += "    const i64 wbase0 = tile * " + std::to_string(WT) + " + (i64)wid * " + std::to_string(1024 * W) + ";\n";
-      src += "    u32 mymask[" + sW + "];\n";
+    const int WT = NW * 1024 * W;
+    const std::string sW = std::to_string(W);
+    src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
+    src += "  __shared__ i64 s_tile;\n";
+    src += "  __shared__ u64 s_excl;\n";
+    src += "  const i64 n_tiles = (A.n + " + std::to_string(WT - 1) + ") / " + std::to_string(WT) + ";\n";
+    src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
+    src += "  const u32 lt = gdv_lanemask_lt();\n";
+    src += "  while (true) {\n";
+    src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
+    src += "    __syncthreads();\n";
+    src += "    const i64 tile = s_tile;\n";
+    src += "    if (tile >= n_tiles) break;\n";
+    src += "    const i64 wbase0 = tile * " + std::to_string(WT) + " + (i64)wid * " + std::to_string(1024 * W) + ";\n";
+    src += "    u32 mymask[" + sW + "];\n";
+    const std::string step_tail =
+        "          { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
+        results[0].v + ")); if (lane == (u32)(g + k)) cur = m; }\n";
+    if (n_varlen == 0) {
+      // Fixed-width columns.  Every warp walks W consecutive 1024-row chunks per tile, so a
+      // 32K-row tile needs 256 threads at W = 4 and eight small CTAs share an SM: while one sits in
+      // its tile-end barriers and look-back, seven keep streaming (measured on Q6, 1e9 rows:
+      // 256 threads x W=4 x R=4 2.95 ms against 3.25 ms for 1024 threads x W=1, profiles/r02_q6_sweeps.md).
       src += "    #pragma unroll\n";
       src += "    for (int w = 0; w < " + sW + "; ++w) {\n";
       src += "      const i64 wbase = wbase0 + 1024 * w;\n";
@@ -2539,92 +2725,18 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
       src += "        const i64 base = wbase + 32 * g;\n";
       src += "        if (base >= A.n) break;\n";
       src += "        if (base + " + s32R + " <= A.n) {\n";
-      EmitGroup(slots, spec, R, kFast, body, walk_tail, &src, 5, 0, std::string(), coop);
+      EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 5, 0, std::string(), coop);
       src += "        } else {\n";
-      EmitGroup(slots, spec, R, kPred, body, walk_tail, &src, 5, 0, std::string(), coop);
+      EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 5, 0, std::string(), coop);
       src += "        }\n";
       src += "      }\n";
       src += "      mymask[w] = cur;\n";
       src += "    }\n";
-      // per chunk: lane k holds step k's mask; exclusive positions run over chunks, then steps
-      src += "    u32 step_excl[" + sW + "];\n";
-      src += "    u32 run = 0u;\n";
-      src += "    #pragma unroll\n";
-      src += "    for (int w = 0; w < " + sW + "; ++w) {\n";
-      src += "      const u32 c = (u32)__popc(mymask[w]);\n";
-      src += "      u32 incl = c;\n";
-      src += "      #pragma unroll\n";
-      src += "      for (int o = 1; o < 32; o <<= 1) {\n";
-      src += "        const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
-      src += "        if (lane >= (u32)o) incl += t;\n";
-      src += "      }\n";
-      src += "      step_excl[w] = run + incl - c;\n";
-      src += "      run += __shfl_sync(GDV_FULL, incl, 31);\n";
-      src += "    }\n";
-      src += "    if (lane == 0u) s_wcount[wid] = run;\n";
-      src += "    __syncthreads();\n";
-      src += "    if (wid == 0u) {\n";
-      src += "      const u32 wc = lane < " + std::to_string(NW) + "u ? s_wcount[lane] : 0u;\n";
-      src += "      u32 winc = wc;\n";
-      src += "      #pragma unroll\n";
-      src += "      for (int o = 1; o < 32; o <<= 1) {\n";
-      src += "        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);\n";
-      src += "        if (lane >= (u32)o) winc += t;\n";
-      src += "      }\n";
-      src += "      const u32 total = __shfl_sync(GDV_FULL, winc, 31);\n";
-      src += "      if (lane < " + std::to_string(NW) + "u) s_wcount[lane] = winc - wc;\n";
-      src += "      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);\n";
-      src += "      if (lane == 0u) {\n";
-      src += "        s_excl = excl;\n";
-      src += "        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;\n";
-      src += "      }\n";
-      src += "    }\n";
-      src += "    __syncthreads();\n";
-      src += "    const u64 wpos = s_excl + (u64)s_wcount[wid];\n";
-      src += "    if (run != 0u) {\n";
-      src += "      #pragma unroll\n";
-      src += "      for (int w = 0; w < " + sW + "; ++w) {\n";
-      src += "        if (__ballot_sync(GDV_FULL, mymask[w] != 0u) == 0u) continue;\n";
-      src += "        #pragma unroll 4\n";
-      src += "        for (int k = 0; k < 32; ++k) {\n";
-      src += "          const u32 m = __shfl_sync(GDV_FULL, mymask[w], k);\n";
-      src += "          const u32 off = __shfl_sync(GDV_FULL, step_excl[w], k);\n";
-      src += "          const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
-      src += "          if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
-      src += "            out_idx[pos] = (" + IDX + ")(A.row_base + wbase0 + 1024 * w + 32 * k + (i64)lane);\n";
-      src += "        }\n";
-      src += "      }\n";
-      src += "    }\n";
-      src += "  }\n";
-      src += "}\n";
     } else {
-    const int TILE = warp_tiles ? 1024 : NW * 1024;
-    const std::string step_tail =
-        "        { const u32 m = __ballot_sync(GDV_FULL, in && (" + results[0].ok + ") && (" +
-        results[0].v + ")); if (lane == (u32)(g + k)) mymask = m; }\n";
-    src += "  __shared__ u32 s_wcount[" + std::to_string(NW) + "];\n";
-    src += "  __shared__ i64 s_tile;\n";
-    src += "  __shared__ u64 s_excl;\n";
-    src += "  const i64 n_tiles = (A.n + " + std::to_string(TILE - 1) + ") / " +
-           std::to_string(TILE) + ";\n";
-    src += "  " + IDX + "* out_idx = reinterpret_cast<" + IDX + "*>(A.out_idx);\n";
-    src += "  const u32 lt = gdv_lanemask_lt();\n";
-    src += "  while (true) {\n";
-    if (warp_tiles) {
-      src += "    i64 tile = 0;\n";
-      src += "    if (lane == 0u) tile = (i64)atomicAdd(A.ticket, 1ull);\n";
-      src += "    tile = __shfl_sync(GDV_FULL, tile, 0);\n";
-      src += "    if (tile >= n_tiles) break;\n";
-      src += "    const i64 wbase = tile * 1024;\n";
-    } else {
-      src += "    if (threadIdx.x == 0) s_tile = (i64)atomicAdd(A.ticket, 1ull);\n";
-      src += "    __syncthreads();\n";
-      src += "    const i64 tile = s_tile;\n";
-      src += "    if (tile >= n_tiles) break;\n";
-      src += "    const i64 wbase = tile * " + std::to_string(TILE) + " + (i64)wid * 1024;\n";
-    }
-    src += "    u32 mymask = 0u;\n";
-    if (prefetch) {
+      // String columns: one 1024-row chunk per warp; the bytes of the NEXT group are copied into a
+      // second shared-memory stage with cp.async while the current group is scanned.
+      src += "    const i64 wbase = wbase0;\n";
+      src += "    u32 cur = 0u;\n";
       // issue(b, par): cp.async the bytes of the full group that starts at row b into stage `par`
       src += "    auto issue = [&](i64 b, u32 par) {\n";
       for (size_t j = 0; j < slots.size(); ++j) {
@@ -2647,19 +2759,15 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
       src += "    };\n";
       src += "    u32 par = 0u;\n";
       src += "    if (wbase + " + s32R + " <= A.n) issue(wbase, 0u);\n";
-    }
-    src += "    #pragma unroll 1\n";
-    src += "    for (int g = 0; g < 32; g += " + sR + ") {\n";
-    src += "      const i64 base = wbase + 32 * g;\n";
-    src += "      if (base >= A.n) break;\n";
-    if (prefetch) {
+      src += "    #pragma unroll 1\n";
+      src += "    for (int g = 0; g < 32; g += " + sR + ") {\n";
+      src += "      const i64 base = wbase + 32 * g;\n";
+      src += "      if (base >= A.n) break;\n";
       for (size_t j = 0; j < slots.size(); ++j)
         if (slots[j].type.is_varlen())
           src += "      u8* const stage" + std::to_string(j) + " = stage" + std::to_string(j) +
                  "_0 + (size_t)par * " + std::to_string(stage_bytes) + "u;\n";
-    }
-    src += "      if (base + " + s32R + " <= A.n) {\n";
-    if (prefetch) {
+      src += "      if (base + " + s32R + " <= A.n) {\n";
       src += "        if (g + " + sR + " < 32 && base + " + std::to_string(64 * R) + " <= A.n) {\n";
       src += "          issue(base + " + s32R + ", par ^ 1u);\n";
       src += "          gdv_cp_async_wait<1>();\n";
@@ -2668,84 +2776,16 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
       src += "        }\n";
       src += "        __syncwarp();\n";
       src += "        par ^= 1u;\n";
-    }
-    EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes, std::string(), coop, prefetch);
-    src += "      } else {\n";
-    EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 4, 0, std::string(), coop);
-    src += "      }\n";
-    src += "    }\n";
-    // lane k: c = selected rows of step k; exclusive scan over steps; warp total
-    src += "    const u32 c = (u32)__popc(mymask);\n";
-    src += "    u32 incl = c;\n";
-    src += "    #pragma unroll\n";
-    src += "    for (int o = 1; o < 32; o <<= 1) {\n";
-    src += "      const u32 t = __shfl_up_sync(GDV_FULL, incl, o);\n";
-    src += "      if (lane >= (u32)o) incl += t;\n";
-    src += "    }\n";
-    src += "    const u32 step_excl = incl - c;\n";
-    if (warp_tiles) {
-      src += "    const u32 wtotal = __shfl_sync(GDV_FULL, incl, 31);\n";
-      src += "    const u64 wpos = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)wtotal, lane);\n";
-      src += "    if (lane == 0u && tile == n_tiles - 1) *A.out_count = wpos + (u64)wtotal;\n";
-      src += "    if (wtotal != 0u) {\n";
-      src += "      #pragma unroll 4\n";
-      src += "      for (int k = 0; k < 32; ++k) {\n";
-      src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
-      src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
-      src += "        const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
-      src += "        if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
-      src += "          out_idx[pos] = (" + IDX + ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
+      EmitGroup(slots, spec, R, kFast, body, step_tail, &src, 4, stage_bytes, std::string(), coop, true);
+      src += "      } else {\n";
+      EmitGroup(slots, spec, R, kPred, body, step_tail, &src, 4, 0, std::string(), coop);
       src += "      }\n";
       src += "    }\n";
-      src += "  }\n";
-      src += "}\n";
-    } else {
-    src += "    if (lane == 31u) s_wcount[wid] = incl;\n";
-    src += "    __syncthreads();\n";
-    src += "    if (wid == 0u) {\n";
-    src += "      const u32 wc = lane < " + std::to_string(NW) + "u ? s_wcount[lane] : 0u;\n";
-    src += "      u32 winc = wc;\n";
-    src += "      #pragma unroll\n";
-    src += "      for (int o = 1; o < 32; o <<= 1) {\n";
-    src += "        const u32 t = __shfl_up_sync(GDV_FULL, winc, o);\n";
-    src += "        if (lane >= (u32)o) winc += t;\n";
-    src += "      }\n";
-    src += "      const u32 total = __shfl_sync(GDV_FULL, winc, 31);\n";
-    src += "      if (lane < " + std::to_string(NW) + "u) s_wcount[lane] = winc - wc;\n";
-    src += "      const u64 excl = gdv_tile_exclusive_prefix(A.tile_state, tile, (u64)total, lane);\n";
-    src += "      if (lane == 0u) {\n";
-    src += "        s_excl = excl;\n";
-    src += "        if (tile == n_tiles - 1) *A.out_count = excl + (u64)total;\n";
-    src += "      }\n";
-    src += "    }\n";
-    src += "    __syncthreads();\n";
-    src += "    const u64 wpos = s_excl + (u64)s_wcount[wid];\n";
-    src += "    const u32 wtotal = __shfl_sync(GDV_FULL, incl, 31);\n";
-    // The whole run of this warp fits the vector (always, unless GDV_SEL_BOUNDED): 32-bit offsets
-    // from one 64-bit base and no per-row capacity test.
-    src += "    if (wtotal != 0u && wpos + (u64)wtotal <= (u64)A.out_cap) {\n";
-    src += "      " + IDX + "* const wout = out_idx + wpos;\n";
-    src += "      #pragma unroll 4\n";
-    src += "      for (int k = 0; k < 32; ++k) {\n";
-    src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
-    src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
-    src += "        if ((m >> lane) & 1u)\n";
-    src += "          wout[off + (u32)__popc(m & lt)] = (" + IDX + ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
-    src += "      }\n";
-    src += "    } else if (wtotal != 0u) {\n";
-    src += "      #pragma unroll 1\n";
-    src += "      for (int k = 0; k < 32; ++k) {\n";
-    src += "        const u32 m = __shfl_sync(GDV_FULL, mymask, k);\n";
-    src += "        const u32 off = __shfl_sync(GDV_FULL, step_excl, k);\n";
-    src += "        const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
-    src += "        if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
-    src += "          out_idx[pos] = (" + IDX + ")(A.row_base + wbase + 32 * k + (i64)lane);\n";
-    src += "      }\n";
-    src += "    }\n";
+      src += "    mymask[0] = cur;\n";
+    }
+    EmitFilterEpilogue(slots, spec, NW, W, IDX, &src);
     src += "  }\n";
     src += "}\n";
-    }  // !warp_tiles
-    }  // W == 1
   }
 
   out->source = std::move(src);
@@ -2764,11 +2804,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   out->out_bytes_per_row = out_bytes;
   out->args_size = L.size;
   out->dynamic_smem = dynamic_smem;
-  const int walk = (spec.kind == KernelKind::kFilter && n_varlen == 0 &&
-                    (spec.stages == 2 || spec.stages == 4 || spec.stages == 8)) ? spec.stages : 1;
-  out->tile_rows = spec.kind == KernelKind::kFilter
-                       ? ((n_varlen > 0 && (spec.string_scan & 4) != 0) ? 1024 : static_cast<int64_t>(BT / 32) * 1024 * walk)
-                       : 0;
+  out->tile_rows = spec.kind == KernelKind::kFilter ? static_cast<int64_t>(BT / 32) * 1024 * W : 0;
   out->staged = staged;
   out->stages = staged ? S : 0;
   out->cta_tile_rows = static_cast<int64_t>(BT) * R;

@@ -37,18 +37,24 @@ struct KernelSpec {
   KernelKind kind = KernelKind::kProject;
   int selection_mode = GDV_SEL_NONE;  // project: input selection; filter: output index width
   int rows_per_thread = 0;            // 0 = pick from bytes/row
-  int block_threads = 256;
+  int block_threads = 0;              // 0 = pick per kernel shape
+  bool large_batch = false;           // filter: the batch has >= 32 M rows (big tiles)
   std::string name;                   // kernel symbol
   bool nullable = true;               // false: specialised for batches where no input has nulls
   int loader = 0;                     // 0 = engine picks, 1 = direct LDG, 2 = TMA bulk -> shared
-  int stages = 0;                     // TMA loader: shared-memory stages per CTA (0 = pick)
-  int string_scan = 0;                // 0 = engine picks (cooperative LIKE scan), 1 = per-lane only
-  int key_scan_seg = 0;               // key-scan filter: bytes of the data buffer per warp and tile
+  int stages = 0;                     // projector, TMA loader: shared-memory stages per CTA (0 = pick);
+                                      // fixed-width filter: 1024-row chunks every warp walks per tile (1/2/4/8)
+  int string_scan = 0;                // bit 0: LIKE with the per-lane matcher only (no cooperative scan);
+                                      // bit 2: row-driven string filter even where the key-driven one applies
 };
 
 struct ColumnSlot {
   int schema_index;
   DataType type;
+  // Filter kernels: a null in this column makes the condition not-true whatever the other columns
+  // hold, so its validity is ANDed into the tile's keep-mask 32 rows at a time after the row loop
+  // instead of being read per row (BodyGen::TruthStrict).
+  bool hoist = false;
 };
 
 struct GeneratedKernel {
@@ -67,7 +73,7 @@ struct GeneratedKernel {
   size_t args_size = 0;             // sizeof(gdv_args) for this kernel
   int dynamic_smem = 0;             // bytes of dynamic shared memory (string staging)
   int64_t tile_rows = 0;            // filter: rows per CTA tile (one look-back descriptor each)
-  int64_t tile_bytes = 0;           // key-scan filter: bytes of the string column per CTA tile (tile_rows == 0)
+  bool key_driven = false;          // string filter driven by the occurrences of a literal key in the column's bytes
   bool staged = false;              // project: inputs staged through shared memory by TMA bulk copies
   int stages = 0;                   // staged: shared-memory stages per CTA
   int64_t cta_tile_rows = 0;        // staged: rows per CTA tile (block_threads * rows_per_thread)

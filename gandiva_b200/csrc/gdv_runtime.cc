@@ -261,11 +261,11 @@ Status BuildKernel(const Schema& schema, const std::vector<ExpressionPtr>& exprs
   spec.nullable = nullable;
   spec.selection_mode = selection_mode;
   spec.rows_per_thread = cfg.rows_per_thread;
-  spec.block_threads = cfg.block_threads > 0 ? cfg.block_threads : 256;
+  spec.block_threads = cfg.block_threads;  // 0: the fuser picks per kernel shape
   spec.loader = cfg.loader;
   spec.stages = cfg.stages;
   spec.string_scan = cfg.string_scan;
-  spec.key_scan_seg = cfg.key_scan_seg;
+  spec.large_batch = cfg.large_batch;
   const std::string placeholder = std::string(KernelPrefix(kind)) + "PLACEHOLDER";
   spec.name = placeholder;
   std::unique_ptr<CompiledKernel> k(new CompiledKernel());
@@ -954,19 +954,10 @@ Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** o
   if (it == kernels_.end()) {
     std::unique_ptr<CompiledKernel> k;
     std::vector<ExpressionPtr> exprs = {cond_};
-    // Tile = block_threads / 32 * 1024 rows.  Big batches want big tiles (few look-back
-    // descriptors: 94% of HBM peak at 1024 threads vs 88% at 256 on Q6, profiles/r01_sweeps.md);
-    // small batches want enough tiles to occupy the 148 SMs.
+    // Big batches want big tiles (few look-back descriptors), small ones enough tiles to occupy the
+    // 148 SMs: the fuser picks block size and chunks per warp from this flag (GenerateKernelImpl).
     Config cfg = cfg_;
-    // String predicates are instruction-bound and stage bytes per warp in shared memory: 512
-    // threads measured best at every batch size (profiles/r01_string_filter.md).
-    bool has_varlen = false;
-    for (const auto& f : schema_->fields()) has_varlen = has_varlen || f.type.is_varlen();
-    if (cfg.block_threads == 0)
-      cfg.block_threads = large ? (has_varlen ? 512 : 1024) : 256;
-    // key-scan filters (string_scan bit 4): 64 KB of the string column per warp and tile on big
-    // batches (few look-back descriptors), 4 KB on small ones (enough tiles for 148 SMs)
-    cfg.key_scan_seg = large ? 65536 : 4096;
+    cfg.large_batch = large;
     GDV_RETURN_NOT_OK(BuildKernel(*schema_, exprs, KernelKind::kFilter, mode, nullable, cfg, &k));
     it = kernels_.emplace(key, std::move(k)).first;
   }
@@ -1019,9 +1010,6 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   const bool large = batch->num_rows >= (int64_t(32) << 20);
   GDV_RETURN_NOT_OK(
       KernelFor(sel_mode, AnyValidity(general->gen, batch), large, &kernel));
-  if (cfg_.loader == 3 && !host)
-    return EvaluateTwoPass(batch, out_sel, sel_mode, bounded, AnyValidity(general->gen, batch), stream_v,
-                           async, d_count_user);
   last_used_ = kernel;
   CompiledKernel::Loaded l;
   GDV_RETURN_NOT_OK(kernel->Load(dev, &l));
@@ -1033,11 +1021,9 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
 
-  // Row tiles: ceil(n / tile_rows) descriptors.  Key-scan kernels tile the BYTES of a string
-  // column, whose amount the host does not know for device batches: int32 offsets bound it.
+  // Row tiles: ceil(n / tile_rows) look-back descriptors.
   const int64_t tile_rows = gen.tile_rows;
-  const int64_t n_tiles = tile_rows > 0 ? (n + tile_rows - 1) / tile_rows
-                                        : ((int64_t(1) << 31) / gen.tile_bytes + 2);
+  const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
 
   // Per-stream persistent scratch: [ticket u64][count u64][tile_state n_tiles x u64]
   const size_t state_bytes = 16 + static_cast<size_t>(n_tiles) * 8;
@@ -1118,78 +1104,6 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   return Status::OK();
 }
 
-Status Filter::EvaluateTwoPass(const gdv_batch_t* batch, gdv_selection_t* out_sel, int sel_mode,
-                               bool bounded, bool any_validity, void* stream_v, bool async,
-                               void* d_count_user) {
-  const int64_t n = batch->num_rows;
-  Device* dev = nullptr;
-  GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
-  const DriverApi& d = Driver();
-  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
-  {
-    std::lock_guard<std::mutex> lock(mu_);
-    if (truth_proj_ == nullptr) {
-      Config pc = cfg_;
-      pc.loader = 0;  // the projector picks its own loader
-      std::vector<ExpressionPtr> one = {std::make_shared<Expression>(cond_->root(), Field{"cond", boolean()})};
-      GDV_RETURN_NOT_OK(Projector::Make(schema_, std::move(one), GDV_SEL_NONE, pc, &truth_proj_));
-    }
-  }
-  const size_t words = static_cast<size_t>((n + 31) / 32);
-  const int64_t tile_words = 256 * 16;  // GDV_B2S_WPT words per thread, 256 threads
-  const int64_t n_tiles = (static_cast<int64_t>(words) + tile_words - 1) / tile_words;
-  const size_t state_bytes = 16 + static_cast<size_t>(n_tiles) * 8;
-  CUdeviceptr d_state = 0, d_data = 0, d_vld = 0;
-  {
-    std::lock_guard<std::mutex> lock(mu_);
-    Pending& pend = pending_[stream];
-    pend.dev = dev;
-    // per-launch blocks, alive until Sync(): queued launches may still be using earlier ones
-    GDV_RETURN_NOT_OK(dev->Alloc(state_bytes, &d_state));
-    pend.scratch.push_back(d_state);
-    GDV_RETURN_NOT_OK(dev->Alloc(words * 4 + 64, &d_data));
-    pend.scratch.push_back(d_data);
-    if (any_validity) {
-      GDV_RETURN_NOT_OK(dev->Alloc(words * 4 + 64, &d_vld));
-      pend.scratch.push_back(d_vld);
-    }
-    pend.d_count = d_count_user != nullptr ? reinterpret_cast<CUdeviceptr>(d_count_user) : d_state + 8;
-  }
-  GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(d_state, 0, state_bytes, stream), "memset tile state"));
-  CUdeviceptr d_count = d_state + 8;
-  if (d_count_user != nullptr) {
-    d_count = reinterpret_cast<CUdeviceptr>(d_count_user);
-    GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(d_count, 0, 8, stream), "memset count"));
-  }
-  // pass 1: condition -> value bits (+ validity bits when some input carries a bitmap)
-  gdv_out_column_t truth;
-  std::memset(&truth, 0, sizeof(truth));
-  truth.values = reinterpret_cast<void*>(d_data);
-  truth.validity = any_validity ? reinterpret_cast<void*>(d_vld) : nullptr;
-  GDV_RETURN_NOT_OK(truth_proj_->Evaluate(batch, nullptr, &truth, 1, stream, /*async=*/true));
-  last_used_ = &truth_proj_->kernel();
-  // pass 2: bitmap -> ascending row indices
-  CUfunction fn = nullptr;
-  GDV_RETURN_NOT_OK(dev->StaticFunction("gdv_bitmap_to_sel", &fn));
-  int64_t nn = n, row_base = out_sel->index_base, out_cap = bounded ? out_sel->max_slots : n;
-  CUdeviceptr d_idx = reinterpret_cast<CUdeviceptr>(out_sel->indices);
-  int elem_bytes = SelWidth(sel_mode);
-  CUdeviceptr tiles = d_state + 16, ticket = d_state;
-  void* params[] = {&d_data, &d_vld, &nn, &row_base, &d_idx, &elem_bytes, &out_cap, &d_count, &tiles, &ticket};
-  const int64_t cap = static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * 8;
-  const unsigned grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, cap)));
-  g_launch_count.fetch_add(1);
-  GDV_RETURN_NOT_OK(CuCheck(d.LaunchKernel(fn, grid, 1, 1, 256, 1, 1, 0, stream, params, nullptr),
-                            "cuLaunchKernel(gdv_bitmap_to_sel)"));
-  out_sel->num_slots = -1;
-  if (!async) {
-    int64_t count = 0;
-    GDV_RETURN_NOT_OK(Sync(stream, &count));
-    out_sel->num_slots = count;
-  }
-  return Status::OK();
-}
-
 Status Filter::Sync(void* stream_v, int64_t* num_slots) {
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
@@ -1220,12 +1134,6 @@ Status Filter::Sync(void* stream_v, int64_t* num_slots) {
   }
   GDV_RETURN_NOT_OK(s);
   if (err != 0) return Status::Make(GDV_EXECUTION_ERROR, ExecutionErrorMessage(err));
-  std::shared_ptr<Projector> tp;
-  {
-    std::lock_guard<std::mutex> lock(mu_);
-    tp = truth_proj_;
-  }
-  if (tp != nullptr) GDV_RETURN_NOT_OK(tp->Sync(stream_v));  // pass 1 of a two-pass filter: its errors
   if (num_slots != nullptr) *num_slots = have ? static_cast<int64_t>(count) : -1;
   return Status::OK();
 }

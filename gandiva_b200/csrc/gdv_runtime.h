@@ -90,7 +90,7 @@ struct Config {
   int stages = 0;
   int sm_reserve = 0;
   int string_scan = 0;
-  int key_scan_seg = 0;  // set per kernel variant by Filter::KernelFor
+  bool large_batch = false;  // set per kernel variant by Filter::KernelFor (batches >= 32 M rows)
 };
 
 class CompiledKernel {
@@ -188,13 +188,6 @@ class Filter {
   CompiledKernel* last_used() const { return last_used_.load(); }
 
  private:
-  // Configuration.loader = 3, device batches: the condition is evaluated by a Projector kernel
-  // into a truth bitmap (pass 1, no tile waits for another), gdv_bitmap_to_sel turns the bitmap
-  // into the ordered SelectionVector (pass 2).
-  Status EvaluateTwoPass(const gdv_batch_t* batch, gdv_selection_t* out_sel, int sel_mode,
-                         bool bounded, bool any_validity, void* stream, bool async,
-                         void* d_count_user);
-  std::shared_ptr<Projector> truth_proj_;
   std::atomic<CompiledKernel*> last_used_{nullptr};
   SchemaPtr schema_;
   ConditionPtr cond_;

@@ -105,24 +105,18 @@ typedef struct gdv_config {
   int32_t device;       /* CUDA device ordinal (default 0) */
   int32_t rows_per_thread; /* 0 = engine picks; otherwise unroll factor override */
   int32_t block_threads;   /* 0 = engine picks (256) */
-  int32_t loader;          /* Projector: 0 = engine picks; 1 = direct coalesced LDG; 2 = TMA bulk -> shared.
-                              Filter: 3 = two-pass on device batches (condition -> truth bitmap by the
-                              projector kernel, bitmap -> SelectionVector by gdv_bitmap_to_sel); opt-in
-                              until measured against the fused filter kernel */
+  int32_t loader;          /* Projector: 0 = engine picks; 1 = direct coalesced LDG; 2 = TMA bulk -> shared */
   int32_t sm_reserve;      /* SMs left without CTAs of the persistent kernels, so that a
-                              concurrent stream (e.g. NCCL's gather of the previous batch's
+                              concurrent stream (e.g. the push of the previous batch's
                               SelectionVector) can run; default 0 */
   int32_t stages;          /* Projector, TMA loader: shared-memory stages per CTA (0 = engine picks).
-                              Fixed-width Filter: 2 / 4 / 8 = 1024-row chunks every warp walks per tile
-                              (smaller CTAs for the same tile; opt-in until measured) */
+                              Fixed-width Filter: 1 / 2 / 4 / 8 = 1024-row chunks every warp walks per
+                              tile (0 = engine picks: 4 on batches >= 32 M rows, else 1) */
   int32_t string_scan;     /* string columns, bit mask; 0 = engine picks (everything on):
                               bit 0: LIKE with the per-lane matcher only (no warp-cooperative scan),
-                              bit 1: filters stage string bytes without the cp.async prefetch,
-                              bit 2: string filters use one 1024-row tile per warp,
-                              bit 3: look-back waits for its whole 32-tile window (A/B switch),
-                              bit 4: key-scan filter: a condition with a LIKE conjunct over a literal
-                                     segment is driven by that segment's occurrences in the column's
-                                     bytes instead of by rows (opt-in until measured on B200) */
+                              bit 2: row-driven string Filter kernel even where the condition implies a
+                                     literal and the key-driven kernel (driven by the literal's
+                                     occurrences in the column's bytes) would apply */
   int32_t reserved[3];
 } gdv_config_t;
 void gdv_config_default(gdv_config_t* cfg);

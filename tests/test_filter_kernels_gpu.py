@@ -1,7 +1,8 @@
-"""Parity tests of the OPT-IN kernel variants (none is a default): the key-scan string filter
-(string_scan bit 4), the two-pass filter (Configuration(loader=3)) and the W-walk filter tiles
-(Configuration(stages=W)).  Same bar as test_parity_gpu.py -- bit-exact against the oracle through
-the C-ABI -- kept in a file that sorts last so that the default paths are judged first."""
+"""Parity tests of the Filter kernel shapes: the key-driven string filter (default wherever the
+condition implies a literal; Configuration(string_scan=4) keeps the row-driven kernel, which must
+agree), the fixed-width filter with W chunks per warp (Configuration(stages=W); W=4 is what big
+batches get) and the validity words hoisted out of the row loop.  Same bar as test_parity_gpu.py:
+bit-exact against the oracle through the C-ABI."""
 import numpy as np
 import pyarrow as pa
 import pytest
@@ -20,16 +21,18 @@ KEY_SCAN_CASES = [cases.case_like_scan(p, v, "filter") for p, v in
 
 
 @pytest.mark.parametrize("case", KEY_SCAN_CASES, ids=[c.__name__ for c in KEY_SCAN_CASES])
-def test_key_scan_filter(case, gandiva, oracle):
-    """string_scan bit 4: the filter is driven by the occurrences of a literal LIKE segment in the
-    column's bytes (rows without one are never looked at).  Same answers as the oracle on sparse
-    and dense matches (list overflow -> second pass), rows longer than a segment, non-ASCII text,
-    sliced arrays, 16/32/64-bit indices and a row base."""
+def test_key_driven_filter(case, gandiva, oracle):
+    """The filter is driven by the occurrences of a literal LIKE segment in the column's bytes (rows
+    without one are never looked at).  Same answers as the oracle -- and as the row-driven kernel --
+    on sparse and dense matches (anchor list drained many times / overflowing), long rows, non-ASCII
+    text, sliced arrays and 16/32/64-bit indices."""
     b = gandiva.TreeExprBuilder()
     schema, outs, _ = case(b)
     cond = outs[0][0]
-    f = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(string_scan=16))
-    assert "key-scan string Filter" in f.llvm_ir
+    f = gandiva.make_filter(schema, b.make_condition(cond))
+    assert "key-driven string Filter" in f.llvm_ir
+    f_rows = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(string_scan=4))
+    assert "key-driven string Filter" not in f_rows.llvm_ir
     for n, seed, offset, dense, long_rows in [(1, 1, 0, False, False), (64, 1, 0, False, False),
                                               (5000, 2, 0, False, False), (20011, 3, 7, True, False),
                                               (9000, 4, 1, False, True), (60_001, 5, 3, True, True)]:
@@ -39,16 +42,17 @@ def test_key_scan_filter(case, gandiva, oracle):
             sel = f.evaluate(batch, None, dtype)
             assert sel.num_slots == len(want), (n, dtype, sel.num_slots, len(want))
             assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want), (n, dtype)
+        assert np.array_equal(f_rows.evaluate(batch).to_array().to_numpy().astype(np.uint64), want), n
 
 
-def test_key_scan_filter_conjunction_and_fallback(gandiva, oracle):
+def test_key_driven_filter_conjunction_and_fallback(gandiva, oracle):
     """The LIKE may sit anywhere on the AND spine next to other predicates (evaluated for the
     candidate rows only); conditions that do not imply a key keep the row-driven kernel."""
     b = gandiva.TreeExprBuilder()
     cond = cases.comment_condition(b)
-    cfg = gandiva.Configuration(string_scan=16)
+    cfg = None
     f = gandiva.make_filter(cases.COMMENT_SCHEMA, b.make_condition(cond), cfg)
-    assert "key-scan string Filter" in f.llvm_ir
+    assert "key-driven string Filter" in f.llvm_ir and "'REQUESTS'" in f.llvm_ir
     for n in (70_001, 300_000):
         batch = cases.comment_batch(n, seed=n)
         want = oracle.filter_indices(cond, batch, threads=4)
@@ -63,7 +67,7 @@ def test_key_scan_filter_conjunction_and_fallback(gandiva, oracle):
     either = b.make_or([small, like])
     batch = cases.random_batch(schema, 30_011, seed=9, null_prob=0.1, offset=5)
     f_and = gandiva.make_filter(schema, b.make_condition(both), cfg)
-    assert "key-scan string Filter" in f_and.llvm_ir
+    assert "key-driven string Filter" in f_and.llvm_ir
     assert np.array_equal(f_and.evaluate(batch).to_array().to_numpy().astype(np.uint64),
                           oracle.filter_indices(both, batch, threads=4))
     # other ways of saying "the column holds this literal": is_substr / starts_with / ends_with / equal
@@ -72,24 +76,25 @@ def test_key_scan_filter_conjunction_and_fallback(gandiva, oracle):
         arg = s if view is None else b.make_function(view, [s], S)
         c2 = b.make_and([b.make_function(fname, [arg, b.make_literal(lit, S)], B), b.make_function("isnotnull", [k], B)])
         f2 = gandiva.make_filter(schema, b.make_condition(c2), cfg)
-        assert "key-scan string Filter" in f2.llvm_ir, fname
+        assert "key-driven string Filter" in f2.llvm_ir, fname
         want2 = oracle.filter_indices(c2, batch, threads=4)
         assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want2), fname
     f_or = gandiva.make_filter(schema, b.make_condition(either), cfg)
-    assert "key-scan string Filter" not in f_or.llvm_ir   # an OR does not imply the key
+    assert "key-driven string Filter" not in f_or.llvm_ir   # an OR does not imply the key
     assert np.array_equal(f_or.evaluate(batch).to_array().to_numpy().astype(np.uint64),
                           oracle.filter_indices(either, batch, threads=4))
 
 
-def test_key_scan_filter_dense_and_empty(gandiva, oracle):
-    """More accepted rows per warp segment than the shared-memory list holds (second, direct-write
-    pass over the tile), a column of empty strings (no bytes at all), and a bounded vector."""
+def test_key_driven_filter_dense_and_empty(gandiva, oracle):
+    """More anchors per warp than the shared-memory list holds (many drains; with every chunk full
+    of matches the warp evaluates all its rows), a column of empty strings (no bytes at all), a
+    3-byte key (halfword test + verification) and rows with several occurrences."""
     b = gandiva.TreeExprBuilder()
     S, B = pa.string(), pa.bool_()
     schema = pa.schema([("s", S)])
     cond = b.make_function("like", [cases.F(b, "s", S), b.make_literal("%ark%", S)], B)
-    f = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(string_scan=16))
-    assert "key-scan string Filter" in f.llvm_ir
+    f = gandiva.make_filter(schema, b.make_condition(cond))
+    assert "key-driven string Filter" in f.llvm_ir
     rng = np.random.default_rng(3)
     rows = [None if rng.random() < 0.02 else ("ark" if rng.random() < 0.97 else "xy") for _ in range(40_003)]
     batch = pa.RecordBatch.from_arrays([pa.array(rows, S)], schema=schema)
@@ -99,68 +104,62 @@ def test_key_scan_filter_dense_and_empty(gandiva, oracle):
     assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
     empty = pa.RecordBatch.from_arrays([pa.array([""] * 1000 + [None] * 5, S)], schema=schema)
     assert f.evaluate(empty).num_slots == 0
-    # big segments / big CTAs (the variant large batches get): rows_per_thread = KB per warp segment
-    for bt, seg_kb in ((1024, 64), (64, 1), (512, 16)):
-        f2 = gandiva.make_filter(schema, b.make_condition(cond),
-                                 gandiva.Configuration(string_scan=16, block_threads=bt, rows_per_thread=seg_kb))
-        assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want), (bt, seg_kb)
+    for bt in (1024, 64, 512):
+        f2 = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(block_threads=bt))
+        assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want), bt
+    # a long key in every row: far more than 128 anchors per 2 KB of bytes -> the all-rows fallback
+    cond8 = b.make_function("like", [cases.F(b, "s", S), b.make_literal("%requests%", S)], B)
+    f8 = gandiva.make_filter(schema, b.make_condition(cond8))
+    assert "key-driven string Filter" in f8.llvm_ir
+    full = pa.RecordBatch.from_arrays([pa.array(["requestsrequests", "xrequests", None, "request"] * 9000, S)], schema=schema)
+    assert np.array_equal(f8.evaluate(full).to_array().to_numpy().astype(np.uint64), oracle.filter_indices(cond8, full, threads=4))
     # "arkark": two occurrences in one row, the row is reported once
     twice = pa.RecordBatch.from_arrays([pa.array(["arkark", "xarkxxark", "ar", "k", "ark"] * 700, S)], schema=schema)
     sel = f.evaluate(twice)
     assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), oracle.filter_indices(cond, twice))
 
 
-@pytest.mark.parametrize("nullp", [0, 15])
-def test_two_pass_filter(nullp, gandiva, oracle):
-    """Configuration(loader=3) on device batches: condition -> truth bitmap with the projector
-    kernel, bitmap -> ordered SelectionVector with gdv_bitmap_to_sel.  Same indices as the oracle
-    for every index width, with a row base and a bounded vector, at tile and word boundaries."""
-    b = gandiva.TreeExprBuilder()
-    cond = cases.q6_condition(b)
-    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cond), gandiva.Configuration(loader=3))
-    st = devmem.stream()
-    for n in (1, 31, 32, 33, 4095, 131072, 131073, 300_011):
-        ship, disc, qty = devmem.DevBuf(n, np.int32), devmem.DevBuf(n, np.float64), devmem.DevBuf(n, np.float64)
-        vl = [devmem.DevBuf((n + 31) // 32, np.int32) if nullp else None for _ in range(3)]
-        for kind, t, v in ((0, ship, vl[0]), (1, disc, vl[1]), (2, qty, vl[2])):
-            gandiva.generate_lineitem(0, kind, 42, 0, n, t.ptr, v.ptr if v is not None else 0, nullp, st)
-        cols = [(v.ptr if v is not None else 0, t.ptr, 0, 0) for t, v in zip((ship, disc, qty), vl)]
-        batch = cases.q6_batch(n, seed=42, null_permille=nullp)
-        want = oracle.filter_indices(cond, batch, threads=4)
-        modes = [("UINT32", np.uint32, 0), ("UINT64", np.uint64, 7_000_000_000)]
-        if n <= 65536:
-            modes.append(("UINT16", np.uint16, 0))
-        for mode, npdt, base in modes:
-            out = devmem.DevBuf(n + 8, npdt, fill=0)
-            cnt = devmem.DevBuf(1, np.int64, fill=0)
-            f.evaluate_device(n, cols, out.ptr, n, mode, st, cnt.ptr, index_base=base)
-            count = f.sync(st)
-            assert count == len(want) == int(cnt.numpy()[0]), (n, mode)
-            assert np.array_equal(out.numpy()[:count].astype(np.uint64), want + base), (n, mode)
-        if n > 1000:
-            cap = max(1, len(want) // 2)
-            out = devmem.DevBuf(cap + 16, np.int64, fill=-1)
-            cnt = devmem.DevBuf(1, np.int64, fill=0)
-            f.evaluate_device(n, cols, out.ptr, cap, "UINT64|BOUNDED", st, cnt.ptr)
-            assert f.sync(st) == len(want)
-            got = out.numpy()
-            assert np.array_equal(got[:cap].astype(np.uint64), want[:cap]) and (got[cap:] == -1).all()
-    assert "gdv_project_expr_" in f.kernel_info["name"]
-
-
-@pytest.mark.parametrize("walk,bt", [(2, 256), (4, 256), (8, 128), (4, 64)])
+@pytest.mark.parametrize("walk,bt", [(1, 256), (2, 256), (4, 256), (8, 128), (4, 64), (1, 1024)])
 def test_filter_walk_variant(walk, bt, gandiva, oracle):
     """Configuration(stages = W) on a fixed-width filter: every warp walks W 1024-row chunks per
     tile (same fused kernel, smaller CTAs).  Same indices as the oracle, tails and bounded vectors."""
     b = gandiva.TreeExprBuilder()
     cond = cases.q6_condition(b)
     f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cond), gandiva.Configuration(stages=walk, block_threads=bt))
-    assert "mymask[%d]" % walk in f.llvm_ir
+    assert "u32 mymask[%d];" % walk in f.llvm_ir
     for n, nullp in ((1, 0), (1023, 10), (1024 * walk * (bt // 32) + 5, 0), (300_007, 15)):
         batch = cases.q6_batch(n, seed=7, null_permille=nullp)
         want = oracle.filter_indices(cond, batch, threads=4)
         for dtype in ("int32", "int64"):
             sel = f.evaluate(batch, None, dtype)
             assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want), (n, nullp, dtype)
+
+
+def test_filter_hoisted_validity(gandiva, oracle):
+    """Columns whose NULL makes the condition not-true lose their per-row validity loads: their bitmap
+    words are ANDed into the keep-mask after the row loop (gdv_ldwin_rows).  Q6 hoists all three
+    columns; an OR keeps the per-row form for the column only one side needs; sliced batches (validity
+    offsets that are not multiples of 8 or 32) and every tail length must agree with the oracle."""
+    b = gandiva.TreeExprBuilder()
+    cond = cases.q6_condition(b)
+    f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cond))
+    src = f.llvm_ir
+    assert src.count("gdv_ldwin_rows(") == 3 and "gdv_ldwin(in_vp" not in src
+    full = cases.q6_batch(70_000, seed=11, null_permille=200)
+    for off, n in ((0, 70_000), (1, 1), (3, 33), (5, 1024), (7, 1025), (31, 2047), (33, 32_768), (64, 65_536 + 13), (13, 69_000)):
+        batch = full.slice(off, n)
+        want = oracle.filter_indices(cond, batch, threads=2)
+        got = f.evaluate(batch).to_array().to_numpy().astype(np.uint64)
+        assert np.array_equal(got, want), (off, n)
+    # a OR (b AND c): nothing is strict in every branch except what both sides share
+    t, B = pa.int32(), pa.bool_()
+    schema = pa.schema([("a", t), ("b", t), ("c", t)])
+    A_, B_, C_ = (cases.F(b, x, t) for x in "abc")
+    lt = lambda x, v: b.make_function("less_than", [x, b.make_literal(v, t)], B)   # noqa: E731
+    mixed = b.make_and([lt(A_, 0), b.make_or([lt(B_, 0), b.make_and([lt(C_, 0), b.make_function("isnull", [B_], B)])])])
+    fm = gandiva.make_filter(schema, b.make_condition(mixed))
+    assert fm.llvm_ir.count("gdv_ldwin_rows(") == 1      # only `a` is strict
+    rb = cases.random_batch(schema, 50_021, seed=4, null_prob=0.3, offset=9)
+    assert np.array_equal(fm.evaluate(rb).to_array().to_numpy().astype(np.uint64), oracle.filter_indices(mixed, rb, threads=2))
 
 

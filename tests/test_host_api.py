@@ -185,7 +185,7 @@ def test_like_scan_kernels_compile(gandiva):
         b = gandiva.TreeExprBuilder()
         schema, outs, kind = case(b)
         for scan in (0, 1):
-            cfg = gandiva.Configuration(string_scan=scan)
+            cfg = gandiva.Configuration(string_scan=scan | 4)   # bit 2: the row-driven filter kernel
             if kind == "project":
                 src = gandiva.make_projector(schema, [b.make_expression(outs[0][0], pa.field("o", pa.bool_()))],
                                              None, "NONE", cfg).llvm_ir

@@ -120,11 +120,13 @@ def test_like_cooperative_scan(case, gandiva, oracle):
 
 @pytest.mark.parametrize("bt,rpt", [(256, 2), (512, 2), (1024, 2), (512, 4), (256, 1)])
 def test_like_scan_filter(bt, rpt, gandiva, oracle):
-    """The config-4 condition as a Filter on l_comment-like rows, block sizes and rows/thread."""
+    """The config-4 condition as a Filter on l_comment-like rows through the ROW-DRIVEN string kernel
+    (string_scan bit 2; the key-driven default is covered by test_filter_kernels_gpu.py): cooperative
+    scan + cp.async stages at several block sizes and rows/thread."""
     b = gandiva.TreeExprBuilder()
     cond = cases.comment_condition(b)
     f = gandiva.make_filter(cases.COMMENT_SCHEMA, b.make_condition(cond),
-                            gandiva.Configuration(rows_per_thread=rpt, block_threads=bt))
+                            gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, string_scan=4))
     assert "gdv_likeh_" in f.llvm_ir
     for n in (70_001, 300_000):
         batch = cases.comment_batch(n, seed=bt + rpt)

@@ -132,7 +132,7 @@ def test_random_filter_trees(seed, gandiva, oracle):
     b = gandiva.TreeExprBuilder()
     g = TreeGen(gandiva, b, rng)
     cond = g.gen(B, int(rng.integers(2, 5)))
-    cfg = gandiva.Configuration(string_scan=16) if seed % 2 else None   # odd seeds: key-scan when it applies
+    cfg = gandiva.Configuration(string_scan=4) if seed % 2 else None   # odd seeds: the row-driven kernel even where a key would drive it
     f = gandiva.make_filter(SCHEMA, b.make_condition(cond), cfg)
     for n in (1, 2000 + seed, 9001):
         batch = _batch(n, seed + n)
