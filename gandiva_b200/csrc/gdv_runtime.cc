@@ -1,5 +1,7 @@
 #include "gdv_runtime.h"
 
+#include "gdv_staging.h"
+
 #include <unistd.h>
 
 #include <algorithm>
@@ -79,6 +81,7 @@ Status Device::Get(int ordinal, Device** out) {
     GDV_RETURN_NOT_OK(
         CuCheck(d.StreamCreate(&dev->copy_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate"));
     dev->owner_thread_ = std::this_thread::get_id();
+    if (const char* lim = std::getenv("GDV_POOL_LIMIT_MB")) dev->pool_limit_ = static_cast<size_t>(std::atoll(lim)) << 20;
     g_devices[ordinal] = dev.release();
   }
   *out = g_devices[ordinal];
@@ -128,6 +131,7 @@ Status Device::Alloc(size_t bytes, CUdeviceptr* out) {
     auto it = free_.lower_bound(want);
     if (it != free_.end() && it->first <= want * 2) {
       *out = it->second;
+      idle_bytes_ -= it->first;
       free_.erase(it);
       return Status::OK();
     }
@@ -145,6 +149,7 @@ Status Device::Alloc(size_t bytes, CUdeviceptr* out) {
         sizes_.erase(kv.second);
       }
       free_.clear();
+      idle_bytes_ = 0;
     }
     for (auto q : drop) Driver().MemFree(q);
     r = Driver().MemAlloc(&p, want);
@@ -164,10 +169,44 @@ Status Device::Alloc(size_t bytes, CUdeviceptr* out) {
 
 void Device::Free(CUdeviceptr p) {
   if (p == 0) return;
-  std::lock_guard<std::mutex> lock(mu_);
-  auto it = sizes_.find(p);
-  if (it == sizes_.end()) return;
-  free_.emplace(it->second, p);
+  std::vector<CUdeviceptr> drop;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = sizes_.find(p);
+    if (it == sizes_.end()) return;
+    free_.emplace(it->second, p);
+    idle_bytes_ += it->second;
+    // over the limit: the largest idle blocks go back to the driver (cuMemFree waits for work that
+    // still uses a block, so releasing one that a queued kernel reads is safe, only slow)
+    while (idle_bytes_ > pool_limit_ && !free_.empty()) {
+      auto big = std::prev(free_.end());
+      idle_bytes_ -= big->first;
+      sizes_.erase(big->second);
+      drop.push_back(big->second);
+      free_.erase(big);
+    }
+  }
+  if (!drop.empty() && MakeCurrent().ok())
+    for (auto q : drop) Driver().MemFree(q);
+}
+
+size_t Device::Trim(size_t keep_bytes) {
+  std::vector<CUdeviceptr> drop;
+  size_t released = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    while (idle_bytes_ > keep_bytes && !free_.empty()) {
+      auto big = std::prev(free_.end());
+      idle_bytes_ -= big->first;
+      released += big->first;
+      sizes_.erase(big->second);
+      drop.push_back(big->second);
+      free_.erase(big);
+    }
+  }
+  if (!drop.empty() && MakeCurrent().ok())
+    for (auto q : drop) Driver().MemFree(q);
+  return released;
 }
 
 Status Device::StaticFunction(const char* name, CUfunction* out) {
@@ -382,7 +421,6 @@ inline int64_t BitBytes(int64_t bit_begin, int64_t nbits) {
 
 Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t* batch,
                      CUstream stream, ScratchScope* scratch, std::vector<ResolvedIn>* out) {
-  const DriverApi& d = Driver();
   const bool host = batch->mem_space == GDV_MEM_HOST;
   const int64_t n = batch->num_rows;
   out->resize(gen.inputs.size());
@@ -406,7 +444,7 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
         const size_t bytes = static_cast<size_t>(BitBytes(off, n));
         CUdeviceptr dp;
         GDV_RETURN_NOT_OK(scratch->Alloc(bytes + 8, &dp));
-        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D validity"));
+        GDV_RETURN_NOT_OK(StagedHtoD(dev, dp, p, bytes, stream));
         r.vld = dp;
       } else {
         const uintptr_t mis = reinterpret_cast<uintptr_t>(p) & 3u;
@@ -422,7 +460,7 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
         const size_t bytes = static_cast<size_t>(BitBytes(off, n));
         CUdeviceptr dp;
         GDV_RETURN_NOT_OK(scratch->Alloc(bytes + 8, &dp));
-        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D bool values"));
+        GDV_RETURN_NOT_OK(StagedHtoD(dev, dp, p, bytes, stream));
         r.val = dp;
       } else {
         const uintptr_t mis = reinterpret_cast<uintptr_t>(p) & 3u;
@@ -435,17 +473,14 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
         const size_t obytes = static_cast<size_t>(n + 1) * 4;
         CUdeviceptr dp;
         GDV_RETURN_NOT_OK(scratch->Alloc(obytes, &dp));
-        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, offs, obytes, stream), "H2D offsets"));
+        GDV_RETURN_NOT_OK(StagedHtoD(dev, dp, offs, obytes, stream));
         r.val = dp;
         const int64_t first = n > 0 ? offs[0] : 0, last = n > 0 ? offs[n] : 0;
         const size_t vbytes = static_cast<size_t>(last - first);
         CUdeviceptr dv;
         GDV_RETURN_NOT_OK(scratch->Alloc(vbytes + 16, &dv));
         if (vbytes > 0)
-          GDV_RETURN_NOT_OK(CuCheck(
-              d.MemcpyHtoDAsync(dv, static_cast<const uint8_t*>(c.var_data) + first, vbytes,
-                                stream),
-              "H2D string bytes"));
+          GDV_RETURN_NOT_OK(StagedHtoD(dev, dv, static_cast<const uint8_t*>(c.var_data) + first, vbytes, stream));
         // kernel addresses bytes as var + offs[r]; rebase so offs[0] lands on dv
         r.var = dv - static_cast<CUdeviceptr>(first);
       } else {
@@ -460,7 +495,7 @@ Status ResolveInputs(Device* dev, const GeneratedKernel& gen, const gdv_batch_t*
         CUdeviceptr dp;
         GDV_RETURN_NOT_OK(scratch->Alloc(bytes + 16, &dp));
         if (bytes > 0)
-          GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dp, p, bytes, stream), "H2D values"));
+          GDV_RETURN_NOT_OK(StagedHtoD(dev, dp, p, bytes, stream));
         r.val = dp;
       } else {
         if (reinterpret_cast<uintptr_t>(p) % static_cast<uintptr_t>(w) != 0)
@@ -656,6 +691,7 @@ Status Projector::EvaluateString(StringKernels* sk, const gdv_batch_t* batch,
   const GeneratedKernel& gen = ksize->gen;  // both kernels read the same input slots
 
   ScratchScope scratch(dev);
+  scratch.Guard(stream);
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
   ArgsLayout L(static_cast<int>(gen.inputs.size()), 1);
@@ -674,7 +710,7 @@ Status Projector::EvaluateString(StringKernels* sk, const gdv_batch_t* batch,
       const size_t bytes = static_cast<size_t>(n) * SelWidth(selection_mode_);
       GDV_RETURN_NOT_OK(scratch.Alloc(bytes + 16, &dsel));
       if (bytes > 0)
-        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dsel, sel->indices, bytes, stream), "H2D sel"));
+        GDV_RETURN_NOT_OK(StagedHtoD(dev, dsel, sel->indices, bytes, stream));
     }
     Put<CUdeviceptr>(args, L.off_sel, dsel);
   }
@@ -758,14 +794,10 @@ Status Projector::EvaluateString(StringKernels* sk, const gdv_batch_t* batch,
   grid = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, cap_w)));
   GDV_RETURN_NOT_OK(LaunchKernel(dev, lwrite, kwrite->gen, args, grid, stream));
   if (host) {
-    GDV_RETURN_NOT_OK(CuCheck(
-        d.MemcpyDtoHAsync(out->values, d_offs, static_cast<size_t>(n + 1) * 4, stream), "D2H offsets"));
-    if (total > 0)
-      GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(out->var_data, d_data, static_cast<size_t>(total), stream),
-                                "D2H string bytes"));
+    GDV_RETURN_NOT_OK(StagedDtoH(dev, out->values, d_offs, static_cast<size_t>(n + 1) * 4, stream));
+    if (total > 0) GDV_RETURN_NOT_OK(StagedDtoH(dev, out->var_data, d_data, static_cast<size_t>(total), stream));
     if (out->validity != nullptr)
-      GDV_RETURN_NOT_OK(CuCheck(
-          d.MemcpyDtoHAsync(out->validity, d_vld, static_cast<size_t>((n + 7) / 8), stream), "D2H validity"));
+      GDV_RETURN_NOT_OK(StagedDtoH(dev, out->validity, d_vld, static_cast<size_t>((n + 7) / 8), stream));
     // the staging blocks go back to the pool when `scratch` dies: wait for the copies first
     GDV_RETURN_NOT_OK(CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize"));
   }
@@ -808,6 +840,7 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   const GeneratedKernel& gen = kernel->gen;
 
   ScratchScope scratch(dev);
+  scratch.Guard(stream);
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
 
@@ -828,7 +861,7 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
       const size_t bytes = static_cast<size_t>(n) * SelWidth(selection_mode_);
       GDV_RETURN_NOT_OK(scratch.Alloc(bytes + 16, &dsel));
       if (bytes > 0)
-        GDV_RETURN_NOT_OK(CuCheck(d.MemcpyHtoDAsync(dsel, sel->indices, bytes, stream), "H2D sel"));
+        GDV_RETURN_NOT_OK(StagedHtoD(dev, dsel, sel->indices, bytes, stream));
     }
     Put<CUdeviceptr>(args, L.off_sel, dsel);
   }
@@ -882,12 +915,9 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   if (host) {
     for (int o = 0; o < n_outs; ++o) {
       if (stage[o].val_bytes > 0)
-        GDV_RETURN_NOT_OK(CuCheck(
-            d.MemcpyDtoHAsync(outs[o].values, stage[o].val, stage[o].val_bytes, stream), "D2H values"));
+        GDV_RETURN_NOT_OK(StagedDtoH(dev, outs[o].values, stage[o].val, stage[o].val_bytes, stream));
       if (outs[o].validity != nullptr && stage[o].vld_bytes > 0)
-        GDV_RETURN_NOT_OK(CuCheck(
-            d.MemcpyDtoHAsync(outs[o].validity, stage[o].vld, stage[o].vld_bytes, stream),
-            "D2H validity"));
+        GDV_RETURN_NOT_OK(StagedDtoH(dev, outs[o].validity, stage[o].vld, stage[o].vld_bytes, stream));
     }
     return Sync(stream);
   }
@@ -913,13 +943,14 @@ Status Projector::Sync(void* stream_v) {
     }
   }
   int err = 0;
-  if (have && pend.d_err != 0)
-    GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(&err, pend.d_err, sizeof(int), stream), "D2H err"));
+  Status copy = Status::OK();
+  if (have && pend.d_err != 0) copy = CuCheck(d.MemcpyDtoHAsync(&err, pend.d_err, sizeof(int), stream), "D2H err");
   Status s = CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize");
-  if (have) {
+  if (have) {  // on every path: the pending blocks go back to the pool once the stream is idle
     if (pend.d_err != 0) dev->Free(pend.d_err);
     for (auto p : pend.scratch) dev->Free(p);
   }
+  GDV_RETURN_NOT_OK(copy);
   GDV_RETURN_NOT_OK(s);
   if (err != 0) return Status::Make(GDV_EXECUTION_ERROR, ExecutionErrorMessage(err));
   return Status::OK();
@@ -1018,6 +1049,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   const GeneratedKernel& gen = kernel->gen;
 
   ScratchScope scratch(dev);
+  scratch.Guard(stream);
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
 
@@ -1088,9 +1120,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
     int64_t count = 0;
     GDV_RETURN_NOT_OK(Sync(stream, &count));
     if (count > 0) {
-      GDV_RETURN_NOT_OK(CuCheck(
-          d.MemcpyDtoHAsync(out_sel->indices, d_idx, static_cast<size_t>(count) * iw, stream),
-          "D2H selection"));
+      GDV_RETURN_NOT_OK(StagedDtoH(dev, out_sel->indices, d_idx, static_cast<size_t>(count) * iw, stream));
       GDV_RETURN_NOT_OK(CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize"));
     }
     out_sel->num_slots = count;
@@ -1122,16 +1152,16 @@ Status Filter::Sync(void* stream_v, int64_t* num_slots) {
   }
   int err = 0;
   uint64_t count = 0;
-  if (have && pend.d_err != 0)
-    GDV_RETURN_NOT_OK(CuCheck(d.MemcpyDtoHAsync(&err, pend.d_err, sizeof(int), stream), "D2H err"));
-  if (have && pend.d_count != 0)
-    GDV_RETURN_NOT_OK(
-        CuCheck(d.MemcpyDtoHAsync(&count, pend.d_count, sizeof(count), stream), "D2H count"));
+  Status copy = Status::OK();
+  if (have && pend.d_err != 0) copy = CuCheck(d.MemcpyDtoHAsync(&err, pend.d_err, sizeof(int), stream), "D2H err");
+  if (copy.ok() && have && pend.d_count != 0)
+    copy = CuCheck(d.MemcpyDtoHAsync(&count, pend.d_count, sizeof(count), stream), "D2H count");
   Status s = CuCheck(d.StreamSynchronize(stream), "cuStreamSynchronize");
-  if (have) {
+  if (have) {  // on every path: the pending blocks go back to the pool once the stream is idle
     if (pend.d_err != 0) dev->Free(pend.d_err);
     for (auto p : pend.scratch) dev->Free(p);
   }
+  GDV_RETURN_NOT_OK(copy);
   GDV_RETURN_NOT_OK(s);
   if (err != 0) return Status::Make(GDV_EXECUTION_ERROR, ExecutionErrorMessage(err));
   if (num_slots != nullptr) *num_slots = have ? static_cast<int64_t>(count) : -1;

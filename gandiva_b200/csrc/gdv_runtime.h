@@ -34,9 +34,16 @@ class Device {
   CUstream stream() const;
   CUstream copy_stream() const { return copy_stream_; }
 
-  // Pooled device scratch: freed blocks are cached and reused (no cuMemFree on the hot path).
+  // Pooled device scratch: freed blocks are cached and reused (no cuMemFree on the hot path).  The
+  // cache is bounded: once the idle blocks hold more than the limit (default 4 GiB, GDV_POOL_LIMIT_MB
+  // or SetPoolLimit), the largest idle blocks go back to the driver, so one multi-GB batch does not
+  // pin that much HBM for the life of the process.
   Status Alloc(size_t bytes, CUdeviceptr* out);
   void Free(CUdeviceptr p);
+  // Returns idle blocks to the driver until at most keep_bytes stay cached; returns the bytes released.
+  size_t Trim(size_t keep_bytes);
+  void SetPoolLimit(size_t bytes) { pool_limit_ = bytes; }
+  size_t idle_bytes() const { return idle_bytes_; }
 
   // Kernels of device/static_kernels.cu (embedded sm_100a cubin).
   Status StaticFunction(const char* name, CUfunction* out);
@@ -53,6 +60,8 @@ class Device {
   std::mutex mu_;
   std::multimap<size_t, CUdeviceptr> free_;
   std::unordered_map<CUdeviceptr, size_t> sizes_;
+  size_t idle_bytes_ = 0;                  // bytes held by free_
+  size_t pool_limit_ = size_t(4) << 30;
   CUmodule static_mod_ = nullptr;
   std::map<std::string, CUfunction> static_fns_;
 };
@@ -61,7 +70,17 @@ class Device {
 class ScratchScope {
  public:
   explicit ScratchScope(Device* d) : dev_(d) {}
+  // Work that reads or writes the blocks may still be queued on `stream` when an Evaluate returns
+  // early with an error: the destructor then waits for the stream before the blocks go back to the
+  // pool (where another thread could be handed them).  Settled() after the call's own final
+  // synchronisation skips that wait.
+  void Guard(CUstream stream) {
+    stream_ = stream;
+    guarded_ = true;
+  }
+  void Settled() { guarded_ = false; }
   ~ScratchScope() {
+    if (guarded_ && !blocks_.empty()) Driver().StreamSynchronize(stream_);
     for (auto p : blocks_) dev_->Free(p);
   }
   Status Alloc(size_t bytes, CUdeviceptr* out) {
@@ -78,6 +97,8 @@ class ScratchScope {
  private:
   Device* dev_;
   std::vector<CUdeviceptr> blocks_;
+  CUstream stream_ = nullptr;
+  bool guarded_ = false;
 };
 
 struct Config {

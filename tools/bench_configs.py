@@ -119,9 +119,8 @@ def bench_str(rows_per_batch, batches):
         out = torch.empty(n, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         cols = [(d_vld.data_ptr(), d_offs.data_ptr(), d_bytes.data_ptr(), 0)]
-        combos = [(bt, rpt, 0) for bt in (256, 512, 1024) for rpt in (1, 2, 4)] + [(1024, 2, 1), (512, 2, 1)]
-        # key-scan filter (string_scan bit 4): rows_per_thread = KB of the column per warp segment (0 = 64)
-        combos += [(bt, kb, 16) for bt in (128, 256, 512, 1024) for kb in (0, 16, 256)]
+        # (block_threads, rows_per_thread, string_scan): 0 = key-driven filter (the default), 4 = row-driven kernel
+        combos = [(0, 0, 0)] + [(bt, 0, 0) for bt in (128, 256, 512, 1024)] + [(512, 2, 4), (256, 2, 4)]
         if os.environ.get("GDV_STR_COMBOS"):
             combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_STR_COMBOS"].split(";")]
         for bt, rpt, scan in combos:
@@ -138,9 +137,9 @@ def bench_str(rows_per_batch, batches):
                 rows = n * batches
                 bytes_ = batches * (4.0 * n + block_bytes * reps + n / 8.0 + 4.0 * count)
                 gbs = bytes_ / ms / 1e6
-                r = {"config": "string_filter_like_upper_substr", "block_threads": bt, "rows_per_thread": rpt,
-                     "matcher": "key scan over the column bytes" if scan & 16 else
-                     ("per-lane" if scan & 1 else "cooperative scan") + (", no prefetch" if scan & 2 else ", cp.async prefetch"),
+                r = {"config": "string_filter_like_upper_substr", "block_threads": f.kernel_info["block_threads"], "rows_per_thread": rpt,
+                     "matcher": ("row-driven: " + ("per-lane" if scan & 1 else "cooperative scan") + ", cp.async prefetch") if scan & 4
+                     else "key-driven: aligned-word scan of the column bytes",
                      "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "gbs": gbs, "frac": gbs / PEAK,
                      "bytes_per_row": bytes_ / rows, "selected_per_batch": count, "regs": f.kernel_info["regs"],
                      "smem": f.kernel_info.get("dynamic_smem"), "ctas_per_sm": f.kernel_info.get("blocks_per_sm")}

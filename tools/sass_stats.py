@@ -26,16 +26,16 @@ def main():
 
     def note(label, obj):
         made.append((label, obj.kernel_info["name"]))
-    note("config 2: Q6 filter, fused (1024 threads)", g.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)),
-                                                               g.Configuration(block_threads=1024)))
-    note("config 2: Q6 filter, W-walk (stages=4, 256 threads)", g.make_filter(
+    note("config 2: Q6 filter, 256 threads x 4 chunks per warp (what batches >= 32 M rows get)", g.make_filter(
         cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)), g.Configuration(block_threads=256, stages=4)))
+    note("config 2: Q6 filter, 256 threads x 1 chunk (small batches)", g.make_filter(
+        cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)), g.Configuration(block_threads=256, stages=1)))
     exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(cases.q1_outputs(b))]
     note("config 3: Q1 projector, TMA loader", g.make_projector(cases.Q1_SCHEMA, exprs, None, "NONE", g.Configuration(loader=2)))
-    note("config 4: string filter, cooperative scan (512 threads)", g.make_filter(
-        cases.COMMENT_SCHEMA, b.make_condition(cases.comment_condition(b)), g.Configuration(block_threads=512)))
-    note("config 4: string filter, key scan (512 threads)", g.make_filter(
-        cases.COMMENT_SCHEMA, b.make_condition(cases.comment_condition(b)), g.Configuration(block_threads=512, string_scan=16)))
+    note("config 4: string filter, key-driven (256 threads)", g.make_filter(
+        cases.COMMENT_SCHEMA, b.make_condition(cases.comment_condition(b))))
+    note("config 4: string filter, row-driven cooperative scan (512 threads)", g.make_filter(
+        cases.COMMENT_SCHEMA, b.make_condition(cases.comment_condition(b)), g.Configuration(block_threads=512, string_scan=4)))
     schema, outs, _ = cases.case_arith("add", pa.int32())(b)
     note("config 1: add(int32, int32) projector", g.make_projector(schema, [b.make_expression(outs[0][0], pa.field("c", pa.int32()))], None))
     labels = dict((name, label) for label, name in made)

@@ -33,20 +33,16 @@ def main():
         cols = [(v.data_ptr() if v is not None else 0, t.data_ptr(), 0, 0) for t, v in zip((ship, disc, qty), vl)]
         results = []
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        combos = [(bt, rpt, 0) for bt in (256, 512, 1024) for rpt in (2, 4, 8, 16)]
-        if os.environ.get("GDV_Q6_COMBOS"):
-            combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_Q6_COMBOS"].split(";")]
-        combos += [(bt, rpt, 0, 3) for bt in (128, 256, 512) for rpt in (0, 4, 8)]   # two-pass filter (loader=3)
-        combos += [(bt, rpt, 0, 0, w) for (bt, w) in ((256, 4), (512, 2), (128, 8), (256, 2)) for rpt in (2, 4)]  # W-walk
+        # (block_threads, rows_per_thread, string_scan flags, chunks per warp W); 0 = engine default
+        combos = [(0, 0, 0, 0)] + [(bt, rpt, 0, w) for (bt, w) in ((256, 4), (256, 2), (512, 2), (128, 8), (1024, 1), (256, 8))
+                                   for rpt in (2, 4, 8)]
         if os.environ.get("GDV_Q6_COMBOS"):
             combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_Q6_COMBOS"].split(";")]
         for combo in combos:
             bt, rpt, flags = combo[:3]
-            loader = combo[3] if len(combo) > 3 else 0
-            walk = combo[4] if len(combo) > 4 else 0
+            walk = combo[3] if len(combo) > 3 else 0
             if True:
-                cfg = gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, string_scan=flags, loader=loader,
-                                            stages=walk)
+                cfg = gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, string_scan=flags, stages=walk)
                 b = gandiva.TreeExprBuilder()
                 f = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)), cfg)
                 for _ in range(3):
@@ -64,7 +60,8 @@ def main():
                 bytes_ = n * (20.0 + (3 / 8.0 if nullp else 0.0)) + 4.0 * count
                 gbs = bytes_ / (ms * 1e-3) / 1e9
                 info = f.kernel_info
-                r = {"block_threads": bt, "rows_per_thread": rpt, "flags": flags, "loader": loader, "walk": walk, "ms": ms, "gbs": gbs, "frac": gbs / peak,
+                r = {"block_threads": info["block_threads"], "rows_per_thread": info["rows_per_thread"], "flags": flags,
+                     "walk": walk, "asked": list(combo), "ms": ms, "gbs": gbs, "frac": gbs / peak,
                      "regs": info["regs"], "rows_per_s": n / (ms * 1e-3), "count": count}
                 results.append(r)
                 print(json.dumps(r), flush=True)
