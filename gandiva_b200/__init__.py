@@ -86,7 +86,8 @@ class gdv_out_column_t(C.Structure):
 
 class gdv_selection_t(C.Structure):
     _fields_ = [("indices", C.c_void_p), ("max_slots", C.c_int64), ("num_slots", C.c_int64),
-                ("mode", C.c_int32), ("mem_space", C.c_int32), ("index_base", C.c_int64)]
+                ("mode", C.c_int32), ("mem_space", C.c_int32), ("index_base", C.c_int64),
+                ("d_num_slots", C.c_void_p)]
 
 
 def _load() -> C.CDLL:
@@ -125,6 +126,9 @@ def _load() -> C.CDLL:
         "gdv_projector_evaluate": (i32, [vp, P(gdv_batch_t), P(gdv_selection_t),
                                          P(gdv_out_column_t), i32, vp, i32]),
         "gdv_projector_sync": (i32, [vp, vp]),
+        "gdv_device_alloc": (i32, [i32, C.c_size_t, P(vp)]),
+        "gdv_device_free": (i32, [i32, vp]),
+        "gdv_device_trim": (i32, [i32, C.c_size_t, P(C.c_size_t)]),
         "gdv_projector_output_var_size": (i32, [vp, P(gdv_batch_t), P(gdv_selection_t), i32, vp,
                                                 P(i64)]),
         "gdv_projector_dump_ir": (i64, [vp, C.c_char_p, i64]),
@@ -676,7 +680,9 @@ class Projector:
     def evaluate_device(self, num_rows: int, columns: Sequence[tuple], outputs: Sequence[tuple],
                         stream: int = 0, selection: tuple | None = None, sync: bool = False) -> None:
         """columns: per schema field (validity_ptr|0, values_ptr, var_data_ptr|0, offset);
-        outputs: per expression (validity_ptr|0, values_ptr); selection: (ptr, num_slots)."""
+        outputs: per expression (validity_ptr|0, values_ptr); selection: (ptr, num_slots) or
+        (ptr, max_slots, d_count_ptr): the slot count is read from device memory (the d_count a
+        Filter.evaluate_device(..., sync=False) wrote on the same stream), no host round trip."""
         cols = (gdv_column_t * max(len(columns), 1))()
         for i, (vld, val, var, off) in enumerate(columns):
             cols[i].validity, cols[i].values, cols[i].var_data, cols[i].offset = \
@@ -687,7 +693,8 @@ class Projector:
             outs[i].validity, outs[i].values = (vld or None), (val or None)
         csel = None
         if selection is not None:
-            s = gdv_selection_t(selection[0], selection[1], selection[1], self._mode, GDV_MEM_DEVICE)
+            s = gdv_selection_t(selection[0], selection[1], selection[1], self._mode, GDV_MEM_DEVICE, 0,
+                                selection[2] if len(selection) > 2 else None)
             csel = C.byref(s)
         _check(lib.gdv_projector_evaluate(self._h, C.byref(cb), csel, outs, len(outputs),
                                           _stream_handle(stream), 0 if sync else 1))

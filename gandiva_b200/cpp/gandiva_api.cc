@@ -5,8 +5,10 @@
 
 #include "arrow/array/util.h"
 #include "arrow/buffer.h"
+#include "arrow/device.h"
 #include "arrow/util/bit_util.h"
 #include "gandiva/condition.h"
+#include "gandiva/device.h"
 #include "gandiva/configuration.h"
 #include "gandiva/expression.h"
 #include "gandiva/expression_registry.h"
@@ -172,26 +174,45 @@ gdv_config_t ConfigToC(const std::shared_ptr<Configuration>& c) {
   return cfg;
 }
 
-// RecordBatch -> raw buffer addresses (arrow::ArrayData, P/include/arrow/array/data.h:468-474)
-Status ToColumns(const arrow::RecordBatch& batch, std::vector<gdv_column_t>* cols) {
+// RecordBatch -> raw buffer addresses (arrow::ArrayData, P/include/arrow/array/data.h:468-474).
+// All buffers of a batch must live in one memory space: CPU (GDV_MEM_HOST, staged by the engine) or the
+// HBM of one GPU (GDV_MEM_DEVICE: kernels read them in place).  *mm = the MemoryManager of the first
+// device buffer, from which device outputs are allocated.
+Status ToColumns(const arrow::RecordBatch& batch, std::vector<gdv_column_t>* cols, int* mem_space,
+                 std::shared_ptr<arrow::MemoryManager>* mm) {
+  int n_cpu = 0, n_dev = 0;
   for (int i = 0; i < batch.num_columns(); ++i) {
     const arrow::ArrayData& a = *batch.column_data(i);
     gdv_column_t c;
     std::memset(&c, 0, sizeof(c));
-    for (const auto& b : a.buffers)
-      if (b != nullptr && !b->is_cpu())
-        return Status::NotImplemented(
-            "device-resident buffers go through the C-ABI (GDV_MEM_DEVICE), not this overload");
-    if (a.buffers.size() > 0 && a.buffers[0] != nullptr && a.GetNullCount() != 0)
-      c.validity = a.buffers[0]->data();
-    if (a.buffers.size() > 1 && a.buffers[1] != nullptr) c.values = a.buffers[1]->data();
+    for (const auto& b : a.buffers) {
+      if (b == nullptr) continue;
+      if (b->is_cpu()) {
+        ++n_cpu;
+      } else {
+        if (b->device_type() != arrow::DeviceAllocationType::kCUDA &&
+            b->device_type() != arrow::DeviceAllocationType::kCUDA_MANAGED)
+          return Status::NotImplemented("buffers of device type ", static_cast<int>(b->device_type()),
+                                        " (only CPU and CUDA memory can be evaluated)");
+        ++n_dev;
+        if (mm != nullptr && *mm == nullptr) *mm = b->memory_manager();
+      }
+    }
+    // address() is valid for both spaces (data() is null for non-CPU buffers).  null_count is read as
+    // stored: computing it would walk a bitmap that may live in HBM.
+    if (a.buffers.size() > 0 && a.buffers[0] != nullptr && a.null_count.load() != 0)
+      c.validity = reinterpret_cast<const void*>(a.buffers[0]->address());
+    if (a.buffers.size() > 1 && a.buffers[1] != nullptr) c.values = reinterpret_cast<const void*>(a.buffers[1]->address());
     if (a.buffers.size() > 2 && a.buffers[2] != nullptr) {
-      c.var_data = a.buffers[2]->data();
+      c.var_data = reinterpret_cast<const void*>(a.buffers[2]->address());
       c.var_data_size = a.buffers[2]->size();
     }
     c.offset = a.offset;
     cols->push_back(c);
   }
+  if (n_cpu > 0 && n_dev > 0)
+    return Status::Invalid("the buffers of a RecordBatch must all be in host memory or all in device memory");
+  *mem_space = n_dev > 0 ? GDV_MEM_DEVICE : GDV_MEM_HOST;
   return Status::OK();
 }
 
@@ -387,7 +408,14 @@ static int ModeWidth(SelectionVector::Mode m) {
 }
 
 uint64_t SelectionVector::GetIndex(int64_t index) const {
+  uint64_t host_copy = 0;
   const uint8_t* p = buffer_->data();
+  if (!buffer_->is_cpu()) {  // a vector in HBM: one element over PCIe (debugging aid, not a hot path)
+    const int w = mode_ == MODE_UINT16 ? 2 : (mode_ == MODE_UINT32 ? 4 : 8);
+    if (arrow::MemoryManager::CopyBufferSliceToCPU(buffer_, index * w, w, reinterpret_cast<uint8_t*>(&host_copy)).ok())
+      return host_copy;
+    return 0;
+  }
   switch (mode_) {
     case MODE_UINT16: return reinterpret_cast<const uint16_t*>(p)[index];
     case MODE_UINT32: return reinterpret_cast<const uint32_t*>(p)[index];
@@ -511,8 +539,11 @@ Status Projector::Evaluate(const arrow::RecordBatch& batch, const SelectionVecto
   if (mode_ != SelectionVector::MODE_NONE && selection_vector == nullptr)
     return Status::Invalid("Selection vector must be non-null.");
   std::vector<gdv_column_t> cols;
-  ARROW_RETURN_NOT_OK(ToColumns(batch, &cols));
-  gdv_batch_t b{batch.num_rows(), batch.num_columns(), GDV_MEM_HOST, cols.data()};
+  int space = GDV_MEM_HOST;
+  std::shared_ptr<arrow::MemoryManager> mm;
+  ARROW_RETURN_NOT_OK(ToColumns(batch, &cols, &space, &mm));
+  const bool on_device = space == GDV_MEM_DEVICE;
+  gdv_batch_t b{batch.num_rows(), batch.num_columns(), space, cols.data()};
   const int64_t n = selection_vector != nullptr && mode_ != SelectionVector::MODE_NONE
                         ? selection_vector->GetNumSlots()
                         : batch.num_rows();
@@ -520,49 +551,52 @@ Status Projector::Evaluate(const arrow::RecordBatch& batch, const SelectionVecto
   std::memset(&sel, 0, sizeof(sel));
   const gdv_selection_t* psel = nullptr;
   if (mode_ != SelectionVector::MODE_NONE) {
-    sel.indices = const_cast<uint8_t*>(selection_vector->GetBuffer().data());
+    if (selection_vector->GetBuffer().is_cpu() == on_device)
+      return Status::Invalid("the selection vector and the RecordBatch must live in the same memory space");
+    sel.indices = reinterpret_cast<void*>(selection_vector->GetBuffer().address());
     sel.max_slots = selection_vector->GetMaxSlots();
     sel.num_slots = selection_vector->GetNumSlots();
     sel.mode = SelModeToC(selection_vector->GetMode());
-    sel.mem_space = GDV_MEM_HOST;
+    sel.mem_space = space;
     psel = &sel;
   }
+  // Outputs: from the caller's pool for host batches (as the reference does); for device batches from
+  // the MemoryManager of the batch's buffers, so that results stay next to their inputs in HBM.
+  auto alloc = [&](int64_t bytes, bool zero) -> arrow::Result<std::shared_ptr<arrow::Buffer>> {
+    if (on_device) {
+      ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> buf, mm->AllocateBuffer(bytes));
+      return std::shared_ptr<arrow::Buffer>(std::move(buf));
+    }
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> buf, arrow::AllocateBuffer(bytes, pool));
+    if (zero) std::memset(buf->mutable_data(), 0, static_cast<size_t>(bytes));
+    return std::shared_ptr<arrow::Buffer>(std::move(buf));
+  };
   std::vector<gdv_out_column_t> outs(output_fields_.size());
   std::vector<ArrayDataPtr> datas;
   for (size_t i = 0; i < outs.size(); ++i) {
     std::memset(&outs[i], 0, sizeof(outs[i]));
     const DataTypePtr& t = output_fields_[i]->type();
     const int64_t bitmap_bytes = arrow::bit_util::RoundUpToMultipleOf8(arrow::bit_util::BytesForBits(n)) + 8;
-    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> validity, arrow::AllocateBuffer(bitmap_bytes, pool));
-    std::memset(validity->mutable_data(), 0, static_cast<size_t>(bitmap_bytes));
-    outs[i].validity = validity->mutable_data();
+    ARROW_ASSIGN_OR_RAISE(std::shared_ptr<arrow::Buffer> validity, alloc(bitmap_bytes, true));
+    outs[i].validity = reinterpret_cast<void*>(validity->address());
     if (t->id() == arrow::Type::STRING || t->id() == arrow::Type::BINARY) {
       // utf8/binary: the sizing pass says how many bytes the data buffer needs, then the
-      // offsets (n + 1 int32) and the bytes are allocated from the caller's pool
+      // offsets (n + 1 int32) and the bytes are allocated
       int64_t need = 0;
       ARROW_RETURN_NOT_OK(ToStatus(gdv_projector_output_var_size(
           static_cast<gdv_projector_t>(handle_), &b, psel, static_cast<int32_t>(i), nullptr, &need)));
-      ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> offsets, arrow::AllocateBuffer((n + 1) * 4 + 8, pool));
-      ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> bytes, arrow::AllocateBuffer(need + 8, pool));
-      outs[i].values = offsets->mutable_data();
-      outs[i].var_data = bytes->mutable_data();
+      ARROW_ASSIGN_OR_RAISE(std::shared_ptr<arrow::Buffer> offsets, alloc((n + 1) * 4 + 8, false));
+      ARROW_ASSIGN_OR_RAISE(std::shared_ptr<arrow::Buffer> bytes, alloc(need + 8, false));
+      outs[i].values = reinterpret_cast<void*>(offsets->address());
+      outs[i].var_data = reinterpret_cast<void*>(bytes->address());
       outs[i].var_capacity = need;
-      datas.push_back(arrow::ArrayData::Make(
-          t, n, {std::shared_ptr<arrow::Buffer>(std::move(validity)), std::shared_ptr<arrow::Buffer>(std::move(offsets)),
-                 std::shared_ptr<arrow::Buffer>(std::move(bytes))}));
+      datas.push_back(arrow::ArrayData::Make(t, n, {validity, offsets, bytes}));
       continue;
     }
-    int64_t value_bytes;
-    if (t->id() == arrow::Type::BOOL) {
-      value_bytes = bitmap_bytes;
-    } else {
-      value_bytes = n * (t->bit_width() / 8) + 8;
-    }
-    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> values, arrow::AllocateBuffer(value_bytes, pool));
-    if (t->id() == arrow::Type::BOOL) std::memset(values->mutable_data(), 0, static_cast<size_t>(value_bytes));
-    outs[i].values = values->mutable_data();
-    datas.push_back(arrow::ArrayData::Make(
-        t, n, {std::shared_ptr<arrow::Buffer>(std::move(validity)), std::shared_ptr<arrow::Buffer>(std::move(values))}));
+    const int64_t value_bytes = t->id() == arrow::Type::BOOL ? bitmap_bytes : n * (t->bit_width() / 8) + 8;
+    ARROW_ASSIGN_OR_RAISE(std::shared_ptr<arrow::Buffer> values, alloc(value_bytes, t->id() == arrow::Type::BOOL));
+    outs[i].values = reinterpret_cast<void*>(values->address());
+    datas.push_back(arrow::ArrayData::Make(t, n, {validity, values}));
   }
   ARROW_RETURN_NOT_OK(ToStatus(gdv_projector_evaluate(static_cast<gdv_projector_t>(handle_), &b, psel,
                                                       outs.data(), static_cast<int32_t>(outs.size()),
@@ -611,14 +645,18 @@ Status Filter::Evaluate(const arrow::RecordBatch& batch, std::shared_ptr<Selecti
   if (out_selection->GetMaxSlots() < batch.num_rows())
     return Status::Invalid("Output selection vector capacity too small");
   std::vector<gdv_column_t> cols;
-  ARROW_RETURN_NOT_OK(ToColumns(batch, &cols));
-  gdv_batch_t b{batch.num_rows(), batch.num_columns(), GDV_MEM_HOST, cols.data()};
+  int space = GDV_MEM_HOST;
+  ARROW_RETURN_NOT_OK(ToColumns(batch, &cols, &space, nullptr));
+  if (out_selection->GetBuffer().is_cpu() == (space == GDV_MEM_DEVICE))
+    return Status::Invalid("the selection vector and the RecordBatch must live in the same memory space "
+                           "(SelectionVector::MakeInt32(max_slots, <device buffer>, &out) for device batches)");
+  gdv_batch_t b{batch.num_rows(), batch.num_columns(), space, cols.data()};
   gdv_selection_t sel;
   std::memset(&sel, 0, sizeof(sel));
-  sel.indices = out_selection->GetBuffer().mutable_data();
+  sel.indices = reinterpret_cast<void*>(out_selection->GetBuffer().address());
   sel.max_slots = out_selection->GetMaxSlots();
   sel.mode = SelModeToC(out_selection->GetMode());
-  sel.mem_space = GDV_MEM_HOST;
+  sel.mem_space = space;
   ARROW_RETURN_NOT_OK(
       ToStatus(gdv_filter_evaluate(static_cast<gdv_filter_t>(handle_), &b, &sel, nullptr, 0, nullptr)));
   out_selection->SetNumSlots(sel.num_slots);
@@ -651,6 +689,108 @@ std::vector<std::shared_ptr<FunctionSignature>> GetRegisteredFunctionSignatures(
     out.push_back(std::make_shared<FunctionSignature>(name, std::move(pts), FromC(ret)));
   }
   return out;
+}
+
+// ---- HBM as an arrow::MemoryManager ------------------------------------------------------------
+namespace {
+
+class HbmDevice : public arrow::Device {
+ public:
+  explicit HbmDevice(int ordinal) : arrow::Device(false), ordinal_(ordinal) {}
+  const char* type_name() const override { return "gandiva_b200::HbmDevice"; }
+  std::string ToString() const override { return "gandiva_b200 CUDA device " + std::to_string(ordinal_); }
+  bool Equals(const arrow::Device& other) const override {
+    return other.device_type() == device_type() && other.device_id() == device_id();
+  }
+  int64_t device_id() const override { return ordinal_; }
+  arrow::DeviceAllocationType device_type() const override { return arrow::DeviceAllocationType::kCUDA; }
+  std::shared_ptr<arrow::MemoryManager> default_memory_manager() override;
+
+ private:
+  int ordinal_;
+};
+
+// A block of the engine's pooled allocator; goes back to the pool with the buffer.
+class HbmBuffer : public arrow::MutableBuffer {
+ public:
+  HbmBuffer(int ordinal, void* p, int64_t size, std::shared_ptr<arrow::MemoryManager> mm)
+      : arrow::MutableBuffer(static_cast<uint8_t*>(p), size, std::move(mm)), ordinal_(ordinal), p_(p) {}
+  ~HbmBuffer() override { gdv_device_free(ordinal_, p_); }
+
+ private:
+  int ordinal_;
+  void* p_;
+};
+
+class HbmMemoryManager : public arrow::MemoryManager {
+ public:
+  HbmMemoryManager(const std::shared_ptr<arrow::Device>& dev, int ordinal) : arrow::MemoryManager(dev), ordinal_(ordinal) {}
+  arrow::Result<std::shared_ptr<arrow::io::RandomAccessFile>> GetBufferReader(std::shared_ptr<arrow::Buffer>) override {
+    return Status::NotImplemented("no file interface over HBM buffers: copy them to the host first");
+  }
+  arrow::Result<std::shared_ptr<arrow::io::OutputStream>> GetBufferWriter(std::shared_ptr<arrow::Buffer>) override {
+    return Status::NotImplemented("no file interface over HBM buffers");
+  }
+  arrow::Result<std::unique_ptr<arrow::Buffer>> AllocateBuffer(int64_t size) override {
+    void* p = nullptr;
+    ARROW_RETURN_NOT_OK(ToStatus(gdv_device_alloc(ordinal_, static_cast<size_t>(size > 0 ? size : 1), &p)));
+    return std::unique_ptr<arrow::Buffer>(new HbmBuffer(ordinal_, p, size, shared_from_this()));
+  }
+
+ protected:
+  arrow::Result<std::shared_ptr<arrow::Buffer>> CopyBufferFrom(const std::shared_ptr<arrow::Buffer>& buf,
+                                                              const std::shared_ptr<arrow::MemoryManager>& from) override {
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> out, CopyNonOwnedFrom(*buf, from));
+    return std::shared_ptr<arrow::Buffer>(std::move(out));
+  }
+  arrow::Result<std::unique_ptr<arrow::Buffer>> CopyNonOwnedFrom(const arrow::Buffer& buf,
+                                                               const std::shared_ptr<arrow::MemoryManager>& from) override {
+    if (!from->is_cpu()) return std::unique_ptr<arrow::Buffer>();  // unsupported here: let the other side try
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> out, AllocateBuffer(buf.size()));
+    ARROW_RETURN_NOT_OK(ToStatus(gdv_memcpy(ordinal_, reinterpret_cast<void*>(out->address()), buf.data(),
+                                            static_cast<size_t>(buf.size()), 1)));
+    return out;
+  }
+  arrow::Result<std::shared_ptr<arrow::Buffer>> CopyBufferTo(const std::shared_ptr<arrow::Buffer>& buf,
+                                                            const std::shared_ptr<arrow::MemoryManager>& to) override {
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> out, CopyNonOwnedTo(*buf, to));
+    return std::shared_ptr<arrow::Buffer>(std::move(out));
+  }
+  arrow::Result<std::unique_ptr<arrow::Buffer>> CopyNonOwnedTo(const arrow::Buffer& buf,
+                                                             const std::shared_ptr<arrow::MemoryManager>& to) override {
+    if (!to->is_cpu()) return std::unique_ptr<arrow::Buffer>();
+    ARROW_ASSIGN_OR_RAISE(std::unique_ptr<arrow::Buffer> out, to->AllocateBuffer(buf.size()));
+    ARROW_RETURN_NOT_OK(ToStatus(gdv_memcpy(ordinal_, out->mutable_data(), reinterpret_cast<const void*>(buf.address()),
+                                            static_cast<size_t>(buf.size()), 2)));
+    return out;
+  }
+
+ private:
+  int ordinal_;
+};
+
+std::shared_ptr<arrow::MemoryManager> HbmDevice::default_memory_manager() {
+  return std::make_shared<HbmMemoryManager>(shared_from_this(), ordinal_);
+}
+
+}  // namespace
+
+arrow::Result<std::shared_ptr<arrow::MemoryManager>> DeviceMemoryManager(int device) {
+  if (!gdv_cuda_available()) return Status::ExecutionError("CUDA: no usable device (", gdv_last_error(), ")");
+  if (device < 0 || device >= gdv_device_count()) return Status::Invalid("no CUDA device ", device);
+  auto dev = std::make_shared<HbmDevice>(device);
+  return dev->default_memory_manager();
+}
+
+arrow::Result<std::shared_ptr<arrow::RecordBatch>> CopyToDevice(const arrow::RecordBatch& batch, int device) {
+  ARROW_ASSIGN_OR_RAISE(std::shared_ptr<arrow::MemoryManager> mm, DeviceMemoryManager(device));
+  return batch.CopyTo(mm);
+}
+arrow::Result<std::shared_ptr<arrow::RecordBatch>> CopyToHost(const arrow::RecordBatch& batch) {
+  return batch.CopyTo(arrow::default_cpu_memory_manager());
+}
+arrow::Result<std::shared_ptr<arrow::Array>> CopyToHost(const arrow::Array& array) {
+  return array.CopyTo(arrow::default_cpu_memory_manager());
 }
 
 }  // namespace gandiva

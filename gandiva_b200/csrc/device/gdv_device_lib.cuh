@@ -42,11 +42,29 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_CAST_DECIMAL 7     /* castDECIMAL of a string that is not a decimal number */
 #define GDV_ERR_CAST_FLOAT 8       /* castFLOAT4 / castFLOAT8 of a string that is not a number */
 #define GDV_ERR_CAST_BOOL 9        /* castBIT / castBOOLEAN of a string that is not true / false / 1 / 0 */
+#define GDV_ERR_NEG_LENGTH 10      /* castVARCHAR(x, n) with n < 0 */
+#define GDV_ERR_LOCATE_START 11    /* locate(sub, s, start) with start < 1 */
 struct gdv_ctx {
   int* err;
 };
 GDV_DEV void gdv_set_error(gdv_ctx* c, int code) {
   if (c->err != nullptr) atomicCAS(c->err, 0, code);
+}
+// Argument checks of castVARCHAR(x, n) and locate(sub, s, start): the reference raises on a negative
+// length / a start position below 1.  Called only on rows where every argument is valid.
+GDV_DEV long long gdv_check_len(gdv_ctx* c, long long n) {
+  if (n < 0) {
+    gdv_set_error(c, GDV_ERR_NEG_LENGTH);
+    return 0;
+  }
+  return n;
+}
+GDV_DEV int gdv_check_start(gdv_ctx* c, int start) {
+  if (start < 1) {
+    gdv_set_error(c, GDV_ERR_LOCATE_START);
+    return 1;
+  }
+  return start;
 }
 
 // ---- strings: a view on Arrow bytes plus a lazy ASCII case map ------------------------
@@ -2457,7 +2475,8 @@ GDV_DEV gdv_str right_utf8_int32(gdv_str s, i32 n) {
   return substr_utf8_int64_int64(s, g - (i64)n + 1, (i64)n);
 }
 // locate(sub, s[, start]): 1-based glyph position of the first occurrence of sub in s at or after
-// glyph `start`, 0 when there is none (or start < 1); the empty string is found at `start`.
+// glyph `start`, 0 when there is none; the empty string is found at `start` (start < 1 raises: the
+// fuser checks it with gdv_check_start before this is called).
 GDV_DEV i32 locate_utf8_utf8_int32(gdv_str sub, gdv_str s, i32 start) {
   if (start < 1) return 0;
   i32 pos = 0, g = 1;

@@ -416,6 +416,37 @@ gdv_status gdv_registry_get(int32_t i, const char** name, gdv_type_t* ret, gdv_t
 }
 
 // ---- harness helpers ----------------------------------------------------------------------
+gdv_status gdv_device_alloc(int32_t device, size_t bytes, void** out) {
+  if (out == nullptr) return Fail(GDV_INVALID, "null argument");
+  *out = nullptr;
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  CUdeviceptr p = 0;
+  s = dev->Alloc(bytes > 0 ? bytes : 1, &p);
+  if (!s.ok()) return Fail(s);
+  *out = reinterpret_cast<void*>(p);
+  return GDV_OK;
+}
+
+gdv_status gdv_device_free(int32_t device, void* p) {
+  if (p == nullptr) return GDV_OK;
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  dev->Free(reinterpret_cast<CUdeviceptr>(p));
+  return GDV_OK;
+}
+
+gdv_status gdv_device_trim(int32_t device, size_t keep_bytes, size_t* released) {
+  Device* dev = nullptr;
+  Status s = Device::Get(device, &dev);
+  if (!s.ok()) return Fail(s);
+  const size_t r = dev->Trim(keep_bytes);
+  if (released != nullptr) *released = r;
+  return GDV_OK;
+}
+
 gdv_status gdv_host_alloc(size_t bytes, void** out) {
   if (out == nullptr) return Fail(GDV_INVALID, "null argument");
   Device* dev = nullptr;

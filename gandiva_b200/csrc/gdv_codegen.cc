@@ -2,6 +2,7 @@
 #include "gdv_regex.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <map>
 #include <sstream>
@@ -90,6 +91,19 @@ Status ValidateNode(const Schema& schema, const Node& node) {
         if (fn.children().size() == 3 &&
             static_cast<const LiteralNode&>(*fn.children()[2]).bytes().size() != 1)
           return VErr("The length of escape char in 'like' function must be 1");
+        if (fn.children().size() == 3 && (fn.name() == "like" || fn.name() == "ilike")) {
+          // the reference's pattern translation accepts the escape character only in front of
+          // '_', '%' or itself, and never as the last character of the pattern
+          const std::string& pat = static_cast<const LiteralNode&>(*fn.children()[1]).bytes();
+          const char esc = static_cast<const LiteralNode&>(*fn.children()[2]).bytes()[0];
+          for (size_t i = 0; i < pat.size(); ++i) {
+            if (pat[i] != esc) continue;
+            if (i + 1 == pat.size()) return VErr("Unexpected escape char at the end of pattern " + pat);
+            const char nx = pat[++i];
+            if (nx != '_' && nx != '%' && nx != esc)
+              return VErr("Invalid escape sequence in pattern " + pat + " at offset " + std::to_string(i));
+          }
+        }
       }
       return Status::OK();
     }
@@ -161,7 +175,7 @@ Status ValidateExpression(const Schema& schema, const Expression& expr) {
 // ======================================================================================
 ArgsLayout::ArgsLayout(int n_inputs, int n_outputs)
     : ni(std::max(n_inputs, 1)), no(std::max(n_outputs, 1)) {
-  size_t o = 72;
+  size_t o = 80;
   off_in_val = o; o += 8u * ni;
   off_in_vld = o; o += 8u * ni;
   off_in_var = o; o += 8u * ni;
@@ -441,6 +455,28 @@ class BodyGen {
 
   static double PairScore(unsigned char a, unsigned char b, unsigned xf) { return DigramScore(a, b, xf); }
 
+  // castVARCHAR(x, n) raises on n < 0 ("Output buffer length can't be negative"), locate(sub, s, start)
+  // on start < 1 ("Start position must be greater than 0"), as the reference's functions do.  Returns
+  // the index of the argument a can-fail helper must check, or -1 (literals that can never raise).
+  static int ArgGuard(const FunctionNode& fn) {
+    int arg = -1;
+    int64_t least = 0;
+    if (fn.name() == "castVARCHAR" && fn.children().size() == 2) arg = 1;
+    if ((fn.name() == "locate" || fn.name() == "position") && fn.children().size() == 3) {
+      arg = 2;
+      least = 1;
+    }
+    if (arg < 0) return -1;
+    const Node& c = *fn.children()[static_cast<size_t>(arg)];
+    if (c.kind() == NodeKind::kLiteral) {
+      const auto& lit = static_cast<const LiteralNode&>(c);
+      if (lit.is_null()) return -1;  // a null argument makes the row null: nothing is called
+      const int64_t v = c.return_type().id == GDV_TYPE_INT32 ? static_cast<int64_t>(lit.as<int32_t>()) : lit.as<int64_t>();
+      if (v >= least) return -1;
+    }
+    return arg;
+  }
+
   static bool CanFail(const Node& node) {
     switch (node.kind()) {
       case NodeKind::kField: case NodeKind::kLiteral: return false;
@@ -450,6 +486,7 @@ class BodyGen {
         for (const auto& c : fn.children()) params.push_back(c->return_type());
         const FunctionDef* def = Registry::Get().Lookup(fn.name(), params);
         if (def != nullptr && (def->flags & kCanFail)) return true;
+        if (ArgGuard(fn) >= 0) return true;
         for (const auto& c : fn.children())
           if (CanFail(*c)) return true;
         return false;
@@ -985,6 +1022,19 @@ class BodyGen {
       return r;
     }
 
+    if (const int ga = ArgGuard(fn); ga >= 0) {
+      std::vector<std::string> goks;
+      for (const auto& a : args) goks.push_back(a.ok);
+      const std::string gok = AndOk(goks);
+      const std::string gv = NewVar("v");
+      Val& g = args[static_cast<size_t>(ga)];
+      *out += Ind(indent) + g.type.ctype() + " " + gv + " = " + (ga == 1 ? "0" : "1") + ";\n";
+      *out += Ind(indent) + "if (in && (" + gok + ")) " + gv + " = " + (ga == 1 ? "gdv_check_len" : "gdv_check_start") +
+              "(&ctx, " + g.v + ");\n";
+      g.v = gv;
+      uses_ctx_ = true;
+    }
+
     if (fn.name() == "nvl") {
       // nvl(a, b) = a where a is valid, else b: a select on a's validity, no device function
       const Val& a = args[0];
@@ -1215,6 +1265,7 @@ std::string EmitArgsStruct(const ArgsLayout& L) {
     << "  u64* ticket;      // filter: dynamic tile counter\n"
     << "  int* err;         // first ExecutionError code raised by a device function\n"
     << "  i64 out_cap;      // filter: capacity of out_idx; selected rows past it are counted, not stored\n"
+    << "  const u64* n_ptr; // project with a selection vector: slot count in device memory (or null: n)\n"
     << "  const void* in_val[" << L.ni << "];\n"
     << "  const u8* in_vld[" << L.ni << "];\n"
     << "  const u8* in_var[" << L.ni << "];\n"
@@ -1667,6 +1718,7 @@ void EmitFilterEpilogue(const std::vector<ColumnSlot>& slots, const KernelSpec& 
   src += "        #pragma unroll 4\n";
   src += "        for (int k = 0; k < 32; ++k) {\n";
   src += "          const u32 m = __shfl_sync(GDV_FULL, mymask[w], k);\n";
+  src += "          if (m == 0u) continue;  // warp-uniform: most steps of a selective filter keep nothing\n";
   src += "          const u32 off = __shfl_sync(GDV_FULL, step_excl[w], k);\n";
   src += "          if ((m >> lane) & 1u)\n";
   src += "            wout[off + (u32)__popc(m & lt)] = (" + IDX + ")(A.row_base + wbase0 + 1024 * w + 32 * k + (i64)lane);\n";
@@ -1678,6 +1730,7 @@ void EmitFilterEpilogue(const std::vector<ColumnSlot>& slots, const KernelSpec& 
   src += "        #pragma unroll 1\n";
   src += "        for (int k = 0; k < 32; ++k) {\n";
   src += "          const u32 m = __shfl_sync(GDV_FULL, mymask[w], k);\n";
+  src += "          if (m == 0u) continue;\n";
   src += "          const u32 off = __shfl_sync(GDV_FULL, step_excl[w], k);\n";
   src += "          const u64 pos = wpos + (u64)off + (u64)__popc(m & lt);\n";
   src += "          if (((m >> lane) & 1u) && pos < (u64)A.out_cap)\n";
@@ -1705,7 +1758,7 @@ void EmitFilterEpilogue(const std::vector<ColumnSlot>& slots, const KernelSpec& 
 // outside the column (first / last chunk of the batch) are not loaded as chunks: every such byte is
 // an anchor.  More anchors than the list holds between two drains: the warp evaluates all its rows.
 std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec& spec,
-                          const KeyPlan& plan, const std::string& body, const Val& result, int BT,
+                          const KeyPlan& plan, const std::string& body, const Val& result, int BT, int W,
                           const std::string& scratch_decl) {
   const int NW = BT / 32;
   const int L = static_cast<int>(plan.key.size());
@@ -1804,9 +1857,9 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
   gdv_ctx ctx;
   ctx.err = A.err;
 @PROLOGUE@  extern __shared__ uint4 gdv_smem[];
-  u32* const wmask = reinterpret_cast<u32*>(gdv_smem) + (size_t)wid * (@CAP@ + 36);  // keep-mask of step k of this warp's rows
-  u32* const wctr = wmask + 32;   // [0] anchors queued since the last drain
-  u32* const wanch = wmask + 36;  // their byte positions in the column's data buffer
+  u32* const wmask = reinterpret_cast<u32*>(gdv_smem) + (size_t)wid * (@CAP@ + 32 * @W@ + 4);  // keep-mask of step k of this warp's rows
+  u32* const wctr = wmask + 32 * @W@;      // [0] anchors queued since the last drain
+  u32* const wanch = wmask + 32 * @W@ + 4; // their byte positions in the column's data buffer
   __shared__ u32 s_wcount[@NW@];
   __shared__ i64 s_tile;
   __shared__ u64 s_excl;
@@ -1826,13 +1879,15 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
     __syncthreads();
     const i64 tile = s_tile;
     if (tile >= n_tiles) break;
-    const i64 wbase0 = tile * @TILE@ + (i64)wid * 1024;
-    wmask[lane] = 0u;
+    // every warp owns @W@ consecutive 1024-row chunks: one run of bytes, one anchor list, one drain
+    const i64 wbase0 = tile * @TILE@ + (i64)wid * (1024 * @W@);
+    #pragma unroll
+    for (int w = 0; w < @W@; ++w) wmask[32 * w + lane] = 0u;
     if (lane == 0u) wctr[0] = 0u;
     __syncwarp();
     if (wbase0 < A.n) {
       const i64 r0 = wbase0;
-      const i64 r1 = r0 + 1024 < A.n ? r0 + 1024 : A.n;
+      const i64 r1 = r0 + 1024 * @W@ < A.n ? r0 + 1024 * @W@ : A.n;
       const i64 b0 = (i64)offs[r0], b1 = (i64)offs[r1];
       auto push = [&](i64 pos) {
         const u32 ix = atomicAdd(wctr, 1u);
@@ -1945,8 +2000,9 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
         }
       }
     }
-    u32 mymask[1];
-    mymask[0] = wmask[lane];
+    u32 mymask[@W@];
+    #pragma unroll
+    for (int w = 0; w < @W@; ++w) mymask[w] = wmask[32 * w + lane];
     __syncwarp();
 @EPILOGUE@  }
 }
@@ -1979,7 +2035,7 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
   std::string prologue, epilogue;
   EmitPrologue(slots, spec, &prologue);
   prologue += scratch_decl;
-  EmitFilterEpilogue(slots, spec, NW, 1, SelCType(spec.selection_mode), &epilogue);
+  EmitFilterEpilogue(slots, spec, NW, W, SelCType(spec.selection_mode), &epilogue);
   ReplaceAll(&k, "@PROLOGUE@", prologue);
   ReplaceAll(&k, "@EPILOGUE@", epilogue);
   ReplaceAll(&k, "@PRED@", pred);
@@ -1991,10 +2047,35 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
   ReplaceAll(&k, "@NAME@", spec.name);
   ReplaceAll(&k, "@CAP@", std::to_string(kKeyAnchorCap));
   ReplaceAll(&k, "@J@", std::to_string(plan.slot));
-  ReplaceAll(&k, "@TILE@", std::to_string(static_cast<long long>(NW) * 1024) + "ll");
+  ReplaceAll(&k, "@TILE@", std::to_string(static_cast<long long>(NW) * 1024 * W) + "ll");
+  ReplaceAll(&k, "@W@", std::to_string(W));
   ReplaceAll(&k, "@IDX@", SelCType(spec.selection_mode));
   ReplaceAll(&k, "@UNIT@", std::to_string(unit));
   return k;
+}
+
+// Projector kernels that read their rows through a selection vector may get the slot count from
+// device memory (gdv_selection_t.d_num_slots: the count a Filter left there, so that a Filter ->
+// Projector chain never returns to the host): every use of A.n in the kernel body becomes gdv_n, the
+// smaller of *A.n_ptr and A.n (the host-side upper bound the grid was sized with).
+void ApplyDeviceCount(std::string* src) {
+  const std::string sig = "(const __grid_constant__ gdv_args A) {\n";
+  const size_t at = src->find(sig);
+  if (at == std::string::npos) return;
+  const size_t body = at + sig.size();
+  std::string tail = src->substr(body);
+  std::string out;
+  out.reserve(tail.size() + 64);
+  for (size_t i = 0; i < tail.size();) {
+    if (tail.compare(i, 3, "A.n") == 0 && (i + 3 >= tail.size() || !(std::isalnum(static_cast<unsigned char>(tail[i + 3])) || tail[i + 3] == '_'))) {
+      out += "gdv_n";
+      i += 3;
+    } else {
+      out.push_back(tail[i++]);
+    }
+  }
+  *src = src->substr(0, body) +
+         "  const i64 gdv_n = A.n_ptr != nullptr ? ((i64)*A.n_ptr < A.n ? (i64)*A.n_ptr : A.n) : A.n;\n" + out;
 }
 
 // Filter kernels: columns whose NULL makes the condition not-true (BodyGen::TruthStrict) have their
@@ -2347,6 +2428,9 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     BodyGen kgen(schema, &kslots, spec.nullable, /*coop=*/false);
     KeyPlan plan;
     const int kBT = spec.block_threads > 0 ? spec.block_threads : 256;
+    // chunks of 1024 rows per warp and tile: more rows per anchor drain and per tile-end barrier on
+    // big batches (Configuration.stages overrides), one on small ones (enough tiles for 148 SMs)
+    const int kW = (spec.stages == 1 || spec.stages == 2 || spec.stages == 4) ? spec.stages : (spec.large_batch ? 2 : 1);
     if (kBT % 32 == 0 && kBT <= 1024 && kgen.PlanKey(*exprs[0]->root(), &plan)) {
       std::string kbody;
       const Val kres = kgen.GenTruth(*exprs[0]->root(), &kbody, 6);
@@ -2361,7 +2445,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
         src += "#include \"gdv_device_lib.cuh\"\n";
         src += EmitArgsStruct(KL);
         src += kgen.globals();
-        src += EmitKeyFilter(kslots, spec, plan, kbody, kres, kBT, kgen.ScratchDecl(1));
+        src += EmitKeyFilter(kslots, spec, plan, kbody, kres, kBT, kW, kgen.ScratchDecl(1));
         int in_bytes = 0;
         for (const auto& sl : kslots) in_bytes += sl.type.is_varlen() ? 32 : std::max(sl.type.width(), 1);
         out->source = std::move(src);
@@ -2377,8 +2461,8 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
         out->in_bytes_per_row = in_bytes;
         out->out_bytes_per_row = 0;
         out->args_size = KL.size;
-        out->dynamic_smem = (kBT / 32) * (kKeyAnchorCap + 36) * 4;
-        out->tile_rows = static_cast<int64_t>(kBT / 32) * 1024;
+        out->dynamic_smem = (kBT / 32) * (kKeyAnchorCap + 32 * kW + 4) * 4;
+        out->tile_rows = static_cast<int64_t>(kBT / 32) * 1024 * kW;
         out->key_driven = true;
         out->staged = false;
         out->stages = 0;
@@ -2788,6 +2872,7 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
     src += "}\n";
   }
 
+  if (has_sel) ApplyDeviceCount(&src);
   out->source = std::move(src);
   out->name = spec.name;
   out->kind = spec.kind;

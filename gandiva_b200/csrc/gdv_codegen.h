@@ -83,7 +83,7 @@ struct GeneratedKernel {
 struct ArgsLayout {
   int ni, no;  // array extents (>= 1)
   size_t off_n = 0, off_row_base = 8, off_sel = 16, off_out_idx = 24, off_out_count = 32,
-         off_tile_state = 40, off_ticket = 48, off_err = 56, off_out_cap = 64;
+         off_tile_state = 40, off_ticket = 48, off_err = 56, off_out_cap = 64, off_n_ptr = 72;
   size_t off_in_val, off_in_vld, off_in_var, off_out_val, off_out_vld, off_out_var, off_in_vsh,
       off_in_dsh, size;
   ArgsLayout(int n_inputs, int n_outputs);

@@ -166,6 +166,25 @@ class Parser {
       if (More() && Peek() == '?') ++i_;  // lazy: the same set of matching rows
       if (More() && Peek() == '+') { Fail(2, "possessive repetition"); break; }
       atom = Expand(atom, lo, hi);
+      // the reference's RE2 does not stack repetition operators: a** / a+* / a{2}* are syntax errors
+      if (code == 0 && More()) {
+        const unsigned char q = Peek();
+        bool again = q == '*' || q == '+' || q == '?';
+        if (q == '{') {
+          const size_t save = i_;
+          int a = 0, b2 = 0;
+          ++i_;
+          if (Number(&a)) {
+            if (More() && Peek() == ',') {
+              ++i_;
+              (void)Number(&b2);
+            }
+            again = More() && Peek() == '}';
+          }
+          i_ = save;
+        }
+        if (again) { Fail(1, "bad repetition operator: a repetition cannot follow another one"); break; }
+      }
     }
     return atom;
   }

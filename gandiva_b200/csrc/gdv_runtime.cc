@@ -25,6 +25,8 @@ const char* ExecutionErrorMessage(int code) {
     case 7: return "Failed to cast the string to a decimal (not a decimal number)";
     case 8: return "Failed to cast the string to a float (not a number)";
     case 9: return "Invalid value for boolean";
+    case 10: return "Output buffer length can't be negative";
+    case 11: return "Start position must be greater than 0";
     default: return "execution error in device function";
   }
 }
@@ -677,6 +679,8 @@ Status Projector::EvaluateString(StringKernels* sk, const gdv_batch_t* batch,
                                  bool async, bool size_only, int64_t* total_out) {
   int64_t n = 0;
   GDV_RETURN_NOT_OK(CheckEvaluateArgs(batch, sel, &n));
+  if (sel != nullptr && sel->d_num_slots != nullptr)
+    return Status::Make(GDV_NOT_IMPLEMENTED, "utf8/binary outputs need the slot count on the host (d_num_slots is for fixed-width outputs)");
   const bool host = batch->mem_space == GDV_MEM_HOST;
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
@@ -864,6 +868,10 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
         GDV_RETURN_NOT_OK(StagedHtoD(dev, dsel, sel->indices, bytes, stream));
     }
     Put<CUdeviceptr>(args, L.off_sel, dsel);
+    if (sel->d_num_slots != nullptr) {
+      if (host) return Status::Make(GDV_INVALID, "d_num_slots needs device buffers");
+      Put<CUdeviceptr>(args, L.off_n_ptr, reinterpret_cast<CUdeviceptr>(sel->d_num_slots));
+    }
   }
   // outputs
   struct OutStage {

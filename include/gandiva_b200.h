@@ -179,6 +179,11 @@ typedef struct gdv_selection {
   int32_t mem_space;  /* GDV_MEM_* */
   int64_t index_base; /* filter: added to every emitted index (row-range sharding: the
                          shard's first global row); projector: ignored */
+  const void* d_num_slots; /* projector, device buffers, may be NULL: device uint64 holding the slot
+                         count (e.g. the d_count a Filter wrote on the same stream).  The kernel reads
+                         it on the device, so a Filter -> Projector chain needs no host round trip;
+                         num_slots is then only an upper bound (grid size, output capacity).  Rows past
+                         the device count are not written.  Fixed-width outputs only. */
 } gdv_selection_t;
 
 /* ---- library / device ---------------------------------------------------- */
@@ -276,6 +281,17 @@ int32_t gdv_registry_size(void);
 /* Signature i: name, return type, parameter types (up to max_params written; returns count). */
 gdv_status gdv_registry_get(int32_t i, const char** name, gdv_type_t* ret, gdv_type_t* params,
                             int32_t max_params, int32_t* n_params);
+
+/* ---- device memory (the engine's pooled allocator; what the C++ layer's arrow::MemoryManager
+ *      for HBM, include/gandiva/device.h, allocates from) ---------------------------------- */
+gdv_status gdv_device_alloc(int32_t device, size_t bytes, void** out);
+gdv_status gdv_device_free(int32_t device, void* p);
+/* Returns idle pool blocks to the driver until at most keep_bytes stay cached (the pool also trims
+ * itself above GDV_POOL_LIMIT_MB, default 4096); *released (may be NULL) = bytes given back. */
+gdv_status gdv_device_trim(int32_t device, size_t keep_bytes, size_t* released);
+/* Copy between host and device memory on the engine's stream, synchronously.
+ * kind 1 = host -> device, 2 = device -> host. */
+gdv_status gdv_memcpy(int32_t device, void* dst, const void* src, size_t bytes, int32_t kind);
 
 /* ---- device helpers used by the harness (bench.py, tests) ---------------- */
 /* Pinned host memory (cuMemHostAlloc) so H2D staging runs at PCIe speed. */

@@ -2602,6 +2602,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
                      : Substr(a[0].s, a[1].i, static_cast<int64_t>(a[0].s.size()));
     return;
   }
+  if (f == "castVARCHAR" && na == 2 && a[1].i < 0) { cx.error = 10; return; }   // "Output buffer length can't be negative"
   if (f == "castVARCHAR" && t0.id == T_DECIMAL) {
     // unscaled digits with the point `scale` places from the right
     u128 m = a[0].dec < 0 ? (~static_cast<u128>(a[0].dec) + 1) : static_cast<u128>(a[0].dec);
@@ -2796,7 +2797,7 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     const std::string& str = text_first ? a[0].s : a[1].s;
     const int64_t start = na == 3 ? a[2].i : 1;
     out->i = 0;
-    if (start < 1) return;
+    if (start < 1) { cx.error = 11; return; }   // "Start position must be greater than 0"
     const std::vector<size_t> st = GlyphStarts(str);
     const int64_t g = static_cast<int64_t>(st.size());
     if (start > g + 1) return;

@@ -274,7 +274,8 @@ def case_string_positions(b):
         (fn("octet_length", [fn("right", [s, kk], S)], I), I),
         (fn("locate", [lit("ar", S), s], I), I), (fn("locate", [lit("", S), s], I), I),
         (fn("locate", [lit("本", S), s], I), I), (fn("locate", [lit("e", S), s, lit(3, I)], I), I),
-        (fn("locate", [lit("s", S), s, kk], I), I), (fn("locate", [u, s], I), I),
+        (fn("locate", [lit("s", S), s, b.make_if(fn("greater_than", [kk, lit(0, I)], B), kk, lit(1, I), I)], I), I),
+        (fn("locate", [u, s], I), I),
         (fn("position", [lit("re", S), s], I), I),
         (fn("strpos", [s, lit("re", S)], I), I), (fn("strpos", [fn("upper", [s], S), lit("RE", S)], I), I),
         (fn("octet_length", [fn("byte_substr", [z, lit(2, I), lit(5, I)], BIN)], I), I),
@@ -721,8 +722,10 @@ def case_cast_varchar(b):
     I = pa.int32()
     L = lambda v: b.make_literal(v, pa.int64())
     cv = lambda n: b.make_function("castVARCHAR", [s, n], t)
+    # a negative length raises (test_raising_arguments): the variable length is clamped at 0 here
+    kpos = b.make_if(b.make_function("greater_than_or_equal_to", [k, L(0)], pa.bool_()), k, L(0), pa.int64())
     return schema, [(b.make_function("octet_length", [cv(L(5))], I), I),
-                    (b.make_function("char_length", [cv(k)], I), I),
+                    (b.make_function("char_length", [cv(kpos)], I), I),
                     (b.make_function("like", [cv(L(7)), b.make_literal("%spa%", t)], pa.bool_()), pa.bool_()),
                     (b.make_function("equal", [cv(L(0)), b.make_literal("", t)], pa.bool_()), pa.bool_())], "project"
 
@@ -872,7 +875,7 @@ def case_string_outputs(b):
         (up, t),
         (b.make_function("lower", [b.make_function("substr", [s, L(2), L(9)], t)], t), t),
         (b.make_function("btrim", [u], t), t),
-        (b.make_if(cond, up, b.make_function("castVARCHAR", [u, k], t), t), t),
+        (b.make_if(cond, up, b.make_function("castVARCHAR", [u, b.make_if(b.make_function("greater_than_or_equal_to", [k, L(0)], B), k, L(2), pa.int64())], t), t), t),
         (b.make_if(b.make_function("like", [s, b.make_literal("%spark%", t)], B),
                    b.make_literal("SPARK!", t), b.make_if(cond, b.make_literal("", t), b.make_literal(None, t), t), t), t),
         (b.make_function("char_length", [s], pa.int32()), pa.int32()),

@@ -104,9 +104,10 @@ def test_key_driven_filter_dense_and_empty(gandiva, oracle):
     assert np.array_equal(sel.to_array().to_numpy().astype(np.uint64), want)
     empty = pa.RecordBatch.from_arrays([pa.array([""] * 1000 + [None] * 5, S)], schema=schema)
     assert f.evaluate(empty).num_slots == 0
-    for bt in (1024, 64, 512):
-        f2 = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(block_threads=bt))
-        assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want), bt
+    for bt, w in ((1024, 1), (64, 2), (512, 4), (256, 2)):     # stages = 1024-row chunks per warp and tile
+        f2 = gandiva.make_filter(schema, b.make_condition(cond), gandiva.Configuration(block_threads=bt, stages=w))
+        assert "u32 mymask[%d];" % w in f2.llvm_ir
+        assert np.array_equal(f2.evaluate(batch).to_array().to_numpy().astype(np.uint64), want), (bt, w)
     # a long key in every row: far more than 128 anchors per 2 KB of bytes -> the all-rows fallback
     cond8 = b.make_function("like", [cases.F(b, "s", S), b.make_literal("%requests%", S)], B)
     f8 = gandiva.make_filter(schema, b.make_condition(cond8))

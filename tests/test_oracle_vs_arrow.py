@@ -457,7 +457,8 @@ def test_cast_varchar(oracle, gandiva):
     got = run_oracle(oracle, gandiva, cases.case_cast_varchar, batch)
     s, k = batch.column(0), batch.column(1)
     assert_arrays_match(got[0], pc.binary_length(pc.utf8_slice_codeunits(s, 0, 5)), "castVARCHAR 5")
-    want = [None if a is None or b is None else len(a[:max(b, 0)]) for a, b in zip(s.to_pylist(), k.to_pylist())]
+    # the case clamps the length: if (k >= 0) k else 0 -- a NULL k takes the else branch
+    want = [None if a is None else len(a[:max(b or 0, 0)]) for a, b in zip(s.to_pylist(), k.to_pylist())]
     assert_arrays_match(got[1], pa.array(want, type=pa.int32()), "castVARCHAR k")
 
 
@@ -1498,3 +1499,57 @@ def test_mod_of_doubles_against_math_fmod(oracle, gandiva):
     bad = pa.RecordBatch.from_arrays([pa.array([1.0], D), pa.array([0.0], D), pa.array([1], I), pa.array([1], I)], schema=schema)
     with pytest.raises(Exception, match="divide by zero"):
         oracle.project([b.make_function("modulo", [x, y], D)], [D], bad)
+
+
+def test_raising_arguments(oracle, gandiva):
+    """castVARCHAR(x, n) raises on a negative n, locate(sub, s, start) on start < 1 -- on the rows where
+    every argument is valid only (a NULL argument makes the row NULL, nothing is called), and not at
+    all under an if/else branch that is not taken."""
+    b = gandiva.TreeExprBuilder()
+    S, L, I, B = pa.string(), pa.int64(), pa.int32(), pa.bool_()
+    schema = pa.schema([("s", S), ("n", L), ("p", I)])
+    s, n, p = cases.F(b, "s", S), cases.F(b, "n", L), cases.F(b, "p", I)
+    fn = b.make_function
+    cv = fn("char_length", [fn("castVARCHAR", [s, n], S)], I)
+    loc = fn("locate", [b.make_literal("a", S), s, p], I)
+    ok = pa.RecordBatch.from_arrays([pa.array(["banana", "x", None, "abc"]), pa.array([3, 0, -5, None], L),
+                                     pa.array([1, 2, 0, None], I)], schema=schema)
+    got = oracle.project([cv, loc], [I, I], ok)
+    assert got[0].to_pylist() == [3, 0, None, None] and got[1].to_pylist() == [2, 0, None, None]
+    bad_len = pa.RecordBatch.from_arrays([pa.array(["banana", "x"]), pa.array([3, -1], L), pa.array([1, 1], I)], schema=schema)
+    with pytest.raises(Exception, match="Output buffer length can't be negative"):
+        oracle.project([cv], [I], bad_len)
+    bad_start = pa.RecordBatch.from_arrays([pa.array(["banana", "x"]), pa.array([3, 1], L), pa.array([1, 0], I)], schema=schema)
+    with pytest.raises(Exception, match="Start position must be greater than 0"):
+        oracle.project([loc], [I], bad_start)
+    # guarded by if/else: the untaken branch never raises
+    guarded = b.make_if(fn("greater_than_or_equal_to", [n, b.make_literal(0, L)], B), cv, b.make_literal(-1, I), I)
+    assert oracle.project([guarded], [I], bad_len)[0].to_pylist() == [3, -1]
+    # literal arguments that can never raise lower to the plain functions (no error plumbing in the kernel)
+    plain = gandiva.make_projector(schema, [b.make_expression(fn("char_length", [fn("castVARCHAR", [s, b.make_literal(5, L)], S)], I),
+                                                              pa.field("o", I))], None)
+    assert "gdv_check_len" not in plain.llvm_ir
+    checked = gandiva.make_projector(schema, [b.make_expression(cv, pa.field("o", I))], None)
+    assert "gdv_check_len" in checked.llvm_ir
+
+
+def test_like_escape_and_regex_repetition_are_validated(gandiva):
+    """The reference's pattern holders reject an escape character that is not followed by '_', '%' or
+    itself (or that ends the pattern), and RE2 rejects stacked repetition operators: Make() must too."""
+    b = gandiva.TreeExprBuilder()
+    S, B = pa.string(), pa.bool_()
+    schema = pa.schema([("s", S)])
+    s = cases.F(b, "s", S)
+
+    def like(pat, esc):
+        return b.make_condition(b.make_function("like", [s, b.make_literal(pat, S), b.make_literal(esc, S)], B))
+    for pat in ("100\\\\%", "a\\\\_b", "a\\\\\\\\b", "%x\\\\%%"):
+        gandiva.make_filter(schema, like(pat.replace("\\\\", "\\"), "\\"))
+    for pat in ("ab\\", "a\\bc", "\\x%"):
+        with pytest.raises(Exception, match="escape"):
+            gandiva.make_filter(schema, like(pat, "\\"))
+    for pat in ("a**", "a+*", "a{2}*", "a*{2}", "(ab)?+"):
+        with pytest.raises(Exception):
+            gandiva.make_filter(schema, b.make_condition(b.make_function("regexp_matches", [s, b.make_literal(pat, S)], B)))
+    for pat in ("a*?", "(a*)*", "a{2,3}?b", "a+b*"):
+        gandiva.make_filter(schema, b.make_condition(b.make_function("regexp_matches", [s, b.make_literal(pat, S)], B)))
