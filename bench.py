@@ -74,9 +74,10 @@ def parse_args():
                          "gdv_selection_push, device-side NVLink stores into rank 0's vector, no host "
                          "sync; nccl: all-gather of counts + send/recv (host reads the count)")
     ap.add_argument("--no-overlap", action="store_true", help="--gather nccl: gather inside each step, no pipelining")
-    ap.add_argument("--push-ctas", type=int, default=4, help="--gather push: CTAs of the push kernel")
+    ap.add_argument("--push-ctas", type=int, default=8, help="--gather push: CTAs (256 threads) of the push kernel")
     ap.add_argument("--sm-reserve", type=int, default=-1,
-                    help="SMs left free for the push / NCCL kernels (default: --push-ctas when N>1)")
+                    help="SMs the filter leaves free for the push / NCCL kernels (default with N>1: 2, i.e. twelve "
+                         "256-thread CTA slots for the eight push CTAs)")
     return ap.parse_args()
 
 
@@ -682,7 +683,7 @@ def main():
     idx_mode = "UINT32" if (world == 1 and n <= (1 << 32)) else "UINT64"
     idx_dtype = torch.int32 if idx_mode == "UINT32" else torch.int64
     use_push = world > 1 and not args.no_gather and args.gather == "push"
-    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else (args.push_ctas if use_push else 0)
+    sm_reserve = args.sm_reserve if args.sm_reserve >= 0 else ((2 if use_push else 4) if world > 1 and not args.no_gather else 0)
     cfg = gandiva.Configuration(device=local_rank, rows_per_thread=args.rows_per_thread,
                                 block_threads=args.block_threads, sm_reserve=sm_reserve)
     filt, _ = q6_filter(gandiva, cases, cfg)

@@ -150,23 +150,49 @@ __device__ __forceinline__ void gdv_st_release_sys(u64* p, u64 v) {
 }
 #endif
 
+// Moves one index run into peer memory.  Measured on two B200s (profiles/r02_p2p_store_bench.txt): a
+// kernel's peer stores reach 579 GB/s with 16-byte stores (497 with 8-byte ones, copy engine 731), and
+// what limits a FEW CTAs is bytes in flight per thread: 8 CTAs x 256 threads move 320 GB/s with eight
+// 16-byte stores in flight per thread, 200 with four.  The CTAs are 256 threads wide because they must
+// fit the slots the persistent filter kernel (256-thread CTAs) leaves free (gdv_config_t.sm_reserve).
 template <typename T>
-__device__ __forceinline__ void gdv_copy_run(const T* __restrict__ src, T* dst, u64 n) {
+__device__ __forceinline__ void gdv_copy_run_scalar(const T* __restrict__ src, T* dst, u64 n) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  // eight independent local loads in flight per thread, then eight fire-and-forget peer stores:
-  // a few CTAs are enough to move one run per step while the next filter kernel owns the GPU
-  for (; i + 7 * stride < n; i += 8 * stride) {
-    T v[8];
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+// 8-byte elements: the destination (run offset in the root's vector) is only 8-byte aligned, so the
+// first element goes alone when needed; after that every store is one aligned 16-byte peer store fed
+// by two local 8-byte loads (the source is then off by one element, which local loads do not mind).
+__device__ __forceinline__ void gdv_copy_run_u64(const u64* __restrict__ src, u64* dst, u64 n) {
+  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 head = (((unsigned long long)dst & 15ull) != 0ull && n > 0) ? 1ull : 0ull;
+  if (head != 0ull && tid == 0) dst[0] = src[0];
+  const u64* s = src + head;
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(dst + head);
+  const u64 pairs = (n - head) >> 1;
+  u64 i = tid;
+  for (; i + 7 * stride < pairs; i += 8 * stride) {
+    ulonglong2 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + i + k * stride);
+    for (int k = 0; k < 8; ++k) {
+      const u64 e = 2 * (i + k * stride);
+      v[k].x = __ldcs(s + e);
+      v[k].y = __ldcs(s + e + 1);
+    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dst[i + k * stride] = v[k];
+    for (int k = 0; k < 8; ++k) d[i + k * stride] = v[k];
   }
-  for (; i < n; i += stride) dst[i] = src[i];
+  for (; i < pairs; i += stride) {
+    ulonglong2 v;
+    v.x = s[2 * i];
+    v.y = s[2 * i + 1];
+    d[i] = v;
+  }
+  if (((n - head) & 1ull) != 0ull && tid == 0) dst[n - 1] = src[n - 1];
 }
 
-extern "C" __global__ void __launch_bounds__(1024)
+extern "C" __global__ void __launch_bounds__(256)
 gdv_sel_push(const void* src, const u64* d_count, void* dst, i64 dst_cap, u64* board_count,
              u64* board_done, u64* board_consumed, u64* board_err, int rank, int world, u64 seq,
              u64 need_consumed, int elem_bytes, u64* local_ctr, u64 done_target, u64* total_out) {
@@ -193,11 +219,11 @@ gdv_sel_push(const void* src, const u64* d_count, void* dst, i64 dst_cap, u64* b
   if (rank != 0) {
     if (off + cnt <= (u64)dst_cap) {
       if (elem_bytes == 8)
-        gdv_copy_run(reinterpret_cast<const u64*>(src), reinterpret_cast<u64*>(dst) + off, cnt);
+        gdv_copy_run_u64(reinterpret_cast<const u64*>(src), reinterpret_cast<u64*>(dst) + off, cnt);
       else if (elem_bytes == 4)
-        gdv_copy_run(reinterpret_cast<const u32*>(src), reinterpret_cast<u32*>(dst) + off, cnt);
+        gdv_copy_run_scalar(reinterpret_cast<const u32*>(src), reinterpret_cast<u32*>(dst) + off, cnt);
       else
-        gdv_copy_run(reinterpret_cast<const u16*>(src), reinterpret_cast<u16*>(dst) + off, cnt);
+        gdv_copy_run_scalar(reinterpret_cast<const u16*>(src), reinterpret_cast<u16*>(dst) + off, cnt);
     } else if (threadIdx.x == 0 && blockIdx.x == 0) {
       gdv_st_release_sys(board_err, seq);
     }

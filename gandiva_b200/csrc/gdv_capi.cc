@@ -592,7 +592,7 @@ gdv_status gdv_selection_push(int32_t device, const void* d_src, const void* d_c
                     &rank, &world, &seq, &need_consumed, &elem_bytes, &d_local_counter, &done_target,
                     &d_total_out};
   const unsigned grid = rank == 0 ? 1u : static_cast<unsigned>(std::max(1, ctas));
-  const unsigned threads = rank == 0 ? 32u : 1024u;
+  const unsigned threads = rank == 0 ? 32u : 256u;  // fits the slots a 256-thread persistent filter leaves free
   g_launch_count.fetch_add(1);
   s = CuCheck(Driver().LaunchKernel(fn, grid, 1, 1, threads, 1, 1, 0, st, params, nullptr),
               "cuLaunchKernel(gdv_sel_push)");

@@ -15,7 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIBDIR = os.path.join(HERE, "lib")              # libcuda.so.1 stand-in: goes on LD_LIBRARY_PATH
 NVRTC_DIR = os.path.join(HERE, "lib_nvrtc")     # libnvrtc.so.12 stand-in: named by GDV_NVRTC_PATH only (a
 #                                                 real NVRTC must never find it on the loader path)
-CACHE = os.path.join(HERE, "cache")
+# compiled host builds of the generated kernels (hundreds of MB over a session): kept OUTSIDE the repo so that
+# they never travel with a gpurun snapshot (the snapshot has a 512 MiB limit); GDV_EMU_CACHE overrides
+CACHE = os.environ.get("GDV_EMU_CACHE_DIR", os.path.join("/tmp", "gdv_emu_cache_%d" % os.getuid()))
 CUDA_INC = "/usr/local/cuda/include"
 DEVICE_DIR = os.path.join(ROOT, "gandiva_b200", "csrc", "device")
 

@@ -35,9 +35,9 @@ def main():
     qty = torch.empty(n, dtype=torch.float64, device=dev)
     b = gandiva.TreeExprBuilder()
     filt = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)),
-                               gandiva.Configuration(device=local, sm_reserve=4))
+                               gandiva.Configuration(device=local, sm_reserve=2))
     ps = PeerSelection(capacity=int(total_rows * 0.05) + 1024, local_rows=n, mode="UINT64", device=dev,
-                       slots=2, ctas=4)
+                       slots=2, ctas=8)
     cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
     ok = True
     for step in range(steps):
