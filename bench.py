@@ -57,8 +57,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=int(os.environ.get("GDV_BENCH_ROWS", 1_000_000_000)),
-                    help="lineitem rows per GPU per step")
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("GDV_BENCH_ROWS", 0)),
+                    help="lineitem rows per GPU per step (default: 1e9 at N=1 = BASELINE.json configs[1]; 1.25e9 at N>1 = "
+                         "configs[4]'s 10 B rows over 8 GPUs, the same per-GPU shard at every N>1)")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows per e2e step (0 = same as --rows)")
     ap.add_argument("--e2e-chunk", type=int, default=32 * 1024 * 1024, help="rows per host RecordBatch")
     ap.add_argument("--cpu-rows", type=int, default=0, help="CPU arm rows per step (0 = same as --rows)")
@@ -246,7 +247,7 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rows = args.cpu_rows or args.rows
+    rows = args.cpu_rows or args.rows or (1_000_000_000 if world == 1 else 1_250_000_000)
     res = cpu_q6(rows, max(args.steps, 1), max(args.warmup, 1))
     rps = res["value"]
     line = {
@@ -678,7 +679,7 @@ def main():
     torch.cuda.set_stream(stream)     # NCCL ops are all ordered on it
     st = stream.cuda_stream
 
-    n = args.rows
+    n = args.rows or (1_000_000_000 if world == 1 else 1_250_000_000)
     first_row = rank * n
     idx_mode = "UINT32" if (world == 1 and n <= (1 << 32)) else "UINT64"
     idx_dtype = torch.int32 if idx_mode == "UINT32" else torch.int64
@@ -965,10 +966,12 @@ def run_e2e(args, gandiva, cases, torch, np, dev, local_rank, rank, world, n, sh
     import ctypes as C
     import psutil
     rows = args.e2e_rows or n
+    if world > 1:   # every rank stages its own host copy: bound the node's total (the per-GPU rate is the PCIe link's)
+        rows = min(rows, 512 * 1024 * 1024)
     avail = psutil.virtual_memory().available
-    need = rows * 24 * 2 + (1 << 30)
-    if need > avail * 0.6:
-        rows = int(avail * 0.6 - (1 << 30)) // 48 // 1024 * 1024
+    need = rows * 24 + (1 << 30)
+    if need * world > avail * 0.5:
+        rows = int(avail * 0.5 / world - (1 << 30)) // 24 // 1024 * 1024
     chunk = min(args.e2e_chunk, rows)
     rows = rows // chunk * chunk
     if rows <= 0:

@@ -1920,7 +1920,10 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
       while (true) {
         bool last;
         if (!redo) {
-          if (ci < nch) {
+          // four blocks (8 KB) between two looks at the anchor list: the warp-wide hand-shake below
+          // costs as much as a quarter of a block's compares
+          #pragma unroll 1
+          for (int rep = 0; rep < 4 && ci < nch; ++rep, ci += 128) {
             bool any[4];
             if (ci + 128 <= nch) {
               uint4 v[4];
@@ -1951,7 +1954,6 @@ std::string EmitKeyFilter(const std::vector<ColumnSlot>& slots, const KernelSpec
               }
             }
           }
-          ci += 128;
           last = ci >= nch;
         } else {
           #pragma unroll

@@ -119,15 +119,18 @@ def bench_str(rows_per_batch, batches):
         out = torch.empty(n, dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         cols = [(d_vld.data_ptr(), d_offs.data_ptr(), d_bytes.data_ptr(), 0)]
-        # (block_threads, rows_per_thread, string_scan): 0 = key-driven filter (the default), 4 = row-driven kernel
-        combos = [(0, 0, 0)] + [(bt, 0, 0) for bt in (128, 256, 512, 1024)] + [(512, 2, 4), (256, 2, 4)]
+        # (block_threads, rows_per_thread, string_scan[, stages]): string_scan 0 = key-driven filter (the default),
+        # 4 = row-driven kernel; stages = 1024-row chunks per warp and tile of the key-driven kernel (0 = engine picks)
+        combos = [(0, 0, 0, 0)] + [(bt, 0, 0, w) for bt in (128, 256, 512) for w in (1, 2, 4)] + [(512, 2, 4, 0)]
         if os.environ.get("GDV_STR_COMBOS"):
             combos = [tuple(int(x) for x in c.split(",")) for c in os.environ["GDV_STR_COMBOS"].split(";")]
-        for bt, rpt, scan in combos:
+        for combo in combos:
+            bt, rpt, scan = combo[:3]
+            stages = combo[3] if len(combo) > 3 else 0
             if True:
                 b = gandiva.TreeExprBuilder()
                 f = gandiva.make_filter(cases.COMMENT_SCHEMA, b.make_condition(cases.comment_condition(b)),
-                                        gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, string_scan=scan))
+                                        gandiva.Configuration(rows_per_thread=rpt, block_threads=bt, string_scan=scan, stages=stages))
 
                 def run():
                     for _ in range(batches):
@@ -138,6 +141,7 @@ def bench_str(rows_per_batch, batches):
                 bytes_ = batches * (4.0 * n + block_bytes * reps + n / 8.0 + 4.0 * count)
                 gbs = bytes_ / ms / 1e6
                 r = {"config": "string_filter_like_upper_substr", "block_threads": f.kernel_info["block_threads"], "rows_per_thread": rpt,
+                     "stages": stages, "tile_rows": f.kernel_info.get("tile_rows"),
                      "matcher": ("row-driven: " + ("per-lane" if scan & 1 else "cooperative scan") + ", cp.async prefetch") if scan & 4
                      else "key-driven: aligned-word scan of the column bytes",
                      "rows": rows, "ms": ms, "rows_per_s": rows / ms * 1e3, "gbs": gbs, "frac": gbs / PEAK,
