@@ -1047,15 +1047,23 @@ GDV_DEV i64 gdv_add_months(i64 ms, i64 months) {
 }
 #define GDV_TSADD(NAME, UNIT_MS)                                                                  \
   GDV_DEV i64 NAME##_int32_timestamp(i32 n, i64 ts) { return (i64)((u64)ts + (u64)((i64)n * (UNIT_MS))); } \
-  GDV_DEV i64 NAME##_int64_timestamp(i64 n, i64 ts) { return (i64)((u64)ts + (u64)n * (u64)(UNIT_MS)); }
+  GDV_DEV i64 NAME##_int64_timestamp(i64 n, i64 ts) { return (i64)((u64)ts + (u64)n * (u64)(UNIT_MS)); } \
+  GDV_DEV i64 NAME##_timestamp_int32(i64 ts, i32 n) { return NAME##_int32_timestamp(n, ts); }     \
+  GDV_DEV i64 NAME##_timestamp_int64(i64 ts, i64 n) { return NAME##_int64_timestamp(n, ts); }
 GDV_TSADD(timestampaddSecond, 1000ll)
 GDV_TSADD(timestampaddMinute, 60000ll)
 GDV_TSADD(timestampaddHour, 3600000ll)
 GDV_TSADD(timestampaddDay, 86400000ll)
 GDV_TSADD(timestampaddWeek, 604800000ll)
-GDV_DEV i64 timestampaddMonth_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, (i64)n); }
-GDV_DEV i64 timestampaddQuarter_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, 3 * (i64)n); }
-GDV_DEV i64 timestampaddYear_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, 12 * (i64)n); }
+// calendar units: month counts wrap in 64 bits (an int64 count times 3 or 12), like the millisecond units
+#define GDV_TSADD_MONTHS(NAME, K)                                                                 \
+  GDV_DEV i64 NAME##_int32_timestamp(i32 n, i64 ts) { return gdv_add_months(ts, (K) * (i64)n); }  \
+  GDV_DEV i64 NAME##_int64_timestamp(i64 n, i64 ts) { return gdv_add_months(ts, (i64)((u64)(K) * (u64)n)); } \
+  GDV_DEV i64 NAME##_timestamp_int32(i64 ts, i32 n) { return NAME##_int32_timestamp(n, ts); }     \
+  GDV_DEV i64 NAME##_timestamp_int64(i64 ts, i64 n) { return NAME##_int64_timestamp(n, ts); }
+GDV_TSADD_MONTHS(timestampaddMonth, 1ll)
+GDV_TSADD_MONTHS(timestampaddQuarter, 3ll)
+GDV_TSADD_MONTHS(timestampaddYear, 12ll)
 GDV_DEV i64 date_add_date64_int32(i64 d, i32 n) { return (i64)((u64)d + (u64)((i64)n * 86400000ll)); }
 GDV_DEV i64 date_sub_date64_int32(i64 d, i32 n) { return (i64)((u64)d - (u64)((i64)n * 86400000ll)); }
 GDV_DEV i64 date_add_timestamp_int32(i64 d, i32 n) { return date_add_date64_int32(d, n); }

@@ -204,12 +204,14 @@ Registry::Registry() {
   Add("truncate", {I64, I32}, I64, NullMode::kIfNull, 0, {"trunc"});
 
   // ---- date / time arithmetic -------------------------------------------------------------
+  // every unit in both argument orders (count, timestamp) / (timestamp, count) and with int32 / int64 counts
   for (const char* f : {"timestampaddSecond", "timestampaddMinute", "timestampaddHour", "timestampaddDay",
-                        "timestampaddWeek"}) {
+                        "timestampaddWeek", "timestampaddMonth", "timestampaddQuarter", "timestampaddYear"}) {
     Add(f, {I32, TS}, TS);
     Add(f, {I64, TS}, TS);
+    Add(f, {TS, I32}, TS);
+    Add(f, {TS, I64}, TS);
   }
-  for (const char* f : {"timestampaddMonth", "timestampaddQuarter", "timestampaddYear"}) Add(f, {I32, TS}, TS);
   Add("date_add", {D64, I32}, D64);
   Add("date_sub", {D64, I32}, D64);
   Add("date_add", {TS, I32}, TS);

@@ -306,6 +306,19 @@ int64_t proxy_q6_filter(const int32_t* ship, const double* disc, const double* q
   });
 }
 
+// The same on the calling thread alone: Gandiva evaluates one RecordBatch on one thread.
+void proxy_add_i32_inline(const int32_t* a, const int32_t* b, const uint8_t* va, const uint8_t* vb, int64_t n,
+                          int32_t* out, uint8_t* vout) {
+  for (int64_t i = 0; i < n; ++i) out[i] = (int32_t)((uint32_t)a[i] + (uint32_t)b[i]);
+  if (vout != nullptr) {
+    for (int64_t r = 0; r < n; r += 64) {
+      const uint64_t w = Valid64(va, r, n) & Valid64(vb, r, n) & TailMask(r, n);
+      const int64_t bytes = (n + 7) / 8 - r / 8;
+      memcpy(vout + r / 8, &w, bytes >= 8 ? 8 : (size_t)bytes);
+    }
+  }
+}
+
 // Projector add(int32, int32): values + validity (AND of the inputs') in one pass.
 void proxy_add_i32(const int32_t* a, const int32_t* b, const uint8_t* va, const uint8_t* vb, int64_t n, int32_t* out,
                    uint8_t* vout, int threads) {

@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
         L.proxy_q6_filter.restype = i64
         L.proxy_q6_filter.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, C.c_int]
         L.proxy_add_i32.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.c_int]
+        L.proxy_add_i32_inline.argtypes = [vp, vp, vp, vp, i64, vp, vp]
         L.proxy_comment_filter.restype = i64
         L.proxy_comment_filter.argtypes = [vp, vp, vp, i64, vp, vp, C.c_int]
         L.proxy_q1_project.argtypes = [C.POINTER(vp), C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), C.c_int]
@@ -136,6 +137,11 @@ def q6_filter(ship, disc, qty, v_ship, v_disc, v_qty, n: int, out, bits) -> int:
 
 def add_i32(a, b, va, vb, n: int, out, vout) -> None:
     lib().proxy_add_i32(_p(a), _p(b), _p(va), _p(vb), n, _p(out), _p(vout), 0)
+
+
+def add_i32_inline(a, b, va, vb, n: int, out, vout) -> None:
+    """On the calling thread only (one batch, one thread: how the reference evaluates a RecordBatch)."""
+    lib().proxy_add_i32_inline(_p(a), _p(b), _p(va), _p(vb), n, _p(out), _p(vout))
 
 
 def comment_filter(offsets, data, validity, n: int, out, bits) -> int:

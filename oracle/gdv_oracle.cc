@@ -2418,7 +2418,9 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   // ---- date/time arithmetic -----------------------------------------------------------------
   if (f.rfind("timestampadd", 0) == 0) {
     const std::string unit = f.substr(12);
-    const int64_t n = a[0].i, ts = a[1].i;
+    // (count, timestamp) or (timestamp, count)
+    const bool ts_first = t0.id == T_TIMESTAMP;
+    const int64_t n = ts_first ? a[1].i : a[0].i, ts = ts_first ? a[0].i : a[1].i;
     int64_t unit_ms = 0;
     if (unit == "Second") unit_ms = 1000;
     else if (unit == "Minute") unit_ms = 60000;
@@ -2429,7 +2431,8 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
       out->i = static_cast<int64_t>(static_cast<uint64_t>(ts) + static_cast<uint64_t>(n) * static_cast<uint64_t>(unit_ms));
       return;
     }
-    const int64_t months = unit == "Month" ? n : (unit == "Quarter" ? 3 * n : 12 * n);
+    const int64_t months = static_cast<int64_t>(static_cast<uint64_t>(unit == "Month" ? 1 : (unit == "Quarter" ? 3 : 12)) *
+                                                static_cast<uint64_t>(n));
     const int64_t days = FloorDiv(ts, 86400000);
     const int64_t in_day = ts - days * 86400000;
     const Ymd c = CivilFromDays(days);

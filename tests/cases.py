@@ -566,6 +566,12 @@ def case_date_arith(b):
         outs.append((b.make_function(fn, [t, u], pa.int32()), pa.int32()))
     outs.append((b.make_function("months_between", [t, u], pa.float64()), pa.float64()))
     outs.append((b.make_function("months_between", [d, b.make_function("castDATE", [t], d64)], pa.float64()), pa.float64()))
+    # the other argument order and int64 counts (small ones for the calendar units: the year must stay in range)
+    outs.append((b.make_function("timestampaddHour", [t, n], ts), ts))
+    outs.append((b.make_function("timestampaddWeek", [t, m], ts), ts))
+    outs.append((b.make_function("timestampaddMonth", [t, n], ts), ts))
+    outs.append((b.make_function("timestampaddYear", [t, b.make_function("castBIGINT", [n], pa.int64())], ts), ts))
+    outs.append((b.make_function("timestampaddQuarter", [b.make_function("castBIGINT", [n], pa.int64()), t], ts), ts))
     return schema, outs, "project"
 
 

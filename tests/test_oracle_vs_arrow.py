@@ -540,6 +540,15 @@ def test_date_arithmetic(oracle, gandiva):
                 w.append(q - (1 << 32) if q >> 31 else q)
         want.append(w)
     schema_b = cases.case_date_arith(gandiva.TreeExprBuilder())[1]
+    # the last five outputs: (timestamp, count) argument order and int64 counts
+    tail = [[None if a is None or b is None else b + a * unit["Hour"] for a, b in zip(n, t)],
+            [None if a is None or b is None else b + a * unit["Week"] for a, b in zip(m, t)],
+            [None if a is None or b is None else add_months(b, a) for a, b in zip(n, t)],
+            [None if a is None or b is None else add_months(b, 12 * a) for a, b in zip(n, t)],
+            [None if a is None or b is None else add_months(b, 3 * a) for a, b in zip(n, t)]]
+    assert len(got) == len(schema_b)
+    for g, w, (_, ty) in zip(got[-5:], tail, schema_b[-5:]):
+        assert_arrays_match(g, pa.array(w, type=pa.int64()).cast(ty), "date arithmetic, swapped / int64 arguments")
     for i, (g, w, (_, ty)) in enumerate(zip(got, want, schema_b)):
         exp = pa.array(w, type=pa.int64()).cast(ty) if not pa.types.is_int32(ty) else pa.array(w, type=pa.int32())
         assert_arrays_match(g, exp, "date arithmetic out %d" % i)
