@@ -70,6 +70,9 @@ def parse_args():
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` object (N=1)")
     ap.add_argument("--only", default="", help="comma list of configs entries to run (q6_nulls,q1,str,ab_1m)")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--equal-shards", action="store_true",
+                    help="N>1, --gather push: keep equal row ranges (default: rank 0's shard is smaller by what absorbing the "
+                         "other ranks' runs costs it)")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"],
                     help="N>1: how the SelectionVector reaches rank 0.  push (default): "
                          "gdv_selection_push, device-side NVLink stores into rank 0's vector, no host "
@@ -682,8 +685,9 @@ def main():
     torch.cuda.set_stream(stream)     # NCCL ops are all ordered on it
     st = stream.cuda_stream
 
-    n = args.rows or (1_000_000_000 if world == 1 else 1_250_000_000)
-    first_row = rank * n
+    n_nominal = args.rows or (1_000_000_000 if world == 1 else 1_250_000_000)
+    total_rows = n_nominal * world
+    n, first_row = n_nominal, rank * n_nominal
     idx_mode = "UINT32" if (world == 1 and n <= (1 << 32)) else "UINT64"
     idx_dtype = torch.int32 if idx_mode == "UINT32" else torch.int64
     use_push = world > 1 and not args.no_gather and args.gather == "push"
@@ -693,22 +697,58 @@ def main():
     filt, _ = q6_filter(gandiva, cases, cfg)
 
     # ---- inputs resident in HBM (generated on device; same stream as oracle/lineitem.h) -----
-    ship = torch.empty(n, dtype=torch.int32, device=dev)
-    disc = torch.empty(n, dtype=torch.float64, device=dev)
-    qty = torch.empty(n, dtype=torch.float64, device=dev)
-    for kind, t in ((0, ship), (1, disc), (2, qty)):
-        gandiva.generate_lineitem(local_rank, kind, 42, first_row, n, t.data_ptr(), 0, 0, st)
-    out_idx = None if use_push else torch.empty(n, dtype=idx_dtype, device=dev)
+    cap_rows = n_nominal if world == 1 else (int(n_nominal * 1.05) // 64 + 1) * 64
+    ship_full = torch.empty(cap_rows, dtype=torch.int32, device=dev)
+    disc_full = torch.empty(cap_rows, dtype=torch.float64, device=dev)
+    qty_full = torch.empty(cap_rows, dtype=torch.float64, device=dev)
+
+    def generate(first, rows):
+        for kind, t in ((0, ship_full), (1, disc_full), (2, qty_full)):
+            gandiva.generate_lineitem(local_rank, kind, 42, first, rows, t.data_ptr(), 0, 0, st)
+    generate(first_row, n)
     d_count = torch.zeros(1, dtype=torch.int64, device=dev)
-    cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
+    cols = [(0, ship_full.data_ptr(), 0, 0), (0, disc_full.data_ptr(), 0, 0), (0, qty_full.data_ptr(), 0, 0)]
     torch.cuda.synchronize()
+
+    # ---- N>1 with the SelectionVector reassembled on rank 0: the root's shard is smaller ----------
+    # Rank 0 does everything the other ranks do AND absorbs their runs: (N-1) x selectivity x 8 B per row
+    # land in its HBM while its own filter streams 20 B per row, and an incoming write costs the memory
+    # system about twice what a streamed read does (measured: +0.39 ms per 1.27 GB at N=8, +0.16 ms per
+    # 0.54 GB at N=4, profiles/r02_multi_gpu.md).  With equal shards every step waits for rank 0; shards
+    # sized so that all ranks finish together keep the same total (N x rows) and the same global order.
+    # The selectivity is measured by one calibration pass over the equal shards.
+    shard_rows = [n_nominal] * world
+    shard_note = None
+    if use_push and not args.equal_shards:
+        scratch_idx = torch.empty(1 << 20, dtype=idx_dtype, device=dev)
+        filt.evaluate_device(n, cols, scratch_idx.data_ptr(), scratch_idx.numel(), idx_mode + "|BOUNDED", st,
+                             d_count.data_ptr(), sync=False, index_base=first_row)
+        c = torch.tensor([filt.sync(st)], dtype=torch.int64, device=dev)
+        dist.all_reduce(c)
+        sel = float(c.item()) / total_rows
+        write_cost = 2.0
+        from gandiva_b200.sharding import shard_rows_with_root
+        shard_rows = shard_rows_with_root(total_rows, world, sel, ALGO_IN_BYTES_PER_ROW, 8, write_cost)
+        if max(shard_rows) <= cap_rows and min(shard_rows) > 0:
+            n = shard_rows[rank]
+            first_row = sum(shard_rows[:rank])
+            generate(first_row, n)
+            shard_note = ("rank 0 also absorbs the other ranks' runs: shards sized so that all ranks finish together "
+                          "(selectivity %.4f from a calibration pass, an incoming 8-byte index costed as %.0f B of streaming)"
+                          % (sel, write_cost * 8.0))
+        else:
+            shard_rows = [n_nominal] * world
+        del scratch_idx
+        torch.cuda.synchronize()
+    ship, disc, qty = ship_full[:n], disc_full[:n], qty_full[:n]
+    out_idx = None if use_push else torch.empty(n, dtype=idx_dtype, device=dev)
 
     from gandiva_b200.sharding import gather_selection
     pipelined = world > 1 and not args.no_gather and not args.no_overlap and not use_push
     ps = None
     if use_push:
         from gandiva_b200.sharding import PeerSelection
-        ps = PeerSelection(capacity=int(n * world * 0.03) + 4096, local_rows=n, mode=idx_mode, device=dev,
+        ps = PeerSelection(capacity=int(total_rows * 0.03) + 4096, local_rows=cap_rows, mode=idx_mode, device=dev,
                            slots=2, ctas=args.push_ctas)
     gstep = {"i": 0}
     # N>1: the gather of batch i runs on a second stream while the filter kernel of batch i+1
@@ -819,7 +859,7 @@ def main():
     else:
         total_selected = count
     ms_per_step = total_ms / args.steps
-    value = n * world / (ms_per_step * 1e-3)
+    value = total_rows / (ms_per_step * 1e-3)
     gather_check = None
     full_check = None
     if world == 1:
@@ -944,7 +984,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "TPC-H Q6 filter (BASELINE.json configs[1]%s)" %
                                    ("; configs[4] sharding" if world > 1 else ""),
-                       "rows_per_gpu": n, "total_rows": n * world, "selectivity": total_selected / (n * world),
+                       "rows_per_gpu": n_nominal, "total_rows": total_rows, "selectivity": total_selected / total_rows,
+                       "shard_rows": shard_rows if world > 1 else None, "shard_note": shard_note,
                        "selection_vector": idx_mode + ((" reassembled on rank 0 over NVLink" + (", gdv_selection_push: device-side stores into rank 0's vector (CUDA IPC), counts exchanged through a board in rank 0's HBM, no host sync, overlapped with the next batch's kernel (%d SMs reserved)" % sm_reserve if use_push else (", NCCL send/recv, overlapped with the next batch's kernel" if pipelined else ", NCCL send/recv"))) if world > 1 and not args.no_gather else ""),
                        "gather_check": gather_check, "full_size_check": full_check,
                        "l2_policy": "inputs (20 B/row x %d rows) larger than L2; no flush" % n,

@@ -22,6 +22,23 @@ def shard_range(num_rows: int, world: int, rank: int, align: int = 64) -> Tuple[
     return first, min(first + per, num_rows)
 
 
+def shard_rows_with_root(total_rows: int, world: int, selectivity: float, bytes_per_row: float, index_bytes: int = 8,
+                         write_cost: float = 2.0, align: int = 64) -> list:
+    """Row counts per rank (contiguous ranges, in rank order, summing to total_rows) for a Filter whose
+    SelectionVector is reassembled on rank 0.  The root streams its own rows AND absorbs the other ranks'
+    runs — (world-1) x selectivity x index_bytes per row of a shard, each incoming byte costing the memory
+    system about `write_cost` streamed bytes (measured 2.0 on B200) — so with equal ranges every
+    step waits for it.  The root's range is shortened until all ranks finish together.  Every range but the
+    last is a multiple of `align` rows (no two shards share a validity-bitmap word)."""
+    if world <= 1:
+        return [total_rows]
+    per = total_rows / world
+    delta = write_cost * index_bytes * selectivity * (world - 1) / bytes_per_row
+    r_root = max(align, int(per * (1.0 - delta * (world - 1) / world)) // align * align)
+    r_other = ((total_rows - r_root) // (world - 1)) // align * align
+    return [r_root] + [r_other] * (world - 2) + [total_rows - r_root - r_other * (world - 2)]
+
+
 def gather_selection(local_indices: torch.Tensor, count: int, dst: int = 0,
                      group: Optional[dist.ProcessGroup] = None,
                      out: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], int]:

@@ -74,3 +74,21 @@ def test_gather_selection_world2():
     want = oracle.filter_indices(cases.q6_condition(b), cases.q6_batch(n, seed=42))
     assert total == len(want)
     assert np.array_equal(got.astype(np.uint64), want)
+
+
+def test_shard_rows_with_root():
+    """Shards for a root-gathered Filter: contiguous, aligned, exact total, the root's range shorter by what
+    absorbing (world-1) runs costs; equal ranges when nothing is selected."""
+    from gandiva_b200.sharding import shard_rows_with_root
+    for world in (1, 2, 4, 8):
+        for total in (10_000_000_000, 1_000_003, 64 * world):
+            for sel in (0.0, 0.0181, 0.3):
+                r = shard_rows_with_root(total, world, sel, 20.0)
+                assert len(r) == world and sum(r) == total and min(r) > 0
+                assert all(x % 64 == 0 for x in r[:-1]) or world == 1
+                if world > 1 and sel > 0 and total > 1_000_000:
+                    assert r[0] < r[1]
+                if world > 1 and sel == 0.0 and total % (64 * world) == 0:
+                    assert len(set(r)) == 1
+    r = shard_rows_with_root(10_000_000_000, 8, 0.0181, 20.0)
+    assert abs(r[0] / 1.25e9 - 0.911) < 0.01 and abs(r[1] / 1.25e9 - 1.0127) < 0.005
