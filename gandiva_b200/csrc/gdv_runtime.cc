@@ -5,6 +5,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,15 @@ Device* g_devices[64] = {nullptr};
     ::gdv::Status _s = (expr);       \
     if (!_s.ok()) return _s;         \
   } while (0)
+
+// GDV_TRACE=1: phase timings of host-batch evaluations on stderr (where a call's microseconds go).
+bool TraceOn() {
+  static const bool on = std::getenv("GDV_TRACE") != nullptr;
+  return on;
+}
+double NowUs() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 size_t RoundPool(size_t bytes) {
   if (bytes < 512) return 512;
@@ -843,10 +853,12 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
   const GeneratedKernel& gen = kernel->gen;
 
+  const double t_begin = TraceOn() ? NowUs() : 0.0;
   ScratchScope scratch(dev);
   scratch.Guard(stream);
   std::vector<ResolvedIn> ins;
   GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
+  const double t_inputs = TraceOn() ? NowUs() : 0.0;
 
   ArgsLayout L(static_cast<int>(gen.inputs.size()), n_outs);
   std::vector<uint8_t> args(L.size, 0);
@@ -921,13 +933,20 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   GDV_RETURN_NOT_OK(LaunchKernel(dev, l, gen, args, grid, stream));
 
   if (host) {
+    const double t_launch = TraceOn() ? NowUs() : 0.0;
     for (int o = 0; o < n_outs; ++o) {
       if (stage[o].val_bytes > 0)
         GDV_RETURN_NOT_OK(StagedDtoH(dev, outs[o].values, stage[o].val, stage[o].val_bytes, stream));
       if (outs[o].validity != nullptr && stage[o].vld_bytes > 0)
         GDV_RETURN_NOT_OK(StagedDtoH(dev, outs[o].validity, stage[o].vld, stage[o].vld_bytes, stream));
     }
-    return Sync(stream);
+    const double t_out = TraceOn() ? NowUs() : 0.0;
+    Status st = Sync(stream);
+    if (TraceOn())
+      std::fprintf(stderr, "gdv trace: projector host batch %lld rows: inputs %.0f us, args+launch %.0f us, outputs %.0f us, "
+                           "sync %.0f us\n", static_cast<long long>(n), t_inputs - t_begin, t_launch - t_inputs,
+                   t_out - t_launch, NowUs() - t_out);
+    return st;
   }
   if (!async) return Sync(stream);
   // async with device buffers: inputs were not staged, scratch holds nothing the kernel reads

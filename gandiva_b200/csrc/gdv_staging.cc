@@ -43,10 +43,14 @@ class CopyPool {
       bytes_ = bytes;
       slice_ = slice;
       pending_ = n - 1;
+      pending_pub_.store(n - 1, std::memory_order_release);
       ++epoch_;
+      epoch_pub_.store(epoch_, std::memory_order_release);
     }
     cv_.notify_all();
     Slice(0);  // the calling thread takes the first slice
+    for (int spin = 0; spin < 20000; ++spin)  // the others finish within microseconds of this one
+      if (pending_pub_.load(std::memory_order_acquire) == 0) break;
     std::unique_lock<std::mutex> g(mu_);
     done_.wait(g, [this] { return pending_ == 0; });
   }
@@ -67,13 +71,22 @@ class CopyPool {
   void Loop(int t) {
     unsigned long long seen = 0;
     for (;;) {
+      // A host batch is several copies back to back (one per column, then the results): after a job the
+      // worker polls for the next one for ~100 us before it goes to sleep, because waking a sleeping thread
+      // costs tens of microseconds — as much as copying its whole slice.
+      bool got = false;
+      for (int spin = 0; spin < 20000 && !got; ++spin) {
+        if (epoch_pub_.load(std::memory_order_acquire) != seen) got = true;
+        else if ((spin & 63) == 63) std::this_thread::yield();
+      }
       {
         std::unique_lock<std::mutex> g(mu_);
-        cv_.wait(g, [&] { return epoch_ != seen; });
+        if (!got) cv_.wait(g, [&] { return epoch_ != seen; });
         seen = epoch_;
       }
       Slice(t);
       std::lock_guard<std::mutex> g(mu_);
+      pending_pub_.store(pending_ - 1, std::memory_order_release);
       if (--pending_ == 0) done_.notify_one();
     }
   }
@@ -85,6 +98,8 @@ class CopyPool {
   size_t bytes_ = 0, slice_ = 0;
   int pending_ = 0;
   unsigned long long epoch_ = 0;
+  std::atomic<unsigned long long> epoch_pub_{0};  // epoch_, readable without the lock by polling workers
+  std::atomic<int> pending_pub_{0};               // pending_, for the caller's short poll
 };
 
 // The pinned slots of one device.  One transfer at a time uses the ring (the link is shared anyway).

@@ -566,12 +566,20 @@ def case_date_arith(b):
         outs.append((b.make_function(fn, [t, u], pa.int32()), pa.int32()))
     outs.append((b.make_function("months_between", [t, u], pa.float64()), pa.float64()))
     outs.append((b.make_function("months_between", [d, b.make_function("castDATE", [t], d64)], pa.float64()), pa.float64()))
-    # the other argument order and int64 counts (small ones for the calendar units: the year must stay in range)
-    outs.append((b.make_function("timestampaddHour", [t, n], ts), ts))
-    outs.append((b.make_function("timestampaddWeek", [t, m], ts), ts))
-    outs.append((b.make_function("timestampaddMonth", [t, n], ts), ts))
-    outs.append((b.make_function("timestampaddYear", [t, b.make_function("castBIGINT", [n], pa.int64())], ts), ts))
-    outs.append((b.make_function("timestampaddQuarter", [b.make_function("castBIGINT", [n], pa.int64()), t], ts), ts))
+    return schema, outs, "project"
+
+
+def case_date_arith_swapped(b):
+    """timestampadd* in the (timestamp, count) argument order and with int64 counts (same batch as case_date_arith)."""
+    ts, d64 = pa.timestamp("ms"), pa.date64()
+    schema = pa.schema([("t", ts), ("u", ts), ("d", d64), ("n", pa.int32()), ("m", pa.int64())])
+    t, n, m = F(b, "t", ts), F(b, "n", pa.int32()), F(b, "m", pa.int64())
+    n64 = b.make_function("castBIGINT", [n], pa.int64())
+    outs = [(b.make_function("timestampaddHour", [t, n], ts), ts),
+            (b.make_function("timestampaddWeek", [t, m], ts), ts),
+            (b.make_function("timestampaddMonth", [t, n], ts), ts),
+            (b.make_function("timestampaddYear", [t, n64], ts), ts),       # small counts: the year must stay in range
+            (b.make_function("timestampaddQuarter", [n64, t], ts), ts)]
     return schema, outs, "project"
 
 
@@ -1143,7 +1151,7 @@ def all_project_cases():
               case_decimal_divide(38, 30, 12, 0),
               case_decimal_mod(15, 2, 15, 2), case_decimal_mod(38, 10, 20, 4), case_decimal_mod(20, 0, 38, 30),
               case_decimal_from_double, case_cast_varchar, case_string_outputs, case_binary_output,
-              case_concat_outputs, case_rounding, case_date_arith, case_intmath, case_calendar,
+              case_concat_outputs, case_rounding, case_date_arith, case_date_arith_swapped, case_intmath, case_calendar,
               case_string_positions, case_number_to_text, case_string_misc, case_virtual_strings,
               case_decimal_rounding, case_math, case_trig, case_regexp, case_misc_casts, case_power, case_inverse_trig, case_in_floats, case_concat_consumers]
     cases += [case_hash(t) for t in HASH_TYPES]
