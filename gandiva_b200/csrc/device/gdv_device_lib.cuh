@@ -44,6 +44,8 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_CAST_BOOL 9        /* castBIT / castBOOLEAN of a string that is not true / false / 1 / 0 */
 #define GDV_ERR_NEG_LENGTH 10      /* castVARCHAR(x, n) with n < 0 */
 #define GDV_ERR_LOCATE_START 11    /* locate(sub, s, start) with start < 1 */
+#define GDV_ERR_FACTORIAL_NEG 12   /* factorial of a negative number */
+#define GDV_ERR_FACTORIAL_BIG 13   /* factorial of a number above 20 (does not fit int64) */
 struct gdv_ctx {
   int* err;
 };
@@ -424,6 +426,23 @@ GDV_INTDIV(i32, u32, int32)
 GDV_INTDIV(i64, u64, int64)
 GDV_DEV f32 sign_float32(f32 a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : a); }
 GDV_DEV f64 sign_float64(f64 a) { return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : a); }
+// bround: round half to even (the IEEE default rounding of rint)
+GDV_DEV f64 bround_float64(f64 a) { return rint(a); }
+// factorial(n), 0 <= n <= 20 (21! does not fit int64); anything else raises as the reference does
+GDV_DEV i64 factorial_int64(gdv_ctx* c, i64 n) {
+  if (n < 0) {
+    gdv_set_error(c, GDV_ERR_FACTORIAL_NEG);
+    return 0;
+  }
+  if (n > 20) {
+    gdv_set_error(c, GDV_ERR_FACTORIAL_BIG);
+    return 0;
+  }
+  i64 r = 1;
+  for (i64 k = 2; k <= n; ++k) r *= k;
+  return r;
+}
+GDV_DEV i64 factorial_int32(gdv_ctx* c, i32 n) { return factorial_int64(c, (i64)n); }
 // greatest / least of 2..4 arguments, folded left to right with > / <: a NaN that is not the
 // first argument never wins, a leading NaN is only displaced by a comparison that is true.
 #define GDV_GREATEST_LEAST(T, S)                                                                  \
@@ -1064,6 +1083,11 @@ GDV_TSADD(timestampaddWeek, 604800000ll)
 GDV_TSADD_MONTHS(timestampaddMonth, 1ll)
 GDV_TSADD_MONTHS(timestampaddQuarter, 3ll)
 GDV_TSADD_MONTHS(timestampaddYear, 12ll)
+// add_months(date | timestamp, n): timestampaddMonth with the arguments the other way round
+GDV_DEV i64 add_months_date64_int32(i64 d, i32 n) { return gdv_add_months(d, (i64)n); }
+GDV_DEV i64 add_months_date64_int64(i64 d, i64 n) { return gdv_add_months(d, n); }
+GDV_DEV i64 add_months_timestamp_int32(i64 d, i32 n) { return gdv_add_months(d, (i64)n); }
+GDV_DEV i64 add_months_timestamp_int64(i64 d, i64 n) { return gdv_add_months(d, n); }
 GDV_DEV i64 date_add_date64_int32(i64 d, i32 n) { return (i64)((u64)d + (u64)((i64)n * 86400000ll)); }
 GDV_DEV i64 date_sub_date64_int32(i64 d, i32 n) { return (i64)((u64)d - (u64)((i64)n * 86400000ll)); }
 GDV_DEV i64 date_add_timestamp_int32(i64 d, i32 n) { return date_add_date64_int32(d, n); }

@@ -110,7 +110,9 @@ Registry::Registry() {
   for (const auto& t : {I32, I64}) {
     Add("div", {t, t}, t, NullMode::kIfNull, kCanFail);
     Add("pmod", {t, t}, t);
+    Add("factorial", {t}, I64, NullMode::kIfNull, kCanFail);
   }
+  Add("bround", {F64}, F64);
   for (const auto& t : {I32, I64, F32, F64}) {
     Add("sign", {t}, t);
     for (size_t n = 2; n <= 4; ++n) {
@@ -211,6 +213,10 @@ Registry::Registry() {
     Add(f, {I64, TS}, TS);
     Add(f, {TS, I32}, TS);
     Add(f, {TS, I64}, TS);
+  }
+  for (const auto& t : {D64, TS}) {
+    Add("add_months", {t, I32}, t);
+    Add("add_months", {t, I64}, t);
   }
   Add("date_add", {D64, I32}, D64);
   Add("date_sub", {D64, I32}, D64);

@@ -28,6 +28,8 @@ const char* ExecutionErrorMessage(int code) {
     case 9: return "Invalid value for boolean";
     case 10: return "Output buffer length can't be negative";
     case 11: return "Start position must be greater than 0";
+    case 12: return "Factorial of negative number not exist!";
+    case 13: return "Factorial of number greater than 20 not supported!";
     default: return "execution error in device function";
   }
 }

@@ -2084,6 +2084,15 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
     out->i = WrapSigned(r, rt.bits());
     return;
   }
+  if (f == "bround") { out->d = std::nearbyint(a[0].d); return; }   // default rounding mode: to nearest, ties to even
+  if (f == "factorial") {
+    if (a[0].i < 0) { cx.error = 12; return; }
+    if (a[0].i > 20) { cx.error = 13; return; }
+    int64_t r = 1;
+    for (int64_t k = 2; k <= a[0].i; ++k) r *= k;
+    out->i = r;
+    return;
+  }
   if (f == "sign") {
     if (rt.id == T_FLOAT) out->f = a[0].f > 0.0f ? 1.0f : (a[0].f < 0.0f ? -1.0f : a[0].f);
     else if (rt.id == T_DOUBLE) out->d = a[0].d > 0.0 ? 1.0 : (a[0].d < 0.0 ? -1.0 : a[0].d);
@@ -2416,10 +2425,10 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   if (f == "truncate" || f == "trunc") { out->d = std::trunc(a[0].d); return; }
 
   // ---- date/time arithmetic -----------------------------------------------------------------
-  if (f.rfind("timestampadd", 0) == 0) {
-    const std::string unit = f.substr(12);
+  if (f.rfind("timestampadd", 0) == 0 || f == "add_months") {
+    const std::string unit = f == "add_months" ? std::string("Month") : f.substr(12);
     // (count, timestamp) or (timestamp, count)
-    const bool ts_first = t0.id == T_TIMESTAMP;
+    const bool ts_first = t0.id == T_TIMESTAMP || t0.id == T_DATE64;
     const int64_t n = ts_first ? a[1].i : a[0].i, ts = ts_first ? a[0].i : a[1].i;
     int64_t unit_ms = 0;
     if (unit == "Second") unit_ms = 1000;

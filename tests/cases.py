@@ -228,6 +228,9 @@ def case_intmath(b):
         (fn("round", [i, lit(3, I)], I), I), (fn("round", [l, lit(-19, I)], L), L), (fn("round", [l, lit(-40, I)], L), L),
         (fn("truncate", [l, lit(-3, I)], L), L), (fn("truncate", [i, lit(-1, I)], I), I),
         (fn("truncate", [d, lit(2, I)], D), D), (fn("truncate", [d, lit(-2, I)], D), D), (fn("trunc", [d, j], D), D),
+        (fn("bround", [d], D), D), (fn("bround", [fn("divide", [fn("castFLOAT8", [i], D), lit(2.0, D)], D)], D), D),
+        # factorial raises outside 0..20: pmod(i, 21) keeps it inside
+        (fn("factorial", [fn("pmod", [i, lit(21, I)], I)], L), L), (fn("factorial", [fn("pmod", [l, lit(21, L)], L)], L), L),
     ]
     return schema, outs, "project"
 
@@ -579,7 +582,8 @@ def case_date_arith_swapped(b):
             (b.make_function("timestampaddWeek", [t, m], ts), ts),
             (b.make_function("timestampaddMonth", [t, n], ts), ts),
             (b.make_function("timestampaddYear", [t, n64], ts), ts),       # small counts: the year must stay in range
-            (b.make_function("timestampaddQuarter", [n64, t], ts), ts)]
+            (b.make_function("timestampaddQuarter", [n64, t], ts), ts),
+            (b.make_function("add_months", [t, n], ts), ts), (b.make_function("add_months", [F(b, "d", d64), n64], d64), d64)]
     return schema, outs, "project"
 
 

@@ -115,3 +115,23 @@ def test_raising_arguments_on_the_gpu(gandiva, oracle):
     assert np.array_equal(f.evaluate(ok).to_array().to_numpy().astype(np.uint64), oracle.filter_indices(cond, ok))
     with pytest.raises(gandiva.GandivaError, match="can't be negative"):
         f.evaluate(bad_len)
+
+
+def test_factorial_and_bround_on_the_gpu(gandiva, oracle):
+    """factorial raises outside 0..20 with the reference's messages; bround rounds half to even."""
+    b = gandiva.TreeExprBuilder()
+    L, D = pa.int64(), pa.float64()
+    schema = pa.schema([("l", L), ("d", D)])
+    fact = b.make_function("factorial", [cases.F(b, "l", L)], L)
+    br = b.make_function("bround", [cases.F(b, "d", D)], D)
+    p = gandiva.make_projector(schema, [b.make_expression(fact, pa.field("f", L)), b.make_expression(br, pa.field("r", D))], None)
+    ok = pa.RecordBatch.from_arrays([pa.array([0, 1, 5, 20, None] * 40, L), pa.array([0.5, 1.5, 2.5, -0.5, None] * 40, D)], schema=schema)
+    got = p.evaluate(ok)
+    want = oracle.project([fact, br], [L, D], ok)
+    assert_arrays_match(got[0], want[0], "factorial")
+    assert_arrays_match(got[1], want[1], "bround")
+    assert got[1].to_pylist()[:4] == [0.0, 2.0, 2.0, -0.0]
+    for bad, msg in (([3, -1], "Factorial of negative number not exist!"), ([21, 2], "Factorial of number greater than 20 not supported!")):
+        batch = pa.RecordBatch.from_arrays([pa.array(bad * 50, L), pa.array([1.0, 2.0] * 50, D)], schema=schema)
+        with pytest.raises(gandiva.GandivaError, match="ExecutionError: " + msg):
+            p.evaluate(batch)

@@ -546,9 +546,13 @@ def test_date_arithmetic(oracle, gandiva):
             [None if a is None or b is None else b + a * unit["Week"] for a, b in zip(m, t)],
             [None if a is None or b is None else add_months(b, a) for a, b in zip(n, t)],
             [None if a is None or b is None else add_months(b, 12 * a) for a, b in zip(n, t)],
-            [None if a is None or b is None else add_months(b, 3 * a) for a, b in zip(n, t)]]
-    for g, w in zip(swapped, tail):
-        assert_arrays_match(g, pa.array(w, type=pa.int64()).cast(pa.timestamp("ms")), "date arithmetic, swapped / int64 arguments")
+            [None if a is None or b is None else add_months(b, 3 * a) for a, b in zip(n, t)],
+            [None if a is None or b is None else add_months(b, a) for a, b in zip(n, t)],      # add_months(timestamp, int32)
+            [None if a is None or b is None else add_months(b, a) for a, b in zip(n, d)]]      # add_months(date64, int64)
+    assert len(swapped) == len(tail)
+    for k, (g, w) in enumerate(zip(swapped, tail)):
+        ty = pa.date64() if k == 6 else pa.timestamp("ms")
+        assert_arrays_match(g, pa.array(w, type=pa.int64()).cast(ty), "date arithmetic, swapped / int64 arguments, out %d" % k)
     for i, (g, w, (_, ty)) in enumerate(zip(got, want, schema_b)):
         exp = pa.array(w, type=pa.int64()).cast(ty) if not pa.types.is_int32(ty) else pa.array(w, type=pa.int32())
         assert_arrays_match(g, exp, "date arithmetic out %d" % i)
@@ -631,6 +635,25 @@ def test_integer_math_family(oracle, gandiva):
         expect(28, lambda r: None if none(i[r]) else dec_round(i[r], -1, down), 32)
     assert_arrays_match(got[29], pc.round(cd, 2, round_mode="towards_zero"), "truncate(d, 2)")
     assert_arrays_match(got[30], pc.round(cd, -2, round_mode="towards_zero"), "truncate(d, -2)")
+    # bround: round half to even (Arrow's half_to_even), incl. exact ties i / 2
+    assert_arrays_match(got[32], pc.round(cd, 0, round_mode="half_to_even"), "bround(d)")
+    halves = pc.divide(pc.cast(ci, D), pa.scalar(2.0, D))
+    assert_arrays_match(got[33], pc.round(halves, 0, round_mode="half_to_even"), "bround(i / 2)")
+    import math
+    expect(34, lambda r: None if none(i[r]) else math.factorial(i[r] % 21))
+    expect(35, lambda r: None if none(l[r]) else math.factorial(l[r] % 21))
+
+
+def test_factorial_raises_outside_its_range(oracle, gandiva):
+    b = gandiva.TreeExprBuilder()
+    L = pa.int64()
+    schema = pa.schema([("l", L)])
+    root = b.make_function("factorial", [cases.F(b, "l", L)], L)
+    ok = pa.RecordBatch.from_arrays([pa.array([0, 1, 5, 20, None], L)], schema=schema)
+    assert oracle.project([root], [L], ok)[0].to_pylist() == [1, 1, 120, 2432902008176640000, None]
+    for bad, msg in (([3, -1], "negative"), ([21, 2], "greater than 20")):
+        with pytest.raises(Exception, match=msg):
+            oracle.project([root], [L], pa.RecordBatch.from_arrays([pa.array(bad, L)], schema=schema))
 
 
 def test_calendar_functions(oracle, gandiva):
