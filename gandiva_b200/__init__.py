@@ -129,6 +129,7 @@ def _load() -> C.CDLL:
         "gdv_device_alloc": (i32, [i32, C.c_size_t, P(vp)]),
         "gdv_device_free": (i32, [i32, vp]),
         "gdv_device_trim": (i32, [i32, C.c_size_t, P(C.c_size_t)]),
+        "gdv_staged_bytes": (C.c_int64, []),
         "gdv_projector_output_var_size": (i32, [vp, P(gdv_batch_t), P(gdv_selection_t), i32, vp,
                                                 P(i64)]),
         "gdv_projector_dump_ir": (i64, [vp, C.c_char_p, i64]),

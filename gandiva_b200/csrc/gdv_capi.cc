@@ -8,6 +8,7 @@
 #include "gdv_node.h"
 #include "gdv_registry.h"
 #include "gdv_runtime.h"
+#include "gdv_staging.h"
 
 using namespace gdv;
 using namespace gdv::capi;
@@ -446,6 +447,8 @@ gdv_status gdv_device_trim(int32_t device, size_t keep_bytes, size_t* released) 
   if (released != nullptr) *released = r;
   return GDV_OK;
 }
+
+int64_t gdv_staged_bytes(void) { return static_cast<int64_t>(StagedBytes()); }
 
 gdv_status gdv_host_alloc(size_t bytes, void** out) {
   if (out == nullptr) return Fail(GDV_INVALID, "null argument");

@@ -1,6 +1,7 @@
 #include "gdv_staging.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -29,77 +30,112 @@ class CopyPool {
     static CopyPool* p = new CopyPool();  // never destroyed: threads may outlive static destructors
     return *p;
   }
+  // Copies in kChunk pieces that the calling thread and the workers CLAIM one at a time, so the call
+  // never waits for a worker to wake up: a worker that is asleep (or descheduled) simply claims nothing
+  // and the caller copies those pieces itself.  (The first version gave every thread a fixed slice and
+  // waited for all of them; waking seven sleeping workers cost ~1 ms on the bench box — the D2H half of a
+  // 1M-row a+b call took 1.1 ms against 0.11 ms for the H2D half, profiles/r02_host_latency.md.)
   void Copy(void* dst, const void* src, size_t bytes) {
-    const int n = static_cast<int>(workers_.size()) + 1;
-    if (bytes < (size_t(256) << 10) || n == 1) {
+    if (bytes < 2 * kChunk || workers_ == 0) {
       std::memcpy(dst, src, bytes);
       return;
     }
-    const size_t slice = ((bytes + n - 1) / n + 4095) & ~size_t(4095);
-    {
+    std::lock_guard<std::mutex> one_caller(caller_mu_);
+    const unsigned long long e = (ticket_.load(std::memory_order_relaxed) >> 32) + 1;
+    const unsigned nchunks = static_cast<unsigned>((bytes + kChunk - 1) / kChunk);
+    dst_.store(static_cast<char*>(dst), std::memory_order_relaxed);
+    src_.store(static_cast<const char*>(src), std::memory_order_relaxed);
+    bytes_.store(bytes, std::memory_order_relaxed);
+    nchunks_.store(nchunks, std::memory_order_relaxed);
+    done_.store(0, std::memory_order_relaxed);
+    ticket_.store(e << 32, std::memory_order_seq_cst);  // publishes the fields above
+    // (seq_cst here and on the sleeper's side: either this load sees the sleeper or its predicate sees the
+    // job.  A missed wake-up would only cost parallelism — the caller copies every unclaimed piece.)
+    if (sleepers_.load(std::memory_order_seq_cst) > 0) {
       std::lock_guard<std::mutex> g(mu_);
-      dst_ = static_cast<char*>(dst);
-      src_ = static_cast<const char*>(src);
-      bytes_ = bytes;
-      slice_ = slice;
-      pending_ = n - 1;
-      pending_pub_.store(n - 1, std::memory_order_release);
-      ++epoch_;
-      epoch_pub_.store(epoch_, std::memory_order_release);
+      cv_.notify_one();  // a woken worker wakes the next one: the caller pays for one wake-up, not seven
     }
-    cv_.notify_all();
-    Slice(0);  // the calling thread takes the first slice
-    for (int spin = 0; spin < 20000; ++spin)  // the others finish within microseconds of this one
-      if (pending_pub_.load(std::memory_order_acquire) == 0) break;
-    std::unique_lock<std::mutex> g(mu_);
-    done_.wait(g, [this] { return pending_ == 0; });
+    Work(e);
+    while (done_.load(std::memory_order_acquire) != nchunks) {  // pieces still in a worker's hands
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
   }
 
  private:
+  static constexpr size_t kChunk = size_t(256) << 10;
+
   CopyPool() {
     int want = 8;
     if (const char* e = std::getenv("GDV_STAGE_THREADS")) want = std::atoi(e);
     const int hw = static_cast<int>(std::thread::hardware_concurrency());
     if (hw > 0 && want > hw) want = hw;
-    for (int t = 1; t < want; ++t) workers_.emplace_back([this, t] { Loop(t); });
-    for (auto& w : workers_) w.detach();
-  }
-  void Slice(int t) {
-    const size_t b = slice_ * static_cast<size_t>(t);
-    if (b < bytes_) std::memcpy(dst_ + b, src_ + b, std::min(slice_, bytes_ - b));
-  }
-  void Loop(int t) {
-    unsigned long long seen = 0;
-    for (;;) {
-      // A host batch is several copies back to back (one per column, then the results): after a job the
-      // worker polls for the next one for ~100 us before it goes to sleep, because waking a sleeping thread
-      // costs tens of microseconds — as much as copying its whole slice.
-      bool got = false;
-      for (int spin = 0; spin < 20000 && !got; ++spin) {
-        if (epoch_pub_.load(std::memory_order_acquire) != seen) got = true;
-        else if ((spin & 63) == 63) std::this_thread::yield();
-      }
-      {
-        std::unique_lock<std::mutex> g(mu_);
-        if (!got) cv_.wait(g, [&] { return epoch_ != seen; });
-        seen = epoch_;
-      }
-      Slice(t);
-      std::lock_guard<std::mutex> g(mu_);
-      pending_pub_.store(pending_ - 1, std::memory_order_release);
-      if (--pending_ == 0) done_.notify_one();
+    for (int t = 1; t < want; ++t) {
+      std::thread([this] { Loop(); }).detach();
+      ++workers_;
     }
   }
-  std::vector<std::thread> workers_;
-  std::mutex mu_;
-  std::condition_variable cv_, done_;
-  char* dst_ = nullptr;
-  const char* src_ = nullptr;
-  size_t bytes_ = 0, slice_ = 0;
-  int pending_ = 0;
-  unsigned long long epoch_ = 0;
-  std::atomic<unsigned long long> epoch_pub_{0};  // epoch_, readable without the lock by polling workers
-  std::atomic<int> pending_pub_{0};               // pending_, for the caller's short poll
+  // Claims and copies pieces of job `e` until none is left.  A claim is a CAS on (epoch << 32 | next
+  // piece): it can only succeed while job `e` is still the published one, and the caller does not return
+  // (so the fields do not change) before every claimed piece is counted in done_.
+  void Work(unsigned long long e) {
+    for (;;) {
+      unsigned long long t = ticket_.load(std::memory_order_acquire);
+      if ((t >> 32) != e) return;
+      const unsigned idx = static_cast<unsigned>(t & 0xffffffffu);
+      if (idx >= nchunks_.load(std::memory_order_relaxed)) return;
+      char* d = dst_.load(std::memory_order_relaxed);
+      const char* s = src_.load(std::memory_order_relaxed);
+      const size_t bytes = bytes_.load(std::memory_order_relaxed);
+      if (!ticket_.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel)) continue;
+      const size_t off = static_cast<size_t>(idx) * kChunk;
+      std::memcpy(d + off, s + off, std::min(kChunk, bytes - off));
+      done_.fetch_add(1, std::memory_order_acq_rel);
+    }
+  }
+  bool HasWork(unsigned long long e) const {
+    const unsigned long long t = ticket_.load(std::memory_order_acquire);
+    return (t >> 32) == e && static_cast<unsigned>(t & 0xffffffffu) < nchunks_.load(std::memory_order_relaxed);
+  }
+  void Loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      // A host batch is several copies back to back (one per column, then — a DMA and a kernel later —
+      // the results): after a job the worker polls for the next one for 2 ms before it goes to sleep.
+      bool got = false;
+      const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+      for (unsigned spin = 0; !got; ++spin) {
+        if ((ticket_.load(std::memory_order_acquire) >> 32) != seen) {
+          got = true;
+        } else if ((spin & 255u) == 255u) {
+          if (std::chrono::steady_clock::now() >= t_end) break;
+          std::this_thread::yield();
+        }
+      }
+      if (!got) {
+        std::unique_lock<std::mutex> g(mu_);
+        sleepers_.fetch_add(1, std::memory_order_seq_cst);
+        cv_.wait(g, [&] { return (ticket_.load(std::memory_order_seq_cst) >> 32) != seen; });
+        sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+      }
+      seen = ticket_.load(std::memory_order_acquire) >> 32;
+      if (!got && sleepers_.load(std::memory_order_acquire) > 0 && HasWork(seen)) {
+        std::lock_guard<std::mutex> g(mu_);
+        cv_.notify_one();
+      }
+      Work(seen);
+    }
+  }
+  int workers_ = 0;
+  std::mutex mu_, caller_mu_;
+  std::condition_variable cv_;
+  std::atomic<char*> dst_{nullptr};
+  std::atomic<const char*> src_{nullptr};
+  std::atomic<size_t> bytes_{0};
+  std::atomic<unsigned> nchunks_{0}, done_{0};
+  std::atomic<int> sleepers_{0};
+  std::atomic<unsigned long long> ticket_{0};  // (job number << 32) | next unclaimed piece
 };
 
 // The pinned slots of one device.  One transfer at a time uses the ring (the link is shared anyway).

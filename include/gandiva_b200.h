@@ -297,6 +297,9 @@ gdv_status gdv_memcpy(int32_t device, void* dst, const void* src, size_t bytes, 
 /* Pinned host memory (cuMemHostAlloc) so H2D staging runs at PCIe speed. */
 gdv_status gdv_host_alloc(size_t bytes, void** out);
 gdv_status gdv_host_free(void* p);
+/* Bytes that host batches in PAGEABLE memory have moved through the pinned staging ring since the
+ * library was loaded (csrc/gdv_staging.cc); pinned and device-resident batches never add to it. */
+int64_t gdv_staged_bytes(void);
 /* Synthetic TPC-H lineitem columns generated straight into device memory (counter-based
  * hash RNG, identical stream to oracle/lineitem.c):
  *  kind 0: l_shipdate date32  1: l_discount f64  2: l_quantity f64 ... see DESIGN.md */

@@ -331,11 +331,24 @@ CUresult cuMemGetAddressRange_v2(CUdeviceptr* base, size_t* size, CUdeviceptr p)
   if (size) *size = it->second;
   EMU_OK;
 }
+// pinned ranges, so cuPointerGetAttribute can tell them from pageable memory like the driver does
+static std::mutex g_pinned_mu;
+static std::map<uintptr_t, size_t> g_pinned;
 CUresult cuMemHostAlloc(void** p, size_t n, unsigned int) {
   *p = std::malloc(n ? n : 1);
-  return *p ? CUDA_SUCCESS : CUDA_ERROR_OUT_OF_MEMORY;
+  if (*p == nullptr) return CUDA_ERROR_OUT_OF_MEMORY;
+  std::lock_guard<std::mutex> g(g_pinned_mu);
+  g_pinned[reinterpret_cast<uintptr_t>(*p)] = n ? n : 1;
+  return CUDA_SUCCESS;
 }
-CUresult cuMemFreeHost(void* p) { std::free(p); EMU_OK; }
+CUresult cuMemFreeHost(void* p) {
+  {
+    std::lock_guard<std::mutex> g(g_pinned_mu);
+    g_pinned.erase(reinterpret_cast<uintptr_t>(p));
+  }
+  std::free(p);
+  EMU_OK;
+}
 CUresult cuMemcpyHtoDAsync_v2(CUdeviceptr d, const void* s, size_t n, CUstream) {
   std::memcpy(reinterpret_cast<void*>(d), s, n);
   EMU_OK;
@@ -467,7 +480,15 @@ CUresult cuGetErrorString(CUresult r, const char** s) {
   *s = r == CUDA_SUCCESS ? "no error" : "emulated driver error";
   EMU_OK;
 }
-CUresult cuPointerGetAttribute(void*, CUpointer_attribute, CUdeviceptr) { return CUDA_ERROR_INVALID_VALUE; }
+CUresult cuPointerGetAttribute(void* out, CUpointer_attribute, CUdeviceptr ptr) {
+  std::lock_guard<std::mutex> g(g_pinned_mu);
+  auto it = g_pinned.upper_bound(static_cast<uintptr_t>(ptr));
+  if (it == g_pinned.begin()) return CUDA_ERROR_INVALID_VALUE;
+  --it;
+  if (static_cast<uintptr_t>(ptr) >= it->first + it->second) return CUDA_ERROR_INVALID_VALUE;
+  *static_cast<unsigned int*>(out) = 1;  // CU_MEMORYTYPE_HOST
+  return CUDA_SUCCESS;
+}
 CUresult cuCtxEnablePeerAccess(CUcontext, unsigned int) { EMU_OK; }
 CUresult cuDeviceCanAccessPeer(int* can, CUdevice, CUdevice) { *can = 0; EMU_OK; }
 CUresult cuIpcGetMemHandle(CUipcMemHandle*, CUdeviceptr) { return CUDA_ERROR_NOT_SUPPORTED; }
