@@ -78,6 +78,10 @@ def parse_args():
                          "gdv_selection_push, device-side NVLink stores into rank 0's vector, no host "
                          "sync; nccl: all-gather of counts + send/recv (host reads the count)")
     ap.add_argument("--no-overlap", action="store_true", help="--gather nccl: gather inside each step, no pipelining")
+    ap.add_argument("--waves", type=int, default=4,
+                    help="N>1, --gather push: filter each step's batch in this many row slices (wave-major global row "
+                         "order) so that the NVLink push of slice j hides under the filter kernel of slice j+1 and only "
+                         "the last slice's push is exposed (1 = one run per rank, the whole push of the last step exposed)")
     ap.add_argument("--push-ctas", type=int, default=8, help="--gather push: CTAs (256 threads) of the push kernel")
     ap.add_argument("--sm-reserve", type=int, default=-1,
                     help="SMs the filter leaves free for the push / NCCL kernels (default with N>1: 2, i.e. twelve "
@@ -702,9 +706,9 @@ def main():
     disc_full = torch.empty(cap_rows, dtype=torch.float64, device=dev)
     qty_full = torch.empty(cap_rows, dtype=torch.float64, device=dev)
 
-    def generate(first, rows):
+    def generate(first, rows, at=0):
         for kind, t in ((0, ship_full), (1, disc_full), (2, qty_full)):
-            gandiva.generate_lineitem(local_rank, kind, 42, first, rows, t.data_ptr(), 0, 0, st)
+            gandiva.generate_lineitem(local_rank, kind, 42, first, rows, t.data_ptr() + at * t.element_size(), 0, 0, st)
     generate(first_row, n)
     d_count = torch.zeros(1, dtype=torch.int64, device=dev)
     cols = [(0, ship_full.data_ptr(), 0, 0), (0, disc_full.data_ptr(), 0, 0), (0, qty_full.data_ptr(), 0, 0)]
@@ -740,6 +744,21 @@ def main():
             shard_rows = [n_nominal] * world
         del scratch_idx
         torch.cuda.synchronize()
+    # ---- waves: the shard is filtered in slices, global row order wave-major -------------------------
+    waves = max(1, args.waves) if use_push else 1
+    wave_rows, wave_first = None, None
+    if waves > 1:
+        from gandiva_b200.sharding import wave_layout
+        all_rows, all_first = wave_layout(shard_rows, waves)
+        wave_rows, wave_first = all_rows[rank], all_first[rank]
+        if min(wave_rows) <= 0:
+            waves, wave_rows, wave_first = 1, None, None
+        else:
+            at = 0
+            for j in range(waves):
+                generate(wave_first[j], wave_rows[j], at)
+                at += wave_rows[j]
+            torch.cuda.synchronize()
     ship, disc, qty = ship_full[:n], disc_full[:n], qty_full[:n]
     out_idx = None if use_push else torch.empty(n, dtype=idx_dtype, device=dev)
 
@@ -748,15 +767,16 @@ def main():
     ps = None
     if use_push:
         from gandiva_b200.sharding import PeerSelection
-        ps = PeerSelection(capacity=int(total_rows * 0.03) + 4096, local_rows=cap_rows, mode=idx_mode, device=dev,
-                           slots=2, ctas=args.push_ctas)
+        ps = PeerSelection(capacity=int(total_rows * 0.03) + 4096,
+                           local_rows=cap_rows if waves == 1 else max(wave_rows), mode=idx_mode, device=dev,
+                           slots=2, ctas=args.push_ctas, waves=waves)
     gstep = {"i": 0}
     # N>1: the gather of batch i runs on a second stream while the filter kernel of batch i+1
     # runs (double-buffered index buffers).  The filter was built with sm_reserve so that the
     # copy CTAs find free slots next to the persistent filter CTAs.
     comm_stream = torch.cuda.Stream(dev) if world > 1 else None
     if use_push:                       # the kernel-only timing below writes here
-        out_idx = ps.local[0] if rank != 0 else torch.empty(n, dtype=idx_dtype, device=dev)
+        out_idx = ps.local[0] if (rank != 0 and waves == 1) else torch.empty(n, dtype=idx_dtype, device=dev)
     bufs = [out_idx, torch.empty(n, dtype=idx_dtype, device=dev) if pipelined else out_idx]
     cnts = [d_count, torch.zeros(1, dtype=torch.int64, device=dev)]
     host_cnt = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
@@ -790,11 +810,23 @@ def main():
         for i in range(k):
             g = gstep["i"]
             gstep["i"] += 1
-            ps.before_filter(g, stream)
-            ptr, cap, mode, cnt_ptr = ps.filter_target(g)
-            filt.evaluate_device(n, cols, ptr, cap, mode, st, cnt_ptr, sync=False, index_base=first_row)
-            # the last run of the job has no filter kernel to hide under: push it with the whole GPU
-            ps.after_filter(g, stream, ctas=(2 * 148 if i == k - 1 else 0))
+            if waves == 1:
+                ps.before_filter(g, stream)
+                ptr, cap, mode, cnt_ptr = ps.filter_target(g)
+                filt.evaluate_device(n, cols, ptr, cap, mode, st, cnt_ptr, sync=False, index_base=first_row)
+                # the last run of the job has no filter kernel to hide under: push it with the whole GPU
+                ps.after_filter(g, stream, ctas=(2 * 148 if i == k - 1 else 0))
+            else:
+                at = 0
+                for j in range(waves):
+                    ps.before_filter(g, stream, wave=j)
+                    ptr, cap, mode, cnt_ptr = ps.filter_target(g, wave=j)
+                    wcols = [(0, ship_full.data_ptr() + 4 * at, 0, 0), (0, disc_full.data_ptr() + 8 * at, 0, 0),
+                             (0, qty_full.data_ptr() + 8 * at, 0, 0)]
+                    filt.evaluate_device(wave_rows[j], wcols, ptr, cap, mode, st, cnt_ptr, sync=False,
+                                         index_base=wave_first[j])
+                    ps.after_filter(g, stream, ctas=(2 * 148 if (i == k - 1 and j == waves - 1) else 0), wave=j)
+                    at += wave_rows[j]
             if events is not None and i + 1 < k:
                 events[i + 1].record(stream)
         ps.finish(stream)                          # the last step closes after its push landed
@@ -890,31 +922,39 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         mask = (ship >= 8766) & (ship < 9131) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24)
-        mine = torch.nonzero(mask).flatten() + first_row
+        if waves == 1:
+            mine = [torch.nonzero(mask).flatten() + first_row]
+        else:                               # wave-major global row order: one run per (wave, rank)
+            mine, at = [], 0
+            for j in range(waves):
+                mine.append(torch.nonzero(mask[at:at + wave_rows[j]]).flatten() + wave_first[j])
+                at += wave_rows[j]
         del mask
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([mine.numel()], dtype=torch.int64, device=dev))
-        sizes = [int(s.item()) for s in sizes]
+        sizes = [torch.zeros(waves, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([m.numel() for m in mine], dtype=torch.int64, device=dev))
+        sizes = [[int(x) for x in s_.tolist()] for s_ in sizes]
+        total_selected = sum(sum(s_) for s_ in sizes)
         ok = True
         if rank == 0:
             vec, total = ps.result(gstep["i"] - 1)
-            ok = (total == total_selected == sum(sizes)) and not ps.overflowed()
+            ok = (total == total_selected) and not ps.overflowed()
             pos = 0
-            for r in range(world):
-                part = mine if r == 0 else torch.empty(sizes[r], dtype=torch.int64, device=dev)
-                if r != 0:
-                    dist.recv(part, src=r)
-                ok = ok and bool(torch.equal(vec[pos:pos + sizes[r]].to(torch.int64), part))
-                pos += sizes[r]
-            gather_check = ("ok: %d global indices on rank 0 == concat over ranks of nonzero(torch mask) + shard base"
-                            % total) if ok else "FAILED"
+            for j in range(waves):
+                for r in range(world):
+                    part = mine[j] if r == 0 else torch.empty(sizes[r][j], dtype=torch.int64, device=dev)
+                    if r != 0:
+                        dist.recv(part, src=r)
+                    ok = ok and bool(torch.equal(vec[pos:pos + sizes[r][j]].to(torch.int64), part))
+                    pos += sizes[r][j]
+            gather_check = ("ok: %d global indices on rank 0 == concat over %s of nonzero(torch mask) + slice base"
+                            % (total, "ranks" if waves == 1 else "(wave, rank)")) if ok else "FAILED"
         else:
-            dist.send(mine, dst=0)
+            for j in range(waves):
+                dist.send(mine[j], dst=0)
         del mine
 
     # ---- roofline of the dominant (only) kernel ----------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    algo_bytes = ALGO_IN_BYTES_PER_ROW * n + (IDX_BYTES if idx_mode == "UINT32" else 8.0) * count
     # kernel-only duration: time K evaluate calls without the gather
     kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kreps = max(3, min(args.steps, 10))
@@ -925,7 +965,8 @@ def main():
                              sync=False, index_base=first_row)
     kev[1].record(stream)
     torch.cuda.synchronize()
-    filt.sync(st)
+    count = filt.sync(st)
+    algo_bytes = ALGO_IN_BYTES_PER_ROW * n + (IDX_BYTES if idx_mode == "UINT32" else 8.0) * count
     kernel_ms = kev[0].elapsed_time(kev[1]) / kreps
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     info = filt.kernel_info

@@ -141,7 +141,7 @@ def _load() -> C.CDLL:
         "gdv_filter_dump_ir": (i64, [vp, C.c_char_p, i64]),
         "gdv_filter_kernel_info": (i32, [vp, C.c_char_p, i64, P(i32), P(i32), P(i32), P(i32)]),
         "gdv_selection_push": (i32, [i32, vp, vp, vp, i64, vp, i32, i32, i32, C.c_uint64, C.c_uint64, i32,
-                                     i32, vp, C.c_uint64, vp, vp]),
+                                     i32, vp, C.c_uint64, vp, vp, i32, i32, vp]),
         "gdv_selection_release": (i32, [i32, vp, i32, C.c_uint64, vp]),
         "gdv_enable_peer_access": (i32, [i32, i32]),
         "gdv_ipc_export": (i32, [i32, vp, C.c_char_p, P(i64)]),
@@ -513,6 +513,7 @@ class Configuration:
 
 
 # ---- selection vector --------------------------------------------------------------------
+GDV_WAVE_FIRST, GDV_WAVE_LAST = 1, 2
 _SEL_MODE = {"NONE": GDV_SEL_NONE, "UINT16": GDV_SEL_UINT16, "UINT32": GDV_SEL_UINT32,
              "UINT64": GDV_SEL_UINT64}
 _SEL_NP = {GDV_SEL_UINT16: np.uint16, GDV_SEL_UINT32: np.uint32, GDV_SEL_UINT64: np.uint64}

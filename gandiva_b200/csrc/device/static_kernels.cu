@@ -192,18 +192,34 @@ __device__ __forceinline__ void gdv_copy_run_u64(const u64* __restrict__ src, u6
   if (((n - head) & 1ull) != 0ull && tid == 0) dst[n - 1] = src[n - 1];
 }
 
+// One rank's part of the SelectionVector reassembly on the root (C-ABI gdv_selection_push).
+//  base == nullptr: the vector is one run per rank.  The root's filter wrote its run in place at
+//                   offset 0; every other rank stores its run behind the lower ranks' runs.
+//  base != nullptr: the vector is built from several WAVES (the batch is filtered in slices so that
+//                   the transfer of slice j hides under the filter kernel of slice j+1 and only the
+//                   last slice's transfer is exposed).  Every rank, the root included, stores the
+//                   run of this wave at  *base + runs of the lower ranks in this wave ; the last CTA
+//                   of the push then adds the wave's total (all ranks) to *base, a device word owned
+//                   by the calling rank.  GDV_WAVE_FIRST starts a vector (*base is taken as 0),
+//                   GDV_WAVE_LAST makes the root wait for every rank's stores and write the total.
+#define GDV_WAVE_FIRST 1
+#define GDV_WAVE_LAST 2
 extern "C" __global__ void __launch_bounds__(256)
 gdv_sel_push(const void* src, const u64* d_count, void* dst, i64 dst_cap, u64* board_count,
              u64* board_done, u64* board_consumed, u64* board_err, int rank, int world, u64 seq,
-             u64 need_consumed, int elem_bytes, u64* local_ctr, u64 done_target, u64* total_out) {
-  __shared__ u64 s_off, s_cnt;
+             u64 need_consumed, int elem_bytes, u64* local_ctr, u64 done_target, u64* total_out,
+             u64* base, int wave_flags) {
+  __shared__ u64 s_off, s_cnt, s_base;
+  const bool waves = base != nullptr;
   if (threadIdx.x == 0) {
     const u64 cnt = *d_count;
     if (blockIdx.x == 0) gdv_st_release_sys(&board_count[rank], (seq << GDV_BOARD_SEQ_SHIFT) | cnt);
     if (need_consumed != 0ull)
       while (gdv_ld_acquire_sys(board_consumed) < need_consumed) {
       }
-    u64 off = 0;
+    // *base was written by the previous wave's push, a kernel earlier on this stream
+    const u64 b0 = (waves && (wave_flags & GDV_WAVE_FIRST) == 0) ? *base : 0ull;
+    u64 off = b0;
     for (int q = 0; q < rank; ++q) {
       u64 v;
       do {
@@ -213,10 +229,11 @@ gdv_sel_push(const void* src, const u64* d_count, void* dst, i64 dst_cap, u64* b
     }
     s_off = off;
     s_cnt = cnt;
+    s_base = b0;
   }
   __syncthreads();
   const u64 off = s_off, cnt = s_cnt;
-  if (rank != 0) {
+  if (rank != 0 || waves) {
     if (off + cnt <= (u64)dst_cap) {
       if (elem_bytes == 8)
         gdv_copy_run_u64(reinterpret_cast<const u64*>(src), reinterpret_cast<u64*>(dst) + off, cnt);
@@ -231,10 +248,31 @@ gdv_sel_push(const void* src, const u64* d_count, void* dst, i64 dst_cap, u64* b
     __syncthreads();
     if (threadIdx.x == 0) {
       const u64 prev = atomicAdd(reinterpret_cast<unsigned long long*>(local_ctr), 1ull);
-      if (prev + 1ull == done_target) gdv_st_release_sys(&board_done[rank], seq);
+      if (prev + 1ull == done_target) {  // the last CTA of this push: every store of the rank is out
+        if (waves) {
+          u64 total = s_base;
+          for (int q = 0; q < world; ++q) {
+            u64 v;
+            do {
+              v = gdv_ld_acquire_sys(&board_count[q]);
+            } while ((v >> GDV_BOARD_SEQ_SHIFT) != seq);
+            total += v & GDV_BOARD_COUNT_MASK;
+          }
+          *base = total;
+          gdv_st_release_sys(&board_done[rank], seq);
+          if (rank == 0 && (wave_flags & GDV_WAVE_LAST) != 0) {
+            for (int q = 1; q < world; ++q)
+              while (gdv_ld_acquire_sys(&board_done[q]) != seq) {
+              }
+            if (total_out != nullptr) *total_out = total;
+          }
+        } else {
+          gdv_st_release_sys(&board_done[rank], seq);
+        }
+      }
     }
   } else if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // root: its own run was written in place by the filter kernel (offset 0)
+    // root, one run per rank: its own run was written in place by the filter kernel (offset 0)
     if (cnt > (u64)dst_cap) gdv_st_release_sys(board_err, seq);
     gdv_st_release_sys(&board_done[0], seq);
     u64 total = cnt;

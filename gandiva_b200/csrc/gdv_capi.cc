@@ -571,7 +571,10 @@ gdv_status gdv_selection_push(int32_t device, const void* d_src, const void* d_c
                               int64_t dst_capacity, void* board, int32_t board_slot, int32_t rank,
                               int32_t world, uint64_t seq, uint64_t need_consumed, int32_t mode,
                               int32_t ctas, void* d_local_counter, uint64_t done_target,
-                              void* d_total_out, void* stream) {
+                              void* d_total_out, void* d_base, int32_t wave_flags,
+                              int32_t consumed_slot, void* stream) {
+  if (d_base != nullptr && (consumed_slot < 0 || consumed_slot >= GDV_BOARD_SLOTS))
+    return Fail(GDV_INVALID, "gdv_selection_push: bad consumed_slot");
   if (world < 1 || world > GDV_BOARD_MAX_WORLD || rank < 0 || rank >= world || board == nullptr ||
       d_count == nullptr || board_slot < 0 || board_slot >= GDV_BOARD_SLOTS)
     return Fail(GDV_INVALID, "gdv_selection_push: bad arguments");
@@ -588,14 +591,16 @@ gdv_status gdv_selection_push(int32_t device, const void* d_src, const void* d_c
   uint64_t* b = static_cast<uint64_t*>(board);
   uint64_t* b_count = b + static_cast<size_t>(board_slot) * GDV_BOARD_MAX_WORLD;
   uint64_t* b_done = b + static_cast<size_t>(GDV_BOARD_SLOTS + board_slot) * GDV_BOARD_MAX_WORLD;
-  uint64_t* b_cons = b + static_cast<size_t>(2 * GDV_BOARD_SLOTS) * GDV_BOARD_MAX_WORLD + board_slot;
+  uint64_t* b_cons = b + static_cast<size_t>(2 * GDV_BOARD_SLOTS) * GDV_BOARD_MAX_WORLD +
+                     (d_base != nullptr ? consumed_slot : board_slot);
   uint64_t* b_err = b + static_cast<size_t>(2 * GDV_BOARD_SLOTS) * GDV_BOARD_MAX_WORLD + GDV_BOARD_SLOTS;
   int elem_bytes = elem;
   void* params[] = {&d_src, &d_count, &d_dst, &dst_capacity, &b_count, &b_done, &b_cons, &b_err,
                     &rank, &world, &seq, &need_consumed, &elem_bytes, &d_local_counter, &done_target,
-                    &d_total_out};
-  const unsigned grid = rank == 0 ? 1u : static_cast<unsigned>(std::max(1, ctas));
-  const unsigned threads = rank == 0 ? 32u : 256u;  // fits the slots a 256-thread persistent filter leaves free
+                    &d_total_out, &d_base, &wave_flags};
+  const bool one_thread = rank == 0 && d_base == nullptr;  // the root of a one-run-per-rank vector only waits
+  const unsigned grid = one_thread ? 1u : static_cast<unsigned>(std::max(1, ctas));
+  const unsigned threads = one_thread ? 32u : 256u;  // fits the slots a 256-thread persistent filter leaves free
   g_launch_count.fetch_add(1);
   s = CuCheck(Driver().LaunchKernel(fn, grid, 1, 1, threads, 1, 1, 0, st, params, nullptr),
               "cuLaunchKernel(gdv_sel_push)");

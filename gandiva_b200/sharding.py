@@ -39,6 +39,30 @@ def shard_rows_with_root(total_rows: int, world: int, selectivity: float, bytes_
     return [r_root] + [r_other] * (world - 2) + [total_rows - r_root - r_other * (world - 2)]
 
 
+def wave_layout(shard_rows: list, waves: int, align: int = 1024):
+    """Row slices for a batch that is filtered in `waves` waves (PeerSelection(waves=...)).
+    Rank r's shard of shard_rows[r] rows is cut into `waves` slices (all but the last a multiple of `align`
+    rows); the GLOBAL row order is wave-major — every rank's slice 0 in rank order, then every rank's
+    slice 1, ... — so that the runs of one wave are contiguous in the SelectionVector and a wave can be
+    pushed as soon as it is filtered.  Returns (rows, first): rows[r][j] = size of rank r's slice j,
+    first[r][j] = its first global row (the Filter call's index_base)."""
+    world = len(shard_rows)
+    rows = []
+    for n in shard_rows:
+        per = (n // waves) // align * align
+        if per == 0:
+            rows.append([n] + [0] * (waves - 1))
+        else:
+            rows.append([per] * (waves - 1) + [n - per * (waves - 1)])
+    first = [[0] * waves for _ in range(world)]
+    g = 0
+    for j in range(waves):
+        for r in range(world):
+            first[r][j] = g
+            g += rows[r][j]
+    return rows, first
+
+
 def gather_selection(local_indices: torch.Tensor, count: int, dst: int = 0,
                      group: Optional[dist.ProcessGroup] = None,
                      out: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], int]:
@@ -153,10 +177,16 @@ class PeerSelection:
         total count next to the vector.
 
     Nothing is synchronised through the host; `torch.distributed` (gloo) is used once, at
-    construction, to hand the IPC handles around."""
+    construction, to hand the IPC handles around.
+
+    `waves` > 1: a step's batch is filtered in `waves` row slices (wave-major global row order: all
+    ranks' slice 0, then all ranks' slice 1, ...; `wave_rows`) and each slice's run is pushed while the
+    next slice is being filtered, so only the LAST slice's transfer is not hidden.  Every rank, the root
+    included, then writes local runs (two buffers, alternating) and the push kernel carries the vector's
+    fill level from wave to wave in a device word (`gdv_selection_push`'s d_base)."""
 
     def __init__(self, capacity: int, local_rows: int, mode: str, device: torch.device,
-                 slots: int = 2, ctas: int = 8, root: int = 0):
+                 slots: int = 2, ctas: int = 8, root: int = 0, waves: int = 1):
         import ctypes as C
         import gandiva_b200 as gandiva
         assert root == 0, "the root is rank 0 (its run has offset 0 and is written in place)"
@@ -164,6 +194,8 @@ class PeerSelection:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         assert self.world <= gandiva.GDV_BOARD_MAX_WORLD and 1 <= slots <= gandiva.GDV_BOARD_SLOTS
         self.device, self.slots, self.ctas = device, slots, ctas
+        self.waves = int(waves)
+        assert self.waves >= 1
         self.mode = mode
         self.dtype = {"UINT16": torch.int16, "UINT32": torch.int32, "UINT64": torch.int64}[mode]
         self.capacity = int(capacity)
@@ -195,6 +227,12 @@ class PeerSelection:
                     self._opened.append(p.value)
                 ptrs.append(seen[raw] + off)
             self.vector_ptrs, self.board_ptr = ptrs[:-1], ptrs[-1]
+        if self.waves > 1:      # local_rows = the largest slice; runs alternate between two buffers
+            self.local = [torch.empty(local_rows, dtype=self.dtype, device=device) for _ in range(2)]
+            self.ev_wave = [torch.cuda.Event() for _ in range(2)]
+            self.wave_counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(2)]
+            self.base = torch.zeros(1, dtype=torch.int64, device=device)
+        elif self.rank != 0:
             self.local = [torch.empty(local_rows, dtype=self.dtype, device=device) for _ in range(slots)]
         self.counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(slots)]
         self.totals = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(slots)]
@@ -215,25 +253,54 @@ class PeerSelection:
         self._opened = []
         dist.barrier(group=self.cpu_group)
 
-    def filter_target(self, step: int):
-        """(device pointer, max_slots, mode string, count pointer) for this step's Filter call."""
+    def filter_target(self, step: int, wave: int = 0):
+        """(device pointer, max_slots, mode string, count pointer) for the Filter call of this step (and wave)."""
+        if self.waves > 1:
+            lb = (step * self.waves + wave) % 2
+            return self.local[lb].data_ptr(), self.local_rows, self.mode, self.wave_counts[lb].data_ptr()
         b = step % self.slots
         if self.rank == 0:
             return self.vector_ptrs[b], self.capacity, self.mode + "|BOUNDED", self.counts[b].data_ptr()
         return self.local[b].data_ptr(), self.local_rows, self.mode, self.counts[b].data_ptr()
 
-    def before_filter(self, step: int, stream: torch.cuda.Stream) -> None:
-        """The step's buffers are free again once the push that last used them has finished."""
+    def before_filter(self, step: int, stream: torch.cuda.Stream, wave: int = 0) -> None:
+        """The buffers the Filter is about to write are free again once the push that last read them has finished."""
+        if self.waves > 1:
+            w = step * self.waves + wave
+            if w >= 2:
+                stream.wait_event(self.ev_wave[w % 2])
+            return
         if step >= self.slots:
             stream.wait_event(self.ev_pushed[step % self.slots])
 
-    def after_filter(self, step: int, stream: torch.cuda.Stream, ctas: int = 0) -> None:
-        """Enqueue the push of this step's run (and, on the root, the wait for all runs).
+    def after_filter(self, step: int, stream: torch.cuda.Stream, ctas: int = 0, wave: int = 0) -> None:
+        """Enqueue the push of this step's (wave's) run (and, on the root, the wait for all runs).
         `ctas` overrides the copy kernel's grid for this call (e.g. the whole GPU for the last
-        step of a job, when no filter kernel follows)."""
-        g, b, seq = self.g, step % self.slots, step + 1
+        push of a job, when no filter kernel follows)."""
+        g, b = self.g, step % self.slots
         ctas = ctas or self.ctas
         self.ctas_issued += ctas
+        if self.waves > 1:
+            w = step * self.waves + wave
+            lb, seq = w % 2, w + 1
+            first, last = wave == 0, wave == self.waves - 1
+            self.ev_wave[lb].record(stream)
+            self.side.wait_event(self.ev_wave[lb])
+            need = step + 1 - self.slots if (first and self.rank != 0 and step >= self.slots) else 0
+            g._check(g.lib.gdv_selection_push(
+                self.device.index, self.local[lb].data_ptr(), self.wave_counts[lb].data_ptr(), self.vector_ptrs[b],
+                self.capacity, self.board_ptr, seq % g.GDV_BOARD_SLOTS, self.rank, self.world, seq, need,
+                g._SEL_MODE[self.mode], ctas, self.local_ctr.data_ptr(), self.ctas_issued, self.totals[b].data_ptr(),
+                self.base.data_ptr(), (g.GDV_WAVE_FIRST if first else 0) | (g.GDV_WAVE_LAST if last else 0), b,
+                g._stream_handle(self.side.cuda_stream)))
+            if self.rank == 0 and last:
+                g._check(g.lib.gdv_selection_release(self.device.index, self.board_ptr, b, step + 1,
+                                                     g._stream_handle(self.side.cuda_stream)))
+            self.ev_wave[lb].record(self.side)
+            if last:
+                self.ev_pushed[b].record(self.side)
+            return
+        seq = step + 1
         self.ev_filter[b].record(stream)
         self.side.wait_event(self.ev_filter[b])
         need = seq - self.slots if (self.rank != 0 and seq > self.slots) else 0
@@ -241,7 +308,7 @@ class PeerSelection:
         g._check(g.lib.gdv_selection_push(
             self.device.index, src, self.counts[b].data_ptr(), self.vector_ptrs[b], self.capacity,
             self.board_ptr, b, self.rank, self.world, seq, need, g._SEL_MODE[self.mode], ctas,
-            self.local_ctr.data_ptr(), self.ctas_issued, self.totals[b].data_ptr(),
+            self.local_ctr.data_ptr(), self.ctas_issued, self.totals[b].data_ptr(), None, 0, 0,
             g._stream_handle(self.side.cuda_stream)))
         if self.rank == 0:
             # bench / tests have no consumer: the vector is released as soon as it is complete
@@ -251,7 +318,7 @@ class PeerSelection:
 
     def finish(self, stream: torch.cuda.Stream) -> None:
         """Make `stream` wait for every push issued so far."""
-        for e in self.ev_pushed:
+        for e in self.ev_pushed + (self.ev_wave if self.waves > 1 else []):
             stream.wait_event(e)
 
     def result(self, step: int):

@@ -326,7 +326,20 @@ gdv_status gdv_generate_lineitem(int32_t device, int32_t column_kind, uint64_t s
  *  d_local_counter: zero-initialised device uint64 owned by the calling rank; every CTA of every
  *                push adds one to it.  done_target: the value it reaches when this call's last
  *                CTA has finished (= sum of `ctas` over all pushes issued so far, this one
- *                included), so `ctas` may differ from call to call. */
+ *                included), so `ctas` may differ from call to call.
+ *  d_base      : NULL = the vector is one run per rank (above).  Otherwise the batch is filtered in
+ *                several WAVES (row slices, wave-major global row order) so that the transfer of
+ *                wave j hides under the filter kernel of wave j+1 and only the last wave's
+ *                transfer is exposed: d_base is a device uint64 owned by the calling rank that
+ *                carries the vector's fill level from wave to wave; every rank, the root included
+ *                (its filter then writes a local run like everyone else), stores this wave's run
+ *                at *d_base + the lower ranks' runs of this wave and then adds the wave's total.
+ *                Each wave is one call with its own seq; board_slot = seq % GDV_BOARD_SLOTS;
+ *                consumed_slot = which vector of the ring (need_consumed only on the first wave).
+ *  wave_flags  : GDV_WAVE_FIRST starts a vector, GDV_WAVE_LAST completes it (the root waits for
+ *                every rank and writes d_total_out). */
+#define GDV_WAVE_FIRST 1
+#define GDV_WAVE_LAST 2
 /* Lets kernels running on `device` dereference memory of `peer_device` (cuCtxEnablePeerAccess);
  * required once per process before gdv_selection_push stores into the root's vector. */
 gdv_status gdv_enable_peer_access(int32_t device, int32_t peer_device);
@@ -344,7 +357,8 @@ gdv_status gdv_selection_push(int32_t device, const void* d_src, const void* d_c
                               int64_t dst_capacity, void* board, int32_t board_slot, int32_t rank,
                               int32_t world, uint64_t seq, uint64_t need_consumed, int32_t mode,
                               int32_t ctas, void* d_local_counter, uint64_t done_target,
-                              void* d_total_out, void* stream);
+                              void* d_total_out, void* d_base, int32_t wave_flags,
+                              int32_t consumed_slot, void* stream);
 /* root: marks slot `board_slot`'s vector of step `seq` as consumed (its buffer may be reused). */
 gdv_status gdv_selection_release(int32_t device, void* board, int32_t board_slot, uint64_t seq,
                                  void* stream);

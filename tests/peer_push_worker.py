@@ -14,7 +14,7 @@ import torch.distributed as dist  # noqa: E402
 
 import cases  # noqa: E402
 import gandiva_b200 as gandiva  # noqa: E402
-from gandiva_b200.sharding import PeerSelection, shard_range  # noqa: E402
+from gandiva_b200.sharding import PeerSelection, shard_range, wave_layout  # noqa: E402
 
 
 def main():
@@ -25,8 +25,14 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     total_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_003
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    first, last = shard_range(total_rows, world, rank)
+    waves = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    ranges = [shard_range(total_rows, world, r) for r in range(world)]
+    first, last = ranges[rank]
     n = last - first
+    # waves > 1: every rank's shard is filtered in slices; the global row order is wave-major, i.e. slice
+    # (rank r, wave j) IS the global row range [wfirst[j], wfirst[j] + wrows[j]) of the same table
+    all_rows, all_first = wave_layout([b_ - a_ for a_, b_ in ranges], waves)
+    wrows, wfirst = all_rows[rank], all_first[rank]
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     st = stream.cuda_stream
@@ -36,18 +42,32 @@ def main():
     b = gandiva.TreeExprBuilder()
     filt = gandiva.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)),
                                gandiva.Configuration(device=local, sm_reserve=2))
-    ps = PeerSelection(capacity=int(total_rows * 0.05) + 1024, local_rows=n, mode="UINT64", device=dev,
-                       slots=2, ctas=8)
+    ps = PeerSelection(capacity=int(total_rows * 0.05) + 1024, local_rows=n if waves == 1 else max(wrows),
+                       mode="UINT64", device=dev, slots=2, ctas=8, waves=waves)
     cols = [(0, ship.data_ptr(), 0, 0), (0, disc.data_ptr(), 0, 0), (0, qty.data_ptr(), 0, 0)]
     ok = True
     for step in range(steps):
         seed = 42 + step // 2          # two consecutive steps share a table, then it changes
-        ps.before_filter(step, stream)
-        for kind, t in ((0, ship), (1, disc), (2, qty)):
-            gandiva.generate_lineitem(local, kind, seed, first, n, t.data_ptr(), 0, 0, st)
-        ptr, cap, mode, cnt = ps.filter_target(step)
-        filt.evaluate_device(n, cols, ptr, cap, mode, st, cnt, sync=False, index_base=first)
-        ps.after_filter(step, stream)
+        if waves == 1:
+            ps.before_filter(step, stream)
+            for kind, t in ((0, ship), (1, disc), (2, qty)):
+                gandiva.generate_lineitem(local, kind, seed, first, n, t.data_ptr(), 0, 0, st)
+            ptr, cap, mode, cnt = ps.filter_target(step)
+            filt.evaluate_device(n, cols, ptr, cap, mode, st, cnt, sync=False, index_base=first)
+            ps.after_filter(step, stream)
+        else:
+            at = 0
+            for j in range(waves):
+                ps.before_filter(step, stream, wave=j)
+                for kind, t in ((0, ship), (1, disc), (2, qty)):
+                    gandiva.generate_lineitem(local, kind, seed, wfirst[j], wrows[j],
+                                              t.data_ptr() + at * t.element_size(), 0, 0, st)
+                wcols = [(0, ship.data_ptr() + 4 * at, 0, 0), (0, disc.data_ptr() + 8 * at, 0, 0),
+                         (0, qty.data_ptr() + 8 * at, 0, 0)]
+                ptr, cap, mode, cnt = ps.filter_target(step, wave=j)
+                filt.evaluate_device(wrows[j], wcols, ptr, cap, mode, st, cnt, sync=False, index_base=wfirst[j])
+                ps.after_filter(step, stream, wave=j)
+                at += wrows[j]
         if step == steps - 1 or step == 1:
             ps.finish(stream)
             torch.cuda.synchronize()

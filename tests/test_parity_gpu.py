@@ -421,8 +421,10 @@ def test_filter_bounded_selection_vector(gandiva, oracle):
         f.evaluate_device(n, cols, out.ptr, 7, "UINT64", st, cnt.ptr)
 
 
-def test_peer_selection_push(gandiva):
-    """Multi-GPU reassembly of the SelectionVector (needs >= 2 GPUs on the box)."""
+@pytest.mark.parametrize("waves", [1, 3])
+def test_peer_selection_push(waves, gandiva):
+    """Multi-GPU reassembly of the SelectionVector (needs >= 2 GPUs on the box); one run per rank, and the
+    batch filtered in waves whose pushes hide under the next wave's filter kernel."""
     import os
     import subprocess
     import sys
@@ -432,7 +434,7 @@ def test_peer_selection_push(gandiva):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(root, "tests", "peer_push_worker.py")],
+                          os.path.join(root, "tests", "peer_push_worker.py"), "5000003", "5", str(waves)],
                          capture_output=True, text=True, timeout=600)
     assert "PEER_PUSH_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 

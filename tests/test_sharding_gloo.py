@@ -92,3 +92,22 @@ def test_shard_rows_with_root():
                     assert len(set(r)) == 1
     r = shard_rows_with_root(10_000_000_000, 8, 0.0181, 20.0)
     assert abs(r[0] / 1.25e9 - 0.911) < 0.01 and abs(r[1] / 1.25e9 - 1.0127) < 0.005
+
+
+def test_wave_layout_is_a_wave_major_partition():
+    """Slices of a batch filtered in waves: every rank's rows are all used, slices are aligned, and walking the
+    slices wave by wave, rank by rank, walks the global row space from 0 to the total without gap or overlap —
+    which is why the concatenated runs are the ascending SelectionVector of the whole table."""
+    from gandiva_b200.sharding import shard_rows_with_root, wave_layout
+    for shard in ([1000], [5_000_003, 4_999_936], shard_rows_with_root(10_000_000_000, 8, 0.0127, 20.0)):
+        for waves in (1, 2, 4, 7):
+            rows, first = wave_layout(shard, waves)
+            assert [sum(r) for r in rows] == list(shard)
+            pos = 0
+            for j in range(waves):
+                for r in range(len(shard)):
+                    assert first[r][j] == pos
+                    pos += rows[r][j]
+                    if j < waves - 1 and rows[r][j] and rows[r][j] != shard[r]:   # (a tiny shard is one slice)
+                        assert rows[r][j] % 1024 == 0
+            assert pos == sum(shard)
