@@ -44,6 +44,22 @@ def _run(gandiva, world, waves, steps, shard_rows, ctas=2, slots=2):
     b = g.TreeExprBuilder()
     filt = [g.make_filter(cases.Q6_SCHEMA, b.make_condition(cases.q6_condition(b)), g.Configuration(device=0, sm_reserve=4))
             for _ in range(world)]
+    # Everything a rank will launch is launched once and waited for BEFORE any rank waits for another on the
+    # device: the first launch of a kernel loads its module (CUDA loads lazily), and a module load that has to
+    # wait for the device would wait forever behind a push kernel that is itself waiting for that rank.
+    warm = [devmem.DevBuf(4096, np.int32), devmem.DevBuf(4096, np.float64), devmem.DevBuf(4096, np.float64),
+            devmem.DevBuf(4096, np.int64), devmem.DevBuf(1, np.int64, fill=0)]
+    for kind, t in ((0, warm[0]), (1, warm[1]), (2, warm[2])):
+        g.generate_lineitem(0, kind, 1, 0, 4096, t.ptr, 0, 0, 0)
+    for f in filt:
+        f.evaluate_device(4096, [(0, warm[0].ptr, 0, 0), (0, warm[1].ptr, 0, 0), (0, warm[2].ptr, 0, 0)], warm[3].ptr,
+                          4096, "UINT64", 0, warm[4].ptr, sync=True)
+    wb = devmem.DevBuf(g.GDV_BOARD_BYTES // 8, np.int64, fill=0)
+    wc = devmem.DevBuf(1, np.int64, fill=0)
+    g._check(g.lib.gdv_selection_push(0, warm[3].ptr, warm[4].ptr, warm[3].ptr, 4096, wb.ptr, 0, 0, 1, 1, 0,
+                                      g.GDV_SEL_UINT64, 1, wc.ptr, 1, None, None, 0, 0, None))
+    g._check(g.lib.gdv_selection_release(0, wb.ptr, 0, 1, None))
+    devmem.synchronize()
     cap = int(total_rows * 0.05) + 1024
     vectors = [devmem.DevBuf(cap, np.int64, fill=-1) for _ in range(slots)]
     board = devmem.DevBuf(g.GDV_BOARD_BYTES // 8, np.int64, fill=0)
@@ -119,13 +135,18 @@ def _run(gandiva, world, waves, steps, shard_rows, ctas=2, slots=2):
         f.sync(0)
 
 
-needs_concurrency = pytest.mark.skipif(devmem.EMU,
-                                       reason="ranks wait for each other on the device: needs kernels of several "
-                                              "streams in flight at once, the CPU simulator runs one at a time")
+import os  # noqa: E402
+
+# Several virtual ranks on ONE device wait for each other inside kernels: that needs the kernels of several
+# streams to be resident at the same time, which CUDA does not promise (and the CPU simulator runs one kernel
+# at a time).  It works on B200 (tools/r02_call6.sh runs it under a timeout) but a test that could hang a
+# box is opt-in; the real multi-GPU path is tests/peer_push_worker.py.
+needs_concurrency = pytest.mark.skipif(devmem.EMU or os.environ.get("GDV_TEST_VIRTUAL_RANKS") != "1",
+                                       reason="opt-in: GDV_TEST_VIRTUAL_RANKS=1 (ranks wait for each other on one device)")
 
 
 @needs_concurrency
-@pytest.mark.timeout(300)
+@pytest.mark.timeout(60)
 @pytest.mark.parametrize("world,waves", [(2, 1), (3, 1), (2, 4), (3, 3), (4, 2)])
 def test_virtual_ranks_on_one_gpu(world, waves, gandiva):
     shard_rows = shard_rows_with_root(1_500_000 * world + 12_345, world, 0.0127, 20.0)
