@@ -42,7 +42,13 @@ class CopyPool {
     }
     std::lock_guard<std::mutex> one_caller(caller_mu_);
     const unsigned long long e = (ticket_.load(std::memory_order_relaxed) >> 32) + 1;
-    const unsigned nchunks = static_cast<unsigned>((bytes + kChunk - 1) / kChunk);
+    // Full ring slots (the pieces of a bulk transfer) go in 1 MB pieces: memcpy then takes its streaming
+    // (non-temporal store) path and the 8 threads each get one piece — 46.9 GB/s pageable->device on the
+    // bench box against 37.7 GB/s in 256 KB pieces (profiles/r02_host_latency.md).  Smaller copies (one
+    // column of a 1M-row batch) go in 256 KB pieces so that every thread has something to claim.
+    const size_t chunk = bytes >= kSlotBytes ? 4 * kChunk : kChunk;
+    const unsigned nchunks = static_cast<unsigned>((bytes + chunk - 1) / chunk);
+    chunk_.store(chunk, std::memory_order_relaxed);
     dst_.store(static_cast<char*>(dst), std::memory_order_relaxed);
     src_.store(static_cast<const char*>(src), std::memory_order_relaxed);
     bytes_.store(bytes, std::memory_order_relaxed);
@@ -88,9 +94,10 @@ class CopyPool {
       char* d = dst_.load(std::memory_order_relaxed);
       const char* s = src_.load(std::memory_order_relaxed);
       const size_t bytes = bytes_.load(std::memory_order_relaxed);
+      const size_t chunk = chunk_.load(std::memory_order_relaxed);
       if (!ticket_.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel)) continue;
-      const size_t off = static_cast<size_t>(idx) * kChunk;
-      std::memcpy(d + off, s + off, std::min(kChunk, bytes - off));
+      const size_t off = static_cast<size_t>(idx) * chunk;
+      std::memcpy(d + off, s + off, std::min(chunk, bytes - off));
       done_.fetch_add(1, std::memory_order_acq_rel);
     }
   }
@@ -132,7 +139,7 @@ class CopyPool {
   std::condition_variable cv_;
   std::atomic<char*> dst_{nullptr};
   std::atomic<const char*> src_{nullptr};
-  std::atomic<size_t> bytes_{0};
+  std::atomic<size_t> bytes_{0}, chunk_{0};
   std::atomic<unsigned> nchunks_{0}, done_{0};
   std::atomic<int> sleepers_{0};
   std::atomic<unsigned long long> ticket_{0};  // (job number << 32) | next unclaimed piece
