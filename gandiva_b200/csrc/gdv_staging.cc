@@ -1,8 +1,12 @@
 #include "gdv_staging.h"
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -46,7 +50,7 @@ class CopyPool {
     // (non-temporal store) path and the 8 threads each get one piece — 46.9 GB/s pageable->device on the
     // bench box against 37.7 GB/s in 256 KB pieces (profiles/r02_host_latency.md).  Smaller copies (one
     // column of a 1M-row batch) go in 256 KB pieces so that every thread has something to claim.
-    const size_t chunk = bytes >= kSlotBytes ? 4 * kChunk : kChunk;
+    const size_t chunk = chunk_override_ != 0 ? chunk_override_ : (bytes >= kSlotBytes ? 4 * kChunk : kChunk);
     const unsigned nchunks = static_cast<unsigned>((bytes + chunk - 1) / chunk);
     chunk_.store(chunk, std::memory_order_relaxed);
     dst_.store(static_cast<char*>(dst), std::memory_order_relaxed);
@@ -77,10 +81,65 @@ class CopyPool {
     if (const char* e = std::getenv("GDV_STAGE_THREADS")) want = std::atoi(e);
     const int hw = static_cast<int>(std::thread::hardware_concurrency());
     if (hw > 0 && want > hw) want = hw;
+    if (const char* e = std::getenv("GDV_STAGE_CHUNK_KB")) chunk_override_ = static_cast<size_t>(std::atoi(e)) << 10;
+    // The workers stay on the NUMA node of the thread that first stages a batch: that thread allocated the
+    // pinned ring (first touch) and usually filled the batch, so every copy is node-local; threads floating
+    // over both sockets made the pageable path vary by 1.6x between runs (GDV_STAGE_PIN=0 turns this off).
+    cpu_set_t node_cpus;
+    bool pin = false;
+    const char* pe = std::getenv("GDV_STAGE_PIN");
+    if (pe == nullptr || std::atoi(pe) != 0) pin = NodeCpusOfCaller(&node_cpus);
     for (int t = 1; t < want; ++t) {
-      std::thread([this] { Loop(); }).detach();
+      std::thread th([this] { Loop(); });
+      if (pin) pthread_setaffinity_np(th.native_handle(), sizeof(node_cpus), &node_cpus);
+      th.detach();
       ++workers_;
     }
+  }
+  // CPUs of the NUMA node the calling thread runs on (/sys/devices/system/node/nodeN/cpulist), intersected
+  // with the process's affinity mask.  false if that cannot be read (no sysfs, one node, ...).
+  static bool NodeCpusOfCaller(cpu_set_t* out) {
+    const int cpu = sched_getcpu();
+    if (cpu < 0) return false;
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
+    for (int node = 0; node < 64; ++node) {
+      char path[96];
+      std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+      FILE* f = std::fopen(path, "r");
+      if (f == nullptr) {
+        if (node == 0) return false;
+        break;
+      }
+      char buf[4096];
+      const size_t len = std::fread(buf, 1, sizeof(buf) - 1, f);
+      std::fclose(f);
+      buf[len] = 0;
+      CPU_ZERO(out);
+      bool mine = false;
+      int count = 0;
+      for (const char* p = buf; *p != 0;) {  // "0-31,64-95"
+        char* end = nullptr;
+        const long a = std::strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') {
+          b = std::strtol(p + 1, &end, 10);
+          p = end;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+          if (c == cpu) mine = true;
+          if (CPU_ISSET(c, &allowed)) {
+            CPU_SET(c, out);
+            ++count;
+          }
+        }
+        while (*p == ',' || *p == '\n' || *p == ' ') ++p;
+      }
+      if (mine) return count >= 2;
+    }
+    return false;
   }
   // Claims and copies pieces of job `e` until none is left.  A claim is a CAS on (epoch << 32 | next
   // piece): it can only succeed while job `e` is still the published one, and the caller does not return
@@ -135,6 +194,7 @@ class CopyPool {
     }
   }
   int workers_ = 0;
+  size_t chunk_override_ = 0;
   std::mutex mu_, caller_mu_;
   std::condition_variable cv_;
   std::atomic<char*> dst_{nullptr};
