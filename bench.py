@@ -78,10 +78,15 @@ def parse_args():
                          "gdv_selection_push, device-side NVLink stores into rank 0's vector, no host "
                          "sync; nccl: all-gather of counts + send/recv (host reads the count)")
     ap.add_argument("--no-overlap", action="store_true", help="--gather nccl: gather inside each step, no pipelining")
-    ap.add_argument("--waves", type=int, default=4,
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="leave the process unbound (default: run on the CPUs of the GPU's NUMA node, restored for the CPU arms)")
+    ap.add_argument("--waves", type=int, default=1,
                     help="N>1, --gather push: filter each step's batch in this many row slices (wave-major global row "
                          "order) so that the NVLink push of slice j hides under the filter kernel of slice j+1 and only "
-                         "the last slice's push is exposed (1 = one run per rank, the whole push of the last step exposed)")
+                         "the last slice's push is exposed.  Default 1 (one run per rank: the push of batch i hides under the filter of "
+                         "batch i+1, only the LAST batch's push is exposed).  Measured at N=2, 1.25e9 rows/GPU: 4 waves cost "
+                         "+0.23 ms per step (four kernel ramps instead of one) and take the last step from +0.28 ms to +0.09 ms "
+                         "— worth it for one isolated batch, not for a stream of batches (profiles/r02_multi_gpu.md)")
     ap.add_argument("--push-ctas", type=int, default=8, help="--gather push: CTAs (256 threads) of the push kernel")
     ap.add_argument("--sm-reserve", type=int, default=-1,
                     help="SMs the filter leaves free for the push / NCCL kernels (default with N>1: 2, i.e. twelve "
@@ -665,6 +670,24 @@ def run_configs(ctx, only):
 
 
 # =================================================================================================
+def gpu_numa_cpus(torch, dev):
+    """(node, cpus) of the NUMA node the GPU hangs off (sysfs), or (None, None)."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else (None, None)
+    except Exception:  # noqa: BLE001 - no sysfs / attribute: run unbound
+        return None, None
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -685,6 +708,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # The process that feeds a GPU runs on the CPUs of the GPU's NUMA node (what a one-process-per-GPU launcher
+    # does with numactl / --cpunodebind): host batches are then allocated next to the link.  On the two-socket
+    # bench box the pageable e2e path varied 25-47 GB/s with the feeding thread left to float.  Undone before
+    # the CPU arms run, which use every core of the box.
+    affinity0 = os.sched_getaffinity(0)
+    numa_node, numa_cpus = gpu_numa_cpus(torch, dev)
+    if numa_cpus and not args.no_numa_bind:
+        os.sched_setaffinity(0, numa_cpus)
     stream = torch.cuda.Stream(dev)   # a real (non-default) stream: events, kernels and
     torch.cuda.set_stream(stream)     # NCCL ops are all ordered on it
     st = stream.cuda_stream
@@ -1006,6 +1037,11 @@ def main():
         del ship, disc, qty, out_idx, bufs, cols
         configs = run_configs(ctx, only)
 
+    for tid in os.listdir("/proc/self/task"):      # threads created while bound inherited the mask
+        try:
+            os.sched_setaffinity(int(tid), affinity0)
+        except OSError:
+            pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -1030,6 +1066,8 @@ def main():
                        "selection_vector": idx_mode + ((" reassembled on rank 0 over NVLink" + (", gdv_selection_push: device-side stores into rank 0's vector (CUDA IPC), counts exchanged through a board in rank 0's HBM, no host sync, overlapped with the next batch's kernel (%d SMs reserved)" % sm_reserve if use_push else (", NCCL send/recv, overlapped with the next batch's kernel" if pipelined else ", NCCL send/recv"))) if world > 1 and not args.no_gather else ""),
                        "gather_check": gather_check, "full_size_check": full_check,
                        "l2_policy": "inputs (20 B/row x %d rows) larger than L2; no flush" % n,
+                       "host_numa": ("process bound to NUMA node %d, the GPU's (%d CPUs), for the GPU arm" % (numa_node, len(numa_cpus)))
+                                    if (numa_cpus and not args.no_numa_bind) else "unbound",
                        "parallelism": "row-range shards, %d" % world},
             "hbm_gbs": achieved, "per_step_ms": per_step,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

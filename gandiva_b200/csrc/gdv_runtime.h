@@ -26,6 +26,7 @@ class Device {
   Status MakeCurrent() const;
   int ordinal() const { return ordinal_; }
   int sm_count() const { return sm_count_; }
+  CUdevice cu_device() const { return dev_; }
   std::string arch() const;
   // The engine's own stream for calls that pass stream == NULL: one non-blocking stream per
   // (host thread, device), so that concurrent Evaluate calls from different threads never share

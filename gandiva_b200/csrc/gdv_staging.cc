@@ -28,10 +28,96 @@ std::atomic<long long> g_staged_bytes{0};
 
 // A few threads that copy slices of one piece in parallel (one memcpy stream does ~10 GB/s, the
 // link wants ~55).  Started on first use, parked on a condition variable in between.
+// ---- NUMA placement ---------------------------------------------------------------------------------------
+// The pinned ring and the copy threads belong on the NUMA node the GPU hangs off: a slot on the other socket
+// makes every DMA cross the socket interconnect, and copy threads floating over both sockets made the pageable
+// path vary between 25 and 47 GB/s from run to run on the two-socket bench box (profiles/r02_host_latency.md).
+
+// CPUs of NUMA node `node` that this process may run on ("0-31,64-95" in sysfs); false if unreadable.
+bool NodeCpus(int node, cpu_set_t* out) {
+  char path[96];
+  std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = std::fopen(path, "r");
+  if (f == nullptr) return false;
+  char buf[4096];
+  const size_t len = std::fread(buf, 1, sizeof(buf) - 1, f);
+  std::fclose(f);
+  buf[len] = 0;
+  cpu_set_t allowed;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
+  CPU_ZERO(out);
+  int count = 0;
+  for (const char* p = buf; *p != 0;) {
+    char* end = nullptr;
+    const long a = std::strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    p = end;
+    if (*p == '-') {
+      b = std::strtol(p + 1, &end, 10);
+      p = end;
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &allowed)) {
+        CPU_SET(c, out);
+        ++count;
+      }
+    while (*p == ',' || *p == '\n' || *p == ' ') ++p;
+  }
+  return count >= 1;
+}
+
+// NUMA node of the GPU (sysfs numa_node of its PCI function), else of the calling thread, else -1.
+int StagingNode(Device* dev) {
+  if (const char* e = std::getenv("GDV_STAGE_PIN"))
+    if (std::atoi(e) == 0) return -1;
+  const DriverApi& d = Driver();
+  int bus = -1, slot = -1, domain = 0;
+  if (d.DeviceGetAttribute(&bus, CU_DEVICE_ATTRIBUTE_PCI_BUS_ID, dev->cu_device()) == CUDA_SUCCESS &&
+      d.DeviceGetAttribute(&slot, CU_DEVICE_ATTRIBUTE_PCI_DEVICE_ID, dev->cu_device()) == CUDA_SUCCESS &&
+      d.DeviceGetAttribute(&domain, CU_DEVICE_ATTRIBUTE_PCI_DOMAIN_ID, dev->cu_device()) == CUDA_SUCCESS && bus >= 0) {
+    char path[128];
+    std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node", domain, bus, slot);
+    if (FILE* f = std::fopen(path, "r")) {
+      int node = -1;
+      const int got = std::fscanf(f, "%d", &node);
+      std::fclose(f);
+      if (got == 1 && node >= 0) return node;
+    }
+  }
+  const int cpu = sched_getcpu();
+  if (cpu < 0) return -1;
+  for (int node = 0; node < 64; ++node) {
+    cpu_set_t set;
+    if (!NodeCpus(node, &set)) break;
+    if (CPU_ISSET(cpu, &set)) return node;
+  }
+  return -1;
+}
+
+// Runs the calling thread on `node` for the lifetime of the object (memory it allocates and first touches
+// lands there), then restores its affinity mask.
+class OnNode {
+ public:
+  explicit OnNode(int node) {
+    cpu_set_t set;
+    if (node >= 0 && NodeCpus(node, &set) && sched_getaffinity(0, sizeof(saved_), &saved_) == 0)
+      moved_ = sched_setaffinity(0, sizeof(set), &set) == 0;
+  }
+  ~OnNode() {
+    if (moved_) sched_setaffinity(0, sizeof(saved_), &saved_);
+  }
+
+ private:
+  cpu_set_t saved_;
+  bool moved_ = false;
+};
+
 class CopyPool {
  public:
-  static CopyPool& Get() {
-    static CopyPool* p = new CopyPool();  // never destroyed: threads may outlive static destructors
+  // `node`: where the workers run (the first caller decides; one process drives one GPU).
+  static CopyPool& Get(int node) {
+    static CopyPool* p = new CopyPool(node);  // never destroyed: threads may outlive static destructors
     return *p;
   }
   // Copies in kChunk pieces that the calling thread and the workers CLAIM one at a time, so the call
@@ -76,70 +162,20 @@ class CopyPool {
  private:
   static constexpr size_t kChunk = size_t(256) << 10;
 
-  CopyPool() {
+  explicit CopyPool(int node) {
     int want = 8;
     if (const char* e = std::getenv("GDV_STAGE_THREADS")) want = std::atoi(e);
     const int hw = static_cast<int>(std::thread::hardware_concurrency());
     if (hw > 0 && want > hw) want = hw;
     if (const char* e = std::getenv("GDV_STAGE_CHUNK_KB")) chunk_override_ = static_cast<size_t>(std::atoi(e)) << 10;
-    // The workers stay on the NUMA node of the thread that first stages a batch: that thread allocated the
-    // pinned ring (first touch) and usually filled the batch, so every copy is node-local; threads floating
-    // over both sockets made the pageable path vary by 1.6x between runs (GDV_STAGE_PIN=0 turns this off).
     cpu_set_t node_cpus;
-    bool pin = false;
-    const char* pe = std::getenv("GDV_STAGE_PIN");
-    if (pe == nullptr || std::atoi(pe) != 0) pin = NodeCpusOfCaller(&node_cpus);
+    const bool pin = node >= 0 && NodeCpus(node, &node_cpus);
     for (int t = 1; t < want; ++t) {
       std::thread th([this] { Loop(); });
       if (pin) pthread_setaffinity_np(th.native_handle(), sizeof(node_cpus), &node_cpus);
       th.detach();
       ++workers_;
     }
-  }
-  // CPUs of the NUMA node the calling thread runs on (/sys/devices/system/node/nodeN/cpulist), intersected
-  // with the process's affinity mask.  false if that cannot be read (no sysfs, one node, ...).
-  static bool NodeCpusOfCaller(cpu_set_t* out) {
-    const int cpu = sched_getcpu();
-    if (cpu < 0) return false;
-    cpu_set_t allowed;
-    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
-    for (int node = 0; node < 64; ++node) {
-      char path[96];
-      std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
-      FILE* f = std::fopen(path, "r");
-      if (f == nullptr) {
-        if (node == 0) return false;
-        break;
-      }
-      char buf[4096];
-      const size_t len = std::fread(buf, 1, sizeof(buf) - 1, f);
-      std::fclose(f);
-      buf[len] = 0;
-      CPU_ZERO(out);
-      bool mine = false;
-      int count = 0;
-      for (const char* p = buf; *p != 0;) {  // "0-31,64-95"
-        char* end = nullptr;
-        const long a = std::strtol(p, &end, 10);
-        if (end == p) break;
-        long b = a;
-        p = end;
-        if (*p == '-') {
-          b = std::strtol(p + 1, &end, 10);
-          p = end;
-        }
-        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
-          if (c == cpu) mine = true;
-          if (CPU_ISSET(c, &allowed)) {
-            CPU_SET(c, out);
-            ++count;
-          }
-        }
-        while (*p == ',' || *p == '\n' || *p == ' ') ++p;
-      }
-      if (mine) return count >= 2;
-    }
-    return false;
   }
   // Claims and copies pieces of job `e` until none is left.  A claim is a CAS on (epoch << 32 | next
   // piece): it can only succeed while job `e` is still the published one, and the caller does not return
@@ -214,9 +250,13 @@ struct Ring {
   bool busy[kSlots] = {false};
   int next = 0;
 
-  Status Init() {
+  int node = -1;
+
+  Status Init(Device* dev) {
     if (ready) return Status::OK();
     const DriverApi& d = Driver();
+    node = StagingNode(dev);
+    OnNode here(node);  // the slots are allocated (and so placed) from a CPU of the GPU's node
     for (int i = 0; i < kSlots; ++i) {
       Status s = CuCheck(d.MemHostAlloc(&slot[i], kSlotBytes, 0), "cuMemHostAlloc(staging slot)");
       if (!s.ok()) return s;
@@ -259,9 +299,9 @@ Status StagedHtoD(Device* dev, CUdeviceptr dst, const void* src, size_t bytes, C
     return CuCheck(d.MemcpyHtoDAsync(dst, src, bytes, stream), "cuMemcpyHtoDAsync");
   Ring* ring = RingFor(dev);
   std::lock_guard<std::mutex> lock(ring->mu);
-  Status st = ring->Init();
+  Status st = ring->Init(dev);
   if (!st.ok()) return st;
-  CopyPool& pool = CopyPool::Get();
+  CopyPool& pool = CopyPool::Get(ring->node);
   const char* s = static_cast<const char*>(src);
   for (size_t off = 0; off < bytes; off += kSlotBytes) {
     const size_t n = std::min(kSlotBytes, bytes - off);
@@ -290,9 +330,9 @@ Status StagedDtoH(Device* dev, void* dst, CUdeviceptr src, size_t bytes, CUstrea
     return CuCheck(d.MemcpyDtoHAsync(dst, src, bytes, stream), "cuMemcpyDtoHAsync");
   Ring* ring = RingFor(dev);
   std::lock_guard<std::mutex> lock(ring->mu);
-  Status st = ring->Init();
+  Status st = ring->Init(dev);
   if (!st.ok()) return st;
-  CopyPool& pool = CopyPool::Get();
+  CopyPool& pool = CopyPool::Get(ring->node);
   char* out = static_cast<char*>(dst);
   // every slot may still be read by an earlier H2D: wait for those first
   for (int i = 0; i < kSlots; ++i)
