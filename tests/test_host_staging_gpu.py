@@ -35,9 +35,9 @@ def test_pageable_batches_go_through_the_ring(n, gandiva, oracle):
     want = oracle.project([outs[0][0]], [pa.int32()], batch)
     assert_arrays_match(got[0], want[0])
     # copies of 1 MB and more are staged: two value columns in, one out (validity bitmaps are below the threshold
-    # at the two smaller sizes)
+    # at the two smaller sizes; batches of 0.5M rows and more travel in slices, whose last one may be below it too)
     expect = 3 * 4 * n if 4 * n >= (1 << 20) else 0
-    assert moved >= expect and (expect > 0 or moved == 0)
+    assert moved >= 0.7 * expect and (expect > 0 or moved == 0)
 
 
 def test_back_to_back_and_after_a_pause(gandiva, oracle):
@@ -86,3 +86,46 @@ def test_pinned_buffers_bypass_the_ring(gandiva):
     finally:
         for q in ptrs:
             gandiva.lib.gdv_host_free(q)
+
+
+def test_host_batch_in_slices_matches_oracle(gandiva, oracle):
+    """A host batch of 0.5M rows and more is evaluated in slices on two streams (results of one slice travel back
+    while the next slices' inputs arrive): fixed-width, bool and string INPUTS, fixed-width and bool OUTPUTS,
+    nulls, and columns that are themselves Arrow slices (offset != 0)."""
+    I32, F64, B, S = pa.int32(), pa.float64(), pa.bool_(), pa.string()
+    schema = pa.schema([("i", I32), ("j", I32), ("d", F64), ("p", B), ("s", S)])
+    b = gandiva.TreeExprBuilder()
+    f = {x.name: b.make_field(x) for x in schema}
+    fn = b.make_function
+    roots = [(fn("add", [f["i"], f["j"]], I32), I32),
+             (fn("less_than", [f["d"], b.make_literal(0.25, F64)], B), B),
+             (b.make_if(f["p"], fn("multiply", [f["d"], b.make_literal(2.0, F64)], F64), fn("castFLOAT8", [f["i"]], F64), F64),
+              F64),
+             (fn("octet_length", [f["s"]], I32), I32)]
+    p = gandiva.make_projector(schema, [b.make_expression(r, pa.field("o%d" % k, t)) for k, (r, t) in enumerate(roots)], None)
+    for n, off in ((524_288, 0), (700_001, 3), (1_300_000, 13)):
+        batch = cases.random_batch(schema, n, seed=n, null_prob=0.15, offset=off)
+        got = p.evaluate(batch)
+        want = oracle.project([r for r, _ in roots], [t for _, t in roots], batch, threads=8)
+        for k, (gv, wv) in enumerate(zip(got, want)):
+            assert_arrays_match(gv, wv, "n=%d offset=%d output %d" % (n, off, k))
+
+
+def test_error_in_a_later_slice_is_reported(gandiva):
+    """divide by zero in the LAST slice of a sliced host batch raises like it does in an unsliced one."""
+    I32 = pa.int32()
+    schema = pa.schema([("a", I32), ("b", I32)])
+    b = gandiva.TreeExprBuilder()
+    p = gandiva.make_projector(schema, [b.make_expression(
+        b.make_function("divide", [b.make_field(schema.field(0)), b.make_field(schema.field(1))], I32), pa.field("q", I32))],
+        None)
+    n = 1_200_000
+    a = np.arange(n, dtype=np.int32)
+    d = np.full(n, 7, dtype=np.int32)
+    ok = p.evaluate(pa.record_batch([pa.array(a), pa.array(d)], schema=schema))[0].to_numpy()
+    assert np.array_equal(ok, a // 7)
+    d[n - 5] = 0
+    with pytest.raises(gandiva.GandivaError, match="divide by zero"):
+        p.evaluate(pa.record_batch([pa.array(a), pa.array(d)], schema=schema))
+    again = p.evaluate(pa.record_batch([pa.array(a), pa.array(np.full(n, 7, dtype=np.int32))], schema=schema))[0].to_numpy()
+    assert np.array_equal(again, a // 7)        # the error flag of both streams was cleared
