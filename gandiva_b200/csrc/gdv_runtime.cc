@@ -106,14 +106,11 @@ namespace {
 // Streams of the threads that did not create the Device; released at thread exit.
 struct ThreadStreams {
   CUstream by_device[64] = {nullptr};
-  CUstream side_by_device[64] = {nullptr};
   ~ThreadStreams() {
     const DriverApi& d = Driver();
     if (!d.loaded) return;
     for (CUstream s : by_device)
       if (s != nullptr) d.StreamDestroy(s);  // fails harmlessly once the context is gone
-    for (CUstream s : side_by_device)
-      if (s != nullptr) d.StreamDestroy(s);
   }
 };
 thread_local ThreadStreams tl_streams;
@@ -126,14 +123,6 @@ CUstream Device::stream() const {
     if (!MakeCurrent().ok() ||
         Driver().StreamCreate(&s, CU_STREAM_NON_BLOCKING) != CUDA_SUCCESS)
       return stream_;  // out of streams: fall back to the shared one
-  }
-  return s;
-}
-
-CUstream Device::side_stream() const {
-  CUstream& s = tl_streams.side_by_device[ordinal_];
-  if (s == nullptr) {
-    if (!MakeCurrent().ok() || Driver().StreamCreate(&s, CU_STREAM_NON_BLOCKING) != CUDA_SUCCESS) return nullptr;
   }
   return s;
 }
@@ -831,24 +820,6 @@ Status Projector::EvaluateString(StringKernels* sk, const gdv_batch_t* batch,
   return Status::OK();
 }
 
-namespace {
-// Rows per slice of a host batch (0 = evaluate it in one piece).  GDV_HOST_SLICE_ROWS overrides (0 = never).
-int64_t HostSliceRows(int64_t n) {
-  static const int64_t forced = [] {
-    const char* e = std::getenv("GDV_HOST_SLICE_ROWS");
-    return e != nullptr ? static_cast<int64_t>(std::atoll(e)) : int64_t(-1);
-  }();
-  int64_t rows;
-  if (forced >= 0) {
-    rows = (forced + 4095) / 4096 * 4096;
-  } else {
-    if (n < (int64_t(1) << 19)) return 0;  // below ~0.5M rows the extra launches cost more than the overlap gives
-    rows = std::max<int64_t>(int64_t(1) << 18, ((n + 7) / 8 + 4095) / 4096 * 4096);
-  }
-  return (rows <= 0 || rows >= n) ? 0 : rows;
-}
-}  // namespace
-
 Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
                            gdv_out_column_t* all_outs, int n_all_outs, void* stream_v, bool async) {
   if (batch == nullptr || all_outs == nullptr) return Status::Make(GDV_INVALID, "null argument");
@@ -884,167 +855,99 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
   const GeneratedKernel& gen = kernel->gen;
 
+  const double t_begin = TraceOn() ? NowUs() : 0.0;
+  ScratchScope scratch(dev);
+  scratch.Guard(stream);
+  std::vector<ResolvedIn> ins;
+  GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, batch, stream, &scratch, &ins));
+  const double t_inputs = TraceOn() ? NowUs() : 0.0;
+
+  ArgsLayout L(static_cast<int>(gen.inputs.size()), n_outs);
+  std::vector<uint8_t> args(L.size, 0);
+  Put<int64_t>(args, L.off_n, n);
+  for (size_t j = 0; j < ins.size(); ++j) {
+    Put<CUdeviceptr>(args, L.off_in_val + 8 * j, ins[j].val);
+    Put<CUdeviceptr>(args, L.off_in_vld + 8 * j, ins[j].vld);
+    Put<CUdeviceptr>(args, L.off_in_var + 8 * j, ins[j].var);
+    Put<uint32_t>(args, L.off_in_vsh + 4 * j, ins[j].vsh);
+    Put<uint32_t>(args, L.off_in_dsh + 4 * j, ins[j].dsh);
+  }
+  // selection vector
+  if (selection_mode_ != GDV_SEL_NONE) {
+    CUdeviceptr dsel = reinterpret_cast<CUdeviceptr>(sel->indices);
+    if (host) {
+      const size_t bytes = static_cast<size_t>(n) * SelWidth(selection_mode_);
+      GDV_RETURN_NOT_OK(scratch.Alloc(bytes + 16, &dsel));
+      if (bytes > 0)
+        GDV_RETURN_NOT_OK(StagedHtoD(dev, dsel, sel->indices, bytes, stream));
+    }
+    Put<CUdeviceptr>(args, L.off_sel, dsel);
+    if (sel->d_num_slots != nullptr) {
+      if (host) return Status::Make(GDV_INVALID, "d_num_slots needs device buffers");
+      Put<CUdeviceptr>(args, L.off_n_ptr, reinterpret_cast<CUdeviceptr>(sel->d_num_slots));
+    }
+  }
+  // outputs
   struct OutStage {
     CUdeviceptr val = 0, vld = 0;
     size_t val_bytes = 0, vld_bytes = 0;
   };
-  // Inputs to the device (staged for host batches), arguments, launch — everything of one Evaluate up
-  // to, not including, the way back of the results.  `b` / `o` / `nn` are the whole batch or one slice.
-  auto enqueue = [&](const gdv_batch_t* b, gdv_out_column_t* o, int64_t nn, CUstream s, ScratchScope* sc,
-                     std::vector<OutStage>* stage) -> Status {
-    std::vector<ResolvedIn> ins;
-    GDV_RETURN_NOT_OK(ResolveInputs(dev, gen, b, s, sc, &ins));
-    ArgsLayout L(static_cast<int>(gen.inputs.size()), n_outs);
-    std::vector<uint8_t> args(L.size, 0);
-    Put<int64_t>(args, L.off_n, nn);
-    for (size_t j = 0; j < ins.size(); ++j) {
-      Put<CUdeviceptr>(args, L.off_in_val + 8 * j, ins[j].val);
-      Put<CUdeviceptr>(args, L.off_in_vld + 8 * j, ins[j].vld);
-      Put<CUdeviceptr>(args, L.off_in_var + 8 * j, ins[j].var);
-      Put<uint32_t>(args, L.off_in_vsh + 4 * j, ins[j].vsh);
-      Put<uint32_t>(args, L.off_in_dsh + 4 * j, ins[j].dsh);
+  std::vector<OutStage> stage(n_outs);
+  const size_t words = static_cast<size_t>((n + 31) / 32);
+  for (int o = 0; o < n_outs; ++o) {
+    const DataType& t = gen.outputs[o];
+    if (outs[o].values == nullptr && n > 0)
+      return Status::Make(GDV_INVALID, "output values buffer is null");
+    OutStage& st = stage[o];
+    st.val_bytes = t.is_bool() ? static_cast<size_t>((n + 7) / 8) : static_cast<size_t>(n) * t.width();
+    st.vld_bytes = static_cast<size_t>((n + 7) / 8);
+    if (host) {
+      GDV_RETURN_NOT_OK(scratch.Alloc(t.is_bool() ? words * 4 + 8 : st.val_bytes + 16, &st.val));
+      if (outs[o].validity != nullptr) GDV_RETURN_NOT_OK(scratch.Alloc(words * 4 + 8, &st.vld));
+    } else {
+      st.val = reinterpret_cast<CUdeviceptr>(outs[o].values);
+      st.vld = reinterpret_cast<CUdeviceptr>(outs[o].validity);
     }
-    // selection vector
-    if (selection_mode_ != GDV_SEL_NONE) {
-      CUdeviceptr dsel = reinterpret_cast<CUdeviceptr>(sel->indices);
-      if (host) {
-        const size_t bytes = static_cast<size_t>(nn) * SelWidth(selection_mode_);
-        GDV_RETURN_NOT_OK(sc->Alloc(bytes + 16, &dsel));
-        if (bytes > 0)
-          GDV_RETURN_NOT_OK(StagedHtoD(dev, dsel, sel->indices, bytes, s));
-      }
-      Put<CUdeviceptr>(args, L.off_sel, dsel);
-      if (sel->d_num_slots != nullptr) {
-        if (host) return Status::Make(GDV_INVALID, "d_num_slots needs device buffers");
-        Put<CUdeviceptr>(args, L.off_n_ptr, reinterpret_cast<CUdeviceptr>(sel->d_num_slots));
-      }
+    Put<CUdeviceptr>(args, L.off_out_val + 8 * o, st.val);
+    Put<CUdeviceptr>(args, L.off_out_vld + 8 * o, st.vld);
+  }
+  // error flag
+  CUdeviceptr d_err = 0;
+  if (gen.uses_ctx) {
+    std::lock_guard<std::mutex> lock(mu_);
+    Pending& pend = pending_[stream];
+    if (pend.d_err == 0) {
+      pend.dev = dev;
+      pend.uses_ctx = true;
+      GDV_RETURN_NOT_OK(dev->Alloc(256, &pend.d_err));
+      GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(pend.d_err, 0, 256, stream), "memset err"));
     }
-    // outputs
-    stage->assign(n_outs, OutStage());
-    const size_t words = static_cast<size_t>((nn + 31) / 32);
-    for (int k = 0; k < n_outs; ++k) {
-      const DataType& t = gen.outputs[k];
-      if (o[k].values == nullptr && nn > 0)
-        return Status::Make(GDV_INVALID, "output values buffer is null");
-      OutStage& st = (*stage)[k];
-      st.val_bytes = t.is_bool() ? static_cast<size_t>((nn + 7) / 8) : static_cast<size_t>(nn) * t.width();
-      st.vld_bytes = static_cast<size_t>((nn + 7) / 8);
-      if (host) {
-        GDV_RETURN_NOT_OK(sc->Alloc(t.is_bool() ? words * 4 + 8 : st.val_bytes + 16, &st.val));
-        if (o[k].validity != nullptr) GDV_RETURN_NOT_OK(sc->Alloc(words * 4 + 8, &st.vld));
-      } else {
-        st.val = reinterpret_cast<CUdeviceptr>(o[k].values);
-        st.vld = reinterpret_cast<CUdeviceptr>(o[k].validity);
-      }
-      Put<CUdeviceptr>(args, L.off_out_val + 8 * k, st.val);
-      Put<CUdeviceptr>(args, L.off_out_vld + 8 * k, st.vld);
-    }
-    // error flag
-    if (gen.uses_ctx) {
-      CUdeviceptr d_err = 0;
-      std::lock_guard<std::mutex> lock(mu_);
-      Pending& pend = pending_[s];
-      if (pend.d_err == 0) {
-        pend.dev = dev;
-        pend.uses_ctx = true;
-        GDV_RETURN_NOT_OK(dev->Alloc(256, &pend.d_err));
-        GDV_RETURN_NOT_OK(CuCheck(d.MemsetD8Async(pend.d_err, 0, 256, s), "memset err"));
-      }
-      d_err = pend.d_err;
-      Put<CUdeviceptr>(args, L.off_err, d_err);
-    }
-    const int R = gen.rows_per_thread, BT = gen.block_threads;
-    const int64_t wtiles = (nn + 32 * R - 1) / (32 * R);
-    const int64_t blocks_needed = (wtiles + BT / 32 - 1) / (BT / 32);
-    const int64_t cap =
-        static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * l.blocks_per_sm;
-    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(blocks_needed, cap));
-    return LaunchKernel(dev, l, gen, args, grid, s);
-  };
-  auto copy_out = [&](gdv_out_column_t* o, CUstream s, const std::vector<OutStage>& stage) -> Status {
-    for (int k = 0; k < n_outs; ++k) {
-      if (stage[k].val_bytes > 0)
-        GDV_RETURN_NOT_OK(StagedDtoH(dev, o[k].values, stage[k].val, stage[k].val_bytes, s));
-      if (o[k].validity != nullptr && stage[k].vld_bytes > 0)
-        GDV_RETURN_NOT_OK(StagedDtoH(dev, o[k].validity, stage[k].vld, stage[k].vld_bytes, s));
-    }
-    return Status::OK();
-  };
-
-  const double t_begin = TraceOn() ? NowUs() : 0.0;
-  // ---- host batch, no selection vector: in slices on two streams ---------------------------------------
-  // One slice's results travel back (the link is full duplex, and for pageable buffers the copy threads are
-  // free) while the next slices' inputs are still arriving; the call costs about max(in, out) instead of
-  // in + kernel + out.  Slices are ArrayData offsets into the same buffers (multiples of 4096 rows, so every
-  // output bitmap slice starts on a byte).
-  const int64_t slice_rows = (host && selection_mode_ == GDV_SEL_NONE) ? HostSliceRows(n) : 0;
-  CUstream side = slice_rows > 0 ? dev->side_stream() : nullptr;
-  if (side != nullptr) {
-    struct Slice {
-      int64_t first = 0, rows = 0;
-      CUstream s = nullptr;
-      std::unique_ptr<ScratchScope> scratch;
-      std::vector<OutStage> stage;
-      std::vector<gdv_out_column_t> outs;
-    };
-    std::vector<Slice> slices;
-    for (int64_t first = 0; first < n; first += slice_rows) {
-      Slice sl;
-      sl.first = first;
-      sl.rows = std::min(slice_rows, n - first);
-      sl.s = (slices.size() & 1u) != 0u ? side : stream;
-      slices.push_back(std::move(sl));
-    }
-    std::vector<gdv_column_t> cols(batch->columns, batch->columns + batch->num_columns);
-    Status st = Status::OK();
-    for (Slice& sl : slices) {
-      for (int c = 0; c < batch->num_columns; ++c) cols[c].offset = batch->columns[c].offset + sl.first;
-      gdv_batch_t sub = *batch;
-      sub.num_rows = sl.rows;
-      sub.columns = cols.data();
-      sl.outs.assign(outs, outs + n_outs);
-      for (int k = 0; k < n_outs; ++k) {
-        const DataType& t = gen.outputs[k];
-        const size_t skip = t.is_bool() ? static_cast<size_t>(sl.first / 8) : static_cast<size_t>(sl.first) * t.width();
-        if (sl.outs[k].values != nullptr) sl.outs[k].values = static_cast<uint8_t*>(sl.outs[k].values) + skip;
-        if (sl.outs[k].validity != nullptr)
-          sl.outs[k].validity = static_cast<uint8_t*>(sl.outs[k].validity) + sl.first / 8;
-      }
-      sl.scratch.reset(new ScratchScope(dev));
-      sl.scratch->Guard(sl.s);
-      st = enqueue(&sub, sl.outs.data(), sl.rows, sl.s, sl.scratch.get(), &sl.stage);
-      if (!st.ok()) break;
-    }
-    const double t_launch = TraceOn() ? NowUs() : 0.0;
-    if (st.ok())
-      for (Slice& sl : slices) {
-        st = copy_out(sl.outs.data(), sl.s, sl.stage);
-        if (!st.ok()) break;
-      }
-    const double t_out = TraceOn() ? NowUs() : 0.0;
-    const Status s0 = Sync(stream), s1 = Sync(side);  // both, always: they release the pending blocks
-    if (TraceOn())
-      std::fprintf(stderr, "gdv trace: projector host batch %lld rows in %zu slices: inputs+launch %.0f us, outputs %.0f us, "
-                           "sync %.0f us\n", static_cast<long long>(n), slices.size(), t_launch - t_begin, t_out - t_launch,
-                   NowUs() - t_out);
-    GDV_RETURN_NOT_OK(st);
-    GDV_RETURN_NOT_OK(s0);
-    return s1;
+    d_err = pend.d_err;
+    Put<CUdeviceptr>(args, L.off_err, d_err);
   }
 
-  ScratchScope scratch(dev);
-  scratch.Guard(stream);
-  std::vector<OutStage> stage;
-  GDV_RETURN_NOT_OK(enqueue(batch, outs, n, stream, &scratch, &stage));
+  const int R = gen.rows_per_thread, BT = gen.block_threads;
+  const int64_t wtiles = (n + 32 * R - 1) / (32 * R);
+  const int64_t blocks_needed = (wtiles + BT / 32 - 1) / (BT / 32);
+  const int64_t cap =
+      static_cast<int64_t>(std::max(1, dev->sm_count() - cfg_.sm_reserve)) * l.blocks_per_sm;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(blocks_needed, cap));
+  GDV_RETURN_NOT_OK(LaunchKernel(dev, l, gen, args, grid, stream));
+
   if (host) {
     const double t_launch = TraceOn() ? NowUs() : 0.0;
-    GDV_RETURN_NOT_OK(copy_out(outs, stream, stage));
+    for (int o = 0; o < n_outs; ++o) {
+      if (stage[o].val_bytes > 0)
+        GDV_RETURN_NOT_OK(StagedDtoH(dev, outs[o].values, stage[o].val, stage[o].val_bytes, stream));
+      if (outs[o].validity != nullptr && stage[o].vld_bytes > 0)
+        GDV_RETURN_NOT_OK(StagedDtoH(dev, outs[o].validity, stage[o].vld, stage[o].vld_bytes, stream));
+    }
     const double t_out = TraceOn() ? NowUs() : 0.0;
     Status st = Sync(stream);
     if (TraceOn())
-      std::fprintf(stderr, "gdv trace: projector host batch %lld rows: inputs+launch %.0f us, outputs %.0f us, "
-                           "sync %.0f us\n", static_cast<long long>(n), t_launch - t_begin, t_out - t_launch,
-                   NowUs() - t_out);
+      std::fprintf(stderr, "gdv trace: projector host batch %lld rows: inputs %.0f us, args+launch %.0f us, outputs %.0f us, "
+                           "sync %.0f us\n", static_cast<long long>(n), t_inputs - t_begin, t_launch - t_inputs,
+                   t_out - t_launch, NowUs() - t_out);
     return st;
   }
   if (!async) return Sync(stream);

@@ -34,10 +34,6 @@ class Device {
   // stream_; other threads get theirs on first use (destroyed when the thread exits).
   CUstream stream() const;
   CUstream copy_stream() const { return copy_stream_; }
-  // A second stream of the calling thread (created on first use; NULL if the driver is out of streams):
-  // host batches are evaluated in slices that alternate between stream() and this one, so that the
-  // device-to-host copy of one slice runs while the next slice's inputs are still arriving.
-  CUstream side_stream() const;
 
   // Pooled device scratch: freed blocks are cached and reused (no cuMemFree on the hot path).  The
   // cache is bounded: once the idle blocks hold more than the limit (default 4 GiB, GDV_POOL_LIMIT_MB

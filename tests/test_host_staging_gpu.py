@@ -35,9 +35,9 @@ def test_pageable_batches_go_through_the_ring(n, gandiva, oracle):
     want = oracle.project([outs[0][0]], [pa.int32()], batch)
     assert_arrays_match(got[0], want[0])
     # copies of 1 MB and more are staged: two value columns in, one out (validity bitmaps are below the threshold
-    # at the two smaller sizes; batches of 0.5M rows and more travel in slices, whose last one may be below it too)
+    # at the two smaller sizes)
     expect = 3 * 4 * n if 4 * n >= (1 << 20) else 0
-    assert moved >= 0.7 * expect and (expect > 0 or moved == 0)
+    assert moved >= expect and (expect > 0 or moved == 0)
 
 
 def test_back_to_back_and_after_a_pause(gandiva, oracle):
@@ -88,10 +88,9 @@ def test_pinned_buffers_bypass_the_ring(gandiva):
             gandiva.lib.gdv_host_free(q)
 
 
-def test_host_batch_in_slices_matches_oracle(gandiva, oracle):
-    """A host batch of 0.5M rows and more is evaluated in slices on two streams (results of one slice travel back
-    while the next slices' inputs arrive): fixed-width, bool and string INPUTS, fixed-width and bool OUTPUTS,
-    nulls, and columns that are themselves Arrow slices (offset != 0)."""
+def test_large_host_batch_of_every_buffer_kind(gandiva, oracle):
+    """Host batches of 0.5M-1.3M rows through the staging ring: fixed-width, bool and string INPUTS, fixed-width
+    and bool OUTPUTS, nulls, and columns that are themselves Arrow slices (offset != 0)."""
     I32, F64, B, S = pa.int32(), pa.float64(), pa.bool_(), pa.string()
     schema = pa.schema([("i", I32), ("j", I32), ("d", F64), ("p", B), ("s", S)])
     b = gandiva.TreeExprBuilder()
@@ -111,8 +110,8 @@ def test_host_batch_in_slices_matches_oracle(gandiva, oracle):
             assert_arrays_match(gv, wv, "n=%d offset=%d output %d" % (n, off, k))
 
 
-def test_error_in_a_later_slice_is_reported(gandiva):
-    """divide by zero in the LAST slice of a sliced host batch raises like it does in an unsliced one."""
+def test_error_late_in_a_large_host_batch_is_reported(gandiva):
+    """divide by zero near the end of a 1.2M-row host batch raises, and the next call starts clean."""
     I32 = pa.int32()
     schema = pa.schema([("a", I32), ("b", I32)])
     b = gandiva.TreeExprBuilder()
@@ -128,4 +127,4 @@ def test_error_in_a_later_slice_is_reported(gandiva):
     with pytest.raises(gandiva.GandivaError, match="divide by zero"):
         p.evaluate(pa.record_batch([pa.array(a), pa.array(d)], schema=schema))
     again = p.evaluate(pa.record_batch([pa.array(a), pa.array(np.full(n, 7, dtype=np.int32))], schema=schema))[0].to_numpy()
-    assert np.array_equal(again, a // 7)        # the error flag of both streams was cleared
+    assert np.array_equal(again, a // 7)        # the error flag was cleared
