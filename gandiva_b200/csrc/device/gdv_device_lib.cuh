@@ -46,6 +46,7 @@ typedef unsigned __int128 u128;
 #define GDV_ERR_LOCATE_START 11    /* locate(sub, s, start) with start < 1 */
 #define GDV_ERR_FACTORIAL_NEG 12   /* factorial of a negative number */
 #define GDV_ERR_FACTORIAL_BIG 13   /* factorial of a number above 20 (does not fit int64) */
+#define GDV_ERR_TO_DATE 14         /* to_date: the text does not match the format (and errors are not suppressed) */
 struct gdv_ctx {
   int* err;
 };
@@ -71,7 +72,9 @@ GDV_DEV int gdv_check_start(gdv_ctx* c, int start) {
 
 // ---- strings: a view on Arrow bytes plus a lazy ASCII case map ------------------------
 // upper()/lower()/substr()/trim() never materialise: they return a view, and consumers read
-// bytes through gdv_ch().  xf bits 0-1: 0 = as stored, 1 = upper-cased, 2 = lower-cased;
+// bytes through gdv_ch().  xf bits 0-1: 0 = as stored, 1 = upper-cased, 2 = lower-cased,
+// 3 = initcap (a letter is upper-cased at the start of the view or after a byte that is not part of a
+// word, lower-cased inside a word; the fuser never narrows a view from the left after initcap);
 // GDV_XF_ASCII: every stored byte of the row is known to be < 0x80 (set by the cooperative
 // scan of the staged bytes), so glyph positions are byte positions.
 #define GDV_XF_CASE 3u
@@ -87,6 +90,11 @@ struct gdv_str {
   i32 len;
   u32 xf;
 };
+// Part of a word for initcap: ASCII letters and digits, and every byte of a multi-byte glyph (the case
+// maps are ASCII-only, DESIGN.md §5: a non-ASCII letter continues a word but is never re-cased itself).
+GDV_DEV bool gdv_is_word_byte(u8 c) {
+  return (u32)((c | 0x20u) - (u32)'a') <= 25u || (u32)(c - (u32)'0') <= 9u || c >= 0x80u;
+}
 GDV_DEV u8 gdv_ch(const gdv_str& s, i32 i) {
   u8 c = s.p[i];
   const u32 cm = s.xf & GDV_XF_CASE;
@@ -94,6 +102,9 @@ GDV_DEV u8 gdv_ch(const gdv_str& s, i32 i) {
     if (c >= (u8)'a' && c <= (u8)'z') c = (u8)(c - 32);
   } else if (cm == 2u) {
     if (c >= (u8)'A' && c <= (u8)'Z') c = (u8)(c + 32);
+  } else if (cm == 3u) {
+    const u32 low = (u32)c | 0x20u;
+    if (low - (u32)'a' <= 25u) c = (i > 0 && gdv_is_word_byte(s.p[i - 1])) ? (u8)low : (u8)(low - 32u);
   }
   return c;
 }
@@ -102,6 +113,7 @@ GDV_DEV u8 gdv_ch(const gdv_str& s, i32 i) {
 GDV_DEV bool gdv_ch_eq(const gdv_str& s, i32 i, u32 lit) {
   const u32 c = s.p[i];
   const u32 cm = s.xf & GDV_XF_CASE;
+  if (cm == 3u) return (u32)gdv_ch(s, i) == lit;
   if (cm == 1u) {
     if (lit >= (u32)'a' && lit <= (u32)'z') return false;  // upper-cased text has no a-z
     if (lit >= (u32)'A' && lit <= (u32)'Z') return (c | 0x20u) == (lit | 0x20u);
@@ -2371,6 +2383,93 @@ GDV_DEV gdv_str upper_utf8(gdv_str s) {
 }
 GDV_DEV gdv_str lower_utf8(gdv_str s) {
   s.xf = (s.xf & ~GDV_XF_CASE) | 2u;
+  return s;
+}
+// ---- to_date(text, format): interpreter of the program csrc/gdv_datefmt.cc compiles from the format literal.
+// The rules are glibc strptime's for %Y %y %m %d %H %I %M %S %b/%B %p, white space and literal bytes; trailing
+// text is allowed, the time of day is parsed but ignored, the day defaults to 1 (gdv_datefmt.h).
+GDV_DEV bool gdv_fmt_space(u8 c) { return c == (u8)' ' || (u32)(c - 9u) <= 4u; }
+// up to `width` digits after optional white space, stopping early when another digit would exceed `hi`
+GDV_DEV bool gdv_fmt_number(const gdv_str& s, i32* pos, i32 lo, i32 hi, i32 width, i32* out) {
+  i32 i = *pos;
+  while (i < s.len && gdv_fmt_space(gdv_ch(s, i))) ++i;
+  if (i >= s.len || (u32)(gdv_ch(s, i) - (u32)'0') > 9u) return false;
+  i32 val = 0;
+  do {
+    val = val * 10 + (i32)(gdv_ch(s, i) - (u32)'0');
+    ++i;
+  } while (--width > 0 && val * 10 <= hi && i < s.len && (u32)(gdv_ch(s, i) - (u32)'0') <= 9u);
+  *pos = i;
+  *out = val;
+  return val >= lo && val <= hi;
+}
+// case-insensitive match of `word` (lower case, n bytes) at s[pos..]
+GDV_DEV bool gdv_fmt_word(const gdv_str& s, i32 pos, const char* word, i32 n) {
+  if (pos + n > s.len) return false;
+  for (i32 k = 0; k < n; ++k)
+    if (((u32)gdv_ch(s, pos + k) | 0x20u) != (u32)(u8)word[k]) return false;
+  return true;
+}
+GDV_DEV i64 gdv_to_date_fmt(gdv_ctx* c, gdv_str s, const u8* prog, i32 nprog, bool suppress, bool* ok) {
+  const char names[12][10] = {"january", "february", "march", "april", "may", "june", "july", "august", "september",
+                              "october", "november", "december"};
+  const int name_len[12] = {7, 8, 5, 5, 3, 4, 4, 6, 9, 7, 8, 8};
+  i32 pos = 0, year = 1900, mon = 1, day = 0, tmp = 0;
+  bool good = true;
+  for (i32 k = 0; k < nprog && good; ++k) {
+    const u32 op = prog[k];
+    if (op == 11u) {  // white space in the format: any run of white space in the text
+      while (pos < s.len && gdv_fmt_space(gdv_ch(s, pos))) ++pos;
+    } else if (op == 12u) {  // literal byte
+      ++k;
+      good = pos < s.len && (u32)gdv_ch(s, pos) == (u32)prog[k];
+      ++pos;
+    } else if (op == 1u) {
+      good = gdv_fmt_number(s, &pos, 0, 9999, 4, &year);
+    } else if (op == 2u) {
+      good = gdv_fmt_number(s, &pos, 0, 99, 2, &tmp);
+      year = tmp >= 69 ? 1900 + tmp : 2000 + tmp;
+    } else if (op == 3u) {
+      good = gdv_fmt_number(s, &pos, 1, 12, 2, &mon);
+    } else if (op == 4u) {
+      good = gdv_fmt_number(s, &pos, 1, 31, 2, &day);
+    } else if (op == 5u) {
+      good = gdv_fmt_number(s, &pos, 0, 23, 2, &tmp);
+    } else if (op == 6u) {
+      good = gdv_fmt_number(s, &pos, 1, 12, 2, &tmp);
+    } else if (op == 7u) {
+      good = gdv_fmt_number(s, &pos, 0, 59, 2, &tmp);
+    } else if (op == 8u) {
+      good = gdv_fmt_number(s, &pos, 0, 61, 2, &tmp);
+    } else if (op == 9u) {  // month name, full or three letters, any case
+      good = false;
+      for (i32 m = 0; m < 12 && !good; ++m) {
+        if (gdv_fmt_word(s, pos, names[m], name_len[m])) {
+          pos += name_len[m];
+          good = true;
+        } else if (gdv_fmt_word(s, pos, names[m], 3)) {
+          pos += 3;
+          good = true;
+        }
+        if (good) mon = m + 1;
+      }
+    } else {  // AM / PM
+      good = gdv_fmt_word(s, pos, "am", 2) || gdv_fmt_word(s, pos, "pm", 2);
+      pos += 2;
+    }
+  }
+  *ok = good;
+  if (!good) {
+    if (!suppress) gdv_set_error(c, GDV_ERR_TO_DATE);
+    return 0;
+  }
+  if (day < 1) day = 1;
+  // midnight of year / month / day; a day past the month's end runs into the next month (plain day arithmetic)
+  return (gdv_days_from_civil((i64)year, mon, 1) + (i64)(day - 1)) * 86400000ll;
+}
+
+GDV_DEV gdv_str initcap_utf8(gdv_str s) {
+  s.xf = (s.xf & ~GDV_XF_CASE) | 3u;
   return s;
 }
 GDV_DEV i32 octet_length_utf8(gdv_str s) { return s.len; }

@@ -1,4 +1,5 @@
 #include "gdv_codegen.h"
+#include "gdv_datefmt.h"
 #include "gdv_regex.h"
 
 #include <algorithm>
@@ -29,6 +30,22 @@ bool IsSupportedType(const DataType& t) {
       return t.precision == 1;  // milliseconds, as in the reference
     default: return false;
   }
+}
+
+// True when the string this node yields carries the initcap case map: initcap itself, or a function that
+// hands its argument through with the start of the view untouched.
+static bool EndsInInitcap(const Node& node) {
+  if (node.kind() == NodeKind::kIf) {
+    const auto& n = static_cast<const IfNode&>(node);
+    return EndsInInitcap(*n.then_node()) || EndsInInitcap(*n.else_node());
+  }
+  if (node.kind() != NodeKind::kFunction) return false;
+  const auto& fn = static_cast<const FunctionNode&>(node);
+  if (fn.name() == "initcap") return true;
+  if (fn.name() == "rtrim" || fn.name() == "nvl")
+    for (const auto& c : fn.children())
+      if (c->return_type().id == GDV_TYPE_STRING && EndsInInitcap(*c)) return true;
+  return false;
 }
 
 Status ValidateNode(const Schema& schema, const Node& node) {
@@ -72,6 +89,30 @@ Status ValidateNode(const Schema& schema, const Node& node) {
           (def->ret.id != GDV_TYPE_DECIMAL128 && def->ret != fn.return_type()))
         return VErr("Function " + def->signature() + " not supported yet: return type " +
                     fn.return_type().ToString() + " does not match");
+      // initcap is a lazy case map that looks one byte back (csrc/device/gdv_device_lib.cuh, gdv_ch): a
+      // function that then moves the START of the view (substr, ltrim, right, ...) or re-orders its bytes
+      // would make the first byte of its result depend on a byte it no longer has.
+      if ((def->ret.id == GDV_TYPE_STRING || def->ret.id == GDV_TYPE_BINARY) && fn.name() != "upper" &&
+          fn.name() != "lower" && fn.name() != "initcap" && fn.name() != "rtrim" && fn.name() != "nvl" &&
+          fn.name() != "concat" && fn.name() != "concatOperator") {
+        for (const auto& c : fn.children())
+          if (c->return_type().id == GDV_TYPE_STRING && EndsInInitcap(*c))
+            return Status::Make(GDV_NOT_IMPLEMENTED, "'" + fn.name() + "' over the result of initcap is not supported: "
+                                                      "apply initcap last (initcap(" + fn.name() + "(...)))");
+      }
+      if (def->flags & kDateFormat) {
+        for (size_t i = 1; i < fn.children().size(); ++i) {
+          const Node& c = *fn.children()[i];
+          if (c.kind() != NodeKind::kLiteral || static_cast<const LiteralNode&>(c).is_null())
+            return VErr(i == 1 ? "'to_date' function requires a literal as the second parameter"
+                               : "The third parameter of 'to_date' (suppress errors) must be a literal 0 or 1");
+        }
+        std::vector<uint8_t> prog;
+        std::string why;
+        const int rc = CompileDateFormat(static_cast<const LiteralNode&>(*fn.children()[1]).bytes(), &prog, &why);
+        if (rc == 1) return VErr(why);
+        if (rc != 0) return Status::Make(GDV_NOT_IMPLEMENTED, why);
+      }
       if (def->flags & kRegexHolder) {
         const Node& c = *fn.children()[1];
         if (c.kind() != NodeKind::kLiteral || static_cast<const LiteralNode&>(c).is_null())
@@ -858,6 +899,32 @@ class BodyGen {
     for (const auto& c : fn.children()) ptypes.push_back(c->return_type());
     const FunctionDef* def = Registry::Get().Lookup(fn.name(), ptypes);
     const DataType& rt = fn.return_type();
+
+    if (def->flags & kDateFormat) {
+      Val s = Gen(*fn.children()[0], out, indent);
+      if (!s.parts.empty() && error_.empty()) error_ = fn.name() + "(concat(...)) is not supported yet";
+      std::vector<uint8_t> prog;
+      std::string why;
+      if (CompileDateFormat(static_cast<const LiteralNode&>(*fn.children()[1]).bytes(), &prog, &why) != 0 && error_.empty())
+        error_ = why;
+      bool suppress = false;
+      if (fn.children().size() == 3) {
+        const auto& lit = static_cast<const LiteralNode&>(*fn.children()[2]);
+        suppress = lit.as<int32_t>() != 0;
+      }
+      const std::string arr = NewVar("gdv_datefmt_");
+      std::string t = "__device__ const u8 " + arr + "[" + std::to_string(prog.size() + 1) + "] = {";
+      for (uint8_t b : prog) t += std::to_string(static_cast<unsigned>(b)) + ",";
+      t += "0};\n";
+      globals_ += t;
+      const std::string v = NewVar("v"), okv = NewVar("ok");
+      uses_ctx_ = true;
+      *out += Ind(indent) + "i64 " + v + " = 0;\n";
+      *out += Ind(indent) + "bool " + okv + " = false;\n";
+      *out += Ind(indent) + "if (in && (" + s.ok + ")) " + v + " = gdv_to_date_fmt(&ctx, " + s.v + ", " + arr + ", " +
+              std::to_string(prog.size()) + ", " + (suppress ? "true" : "false") + ", &" + okv + ");\n";
+      return Val{v, okv, rt};
+    }
 
     if (def->flags & kRegexHolder) {
       Val s = Gen(*fn.children()[0], out, indent);

@@ -180,15 +180,18 @@ Registry::Registry() {
   Add("castDATE", {I32}, D32);
 
   // ---- date / time extraction (date64 and timestamp are milliseconds since epoch) ----
+  // SQL-style short names are aliases of the extract* functions (same device function, same signature)
+  static const std::pair<const char*, std::vector<std::string>> kExtract[] = {
+      {"extractYear", {"year"}},       {"extractMonth", {"month"}},     {"extractDay", {"day", "dayofmonth"}},
+      {"extractHour", {"hour"}},       {"extractMinute", {"minute"}},   {"extractSecond", {"second"}},
+      {"extractDoy", {"dayofyear"}},   {"extractDow", {"dayofweek"}},   {"extractQuarter", {"quarter"}},
+      {"extractEpoch", {}}};
   for (const auto& t : {D64, TS}) {
-    for (const char* f : {"extractYear", "extractMonth", "extractDay", "extractHour",
-                          "extractMinute", "extractSecond", "extractDoy", "extractDow",
-                          "extractQuarter", "extractEpoch"})
-      Add(f, {t}, I64);
+    for (const auto& e : kExtract) Add(e.first, {t}, I64, NullMode::kIfNull, 0, e.second);
   }
-  Add("extractYear", {D32}, I64);
-  Add("extractMonth", {D32}, I64);
-  Add("extractDay", {D32}, I64);
+  Add("extractYear", {D32}, I64, NullMode::kIfNull, 0, {"year"});
+  Add("extractMonth", {D32}, I64, NullMode::kIfNull, 0, {"month"});
+  Add("extractDay", {D32}, I64, NullMode::kIfNull, 0, {"day", "dayofmonth"});
 
   // ---- rounding ------------------------------------------------------------------------
   Add("round", {F64}, F64);
@@ -228,7 +231,8 @@ Registry::Registry() {
 
   // ---- calendar fields, truncation, time of day ----------------------------------------------
   for (const auto& t : {D64, TS}) {
-    for (const char* f : {"extractWeek", "extractDecade", "extractCentury", "extractMillennium"}) Add(f, {t}, I64);
+    Add("extractWeek", {t}, I64, NullMode::kIfNull, 0, {"weekofyear", "yearweek"});
+    for (const char* f : {"extractDecade", "extractCentury", "extractMillennium"}) Add(f, {t}, I64);
     for (const char* u : {"Second", "Minute", "Hour", "Day", "Week", "Month", "Quarter", "Year", "Decade",
                           "Century", "Millennium"})
       Add(std::string("date_trunc_") + u, {t}, t);
@@ -240,9 +244,9 @@ Registry::Registry() {
   Add("datediff", {TS, TS}, I32);
   Add("datediff", {D64, D64}, I32);
   Add("castTIME", {TS}, T32);
-  Add("extractHour", {T32}, I64);
-  Add("extractMinute", {T32}, I64);
-  Add("extractSecond", {T32}, I64);
+  Add("extractHour", {T32}, I64, NullMode::kIfNull, 0, {"hour"});
+  Add("extractMinute", {T32}, I64, NullMode::kIfNull, 0, {"minute"});
+  Add("extractSecond", {T32}, I64, NullMode::kIfNull, 0, {"second"});
 
   // ---- decimal128 ---------------------------------------------------------------------
   Add("add", {DEC, DEC}, DEC, NullMode::kIfNull, kDecimalArgs);
@@ -294,6 +298,9 @@ Registry::Registry() {
   Add("substr", {S, I64}, S, NullMode::kIfNull, kStringView, {"substring"});
   Add("upper", {S}, S, NullMode::kIfNull, kStringView);
   Add("lower", {S}, S, NullMode::kIfNull, kStringView);
+  Add("initcap", {S}, S, NullMode::kIfNull, kStringView);
+  Add("to_date", {S, S}, D64, NullMode::kInternal, kDateFormat | kCanFail);
+  Add("to_date", {S, S, I32}, D64, NullMode::kInternal, kDateFormat | kCanFail);
   Add("char_length", {S}, I32, NullMode::kIfNull, 0, {"length", "lengthUtf8"});
   Add("octet_length", {S}, I32);
   Add("octet_length", {BIN}, I32);

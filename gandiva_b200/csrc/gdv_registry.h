@@ -25,6 +25,8 @@ enum FnFlags : uint32_t {
   kConcat = 1u << 4,       // result = the pieces of its arguments in order (a rope, see the fuser)
   kScratch = 1u << 5,      // writes its result bytes into a per-row scratch slot passed as last argument
   kRegexHolder = 1u << 7,  // second arg is a literal regular expression, compiled at Make() (gdv_regex.h)
+  kDateFormat = 1u << 8,   // second arg is a literal date format, compiled at Make() (gdv_datefmt.h); a third
+                           // (int32 literal) argument suppresses parse errors: the row is NULL instead
   kVirtual = 1u << 6,      // result is a rope of "virtual" pieces (repeated / reversed bytes) that only the
                            // string write pass can read: projectable, concat-able, if/else-able, nothing else
 };

@@ -30,6 +30,7 @@ const char* ExecutionErrorMessage(int code) {
     case 11: return "Start position must be greater than 0";
     case 12: return "Factorial of negative number not exist!";
     case 13: return "Factorial of number greater than 20 not supported!";
+    case 14: return "Error parsing value for given format (to_date)";
     default: return "execution error in device function";
   }
 }

@@ -34,6 +34,7 @@
 #include <functional>
 #include <limits>
 #include <memory>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1915,8 +1916,19 @@ std::string OrcFloatText(double v, bool is_float) {
   return out;
 }
 
+// SQL-style short names of the date-part functions (registered as aliases, csrc/gdv_registry.cc).
+static const std::string& CanonicalName(const std::string& name) {
+  static const std::map<std::string, std::string> kAlias = {
+      {"year", "extractYear"},       {"month", "extractMonth"},       {"day", "extractDay"},
+      {"dayofmonth", "extractDay"},  {"hour", "extractHour"},         {"minute", "extractMinute"},
+      {"second", "extractSecond"},   {"dayofyear", "extractDoy"},     {"dayofweek", "extractDow"},
+      {"quarter", "extractQuarter"}, {"weekofyear", "extractWeek"},   {"yearweek", "extractWeek"}};
+  const auto it = kAlias.find(name);
+  return it == kAlias.end() ? name : it->second;
+}
+
 void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
-  const std::string& f = n.name;
+  const std::string& f = CanonicalName(n.name);
   const size_t na = n.kids.size();
   if (f == "concat" || f == "concatOperator") {
     // concat: null arguments are empty strings, never null; concatOperator: null if any is null
@@ -1943,6 +1955,101 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   }
   const Type& rt = n.type;
   const Type& t0 = n.kids[0]->type;
+
+  // ---- to_date(text, format [, suppress_errors]) ---------------------------------------------------------
+  // The reference's holder (from memory; unpinned): translate the SQL-style format into a strptime format,
+  // parse with strptime, allow trailing characters, ignore the time of day, year / month / max(day, 1) at
+  // midnight.  Restated here as a walk over the FORMAT TEXT itself (no compiled program: that is the product's
+  // way, csrc/gdv_datefmt.cc), with glibc's field rules; tests/test_oracle_vs_arrow.py referees against libc.
+  if (f == "to_date" && t0.id == T_STRING) {
+    out->ok = false;
+    if (!a[0].ok) return;
+    const std::string& text = a[0].s;
+    const std::string& fmt = n.kids[1]->lit.s;
+    const bool suppress = na == 3 && n.kids[2]->lit.i != 0;
+    size_t pos = 0, fp = 0;
+    auto is_space = [](unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); };
+    auto number = [&](int lo, int hi, int width, int* v) {
+      while (pos < text.size() && is_space(static_cast<unsigned char>(text[pos]))) ++pos;
+      if (pos >= text.size() || text[pos] < '0' || text[pos] > '9') return false;
+      int val = 0;
+      do {
+        val = val * 10 + (text[pos] - '0');
+        ++pos;
+      } while (--width > 0 && val * 10 <= hi && pos < text.size() && text[pos] >= '0' && text[pos] <= '9');
+      *v = val;
+      return val >= lo && val <= hi;
+    };
+    auto word = [&](const std::string& w) {   // case-insensitive, does not consume
+      if (pos + w.size() > text.size()) return false;
+      for (size_t k = 0; k < w.size(); ++k)
+        if (std::tolower(static_cast<unsigned char>(text[pos + k])) != w[k]) return false;
+      return true;
+    };
+    auto token = [&](const char* t) {   // case-insensitive match of a format token at fp
+      size_t k = 0;
+      while (t[k] != 0 && fp + k < fmt.size() && std::toupper(static_cast<unsigned char>(fmt[fp + k])) == t[k]) ++k;
+      if (t[k] != 0) return false;
+      fp += k;
+      return true;
+    };
+    static const char* kMonths[12] = {"january", "february", "march", "april", "may", "june", "july", "august",
+                                      "september", "october", "november", "december"};
+    int year = 1900, mon = 1, day = 0, tmp = 0;
+    bool good = true;
+    while (good && fp < fmt.size()) {
+      const unsigned char fc = static_cast<unsigned char>(fmt[fp]);
+      if (is_space(fc)) {
+        while (pos < text.size() && is_space(static_cast<unsigned char>(text[pos]))) ++pos;
+        ++fp;
+      } else if (token("YYYY")) {
+        good = number(0, 9999, 4, &year);
+      } else if (token("YY")) {
+        good = number(0, 99, 2, &tmp);
+        year = tmp >= 69 ? 1900 + tmp : 2000 + tmp;
+      } else if (token("MONTH") || token("MON")) {
+        good = false;
+        for (int m = 0; m < 12 && !good; ++m) {
+          const std::string full = kMonths[m];
+          if (word(full)) { pos += full.size(); good = true; }
+          else if (word(full.substr(0, 3))) { pos += 3; good = true; }
+          if (good) mon = m + 1;
+        }
+      } else if (token("MM")) {
+        good = number(1, 12, 2, &mon);
+      } else if (token("MI")) {
+        good = number(0, 59, 2, &tmp);
+      } else if (token("DD")) {
+        good = number(1, 31, 2, &day);
+      } else if (token("HH24")) {
+        good = number(0, 23, 2, &tmp);
+      } else if (token("HH12") || token("HH")) {
+        good = number(1, 12, 2, &tmp);
+      } else if (token("SS")) {
+        good = number(0, 61, 2, &tmp);
+      } else if (token("AM") || token("PM")) {
+        good = word("am") || word("pm");
+        pos += 2;
+      } else {
+        good = pos < text.size() && static_cast<unsigned char>(text[pos]) == fc;
+        ++pos;
+        ++fp;
+      }
+    }
+    if (!good) {
+      if (!suppress) cx.error = 14;
+      return;
+    }
+    if (day < 1) day = 1;
+    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    const int64_t y1 = static_cast<int64_t>(year) - 1;
+    int64_t dn = y1 * 365 + FloorDiv(y1, 4) - FloorDiv(y1, 100) + FloorDiv(y1, 400) - 719162;
+    for (int m = 1; m < mon; ++m) dn += mdays[m - 1] + ((m == 2 && IsLeap(year)) ? 1 : 0);
+    dn += day - 1;
+    out->ok = true;
+    out->i = DaysToMs(dn);
+    return;
+  }
 
   // ---- never-null functions -------------------------------------------------------------
   if (f == "nvl") { *out = a[0].ok ? a[0] : a[1]; return; }
@@ -2601,6 +2708,19 @@ void ApplyFunction(const Node& n, EvalCtx& cx, int64_t row, Val* out) {
   // ---- strings ---------------------------------------------------------------------------
   if (f == "like") { out->b = LikeRec(a[0].s, 0, n.like, 0); return; }
   if (f == "regexp_matches" || f == "regexp_like") { out->b = OrcReSearch(n.regex.get(), a[0].s); return; }
+  if (f == "initcap") {
+    // ASCII letters only, like upper / lower: upper-case at the start and after a byte that is not part of a
+    // word (ASCII letter / digit, or any byte of a multi-byte glyph), lower-case inside a word
+    out->s = a[0].s;
+    bool in_word = false;
+    for (auto& ch : out->s) {
+      const unsigned char c = static_cast<unsigned char>(ch);
+      const bool letter = (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
+      if (letter) ch = static_cast<char>(in_word ? (c | 0x20) : (c & ~0x20));
+      in_word = letter || (c >= '0' && c <= '9') || c >= 0x80;
+    }
+    return;
+  }
   if (f == "upper" || f == "lower") {
     out->s = a[0].s;
     for (auto& ch : out->s) {

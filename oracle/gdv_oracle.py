@@ -51,7 +51,7 @@ _lib = _load()
 
 class OracleExecutionError(Exception):
     def __init__(self, code: int):
-        super().__init__({1: "divide by zero error", 4: "Failed to cast the string to an integer", 5: "Failed to cast the string to a date / timestamp", 6: "Index in split_part must be positive", 7: "Failed to cast the string to a decimal", 8: "Failed to cast the string to a float", 9: "Invalid value for boolean", 10: "Output buffer length can't be negative", 11: "Start position must be greater than 0", 12: "Factorial of negative number not exist!", 13: "Factorial of number greater than 20 not supported!"}.get(code, "oracle error %d" % code))
+        super().__init__({1: "divide by zero error", 4: "Failed to cast the string to an integer", 5: "Failed to cast the string to a date / timestamp", 6: "Index in split_part must be positive", 7: "Failed to cast the string to a decimal", 8: "Failed to cast the string to a float", 9: "Invalid value for boolean", 10: "Output buffer length can't be negative", 11: "Start position must be greater than 0", 12: "Factorial of negative number not exist!", 13: "Factorial of number greater than 20 not supported!", 14: "Error parsing value for given format (to_date)"}.get(code, "oracle error %d" % code))
         self.code = code
 
 

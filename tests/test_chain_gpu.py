@@ -135,3 +135,123 @@ def test_factorial_and_bround_on_the_gpu(gandiva, oracle):
         batch = pa.RecordBatch.from_arrays([pa.array(bad * 50, L), pa.array([1.0, 2.0] * 50, D)], schema=schema)
         with pytest.raises(gandiva.GandivaError, match="ExecutionError: " + msg):
             p.evaluate(batch)
+
+
+def test_initcap_views_and_consumers(gandiva, oracle):
+    """initcap is a lazy case map (it looks one byte back): projected, under concat / if / rtrim / upper / lower,
+    over substr / trim, and read by like / equal / starts_with / length in a Filter — bit-exact against the oracle;
+    a function that would move the start of the view AFTER initcap is refused at Make()."""
+    S, B, I32, I64 = pa.string(), pa.bool_(), pa.int32(), pa.int64()
+    schema = pa.schema([("s", S), ("u", S), ("p", B)])
+    rng = np.random.default_rng(21)
+    alphabet = list("abcdXYZ019 _-.,'") + ["é", "日"]
+    n = 3000
+    mk = lambda: pa.array([None if rng.random() < 0.1 else "".join(rng.choice(alphabet, size=int(rng.integers(0, 30))))
+                           for _ in range(n)], S)
+    batch = pa.RecordBatch.from_arrays([mk(), mk(), pa.array(rng.random(n) < 0.5, mask=rng.random(n) < 0.1)], schema=schema)
+    b = gandiva.TreeExprBuilder()
+    f = {x.name: b.make_field(x) for x in schema}
+    fn = b.make_function
+    ic = lambda x: fn("initcap", [x], S)
+    roots = [(ic(f["s"]), S),
+             (ic(fn("substr", [f["s"], b.make_literal(3, I64), b.make_literal(12, I64)], S)), S),
+             (ic(fn("upper", [f["s"]], S)), S),
+             (fn("upper", [ic(f["s"])], S), S),
+             (fn("lower", [ic(f["s"])], S), S),
+             (fn("rtrim", [ic(f["s"])], S), S),
+             (ic(fn("btrim", [f["s"]], S)), S),
+             (fn("concat", [ic(f["s"]), b.make_literal("|", S), ic(f["u"])], S), S),
+             (b.make_if(f["p"], ic(f["s"]), f["u"], S), S),
+             (fn("char_length", [ic(f["s"])], I32), I32)]
+    for k, (root, t) in enumerate(roots):
+        p = gandiva.make_projector(schema, [b.make_expression(root, pa.field("o", t))], None)
+        got = p.evaluate(batch)[0]
+        want = oracle.project([root], [t], batch)[0]
+        assert_arrays_match(got, want, "initcap projection %d" % k)
+    conds = [fn("like", [ic(f["s"]), b.make_literal("%Ab%", S)], B),
+             fn("equal", [ic(f["s"]), ic(f["u"])], B),
+             fn("starts_with", [ic(f["s"]), b.make_literal("A", S)], B),
+             fn("ends_with", [ic(f["s"]), b.make_literal("b", S)], B),
+             fn("less_than", [ic(f["s"]), f["u"]], B)]
+    for k, cond in enumerate(conds):
+        flt = gandiva.make_filter(schema, b.make_condition(cond))
+        got = flt.evaluate(batch).to_array().to_numpy().astype(np.uint64)
+        want = oracle.filter_indices(cond, batch)
+        assert np.array_equal(got, want), "initcap filter %d" % k
+    for bad in (fn("substr", [ic(f["s"]), b.make_literal(2, I64)], S), fn("ltrim", [ic(f["s"])], S),
+                fn("reverse", [ic(f["s"])], S), fn("right", [ic(f["s"]), b.make_literal(3, I32)], S)):
+        with pytest.raises(pa.ArrowNotImplementedError, match="initcap"):
+            gandiva.make_projector(schema, [b.make_expression(bad, pa.field("o", S))], None)
+
+
+def test_date_part_aliases_on_the_device(gandiva, oracle):
+    ts, d64, I64 = pa.timestamp("ms"), pa.date64(), pa.int64()
+    schema = pa.schema([("t", ts), ("d", d64)])
+    rng = np.random.default_rng(4)
+    n = 5000
+    batch = pa.RecordBatch.from_arrays(
+        [pa.array(rng.integers(-10**13, 10**13, n).astype(np.int64), ts, mask=rng.random(n) < 0.1),
+         pa.array(rng.integers(-10**5, 10**5, n).astype(np.int64) * 86400000, d64, mask=rng.random(n) < 0.1)], schema=schema)
+    b = gandiva.TreeExprBuilder()
+    roots = []
+    for name in ("year", "month", "day", "dayofmonth", "hour", "minute", "second", "dayofyear", "dayofweek", "quarter",
+                 "weekofyear", "yearweek"):
+        roots.append(b.make_function(name, [b.make_field(schema.field(0))], I64))
+        roots.append(b.make_function(name, [b.make_field(schema.field(1))], I64))
+    p = gandiva.make_projector(schema, [b.make_expression(r, pa.field("o%d" % k, I64)) for k, r in enumerate(roots)], None)
+    got = p.evaluate(batch)
+    want = oracle.project(roots, [I64] * len(roots), batch)
+    for k, (gv, wv) in enumerate(zip(got, want)):
+        assert_arrays_match(gv, wv, "alias output %d" % k)
+
+
+def test_to_date_with_format(gandiva, oracle):
+    """to_date(text, format literal [, suppress]): the format is compiled at Make() into a program the device
+    function interprets; bit-exact against the oracle (itself refereed against libc's strptime), raising on the first
+    text that does not parse unless errors are suppressed (NULL then)."""
+    S, D64, I32 = pa.string(), pa.date64(), pa.int32()
+    schema = pa.schema([("s", S)])
+    rng = np.random.default_rng(23)
+    b = gandiva.TreeExprBuilder()
+    fs = b.make_field(schema.field(0))
+    mons = ["Jan", "feb", "MARCH", "April", "may", "June", "jul", "AUGUST", "Sep", "october", "Nov", "DEC"]
+    n = 4000
+
+    def texts(kind):
+        out = []
+        for _ in range(n):
+            y, m, d = int(rng.integers(1, 9999)), int(rng.integers(1, 13)), int(rng.integers(1, 29))
+            if kind == 0:
+                t = "%04d-%02d-%02d" % (y, m, d)
+            elif kind == 1:
+                t = "%d %s %d %02d:%02d" % (d, mons[m - 1], y, int(rng.integers(0, 24)), int(rng.integers(0, 60)))
+            else:
+                t = "%02d/%02d/%02d" % (m, d, y % 100)
+            r = rng.random()
+            if r < 0.05:
+                t = t[: int(rng.integers(0, len(t)))]
+            elif r < 0.10:
+                t += "Z"
+            elif r < 0.13:
+                t = None
+            out.append(t)
+        return pa.array(out, S)
+    for kind, fmt in enumerate(["YYYY-MM-DD", "DD MON YYYY HH24:MI", "MM/DD/YY"]):
+        batch = pa.RecordBatch.from_arrays([texts(kind)], schema=schema)
+        lenient = b.make_function("to_date", [fs, b.make_literal(fmt, S), b.make_literal(1, I32)], D64)
+        p = gandiva.make_projector(schema, [b.make_expression(lenient, pa.field("d", D64))], None)
+        got = p.evaluate(batch)[0]
+        want = oracle.project([lenient], [D64], batch)[0]
+        assert_arrays_match(got, want, "to_date %s" % fmt)
+        assert 0 < want.null_count < n // 3
+        strict = b.make_function("to_date", [fs, b.make_literal(fmt, S)], D64)
+        ps = gandiva.make_projector(schema, [b.make_expression(strict, pa.field("d", D64))], None)
+        with pytest.raises(gandiva.GandivaError, match="Error parsing value"):
+            ps.evaluate(batch)
+        clean = batch.filter(pa.compute.is_valid(want))
+        assert_arrays_match(ps.evaluate(clean)[0], oracle.project([strict], [D64], clean)[0], "strict to_date %s" % fmt)
+    with pytest.raises(pa.ArrowNotImplementedError, match="DDD"):
+        gandiva.make_projector(schema, [b.make_expression(b.make_function("to_date", [fs, b.make_literal("YYYY-DDD", S)], D64),
+                                                          pa.field("d", D64))], None)
+    with pytest.raises(gandiva.GandivaError, match="requires a literal"):
+        gandiva.make_projector(schema, [b.make_expression(b.make_function("to_date", [fs, fs], D64), pa.field("d", D64))], None)

@@ -1587,3 +1587,157 @@ def test_like_escape_and_regex_repetition_are_validated(gandiva):
             gandiva.make_filter(schema, b.make_condition(b.make_function("regexp_matches", [s, b.make_literal(pat, S)], B)))
     for pat in ("a*?", "(a*)*", "a{2,3}?b", "a+b*"):
         gandiva.make_filter(schema, b.make_condition(b.make_function("regexp_matches", [s, b.make_literal(pat, S)], B)))
+
+
+def test_initcap_against_a_python_restatement(oracle, gandiva):
+    """initcap: first letter of every word upper-cased, the rest lower-cased, words delimited by anything that is not
+    a letter or digit; ASCII letters only (like upper / lower) — referee: a regular expression."""
+    import re
+    b = gandiva.TreeExprBuilder()
+    S = pa.string()
+    schema = pa.schema([("s", S)])
+    root = b.make_function("initcap", [cases.F(b, "s", S)], S)
+    rng = np.random.default_rng(11)
+    alphabet = list("abcXYZ019 _-.,'\t") + ["é", "日", "ß"]
+    rows = ["", "a", "A", "hELLO wORLD", "1abc def2ghi", "o'neil mc-donald", "  two  spaces ", "éa bé", "日本語 text", None,
+            "ALL CAPS HERE", "x", "_x_y_"]
+    rows += ["".join(rng.choice(alphabet, size=int(rng.integers(0, 24)))) for _ in range(300)]
+    batch = pa.RecordBatch.from_arrays([pa.array(rows, S)], schema=schema)
+    got = oracle.project([root], [S], batch)[0].to_pylist()
+
+    def ref(s):
+        if s is None:
+            return None
+        # a "word" = maximal run of ASCII letters / digits / non-ASCII characters; only ASCII letters change case
+        def cap(m):
+            w = m.group(0)
+            out, first = [], True
+            for ch in w:
+                if ch.isascii() and ch.isalpha():
+                    out.append(ch.upper() if first else ch.lower())
+                else:
+                    out.append(ch)
+                first = False
+            return "".join(out)
+        return re.sub(r"(?:[A-Za-z0-9]|[^\x00-\x7f])+", cap, s)
+    assert got == [ref(s) for s in rows]
+
+
+def test_date_part_aliases(oracle, gandiva):
+    """year / month / day / dayofmonth / hour / minute / second / dayofyear / dayofweek / quarter / weekofyear /
+    yearweek are the extract* functions under their SQL names."""
+    b = gandiva.TreeExprBuilder()
+    ts, I64 = pa.timestamp("ms"), pa.int64()
+    schema = pa.schema([("t", ts)])
+    rng = np.random.default_rng(3)
+    vals = rng.integers(-10**13, 10**13, 200).astype(np.int64)
+    batch = pa.RecordBatch.from_arrays([pa.array(vals, ts, mask=rng.random(200) < 0.1)], schema=schema)
+    pairs = [("year", "extractYear"), ("month", "extractMonth"), ("day", "extractDay"), ("dayofmonth", "extractDay"),
+             ("hour", "extractHour"), ("minute", "extractMinute"), ("second", "extractSecond"),
+             ("dayofyear", "extractDoy"), ("dayofweek", "extractDow"), ("quarter", "extractQuarter"),
+             ("weekofyear", "extractWeek"), ("yearweek", "extractWeek")]
+    names = {s.name() for s in gandiva.get_registered_function_signatures()}
+    for alias, canon in pairs:
+        assert alias in names
+        a = oracle.project([b.make_function(alias, [cases.F(b, "t", ts)], I64)], [I64], batch)[0]
+        c = oracle.project([b.make_function(canon, [cases.F(b, "t", ts)], I64)], [I64], batch)[0]
+        assert a.equals(c), alias
+
+
+def test_to_date_with_format_against_libc_strptime(oracle, gandiva):
+    """to_date(text, format): the reference's holder translates the format to strptime, allows trailing text, drops
+    the time of day and defaults the day to 1 (from memory; unpinned).  Referee: the C library's own strptime on
+    the translated format, for texts that match, nearly match and do not match."""
+    import ctypes as C
+
+    class Tm(C.Structure):
+        _fields_ = [(k, C.c_int) for k in ("sec", "min", "hour", "mday", "mon", "year", "wday", "yday", "isdst")] + \
+                   [("gmtoff", C.c_long), ("zone", C.c_char_p)]
+    libc = C.CDLL(None)
+    libc.strptime.restype = C.c_void_p
+    libc.strptime.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Tm)]
+    trans = [("YYYY", "%Y"), ("YY", "%y"), ("MONTH", "%B"), ("MON", "%b"), ("MM", "%m"), ("MI", "%M"), ("DD", "%d"),
+             ("HH24", "%H"), ("HH12", "%I"), ("HH", "%I"), ("SS", "%S"), ("AM", "%p"), ("PM", "%p")]
+
+    def to_strptime(fmt):
+        out, i = "", 0
+        while i < len(fmt):
+            for tok, rep in trans:
+                if fmt[i:i + len(tok)].upper() == tok:
+                    out += rep
+                    i += len(tok)
+                    break
+            else:
+                out += fmt[i]
+                i += 1
+        return out
+
+    def referee(text, fmt):
+        tm = Tm()
+        if not libc.strptime(text.encode(), to_strptime(fmt).encode(), C.byref(tm)):
+            return None
+        first = np.datetime64("%04d-%02d-01" % (tm.year + 1900, tm.mon + 1), "D")
+        return int((first + (max(tm.mday, 1) - 1)).astype("int64")) * 86400000
+
+    formats = ["YYYY-MM-DD", "yyyy-mm-dd", "DD/MM/YYYY", "YYYY-MM-DD HH24:MI:SS", "DD MON YYYY", "MONTH DD, YYYY", "YYYYMMDD",
+               "YY.MM.DD", "YYYY-MM", "HH12:MI AM DD-MM-YYYY", "YYYY-MM-DDTHH24:MI", "MM/DD/YY HH:MI:SS PM", "DD-MON-YY"]
+    rng = np.random.default_rng(17)
+    months = ["January", "February", "March", "April", "May", "June", "July", "August", "September", "October",
+              "November", "December"]
+
+    def render(fmt):
+        y, m, d = int(rng.integers(0, 10000)), int(rng.integers(1, 13)), int(rng.integers(1, 32))
+        hh, mi, ss = int(rng.integers(0, 24)), int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        pad = rng.random() < 0.7
+        num = lambda v, w: ("%0*d" % (w, v)) if pad else str(v)
+        sub = {"YYYY": num(y, 4), "YY": num(y % 100, 2), "MONTH": months[m - 1] if rng.random() < 0.6 else months[m - 1].upper(),
+               "MON": months[m - 1][:3] if rng.random() < 0.6 else months[m - 1][:3].lower(), "MM": num(m, 2), "MI": num(mi, 2),
+               "DD": num(d, 2), "HH24": num(hh, 2), "HH12": num((hh % 12) or 12, 2), "HH": num((hh % 12) or 12, 2),
+               "SS": num(ss, 2), "AM": "AM" if hh < 12 else "pm", "PM": "AM" if hh < 12 else "PM"}
+        out, i = "", 0
+        while i < len(fmt):
+            for tok, _ in trans:
+                if fmt[i:i + len(tok)].upper() == tok:
+                    out += sub[tok]
+                    i += len(tok)
+                    break
+            else:
+                out += fmt[i]
+                i += 1
+        r = rng.random()
+        if r < 0.15:
+            out += " trailing"
+        elif r < 0.25 and out:
+            k = int(rng.integers(0, len(out)))
+            out = out[:k] + str(rng.choice(list("x-/ 9"))) + out[k + 1:]
+        elif r < 0.30:
+            out = "  " + out
+        elif r < 0.33:
+            out = out[: int(rng.integers(0, len(out) + 1))]
+        return out
+
+    b = gandiva.TreeExprBuilder()
+    S, D64, I32 = pa.string(), pa.date64(), pa.int32()
+    schema = pa.schema([("s", S)])
+    checked = failed = 0
+    for fmt in formats:
+        texts = [render(fmt) for _ in range(400)] + ["", " ", "0000-00-00", "2024-02-30", "2023-2-3", "12/31/1999"]
+        want = [referee(t, fmt) for t in texts]
+        root = b.make_function("to_date", [cases.F(b, "s", S), b.make_literal(fmt, S), b.make_literal(1, I32)], D64)
+        batch = pa.RecordBatch.from_arrays([pa.array(texts + [None], S)], schema=schema)
+        got = oracle.project([root], [D64], batch)[0].cast(pa.int64()).to_pylist()
+        assert got[-1] is None
+        for t, g, w in zip(texts, got, want):
+            assert g == w, (fmt, t, g, w)
+        checked += len(texts)
+        failed += sum(w is None for w in want)
+        # without suppress_errors a text that does not parse raises
+        strict = b.make_function("to_date", [cases.F(b, "s", S), b.make_literal(fmt, S)], D64)
+        bad = [t for t, w in zip(texts, want) if w is None]
+        if bad:
+            with pytest.raises(Exception, match="Error parsing value"):
+                oracle.project([strict], [D64], pa.RecordBatch.from_arrays([pa.array(bad[:1], S)], schema=schema))
+        good = [t for t, w in zip(texts, want) if w is not None]
+        ok = oracle.project([strict], [D64], pa.RecordBatch.from_arrays([pa.array(good, S)], schema=schema))[0]
+        assert ok.cast(pa.int64()).to_pylist() == [w for w in want if w is not None]
+    assert checked > 5000 and 200 < failed < checked // 2

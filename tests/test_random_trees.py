@@ -27,7 +27,10 @@ SKIP = {"divide", "div", "like", "ilike", "regexp_matches", "regexp_like", "conc
         "repeat", "space", "reverse", "lpad", "rpad", "replace",
         "power", "pow", "cot", "sinh", "cosh",   # same as exp below: inf arrives quickly
         "exp",   # overflows to inf on the random doubles; inf - inf then makes a hardware NaN whose sign differs between x86 and sm_100a
-        "timestampaddMonth", "timestampaddQuarter", "timestampaddYear", "mod", "modulo"}
+        "timestampaddMonth", "timestampaddQuarter", "timestampaddYear", "mod", "modulo",
+        "factorial",   # raises outside 0..20 (dedicated tests)
+        "initcap",   # a lazy case map that may not be narrowed from the left afterwards (dedicated test)
+        "to_date"}   # needs a literal format (dedicated test)
 LIKE_PATTERNS = ["%spark%", "s%", "%s", "%special%requests%", "_a%", "%", "", "%re%e%", "fire", "%日本%"]
 STR_LITS = ["", "s", "re", "park", "special", "日本", " ", "Quick", "x_y"]
 
