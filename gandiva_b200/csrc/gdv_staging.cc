@@ -26,8 +26,6 @@ constexpr size_t kDirectBelow = size_t(1) << 20; // smaller copies are not worth
 
 std::atomic<long long> g_staged_bytes{0};
 
-// A few threads that copy slices of one piece in parallel (one memcpy stream does ~10 GB/s, the
-// link wants ~55).  Started on first use, parked on a condition variable in between.
 // ---- NUMA placement ---------------------------------------------------------------------------------------
 // The pinned ring and the copy threads belong on the NUMA node the GPU hangs off: a slot on the other socket
 // makes every DMA cross the socket interconnect, and copy threads floating over both sockets made the pageable
@@ -113,6 +111,8 @@ class OnNode {
   bool moved_ = false;
 };
 
+// A few threads that copy pieces of one transfer in parallel (one memcpy stream does ~10 GB/s, the link wants
+// ~55).  Started on first use; they poll for 2 ms after a job and park on a condition variable after that.
 class CopyPool {
  public:
   // `node`: where the workers run (the first caller decides; one process drives one GPU).
