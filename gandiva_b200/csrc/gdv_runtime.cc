@@ -1,4 +1,5 @@
 #include "gdv_runtime.h"
+#include "gdv_rope_temps.h"
 
 #include "gdv_staging.h"
 
@@ -568,6 +569,23 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
   p->exprs_ = std::move(exprs);
   p->selection_mode_ = selection_mode;
   p->cfg_ = cfg;
+  Status st = p->BuildKernels();
+  if (!st.ok()) {
+    // something other than projection / concat / if-else reads a rope: materialise the ropes first
+    if (!IsRopeConsumerError(st) || !MakeWithRopeTemps(schema, p->exprs_, selection_mode, cfg, p.get()).ok()) return st;
+  }
+  *out = std::move(p);
+  return Status::OK();
+}
+
+Status Projector::BuildKernels() {
+  Projector* p = this;
+  const SchemaPtr& schema = schema_;
+  const int selection_mode = selection_mode_;
+  const Config& cfg = cfg_;
+  p->strings_.clear();
+  p->fixed_exprs_.clear();
+  p->fixed_idx_.clear();
   // Fixed-width outputs share ONE fused kernel; every utf8/binary output gets its own
   // sizing + write kernel pair (its bytes cannot be placed before all lengths are known).
   for (size_t i = 0; i < p->exprs_.size(); ++i) {
@@ -592,11 +610,110 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
     CompiledKernel* k = nullptr;
     GDV_RETURN_NOT_OK(p->KernelFor(false, &k));
   }
-  *out = std::move(p);
   return Status::OK();
 }
 
+// ---- consumers of a rope: temps first (gdv_rope_temps.h) ---------------------------------------------------
+namespace {
+SchemaPtr ExtendedSchema(const SchemaPtr& schema, const RopeTemps& rt) {
+  std::vector<Field> fields = schema->fields();
+  fields.insert(fields.end(), rt.fields.begin(), rt.fields.end());
+  return std::make_shared<Schema>(std::move(fields));
+}
+}  // namespace
+
+Status Projector::MakeWithRopeTemps(const SchemaPtr& schema, const std::vector<ExpressionPtr>& exprs,
+                                    int selection_mode, const Config& cfg, Projector* into) {
+  RopeTemps rt;
+  std::vector<ExpressionPtr> rewritten;
+  for (const auto& e : exprs) {
+    NodePtr r;
+    if (!ExtractRopes(e->root(), e->result().type.is_varlen(), &rt, &r))
+      return Status::Make(GDV_NOT_IMPLEMENTED, "a rope consumer inside the arguments of another rope");
+    rewritten.push_back(std::make_shared<Expression>(r, e->result()));
+  }
+  if (rt.temps.empty()) return Status::Make(GDV_NOT_IMPLEMENTED, "no rope to materialise");
+  std::shared_ptr<Projector> pre, main;
+  GDV_RETURN_NOT_OK(Projector::Make(schema, rt.temps, GDV_SEL_NONE, cfg, &pre));
+  if (pre->rope_main_ != nullptr) return Status::Make(GDV_NOT_IMPLEMENTED, "nested rope consumers");
+  GDV_RETURN_NOT_OK(Projector::Make(ExtendedSchema(schema, rt), rewritten, selection_mode, cfg, &main));
+  if (main->rope_main_ != nullptr) return Status::Make(GDV_NOT_IMPLEMENTED, "nested rope consumers");
+  into->rope_pre_ = std::move(pre);
+  into->rope_main_ = std::move(main);
+  return Status::OK();
+}
+
+TempColumns::~TempColumns() {
+  if (dev != nullptr)
+    for (CUdeviceptr p : device) dev->Free(p);
+}
+
+// Runs the pre-projector over `in` (all rows, no selection vector) and appends its utf8 outputs to the batch's
+// columns: in host vectors for a host batch, in pooled device memory for a device batch.  Synchronous.
+Status TempColumns::Build(Projector* pre, const gdv_batch_t* in, void* stream) {
+  const int n_temps = pre->num_outputs();
+  const int64_t n = in->num_rows;
+  const bool on_host = in->mem_space == GDV_MEM_HOST;
+  cols.assign(in->columns, in->columns + in->num_columns);
+  std::vector<gdv_out_column_t> outs(static_cast<size_t>(n_temps));
+  const size_t off_bytes = static_cast<size_t>(n + 1) * 4 + 16, vld_bytes = static_cast<size_t>((n + 63) / 64) * 8 + 8;
+  if (!on_host) GDV_RETURN_NOT_OK(Device::Get(pre->config().device, &dev));
+  for (int k = 0; k < n_temps; ++k) {
+    int64_t bytes = 0;
+    GDV_RETURN_NOT_OK(pre->OutputVarSize(in, nullptr, k, stream, &bytes));
+    gdv_out_column_t& o = outs[static_cast<size_t>(k)];
+    std::memset(&o, 0, sizeof(o));
+    const size_t data_bytes = static_cast<size_t>(bytes) + 16;
+    if (on_host) {
+      host.emplace_back(off_bytes);
+      o.values = host.back().data();
+      host.emplace_back(vld_bytes);
+      o.validity = host.back().data();
+      host.emplace_back(data_bytes);
+      o.var_data = host.back().data();
+    } else {
+      CUdeviceptr p = 0;
+      GDV_RETURN_NOT_OK(dev->Alloc(off_bytes, &p));
+      device.push_back(p);
+      o.values = reinterpret_cast<void*>(p);
+      GDV_RETURN_NOT_OK(dev->Alloc(vld_bytes, &p));
+      device.push_back(p);
+      o.validity = reinterpret_cast<void*>(p);
+      GDV_RETURN_NOT_OK(dev->Alloc(data_bytes, &p));
+      device.push_back(p);
+      o.var_data = reinterpret_cast<void*>(p);
+    }
+    o.var_capacity = bytes;
+  }
+  GDV_RETURN_NOT_OK(pre->Evaluate(in, nullptr, outs.data(), n_temps, stream, /*async=*/false));
+  for (int k = 0; k < n_temps; ++k) {
+    gdv_column_t c;
+    std::memset(&c, 0, sizeof(c));
+    c.validity = outs[static_cast<size_t>(k)].validity;
+    c.values = outs[static_cast<size_t>(k)].values;
+    c.var_data = outs[static_cast<size_t>(k)].var_data;
+    c.offset = 0;
+    c.var_data_size = outs[static_cast<size_t>(k)].var_capacity;
+    cols.push_back(c);
+  }
+  batch = *in;
+  batch.num_columns = static_cast<int32_t>(cols.size());
+  batch.columns = cols.data();
+  return Status::OK();
+}
+
+namespace {
+// The temps of a device batch go back to the pool when TempColumns dies: not before the work that reads them.
+Status WaitForStream(int device, void* stream_v) {
+  Device* dev = nullptr;
+  GDV_RETURN_NOT_OK(Device::Get(device, &dev));
+  CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
+  return CuCheck(Driver().StreamSynchronize(stream), "cuStreamSynchronize");
+}
+}  // namespace
+
 CompiledKernel& Projector::kernel() {
+  if (rope_main_ != nullptr) return rope_main_->kernel();
   if (last_used_ != nullptr) return *last_used_;
   if (kernel_ != nullptr) return *kernel_;
   return *strings_.front().write[0];
@@ -621,6 +738,7 @@ Status Projector::StringKernelsFor(StringKernels* sk, bool nullable, CompiledKer
 }
 
 Status Projector::KernelFor(bool nullable, CompiledKernel** out) {
+  if (rope_main_ != nullptr) return rope_main_->KernelFor(nullable, out);
   if (kernel_ == nullptr) return Status::Make(GDV_INVALID, "projector has no fixed-width output");
   if (nullable) {
     *out = kernel_.get();
@@ -644,6 +762,7 @@ static bool AnyValidity(const GeneratedKernel& gen, const gdv_batch_t* batch) {
 }
 
 std::string Projector::DumpIR() const {
+  if (rope_main_ != nullptr) return rope_pre_->DumpIR() + "\n" + rope_main_->DumpIR();
   std::string ir;
   if (kernel_ != nullptr)
     ir += kernel_->gen.source + (kernel_->ptx.empty() ? "" : "\n// ---- PTX ----\n" + kernel_->ptx);
@@ -679,6 +798,12 @@ Status Projector::OutputVarSize(const gdv_batch_t* batch, const gdv_selection_t*
   *bytes = 0;
   if (out_index < 0 || out_index >= num_outputs())
     return Status::Make(GDV_INVALID, "output index out of range");
+  if (rope_main_ != nullptr) {
+    if (batch == nullptr) return Status::Make(GDV_INVALID, "null argument");
+    TempColumns tc;
+    GDV_RETURN_NOT_OK(tc.Build(rope_pre_.get(), batch, stream));
+    return rope_main_->OutputVarSize(&tc.batch, sel, out_index, stream, bytes);  // synchronous: reads the total back
+  }
   for (auto& sk : strings_)
     if (sk.out_index == out_index)
       return EvaluateString(&sk, batch, sel, nullptr, stream, false, true, bytes);
@@ -827,6 +952,18 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
   if (n_all_outs != num_outputs())
     return Status::Make(GDV_INVALID, "expected " + std::to_string(num_outputs()) +
                                          " output columns, got " + std::to_string(n_all_outs));
+  if (rope_main_ != nullptr) {
+    if (batch->num_columns != static_cast<int>(schema_->fields().size()))
+      return Status::Make(GDV_INVALID, "RecordBatch schema must match the schema of Make()");
+    TempColumns tc;
+    GDV_RETURN_NOT_OK(tc.Build(rope_pre_.get(), batch, stream_v));
+    Status st = rope_main_->Evaluate(&tc.batch, sel, all_outs, n_all_outs, stream_v, async);
+    if (batch->mem_space != GDV_MEM_HOST) {
+      const Status w = WaitForStream(cfg_.device, stream_v);
+      if (st.ok()) st = w;
+    }
+    return st;
+  }
   int64_t n = 0;
   GDV_RETURN_NOT_OK(CheckEvaluateArgs(batch, sel, &n));
   const bool host = batch->mem_space == GDV_MEM_HOST;
@@ -957,6 +1094,7 @@ Status Projector::Evaluate(const gdv_batch_t* batch, const gdv_selection_t* sel,
 }
 
 Status Projector::Sync(void* stream_v) {
+  if (rope_main_ != nullptr) return rope_main_->Sync(stream_v);
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
   CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();
@@ -1001,7 +1139,24 @@ Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
   // The default Python/Cython path uses UINT32 indices: compile that variant eagerly so
   // Make() surfaces code-generation errors, as the reference does.
   CompiledKernel* k = nullptr;
-  GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, true, false, &k));
+  Status st = f->KernelFor(GDV_SEL_UINT32, true, false, &k);
+  if (!st.ok()) {
+    if (!IsRopeConsumerError(st)) return st;
+    // something in the condition reads a rope: materialise the ropes first (gdv_rope_temps.h)
+    RopeTemps rt;
+    NodePtr r;
+    if (!ExtractRopes(cond->root(), false, &rt, &r) || rt.temps.empty()) return st;
+    std::shared_ptr<Projector> pre;
+    std::shared_ptr<Filter> main;
+    if (!Projector::Make(schema, rt.temps, GDV_SEL_NONE, cfg, &pre).ok()) return st;
+    if (!Filter::Make(ExtendedSchema(schema, rt), std::make_shared<Condition>(r), cfg, &main).ok() ||
+        main->rope_main_ != nullptr)
+      return st;
+    f->rope_pre_ = std::move(pre);
+    f->rope_main_ = std::move(main);
+    *out = std::move(f);
+    return Status::OK();
+  }
   if (std::getenv("GDV_EAGER_NONULL") != nullptr)
     GDV_RETURN_NOT_OK(f->KernelFor(GDV_SEL_UINT32, false, true, &k));
   *out = std::move(f);
@@ -1009,6 +1164,7 @@ Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
 }
 
 Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** out) {
+  if (rope_main_ != nullptr) return rope_main_->KernelFor(mode, nullable, large, out);
   std::lock_guard<std::mutex> lock(mu_);
   const int key = mode * 4 + (nullable ? 1 : 0) + (large ? 2 : 0);
   auto it = kernels_.find(key);
@@ -1027,6 +1183,7 @@ Status Filter::KernelFor(int mode, bool nullable, bool large, CompiledKernel** o
 }
 
 std::string Filter::DumpIR() const {
+  if (rope_main_ != nullptr) return rope_pre_->DumpIR() + "\n" + rope_main_->DumpIR();
   std::lock_guard<std::mutex> lock(mu_);
   auto it = kernels_.find(GDV_SEL_UINT32 * 4 + 1);
   if (it == kernels_.end()) return "";
@@ -1039,6 +1196,16 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
   if (batch == nullptr || out_sel == nullptr) return Status::Make(GDV_INVALID, "null argument");
   if (batch->num_columns != static_cast<int>(schema_->fields().size()))
     return Status::Make(GDV_INVALID, "RecordBatch schema must match the schema of Make()");
+  if (rope_main_ != nullptr) {
+    TempColumns tc;
+    GDV_RETURN_NOT_OK(tc.Build(rope_pre_.get(), batch, stream_v));
+    Status st = rope_main_->Evaluate(&tc.batch, out_sel, stream_v, async, d_count_user);
+    if (batch->mem_space != GDV_MEM_HOST) {
+      const Status w = WaitForStream(cfg_.device, stream_v);
+      if (st.ok()) st = w;
+    }
+    return st;
+  }
   if (batch->num_rows <= 0) return Status::Make(GDV_INVALID, "RecordBatch must be non-empty.");
   // GDV_SEL_BOUNDED: the caller sized the index buffer for the rows it expects to be selected
   // (row-range shards writing into a shared SelectionVector); rows past max_slots are counted
@@ -1165,6 +1332,7 @@ Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void
 }
 
 Status Filter::Sync(void* stream_v, int64_t* num_slots) {
+  if (rope_main_ != nullptr) return rope_main_->Sync(stream_v, num_slots);
   Device* dev = nullptr;
   GDV_RETURN_NOT_OK(Device::Get(cfg_.device, &dev));
   CUstream stream = stream_v != nullptr ? static_cast<CUstream>(stream_v) : dev->stream();

@@ -67,6 +67,18 @@ class Device {
   std::map<std::string, CUfunction> static_fns_;
 };
 
+class Projector;
+// A batch extended by the temporary columns a rope pre-projector produced (gdv_rope_temps.h); owns them.
+struct TempColumns {
+  std::vector<gdv_column_t> cols;
+  gdv_batch_t batch;
+  std::vector<std::vector<uint8_t>> host;
+  Device* dev = nullptr;
+  std::vector<CUdeviceptr> device;
+  ~TempColumns();
+  Status Build(Projector* pre, const gdv_batch_t* in, void* stream);
+};
+
 // RAII list of scratch blocks returned to the pool when the evaluation ends.
 class ScratchScope {
  public:
@@ -168,6 +180,12 @@ class Projector {
   const std::vector<ExpressionPtr>& expressions() const { return exprs_; }
 
  private:
+  // Consumers of a rope (gdv_rope_temps.h): the ropes are materialised by rope_pre_ into temporary utf8
+  // columns and rope_main_ evaluates the caller's expressions over the batch plus those columns.
+  std::shared_ptr<Projector> rope_pre_, rope_main_;
+  Status BuildKernels();
+  static Status MakeWithRopeTemps(const SchemaPtr& schema, const std::vector<ExpressionPtr>& exprs,
+                                  int selection_mode, const Config& cfg, Projector* into);
   // One utf8/binary output expression: sizing + write kernels, [0] nullable inputs, [1] no nulls.
   struct StringKernels {
     int out_index = 0;
@@ -207,9 +225,11 @@ class Filter {
   Status KernelFor(int mode, bool nullable, bool large, CompiledKernel** out);
   const Config& config() const { return cfg_; }
   const SchemaPtr& schema() const { return schema_; }
-  CompiledKernel* last_used() const { return last_used_.load(); }
+  CompiledKernel* last_used() const { return rope_main_ != nullptr ? rope_main_->last_used() : last_used_.load(); }
 
  private:
+  std::shared_ptr<Projector> rope_pre_;  // consumers of a rope (gdv_rope_temps.h): temps first,
+  std::shared_ptr<Filter> rope_main_;    // then the condition over the batch plus the temp columns
   std::atomic<CompiledKernel*> last_used_{nullptr};
   SchemaPtr schema_;
   ConditionPtr cond_;

@@ -21,13 +21,20 @@ def child(first, last, what):
     import oracle
     import test_random_trees as T
     from helpers import assert_arrays_match
-    bad = 0
+    bad = skipped = 0
+    if what in ("rope", "ropefilt"):
+        # ropes read by arbitrary consumers (materialised through a temporary column, csrc/gdv_rope_temps.h);
+        # trees that nest a consumer inside another rope's arguments are refused at Make() and counted as skipped
+        T.SKIP -= {"concat", "concatOperator", "reverse"}
+        what_kind = "proj" if what == "rope" else "filt"
+    else:
+        what_kind = what
     for seed in range(first, last):
         try:
             rng = np.random.default_rng(77_000 + seed)
             b = gandiva.TreeExprBuilder()
             g = T.TreeGen(gandiva, b, rng)
-            if what == "proj":
+            if what_kind == "proj":
                 out_types = [T.TYPES[int(rng.integers(len(T.TYPES)))] for _ in range(int(rng.integers(1, 5)))]
                 roots = [g.gen(t, int(rng.integers(2, 6))) for t in out_types]
                 exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(zip(roots, out_types))]
@@ -39,7 +46,7 @@ def child(first, last, what):
                     want = oracle.project(roots, out_types, batch, threads=2)
                     for i, (gv, wv) in enumerate(zip(got, want)):
                         assert_arrays_match(gv, wv, "seed %d n=%d out %d: %s" % (seed, n, i, roots[i]))
-            elif what == "filt":
+            elif what_kind == "filt":
                 cond = g.gen(T.B, int(rng.integers(2, 6)))
                 cfg = gandiva.Configuration(string_scan=4) if seed % 3 == 0 else None
                 f = gandiva.make_filter(T.SCHEMA, b.make_condition(cond), cfg)
@@ -113,11 +120,13 @@ def child(first, last, what):
                 got = f.evaluate(batch).to_array().to_numpy().astype(np.uint64)
                 want = oracle.filter_indices(cond, batch, threads=2)
                 assert np.array_equal(got, want), "seed %d n=%d key_driven=%s: %s" % (seed, n, f.kernel_info.get("key_driven"), cond)
+        except pa.ArrowNotImplementedError:
+            skipped += 1
         except Exception as e:  # noqa: BLE001 - report and go on
             bad += 1
             msg = traceback.format_exc().strip().splitlines()
             print("FAIL %s seed %d: %s" % (what, seed, " | ".join(msg[-3:])[:1500]), flush=True)
-    print("done %s %d..%d: %d failures" % (what, first, last, bad), flush=True)
+    print("done %s %d..%d: %d failures, %d refused at Make()" % (what, first, last, bad, skipped), flush=True)
 
 
 def main():
