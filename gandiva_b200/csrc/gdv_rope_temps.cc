@@ -29,18 +29,16 @@ bool IsRope(const Node& node) {
 
 struct Extractor {
   RopeTemps* out;
-  bool nested = false;   // a rope was found inside a rope that is being materialised
   bool in_temp = false;  // walking the expression of a temp
 
   // `rope_ok`: the parent can read a rope (it is the output root, a concat, or an if/else in such a position)
   NodePtr Walk(const NodePtr& node, bool rope_ok) {
     if (IsRope(*node) && !rope_ok) {
-      if (in_temp) {
-        nested = true;
-        return node;
-      }
+      // a consumer inside the arguments of a rope that is itself being materialised stays where it is: the
+      // internal Projector that evaluates the temp is built the same way and takes care of it (next level)
+      if (in_temp) return node;
       in_temp = true;
-      const NodePtr inner = Walk(node, true);  // consumers inside the rope's own arguments: not supported (nested)
+      const NodePtr inner = Walk(node, true);
       in_temp = false;
       const std::string text = inner->ToString();
       for (size_t k = 0; k < out->temps.size(); ++k)
@@ -95,7 +93,7 @@ struct Extractor {
 bool ExtractRopes(const NodePtr& root, bool root_is_output, RopeTemps* out, NodePtr* rewritten) {
   Extractor x{out};
   *rewritten = x.Walk(root, root_is_output);
-  return !x.nested;
+  return true;
 }
 
 }  // namespace gdv

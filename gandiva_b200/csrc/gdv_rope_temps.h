@@ -26,7 +26,8 @@ bool IsRopeConsumerError(const Status& s);
 
 // Replaces every rope that is read by such a consumer in `root` with a field (`__gdv_rope_<k>`), adding the
 // rope's expression to `out`.  `root_is_output`: a rope AT the root of a projector output stays where it is.
-// Ropes nested inside a materialised rope's own arguments are not supported (one level): returns false then.
+// A consumer inside the arguments of a materialised rope is left in the temp's expression: the internal
+// Projector for the temps is built through the same path, one level of temporaries per nesting level.
 bool ExtractRopes(const NodePtr& root, bool root_is_output, RopeTemps* out, NodePtr* rewritten);
 
 }  // namespace gdv

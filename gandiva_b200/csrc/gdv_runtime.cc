@@ -628,16 +628,22 @@ Status Projector::MakeWithRopeTemps(const SchemaPtr& schema, const std::vector<E
   std::vector<ExpressionPtr> rewritten;
   for (const auto& e : exprs) {
     NodePtr r;
-    if (!ExtractRopes(e->root(), e->result().type.is_varlen(), &rt, &r))
-      return Status::Make(GDV_NOT_IMPLEMENTED, "a rope consumer inside the arguments of another rope");
+    ExtractRopes(e->root(), e->result().type.is_varlen(), &rt, &r);
     rewritten.push_back(std::make_shared<Expression>(r, e->result()));
   }
   if (rt.temps.empty()) return Status::Make(GDV_NOT_IMPLEMENTED, "no rope to materialise");
+  // nesting: the temps' own Projector may need temporaries of its own (a consumer inside a rope's arguments)
+  static thread_local int depth = 0;
+  if (depth >= 8) return Status::Make(GDV_NOT_IMPLEMENTED, "rope consumers nested more than 8 levels deep");
+  struct Level {
+    int& d;
+    explicit Level(int& x) : d(x) { ++d; }
+    ~Level() { --d; }
+  } level(depth);
   std::shared_ptr<Projector> pre, main;
   GDV_RETURN_NOT_OK(Projector::Make(schema, rt.temps, GDV_SEL_NONE, cfg, &pre));
-  if (pre->rope_main_ != nullptr) return Status::Make(GDV_NOT_IMPLEMENTED, "nested rope consumers");
   GDV_RETURN_NOT_OK(Projector::Make(ExtendedSchema(schema, rt), rewritten, selection_mode, cfg, &main));
-  if (main->rope_main_ != nullptr) return Status::Make(GDV_NOT_IMPLEMENTED, "nested rope consumers");
+  if (main->rope_main_ != nullptr) return Status::Make(GDV_NOT_IMPLEMENTED, "rope consumer left after materialisation");
   into->rope_pre_ = std::move(pre);
   into->rope_main_ = std::move(main);
   return Status::OK();
@@ -1145,7 +1151,8 @@ Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
     // something in the condition reads a rope: materialise the ropes first (gdv_rope_temps.h)
     RopeTemps rt;
     NodePtr r;
-    if (!ExtractRopes(cond->root(), false, &rt, &r) || rt.temps.empty()) return st;
+    ExtractRopes(cond->root(), false, &rt, &r);
+    if (rt.temps.empty()) return st;
     std::shared_ptr<Projector> pre;
     std::shared_ptr<Filter> main;
     if (!Projector::Make(schema, rt.temps, GDV_SEL_NONE, cfg, &pre).ok()) return st;

@@ -145,11 +145,18 @@ def test_device_resident_batch_over_ropes(gandiva, oracle):
     assert np.array_equal(out.numpy()[:got_n].astype(np.uint64), want)
 
 
-def test_nested_rope_consumers_are_still_refused(gandiva):
+def test_nested_rope_consumers(gandiva, oracle):
+    """A consumer inside the arguments of a rope that is itself consumed: one level of temporaries per nesting level."""
     b = gandiva.TreeExprBuilder()
     f = {x.name: b.make_field(x) for x in SCHEMA}
     fn = b.make_function
     inner = fn("substr", [fn("reverse", [f["s"]], S), b.make_literal(1, I64), b.make_literal(3, I64)], S)
-    root = fn("like", [fn("concat", [inner, f["u"]], S), b.make_literal("a%", S)], B)
-    with pytest.raises(pa.ArrowNotImplementedError):
-        gandiva.make_projector(SCHEMA, [b.make_expression(root, pa.field("o", B))], None)
+    deeper = fn("upper", [fn("lpad", [fn("substr", [fn("concat", [inner, f["u"]], S), b.make_literal(2, I64)], S),
+                                      b.make_literal(8, I32), b.make_literal("*", S)], S)], S)
+    roots = [(fn("like", [fn("concat", [inner, f["u"]], S), b.make_literal("a%", S)], B), B), (deeper, S)]
+    batch = _batch(2500, seed=77)
+    for root, t in roots:
+        p = gandiva.make_projector(SCHEMA, [b.make_expression(root, pa.field("o", t))], None)
+        assert_arrays_match(p.evaluate(batch)[0], oracle.project([root], [t], batch)[0], str(root))
+    flt = gandiva.make_filter(SCHEMA, b.make_condition(roots[0][0]))
+    assert np.array_equal(flt.evaluate(batch).to_array().to_numpy().astype(np.uint64), oracle.filter_indices(roots[0][0], batch))
