@@ -2192,13 +2192,22 @@ Status GenerateStringKernel(const Schema& schema, const ExpressionPtr& expr, con
     n_varlen += s.type.is_varlen() ? 1 : 0;
     in_bytes += s.type.is_varlen() ? 32 : std::max(s.type.width(), 1);
   }
-  const int R = spec.rows_per_thread > 0 ? std::min(spec.rows_per_thread, 8) : 2;
+  int R = spec.rows_per_thread > 0 ? std::min(spec.rows_per_thread, 8) : 2;
   // String predicates are instruction-bound and stage bytes per warp in shared memory: 512 threads
   // measured best on big batches (profiles/r01_string_filter.md); everything else runs 256.
-  const int BT = spec.block_threads > 0 ? spec.block_threads
-                                        : (spec.kind == KernelKind::kFilter && n_varlen > 0 && spec.large_batch ? 512 : 256);
+  int BT = spec.block_threads > 0 ? spec.block_threads
+                                  : (spec.kind == KernelKind::kFilter && n_varlen > 0 && spec.large_batch ? 512 : 256);
   if (BT % 32 != 0 || BT > 1024)
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
+  {  // many string columns: the per-warp stages of all of them must fit the CTA's shared memory
+    const int hit = gen.coop_segs().empty() ? 0 : 8 * kHitCap + 16;
+    auto need = [&](int r, int bt) { return (48 * 32 * r + hit) * (bt / 32) * n_varlen; };
+    const int kMaxStage = 200 * 1024;
+    while (need(R, BT) > kMaxStage && R > 1) R /= 2;
+    while (need(R, BT) > kMaxStage && BT > 64 && spec.block_threads == 0) BT /= 2;
+    if (need(R, BT) > kMaxStage)
+      return Status::Make(GDV_NOT_IMPLEMENTED, "too many utf8/binary columns for one kernel (" + std::to_string(n_varlen) + ")");
+  }
   const int NW = BT / 32;
   const int T = BT * R;
   const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
@@ -2585,18 +2594,29 @@ Status GenerateKernelImpl(const Schema& schema, const std::vector<ExpressionPtr>
   }
   // String predicates are instruction-bound and stage bytes per warp in shared memory: 512 threads
   // measured best on big batches (profiles/r01_string_filter.md); everything else runs 256.
-  const int BT = spec.block_threads > 0 ? spec.block_threads
-                                        : (spec.kind == KernelKind::kFilter && n_varlen > 0 && spec.large_batch ? 512 : 256);
+  int BT = spec.block_threads > 0 ? spec.block_threads
+                                  : (spec.kind == KernelKind::kFilter && n_varlen > 0 && spec.large_batch ? 512 : 256);
   if (BT % 32 != 0 || BT > 1024)
     return Status::Make(GDV_INVALID, "block_threads must be a multiple of 32 and <= 1024");
 
-  // shared-memory stage for string bytes: 48 B per row of a group, per warp and string column
-  const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
   // Filters copy the string bytes of the NEXT group into a second stage with cp.async while the
   // current group is scanned (per-warp double buffering): the copy costs no registers and its
   // latency is hidden behind the scan instead of behind other warps.
   const bool prefetch = spec.kind == KernelKind::kFilter && n_varlen > 0;
   const int n_stages = prefetch ? 2 : 1;
+  // Many string columns (e.g. a schema extended by materialised ropes, gdv_rope_temps.h): the per-warp stages
+  // of all of them must fit the CTA's shared memory — fewer rows per thread first, then fewer warps per CTA.
+  {
+    const int hit = gen.coop_segs().empty() ? 0 : 8 * kHitCap + 16;
+    auto need = [&](int r, int bt) { return (n_stages * 48 * 32 * r + hit) * (bt / 32) * n_varlen; };
+    const int kMaxStage = 200 * 1024;
+    while (need(R, BT) > kMaxStage && R > 1) R /= 2;
+    while (need(R, BT) > kMaxStage && BT > 64 && spec.block_threads == 0) BT /= 2;
+    if (need(R, BT) > kMaxStage)
+      return Status::Make(GDV_NOT_IMPLEMENTED, "too many utf8/binary columns for one kernel (" + std::to_string(n_varlen) + ")");
+  }
+  // shared-memory stage for string bytes: 48 B per row of a group, per warp and string column
+  const int stage_bytes = n_varlen > 0 ? 48 * 32 * R : 0;
   // fixed-width filters: 1024-row chunks every warp walks per tile (Configuration.stages; 1 unless asked)
   const int W = (spec.kind != KernelKind::kFilter || n_varlen != 0) ? 1
                 : (spec.stages == 1 || spec.stages == 2 || spec.stages == 4 || spec.stages == 8) ? spec.stages
