@@ -767,14 +767,23 @@ static bool AnyValidity(const GeneratedKernel& gen, const gdv_batch_t* batch) {
   return false;
 }
 
+namespace {
+// Source + PTX of one kernel.  NVRTC's PTX text ends with a NUL: dropped, or a char* reader would stop there and
+// lose every kernel after the first one.
+std::string KernelText(const CompiledKernel& k) {
+  std::string ptx = k.ptx;
+  while (!ptx.empty() && ptx.back() == '\0') ptx.pop_back();
+  return k.gen.source + (ptx.empty() ? "" : "\n// ---- PTX ----\n" + ptx);
+}
+}  // namespace
+
 std::string Projector::DumpIR() const {
   if (rope_main_ != nullptr) return rope_pre_->DumpIR() + "\n" + rope_main_->DumpIR();
   std::string ir;
-  if (kernel_ != nullptr)
-    ir += kernel_->gen.source + (kernel_->ptx.empty() ? "" : "\n// ---- PTX ----\n" + kernel_->ptx);
+  if (kernel_ != nullptr) ir += KernelText(*kernel_);
   for (const auto& sk : strings_)
     for (const auto* k : {sk.size[0].get(), sk.write[0].get()})
-      if (k != nullptr) ir += "\n" + k->gen.source + (k->ptx.empty() ? "" : "\n// ---- PTX ----\n" + k->ptx);
+      if (k != nullptr) ir += "\n" + KernelText(*k);
   return ir;
 }
 
@@ -1194,8 +1203,7 @@ std::string Filter::DumpIR() const {
   std::lock_guard<std::mutex> lock(mu_);
   auto it = kernels_.find(GDV_SEL_UINT32 * 4 + 1);
   if (it == kernels_.end()) return "";
-  return it->second->gen.source +
-         (it->second->ptx.empty() ? "" : "\n// ---- PTX ----\n" + it->second->ptx);
+  return KernelText(*it->second);
 }
 
 Status Filter::Evaluate(const gdv_batch_t* batch, gdv_selection_t* out_sel, void* stream_v,

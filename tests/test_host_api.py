@@ -201,32 +201,37 @@ def test_like_scan_kernels_compile(gandiva):
         assert "gdv_likeh_" not in src
 
 
-def test_concat_consumers_are_rejected(gandiva):
-    """concat() results are ropes of views: they can be projected, concatenated again or chosen by
-    if/else; feeding one to another function is a Make()-time error, not a wrong answer."""
+def test_rope_consumers_build_a_two_stage_plan(gandiva):
+    """concat() / repeat / pad / reverse results are ropes of views: projected, concatenated again or chosen by
+    if/else directly; any other consumer makes Make() build a two-stage plan (the rope is materialised into a
+    temporary column first, csrc/gdv_rope_temps.h) instead of failing.  (Results: tests/test_rope_consumers_gpu.py.)"""
     b = gandiva.TreeExprBuilder()
     t = pa.string()
     schema = pa.schema([("s", t), ("u", t)])
+    cfg = gandiva.Configuration(dump_ir=True)
     cc = b.make_function("concat", [cases.F(b, "s", t), cases.F(b, "u", t)], t)
-    bad = b.make_function("hash32", [cc], pa.int32())
-    with pytest.raises(pa.ArrowNotImplementedError, match="concat"):
-        gandiva.make_projector(schema, [b.make_expression(bad, pa.field("r", pa.int32()))], None)
-    # the length functions and the ASCII case maps distribute over the pieces instead
+    p = gandiva.make_projector(schema, [b.make_expression(b.make_function("hash32", [cc], pa.int32()), pa.field("r", pa.int32()))],
+                               None, configuration=cfg)
+    assert "__gdv_rope_0" in p.llvm_ir
+    # the length functions and the ASCII case maps distribute over the pieces instead: no temporary
     for ok_fn, rt in (("octet_length", pa.int32()), ("char_length", pa.int32()), ("upper", t)):
-        gandiva.make_projector(schema, [b.make_expression(b.make_function(ok_fn, [cc], rt), pa.field("r", rt))], None)
+        q = gandiva.make_projector(schema, [b.make_expression(b.make_function(ok_fn, [cc], rt), pa.field("r", rt))], None,
+                                   configuration=cfg)
+        assert "__gdv_rope_" not in q.llvm_ir
     like = b.make_function("like", [cc, b.make_literal("%ab%", t)], pa.bool_())
-    with pytest.raises(pa.ArrowNotImplementedError, match="concat"):
-        gandiva.make_filter(schema, b.make_condition(like))
+    f = gandiva.make_filter(schema, b.make_condition(like), cfg)
+    assert "__gdv_rope_0" in f.llvm_ir
     # replace() needs literal from / to
     with pytest.raises(pa.ArrowNotImplementedError, match="literal"):
         gandiva.make_projector(schema, [b.make_expression(
             b.make_function("replace", [cases.F(b, "s", t), cases.F(b, "u", t), b.make_literal("x", t)], t), pa.field("r", t))], None)
-    # the same holds for the virtual pieces of repeat / space / lpad / rpad / reverse
+    # the virtual pieces of repeat / space / lpad / rpad / reverse go the same way
     for inner in (b.make_function("repeat", [cases.F(b, "s", t), b.make_literal(2, pa.int32())], t),
                   b.make_function("reverse", [cases.F(b, "s", t)], t),
                   b.make_function("lpad", [cases.F(b, "s", t), b.make_literal(9, pa.int32())], t)):
-        with pytest.raises(pa.ArrowNotImplementedError, match="only be projected"):
-            gandiva.make_projector(schema, [b.make_expression(b.make_function("upper", [inner], t), pa.field("r", t))], None)
+        q = gandiva.make_projector(schema, [b.make_expression(b.make_function("upper", [inner], t), pa.field("r", t))], None,
+                                   configuration=cfg)
+        assert "__gdv_rope_0" in q.llvm_ir
 
 
 def test_cubin_cache(gandiva):
