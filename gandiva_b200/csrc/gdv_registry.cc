@@ -378,8 +378,9 @@ Registry::Registry() {
     nvl_types.push_back(BIN);
     for (const auto& t : nvl_types) Add("nvl", {t, t}, t, NullMode::kInternal);
   }
-  // concat: null arguments are empty strings, never null; concatOperator: null if any is null
-  for (int n = 2; n <= 6; ++n) {
+  // concat: null arguments are empty strings, never null; concatOperator: null if any is null.  2..10 arguments
+  // like the reference; a rope holds 8 pieces, wider concats are folded through temporaries (gdv_rope_temps.h)
+  for (int n = 2; n <= 10; ++n) {
     Add("concat", std::vector<DataType>(static_cast<size_t>(n), S), S, NullMode::kNever, kConcat);
     Add("concatOperator", std::vector<DataType>(static_cast<size_t>(n), S), S, NullMode::kIfNull, kConcat);
   }

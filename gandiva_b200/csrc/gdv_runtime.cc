@@ -572,7 +572,10 @@ Status Projector::Make(SchemaPtr schema, std::vector<ExpressionPtr> exprs, int s
   Status st = p->BuildKernels();
   if (!st.ok()) {
     // something other than projection / concat / if-else reads a rope: materialise the ropes first
-    if (!IsRopeConsumerError(st) || !MakeWithRopeTemps(schema, p->exprs_, selection_mode, cfg, p.get()).ok()) return st;
+    if (!IsRopeConsumerError(st)) return st;
+    const Status two_stage = MakeWithRopeTemps(schema, p->exprs_, selection_mode, cfg, p.get());
+    // the plan can still hit another limit of the fuser (e.g. a concat of more than 8 pieces): say that one
+    if (!two_stage.ok()) return IsRopeConsumerError(two_stage) ? st : two_stage;
   }
   *out = std::move(p);
   return Status::OK();
@@ -1164,10 +1167,10 @@ Status Filter::Make(SchemaPtr schema, ConditionPtr cond, const Config& cfg,
     if (rt.temps.empty()) return st;
     std::shared_ptr<Projector> pre;
     std::shared_ptr<Filter> main;
-    if (!Projector::Make(schema, rt.temps, GDV_SEL_NONE, cfg, &pre).ok()) return st;
-    if (!Filter::Make(ExtendedSchema(schema, rt), std::make_shared<Condition>(r), cfg, &main).ok() ||
-        main->rope_main_ != nullptr)
-      return st;
+    Status two_stage = Projector::Make(schema, rt.temps, GDV_SEL_NONE, cfg, &pre);
+    if (two_stage.ok()) two_stage = Filter::Make(ExtendedSchema(schema, rt), std::make_shared<Condition>(r), cfg, &main);
+    if (two_stage.ok() && main->rope_main_ != nullptr) two_stage = st;
+    if (!two_stage.ok()) return IsRopeConsumerError(two_stage) ? st : two_stage;  // another limit of the fuser: say that one
     f->rope_pre_ = std::move(pre);
     f->rope_main_ = std::move(main);
     *out = std::move(f);

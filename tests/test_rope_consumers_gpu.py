@@ -160,3 +160,24 @@ def test_nested_rope_consumers(gandiva, oracle):
         assert_arrays_match(p.evaluate(batch)[0], oracle.project([root], [t], batch)[0], str(root))
     flt = gandiva.make_filter(SCHEMA, b.make_condition(roots[0][0]))
     assert np.array_equal(flt.evaluate(batch).to_array().to_numpy().astype(np.uint64), oracle.filter_indices(roots[0][0], batch))
+
+
+def test_concat_wider_than_one_rope(gandiva, oracle):
+    """A rope holds 8 pieces.  A concat of more arguments (or of ropes that add up to more) reads its widest rope
+    arguments through temporaries, and a concat of more than 8 scalar arguments is folded 8 at a time — the same
+    strings as the oracle's plain left-to-right concatenation, NULL rules of concat / concatOperator included."""
+    b = gandiva.TreeExprBuilder()
+    f = {x.name: b.make_field(x) for x in SCHEMA}
+    fn = b.make_function
+    lit = lambda v, t=S: b.make_literal(v, t)
+    ten = [f["s"], lit("-"), f["u"], lit("+"), f["s"], f["u"], lit("日"), f["s"], lit(""), f["u"]]   # the registry's widest concat
+    nested = fn("concat", [fn("concatOperator", [f["s"], f["u"], f["s"], f["u"], f["s"]], S),
+                           fn("lpad", [f["u"], lit(6, I32), lit("ab")], S), fn("reverse", [f["s"]], S),
+                           fn("concat", [f["u"], lit("/"), f["s"], lit("/"), f["u"]], S), f["s"]], S)
+    roots = [(fn("concat", ten, S), S), (fn("concatOperator", ten, S), S), (nested, S),
+             (fn("char_length", [fn("concat", [fn("concat", ten, S), lit("|"), fn("concatOperator", ten, S)], S)], I32), I32),
+             (fn("like", [fn("concatOperator", ten, S), lit("%a-%")], B), B)]
+    batch = _batch(3000, seed=41, null_prob=0.08)
+    for root, t in roots:
+        p = gandiva.make_projector(SCHEMA, [b.make_expression(root, pa.field("o", t))], None)
+        assert_arrays_match(p.evaluate(batch)[0], oracle.project([root], [t], batch)[0], str(root)[:80])

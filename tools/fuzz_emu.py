@@ -120,8 +120,10 @@ def child(first, last, what):
                 got = f.evaluate(batch).to_array().to_numpy().astype(np.uint64)
                 want = oracle.filter_indices(cond, batch, threads=2)
                 assert np.array_equal(got, want), "seed %d n=%d key_driven=%s: %s" % (seed, n, f.kernel_info.get("key_driven"), cond)
-        except pa.ArrowNotImplementedError:
+        except pa.ArrowNotImplementedError as e:
             skipped += 1
+            if os.environ.get("FUZZ_VERBOSE"):
+                print("refused %s seed %d: %s" % (what, seed, str(e)[:300]), flush=True)
         except Exception as e:  # noqa: BLE001 - report and go on
             bad += 1
             msg = traceback.format_exc().strip().splitlines()
