@@ -985,9 +985,9 @@ def get_registered_function_signatures() -> list:
     for i in range(lib.gdv_registry_size()):
         name = C.c_char_p()
         ret = gdv_type_t()
-        params = (gdv_type_t * 8)()
+        params = (gdv_type_t * 16)()
         n = C.c_int32()
-        _check(lib.gdv_registry_get(i, C.byref(name), C.byref(ret), params, 8, C.byref(n)))
+        _check(lib.gdv_registry_get(i, C.byref(name), C.byref(ret), params, 16, C.byref(n)))
         out.append(FunctionSignature(name.value.decode(), _from_c_type(ret),
                                      [_from_c_type(params[k]) for k in range(n.value)]))
     return out

@@ -681,11 +681,11 @@ std::vector<std::shared_ptr<FunctionSignature>> GetRegisteredFunctionSignatures(
   for (int32_t i = 0; i < n; ++i) {
     const char* name = nullptr;
     gdv_type_t ret;
-    gdv_type_t params[8];
+    gdv_type_t params[16];
     int32_t np = 0;
-    if (gdv_registry_get(i, &name, &ret, params, 8, &np) != GDV_OK) continue;
+    if (gdv_registry_get(i, &name, &ret, params, 16, &np) != GDV_OK) continue;
     DataTypeVector pts;
-    for (int32_t k = 0; k < np && k < 8; ++k) pts.push_back(FromC(params[k]));
+    for (int32_t k = 0; k < np && k < 16; ++k) pts.push_back(FromC(params[k]));
     out.push_back(std::make_shared<FunctionSignature>(name, std::move(pts), FromC(ret)));
   }
   return out;
