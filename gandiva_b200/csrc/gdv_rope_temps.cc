@@ -81,6 +81,8 @@ struct Extractor {
         // 8 arguments is folded from the left, 8 at a time.  Not inside a temp: its own Projector does that.
         if (is_concat && !in_temp && Pieces(*node) > 8) {
           NodeVector args = fn.children();
+          NodeVector orig = fn.children();  // what each argument stands for, over the ORIGINAL schema: the
+                                            // expression of a temp may not name another temp's field
           auto total = [&] {
             int n = 0;
             for (const auto& a : args) n += Pieces(*a);
@@ -92,17 +94,19 @@ struct Extractor {
               if (Pieces(*args[i]) > Pieces(*args[widest])) widest = i;
             if (Pieces(*args[widest]) > 1) {
               in_temp = true;
-              const NodePtr inner = Walk(args[widest], true);
+              const NodePtr inner = Walk(orig[widest], true);
               in_temp = false;
-              args[widest] = Temp(inner, args[widest]->return_type());
+              args[widest] = Temp(inner, orig[widest]->return_type());
             } else {  // every argument is one piece: fold the first eight into one
-              NodeVector head(args.begin(), args.begin() + 8);
+              NodeVector head(orig.begin(), orig.begin() + 8);
               const NodePtr folded = std::make_shared<FunctionNode>(fn.name(), std::move(head), fn.return_type());
               in_temp = true;
               const NodePtr inner = Walk(folded, true);
               in_temp = false;
               args.erase(args.begin(), args.begin() + 8);
               args.insert(args.begin(), Temp(inner, fn.return_type()));
+              orig.erase(orig.begin(), orig.begin() + 8);
+              orig.insert(orig.begin(), folded);
             }
           }
           NodeVector kids;
