@@ -30,6 +30,8 @@ def child(first, last, what):
     else:
         what_kind = what
     for seed in range(first, last):
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("seed %d" % seed, flush=True)
         try:
             rng = np.random.default_rng(77_000 + seed)
             b = gandiva.TreeExprBuilder()
@@ -39,7 +41,7 @@ def child(first, last, what):
                 roots = [g.gen(t, int(rng.integers(2, 6))) for t in out_types]
                 exprs = [b.make_expression(r, pa.field("o%d" % i, t)) for i, (r, t) in enumerate(zip(roots, out_types))]
                 p = gandiva.make_projector(T.SCHEMA, exprs, None)
-                for n in (int(rng.integers(1, 70)), int(rng.integers(1000, 6000))):
+                for n in (int(rng.integers(1, 70)), int(rng.integers(200, 700)) if what == "rope" else int(rng.integers(1000, 6000))):
                     batch = cases.random_batch(T.SCHEMA, n, seed=seed + n, null_prob=float(rng.choice([0.0, 0.12, 0.5])),
                                                offset=int(rng.integers(0, 9)))
                     got = p.evaluate(batch)
@@ -47,10 +49,10 @@ def child(first, last, what):
                     for i, (gv, wv) in enumerate(zip(got, want)):
                         assert_arrays_match(gv, wv, "seed %d n=%d out %d: %s" % (seed, n, i, roots[i]))
             elif what_kind == "filt":
-                cond = g.gen(T.B, int(rng.integers(2, 6)))
+                cond = g.gen(T.B, int(rng.integers(2, 4 if what == "ropefilt" else 6)))   # (deep rope trees: many plan levels)
                 cfg = gandiva.Configuration(string_scan=4) if seed % 3 == 0 else None
                 f = gandiva.make_filter(T.SCHEMA, b.make_condition(cond), cfg)
-                for n in (int(rng.integers(1, 70)), int(rng.integers(2000, 12000))):
+                for n in (int(rng.integers(1, 70)), int(rng.integers(200, 700)) if what == "ropefilt" else int(rng.integers(2000, 12000))):
                     batch = cases.random_batch(T.SCHEMA, n, seed=seed + n, null_prob=float(rng.choice([0.0, 0.12, 0.5])),
                                                offset=int(rng.integers(0, 9)))
                     got = f.evaluate(batch).to_array().to_numpy().astype(np.uint64)
