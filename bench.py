@@ -715,7 +715,10 @@ def main():
     affinity0 = os.sched_getaffinity(0)
     numa_node, numa_cpus = gpu_numa_cpus(torch, dev)
     if numa_cpus and not args.no_numa_bind:
-        os.sched_setaffinity(0, numa_cpus)
+        try:
+            os.sched_setaffinity(0, numa_cpus)
+        except OSError:       # a container that forbids it: run unbound
+            numa_cpus = None
     stream = torch.cuda.Stream(dev)   # a real (non-default) stream: events, kernels and
     torch.cuda.set_stream(stream)     # NCCL ops are all ordered on it
     st = stream.cuda_stream
