@@ -9,7 +9,7 @@ look-back, staging protocols, function semantics) against the oracle without a G
 run of the very same test functions on the B200 box stays the parity gate.
 
 Every `gpu`-marked test runs (about a minute on 8 cores, compiled kernels are cached under
-tests/emu/cache); GDV_EMU_SELECT=<pytest -k expression> narrows it while developing."""
+/tmp/gdv_emu_cache_<uid>, outside the tree); GDV_EMU_SELECT=<pytest -k expression> narrows it while developing."""
 import os
 import subprocess
 import sys
