@@ -660,6 +660,16 @@ TempColumns::~TempColumns() {
 // Runs the pre-projector over `in` (all rows, no selection vector) and appends its utf8 outputs to the batch's
 // columns: in host vectors for a host batch, in pooled device memory for a device batch.  Synchronous.
 Status TempColumns::Build(Projector* pre, const gdv_batch_t* in, void* stream) {
+  if (pre->rope_main() != nullptr) {
+    lower.reset(new TempColumns());
+    GDV_RETURN_NOT_OK(lower->Build(pre->rope_pre(), in, stream));
+    return Run(pre->rope_main(), &lower->batch, in, stream);
+  }
+  return Run(pre, in, in, stream);
+}
+
+// `pre` evaluated over `eval` (which may carry lower-level temporaries); its outputs appended to the columns of `in`.
+Status TempColumns::Run(Projector* pre, const gdv_batch_t* eval, const gdv_batch_t* in, void* stream) {
   const int n_temps = pre->num_outputs();
   const int64_t n = in->num_rows;
   const bool on_host = in->mem_space == GDV_MEM_HOST;
@@ -669,7 +679,7 @@ Status TempColumns::Build(Projector* pre, const gdv_batch_t* in, void* stream) {
   if (!on_host) GDV_RETURN_NOT_OK(Device::Get(pre->config().device, &dev));
   for (int k = 0; k < n_temps; ++k) {
     int64_t bytes = 0;
-    GDV_RETURN_NOT_OK(pre->OutputVarSize(in, nullptr, k, stream, &bytes));
+    GDV_RETURN_NOT_OK(pre->OutputVarSize(eval, nullptr, k, stream, &bytes));
     gdv_out_column_t& o = outs[static_cast<size_t>(k)];
     std::memset(&o, 0, sizeof(o));
     const size_t data_bytes = static_cast<size_t>(bytes) + 16;
@@ -694,7 +704,7 @@ Status TempColumns::Build(Projector* pre, const gdv_batch_t* in, void* stream) {
     }
     o.var_capacity = bytes;
   }
-  GDV_RETURN_NOT_OK(pre->Evaluate(in, nullptr, outs.data(), n_temps, stream, /*async=*/false));
+  GDV_RETURN_NOT_OK(pre->Evaluate(eval, nullptr, outs.data(), n_temps, stream, /*async=*/false));
   for (int k = 0; k < n_temps; ++k) {
     gdv_column_t c;
     std::memset(&c, 0, sizeof(c));

@@ -75,8 +75,14 @@ struct TempColumns {
   std::vector<std::vector<uint8_t>> host;
   Device* dev = nullptr;
   std::vector<CUdeviceptr> device;
+  std::unique_ptr<TempColumns> lower;  // the temporaries `pre` itself reads, when it is a two-stage plan
   ~TempColumns();
+  // batch = `in` + one utf8 column per output of `pre`.  A two-stage `pre` has its own temporaries built ONCE
+  // here (not once per sizing pass and once more for the write pass, which would multiply per nesting level).
   Status Build(Projector* pre, const gdv_batch_t* in, void* stream);
+
+ private:
+  Status Run(Projector* proj, const gdv_batch_t* eval, const gdv_batch_t* in, void* stream);
 };
 
 // RAII list of scratch blocks returned to the pool when the evaluation ends.
@@ -178,6 +184,8 @@ class Projector {
   int num_outputs() const { return static_cast<int>(exprs_.size()); }
   const SchemaPtr& schema() const { return schema_; }
   const std::vector<ExpressionPtr>& expressions() const { return exprs_; }
+  Projector* rope_pre() const { return rope_pre_.get(); }
+  Projector* rope_main() const { return rope_main_.get(); }
 
  private:
   // Consumers of a rope (gdv_rope_temps.h): the ropes are materialised by rope_pre_ into temporary utf8
